@@ -1,0 +1,293 @@
+"""CPU oracle for the D8 flow-network hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+ctypes wrappers around ``oracle/libpfd_oracle.so`` (built from ``pfd_oracle.c`` by ``oracle/Makefile``)
+exposing the reference's L1/L2 function signatures so parity tests read like the reference's own:
+
+    oracle.core_d8.from_array / to_array / isvalid      (pyflwdir/core_d8.py:42-67,86-102,105-122)
+    oracle.core.rank / upstream_count / idxs_seq / fillnodata_upstream / pit_indices
+                                                          (pyflwdir/core.py:17-47,50-61,87-117,120-146,225-232)
+    oracle.streams.accuflux / accuflux_ds / strahler_order (pyflwdir/streams.py:15-41,44-70,228-269)
+    oracle.basins.basins                                 (pyflwdir/basins.py:12-18)
+    oracle.dem.height_above_nearest_drain                (pyflwdir/dem.py:299-330)
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may
+import this package. ``pyflwdir_b200`` never does. Parity of this oracle with the real reference is pinned by
+``tests/golden`` (see ``tests/golden/make_golden.py``).
+"""
+import ctypes as C
+import os
+import subprocess
+import types
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libpfd_oracle.so")
+_lib = None
+
+_SFX = {np.dtype(np.int32): "i32", np.dtype(np.uint32): "u32", np.dtype(np.int64): "i64"}
+_DATA_SFX = {
+    np.dtype(np.int8): "i8",
+    np.dtype(np.uint8): "u8",
+    np.dtype(np.int16): "i16",
+    np.dtype(np.uint16): "u16",
+    np.dtype(np.int32): "i32",
+    np.dtype(np.uint32): "u32",
+    np.dtype(np.int64): "i64",
+    np.dtype(np.float32): "f32",
+    np.dtype(np.float64): "f64",
+}
+
+
+def build(force=False):
+    """Compile the oracle shared library (gcc). Building the checker is not using it."""
+    if force or not os.path.exists(_LIB_PATH):
+        subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []), stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _idx(a):
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.dtype(np.intp) and a.dtype not in _SFX:  # pragma: no cover
+        a = a.astype(np.int64)
+    if a.dtype == np.uint64:
+        # the reference's uint64 fixtures (tests/conftest.py:88-108) -> same values as int64, mv -> -1
+        a = a.astype(np.int64)
+    if a.dtype not in _SFX:
+        raise TypeError(f"unsupported index dtype {a.dtype}")
+    return a, _SFX[a.dtype]
+
+
+def _fn(name, sfx, restype=None):
+    f = getattr(lib(), f"{name}_{sfx}")
+    f.restype = restype
+    return f
+
+
+# ----------------------------------------------------------------------------- core_d8
+def _d8_from_array(flwdir, _mv=np.uint8(247), dtype=np.intp):
+    flwdir = np.ascontiguousarray(flwdir, dtype=np.uint8)
+    nrow, ncol = flwdir.shape
+    dt = np.dtype(dtype)
+    if dt == np.uint64:
+        dt = np.dtype(np.int64)
+    sfx = _SFX[dt]
+    idxs_ds = np.empty(flwdir.size, dtype=dt)
+    pits = np.empty(flwdir.size, dtype=dt)
+    npits = C.c_int64(0)
+    n = _fn("orc_d8_from_array", sfx, C.c_int64)(
+        _p(flwdir), C.c_int64(nrow), C.c_int64(ncol), _p(idxs_ds), _p(pits), C.byref(npits)
+    )
+    out_pits = pits[: npits.value].copy()
+    if np.dtype(dtype) == np.uint64:
+        return idxs_ds.astype(np.uint64), out_pits.astype(np.uint64), int(n)
+    return idxs_ds, out_pits, int(n)
+
+
+def _d8_to_array(idxs_ds, shape, mv=None):
+    a, sfx = _idx(idxs_ds)
+    out = np.empty(a.size, dtype=np.uint8)
+    rc = _fn("orc_d8_to_array", sfx, C.c_int)(_p(a), C.c_int64(a.size), C.c_int64(shape[1]), _p(out))
+    if rc != 0:
+        raise ValueError("Invalid data downstream index outside 8 neighbors.")
+    return out.reshape(shape)
+
+
+def _d8_isvalid(flwdir):
+    if not (isinstance(flwdir, np.ndarray) and flwdir.dtype == np.uint8 and flwdir.ndim == 2):
+        return False
+    f = lib().orc_d8_check_values
+    f.restype = C.c_int
+    a = np.ascontiguousarray(flwdir)
+    return bool(f(_p(a), C.c_int64(a.size)))
+
+
+def _drdc_table():
+    dr = np.empty(256, np.int8)
+    dc = np.empty(256, np.int8)
+    lib().orc_drdc_table(_p(dr), _p(dc))
+    return dr, dc
+
+
+core_d8 = types.SimpleNamespace(
+    from_array=_d8_from_array, to_array=_d8_to_array, isvalid=_d8_isvalid, drdc_table=_drdc_table
+)
+
+
+# ----------------------------------------------------------------------------- core
+def _rank(idxs_ds, mv=None):
+    a, sfx = _idx(idxs_ds)
+    ranks = np.empty(a.size, dtype=np.int32)
+    n = _fn("orc_rank", sfx, C.c_int64)(_p(a), C.c_int64(a.size), _p(ranks))
+    return ranks, int(n)
+
+
+def _upstream_count(idxs_ds, mv=None, mask=None):
+    a, sfx = _idx(idxs_ds)
+    n_up = np.empty(a.size, dtype=np.int8)
+    m = None if mask is None else np.ascontiguousarray(mask).astype(np.uint8)
+    _fn("orc_upstream_count", sfx)(_p(a), C.c_int64(a.size), None if m is None else _p(m), _p(n_up))
+    return n_up
+
+
+def _idxs_seq(idxs_ds, idxs_pit, mv=None):
+    a, sfx = _idx(idxs_ds)
+    pits = np.ascontiguousarray(idxs_pit).astype(a.dtype)
+    seq = np.empty(a.size, dtype=a.dtype)
+    n = _fn("orc_idxs_seq", sfx, C.c_int64)(_p(a), C.c_int64(a.size), _p(pits), C.c_int64(pits.size), _p(seq))
+    out = seq[: int(n)].copy()
+    return out.astype(idxs_ds.dtype) if idxs_ds.dtype != out.dtype else out
+
+
+def _pit_indices(idxs_ds):
+    a, sfx = _idx(idxs_ds)
+    pits = np.empty(a.size, dtype=a.dtype)
+    n = _fn("orc_pit_indices", sfx, C.c_int64)(_p(a), C.c_int64(a.size), _p(pits))
+    return pits[: int(n)].copy()
+
+
+_UINT_OF_SIZE = {1: (np.uint8, "u8", C.c_uint8), 2: (np.uint16, "u16", C.c_uint16),
+                 4: (np.uint32, "u32", C.c_uint32), 8: (np.uint64, "u64", C.c_uint64)}
+
+
+def _fillnodata_upstream(idxs_ds, seq, data, nodata):
+    a, sfx = _idx(idxs_ds)
+    s = np.ascontiguousarray(seq).astype(a.dtype)
+    data = np.ascontiguousarray(data)
+    if data.dtype.kind not in "iub":
+        raise TypeError("oracle fillnodata_upstream: integer data only")
+    udt, tsfx, ctype = _UINT_OF_SIZE[data.dtype.itemsize]
+    nd = np.array([nodata]).astype(data.dtype).view(udt)[0]
+    out = np.empty(data.size, dtype=data.dtype)
+    _fn(f"orc_fillnodata_upstream_{tsfx}", sfx)(
+        _p(a), _p(s), C.c_int64(s.size), _p(data), C.c_int64(data.size), ctype(int(nd)), _p(out)
+    )
+    return out
+
+
+core = types.SimpleNamespace(
+    rank=_rank,
+    upstream_count=_upstream_count,
+    idxs_seq=_idxs_seq,
+    pit_indices=_pit_indices,
+    fillnodata_upstream=_fillnodata_upstream,
+)
+
+
+# ----------------------------------------------------------------------------- streams
+def _nodata_args(nodata):
+    is_int = isinstance(nodata, (int, np.integer)) and not isinstance(nodata, (bool, np.bool_))
+    nd_f = float(nodata)
+    nd_i = int(nodata) if is_int else 0
+    return C.c_double(nd_f), C.c_int64(nd_i), C.c_int(1 if is_int else 0)
+
+
+def _accuflux_impl(idxs_ds, seq, data, nodata, downstream):
+    a, sfx = _idx(idxs_ds)
+    s = np.ascontiguousarray(seq).astype(a.dtype)
+    data = np.ascontiguousarray(data)
+    if data.dtype not in _DATA_SFX:
+        raise TypeError(f"oracle accuflux: unsupported data dtype {data.dtype}")
+    tsfx = _DATA_SFX[data.dtype]
+    out = np.empty(data.size, dtype=data.dtype)
+    nd_f, nd_i, nd_is_int = _nodata_args(nodata)
+    _fn(f"orc_accuflux_{tsfx}", sfx)(
+        _p(a), _p(s), C.c_int64(s.size), _p(data), C.c_int64(data.size), nd_f, nd_i, nd_is_int,
+        C.c_int(downstream), _p(out)
+    )
+    return out
+
+
+def _accuflux(idxs_ds, seq, data, nodata):
+    return _accuflux_impl(idxs_ds, seq, data, nodata, 0)
+
+
+def _accuflux_ds(idxs_ds, seq, data, nodata):
+    return _accuflux_impl(idxs_ds, seq, data, nodata, 1)
+
+
+def _strahler_order(idxs_ds, seq, mask=None):
+    a, sfx = _idx(idxs_ds)
+    s = np.ascontiguousarray(seq).astype(a.dtype)
+    m = None if mask is None else np.ascontiguousarray(mask).astype(np.uint8)
+    out = np.empty(a.size, dtype=np.uint8)
+    _fn("orc_strahler", sfx)(
+        _p(a), _p(s), C.c_int64(s.size), None if m is None else _p(m), C.c_int64(a.size), _p(out)
+    )
+    return out
+
+
+streams = types.SimpleNamespace(accuflux=_accuflux, accuflux_ds=_accuflux_ds, strahler_order=_strahler_order)
+
+
+# ----------------------------------------------------------------------------- basins / dem
+def _basins(idxs_ds, idxs_pit, seq, ids=None):
+    """pyflwdir/basins.py:12-18"""
+    if ids is None:
+        ids = np.arange(1, idxs_pit.size + 1, dtype=np.uint32)
+    b = np.zeros(idxs_ds.size, dtype=ids.dtype)
+    b[idxs_pit] = ids
+    return _fillnodata_upstream(idxs_ds, seq, b, 0)
+
+
+basins = types.SimpleNamespace(basins=_basins)
+
+
+def _hand(idxs_ds, seq, drain, elevtn):
+    a, sfx = _idx(idxs_ds)
+    s = np.ascontiguousarray(seq).astype(a.dtype)
+    d = np.ascontiguousarray(drain).astype(np.uint8)
+    e = np.ascontiguousarray(elevtn)
+    if e.dtype == np.float32:
+        tsfx = "f32"
+    elif e.dtype == np.float64:
+        tsfx = "f64"
+    else:
+        raise TypeError("oracle hand: elevtn must be float32/float64")
+    out = np.empty(a.size, dtype=np.float64)
+    _fn(f"orc_hand_{tsfx}", sfx)(_p(a), _p(s), C.c_int64(s.size), _p(d), _p(e), C.c_int64(a.size), _p(out))
+    return out
+
+
+dem = types.SimpleNamespace(height_above_nearest_drain=_hand)
+
+
+# ----------------------------------------------------------------------------- synthetic input (host)
+def synth_elevation(nrow, ncol, seed=0, octaves=None, nref=None):
+    """Host version of the SURVEY §8(d) generator (bit-identical to the CUDA one)."""
+    if nref is None:
+        nref = 1 << int(np.ceil(np.log2(max(nrow, ncol, 8))))
+    if octaves is None:
+        octaves = max(1, int(np.log2(nref)) - 2)
+    z = np.empty((nrow, ncol), dtype=np.float32)
+    lib().orc_synth_elevation(C.c_int64(nrow), C.c_int64(ncol), C.c_int64(nref), C.c_int(octaves),
+                              C.c_uint32(seed), _p(z))
+    return z
+
+
+def synth_d8(z, sea_level=-np.inf):
+    z = np.ascontiguousarray(z, dtype=np.float32)
+    d8 = np.empty(z.shape, dtype=np.uint8)
+    lib().orc_synth_d8(_p(z), C.c_int64(z.shape[0]), C.c_int64(z.shape[1]), C.c_float(sea_level), _p(d8))
+    return d8
+
+
+def get_idxs_dtype(n):
+    """pyflwdir/pyflwdir.py:105-127"""
+    if n < 2147483647:
+        return np.int32
+    elif n < 4294967294:
+        return np.uint32
+    return np.int64

@@ -1,0 +1,118 @@
+"""Host-side georeferencing helpers needed by the hot path's wrappers.
+
+Only what `FlwdirRaster.upstream_area(unit != "cell")` and `set_transform` touch: an `Affine` value type (the
+`affine` package is not a dependency here), `IDENTITY`, `AREA_FACTORS`, and the per-row cell-area grid.
+Mirrors /root/reference/pyflwdir/gis_utils.py:10-13 (constants), :340-358 (pixel-centre coordinates),
+:379-402 (reggrid_area / area_grid), :405-412 (cellarea). The area grid is an O(nrow) host computation that
+only produces the `data` vector of an accumulation; it stays on the host.
+"""
+import math
+from collections import namedtuple
+
+import numpy as np
+
+_R = 6371e3  # earth radius [m], gis_utils.py:10
+AREA_FACTORS = {"m2": 1.0, "ha": 1e4, "km2": 1e6, "cell": 1}  # gis_utils.py:11
+
+_AffineBase = namedtuple("Affine", "a b c d e f g h i")
+
+
+class Affine(_AffineBase):
+    """2-D affine transform (x, y) = A * (col, row); a 9-tuple like `affine.Affine` (indexable, iterable)."""
+
+    __slots__ = ()
+
+    def __new__(cls, a, b, c, d, e, f, g=0.0, h=0.0, i=1.0):
+        vals = [float(v) for v in (a, b, c, d, e, f)]
+        return super().__new__(cls, *vals, float(g), float(h), float(i))
+
+    @classmethod
+    def identity(cls):
+        return cls(1.0, 0.0, 0.0, 0.0, 1.0, 0.0)
+
+    @classmethod
+    def translation(cls, xoff, yoff):
+        return cls(1.0, 0.0, xoff, 0.0, 1.0, yoff)
+
+    @classmethod
+    def scale(cls, sx, sy=None):
+        return cls(sx, 0.0, 0.0, 0.0, sx if sy is None else sy, 0.0)
+
+    @property
+    def xoff(self):
+        return self.c
+
+    @property
+    def yoff(self):
+        return self.f
+
+    def __mul__(self, other):
+        if isinstance(other, Affine):
+            return Affine(
+                self.a * other.a + self.b * other.d,
+                self.a * other.b + self.b * other.e,
+                self.a * other.c + self.b * other.f + self.c,
+                self.d * other.a + self.e * other.d,
+                self.d * other.b + self.e * other.e,
+                self.d * other.c + self.e * other.f + self.f,
+            )
+        x, y = other
+        return (x * self.a + y * self.b + self.c, x * self.d + y * self.e + self.f)
+
+    def __invert__(self):
+        det = self.a * self.e - self.b * self.d
+        if det == 0:
+            raise ValueError("Affine transform is not invertible")
+        ia, ib, id_, ie = self.e / det, -self.b / det, -self.d / det, self.a / det
+        return Affine(ia, ib, -self.c * ia - self.f * ib, id_, ie, -self.c * id_ - self.f * ie)
+
+
+# N->S oriented identity, gis_utils.py:13
+IDENTITY = Affine(1.0, 0.0, 0.0, 0.0, -1.0, 0.0)
+
+
+def affine_to_coords(affine, shape):
+    """Pixel-centre x (per column) and y (per row) coordinates; gis_utils.py:340-358."""
+    height, width = shape
+    xs, _ = affine * (np.arange(width) + 0.5, np.zeros(width) + 0.5)
+    _, ys = affine * (np.zeros(height) + 0.5, np.arange(height) + 0.5)
+    return xs, ys
+
+
+def cellarea(lat, xres, yres):
+    """Area [m2] of a (xres x yres) degree cell centred at latitude `lat`; gis_utils.py:405-412.
+
+    The reference evaluates this inside numba (libm `sin`); `math.sin` is the same libm call, whereas numpy's
+    vectorised `np.sin` may differ in the last bit, so rows are evaluated one by one."""
+    lat = np.atleast_1d(np.asarray(lat, dtype=np.float64))
+    out = np.empty(lat.shape, dtype=np.float64)
+    half = abs(yres) / 2.0
+    dx = math.radians(abs(xres))
+    for k, la in enumerate(lat.tolist()):
+        l1 = math.radians(la - half)
+        l2 = math.radians(la + half)
+        out[k] = _R**2 * dx * (math.sin(l2) - math.sin(l1))
+    return out
+
+
+def reggrid_area(lats, lons):
+    """Cell-area grid [m2] of a regular lat/lon grid; gis_utils.py:379-385 (float64 result)."""
+    xres = np.abs(np.mean(np.diff(lons)))
+    yres = np.abs(np.mean(np.diff(lats)))
+    ones = np.ones((lats.size, lons.size), dtype=np.float32)
+    return cellarea(lats, xres, yres)[:, None] * ones
+
+
+def area_grid(transform, shape, latlon=False, unit="m2"):
+    """Regular grid of cell areas; gis_utils.py:388-402 (int32 ones for "cell", float64 if latlon, else float32)."""
+    unit = str(unit).lower()
+    if unit not in AREA_FACTORS:
+        fstr = '", "'.join(AREA_FACTORS.keys())
+        raise ValueError(f'Unknown unit: {unit}, select from "{fstr}".')
+    if unit == "cell":
+        return np.ones(shape, dtype=np.int32)
+    if latlon:
+        lon, lat = affine_to_coords(transform, shape)
+        return reggrid_area(lat, lon) / AREA_FACTORS[unit]
+    area0 = abs(transform[0] * transform[4]) / AREA_FACTORS[unit]
+    return np.full(shape, area0, dtype=np.float32)

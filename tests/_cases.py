@@ -1,0 +1,142 @@
+"""Shared helpers for the parity tests: golden fixtures (generated from the real reference by
+tests/golden/make_golden.py) and the deterministic auxiliary inputs of every case."""
+import hashlib
+import json
+import os
+
+import numpy as np
+
+import oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden")
+
+RHINE_TRANSFORM = (0.008333333333325754, 0.0, 3.5666666664997138, 0.0, -0.008333333333339965, 52.00833333330708)
+
+SMALL_CASES = ["flwdir_asc", "flwdir1_asc", "loop3x3", "random48x61", "synth96x130"]
+HASH_CASES = ["rhine", "synth512x768"]
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def case_inputs(name, d8, seed):
+    """Deterministic auxiliary inputs for a case (identical in make_golden.py and in the tests)."""
+    rng = np.random.default_rng(seed)
+    shape = d8.shape
+    data_f32 = rng.random(shape, dtype=np.float32) * np.float32(10.0)
+    data_f64 = rng.random(shape) * 1e3
+    holes = rng.random(shape) < 0.01
+    data_f32_nd = np.where(holes, np.float32(-9999.0), data_f32)
+    data_i64 = rng.integers(-50, 1000, size=shape, dtype=np.int64)
+    elevtn = (oracle.synth_elevation(shape[0], shape[1], seed=seed + 7) * np.float32(1000.0)).astype(np.float32)
+    smask = rng.random(shape) < 0.6
+    return dict(data_f32=data_f32, data_f64=data_f64, data_f32_nd=data_f32_nd, data_i64=data_i64,
+                elevtn=elevtn, smask=smask)
+
+
+_small = None
+_hashes = None
+
+
+def small():
+    global _small
+    if _small is None:
+        _small = dict(np.load(os.path.join(GOLDEN, "small_cases.npz")))
+    return _small
+
+
+def hashes():
+    global _hashes
+    if _hashes is None:
+        with open(os.path.join(GOLDEN, "hashes.json")) as f:
+            _hashes = json.load(f)
+    return _hashes["cases"]
+
+
+def case_d8(name):
+    if name in SMALL_CASES:
+        return small()[f"in/{name}/d8"]
+    if name == "rhine":
+        return np.load(os.path.join(GOLDEN, "rhine_d8.npz"))["d8"]
+    if name == "synth512x768":
+        h = hashes()[name]
+        z = oracle.synth_elevation(512, 768, seed=h["_synth_seed"])
+        d8 = oracle.synth_d8(z, sea_level=h["_sea_level"])
+        assert sha(d8) == h["_d8"], "synthetic generator drifted from the golden input"
+        return d8
+    raise KeyError(name)
+
+
+def case_seed(name):
+    return hashes()[name]["_seed"]
+
+
+def golden(name, key):
+    """Full golden array for small cases, else None (hash-only)."""
+    return small().get(f"out/{name}/{key}")
+
+
+def check(name, key, arr):
+    """Assert `arr` equals the reference output `key` of case `name` bit for bit."""
+    arr = np.asarray(arr)
+    g = golden(name, key)
+    if g is not None:
+        assert arr.dtype == g.dtype, f"{name}/{key}: dtype {arr.dtype} != {g.dtype}"
+        assert arr.shape == g.shape, f"{name}/{key}: shape {arr.shape} != {g.shape}"
+        if not np.array_equal(arr, g, equal_nan=True):
+            bad = np.flatnonzero(arr.ravel() != g.ravel())
+            raise AssertionError(f"{name}/{key}: {bad.size} mismatches, first at {bad[:5]}: "
+                                 f"{arr.ravel()[bad[:5]]} != {g.ravel()[bad[:5]]}")
+    assert sha(arr) == hashes()[name][key], f"{name}/{key}: SHA-256 differs from the reference's"
+
+
+def run_oracle_case(d8, aux, area=None):
+    """The whole hot path on the CPU oracle, mirroring make_golden.run_case (which runs the real reference).
+    `area` = flat cell-area vector [m2] for upstream_area("km2") (host-side input, see gis_utils.area_grid)."""
+    o = oracle
+    shape = d8.shape
+    dtype = o.get_idxs_dtype(d8.size)
+    idxs_ds, idxs_pit, n = o.core_d8.from_array(d8, dtype=dtype)
+    out = {}
+    out["idxs_ds"] = idxs_ds
+    out["idxs_pit"] = idxs_pit
+    out["idxs_outlet"] = idxs_pit[np.isin(d8.flat[idxs_pit], [0, 255])]
+    rank, nn = o.core.rank(idxs_ds)
+    out["rank"] = rank.reshape(shape)
+    seq = o.core.idxs_seq(idxs_ds, idxs_pit)
+    out["idxs_seq"] = seq
+    out["nnodes"] = np.int64(seq.size)
+    out["isvalid"] = np.bool_(np.all(rank != -1))
+    out["n_upstream"] = o.core.upstream_count(idxs_ds).reshape(shape)
+    mask = idxs_ds != idxs_ds.dtype.type(-1)
+
+    def uparea(a):
+        u = o.streams.accuflux(idxs_ds, seq, a, -9999)
+        u[~mask] = -9999
+        return u.reshape(shape)
+
+    out["uparea_cell"] = uparea(np.ones(d8.size, dtype=np.int32))
+    if area is not None:
+        out["uparea_km2"] = uparea(area / 1e6)
+    out["basins"] = o.basins.basins(idxs_ds, idxs_pit, seq).reshape(shape)
+    out["strord"] = o.streams.strahler_order(idxs_ds, seq).reshape(shape)
+    out["strord_mask"] = o.streams.strahler_order(idxs_ds, seq, mask=aux["smask"].ravel()).reshape(shape)
+    out["accu_f32"] = o.streams.accuflux(idxs_ds, seq, aux["data_f32"].ravel(), -9999).reshape(shape)
+    out["accu_f64"] = o.streams.accuflux(idxs_ds, seq, aux["data_f64"].ravel(), -9999.0).reshape(shape)
+    out["accu_f32_nd"] = o.streams.accuflux(idxs_ds, seq, aux["data_f32_nd"].ravel(), -9999).reshape(shape)
+    out["accu_i64"] = o.streams.accuflux(idxs_ds, seq, aux["data_i64"].ravel(), -9999).reshape(shape)
+    out["accu_ds_f64"] = o.streams.accuflux_ds(idxs_ds, seq, aux["data_f64"].ravel(), -9999.0).reshape(shape)
+    out["accu_ds_i64"] = o.streams.accuflux_ds(idxs_ds, seq, aux["data_i64"].ravel(), -9999).reshape(shape)
+    drain = out["uparea_cell"] > max(4, int(0.002 * d8.size))
+    out["hand_f32"] = o.dem.height_above_nearest_drain(idxs_ds, seq, drain.ravel(), aux["elevtn"].ravel()).reshape(shape)
+    out["hand_f64"] = o.dem.height_above_nearest_drain(
+        idxs_ds, seq, drain.ravel(), (aux["elevtn"].astype(np.float64) * 1.1).ravel()).reshape(shape)
+    sub_idxs = seq[:: max(1, seq.size // 23)][:40]
+    sub_ids = (np.arange(sub_idxs.size, dtype=np.int64) * 3 + 5).astype(np.int32)
+    out["sub_idxs"] = sub_idxs
+    out["sub_ids"] = sub_ids
+    out["basins_sub"] = o.basins.basins(idxs_ds, sub_idxs, seq, sub_ids).reshape(shape)
+    out["to_array"] = o.core_d8.to_array(idxs_ds, shape)
+    return out

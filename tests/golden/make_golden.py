@@ -1,0 +1,160 @@
+"""Generate the golden vectors under tests/golden/ by running the REAL reference (Deltares/pyflwdir v0.5.12,
+numba) in the build container, where it is mounted read-only at /root/reference.
+
+    python tests/golden/make_golden.py
+
+Outputs (committed):
+    tests/golden/small_cases.npz   inputs + full reference outputs for the small rasters
+    tests/golden/rhine_d8.npz      the 682x997 D8 raster of examples/rhine_d8.tif (input data only)
+    tests/golden/hashes.json       SHA-256 of every reference output (all cases), plus scalars
+
+The reference cannot travel to the GPU box; these files can. Nothing here is product code.
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import reference  # noqa: E402
+import oracle  # noqa: E402
+
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from _cases import RHINE_TRANSFORM, case_inputs, sha  # noqa: E402
+
+
+def run_case(pf, name, d8, seed, transform=None, latlon=False, dtype_override=None):
+    """Returns dict of reference outputs for one D8 raster."""
+    kw = {}
+    if transform is not None:
+        kw = dict(transform=transform, latlon=latlon)
+    flw = pf.from_array(d8, ftype="d8", cache=False, **kw)
+    aux = case_inputs(name, d8, seed)
+    out = {}
+    out["idxs_ds"] = flw.idxs_ds
+    out["idxs_pit"] = flw.idxs_pit
+    out["idxs_outlet"] = flw.idxs_outlet
+    out["rank"] = flw.rank
+    out["idxs_seq"] = flw.idxs_seq
+    out["nnodes"] = np.int64(flw.nnodes)
+    out["isvalid"] = np.bool_(flw.isvalid)
+    out["n_upstream"] = flw.n_upstream
+    out["uparea_cell"] = flw.upstream_area()
+    out["uparea_km2"] = flw.upstream_area("km2")
+    out["basins"] = flw.basins()
+    out["strord"] = flw.stream_order()
+    out["strord_mask"] = flw.stream_order(mask=aux["smask"])
+    out["accu_f32"] = flw.accuflux(aux["data_f32"], nodata=-9999)
+    out["accu_f64"] = flw.accuflux(aux["data_f64"], nodata=-9999.0)
+    out["accu_f32_nd"] = flw.accuflux(aux["data_f32_nd"], nodata=-9999)
+    out["accu_i64"] = flw.accuflux(aux["data_i64"], nodata=-9999)
+    out["accu_ds_f64"] = flw.accuflux(aux["data_f64"], nodata=-9999.0, direction="down")
+    out["accu_ds_i64"] = flw.accuflux(aux["data_i64"], nodata=-9999, direction="down")
+    drain = out["uparea_cell"] > max(4, int(0.002 * d8.size))
+    out["hand_f32"] = flw.hand(drain, aux["elevtn"])
+    out["hand_f64"] = flw.hand(drain, aux["elevtn"].astype(np.float64) * 1.1)
+    # sub-basins from custom outlets with custom ids (every 37th cell of the sequence)
+    seq = flw.idxs_seq
+    sub_idxs = seq[:: max(1, seq.size // 23)][:40]
+    sub_ids = (np.arange(sub_idxs.size, dtype=np.int64) * 3 + 5).astype(np.int32)
+    out["sub_idxs"] = sub_idxs
+    out["sub_ids"] = sub_ids
+    out["basins_sub"] = flw.basins(idxs=sub_idxs, ids=sub_ids)
+    out["to_array"] = flw.to_array()
+    return out, aux
+
+
+def main():
+    pf = reference.load()
+    import pyflwdir.core as rcore  # noqa: F401
+
+    small_inputs = {}
+    small_outputs = {}
+    hashes = {"reference_version": pf.__version__, "cases": {}}
+
+    # --- the reference's own test rasters (tests/data/*.asc, tests/conftest.py:18-20,116-124)
+    d8_small = np.loadtxt(os.path.join(reference.REFERENCE_ROOT, "tests/data/flwdir.asc"), dtype=np.uint8)
+    d8_large = np.loadtxt(os.path.join(reference.REFERENCE_ROOT, "tests/data/flwdir1.asc"), dtype=np.uint8)
+    # --- hand-made loop KAT
+    d8_loop = np.array([[1, 16, 4], [1, 4, 4], [247, 0, 16]], dtype=np.uint8)
+    # --- random legal codes: many loops, forced pits at the border and next to nodata
+    rng = np.random.default_rng(4242)
+    legal = np.array([32, 64, 128, 16, 0, 1, 8, 4, 2, 247, 255], dtype=np.uint8)
+    p = np.array([1, 1, 1, 1, 0.1, 1, 1, 1, 1, 0.4, 0.1])
+    d8_rand = legal[rng.choice(legal.size, size=(48, 61), p=p / p.sum())]
+    # --- synthetic terrain with a "sea" (nodata) from the repo's own generator
+    z = oracle.synth_elevation(96, 130, seed=11)
+    d8_syn = oracle.synth_d8(z, sea_level=float(np.quantile(z, 0.08)))
+
+    cases = {
+        "flwdir_asc": (d8_small, 1),
+        "flwdir1_asc": (d8_large, 2),
+        "loop3x3": (d8_loop, 3),
+        "random48x61": (d8_rand, 4),
+        "synth96x130": (d8_syn, 5),
+    }
+    for name, (d8, seed) in cases.items():
+        out, _ = run_case(pf, name, d8, seed)
+        small_inputs[f"{name}/d8"] = d8
+        for k, v in out.items():
+            small_outputs[f"{name}/{k}"] = np.asarray(v)
+        hashes["cases"][name] = {k: sha(np.asarray(v)) for k, v in out.items()}
+        hashes["cases"][name]["_shape"] = list(d8.shape)
+        hashes["cases"][name]["_seed"] = seed
+
+    # --- index dtypes: the reference's fixtures parse with uint32 / uint64 (tests/conftest.py:23-26,88-108)
+    import pyflwdir.core_d8 as rd8
+    for dt in (np.uint32, np.int64):
+        ids, pits, n = rd8.from_array(d8_small, dtype=dt)
+        small_outputs[f"flwdir_asc/idxs_ds_{np.dtype(dt).name}"] = ids
+        small_outputs[f"flwdir_asc/idxs_pit_{np.dtype(dt).name}"] = pits
+
+    # --- drdc over all 256 codes (core_d8.py:22-39), including the illegal ones
+    drdc = np.array([rd8.drdc(np.uint8(i)) for i in range(256)], dtype=np.int8)
+    small_outputs["drdc_table"] = drdc
+
+    # --- rhine (config 1 of BASELINE.json): hashes only + the input raster
+    from PIL import Image
+
+    rhine = np.array(Image.open(os.path.join(reference.REFERENCE_ROOT, "examples/rhine_d8.tif")))
+    out, aux = run_case(pf, "rhine", rhine, 6, transform=RHINE_TRANSFORM, latlon=True)
+    hashes["cases"]["rhine"] = {k: sha(np.asarray(v)) for k, v in out.items()}
+    hashes["cases"]["rhine"]["_shape"] = list(rhine.shape)
+    hashes["cases"]["rhine"]["_seed"] = 6
+    hashes["cases"]["rhine"]["_transform"] = list(RHINE_TRANSFORM)
+    hashes["cases"]["rhine"]["_max_rank"] = int(out["rank"].max())
+    hashes["cases"]["rhine"]["_max_uparea_km2"] = float(out["uparea_km2"].max())
+    hashes["cases"]["rhine"]["_strord_hist"] = np.bincount(out["strord"].ravel(), minlength=10).tolist()
+    hashes["cases"]["rhine"]["_aux"] = {k: sha(v) for k, v in aux.items()}
+    # area grid rows (input of upstream_area("km2")), to pin the host-side cellarea restatement
+    small_outputs["rhine/area_col0"] = np.asarray(
+        pf.from_array(rhine, ftype="d8", transform=RHINE_TRANSFORM, latlon=True).area[:, 0]
+    )
+
+    # --- a mid-size synthetic (512 x 768, with sea): hashes only, input regenerated in the tests
+    z = oracle.synth_elevation(512, 768, seed=21)
+    sea = float(np.quantile(z, 0.05))
+    d8_mid = oracle.synth_d8(z, sea_level=sea)
+    out, aux = run_case(pf, "synth512x768", d8_mid, 8)
+    hashes["cases"]["synth512x768"] = {k: sha(np.asarray(v)) for k, v in out.items()}
+    hashes["cases"]["synth512x768"].update(
+        {"_shape": [512, 768], "_seed": 8, "_synth_seed": 21, "_sea_level": sea, "_d8": sha(d8_mid),
+         "_max_rank": int(out["rank"].max()), "_npits": int(out["idxs_pit"].size),
+         "_aux": {k: sha(v) for k, v in aux.items()}}
+    )
+
+    np.savez_compressed(os.path.join(HERE, "small_cases.npz"), **{f"in/{k}": v for k, v in small_inputs.items()},
+                        **{f"out/{k}": v for k, v in small_outputs.items()})
+    np.savez_compressed(os.path.join(HERE, "rhine_d8.npz"), d8=rhine)
+    with open(os.path.join(HERE, "hashes.json"), "w") as f:
+        json.dump(hashes, f, indent=1, sort_keys=True)
+    print("wrote", os.listdir(HERE))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,96 @@
+"""CPU tests: the C oracle (oracle/pfd_oracle.c) against the golden vectors that tests/golden/make_golden.py
+generated from the REAL reference (numba) -- this is what pins the oracle. When /root/reference is mounted
+(build container) the oracle is additionally checked against the live reference on fresh random inputs."""
+import numpy as np
+import pytest
+
+import _cases as cs
+import oracle
+from oracle import reference
+
+
+@pytest.mark.parametrize("name", cs.SMALL_CASES + ["synth512x768"])
+def test_oracle_matches_reference_golden(name, oracle_lib):
+    d8 = cs.case_d8(name)
+    aux = cs.case_inputs(name, d8, cs.case_seed(name))
+    out = cs.run_oracle_case(d8, aux, area=np.ones(d8.size, dtype=np.float32))
+    for key, val in out.items():
+        cs.check(name, key, val)
+
+
+def test_oracle_rhine_golden(oracle_lib):
+    from pyflwdir_b200 import gis_utils
+
+    d8 = cs.case_d8("rhine")
+    aux = cs.case_inputs("rhine", d8, cs.case_seed("rhine"))
+    for k, v in aux.items():
+        assert cs.sha(v) == cs.hashes()["rhine"]["_aux"][k], f"aux input {k} drifted"
+    area = gis_utils.area_grid(gis_utils.Affine(*cs.RHINE_TRANSFORM), d8.shape, latlon=True)
+    assert np.array_equal(area[:, 0], cs.small()["out/rhine/area_col0"])
+    out = cs.run_oracle_case(d8, aux, area=area.ravel())
+    for key, val in out.items():
+        cs.check("rhine", key, val)
+    assert int(out["rank"].max()) == cs.hashes()["rhine"]["_max_rank"] == 1674
+
+
+def test_oracle_drdc_table(oracle_lib):
+    dr, dc = oracle.core_d8.drdc_table()
+    g = cs.small()["out/drdc_table"]
+    assert np.array_equal(dr, g[:, 0]) and np.array_equal(dc, g[:, 1])
+
+
+@pytest.mark.parametrize("dt", [np.uint32, np.int64])
+def test_oracle_index_dtypes(dt, oracle_lib):
+    d8 = cs.case_d8("flwdir_asc")
+    ids, pits, n = oracle.core_d8.from_array(d8, dtype=dt)
+    name = np.dtype(dt).name
+    assert np.array_equal(ids, cs.small()[f"out/flwdir_asc/idxs_ds_{name}"]) and ids.dtype == dt
+    assert np.array_equal(pits, cs.small()[f"out/flwdir_asc/idxs_pit_{name}"])
+    assert n == 407
+
+
+def test_loop_kat(oracle_lib):
+    """SURVEY.md §8c hand-made 3x3 raster with a 2-cell loop."""
+    d8 = np.array([[1, 16, 4], [1, 4, 4], [247, 0, 16]], dtype=np.uint8)
+    ids, pits, n = oracle.core_d8.from_array(d8, dtype=np.int32)
+    assert ids.tolist() == [1, 0, 5, 4, 7, 8, -1, 7, 7] and pits.tolist() == [7] and n == 8
+    rank, nn = oracle.core.rank(ids)
+    assert rank.tolist() == [-1, -1, 3, 2, 1, 2, -9999, 0, 1] and nn == 6
+    seq = oracle.core.idxs_seq(ids, pits)
+    assert seq.tolist() == [7, 4, 8, 3, 5, 2]
+    upa = oracle.streams.accuflux(ids, seq, np.ones(9, np.int32), -9999)
+    assert upa.tolist() == [1, 1, 1, 1, 2, 2, 1, 6, 3]
+    assert oracle.basins.basins(ids, pits, seq).tolist() == [0, 0, 1, 1, 1, 1, 0, 1, 1]
+    assert oracle.streams.strahler_order(ids, seq).tolist() == [0, 0, 1, 1, 1, 1, 0, 2, 1]
+    assert oracle.core.upstream_count(ids).tolist() == [1, 1, 0, 0, 1, 1, -9, 2, 1]
+    hand = oracle.dem.height_above_nearest_drain(ids, seq, np.zeros(9, bool), np.arange(9, dtype=np.float32))
+    assert hand.tolist() == [-9999, -9999, -5, -4, -3, -2, -9999, 0, 1]
+
+
+@pytest.mark.skipif(not reference.available(), reason="reference not mounted (GPU box)")
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_oracle_vs_live_reference(seed, oracle_lib):
+    """Fresh random rasters (legal codes, loops, nodata) through the real numba reference and the oracle."""
+    pf = reference.load()
+    rng = np.random.default_rng(100 + seed)
+    if seed == 0:
+        legal = np.array([32, 64, 128, 16, 0, 1, 8, 4, 2, 247, 255], dtype=np.uint8)
+        d8 = legal[rng.integers(0, legal.size, size=(37, 53))]
+    else:
+        z = oracle.synth_elevation(150 + 13 * seed, 211, seed=50 + seed)
+        d8 = oracle.synth_d8(z, sea_level=float(np.quantile(z, 0.1)))
+    aux = cs.case_inputs("live", d8, 77 + seed)
+    flw = pf.from_array(d8, ftype="d8", cache=False)
+    out = cs.run_oracle_case(d8, aux)
+    assert np.array_equal(out["idxs_ds"], flw.idxs_ds) and out["idxs_ds"].dtype == flw.idxs_ds.dtype
+    assert np.array_equal(out["idxs_pit"], flw.idxs_pit)
+    assert np.array_equal(out["rank"], flw.rank)
+    assert np.array_equal(out["idxs_seq"], flw.idxs_seq)
+    assert np.array_equal(out["uparea_cell"], flw.upstream_area())
+    assert np.array_equal(out["basins"], flw.basins())
+    assert np.array_equal(out["strord"], flw.stream_order())
+    assert np.array_equal(out["strord_mask"], flw.stream_order(mask=aux["smask"]))
+    assert np.array_equal(out["accu_f32_nd"], flw.accuflux(aux["data_f32_nd"], nodata=-9999))
+    assert np.array_equal(out["accu_f64"], flw.accuflux(aux["data_f64"], nodata=-9999.0))
+    drain = out["uparea_cell"] > max(4, int(0.002 * d8.size))
+    assert np.array_equal(out["hand_f32"], flw.hand(drain, aux["elevtn"]))
