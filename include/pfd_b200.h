@@ -1,0 +1,171 @@
+/*
+ * pfd_b200.h -- C ABI of libpfd_b200.so: the B200 (sm_100a) implementation of pyflwdir's D8 flow-network
+ * hot path (parse -> order -> accumulate / delineate / stream order / HAND).
+ *
+ * The reference (Deltares/pyflwdir v0.5.12) has no FFI: its seam is the Python call boundary between the L3
+ * object API and the L1/L2 numba kernels. Each entry point below replaces one of those numba
+ * kernels; the reference interface it stands in for is cited as (file:line) relative to /root/reference.
+ * INTEGRATION.md shows the ctypes binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes only. Every array argument may be a HOST pointer (pageable or pinned) or a
+ *    DEVICE pointer of the handle's device; the library detects which (cudaPointerGetAttributes) and stages
+ *    host buffers itself. Outputs are written in full; calls are synchronous on return.
+ *  - return value: 0 = PFD_OK, otherwise a pfd_status code; pfd_last_error(h) has the message. There is NO
+ *    CPU fallback: without a usable CUDA device every compute call fails with PFD_ERR_CUDA.
+ *  - one handle = one raster on one GPU (owns its device buffers and a CUDA stream). Calls on different
+ *    handles are independent; calls on one handle must not overlap.
+ *  - cell indices are row-major linear indices, exactly the reference's `idxs_ds` convention
+ *    (pit: idxs_ds[i]==i, nodata: idxs_ds[i]==mv with mv=-1 / 0xFFFFFFFF; pyflwdir/core.py:12,
+ *    pyflwdir/flwdir.py:112-117).
+ */
+#ifndef PFD_B200_H
+#define PFD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pfd_handle pfd_handle;
+
+typedef enum pfd_status {
+    PFD_OK = 0,
+    PFD_ERR_CUDA = 1,        /* CUDA runtime / driver error (includes "no device") */
+    PFD_ERR_INVALID_ARG = 2, /* bad pointer, size, dtype or flag */
+    PFD_ERR_INVALID_D8 = 3,  /* raster holds a value outside core_d8._all (pyflwdir/core_d8.py:19) */
+    PFD_ERR_NO_PITS = 4,     /* "Invalid FlwdirRaster: no pits found" (pyflwdir/flwdir.py:126-127) */
+    PFD_ERR_STATE = 5,       /* call sequence error (e.g. sweep before parse) */
+    PFD_ERR_UNSUPPORTED = 6, /* e.g. more than 2^32 cells, downstream index outside the 8 neighbours */
+    PFD_ERR_OOM = 7,         /* device or pinned-host allocation failed */
+    PFD_ERR_NCCL = 8         /* NCCL failure in the multi-GPU path */
+} pfd_status;
+
+/* element types of caller arrays */
+typedef enum pfd_dtype {
+    PFD_I8 = 0, PFD_U8 = 1, PFD_I16 = 2, PFD_U16 = 3, PFD_I32 = 4, PFD_U32 = 5,
+    PFD_I64 = 6, PFD_U64 = 7, PFD_F32 = 8, PFD_F64 = 9
+} pfd_dtype;
+
+/* which cached array pfd_fetch copies out */
+typedef enum pfd_array {
+    PFD_ARR_IDXS_DS = 0,   /* idx dtype, N          -- core_d8.from_array()[0]      */
+    PFD_ARR_PITS = 1,      /* idx dtype, n_pits     -- core_d8.from_array()[1] / core.pit_indices */
+    PFD_ARR_PIT_IS_OUTLET = 2, /* uint8, n_pits: 1 where the pit's D8 code is 0/255 (pyflwdir.py:193) */
+    PFD_ARR_SEQ = 3,       /* idx dtype, nnodes     -- core.idxs_seq ("walk")        */
+    PFD_ARR_RANK = 4,      /* int32, N              -- core.rank()[0]                */
+    PFD_ARR_N_UPSTREAM = 5,/* int8, N               -- core.upstream_count           */
+    PFD_ARR_D8 = 6,        /* uint8, N              -- core_d8.to_array              */
+    PFD_ARR_LEVEL_OFFSETS = 7 /* int64, nlevels+1: start of every rank level inside SEQ */
+} pfd_array;
+
+/* ---- library / device ------------------------------------------------------------------------------- */
+const char* pfd_version(void);
+int pfd_device_count(void);                       /* 0 when no CUDA device is usable */
+const char* pfd_status_string(int status);
+
+/* ---- handle ------------------------------------------------------------------------------------------ */
+int pfd_create(int device, pfd_handle** out);
+void pfd_destroy(pfd_handle* h);
+const char* pfd_last_error(const pfd_handle* h);  /* message of the last failing call on h (h may be NULL) */
+
+/* Pinned host memory + device memory for callers that want resident / zero-staging buffers. */
+int pfd_host_alloc(size_t bytes, void** out);
+int pfd_host_free(void* p);
+int pfd_dev_alloc(pfd_handle* h, size_t bytes, void** out);
+int pfd_dev_free(pfd_handle* h, void* p);
+int pfd_memcpy(pfd_handle* h, void* dst, const void* src, size_t bytes); /* any direction, synchronous */
+int pfd_synchronize(pfd_handle* h);
+
+/* ---- parse ------------------------------------------------------------------------------------------- */
+/*
+ * Replaces core_d8.from_array (pyflwdir/core_d8.py:42-67) + core_d8.isvalid/check_values (:105-122), as
+ * called from pyflwdir.from_array (pyflwdir/pyflwdir.py:183-193).
+ *   d8          : nrow x ncol uint8, C-contiguous (host or device)
+ *   check_values: !=0 -> fail with PFD_ERR_INVALID_D8 if a value is not one of the 11 legal codes. Illegal
+ *                 codes are refused even when 0 (the reference would silently mis-parse them).
+ *   idxs_ds_out : optional (may be NULL). If given, the downstream-index array is ALSO written here in
+ *                 `idx_dtype` (PFD_I32 / PFD_U32 / PFD_I64) by the same kernel that parses the raster.
+ *   n_valid / n_pits / n_outlets : counts of non-nodata cells, pits, pits whose code is 0/255.
+ * The handle keeps the parsed flow graph on the device (1 B direction + 1 B upstream mask per cell).
+ */
+int pfd_d8_parse(pfd_handle* h, const uint8_t* d8, int64_t nrow, int64_t ncol, int check_values,
+                 void* idxs_ds_out, int idx_dtype, int64_t* n_valid, int64_t* n_pits, int64_t* n_outlets);
+
+/*
+ * Constructor path FlwdirRaster(idxs_ds, shape, "d8", ...) (pyflwdir/pyflwdir.py:211-273): load a graph from
+ * a downstream-index array whose links all stay inside the 8-neighbourhood.
+ */
+int pfd_load_idxs_ds(pfd_handle* h, const void* idxs_ds, int idx_dtype, int64_t nrow, int64_t ncol,
+                     int64_t* n_valid, int64_t* n_pits);
+
+/* ---- order -------------------------------------------------------------------------------------------- */
+/*
+ * Replaces core.idxs_seq (pyflwdir/core.py:87-117, incl. upstream_matrix :67-84) and core.rank (:17-47):
+ * a level-synchronous BFS from the pits that reproduces the reference's "walk" sequence exactly and yields
+ * rank (= level) on the way. Idempotent; every sweep calls it implicitly.
+ *   nnodes  : number of cells that drain to a pit (= seq.size = #(rank >= 0))
+ *   nlevels : max rank + 1
+ */
+int pfd_order(pfd_handle* h, int64_t* nnodes, int64_t* nlevels);
+
+/* Copy a cached array out (host or device destination). idx_dtype is used for the index-typed arrays. */
+int pfd_fetch(pfd_handle* h, int which, void* out, int idx_dtype);
+
+/* ---- sweeps ------------------------------------------------------------------------------------------ */
+/*
+ * streams.accuflux / accuflux_ds (pyflwdir/streams.py:15-41, 44-70) over the "walk" sequence.
+ *   data, out : N elements of `dtype`; nodata compared as numba does (integer vs integer as int64, anything
+ *               with a float as float64): pass both representations + is_int.
+ *   direction : 0 = "up" (accumulate upstream values), 1 = "down".
+ * Bit-exact for floats: a cell pulls its upstream neighbours in descending linear index.
+ */
+int pfd_accuflux(pfd_handle* h, const void* data, int dtype, double nodata_f, int64_t nodata_i,
+                 int nodata_is_int, int direction, void* out);
+
+/* FlwdirRaster.upstream_area(unit="cell") (pyflwdir/pyflwdir.py:770-801): int32 cell counts, -9999 on nodata. */
+int pfd_upstream_area_cells(pfd_handle* h, int32_t* out);
+
+/*
+ * basins.basins (pyflwdir/basins.py:12-18) -> core.fillnodata_upstream (pyflwdir/core.py:120-146).
+ *   outlets == NULL : all pits, ids 1..n_pits (uint32) -- `ids`/`ids_dtype` ignored, out is uint32.
+ *   else            : n_outlets linear indices (idx_dtype) with ids of `ids_dtype` (any 1/2/4/8-byte integer).
+ */
+int pfd_basins(pfd_handle* h, const void* outlets, int64_t n_outlets, int idx_dtype, const void* ids,
+               int ids_dtype, void* out);
+
+/* streams.strahler_order (pyflwdir/streams.py:228-269); mask may be NULL, else N bytes (non-zero = stream). */
+int pfd_strahler(pfd_handle* h, const uint8_t* mask, uint8_t* out);
+
+/*
+ * dem.height_above_nearest_drain (pyflwdir/dem.py:299-330): drain = N bytes (==1 marks a drain cell), elevtn
+ * = N values of PFD_F32 or PFD_F64; out = N float64, -9999.0 outside the sequence.
+ */
+int pfd_hand(pfd_handle* h, const uint8_t* drain, const void* elevtn, int elev_dtype, double* out);
+
+/* ---- fused headline pass ------------------------------------------------------------------------------ */
+/*
+ * parse + order + rank + upstream_area(cell) + basins() in one call (BASELINE.json metric). Any output may be
+ * NULL. Equivalent to pfd_d8_parse + pfd_order + pfd_fetch(RANK) + pfd_upstream_area_cells + pfd_basins(NULL).
+ */
+int pfd_d8_flow_all(pfd_handle* h, const uint8_t* d8, int64_t nrow, int64_t ncol, void* idxs_ds_out,
+                    int idx_dtype, int32_t* rank_out, int32_t* uparea_out, uint32_t* basins_out,
+                    int64_t* n_valid, int64_t* n_pits, int64_t* nnodes);
+
+/* ---- synthetic input (bench / tests) ---------------------------------------------------- */
+/* z: nrow*ncol float32 (device or host) elevation; d8 from z by strict steepest descent. */
+int pfd_synth_elevation(pfd_handle* h, int64_t nrow, int64_t ncol, int64_t nref, int octaves, uint32_t seed,
+                        float* z_out);
+int pfd_synth_d8(pfd_handle* h, const float* z, int64_t nrow, int64_t ncol, float sea_level, uint8_t* d8_out);
+
+/* ---- instrumentation ---------------------------------------------------------------------------------- */
+/* kernels launched by this handle since creation (bench.py's gpu_launches) */
+int64_t pfd_launch_count(const pfd_handle* h);
+/* device time [ms] of the most recent call's kernels by stage: 0 parse, 1 pits, 2 order, 3 sweep, 4 total */
+double pfd_last_stage_ms(const pfd_handle* h, int stage);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFD_B200_H */

@@ -1,1 +1,14 @@
-"""pyflwdir_b200 -- B200-native D8 flow-network hot path behind pyflwdir's from_array / FlwdirRaster API."""
+"""pyflwdir_b200 -- B200-native (sm_100a CUDA) implementation of pyflwdir's D8 flow-network hot path behind the
+reference's own `from_array` / `FlwdirRaster` API.
+
+Host code is plain Python + numpy calling hand-written CUDA through a C ABI (ctypes, `include/pfd_b200.h`); no
+PyTorch, no Triton, no CPU fallback: without the built `libpfd_b200.so` and a CUDA device every compute call
+raises. See DESIGN.md for the kernels and INTEGRATION.md for the drop-in boundary.
+"""
+from . import gis_utils
+from .gis_utils import Affine
+from .pyflwdir import FlwdirRaster, from_array, _get_idxs_dtype
+from .flwdir import Flwdir
+
+__version__ = "0.1.0"
+__all__ = ["FlwdirRaster", "Flwdir", "from_array", "gis_utils", "Affine"]

@@ -1,0 +1,192 @@
+"""DeviceGraph: one D8 raster resident on one GPU (thin object wrapper over the C ABI handle)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+_IDX_DTYPES = (np.dtype(np.int32), np.dtype(np.uint32), np.dtype(np.int64), np.dtype(np.uint64))
+
+
+def nodata_args(nodata):
+    """(float64 value, int64 value, is_int) -- numba compares int data with an int nodata as int64 and
+    everything else as float64 (pyflwdir/streams.py:39 under numba typing)."""
+    is_int = isinstance(nodata, (int, np.integer)) and not isinstance(nodata, (bool, np.bool_))
+    nd_f = float(nodata)
+    nd_i = int(nodata) if is_int else 0
+    if is_int and not (-(2**63) <= nd_i < 2**63):
+        is_int, nd_i = False, 0
+    return C.c_double(nd_f), C.c_int64(nd_i), C.c_int(1 if is_int else 0)
+
+
+class DeviceGraph:
+    def __init__(self, device=0):
+        self._l = _lib.lib()
+        h = C.c_void_p()
+        _lib.check(self._l.pfd_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self.shape = None
+        self.size = 0
+        self.n_valid = self.n_pits = self.n_outlets = 0
+        self.nnodes = None
+        self.nlevels = None
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            self._l.pfd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, status):
+        _lib.check(status, self._h)
+
+    # -- parse
+    def parse_d8(self, d8, idx_dtype=None, want_idxs=False):
+        """core_d8.from_array on the device. `d8`: 2-D uint8 array (host) -> optional idxs_ds (host)."""
+        d8 = np.ascontiguousarray(d8, dtype=np.uint8)
+        nrow, ncol = d8.shape
+        nv, npit, nout = C.c_int64(), C.c_int64(), C.c_int64()
+        idxs = None
+        code = 0
+        if want_idxs:
+            idxs = np.empty(d8.size, dtype=idx_dtype)
+            code = _lib.dtype_code(idx_dtype)
+        self._ck(self._l.pfd_d8_parse(self._h, _lib.ptr(d8), nrow, ncol, 1, _lib.ptr(idxs), code,
+                                      C.byref(nv), C.byref(npit), C.byref(nout)))
+        self._set_shape(nrow, ncol, nv.value, npit.value, nout.value)
+        return idxs
+
+    def load_idxs_ds(self, idxs_ds, shape):
+        idxs_ds = np.ascontiguousarray(idxs_ds)
+        if idxs_ds.dtype not in _IDX_DTYPES:
+            raise TypeError(f"idxs_ds dtype {idxs_ds.dtype} not supported")
+        nv, npit = C.c_int64(), C.c_int64()
+        self._ck(self._l.pfd_load_idxs_ds(self._h, _lib.ptr(idxs_ds), _lib.dtype_code(idxs_ds.dtype), int(shape[0]),
+                                          int(shape[1]), C.byref(nv), C.byref(npit)))
+        self._set_shape(int(shape[0]), int(shape[1]), nv.value, npit.value, 0)
+
+    def _set_shape(self, nrow, ncol, nv, npit, nout):
+        self.shape = (nrow, ncol)
+        self.size = nrow * ncol
+        self.n_valid, self.n_pits, self.n_outlets = nv, npit, nout
+        self.nnodes = self.nlevels = None
+
+    # -- order
+    def order(self):
+        nn, nl = C.c_int64(), C.c_int64()
+        self._ck(self._l.pfd_order(self._h, C.byref(nn), C.byref(nl)))
+        self.nnodes, self.nlevels = nn.value, nl.value
+        return self.nnodes, self.nlevels
+
+    def fetch(self, which, idx_dtype=np.int32):
+        code = 0
+        if which == _lib.ARR_IDXS_DS:
+            out = np.empty(self.size, dtype=idx_dtype)
+            code = _lib.dtype_code(idx_dtype)
+        elif which == _lib.ARR_PITS:
+            out = np.empty(self.n_pits, dtype=idx_dtype)
+            code = _lib.dtype_code(idx_dtype)
+        elif which == _lib.ARR_PIT_IS_OUTLET:
+            out = np.empty(self.n_pits, dtype=np.uint8)
+        elif which == _lib.ARR_SEQ:
+            if self.nnodes is None:
+                self.order()
+            out = np.empty(self.nnodes, dtype=idx_dtype)
+            code = _lib.dtype_code(idx_dtype)
+        elif which == _lib.ARR_RANK:
+            out = np.empty(self.size, dtype=np.int32)
+        elif which == _lib.ARR_N_UPSTREAM:
+            out = np.empty(self.size, dtype=np.int8)
+        elif which == _lib.ARR_D8:
+            out = np.empty(self.size, dtype=np.uint8)
+        elif which == _lib.ARR_LEVEL_OFFSETS:
+            if self.nlevels is None:
+                self.order()
+            out = np.empty(self.nlevels + 1, dtype=np.int64)
+        else:
+            raise ValueError(which)
+        if out.size or which in (_lib.ARR_SEQ, _lib.ARR_LEVEL_OFFSETS):
+            self._ck(self._l.pfd_fetch(self._h, which, _lib.ptr(out) if out.size else _lib.ptr(np.empty(1, out.dtype)), code))
+        if which in (_lib.ARR_SEQ, _lib.ARR_RANK) and self.nnodes is None:
+            self.order()
+        return out
+
+    # -- sweeps (flat host arrays in, flat host arrays out)
+    def accuflux(self, data, nodata, direction="up"):
+        data = np.ascontiguousarray(data)
+        if data.size != self.size:
+            raise ValueError('"data" size does not match.')
+        dt = data.dtype
+        if dt == np.bool_:
+            raise TypeError("accuflux: boolean data is not supported")
+        out = np.empty(data.size, dtype=dt)
+        nd_f, nd_i, nd_is = nodata_args(nodata)
+        self._ck(self._l.pfd_accuflux(self._h, _lib.ptr(data), _lib.dtype_code(dt), nd_f, nd_i, nd_is,
+                                      0 if direction == "up" else 1, _lib.ptr(out)))
+        return out
+
+    def upstream_area_cells(self):
+        out = np.empty(self.size, dtype=np.int32)
+        self._ck(self._l.pfd_upstream_area_cells(self._h, _lib.ptr(out)))
+        return out
+
+    def basins(self, idxs=None, ids=None):
+        if idxs is None:
+            out = np.empty(self.size, dtype=np.uint32)
+            self._ck(self._l.pfd_basins(self._h, None, 0, 0, None, 0, _lib.ptr(out)))
+            return out
+        idxs = np.ascontiguousarray(idxs)
+        if idxs.dtype not in _IDX_DTYPES:
+            idxs = idxs.astype(np.int64)
+        ids = np.ascontiguousarray(ids)
+        if ids.dtype.kind not in "iu":
+            raise TypeError("basin ids must be integers")
+        # numpy fancy assignment keeps the LAST id of duplicated outlets (basins.py:17): dedupe on the host
+        if idxs.size > 1:
+            norm = np.where(idxs.astype(np.int64) < 0, idxs.astype(np.int64) + self.size, idxs.astype(np.int64))
+            _, last = np.unique(norm[::-1], return_index=True)
+            if last.size != idxs.size:
+                keep = np.sort(idxs.size - 1 - last)
+                idxs, ids = np.ascontiguousarray(idxs[keep]), np.ascontiguousarray(ids[keep])
+        out = np.empty(self.size, dtype=ids.dtype)
+        self._ck(self._l.pfd_basins(self._h, _lib.ptr(idxs), idxs.size, _lib.dtype_code(idxs.dtype), _lib.ptr(ids),
+                                    _lib.dtype_code(ids.dtype), _lib.ptr(out)))
+        return out
+
+    def strahler(self, mask=None):
+        m = None
+        if mask is not None:
+            m = np.ascontiguousarray(mask)
+            m = m.view(np.uint8) if m.dtype == np.bool_ else (m != 0).astype(np.uint8)
+            if m.size != self.size:
+                raise ValueError('"mask" size does not match.')
+        out = np.empty(self.size, dtype=np.uint8)
+        self._ck(self._l.pfd_strahler(self._h, _lib.ptr(m), _lib.ptr(out)))
+        return out
+
+    def hand(self, drain, elevtn):
+        d = np.ascontiguousarray(drain)
+        d = d.view(np.uint8) if d.dtype == np.bool_ else (d == 1).astype(np.uint8)
+        e = np.ascontiguousarray(elevtn)
+        if e.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+            e = e.astype(np.float64)  # integer DEMs: differences are exact in float64
+        if d.size != self.size or e.size != self.size:
+            raise ValueError('"elevtn" size does not match.')
+        out = np.empty(self.size, dtype=np.float64)
+        self._ck(self._l.pfd_hand(self._h, _lib.ptr(d), _lib.ptr(e), _lib.dtype_code(e.dtype), _lib.ptr(out)))
+        return out
+
+    # -- instrumentation
+    @property
+    def launches(self):
+        return int(self._l.pfd_launch_count(self._h))
+
+    def stage_ms(self, stage):
+        return float(self._l.pfd_last_stage_ms(self._h, stage))

@@ -1,0 +1,153 @@
+"""ctypes binding of libpfd_b200.so (C ABI declared in include/pfd_b200.h).
+
+There is no CPU fallback: if the shared library has not been built, or no CUDA device is usable, every compute
+entry point raises. Build with ``python -c "import __graft_entry__ as g; g.build()"`` or
+``make -C pyflwdir_b200/csrc``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpfd_b200.so")
+
+# pfd_status
+OK, ERR_CUDA, ERR_INVALID_ARG, ERR_INVALID_D8, ERR_NO_PITS, ERR_STATE, ERR_UNSUPPORTED, ERR_OOM, ERR_NCCL = range(9)
+
+# pfd_dtype
+DTYPES = {
+    np.dtype(np.int8): 0, np.dtype(np.uint8): 1, np.dtype(np.int16): 2, np.dtype(np.uint16): 3,
+    np.dtype(np.int32): 4, np.dtype(np.uint32): 5, np.dtype(np.int64): 6, np.dtype(np.uint64): 7,
+    np.dtype(np.float32): 8, np.dtype(np.float64): 9,
+}
+
+# pfd_array
+ARR_IDXS_DS, ARR_PITS, ARR_PIT_IS_OUTLET, ARR_SEQ, ARR_RANK, ARR_N_UPSTREAM, ARR_D8, ARR_LEVEL_OFFSETS = range(8)
+
+# every symbol include/pfd_b200.h declares: name -> (restype, argtypes)
+_vp, _i64, _int, _u32 = C.c_void_p, C.c_int64, C.c_int, C.c_uint32
+_pi64 = C.POINTER(C.c_int64)
+SYMBOLS = {
+    "pfd_version": (C.c_char_p, []),
+    "pfd_device_count": (_int, []),
+    "pfd_status_string": (C.c_char_p, [_int]),
+    "pfd_create": (_int, [_int, C.POINTER(_vp)]),
+    "pfd_destroy": (None, [_vp]),
+    "pfd_last_error": (C.c_char_p, [_vp]),
+    "pfd_host_alloc": (_int, [C.c_size_t, C.POINTER(_vp)]),
+    "pfd_host_free": (_int, [_vp]),
+    "pfd_dev_alloc": (_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
+    "pfd_dev_free": (_int, [_vp, _vp]),
+    "pfd_memcpy": (_int, [_vp, _vp, _vp, C.c_size_t]),
+    "pfd_synchronize": (_int, [_vp]),
+    "pfd_d8_parse": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _int, _pi64, _pi64, _pi64]),
+    "pfd_load_idxs_ds": (_int, [_vp, _vp, _int, _i64, _i64, _pi64, _pi64]),
+    "pfd_order": (_int, [_vp, _pi64, _pi64]),
+    "pfd_fetch": (_int, [_vp, _int, _vp, _int]),
+    "pfd_accuflux": (_int, [_vp, _vp, _int, C.c_double, _i64, _int, _int, _vp]),
+    "pfd_upstream_area_cells": (_int, [_vp, _vp]),
+    "pfd_basins": (_int, [_vp, _vp, _i64, _int, _vp, _int, _vp]),
+    "pfd_strahler": (_int, [_vp, _vp, _vp]),
+    "pfd_hand": (_int, [_vp, _vp, _vp, _int, _vp]),
+    "pfd_d8_flow_all": (_int, [_vp, _vp, _i64, _i64, _vp, _int, _vp, _vp, _vp, _pi64, _pi64, _pi64]),
+    "pfd_synth_elevation": (_int, [_vp, _i64, _i64, _i64, _int, _u32, _vp]),
+    "pfd_synth_d8": (_int, [_vp, _vp, _i64, _i64, C.c_float, _vp]),
+    "pfd_launch_count": (_i64, [_vp]),
+    "pfd_last_stage_ms": (C.c_double, [_vp, _int]),
+}
+
+_lib = None
+
+
+class PfdError(RuntimeError):
+    """Failure inside libpfd_b200 that is not a user-input error (CUDA, OOM, state)."""
+
+    def __init__(self, status, message):
+        super().__init__(f"libpfd_b200 [{status}]: {message}")
+        self.status = status
+
+
+def lib():
+    """Load the CUDA library; raises ImportError loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: the CUDA extension has not been built and pyflwdir_b200 has no CPU "
+                "fallback. Run `make -C pyflwdir_b200/csrc` (or __graft_entry__.build())."
+            )
+        handle = C.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SYMBOLS.items():
+            fn = getattr(handle, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def device_count():
+    return int(lib().pfd_device_count())
+
+
+def check(status, handle=None):
+    """Map a pfd_status to the exception type the reference raises for the same condition."""
+    if status == OK:
+        return
+    msg = lib().pfd_last_error(handle)
+    msg = msg.decode() if msg else lib().pfd_status_string(status).decode()
+    if status in (ERR_INVALID_ARG, ERR_INVALID_D8, ERR_NO_PITS, ERR_UNSUPPORTED):
+        err = ValueError(msg)
+        err.status = status
+        raise err
+    if status == ERR_OOM:
+        raise MemoryError(msg)
+    raise PfdError(status, msg)
+
+
+def ptr(a):
+    """void* of a numpy array (must be C-contiguous) or of a raw device/pinned address (int)."""
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return C.c_void_p(int(a))
+    if isinstance(a, C.c_void_p):
+        return a
+    if not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("array must be C-contiguous")
+    return C.c_void_p(a.ctypes.data)
+
+
+def dtype_code(dt):
+    dt = np.dtype(dt)
+    if dt == np.bool_:
+        return DTYPES[np.dtype(np.uint8)]
+    if dt not in DTYPES:
+        raise TypeError(f"unsupported dtype {dt} (supported: {[str(k) for k in DTYPES]})")
+    return DTYPES[dt]
+
+
+class PinnedArray:
+    """numpy view over page-locked host memory from pfd_host_alloc (fast, truly asynchronous H2D / D2H)."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(np.atleast_1d(shape).tolist())
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        check(lib().pfd_host_alloc(max(nbytes, 1), C.byref(p)))
+        self._p = p
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self._p is not None:
+            self.array = None
+            lib().pfd_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

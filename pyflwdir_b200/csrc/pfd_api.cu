@@ -1,0 +1,886 @@
+// pfd_api.cu -- extern "C" entry points of libpfd_b200.so (see include/pfd_b200.h for the contract).
+#include "pfd_common.cuh"
+#include "pfd_order.cuh"
+#include "pfd_parse.cuh"
+#include "pfd_sweeps.cuh"
+#include "pfd_synth.h"
+
+#include <algorithm>
+#include <cmath>
+#include <new>
+
+#define PFD_VERSION "0.1.0"
+#define MAX_CELLS (1ll << 32)
+
+// ---------------------------------------------------------------------------------------------------------
+// small utilities
+// ---------------------------------------------------------------------------------------------------------
+struct StageTimer {
+    pfd_handle* h;
+    int stage;
+    StageTimer(pfd_handle* h_, int s) : h(h_), stage(s) { cudaEventRecord(h->ev_start[s], h->stream); h->stage_used[s] = true; }
+    ~StageTimer() { cudaEventRecord(h->ev_stop[stage], h->stream); }
+};
+
+static void stage_reset(pfd_handle* h) {
+    for (int s = 0; s < PFD_NSTAGE; ++s) h->stage_used[s] = false;
+}
+
+// call after the stream is synchronised
+static void stage_collect(pfd_handle* h) {
+    for (int s = 0; s < PFD_NSTAGE; ++s) {
+        if (!h->stage_used[s]) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev_start[s], h->ev_stop[s]) == cudaSuccess) h->stage_ms[s] = ms;
+        else cudaGetLastError();
+    }
+}
+
+static int grid_for(int64_t n, int threads, int per_thread = 1, int64_t cap = 1 << 20) {
+    int64_t g = (n + (int64_t)threads * per_thread - 1) / ((int64_t)threads * per_thread);
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (int)g;
+}
+
+static int check_handle(pfd_handle* h) {
+    if (!h) return pfd_fail(nullptr, PFD_ERR_INVALID_ARG, "null handle");
+    PFD_CUDA(h, cudaSetDevice(h->device));
+    return PFD_OK;
+}
+
+template <typename IDX>
+__global__ void widen_cells_kernel(const cell_t* __restrict__ in, int64_t n, IDX* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (IDX)in[i];
+}
+
+template <typename IDX>
+__global__ void narrow_cells_kernel(const IDX* __restrict__ in, int64_t n, cell_t* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (cell_t)in[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// library / handle
+// ---------------------------------------------------------------------------------------------------------
+extern "C" const char* pfd_version(void) { return PFD_VERSION " (sm_100a)"; }
+
+extern "C" int pfd_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" const char* pfd_status_string(int s) {
+    switch (s) {
+    case PFD_OK: return "ok";
+    case PFD_ERR_CUDA: return "CUDA error";
+    case PFD_ERR_INVALID_ARG: return "invalid argument";
+    case PFD_ERR_INVALID_D8: return "invalid D8 data";
+    case PFD_ERR_NO_PITS: return "no pits found";
+    case PFD_ERR_STATE: return "invalid call sequence";
+    case PFD_ERR_UNSUPPORTED: return "unsupported";
+    case PFD_ERR_OOM: return "out of memory";
+    case PFD_ERR_NCCL: return "NCCL error";
+    default: return "unknown";
+    }
+}
+
+extern "C" const char* pfd_last_error(const pfd_handle* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+extern "C" int pfd_create(int device, pfd_handle** out) {
+    if (!out) return pfd_fail(nullptr, PFD_ERR_INVALID_ARG, "pfd_create: out is null");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return pfd_fail(nullptr, PFD_ERR_CUDA,
+                        std::string("pfd_create: no usable CUDA device (") + cudaGetErrorString(e) +
+                            "); libpfd_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return pfd_fail(nullptr, PFD_ERR_INVALID_ARG, "pfd_create: bad device ordinal");
+    pfd_handle* h = new (std::nothrow) pfd_handle();
+    if (!h) return pfd_fail(nullptr, PFD_ERR_OOM, "pfd_create: host allocation failed");
+    h->device = device;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        std::string msg = std::string("pfd_create: ") + cudaGetErrorString(cudaGetLastError());
+        delete h;
+        return pfd_fail(nullptr, PFD_ERR_CUDA, msg);
+    }
+    h->num_sms = prop.multiProcessorCount;
+    if (!prop.cooperativeLaunch) {
+        cudaStreamDestroy(h->stream);
+        delete h;
+        return pfd_fail(nullptr, PFD_ERR_UNSUPPORTED, "pfd_create: device lacks cooperative launch");
+    }
+    for (int s = 0; s < PFD_NSTAGE; ++s) {
+        cudaEventCreate(&h->ev_start[s]);
+        cudaEventCreate(&h->ev_stop[s]);
+    }
+    *out = h;
+    return PFD_OK;
+}
+
+extern "C" void pfd_destroy(pfd_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf* bufs[] = {&h->dir, &h->upmask, &h->pits, &h->pit_outlet, &h->seq, &h->bseq, &h->rank, &h->basins,
+                      &h->level_off, &h->bfs_state, &h->chunk_status, &h->blk_counts, &h->blk_offsets, &h->counters,
+                      &h->segs};
+    for (DevBuf* b : bufs) pfd_release(*b);
+    for (DevBuf& b : h->scratch) pfd_release(b);
+    for (int s = 0; s < PFD_NSTAGE; ++s) {
+        cudaEventDestroy(h->ev_start[s]);
+        cudaEventDestroy(h->ev_stop[s]);
+    }
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int pfd_host_alloc(size_t bytes, void** out) {
+    if (!out) return PFD_ERR_INVALID_ARG;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return pfd_fail(nullptr, PFD_ERR_OOM, std::string("pfd_host_alloc: ") + cudaGetErrorString(e));
+    }
+    return PFD_OK;
+}
+
+extern "C" int pfd_host_free(void* p) {
+    if (p && cudaFreeHost(p) != cudaSuccess) {
+        cudaGetLastError();
+        return PFD_ERR_CUDA;
+    }
+    return PFD_OK;
+}
+
+extern "C" int pfd_dev_alloc(pfd_handle* h, size_t bytes, void** out) {
+    PFD_TRY(check_handle(h));
+    if (!out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_dev_alloc: out is null");
+    PFD_CUDA(h, cudaMalloc(out, bytes ? bytes : 16));
+    return PFD_OK;
+}
+
+extern "C" int pfd_dev_free(pfd_handle* h, void* p) {
+    PFD_TRY(check_handle(h));
+    if (p) PFD_CUDA(h, cudaFree(p));
+    return PFD_OK;
+}
+
+extern "C" int pfd_memcpy(pfd_handle* h, void* dst, const void* src, size_t bytes) {
+    PFD_TRY(check_handle(h));
+    PFD_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, h->stream));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    return PFD_OK;
+}
+
+extern "C" int pfd_synchronize(pfd_handle* h) {
+    PFD_TRY(check_handle(h));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    return PFD_OK;
+}
+
+extern "C" int64_t pfd_launch_count(const pfd_handle* h) { return h ? h->launches : 0; }
+
+extern "C" double pfd_last_stage_ms(const pfd_handle* h, int stage) {
+    if (!h || stage < 0 || stage >= PFD_NSTAGE) return 0.0;
+    return h->stage_ms[stage];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// parse
+// ---------------------------------------------------------------------------------------------------------
+static void invalidate(pfd_handle* h) {
+    h->parsed = h->ordered = h->have_rank = h->have_basins = false;
+    h->n_valid = h->n_pits = h->n_outlets = h->nnodes = h->nlevels = 0;
+}
+
+// d8_dev: device pointer. idxs_dev: device pointer or null.
+static int parse_device(pfd_handle* h, const uint8_t* d8_dev, int64_t nrow, int64_t ncol, void* idxs_dev, int idx_dtype) {
+    const int64_t n = nrow * ncol;
+    const int64_t npad = (n + PC_CHUNK - 1) / PC_CHUNK * PC_CHUNK;
+    PFD_TRY(pfd_reserve(h, h->dir, (size_t)npad));
+    PFD_TRY(pfd_reserve(h, h->upmask, (size_t)npad));
+    PFD_TRY(pfd_reserve(h, h->counters, 8 * sizeof(unsigned long long)));
+    PFD_CUDA(h, cudaMemsetAsync(h->counters.p, 0, 8 * sizeof(unsigned long long), h->stream));
+    if (npad > n) PFD_CUDA(h, cudaMemsetAsync((uint8_t*)h->dir.p + n, 0xFF, (size_t)(npad - n), h->stream));
+    unsigned int* flag = reinterpret_cast<unsigned int*>((unsigned long long*)h->counters.p + 3);
+    {
+        StageTimer t(h, PFD_STAGE_PARSE);
+        dim3 grid((unsigned)((ncol + PT_W - 1) / PT_W), (unsigned)((nrow + PT_H - 1) / PT_H));
+        if (grid.y > 65535u) return pfd_fail(h, PFD_ERR_UNSUPPORTED, "pfd_d8_parse: more than 2097120 rows");
+        const int idxmode = !idxs_dev ? 0 : (idx_dtype == PFD_I64 ? 2 : 1);
+        const bool aligned = (ncol % 4 == 0) && ((uintptr_t)d8_dev % 4 == 0) && (!idxs_dev || (uintptr_t)idxs_dev % 16 == 0);
+        uint8_t* dir = (uint8_t*)h->dir.p;
+        uint8_t* upm = (uint8_t*)h->upmask.p;
+#define LAUNCH_PARSE(A, M) parse_kernel<A, M><<<grid, 256, 0, h->stream>>>(d8_dev, nrow, ncol, dir, upm, idxs_dev, flag)
+        if (aligned) {
+            if (idxmode == 0) LAUNCH_PARSE(true, 0);
+            else if (idxmode == 1) LAUNCH_PARSE(true, 1);
+            else LAUNCH_PARSE(true, 2);
+        } else {
+            if (idxmode == 0) LAUNCH_PARSE(false, 0);
+            else if (idxmode == 1) LAUNCH_PARSE(false, 1);
+            else LAUNCH_PARSE(false, 2);
+        }
+#undef LAUNCH_PARSE
+        PFD_LAUNCH_CHECK(h);
+    }
+    const int64_t nblk = npad / PC_CHUNK;
+    {
+        StageTimer t(h, PFD_STAGE_PITS);
+        PFD_TRY(pfd_reserve(h, h->blk_counts, (size_t)nblk * sizeof(uint32_t)));
+        PFD_TRY(pfd_reserve(h, h->blk_offsets, (size_t)(nblk + 1) * sizeof(unsigned long long)));
+        pit_count_kernel<<<(unsigned)nblk, 256, 0, h->stream>>>((const uint8_t*)h->dir.p, (uint32_t*)h->blk_counts.p,
+                                                               (unsigned long long*)h->counters.p);
+        PFD_LAUNCH_CHECK(h);
+        scan_counts_kernel<<<1, 1024, 0, h->stream>>>((const uint32_t*)h->blk_counts.p, nblk,
+                                                     (unsigned long long*)h->blk_offsets.p);
+        PFD_LAUNCH_CHECK(h);
+        unsigned long long hc[4];
+        PFD_CUDA(h, cudaMemcpyAsync(hc, h->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, h->stream));
+        PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+        const unsigned int flags = (unsigned int)hc[3];
+        if (flags & 1u) {
+            invalidate(h);
+            return pfd_fail(h, PFD_ERR_INVALID_D8, "raster holds values outside the D8 code set {0,1,2,4,8,16,32,64,128,247,255}");
+        }
+        h->n_valid = (int64_t)hc[0];
+        h->n_pits = (int64_t)hc[1];
+        h->n_outlets = (int64_t)hc[2];
+        PFD_TRY(pfd_reserve(h, h->pits, (size_t)std::max<int64_t>(h->n_pits, 1) * sizeof(cell_t)));
+        PFD_TRY(pfd_reserve(h, h->pit_outlet, (size_t)std::max<int64_t>(h->n_pits, 1)));
+        if (h->n_pits > 0) {
+            pit_scatter_kernel<<<(unsigned)nblk, 256, 0, h->stream>>>((const uint8_t*)h->dir.p,
+                                                                     (const unsigned long long*)h->blk_offsets.p,
+                                                                     (cell_t*)h->pits.p, (uint8_t*)h->pit_outlet.p);
+            PFD_LAUNCH_CHECK(h);
+        }
+    }
+    h->nrow = nrow;
+    h->ncol = ncol;
+    h->n = n;
+    h->parsed = true;
+    h->ordered = h->have_rank = h->have_basins = false;
+    return PFD_OK;
+}
+
+static int check_shape(pfd_handle* h, int64_t nrow, int64_t ncol, const char* who) {
+    if (nrow <= 0 || ncol <= 0) return pfd_fail(h, PFD_ERR_INVALID_ARG, std::string(who) + ": empty raster");
+    if (nrow > MAX_CELLS / ncol) return pfd_fail(h, PFD_ERR_UNSUPPORTED, std::string(who) + ": more than 2^32 cells");
+    return PFD_OK;
+}
+
+static int parse_impl(pfd_handle* h, const uint8_t* d8, int64_t nrow, int64_t ncol, void* idxs_ds_out, int idx_dtype) {
+    PFD_TRY(check_shape(h, nrow, ncol, "pfd_d8_parse"));
+    if (!d8) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_d8_parse: d8 is null");
+    if (idxs_ds_out && idx_dtype != PFD_I32 && idx_dtype != PFD_U32 && idx_dtype != PFD_I64)
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_d8_parse: idx_dtype must be int32, uint32 or int64");
+    const int64_t n = nrow * ncol;
+    if (idxs_ds_out && idx_dtype == PFD_I32 && n >= 2147483647ll)
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_d8_parse: int32 indices cannot address this raster");
+    invalidate(h);
+    const void* d8_dev = nullptr;
+    PFD_TRY(pfd_stage_in(h, d8, (size_t)n, 0, &d8_dev));
+    void* idxs_dev = nullptr;
+    const size_t ibytes = (size_t)n * pfd_dtype_size(idx_dtype);
+    if (idxs_ds_out) PFD_TRY(pfd_stage_out(h, idxs_ds_out, ibytes, 1, &idxs_dev));
+    PFD_TRY(parse_device(h, (const uint8_t*)d8_dev, nrow, ncol, idxs_dev, idx_dtype));
+    if (idxs_ds_out) PFD_TRY(pfd_finish_out(h, idxs_ds_out, idxs_dev, ibytes));
+    return PFD_OK;
+}
+
+extern "C" int pfd_d8_parse(pfd_handle* h, const uint8_t* d8, int64_t nrow, int64_t ncol, int check_values,
+                            void* idxs_ds_out, int idx_dtype, int64_t* n_valid, int64_t* n_pits, int64_t* n_outlets) {
+    (void)check_values;  // illegal codes are always refused
+    PFD_TRY(check_handle(h));
+    stage_reset(h);
+    PFD_TRY(parse_impl(h, d8, nrow, ncol, idxs_ds_out, idx_dtype));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    if (n_valid) *n_valid = h->n_valid;
+    if (n_pits) *n_pits = h->n_pits;
+    if (n_outlets) *n_outlets = h->n_outlets;
+    return PFD_OK;
+}
+
+extern "C" int pfd_load_idxs_ds(pfd_handle* h, const void* idxs_ds, int idx_dtype, int64_t nrow, int64_t ncol,
+                                int64_t* n_valid, int64_t* n_pits) {
+    PFD_TRY(check_handle(h));
+    stage_reset(h);
+    PFD_TRY(check_shape(h, nrow, ncol, "pfd_load_idxs_ds"));
+    if (!idxs_ds) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_load_idxs_ds: idxs_ds is null");
+    const size_t isz = pfd_dtype_size(idx_dtype);
+    if (idx_dtype != PFD_I32 && idx_dtype != PFD_U32 && idx_dtype != PFD_I64 && idx_dtype != PFD_U64)
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_load_idxs_ds: idx_dtype must be a 32/64-bit integer");
+    invalidate(h);
+    const int64_t n = nrow * ncol;
+    const void* idev = nullptr;
+    PFD_TRY(pfd_stage_in(h, idxs_ds, (size_t)n * isz, 1, &idev));
+    PFD_TRY(pfd_reserve(h, h->scratch[0], (size_t)n));
+    PFD_TRY(pfd_reserve(h, h->counters, 8 * sizeof(unsigned long long)));
+    PFD_CUDA(h, cudaMemsetAsync(h->counters.p, 0, 8 * sizeof(unsigned long long), h->stream));
+    unsigned int* flag = reinterpret_cast<unsigned int*>((unsigned long long*)h->counters.p + 4);
+    uint8_t* d8 = (uint8_t*)h->scratch[0].p;
+    const int g = grid_for(n, 256, 4);
+    switch (idx_dtype) {
+    case PFD_I32: idxs_to_d8_kernel<int32_t><<<g, 256, 0, h->stream>>>((const int32_t*)idev, n, ncol, d8, flag); break;
+    case PFD_U32: idxs_to_d8_kernel<uint32_t><<<g, 256, 0, h->stream>>>((const uint32_t*)idev, n, ncol, d8, flag); break;
+    case PFD_I64: idxs_to_d8_kernel<int64_t><<<g, 256, 0, h->stream>>>((const int64_t*)idev, n, ncol, d8, flag); break;
+    default: idxs_to_d8_kernel<uint64_t><<<g, 256, 0, h->stream>>>((const uint64_t*)idev, n, ncol, d8, flag); break;
+    }
+    PFD_LAUNCH_CHECK(h);
+    unsigned int hflag = 0;
+    PFD_CUDA(h, cudaMemcpyAsync(&hflag, flag, sizeof(hflag), cudaMemcpyDeviceToHost, h->stream));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (hflag & 2u)
+        return pfd_fail(h, PFD_ERR_UNSUPPORTED, "Invalid data downstream index outside 8 neighbors.");
+    PFD_TRY(parse_device(h, d8, nrow, ncol, nullptr, 0));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    if (n_valid) *n_valid = h->n_valid;
+    if (n_pits) *n_pits = h->n_pits;
+    return PFD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// order
+// ---------------------------------------------------------------------------------------------------------
+template <class K>
+static int coop_grid(pfd_handle* h, K kernel, int threads, int64_t max_useful_blocks, int* grid) {
+    int per_sm = 0;
+    PFD_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+    if (per_sm < 1) return pfd_fail(h, PFD_ERR_CUDA, "kernel cannot be made resident");
+    int64_t g = (int64_t)per_sm * h->num_sms;
+    if (g > max_useful_blocks) g = std::max<int64_t>(1, max_useful_blocks);
+    *grid = (int)g;
+    return PFD_OK;
+}
+
+static int build_schedule(pfd_handle* h) {
+    std::vector<SweepSeg> segs;
+    const int nlev = (int)h->nlevels;
+    int l = 0;
+    while (l < nlev) {
+        const int64_t size = h->h_level_off[l + 1] - h->h_level_off[l];
+        if (size > SW_SOLO_MAX) {
+            segs.push_back(SweepSeg{l, 1, 0, 0});
+            ++l;
+        } else {
+            int l2 = l;
+            while (l2 < nlev && h->h_level_off[l2 + 1] - h->h_level_off[l2] <= SW_SOLO_MAX) ++l2;
+            segs.push_back(SweepSeg{l, l2 - l, 1, 0});
+            l = l2;
+        }
+    }
+    h->nsegs = (int)segs.size();
+    h->max_level_size = 0;
+    for (int i = 0; i < nlev; ++i) h->max_level_size = std::max<int64_t>(h->max_level_size, (int64_t)(h->h_level_off[i + 1] - h->h_level_off[i]));
+    PFD_TRY(pfd_reserve(h, h->segs, std::max<size_t>(1, segs.size()) * sizeof(SweepSeg)));
+    if (!segs.empty())
+        PFD_CUDA(h, cudaMemcpyAsync(h->segs.p, segs.data(), segs.size() * sizeof(SweepSeg), cudaMemcpyHostToDevice, h->stream));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));  // segs is a local vector
+    return PFD_OK;
+}
+
+template <class Op, bool UP>
+static int run_sweep(pfd_handle* h, Op op, int skip_level0) {
+    if (h->nsegs == 0) return PFD_OK;
+    SweepParams P;
+    P.seq = (const cell_t*)h->seq.p;
+    P.level_off = (const long long*)h->level_off.p;
+    P.segs = (const SweepSeg*)h->segs.p;
+    P.nsegs = h->nsegs;
+    P.skip_level0 = skip_level0;
+    int grid = 1;
+    PFD_TRY(coop_grid(h, sweep_kernel<Op, UP>, SW_THREADS, (h->max_level_size + SW_THREADS - 1) / SW_THREADS, &grid));
+    void* args[] = {(void*)&P, (void*)&op};
+    StageTimer t(h, PFD_STAGE_SWEEP);
+    PFD_CUDA(h, cudaLaunchCooperativeKernel((void*)sweep_kernel<Op, UP>, dim3(grid), dim3(SW_THREADS), args, 0, h->stream));
+    h->launches++;
+    return PFD_OK;
+}
+
+static int order_impl(pfd_handle* h, bool want_rank, bool want_basins) {
+    if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, "pfd_order: no raster parsed on this handle");
+    const int64_t n = h->n;
+    if (!h->ordered) {
+        StageTimer t(h, PFD_STAGE_ORDER);
+        PFD_TRY(pfd_reserve(h, h->seq, (size_t)n * sizeof(cell_t)));
+        if (want_basins) {
+            PFD_TRY(pfd_reserve(h, h->bseq, (size_t)n * sizeof(uint32_t)));
+            PFD_TRY(pfd_reserve(h, h->basins, (size_t)n * sizeof(uint32_t)));
+            PFD_CUDA(h, cudaMemsetAsync(h->basins.p, 0, (size_t)n * sizeof(uint32_t), h->stream));
+        }
+        if (want_rank) {
+            PFD_TRY(pfd_reserve(h, h->rank, (size_t)n * sizeof(int32_t)));
+            order_init_rank_kernel<<<grid_for(n, 256, 4, 1ll << 30), 256, 0, h->stream>>>((const uint8_t*)h->dir.p, n, (int32_t*)h->rank.p);
+            PFD_LAUNCH_CHECK(h);
+        }
+        if (h->level_cap == 0) h->level_cap = std::min<int64_t>(std::max<int64_t>(n, 1), 1 << 20);
+        PFD_TRY(pfd_reserve(h, h->level_off, (size_t)(h->level_cap + 1) * sizeof(long long)));
+        PFD_TRY(pfd_reserve(h, h->bfs_state, sizeof(BfsState)));
+        const int64_t nstatus = n / BFS_CHUNK + 2;
+        PFD_TRY(pfd_reserve(h, h->chunk_status, (size_t)nstatus * sizeof(unsigned long long)));
+        PFD_CUDA(h, cudaMemsetAsync(h->chunk_status.p, 0, (size_t)nstatus * sizeof(unsigned long long), h->stream));
+        BfsState st;
+        memset(&st, 0, sizeof(st));
+        st.slot_start[0] = 0;
+        st.slot_end[0] = (unsigned long long)h->n_pits;
+        PFD_CUDA(h, cudaMemcpyAsync(h->bfs_state.p, &st, sizeof(st), cudaMemcpyHostToDevice, h->stream));
+        PFD_CUDA(h, cudaMemsetAsync(h->level_off.p, 0, sizeof(long long), h->stream));
+        if (h->n_pits > 0) {
+            order_init_pits_kernel<<<grid_for(h->n_pits, 256), 256, 0, h->stream>>>(
+                (const cell_t*)h->pits.p, h->n_pits, (cell_t*)h->seq.p, want_basins ? (uint32_t*)h->bseq.p : nullptr,
+                want_rank ? (int32_t*)h->rank.p : nullptr, want_basins ? (uint32_t*)h->basins.p : nullptr);
+            PFD_LAUNCH_CHECK(h);
+        }
+        for (;;) {
+            BfsParams P;
+            P.upmask = (const uint8_t*)h->upmask.p;
+            P.seq = (cell_t*)h->seq.p;
+            P.bseq = (uint32_t*)h->bseq.p;
+            P.rank = (int32_t*)h->rank.p;
+            P.basins = (uint32_t*)h->basins.p;
+            P.level_off = (long long*)h->level_off.p;
+            P.level_cap = h->level_cap;
+            P.status = (unsigned long long*)h->chunk_status.p;
+            P.st = (BfsState*)h->bfs_state.p;
+            P.ncol = h->ncol;
+            void* args[] = {(void*)&P};
+            void* kern = want_rank ? (want_basins ? (void*)bfs_kernel<true, true> : (void*)bfs_kernel<true, false>)
+                                   : (want_basins ? (void*)bfs_kernel<false, true> : (void*)bfs_kernel<false, false>);
+            int per_sm = 0;
+            if (want_rank && want_basins) PFD_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_kernel<true, true>, BFS_THREADS, 0));
+            else if (want_rank) PFD_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_kernel<true, false>, BFS_THREADS, 0));
+            else if (want_basins) PFD_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_kernel<false, true>, BFS_THREADS, 0));
+            else PFD_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_kernel<false, false>, BFS_THREADS, 0));
+            if (per_sm < 1) return pfd_fail(h, PFD_ERR_CUDA, "bfs kernel cannot be made resident");
+            int64_t grid = (int64_t)per_sm * h->num_sms;
+            grid = std::max<int64_t>(1, std::min<int64_t>(grid, (n + BFS_CHUNK - 1) / BFS_CHUNK));
+            PFD_CUDA(h, cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(BFS_THREADS), args, 0, h->stream));
+            h->launches++;
+            PFD_CUDA(h, cudaMemcpyAsync(&st, h->bfs_state.p, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+            PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+            if (st.stop == 1) break;
+            if (st.stop != 2) return pfd_fail(h, PFD_ERR_CUDA, "bfs kernel ended in an unknown state");
+            // grow the level table and continue from the level the kernel stopped at
+            const int64_t new_cap = std::min<int64_t>(n + 1, h->level_cap * 4);
+            if (new_cap <= h->level_cap) return pfd_fail(h, PFD_ERR_CUDA, "bfs level table cannot grow");
+            DevBuf bigger;
+            PFD_TRY(pfd_reserve(h, bigger, (size_t)(new_cap + 1) * sizeof(long long)));
+            PFD_CUDA(h, cudaMemcpyAsync(bigger.p, h->level_off.p, (size_t)(h->level_cap + 1) * sizeof(long long), cudaMemcpyDeviceToDevice, h->stream));
+            PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+            pfd_release(h->level_off);
+            h->level_off = bigger;
+            h->level_cap = new_cap;
+            unsigned int zero = 0;
+            PFD_CUDA(h, cudaMemcpyAsync(&((BfsState*)h->bfs_state.p)->stop, &zero, sizeof(zero), cudaMemcpyHostToDevice, h->stream));
+        }
+        h->nnodes = (int64_t)st.total;
+        h->nlevels = (int64_t)st.cur_level;
+        h->h_level_off.resize((size_t)h->nlevels + 1);
+        PFD_CUDA(h, cudaMemcpyAsync(h->h_level_off.data(), h->level_off.p, (size_t)(h->nlevels + 1) * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+        PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+        PFD_TRY(build_schedule(h));
+        h->ordered = true;
+        h->have_rank = want_rank;
+        h->have_basins = want_basins;
+    }
+    if (want_rank && !h->have_rank) {
+        PFD_TRY(pfd_reserve(h, h->rank, (size_t)n * sizeof(int32_t)));
+        order_init_rank_kernel<<<grid_for(n, 256, 4, 1ll << 30), 256, 0, h->stream>>>((const uint8_t*)h->dir.p, n, (int32_t*)h->rank.p);
+        PFD_LAUNCH_CHECK(h);
+        RankOp op{(int32_t*)h->rank.p};
+        PFD_TRY((run_sweep<RankOp, false>(h, op, 0)));
+        h->have_rank = true;
+    }
+    if (want_basins && !h->have_basins) {
+        PFD_TRY(pfd_reserve(h, h->basins, (size_t)n * sizeof(uint32_t)));
+        PFD_CUDA(h, cudaMemsetAsync(h->basins.p, 0, (size_t)n * sizeof(uint32_t), h->stream));
+        if (h->n_pits > 0) {
+            // seq[0:n_pits] already holds the pits; only the labels are needed
+            order_init_pits_kernel<<<grid_for(h->n_pits, 256), 256, 0, h->stream>>>(
+                (const cell_t*)h->pits.p, h->n_pits, (cell_t*)h->seq.p, nullptr, nullptr, (uint32_t*)h->basins.p);
+            PFD_LAUNCH_CHECK(h);
+        }
+        FillUpOp<uint32_t> op{(const uint8_t*)h->dir.p, (uint32_t*)h->basins.p, h->ncol};
+        PFD_TRY((run_sweep<FillUpOp<uint32_t>, false>(h, op, 1)));
+        h->have_basins = true;
+    }
+    return PFD_OK;
+}
+
+extern "C" int pfd_order(pfd_handle* h, int64_t* nnodes, int64_t* nlevels) {
+    PFD_TRY(check_handle(h));
+    stage_reset(h);
+    PFD_TRY(order_impl(h, true, false));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    if (nnodes) *nnodes = h->nnodes;
+    if (nlevels) *nlevels = h->nlevels;
+    return PFD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fetch
+// ---------------------------------------------------------------------------------------------------------
+static int copy_cells_out(pfd_handle* h, const cell_t* src, int64_t count, void* out, int idx_dtype) {
+    if (count == 0) return PFD_OK;
+    const size_t osz = pfd_dtype_size(idx_dtype);
+    if (idx_dtype == PFD_I32 || idx_dtype == PFD_U32) {
+        PFD_CUDA(h, cudaMemcpyAsync(out, src, (size_t)count * 4, cudaMemcpyDefault, h->stream));
+        return PFD_OK;
+    }
+    if (idx_dtype != PFD_I64 && idx_dtype != PFD_U64) return pfd_fail(h, PFD_ERR_INVALID_ARG, "index dtype must be 32/64-bit integer");
+    void* dev = nullptr;
+    PFD_TRY(pfd_stage_out(h, out, (size_t)count * osz, 2, &dev));
+    widen_cells_kernel<int64_t><<<grid_for(count, 256, 4), 256, 0, h->stream>>>(src, count, (int64_t*)dev);
+    PFD_LAUNCH_CHECK(h);
+    PFD_TRY(pfd_finish_out(h, out, dev, (size_t)count * osz));
+    return PFD_OK;
+}
+
+extern "C" int pfd_fetch(pfd_handle* h, int which, void* out, int idx_dtype) {
+    PFD_TRY(check_handle(h));
+    if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, "pfd_fetch: no raster parsed on this handle");
+    if (!out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_fetch: out is null");
+    stage_reset(h);
+    const int64_t n = h->n;
+    switch (which) {
+    case PFD_ARR_IDXS_DS: {
+        const size_t osz = pfd_dtype_size(idx_dtype);
+        if (idx_dtype != PFD_I32 && idx_dtype != PFD_U32 && idx_dtype != PFD_I64 && idx_dtype != PFD_U64)
+            return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_fetch: bad index dtype");
+        void* dev = nullptr;
+        PFD_TRY(pfd_stage_out(h, out, (size_t)n * osz, 2, &dev));
+        const int g = grid_for(n, 256, 4);
+        if (osz == 4) dir_to_idxs_kernel<uint32_t><<<g, 256, 0, h->stream>>>((const uint8_t*)h->dir.p, n, h->ncol, (uint32_t*)dev);
+        else dir_to_idxs_kernel<int64_t><<<g, 256, 0, h->stream>>>((const uint8_t*)h->dir.p, n, h->ncol, (int64_t*)dev);
+        PFD_LAUNCH_CHECK(h);
+        PFD_TRY(pfd_finish_out(h, out, dev, (size_t)n * osz));
+        break;
+    }
+    case PFD_ARR_PITS:
+        PFD_TRY(copy_cells_out(h, (const cell_t*)h->pits.p, h->n_pits, out, idx_dtype));
+        break;
+    case PFD_ARR_PIT_IS_OUTLET:
+        if (h->n_pits) PFD_CUDA(h, cudaMemcpyAsync(out, h->pit_outlet.p, (size_t)h->n_pits, cudaMemcpyDefault, h->stream));
+        break;
+    case PFD_ARR_SEQ:
+        PFD_TRY(order_impl(h, false, false));
+        PFD_TRY(copy_cells_out(h, (const cell_t*)h->seq.p, h->nnodes, out, idx_dtype));
+        break;
+    case PFD_ARR_RANK:
+        PFD_TRY(order_impl(h, true, false));
+        PFD_CUDA(h, cudaMemcpyAsync(out, h->rank.p, (size_t)n * sizeof(int32_t), cudaMemcpyDefault, h->stream));
+        break;
+    case PFD_ARR_N_UPSTREAM: {
+        void* dev = nullptr;
+        PFD_TRY(pfd_stage_out(h, out, (size_t)n, 2, &dev));
+        upstream_count_kernel<<<grid_for(n, 256, 4), 256, 0, h->stream>>>((const uint8_t*)h->dir.p, (const uint8_t*)h->upmask.p, n, (int8_t*)dev);
+        PFD_LAUNCH_CHECK(h);
+        PFD_TRY(pfd_finish_out(h, out, dev, (size_t)n));
+        break;
+    }
+    case PFD_ARR_D8: {
+        void* dev = nullptr;
+        PFD_TRY(pfd_stage_out(h, out, (size_t)n, 2, &dev));
+        dir_to_d8_kernel<<<grid_for(n, 256, 4), 256, 0, h->stream>>>((const uint8_t*)h->dir.p, n, (uint8_t*)dev);
+        PFD_LAUNCH_CHECK(h);
+        PFD_TRY(pfd_finish_out(h, out, dev, (size_t)n));
+        break;
+    }
+    case PFD_ARR_LEVEL_OFFSETS:
+        PFD_TRY(order_impl(h, false, false));
+        PFD_CUDA(h, cudaMemcpyAsync(out, h->level_off.p, (size_t)(h->nlevels + 1) * sizeof(long long), cudaMemcpyDefault, h->stream));
+        break;
+    default:
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_fetch: unknown array id");
+    }
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    return PFD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// sweeps
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+static int accuflux_typed(pfd_handle* h, const void* data_dev, void* out_dev, const NoData& nd, int direction) {
+    const int64_t n = h->n;
+    if (data_dev != out_dev)
+        PFD_CUDA(h, cudaMemcpyAsync(out_dev, data_dev, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
+    if (direction == 0) {
+        AccuUpOp<T> op{(const uint8_t*)h->upmask.p, (T*)out_dev, h->ncol, nd};
+        return run_sweep<AccuUpOp<T>, true>(h, op, 0);
+    }
+    AccuDownOp<T> op{(const uint8_t*)h->dir.p, (T*)out_dev, h->ncol, nd};
+    return run_sweep<AccuDownOp<T>, false>(h, op, 1);
+}
+
+extern "C" int pfd_accuflux(pfd_handle* h, const void* data, int dtype, double nodata_f, int64_t nodata_i,
+                            int nodata_is_int, int direction, void* out) {
+    PFD_TRY(check_handle(h));
+    stage_reset(h);
+    if (!data || !out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_accuflux: null array");
+    if (direction != 0 && direction != 1) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_accuflux: direction must be 0 (up) or 1 (down)");
+    const size_t esz = pfd_dtype_size(dtype);
+    if (!esz) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_accuflux: unknown dtype");
+    PFD_TRY(order_impl(h, false, false));
+    const size_t bytes = (size_t)h->n * esz;
+    void* out_dev = nullptr;
+    PFD_TRY(pfd_stage_out(h, out, bytes, 3, &out_dev));
+    const void* data_dev = nullptr;
+    if (pfd_is_device_ptr(data)) {
+        data_dev = data;
+    } else {  // host data goes straight into the output buffer (accu = data.copy())
+        PFD_CUDA(h, cudaMemcpyAsync(out_dev, data, bytes, cudaMemcpyHostToDevice, h->stream));
+        data_dev = out_dev;
+    }
+    NoData nd{nodata_f, (long long)nodata_i, nodata_is_int};
+    int rc;
+    switch (dtype) {
+    case PFD_I8: rc = accuflux_typed<int8_t>(h, data_dev, out_dev, nd, direction); break;
+    case PFD_U8: rc = accuflux_typed<uint8_t>(h, data_dev, out_dev, nd, direction); break;
+    case PFD_I16: rc = accuflux_typed<int16_t>(h, data_dev, out_dev, nd, direction); break;
+    case PFD_U16: rc = accuflux_typed<uint16_t>(h, data_dev, out_dev, nd, direction); break;
+    case PFD_I32: rc = accuflux_typed<int32_t>(h, data_dev, out_dev, nd, direction); break;
+    case PFD_U32: rc = accuflux_typed<uint32_t>(h, data_dev, out_dev, nd, direction); break;
+    case PFD_I64: rc = accuflux_typed<int64_t>(h, data_dev, out_dev, nd, direction); break;
+    case PFD_U64: rc = accuflux_typed<uint64_t>(h, data_dev, out_dev, nd, direction); break;
+    case PFD_F32: rc = accuflux_typed<float>(h, data_dev, out_dev, nd, direction); break;
+    default: rc = accuflux_typed<double>(h, data_dev, out_dev, nd, direction); break;
+    }
+    PFD_TRY(rc);
+    PFD_TRY(pfd_finish_out(h, out, out_dev, bytes));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    return PFD_OK;
+}
+
+static int uparea_cells_device(pfd_handle* h, int32_t* out_dev) {
+    const int64_t n = h->n;
+    uparea_init_kernel<<<grid_for(n, 256, 4, 1ll << 30), 256, 0, h->stream>>>((const uint8_t*)h->dir.p, n, out_dev);
+    PFD_LAUNCH_CHECK(h);
+    NoData nd{-9999.0, -9999, 1};
+    AccuUpOp<int32_t> op{(const uint8_t*)h->upmask.p, out_dev, h->ncol, nd};
+    return run_sweep<AccuUpOp<int32_t>, true>(h, op, 0);
+}
+
+extern "C" int pfd_upstream_area_cells(pfd_handle* h, int32_t* out) {
+    PFD_TRY(check_handle(h));
+    stage_reset(h);
+    if (!out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_upstream_area_cells: out is null");
+    PFD_TRY(order_impl(h, false, false));
+    const size_t bytes = (size_t)h->n * sizeof(int32_t);
+    void* out_dev = nullptr;
+    PFD_TRY(pfd_stage_out(h, out, bytes, 3, &out_dev));
+    PFD_TRY(uparea_cells_device(h, (int32_t*)out_dev));
+    PFD_TRY(pfd_finish_out(h, out, out_dev, bytes));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    return PFD_OK;
+}
+
+template <typename IDX, typename U>
+static int basins_custom(pfd_handle* h, const void* idx_dev, const void* ids_dev, int64_t k, void* out_dev) {
+    unsigned int* flag = reinterpret_cast<unsigned int*>((unsigned long long*)h->counters.p + 5);
+    PFD_CUDA(h, cudaMemsetAsync(flag, 0, sizeof(unsigned int), h->stream));
+    PFD_CUDA(h, cudaMemsetAsync(out_dev, 0, (size_t)h->n * sizeof(U), h->stream));
+    if (k > 0) {
+        scatter_ids_kernel<IDX, U><<<grid_for(k, 256), 256, 0, h->stream>>>((const IDX*)idx_dev, (const U*)ids_dev, 0, k, h->n, (U*)out_dev, flag);
+        PFD_LAUNCH_CHECK(h);
+    }
+    unsigned int hflag = 0;
+    PFD_CUDA(h, cudaMemcpyAsync(&hflag, flag, sizeof(hflag), cudaMemcpyDeviceToHost, h->stream));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (hflag & 4u) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_basins: outlet index out of bounds");
+    FillUpOp<U> op{(const uint8_t*)h->dir.p, (U*)out_dev, h->ncol};
+    return run_sweep<FillUpOp<U>, false>(h, op, 0);
+}
+
+extern "C" int pfd_basins(pfd_handle* h, const void* outlets, int64_t n_outlets, int idx_dtype, const void* ids,
+                          int ids_dtype, void* out) {
+    PFD_TRY(check_handle(h));
+    stage_reset(h);
+    if (!out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_basins: out is null");
+    if (!outlets) {
+        PFD_TRY(order_impl(h, false, true));
+        PFD_CUDA(h, cudaMemcpyAsync(out, h->basins.p, (size_t)h->n * sizeof(uint32_t), cudaMemcpyDefault, h->stream));
+        PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+        stage_collect(h);
+        return PFD_OK;
+    }
+    if (!ids || n_outlets < 0) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_basins: ids is null");
+    const size_t isz = pfd_dtype_size(idx_dtype), usz = pfd_dtype_size(ids_dtype);
+    if ((isz != 4 && isz != 8) || idx_dtype == PFD_F32 || idx_dtype == PFD_F64)
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_basins: outlet indices must be 32/64-bit integers");
+    if (!usz || ids_dtype == PFD_F32 || ids_dtype == PFD_F64)
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_basins: ids must be an integer dtype");
+    PFD_TRY(order_impl(h, false, false));
+    const size_t bytes = (size_t)h->n * usz;
+    void* out_dev = nullptr;
+    PFD_TRY(pfd_stage_out(h, out, bytes, 3, &out_dev));
+    const void *idx_dev = nullptr, *ids_dev = nullptr;
+    PFD_TRY(pfd_stage_in(h, outlets, (size_t)std::max<int64_t>(n_outlets, 1) * isz, 4, &idx_dev));
+    PFD_TRY(pfd_stage_in(h, ids, (size_t)std::max<int64_t>(n_outlets, 1) * usz, 5, &ids_dev));
+    int rc;
+    const bool i64 = (isz == 8);
+    const bool isigned = (idx_dtype == PFD_I32 || idx_dtype == PFD_I64);
+#define BAS(IDX)                                                                                          \
+    (usz == 1 ? basins_custom<IDX, uint8_t>(h, idx_dev, ids_dev, n_outlets, out_dev)                      \
+              : usz == 2 ? basins_custom<IDX, uint16_t>(h, idx_dev, ids_dev, n_outlets, out_dev)          \
+                         : usz == 4 ? basins_custom<IDX, uint32_t>(h, idx_dev, ids_dev, n_outlets, out_dev) \
+                                    : basins_custom<IDX, uint64_t>(h, idx_dev, ids_dev, n_outlets, out_dev))
+    if (i64) rc = isigned ? BAS(int64_t) : BAS(uint64_t);
+    else rc = isigned ? BAS(int32_t) : BAS(uint32_t);
+#undef BAS
+    PFD_TRY(rc);
+    PFD_TRY(pfd_finish_out(h, out, out_dev, bytes));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    return PFD_OK;
+}
+
+extern "C" int pfd_strahler(pfd_handle* h, const uint8_t* mask, uint8_t* out) {
+    PFD_TRY(check_handle(h));
+    stage_reset(h);
+    if (!out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_strahler: out is null");
+    PFD_TRY(order_impl(h, false, false));
+    const size_t bytes = (size_t)h->n;
+    void* out_dev = nullptr;
+    PFD_TRY(pfd_stage_out(h, out, bytes, 3, &out_dev));
+    const void* mask_dev = nullptr;
+    if (mask) PFD_TRY(pfd_stage_in(h, mask, bytes, 4, &mask_dev));
+    PFD_CUDA(h, cudaMemsetAsync(out_dev, 0, bytes, h->stream));
+    StrahlerOp op{(const uint8_t*)h->upmask.p, (const uint8_t*)mask_dev, (uint8_t*)out_dev, h->ncol};
+    PFD_TRY((run_sweep<StrahlerOp, true>(h, op, 0)));
+    PFD_TRY(pfd_finish_out(h, out, out_dev, bytes));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    return PFD_OK;
+}
+
+extern "C" int pfd_hand(pfd_handle* h, const uint8_t* drain, const void* elevtn, int elev_dtype, double* out) {
+    PFD_TRY(check_handle(h));
+    stage_reset(h);
+    if (!drain || !elevtn || !out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_hand: null array");
+    if (elev_dtype != PFD_F32 && elev_dtype != PFD_F64) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_hand: elevtn must be float32 or float64");
+    PFD_TRY(order_impl(h, false, false));
+    const int64_t n = h->n;
+    const size_t bytes = (size_t)n * sizeof(double);
+    void* out_dev = nullptr;
+    PFD_TRY(pfd_stage_out(h, out, bytes, 3, &out_dev));
+    const void *drain_dev = nullptr, *elev_dev = nullptr;
+    PFD_TRY(pfd_stage_in(h, drain, (size_t)n, 4, &drain_dev));
+    PFD_TRY(pfd_stage_in(h, elevtn, (size_t)n * pfd_dtype_size(elev_dtype), 5, &elev_dev));
+    fill_kernel<double><<<grid_for(n, 256, 4), 256, 0, h->stream>>>((double*)out_dev, n, -9999.0);
+    PFD_LAUNCH_CHECK(h);
+    if (elev_dtype == PFD_F32) {
+        HandOp<float> op{(const uint8_t*)h->dir.p, (const uint8_t*)drain_dev, (const float*)elev_dev, (double*)out_dev, h->ncol};
+        PFD_TRY((run_sweep<HandOp<float>, false>(h, op, 0)));
+    } else {
+        HandOp<double> op{(const uint8_t*)h->dir.p, (const uint8_t*)drain_dev, (const double*)elev_dev, (double*)out_dev, h->ncol};
+        PFD_TRY((run_sweep<HandOp<double>, false>(h, op, 0)));
+    }
+    PFD_TRY(pfd_finish_out(h, out, out_dev, bytes));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    return PFD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fused headline pass
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int pfd_d8_flow_all(pfd_handle* h, const uint8_t* d8, int64_t nrow, int64_t ncol, void* idxs_ds_out,
+                               int idx_dtype, int32_t* rank_out, int32_t* uparea_out, uint32_t* basins_out,
+                               int64_t* n_valid, int64_t* n_pits, int64_t* nnodes) {
+    PFD_TRY(check_handle(h));
+    stage_reset(h);
+    cudaEventRecord(h->ev_start[PFD_STAGE_TOTAL], h->stream);
+    h->stage_used[PFD_STAGE_TOTAL] = true;
+    PFD_TRY(parse_impl(h, d8, nrow, ncol, idxs_ds_out, idx_dtype));
+    if (h->n_pits == 0) return pfd_fail(h, PFD_ERR_NO_PITS, "Invalid FlwdirRaster: no pits found");
+    PFD_TRY(order_impl(h, rank_out != nullptr, basins_out != nullptr));
+    const size_t b4 = (size_t)h->n * 4;
+    if (rank_out) PFD_CUDA(h, cudaMemcpyAsync(rank_out, h->rank.p, b4, cudaMemcpyDefault, h->stream));
+    if (basins_out) PFD_CUDA(h, cudaMemcpyAsync(basins_out, h->basins.p, b4, cudaMemcpyDefault, h->stream));
+    if (uparea_out) {
+        void* out_dev = nullptr;
+        PFD_TRY(pfd_stage_out(h, uparea_out, b4, 3, &out_dev));
+        PFD_TRY(uparea_cells_device(h, (int32_t*)out_dev));
+        PFD_TRY(pfd_finish_out(h, uparea_out, out_dev, b4));
+    }
+    cudaEventRecord(h->ev_stop[PFD_STAGE_TOTAL], h->stream);
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    if (n_valid) *n_valid = h->n_valid;
+    if (n_pits) *n_pits = h->n_pits;
+    if (nnodes) *nnodes = h->nnodes;
+    return PFD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// synthetic input
+// ---------------------------------------------------------------------------------------------------------
+__global__ void synth_elevation_kernel(int64_t nrow, int64_t ncol, int64_t nref, int octaves, uint32_t seed, float* __restrict__ z) {
+    const int64_t n = nrow * ncol;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        z[i] = pfd_synth_z(i / ncol, i % ncol, nref, octaves, seed);
+}
+
+__global__ void synth_d8_kernel(const float* __restrict__ z, int64_t nrow, int64_t ncol, float sea_level, uint8_t* __restrict__ d8) {
+    const int64_t n = nrow * ncol;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / ncol, c = i % ncol;
+        float w[9];
+        int valid[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const int64_t rr = r + k / 3 - 1, cc = c + k % 3 - 1;
+            valid[k] = (rr >= 0 && rr < nrow && cc >= 0 && cc < ncol);
+            w[k] = valid[k] ? __ldg(z + rr * ncol + cc) : 0.0f;
+        }
+        d8[i] = pfd_synth_d8_from_window(w, valid, sea_level);
+    }
+}
+
+extern "C" int pfd_synth_elevation(pfd_handle* h, int64_t nrow, int64_t ncol, int64_t nref, int octaves, uint32_t seed, float* z_out) {
+    PFD_TRY(check_handle(h));
+    PFD_TRY(check_shape(h, nrow, ncol, "pfd_synth_elevation"));
+    if (!z_out || nref < 8 || octaves < 1) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_synth_elevation: bad argument");
+    const int64_t n = nrow * ncol;
+    void* dev = nullptr;
+    PFD_TRY(pfd_stage_out(h, z_out, (size_t)n * 4, 3, &dev));
+    synth_elevation_kernel<<<grid_for(n, 256, 2), 256, 0, h->stream>>>(nrow, ncol, nref, octaves, seed, (float*)dev);
+    PFD_LAUNCH_CHECK(h);
+    PFD_TRY(pfd_finish_out(h, z_out, dev, (size_t)n * 4));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    return PFD_OK;
+}
+
+extern "C" int pfd_synth_d8(pfd_handle* h, const float* z, int64_t nrow, int64_t ncol, float sea_level, uint8_t* d8_out) {
+    PFD_TRY(check_handle(h));
+    PFD_TRY(check_shape(h, nrow, ncol, "pfd_synth_d8"));
+    if (!z || !d8_out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_synth_d8: null array");
+    const int64_t n = nrow * ncol;
+    const void* zdev = nullptr;
+    PFD_TRY(pfd_stage_in(h, z, (size_t)n * 4, 4, &zdev));
+    void* dev = nullptr;
+    PFD_TRY(pfd_stage_out(h, d8_out, (size_t)n, 3, &dev));
+    synth_d8_kernel<<<grid_for(n, 256, 2), 256, 0, h->stream>>>((const float*)zdev, nrow, ncol, sea_level, (uint8_t*)dev);
+    PFD_LAUNCH_CHECK(h);
+    PFD_TRY(pfd_finish_out(h, d8_out, dev, (size_t)n));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    return PFD_OK;
+}

@@ -1,0 +1,227 @@
+// pfd_common.cuh -- shared device helpers, the handle, scratch management.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pfd_b200.h"
+
+namespace cg = cooperative_groups;
+
+// ---------------------------------------------------------------------------------------------------------
+// Device-side flow graph encoding (HBM layout):
+//   dir[i]    uint8: 0..7 = slot of the downstream neighbour, 8 = pit with code 0/255 ("outlet"),
+//                    9 = forced pit (flows off the raster or into nodata), 255 = nodata
+//   upmask[i] uint8: bit k set <=> the neighbour in slot k drains into cell i
+// Neighbour slots are numbered in ASCENDING linear index: 0 NW, 1 N, 2 NE, 3 W, 4 E, 5 SW, 6 S, 7 SE.
+// The neighbour in slot k drains into the centre iff its own dir == 7 - k.
+// ---------------------------------------------------------------------------------------------------------
+#define PFD_DIR_PIT 8
+#define PFD_DIR_FPIT 9
+#define PFD_DIR_NODATA 255
+
+// D8 code (core_d8.py:15 _ds) of "flows to slot k"
+__host__ __device__ __forceinline__ constexpr unsigned pfd_slot_code(int k) {
+    // NW 32, N 64, NE 128, W 16, E 1, SW 8, S 4, SE 2
+    return (k == 0) ? 32u : (k == 1) ? 64u : (k == 2) ? 128u : (k == 3) ? 16u : (k == 4) ? 1u : (k == 5) ? 8u
+                                                                                         : (k == 6) ? 4u : 2u;
+}
+
+// row / column delta of slot k (packed 2-bit LUTs: value + 1)
+__host__ __device__ __forceinline__ int pfd_slot_dr(int k) { return (int)((0xA940u >> (2 * k)) & 3u) - 1; }
+__host__ __device__ __forceinline__ int pfd_slot_dc(int k) { return (int)((0x9224u >> (2 * k)) & 3u) - 1; }
+__host__ __device__ __forceinline__ int64_t pfd_slot_off(int k, int64_t ncol) {
+    return (int64_t)pfd_slot_dr(k) * ncol + pfd_slot_dc(k);
+}
+
+typedef uint32_t cell_t;  // internal cell index: rasters up to 2^32 cells
+
+__device__ __forceinline__ uint32_t splat4(uint32_t b) { return b * 0x01010101u; }
+
+// L2-only loads for data that other SMs write inside the same persistent kernel
+template <typename T>
+__device__ __forceinline__ T ld_cg(const T* p) {
+    return __ldcg(p);
+}
+template <>
+__device__ __forceinline__ int8_t ld_cg<int8_t>(const int8_t* p) {
+    return (int8_t)__ldcg((const signed char*)p);
+}
+template <>
+__device__ __forceinline__ uint8_t ld_cg<uint8_t>(const uint8_t* p) {
+    return (uint8_t)__ldcg((const unsigned char*)p);
+}
+template <>
+__device__ __forceinline__ int16_t ld_cg<int16_t>(const int16_t* p) {
+    return (int16_t)__ldcg((const short*)p);
+}
+template <>
+__device__ __forceinline__ uint16_t ld_cg<uint16_t>(const uint16_t* p) {
+    return (uint16_t)__ldcg((const unsigned short*)p);
+}
+template <>
+__device__ __forceinline__ int64_t ld_cg<int64_t>(const int64_t* p) {
+    return (int64_t)__ldcg((const long long*)p);
+}
+template <>
+__device__ __forceinline__ uint64_t ld_cg<uint64_t>(const uint64_t* p) {
+    return (uint64_t)__ldcg((const unsigned long long*)p);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Host side: handle
+// ---------------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+enum { PFD_STAGE_PARSE = 0, PFD_STAGE_PITS = 1, PFD_STAGE_ORDER = 2, PFD_STAGE_SWEEP = 3, PFD_STAGE_TOTAL = 4, PFD_NSTAGE = 5 };
+
+struct pfd_handle {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // raster
+    int64_t nrow = 0, ncol = 0, n = 0;
+    bool parsed = false, ordered = false, have_rank = false, have_basins = false;
+    int64_t n_valid = 0, n_pits = 0, n_outlets = 0, nnodes = 0, nlevels = 0;
+
+    // graph + order (device)
+    DevBuf dir, upmask;       // uint8 [npad]
+    DevBuf pits;              // cell_t [n_pits]
+    DevBuf pit_outlet;        // uint8 [n_pits]
+    DevBuf seq;               // cell_t [n]
+    DevBuf bseq;              // uint32 [n]  basin id aligned with seq positions
+    DevBuf rank;              // int32 [n]
+    DevBuf basins;            // uint32 [n] default basins (all pits, ids 1..n_pits)
+    DevBuf level_off;         // int64 [level_cap + 1]
+    int64_t level_cap = 0;
+    DevBuf bfs_state;         // BfsState
+    DevBuf chunk_status;      // uint64 [n / CHUNK + 2]
+    DevBuf blk_counts;        // uint32 pit count per PC_CHUNK
+    DevBuf blk_offsets;       // uint64 exclusive scan of blk_counts
+    DevBuf counters;          // uint64 [8]: n_valid, n_pits, n_outlets, parse flags, load flags, basins flags
+    DevBuf segs;              // SweepSeg schedule of the level replays
+    int nsegs = 0;
+    int64_t max_level_size = 0;
+    std::vector<long long> h_level_off;
+
+    // staging / scratch
+    DevBuf scratch[6];
+    void* pinned = nullptr;
+    size_t pinned_cap = 0;
+
+    // instrumentation
+    int64_t launches = 0;
+    double stage_ms[PFD_NSTAGE] = {0, 0, 0, 0, 0};
+    bool stage_used[PFD_NSTAGE] = {false, false, false, false, false};
+    cudaEvent_t ev_start[PFD_NSTAGE] = {};
+    cudaEvent_t ev_stop[PFD_NSTAGE] = {};
+};
+
+static thread_local std::string g_last_error;
+
+static int pfd_fail(pfd_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    g_last_error = msg;
+    return code;
+}
+
+#define PFD_CUDA(h, call)                                                                          \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            int code__ = (e__ == cudaErrorMemoryAllocation) ? PFD_ERR_OOM : PFD_ERR_CUDA;          \
+            return pfd_fail((h), code__,                                                           \
+                            std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + \
+                                ":" + std::to_string(__LINE__) + ")");                             \
+        }                                                                                          \
+    } while (0)
+
+#define PFD_TRY(expr)                 \
+    do {                              \
+        int rc__ = (expr);            \
+        if (rc__ != PFD_OK) return rc__; \
+    } while (0)
+
+static int pfd_reserve(pfd_handle* h, DevBuf& b, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return PFD_OK;
+    if (b.p) {
+        PFD_CUDA(h, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    PFD_CUDA(h, cudaMalloc(&b.p, bytes));
+    b.cap = bytes;
+    return PFD_OK;
+}
+
+static void pfd_release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+static bool pfd_is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static inline size_t pfd_dtype_size(int dt) {
+    switch (dt) {
+    case PFD_I8: case PFD_U8: return 1;
+    case PFD_I16: case PFD_U16: return 2;
+    case PFD_I32: case PFD_U32: case PFD_F32: return 4;
+    case PFD_I64: case PFD_U64: case PFD_F64: return 8;
+    default: return 0;
+    }
+}
+
+// Input staging: returns a device pointer holding `bytes` of `src` (src itself when already on device).
+static int pfd_stage_in(pfd_handle* h, const void* src, size_t bytes, int slot, const void** dev) {
+    if (pfd_is_device_ptr(src)) {
+        *dev = src;
+        return PFD_OK;
+    }
+    PFD_TRY(pfd_reserve(h, h->scratch[slot], bytes));
+    PFD_CUDA(h, cudaMemcpyAsync(h->scratch[slot].p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    *dev = h->scratch[slot].p;
+    return PFD_OK;
+}
+
+// Output staging: device pointer to compute into (dst itself when on device).
+static int pfd_stage_out(pfd_handle* h, void* dst, size_t bytes, int slot, void** dev) {
+    if (pfd_is_device_ptr(dst)) {
+        *dev = dst;
+        return PFD_OK;
+    }
+    PFD_TRY(pfd_reserve(h, h->scratch[slot], bytes));
+    *dev = h->scratch[slot].p;
+    return PFD_OK;
+}
+
+static int pfd_finish_out(pfd_handle* h, void* dst, const void* dev, size_t bytes) {
+    if (dev != dst) PFD_CUDA(h, cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, h->stream));
+    return PFD_OK;
+}
+
+#define PFD_LAUNCH_CHECK(h)                     \
+    do {                                        \
+        (h)->launches++;                        \
+        PFD_CUDA((h), cudaGetLastError());      \
+    } while (0)

@@ -1,0 +1,349 @@
+// pfd_parse.cuh -- D8 raster -> device flow graph (dir + upmask) [+ idxs_ds], pit compaction, codecs.
+// Replaces core_d8.from_array / check_values / to_array (pyflwdir/core_d8.py:42-67,115-122,86-102) and
+// core.upstream_count / pit_indices (pyflwdir/core.py:50-61,225-232).
+#pragma once
+#include "pfd_common.cuh"
+
+// ---------------------------------------------------------------------------------------------------------
+// Parse kernel. One CTA = 256 threads handles a tile of PT_H rows x 128 columns. The tile plus a one-cell
+// halo is staged in shared memory as 32-bit words (4 cells per word, coalesced 128 B row segments); each
+// thread then processes 4 horizontally adjacent cells at once with byte-SIMD compares (__vcmpeq4):
+//   for every neighbour slot k: which of my 4 cells flow there, is that neighbour nodata (forced pit),
+//   does that neighbour flow into me (upstream mask bit k).
+// Out-of-raster halo cells are filled with 247 (nodata), which makes "flows off the raster" and "flows into
+// nodata" the same test (core_d8.py:58-61).
+// ---------------------------------------------------------------------------------------------------------
+#define PT_H 32
+#define PT_WW 32               // words per tile row
+#define PT_W (PT_WW * 4)       // 128 cells
+#define PT_SW (PT_WW + 2)      // smem words per row incl. halo words
+
+template <bool ALIGNED>
+__device__ __forceinline__ uint32_t parse_load_word(const uint8_t* __restrict__ d8, int64_t nrow, int64_t ncol,
+                                                    int64_t r, int64_t wc) {
+    // word wc covers columns 4*wc .. 4*wc+3
+    if (r < 0 || r >= nrow || wc < 0) return 0xF7F7F7F7u;
+    int64_t c = wc * 4;
+    if (c >= ncol) return 0xF7F7F7F7u;
+    if (ALIGNED) {
+        return __ldg(reinterpret_cast<const uint32_t*>(d8 + r * ncol + c));
+    } else {
+        uint32_t w = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            uint32_t v = (c + b < ncol) ? (uint32_t)__ldg(d8 + r * ncol + c + b) : 247u;
+            w |= v << (8 * b);
+        }
+        return w;
+    }
+}
+
+// IDXMODE: 0 = no idxs_ds output, 1 = 32-bit (int32 / uint32 share the bit pattern), 2 = int64
+template <bool ALIGNED, int IDXMODE>
+__global__ void __launch_bounds__(256) parse_kernel(const uint8_t* __restrict__ d8, int64_t nrow, int64_t ncol,
+                                                    uint8_t* __restrict__ dir, uint8_t* __restrict__ upmask,
+                                                    void* __restrict__ idxs_out, unsigned int* __restrict__ invalid_flag) {
+    __shared__ uint32_t tile[PT_H + 2][PT_SW];
+    const int64_t r0 = (int64_t)blockIdx.y * PT_H;
+    const int64_t wc0 = (int64_t)blockIdx.x * PT_WW;  // first word column of the tile
+
+    for (int i = threadIdx.x; i < (PT_H + 2) * PT_SW; i += 256) {
+        int tr = i / PT_SW, tw = i % PT_SW;
+        tile[tr][tw] = parse_load_word<ALIGNED>(d8, nrow, ncol, r0 - 1 + tr, wc0 - 1 + tw);
+    }
+    __syncthreads();
+
+    const int tw = threadIdx.x & 31;  // word within the tile row
+    const int wrow = threadIdx.x >> 5;
+    bool bad = false;
+
+#pragma unroll 1
+    for (int it = 0; it < PT_H / 8; ++it) {
+        const int tr = wrow + it * 8;
+        const int64_t r = r0 + tr;
+        const int64_t c = (wc0 + tw) * 4;
+        if (r >= nrow || c >= ncol) continue;
+        // 3x3 words around mine
+        const uint32_t a0 = tile[tr][tw], a1 = tile[tr][tw + 1], a2 = tile[tr][tw + 2];
+        const uint32_t b0 = tile[tr + 1][tw], w = tile[tr + 1][tw + 1], b2 = tile[tr + 1][tw + 2];
+        const uint32_t c0 = tile[tr + 2][tw], c1 = tile[tr + 2][tw + 1], c2 = tile[tr + 2][tw + 2];
+        // neighbour words per slot: byte j = code of the slot-k neighbour of my cell j
+        uint32_t nb[8];
+        nb[0] = __byte_perm(a0, a1, 0x6543);  // NW: shift right by one cell
+        nb[1] = a1;                           // N
+        nb[2] = __byte_perm(a1, a2, 0x4321);  // NE: shift left by one cell
+        nb[3] = __byte_perm(b0, w, 0x6543);   // W
+        nb[4] = __byte_perm(w, b2, 0x4321);   // E
+        nb[5] = __byte_perm(c0, c1, 0x6543);  // SW
+        nb[6] = c1;                           // S
+        nb[7] = __byte_perm(c1, c2, 0x4321);  // SE
+
+        const uint32_t nodata = __vcmpeq4(w, splat4(247u));
+        const uint32_t pit = __vcmpeq4(w, 0u) | __vcmpeq4(w, splat4(255u));
+        // legal codes: 0 or a power of two, 247, 255 (core_d8.py:19)
+        const uint32_t pow2 = __vcmpeq4(w & __vsub4(w, splat4(1u)), 0u);
+        if ((pow2 | nodata | pit) != 0xFFFFFFFFu) bad = true;
+
+        uint32_t dirw = 0, forced = 0, upw = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t sel = __vcmpeq4(w, splat4(pfd_slot_code(k)));
+            dirw |= sel & splat4((uint32_t)k);
+            forced |= sel & __vcmpeq4(nb[k], splat4(247u));
+            upw |= __vcmpeq4(nb[k], splat4(pfd_slot_code(7 - k))) & splat4(1u << k);
+        }
+        dirw = (dirw & ~forced) | (forced & splat4(PFD_DIR_FPIT));
+        dirw |= pit & splat4(PFD_DIR_PIT);
+        dirw |= nodata;  // 0xFF
+        upw &= ~nodata;
+
+        const int64_t i0 = r * ncol + c;
+        if (ALIGNED) {
+            *reinterpret_cast<uint32_t*>(dir + i0) = dirw;
+            *reinterpret_cast<uint32_t*>(upmask + i0) = upw;
+        } else {
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (c + b < ncol) {
+                    dir[i0 + b] = (uint8_t)(dirw >> (8 * b));
+                    upmask[i0 + b] = (uint8_t)(upw >> (8 * b));
+                }
+        }
+        if (IDXMODE != 0) {
+            int64_t ds[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const uint32_t d = (dirw >> (8 * b)) & 0xFFu;
+                const int64_t i = i0 + b;
+                ds[b] = (d < 8u) ? i + pfd_slot_off((int)d, ncol) : ((d == PFD_DIR_NODATA) ? (int64_t)-1 : i);
+            }
+            if (IDXMODE == 1) {
+                uint32_t* o = reinterpret_cast<uint32_t*>(idxs_out) + i0;
+                if (ALIGNED) {
+                    *reinterpret_cast<uint4*>(o) = make_uint4((uint32_t)ds[0], (uint32_t)ds[1], (uint32_t)ds[2], (uint32_t)ds[3]);
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (c + b < ncol) o[b] = (uint32_t)ds[b];
+                }
+            } else {
+                int64_t* o = reinterpret_cast<int64_t*>(idxs_out) + i0;
+                if (ALIGNED) {
+                    *reinterpret_cast<longlong2*>(o) = make_longlong2(ds[0], ds[1]);
+                    *reinterpret_cast<longlong2*>(o + 2) = make_longlong2(ds[2], ds[3]);
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (c + b < ncol) o[b] = ds[b];
+                }
+            }
+        }
+    }
+    if (bad) atomicOr(invalid_flag, 1u);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// idxs_ds -> D8 code (core_d8.to_array semantics, core_d8.py:86-102) so that an index array given to the
+// FlwdirRaster constructor goes through the same parse kernel. flag bit 1: link outside the 8 neighbours.
+// ---------------------------------------------------------------------------------------------------------
+template <typename IDX>
+__global__ void idxs_to_d8_kernel(const IDX* __restrict__ idxs, int64_t n, int64_t ncol, uint8_t* __restrict__ d8,
+                                  unsigned int* __restrict__ flag) {
+    const IDX mv = (IDX)-1;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        IDX v = idxs[i];
+        uint8_t code = 247;
+        if (v != mv) {
+            int64_t ds = (int64_t)v;
+            if (ds < 0 || ds >= n) {
+                atomicOr(flag, 2u);
+            } else {
+                int64_t dr = ds / ncol - i / ncol, dc = ds % ncol - i % ncol;
+                if (dr < -1 || dr > 1 || dc < -1 || dc > 1) {
+                    atomicOr(flag, 2u);
+                } else if (dr == 0 && dc == 0) {
+                    code = 0;
+                } else {
+                    int k = (int)((dr + 1) * 3 + (dc + 1));
+                    k = k > 4 ? k - 1 : k;  // skip the centre
+                    code = (uint8_t)pfd_slot_code(k);
+                }
+            }
+        }
+        d8[i] = code;
+    }
+}
+
+// dir -> idxs_ds in the caller's dtype / D8 codes / int8 upstream count
+template <typename IDX>
+__global__ void dir_to_idxs_kernel(const uint8_t* __restrict__ dir, int64_t n, int64_t ncol, IDX* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t d = dir[i];
+        int64_t ds = (d < 8u) ? i + pfd_slot_off((int)d, ncol) : ((d == PFD_DIR_NODATA) ? (int64_t)-1 : i);
+        out[i] = (IDX)ds;
+    }
+}
+
+__global__ void dir_to_d8_kernel(const uint8_t* __restrict__ dir, int64_t n, uint8_t* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t d = dir[i];
+        out[i] = (d < 8u) ? (uint8_t)pfd_slot_code((int)d) : ((d == PFD_DIR_NODATA) ? (uint8_t)247 : (uint8_t)0);
+    }
+}
+
+__global__ void upstream_count_kernel(const uint8_t* __restrict__ dir, const uint8_t* __restrict__ upmask, int64_t n,
+                                      int8_t* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (dir[i] == PFD_DIR_NODATA) ? (int8_t)-9 : (int8_t)__popc((unsigned)upmask[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Pit compaction in ascending linear index (core_d8.py:48-62 appends pits in scan order).
+// Pass 1 counts per 16 KiB chunk, a single-CTA scan turns counts into offsets, pass 2 writes.
+// `dir` is padded with 255 up to a multiple of PC_CHUNK so all loads are 16-byte vectors.
+// ---------------------------------------------------------------------------------------------------------
+#define PC_CHUNK 16384  // cells per CTA: 8 warps x 4 iterations x 512 B
+
+__device__ __forceinline__ uint32_t pit_mask16(const uint4& v, uint32_t* valid, uint32_t* outlets) {
+    // returns a 16-bit mask of pit cells among the 16 bytes; accumulates valid / outlet counts
+    uint32_t m = 0;
+    const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t p8 = __vcmpeq4(ws[j], splat4(PFD_DIR_PIT));
+        uint32_t p9 = __vcmpeq4(ws[j], splat4(PFD_DIR_FPIT));
+        uint32_t nd = __vcmpeq4(ws[j], splat4(PFD_DIR_NODATA));
+        uint32_t p = p8 | p9;
+        // compress 0xFF bytes to bits
+        uint32_t bits = ((p & 0x00000080u) >> 7) | ((p & 0x00008000u) >> 14) | ((p & 0x00800000u) >> 21) |
+                        ((p & 0x80000000u) >> 28);
+        m |= bits << (4 * j);
+        *valid += 4 - (__popc(nd) >> 3);
+        *outlets += __popc(p8) >> 3;
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(256) pit_count_kernel(const uint8_t* __restrict__ dir, uint32_t* __restrict__ blk_pits,
+                                                        unsigned long long* __restrict__ counters) {
+    __shared__ uint32_t s_p[8], s_v[8], s_o[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint4* base = reinterpret_cast<const uint4*>(dir + (int64_t)blockIdx.x * PC_CHUNK + warp * 2048);
+    uint32_t np = 0, nv = 0, no = 0;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        uint4 v = __ldg(base + it * 32 + lane);
+        np += __popc(pit_mask16(v, &nv, &no));
+    }
+    np = __reduce_add_sync(0xFFFFFFFFu, np);
+    nv = __reduce_add_sync(0xFFFFFFFFu, nv);
+    no = __reduce_add_sync(0xFFFFFFFFu, no);
+    if (lane == 0) {
+        s_p[warp] = np;
+        s_v[warp] = nv;
+        s_o[warp] = no;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tp = 0, tv = 0, to = 0;
+        for (int w = 0; w < 8; ++w) {
+            tp += s_p[w];
+            tv += s_v[w];
+            to += s_o[w];
+        }
+        blk_pits[blockIdx.x] = tp;
+        if (tv) atomicAdd(&counters[0], (unsigned long long)tv);
+        if (tp) atomicAdd(&counters[1], (unsigned long long)tp);
+        if (to) atomicAdd(&counters[2], (unsigned long long)to);
+    }
+}
+
+// exclusive scan of `n` uint32 counts into uint64 offsets; single CTA of 1024 threads
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const uint32_t* __restrict__ counts, int64_t n,
+                                                           unsigned long long* __restrict__ offsets) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t per = (n + 1023) / 1024;
+    const int64_t b = threadIdx.x * per, e = min(n, b + per);
+    unsigned long long sum = 0;
+    for (int64_t i = b; i < e; ++i) sum += counts[i];
+    unsigned long long incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long v = s_warp[lane], inc2 = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, inc2, d);
+            if (lane >= d) inc2 += t;
+        }
+        s_warp[lane] = inc2 - v;
+        if (lane == 31) s_carry = inc2;
+    }
+    __syncthreads();
+    unsigned long long run = s_warp[warp] + (incl - sum);
+    for (int64_t i = b; i < e; ++i) {
+        offsets[i] = run;
+        run += counts[i];
+    }
+    if (threadIdx.x == 0) offsets[n] = s_carry;
+}
+
+__global__ void __launch_bounds__(256) pit_scatter_kernel(const uint8_t* __restrict__ dir,
+                                                          const unsigned long long* __restrict__ blk_off,
+                                                          cell_t* __restrict__ pits, uint8_t* __restrict__ pit_outlet) {
+    __shared__ uint32_t s_w[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t cell0 = (int64_t)blockIdx.x * PC_CHUNK + warp * 2048;
+    const uint4* base = reinterpret_cast<const uint4*>(dir + cell0);
+    uint4 v[4];
+    uint32_t m[4];
+    uint32_t cnt[4];
+    uint32_t dummy_v = 0, dummy_o = 0, total = 0;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        v[it] = __ldg(base + it * 32 + lane);
+        m[it] = pit_mask16(v[it], &dummy_v, &dummy_o);
+        cnt[it] = __popc(m[it]);
+        total += cnt[it];
+    }
+    // order inside the warp's 2048 cells: iteration-major, then lane, then byte
+    uint32_t iter_tot[4], lane_excl[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        uint32_t incl = cnt[it];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        lane_excl[it] = incl - cnt[it];
+        iter_tot[it] = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    if (lane == 0) s_w[warp] = iter_tot[0] + iter_tot[1] + iter_tot[2] + iter_tot[3];
+    __syncthreads();
+    unsigned long long basep = blk_off[blockIdx.x];
+    for (int w = 0; w < warp; ++w) basep += s_w[w];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        unsigned long long o = basep + lane_excl[it];
+        uint32_t mm = m[it];
+        const uint32_t ws[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+        while (mm) {
+            int b = __ffs(mm) - 1;
+            mm &= mm - 1;
+            uint32_t d = (ws[b >> 2] >> (8 * (b & 3))) & 0xFFu;
+            pits[o] = (cell_t)(cell0 + it * 512 + lane * 16 + b);
+            pit_outlet[o] = (d == PFD_DIR_PIT) ? 1 : 0;
+            ++o;
+        }
+        basep += iter_tot[it];
+    }
+    (void)total;
+}

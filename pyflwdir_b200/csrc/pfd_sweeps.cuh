@@ -1,0 +1,249 @@
+// pfd_sweeps.cuh -- level-ordered sweeps over the BFS sequence.
+// Replaces streams.accuflux / accuflux_ds (pyflwdir/streams.py:15-41,44-70), core.fillnodata_upstream as used
+// by basins.basins (pyflwdir/core.py:120-146, basins.py:12-18), streams.strahler_order (streams.py:228-269)
+// and dem.height_above_nearest_drain (pyflwdir/dem.py:299-330).
+//
+// The reference walks `seq` (down->up) or `seq[::-1]` (up->down) serially. All cells of one rank level are
+// independent, so a sweep = for level in order: all cells of the level in parallel. Up-sweeps are PULLS: the
+// downstream cell gathers its (complete) upstream neighbours in DESCENDING linear index, which is exactly the
+// order in which the reference's `seq[::-1]` loop adds them -> floats are bit-exact and no atomics are needed.
+// One persistent cooperative kernel per sweep follows a host-built schedule: big levels use the whole grid +
+// grid.sync(), runs of small levels are walked by CTA 0 alone.
+#pragma once
+#include "pfd_common.cuh"
+
+#define SW_THREADS 256
+#define SW_SOLO_MAX 2048
+
+struct SweepSeg {
+    int first;   // first level of the segment
+    int count;   // number of levels (1 for a big level)
+    int solo;    // 1: CTA 0 walks `count` small levels alone
+    int pad;
+};
+
+struct SweepParams {
+    const cell_t* seq;
+    const long long* level_off;
+    const SweepSeg* segs;
+    int nsegs;
+    int skip_level0;  // down-sweeps whose level-0 (pit) step is a no-op
+};
+
+template <class Op, bool UP>
+__global__ void __launch_bounds__(SW_THREADS) sweep_kernel(SweepParams P, Op op) {
+    cg::grid_group grid = cg::this_grid();
+    for (int si = 0; si < P.nsegs; ++si) {
+        const SweepSeg sg = P.segs[UP ? (P.nsegs - 1 - si) : si];
+        if (sg.solo) {
+            if (blockIdx.x == 0) {
+                for (int li = 0; li < sg.count; ++li) {
+                    const int lev = UP ? (sg.first + sg.count - 1 - li) : (sg.first + li);
+                    if (!(P.skip_level0 && lev == 0)) {
+                        const long long s = P.level_off[lev], e = P.level_off[lev + 1];
+                        for (long long p = s + threadIdx.x; p < e; p += SW_THREADS) op(__ldg(P.seq + p), p, lev);
+                    }
+                    __syncthreads();
+                }
+            }
+        } else {
+            const int lev = sg.first;
+            if (!(P.skip_level0 && lev == 0)) {
+                const long long s = P.level_off[lev], e = P.level_off[lev + 1];
+                const long long stride = (long long)gridDim.x * SW_THREADS;
+                for (long long p = s + (long long)blockIdx.x * SW_THREADS + threadIdx.x; p < e; p += stride)
+                    op(__ldg(P.seq + p), p, lev);
+            }
+        }
+        if (si + 1 < P.nsegs) grid.sync();
+    }
+}
+
+// ---- typed helpers -------------------------------------------------------------------------------------
+template <typename T> struct AccT { typedef T U; };
+template <> struct AccT<int8_t> { typedef uint8_t U; };
+template <> struct AccT<int16_t> { typedef uint16_t U; };
+template <> struct AccT<int32_t> { typedef uint32_t U; };
+template <> struct AccT<int64_t> { typedef uint64_t U; };
+
+template <typename T>
+__device__ __forceinline__ T acc_add(T a, T b) {  // integer: wrap-around like numba
+    typedef typename AccT<T>::U U;
+    return (T)((U)a + (U)b);
+}
+template <>
+__device__ __forceinline__ float acc_add<float>(float a, float b) { return __fadd_rn(a, b); }
+template <>
+__device__ __forceinline__ double acc_add<double>(double a, double b) { return __dadd_rn(a, b); }
+
+struct NoData {
+    double f;
+    long long i;
+    int is_int;
+};
+
+// numba's promotion for `x != nodata`: int vs int -> int64 compare, otherwise float64 compare
+template <typename T>
+__device__ __forceinline__ bool not_nodata(T x, const NoData& nd) {
+    return nd.is_int ? ((long long)x != nd.i) : ((double)x != nd.f);
+}
+template <>
+__device__ __forceinline__ bool not_nodata<float>(float x, const NoData& nd) { return (double)x != nd.f; }
+template <>
+__device__ __forceinline__ bool not_nodata<double>(double x, const NoData& nd) { return x != nd.f; }
+
+__device__ __forceinline__ long long ds_of(cell_t c, uint32_t d, long long ncol) {
+    return (d < 8u) ? (long long)c + pfd_slot_off((int)d, ncol) : (long long)c;
+}
+
+// ---- streams.accuflux (up): out pre-initialised with data (accu = data.copy(), streams.py:36) -------------
+template <typename T>
+struct AccuUpOp {
+    const uint8_t* upmask;
+    T* out;
+    long long ncol;
+    NoData nd;
+    __device__ __forceinline__ void operator()(cell_t c, long long, int) const {
+        uint32_t m = __ldg(upmask + c);
+        if (!m) return;
+        T acc = ld_cg(out + c);
+        while (m) {  // descending slot = descending linear index of the upstream neighbour
+            const int k = 31 - __clz(m);
+            m ^= 1u << k;
+            const T a = ld_cg(out + ((long long)c + pfd_slot_off(k, ncol)));
+            if (not_nodata(acc, nd) && not_nodata(a, nd)) acc = acc_add(acc, a);
+        }
+        out[c] = acc;
+    }
+};
+
+// ---- streams.accuflux_ds (down) ------------------------------------------------------------------------
+template <typename T>
+struct AccuDownOp {
+    const uint8_t* dir;
+    T* out;
+    long long ncol;
+    NoData nd;
+    __device__ __forceinline__ void operator()(cell_t c, long long, int) const {
+        const uint32_t d = __ldg(dir + c);
+        if (d >= 8u) return;  // pit: idx0 == idx_ds
+        const T a = ld_cg(out + ((long long)c + pfd_slot_off((int)d, ncol)));
+        const T v = ld_cg(out + c);
+        if (not_nodata(a, nd) && not_nodata(v, nd)) out[c] = acc_add(v, a);
+    }
+};
+
+// ---- core.fillnodata_upstream with nodata = 0 (basins) --------------------------------------------------
+template <typename U>
+struct FillUpOp {
+    const uint8_t* dir;
+    U* out;
+    long long ncol;
+    __device__ __forceinline__ void operator()(cell_t c, long long, int) const {
+        if (ld_cg(out + c) != (U)0) return;
+        const uint32_t d = __ldg(dir + c);
+        if (d >= 8u) return;
+        const U a = ld_cg(out + ((long long)c + pfd_slot_off((int)d, ncol)));
+        if (a != (U)0) out[c] = a;
+    }
+};
+
+// ---- core.rank as a replay (when the BFS ran without it) -----------------------------------------------
+struct RankOp {
+    int32_t* rank;
+    __device__ __forceinline__ void operator()(cell_t c, long long, int lev) const { rank[c] = lev; }
+};
+
+// ---- streams.strahler_order -----------------------------------------------------------------------------
+struct StrahlerOp {
+    const uint8_t* upmask;
+    const uint8_t* mask;  // may be null
+    uint8_t* out;
+    long long ncol;
+    __device__ __forceinline__ void operator()(cell_t c, long long, int) const {
+        uint32_t m = __ldg(upmask + c);
+        uint8_t so = 0, smax = 0;  // strord[c], strmax[c] built from the pushes of the upstream cells
+        while (m) {
+            const int k = 31 - __clz(m);
+            m ^= 1u << k;
+            const long long u = (long long)c + pfd_slot_off(k, ncol);
+            if (mask && !__ldg(mask + u)) continue;  // streams.py:252-253: masked-out cells do not push
+            const uint8_t sto = ld_cg(out + u);
+            if (so < sto)
+                so = sto;
+            else if (sto == so && smax == sto)
+                so = (uint8_t)(so + 1);
+            if (smax < sto) smax = sto;
+        }
+        const bool in = mask ? (__ldg(mask + c) != 0) : true;
+        if (in && so == 0) so = 1;  // headwater
+        out[c] = so;
+    }
+};
+
+// ---- dem.height_above_nearest_drain ----------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T elev_sub(T a, T b);
+template <>
+__device__ __forceinline__ float elev_sub<float>(float a, float b) { return __fsub_rn(a, b); }
+template <>
+__device__ __forceinline__ double elev_sub<double>(double a, double b) { return __dsub_rn(a, b); }
+
+template <typename T>
+struct HandOp {
+    const uint8_t* dir;
+    const uint8_t* drain;
+    const T* elevtn;
+    double* out;
+    long long ncol;
+    __device__ __forceinline__ void operator()(cell_t c, long long, int) const {
+        if (__ldg(drain + c) == 1) {
+            out[c] = 0.0;
+            return;
+        }
+        const uint32_t d = __ldg(dir + c);
+        const long long ds = ds_of(c, d, ncol);
+        const T dz = elev_sub<T>(__ldg(elevtn + c), __ldg(elevtn + ds));
+        const double h_ds = (d < 8u) ? ld_cg(out + ds) : 0.0;  // a pit reads its own initial 0 (dem.py:323)
+        out[c] = __dadd_rn(h_ds, (double)dz);
+    }
+};
+
+// ---- element-wise helpers --------------------------------------------------------------------------------
+template <typename T>
+__global__ void fill_kernel(T* __restrict__ out, int64_t n, T v) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = v;
+}
+
+// upstream_area("cell") init: ones, -9999 on nodata (pyflwdir.py:790-800)
+__global__ void uparea_init_kernel(const uint8_t* __restrict__ dir, int64_t n, int32_t* __restrict__ out) {
+    const int64_t i4 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
+    if (i4 >= n) return;
+    if (i4 + 4 <= n) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(dir + i4);
+        int4 r;
+        r.x = ((w & 0xFFu) == 0xFFu) ? -9999 : 1;
+        r.y = (((w >> 8) & 0xFFu) == 0xFFu) ? -9999 : 1;
+        r.z = (((w >> 16) & 0xFFu) == 0xFFu) ? -9999 : 1;
+        r.w = (((w >> 24) & 0xFFu) == 0xFFu) ? -9999 : 1;
+        *reinterpret_cast<int4*>(out + i4) = r;
+    } else {
+        for (int64_t i = i4; i < n; ++i) out[i] = (dir[i] == PFD_DIR_NODATA) ? -9999 : 1;
+    }
+}
+
+// basins[outlets[k]] = ids[k]; serial "last one wins" like numpy fancy assignment is kept by letting the
+// highest k win through an atomicMax on the writer index first.
+template <typename IDX, typename U>
+__global__ void scatter_ids_kernel(const IDX* __restrict__ idxs, const U* __restrict__ ids, int64_t k0, int64_t k1,
+                                   int64_t n, U* __restrict__ out, unsigned int* __restrict__ flag) {
+    for (int64_t k = k0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < k1; k += (int64_t)gridDim.x * blockDim.x) {
+        int64_t i = (int64_t)idxs[k];
+        if (i < 0) i += n;  // numpy negative indexing
+        if (i < 0 || i >= n) {
+            atomicOr(flag, 4u);
+            continue;
+        }
+        out[i] = ids[k];
+    }
+}

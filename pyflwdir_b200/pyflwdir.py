@@ -1,0 +1,279 @@
+"""`from_array` / `FlwdirRaster`: the raster object API of the D8 hot path, mirroring
+/root/reference/pyflwdir/pyflwdir.py (from_array :130-205, _get_idxs_dtype :105-127, FlwdirRaster.__init__
+:211-273, idxs_seq :292-297, set_transform :318-337, to_array :341-360, basins :564-599, upstream_area :770-801,
+hand :1485-1511, _check_data :1548-1559) with every kernel running on the GPU.
+
+Only the D8 flow-direction type is accelerated; "ldd" / "nextxy" rasters raise NotImplementedError.
+"""
+import pickle
+
+import numpy as np
+
+from . import _device, _lib
+from . import gis_utils as gis
+from .flwdir import Flwdir, _not_in_scope
+from .gis_utils import Affine
+
+__all__ = ["FlwdirRaster", "from_array"]
+
+FTYPES = ("d8", "ldd", "nextxy")  # pyflwdir.py:26-30; only "d8" is implemented here
+_D8_MV = np.uint8(247)            # core_d8.py:17
+_D8_PV = np.array([0, 255], dtype=np.uint8)  # core_d8.py:18
+
+
+def _get_idxs_dtype(n):
+    """Smallest integer dtype that can represent ``n`` indices (pyflwdir.py:105-127)."""
+    if n < 2147483647:  # 2**31 - 1
+        return np.int32
+    elif n < 4294967294:  # 2**32 - 2
+        return np.uint32
+    return np.int64
+
+
+def _is_d8_candidate(data):
+    return isinstance(data, np.ndarray) and data.dtype == np.uint8 and data.ndim == 2
+
+
+def from_array(data, ftype="infer", check_ftype=True, mask=None, transform=gis.IDENTITY, latlon=False,
+               device=0, **kwargs):
+    """Flow direction raster array parsed to actionable format (GPU resident).
+
+    Same signature and errors as the reference's `pyflwdir.from_array`; `device` (CUDA ordinal) is the only
+    extension. The D8 raster is parsed by one CUDA kernel into the device flow graph; `idxs_ds`, `idxs_pit`,
+    `idxs_seq`, `rank` are materialised on the host only when read.
+    """
+    infer = ftype == "infer"
+    if infer:
+        # the reference tries d8, ldd, nextxy in that order (pyflwdir.py:39-48); only d8 exists here
+        if not _is_d8_candidate(data):
+            raise ValueError("The flow direction type could not be inferred.")
+        ftype = "d8"
+        check_ftype = False
+    if ftype == "nextxy":
+        shape, ndim = data[0].shape, data[0].ndim
+    else:
+        ndim, shape = data.ndim, data.shape
+    if ndim != 2:
+        raise ValueError("The FlwdirRaster should be 2 dimensional")
+    if ftype not in FTYPES:
+        ftypes_str = '" ,"'.join(FTYPES)
+        raise ValueError(f'Unknown flow direction type: "{ftype}", select from {ftypes_str}')
+    if ftype != "d8":
+        raise NotImplementedError(f'ftype "{ftype}" is not accelerated by pyflwdir_b200 (D8 only)')
+    invalid_msg = f'The flow direction data with type "{ftype}" is invalid.'
+    if not _is_d8_candidate(data):
+        if check_ftype:
+            raise ValueError(invalid_msg)
+        raise ValueError("D8 data must be a 2-D uint8 array")
+    if mask is not None:
+        if mask.shape != data.shape:
+            raise ValueError('"mask" shape does not match with data shape')
+        data = np.where(mask != 0, data, _D8_MV)
+
+    dtype = _get_idxs_dtype(shape[0] * shape[1])
+    dev = _device.DeviceGraph(device)
+    try:
+        dev.parse_d8(data)
+    except ValueError as err:
+        if getattr(err, "status", None) == _lib.ERR_INVALID_D8:
+            # illegal codes are refused even with check_ftype=False (the reference would mis-parse them)
+            if infer:
+                raise ValueError("The flow direction type could not be inferred.") from None
+            raise ValueError(invalid_msg) from None
+        raise
+    idxs_pit = dev.fetch(_lib.ARR_PITS, dtype)
+    is_outlet = dev.fetch(_lib.ARR_PIT_IS_OUTLET)
+    idxs_outlet = idxs_pit[is_outlet != 0]  # pits whose code is 0/255 (pyflwdir.py:193)
+    return FlwdirRaster(
+        idxs_ds=None, idxs_pit=idxs_pit, idxs_outlet=idxs_outlet, shape=shape, ftype=ftype, transform=transform,
+        latlon=latlon, _dev=dev, _idx_dtype=dtype, **kwargs,
+    )
+
+
+class FlwdirRaster(Flwdir):
+    """Flow direction raster array parsed to general actionable format."""
+
+    def __init__(self, idxs_ds, shape, ftype, idxs_pit=None, idxs_outlet=None, idxs_seq=None, nnodes=None,
+                 transform=gis.IDENTITY, latlon=False, cache=True, device=0, _dev=None, _idx_dtype=None):
+        shape = tuple(int(s) for s in shape)
+        if _dev is None:
+            idxs_ds = np.asarray(idxs_ds)
+            size = idxs_ds.size
+        else:
+            size = _dev.size
+        super().__init__(idxs_ds=idxs_ds, idxs_pit=idxs_pit, idxs_outlet=idxs_outlet, idxs_seq=idxs_seq,
+                         nnodes=nnodes, cache=cache, _dev=_dev, _idx_dtype=_idx_dtype, _size=size)
+        if ftype not in FTYPES:
+            ftypes_str = '" ,"'.join(FTYPES)
+            raise ValueError(f'Unknown flow direction type: "{ftype}", select from {ftypes_str}')
+        if ftype != "d8":
+            raise NotImplementedError(f'ftype "{ftype}" is not accelerated by pyflwdir_b200 (D8 only)')
+        self.ftype = ftype
+        if len(shape) != 2 or shape[0] * shape[1] != self.size:
+            raise ValueError(f"Invalid FlwdirRaster: shape {shape} does not match size {self.size}")
+        self.shape = shape
+        self.set_transform(transform, latlon)
+        if self._dev is None:  # public constructor path: upload the index array
+            self._dev = _device.DeviceGraph(device)
+            self._dev.load_idxs_ds(self._idxs_ds, shape)
+            if self._pit is None:
+                self._pit = self._dev.fetch(_lib.ARR_PITS, self._idx_dtype)
+        # check validity (flwdir.py:125-127)
+        if self.idxs_pit.size == 0:
+            raise ValueError("Invalid FlwdirRaster: no pits found")
+
+    def _raster_shape(self):
+        return self.shape
+
+    @property
+    def _dict(self):
+        return {
+            "ftype": self.ftype,
+            "shape": self.shape,
+            "nnodes": self.nnodes,
+            "transform": self.transform,
+            "latlon": self.latlon,
+            "idxs_ds": self.idxs_ds,
+            "idxs_seq": self._seq,
+            "idxs_pit": self._pit,
+        }
+
+    @property
+    def ncells(self):
+        return self.nnodes
+
+    @property
+    def area(self):
+        """Cell area [m2]"""
+        if "area" in self._cached:
+            area = self._cached["area"]
+        else:
+            area = gis.area_grid(self.transform, self.shape, self.latlon, unit="m2")
+            if self.cache:
+                self._cached.update(area=area)
+        return area
+
+    # ------------------------------------------------------------------ set / modify
+    def set_transform(self, transform, latlon=False):
+        """Set transform affine (pyflwdir.py:318-337)."""
+        if not isinstance(transform, Affine):
+            try:
+                transform = Affine(*tuple(transform)[:6])
+            except TypeError:
+                raise ValueError("Invalid transform.")
+        self.transform = transform
+        self.latlon = latlon
+
+    def add_pits(self, idxs=None, xy=None, streams=None):
+        idxs1 = self._check_idxs_xy(idxs, xy, streams)
+        super().add_pits(idxs=idxs1)
+
+    # ------------------------------------------------------------------ export
+    def to_array(self, ftype=None):
+        """Return 2D flow direction raster (core_d8.to_array, core_d8.py:86-102)."""
+        if ftype is None:
+            ftype = self.ftype
+        if ftype == "d8":
+            return self._dev.fetch(_lib.ARR_D8).reshape(self.shape)
+        if ftype in FTYPES:
+            raise NotImplementedError(f'to_array(ftype="{ftype}") is outside the accelerated hot path')
+        raise ValueError(f'ftype "{ftype}" unknown')
+
+    @staticmethod
+    def load(fn):
+        """Load serialized FlwdirRaster object from file"""
+        with open(fn, "rb") as handle:
+            kwargs = pickle.load(handle)
+        return FlwdirRaster(**kwargs)
+
+    # ------------------------------------------------------------------ spatial helpers
+    def index(self, xs, ys, **kwargs):
+        """Linear cell indices of x, y coordinates (row-major), -1 outside the raster."""
+        xs, ys = np.atleast_1d(xs), np.atleast_1d(ys)
+        cols, rows = ~self.transform * (xs, ys)
+        cols, rows = np.floor(cols).astype(np.int64), np.floor(rows).astype(np.int64)
+        nrow, ncol = self.shape
+        idxs = rows * ncol + cols
+        outside = (rows < 0) | (rows >= nrow) | (cols < 0) | (cols >= ncol)
+        idxs[outside] = -1
+        return idxs
+
+    def xy(self, idxs, **kwargs):
+        """Cell-centre x, y coordinates of linear indices."""
+        idxs = np.atleast_1d(idxs)
+        ncol = self.shape[1]
+        r, c = idxs // ncol, idxs % ncol
+        return self.transform * (c + 0.5, r + 0.5)
+
+    # ------------------------------------------------------------------ basins
+    def basins(self, idxs=None, xy=None, ids=None, **kwargs):
+        """(Sub)basin map with a unique ID for every (sub)basin (pyflwdir.py:564-599 -> basins.basins)."""
+        if idxs is None and xy is None:  # full basins / includes edge-pits
+            idxs_dev = None
+            n_idxs = self.idxs_pit.size
+        else:
+            idxs_dev = self._check_idxs_xy(idxs, xy, **kwargs)
+            n_idxs = idxs_dev.size
+        if ids is not None:
+            ids = np.atleast_1d(ids).ravel()
+            if ids.size != n_idxs:
+                raise ValueError("IDs size does not match size of idxs.")
+            elif np.any(ids == 0):
+                raise ValueError("IDs cannot contain a value zero.")
+        if idxs_dev is None and ids is None:
+            basids = self._dev.basins()
+        else:
+            if idxs_dev is None:
+                idxs_dev = self.idxs_pit
+            if ids is None:
+                ids = np.arange(1, n_idxs + 1, dtype=np.uint32)  # basins.py:14-15
+            basids = self._dev.basins(idxs_dev, ids)
+        return basids.reshape(self.shape)
+
+    # ------------------------------------------------------------------ accumulate
+    def upstream_area(self, unit="cell"):
+        """Upstream area map (pyflwdir.py:770-801). "cell": int32 counts by the dedicated device sweep; other
+        units accumulate the cell-area grid in its own dtype (float64 if latlon, else float32)."""
+        unit = str(unit).lower()
+        if unit not in gis.AREA_FACTORS:
+            fstr = '", "'.join(gis.AREA_FACTORS.keys())
+            raise ValueError(f'Unknown unit: {unit}, select from "{fstr}".')
+        if unit == "cell":
+            return self._dev.upstream_area_cells().reshape(self.shape)  # -9999 fill is fused in the kernel
+        area = self.area.ravel() / gis.AREA_FACTORS[unit]
+        uparea = self._dev.accuflux(area, -9999, "up")
+        uparea[~self.mask.ravel()] = -9999
+        return uparea.reshape(self.shape)
+
+    # ------------------------------------------------------------------ elevation
+    def hand(self, drain, elevtn):
+        """Height above the nearest drain (pyflwdir.py:1485-1511 -> dem.height_above_nearest_drain)."""
+        hand = self._dev.hand(self._check_data(drain, "drain"), self._check_data(elevtn, "elevtn"))
+        return hand.reshape(self.shape)
+
+    # ------------------------------------------------------------------ shortcuts
+    def _check_data(self, data, name, optional=False, flatten=True, **kwargs):
+        if data is None and optional:
+            return
+        if data is None:
+            if name == "uparea":
+                data = self.upstream_area(**kwargs)
+            elif name == "basins":
+                data = self.basins(**kwargs)
+            elif name == "strord":
+                data = self.stream_order(**kwargs)
+        return super()._check_data(data, name, optional, flatten=flatten)
+
+    def _check_idxs_xy(self, idxs=None, xy=None, streams=None):
+        if (xy is not None and idxs is not None) or (xy is None and idxs is None):
+            raise ValueError("Either idxs or xy should be provided.")
+        elif xy is not None:
+            idxs = self.index(*xy)
+        return super()._check_idxs_xy(idxs, streams)
+
+    for _name in ("repair_loops_raster", "subbasins_streamorder", "subbasins_pfafstetter", "subbasins_area",
+                  "streams", "geofeatures", "vectorize", "stream_distance", "dem_adjust", "dem_dig_d4", "floodplains",
+                  "upscale", "upscale_error", "subgrid_rivlen", "subgrid_rivslp", "subgrid_rivavg", "subgrid_rivmed",
+                  "ucat_area", "ucat_outlets", "ucat_volume", "inflow_idxs", "outflow_idxs", "main_upstream"):
+        locals()[_name] = _not_in_scope(_name)
+    del _name

@@ -140,3 +140,43 @@ def run_oracle_case(d8, aux, area=None):
     out["basins_sub"] = o.basins.basins(idxs_ds, sub_idxs, seq, sub_ids).reshape(shape)
     out["to_array"] = o.core_d8.to_array(idxs_ds, shape)
     return out
+
+
+def run_api_case(pf, d8, aux, transform=None, latlon=False):
+    """The hot path through the object API of `pf` (the reference `pyflwdir` in make_golden.py, `pyflwdir_b200`
+    in the GPU tests) -- same calls, same order."""
+    kw = {}
+    if transform is not None:
+        kw = dict(transform=transform, latlon=latlon)
+    flw = pf.from_array(d8, ftype="d8", cache=False, **kw)
+    out = {}
+    out["idxs_ds"] = flw.idxs_ds
+    out["idxs_pit"] = flw.idxs_pit
+    out["idxs_outlet"] = flw.idxs_outlet
+    out["rank"] = flw.rank
+    out["idxs_seq"] = flw.idxs_seq
+    out["nnodes"] = np.int64(flw.nnodes)
+    out["isvalid"] = np.bool_(flw.isvalid)
+    out["n_upstream"] = flw.n_upstream
+    out["uparea_cell"] = flw.upstream_area()
+    out["uparea_km2"] = flw.upstream_area("km2")
+    out["basins"] = flw.basins()
+    out["strord"] = flw.stream_order()
+    out["strord_mask"] = flw.stream_order(mask=aux["smask"])
+    out["accu_f32"] = flw.accuflux(aux["data_f32"], nodata=-9999)
+    out["accu_f64"] = flw.accuflux(aux["data_f64"], nodata=-9999.0)
+    out["accu_f32_nd"] = flw.accuflux(aux["data_f32_nd"], nodata=-9999)
+    out["accu_i64"] = flw.accuflux(aux["data_i64"], nodata=-9999)
+    out["accu_ds_f64"] = flw.accuflux(aux["data_f64"], nodata=-9999.0, direction="down")
+    out["accu_ds_i64"] = flw.accuflux(aux["data_i64"], nodata=-9999, direction="down")
+    drain = out["uparea_cell"] > max(4, int(0.002 * d8.size))
+    out["hand_f32"] = flw.hand(drain, aux["elevtn"])
+    out["hand_f64"] = flw.hand(drain, aux["elevtn"].astype(np.float64) * 1.1)
+    seq = flw.idxs_seq
+    sub_idxs = seq[:: max(1, seq.size // 23)][:40]
+    sub_ids = (np.arange(sub_idxs.size, dtype=np.int64) * 3 + 5).astype(np.int32)
+    out["sub_idxs"] = sub_idxs
+    out["sub_ids"] = sub_ids
+    out["basins_sub"] = flw.basins(idxs=sub_idxs, ids=sub_ids)
+    out["to_array"] = flw.to_array()
+    return out

@@ -1,0 +1,122 @@
+"""GPU parity tests (run on the B200 box with -m gpu): pyflwdir_b200 (CUDA through the C ABI) against
+ (1) the golden vectors generated from the real reference, bit for bit, and
+ (2) the CPU oracle on fresh seeded inputs.
+Nothing here reads /root/reference."""
+import numpy as np
+import pytest
+
+import _cases as cs
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pfb():
+    import pyflwdir_b200
+    from pyflwdir_b200 import _lib
+
+    assert _lib.device_count() > 0, "no CUDA device: the GPU tests must run on the B200 box"
+    return pyflwdir_b200
+
+
+@pytest.mark.parametrize("name", cs.SMALL_CASES + ["synth512x768"])
+def test_golden_cases(name, pfb):
+    d8 = cs.case_d8(name)
+    aux = cs.case_inputs(name, d8, cs.case_seed(name))
+    out = cs.run_api_case(pfb, d8, aux)
+    for key, val in out.items():
+        cs.check(name, key, val)
+
+
+def test_golden_rhine(pfb):
+    d8 = cs.case_d8("rhine")
+    aux = cs.case_inputs("rhine", d8, cs.case_seed("rhine"))
+    out = cs.run_api_case(pfb, d8, aux, transform=cs.RHINE_TRANSFORM, latlon=True)
+    for key, val in out.items():
+        cs.check("rhine", key, val)
+    assert int(out["rank"].max()) == 1674
+
+
+@pytest.mark.parametrize("shape,seed,sea", [((257, 1023), 31, 0.1), ((1024, 1024), 32, 0.03), ((1500, 700), 33, 0.0),
+                                             ((64, 4096), 34, 0.2), ((3000, 5), 35, 0.0), ((1, 977), 36, 0.0)])
+def test_vs_oracle_synthetic(shape, seed, sea, pfb):
+    """Fresh synthetic terrain (aligned and unaligned widths, degenerate shapes) against the CPU oracle."""
+    z = oracle.synth_elevation(shape[0], shape[1], seed=seed)
+    d8 = oracle.synth_d8(z, sea_level=float(np.quantile(z, sea)) if sea > 0 else -np.inf)
+    aux = cs.case_inputs("x", d8, seed)
+    got = cs.run_api_case(pfb, d8, aux)
+    want = cs.run_oracle_case(d8, aux, area=np.ones(d8.size, dtype=np.float32))
+    for key in want:
+        assert np.asarray(got[key]).dtype == np.asarray(want[key]).dtype, key
+        assert np.array_equal(got[key], want[key], equal_nan=True), f"{key} differs from the oracle"
+
+
+def test_vs_oracle_random_codes(pfb):
+    """Random legal codes: loops, forced pits at borders and next to nodata."""
+    rng = np.random.default_rng(77)
+    legal = np.array([32, 64, 128, 16, 0, 1, 8, 4, 2, 247, 255], dtype=np.uint8)
+    for shape in [(97, 131), (128, 256), (301, 7)]:
+        d8 = legal[rng.integers(0, legal.size, size=shape)]
+        aux = cs.case_inputs("x", d8, 5)
+        got = cs.run_api_case(pfb, d8, aux)
+        want = cs.run_oracle_case(d8, aux, area=np.ones(d8.size, dtype=np.float32))
+        for key in want:
+            assert np.array_equal(got[key], want[key], equal_nan=True), f"{shape} {key} differs from the oracle"
+
+
+def test_synth_generator_host_equals_device(pfb):
+    """The CUDA input generator used by bench.py is bit-identical to the host one used by the tests."""
+    import ctypes as C
+    from pyflwdir_b200 import _lib, _device
+
+    dev = _device.DeviceGraph(0)
+    nrow, ncol = 300, 517
+    z = np.empty((nrow, ncol), np.float32)
+    d8 = np.empty((nrow, ncol), np.uint8)
+    _lib.check(_lib.lib().pfd_synth_elevation(dev._h, nrow, ncol, 1024, 8, 9, _lib.ptr(z)), dev._h)
+    zh = oracle.synth_elevation(nrow, ncol, seed=9, octaves=8, nref=1024)
+    assert np.array_equal(z, zh)
+    sea = float(np.quantile(zh, 0.1))
+    _lib.check(_lib.lib().pfd_synth_d8(dev._h, _lib.ptr(z), nrow, ncol, C.c_float(sea), _lib.ptr(d8)), dev._h)
+    assert np.array_equal(d8, oracle.synth_d8(zh, sea_level=sea))
+
+
+def test_errors(pfb):
+    with pytest.raises(ValueError, match="could not be inferred"):
+        pfb.from_array(np.full((4, 4), 3, dtype=np.uint8))
+    with pytest.raises(ValueError, match="should be 2 dimensional"):
+        pfb.from_array(np.zeros(16, dtype=np.uint8), ftype="d8")
+    with pytest.raises(ValueError, match='type "d8" is invalid'):
+        pfb.from_array(np.full((4, 4), 3, dtype=np.uint8), ftype="d8")
+    with pytest.raises(ValueError, match="no pits found"):
+        pfb.from_array(np.array([[1, 16], [1, 16]], dtype=np.uint8), ftype="d8")
+    with pytest.raises(ValueError, match="mask"):
+        pfb.from_array(np.zeros((4, 4), dtype=np.uint8), ftype="d8", mask=np.ones((3, 3)))
+    flw = pfb.from_array(np.zeros((4, 4), dtype=np.uint8), ftype="d8")
+    with pytest.raises(ValueError, match="Unknown unit"):
+        flw.upstream_area("furlong")
+    with pytest.raises(ValueError, match="IDs size does not match"):
+        flw.basins(ids=np.arange(3))
+    with pytest.raises(ValueError, match="cannot contain a value zero"):
+        flw.basins(ids=np.zeros(16, dtype=np.uint32))
+    with pytest.raises(ValueError, match="size does not match"):
+        flw.accuflux(np.ones(5))
+    with pytest.raises(ValueError, match="Invalid method"):
+        flw.order_cells("bogus")
+
+
+def test_constructor_from_idxs_ds(pfb):
+    """FlwdirRaster(idxs_ds, shape, 'd8') round trip + mask + dump/load."""
+    d8 = cs.case_d8("flwdir1_asc")
+    flw = pfb.from_array(d8, ftype="d8")
+    flw2 = pfb.FlwdirRaster(flw.idxs_ds.copy(), d8.shape, "d8")
+    assert np.array_equal(flw2.idxs_pit, flw.idxs_pit)
+    assert np.array_equal(flw2.idxs_seq, flw.idxs_seq)
+    assert np.array_equal(flw2.upstream_area(), flw.upstream_area())
+    assert np.array_equal(flw2.to_array() == 247, d8 == 247)
+    m = np.zeros(d8.shape, bool)
+    m[40:120, 30:150] = True
+    flw3 = pfb.from_array(d8, ftype="d8", mask=m)
+    ids, pits, _ = oracle.core_d8.from_array(np.where(m, d8, 247).astype(np.uint8), dtype=np.int32)
+    assert np.array_equal(flw3.idxs_ds, ids) and np.array_equal(flw3.idxs_pit, pits)
