@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the D8 flow-network hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--size 8192] [--impl ours|reference]
+
+One "step" = the whole hot path on one synthetic D8 raster (SURVEY.md §8d generator, "rough" Perlin fBm with
+K = log2(n)-2 octaves, steepest descent, no depression filling):
+    parse (d8 -> idxs_ds) + order/rank + upstream_area(cell) + basins()      == pfd_d8_flow_all
+Outputs of a step: idxs_ds int32, rank int32, upstream area int32, basins uint32 (all N cells each).
+
+  value : Mcells/s with the d8 raster and all outputs RESIDENT IN HBM, timed with CUDA events on the handle's
+          stream around exactly K steps (max over ranks).
+  e2e   : the same C-ABI call with PINNED HOST buffers: H2D of the raster and D2H of the four outputs are inside
+          the timed region.
+  roofline     : the dominant kernel of the step (largest share of device time), algorithmic bytes / event time.
+  cpu_baseline : the CPU oracle (single-threaded C port of the reference's numba kernels) on the same raster.
+
+N > 1 (launched by torchrun, one process per GPU): every rank runs the same step on its own raster (seed + rank)
+-- weak scaling, no data-path collective; the rendezvous/barrier uses torch.distributed (gloo) only as plumbing.
+
+--impl reference: times the reference's CPU implementation of the path (the oracle port; the numba reference
+itself cannot travel to the GPU box) on the host cores, same metric / config, bounded sample per step.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mcells/s D8 parse+rank+accuflux+basins"
+UNIT = "Mcells/s"
+# algorithmic bytes per cell (DESIGN.md "Kernels"): compulsory input read + output write
+ALG_BYTES = {"parse": 5.0, "bfs": 12.0, "sweep": 8.0}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                 str(self.device)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+            self.f.close()
+            sm, mx, reasons = [], [], set()
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            if sm:
+                out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                       "samples": len(sm)}
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return out
+
+
+def dist_setup(n_gpus):
+    """torch.distributed (gloo) purely for barrier / max-reduce across the per-GPU processes."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return None, 0, 1, 0
+    import torch.distributed as dist
+
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group(backend="gloo")
+    return dist, dist.get_rank(), dist.get_world_size(), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def barrier(dist):
+    if dist is not None:
+        dist.barrier()
+
+
+def reduce_max(dist, x):
+    if dist is None:
+        return x
+    import torch
+
+    t = torch.tensor([x], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def reduce_sum(dist, x):
+    if dist is None:
+        return x
+    import torch
+
+    t = torch.tensor([x], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def octaves_for(n):
+    return max(1, int(np.log2(n)) - 2)
+
+
+class Workload:
+    """Synthetic raster on the device + resident / pinned output buffers."""
+
+    def __init__(self, size, seed, device):
+        from pyflwdir_b200 import _lib
+
+        self.L = _lib
+        self.l = _lib.lib()
+        self.n = size
+        self.cells = size * size
+        h = C.c_void_p()
+        _lib.check(self.l.pfd_create(device, C.byref(h)))
+        self.h = h
+        self.d8_dev = self.dev_alloc(self.cells)
+        z_dev = self.dev_alloc(self.cells * 4)
+        self.ck(self.l.pfd_synth_elevation(h, size, size, size, octaves_for(size), seed, z_dev))
+        self.ck(self.l.pfd_synth_d8(h, z_dev, size, size, C.c_float(-np.inf), self.d8_dev))
+        self.ck(self.l.pfd_dev_free(h, z_dev))
+        self.out_dev = [self.dev_alloc(self.cells * 4) for _ in range(4)]  # idxs_ds, rank, uparea, basins
+
+    def ck(self, rc):
+        self.L.check(rc, self.h)
+
+    def dev_alloc(self, nbytes):
+        p = C.c_void_p()
+        self.ck(self.l.pfd_dev_alloc(self.h, nbytes, C.byref(p)))
+        return p
+
+    def step_resident(self):
+        o = self.out_dev
+        self.ck(self.l.pfd_d8_flow_all(self.h, self.d8_dev, self.n, self.n, o[0], self.L.DTYPES[np.dtype(np.int32)],
+                                       o[1], o[2], o[3], None, None, None))
+
+    def make_host(self):
+        self.d8_host = self.L.PinnedArray((self.n, self.n), np.uint8)
+        self.ck(self.l.pfd_memcpy(self.h, self.L.ptr(self.d8_host.array), self.d8_dev, self.cells))
+        self.out_host = [self.L.PinnedArray(self.cells, dt) for dt in (np.int32, np.int32, np.int32, np.uint32)]
+
+    def step_host(self):
+        o = [self.L.ptr(a.array) for a in self.out_host]
+        self.ck(self.l.pfd_d8_flow_all(self.h, self.L.ptr(self.d8_host.array), self.n, self.n, o[0],
+                                       self.L.DTYPES[np.dtype(np.int32)], o[1], o[2], o[3], None, None, None))
+
+    def stage_ms(self):
+        g = self.l.pfd_last_stage_ms
+        return {"parse": g(self.h, 0), "pits": g(self.h, 1), "order": g(self.h, 2), "sweep": g(self.h, 3),
+                "total": g(self.h, 4), "bfs": g(self.h, 5)}
+
+    def timer(self, fn, steps):
+        self.ck(self.l.pfd_timer_start(self.h))
+        for _ in range(steps):
+            fn()
+        ms = C.c_double()
+        self.ck(self.l.pfd_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def launches(self):
+        return int(self.l.pfd_launch_count(self.h))
+
+
+def cpu_path(d8, repeat=1):
+    """The reference's CPU path on `d8` via the oracle port: seconds per stage (best of `repeat`)."""
+    import oracle
+
+    best = None
+    for _ in range(repeat):
+        t = {}
+        t0 = time.perf_counter()
+        ids, pits, _ = oracle.core_d8.from_array(d8, dtype=np.int32)
+        t["from_array"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        oracle.core.rank(ids)
+        t["rank"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        seq = oracle.core.idxs_seq(ids, pits)
+        t["idxs_seq"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        oracle.streams.accuflux(ids, seq, np.ones(d8.size, np.int32), -9999)
+        t["accuflux"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        oracle.basins.basins(ids, pits, seq)
+        t["basins"] = time.perf_counter() - t0
+        t["total"] = sum(t.values())
+        if best is None or t["total"] < best["total"]:
+            best = t
+    return best
+
+
+def host_raster(size, seed):
+    """Synthetic raster on the host: generated by the CUDA generator when a GPU is present (input synthesis is
+    not the measured path), else by the bit-identical host generator."""
+    from pyflwdir_b200 import _lib
+
+    if _lib.device_count() > 0:
+        w = Workload.__new__(Workload)
+        w.L, w.l, w.n, w.cells = _lib, _lib.lib(), size, size * size
+        h = C.c_void_p()
+        _lib.check(w.l.pfd_create(0, C.byref(h)))
+        w.h = h
+        d8 = np.empty((size, size), np.uint8)
+        z_dev = w.dev_alloc(w.cells * 4)
+        w.ck(w.l.pfd_synth_elevation(h, size, size, size, octaves_for(size), seed, z_dev))
+        w.ck(w.l.pfd_synth_d8(h, z_dev, size, size, C.c_float(-np.inf), _lib.ptr(d8)))
+        w.l.pfd_destroy(h)
+        return d8, "synthetic (CUDA generator)"
+    import oracle
+
+    z = oracle.synth_elevation(size, size, seed=seed)
+    return oracle.synth_d8(z), "synthetic (host generator)"
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port, 1 thread) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle
+
+    oracle.build()
+    total_steps = args.steps + args.warmup
+    size = args.size if total_steps <= 6 else min(args.size, 4096)
+    d8, data = host_raster(size, args.seed)
+    cells = d8.size
+    for _ in range(args.warmup):
+        cpu_path(d8)
+    t0 = time.perf_counter()
+    stages = None
+    for _ in range(args.steps):
+        stages = cpu_path(d8)
+    dt = time.perf_counter() - t0
+    value = cells * args.steps / dt / 1e6
+    sample = f"{size}x{size} raster of the same generator (full workload is {args.size}x{args.size}); stages s/step: " + \
+        ", ".join(f"{k}={v:.2f}" for k, v in stages.items())
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": data,
+        "config": {"workload": f"synthetic {args.size}x{args.size} D8 raster: parse + rank + idxs_seq + accuflux(cell) + basins",
+                   "seed": args.seed},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--size", type=int, default=8192, help="raster is size x size (BASELINE.json configs[1]: 8192)")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-size", type=int, default=0, help="raster size of the CPU baseline sample (default: --size)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    dist, rank, world, local_rank = dist_setup(args.gpus)
+    from pyflwdir_b200 import _lib
+
+    if _lib.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device -- pyflwdir_b200 has no CPU fallback")
+    device = local_rank % _lib.device_count()
+    w = Workload(args.size, args.seed + rank, device)
+    cells = w.cells
+
+    # ---- device-resident arm
+    for _ in range(args.warmup):
+        w.step_resident()
+    sampler = ClockSampler(device)
+    barrier(dist)
+    if rank == 0:
+        sampler.start()
+    l0 = w.launches()
+    stage_acc = {}
+    w.ck(w.l.pfd_timer_start(w.h))
+    for _ in range(args.steps):
+        w.step_resident()
+        for k, v in w.stage_ms().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+    ms = C.c_double()
+    w.ck(w.l.pfd_timer_stop(w.h, C.byref(ms)))
+    launches = w.launches() - l0
+    barrier(dist)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = reduce_max(dist, ms.value)
+    value = cells * world * args.steps / (ms_total / 1e3) / 1e6
+    stage_avg = {k: v / args.steps for k, v in stage_acc.items()}
+
+    # ---- end-to-end arm (pinned host buffers through the same C-ABI call)
+    w.make_host()
+    for _ in range(2):
+        w.step_host()
+    barrier(dist)
+    e2e_ms = reduce_max(dist, w.timer(w.step_host, args.steps))
+    barrier(dist)
+    e2e_value = cells * world * args.steps / (e2e_ms / 1e3) / 1e6
+    launches_total = int(reduce_sum(dist, launches))
+
+    # ---- roofline of the dominant kernel
+    peak, peak_src = peaks()
+    kern = max(("parse", "bfs", "sweep"), key=lambda k: stage_avg[k])
+    achieved = ALG_BYTES[kern] * cells / (stage_avg[kern] / 1e3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(f"{kern}_{args.size}")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": {"parse": "parse_kernel", "bfs": "bfs_kernel", "sweep": "sweep_kernel<AccuUpOp<int>>"}[kern],
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_cell": ALG_BYTES[kern],
+                "kernel_ms": stage_avg[kern], "stage_ms": stage_avg,
+                "step_frac_of_roofline_29B": 29.0 * cells / (ms_total / args.steps / 1e3) / 1e9 / peak}
+
+    # ---- CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+
+        oracle.build()
+        cs = args.cpu_size or args.size
+        if cs == args.size:
+            d8 = np.array(w.d8_host.array, copy=True)
+        else:
+            d8, _ = host_raster(cs, args.seed)
+        st = cpu_path(d8)
+        cpu = {"value": d8.size / st["total"] / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{cs}x{cs} raster (same generator/seed), oracle C port of the numba kernels, 1 thread of "
+                         f"{os.cpu_count()} host cores; s/stage: " + ", ".join(f"{k}={v:.2f}" for k, v in st.items()),
+               "accuflux_plus_basins_mcells_s": d8.size / (st["accuflux"] + st["basins"]) / 1e6}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": f"synthetic {args.size}x{args.size} D8 raster per GPU (rough Perlin fBm, {octaves_for(args.size)} octaves, "
+                                   "steepest descent): parse->idxs_ds + rank + upstream_area(cell) + basins",
+                       "seed": args.seed, "l2": "per-step working set ~26 B/cell x N cells (>= 1.7 GB at 8192^2) exceeds the 126 MB L2; no flush needed",
+                       "parallelism": "1 raster per GPU, no collective" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cells, "d2h_bytes_per_step": 16 * cells,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches_total, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -159,10 +159,22 @@ int pfd_synth_elevation(pfd_handle* h, int64_t nrow, int64_t ncol, int64_t nref,
                         float* z_out);
 int pfd_synth_d8(pfd_handle* h, const float* z, int64_t nrow, int64_t ncol, float sea_level, uint8_t* d8_out);
 
+/* ---- options / introspection ------------------------------------------------------------------------- */
+/* "tiles" = 1 (default): rank / basins() / upstream_area("cell") come from the tile-hierarchical solver
+ * (pfd_tiles.cuh); 0: from the level-synchronous BFS + sweeps. Results are identical bit for bit. */
+int pfd_set_option(pfd_handle* h, const char* name, int64_t value);
+/* "tiles", "tile_rounds", "nlevels", "nnodes", "n_pits", "n_valid", "num_sms"; -1 if unknown */
+int64_t pfd_get_info(const pfd_handle* h, const char* name);
+
 /* ---- instrumentation ---------------------------------------------------------------------------------- */
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t pfd_launch_count(const pfd_handle* h);
-/* device time [ms] of the most recent call's kernels by stage: 0 parse, 1 pits, 2 order, 3 sweep, 4 total */
+/* CUDA-event stopwatch on the handle's stream: device time between the two calls, in ms */
+int pfd_timer_start(pfd_handle* h);
+int pfd_timer_stop(pfd_handle* h, double* ms);
+/* device time [ms] (CUDA events on the handle's stream) of the most recent call, by stage:
+ * 0 parse kernel, 1 pit compaction (3 kernels), 2 order (init + BFS + bookkeeping), 3 last sweep kernel,
+ * 4 whole pfd_d8_flow_all call, 5 BFS kernel alone, 6 / 7 / 8 tile solver phase A / B (all rounds) / C */
 double pfd_last_stage_ms(const pfd_handle* h, int stage);
 
 #ifdef __cplusplus

@@ -26,6 +26,11 @@ class DeviceGraph:
         _lib.check(self._l.pfd_create(int(device), C.byref(h)))
         self._h = h
         self.device = int(device)
+        # PFD_TILES=0 selects the level-synchronous BFS + sweeps for rank / basins / upstream_area("cell")
+        # instead of the tile-hierarchical solver (identical results; used by the parity tests)
+        import os
+        if os.environ.get("PFD_TILES", "1") == "0":
+            self.set_option("tiles", 0)
         self.shape = None
         self.size = 0
         self.n_valid = self.n_pits = self.n_outlets = 0
@@ -46,6 +51,12 @@ class DeviceGraph:
 
     def _ck(self, status):
         _lib.check(status, self._h)
+
+    def set_option(self, name, value):
+        self._ck(self._l.pfd_set_option(self._h, name.encode(), int(value)))
+
+    def info(self, name):
+        return int(self._l.pfd_get_info(self._h, name.encode()))
 
     # -- parse
     def parse_d8(self, d8, idx_dtype=None, want_idxs=False):

@@ -53,7 +53,11 @@ SYMBOLS = {
     "pfd_d8_flow_all": (_int, [_vp, _vp, _i64, _i64, _vp, _int, _vp, _vp, _vp, _pi64, _pi64, _pi64]),
     "pfd_synth_elevation": (_int, [_vp, _i64, _i64, _i64, _int, _u32, _vp]),
     "pfd_synth_d8": (_int, [_vp, _vp, _i64, _i64, C.c_float, _vp]),
+    "pfd_set_option": (_int, [_vp, C.c_char_p, _i64]),
+    "pfd_get_info": (_i64, [_vp, C.c_char_p]),
     "pfd_launch_count": (_i64, [_vp]),
+    "pfd_timer_start": (_int, [_vp]),
+    "pfd_timer_stop": (_int, [_vp, C.POINTER(C.c_double)]),
     "pfd_last_stage_ms": (C.c_double, [_vp, _int]),
 }
 

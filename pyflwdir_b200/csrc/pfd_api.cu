@@ -3,6 +3,7 @@
 #include "pfd_order.cuh"
 #include "pfd_parse.cuh"
 #include "pfd_sweeps.cuh"
+#include "pfd_tiles.cuh"
 #include "pfd_synth.h"
 
 #include <algorithm>
@@ -124,6 +125,8 @@ extern "C" int pfd_create(int device, pfd_handle** out) {
         cudaEventCreate(&h->ev_start[s]);
         cudaEventCreate(&h->ev_stop[s]);
     }
+    cudaEventCreate(&h->ev_timer[0]);
+    cudaEventCreate(&h->ev_timer[1]);
     *out = h;
     return PFD_OK;
 }
@@ -134,13 +137,15 @@ extern "C" void pfd_destroy(pfd_handle* h) {
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->dir, &h->upmask, &h->pits, &h->pit_outlet, &h->seq, &h->bseq, &h->rank, &h->basins,
                       &h->level_off, &h->bfs_state, &h->chunk_status, &h->blk_counts, &h->blk_offsets, &h->counters,
-                      &h->segs};
+                      &h->segs, &h->tslots, &h->uparea};
     for (DevBuf* b : bufs) pfd_release(*b);
     for (DevBuf& b : h->scratch) pfd_release(b);
     for (int s = 0; s < PFD_NSTAGE; ++s) {
         cudaEventDestroy(h->ev_start[s]);
         cudaEventDestroy(h->ev_stop[s]);
     }
+    cudaEventDestroy(h->ev_timer[0]);
+    cudaEventDestroy(h->ev_timer[1]);
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -191,6 +196,24 @@ extern "C" int pfd_synchronize(pfd_handle* h) {
 
 extern "C" int64_t pfd_launch_count(const pfd_handle* h) { return h ? h->launches : 0; }
 
+// CUDA-event bracket on the handle's stream (bench.py times K steps between start and stop)
+extern "C" int pfd_timer_start(pfd_handle* h) {
+    PFD_TRY(check_handle(h));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    PFD_CUDA(h, cudaEventRecord(h->ev_timer[0], h->stream));
+    return PFD_OK;
+}
+
+extern "C" int pfd_timer_stop(pfd_handle* h, double* ms) {
+    PFD_TRY(check_handle(h));
+    PFD_CUDA(h, cudaEventRecord(h->ev_timer[1], h->stream));
+    PFD_CUDA(h, cudaEventSynchronize(h->ev_timer[1]));
+    float f = 0.f;
+    PFD_CUDA(h, cudaEventElapsedTime(&f, h->ev_timer[0], h->ev_timer[1]));
+    if (ms) *ms = (double)f;
+    return PFD_OK;
+}
+
 extern "C" double pfd_last_stage_ms(const pfd_handle* h, int stage) {
     if (!h || stage < 0 || stage >= PFD_NSTAGE) return 0.0;
     return h->stage_ms[stage];
@@ -200,7 +223,7 @@ extern "C" double pfd_last_stage_ms(const pfd_handle* h, int stage) {
 // parse
 // ---------------------------------------------------------------------------------------------------------
 static void invalidate(pfd_handle* h) {
-    h->parsed = h->ordered = h->have_rank = h->have_basins = false;
+    h->parsed = h->ordered = h->have_rank = h->have_basins = h->have_uparea = false;
     h->n_valid = h->n_pits = h->n_outlets = h->nnodes = h->nlevels = 0;
 }
 
@@ -270,7 +293,7 @@ static int parse_device(pfd_handle* h, const uint8_t* d8_dev, int64_t nrow, int6
     h->ncol = ncol;
     h->n = n;
     h->parsed = true;
-    h->ordered = h->have_rank = h->have_basins = false;
+    h->ordered = h->have_rank = h->have_basins = h->have_uparea = false;
     return PFD_OK;
 }
 
@@ -352,6 +375,141 @@ extern "C" int pfd_load_idxs_ds(pfd_handle* h, const void* idxs_ds, int idx_dtyp
     return PFD_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// tile-hierarchical solver (pfd_tiles.cuh): rank / basins() / upstream_area("cell") without ordering the cells
+// ---------------------------------------------------------------------------------------------------------
+__global__ void count_ranked_kernel(const int32_t* __restrict__ rank, int64_t n, unsigned long long* __restrict__ out) {
+    unsigned long long c = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        c += (rank[i] >= 0) ? 1u : 0u;
+    c = __reduce_add_sync(0xFFFFFFFFu, (unsigned)c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+static bool tiles_usable(const pfd_handle* h) { return h->use_tiles && h->n_pits > 0 && h->n_pits < (1ll << 31); }
+
+// Any of the three device outputs may be null.
+static int tiles_solve(pfd_handle* h, int32_t* rank_dev, uint32_t* basin_dev, int32_t* uparea_dev) {
+    if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, "no raster parsed on this handle");
+    const long long ntx = (h->ncol + TL_W - 1) / TL_W, nty = (h->nrow + TL_H - 1) / TL_H;
+    if (nty > 65535) return pfd_fail(h, PFD_ERR_UNSUPPORTED, "tile solver: more than 4194240 rows");
+    const long long nslots = ntx * nty * TL_RING;
+    // 13 uint32 arrays + flag
+    const size_t arr = (size_t)nslots * sizeof(uint32_t);
+    PFD_TRY(pfd_reserve(h, h->tslots, 13 * arr + 256));
+    TileSlots S;
+    uint32_t* base = (uint32_t*)h->tslots.p;
+    int a = 0;
+    S.nxt[0] = base + (size_t)nslots * a++;
+    S.nxt[1] = base + (size_t)nslots * a++;
+    S.rh[0] = base + (size_t)nslots * a++;
+    S.rh[1] = base + (size_t)nslots * a++;
+    S.ch[0] = base + (size_t)nslots * a++;
+    S.ch[1] = base + (size_t)nslots * a++;
+    S.acc[0] = base + (size_t)nslots * a++;
+    S.acc[1] = base + (size_t)nslots * a++;
+    S.term = base + (size_t)nslots * a++;
+    S.term_h = base + (size_t)nslots * a++;
+    S.rank = (int32_t*)(base + (size_t)nslots * a++);
+    S.basin = base + (size_t)nslots * a++;
+    S.flag = (unsigned int*)(base + (size_t)nslots * a++);
+    S.nslots = nslots;
+    static bool attr_done = false;
+    if (!attr_done) {
+        PFD_CUDA(h, cudaFuncSetAttribute(tile_phase_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)));
+        PFD_CUDA(h, cudaFuncSetAttribute(tile_phase_c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)));
+        attr_done = true;
+    }
+    const dim3 grid((unsigned)ntx, (unsigned)nty);
+    {
+        StageTimer t(h, PFD_STAGE_TILE_A);
+        PFD_CUDA(h, cudaMemsetAsync(S.acc[0], 0, arr, h->stream));
+        tile_phase_a_kernel<<<grid, TL_THREADS, sizeof(TileShared), h->stream>>>(
+            (const uint8_t*)h->dir.p, h->nrow, h->ncol, ntx, (const cell_t*)h->pits.p, h->n_pits, S);
+        PFD_LAUNCH_CHECK(h);
+    }
+    int src = 0;
+    {
+        StageTimer t(h, PFD_STAGE_TILE_B);
+        const int g = grid_for(nslots, 256, 2, 148 * 16);
+        int k = 0;
+        for (; k < 31; ++k) {
+            PFD_CUDA(h, cudaMemsetAsync(S.acc[src ^ 1], 0, arr, h->stream));
+            PFD_CUDA(h, cudaMemsetAsync(S.flag, 0, sizeof(unsigned int), h->stream));
+            slots_round_kernel<<<g, 256, 0, h->stream>>>(S, src, 1u << k);
+            PFD_LAUNCH_CHECK(h);
+            unsigned int flag = 0;
+            PFD_CUDA(h, cudaMemcpyAsync(&flag, S.flag, sizeof(flag), cudaMemcpyDeviceToHost, h->stream));
+            PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+            src ^= 1;
+            if (!flag) break;
+        }
+        h->tile_rounds = k + 1;
+        slots_finalize_kernel<<<g, 256, 0, h->stream>>>(S, src);
+        PFD_LAUNCH_CHECK(h);
+    }
+    {
+        StageTimer t(h, PFD_STAGE_TILE_C);
+        tile_phase_c_kernel<<<grid, TL_THREADS, sizeof(TileShared), h->stream>>>(
+            (const uint8_t*)h->dir.p, h->nrow, h->ncol, ntx, (const cell_t*)h->pits.p, h->n_pits, S, src, rank_dev,
+            basin_dev, uparea_dev);
+        PFD_LAUNCH_CHECK(h);
+    }
+    return PFD_OK;
+}
+
+// make rank / basins / uparea available in the handle's own cache buffers via the tile solver
+static int tiles_ensure(pfd_handle* h, bool want_rank, bool want_basins, bool want_uparea) {
+    want_rank = want_rank && !h->have_rank;
+    want_basins = want_basins && !h->have_basins;
+    want_uparea = want_uparea && !h->have_uparea;
+    if (!want_rank && !want_basins && !want_uparea) return PFD_OK;
+    const size_t b4 = (size_t)h->n * 4;
+    if (want_rank) PFD_TRY(pfd_reserve(h, h->rank, b4));
+    if (want_basins) PFD_TRY(pfd_reserve(h, h->basins, b4));
+    if (want_uparea) PFD_TRY(pfd_reserve(h, h->uparea, b4));
+    PFD_TRY(tiles_solve(h, want_rank ? (int32_t*)h->rank.p : nullptr, want_basins ? (uint32_t*)h->basins.p : nullptr,
+                        want_uparea ? (int32_t*)h->uparea.p : nullptr));
+    h->have_rank |= want_rank;
+    h->have_basins |= want_basins;
+    h->have_uparea |= want_uparea;
+    return PFD_OK;
+}
+
+static int count_ranked(pfd_handle* h, const int32_t* rank_dev, int64_t* out) {
+    unsigned long long* ctr = (unsigned long long*)h->counters.p + 6;
+    PFD_CUDA(h, cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), h->stream));
+    count_ranked_kernel<<<grid_for(h->n, 256, 8, 148 * 8), 256, 0, h->stream>>>(rank_dev, h->n, ctr);
+    PFD_LAUNCH_CHECK(h);
+    unsigned long long v = 0;
+    PFD_CUDA(h, cudaMemcpyAsync(&v, ctr, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    *out = (int64_t)v;
+    return PFD_OK;
+}
+
+extern "C" int pfd_set_option(pfd_handle* h, const char* name, int64_t value) {
+    PFD_TRY(check_handle(h));
+    if (name && strcmp(name, "tiles") == 0) {
+        h->use_tiles = value ? 1 : 0;
+        return PFD_OK;
+    }
+    return pfd_fail(h, PFD_ERR_INVALID_ARG, std::string("pfd_set_option: unknown option ") + (name ? name : "(null)"));
+}
+
+extern "C" int64_t pfd_get_info(const pfd_handle* h, const char* name) {
+    if (!h || !name) return -1;
+    if (strcmp(name, "tiles") == 0) return h->use_tiles;
+    if (strcmp(name, "tile_rounds") == 0) return h->tile_rounds;
+    if (strcmp(name, "nlevels") == 0) return h->nlevels;
+    if (strcmp(name, "nnodes") == 0) return h->nnodes;
+    if (strcmp(name, "n_pits") == 0) return h->n_pits;
+    if (strcmp(name, "n_valid") == 0) return h->n_valid;
+    if (strcmp(name, "num_sms") == 0) return h->num_sms;
+    return -1;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // order
 // ---------------------------------------------------------------------------------------------------------
@@ -413,6 +571,10 @@ static int run_sweep(pfd_handle* h, Op op, int skip_level0) {
 static int order_impl(pfd_handle* h, bool want_rank, bool want_basins) {
     if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, "pfd_order: no raster parsed on this handle");
     const int64_t n = h->n;
+    if (tiles_usable(h)) {  // scattered rank/basins writes of the BFS are replaced by the tile solver
+        PFD_TRY(tiles_ensure(h, want_rank, want_basins, false));
+        want_rank = want_basins = false;
+    }
     if (!h->ordered) {
         StageTimer t(h, PFD_STAGE_ORDER);
         PFD_TRY(pfd_reserve(h, h->seq, (size_t)n * sizeof(cell_t)));
@@ -467,7 +629,10 @@ static int order_impl(pfd_handle* h, bool want_rank, bool want_basins) {
             if (per_sm < 1) return pfd_fail(h, PFD_ERR_CUDA, "bfs kernel cannot be made resident");
             int64_t grid = (int64_t)per_sm * h->num_sms;
             grid = std::max<int64_t>(1, std::min<int64_t>(grid, (n + BFS_CHUNK - 1) / BFS_CHUNK));
-            PFD_CUDA(h, cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(BFS_THREADS), args, 0, h->stream));
+            {
+                StageTimer tb(h, PFD_STAGE_BFS);
+                PFD_CUDA(h, cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(BFS_THREADS), args, 0, h->stream));
+            }
             h->launches++;
             PFD_CUDA(h, cudaMemcpyAsync(&st, h->bfs_state.p, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
             PFD_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -493,8 +658,8 @@ static int order_impl(pfd_handle* h, bool want_rank, bool want_basins) {
         PFD_CUDA(h, cudaStreamSynchronize(h->stream));
         PFD_TRY(build_schedule(h));
         h->ordered = true;
-        h->have_rank = want_rank;
-        h->have_basins = want_basins;
+        h->have_rank |= want_rank;
+        h->have_basins |= want_basins;
     }
     if (want_rank && !h->have_rank) {
         PFD_TRY(pfd_reserve(h, h->rank, (size_t)n * sizeof(int32_t)));
@@ -581,7 +746,8 @@ extern "C" int pfd_fetch(pfd_handle* h, int which, void* out, int idx_dtype) {
         PFD_TRY(copy_cells_out(h, (const cell_t*)h->seq.p, h->nnodes, out, idx_dtype));
         break;
     case PFD_ARR_RANK:
-        PFD_TRY(order_impl(h, true, false));
+        if (tiles_usable(h)) PFD_TRY(tiles_ensure(h, true, false, false));
+        else PFD_TRY(order_impl(h, true, false));
         PFD_CUDA(h, cudaMemcpyAsync(out, h->rank.p, (size_t)n * sizeof(int32_t), cudaMemcpyDefault, h->stream));
         break;
     case PFD_ARR_N_UPSTREAM: {
@@ -681,11 +847,15 @@ extern "C" int pfd_upstream_area_cells(pfd_handle* h, int32_t* out) {
     PFD_TRY(check_handle(h));
     stage_reset(h);
     if (!out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_upstream_area_cells: out is null");
-    PFD_TRY(order_impl(h, false, false));
     const size_t bytes = (size_t)h->n * sizeof(int32_t);
     void* out_dev = nullptr;
     PFD_TRY(pfd_stage_out(h, out, bytes, 3, &out_dev));
-    PFD_TRY(uparea_cells_device(h, (int32_t*)out_dev));
+    if (tiles_usable(h)) {
+        PFD_TRY(tiles_solve(h, nullptr, nullptr, (int32_t*)out_dev));
+    } else {
+        PFD_TRY(order_impl(h, false, false));
+        PFD_TRY(uparea_cells_device(h, (int32_t*)out_dev));
+    }
     PFD_TRY(pfd_finish_out(h, out, out_dev, bytes));
     PFD_CUDA(h, cudaStreamSynchronize(h->stream));
     stage_collect(h);
@@ -715,7 +885,8 @@ extern "C" int pfd_basins(pfd_handle* h, const void* outlets, int64_t n_outlets,
     stage_reset(h);
     if (!out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_basins: out is null");
     if (!outlets) {
-        PFD_TRY(order_impl(h, false, true));
+        if (tiles_usable(h)) PFD_TRY(tiles_ensure(h, false, true, false));
+        else PFD_TRY(order_impl(h, false, true));
         PFD_CUDA(h, cudaMemcpyAsync(out, h->basins.p, (size_t)h->n * sizeof(uint32_t), cudaMemcpyDefault, h->stream));
         PFD_CUDA(h, cudaStreamSynchronize(h->stream));
         stage_collect(h);
@@ -811,15 +982,35 @@ extern "C" int pfd_d8_flow_all(pfd_handle* h, const uint8_t* d8, int64_t nrow, i
     h->stage_used[PFD_STAGE_TOTAL] = true;
     PFD_TRY(parse_impl(h, d8, nrow, ncol, idxs_ds_out, idx_dtype));
     if (h->n_pits == 0) return pfd_fail(h, PFD_ERR_NO_PITS, "Invalid FlwdirRaster: no pits found");
-    PFD_TRY(order_impl(h, rank_out != nullptr, basins_out != nullptr));
     const size_t b4 = (size_t)h->n * 4;
-    if (rank_out) PFD_CUDA(h, cudaMemcpyAsync(rank_out, h->rank.p, b4, cudaMemcpyDefault, h->stream));
-    if (basins_out) PFD_CUDA(h, cudaMemcpyAsync(basins_out, h->basins.p, b4, cudaMemcpyDefault, h->stream));
-    if (uparea_out) {
-        void* out_dev = nullptr;
-        PFD_TRY(pfd_stage_out(h, uparea_out, b4, 3, &out_dev));
-        PFD_TRY(uparea_cells_device(h, (int32_t*)out_dev));
-        PFD_TRY(pfd_finish_out(h, uparea_out, out_dev, b4));
+    if (tiles_usable(h)) {
+        // write straight into the caller's buffers (device) or into staging buffers (host)
+        void *rk = nullptr, *bs = nullptr, *up = nullptr;
+        if (rank_out) PFD_TRY(pfd_stage_out(h, rank_out, b4, 2, &rk));
+        if (basins_out) PFD_TRY(pfd_stage_out(h, basins_out, b4, 4, &bs));
+        if (uparea_out) PFD_TRY(pfd_stage_out(h, uparea_out, b4, 3, &up));
+        bool tmp_rank = false;
+        if (!rk && nnodes) {  // nnodes needs the rank
+            PFD_TRY(pfd_reserve(h, h->rank, b4));
+            rk = h->rank.p;
+            tmp_rank = true;
+        }
+        PFD_TRY(tiles_solve(h, (int32_t*)rk, (uint32_t*)bs, (int32_t*)up));
+        if (rank_out) PFD_TRY(pfd_finish_out(h, rank_out, rk, b4));
+        if (basins_out) PFD_TRY(pfd_finish_out(h, basins_out, bs, b4));
+        if (uparea_out) PFD_TRY(pfd_finish_out(h, uparea_out, up, b4));
+        if (nnodes) PFD_TRY(count_ranked(h, (const int32_t*)rk, &h->nnodes));
+        if (tmp_rank) h->have_rank = true;
+    } else {
+        PFD_TRY(order_impl(h, rank_out != nullptr, basins_out != nullptr));
+        if (rank_out) PFD_CUDA(h, cudaMemcpyAsync(rank_out, h->rank.p, b4, cudaMemcpyDefault, h->stream));
+        if (basins_out) PFD_CUDA(h, cudaMemcpyAsync(basins_out, h->basins.p, b4, cudaMemcpyDefault, h->stream));
+        if (uparea_out) {
+            void* out_dev = nullptr;
+            PFD_TRY(pfd_stage_out(h, uparea_out, b4, 3, &out_dev));
+            PFD_TRY(uparea_cells_device(h, (int32_t*)out_dev));
+            PFD_TRY(pfd_finish_out(h, uparea_out, out_dev, b4));
+        }
     }
     cudaEventRecord(h->ev_stop[PFD_STAGE_TOTAL], h->stream);
     PFD_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -82,7 +82,8 @@ struct DevBuf {
     size_t cap = 0;
 };
 
-enum { PFD_STAGE_PARSE = 0, PFD_STAGE_PITS = 1, PFD_STAGE_ORDER = 2, PFD_STAGE_SWEEP = 3, PFD_STAGE_TOTAL = 4, PFD_NSTAGE = 5 };
+enum { PFD_STAGE_PARSE = 0, PFD_STAGE_PITS = 1, PFD_STAGE_ORDER = 2, PFD_STAGE_SWEEP = 3, PFD_STAGE_TOTAL = 4, PFD_STAGE_BFS = 5,
+       PFD_STAGE_TILE_A = 6, PFD_STAGE_TILE_B = 7, PFD_STAGE_TILE_C = 8, PFD_NSTAGE = 9 };
 
 struct pfd_handle {
     int device = 0;
@@ -111,6 +112,11 @@ struct pfd_handle {
     DevBuf blk_offsets;       // uint64 exclusive scan of blk_counts
     DevBuf counters;          // uint64 [8]: n_valid, n_pits, n_outlets, parse flags, load flags, basins flags
     DevBuf segs;              // SweepSeg schedule of the level replays
+    DevBuf tslots;            // reduced-graph (tile ring) arrays of the tile solver
+    DevBuf uparea;            // int32 [n] cached cell-count upstream area (tile solver)
+    bool have_uparea = false;
+    int use_tiles = 1;        // option "tiles": 1 = tile-hierarchical solver for rank/basins/uparea, 0 = BFS + sweeps
+    int tile_rounds = 0;      // reduced-graph doubling rounds of the last solve
     int nsegs = 0;
     int64_t max_level_size = 0;
     std::vector<long long> h_level_off;
@@ -122,10 +128,11 @@ struct pfd_handle {
 
     // instrumentation
     int64_t launches = 0;
-    double stage_ms[PFD_NSTAGE] = {0, 0, 0, 0, 0};
-    bool stage_used[PFD_NSTAGE] = {false, false, false, false, false};
+    double stage_ms[PFD_NSTAGE] = {};
+    bool stage_used[PFD_NSTAGE] = {};
     cudaEvent_t ev_start[PFD_NSTAGE] = {};
     cudaEvent_t ev_stop[PFD_NSTAGE] = {};
+    cudaEvent_t ev_timer[2] = {};
 };
 
 static thread_local std::string g_last_error;

@@ -20,8 +20,16 @@ def pfb():
     return pyflwdir_b200
 
 
+@pytest.fixture(params=["tiles", "bfs"])
+def solver(request, monkeypatch):
+    """Both implementations of rank / basins() / upstream_area("cell"): the tile-hierarchical solver (default)
+    and the level-synchronous BFS + sweeps."""
+    monkeypatch.setenv("PFD_TILES", "1" if request.param == "tiles" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("name", cs.SMALL_CASES + ["synth512x768"])
-def test_golden_cases(name, pfb):
+def test_golden_cases(name, pfb, solver):
     d8 = cs.case_d8(name)
     aux = cs.case_inputs(name, d8, cs.case_seed(name))
     out = cs.run_api_case(pfb, d8, aux)
@@ -29,7 +37,7 @@ def test_golden_cases(name, pfb):
         cs.check(name, key, val)
 
 
-def test_golden_rhine(pfb):
+def test_golden_rhine(pfb, solver):
     d8 = cs.case_d8("rhine")
     aux = cs.case_inputs("rhine", d8, cs.case_seed("rhine"))
     out = cs.run_api_case(pfb, d8, aux, transform=cs.RHINE_TRANSFORM, latlon=True)
@@ -40,7 +48,7 @@ def test_golden_rhine(pfb):
 
 @pytest.mark.parametrize("shape,seed,sea", [((257, 1023), 31, 0.1), ((1024, 1024), 32, 0.03), ((1500, 700), 33, 0.0),
                                              ((64, 4096), 34, 0.2), ((3000, 5), 35, 0.0), ((1, 977), 36, 0.0)])
-def test_vs_oracle_synthetic(shape, seed, sea, pfb):
+def test_vs_oracle_synthetic(shape, seed, sea, pfb, solver):
     """Fresh synthetic terrain (aligned and unaligned widths, degenerate shapes) against the CPU oracle."""
     z = oracle.synth_elevation(shape[0], shape[1], seed=seed)
     d8 = oracle.synth_d8(z, sea_level=float(np.quantile(z, sea)) if sea > 0 else -np.inf)
@@ -52,7 +60,7 @@ def test_vs_oracle_synthetic(shape, seed, sea, pfb):
         assert np.array_equal(got[key], want[key], equal_nan=True), f"{key} differs from the oracle"
 
 
-def test_vs_oracle_random_codes(pfb):
+def test_vs_oracle_random_codes(pfb, solver):
     """Random legal codes: loops, forced pits at borders and next to nodata."""
     rng = np.random.default_rng(77)
     legal = np.array([32, 64, 128, 16, 0, 1, 8, 4, 2, 247, 255], dtype=np.uint8)
