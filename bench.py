@@ -39,7 +39,9 @@ sys.path.insert(0, ROOT)
 METRIC = "Mcells/s D8 parse+rank+accuflux+basins"
 UNIT = "Mcells/s"
 # algorithmic bytes per cell (DESIGN.md "Kernels"): compulsory input read + output write
-ALG_BYTES = {"parse": 5.0, "bfs": 12.0, "sweep": 8.0}
+ALG_BYTES = {"parse": 5.0, "bfs": 12.0, "sweep": 8.0, "tile_a": 1.0, "tile_b": 0.0, "tile_c": 13.0}
+KERNEL_NAMES = {"parse": "parse_kernel", "bfs": "bfs_kernel", "sweep": "sweep_kernel<AccuUpOp<int>>",
+                "tile_a": "tile_phase_a_kernel", "tile_b": "slots_round_kernel", "tile_c": "tile_phase_c_kernel"}
 
 
 def peaks():
@@ -189,6 +191,10 @@ class Workload:
 
     def stage_ms(self):
         g = self.l.pfd_last_stage_ms
+        tiles = self.l.pfd_get_info(self.h, b"tiles") == 1
+        if tiles:
+            return {"parse": g(self.h, 0), "pits": g(self.h, 1), "tile_a": g(self.h, 6), "tile_b": g(self.h, 7),
+                    "tile_c": g(self.h, 8), "total": g(self.h, 4)}
         return {"parse": g(self.h, 0), "pits": g(self.h, 1), "order": g(self.h, 2), "sweep": g(self.h, 3),
                 "total": g(self.h, 4), "bfs": g(self.h, 5)}
 
@@ -301,6 +307,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-size", type=int, default=0, help="raster size of the CPU baseline sample (default: --size)")
+    ap.add_argument("--solver", default="tiles", choices=["tiles", "bfs"], help="rank/basins/uparea solver")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -314,6 +321,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- pyflwdir_b200 has no CPU fallback")
     device = local_rank % _lib.device_count()
     w = Workload(args.size, args.seed + rank, device)
+    w.ck(w.l.pfd_set_option(w.h, b"tiles", 1 if args.solver == "tiles" else 0))
     cells = w.cells
 
     # ---- device-resident arm
@@ -351,7 +359,7 @@ def main():
 
     # ---- roofline of the dominant kernel
     peak, peak_src = peaks()
-    kern = max(("parse", "bfs", "sweep"), key=lambda k: stage_avg[k])
+    kern = max((k for k in ("parse", "bfs", "sweep", "tile_a", "tile_c") if k in stage_avg), key=lambda k: stage_avg[k])
     achieved = ALG_BYTES[kern] * cells / (stage_avg[kern] / 1e3) / 1e9
     traffic = None
     try:
@@ -359,7 +367,7 @@ def main():
             traffic = json.load(f).get(f"{kern}_{args.size}")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": {"parse": "parse_kernel", "bfs": "bfs_kernel", "sweep": "sweep_kernel<AccuUpOp<int>>"}[kern],
+    roofline = {"bound": "hbm", "kernel": KERNEL_NAMES[kern],
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_cell": ALG_BYTES[kern],
                 "kernel_ms": stage_avg[kern], "stage_ms": stage_avg,

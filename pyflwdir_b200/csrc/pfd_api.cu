@@ -137,7 +137,7 @@ extern "C" void pfd_destroy(pfd_handle* h) {
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->dir, &h->upmask, &h->pits, &h->pit_outlet, &h->seq, &h->bseq, &h->rank, &h->basins,
                       &h->level_off, &h->bfs_state, &h->chunk_status, &h->blk_counts, &h->blk_offsets, &h->counters,
-                      &h->segs, &h->tslots, &h->uparea};
+                      &h->segs, &h->tslots, &h->uparea, &h->tile_loc, &h->tile_cnt};
     for (DevBuf* b : bufs) pfd_release(*b);
     for (DevBuf& b : h->scratch) pfd_release(b);
     for (int s = 0; s < PFD_NSTAGE; ++s) {
@@ -395,38 +395,36 @@ static int tiles_solve(pfd_handle* h, int32_t* rank_dev, uint32_t* basin_dev, in
     const long long ntx = (h->ncol + TL_W - 1) / TL_W, nty = (h->nrow + TL_H - 1) / TL_H;
     if (nty > 65535) return pfd_fail(h, PFD_ERR_UNSUPPORTED, "tile solver: more than 4194240 rows");
     const long long nslots = ntx * nty * TL_RING;
-    // 13 uint32 arrays + flag
+    // 12 uint32 arrays of nslots + flag
     const size_t arr = (size_t)nslots * sizeof(uint32_t);
-    PFD_TRY(pfd_reserve(h, h->tslots, 13 * arr + 256));
-    TileSlots S;
+    PFD_TRY(pfd_reserve(h, h->tslots, 12 * arr + 256));
     uint32_t* base = (uint32_t*)h->tslots.p;
     int a = 0;
-    S.nxt[0] = base + (size_t)nslots * a++;
-    S.nxt[1] = base + (size_t)nslots * a++;
-    S.rh[0] = base + (size_t)nslots * a++;
-    S.rh[1] = base + (size_t)nslots * a++;
-    S.ch[0] = base + (size_t)nslots * a++;
-    S.ch[1] = base + (size_t)nslots * a++;
-    S.acc[0] = base + (size_t)nslots * a++;
-    S.acc[1] = base + (size_t)nslots * a++;
-    S.term = base + (size_t)nslots * a++;
-    S.term_h = base + (size_t)nslots * a++;
-    S.rank = (int32_t*)(base + (size_t)nslots * a++);
-    S.basin = base + (size_t)nslots * a++;
-    S.flag = (unsigned int*)(base + (size_t)nslots * a++);
-    S.nslots = nslots;
-    static bool attr_done = false;
-    if (!attr_done) {
-        PFD_CUDA(h, cudaFuncSetAttribute(tile_phase_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)));
-        PFD_CUDA(h, cudaFuncSetAttribute(tile_phase_c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)));
-        attr_done = true;
+    SlotBuf B[2];
+    for (int side = 0; side < 2; ++side) {
+        B[side].nxt = base + (size_t)nslots * a++;
+        B[side].rh = base + (size_t)nslots * a++;
+        B[side].ch = base + (size_t)nslots * a++;
+        B[side].acc = base + (size_t)nslots * a++;
     }
+    uint32_t* term = base + (size_t)nslots * a++;
+    uint32_t* term_h = base + (size_t)nslots * a++;
+    int32_t* srank = (int32_t*)(base + (size_t)nslots * a++);
+    uint32_t* sbasin = base + (size_t)nslots * a++;
+    unsigned int* flag = (unsigned int*)(base + (size_t)nslots * a);
     const dim3 grid((unsigned)ntx, (unsigned)nty);
+    PFD_TRY(pfd_reserve(h, h->tile_loc, (size_t)h->n * sizeof(uint32_t)));
+    PFD_TRY(pfd_reserve(h, h->tile_cnt, (size_t)h->n * sizeof(uint32_t)));
     {
         StageTimer t(h, PFD_STAGE_TILE_A);
-        PFD_CUDA(h, cudaMemsetAsync(S.acc[0], 0, arr, h->stream));
-        tile_phase_a_kernel<<<grid, TL_THREADS, sizeof(TileShared), h->stream>>>(
-            (const uint8_t*)h->dir.p, h->nrow, h->ncol, ntx, (const cell_t*)h->pits.p, h->n_pits, S);
+        PFD_CUDA(h, cudaMemsetAsync(B[0].acc, 0, arr, h->stream));
+        if (basin_dev) {
+            stash_pit_ids_kernel<<<grid_for(h->n_pits, 256, 1, 148 * 16), 256, 0, h->stream>>>((const cell_t*)h->pits.p, h->n_pits, basin_dev);
+            PFD_LAUNCH_CHECK(h);
+        }
+        tile_phase_a_kernel<TLA_THREADS, TLA_MINBLOCKS><<<grid, TLA_THREADS, 0, h->stream>>>(
+            (const uint8_t*)h->dir.p, h->nrow, h->ncol, ntx, basin_dev, (uint32_t*)h->tile_loc.p, (uint32_t*)h->tile_cnt.p,
+            B[0].acc, B[0].nxt, B[0].rh, B[0].ch, term, term_h);
         PFD_LAUNCH_CHECK(h);
     }
     int src = 0;
@@ -435,25 +433,25 @@ static int tiles_solve(pfd_handle* h, int32_t* rank_dev, uint32_t* basin_dev, in
         const int g = grid_for(nslots, 256, 2, 148 * 16);
         int k = 0;
         for (; k < 31; ++k) {
-            PFD_CUDA(h, cudaMemsetAsync(S.acc[src ^ 1], 0, arr, h->stream));
-            PFD_CUDA(h, cudaMemsetAsync(S.flag, 0, sizeof(unsigned int), h->stream));
-            slots_round_kernel<<<g, 256, 0, h->stream>>>(S, src, 1u << k);
+            PFD_CUDA(h, cudaMemcpyAsync(B[src ^ 1].acc, B[src].acc, arr, cudaMemcpyDeviceToDevice, h->stream));
+            PFD_CUDA(h, cudaMemsetAsync(flag, 0, sizeof(unsigned int), h->stream));
+            slots_round_kernel<<<g, 256, 0, h->stream>>>(B[src], B[src ^ 1], nslots, 1u << k, flag);
             PFD_LAUNCH_CHECK(h);
-            unsigned int flag = 0;
-            PFD_CUDA(h, cudaMemcpyAsync(&flag, S.flag, sizeof(flag), cudaMemcpyDeviceToHost, h->stream));
+            unsigned int hflag = 0;
+            PFD_CUDA(h, cudaMemcpyAsync(&hflag, flag, sizeof(hflag), cudaMemcpyDeviceToHost, h->stream));
             PFD_CUDA(h, cudaStreamSynchronize(h->stream));
             src ^= 1;
-            if (!flag) break;
+            if (!hflag) break;
         }
         h->tile_rounds = k + 1;
-        slots_finalize_kernel<<<g, 256, 0, h->stream>>>(S, src);
+        slots_finalize_kernel<<<g, 256, 0, h->stream>>>(B[src], term, term_h, nslots, srank, sbasin);
         PFD_LAUNCH_CHECK(h);
     }
     {
         StageTimer t(h, PFD_STAGE_TILE_C);
-        tile_phase_c_kernel<<<grid, TL_THREADS, sizeof(TileShared), h->stream>>>(
-            (const uint8_t*)h->dir.p, h->nrow, h->ncol, ntx, (const cell_t*)h->pits.p, h->n_pits, S, src, rank_dev,
-            basin_dev, uparea_dev);
+        tile_phase_c_kernel<TLC_THREADS, TLC_MINBLOCKS><<<grid, TLC_THREADS, 0, h->stream>>>(
+            (const uint8_t*)h->dir.p, h->nrow, h->ncol, ntx, (const uint32_t*)h->tile_loc.p, (const uint32_t*)h->tile_cnt.p,
+            B[src].acc, srank, sbasin, rank_dev, basin_dev, uparea_dev);
         PFD_LAUNCH_CHECK(h);
     }
     return PFD_OK;

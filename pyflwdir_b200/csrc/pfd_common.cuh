@@ -113,6 +113,7 @@ struct pfd_handle {
     DevBuf counters;          // uint64 [8]: n_valid, n_pits, n_outlets, parse flags, load flags, basins flags
     DevBuf segs;              // SweepSeg schedule of the level replays
     DevBuf tslots;            // reduced-graph (tile ring) arrays of the tile solver
+    DevBuf tile_loc, tile_cnt; // uint32 [n] each: per cell (local terminal | hops << 12), in-tile subtree size
     DevBuf uparea;            // int32 [n] cached cell-count upstream area (tile solver)
     bool have_uparea = false;
     int use_tiles = 1;        // option "tiles": 1 = tile-hierarchical solver for rank/basins/uparea, 0 = BFS + sweeps

@@ -25,26 +25,25 @@
 #define TL_H 64
 #define TL_W 64
 #define TL_CELLS (TL_H * TL_W)
-#define TL_THREADS 256
-#define TL_CPT (TL_CELLS / TL_THREADS)  // 16 cells per thread: fixed column, rows tid/64 + 4*it
-#define TL_RING 256                     // ring slots per tile (252 used)
-#define TL_MAXROUNDS 13                 // 2^12 = 4096 >= longest simple path in a tile (+1 accumulate round)
+// Block shapes (tuned on B200, see profiles/): phase A is issue-bound and likes 1024 threads x 2 CTAs/SM (4 cells
+// per thread, few registers), phase C is latency-bound and likes 512 threads x 4 CTAs/SM.
+#ifndef TLA_THREADS
+#define TLA_THREADS 1024
+#endif
+#ifndef TLA_MINBLOCKS
+#define TLA_MINBLOCKS 2
+#endif
+#ifndef TLC_THREADS
+#define TLC_THREADS 512
+#endif
+#ifndef TLC_MINBLOCKS
+#define TLC_MINBLOCKS 4
+#endif
+#define TL_RING 256                       // ring slots per tile (252 used)
+#define TL_MAXROUNDS 13                   // 2^12 = 4096 >= longest simple path in a tile (+1 accumulate round)
 
 #define SLOT_INVALID 0x7FFFFFFFu  // node does not drain to a pit (loop) / unused
 #define TERM_PIT 0x80000000u      // term = TERM_PIT | pit ordinal: node's local path ends in that pit
-
-struct TileSlots {
-    uint32_t* nxt[2];   // next node (self when last)
-    uint32_t* rh[2];    // reduced hops to nxt, saturating doubling: min(2^k, distance to last node)
-    uint32_t* ch[2];    // cell hops to nxt
-    uint32_t* acc[2];   // inflow accumulate (starts as W)
-    uint32_t* term;     // TERM_PIT|ord for last nodes, SLOT_INVALID for nodes on a local loop / nodata
-    uint32_t* term_h;   // cell hops from a last node to its pit
-    int32_t* rank;      // results: rank of the ring cell (-1 invalid)
-    uint32_t* basin;    // basin id of the ring cell (0 invalid)
-    unsigned int* flag; // "another round needed"
-    long long nslots;
-};
 
 __host__ __device__ __forceinline__ int tl_ring_pos(int ly, int lx) {
     if (ly == 0) return lx;
@@ -62,95 +61,97 @@ __device__ __forceinline__ uint32_t tl_slot_of(long long r, long long c, long lo
     return (uint32_t)((ty * ntx + tx) * TL_RING + tl_ring_pos((int)(r % TL_H), (int)(c % TL_W)));
 }
 
-// binary search of `cell` in the ascending pit list -> ordinal
-__device__ __forceinline__ uint32_t tl_pit_ordinal(const cell_t* __restrict__ pits, long long npits, cell_t cell) {
-    long long lo = 0, hi = npits - 1;
-    while (lo < hi) {
-        const long long mid = (lo + hi) >> 1;
-        if (__ldg(pits + mid) < cell) lo = mid + 1;
-        else hi = mid;
-    }
-    return (uint32_t)lo;
+// basin id (= pit ordinal + 1) of every pit cell, pre-written at the pit's own position of the basin output buffer
+// so that the tile kernels find it with one load of a cell they own (no search in the sorted pit list)
+__global__ void stash_pit_ids_kernel(const cell_t* __restrict__ pits, long long npits, uint32_t* __restrict__ basin) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < npits; k += (long long)gridDim.x * blockDim.x)
+        basin[pits[k]] = (uint32_t)(k + 1);
 }
 
+// Shared state of one tile in phase A: P packs (next cell : 12 bits | hops to it : 20 bits), A is the accumulate
+// buffer.
 struct TileShared {
-    uint16_t nxt[TL_CELLS];
-    uint16_t hops[TL_CELLS];
-    uint32_t A[2][TL_CELLS];
+    uint32_t P[TL_CELLS];
+    uint32_t A[TL_CELLS];
 };
+#define TP_PACK(n, h) ((uint32_t)(n) | ((uint32_t)(h) << 12))
+#define TP_N(p) ((p) & 0xFFFu)
+#define TP_H(p) ((p) >> 12)
+#define TL_LOC_INVALID 0xFFFFFFFFu
 
-// Local solve shared by phases A and C. On return: s.nxt = local terminal of every cell, s.hops = hop distance to
-// it, s.A[abuf] = subtree sum of the initial weights w0 inside the tile; bit `it` of inv_mask is set for owned
-// cells that never reach a terminal (they sit on / above a loop inside the tile).
-// Per round k (Jacobi): A_{k+1}[anc(d)] += A_k[d] for cells whose 2^k-th ancestor exists (hops == 2^k, hops being
-// min(2^k, distance to the terminal)), then nxt <- nxt[nxt], hops += hops[nxt].
-__device__ __forceinline__ bool tl_is_terminal(const TileShared& s, uint32_t i) { return s.nxt[i] == i && s.hops[i] == 0; }
+__device__ __forceinline__ uint32_t tl_dir_of(const uint32_t* dirs, int it) { return (dirs[it >> 2] >> (8 * (it & 3))) & 0xFFu; }
 
-__device__ __forceinline__ void tl_local_solve(TileShared& s, const uint32_t* dirs /*[4] packed 16 bytes*/,
-                                               const uint32_t* w0 /*[16]*/, int& abuf, uint32_t& inv_mask) {
+// local index of the next cell inside the tile, or i itself when the link leaves the tile / the cell is a pit
+__device__ __forceinline__ int tl_local_next(int i, uint32_t d) {
+    if (d >= 8u) return i;
+    const int y = (i >> 6) + pfd_slot_dr((int)d), x = (i & (TL_W - 1)) + pfd_slot_dc((int)d);
+    return (y >= 0 && y < TL_H && x >= 0 && x < TL_W) ? y * TL_W + x : i;
+}
+
+// Local solve of phase A. On return own[it] (mirrored in s.P) = packed (local terminal, hop distance) of every owned
+// cell and s.A[i] = subtree sum of the unit weights inside the tile.
+// Round k (Jacobi): every cell whose 2^k-th ancestor exists (hops == 2^k) snapshots its A and its ancestor's P,
+// then -- after a barrier -- adds the snapshot to that ancestor (A_{k+1}[anc] += A_k[d]) and jumps
+// (next <- next[next], hops += hops[next]). A cell stays active only while its hop count is an exact power of two,
+// i.e. its chain is not exhausted; the loop ends when no cell of the tile is active (<= 12 rounds without loops).
+template <int THREADS>
+__device__ __forceinline__ void tl_local_solve(TileShared& s, const uint32_t* dirs, uint32_t* own) {
+    constexpr int TL_CPT = TL_CELLS / THREADS, TL_RPI = THREADS / TL_W;
     const int lx = threadIdx.x & (TL_W - 1);
     const int ly0 = threadIdx.x >> 6;
+    uint32_t active = 0;
 #pragma unroll
     for (int it = 0; it < TL_CPT; ++it) {
-        const int ly = ly0 + 4 * it;
-        const int i = ly * TL_W + lx;
-        const uint32_t d = (dirs[it >> 2] >> (8 * (it & 3))) & 0xFFu;
-        int ni = i;
-        if (d < 8u) {
-            const int y = ly + pfd_slot_dr((int)d), x = lx + pfd_slot_dc((int)d);
-            if (y >= 0 && y < TL_H && x >= 0 && x < TL_W) ni = y * TL_W + x;
-        }
-        s.nxt[i] = (uint16_t)ni;
-        s.hops[i] = (ni != i) ? 1 : 0;
-        s.A[0][i] = w0[it];
+        const int i = (ly0 + TL_RPI * it) * TL_W + lx;
+        const uint32_t d = tl_dir_of(dirs, it);
+        const int ni = tl_local_next(i, d);
+        own[it] = TP_PACK(ni, ni != i ? 1 : 0);
+        if (ni != i) active |= 1u << it;
+        s.P[i] = own[it];
+        s.A[i] = (d != PFD_DIR_NODATA) ? 1u : 0u;
     }
     __syncthreads();
-    abuf = 0;
     for (int k = 0; k < TL_MAXROUNDS; ++k) {
-        uint32_t pk[TL_CPT];  // nxt[nxt] | hops[nxt] << 16
-        int more = 0;
         const uint32_t two_k = 1u << k;
+        uint32_t pn[TL_CPT], a[TL_CPT];
 #pragma unroll
         for (int it = 0; it < TL_CPT; ++it) {
-            const int i = (ly0 + 4 * it) * TL_W + lx;
-            const uint32_t n = s.nxt[i], h = s.hops[i];
-            const uint32_t n2 = s.nxt[n], h2 = s.hops[n];
-            pk[it] = n2 | (h2 << 16);
-            s.A[abuf ^ 1][i] = s.A[abuf][i];
-            more |= (h2 != 0u) | ((h + h2) == (two_k << 1));
+            if (active & (1u << it)) {
+                pn[it] = s.P[TP_N(own[it])];
+                a[it] = s.A[(ly0 + TL_RPI * it) * TL_W + lx];
+            }
         }
-        more = __syncthreads_or(more);
+        __syncthreads();  // every snapshot is taken before any update
+        uint32_t next_active = 0;
 #pragma unroll
         for (int it = 0; it < TL_CPT; ++it) {
-            const int i = (ly0 + 4 * it) * TL_W + lx;
-            const uint32_t n = s.nxt[i], h = s.hops[i];
-            if (h == two_k) atomicAdd(&s.A[abuf ^ 1][n], s.A[abuf][i]);
-            s.nxt[i] = (uint16_t)(pk[it] & 0xFFFFu);
-            s.hops[i] = (uint16_t)min(h + (pk[it] >> 16), 0xFFFFu);
+            if (active & (1u << it)) {
+                if (a[it]) atomicAdd(&s.A[TP_N(own[it])], a[it]);
+                const uint32_t h = two_k + TP_H(pn[it]);
+                own[it] = TP_PACK(TP_N(pn[it]), h);
+                s.P[(ly0 + TL_RPI * it) * TL_W + lx] = own[it];
+                if (h == (two_k << 1)) next_active |= 1u << it;
+            }
         }
-        __syncthreads();
-        abuf ^= 1;
-        if (!more) break;
-    }
-    inv_mask = 0;
-#pragma unroll
-    for (int it = 0; it < TL_CPT; ++it) {
-        const int i = (ly0 + 4 * it) * TL_W + lx;
-        if (!tl_is_terminal(s, s.nxt[i])) inv_mask |= 1u << it;
+        active = next_active;
+        if (!__syncthreads_or((int)active)) break;
     }
 }
 
-// load the 16 direction bytes this thread owns (rows ly0 + 4*it, column lx) -> 4 packed words; cells outside the
+// load the direction bytes this thread owns (rows ly0 + TL_RPI*it, column lx) packed 4 per word; cells outside the
 // raster read as nodata
+template <int THREADS>
 __device__ __forceinline__ void tl_load_dirs(const uint8_t* __restrict__ dir, long long nrow, long long ncol,
                                              long long r0, long long c0, uint32_t* dirs) {
+    constexpr int TL_CPT = TL_CELLS / THREADS, TL_RPI = THREADS / TL_W;
     const int lx = threadIdx.x & (TL_W - 1);
     const int ly0 = threadIdx.x >> 6;
     const long long c = c0 + lx;
-    dirs[0] = dirs[1] = dirs[2] = dirs[3] = 0;
+#pragma unroll
+    for (int w = 0; w < (TL_CPT + 3) / 4; ++w) dirs[w] = 0;
 #pragma unroll
     for (int it = 0; it < TL_CPT; ++it) {
-        const long long r = r0 + ly0 + 4 * it;
+        const long long r = r0 + ly0 + TL_RPI * it;
         uint32_t d = PFD_DIR_NODATA;
         if (r < nrow && c < ncol) d = __ldg(dir + r * ncol + c);
         dirs[it >> 2] |= d << (8 * (it & 3));
@@ -158,62 +159,71 @@ __device__ __forceinline__ void tl_load_dirs(const uint8_t* __restrict__ dir, lo
 }
 
 // terminal descriptor of an owned cell that is a local terminal: exit -> slot id of the target ring cell,
-// pit -> TERM_PIT | ordinal. (valid, non-nodata cells only)
+// pit -> TERM_PIT | ordinal (0 when basins are not requested). (valid, non-nodata cells only)
 __device__ __forceinline__ uint32_t tl_terminal_info(uint32_t d, long long r, long long c, long long ncol, long long ntx,
-                                                     const cell_t* __restrict__ pits, long long npits) {
+                                                     const uint32_t* __restrict__ pit_ids) {
     if (d < 8u) return tl_slot_of(r + pfd_slot_dr((int)d), c + pfd_slot_dc((int)d), ntx);
-    return TERM_PIT | tl_pit_ordinal(pits, npits, (cell_t)(r * ncol + c));
+    return TERM_PIT | (pit_ids ? (pit_ids[r * ncol + c] - 1u) : 0u);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Phase A
+// Phase A: local solve; per cell (local terminal, hops) -> loc[], in-tile subtree size -> cnt[]; ring nodes; W
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TL_THREADS, 4) tile_phase_a_kernel(const uint8_t* __restrict__ dir, long long nrow,
-                                                                     long long ncol, long long ntx,
-                                                                     const cell_t* __restrict__ pits, long long npits,
-                                                                     TileSlots S) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileShared& s = *reinterpret_cast<TileShared*>(smem_raw);
+template <int THREADS, int MINBLOCKS>
+__global__ void __launch_bounds__(THREADS, MINBLOCKS)
+    tile_phase_a_kernel(const uint8_t* __restrict__ dir, long long nrow, long long ncol, long long ntx,
+                        const uint32_t* pit_ids, uint32_t* __restrict__ loc, uint32_t* __restrict__ cnt,
+                        uint32_t* __restrict__ W, uint32_t* __restrict__ s_nxt, uint32_t* __restrict__ s_rh,
+                        uint32_t* __restrict__ s_ch, uint32_t* __restrict__ s_term, uint32_t* __restrict__ s_term_h) {
+    constexpr int TL_CPT = TL_CELLS / THREADS, TL_RPI = THREADS / TL_W;
+    __shared__ TileShared s;
     const long long tile = (long long)blockIdx.y * ntx + blockIdx.x;
     const long long r0 = (long long)blockIdx.y * TL_H, c0 = (long long)blockIdx.x * TL_W;
     const int lx = threadIdx.x & (TL_W - 1);
     const int ly0 = threadIdx.x >> 6;
 
-    uint32_t dirs[4], w0[TL_CPT];
-    tl_load_dirs(dir, nrow, ncol, r0, c0, dirs);
-#pragma unroll
-    for (int it = 0; it < TL_CPT; ++it) w0[it] = (((dirs[it >> 2] >> (8 * (it & 3))) & 0xFFu) != PFD_DIR_NODATA) ? 1u : 0u;
-    int abuf;
-    uint32_t inv;
-    tl_local_solve(s, dirs, w0, abuf, inv);
+    uint32_t dirs[(TL_CPT + 3) / 4], own[TL_CPT];
+    tl_load_dirs<THREADS>(dir, nrow, ncol, r0, c0, dirs);
+    tl_local_solve<THREADS>(s, dirs, own);
 
-    // terminal descriptors go into the spare accumulate buffer
-    uint32_t* tinfo = s.A[abuf ^ 1];
+    // per-cell results for phase C; terminals hand their subtree size to the entry cell they drain into and then
+    // publish their descriptor through their A slot
+    uint32_t inv = 0;
 #pragma unroll
     for (int it = 0; it < TL_CPT; ++it) {
-        const int ly = ly0 + 4 * it;
+        const int ly = ly0 + TL_RPI * it;
         const int i = ly * TL_W + lx;
-        const uint32_t d = (dirs[it >> 2] >> (8 * (it & 3))) & 0xFFu;
-        if (d != PFD_DIR_NODATA && tl_is_terminal(s, i)) {  // local terminal (exit cell or pit)
-            const uint32_t ti = tl_terminal_info(d, r0 + ly, c0 + lx, ncol, ntx, pits, npits);
-            tinfo[i] = ti;
-            if (!(ti & TERM_PIT)) atomicAdd(S.acc[0] + ti, s.A[abuf][i]);  // inflow weight of the entry cell
+        const uint32_t root = TP_N(own[it]);
+        if (s.P[root] != root) inv |= 1u << it;  // a terminal is (next = itself, hops = 0)
+        const long long r = r0 + ly, c = c0 + lx;
+        if (r < nrow && c < ncol) {
+            loc[r * ncol + c] = ((inv >> it) & 1u) ? TL_LOC_INVALID : own[it];
+            cnt[r * ncol + c] = s.A[i];
         }
     }
     __syncthreads();
-    // ring cells publish their reduced-graph node
 #pragma unroll
     for (int it = 0; it < TL_CPT; ++it) {
-        const int ly = ly0 + 4 * it;
-        if (!tl_on_ring(ly, lx)) continue;
+        const int ly = ly0 + TL_RPI * it;
         const int i = ly * TL_W + lx;
-        const uint32_t d = (dirs[it >> 2] >> (8 * (it & 3))) & 0xFFu;
+        const uint32_t d = tl_dir_of(dirs, it);
+        if (d != PFD_DIR_NODATA && own[it] == (uint32_t)i) {
+            const uint32_t ti = tl_terminal_info(d, r0 + ly, c0 + lx, ncol, ntx, pit_ids);
+            if (!(ti & TERM_PIT)) atomicAdd(W + ti, s.A[i]);
+            s.A[i] = ti;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < TL_CPT; ++it) {
+        const int ly = ly0 + TL_RPI * it;
+        if (!tl_on_ring(ly, lx)) continue;
+        const uint32_t d = tl_dir_of(dirs, it);
         const uint32_t slot = (uint32_t)(tile * TL_RING + tl_ring_pos(ly, lx));
         uint32_t nx = slot, rh = 0, ch = 0, term = SLOT_INVALID, th = 0;
         if (d != PFD_DIR_NODATA && !((inv >> it) & 1u)) {
-            const uint32_t root = s.nxt[i];
-            const uint32_t ti = tinfo[root];
-            const uint32_t dist = s.hops[i];
+            const uint32_t ti = s.A[TP_N(own[it])];
+            const uint32_t dist = TP_H(own[it]);
             if (ti & TERM_PIT) {
                 term = ti;
                 th = dist;
@@ -224,148 +234,182 @@ __global__ void __launch_bounds__(TL_THREADS, 4) tile_phase_a_kernel(const uint8
                 term = 0;
             }
         }
-        S.nxt[0][slot] = nx;
-        S.rh[0][slot] = rh;
-        S.ch[0][slot] = ch;
-        S.term[slot] = term;
-        S.term_h[slot] = th;
+        s_nxt[slot] = nx;
+        s_rh[slot] = rh;
+        s_ch[slot] = ch;
+        s_term[slot] = term;
+        s_term_h[slot] = th;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // Phase B: synchronous doubling rounds over the ring slots
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) slots_round_kernel(TileSlots S, int src, uint32_t two_k) {
-    const int dst = src ^ 1;
-    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < S.nslots; s += (long long)gridDim.x * blockDim.x) {
-        const uint32_t n = S.nxt[src][s];
-        const uint32_t h = S.rh[src][s];
-        const uint32_t a = S.acc[src][s];
-        if (a) atomicAdd(S.acc[dst] + s, a);
+struct SlotBuf {  // one side of the double-buffered reduced-graph state
+    uint32_t* nxt;
+    uint32_t* rh;
+    uint32_t* ch;
+    uint32_t* acc;
+};
+
+// acc of the destination side must hold a copy of the source side before the launch (the kernel only adds)
+__global__ void __launch_bounds__(256) slots_round_kernel(SlotBuf src, SlotBuf dst, long long nslots, uint32_t two_k,
+                                                          unsigned int* __restrict__ flag) {
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < nslots; s += (long long)gridDim.x * blockDim.x) {
+        const uint32_t n = src.nxt[s];
+        const uint32_t h = src.rh[s];
         if (n == (uint32_t)s) {  // last node / unused: nothing to jump
-            S.nxt[dst][s] = n;
-            S.rh[dst][s] = h;
-            S.ch[dst][s] = S.ch[src][s];
+            dst.nxt[s] = n;
+            dst.rh[s] = h;
+            dst.ch[s] = src.ch[s];
             continue;
         }
-        if (h == two_k && a) atomicAdd(S.acc[dst] + n, a);
-        const uint32_t n2 = S.nxt[src][n];
-        const uint32_t h2 = S.rh[src][n];
-        S.nxt[dst][s] = n2;
-        S.rh[dst][s] = h + h2;  // saturating in effect: h2 == 0 once n is a last node
-        S.ch[dst][s] = S.ch[src][s] + S.ch[src][n];
-        if (h2 != 0u || (h + h2) == (two_k << 1)) *S.flag = 1u;
+        if (h == two_k) {
+            const uint32_t a = src.acc[s];
+            if (a) atomicAdd(dst.acc + n, a);
+        }
+        const uint32_t n2 = src.nxt[n];
+        const uint32_t h2 = src.rh[n];
+        dst.nxt[s] = n2;
+        dst.rh[s] = h + h2;
+        dst.ch[s] = src.ch[s] + src.ch[n];
+        if ((h + h2) == (two_k << 1)) *flag = 1u;
     }
 }
 
-__global__ void __launch_bounds__(256) slots_finalize_kernel(TileSlots S, int src) {
-    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < S.nslots; s += (long long)gridDim.x * blockDim.x) {
-        const uint32_t last = S.nxt[src][s];
-        const uint32_t t = S.term[last];
+__global__ void __launch_bounds__(256) slots_finalize_kernel(SlotBuf cur, const uint32_t* __restrict__ term,
+                                                             const uint32_t* __restrict__ term_h, long long nslots,
+                                                             int32_t* __restrict__ rank, uint32_t* __restrict__ basin) {
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < nslots; s += (long long)gridDim.x * blockDim.x) {
+        const uint32_t last = cur.nxt[s];
+        const uint32_t t = term[last];
         int32_t rk = -1;
         uint32_t b = 0;
-        if ((t & TERM_PIT) && S.nxt[src][last] == last && S.term[s] != SLOT_INVALID) {
-            rk = (int32_t)(S.ch[src][s] + S.term_h[last]);
+        if ((t & TERM_PIT) && cur.nxt[last] == last && term[s] != SLOT_INVALID) {
+            rk = (int32_t)(cur.ch[s] + term_h[last]);
             b = (t & ~TERM_PIT) + 1u;
         }
-        S.rank[s] = rk;
-        S.basin[s] = b;
+        rank[s] = rk;
+        basin[s] = b;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Phase C
+// Phase C: no second solve. acc = in-tile count (phase A) + the outside inflows of the tile's entry cells walked
+// down their local paths (sparse: ~90 entry cells per tile); rank / basin = hops + solution of the local terminal.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TL_THREADS, 4) tile_phase_c_kernel(const uint8_t* __restrict__ dir, long long nrow,
-                                                                     long long ncol, long long ntx,
-                                                                     const cell_t* __restrict__ pits, long long npits,
-                                                                     TileSlots S, int src, int32_t* __restrict__ rank_out,
-                                                                     uint32_t* __restrict__ basin_out,
-                                                                     int32_t* __restrict__ uparea_out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileShared& s = *reinterpret_cast<TileShared*>(smem_raw);
+struct TileSharedC {
+    uint32_t X[TL_CELLS];   // extra inflow per cell, later basin id per terminal
+    uint32_t T[TL_CELLS];   // rank at the terminal
+    uint8_t dir[TL_CELLS];
+    uint32_t wl_cell[TL_RING];  // walker list
+    uint32_t wl_w[TL_RING];
+    uint32_t wl_count;
+};
+
+template <int THREADS, int MINBLOCKS>
+__global__ void __launch_bounds__(THREADS, MINBLOCKS)
+    tile_phase_c_kernel(const uint8_t* __restrict__ dir, long long nrow, long long ncol, long long ntx,
+                        const uint32_t* __restrict__ loc, const uint32_t* __restrict__ cnt,
+                        const uint32_t* __restrict__ inflow, const int32_t* __restrict__ s_rank,
+                        const uint32_t* __restrict__ s_basin, int32_t* __restrict__ rank_out, uint32_t* basin_out,
+                        int32_t* __restrict__ uparea_out) {
+    constexpr int TL_CPT = TL_CELLS / THREADS, TL_RPI = THREADS / TL_W;
+    __shared__ TileSharedC s;
     const long long tile = (long long)blockIdx.y * ntx + blockIdx.x;
     const long long r0 = (long long)blockIdx.y * TL_H, c0 = (long long)blockIdx.x * TL_W;
     const int lx = threadIdx.x & (TL_W - 1);
     const int ly0 = threadIdx.x >> 6;
 
-    uint32_t dirs[4], w0[TL_CPT];
-    tl_load_dirs(dir, nrow, ncol, r0, c0, dirs);
+    uint32_t dirs[(TL_CPT + 3) / 4], own[TL_CPT], up[TL_CPT];
+    tl_load_dirs<THREADS>(dir, nrow, ncol, r0, c0, dirs);
+    if (threadIdx.x == 0) s.wl_count = 0;
 #pragma unroll
     for (int it = 0; it < TL_CPT; ++it) {
-        const int ly = ly0 + 4 * it;
-        const uint32_t d = (dirs[it >> 2] >> (8 * (it & 3))) & 0xFFu;
-        uint32_t w = (d != PFD_DIR_NODATA) ? 1u : 0u;
-        if (w && tl_on_ring(ly, lx)) w += S.acc[src][tile * TL_RING + tl_ring_pos(ly, lx)];  // inflow from outside
-        w0[it] = w;
-    }
-    int abuf;
-    uint32_t inv;
-    tl_local_solve(s, dirs, w0, abuf, inv);
-
-    // per terminal: rank at the terminal first, then (second pass through the same spare buffer) its basin id
-    uint32_t* tbuf = s.A[abuf ^ 1];
-    uint32_t t_b[TL_CPT];
-#pragma unroll
-    for (int it = 0; it < TL_CPT; ++it) {
-        const int ly = ly0 + 4 * it;
+        const int ly = ly0 + TL_RPI * it;
         const int i = ly * TL_W + lx;
-        const uint32_t d = (dirs[it >> 2] >> (8 * (it & 3))) & 0xFFu;
-        t_b[it] = 0;
-        if (d != PFD_DIR_NODATA && tl_is_terminal(s, i)) {
-            uint32_t rk;
+        const long long r = r0 + ly, c = c0 + lx;
+        const bool inside = r < nrow && c < ncol;
+        own[it] = inside ? __ldg(loc + r * ncol + c) : TL_LOC_INVALID;
+        up[it] = (inside && uparea_out) ? __ldg(cnt + r * ncol + c) : 0u;
+        s.dir[i] = (uint8_t)tl_dir_of(dirs, it);
+        s.X[i] = 0;
+    }
+    __syncthreads();
+    // entry cells with outside inflow become walkers
+#pragma unroll
+    for (int it = 0; it < TL_CPT; ++it) {
+        const int ly = ly0 + TL_RPI * it;
+        if (uparea_out && tl_on_ring(ly, lx) && own[it] != TL_LOC_INVALID) {
+            const uint32_t w = __ldg(inflow + tile * TL_RING + tl_ring_pos(ly, lx));
+            if (w) {
+                const uint32_t k = atomicAdd(&s.wl_count, 1u);
+                s.wl_cell[k] = (uint32_t)(ly * TL_W + lx);
+                s.wl_w[k] = w;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < s.wl_count) {
+        int i = (int)s.wl_cell[threadIdx.x];
+        const uint32_t w = s.wl_w[threadIdx.x];
+        for (int step = 0; step < TL_CELLS; ++step) {
+            atomicAdd(&s.X[i], w);
+            const int ni = tl_local_next(i, s.dir[i]);
+            if (ni == i) break;
+            i = ni;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < TL_CPT; ++it) up[it] += s.X[(ly0 + TL_RPI * it) * TL_W + lx];
+    __syncthreads();
+    // terminals publish (rank at the terminal, basin id)
+#pragma unroll
+    for (int it = 0; it < TL_CPT; ++it) {
+        const int ly = ly0 + TL_RPI * it;
+        const int i = ly * TL_W + lx;
+        const uint32_t d = tl_dir_of(dirs, it);
+        if (d != PFD_DIR_NODATA && own[it] == (uint32_t)i) {
+            uint32_t rk, b;
             if (d < 8u) {  // exit cell: one hop above the entry cell of the neighbouring tile
                 const uint32_t slot = tl_slot_of(r0 + ly + pfd_slot_dr((int)d), c0 + lx + pfd_slot_dc((int)d), ntx);
-                const int32_t rs = S.rank[slot];
+                const int32_t rs = __ldg(s_rank + slot);
                 rk = (rs < 0) ? 0xFFFFFFFFu : (uint32_t)(rs + 1);
-                t_b[it] = (rs < 0) ? 0u : S.basin[slot];
+                b = (rs < 0) ? 0u : __ldg(s_basin + slot);
             } else {
                 rk = 0;
-                t_b[it] = tl_pit_ordinal(pits, npits, (cell_t)((r0 + ly) * ncol + c0 + lx)) + 1u;
+                b = basin_out ? basin_out[(r0 + ly) * ncol + c0 + lx] : 0u;  // stashed by stash_pit_ids_kernel
             }
-            tbuf[i] = rk;
+            s.T[i] = rk;
+            s.X[i] = b;
         }
     }
     __syncthreads();
-    int32_t rks[TL_CPT];
 #pragma unroll
     for (int it = 0; it < TL_CPT; ++it) {
-        const int i = (ly0 + 4 * it) * TL_W + lx;
-        const uint32_t d = (dirs[it >> 2] >> (8 * (it & 3))) & 0xFFu;
-        int32_t rk = -9999;
-        if (d != PFD_DIR_NODATA) {
-            rk = -1;
-            if (!((inv >> it) & 1u)) {
-                const uint32_t tr = tbuf[s.nxt[i]];
-                if (tr != 0xFFFFFFFFu) rk = (int32_t)(tr + s.hops[i]);
-            }
-        }
-        rks[it] = rk;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int it = 0; it < TL_CPT; ++it) {
-        const int i = (ly0 + 4 * it) * TL_W + lx;
-        const uint32_t d = (dirs[it >> 2] >> (8 * (it & 3))) & 0xFFu;
-        if (d != PFD_DIR_NODATA && tl_is_terminal(s, i)) tbuf[i] = t_b[it];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int it = 0; it < TL_CPT; ++it) {
-        const int ly = ly0 + 4 * it;
+        const int ly = ly0 + TL_RPI * it;
         const long long r = r0 + ly, c = c0 + lx;
         if (r >= nrow || c >= ncol) continue;
-        const int i = ly * TL_W + lx;
-        const int32_t rk = rks[it];
-        int32_t up = (rk == -9999) ? -9999 : 1;
+        const uint32_t d = tl_dir_of(dirs, it);
+        int32_t rk = -9999, ua = -9999;
         uint32_t b = 0;
-        if (rk >= 0) {
-            b = tbuf[s.nxt[i]];
-            up = (int32_t)s.A[abuf][i];
+        if (d != PFD_DIR_NODATA) {
+            rk = -1;
+            ua = 1;
+            if (own[it] != TL_LOC_INVALID) {
+                const uint32_t root = TP_N(own[it]);
+                const uint32_t tr = s.T[root];
+                if (tr != 0xFFFFFFFFu) {
+                    rk = (int32_t)(tr + TP_H(own[it]));
+                    b = s.X[root];
+                    ua = (int32_t)up[it];
+                }
+            }
         }
         const long long g = r * ncol + c;
         if (rank_out) rank_out[g] = rk;
         if (basin_out) basin_out[g] = b;
-        if (uparea_out) uparea_out[g] = up;
+        if (uparea_out) uparea_out[g] = ua;
     }
 }

@@ -1,0 +1,92 @@
+"""CPU tests of the host-side logic that mirrors the reference's wrappers (no GPU needed)."""
+import numpy as np
+import pytest
+
+import _cases as cs
+import pyflwdir_b200 as pfb
+from pyflwdir_b200 import gis_utils as gis
+from pyflwdir_b200._device import nodata_args
+
+
+def test_get_idxs_dtype():
+    """tests/test_pyflwdir.py:42-51 of the reference."""
+    assert pfb._get_idxs_dtype(10) == np.int32
+    assert pfb._get_idxs_dtype(2147483646) == np.int32
+    assert pfb._get_idxs_dtype(2147483647) == np.uint32
+    assert pfb._get_idxs_dtype(4294967293) == np.uint32
+    assert pfb._get_idxs_dtype(4294967294) == np.int64
+    assert pfb._get_idxs_dtype(2**40) == np.int64
+
+
+def test_from_array_input_errors():
+    """Error messages of pyflwdir.from_array raised before anything touches the device
+    (reference tests/test_pyflwdir.py:29-39)."""
+    with pytest.raises(ValueError, match="could not be inferred"):
+        pfb.from_array(np.zeros((3, 3), dtype=np.float32))
+    with pytest.raises(ValueError, match="should be 2 dimensional"):
+        pfb.from_array(np.zeros(9, dtype=np.uint8), ftype="d8")
+    with pytest.raises(ValueError, match='type "d8" is invalid'):
+        pfb.from_array(np.zeros((3, 3), dtype=np.int16), ftype="d8")
+    with pytest.raises(ValueError, match="Unknown flow direction type"):
+        pfb.from_array(np.zeros((3, 3), dtype=np.uint8), ftype="d16")
+    with pytest.raises(ValueError, match='"mask" shape does not match'):
+        pfb.from_array(np.zeros((3, 3), dtype=np.uint8), ftype="d8", mask=np.ones((2, 2)))
+    with pytest.raises(NotImplementedError):
+        pfb.from_array(np.ones((3, 3), dtype=np.uint8), ftype="ldd")
+
+
+def test_affine():
+    a = gis.Affine(0.5, 0.0, 10.0, 0.0, -0.5, 50.0)
+    assert tuple(a)[:6] == (0.5, 0.0, 10.0, 0.0, -0.5, 50.0) and a[0] == 0.5 and a[4] == -0.5
+    x, y = a * (np.array([0.0, 2.0]), np.array([0.0, 4.0]))
+    assert np.allclose(x, [10.0, 11.0]) and np.allclose(y, [50.0, 48.0])
+    inv = ~a
+    c, r = inv * (x, y)
+    assert np.allclose(c, [0.0, 2.0]) and np.allclose(r, [0.0, 4.0])
+    assert (a * gis.Affine.identity()) == a
+    assert gis.IDENTITY == gis.Affine(1.0, 0.0, 0.0, 0.0, -1.0, 0.0)
+
+
+def test_area_grid_matches_reference_rows():
+    """gis_utils.area_grid against the reference's own area grid of the rhine raster (golden, float64)."""
+    t = gis.Affine(*cs.RHINE_TRANSFORM)
+    area = gis.area_grid(t, (682, 997), latlon=True)
+    assert area.dtype == np.float64 and area.shape == (682, 997)
+    assert np.array_equal(area[:, 0], cs.small()["out/rhine/area_col0"])
+    assert np.array_equal(area[:, 0], area[:, -1])
+    flat = gis.area_grid(gis.Affine(100.0, 0, 0, 0, -100.0, 0), (4, 5), latlon=False, unit="ha")
+    assert flat.dtype == np.float32 and np.all(flat == np.float32(1.0))
+    assert gis.area_grid(t, (2, 2), unit="cell").dtype == np.int32
+    with pytest.raises(ValueError, match="Unknown unit"):
+        gis.area_grid(t, (2, 2), unit="acre")
+
+
+def test_nodata_args():
+    f, i, is_int = nodata_args(-9999)
+    assert (f.value, i.value, is_int.value) == (-9999.0, -9999, 1)
+    f, i, is_int = nodata_args(-9999.0)
+    assert (f.value, is_int.value) == (-9999.0, 0)
+    f, i, is_int = nodata_args(np.float32(1.5))
+    assert (f.value, is_int.value) == (1.5, 0)
+    f, i, is_int = nodata_args(np.int16(7))
+    assert (i.value, is_int.value) == (7, 1)
+
+
+def test_ring_slot_numbering():
+    """The tile solver's ring-slot numbering (pfd_tiles.cuh tl_ring_pos) is a bijection onto 0..251."""
+    TL = 64
+    seen = set()
+    for ly in range(TL):
+        for lx in range(TL):
+            if ly in (0, TL - 1) or lx in (0, TL - 1):
+                if ly == 0:
+                    p = lx
+                elif ly == TL - 1:
+                    p = TL + lx
+                elif lx == 0:
+                    p = 2 * TL + ly - 1
+                else:
+                    p = 2 * TL + (TL - 2) + ly - 1
+                assert p not in seen
+                seen.add(p)
+    assert seen == set(range(4 * TL - 4))
