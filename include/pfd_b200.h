@@ -153,6 +153,35 @@ int pfd_d8_flow_all(pfd_handle* h, const uint8_t* d8, int64_t nrow, int64_t ncol
                     int idx_dtype, int32_t* rank_out, int32_t* uparea_out, uint32_t* basins_out,
                     int64_t* n_valid, int64_t* n_pits, int64_t* nnodes);
 
+/* ---- row-tiled multi-GPU solve (BASELINE config 4) ------------------------------------- */
+/*
+ * One process per GPU; rank g owns a block of consecutive rows (a multiple of 64 rows except for the last rank)
+ * of ONE raster. d8_block holds halo_top + nrow_owned + halo_bot rows: the owned rows plus one halo row of D8
+ * codes from each existing neighbour (core_d8.from_array's "downstream cell is nodata?" test needs it).
+ * The solve is the tile solver of pfd_d8_flow_all with two exchanges: the pit counts (global basin ids) and ONE
+ * all-reduce (uint32 sum) of the boundary tables, 4 x 2(R-1) x ncol entries. Outputs hold the owned rows only;
+ * idxs_ds are GLOBAL linear indices. Integer outputs => bit-identical to the single-GPU result.
+ *
+ * pfd_d8_flow_all_tiled does everything over the handle's NCCL communicator (pfd_comm_init). The three step
+ * functions expose the same computation with the exchanges left to the caller (tests emulate R ranks on one GPU):
+ *   pfd_tiled_parse  -> n_pits of the block;   caller: pit_id_offset = sum of n_pits of the lower ranks
+ *   pfd_tiled_local  -> *table_dev (device, uint32 x *table_len);   caller: all-reduce(sum) it across ranks
+ *   pfd_tiled_finish -> outputs.   basins_out (if wanted) must be a device buffer, same pointer in both calls.
+ */
+int pfd_comm_unique_id(void* out128, int64_t capacity);     /* ncclGetUniqueId -> 128 bytes, on rank 0 */
+int pfd_comm_init(pfd_handle* h, int rank, int nranks, const void* unique_id128);
+int pfd_comm_barrier(pfd_handle* h);
+int pfd_comm_destroy(pfd_handle* h);
+int pfd_d8_flow_all_tiled(pfd_handle* h, const uint8_t* d8_block, int64_t nrow_owned, int64_t ncol, int halo_top,
+                          int halo_bot, int64_t glob_row0, void* idxs_ds_out, int idx_dtype, int32_t* rank_out,
+                          int32_t* uparea_out, uint32_t* basins_out, int64_t* n_valid, int64_t* n_pits_global);
+int pfd_tiled_parse(pfd_handle* h, const uint8_t* d8_block, int64_t nrow_owned, int64_t ncol, int halo_top,
+                    int halo_bot, int64_t glob_row0, void* idxs_ds_out, int idx_dtype, int64_t* n_valid,
+                    int64_t* n_pits);
+int pfd_tiled_local(pfd_handle* h, int rank, int nranks, int64_t pit_id_offset, uint32_t* basins_out,
+                    void** table_dev, int64_t* table_len);
+int pfd_tiled_finish(pfd_handle* h, int32_t* rank_out, int32_t* uparea_out, uint32_t* basins_out);
+
 /* ---- synthetic input (bench / tests) ---------------------------------------------------- */
 /* z: nrow*ncol float32 (device or host) elevation; d8 from z by strict steepest descent. */
 int pfd_synth_elevation(pfd_handle* h, int64_t nrow, int64_t ncol, int64_t nref, int octaves, uint32_t seed,

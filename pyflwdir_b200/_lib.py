@@ -51,6 +51,14 @@ SYMBOLS = {
     "pfd_strahler": (_int, [_vp, _vp, _vp]),
     "pfd_hand": (_int, [_vp, _vp, _vp, _int, _vp]),
     "pfd_d8_flow_all": (_int, [_vp, _vp, _i64, _i64, _vp, _int, _vp, _vp, _vp, _pi64, _pi64, _pi64]),
+    "pfd_comm_unique_id": (_int, [_vp, _i64]),
+    "pfd_comm_init": (_int, [_vp, _int, _int, _vp]),
+    "pfd_comm_barrier": (_int, [_vp]),
+    "pfd_comm_destroy": (_int, [_vp]),
+    "pfd_d8_flow_all_tiled": (_int, [_vp, _vp, _i64, _i64, _int, _int, _i64, _vp, _int, _vp, _vp, _vp, _pi64, _pi64]),
+    "pfd_tiled_parse": (_int, [_vp, _vp, _i64, _i64, _int, _int, _i64, _vp, _int, _pi64, _pi64]),
+    "pfd_tiled_local": (_int, [_vp, _int, _int, _i64, _vp, C.POINTER(_vp), _pi64]),
+    "pfd_tiled_finish": (_int, [_vp, _vp, _vp, _vp]),
     "pfd_synth_elevation": (_int, [_vp, _i64, _i64, _i64, _int, _u32, _vp]),
     "pfd_synth_d8": (_int, [_vp, _vp, _i64, _i64, C.c_float, _vp]),
     "pfd_set_option": (_int, [_vp, C.c_char_p, _i64]),

@@ -6,6 +6,8 @@
 #include "pfd_tiles.cuh"
 #include "pfd_synth.h"
 
+#include <nccl.h>
+
 #include <algorithm>
 #include <cmath>
 #include <new>
@@ -131,13 +133,16 @@ extern "C" int pfd_create(int device, pfd_handle** out) {
     return PFD_OK;
 }
 
+extern "C" int pfd_comm_destroy(pfd_handle* h);
+
 extern "C" void pfd_destroy(pfd_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    pfd_comm_destroy(h);
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->dir, &h->upmask, &h->pits, &h->pit_outlet, &h->seq, &h->bseq, &h->rank, &h->basins,
                       &h->level_off, &h->bfs_state, &h->chunk_status, &h->blk_counts, &h->blk_offsets, &h->counters,
-                      &h->segs, &h->tslots, &h->uparea, &h->tile_loc, &h->tile_cnt};
+                      &h->segs, &h->tslots, &h->uparea, &h->tile_loc, &h->tile_cnt, &h->btab, &h->bgraph, &h->mg_counts};
     for (DevBuf* b : bufs) pfd_release(*b);
     for (DevBuf& b : h->scratch) pfd_release(b);
     for (int s = 0; s < PFD_NSTAGE; ++s) {
@@ -228,7 +233,11 @@ static void invalidate(pfd_handle* h) {
 }
 
 // d8_dev: device pointer. idxs_dev: device pointer or null.
-static int parse_device(pfd_handle* h, const uint8_t* d8_dev, int64_t nrow, int64_t ncol, void* idxs_dev, int idx_dtype) {
+// d8_dev holds halo_top + nrow + halo_bot rows (halo rows only feed the forced-pit test of the block's edge rows);
+// idxs_dev (optional) receives the nrow owned rows as global linear indices (first owned row = glob_row0).
+static int parse_device(pfd_handle* h, const uint8_t* d8_dev, int64_t nrow_owned, int64_t ncol, void* idxs_dev, int idx_dtype,
+                        int halo_top = 0, int halo_bot = 0, int64_t glob_row0 = 0) {
+    const int64_t nrow = nrow_owned + halo_top + halo_bot;
     const int64_t n = nrow * ncol;
     const int64_t npad = (n + PC_CHUNK - 1) / PC_CHUNK * PC_CHUNK;
     PFD_TRY(pfd_reserve(h, h->dir, (size_t)npad));
@@ -245,7 +254,8 @@ static int parse_device(pfd_handle* h, const uint8_t* d8_dev, int64_t nrow, int6
         const bool aligned = (ncol % 4 == 0) && ((uintptr_t)d8_dev % 4 == 0) && (!idxs_dev || (uintptr_t)idxs_dev % 16 == 0);
         uint8_t* dir = (uint8_t*)h->dir.p;
         uint8_t* upm = (uint8_t*)h->upmask.p;
-#define LAUNCH_PARSE(A, M) parse_kernel<A, M><<<grid, 256, 0, h->stream>>>(d8_dev, nrow, ncol, dir, upm, idxs_dev, flag)
+#define LAUNCH_PARSE(A, M) \
+    parse_kernel<A, M><<<grid, 256, 0, h->stream>>>(d8_dev, nrow, ncol, dir, upm, idxs_dev, flag, (int64_t)halo_top, nrow_owned, glob_row0)
         if (aligned) {
             if (idxmode == 0) LAUNCH_PARSE(true, 0);
             else if (idxmode == 1) LAUNCH_PARSE(true, 1);
@@ -257,6 +267,9 @@ static int parse_device(pfd_handle* h, const uint8_t* d8_dev, int64_t nrow, int6
         }
 #undef LAUNCH_PARSE
         PFD_LAUNCH_CHECK(h);
+        // halo rows must not contribute pits / valid cells: blank them after the owned rows were parsed
+        if (halo_top) PFD_CUDA(h, cudaMemsetAsync(h->dir.p, 0xFF, (size_t)ncol, h->stream));
+        if (halo_bot) PFD_CUDA(h, cudaMemsetAsync((uint8_t*)h->dir.p + (n - ncol), 0xFF, (size_t)ncol, h->stream));
     }
     const int64_t nblk = npad / PC_CHUNK;
     {
@@ -289,9 +302,11 @@ static int parse_device(pfd_handle* h, const uint8_t* d8_dev, int64_t nrow, int6
             PFD_LAUNCH_CHECK(h);
         }
     }
-    h->nrow = nrow;
+    h->nrow = nrow_owned;
     h->ncol = ncol;
-    h->n = n;
+    h->n = nrow_owned * ncol;
+    h->dir_off = (int64_t)halo_top * ncol;
+    h->tiled = (halo_top || halo_bot || glob_row0 != 0);
     h->parsed = true;
     h->ordered = h->have_rank = h->have_basins = h->have_uparea = false;
     return PFD_OK;
@@ -389,71 +404,369 @@ __global__ void count_ranked_kernel(const int32_t* __restrict__ rank, int64_t n,
 
 static bool tiles_usable(const pfd_handle* h) { return h->use_tiles && h->n_pits > 0 && h->n_pits < (1ll << 31); }
 
-// Any of the three device outputs may be null.
-static int tiles_solve(pfd_handle* h, int32_t* rank_dev, uint32_t* basin_dev, int32_t* uparea_dev) {
+struct TileCtx {
+    long long ntx = 0, nty = 0, nslots = 0;
+    size_t arr = 0;
+    SlotBuf B[2];       // double-buffered reduced-graph state
+    SlotBuf init;       // copy of the state after phase A (multi-rank: the local reduced graph is solved twice)
+    uint32_t *term = nullptr, *term_h = nullptr, *sbasin = nullptr;
+    int32_t* srank = nullptr;
+    unsigned int* flag = nullptr;
+    const uint8_t* dir = nullptr;  // first OWNED row
+};
+
+static int tiles_setup(pfd_handle* h, TileCtx& T, bool with_init_copy) {
     if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, "no raster parsed on this handle");
-    const long long ntx = (h->ncol + TL_W - 1) / TL_W, nty = (h->nrow + TL_H - 1) / TL_H;
-    if (nty > 65535) return pfd_fail(h, PFD_ERR_UNSUPPORTED, "tile solver: more than 4194240 rows");
-    const long long nslots = ntx * nty * TL_RING;
-    // 12 uint32 arrays of nslots + flag
-    const size_t arr = (size_t)nslots * sizeof(uint32_t);
-    PFD_TRY(pfd_reserve(h, h->tslots, 12 * arr + 256));
+    T.ntx = (h->ncol + TL_W - 1) / TL_W;
+    T.nty = (h->nrow + TL_H - 1) / TL_H;
+    if (T.nty > 65535) return pfd_fail(h, PFD_ERR_UNSUPPORTED, "tile solver: more than 4194240 rows");
+    T.nslots = T.ntx * (T.nty + 2) * TL_RING;  // + one halo tile row above and below
+    if (T.nslots >= (1ll << 30)) return pfd_fail(h, PFD_ERR_UNSUPPORTED, "tile solver: too many ring slots");
+    T.arr = (size_t)T.nslots * sizeof(uint32_t);
+    const int narr = with_init_copy ? 16 : 12;
+    PFD_TRY(pfd_reserve(h, h->tslots, narr * T.arr + 256));
     uint32_t* base = (uint32_t*)h->tslots.p;
     int a = 0;
-    SlotBuf B[2];
+    auto take = [&]() { return base + (size_t)T.nslots * a++; };
     for (int side = 0; side < 2; ++side) {
-        B[side].nxt = base + (size_t)nslots * a++;
-        B[side].rh = base + (size_t)nslots * a++;
-        B[side].ch = base + (size_t)nslots * a++;
-        B[side].acc = base + (size_t)nslots * a++;
+        T.B[side].nxt = take();
+        T.B[side].rh = take();
+        T.B[side].ch = take();
+        T.B[side].acc = take();
     }
-    uint32_t* term = base + (size_t)nslots * a++;
-    uint32_t* term_h = base + (size_t)nslots * a++;
-    int32_t* srank = (int32_t*)(base + (size_t)nslots * a++);
-    uint32_t* sbasin = base + (size_t)nslots * a++;
-    unsigned int* flag = (unsigned int*)(base + (size_t)nslots * a);
-    const dim3 grid((unsigned)ntx, (unsigned)nty);
+    T.term = take();
+    T.term_h = take();
+    T.srank = (int32_t*)take();
+    T.sbasin = take();
+    if (with_init_copy) {
+        T.init.nxt = take();
+        T.init.rh = take();
+        T.init.ch = take();
+        T.init.acc = take();
+    }
+    T.flag = (unsigned int*)(base + (size_t)T.nslots * a);
+    T.dir = (const uint8_t*)h->dir.p + h->dir_off;
     PFD_TRY(pfd_reserve(h, h->tile_loc, (size_t)h->n * sizeof(uint32_t)));
     PFD_TRY(pfd_reserve(h, h->tile_cnt, (size_t)h->n * sizeof(uint32_t)));
-    {
-        StageTimer t(h, PFD_STAGE_TILE_A);
-        PFD_CUDA(h, cudaMemsetAsync(B[0].acc, 0, arr, h->stream));
-        if (basin_dev) {
-            stash_pit_ids_kernel<<<grid_for(h->n_pits, 256, 1, 148 * 16), 256, 0, h->stream>>>((const cell_t*)h->pits.p, h->n_pits, basin_dev);
-            PFD_LAUNCH_CHECK(h);
+    return PFD_OK;
+}
+
+// phase A: per-tile local solve -> loc / cnt per cell, ring nodes + inflow weights in T.B[0]
+static int tiles_phase_a(pfd_handle* h, TileCtx& T, uint32_t* basin_dev, unsigned long long pit_id_offset) {
+    StageTimer t(h, PFD_STAGE_TILE_A);
+    const dim3 grid((unsigned)T.ntx, (unsigned)T.nty);
+    PFD_CUDA(h, cudaMemsetAsync(T.B[0].acc, 0, T.arr, h->stream));
+    halo_slots_init_kernel<<<grid_for(2 * T.ntx * TL_RING, 256), 256, 0, h->stream>>>(T.B[0], T.term, T.term_h, T.ntx, T.nty);
+    PFD_LAUNCH_CHECK(h);
+    if (basin_dev && h->n_pits > 0) {
+        stash_pit_ids_kernel<<<grid_for(h->n_pits, 256, 1, 148 * 16), 256, 0, h->stream>>>(
+            (const cell_t*)h->pits.p, h->n_pits, h->dir_off, pit_id_offset, basin_dev);
+        PFD_LAUNCH_CHECK(h);
+    }
+    tile_phase_a_kernel<TLA_THREADS, TLA_MINBLOCKS><<<grid, TLA_THREADS, 0, h->stream>>>(
+        T.dir, h->nrow, h->ncol, T.ntx, basin_dev, (uint32_t*)h->tile_loc.p, (uint32_t*)h->tile_cnt.p, T.B[0].acc,
+        T.B[0].nxt, T.B[0].rh, T.B[0].ch, T.term, T.term_h);
+    PFD_LAUNCH_CHECK(h);
+    return PFD_OK;
+}
+
+// phase B: doubling rounds over `n` reduced-graph nodes starting from side 0; *src = side holding the result
+static int slots_solve(pfd_handle* h, SlotBuf* B, long long n, unsigned int* flag, int* src_out, int* rounds_out) {
+    const size_t arr = (size_t)n * sizeof(uint32_t);
+    const int g = grid_for(n, 256, 2, 148 * 16);
+    int src = 0, k = 0;
+    for (; k < 31; ++k) {
+        PFD_CUDA(h, cudaMemcpyAsync(B[src ^ 1].acc, B[src].acc, arr, cudaMemcpyDeviceToDevice, h->stream));
+        PFD_CUDA(h, cudaMemsetAsync(flag, 0, sizeof(unsigned int), h->stream));
+        slots_round_kernel<<<g, 256, 0, h->stream>>>(B[src], B[src ^ 1], n, 1u << k, flag);
+        PFD_LAUNCH_CHECK(h);
+        unsigned int hflag = 0;
+        PFD_CUDA(h, cudaMemcpyAsync(&hflag, flag, sizeof(hflag), cudaMemcpyDeviceToHost, h->stream));
+        PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+        src ^= 1;
+        if (!hflag) break;
+    }
+    *src_out = src;
+    if (rounds_out) *rounds_out = k + 1;
+    return PFD_OK;
+}
+
+static int tiles_phase_b(pfd_handle* h, TileCtx& T, int* src_out) {
+    StageTimer t(h, PFD_STAGE_TILE_B);
+    PFD_TRY(slots_solve(h, T.B, T.nslots, T.flag, src_out, &h->tile_rounds));
+    slots_finalize_kernel<<<grid_for(T.nslots, 256, 2, 148 * 16), 256, 0, h->stream>>>(T.B[*src_out], T.term, T.term_h,
+                                                                                       T.nslots, T.srank, T.sbasin);
+    PFD_LAUNCH_CHECK(h);
+    return PFD_OK;
+}
+
+static int tiles_phase_c(pfd_handle* h, TileCtx& T, int src, int32_t* rank_dev, uint32_t* basin_dev, int32_t* uparea_dev) {
+    StageTimer t(h, PFD_STAGE_TILE_C);
+    const dim3 grid((unsigned)T.ntx, (unsigned)T.nty);
+    tile_phase_c_kernel<TLC_THREADS, TLC_MINBLOCKS><<<grid, TLC_THREADS, 0, h->stream>>>(
+        T.dir, h->nrow, h->ncol, T.ntx, (const uint32_t*)h->tile_loc.p, (const uint32_t*)h->tile_cnt.p, T.B[src].acc,
+        T.srank, T.sbasin, rank_dev, basin_dev, uparea_dev);
+    PFD_LAUNCH_CHECK(h);
+    return PFD_OK;
+}
+
+// Single-GPU solve. Any of the three device outputs may be null.
+static int tiles_solve(pfd_handle* h, int32_t* rank_dev, uint32_t* basin_dev, int32_t* uparea_dev) {
+    TileCtx T;
+    PFD_TRY(tiles_setup(h, T, false));
+    PFD_TRY(tiles_phase_a(h, T, basin_dev, 0));
+    int src = 0;
+    PFD_TRY(tiles_phase_b(h, T, &src));
+    PFD_TRY(tiles_phase_c(h, T, src, rank_dev, basin_dev, uparea_dev));
+    return PFD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Row-tiled multi-GPU solve (BASELINE config 4): every rank owns a block of rows (multiple of 64 except the last),
+// parses it with one halo row of D8 codes from each neighbour, solves its tiles and its local reduced graph, and
+// meets the other ranks in exactly two small exchanges: the pit counts (for global basin ids) and ONE all-reduce of
+// the boundary tables (4 x 2(R-1) x ncol uint32). The boundary graph (entries on the block edges) is then solved
+// redundantly by every rank with the same doubling kernels. Integer payloads only => bit-exact.
+// The steps are exposed separately so the exchange can be NCCL (pfd_comm_*) or an in-process emulation (tests).
+// ---------------------------------------------------------------------------------------------------------
+static long long boundary_entries(const pfd_handle* h) { return 2ll * (h->mg_nranks - 1) * h->ncol; }
+
+static void boundary_tables(pfd_handle* h, BoundaryTables& bt) {
+    const long long nb = boundary_entries(h);
+    uint32_t* p = (uint32_t*)h->btab.p;
+    bt.h1 = p;
+    bt.nxt = p + nb;
+    bt.hop = p + 2 * nb;
+    bt.bas = p + 3 * nb;
+}
+
+extern "C" int pfd_tiled_parse(pfd_handle* h, const uint8_t* d8_block, int64_t nrow_owned, int64_t ncol, int halo_top,
+                               int halo_bot, int64_t glob_row0, void* idxs_ds_out, int idx_dtype, int64_t* n_valid,
+                               int64_t* n_pits) {
+    PFD_TRY(check_handle(h));
+    stage_reset(h);
+    PFD_TRY(check_shape(h, nrow_owned + 2, ncol, "pfd_tiled_parse"));
+    if (!d8_block) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_tiled_parse: d8_block is null");
+    if ((halo_top | halo_bot) & ~1) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_tiled_parse: halo flags must be 0 or 1");
+    if (idxs_ds_out && idx_dtype != PFD_I32 && idx_dtype != PFD_U32 && idx_dtype != PFD_I64)
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_tiled_parse: idx_dtype must be int32, uint32 or int64");
+    invalidate(h);
+    const int64_t next = (nrow_owned + halo_top + halo_bot) * ncol;
+    const void* d8_dev = nullptr;
+    PFD_TRY(pfd_stage_in(h, d8_block, (size_t)next, 0, &d8_dev));
+    void* idxs_dev = nullptr;
+    const size_t ibytes = (size_t)(nrow_owned * ncol) * pfd_dtype_size(idx_dtype);
+    if (idxs_ds_out) PFD_TRY(pfd_stage_out(h, idxs_ds_out, ibytes, 1, &idxs_dev));
+    PFD_TRY(parse_device(h, (const uint8_t*)d8_dev, nrow_owned, ncol, idxs_dev, idx_dtype, halo_top, halo_bot, glob_row0));
+    if (idxs_ds_out) PFD_TRY(pfd_finish_out(h, idxs_ds_out, idxs_dev, ibytes));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    h->mg_halo_top = halo_top;
+    h->mg_halo_bot = halo_bot;
+    if (n_valid) *n_valid = h->n_valid;
+    if (n_pits) *n_pits = h->n_pits;
+    return PFD_OK;
+}
+
+// Local part: tiles + local reduced graph; fills this rank's contribution to the boundary tables.
+// table_dev / table_len: the device buffer to all-reduce (uint32 sum) across ranks before pfd_tiled_finish.
+extern "C" int pfd_tiled_local(pfd_handle* h, int rank, int nranks, int64_t pit_id_offset, uint32_t* basins_out,
+                               void** table_dev, int64_t* table_len) {
+    PFD_TRY(check_handle(h));
+    stage_reset(h);
+    if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, "pfd_tiled_local: call pfd_tiled_parse first");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_tiled_local: bad rank");
+    if (nranks > 1 && rank < nranks - 1 && (h->nrow % TL_H) != 0)
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_tiled_local: row blocks (except the last) must be multiples of 64 rows");
+    if (basins_out && !pfd_is_device_ptr(basins_out))
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_tiled_local: basins_out must be a device buffer (it carries the pit ids)");
+    h->mg_rank = rank;
+    h->mg_nranks = nranks;
+    h->mg_basins = basins_out;
+    TileCtx T;
+    PFD_TRY(tiles_setup(h, T, nranks > 1));
+    PFD_TRY(tiles_phase_a(h, T, basins_out, (unsigned long long)pit_id_offset));
+    const long long nb = boundary_entries(h);
+    PFD_TRY(pfd_reserve(h, h->btab, (size_t)std::max<long long>(4 * nb, 1) * sizeof(uint32_t)));
+    if (nranks > 1) {
+        // keep the state after phase A: the local reduced graph is solved again once the remote inflow is known
+        for (int f = 0; f < 4; ++f) {
+            uint32_t* dst = f == 0 ? T.init.nxt : f == 1 ? T.init.rh : f == 2 ? T.init.ch : T.init.acc;
+            uint32_t* src = f == 0 ? T.B[0].nxt : f == 1 ? T.B[0].rh : f == 2 ? T.B[0].ch : T.B[0].acc;
+            PFD_CUDA(h, cudaMemcpyAsync(dst, src, T.arr, cudaMemcpyDeviceToDevice, h->stream));
         }
-        tile_phase_a_kernel<TLA_THREADS, TLA_MINBLOCKS><<<grid, TLA_THREADS, 0, h->stream>>>(
-            (const uint8_t*)h->dir.p, h->nrow, h->ncol, ntx, basin_dev, (uint32_t*)h->tile_loc.p, (uint32_t*)h->tile_cnt.p,
-            B[0].acc, B[0].nxt, B[0].rh, B[0].ch, term, term_h);
+        int src = 0;
+        {
+            StageTimer t(h, PFD_STAGE_TILE_B);
+            PFD_TRY(slots_solve(h, T.B, T.nslots, T.flag, &src, &h->tile_rounds));
+        }
+        PFD_CUDA(h, cudaMemsetAsync(h->btab.p, 0, (size_t)(4 * nb) * sizeof(uint32_t), h->stream));
+        BoundaryTables bt;
+        boundary_tables(h, bt);
+        boundary_fill_kernel<<<grid_for(2 * h->ncol, 256), 256, 0, h->stream>>>(T.B[src], T.term, T.term_h, h->nrow, h->ncol,
+                                                                                 T.ntx, T.nty, rank, h->mg_halo_top,
+                                                                                 h->mg_halo_bot, bt);
+        PFD_LAUNCH_CHECK(h);
+    }
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    if (table_dev) *table_dev = h->btab.p;
+    if (table_len) *table_len = 4 * nb;
+    return PFD_OK;
+}
+
+// After the boundary tables were all-reduced: boundary graph, second local solve, per-tile finalisation.
+extern "C" int pfd_tiled_finish(pfd_handle* h, int32_t* rank_out, int32_t* uparea_out, uint32_t* basins_out) {
+    PFD_TRY(check_handle(h));
+    stage_reset(h);
+    if (!h->parsed || h->mg_nranks < 1) return pfd_fail(h, PFD_ERR_STATE, "pfd_tiled_finish: call pfd_tiled_local first");
+    if (basins_out != h->mg_basins) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_tiled_finish: basins_out differs from pfd_tiled_local");
+    const size_t b4 = (size_t)h->n * 4;
+    void *rk = nullptr, *up = nullptr;
+    if (rank_out) PFD_TRY(pfd_stage_out(h, rank_out, b4, 2, &rk));
+    if (uparea_out) PFD_TRY(pfd_stage_out(h, uparea_out, b4, 3, &up));
+    TileCtx T;
+    PFD_TRY(tiles_setup(h, T, h->mg_nranks > 1));
+    if (h->mg_nranks > 1) {
+        const long long nb = boundary_entries(h);
+        // boundary graph: 12 node arrays + results, solved redundantly on every rank
+        PFD_TRY(pfd_reserve(h, h->bgraph, (size_t)(13 * nb) * sizeof(uint32_t) + 256));
+        uint32_t* base = (uint32_t*)h->bgraph.p;
+        int a = 0;
+        auto take = [&]() { return base + (size_t)nb * a++; };
+        SlotBuf G[2];
+        for (int side = 0; side < 2; ++side) {
+            G[side].nxt = take();
+            G[side].rh = take();
+            G[side].ch = take();
+            G[side].acc = take();
+        }
+        uint32_t *gterm = take(), *gterm_h = take(), *gbasin = take();
+        int32_t* grank = (int32_t*)take();
+        unsigned int* gflag = (unsigned int*)take();
+        BoundaryTables bt;
+        boundary_tables(h, bt);
+        boundary_build_kernel<<<grid_for(nb, 256), 256, 0, h->stream>>>(bt, nb, G[0], gterm, gterm_h);
+        PFD_LAUNCH_CHECK(h);
+        int gsrc = 0, grounds = 0;
+        PFD_TRY(slots_solve(h, G, nb, gflag, &gsrc, &grounds));
+        slots_finalize_kernel<<<grid_for(nb, 256), 256, 0, h->stream>>>(G[gsrc], gterm, gterm_h, nb, grank, gbasin);
+        PFD_LAUNCH_CHECK(h);
+        // restore the local reduced graph, add the remote inflow, make the halo slots terminals, solve again
+        for (int f = 0; f < 4; ++f) {
+            uint32_t* src = f == 0 ? T.init.nxt : f == 1 ? T.init.rh : f == 2 ? T.init.ch : T.init.acc;
+            uint32_t* dst = f == 0 ? T.B[0].nxt : f == 1 ? T.B[0].rh : f == 2 ? T.B[0].ch : T.B[0].acc;
+            PFD_CUDA(h, cudaMemcpyAsync(dst, src, T.arr, cudaMemcpyDeviceToDevice, h->stream));
+        }
+        boundary_writeback_kernel<<<grid_for(2 * h->ncol, 256), 256, 0, h->stream>>>(
+            grank, gbasin, G[gsrc].acc, h->nrow, h->ncol, T.ntx, h->mg_rank, h->mg_halo_top, h->mg_halo_bot, T.B[0].acc,
+            T.term, T.term_h);
         PFD_LAUNCH_CHECK(h);
     }
     int src = 0;
-    {
-        StageTimer t(h, PFD_STAGE_TILE_B);
-        const int g = grid_for(nslots, 256, 2, 148 * 16);
-        int k = 0;
-        for (; k < 31; ++k) {
-            PFD_CUDA(h, cudaMemcpyAsync(B[src ^ 1].acc, B[src].acc, arr, cudaMemcpyDeviceToDevice, h->stream));
-            PFD_CUDA(h, cudaMemsetAsync(flag, 0, sizeof(unsigned int), h->stream));
-            slots_round_kernel<<<g, 256, 0, h->stream>>>(B[src], B[src ^ 1], nslots, 1u << k, flag);
-            PFD_LAUNCH_CHECK(h);
-            unsigned int hflag = 0;
-            PFD_CUDA(h, cudaMemcpyAsync(&hflag, flag, sizeof(hflag), cudaMemcpyDeviceToHost, h->stream));
-            PFD_CUDA(h, cudaStreamSynchronize(h->stream));
-            src ^= 1;
-            if (!hflag) break;
+    PFD_TRY(tiles_phase_b(h, T, &src));
+    PFD_TRY(tiles_phase_c(h, T, src, (int32_t*)rk, basins_out, (int32_t*)up));
+    if (rank_out) PFD_TRY(pfd_finish_out(h, rank_out, rk, b4));
+    if (uparea_out) PFD_TRY(pfd_finish_out(h, uparea_out, up, b4));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    return PFD_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// NCCL plumbing for the row-tiled solve (one process per GPU; the caller distributes the unique id)
+// ---------------------------------------------------------------------------------------------------------
+#define PFD_NCCL(h, call)                                                                                         \
+    do {                                                                                                          \
+        ncclResult_t r__ = (call);                                                                                \
+        if (r__ != ncclSuccess)                                                                                   \
+            return pfd_fail((h), PFD_ERR_NCCL, std::string(#call) + ": " + ncclGetErrorString(r__));              \
+    } while (0)
+
+extern "C" int pfd_comm_unique_id(void* out, int64_t capacity) {
+    if (!out || capacity < (int64_t)sizeof(ncclUniqueId)) return pfd_fail(nullptr, PFD_ERR_INVALID_ARG, "pfd_comm_unique_id: need 128 bytes");
+    ncclUniqueId id;
+    PFD_NCCL(nullptr, ncclGetUniqueId(&id));
+    memcpy(out, &id, sizeof(id));
+    return PFD_OK;
+}
+
+extern "C" int pfd_comm_init(pfd_handle* h, int rank, int nranks, const void* unique_id) {
+    PFD_TRY(check_handle(h));
+    if (!unique_id || nranks < 1 || rank < 0 || rank >= nranks) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_comm_init: bad argument");
+    if (h->nccl_comm) return pfd_fail(h, PFD_ERR_STATE, "pfd_comm_init: communicator already initialised");
+    ncclUniqueId id;
+    memcpy(&id, unique_id, sizeof(id));
+    ncclComm_t comm;
+    PFD_NCCL(h, ncclCommInitRank(&comm, nranks, id, rank));
+    h->nccl_comm = (void*)comm;
+    h->mg_rank = rank;
+    h->mg_nranks = nranks;
+    return PFD_OK;
+}
+
+extern "C" int pfd_comm_destroy(pfd_handle* h) {
+    if (h && h->nccl_comm) {
+        cudaSetDevice(h->device);
+        ncclCommDestroy((ncclComm_t)h->nccl_comm);
+        h->nccl_comm = nullptr;
+    }
+    return PFD_OK;
+}
+
+extern "C" int pfd_comm_barrier(pfd_handle* h) {
+    PFD_TRY(check_handle(h));
+    if (!h->nccl_comm) return pfd_fail(h, PFD_ERR_STATE, "pfd_comm_barrier: no communicator");
+    PFD_TRY(pfd_reserve(h, h->counters, 8 * sizeof(unsigned long long)));
+    unsigned int* p = (unsigned int*)((unsigned long long*)h->counters.p + 7);
+    PFD_NCCL(h, ncclAllReduce(p, p, 1, ncclUint32, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    return PFD_OK;
+}
+
+// parse + order-free solve of one row block, exchanges over NCCL. Outputs (device or host, any may be NULL except
+// that basins_out, when given, must be a device buffer) hold the nrow_owned rows of this rank.
+extern "C" int pfd_d8_flow_all_tiled(pfd_handle* h, const uint8_t* d8_block, int64_t nrow_owned, int64_t ncol, int halo_top,
+                                     int halo_bot, int64_t glob_row0, void* idxs_ds_out, int idx_dtype, int32_t* rank_out,
+                                     int32_t* uparea_out, uint32_t* basins_out, int64_t* n_valid, int64_t* n_pits_global) {
+    PFD_TRY(check_handle(h));
+    const int nranks = h->nccl_comm ? h->mg_nranks : 1, rank = h->nccl_comm ? h->mg_rank : 0;
+    int64_t nv = 0, np = 0;
+    cudaEventRecord(h->ev_timer[0], h->stream);
+    PFD_TRY(pfd_tiled_parse(h, d8_block, nrow_owned, ncol, halo_top, halo_bot, glob_row0, idxs_ds_out, idx_dtype, &nv, &np));
+    // exchange #1: pit counts -> global basin id offset of this block (blocks are in linear-index order)
+    long long offset = 0, total = np;
+    if (nranks > 1) {
+        PFD_TRY(pfd_reserve(h, h->mg_counts, (size_t)(nranks + 1) * sizeof(unsigned long long)));
+        unsigned long long* d = (unsigned long long*)h->mg_counts.p;
+        unsigned long long mine = (unsigned long long)np;
+        PFD_CUDA(h, cudaMemcpyAsync(d + nranks, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+        PFD_NCCL(h, ncclAllGather(d + nranks, d, 1, ncclUint64, (ncclComm_t)h->nccl_comm, h->stream));
+        std::vector<unsigned long long> all(nranks);
+        PFD_CUDA(h, cudaMemcpyAsync(all.data(), d, (size_t)nranks * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+        total = 0;
+        for (int g = 0; g < nranks; ++g) {
+            if (g < rank) offset += (long long)all[g];
+            total += (long long)all[g];
         }
-        h->tile_rounds = k + 1;
-        slots_finalize_kernel<<<g, 256, 0, h->stream>>>(B[src], term, term_h, nslots, srank, sbasin);
-        PFD_LAUNCH_CHECK(h);
     }
-    {
-        StageTimer t(h, PFD_STAGE_TILE_C);
-        tile_phase_c_kernel<TLC_THREADS, TLC_MINBLOCKS><<<grid, TLC_THREADS, 0, h->stream>>>(
-            (const uint8_t*)h->dir.p, h->nrow, h->ncol, ntx, (const uint32_t*)h->tile_loc.p, (const uint32_t*)h->tile_cnt.p,
-            B[src].acc, srank, sbasin, rank_dev, basin_dev, uparea_dev);
-        PFD_LAUNCH_CHECK(h);
+    if (total >= (1ll << 31)) return pfd_fail(h, PFD_ERR_UNSUPPORTED, "pfd_d8_flow_all_tiled: more than 2^31 pits");
+    void* table = nullptr;
+    int64_t table_len = 0;
+    PFD_TRY(pfd_tiled_local(h, rank, nranks, offset, basins_out, &table, &table_len));
+    // exchange #2: ONE all-reduce of the boundary tables
+    if (nranks > 1 && table_len > 0) {
+        PFD_NCCL(h, ncclAllReduce(table, table, (size_t)table_len, ncclUint32, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
     }
+    PFD_TRY(pfd_tiled_finish(h, rank_out, uparea_out, basins_out));
+    cudaEventRecord(h->ev_timer[1], h->stream);
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev_timer[0], h->ev_timer[1]) == cudaSuccess) h->stage_ms[PFD_STAGE_TOTAL] = ms;
+    if (n_valid) *n_valid = nv;
+    if (n_pits_global) *n_pits_global = total;
     return PFD_OK;
 }
 
@@ -463,6 +776,7 @@ static int tiles_ensure(pfd_handle* h, bool want_rank, bool want_basins, bool wa
     want_basins = want_basins && !h->have_basins;
     want_uparea = want_uparea && !h->have_uparea;
     if (!want_rank && !want_basins && !want_uparea) return PFD_OK;
+    if (h->tiled) return pfd_fail(h, PFD_ERR_UNSUPPORTED, "this handle holds a row block: only the pfd_tiled_* entry points apply");
     const size_t b4 = (size_t)h->n * 4;
     if (want_rank) PFD_TRY(pfd_reserve(h, h->rank, b4));
     if (want_basins) PFD_TRY(pfd_reserve(h, h->basins, b4));
@@ -568,6 +882,7 @@ static int run_sweep(pfd_handle* h, Op op, int skip_level0) {
 
 static int order_impl(pfd_handle* h, bool want_rank, bool want_basins) {
     if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, "pfd_order: no raster parsed on this handle");
+    if (h->tiled) return pfd_fail(h, PFD_ERR_UNSUPPORTED, "this handle holds a row block: only the pfd_tiled_* entry points apply");
     const int64_t n = h->n;
     if (tiles_usable(h)) {  // scattered rank/basins writes of the BFS are replaced by the tile solver
         PFD_TRY(tiles_ensure(h, want_rank, want_basins, false));
@@ -717,6 +1032,8 @@ extern "C" int pfd_fetch(pfd_handle* h, int which, void* out, int idx_dtype) {
     PFD_TRY(check_handle(h));
     if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, "pfd_fetch: no raster parsed on this handle");
     if (!out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_fetch: out is null");
+    if (h->tiled && which != PFD_ARR_PITS && which != PFD_ARR_PIT_IS_OUTLET)
+        return pfd_fail(h, PFD_ERR_UNSUPPORTED, "this handle holds a row block: only the pfd_tiled_* entry points apply");
     stage_reset(h);
     const int64_t n = h->n;
     switch (which) {

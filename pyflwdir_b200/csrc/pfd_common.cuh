@@ -113,6 +113,13 @@ struct pfd_handle {
     DevBuf counters;          // uint64 [8]: n_valid, n_pits, n_outlets, parse flags, load flags, basins flags
     DevBuf segs;              // SweepSeg schedule of the level replays
     DevBuf tslots;            // reduced-graph (tile ring) arrays of the tile solver
+    DevBuf mg_counts;
+    DevBuf btab, bgraph;       // row-tiled multi-GPU solve: boundary tables, boundary graph state
+    int64_t dir_off = 0;       // offset of the first OWNED row inside dir (halo row of a row block)
+    bool tiled = false;        // parsed as a row block of a larger raster (only the tiled entry points apply)
+    int mg_rank = 0, mg_nranks = 0, mg_halo_top = 0, mg_halo_bot = 0;
+    uint32_t* mg_basins = nullptr;
+    void* nccl_comm = nullptr;
     DevBuf tile_loc, tile_cnt; // uint32 [n] each: per cell (local terminal | hops << 12), in-tile subtree size
     DevBuf uparea;            // int32 [n] cached cell-count upstream area (tile solver)
     bool have_uparea = false;

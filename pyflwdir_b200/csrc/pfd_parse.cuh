@@ -42,7 +42,8 @@ __device__ __forceinline__ uint32_t parse_load_word(const uint8_t* __restrict__ 
 template <bool ALIGNED, int IDXMODE>
 __global__ void __launch_bounds__(256) parse_kernel(const uint8_t* __restrict__ d8, int64_t nrow, int64_t ncol,
                                                     uint8_t* __restrict__ dir, uint8_t* __restrict__ upmask,
-                                                    void* __restrict__ idxs_out, unsigned int* __restrict__ invalid_flag) {
+                                                    void* __restrict__ idxs_out, unsigned int* __restrict__ invalid_flag,
+                                                    int64_t out_row0, int64_t out_nrow, int64_t glob_row0) {
     __shared__ uint32_t tile[PT_H + 2][PT_SW];
     const int64_t r0 = (int64_t)blockIdx.y * PT_H;
     const int64_t wc0 = (int64_t)blockIdx.x * PT_WW;  // first word column of the tile
@@ -109,16 +110,20 @@ __global__ void __launch_bounds__(256) parse_kernel(const uint8_t* __restrict__ 
                     upmask[i0 + b] = (uint8_t)(upw >> (8 * b));
                 }
         }
-        if (IDXMODE != 0) {
+        // idxs_ds only for the owned rows [out_row0, out_row0 + out_nrow) of a row block, as GLOBAL linear indices
+        // (single GPU: the whole raster, offset 0)
+        if (IDXMODE != 0 && r >= out_row0 && r < out_row0 + out_nrow) {
+            const int64_t o0 = (r - out_row0) * ncol + c;       // position in the output block
+            const int64_t g0 = (r - out_row0 + glob_row0) * ncol + c;  // global index of my first cell
             int64_t ds[4];
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 const uint32_t d = (dirw >> (8 * b)) & 0xFFu;
-                const int64_t i = i0 + b;
+                const int64_t i = g0 + b;
                 ds[b] = (d < 8u) ? i + pfd_slot_off((int)d, ncol) : ((d == PFD_DIR_NODATA) ? (int64_t)-1 : i);
             }
             if (IDXMODE == 1) {
-                uint32_t* o = reinterpret_cast<uint32_t*>(idxs_out) + i0;
+                uint32_t* o = reinterpret_cast<uint32_t*>(idxs_out) + o0;
                 if (ALIGNED) {
                     *reinterpret_cast<uint4*>(o) = make_uint4((uint32_t)ds[0], (uint32_t)ds[1], (uint32_t)ds[2], (uint32_t)ds[3]);
                 } else {
@@ -127,7 +132,7 @@ __global__ void __launch_bounds__(256) parse_kernel(const uint8_t* __restrict__ 
                         if (c + b < ncol) o[b] = (uint32_t)ds[b];
                 }
             } else {
-                int64_t* o = reinterpret_cast<int64_t*>(idxs_out) + i0;
+                int64_t* o = reinterpret_cast<int64_t*>(idxs_out) + o0;
                 if (ALIGNED) {
                     *reinterpret_cast<longlong2*>(o) = make_longlong2(ds[0], ds[1]);
                     *reinterpret_cast<longlong2*>(o + 2) = make_longlong2(ds[2], ds[3]);

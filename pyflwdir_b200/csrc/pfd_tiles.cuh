@@ -56,16 +56,20 @@ __device__ __forceinline__ bool tl_on_ring(int ly, int lx) {
     return ly == 0 || ly == TL_H - 1 || lx == 0 || lx == TL_W - 1;
 }
 
+// Ring-slot arrays cover the local tile rows PLUS one halo tile row above and below (tile row index shifted by
+// one): exits across the top / bottom edge of a row block (multi-GPU row tiling) land in halo slots, which act as
+// terminals of the local reduced graph. r may be -1 or nrow (one row outside the block).
 __device__ __forceinline__ uint32_t tl_slot_of(long long r, long long c, long long ntx) {
-    const long long ty = r / TL_H, tx = c / TL_W;
-    return (uint32_t)((ty * ntx + tx) * TL_RING + tl_ring_pos((int)(r % TL_H), (int)(c % TL_W)));
+    const long long ty = (r + TL_H) / TL_H, tx = c / TL_W;  // = floor(r / TL_H) + 1 for r >= -TL_H
+    return (uint32_t)((ty * ntx + tx) * TL_RING + tl_ring_pos((int)((r + TL_H) % TL_H), (int)(c % TL_W)));
 }
 
 // basin id (= pit ordinal + 1) of every pit cell, pre-written at the pit's own position of the basin output buffer
 // so that the tile kernels find it with one load of a cell they own (no search in the sorted pit list)
-__global__ void stash_pit_ids_kernel(const cell_t* __restrict__ pits, long long npits, uint32_t* __restrict__ basin) {
+__global__ void stash_pit_ids_kernel(const cell_t* __restrict__ pits, long long npits, long long cell_off,
+                                     unsigned long long id_off, uint32_t* __restrict__ basin) {
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < npits; k += (long long)gridDim.x * blockDim.x)
-        basin[pits[k]] = (uint32_t)(k + 1);
+        basin[(long long)pits[k] - cell_off] = (uint32_t)(id_off + (unsigned long long)k + 1ull);
 }
 
 // Shared state of one tile in phase A: P packs (next cell : 12 bits | hops to it : 20 bits), A is the accumulate
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
                         uint32_t* __restrict__ s_ch, uint32_t* __restrict__ s_term, uint32_t* __restrict__ s_term_h) {
     constexpr int TL_CPT = TL_CELLS / THREADS, TL_RPI = THREADS / TL_W;
     __shared__ TileShared s;
-    const long long tile = (long long)blockIdx.y * ntx + blockIdx.x;
+    const long long tile = ((long long)blockIdx.y + 1) * ntx + blockIdx.x;  // +1: halo tile row
     const long long r0 = (long long)blockIdx.y * TL_H, c0 = (long long)blockIdx.x * TL_W;
     const int lx = threadIdx.x & (TL_W - 1);
     const int ly0 = threadIdx.x >> 6;
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
                         int32_t* __restrict__ uparea_out) {
     constexpr int TL_CPT = TL_CELLS / THREADS, TL_RPI = THREADS / TL_W;
     __shared__ TileSharedC s;
-    const long long tile = (long long)blockIdx.y * ntx + blockIdx.x;
+    const long long tile = ((long long)blockIdx.y + 1) * ntx + blockIdx.x;  // +1: halo tile row
     const long long r0 = (long long)blockIdx.y * TL_H, c0 = (long long)blockIdx.x * TL_W;
     const int lx = threadIdx.x & (TL_W - 1);
     const int ly0 = threadIdx.x >> 6;
@@ -411,5 +415,130 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
         if (rank_out) rank_out[g] = rk;
         if (basin_out) basin_out[g] = b;
         if (uparea_out) uparea_out[g] = ua;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Row-tiled multi-GPU solve: boundary tables.
+// Boundary j (between rank j and j+1) has two sides of ncol entries: side 0 = last row of rank j, side 1 = first
+// row of rank j+1; entry index b = (2*j + side) * ncol + col. Four uint32 tables of NB = 2*(R-1)*ncol entries,
+// exchanged with ONE all-reduce(sum) (every entry is written by exactly one rank, the rest contribute zeros):
+//   H1  : inflow weight arriving at the entry from the neighbouring rank (what that rank's halo slot accumulated)
+//   NXT : 0 invalid | 1 path ends in a pit inside the owner's block | 2 + b' path leaves the block into entry b'
+//   HOP : cell hops from the entry to that pit / to entry b'
+//   BAS : basin id of that pit (NXT == 1)
+// ---------------------------------------------------------------------------------------------------------
+struct BoundaryTables {
+    uint32_t* h1;
+    uint32_t* nxt;
+    uint32_t* hop;
+    uint32_t* bas;
+};
+
+// halo slots of the two halo tile rows: terminals of the local reduced graph
+__global__ void halo_slots_init_kernel(SlotBuf b0, uint32_t* __restrict__ term, uint32_t* __restrict__ term_h,
+                                       long long ntx, long long nty) {
+    const long long per_row = ntx * TL_RING;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < 2 * per_row; k += (long long)gridDim.x * blockDim.x) {
+        const long long s = (k < per_row) ? k : (nty + 1) * per_row + (k - per_row);
+        b0.nxt[s] = (uint32_t)s;
+        b0.rh[s] = 0;
+        b0.ch[s] = 0;
+        b0.acc[s] = 0;
+        term[s] = SLOT_INVALID;
+        term_h[s] = 0;
+    }
+}
+
+// side_sel 0: my top boundary (boundary rank-1), 1: my bottom boundary (boundary rank)
+__global__ void boundary_fill_kernel(SlotBuf cur, const uint32_t* __restrict__ term, const uint32_t* __restrict__ term_h,
+                                     long long nrow, long long ncol, long long ntx, long long nty, int rank, int has_top,
+                                     int has_bot, BoundaryTables T) {
+    const long long per_row = ntx * TL_RING;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < 2 * ncol; k += (long long)gridDim.x * blockDim.x) {
+        const int bottom = k >= ncol;
+        const long long c = bottom ? k - ncol : k;
+        if (bottom ? !has_bot : !has_top) continue;
+        const long long j = bottom ? rank : rank - 1;              // boundary index
+        const long long own_b = (2 * j + (bottom ? 0 : 1)) * ncol + c;   // my entry on that boundary
+        const long long nb_b = (2 * j + (bottom ? 1 : 0)) * ncol + c;    // the neighbour's entry (my halo slot)
+        const uint32_t hs = tl_slot_of(bottom ? nrow : -1, c, ntx);      // halo slot of the neighbour's cell
+        T.h1[nb_b] = cur.acc[hs];
+        const uint32_t s = tl_slot_of(bottom ? nrow - 1 : 0, c, ntx);
+        uint32_t nx = 0, hop = 0, bas = 0;
+        if (term[s] != SLOT_INVALID) {
+            const uint32_t last = cur.nxt[s];
+            const uint32_t t = term[last];
+            const bool in_halo = (long long)last < per_row || (long long)last >= (nty + 1) * per_row;
+            if (cur.nxt[last] == last) {
+                if (in_halo) {
+                    // which entry of which boundary is that halo slot? top halo row -> boundary rank-1 side 0,
+                    // bottom halo row -> boundary rank side 1; column from the slot's tile column + ring position
+                    const bool top_halo = (long long)last < per_row;
+                    const long long within = top_halo ? last : last - (nty + 1) * per_row;
+                    const long long tx = within / TL_RING;
+                    const int rp = (int)(within % TL_RING);
+                    // adjacent ring row of the halo tile: bottom ring row (rp in [TL_W, 2*TL_W)) for the top halo,
+                    // top ring row (rp < TL_W) for the bottom halo
+                    const int lx = top_halo ? rp - TL_W : rp;
+                    if (lx >= 0 && lx < TL_W) {
+                        const long long jj = top_halo ? rank - 1 : rank;
+                        nx = (uint32_t)(2 + (2 * jj + (top_halo ? 0 : 1)) * ncol + tx * TL_W + lx);
+                        hop = cur.ch[s];
+                    }
+                } else if (t & TERM_PIT) {
+                    nx = 1;
+                    hop = cur.ch[s] + term_h[last];
+                    bas = (t & ~TERM_PIT) + 1u;
+                }
+            }
+        }
+        T.nxt[own_b] = nx;
+        T.hop[own_b] = hop;
+        T.bas[own_b] = bas;
+    }
+}
+
+// all-reduced tables -> reduced-graph state of the boundary graph (NB nodes), same layout as the ring slots
+__global__ void boundary_build_kernel(BoundaryTables T, long long nb, SlotBuf b0, uint32_t* __restrict__ term,
+                                      uint32_t* __restrict__ term_h) {
+    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < nb; b += (long long)gridDim.x * blockDim.x) {
+        const uint32_t nx = T.nxt[b];
+        b0.acc[b] = T.h1[b];
+        if (nx >= 2u) {
+            b0.nxt[b] = nx - 2u;
+            b0.rh[b] = 1;
+            b0.ch[b] = T.hop[b];
+            term[b] = 0;
+            term_h[b] = 0;
+        } else {
+            b0.nxt[b] = (uint32_t)b;
+            b0.rh[b] = 0;
+            b0.ch[b] = 0;
+            term[b] = (nx == 1u) ? (TERM_PIT | (T.bas[b] - 1u)) : SLOT_INVALID;
+            term_h[b] = (nx == 1u) ? T.hop[b] : 0;
+        }
+    }
+}
+
+// boundary solution -> my halo slots become pit-like terminals carrying (rank, basin) of the neighbour's entry;
+// my own boundary entries receive the total remote inflow X on top of their local weight
+__global__ void boundary_writeback_kernel(const int32_t* __restrict__ brank, const uint32_t* __restrict__ bbasin,
+                                          const uint32_t* __restrict__ bx, long long nrow, long long ncol, long long ntx,
+                                          int rank, int has_top, int has_bot, uint32_t* __restrict__ w,
+                                          uint32_t* __restrict__ term, uint32_t* __restrict__ term_h) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < 2 * ncol; k += (long long)gridDim.x * blockDim.x) {
+        const int bottom = k >= ncol;
+        const long long c = bottom ? k - ncol : k;
+        if (bottom ? !has_bot : !has_top) continue;
+        const long long j = bottom ? rank : rank - 1;
+        const long long own_b = (2 * j + (bottom ? 0 : 1)) * ncol + c;
+        const long long nb_b = (2 * j + (bottom ? 1 : 0)) * ncol + c;
+        const uint32_t hs = tl_slot_of(bottom ? nrow : -1, c, ntx);
+        const int32_t rk = brank[nb_b];
+        term[hs] = (rk >= 0) ? (TERM_PIT | (bbasin[nb_b] - 1u)) : SLOT_INVALID;
+        term_h[hs] = (rk >= 0) ? (uint32_t)rk : 0u;
+        const uint32_t s = tl_slot_of(bottom ? nrow - 1 : 0, c, ntx);
+        if (bx[own_b]) atomicAdd(w + s, bx[own_b]);  // a 1-row block has the same slot on both of its boundaries
     }
 }

@@ -1,0 +1,79 @@
+"""GPU tests of the row-tiled (multi-GPU) solve: R row blocks solved as R ranks on ONE GPU with the two exchanges
+(pit counts, boundary-table all-reduce) emulated on the host -- the same kernels and step functions the NCCL path
+uses. Compared bit for bit with the CPU oracle on the whole raster."""
+import numpy as np
+import pytest
+
+import _cases as cs
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_whole(d8):
+    dtype = oracle.get_idxs_dtype(d8.size)
+    ids, pits, _ = oracle.core_d8.from_array(d8, dtype=dtype)
+    seq = oracle.core.idxs_seq(ids, pits)
+    rank, _ = oracle.core.rank(ids)
+    upa = oracle.streams.accuflux(ids, seq, np.ones(d8.size, np.int32), -9999)
+    upa[ids == ids.dtype.type(-1)] = -9999
+    bas = oracle.basins.basins(ids, pits, seq)
+    return ids, rank.reshape(d8.shape), upa.reshape(d8.shape), bas.reshape(d8.shape), pits.size
+
+
+def _check(d8, nranks):
+    from pyflwdir_b200 import tiled
+
+    got = tiled.solve_emulated(d8, nranks)
+    ids, rank, upa, bas, npits = _oracle_whole(d8)
+    assert got["n_pits"] == npits
+    assert np.array_equal(got["idxs_ds"], ids), "idxs_ds"
+    assert np.array_equal(got["rank"], rank), "rank"
+    assert np.array_equal(got["uparea"], upa), "uparea"
+    assert np.array_equal(got["basins"], bas), "basins"
+    return got
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3, 5])
+def test_tiled_synthetic(nranks):
+    z = oracle.synth_elevation(448, 333, seed=41)
+    d8 = oracle.synth_d8(z, sea_level=float(np.quantile(z, 0.05)))
+    got = _check(d8, nranks)
+    assert len(got["blocks"]) == min(nranks, 7)
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_tiled_random_codes_with_loops(nranks):
+    """Random legal codes: loops and chains that cross the block boundaries in both directions."""
+    rng = np.random.default_rng(9)
+    legal = np.array([32, 64, 128, 16, 0, 1, 8, 4, 2, 247, 255], dtype=np.uint8)
+    p = np.array([1, 1, 1, 1, 0.02, 1, 1, 1, 1, 0.05, 0.02])
+    d8 = legal[rng.choice(legal.size, size=(256, 200), p=p / p.sum())]
+    _check(d8, nranks)
+
+
+def test_tiled_zigzag_across_boundary():
+    """One long river that crosses the boundary between two blocks many times (row 63 <-> row 64)."""
+    nrow, ncol = 128, 96
+    d8 = np.full((nrow, ncol), 4, dtype=np.uint8)   # everything flows south ...
+    d8[64:, :] = 64                                  # ... or north, towards the boundary
+    # the river alternates between row 63 and row 64 while heading east
+    for c in range(ncol - 1):
+        if c % 2 == 0:
+            d8[63, c] = 2    # SE: (63,c) -> (64,c+1)
+            d8[64, c] = 1    # E
+        else:
+            d8[64, c] = 128  # NE: (64,c) -> (63,c+1)
+            d8[63, c] = 1    # E
+    d8[63, ncol - 1] = 0
+    d8[64, ncol - 1] = 64
+    got = _check(d8, 2)
+    assert got["uparea"].max() > nrow * ncol // 2
+
+
+def test_tiled_rhine():
+    d8 = cs.case_d8("rhine")
+    got = _check(d8, 3)
+    h = cs.hashes()["rhine"]
+    assert cs.sha(got["rank"]) == h["rank"] and cs.sha(got["uparea"]) == h["uparea_cell"]
+    assert cs.sha(got["basins"]) == h["basins"] and cs.sha(got["idxs_ds"]) == h["idxs_ds"]

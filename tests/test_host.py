@@ -90,3 +90,19 @@ def test_ring_slot_numbering():
                 assert p not in seen
                 seen.add(p)
     assert seen == set(range(4 * TL - 4))
+
+
+def test_split_rows():
+    """Row blocks of the multi-GPU decomposition: multiples of 64 rows, contiguous, cover the raster."""
+    from pyflwdir_b200 import tiled
+
+    for nrow, R in [(65536, 8), (682, 3), (100, 4), (64, 2), (8192, 5), (1, 1)]:
+        blocks = tiled.split_rows(nrow, R)
+        assert blocks[0][0] == 0 and blocks[-1][1] == nrow
+        for (a0, a1), (b0, b1) in zip(blocks[:-1], blocks[1:]):
+            assert a1 == b0 and a0 % 64 == 0 and (a1 - a0) % 64 == 0 and a1 > a0
+        assert len(blocks) <= R
+    assert tiled.split_rows(65536, 8) == [(i * 8192, (i + 1) * 8192) for i in range(8)]
+    d8 = np.arange(12, dtype=np.uint8).reshape(4, 3)
+    blk, ht, hb = tiled.block_with_halo(d8, 0, 4)
+    assert (ht, hb) == (0, 0) and blk.shape == (4, 3)
