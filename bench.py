@@ -15,8 +15,10 @@ Outputs of a step: idxs_ds int32, rank int32, upstream area int32, basins uint32
   roofline     : the dominant kernel of the step (largest share of device time), algorithmic bytes / event time.
   cpu_baseline : the CPU oracle (single-threaded C port of the reference's numba kernels) on the same raster.
 
-N > 1 (launched by torchrun, one process per GPU): every rank runs the same step on its own raster (seed + rank)
--- weak scaling, no data-path collective; the rendezvous/barrier uses torch.distributed (gloo) only as plumbing.
+N > 1 (launched by torchrun, one process per GPU): ONE raster of (N*size) x size cells is row-tiled across the GPUs,
+each rank owning `size` rows (+ one halo row per neighbour): weak scaling with the real exchange step of the path
+(pit-count all-gather + one NCCL all-reduce of the boundary tables per step, pfd_d8_flow_all_tiled). torch.distributed
+(gloo) is used only to hand out the NCCL unique id and for the barrier / max-reduce of the timings.
 
 --impl reference: times the reference's CPU implementation of the path (the oracle port; the numba reference
 itself cannot travel to the GPU box) on the host cores, same metric / config, bounded sample per step.
@@ -210,6 +212,57 @@ class Workload:
         return int(self.l.pfd_launch_count(self.h))
 
 
+class TiledWorkload(Workload):
+    """Rank `rank` of `world`: rows [rank*size, (rank+1)*size) of a (world*size) x size raster, one GPU per rank."""
+
+    def __init__(self, size, seed, device, rank, world, dist):
+        from pyflwdir_b200 import _lib, tiled
+
+        self.L = _lib
+        self.l = _lib.lib()
+        self.n = size
+        self.cells = size * size
+        self.rank, self.world = rank, world
+        h = C.c_void_p()
+        _lib.check(self.l.pfd_create(device, C.byref(h)))
+        self.h = h
+        uid = [tiled.RowBlockSolver.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid[0])
+        self.ck(self.l.pfd_comm_init(h, rank, world, buf))
+        self.ht = 1 if rank > 0 else 0
+        self.hb = 1 if rank < world - 1 else 0
+        self.row0 = rank * size
+        ext = (size + self.ht + self.hb) * size
+        self.d8_dev = self.dev_alloc(ext)
+        self.ck(self.l.pfd_synth_d8_block(h, self.row0 - self.ht, size + self.ht + self.hb, size, world * size, size,
+                                          octaves_for(size), seed, C.c_float(-np.inf), self.d8_dev))
+        self.ext_bytes = ext
+        self.idx_dtype = np.int32 if world * size * size < 2**31 - 1 else np.int64
+        self.idx_bytes = self.cells * np.dtype(self.idx_dtype).itemsize
+        self.out_dev = [self.dev_alloc(self.idx_bytes)] + [self.dev_alloc(self.cells * 4) for _ in range(3)]
+        self.n_pits_global = C.c_int64()
+
+    def _call(self, d8, idxs, rank_o, upa_o, bas_dev):
+        self.ck(self.l.pfd_d8_flow_all_tiled(self.h, d8, self.n, self.n, self.ht, self.hb, self.row0, idxs,
+                                             self.L.DTYPES[np.dtype(self.idx_dtype)], rank_o, upa_o, bas_dev, None,
+                                             C.byref(self.n_pits_global)))
+
+    def step_resident(self):
+        o = self.out_dev
+        self._call(self.d8_dev, o[0], o[1], o[2], o[3])
+
+    def make_host(self):
+        self.d8_host = self.L.PinnedArray(self.ext_bytes, np.uint8)
+        self.ck(self.l.pfd_memcpy(self.h, self.L.ptr(self.d8_host.array), self.d8_dev, self.ext_bytes))
+        self.out_host = [self.L.PinnedArray(self.cells, dt) for dt in (self.idx_dtype, np.int32, np.int32, np.uint32)]
+
+    def step_host(self):
+        o = [self.L.ptr(a.array) for a in self.out_host]
+        self._call(self.L.ptr(self.d8_host.array), o[0], o[1], o[2], self.out_dev[3])
+        self.ck(self.l.pfd_memcpy(self.h, o[3], self.out_dev[3], self.cells * 4))  # basins travel through a device buffer
+
+
 def cpu_path(d8, repeat=1):
     """The reference's CPU path on `d8` via the oracle port: seconds per stage (best of `repeat`)."""
     import oracle
@@ -320,8 +373,11 @@ def main():
     if _lib.device_count() == 0:
         raise SystemExit("bench.py: no CUDA device -- pyflwdir_b200 has no CPU fallback")
     device = local_rank % _lib.device_count()
-    w = Workload(args.size, args.seed + rank, device)
-    w.ck(w.l.pfd_set_option(w.h, b"tiles", 1 if args.solver == "tiles" else 0))
+    if world > 1:
+        w = TiledWorkload(args.size, args.seed, device, rank, world, dist)
+    else:
+        w = Workload(args.size, args.seed, device)
+        w.ck(w.l.pfd_set_option(w.h, b"tiles", 1 if args.solver == "tiles" else 0))
     cells = w.cells
 
     # ---- device-resident arm
@@ -395,10 +451,14 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "config": {"workload": f"synthetic {args.size}x{args.size} D8 raster per GPU (rough Perlin fBm, {octaves_for(args.size)} octaves, "
-                                   "steepest descent): parse->idxs_ds + rank + upstream_area(cell) + basins",
+            "config": {"workload": (f"synthetic {args.size}x{args.size} D8 raster" if world == 1 else
+                                    f"ONE synthetic {world * args.size}x{args.size} D8 raster row-tiled over {world} GPUs "
+                                    f"({args.size} rows + halo per GPU)") +
+                                   f" (rough Perlin fBm, {octaves_for(args.size)} octaves, steepest descent): "
+                                   "parse->idxs_ds + rank + upstream_area(cell) + basins",
                        "seed": args.seed, "l2": "per-step working set ~26 B/cell x N cells (>= 1.7 GB at 8192^2) exceeds the 126 MB L2; no flush needed",
-                       "parallelism": "1 raster per GPU, no collective" if world > 1 else "single GPU"},
+                       "parallelism": (f"row-tiled x{world}: pit-count all-gather + 1 NCCL all-reduce of boundary tables per step"
+                                       if world > 1 else "single GPU")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cells, "d2h_bytes_per_step": 16 * cells,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches_total, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,

@@ -187,6 +187,9 @@ int pfd_tiled_finish(pfd_handle* h, int32_t* rank_out, int32_t* uparea_out, uint
 int pfd_synth_elevation(pfd_handle* h, int64_t nrow, int64_t ncol, int64_t nref, int octaves, uint32_t seed,
                         float* z_out);
 int pfd_synth_d8(pfd_handle* h, const float* z, int64_t nrow, int64_t ncol, float sea_level, uint8_t* d8_out);
+/* rows [row0, row0+nrow) of the nrow_global x ncol synthetic D8 raster (row blocks of the multi-GPU bench) */
+int pfd_synth_d8_block(pfd_handle* h, int64_t row0, int64_t nrow, int64_t ncol, int64_t nrow_global, int64_t nref,
+                       int octaves, uint32_t seed, float sea_level, uint8_t* d8_out);
 
 /* ---- options / introspection ------------------------------------------------------------------------- */
 /* "tiles" = 1 (default): rank / basins() / upstream_area("cell") come from the tile-hierarchical solver

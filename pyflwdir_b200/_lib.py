@@ -63,6 +63,7 @@ SYMBOLS = {
     "pfd_synth_d8": (_int, [_vp, _vp, _i64, _i64, C.c_float, _vp]),
     "pfd_set_option": (_int, [_vp, C.c_char_p, _i64]),
     "pfd_get_info": (_i64, [_vp, C.c_char_p]),
+    "pfd_synth_d8_block": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _int, _u32, C.c_float, _vp]),
     "pfd_launch_count": (_i64, [_vp]),
     "pfd_timer_start": (_int, [_vp]),
     "pfd_timer_stop": (_int, [_vp, C.POINTER(C.c_double)]),

@@ -129,6 +129,8 @@ extern "C" int pfd_create(int device, pfd_handle** out) {
     }
     cudaEventCreate(&h->ev_timer[0]);
     cudaEventCreate(&h->ev_timer[1]);
+    cudaEventCreate(&h->ev_total[0]);
+    cudaEventCreate(&h->ev_total[1]);
     *out = h;
     return PFD_OK;
 }
@@ -151,6 +153,8 @@ extern "C" void pfd_destroy(pfd_handle* h) {
     }
     cudaEventDestroy(h->ev_timer[0]);
     cudaEventDestroy(h->ev_timer[1]);
+    cudaEventDestroy(h->ev_total[0]);
+    cudaEventDestroy(h->ev_total[1]);
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -404,6 +408,9 @@ __global__ void count_ranked_kernel(const int32_t* __restrict__ rank, int64_t n,
 
 static bool tiles_usable(const pfd_handle* h) { return h->use_tiles && h->n_pits > 0 && h->n_pits < (1ll << 31); }
 
+template <class K>
+static int coop_grid(pfd_handle* h, K kernel, int threads, int64_t max_useful_blocks, int* grid);
+
 struct TileCtx {
     long long ntx = 0, nty = 0, nslots = 0;
     size_t arr = 0;
@@ -470,24 +477,18 @@ static int tiles_phase_a(pfd_handle* h, TileCtx& T, uint32_t* basin_dev, unsigne
     return PFD_OK;
 }
 
-// phase B: doubling rounds over `n` reduced-graph nodes starting from side 0; *src = side holding the result
-static int slots_solve(pfd_handle* h, SlotBuf* B, long long n, unsigned int* flag, int* src_out, int* rounds_out) {
-    const size_t arr = (size_t)n * sizeof(uint32_t);
-    const int g = grid_for(n, 256, 2, 148 * 16);
-    int src = 0, k = 0;
-    for (; k < 31; ++k) {
-        PFD_CUDA(h, cudaMemcpyAsync(B[src ^ 1].acc, B[src].acc, arr, cudaMemcpyDeviceToDevice, h->stream));
-        PFD_CUDA(h, cudaMemsetAsync(flag, 0, sizeof(unsigned int), h->stream));
-        slots_round_kernel<<<g, 256, 0, h->stream>>>(B[src], B[src ^ 1], n, 1u << k, flag);
-        PFD_LAUNCH_CHECK(h);
-        unsigned int hflag = 0;
-        PFD_CUDA(h, cudaMemcpyAsync(&hflag, flag, sizeof(hflag), cudaMemcpyDeviceToHost, h->stream));
-        PFD_CUDA(h, cudaStreamSynchronize(h->stream));
-        src ^= 1;
-        if (!hflag) break;
-    }
-    *src_out = src;
-    if (rounds_out) *rounds_out = k + 1;
+// phase B: all doubling rounds over `n` reduced-graph nodes in one cooperative launch; the result ends in side 0.
+// flags: 3 x uint32 + 1 int (round count) on the device.
+static int slots_solve(pfd_handle* h, SlotBuf* B, long long n, unsigned int* flags, int* src_out, int* rounds_out) {
+    (void)rounds_out;
+    int grid = 1;
+    PFD_TRY(coop_grid(h, slots_solve_kernel, 256, (n + 255) / 256, &grid));
+    PFD_CUDA(h, cudaMemsetAsync(flags, 0, 4 * sizeof(unsigned int), h->stream));
+    int* rounds_dev = (int*)(flags + 3);
+    void* args[] = {(void*)&B[0], (void*)&B[1], (void*)&n, (void*)&flags, (void*)&rounds_dev};
+    PFD_CUDA(h, cudaLaunchCooperativeKernel((void*)slots_solve_kernel, dim3(grid), dim3(256), args, 0, h->stream));
+    h->launches++;
+    *src_out = 0;
     return PFD_OK;
 }
 
@@ -733,7 +734,7 @@ extern "C" int pfd_d8_flow_all_tiled(pfd_handle* h, const uint8_t* d8_block, int
     PFD_TRY(check_handle(h));
     const int nranks = h->nccl_comm ? h->mg_nranks : 1, rank = h->nccl_comm ? h->mg_rank : 0;
     int64_t nv = 0, np = 0;
-    cudaEventRecord(h->ev_timer[0], h->stream);
+    cudaEventRecord(h->ev_total[0], h->stream);
     PFD_TRY(pfd_tiled_parse(h, d8_block, nrow_owned, ncol, halo_top, halo_bot, glob_row0, idxs_ds_out, idx_dtype, &nv, &np));
     // exchange #1: pit counts -> global basin id offset of this block (blocks are in linear-index order)
     long long offset = 0, total = np;
@@ -761,10 +762,10 @@ extern "C" int pfd_d8_flow_all_tiled(pfd_handle* h, const uint8_t* d8_block, int
         PFD_NCCL(h, ncclAllReduce(table, table, (size_t)table_len, ncclUint32, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
     }
     PFD_TRY(pfd_tiled_finish(h, rank_out, uparea_out, basins_out));
-    cudaEventRecord(h->ev_timer[1], h->stream);
+    cudaEventRecord(h->ev_total[1], h->stream);
     PFD_CUDA(h, cudaStreamSynchronize(h->stream));
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, h->ev_timer[0], h->ev_timer[1]) == cudaSuccess) h->stage_ms[PFD_STAGE_TOTAL] = ms;
+    if (cudaEventElapsedTime(&ms, h->ev_total[0], h->ev_total[1]) == cudaSuccess) h->stage_ms[PFD_STAGE_TOTAL] = ms;
     if (n_valid) *n_valid = nv;
     if (n_pits_global) *n_pits_global = total;
     return PFD_OK;
@@ -1339,10 +1340,11 @@ extern "C" int pfd_d8_flow_all(pfd_handle* h, const uint8_t* d8, int64_t nrow, i
 // ---------------------------------------------------------------------------------------------------------
 // synthetic input
 // ---------------------------------------------------------------------------------------------------------
-__global__ void synth_elevation_kernel(int64_t nrow, int64_t ncol, int64_t nref, int octaves, uint32_t seed, float* __restrict__ z) {
+__global__ void synth_elevation_kernel(int64_t nrow, int64_t ncol, int64_t nref, int octaves, uint32_t seed, float* __restrict__ z,
+                                       int64_t row_off = 0) {
     const int64_t n = nrow * ncol;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        z[i] = pfd_synth_z(i / ncol, i % ncol, nref, octaves, seed);
+        z[i] = pfd_synth_z(i / ncol + row_off, i % ncol, nref, octaves, seed);
 }
 
 __global__ void synth_d8_kernel(const float* __restrict__ z, int64_t nrow, int64_t ncol, float sea_level, uint8_t* __restrict__ d8) {
@@ -1387,6 +1389,31 @@ extern "C" int pfd_synth_d8(pfd_handle* h, const float* z, int64_t nrow, int64_t
     synth_d8_kernel<<<grid_for(n, 256, 2), 256, 0, h->stream>>>((const float*)zdev, nrow, ncol, sea_level, (uint8_t*)dev);
     PFD_LAUNCH_CHECK(h);
     PFD_TRY(pfd_finish_out(h, d8_out, dev, (size_t)n));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    return PFD_OK;
+}
+
+// D8 codes of rows [row0, row0 + nrow) of a synthetic raster with nrow_global rows (row blocks of the multi-GPU
+// bench are generated in place, rank by rank; identical to the same rows of the single-piece generator)
+extern "C" int pfd_synth_d8_block(pfd_handle* h, int64_t row0, int64_t nrow, int64_t ncol, int64_t nrow_global, int64_t nref,
+                                  int octaves, uint32_t seed, float sea_level, uint8_t* d8_out) {
+    PFD_TRY(check_handle(h));
+    PFD_TRY(check_shape(h, nrow + 2, ncol, "pfd_synth_d8_block"));
+    if (!d8_out || row0 < 0 || row0 + nrow > nrow_global || nref < 8 || octaves < 1)
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_synth_d8_block: bad argument");
+    const int64_t top = row0 > 0 ? 1 : 0, bot = (row0 + nrow < nrow_global) ? 1 : 0;
+    const int64_t zrows = nrow + top + bot;
+    PFD_TRY(pfd_reserve(h, h->scratch[4], (size_t)(zrows * ncol) * sizeof(float)));
+    PFD_TRY(pfd_reserve(h, h->scratch[5], (size_t)(zrows * ncol)));
+    float* z = (float*)h->scratch[4].p;
+    uint8_t* tmp = (uint8_t*)h->scratch[5].p;
+    synth_elevation_kernel<<<grid_for(zrows * ncol, 256, 2), 256, 0, h->stream>>>(zrows, ncol, nref, octaves, seed, z, row0 - top);
+    PFD_LAUNCH_CHECK(h);
+    // steepest descent on the extended block: its first / last rows are only correct when they are true raster
+    // edges, which is exactly when they are owned rows
+    synth_d8_kernel<<<grid_for(zrows * ncol, 256, 2), 256, 0, h->stream>>>(z, zrows, ncol, sea_level, tmp);
+    PFD_LAUNCH_CHECK(h);
+    PFD_CUDA(h, cudaMemcpyAsync(d8_out, tmp + top * ncol, (size_t)(nrow * ncol), cudaMemcpyDefault, h->stream));
     PFD_CUDA(h, cudaStreamSynchronize(h->stream));
     return PFD_OK;
 }

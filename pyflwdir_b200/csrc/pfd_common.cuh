@@ -141,6 +141,7 @@ struct pfd_handle {
     cudaEvent_t ev_start[PFD_NSTAGE] = {};
     cudaEvent_t ev_stop[PFD_NSTAGE] = {};
     cudaEvent_t ev_timer[2] = {};
+    cudaEvent_t ev_total[2] = {};
 };
 
 static thread_local std::string g_last_error;

@@ -281,6 +281,64 @@ __global__ void __launch_bounds__(256) slots_round_kernel(SlotBuf src, SlotBuf d
     }
 }
 
+// All doubling rounds in ONE cooperative launch (no host round trip per round): per round copy acc, grid.sync,
+// jump + accumulate, grid.sync, stop when no node asked for another round. The result always ends in side 0.
+__global__ void __launch_bounds__(256, 8) slots_solve_kernel(SlotBuf b0, SlotBuf b1, long long nslots, unsigned int* flags,
+                                                          int* rounds_out) {
+    cg::grid_group grid = cg::this_grid();
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    int src = 0, k = 0;
+    for (; k < 31; ++k) {
+        const SlotBuf S = src ? b1 : b0, D = src ? b0 : b1;
+        const uint32_t two_k = 1u << k;
+#pragma unroll 1
+        for (long long s = tid; s < nslots; s += stride) D.acc[s] = S.acc[s];
+        // three rotating flags: the one zeroed here was last READ at the end of round k-2, two grid.sync()s ago
+        if (tid == 0) flags[(k + 1) % 3] = 0u;
+        grid.sync();
+        unsigned int again = 0;
+#pragma unroll 2
+        for (long long s = tid; s < nslots; s += stride) {
+            const uint32_t n = S.nxt[s];
+            const uint32_t h = S.rh[s];
+            if (n == (uint32_t)s) {
+                D.nxt[s] = n;
+                D.rh[s] = h;
+                D.ch[s] = S.ch[s];
+                continue;
+            }
+            if (h == two_k) {
+                const uint32_t a = S.acc[s];
+                if (a) atomicAdd(D.acc + n, a);
+            }
+            const uint32_t n2 = S.nxt[n];
+            const uint32_t h2 = S.rh[n];
+            D.nxt[s] = n2;
+            D.rh[s] = h + h2;
+            D.ch[s] = S.ch[s] + S.ch[n];
+            again |= ((h + h2) == (two_k << 1)) ? 1u : 0u;
+        }
+        if (again) flags[k % 3] = 1u;
+        grid.sync();
+        src ^= 1;
+        if (*((volatile unsigned int*)&flags[k % 3]) == 0u) {
+            ++k;
+            break;
+        }
+    }
+    if (src == 1) {  // bring the result back to side 0
+#pragma unroll 1
+        for (long long s = tid; s < nslots; s += stride) {
+            b0.nxt[s] = b1.nxt[s];
+            b0.rh[s] = b1.rh[s];
+            b0.ch[s] = b1.ch[s];
+            b0.acc[s] = b1.acc[s];
+        }
+    }
+    if (tid == 0 && rounds_out) *rounds_out = k;
+}
+
 __global__ void __launch_bounds__(256) slots_finalize_kernel(SlotBuf cur, const uint32_t* __restrict__ term,
                                                              const uint32_t* __restrict__ term_h, long long nslots,
                                                              int32_t* __restrict__ rank, uint32_t* __restrict__ basin) {
