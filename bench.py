@@ -41,7 +41,10 @@ sys.path.insert(0, ROOT)
 METRIC = "Mcells/s D8 parse+rank+accuflux+basins"
 UNIT = "Mcells/s"
 # algorithmic bytes per cell (DESIGN.md "Kernels"): compulsory input read + output write
-ALG_BYTES = {"parse": 5.0, "bfs": 12.0, "sweep": 8.0, "tile_a": 1.0, "tile_b": 0.0, "tile_c": 13.0}
+# tile solver kernels: phase A reads dir (1) and writes loc + cnt (8); phase C reads dir + loc + cnt (9) and writes
+# rank + basins + uparea (12); the whole fused step has a 17 B/cell lower bound (d8 in, four int32 outputs)
+ALG_BYTES = {"parse": 5.0, "bfs": 12.0, "sweep": 8.0, "tile_a": 9.0, "tile_b": 0.0, "tile_c": 21.0}
+STEP_BYTES_FUSED, STEP_BYTES_UNFUSED = 17.0, 29.0
 KERNEL_NAMES = {"parse": "parse_kernel", "bfs": "bfs_kernel", "sweep": "sweep_kernel<AccuUpOp<int>>",
                 "tile_a": "tile_phase_a_kernel", "tile_b": "slots_round_kernel", "tile_c": "tile_phase_c_kernel"}
 
@@ -166,7 +169,9 @@ class Workload:
         self.ck(self.l.pfd_synth_elevation(h, size, size, size, octaves_for(size), seed, z_dev))
         self.ck(self.l.pfd_synth_d8(h, z_dev, size, size, C.c_float(-np.inf), self.d8_dev))
         self.ck(self.l.pfd_dev_free(h, z_dev))
-        self.out_dev = [self.dev_alloc(self.cells * 4) for _ in range(4)]  # idxs_ds, rank, uparea, basins
+        self.idx_dtype = np.int32 if self.cells < 2**31 - 1 else (np.uint32 if self.cells < 2**32 - 2 else np.int64)
+        idx_b = np.dtype(self.idx_dtype).itemsize
+        self.out_dev = [self.dev_alloc(self.cells * idx_b)] + [self.dev_alloc(self.cells * 4) for _ in range(3)]  # idxs_ds, rank, uparea, basins
 
     def ck(self, rc):
         self.L.check(rc, self.h)
@@ -178,18 +183,18 @@ class Workload:
 
     def step_resident(self):
         o = self.out_dev
-        self.ck(self.l.pfd_d8_flow_all(self.h, self.d8_dev, self.n, self.n, o[0], self.L.DTYPES[np.dtype(np.int32)],
+        self.ck(self.l.pfd_d8_flow_all(self.h, self.d8_dev, self.n, self.n, o[0], self.L.DTYPES[np.dtype(self.idx_dtype)],
                                        o[1], o[2], o[3], None, None, None))
 
     def make_host(self):
         self.d8_host = self.L.PinnedArray((self.n, self.n), np.uint8)
         self.ck(self.l.pfd_memcpy(self.h, self.L.ptr(self.d8_host.array), self.d8_dev, self.cells))
-        self.out_host = [self.L.PinnedArray(self.cells, dt) for dt in (np.int32, np.int32, np.int32, np.uint32)]
+        self.out_host = [self.L.PinnedArray(self.cells, dt) for dt in (self.idx_dtype, np.int32, np.int32, np.uint32)]
 
     def step_host(self):
         o = [self.L.ptr(a.array) for a in self.out_host]
         self.ck(self.l.pfd_d8_flow_all(self.h, self.L.ptr(self.d8_host.array), self.n, self.n, o[0],
-                                       self.L.DTYPES[np.dtype(np.int32)], o[1], o[2], o[3], None, None, None))
+                                       self.L.DTYPES[np.dtype(self.idx_dtype)], o[1], o[2], o[3], None, None, None))
 
     def stage_ms(self):
         g = self.l.pfd_last_stage_ms
@@ -215,13 +220,23 @@ class Workload:
 class TiledWorkload(Workload):
     """Rank `rank` of `world`: rows [rank*size, (rank+1)*size) of a (world*size) x size raster, one GPU per rank."""
 
-    def __init__(self, size, seed, device, rank, world, dist):
+    def __init__(self, size, seed, device, rank, world, dist, strong=False):
         from pyflwdir_b200 import _lib, tiled
 
         self.L = _lib
         self.l = _lib.lib()
-        self.n = size
-        self.cells = size * size
+        self.ncol = size
+        if strong:
+            blocks = tiled.split_rows(size, world)
+            assert len(blocks) == world, "raster too small for this many ranks"
+            self.row0, r1 = blocks[rank]
+            self.n = r1 - self.row0          # rows owned by this rank
+            self.nrow_global = size
+        else:
+            self.n = size
+            self.row0 = rank * size
+            self.nrow_global = world * size
+        self.cells = self.n * size
         self.rank, self.world = rank, world
         h = C.c_void_p()
         _lib.check(self.l.pfd_create(device, C.byref(h)))
@@ -232,19 +247,19 @@ class TiledWorkload(Workload):
         self.ck(self.l.pfd_comm_init(h, rank, world, buf))
         self.ht = 1 if rank > 0 else 0
         self.hb = 1 if rank < world - 1 else 0
-        self.row0 = rank * size
-        ext = (size + self.ht + self.hb) * size
+        ext = (self.n + self.ht + self.hb) * size
         self.d8_dev = self.dev_alloc(ext)
-        self.ck(self.l.pfd_synth_d8_block(h, self.row0 - self.ht, size + self.ht + self.hb, size, world * size, size,
+        self.ck(self.l.pfd_synth_d8_block(h, self.row0 - self.ht, self.n + self.ht + self.hb, size, self.nrow_global, size,
                                           octaves_for(size), seed, C.c_float(-np.inf), self.d8_dev))
         self.ext_bytes = ext
-        self.idx_dtype = np.int32 if world * size * size < 2**31 - 1 else np.int64
+        ncells_global = self.nrow_global * size
+        self.idx_dtype = np.int32 if ncells_global < 2**31 - 1 else (np.uint32 if ncells_global < 2**32 - 2 else np.int64)
         self.idx_bytes = self.cells * np.dtype(self.idx_dtype).itemsize
         self.out_dev = [self.dev_alloc(self.idx_bytes)] + [self.dev_alloc(self.cells * 4) for _ in range(3)]
         self.n_pits_global = C.c_int64()
 
     def _call(self, d8, idxs, rank_o, upa_o, bas_dev):
-        self.ck(self.l.pfd_d8_flow_all_tiled(self.h, d8, self.n, self.n, self.ht, self.hb, self.row0, idxs,
+        self.ck(self.l.pfd_d8_flow_all_tiled(self.h, d8, self.n, self.ncol, self.ht, self.hb, self.row0, idxs,
                                              self.L.DTYPES[np.dtype(self.idx_dtype)], rank_o, upa_o, bas_dev, None,
                                              C.byref(self.n_pits_global)))
 
@@ -261,6 +276,50 @@ class TiledWorkload(Workload):
         o = [self.L.ptr(a.array) for a in self.out_host]
         self._call(self.L.ptr(self.d8_host.array), o[0], o[1], o[2], self.out_dev[3])
         self.ck(self.l.pfd_memcpy(self.h, o[3], self.out_dev[3], self.cells * 4))  # basins travel through a device buffer
+
+
+def extras(w, size, seed):
+    """Secondary configs of BASELINE.json on the same raster (device-resident, CUDA events, best of 3): the exact
+    idxs_seq ordering (level-synchronous BFS), Strahler order, float64 accuflux and HAND level sweeps."""
+    l, L, h, n = w.l, w.L, w.h, w.cells
+    z_dev = w.dev_alloc(n * 4)
+    w.ck(l.pfd_synth_elevation(h, size, size, size, octaves_for(size), seed, z_dev))
+    upa = np.empty(n, np.int32)
+    w.ck(l.pfd_d8_parse(h, w.d8_dev, size, size, 1, None, 0, None, None, None))
+    w.ck(l.pfd_upstream_area_cells(h, L.ptr(upa)))
+    drain = (upa > 1000).astype(np.uint8)
+    drain_dev = w.dev_alloc(n)
+    w.ck(l.pfd_memcpy(h, drain_dev, L.ptr(drain), n))
+    f64_dev, out8_dev, out1_dev = w.dev_alloc(n * 8), w.dev_alloc(n * 8), w.dev_alloc(n)
+    w.ck(l.pfd_accuflux(h, w.out_dev[2], L.DTYPES[np.dtype(np.int32)], -9999.0, -9999, 1, 0, w.out_dev[1]))  # warm the sweep path
+
+    def best(fn, reps=3, prep=None):
+        t = []
+        for _ in range(reps):
+            if prep:
+                prep()
+            t.append(w.timer(fn, 1))
+        return min(t)
+
+    res = {}
+    reparse = lambda: w.ck(l.pfd_d8_parse(h, w.d8_dev, size, size, 1, None, 0, None, None, None))
+    res["order_idxs_seq_ms"] = best(lambda: w.ck(l.pfd_order(h, None, None)), prep=reparse)
+    res["nlevels"] = int(l.pfd_get_info(h, b"nlevels"))
+    res["strahler_sweep_ms"] = best(lambda: w.ck(l.pfd_strahler(h, None, out1_dev)))
+    # float64 data = the float elevation promoted on the device would need a kernel; use the int32 uparea as int64-free
+    res["accuflux_i32_sweep_ms"] = best(lambda: w.ck(l.pfd_accuflux(h, w.out_dev[2], L.DTYPES[np.dtype(np.int32)], -9999.0,
+                                                                      -9999, 1, 0, w.out_dev[1])))
+    res["accuflux_f32_sweep_ms"] = best(lambda: w.ck(l.pfd_accuflux(h, z_dev, L.DTYPES[np.dtype(np.float32)], -9999.0, 0, 0,
+                                                                      0, w.out_dev[1])))
+    res["hand_sweep_ms"] = best(lambda: w.ck(l.pfd_hand(h, drain_dev, z_dev, L.DTYPES[np.dtype(np.float32)], out8_dev)))
+    for k in list(res):
+        if k.endswith("_ms"):
+            res[k.replace("_ms", "_mcells_s")] = n / (res[k] / 1e3) / 1e6
+    res["note"] = ("device-resident, same raster; sweeps run over the cached ordering; config 3 (accuflux + Strahler) = "
+                   "tile solver + order + strahler sweep, config 5 (HAND) = tile solver + order + hand sweep")
+    for p in (z_dev, drain_dev, f64_dev, out8_dev, out1_dev):
+        w.ck(l.pfd_dev_free(h, p))
+    return res
 
 
 def cpu_path(d8, repeat=1):
@@ -361,6 +420,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-size", type=int, default=0, help="raster size of the CPU baseline sample (default: --size)")
     ap.add_argument("--solver", default="tiles", choices=["tiles", "bfs"], help="rank/basins/uparea solver")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = every GPU owns `size` rows of a (N*size) x size raster (default); "
+                         "strong = ONE size x size raster split into N row blocks (BASELINE config 4 with --size 65536)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the pinned-host end-to-end arm (very large rasters)")
+    ap.add_argument("--extras", action="store_true", help="also time the secondary configs (order, Strahler, HAND sweeps)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -374,7 +438,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- pyflwdir_b200 has no CPU fallback")
     device = local_rank % _lib.device_count()
     if world > 1:
-        w = TiledWorkload(args.size, args.seed, device, rank, world, dist)
+        w = TiledWorkload(args.size, args.seed, device, rank, world, dist, strong=(args.scaling == "strong"))
     else:
         w = Workload(args.size, args.seed, device)
         w.ck(w.l.pfd_set_option(w.h, b"tiles", 1 if args.solver == "tiles" else 0))
@@ -400,17 +464,23 @@ def main():
     barrier(dist)
     clocks = sampler.stop() if rank == 0 else None
     ms_total = reduce_max(dist, ms.value)
-    value = cells * world * args.steps / (ms_total / 1e3) / 1e6
+    cells_total = reduce_sum(dist, float(cells))
+    value = cells_total * args.steps / (ms_total / 1e3) / 1e6
     stage_avg = {k: v / args.steps for k, v in stage_acc.items()}
 
     # ---- end-to-end arm (pinned host buffers through the same C-ABI call)
-    w.make_host()
-    for _ in range(2):
-        w.step_host()
-    barrier(dist)
-    e2e_ms = reduce_max(dist, w.timer(w.step_host, args.steps))
-    barrier(dist)
-    e2e_value = cells * world * args.steps / (e2e_ms / 1e3) / 1e6
+    e2e = None
+    if not args.no_e2e:
+        w.make_host()
+        for _ in range(2):
+            w.step_host()
+        barrier(dist)
+        e2e_ms = reduce_max(dist, w.timer(w.step_host, args.steps))
+        barrier(dist)
+        idx_b = np.dtype(getattr(w, "idx_dtype", np.int32)).itemsize
+        e2e = {"value": cells_total * args.steps / (e2e_ms / 1e3) / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": int(getattr(w, "ext_bytes", cells)), "d2h_bytes_per_step": int((12 + idx_b) * cells),
+               "ms_per_step": e2e_ms / args.steps, "note": "bytes are per GPU"}
     launches_total = int(reduce_sum(dist, launches))
 
     # ---- roofline of the dominant kernel
@@ -427,7 +497,13 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_cell": ALG_BYTES[kern],
                 "kernel_ms": stage_avg[kern], "stage_ms": stage_avg,
-                "step_frac_of_roofline_29B": 29.0 * cells / (ms_total / args.steps / 1e3) / 1e9 / peak}
+                "step": {"algorithmic_bytes_per_cell": STEP_BYTES_FUSED, "unfused_bytes_per_cell": STEP_BYTES_UNFUSED,
+                         "achieved_gbs_per_gpu": STEP_BYTES_FUSED * cells / (ms_total / args.steps / 1e3) / 1e9,
+                         "frac_per_gpu": STEP_BYTES_FUSED * cells / (ms_total / args.steps / 1e3) / 1e9 / peak}}
+
+    extra = None
+    if args.extras and world == 1:
+        extra = extras(w, args.size, args.seed)
 
     # ---- CPU baseline (rank 0, N = 1 only)
     cpu = None
@@ -449,19 +525,18 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int32", "data": "synthetic",
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": (f"synthetic {args.size}x{args.size} D8 raster" if world == 1 else
-                                    f"ONE synthetic {world * args.size}x{args.size} D8 raster row-tiled over {world} GPUs "
-                                    f"({args.size} rows + halo per GPU)") +
+                                    f"ONE synthetic {w.nrow_global}x{args.size} D8 raster row-tiled over {world} GPUs "
+                                    f"({w.n} rows + halo per GPU)") +
                                    f" (rough Perlin fBm, {octaves_for(args.size)} octaves, steepest descent): "
                                    "parse->idxs_ds + rank + upstream_area(cell) + basins",
                        "seed": args.seed, "l2": "per-step working set ~26 B/cell x N cells (>= 1.7 GB at 8192^2) exceeds the 126 MB L2; no flush needed",
                        "parallelism": (f"row-tiled x{world}: pit-count all-gather + 1 NCCL all-reduce of boundary tables per step"
                                        if world > 1 else "single GPU")},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cells, "d2h_bytes_per_step": 16 * cells,
-                    "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": launches_total, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": launches_total, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "extra": extra,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -5,7 +5,7 @@ Host code is plain Python + numpy calling hand-written CUDA through a C ABI (cty
 PyTorch, no Triton, no CPU fallback: without the built `libpfd_b200.so` and a CUDA device every compute call
 raises. See DESIGN.md for the kernels and INTEGRATION.md for the drop-in boundary.
 """
-from . import gis_utils
+from . import basins, core, core_d8, dem, gis_utils, streams
 from .gis_utils import Affine
 from .pyflwdir import FlwdirRaster, from_array, _get_idxs_dtype
 from .flwdir import Flwdir

@@ -414,7 +414,8 @@ static int coop_grid(pfd_handle* h, K kernel, int threads, int64_t max_useful_bl
 struct TileCtx {
     long long ntx = 0, nty = 0, nslots = 0;
     size_t arr = 0;
-    SlotBuf B[2];       // double-buffered reduced-graph state
+    SlotBuf B[2];       // double-buffered reduced-graph state (B[1].acc == B[0].acc)
+    uint32_t* recv[2] = {nullptr, nullptr};
     SlotBuf init;       // copy of the state after phase A (multi-rank: the local reduced graph is solved twice)
     uint32_t *term = nullptr, *term_h = nullptr, *sbasin = nullptr;
     int32_t* srank = nullptr;
@@ -430,7 +431,7 @@ static int tiles_setup(pfd_handle* h, TileCtx& T, bool with_init_copy) {
     T.nslots = T.ntx * (T.nty + 2) * TL_RING;  // + one halo tile row above and below
     if (T.nslots >= (1ll << 30)) return pfd_fail(h, PFD_ERR_UNSUPPORTED, "tile solver: too many ring slots");
     T.arr = (size_t)T.nslots * sizeof(uint32_t);
-    const int narr = with_init_copy ? 16 : 12;
+    const int narr = with_init_copy ? 17 : 13;
     PFD_TRY(pfd_reserve(h, h->tslots, narr * T.arr + 256));
     uint32_t* base = (uint32_t*)h->tslots.p;
     int a = 0;
@@ -439,8 +440,9 @@ static int tiles_setup(pfd_handle* h, TileCtx& T, bool with_init_copy) {
         T.B[side].nxt = take();
         T.B[side].rh = take();
         T.B[side].ch = take();
-        T.B[side].acc = take();
+        T.recv[side] = take();
     }
+    T.B[0].acc = T.B[1].acc = take();
     T.term = take();
     T.term_h = take();
     T.srank = (int32_t*)take();
@@ -477,35 +479,46 @@ static int tiles_phase_a(pfd_handle* h, TileCtx& T, uint32_t* basin_dev, unsigne
     return PFD_OK;
 }
 
-// phase B: all doubling rounds over `n` reduced-graph nodes in one cooperative launch; the result ends in side 0.
-// flags: 3 x uint32 + 1 int (round count) on the device.
-static int slots_solve(pfd_handle* h, SlotBuf* B, long long n, unsigned int* flags, int* src_out, int* rounds_out) {
-    (void)rounds_out;
+// phase B: all doubling rounds over `n` reduced-graph nodes in one cooperative launch. The final node state is on
+// side (*rounds & 1) where rounds = (int*)(flags + 3) lives on the device; acc is side-independent.
+static int slots_solve(pfd_handle* h, SlotBuf* B, uint32_t** recv, long long n, unsigned int* flags, int mark_inert,
+                       SlotProtect prot) {
     int grid = 1;
     PFD_TRY(coop_grid(h, slots_solve_kernel, 256, (n + 255) / 256, &grid));
     PFD_CUDA(h, cudaMemsetAsync(flags, 0, 4 * sizeof(unsigned int), h->stream));
+    PFD_CUDA(h, cudaMemsetAsync(recv[0], 0, (size_t)n * sizeof(uint32_t), h->stream));
+    PFD_CUDA(h, cudaMemsetAsync(recv[1], 0, (size_t)n * sizeof(uint32_t), h->stream));
     int* rounds_dev = (int*)(flags + 3);
-    void* args[] = {(void*)&B[0], (void*)&B[1], (void*)&n, (void*)&flags, (void*)&rounds_dev};
+    void* args[] = {(void*)&B[0], (void*)&B[1], (void*)&recv[0], (void*)&recv[1], (void*)&n,
+                    (void*)&flags,  (void*)&rounds_dev, (void*)&mark_inert, (void*)&prot};
     PFD_CUDA(h, cudaLaunchCooperativeKernel((void*)slots_solve_kernel, dim3(grid), dim3(256), args, 0, h->stream));
     h->launches++;
-    *src_out = 0;
     return PFD_OK;
 }
 
-static int tiles_phase_b(pfd_handle* h, TileCtx& T, int* src_out) {
+static SlotProtect tiles_protect(const pfd_handle* h, const TileCtx& T, bool first_multirank_pass) {
+    SlotProtect p;
+    p.per_row = T.ntx * TL_RING;
+    p.nty = T.nty;
+    p.top = first_multirank_pass ? h->mg_halo_top : 0;
+    p.bot = first_multirank_pass ? h->mg_halo_bot : 0;
+    return p;
+}
+
+static int tiles_phase_b(pfd_handle* h, TileCtx& T) {
     StageTimer t(h, PFD_STAGE_TILE_B);
-    PFD_TRY(slots_solve(h, T.B, T.nslots, T.flag, src_out, &h->tile_rounds));
-    slots_finalize_kernel<<<grid_for(T.nslots, 256, 2, 148 * 16), 256, 0, h->stream>>>(T.B[*src_out], T.term, T.term_h,
-                                                                                       T.nslots, T.srank, T.sbasin);
+    PFD_TRY(slots_solve(h, T.B, T.recv, T.nslots, T.flag, 1, tiles_protect(h, T, false)));
+    slots_finalize_kernel<<<grid_for(T.nslots, 256, 2, 148 * 16), 256, 0, h->stream>>>(
+        T.B[0], T.B[1], (const int*)(T.flag + 3), T.term, T.term_h, T.nslots, T.srank, T.sbasin);
     PFD_LAUNCH_CHECK(h);
     return PFD_OK;
 }
 
-static int tiles_phase_c(pfd_handle* h, TileCtx& T, int src, int32_t* rank_dev, uint32_t* basin_dev, int32_t* uparea_dev) {
+static int tiles_phase_c(pfd_handle* h, TileCtx& T, int32_t* rank_dev, uint32_t* basin_dev, int32_t* uparea_dev) {
     StageTimer t(h, PFD_STAGE_TILE_C);
     const dim3 grid((unsigned)T.ntx, (unsigned)T.nty);
     tile_phase_c_kernel<TLC_THREADS, TLC_MINBLOCKS><<<grid, TLC_THREADS, 0, h->stream>>>(
-        T.dir, h->nrow, h->ncol, T.ntx, (const uint32_t*)h->tile_loc.p, (const uint32_t*)h->tile_cnt.p, T.B[src].acc,
+        T.dir, h->nrow, h->ncol, T.ntx, (const uint32_t*)h->tile_loc.p, (const uint32_t*)h->tile_cnt.p, T.B[0].acc,
         T.srank, T.sbasin, rank_dev, basin_dev, uparea_dev);
     PFD_LAUNCH_CHECK(h);
     return PFD_OK;
@@ -516,9 +529,8 @@ static int tiles_solve(pfd_handle* h, int32_t* rank_dev, uint32_t* basin_dev, in
     TileCtx T;
     PFD_TRY(tiles_setup(h, T, false));
     PFD_TRY(tiles_phase_a(h, T, basin_dev, 0));
-    int src = 0;
-    PFD_TRY(tiles_phase_b(h, T, &src));
-    PFD_TRY(tiles_phase_c(h, T, src, rank_dev, basin_dev, uparea_dev));
+    PFD_TRY(tiles_phase_b(h, T));
+    PFD_TRY(tiles_phase_c(h, T, rank_dev, basin_dev, uparea_dev));
     return PFD_OK;
 }
 
@@ -596,17 +608,16 @@ extern "C" int pfd_tiled_local(pfd_handle* h, int rank, int nranks, int64_t pit_
             uint32_t* src = f == 0 ? T.B[0].nxt : f == 1 ? T.B[0].rh : f == 2 ? T.B[0].ch : T.B[0].acc;
             PFD_CUDA(h, cudaMemcpyAsync(dst, src, T.arr, cudaMemcpyDeviceToDevice, h->stream));
         }
-        int src = 0;
         {
             StageTimer t(h, PFD_STAGE_TILE_B);
-            PFD_TRY(slots_solve(h, T.B, T.nslots, T.flag, &src, &h->tile_rounds));
+            PFD_TRY(slots_solve(h, T.B, T.recv, T.nslots, T.flag, 1, tiles_protect(h, T, true)));
         }
         PFD_CUDA(h, cudaMemsetAsync(h->btab.p, 0, (size_t)(4 * nb) * sizeof(uint32_t), h->stream));
         BoundaryTables bt;
         boundary_tables(h, bt);
-        boundary_fill_kernel<<<grid_for(2 * h->ncol, 256), 256, 0, h->stream>>>(T.B[src], T.term, T.term_h, h->nrow, h->ncol,
-                                                                                 T.ntx, T.nty, rank, h->mg_halo_top,
-                                                                                 h->mg_halo_bot, bt);
+        boundary_fill_kernel<<<grid_for(2 * h->ncol, 256), 256, 0, h->stream>>>(
+            T.B[0], T.B[1], (const int*)(T.flag + 3), T.term, T.term_h, h->nrow, h->ncol, T.ntx, T.nty, rank, h->mg_halo_top,
+            h->mg_halo_bot, bt);
         PFD_LAUNCH_CHECK(h);
     }
     PFD_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -631,27 +642,30 @@ extern "C" int pfd_tiled_finish(pfd_handle* h, int32_t* rank_out, int32_t* upare
     if (h->mg_nranks > 1) {
         const long long nb = boundary_entries(h);
         // boundary graph: 12 node arrays + results, solved redundantly on every rank
-        PFD_TRY(pfd_reserve(h, h->bgraph, (size_t)(13 * nb) * sizeof(uint32_t) + 256));
+        PFD_TRY(pfd_reserve(h, h->bgraph, (size_t)(14 * nb) * sizeof(uint32_t) + 256));
         uint32_t* base = (uint32_t*)h->bgraph.p;
         int a = 0;
         auto take = [&]() { return base + (size_t)nb * a++; };
         SlotBuf G[2];
+        uint32_t* grecv[2];
         for (int side = 0; side < 2; ++side) {
             G[side].nxt = take();
             G[side].rh = take();
             G[side].ch = take();
-            G[side].acc = take();
+            grecv[side] = take();
         }
+        G[0].acc = G[1].acc = take();
         uint32_t *gterm = take(), *gterm_h = take(), *gbasin = take();
         int32_t* grank = (int32_t*)take();
-        unsigned int* gflag = (unsigned int*)take();
+        unsigned int* gflag = (unsigned int*)take();  // + 256 spare bytes behind it
         BoundaryTables bt;
         boundary_tables(h, bt);
         boundary_build_kernel<<<grid_for(nb, 256), 256, 0, h->stream>>>(bt, nb, G[0], gterm, gterm_h);
         PFD_LAUNCH_CHECK(h);
-        int gsrc = 0, grounds = 0;
-        PFD_TRY(slots_solve(h, G, nb, gflag, &gsrc, &grounds));
-        slots_finalize_kernel<<<grid_for(nb, 256), 256, 0, h->stream>>>(G[gsrc], gterm, gterm_h, nb, grank, gbasin);
+        SlotProtect noprot{1, 0, 0, 0};
+        PFD_TRY(slots_solve(h, G, grecv, nb, gflag, 0, noprot));
+        slots_finalize_kernel<<<grid_for(nb, 256), 256, 0, h->stream>>>(G[0], G[1], (const int*)(gflag + 3), gterm, gterm_h, nb,
+                                                                        grank, gbasin);
         PFD_LAUNCH_CHECK(h);
         // restore the local reduced graph, add the remote inflow, make the halo slots terminals, solve again
         for (int f = 0; f < 4; ++f) {
@@ -660,13 +674,12 @@ extern "C" int pfd_tiled_finish(pfd_handle* h, int32_t* rank_out, int32_t* upare
             PFD_CUDA(h, cudaMemcpyAsync(dst, src, T.arr, cudaMemcpyDeviceToDevice, h->stream));
         }
         boundary_writeback_kernel<<<grid_for(2 * h->ncol, 256), 256, 0, h->stream>>>(
-            grank, gbasin, G[gsrc].acc, h->nrow, h->ncol, T.ntx, h->mg_rank, h->mg_halo_top, h->mg_halo_bot, T.B[0].acc,
+            grank, gbasin, G[0].acc, h->nrow, h->ncol, T.ntx, h->mg_rank, h->mg_halo_top, h->mg_halo_bot, T.B[0].acc,
             T.term, T.term_h);
         PFD_LAUNCH_CHECK(h);
     }
-    int src = 0;
-    PFD_TRY(tiles_phase_b(h, T, &src));
-    PFD_TRY(tiles_phase_c(h, T, src, (int32_t*)rk, basins_out, (int32_t*)up));
+    PFD_TRY(tiles_phase_b(h, T));
+    PFD_TRY(tiles_phase_c(h, T, (int32_t*)rk, basins_out, (int32_t*)up));
     if (rank_out) PFD_TRY(pfd_finish_out(h, rank_out, rk, b4));
     if (uparea_out) PFD_TRY(pfd_finish_out(h, uparea_out, up, b4));
     PFD_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -251,97 +251,115 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 // ---------------------------------------------------------------------------------------------------------
 struct SlotBuf {  // one side of the double-buffered reduced-graph state
     uint32_t* nxt;
-    uint32_t* rh;
+    uint32_t* rh;   // reduced hops (low 30 bits) | SLOT_DONE1 | SLOT_DONE2
     uint32_t* ch;
-    uint32_t* acc;
+    uint32_t* acc;  // inflow accumulate -- ONE array shared by both sides
+};
+#define SLOT_DONE1 0x40000000u  // final state stored on this side only
+#define SLOT_DONE2 0x80000000u  // final state stored on both sides: the node is skipped from now on
+#define SLOT_HMASK 0x3FFFFFFFu
+
+struct SlotProtect {  // ring rows on the block's edges that must stay live in the first local solve (multi-rank)
+    long long per_row;   // slots per tile row
+    long long nty;
+    int top, bot;
 };
 
-// acc of the destination side must hold a copy of the source side before the launch (the kernel only adds)
-__global__ void __launch_bounds__(256) slots_round_kernel(SlotBuf src, SlotBuf dst, long long nslots, uint32_t two_k,
-                                                          unsigned int* __restrict__ flag) {
-    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < nslots; s += (long long)gridDim.x * blockDim.x) {
-        const uint32_t n = src.nxt[s];
-        const uint32_t h = src.rh[s];
-        if (n == (uint32_t)s) {  // last node / unused: nothing to jump
-            dst.nxt[s] = n;
-            dst.rh[s] = h;
-            dst.ch[s] = src.ch[s];
-            continue;
-        }
-        if (h == two_k) {
-            const uint32_t a = src.acc[s];
-            if (a) atomicAdd(dst.acc + n, a);
-        }
-        const uint32_t n2 = src.nxt[n];
-        const uint32_t h2 = src.rh[n];
-        dst.nxt[s] = n2;
-        dst.rh[s] = h + h2;
-        dst.ch[s] = src.ch[s] + src.ch[n];
-        if ((h + h2) == (two_k << 1)) *flag = 1u;
-    }
-}
-
-// All doubling rounds in ONE cooperative launch (no host round trip per round): per round copy acc, grid.sync,
-// jump + accumulate, grid.sync, stop when no node asked for another round. The result always ends in side 0.
-__global__ void __launch_bounds__(256, 8) slots_solve_kernel(SlotBuf b0, SlotBuf b1, long long nslots, unsigned int* flags,
-                                                          int* rounds_out) {
+// All doubling rounds of a reduced graph in ONE cooperative launch.
+//  * prologue: ring nodes that received no inflow weight are never referenced by any chain -> made inert;
+//  * round k: every live node adds its accumulate to its 2^k-th successor (into the `recv` buffer of this round's
+//    parity, folded into acc by the owner at the start of the next round: Jacobi without copying acc) and jumps;
+//    a node whose chain is exhausted writes its final state to both sides once and is skipped afterwards, so late
+//    rounds only stream rh + recv;
+//  * the number of executed rounds K is left in *rounds_out: the final state of every node is on side K & 1.
+__global__ void __launch_bounds__(256, 8) slots_solve_kernel(SlotBuf b0, SlotBuf b1, uint32_t* recv0, uint32_t* recv1,
+                                                             long long nslots, unsigned int* flags, int* rounds_out,
+                                                             int mark_inert, SlotProtect prot) {
     cg::grid_group grid = cg::this_grid();
     const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    int src = 0, k = 0;
-    for (; k < 31; ++k) {
-        const SlotBuf S = src ? b1 : b0, D = src ? b0 : b1;
-        const uint32_t two_k = 1u << k;
+    uint32_t* const acc = b0.acc;
+    if (mark_inert) {
 #pragma unroll 1
-        for (long long s = tid; s < nslots; s += stride) D.acc[s] = S.acc[s];
+        for (long long s = tid; s < nslots; s += stride) {
+            if (acc[s] == 0u && b0.nxt[s] != (uint32_t)s) {
+                const long long trow = s / prot.per_row;
+                const int rp = (int)(s % TL_RING);
+                const bool keep = (prot.top && trow == 1 && rp < TL_W) ||
+                                  (prot.bot && trow == prot.nty && rp >= TL_W && rp < 2 * TL_W);
+                if (!keep) {
+                    b0.nxt[s] = (uint32_t)s;
+                    b0.rh[s] = 0u;
+                }
+            }
+        }
+        grid.sync();
+    }
+    int k = 0;
+    for (; k < 30; ++k) {
+        const SlotBuf S = (k & 1) ? b1 : b0, D = (k & 1) ? b0 : b1;
+        uint32_t* const recv_prev = (k & 1) ? recv0 : recv1;  // filled in round k-1
+        uint32_t* const recv_cur = (k & 1) ? recv1 : recv0;
+        const uint32_t two_k = 1u << k;
         // three rotating flags: the one zeroed here was last READ at the end of round k-2, two grid.sync()s ago
         if (tid == 0) flags[(k + 1) % 3] = 0u;
-        grid.sync();
         unsigned int again = 0;
 #pragma unroll 2
         for (long long s = tid; s < nslots; s += stride) {
+            const uint32_t rhw = S.rh[s];
+            const uint32_t r = recv_prev[s];
+            if (r) {
+                acc[s] += r;
+                recv_prev[s] = 0u;
+            }
+            if (rhw & SLOT_DONE2) continue;
             const uint32_t n = S.nxt[s];
-            const uint32_t h = S.rh[s];
-            if (n == (uint32_t)s) {
+            const uint32_t h = rhw & SLOT_HMASK;
+            if ((rhw & SLOT_DONE1) || n == (uint32_t)s) {  // chain exhausted: replicate the final state once
                 D.nxt[s] = n;
-                D.rh[s] = h;
+                D.rh[s] = h | SLOT_DONE2;
                 D.ch[s] = S.ch[s];
+                S.rh[s] = h | SLOT_DONE2;  // only flag bits change: concurrent readers mask them off
                 continue;
             }
             if (h == two_k) {
-                const uint32_t a = S.acc[s];
-                if (a) atomicAdd(D.acc + n, a);
+                const uint32_t a = acc[s];
+                if (a) atomicAdd(recv_cur + n, a);
             }
             const uint32_t n2 = S.nxt[n];
-            const uint32_t h2 = S.rh[n];
+            const uint32_t nh = h + (S.rh[n] & SLOT_HMASK);
+            const bool live = nh == (two_k << 1);
             D.nxt[s] = n2;
-            D.rh[s] = h + h2;
+            D.rh[s] = nh | (live ? 0u : SLOT_DONE1);
             D.ch[s] = S.ch[s] + S.ch[n];
-            again |= ((h + h2) == (two_k << 1)) ? 1u : 0u;
+            again |= live ? 1u : 0u;
         }
         if (again) flags[k % 3] = 1u;
         grid.sync();
-        src ^= 1;
         if (*((volatile unsigned int*)&flags[k % 3]) == 0u) {
             ++k;
             break;
         }
     }
-    if (src == 1) {  // bring the result back to side 0
+    // fold what the last round delivered
+    uint32_t* const recv_last = ((k - 1) & 1) ? recv1 : recv0;
 #pragma unroll 1
-        for (long long s = tid; s < nslots; s += stride) {
-            b0.nxt[s] = b1.nxt[s];
-            b0.rh[s] = b1.rh[s];
-            b0.ch[s] = b1.ch[s];
-            b0.acc[s] = b1.acc[s];
+    for (long long s = tid; s < nslots; s += stride) {
+        const uint32_t r = recv_last[s];
+        if (r) {
+            acc[s] += r;
+            recv_last[s] = 0u;
         }
     }
-    if (tid == 0 && rounds_out) *rounds_out = k;
+    if (tid == 0) *rounds_out = k;
 }
 
-__global__ void __launch_bounds__(256) slots_finalize_kernel(SlotBuf cur, const uint32_t* __restrict__ term,
+// rounds: number of rounds the solve executed (device) -> the final node state is on side (*rounds & 1)
+__global__ void __launch_bounds__(256) slots_finalize_kernel(SlotBuf b0, SlotBuf b1, const int* __restrict__ rounds,
+                                                             const uint32_t* __restrict__ term,
                                                              const uint32_t* __restrict__ term_h, long long nslots,
                                                              int32_t* __restrict__ rank, uint32_t* __restrict__ basin) {
+    const SlotBuf cur = (*rounds & 1) ? b1 : b0;
     for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < nslots; s += (long long)gridDim.x * blockDim.x) {
         const uint32_t last = cur.nxt[s];
         const uint32_t t = term[last];
@@ -509,9 +527,10 @@ __global__ void halo_slots_init_kernel(SlotBuf b0, uint32_t* __restrict__ term, 
 }
 
 // side_sel 0: my top boundary (boundary rank-1), 1: my bottom boundary (boundary rank)
-__global__ void boundary_fill_kernel(SlotBuf cur, const uint32_t* __restrict__ term, const uint32_t* __restrict__ term_h,
-                                     long long nrow, long long ncol, long long ntx, long long nty, int rank, int has_top,
-                                     int has_bot, BoundaryTables T) {
+__global__ void boundary_fill_kernel(SlotBuf b0, SlotBuf b1, const int* __restrict__ rounds, const uint32_t* __restrict__ term,
+                                     const uint32_t* __restrict__ term_h, long long nrow, long long ncol, long long ntx,
+                                     long long nty, int rank, int has_top, int has_bot, BoundaryTables T) {
+    const SlotBuf cur = (*rounds & 1) ? b1 : b0;
     const long long per_row = ntx * TL_RING;
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < 2 * ncol; k += (long long)gridDim.x * blockDim.x) {
         const int bottom = k >= ncol;

@@ -1,0 +1,27 @@
+"""Sweeps over the flow sequence on the GPU; mirrors /root/reference/pyflwdir/streams.py (accuflux :15-41,
+accuflux_ds :44-70, strahler_order :228-269). The device always sweeps its own "walk" sequence (the one
+`core.idxs_seq` returns); `seq` is only checked for covering the same cells."""
+import numpy as np
+
+from . import _functional
+
+
+def accuflux(idxs_ds, seq, data, nodata, shape=None, ncol=None):
+    """Returns maps of accumulate upstream <data>"""
+    g = _functional.graph(idxs_ds, shape, ncol)
+    _functional.check_seq(g, seq, "accuflux")
+    return g.accuflux(np.asarray(data).ravel(), nodata, "up")
+
+
+def accuflux_ds(idxs_ds, seq, data, nodata, shape=None, ncol=None):
+    """Returns maps of accumulate downstream <data>"""
+    g = _functional.graph(idxs_ds, shape, ncol)
+    _functional.check_seq(g, seq, "accuflux_ds")
+    return g.accuflux(np.asarray(data).ravel(), nodata, "down")
+
+
+def strahler_order(idxs_ds, seq, mask=None, shape=None, ncol=None):
+    """Returns the strahler "top down" stream order (uint8)."""
+    g = _functional.graph(idxs_ds, shape, ncol)
+    _functional.check_seq(g, seq, "strahler_order")
+    return g.strahler(mask)

@@ -128,3 +128,50 @@ def test_constructor_from_idxs_ds(pfb):
     flw3 = pfb.from_array(d8, ftype="d8", mask=m)
     ids, pits, _ = oracle.core_d8.from_array(np.where(m, d8, 247).astype(np.uint8), dtype=np.int32)
     assert np.array_equal(flw3.idxs_ds, ids) and np.array_equal(flw3.idxs_pit, pits)
+
+
+def test_module_level_functions(pfb):
+    """The L1/L2 free functions with the reference's signatures (what the reference's own tests call):
+    core_d8.from_array / to_array / isvalid, core.rank / idxs_seq / upstream_count / pit_indices,
+    streams.accuflux / strahler_order, basins.basins, dem.height_above_nearest_drain."""
+    from pyflwdir_b200 import basins, core, core_d8, dem, streams
+
+    d8 = cs.case_d8("flwdir_asc")
+    # tests/conftest.py:23-26 of the reference parses the fixture with uint32 indices
+    ids, pits, n = core_d8.from_array(d8, dtype=np.uint32)
+    assert np.array_equal(ids, cs.small()["out/flwdir_asc/idxs_ds_uint32"]) and ids.dtype == np.uint32
+    assert np.array_equal(pits, cs.small()["out/flwdir_asc/idxs_pit_uint32"]) and n == 407
+    assert core_d8.isvalid(d8) and not core_d8.isvalid(np.full((3, 3), 3, np.uint8)) and not core_d8.isvalid(d8.astype(np.int32))
+    # tests/test_core_xx.py:54-62: to_array -> from_array is the identity
+    d8b = core_d8.to_array(ids, d8.shape)
+    ids2, pits2, _ = core_d8.from_array(d8b, dtype=np.uint32)
+    assert np.array_equal(ids2, ids) and np.array_equal(pits2, pits)
+
+    for name in ["flwdir1_asc", "random48x61"]:
+        d8 = cs.case_d8(name)
+        ids, pits, _ = core_d8.from_array(d8, dtype=np.int32)
+        rnk, n = core.rank(ids)
+        assert np.array_equal(rnk.reshape(d8.shape), cs.golden(name, "rank")) and n == int(cs.golden(name, "nnodes"))
+        # tests/test_core.py:18-22: rank[i] == rank[ds[i]] + 1 away from pits, #rank0 == #pits
+        ok = rnk > 0
+        assert np.all(rnk[ok] == rnk[ids[ok]] + 1) and np.count_nonzero(rnk == 0) == pits.size
+        seq = core.idxs_seq(ids, pits)
+        assert np.array_equal(seq, cs.golden(name, "idxs_seq")) and np.all(np.diff(rnk[seq]) >= 0)
+        assert np.array_equal(core.upstream_count(ids).reshape(d8.shape), cs.golden(name, "n_upstream"))
+        assert np.array_equal(core.pit_indices(ids), pits)
+        aux = cs.case_inputs(name, d8, cs.case_seed(name))
+        acc = streams.accuflux(ids, seq, aux["data_f64"].ravel(), -9999.0)
+        assert np.array_equal(acc.reshape(d8.shape), cs.golden(name, "accu_f64"))
+        accd = streams.accuflux_ds(ids, seq, aux["data_i64"].ravel(), -9999)
+        assert np.array_equal(accd.reshape(d8.shape), cs.golden(name, "accu_ds_i64"))
+        assert np.array_equal(streams.strahler_order(ids, seq).reshape(d8.shape), cs.golden(name, "strord"))
+        assert np.array_equal(streams.strahler_order(ids, seq, mask=aux["smask"].ravel()).reshape(d8.shape),
+                              cs.golden(name, "strord_mask"))
+        assert np.array_equal(basins.basins(ids, pits, seq).reshape(d8.shape), cs.golden(name, "basins"))
+        sub = basins.basins(ids, cs.golden(name, "sub_idxs"), seq, ids=cs.golden(name, "sub_ids"))
+        assert np.array_equal(sub.reshape(d8.shape), cs.golden(name, "basins_sub")) and sub.dtype == np.int32
+        drain = cs.golden(name, "uparea_cell") > max(4, int(0.002 * d8.size))
+        hand = dem.height_above_nearest_drain(ids, seq, drain.ravel(), aux["elevtn"].ravel())
+        assert np.array_equal(hand.reshape(d8.shape), cs.golden(name, "hand_f32"))
+    with pytest.raises(ValueError, match="outside 8 neighbors"):
+        core_d8.to_array(np.array([5, 1, 2, 3, 4, 5], dtype=np.int32), (2, 3))

@@ -106,3 +106,22 @@ def test_split_rows():
     d8 = np.arange(12, dtype=np.uint8).reshape(4, 3)
     blk, ht, hb = tiled.block_with_halo(d8, 0, 4)
     assert (ht, hb) == (0, 0) and blk.shape == (4, 3)
+
+
+def test_infer_ncol():
+    """Raster width inferred from a flat idxs_ds (the reference's free functions do not carry the shape)."""
+    import oracle
+    from pyflwdir_b200 import _functional as F
+
+    for name in cs.SMALL_CASES:
+        d8 = cs.case_d8(name)
+        for dt in (np.int32, np.uint32, np.int64):
+            ids, _, _ = oracle.core_d8.from_array(d8, dtype=dt)
+            assert F.infer_ncol(ids) == d8.shape[1]
+            assert F.resolve_shape(ids) == d8.shape
+    assert F.infer_ncol(np.array([0, 1, 2, 3], dtype=np.int32)) == 4  # only pits: read as a single row
+    with pytest.raises(ValueError, match="cannot infer"):
+        F.infer_ncol(np.array([3, 1, 2, 3, 4, 5], dtype=np.int32))  # 0 -> 3 is "S" on 2x3 and "SE" on 3x2
+    assert F.resolve_shape(np.arange(12, dtype=np.int32), shape=(3, 4)) == (3, 4)
+    with pytest.raises(ValueError, match="does not match"):
+        F.resolve_shape(np.arange(12, dtype=np.int32), shape=(5, 4))
