@@ -75,7 +75,7 @@ class ClockSampler:
             os.close(fd)
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
                  str(self.device)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -444,13 +444,15 @@ def main():
         w.ck(w.l.pfd_set_option(w.h, b"tiles", 1 if args.solver == "tiles" else 0))
     cells = w.cells
 
-    # ---- device-resident arm
-    for _ in range(args.warmup):
-        w.step_resident()
+    # ---- device-resident arm. The clock sampler (rank 0) runs from before the warm-up until after a >= 1.2 s
+    # window of back-to-back steps that directly follows the timed region (the timed region itself is only
+    # K x ~2 ms, shorter than one nvidia-smi sampling period).
     sampler = ClockSampler(device)
-    barrier(dist)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        w.step_resident()
+    barrier(dist)
     l0 = w.launches()
     stage_acc = {}
     w.ck(w.l.pfd_timer_start(w.h))
@@ -461,6 +463,9 @@ def main():
     ms = C.c_double()
     w.ck(w.l.pfd_timer_stop(w.h, C.byref(ms)))
     launches = w.launches() - l0
+    t_probe = time.perf_counter()
+    while time.perf_counter() - t_probe < 1.2:
+        w.step_resident()
     barrier(dist)
     clocks = sampler.stop() if rank == 0 else None
     ms_total = reduce_max(dist, ms.value)

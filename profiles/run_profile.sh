@@ -9,7 +9,7 @@ CMD="python bench.py --size $SIZE --steps 2 --warmup 3 --no-cpu-baseline --solve
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${TAG}.csv \
     $CMD > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
 if [ "$SOLVER" = "tiles" ]; then
-  REGEX="parse_kernel|tile_phase_a_kernel|tile_phase_c_kernel|slots_round_kernel"; SKIP=42; COUNT=14
+  REGEX="parse_kernel|tile_phase_a_kernel|tile_phase_c_kernel|slots_solve_kernel"; SKIP=12; COUNT=4
 else
   REGEX="bfs_kernel|sweep_kernel|parse_kernel"; SKIP=9; COUNT=3
 fi

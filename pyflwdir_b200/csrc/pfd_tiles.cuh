@@ -25,8 +25,8 @@
 #define TL_H 64
 #define TL_W 64
 #define TL_CELLS (TL_H * TL_W)
-// Block shapes (tuned on B200, see profiles/): phase A is issue-bound and likes 1024 threads x 2 CTAs/SM (4 cells
-// per thread, few registers), phase C is latency-bound and likes 512 threads x 4 CTAs/SM.
+// Block shapes (tuned on B200, see profiles/): both phases run best with 1024 threads x 2 CTAs/SM (4 cells per
+// thread keep the per-thread arrays in 32 registers without spills).
 #ifndef TLA_THREADS
 #define TLA_THREADS 1024
 #endif
@@ -34,10 +34,10 @@
 #define TLA_MINBLOCKS 2
 #endif
 #ifndef TLC_THREADS
-#define TLC_THREADS 512
+#define TLC_THREADS 1024
 #endif
 #ifndef TLC_MINBLOCKS
-#define TLC_MINBLOCKS 4
+#define TLC_MINBLOCKS 2
 #endif
 #define TL_RING 256                       // ring slots per tile (252 used)
 #define TL_MAXROUNDS 13                   // 2^12 = 4096 >= longest simple path in a tile (+1 accumulate round)
@@ -54,6 +54,37 @@ __host__ __device__ __forceinline__ int tl_ring_pos(int ly, int lx) {
 
 __device__ __forceinline__ bool tl_on_ring(int ly, int lx) {
     return ly == 0 || ly == TL_H - 1 || lx == 0 || lx == TL_W - 1;
+}
+
+// inverse of tl_ring_pos: local cell index of ring position rp (0 .. 4*TL_W-5)
+__device__ __forceinline__ int tl_ring_cell(int rp) {
+    if (rp < TL_W) return rp;
+    if (rp < 2 * TL_W) return (TL_H - 1) * TL_W + (rp - TL_W);
+    if (rp < 2 * TL_W + TL_H - 2) return (rp - 2 * TL_W + 1) * TL_W;
+    return (rp - 2 * TL_W - (TL_H - 2) + 1) * TL_W + (TL_W - 1);
+}
+#define TL_NRING (2 * TL_W + 2 * (TL_H - 2))
+
+// slot of the cell one step in direction d outside the tile `tile` (slot-array tile index incl. the halo row shift)
+// from local cell (ly, lx): 32-bit arithmetic only
+__device__ __forceinline__ uint32_t tl_exit_slot(uint32_t tile, uint32_t ntx, int ly, int lx, uint32_t d) {
+    int y = ly + pfd_slot_dr((int)d), x = lx + pfd_slot_dc((int)d);
+    uint32_t t = tile;
+    if (y < 0) {
+        t -= ntx;
+        y += TL_H;
+    } else if (y >= TL_H) {
+        t += ntx;
+        y -= TL_H;
+    }
+    if (x < 0) {
+        t -= 1;
+        x += TL_W;
+    } else if (x >= TL_W) {
+        t += 1;
+        x -= TL_W;
+    }
+    return t * TL_RING + (uint32_t)tl_ring_pos(y, x);
 }
 
 // Ring-slot arrays cover the local tile rows PLUS one halo tile row above and below (tile row index shifted by
@@ -77,6 +108,7 @@ __global__ void stash_pit_ids_kernel(const cell_t* __restrict__ pits, long long 
 struct TileShared {
     uint32_t P[TL_CELLS];
     uint32_t A[TL_CELLS];
+    uint8_t dir[TL_CELLS];
 };
 #define TP_PACK(n, h) ((uint32_t)(n) | ((uint32_t)(h) << 12))
 #define TP_N(p) ((p) & 0xFFFu)
@@ -162,14 +194,6 @@ __device__ __forceinline__ void tl_load_dirs(const uint8_t* __restrict__ dir, lo
     }
 }
 
-// terminal descriptor of an owned cell that is a local terminal: exit -> slot id of the target ring cell,
-// pit -> TERM_PIT | ordinal (0 when basins are not requested). (valid, non-nodata cells only)
-__device__ __forceinline__ uint32_t tl_terminal_info(uint32_t d, long long r, long long c, long long ncol, long long ntx,
-                                                     const uint32_t* __restrict__ pit_ids) {
-    if (d < 8u) return tl_slot_of(r + pfd_slot_dr((int)d), c + pfd_slot_dc((int)d), ntx);
-    return TERM_PIT | (pit_ids ? (pit_ids[r * ncol + c] - 1u) : 0u);
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // Phase A: local solve; per cell (local terminal, hops) -> loc[], in-tile subtree size -> cnt[]; ring nodes; W
 // ---------------------------------------------------------------------------------------------------------
@@ -181,53 +205,64 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
                         uint32_t* __restrict__ s_ch, uint32_t* __restrict__ s_term, uint32_t* __restrict__ s_term_h) {
     constexpr int TL_CPT = TL_CELLS / THREADS, TL_RPI = THREADS / TL_W;
     __shared__ TileShared s;
-    const long long tile = ((long long)blockIdx.y + 1) * ntx + blockIdx.x;  // +1: halo tile row
+    const uint32_t tile = (uint32_t)(((long long)blockIdx.y + 1) * ntx + blockIdx.x);  // +1: halo tile row
     const long long r0 = (long long)blockIdx.y * TL_H, c0 = (long long)blockIdx.x * TL_W;
     const int lx = threadIdx.x & (TL_W - 1);
     const int ly0 = threadIdx.x >> 6;
+    const long long g00 = r0 * ncol + c0;  // global index of the tile's first cell
 
     uint32_t dirs[(TL_CPT + 3) / 4], own[TL_CPT];
     tl_load_dirs<THREADS>(dir, nrow, ncol, r0, c0, dirs);
+#pragma unroll
+    for (int it = 0; it < TL_CPT; ++it) s.dir[(ly0 + TL_RPI * it) * TL_W + lx] = (uint8_t)tl_dir_of(dirs, it);
     tl_local_solve<THREADS>(s, dirs, own);
 
-    // per-cell results for phase C; terminals hand their subtree size to the entry cell they drain into and then
-    // publish their descriptor through their A slot
-    uint32_t inv = 0;
+    // (1) per-cell results for phase C
 #pragma unroll
     for (int it = 0; it < TL_CPT; ++it) {
         const int ly = ly0 + TL_RPI * it;
         const int i = ly * TL_W + lx;
         const uint32_t root = TP_N(own[it]);
-        if (s.P[root] != root) inv |= 1u << it;  // a terminal is (next = itself, hops = 0)
-        const long long r = r0 + ly, c = c0 + lx;
-        if (r < nrow && c < ncol) {
-            loc[r * ncol + c] = ((inv >> it) & 1u) ? TL_LOC_INVALID : own[it];
-            cnt[r * ncol + c] = s.A[i];
+        const bool inv = s.P[root] != root;  // a terminal is (next = itself, hops = 0)
+        if (r0 + ly < nrow && c0 + lx < ncol) {
+            const long long g = g00 + (long long)ly * ncol + lx;
+            loc[g] = inv ? TL_LOC_INVALID : own[it];
+            cnt[g] = s.A[i];
         }
     }
     __syncthreads();
+    // (2) terminals publish their descriptor through their A slot: pits by their owner thread, exit cells (always
+    //     ring cells) by one thread per ring position, which also hands the exit cell's in-tile subtree size to the
+    //     entry cell it drains into
 #pragma unroll
     for (int it = 0; it < TL_CPT; ++it) {
-        const int ly = ly0 + TL_RPI * it;
-        const int i = ly * TL_W + lx;
         const uint32_t d = tl_dir_of(dirs, it);
-        if (d != PFD_DIR_NODATA && own[it] == (uint32_t)i) {
-            const uint32_t ti = tl_terminal_info(d, r0 + ly, c0 + lx, ncol, ntx, pit_ids);
-            if (!(ti & TERM_PIT)) atomicAdd(W + ti, s.A[i]);
-            s.A[i] = ti;
+        if (d == PFD_DIR_PIT || d == PFD_DIR_FPIT) {
+            const int ly = ly0 + TL_RPI * it;
+            s.A[ly * TL_W + lx] = TERM_PIT | (pit_ids ? (pit_ids[g00 + (long long)ly * ncol + lx] - 1u) : 0u);
+        }
+    }
+    int ri = -1;
+    uint32_t rd = PFD_DIR_NODATA;
+    if (threadIdx.x < TL_NRING) {
+        ri = tl_ring_cell(threadIdx.x);
+        rd = s.dir[ri];
+        if (rd < 8u && s.P[ri] == (uint32_t)ri) {  // exit cell
+            const uint32_t ti = tl_exit_slot(tile, (uint32_t)ntx, ri >> 6, ri & (TL_W - 1), rd);
+            atomicAdd(W + ti, s.A[ri]);
+            s.A[ri] = ti;
         }
     }
     __syncthreads();
-#pragma unroll
-    for (int it = 0; it < TL_CPT; ++it) {
-        const int ly = ly0 + TL_RPI * it;
-        if (!tl_on_ring(ly, lx)) continue;
-        const uint32_t d = tl_dir_of(dirs, it);
-        const uint32_t slot = (uint32_t)(tile * TL_RING + tl_ring_pos(ly, lx));
+    // (3) ring cells publish their reduced-graph node
+    if (ri >= 0) {
+        const uint32_t slot = tile * TL_RING + threadIdx.x;
         uint32_t nx = slot, rh = 0, ch = 0, term = SLOT_INVALID, th = 0;
-        if (d != PFD_DIR_NODATA && !((inv >> it) & 1u)) {
-            const uint32_t ti = s.A[TP_N(own[it])];
-            const uint32_t dist = TP_H(own[it]);
+        const uint32_t p = s.P[ri];
+        const uint32_t root = TP_N(p);
+        if (rd != PFD_DIR_NODATA && s.P[root] == root) {
+            const uint32_t ti = s.A[root];
+            const uint32_t dist = TP_H(p);
             if (ti & TERM_PIT) {
                 term = ti;
                 th = dist;
@@ -396,11 +431,32 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
                         int32_t* __restrict__ uparea_out) {
     constexpr int TL_CPT = TL_CELLS / THREADS, TL_RPI = THREADS / TL_W;
     __shared__ TileSharedC s;
-    const long long tile = ((long long)blockIdx.y + 1) * ntx + blockIdx.x;  // +1: halo tile row
+    const uint32_t tile = (uint32_t)(((long long)blockIdx.y + 1) * ntx + blockIdx.x);  // +1: halo tile row
     const long long r0 = (long long)blockIdx.y * TL_H, c0 = (long long)blockIdx.x * TL_W;
     const int lx = threadIdx.x & (TL_W - 1);
     const int ly0 = threadIdx.x >> 6;
+    const long long g00 = r0 * ncol + c0;
 
+    // one thread per ring position: everything it needs from global memory is requested up front, together with
+    // the per-cell loads below (entry inflow; for exit cells the solution of the entry cell they drain into)
+    int ri = -1;
+    uint32_t rd = PFD_DIR_NODATA, rloc = TL_LOC_INVALID, rw = 0, rbasin = 0;
+    int32_t rrank = -1;
+    if (threadIdx.x < TL_NRING) {
+        ri = tl_ring_cell(threadIdx.x);
+        const int ly = ri >> 6, lxr = ri & (TL_W - 1);
+        if (r0 + ly < nrow && c0 + lxr < ncol) {
+            const long long g = g00 + (long long)ly * ncol + lxr;
+            rd = __ldg(dir + g);
+            rloc = __ldg(loc + g);
+            if (uparea_out) rw = __ldg(inflow + tile * TL_RING + threadIdx.x);
+            if (rd < 8u && rloc == (uint32_t)ri) {  // exit cell
+                const uint32_t slot = tl_exit_slot(tile, (uint32_t)ntx, ly, lxr, rd);
+                rrank = __ldg(s_rank + slot);
+                rbasin = __ldg(s_basin + slot);
+            }
+        }
+    }
     uint32_t dirs[(TL_CPT + 3) / 4], own[TL_CPT], up[TL_CPT];
     tl_load_dirs<THREADS>(dir, nrow, ncol, r0, c0, dirs);
     if (threadIdx.x == 0) s.wl_count = 0;
@@ -408,26 +464,19 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
     for (int it = 0; it < TL_CPT; ++it) {
         const int ly = ly0 + TL_RPI * it;
         const int i = ly * TL_W + lx;
-        const long long r = r0 + ly, c = c0 + lx;
-        const bool inside = r < nrow && c < ncol;
-        own[it] = inside ? __ldg(loc + r * ncol + c) : TL_LOC_INVALID;
-        up[it] = (inside && uparea_out) ? __ldg(cnt + r * ncol + c) : 0u;
+        const bool inside = r0 + ly < nrow && c0 + lx < ncol;
+        const long long g = g00 + (long long)ly * ncol + lx;
+        own[it] = inside ? __ldg(loc + g) : TL_LOC_INVALID;
+        up[it] = (inside && uparea_out) ? __ldg(cnt + g) : 0u;
         s.dir[i] = (uint8_t)tl_dir_of(dirs, it);
         s.X[i] = 0;
     }
     __syncthreads();
     // entry cells with outside inflow become walkers
-#pragma unroll
-    for (int it = 0; it < TL_CPT; ++it) {
-        const int ly = ly0 + TL_RPI * it;
-        if (uparea_out && tl_on_ring(ly, lx) && own[it] != TL_LOC_INVALID) {
-            const uint32_t w = __ldg(inflow + tile * TL_RING + tl_ring_pos(ly, lx));
-            if (w) {
-                const uint32_t k = atomicAdd(&s.wl_count, 1u);
-                s.wl_cell[k] = (uint32_t)(ly * TL_W + lx);
-                s.wl_w[k] = w;
-            }
-        }
+    if (ri >= 0 && rw != 0u && rloc != TL_LOC_INVALID) {
+        const uint32_t k = atomicAdd(&s.wl_count, 1u);
+        s.wl_cell[k] = (uint32_t)ri;
+        s.wl_w[k] = rw;
     }
     __syncthreads();
     if (threadIdx.x < s.wl_count) {
@@ -444,33 +493,26 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 #pragma unroll
     for (int it = 0; it < TL_CPT; ++it) up[it] += s.X[(ly0 + TL_RPI * it) * TL_W + lx];
     __syncthreads();
-    // terminals publish (rank at the terminal, basin id)
+    // terminals publish (rank at the terminal, basin id): pits by their owner, exit cells by the ring threads
 #pragma unroll
     for (int it = 0; it < TL_CPT; ++it) {
-        const int ly = ly0 + TL_RPI * it;
-        const int i = ly * TL_W + lx;
         const uint32_t d = tl_dir_of(dirs, it);
-        if (d != PFD_DIR_NODATA && own[it] == (uint32_t)i) {
-            uint32_t rk, b;
-            if (d < 8u) {  // exit cell: one hop above the entry cell of the neighbouring tile
-                const uint32_t slot = tl_slot_of(r0 + ly + pfd_slot_dr((int)d), c0 + lx + pfd_slot_dc((int)d), ntx);
-                const int32_t rs = __ldg(s_rank + slot);
-                rk = (rs < 0) ? 0xFFFFFFFFu : (uint32_t)(rs + 1);
-                b = (rs < 0) ? 0u : __ldg(s_basin + slot);
-            } else {
-                rk = 0;
-                b = basin_out ? basin_out[(r0 + ly) * ncol + c0 + lx] : 0u;  // stashed by stash_pit_ids_kernel
-            }
-            s.T[i] = rk;
-            s.X[i] = b;
+        if (d == PFD_DIR_PIT || d == PFD_DIR_FPIT) {
+            const int ly = ly0 + TL_RPI * it;
+            const int i = ly * TL_W + lx;
+            s.T[i] = 0;
+            s.X[i] = basin_out ? basin_out[g00 + (long long)ly * ncol + lx] : 0u;  // stashed by stash_pit_ids_kernel
         }
+    }
+    if (ri >= 0 && rd < 8u && rloc == (uint32_t)ri) {  // exit cell: one hop above the entry cell of the neighbouring tile
+        s.T[ri] = (rrank < 0) ? 0xFFFFFFFFu : (uint32_t)(rrank + 1);
+        s.X[ri] = (rrank < 0) ? 0u : rbasin;
     }
     __syncthreads();
 #pragma unroll
     for (int it = 0; it < TL_CPT; ++it) {
         const int ly = ly0 + TL_RPI * it;
-        const long long r = r0 + ly, c = c0 + lx;
-        if (r >= nrow || c >= ncol) continue;
+        if (r0 + ly >= nrow || c0 + lx >= ncol) continue;
         const uint32_t d = tl_dir_of(dirs, it);
         int32_t rk = -9999, ua = -9999;
         uint32_t b = 0;
@@ -487,7 +529,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
                 }
             }
         }
-        const long long g = r * ncol + c;
+        const long long g = g00 + (long long)ly * ncol + lx;
         if (rank_out) rank_out[g] = rk;
         if (basin_out) basin_out[g] = b;
         if (uparea_out) uparea_out[g] = ua;
