@@ -1,0 +1,112 @@
+"""GPU tests at BASELINE.json sizes. The CPU oracle takes ~6 s at 8192^2 and minutes beyond, so parity at full
+size is established through
+  * the oracle itself at 2048^2 (seconds),
+  * size-independent properties of the reference's definitions checked with numpy on the full outputs:
+        rank[i]   == rank[ds[i]] + 1           (core.py:17-47; pits 0)
+        basins[i] == basins[ds[i]]             (core.py:120-146)
+        uparea[i] == 1 + sum(uparea[upstream]) (streams.py:15-41)  <=>  scatter-add of uparea over ds
+        sum(uparea[pits]) == number of cells that drain to a pit
+  * agreement of the two independent device implementations (tile solver vs level-synchronous BFS + sweeps),
+  * agreement of the row-tiled multi-rank solve with the single-GPU solve."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _synth_on_device(size, seed, sea_quantile=None):
+    from pyflwdir_b200 import _device, _lib
+
+    dev = _device.DeviceGraph(0)
+    l = _lib.lib()
+    z = np.empty((size, size), np.float32)
+    d8 = np.empty((size, size), np.uint8)
+    octaves = max(1, int(np.log2(size)) - 2)
+    _lib.check(l.pfd_synth_elevation(dev._h, size, size, size, octaves, seed, _lib.ptr(z)), dev._h)
+    sea = float(np.quantile(z[::16, ::16], sea_quantile)) if sea_quantile else -np.inf
+    _lib.check(l.pfd_synth_d8(dev._h, _lib.ptr(z), size, size, C.c_float(sea), _lib.ptr(d8)), dev._h)
+    return d8, z
+
+
+def _check_properties(d8, ids, rank, upa, bas, n_pits):
+    n = d8.size
+    ids = ids.astype(np.int64)
+    idx = np.arange(n, dtype=np.int64)
+    valid = ids >= 0
+    pit = valid & (ids == idx)
+    link = valid & ~pit
+    assert int(pit.sum()) == n_pits
+    assert np.all(rank[~valid] == -9999) and np.all(rank[pit] == 0) and np.all(rank[valid] >= 0)  # acyclic by construction
+    assert np.all(rank[link] == rank[ids[link]] + 1)
+    assert np.all(bas[link] == bas[ids[link]]) and np.all(bas[~valid] == 0)
+    assert np.array_equal(bas[pit], np.arange(1, n_pits + 1, dtype=np.uint32))  # pit order = ascending index
+    # uparea: every cell = 1 + sum over cells draining into it
+    inflow = np.zeros(n, dtype=np.int64)
+    np.add.at(inflow, ids[link], upa[link].astype(np.int64))
+    assert np.array_equal(upa[valid].astype(np.int64), 1 + inflow[valid])
+    assert np.all(upa[~valid] == -9999)
+    assert int(upa[pit].astype(np.int64).sum()) == int(valid.sum())
+
+
+def test_oracle_parity_2048():
+    import pyflwdir_b200 as pfb
+
+    d8, _ = _synth_on_device(2048, 5, sea_quantile=0.04)
+    flw = pfb.from_array(d8, ftype="d8")
+    ids, pits, _ = oracle.core_d8.from_array(d8, dtype=np.int32)
+    seq = oracle.core.idxs_seq(ids, pits)
+    assert np.array_equal(flw.idxs_ds, ids) and np.array_equal(flw.idxs_pit, pits)
+    assert np.array_equal(flw.idxs_seq, seq)
+    assert np.array_equal(flw.rank.ravel(), oracle.core.rank(ids)[0])
+    upa = oracle.streams.accuflux(ids, seq, np.ones(d8.size, np.int32), -9999)
+    upa[ids == -1] = -9999
+    assert np.array_equal(flw.upstream_area().ravel(), upa)
+    assert np.array_equal(flw.basins().ravel(), oracle.basins.basins(ids, pits, seq))
+    assert np.array_equal(flw.stream_order().ravel(), oracle.streams.strahler_order(ids, seq))
+
+
+@pytest.mark.parametrize("size", [8192])
+def test_properties_full_size(size):
+    """BASELINE configs[1] size through pfd_d8_flow_all (the benchmarked call), both solvers."""
+    from pyflwdir_b200 import _device, _lib
+
+    d8, _ = _synth_on_device(size, 0)
+    res = {}
+    for tiles in (1, 0):
+        dev = _device.DeviceGraph(0)
+        dev.set_option("tiles", tiles)
+        n = d8.size
+        ids = np.empty(n, np.int32)
+        rank = np.empty(n, np.int32)
+        upa = np.empty(n, np.int32)
+        bas = np.empty(n, np.uint32)
+        nv, npit, nn = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(_lib.lib().pfd_d8_flow_all(dev._h, _lib.ptr(d8), size, size, _lib.ptr(ids), _lib.dtype_code(np.int32),
+                                             _lib.ptr(rank), _lib.ptr(upa), _lib.ptr(bas), C.byref(nv), C.byref(npit),
+                                             C.byref(nn)), dev._h)
+        res[tiles] = (ids, rank, upa, bas, nv.value, npit.value, nn.value)
+        dev.close()
+    ids, rank, upa, bas, nv, npit, nn = res[1]
+    assert nv == n and nn == n  # no nodata, acyclic
+    _check_properties(d8, ids, rank, upa, bas, npit)
+    for a, b in zip(res[1], res[0]):
+        assert np.array_equal(a, b), "tile solver and BFS + sweeps disagree"
+
+
+def test_tiled_equals_single_gpu_4096():
+    """Row-tiled solve (5 emulated ranks) == single-GPU solve on a 4096 x 2048 raster with a sea."""
+    import pyflwdir_b200 as pfb
+    from pyflwdir_b200 import tiled
+
+    d8, _ = _synth_on_device(4096, 3, sea_quantile=0.03)
+    d8 = np.ascontiguousarray(d8[:, :2048])
+    flw = pfb.from_array(d8, ftype="d8")
+    got = tiled.solve_emulated(d8, 5)
+    assert np.array_equal(got["idxs_ds"], flw.idxs_ds)
+    assert np.array_equal(got["rank"], flw.rank)
+    assert np.array_equal(got["uparea"], flw.upstream_area())
+    assert np.array_equal(got["basins"], flw.basins())
