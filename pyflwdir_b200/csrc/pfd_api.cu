@@ -131,6 +131,8 @@ extern "C" int pfd_create(int device, pfd_handle** out) {
     cudaEventCreate(&h->ev_timer[1]);
     cudaEventCreate(&h->ev_total[0]);
     cudaEventCreate(&h->ev_total[1]);
+    cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     *out = h;
     return PFD_OK;
 }
@@ -144,7 +146,7 @@ extern "C" void pfd_destroy(pfd_handle* h) {
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->dir, &h->upmask, &h->pits, &h->pit_outlet, &h->seq, &h->bseq, &h->rank, &h->basins,
                       &h->level_off, &h->bfs_state, &h->chunk_status, &h->blk_counts, &h->blk_offsets, &h->counters,
-                      &h->segs, &h->tslots, &h->uparea, &h->tile_loc, &h->tile_cnt, &h->btab, &h->bgraph, &h->mg_counts};
+                      &h->segs, &h->tslots, &h->uparea, &h->tile_loc, &h->btab, &h->bgraph, &h->mg_counts};
     for (DevBuf* b : bufs) pfd_release(*b);
     for (DevBuf& b : h->scratch) pfd_release(b);
     for (int s = 0; s < PFD_NSTAGE; ++s) {
@@ -155,6 +157,9 @@ extern "C" void pfd_destroy(pfd_handle* h) {
     cudaEventDestroy(h->ev_timer[1]);
     cudaEventDestroy(h->ev_total[0]);
     cudaEventDestroy(h->ev_total[1]);
+    cudaEventDestroy(h->ev_copy);
+    cudaStreamSynchronize(h->copy_stream);
+    cudaStreamDestroy(h->copy_stream);
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -322,7 +327,9 @@ static int check_shape(pfd_handle* h, int64_t nrow, int64_t ncol, const char* wh
     return PFD_OK;
 }
 
-static int parse_impl(pfd_handle* h, const uint8_t* d8, int64_t nrow, int64_t ncol, void* idxs_ds_out, int idx_dtype) {
+// overlap_idxs_copy: the D2H copy of idxs_ds runs on the handle's copy stream (the caller joins it later)
+static int parse_impl(pfd_handle* h, const uint8_t* d8, int64_t nrow, int64_t ncol, void* idxs_ds_out, int idx_dtype,
+                      bool overlap_idxs_copy = false) {
     PFD_TRY(check_shape(h, nrow, ncol, "pfd_d8_parse"));
     if (!d8) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_d8_parse: d8 is null");
     if (idxs_ds_out && idx_dtype != PFD_I32 && idx_dtype != PFD_U32 && idx_dtype != PFD_I64)
@@ -337,7 +344,15 @@ static int parse_impl(pfd_handle* h, const uint8_t* d8, int64_t nrow, int64_t nc
     const size_t ibytes = (size_t)n * pfd_dtype_size(idx_dtype);
     if (idxs_ds_out) PFD_TRY(pfd_stage_out(h, idxs_ds_out, ibytes, 1, &idxs_dev));
     PFD_TRY(parse_device(h, (const uint8_t*)d8_dev, nrow, ncol, idxs_dev, idx_dtype));
-    if (idxs_ds_out) PFD_TRY(pfd_finish_out(h, idxs_ds_out, idxs_dev, ibytes));
+    if (idxs_ds_out && idxs_dev != idxs_ds_out) {
+        if (overlap_idxs_copy) {
+            // parse_device ended with a stream synchronisation (pit counters), so the staging buffer is complete
+            PFD_CUDA(h, cudaMemcpyAsync(idxs_ds_out, idxs_dev, ibytes, cudaMemcpyDeviceToHost, h->copy_stream));
+            h->copy_pending = true;
+        } else {
+            PFD_TRY(pfd_finish_out(h, idxs_ds_out, idxs_dev, ibytes));
+        }
+    }
     return PFD_OK;
 }
 
@@ -455,8 +470,7 @@ static int tiles_setup(pfd_handle* h, TileCtx& T, bool with_init_copy) {
     }
     T.flag = (unsigned int*)(base + (size_t)T.nslots * a);
     T.dir = (const uint8_t*)h->dir.p + h->dir_off;
-    PFD_TRY(pfd_reserve(h, h->tile_loc, (size_t)h->n * sizeof(uint32_t)));
-    PFD_TRY(pfd_reserve(h, h->tile_cnt, (size_t)h->n * sizeof(uint32_t)));
+    PFD_TRY(pfd_reserve(h, h->tile_loc, (size_t)h->n * sizeof(uint2)));  // (loc, cnt) per cell
     return PFD_OK;
 }
 
@@ -473,8 +487,8 @@ static int tiles_phase_a(pfd_handle* h, TileCtx& T, uint32_t* basin_dev, unsigne
         PFD_LAUNCH_CHECK(h);
     }
     tile_phase_a_kernel<TLA_THREADS, TLA_MINBLOCKS><<<grid, TLA_THREADS, 0, h->stream>>>(
-        T.dir, h->nrow, h->ncol, T.ntx, basin_dev, (uint32_t*)h->tile_loc.p, (uint32_t*)h->tile_cnt.p, T.B[0].acc,
-        T.B[0].nxt, T.B[0].rh, T.B[0].ch, T.term, T.term_h);
+        T.dir, h->nrow, h->ncol, T.ntx, basin_dev, (uint2*)h->tile_loc.p, T.B[0].acc, T.B[0].nxt, T.B[0].rh, T.B[0].ch,
+        T.term, T.term_h);
     PFD_LAUNCH_CHECK(h);
     return PFD_OK;
 }
@@ -518,8 +532,8 @@ static int tiles_phase_c(pfd_handle* h, TileCtx& T, int32_t* rank_dev, uint32_t*
     StageTimer t(h, PFD_STAGE_TILE_C);
     const dim3 grid((unsigned)T.ntx, (unsigned)T.nty);
     tile_phase_c_kernel<TLC_THREADS, TLC_MINBLOCKS><<<grid, TLC_THREADS, 0, h->stream>>>(
-        T.dir, h->nrow, h->ncol, T.ntx, (const uint32_t*)h->tile_loc.p, (const uint32_t*)h->tile_cnt.p, T.B[0].acc,
-        T.srank, T.sbasin, rank_dev, basin_dev, uparea_dev);
+        T.dir, h->nrow, h->ncol, T.ntx, (const uint2*)h->tile_loc.p, T.B[0].acc, T.srank, T.sbasin, rank_dev, basin_dev,
+        uparea_dev);
     PFD_LAUNCH_CHECK(h);
     return PFD_OK;
 }
@@ -1309,7 +1323,7 @@ extern "C" int pfd_d8_flow_all(pfd_handle* h, const uint8_t* d8, int64_t nrow, i
     stage_reset(h);
     cudaEventRecord(h->ev_start[PFD_STAGE_TOTAL], h->stream);
     h->stage_used[PFD_STAGE_TOTAL] = true;
-    PFD_TRY(parse_impl(h, d8, nrow, ncol, idxs_ds_out, idx_dtype));
+    PFD_TRY(parse_impl(h, d8, nrow, ncol, idxs_ds_out, idx_dtype, /*overlap_idxs_copy=*/true));
     if (h->n_pits == 0) return pfd_fail(h, PFD_ERR_NO_PITS, "Invalid FlwdirRaster: no pits found");
     const size_t b4 = (size_t)h->n * 4;
     if (tiles_usable(h)) {
@@ -1340,6 +1354,11 @@ extern "C" int pfd_d8_flow_all(pfd_handle* h, const uint8_t* d8, int64_t nrow, i
             PFD_TRY(uparea_cells_device(h, (int32_t*)out_dev));
             PFD_TRY(pfd_finish_out(h, uparea_out, out_dev, b4));
         }
+    }
+    if (h->copy_pending) {  // join the overlapped idxs_ds copy: the timed region ends when BOTH streams are done
+        PFD_CUDA(h, cudaEventRecord(h->ev_copy, h->copy_stream));
+        PFD_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
+        h->copy_pending = false;
     }
     cudaEventRecord(h->ev_stop[PFD_STAGE_TOTAL], h->stream);
     PFD_CUDA(h, cudaStreamSynchronize(h->stream));

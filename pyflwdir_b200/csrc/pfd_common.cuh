@@ -120,7 +120,7 @@ struct pfd_handle {
     int mg_rank = 0, mg_nranks = 0, mg_halo_top = 0, mg_halo_bot = 0;
     uint32_t* mg_basins = nullptr;
     void* nccl_comm = nullptr;
-    DevBuf tile_loc, tile_cnt; // uint32 [n] each: per cell (local terminal | hops << 12), in-tile subtree size
+    DevBuf tile_loc;           // uint2 [n]: per cell (local terminal | hops << 12, in-tile subtree size)
     DevBuf uparea;            // int32 [n] cached cell-count upstream area (tile solver)
     bool have_uparea = false;
     int use_tiles = 1;        // option "tiles": 1 = tile-hierarchical solver for rank/basins/uparea, 0 = BFS + sweeps
@@ -142,6 +142,9 @@ struct pfd_handle {
     cudaEvent_t ev_stop[PFD_NSTAGE] = {};
     cudaEvent_t ev_timer[2] = {};
     cudaEvent_t ev_total[2] = {};
+    cudaEvent_t ev_copy = nullptr;
+    cudaStream_t copy_stream = nullptr;  // D2H copies that overlap compute (pfd_d8_flow_all)
+    bool copy_pending = false;
 };
 
 static thread_local std::string g_last_error;

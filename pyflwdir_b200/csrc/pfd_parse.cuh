@@ -115,23 +115,32 @@ __global__ void __launch_bounds__(256) parse_kernel(const uint8_t* __restrict__ 
         if (IDXMODE != 0 && r >= out_row0 && r < out_row0 + out_nrow) {
             const int64_t o0 = (r - out_row0) * ncol + c;       // position in the output block
             const int64_t g0 = (r - out_row0 + glob_row0) * ncol + c;  // global index of my first cell
-            int64_t ds[4];
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const uint32_t d = (dirw >> (8 * b)) & 0xFFu;
-                const int64_t i = g0 + b;
-                ds[b] = (d < 8u) ? i + pfd_slot_off((int)d, ncol) : ((d == PFD_DIR_NODATA) ? (int64_t)-1 : i);
-            }
             if (IDXMODE == 1) {
+                // 32-bit outputs: wrap-around 32-bit arithmetic gives the right low word for int32 and uint32 alike
+                const uint32_t g32 = (uint32_t)g0, nc32 = (uint32_t)ncol;
+                uint32_t d32[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const uint32_t d = (dirw >> (8 * b)) & 0xFFu;
+                    const uint32_t off = (uint32_t)pfd_slot_dr((int)(d & 7u)) * nc32 + (uint32_t)pfd_slot_dc((int)(d & 7u));
+                    d32[b] = (d < 8u) ? g32 + b + off : ((d == PFD_DIR_NODATA) ? 0xFFFFFFFFu : g32 + b);
+                }
                 uint32_t* o = reinterpret_cast<uint32_t*>(idxs_out) + o0;
                 if (ALIGNED) {
-                    *reinterpret_cast<uint4*>(o) = make_uint4((uint32_t)ds[0], (uint32_t)ds[1], (uint32_t)ds[2], (uint32_t)ds[3]);
+                    *reinterpret_cast<uint4*>(o) = make_uint4(d32[0], d32[1], d32[2], d32[3]);
                 } else {
 #pragma unroll
                     for (int b = 0; b < 4; ++b)
-                        if (c + b < ncol) o[b] = (uint32_t)ds[b];
+                        if (c + b < ncol) o[b] = d32[b];
                 }
             } else {
+                int64_t ds[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const uint32_t d = (dirw >> (8 * b)) & 0xFFu;
+                    const int64_t i = g0 + b;
+                    ds[b] = (d < 8u) ? i + pfd_slot_off((int)d, ncol) : ((d == PFD_DIR_NODATA) ? (int64_t)-1 : i);
+                }
                 int64_t* o = reinterpret_cast<int64_t*>(idxs_out) + o0;
                 if (ALIGNED) {
                     *reinterpret_cast<longlong2*>(o) = make_longlong2(ds[0], ds[1]);

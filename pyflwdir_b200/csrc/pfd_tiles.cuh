@@ -162,7 +162,7 @@ __device__ __forceinline__ void tl_local_solve(TileShared& s, const uint32_t* di
 #pragma unroll
         for (int it = 0; it < TL_CPT; ++it) {
             if (active & (1u << it)) {
-                if (a[it]) atomicAdd(&s.A[TP_N(own[it])], a[it]);
+                atomicAdd(&s.A[TP_N(own[it])], a[it]);
                 const uint32_t h = two_k + TP_H(pn[it]);
                 own[it] = TP_PACK(TP_N(pn[it]), h);
                 s.P[(ly0 + TL_RPI * it) * TL_W + lx] = own[it];
@@ -200,8 +200,7 @@ __device__ __forceinline__ void tl_load_dirs(const uint8_t* __restrict__ dir, lo
 template <int THREADS, int MINBLOCKS>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
     tile_phase_a_kernel(const uint8_t* __restrict__ dir, long long nrow, long long ncol, long long ntx,
-                        const uint32_t* pit_ids, uint32_t* __restrict__ loc, uint32_t* __restrict__ cnt,
-                        uint32_t* __restrict__ W, uint32_t* __restrict__ s_nxt, uint32_t* __restrict__ s_rh,
+                        const uint32_t* pit_ids, uint2* __restrict__ loccnt, uint32_t* __restrict__ W, uint32_t* __restrict__ s_nxt, uint32_t* __restrict__ s_rh,
                         uint32_t* __restrict__ s_ch, uint32_t* __restrict__ s_term, uint32_t* __restrict__ s_term_h) {
     constexpr int TL_CPT = TL_CELLS / THREADS, TL_RPI = THREADS / TL_W;
     __shared__ TileShared s;
@@ -226,8 +225,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
         const bool inv = s.P[root] != root;  // a terminal is (next = itself, hops = 0)
         if (r0 + ly < nrow && c0 + lx < ncol) {
             const long long g = g00 + (long long)ly * ncol + lx;
-            loc[g] = inv ? TL_LOC_INVALID : own[it];
-            cnt[g] = s.A[i];
+            loccnt[g] = make_uint2(inv ? TL_LOC_INVALID : own[it], s.A[i]);  // (local terminal | hops, in-tile count)
         }
     }
     __syncthreads();
@@ -415,18 +413,20 @@ __global__ void __launch_bounds__(256) slots_finalize_kernel(SlotBuf b0, SlotBuf
 // ---------------------------------------------------------------------------------------------------------
 struct TileSharedC {
     uint32_t X[TL_CELLS];   // extra inflow per cell, later basin id per terminal
-    uint32_t T[TL_CELLS];   // rank at the terminal
-    uint8_t dir[TL_CELLS];
+    uint32_t T[TL_CELLS];   // in-tile successor while the walkers run, then rank at the terminal
     uint32_t wl_cell[TL_RING];  // walker list
     uint32_t wl_w[TL_RING];
+    uint32_t ring_t[TL_RING];   // per ring position: rank at the terminal if the cell is an exit cell, else TL_NOT_EXIT
+    uint32_t ring_b[TL_RING];   //                    basin id behind that exit
+    uint32_t ring_w[TL_RING];   //                    outside inflow of the (entry) cell
     uint32_t wl_count;
 };
+#define TL_NOT_EXIT 0xFFFFFFFEu
 
 template <int THREADS, int MINBLOCKS>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
     tile_phase_c_kernel(const uint8_t* __restrict__ dir, long long nrow, long long ncol, long long ntx,
-                        const uint32_t* __restrict__ loc, const uint32_t* __restrict__ cnt,
-                        const uint32_t* __restrict__ inflow, const int32_t* __restrict__ s_rank,
+                        const uint2* __restrict__ loccnt, const uint32_t* __restrict__ inflow, const int32_t* __restrict__ s_rank,
                         const uint32_t* __restrict__ s_basin, int32_t* __restrict__ rank_out, uint32_t* basin_out,
                         int32_t* __restrict__ uparea_out) {
     constexpr int TL_CPT = TL_CELLS / THREADS, TL_RPI = THREADS / TL_W;
@@ -439,23 +439,26 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 
     // one thread per ring position: everything it needs from global memory is requested up front, together with
     // the per-cell loads below (entry inflow; for exit cells the solution of the entry cell they drain into)
-    int ri = -1;
-    uint32_t rd = PFD_DIR_NODATA, rloc = TL_LOC_INVALID, rw = 0, rbasin = 0;
-    int32_t rrank = -1;
+    // (the results are parked in shared memory so that they do not occupy registers across the kernel)
     if (threadIdx.x < TL_NRING) {
-        ri = tl_ring_cell(threadIdx.x);
+        const int ri = tl_ring_cell(threadIdx.x);
         const int ly = ri >> 6, lxr = ri & (TL_W - 1);
+        uint32_t rw = 0, rt = TL_NOT_EXIT, rb = 0;
         if (r0 + ly < nrow && c0 + lxr < ncol) {
             const long long g = g00 + (long long)ly * ncol + lxr;
-            rd = __ldg(dir + g);
-            rloc = __ldg(loc + g);
-            if (uparea_out) rw = __ldg(inflow + tile * TL_RING + threadIdx.x);
+            const uint32_t rd = __ldg(dir + g);
+            const uint32_t rloc = __ldg(&loccnt[g].x);
+            if (uparea_out && rloc != TL_LOC_INVALID) rw = __ldg(inflow + tile * TL_RING + threadIdx.x);
             if (rd < 8u && rloc == (uint32_t)ri) {  // exit cell
                 const uint32_t slot = tl_exit_slot(tile, (uint32_t)ntx, ly, lxr, rd);
-                rrank = __ldg(s_rank + slot);
-                rbasin = __ldg(s_basin + slot);
+                const int32_t rrank = __ldg(s_rank + slot);
+                rt = (rrank < 0) ? 0xFFFFFFFFu : (uint32_t)(rrank + 1);
+                rb = (rrank < 0) ? 0u : __ldg(s_basin + slot);
             }
         }
+        s.ring_w[threadIdx.x] = rw;
+        s.ring_t[threadIdx.x] = rt;
+        s.ring_b[threadIdx.x] = rb;
     }
     uint32_t dirs[(TL_CPT + 3) / 4], own[TL_CPT], up[TL_CPT];
     tl_load_dirs<THREADS>(dir, nrow, ncol, r0, c0, dirs);
@@ -466,29 +469,35 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
         const int i = ly * TL_W + lx;
         const bool inside = r0 + ly < nrow && c0 + lx < ncol;
         const long long g = g00 + (long long)ly * ncol + lx;
-        own[it] = inside ? __ldg(loc + g) : TL_LOC_INVALID;
-        up[it] = (inside && uparea_out) ? __ldg(cnt + g) : 0u;
-        s.dir[i] = (uint8_t)tl_dir_of(dirs, it);
+        const uint2 lc = inside ? __ldg(loccnt + g) : make_uint2(TL_LOC_INVALID, 0u);
+        own[it] = lc.x;
+        up[it] = lc.y;
         s.X[i] = 0;
+        s.T[i] = (uint32_t)tl_local_next(i, tl_dir_of(dirs, it));  // in-tile successor, for the walkers below
     }
     __syncthreads();
     // entry cells with outside inflow become walkers
-    if (ri >= 0 && rw != 0u && rloc != TL_LOC_INVALID) {
-        const uint32_t k = atomicAdd(&s.wl_count, 1u);
-        s.wl_cell[k] = (uint32_t)ri;
-        s.wl_w[k] = rw;
+    if (threadIdx.x < TL_NRING) {
+        const uint32_t my_w = s.ring_w[threadIdx.x];
+        if (my_w != 0u) {
+            const uint32_t k = atomicAdd(&s.wl_count, 1u);
+            s.wl_cell[k] = (uint32_t)tl_ring_cell(threadIdx.x);
+            s.wl_w[k] = my_w;
+        }
     }
     __syncthreads();
+#ifndef TL_EXPERIMENT_NOWALK
     if (threadIdx.x < s.wl_count) {
         int i = (int)s.wl_cell[threadIdx.x];
         const uint32_t w = s.wl_w[threadIdx.x];
         for (int step = 0; step < TL_CELLS; ++step) {
             atomicAdd(&s.X[i], w);
-            const int ni = tl_local_next(i, s.dir[i]);
+            const int ni = (int)s.T[i];
             if (ni == i) break;
             i = ni;
         }
     }
+#endif
     __syncthreads();
 #pragma unroll
     for (int it = 0; it < TL_CPT; ++it) up[it] += s.X[(ly0 + TL_RPI * it) * TL_W + lx];
@@ -504,9 +513,10 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
             s.X[i] = basin_out ? basin_out[g00 + (long long)ly * ncol + lx] : 0u;  // stashed by stash_pit_ids_kernel
         }
     }
-    if (ri >= 0 && rd < 8u && rloc == (uint32_t)ri) {  // exit cell: one hop above the entry cell of the neighbouring tile
-        s.T[ri] = (rrank < 0) ? 0xFFFFFFFFu : (uint32_t)(rrank + 1);
-        s.X[ri] = (rrank < 0) ? 0u : rbasin;
+    if (threadIdx.x < TL_NRING && s.ring_t[threadIdx.x] != TL_NOT_EXIT) {  // exit cell: one hop above the entry cell
+        const int ri = tl_ring_cell(threadIdx.x);                           // of the neighbouring tile
+        s.T[ri] = s.ring_t[threadIdx.x];
+        s.X[ri] = s.ring_b[threadIdx.x];
     }
     __syncthreads();
 #pragma unroll
