@@ -67,7 +67,7 @@ class DeviceGraph:
         idxs = None
         code = 0
         if want_idxs:
-            idxs = np.empty(d8.size, dtype=idx_dtype)
+            idxs = _lib.out_array(d8.size, idx_dtype)
             code = _lib.dtype_code(idx_dtype)
         self._ck(self._l.pfd_d8_parse(self._h, _lib.ptr(d8), nrow, ncol, 1, _lib.ptr(idxs), code,
                                       C.byref(nv), C.byref(npit), C.byref(nout)))
@@ -99,7 +99,7 @@ class DeviceGraph:
     def fetch(self, which, idx_dtype=np.int32):
         code = 0
         if which == _lib.ARR_IDXS_DS:
-            out = np.empty(self.size, dtype=idx_dtype)
+            out = _lib.out_array(self.size, idx_dtype)
             code = _lib.dtype_code(idx_dtype)
         elif which == _lib.ARR_PITS:
             out = np.empty(self.n_pits, dtype=idx_dtype)
@@ -109,14 +109,14 @@ class DeviceGraph:
         elif which == _lib.ARR_SEQ:
             if self.nnodes is None:
                 self.order()
-            out = np.empty(self.nnodes, dtype=idx_dtype)
+            out = _lib.out_array(self.nnodes, idx_dtype)
             code = _lib.dtype_code(idx_dtype)
         elif which == _lib.ARR_RANK:
-            out = np.empty(self.size, dtype=np.int32)
+            out = _lib.out_array(self.size, np.int32)
         elif which == _lib.ARR_N_UPSTREAM:
-            out = np.empty(self.size, dtype=np.int8)
+            out = _lib.out_array(self.size, np.int8)
         elif which == _lib.ARR_D8:
-            out = np.empty(self.size, dtype=np.uint8)
+            out = _lib.out_array(self.size, np.uint8)
         elif which == _lib.ARR_LEVEL_OFFSETS:
             if self.nlevels is None:
                 self.order()
@@ -137,20 +137,20 @@ class DeviceGraph:
         dt = data.dtype
         if dt == np.bool_:
             raise TypeError("accuflux: boolean data is not supported")
-        out = np.empty(data.size, dtype=dt)
+        out = _lib.out_array(data.size, dt)
         nd_f, nd_i, nd_is = nodata_args(nodata)
         self._ck(self._l.pfd_accuflux(self._h, _lib.ptr(data), _lib.dtype_code(dt), nd_f, nd_i, nd_is,
                                       0 if direction == "up" else 1, _lib.ptr(out)))
         return out
 
     def upstream_area_cells(self):
-        out = np.empty(self.size, dtype=np.int32)
+        out = _lib.out_array(self.size, np.int32)
         self._ck(self._l.pfd_upstream_area_cells(self._h, _lib.ptr(out)))
         return out
 
     def basins(self, idxs=None, ids=None):
         if idxs is None:
-            out = np.empty(self.size, dtype=np.uint32)
+            out = _lib.out_array(self.size, np.uint32)
             self._ck(self._l.pfd_basins(self._h, None, 0, 0, None, 0, _lib.ptr(out)))
             return out
         idxs = np.ascontiguousarray(idxs)
@@ -166,7 +166,7 @@ class DeviceGraph:
             if last.size != idxs.size:
                 keep = np.sort(idxs.size - 1 - last)
                 idxs, ids = np.ascontiguousarray(idxs[keep]), np.ascontiguousarray(ids[keep])
-        out = np.empty(self.size, dtype=ids.dtype)
+        out = _lib.out_array(self.size, ids.dtype)
         self._ck(self._l.pfd_basins(self._h, _lib.ptr(idxs), idxs.size, _lib.dtype_code(idxs.dtype), _lib.ptr(ids),
                                     _lib.dtype_code(ids.dtype), _lib.ptr(out)))
         return out
@@ -178,7 +178,7 @@ class DeviceGraph:
             m = m.view(np.uint8) if m.dtype == np.bool_ else (m != 0).astype(np.uint8)
             if m.size != self.size:
                 raise ValueError('"mask" size does not match.')
-        out = np.empty(self.size, dtype=np.uint8)
+        out = _lib.out_array(self.size, np.uint8)
         self._ck(self._l.pfd_strahler(self._h, _lib.ptr(m), _lib.ptr(out)))
         return out
 
@@ -190,7 +190,7 @@ class DeviceGraph:
             e = e.astype(np.float64)  # integer DEMs: differences are exact in float64
         if d.size != self.size or e.size != self.size:
             raise ValueError('"elevtn" size does not match.')
-        out = np.empty(self.size, dtype=np.float64)
+        out = _lib.out_array(self.size, np.float64)
         self._ck(self._l.pfd_hand(self._h, _lib.ptr(d), _lib.ptr(e), _lib.dtype_code(e.dtype), _lib.ptr(out)))
         return out
 

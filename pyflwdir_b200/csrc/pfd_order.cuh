@@ -7,15 +7,19 @@
 // position of its children. The concatenated levels are `seq`; rank = level number; the default basin id is
 // inherited from the parent (it travels in `bseq`, aligned with seq positions, so parents read it coalesced).
 //
-// One persistent cooperative kernel runs all levels: big levels are split into 2048-cell chunks that are
+// One persistent cooperative kernel runs all levels: big levels are split into 4096-cell chunks that are
 // scanned across CTAs with a decoupled look-back (status words tagged with the level, so no reset between
 // levels) followed by one grid.sync(); runs of tiny levels are walked by CTA 0 alone with __syncthreads()
 // only, so the long tail of the flow-path-length distribution costs ~one L2 round trip per level.
 #pragma once
 #include "pfd_common.cuh"
 
-#define BFS_THREADS 256
-#define BFS_ITEMS 8
+#ifndef BFS_THREADS
+#define BFS_THREADS 1024
+#endif
+#ifndef BFS_ITEMS
+#define BFS_ITEMS 4
+#endif
 #define BFS_CHUNK (BFS_THREADS * BFS_ITEMS)
 
 struct BfsState {

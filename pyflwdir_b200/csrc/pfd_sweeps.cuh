@@ -12,8 +12,12 @@
 #pragma once
 #include "pfd_common.cuh"
 
-#define SW_THREADS 256
-#define SW_SOLO_MAX 2048
+#ifndef SW_THREADS
+#define SW_THREADS 1024
+#endif
+#ifndef SW_SOLO_MAX
+#define SW_SOLO_MAX 4096
+#endif
 
 struct SweepSeg {
     int first;   // first level of the segment

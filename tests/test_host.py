@@ -125,3 +125,48 @@ def test_infer_ncol():
     assert F.resolve_shape(np.arange(12, dtype=np.int32), shape=(3, 4)) == (3, 4)
     with pytest.raises(ValueError, match="does not match"):
         F.resolve_shape(np.arange(12, dtype=np.int32), shape=(5, 4))
+
+
+def test_pinned_pool_recycles(monkeypatch):
+    """Result arrays come from a capped pool of page-locked blocks that are recycled when the array and all its
+    views are gone (host logic only: the allocator is faked)."""
+    import ctypes as C
+    import gc
+
+    from pyflwdir_b200 import _lib
+
+    class FakeLib:
+        def __init__(self):
+            self.bufs = {}
+
+        def pfd_host_alloc(self, n, pp):
+            b = (C.c_uint8 * n)()
+            self.bufs[C.addressof(b)] = b
+            pp._obj.value = C.addressof(b)
+            return 0
+
+        def pfd_host_free(self, p):
+            self.bufs.pop(p.value, None)
+            return 0
+
+    fake = FakeLib()
+    monkeypatch.setattr(_lib, "lib", lambda: fake)
+    monkeypatch.setenv("PFD_PINNED_POOL_MB", "16")
+    pool = _lib.PinnedPool()
+    a = pool.empty(1 << 20, np.int32)
+    a[:] = 7
+    v = a.reshape(1024, 1024)
+    assert pool.total == 4 << 20 and not pool.free
+    del a
+    gc.collect()
+    assert not pool.free and v.sum() == 7 * (1 << 20)   # the view keeps the block leased
+    del v
+    gc.collect()
+    assert len(pool.free) == 1
+    b = pool.empty(1 << 20, np.uint32)
+    assert not pool.free and pool.total == 4 << 20        # same block handed out again
+    c = pool.empty(3 << 20, np.int32)                      # 12 MiB more: 16 MiB cap reached exactly
+    d = pool.empty(1 << 20, np.int32)                      # over the cap -> ordinary pageable array
+    assert pool.total == 16 << 20 and d.flags.owndata
+    assert pool.empty(10, np.int32).flags.owndata           # tiny results are never pinned
+    del b, c, d
