@@ -351,25 +351,11 @@ def cpu_path(d8, repeat=1):
 
 
 def host_raster(size, seed):
-    """Synthetic raster on the host: generated by the CUDA generator when a GPU is present (input synthesis is
-    not the measured path), else by the bit-identical host generator."""
-    from pyflwdir_b200 import _lib
-
-    if _lib.device_count() > 0:
-        w = Workload.__new__(Workload)
-        w.L, w.l, w.n, w.cells = _lib, _lib.lib(), size, size * size
-        h = C.c_void_p()
-        _lib.check(w.l.pfd_create(0, C.byref(h)))
-        w.h = h
-        d8 = np.empty((size, size), np.uint8)
-        z_dev = w.dev_alloc(w.cells * 4)
-        w.ck(w.l.pfd_synth_elevation(h, size, size, size, octaves_for(size), seed, z_dev))
-        w.ck(w.l.pfd_synth_d8(h, z_dev, size, size, C.c_float(-np.inf), _lib.ptr(d8)))
-        w.l.pfd_destroy(h)
-        return d8, "synthetic (CUDA generator)"
+    """Synthetic raster built on the HOST (oracle generator, OpenMP over rows, bit-identical to the CUDA one):
+    the reference arm touches nothing of the GPU path."""
     import oracle
 
-    z = oracle.synth_elevation(size, size, seed=seed)
+    z = oracle.synth_elevation(size, size, seed=seed, octaves=octaves_for(size), nref=size)
     return oracle.synth_d8(z), "synthetic (host generator)"
 
 

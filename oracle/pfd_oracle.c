@@ -101,21 +101,75 @@ int orc_d8_check_values(const uint8_t* flwdir, int64_t size) {
 #undef SFX
 
 /* ---- synthetic input (not part of the reference): SURVEY.md §8(d) generator, host version ---- */
-void orc_synth_elevation(int64_t nrow, int64_t ncol, int64_t nref, int octaves, uint32_t seed, float* z) {
-    for (int64_t r = 0; r < nrow; ++r)
-        for (int64_t c = 0; c < ncol; ++c) z[r * ncol + c] = pfd_synth_z(r, c, nref, octaves, seed);
+/* The generator (NOT part of the measured path) is split over rows with pthreads so that the CPU-only reference arm
+ * of bench.py can build its 8192^2 input in seconds; every cell is computed independently, so the result does not
+ * depend on the thread count (ORC_SYNTH_THREADS, default = online cores, capped at 64). */
+#include <pthread.h>
+#include <unistd.h>
+
+typedef struct {
+    int64_t r0, r1, nrow, ncol, nref;
+    int octaves;
+    uint32_t seed;
+    float sea_level;
+    const float* zin;
+    float* z;
+    uint8_t* d8;
+} orc_synth_job;
+
+static void* orc_synth_elev_rows(void* arg) {
+    orc_synth_job* j = (orc_synth_job*)arg;
+    for (int64_t r = j->r0; r < j->r1; ++r)
+        for (int64_t c = 0; c < j->ncol; ++c) j->z[r * j->ncol + c] = pfd_synth_z(r, c, j->nref, j->octaves, j->seed);
+    return NULL;
 }
 
-void orc_synth_d8(const float* z, int64_t nrow, int64_t ncol, float sea_level, uint8_t* d8) {
-    for (int64_t r = 0; r < nrow; ++r)
+static void* orc_synth_d8_rows(void* arg) {
+    orc_synth_job* j = (orc_synth_job*)arg;
+    const int64_t nrow = j->nrow, ncol = j->ncol;
+    for (int64_t r = j->r0; r < j->r1; ++r)
         for (int64_t c = 0; c < ncol; ++c) {
             float w[9];
             int valid[9];
             for (int k = 0; k < 9; ++k) {
                 int64_t rr = r + k / 3 - 1, cc = c + k % 3 - 1;
                 valid[k] = (rr >= 0 && rr < nrow && cc >= 0 && cc < ncol);
-                w[k] = valid[k] ? z[rr * ncol + cc] : 0.0f;
+                w[k] = valid[k] ? j->zin[rr * ncol + cc] : 0.0f;
             }
-            d8[r * ncol + c] = pfd_synth_d8_from_window(w, valid, sea_level);
+            j->d8[r * ncol + c] = pfd_synth_d8_from_window(w, valid, j->sea_level);
         }
+    return NULL;
+}
+
+static void orc_synth_run(void* (*fn)(void*), orc_synth_job proto) {
+    long nt = sysconf(_SC_NPROCESSORS_ONLN);
+    const char* env = getenv("ORC_SYNTH_THREADS");
+    if (env) nt = atol(env);
+    if (nt < 1) nt = 1;
+    if (nt > 64) nt = 64;
+    if (nt > proto.nrow) nt = (long)proto.nrow;
+    pthread_t th[64];
+    orc_synth_job jobs[64];
+    int started[64];
+    for (long t = 0; t < nt; ++t) {
+        jobs[t] = proto;
+        jobs[t].r0 = proto.nrow * t / nt;
+        jobs[t].r1 = proto.nrow * (t + 1) / nt;
+        started[t] = (t > 0) && pthread_create(&th[t], NULL, fn, &jobs[t]) == 0;
+    }
+    fn(&jobs[0]);
+    for (long t = 1; t < nt; ++t) {
+        if (started[t]) pthread_join(th[t], NULL);
+        else fn(&jobs[t]); /* thread creation failed: do the rows here */
+    }
+}
+
+void orc_synth_elevation(int64_t nrow, int64_t ncol, int64_t nref, int octaves, uint32_t seed, float* z) {
+    orc_synth_job j = {0, 0, nrow, ncol, nref, octaves, seed, 0.0f, NULL, z, NULL};
+    orc_synth_run(orc_synth_elev_rows, j);
+}
+
+void orc_synth_d8(const float* z, int64_t nrow, int64_t ncol, float sea_level, uint8_t* d8) {
+    orc_synth_job j = {0, 0, nrow, ncol, 0, 0, 0, sea_level, z, NULL, d8};
+    orc_synth_run(orc_synth_d8_rows, j);
 }
