@@ -57,7 +57,8 @@ typedef enum pfd_array {
     PFD_ARR_RANK = 4,      /* int32, N              -- core.rank()[0]                */
     PFD_ARR_N_UPSTREAM = 5,/* int8, N               -- core.upstream_count           */
     PFD_ARR_D8 = 6,        /* uint8, N              -- core_d8.to_array              */
-    PFD_ARR_LEVEL_OFFSETS = 7 /* int64, nlevels+1: start of every rank level inside SEQ */
+    PFD_ARR_LEVEL_OFFSETS = 7, /* int64, nlevels+1: start of every rank level inside SEQ */
+    PFD_ARR_LDD = 8        /* uint8, N              -- core_ldd.to_array             */
 } pfd_array;
 
 /* ---- library / device ------------------------------------------------------------------------------- */
@@ -92,6 +93,10 @@ int pfd_synchronize(pfd_handle* h);
  */
 int pfd_d8_parse(pfd_handle* h, const uint8_t* d8, int64_t nrow, int64_t ncol, int check_values,
                  void* idxs_ds_out, int idx_dtype, int64_t* n_valid, int64_t* n_pits, int64_t* n_outlets);
+
+/* core_ldd.from_array (pyflwdir/core_ldd.py:41-66): PCRaster LDD codes 1..9 (5 = pit), 255 = nodata; same kernel. */
+int pfd_ldd_parse(pfd_handle* h, const uint8_t* ldd, int64_t nrow, int64_t ncol, void* idxs_ds_out, int idx_dtype,
+                  int64_t* n_valid, int64_t* n_pits);
 
 /*
  * Constructor path FlwdirRaster(idxs_ds, shape, "d8", ...) (pyflwdir/pyflwdir.py:211-273): load a graph from
@@ -143,6 +148,20 @@ int pfd_strahler(pfd_handle* h, const uint8_t* mask, uint8_t* out);
  * = N values of PFD_F32 or PFD_F64; out = N float64, -9999.0 outside the sequence.
  */
 int pfd_hand(pfd_handle* h, const uint8_t* drain, const void* elevtn, int elev_dtype, double* out);
+
+/* ---- next rows: same sweeps, other functors ------------------------------------------------ */
+/* core.fillnodata_upstream / fillnodata_downstream (pyflwdir/core.py:120-146, 149-188), Flwdir.fillnodata
+ * (pyflwdir/flwdir.py:360-392). direction 0 = "up" (fill from the first downstream valid cell), 1 = "down"
+ * (fill from upstream, merging at confluences with how = 0 max / 1 min / 2 sum). */
+int pfd_fillnodata(pfd_handle* h, const void* data, int dtype, double nodata_f, int64_t nodata_i, int nodata_is_int,
+                   int direction, int how, void* out);
+/* core.main_upstream (pyflwdir/core.py:191-219): index of the upstream cell with the largest uparea (> upa_min),
+ * mv (-1) where there is none. uparea: int32 / uint32 / int64 / float32 / float64. */
+int pfd_main_upstream(pfd_handle* h, const void* uparea, int dtype, double upa_min, void* out, int idx_dtype);
+/* core.upstream_count (pyflwdir/core.py:50-61) with an optional mask of the cells that count (N bytes or NULL) */
+int pfd_upstream_count(pfd_handle* h, const uint8_t* mask, int8_t* out);
+/* streams.stream_order, "classic" / Hack (pyflwdir/streams.py:191-225); mask may be NULL */
+int pfd_stream_order_classic(pfd_handle* h, const void* idxs_us_main, int idx_dtype, const uint8_t* mask, uint8_t* out);
 
 /* ---- fused headline pass ------------------------------------------------------------------------------ */
 /*

@@ -126,6 +126,33 @@ core_d8 = types.SimpleNamespace(
 )
 
 
+def _ldd_from_array(flwdir, _mv=np.uint8(255), dtype=np.intp):
+    """pyflwdir/core_ldd.py:41-66"""
+    flwdir = np.ascontiguousarray(flwdir, dtype=np.uint8)
+    nrow, ncol = flwdir.shape
+    dt = np.dtype(dtype)
+    sfx = _SFX[dt]
+    idxs_ds = np.empty(flwdir.size, dtype=dt)
+    pits = np.empty(flwdir.size, dtype=dt)
+    npits = C.c_int64(0)
+    n = _fn("orc_ldd_from_array", sfx, C.c_int64)(
+        _p(flwdir), C.c_int64(nrow), C.c_int64(ncol), _p(idxs_ds), _p(pits), C.byref(npits)
+    )
+    return idxs_ds, pits[: npits.value].copy(), int(n)
+
+
+def _ldd_to_array(idxs_ds, shape, mv=None):
+    a, sfx = _idx(idxs_ds)
+    out = np.empty(a.size, dtype=np.uint8)
+    rc = _fn("orc_ldd_to_array", sfx, C.c_int)(_p(a), C.c_int64(a.size), C.c_int64(shape[1]), _p(out))
+    if rc != 0:
+        raise ValueError("Invalid data downstream index outside 8 neighbors.")
+    return out.reshape(shape)
+
+
+core_ldd = types.SimpleNamespace(from_array=_ldd_from_array, to_array=_ldd_to_array)
+
+
 # ----------------------------------------------------------------------------- core
 def _rank(idxs_ds, mv=None):
     a, sfx = _idx(idxs_ds)
@@ -177,7 +204,57 @@ def _fillnodata_upstream(idxs_ds, seq, data, nodata):
     return out
 
 
+def _fillnodata_typed(name, idxs_ds, seq, data, nodata, how=None):
+    a, sfx = _idx(idxs_ds)
+    s = np.ascontiguousarray(seq).astype(a.dtype)
+    data = np.ascontiguousarray(data)
+    tsfx = _DATA_SFX[data.dtype]
+    out = np.empty(data.size, dtype=data.dtype)
+    nd_f, nd_i, nd_is_int = _nodata_args(nodata)
+    args = [_p(a), _p(s), C.c_int64(s.size), _p(data), C.c_int64(data.size), nd_f, nd_i, nd_is_int]
+    if how is not None:
+        args.append(C.c_int({"max": 0, "min": 1, "sum": 2}[how]))
+    _fn(f"{name}_{tsfx}", sfx)(*args, _p(out))
+    return out
+
+
+def _fillnodata_upstream_any(idxs_ds, seq, data, nodata):
+    """pyflwdir/core.py:120-146 (any dtype / nodata)"""
+    return _fillnodata_typed("orc_fillnodata_up", idxs_ds, seq, data, nodata)
+
+
+def _fillnodata_downstream(idxs_ds, seq, data, nodata, how="max"):
+    """pyflwdir/core.py:149-188"""
+    return _fillnodata_typed("orc_fillnodata_down", idxs_ds, seq, data, nodata, how)
+
+
+def _main_upstream(idxs_ds, uparea, upa_min=0.0, mv=None):
+    """pyflwdir/core.py:191-219"""
+    a, sfx = _idx(idxs_ds)
+    up = np.ascontiguousarray(uparea)
+    tsfx = {np.dtype(np.int32): "i32", np.dtype(np.int64): "i64", np.dtype(np.float32): "f32",
+            np.dtype(np.float64): "f64"}[up.dtype]
+    out = np.empty(a.size, dtype=a.dtype)
+    _fn(f"orc_main_upstream_{tsfx}", sfx)(_p(a), C.c_int64(a.size), _p(up), C.c_double(upa_min), _p(out))
+    return out
+
+
+def _stream_order_classic(idxs_ds, seq, idxs_us_main, mask=None, mv=None):
+    """pyflwdir/streams.py:191-225"""
+    a, sfx = _idx(idxs_ds)
+    s = np.ascontiguousarray(seq).astype(a.dtype)
+    um = np.ascontiguousarray(idxs_us_main).astype(a.dtype)
+    m = None if mask is None else np.ascontiguousarray(mask).astype(np.uint8)
+    out = np.empty(a.size, dtype=np.uint8)
+    _fn("orc_stream_order_classic", sfx)(_p(a), _p(s), C.c_int64(s.size), _p(um), None if m is None else _p(m),
+                                         C.c_int64(a.size), _p(out))
+    return out
+
+
 core = types.SimpleNamespace(
+    fillnodata_upstream_any=_fillnodata_upstream_any,
+    fillnodata_downstream=_fillnodata_downstream,
+    main_upstream=_main_upstream,
     rank=_rank,
     upstream_count=_upstream_count,
     idxs_seq=_idxs_seq,
@@ -229,7 +306,8 @@ def _strahler_order(idxs_ds, seq, mask=None):
     return out
 
 
-streams = types.SimpleNamespace(accuflux=_accuflux, accuflux_ds=_accuflux_ds, strahler_order=_strahler_order)
+streams = types.SimpleNamespace(accuflux=_accuflux, accuflux_ds=_accuflux_ds, strahler_order=_strahler_order,
+                                stream_order=lambda *a, **k: _stream_order_classic(*a, **k))
 
 
 # ----------------------------------------------------------------------------- basins / dem

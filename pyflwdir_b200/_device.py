@@ -59,8 +59,8 @@ class DeviceGraph:
         return int(self._l.pfd_get_info(self._h, name.encode()))
 
     # -- parse
-    def parse_d8(self, d8, idx_dtype=None, want_idxs=False):
-        """core_d8.from_array on the device. `d8`: 2-D uint8 array (host) -> optional idxs_ds (host)."""
+    def parse_d8(self, d8, idx_dtype=None, want_idxs=False, ftype="d8"):
+        """core_d8.from_array / core_ldd.from_array on the device. 2-D uint8 raster (host) -> optional idxs_ds."""
         d8 = np.ascontiguousarray(d8, dtype=np.uint8)
         nrow, ncol = d8.shape
         nv, npit, nout = C.c_int64(), C.c_int64(), C.c_int64()
@@ -69,8 +69,12 @@ class DeviceGraph:
         if want_idxs:
             idxs = _lib.out_array(d8.size, idx_dtype)
             code = _lib.dtype_code(idx_dtype)
-        self._ck(self._l.pfd_d8_parse(self._h, _lib.ptr(d8), nrow, ncol, 1, _lib.ptr(idxs), code,
-                                      C.byref(nv), C.byref(npit), C.byref(nout)))
+        if ftype == "ldd":
+            self._ck(self._l.pfd_ldd_parse(self._h, _lib.ptr(d8), nrow, ncol, _lib.ptr(idxs), code, C.byref(nv),
+                                           C.byref(npit)))
+        else:
+            self._ck(self._l.pfd_d8_parse(self._h, _lib.ptr(d8), nrow, ncol, 1, _lib.ptr(idxs), code,
+                                          C.byref(nv), C.byref(npit), C.byref(nout)))
         self._set_shape(nrow, ncol, nv.value, npit.value, nout.value)
         return idxs
 
@@ -115,7 +119,7 @@ class DeviceGraph:
             out = _lib.out_array(self.size, np.int32)
         elif which == _lib.ARR_N_UPSTREAM:
             out = _lib.out_array(self.size, np.int8)
-        elif which == _lib.ARR_D8:
+        elif which in (_lib.ARR_D8, _lib.ARR_LDD):
             out = _lib.out_array(self.size, np.uint8)
         elif which == _lib.ARR_LEVEL_OFFSETS:
             if self.nlevels is None:
@@ -192,6 +196,57 @@ class DeviceGraph:
             raise ValueError('"elevtn" size does not match.')
         out = _lib.out_array(self.size, np.float64)
         self._ck(self._l.pfd_hand(self._h, _lib.ptr(d), _lib.ptr(e), _lib.dtype_code(e.dtype), _lib.ptr(out)))
+        return out
+
+    def fillnodata(self, data, nodata, direction="down", how="max"):
+        data = np.ascontiguousarray(data)
+        if data.size != self.size:
+            raise ValueError('"data" size does not match.')
+        if data.dtype == np.bool_:
+            raise TypeError("fillnodata: boolean data is not supported")
+        out = _lib.out_array(data.size, data.dtype)
+        nd_f, nd_i, nd_is = nodata_args(nodata)
+        self._ck(self._l.pfd_fillnodata(self._h, _lib.ptr(data), _lib.dtype_code(data.dtype), nd_f, nd_i, nd_is,
+                                        0 if direction == "up" else 1, {"max": 0, "min": 1, "sum": 2}[how],
+                                        _lib.ptr(out)))
+        return out
+
+    def main_upstream(self, uparea, upa_min=0.0, idx_dtype=np.int32):
+        up = np.ascontiguousarray(uparea)
+        if up.size != self.size:
+            raise ValueError('"uparea" size does not match.')
+        if up.dtype not in (np.dtype(np.int32), np.dtype(np.uint32), np.dtype(np.int64), np.dtype(np.float32),
+                            np.dtype(np.float64)):
+            up = up.astype(np.float64)
+        idx_dtype = np.dtype(idx_dtype)
+        fetch = np.dtype(np.int64) if idx_dtype == np.uint64 else idx_dtype
+        out = _lib.out_array(self.size, fetch)
+        self._ck(self._l.pfd_main_upstream(self._h, _lib.ptr(up), _lib.dtype_code(up.dtype), float(upa_min),
+                                           _lib.ptr(out), _lib.dtype_code(fetch)))
+        return out.astype(idx_dtype, copy=False)
+
+    def upstream_count(self, mask=None):
+        m = None
+        if mask is not None:
+            m = np.ascontiguousarray(mask)
+            m = m.view(np.uint8) if m.dtype == np.bool_ else (m != 0).astype(np.uint8)
+            if m.size != self.size:
+                raise ValueError('"mask" size does not match.')
+        out = _lib.out_array(self.size, np.int8)
+        self._ck(self._l.pfd_upstream_count(self._h, _lib.ptr(m), _lib.ptr(out)))
+        return out
+
+    def stream_order_classic(self, idxs_us_main, mask=None):
+        um = np.ascontiguousarray(idxs_us_main)
+        if um.dtype == np.uint64:
+            um = um.astype(np.int64)
+        m = None
+        if mask is not None:
+            m = np.ascontiguousarray(mask)
+            m = m.view(np.uint8) if m.dtype == np.bool_ else (m != 0).astype(np.uint8)
+        out = _lib.out_array(self.size, np.uint8)
+        self._ck(self._l.pfd_stream_order_classic(self._h, _lib.ptr(um), _lib.dtype_code(um.dtype), _lib.ptr(m),
+                                                  _lib.ptr(out)))
         return out
 
     # -- instrumentation

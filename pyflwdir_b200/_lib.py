@@ -23,7 +23,7 @@ DTYPES = {
 }
 
 # pfd_array
-ARR_IDXS_DS, ARR_PITS, ARR_PIT_IS_OUTLET, ARR_SEQ, ARR_RANK, ARR_N_UPSTREAM, ARR_D8, ARR_LEVEL_OFFSETS = range(8)
+ARR_IDXS_DS, ARR_PITS, ARR_PIT_IS_OUTLET, ARR_SEQ, ARR_RANK, ARR_N_UPSTREAM, ARR_D8, ARR_LEVEL_OFFSETS, ARR_LDD = range(9)
 
 # every symbol include/pfd_b200.h declares: name -> (restype, argtypes)
 _vp, _i64, _int, _u32 = C.c_void_p, C.c_int64, C.c_int, C.c_uint32
@@ -42,6 +42,7 @@ SYMBOLS = {
     "pfd_memcpy": (_int, [_vp, _vp, _vp, C.c_size_t]),
     "pfd_synchronize": (_int, [_vp]),
     "pfd_d8_parse": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _int, _pi64, _pi64, _pi64]),
+    "pfd_ldd_parse": (_int, [_vp, _vp, _i64, _i64, _vp, _int, _pi64, _pi64]),
     "pfd_load_idxs_ds": (_int, [_vp, _vp, _int, _i64, _i64, _pi64, _pi64]),
     "pfd_order": (_int, [_vp, _pi64, _pi64]),
     "pfd_fetch": (_int, [_vp, _int, _vp, _int]),
@@ -50,6 +51,10 @@ SYMBOLS = {
     "pfd_basins": (_int, [_vp, _vp, _i64, _int, _vp, _int, _vp]),
     "pfd_strahler": (_int, [_vp, _vp, _vp]),
     "pfd_hand": (_int, [_vp, _vp, _vp, _int, _vp]),
+    "pfd_fillnodata": (_int, [_vp, _vp, _int, C.c_double, _i64, _int, _int, _int, _vp]),
+    "pfd_main_upstream": (_int, [_vp, _vp, _int, C.c_double, _vp, _int]),
+    "pfd_upstream_count": (_int, [_vp, _vp, _vp]),
+    "pfd_stream_order_classic": (_int, [_vp, _vp, _int, _vp, _vp]),
     "pfd_d8_flow_all": (_int, [_vp, _vp, _i64, _i64, _vp, _int, _vp, _vp, _vp, _pi64, _pi64, _pi64]),
     "pfd_comm_unique_id": (_int, [_vp, _i64]),
     "pfd_comm_init": (_int, [_vp, _int, _int, _vp]),

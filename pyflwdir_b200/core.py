@@ -16,10 +16,15 @@ def rank(idxs_ds, mv=_mv, shape=None, ncol=None):
 
 
 def upstream_count(idxs_ds, mv=_mv, mask=None, shape=None, ncol=None):
-    """Returns array with number of upstream cells per cell (int8, -9 on nodata)."""
-    if mask is not None:
-        raise NotImplementedError("upstream_count(mask=...) is outside the accelerated hot path")
-    return _functional.graph(idxs_ds, shape, ncol).fetch(_lib.ARR_N_UPSTREAM)
+    """Returns array with number of upstream cells per cell (int8, -9 on nodata); with `mask`, only the upstream
+    cells inside the mask count."""
+    return _functional.graph(idxs_ds, shape, ncol).upstream_count(mask)
+
+
+def main_upstream(idxs_ds, uparea, upa_min=0.0, mv=_mv, shape=None, ncol=None):
+    """Returns the index of the upstream cell with the largest uparea, mv (-1) at headwaters (core.py:191-219)."""
+    dt = np.asarray(idxs_ds).dtype
+    return _functional.graph(idxs_ds, shape, ncol).main_upstream(np.asarray(uparea).ravel(), upa_min, dt)
 
 
 def idxs_seq(idxs_ds, idxs_pit, mv=_mv, shape=None, ncol=None):
@@ -41,12 +46,17 @@ def pit_indices(idxs_ds, shape=None, ncol=None):
 
 
 def fillnodata_upstream(idxs_ds, seq, data, nodata, shape=None, ncol=None):
-    """Copy of <data> where upstream cells with <nodata> are filled with the first downstream valid value.
-    Only nodata == 0 with integer data (the basins case) runs on the device."""
-    data = np.asarray(data)
-    if nodata != 0 or data.dtype.kind not in "iu":
-        raise NotImplementedError("fillnodata_upstream is accelerated for integer data with nodata=0 (basins) only")
+    """Copy of <data> where upstream cells with <nodata> are filled with the first downstream valid value
+    (core.py:120-146)."""
     g = _functional.graph(idxs_ds, shape, ncol)
     _functional.check_seq(g, seq, "fillnodata_upstream")
-    idxs = np.flatnonzero(data != 0)
-    return g.basins(idxs.astype(np.int64), np.ascontiguousarray(data[idxs]))
+    return g.fillnodata(np.asarray(data).ravel(), nodata, "up")
+
+
+def fillnodata_downstream(idxs_ds, seq, data, nodata, how="max", shape=None, ncol=None):
+    """Copy of <data> where downstream cells with <nodata> are filled from their upstream cells, merged at
+    confluences with how = "max" | "min" | "sum" (core.py:149-188)."""
+    assert how in ["min", "max", "sum"]
+    g = _functional.graph(idxs_ds, shape, ncol)
+    _functional.check_seq(g, seq, "fillnodata_downstream")
+    return g.fillnodata(np.asarray(data).ravel(), nodata, "down", how)

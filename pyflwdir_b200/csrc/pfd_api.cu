@@ -245,7 +245,7 @@ static void invalidate(pfd_handle* h) {
 // d8_dev holds halo_top + nrow + halo_bot rows (halo rows only feed the forced-pit test of the block's edge rows);
 // idxs_dev (optional) receives the nrow owned rows as global linear indices (first owned row = glob_row0).
 static int parse_device(pfd_handle* h, const uint8_t* d8_dev, int64_t nrow_owned, int64_t ncol, void* idxs_dev, int idx_dtype,
-                        int halo_top = 0, int halo_bot = 0, int64_t glob_row0 = 0) {
+                        int halo_top = 0, int halo_bot = 0, int64_t glob_row0 = 0, int ftype = 0) {
     const int64_t nrow = nrow_owned + halo_top + halo_bot;
     const int64_t n = nrow * ncol;
     const int64_t npad = (n + PC_CHUNK - 1) / PC_CHUNK * PC_CHUNK;
@@ -263,17 +263,23 @@ static int parse_device(pfd_handle* h, const uint8_t* d8_dev, int64_t nrow_owned
         const bool aligned = (ncol % 4 == 0) && ((uintptr_t)d8_dev % 4 == 0) && (!idxs_dev || (uintptr_t)idxs_dev % 16 == 0);
         uint8_t* dir = (uint8_t*)h->dir.p;
         uint8_t* upm = (uint8_t*)h->upmask.p;
-#define LAUNCH_PARSE(A, M) \
-    parse_kernel<A, M><<<grid, 256, 0, h->stream>>>(d8_dev, nrow, ncol, dir, upm, idxs_dev, flag, (int64_t)halo_top, nrow_owned, glob_row0)
-        if (aligned) {
-            if (idxmode == 0) LAUNCH_PARSE(true, 0);
-            else if (idxmode == 1) LAUNCH_PARSE(true, 1);
-            else LAUNCH_PARSE(true, 2);
-        } else {
-            if (idxmode == 0) LAUNCH_PARSE(false, 0);
-            else if (idxmode == 1) LAUNCH_PARSE(false, 1);
-            else LAUNCH_PARSE(false, 2);
-        }
+#define LAUNCH_PARSE(A, M, F) \
+    parse_kernel<A, M, F><<<grid, 256, 0, h->stream>>>(d8_dev, nrow, ncol, dir, upm, idxs_dev, flag, (int64_t)halo_top, nrow_owned, glob_row0)
+#define LAUNCH_PARSE_FT(F)                                \
+    do {                                                  \
+        if (aligned) {                                    \
+            if (idxmode == 0) LAUNCH_PARSE(true, 0, F);   \
+            else if (idxmode == 1) LAUNCH_PARSE(true, 1, F); \
+            else LAUNCH_PARSE(true, 2, F);                \
+        } else {                                          \
+            if (idxmode == 0) LAUNCH_PARSE(false, 0, F);  \
+            else if (idxmode == 1) LAUNCH_PARSE(false, 1, F); \
+            else LAUNCH_PARSE(false, 2, F);               \
+        }                                                 \
+    } while (0)
+        if (ftype == 0) LAUNCH_PARSE_FT(0);
+        else LAUNCH_PARSE_FT(1);
+#undef LAUNCH_PARSE_FT
 #undef LAUNCH_PARSE
         PFD_LAUNCH_CHECK(h);
         // halo rows must not contribute pits / valid cells: blank them after the owned rows were parsed
@@ -297,7 +303,8 @@ static int parse_device(pfd_handle* h, const uint8_t* d8_dev, int64_t nrow_owned
         const unsigned int flags = (unsigned int)hc[3];
         if (flags & 1u) {
             invalidate(h);
-            return pfd_fail(h, PFD_ERR_INVALID_D8, "raster holds values outside the D8 code set {0,1,2,4,8,16,32,64,128,247,255}");
+            return pfd_fail(h, PFD_ERR_INVALID_D8, ftype == 0 ? "raster holds values outside the D8 code set {0,1,2,4,8,16,32,64,128,247,255}"
+                                                              : "raster holds values outside the LDD code set {1..9,255}");
         }
         h->n_valid = (int64_t)hc[0];
         h->n_pits = (int64_t)hc[1];
@@ -329,7 +336,7 @@ static int check_shape(pfd_handle* h, int64_t nrow, int64_t ncol, const char* wh
 
 // overlap_idxs_copy: the D2H copy of idxs_ds runs on the handle's copy stream (the caller joins it later)
 static int parse_impl(pfd_handle* h, const uint8_t* d8, int64_t nrow, int64_t ncol, void* idxs_ds_out, int idx_dtype,
-                      bool overlap_idxs_copy = false) {
+                      bool overlap_idxs_copy = false, int ftype = 0) {
     PFD_TRY(check_shape(h, nrow, ncol, "pfd_d8_parse"));
     if (!d8) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_d8_parse: d8 is null");
     if (idxs_ds_out && idx_dtype != PFD_I32 && idx_dtype != PFD_U32 && idx_dtype != PFD_I64)
@@ -343,7 +350,7 @@ static int parse_impl(pfd_handle* h, const uint8_t* d8, int64_t nrow, int64_t nc
     void* idxs_dev = nullptr;
     const size_t ibytes = (size_t)n * pfd_dtype_size(idx_dtype);
     if (idxs_ds_out) PFD_TRY(pfd_stage_out(h, idxs_ds_out, ibytes, 1, &idxs_dev));
-    PFD_TRY(parse_device(h, (const uint8_t*)d8_dev, nrow, ncol, idxs_dev, idx_dtype));
+    PFD_TRY(parse_device(h, (const uint8_t*)d8_dev, nrow, ncol, idxs_dev, idx_dtype, 0, 0, 0, ftype));
     if (idxs_ds_out && idxs_dev != idxs_ds_out) {
         if (overlap_idxs_copy) {
             // parse_device ended with a stream synchronisation (pit counters), so the staging buffer is complete
@@ -367,6 +374,19 @@ extern "C" int pfd_d8_parse(pfd_handle* h, const uint8_t* d8, int64_t nrow, int6
     if (n_valid) *n_valid = h->n_valid;
     if (n_pits) *n_pits = h->n_pits;
     if (n_outlets) *n_outlets = h->n_outlets;
+    return PFD_OK;
+}
+
+// core_ldd.from_array (pyflwdir/core_ldd.py:41-66): same kernel, PCRaster LDD code table
+extern "C" int pfd_ldd_parse(pfd_handle* h, const uint8_t* ldd, int64_t nrow, int64_t ncol, void* idxs_ds_out, int idx_dtype,
+                             int64_t* n_valid, int64_t* n_pits) {
+    PFD_TRY(check_handle(h));
+    stage_reset(h);
+    PFD_TRY(parse_impl(h, ldd, nrow, ncol, idxs_ds_out, idx_dtype, false, 1));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    if (n_valid) *n_valid = h->n_valid;
+    if (n_pits) *n_pits = h->n_pits;
     return PFD_OK;
 }
 
@@ -1101,10 +1121,12 @@ extern "C" int pfd_fetch(pfd_handle* h, int which, void* out, int idx_dtype) {
         PFD_TRY(pfd_finish_out(h, out, dev, (size_t)n));
         break;
     }
-    case PFD_ARR_D8: {
+    case PFD_ARR_D8:
+    case PFD_ARR_LDD: {
         void* dev = nullptr;
         PFD_TRY(pfd_stage_out(h, out, (size_t)n, 2, &dev));
-        dir_to_d8_kernel<<<grid_for(n, 256, 4), 256, 0, h->stream>>>((const uint8_t*)h->dir.p, n, (uint8_t*)dev);
+        if (which == PFD_ARR_D8) dir_to_codes_kernel<0><<<grid_for(n, 256, 4), 256, 0, h->stream>>>((const uint8_t*)h->dir.p, n, (uint8_t*)dev);
+        else dir_to_codes_kernel<1><<<grid_for(n, 256, 4), 256, 0, h->stream>>>((const uint8_t*)h->dir.p, n, (uint8_t*)dev);
         PFD_LAUNCH_CHECK(h);
         PFD_TRY(pfd_finish_out(h, out, dev, (size_t)n));
         break;
@@ -1307,6 +1329,157 @@ extern "C" int pfd_hand(pfd_handle* h, const uint8_t* drain, const void* elevtn,
         HandOp<double> op{(const uint8_t*)h->dir.p, (const uint8_t*)drain_dev, (const double*)elev_dev, (double*)out_dev, h->ncol};
         PFD_TRY((run_sweep<HandOp<double>, false>(h, op, 0)));
     }
+    PFD_TRY(pfd_finish_out(h, out, out_dev, bytes));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    return PFD_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// widening: fillnodata, main_upstream, masked upstream_count, classic stream order
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+static int fillnodata_typed(pfd_handle* h, void* out_dev, const NoData& nd, int direction, int how) {
+    if (direction == 0) {
+        FillUpGenericOp<T> op{(const uint8_t*)h->dir.p, (T*)out_dev, h->ncol, nd};
+        return run_sweep<FillUpGenericOp<T>, false>(h, op, 1);
+    }
+    if (how == 0) {
+        FillDownOp<T, 0> op{(const uint8_t*)h->upmask.p, (T*)out_dev, h->ncol, nd};
+        return run_sweep<FillDownOp<T, 0>, true>(h, op, 0);
+    }
+    if (how == 1) {
+        FillDownOp<T, 1> op{(const uint8_t*)h->upmask.p, (T*)out_dev, h->ncol, nd};
+        return run_sweep<FillDownOp<T, 1>, true>(h, op, 0);
+    }
+    FillDownOp<T, 2> op{(const uint8_t*)h->upmask.p, (T*)out_dev, h->ncol, nd};
+    return run_sweep<FillDownOp<T, 2>, true>(h, op, 0);
+}
+
+extern "C" int pfd_fillnodata(pfd_handle* h, const void* data, int dtype, double nodata_f, int64_t nodata_i,
+                              int nodata_is_int, int direction, int how, void* out) {
+    PFD_TRY(check_handle(h));
+    stage_reset(h);
+    if (!data || !out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_fillnodata: null array");
+    if ((direction != 0 && direction != 1) || how < 0 || how > 2)
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_fillnodata: direction must be 0/1 and how 0 (max) / 1 (min) / 2 (sum)");
+    const size_t esz = pfd_dtype_size(dtype);
+    if (!esz) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_fillnodata: unknown dtype");
+    PFD_TRY(order_impl(h, false, false));
+    const size_t bytes = (size_t)h->n * esz;
+    void* out_dev = nullptr;
+    PFD_TRY(pfd_stage_out(h, out, bytes, 3, &out_dev));
+    if (out_dev != data) PFD_CUDA(h, cudaMemcpyAsync(out_dev, data, bytes, cudaMemcpyDefault, h->stream));
+    NoData nd{nodata_f, (long long)nodata_i, nodata_is_int};
+    int rc;
+    switch (dtype) {
+    case PFD_I8: rc = fillnodata_typed<int8_t>(h, out_dev, nd, direction, how); break;
+    case PFD_U8: rc = fillnodata_typed<uint8_t>(h, out_dev, nd, direction, how); break;
+    case PFD_I16: rc = fillnodata_typed<int16_t>(h, out_dev, nd, direction, how); break;
+    case PFD_U16: rc = fillnodata_typed<uint16_t>(h, out_dev, nd, direction, how); break;
+    case PFD_I32: rc = fillnodata_typed<int32_t>(h, out_dev, nd, direction, how); break;
+    case PFD_U32: rc = fillnodata_typed<uint32_t>(h, out_dev, nd, direction, how); break;
+    case PFD_I64: rc = fillnodata_typed<int64_t>(h, out_dev, nd, direction, how); break;
+    case PFD_U64: rc = fillnodata_typed<uint64_t>(h, out_dev, nd, direction, how); break;
+    case PFD_F32: rc = fillnodata_typed<float>(h, out_dev, nd, direction, how); break;
+    default: rc = fillnodata_typed<double>(h, out_dev, nd, direction, how); break;
+    }
+    PFD_TRY(rc);
+    PFD_TRY(pfd_finish_out(h, out, out_dev, bytes));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    return PFD_OK;
+}
+
+template <typename T>
+static int main_upstream_typed(pfd_handle* h, const void* up_dev, double upa_min, void* out_dev, int idx_dtype) {
+    const int g = grid_for(h->n, 256, 4);
+    const T mn = (T)upa_min;
+    if (pfd_dtype_size(idx_dtype) == 4)
+        main_upstream_kernel<T, uint32_t><<<g, 256, 0, h->stream>>>((const uint8_t*)h->upmask.p, (const T*)up_dev, h->n, h->ncol, mn, (uint32_t*)out_dev);
+    else
+        main_upstream_kernel<T, int64_t><<<g, 256, 0, h->stream>>>((const uint8_t*)h->upmask.p, (const T*)up_dev, h->n, h->ncol, mn, (int64_t*)out_dev);
+    PFD_LAUNCH_CHECK(h);
+    return PFD_OK;
+}
+
+extern "C" int pfd_main_upstream(pfd_handle* h, const void* uparea, int dtype, double upa_min, void* out, int idx_dtype) {
+    PFD_TRY(check_handle(h));
+    stage_reset(h);
+    if (!h->parsed || h->tiled) return pfd_fail(h, PFD_ERR_STATE, "pfd_main_upstream: no (whole) raster parsed on this handle");
+    if (!uparea || !out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_main_upstream: null array");
+    const size_t isz = pfd_dtype_size(idx_dtype), esz = pfd_dtype_size(dtype);
+    if ((isz != 4 && isz != 8) || idx_dtype == PFD_F32 || idx_dtype == PFD_F64)
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_main_upstream: index dtype must be a 32/64-bit integer");
+    const void* up_dev = nullptr;
+    PFD_TRY(pfd_stage_in(h, uparea, (size_t)h->n * esz, 4, &up_dev));
+    void* out_dev = nullptr;
+    PFD_TRY(pfd_stage_out(h, out, (size_t)h->n * isz, 3, &out_dev));
+    int rc;
+    switch (dtype) {
+    case PFD_I32: rc = main_upstream_typed<int32_t>(h, up_dev, upa_min, out_dev, idx_dtype); break;
+    case PFD_U32: rc = main_upstream_typed<uint32_t>(h, up_dev, upa_min, out_dev, idx_dtype); break;
+    case PFD_I64: rc = main_upstream_typed<int64_t>(h, up_dev, upa_min, out_dev, idx_dtype); break;
+    case PFD_F32: rc = main_upstream_typed<float>(h, up_dev, upa_min, out_dev, idx_dtype); break;
+    case PFD_F64: rc = main_upstream_typed<double>(h, up_dev, upa_min, out_dev, idx_dtype); break;
+    default: return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_main_upstream: uparea must be int32/uint32/int64/float32/float64");
+    }
+    PFD_TRY(rc);
+    PFD_TRY(pfd_finish_out(h, out, out_dev, (size_t)h->n * isz));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    return PFD_OK;
+}
+
+extern "C" int pfd_upstream_count(pfd_handle* h, const uint8_t* mask, int8_t* out) {
+    PFD_TRY(check_handle(h));
+    if (!h->parsed || h->tiled) return pfd_fail(h, PFD_ERR_STATE, "pfd_upstream_count: no (whole) raster parsed on this handle");
+    if (!out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_upstream_count: out is null");
+    const int64_t n = h->n;
+    void* dev = nullptr;
+    PFD_TRY(pfd_stage_out(h, out, (size_t)n, 3, &dev));
+    if (mask) {
+        const void* mdev = nullptr;
+        PFD_TRY(pfd_stage_in(h, mask, (size_t)n, 4, &mdev));
+        upstream_count_mask_kernel<<<grid_for(n, 256, 4), 256, 0, h->stream>>>((const uint8_t*)h->dir.p, (const uint8_t*)h->upmask.p,
+                                                                              (const uint8_t*)mdev, n, h->ncol, (int8_t*)dev);
+    } else {
+        upstream_count_kernel<<<grid_for(n, 256, 4), 256, 0, h->stream>>>((const uint8_t*)h->dir.p, (const uint8_t*)h->upmask.p, n, (int8_t*)dev);
+    }
+    PFD_LAUNCH_CHECK(h);
+    PFD_TRY(pfd_finish_out(h, out, dev, (size_t)n));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    return PFD_OK;
+}
+
+extern "C" int pfd_stream_order_classic(pfd_handle* h, const void* idxs_us_main, int idx_dtype, const uint8_t* mask, uint8_t* out) {
+    PFD_TRY(check_handle(h));
+    stage_reset(h);
+    if (!idxs_us_main || !out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_stream_order_classic: null array");
+    const size_t isz = pfd_dtype_size(idx_dtype);
+    if ((isz != 4 && isz != 8) || idx_dtype == PFD_F32 || idx_dtype == PFD_F64)
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_stream_order_classic: index dtype must be a 32/64-bit integer");
+    PFD_TRY(order_impl(h, false, false));
+    const size_t bytes = (size_t)h->n;
+    void* out_dev = nullptr;
+    PFD_TRY(pfd_stage_out(h, out, bytes, 3, &out_dev));
+    const void *mask_dev = nullptr, *main_dev = nullptr;
+    if (mask) PFD_TRY(pfd_stage_in(h, mask, bytes, 4, &mask_dev));
+    PFD_TRY(pfd_stage_in(h, idxs_us_main, (size_t)h->n * isz, 5, &main_dev));
+    PFD_CUDA(h, cudaMemsetAsync(out_dev, 0, bytes, h->stream));
+    const uint8_t *dir = (const uint8_t*)h->dir.p, *upm = (const uint8_t*)h->upmask.p;
+    int rc;
+    if (idx_dtype == PFD_I32) {
+        ClassicOrderOp<int32_t> op{dir, upm, (const uint8_t*)mask_dev, (const int32_t*)main_dev, (uint8_t*)out_dev, h->ncol};
+        rc = run_sweep<ClassicOrderOp<int32_t>, false>(h, op, 0);
+    } else if (idx_dtype == PFD_U32) {
+        ClassicOrderOp<uint32_t> op{dir, upm, (const uint8_t*)mask_dev, (const uint32_t*)main_dev, (uint8_t*)out_dev, h->ncol};
+        rc = run_sweep<ClassicOrderOp<uint32_t>, false>(h, op, 0);
+    } else {
+        ClassicOrderOp<int64_t> op{dir, upm, (const uint8_t*)mask_dev, (const int64_t*)main_dev, (uint8_t*)out_dev, h->ncol};
+        rc = run_sweep<ClassicOrderOp<int64_t>, false>(h, op, 0);
+    }
+    PFD_TRY(rc);
     PFD_TRY(pfd_finish_out(h, out, out_dev, bytes));
     PFD_CUDA(h, cudaStreamSynchronize(h->stream));
     stage_collect(h);

@@ -33,6 +33,16 @@ __host__ __device__ __forceinline__ constexpr unsigned pfd_slot_code(int k) {
                                                                                          : (k == 6) ? 4u : 2u;
 }
 
+// PCRaster LDD code (core_ldd.py:13 _ds = [[7,8,9],[4,5,6],[1,2,3]]) of "flows to slot k"; pit = 5, nodata = 255
+__host__ __device__ __forceinline__ constexpr unsigned pfd_slot_code_ldd(int k) {
+    return (k == 0) ? 7u : (k == 1) ? 8u : (k == 2) ? 9u : (k == 3) ? 4u : (k == 4) ? 6u : (k == 5) ? 1u : (k == 6) ? 2u : 3u;
+}
+// FT: 0 = D8, 1 = LDD
+template <int FT>
+__host__ __device__ __forceinline__ constexpr unsigned pfd_code(int k) { return FT == 0 ? pfd_slot_code(k) : pfd_slot_code_ldd(k); }
+template <int FT>
+__host__ __device__ __forceinline__ constexpr unsigned pfd_nodata_code() { return FT == 0 ? 247u : 255u; }
+
 // row / column delta of slot k (packed 2-bit LUTs: value + 1)
 __host__ __device__ __forceinline__ int pfd_slot_dr(int k) { return (int)((0xA940u >> (2 * k)) & 3u) - 1; }
 __host__ __device__ __forceinline__ int pfd_slot_dc(int k) { return (int)((0x9224u >> (2 * k)) & 3u) - 1; }

@@ -18,20 +18,21 @@
 #define PT_W (PT_WW * 4)       // 128 cells
 #define PT_SW (PT_WW + 2)      // smem words per row incl. halo words
 
-template <bool ALIGNED>
+template <bool ALIGNED, int FT>
 __device__ __forceinline__ uint32_t parse_load_word(const uint8_t* __restrict__ d8, int64_t nrow, int64_t ncol,
                                                     int64_t r, int64_t wc) {
-    // word wc covers columns 4*wc .. 4*wc+3
-    if (r < 0 || r >= nrow || wc < 0) return 0xF7F7F7F7u;
+    // word wc covers columns 4*wc .. 4*wc+3; cells outside the raster read as nodata
+    constexpr uint32_t ND4 = pfd_nodata_code<FT>() * 0x01010101u;
+    if (r < 0 || r >= nrow || wc < 0) return ND4;
     int64_t c = wc * 4;
-    if (c >= ncol) return 0xF7F7F7F7u;
+    if (c >= ncol) return ND4;
     if (ALIGNED) {
         return __ldg(reinterpret_cast<const uint32_t*>(d8 + r * ncol + c));
     } else {
         uint32_t w = 0;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            uint32_t v = (c + b < ncol) ? (uint32_t)__ldg(d8 + r * ncol + c + b) : 247u;
+            uint32_t v = (c + b < ncol) ? (uint32_t)__ldg(d8 + r * ncol + c + b) : pfd_nodata_code<FT>();
             w |= v << (8 * b);
         }
         return w;
@@ -39,7 +40,8 @@ __device__ __forceinline__ uint32_t parse_load_word(const uint8_t* __restrict__ 
 }
 
 // IDXMODE: 0 = no idxs_ds output, 1 = 32-bit (int32 / uint32 share the bit pattern), 2 = int64
-template <bool ALIGNED, int IDXMODE>
+// FT: 0 = D8 codes (core_d8.py:14-19), 1 = PCRaster LDD codes (core_ldd.py:12-17; same algorithm, core_ldd.py:41-66)
+template <bool ALIGNED, int IDXMODE, int FT>
 __global__ void __launch_bounds__(256) parse_kernel(const uint8_t* __restrict__ d8, int64_t nrow, int64_t ncol,
                                                     uint8_t* __restrict__ dir, uint8_t* __restrict__ upmask,
                                                     void* __restrict__ idxs_out, unsigned int* __restrict__ invalid_flag,
@@ -50,7 +52,7 @@ __global__ void __launch_bounds__(256) parse_kernel(const uint8_t* __restrict__ 
 
     for (int i = threadIdx.x; i < (PT_H + 2) * PT_SW; i += 256) {
         int tr = i / PT_SW, tw = i % PT_SW;
-        tile[tr][tw] = parse_load_word<ALIGNED>(d8, nrow, ncol, r0 - 1 + tr, wc0 - 1 + tw);
+        tile[tr][tw] = parse_load_word<ALIGNED, FT>(d8, nrow, ncol, r0 - 1 + tr, wc0 - 1 + tw);
     }
     __syncthreads();
 
@@ -79,19 +81,26 @@ __global__ void __launch_bounds__(256) parse_kernel(const uint8_t* __restrict__ 
         nb[6] = c1;                           // S
         nb[7] = __byte_perm(c1, c2, 0x4321);  // SE
 
-        const uint32_t nodata = __vcmpeq4(w, splat4(247u));
-        const uint32_t pit = __vcmpeq4(w, 0u) | __vcmpeq4(w, splat4(255u));
-        // legal codes: 0 or a power of two, 247, 255 (core_d8.py:19)
-        const uint32_t pow2 = __vcmpeq4(w & __vsub4(w, splat4(1u)), 0u);
-        if ((pow2 | nodata | pit) != 0xFFFFFFFFu) bad = true;
+        const uint32_t nodata = __vcmpeq4(w, splat4(pfd_nodata_code<FT>()));
+        uint32_t pit, legal;
+        if (FT == 0) {
+            pit = __vcmpeq4(w, 0u) | __vcmpeq4(w, splat4(255u));
+            // legal codes: 0 or a power of two, 247, 255 (core_d8.py:19)
+            legal = __vcmpeq4(w & __vsub4(w, splat4(1u)), 0u) | nodata | pit;
+        } else {
+            pit = __vcmpeq4(w, splat4(5u));
+            // legal codes: 1..9 and 255 (core_ldd.py:17)
+            legal = __vcmpltu4(__vsub4(w, splat4(1u)), splat4(9u)) | nodata;
+        }
+        if (legal != 0xFFFFFFFFu) bad = true;
 
         uint32_t dirw = 0, forced = 0, upw = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const uint32_t sel = __vcmpeq4(w, splat4(pfd_slot_code(k)));
+            const uint32_t sel = __vcmpeq4(w, splat4(pfd_code<FT>(k)));
             dirw |= sel & splat4((uint32_t)k);
-            forced |= sel & __vcmpeq4(nb[k], splat4(247u));
-            upw |= __vcmpeq4(nb[k], splat4(pfd_slot_code(7 - k))) & splat4(1u << k);
+            forced |= sel & __vcmpeq4(nb[k], splat4(pfd_nodata_code<FT>()));
+            upw |= __vcmpeq4(nb[k], splat4(pfd_code<FT>(7 - k))) & splat4(1u << k);
         }
         dirw = (dirw & ~forced) | (forced & splat4(PFD_DIR_FPIT));
         dirw |= pit & splat4(PFD_DIR_PIT);
@@ -198,10 +207,13 @@ __global__ void dir_to_idxs_kernel(const uint8_t* __restrict__ dir, int64_t n, i
     }
 }
 
-__global__ void dir_to_d8_kernel(const uint8_t* __restrict__ dir, int64_t n, uint8_t* __restrict__ out) {
+// core_d8.to_array (core_d8.py:86-102) / core_ldd.to_array: pits become 0 (D8) / 5 (LDD)
+template <int FT>
+__global__ void dir_to_codes_kernel(const uint8_t* __restrict__ dir, int64_t n, uint8_t* __restrict__ out) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         uint32_t d = dir[i];
-        out[i] = (d < 8u) ? (uint8_t)pfd_slot_code((int)d) : ((d == PFD_DIR_NODATA) ? (uint8_t)247 : (uint8_t)0);
+        out[i] = (d < 8u) ? (uint8_t)pfd_code<FT>((int)d)
+                          : ((d == PFD_DIR_NODATA) ? (uint8_t)pfd_nodata_code<FT>() : (uint8_t)(FT == 0 ? 0 : 5));
     }
 }
 

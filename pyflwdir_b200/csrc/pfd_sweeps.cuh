@@ -152,6 +152,126 @@ struct FillUpOp {
     }
 };
 
+// ---- core.fillnodata_upstream, any dtype / nodata (core.py:120-146): down-sweep ---------------------------
+template <typename T>
+struct FillUpGenericOp {
+    const uint8_t* dir;
+    T* out;
+    long long ncol;
+    NoData nd;
+    __device__ __forceinline__ void operator()(cell_t c, long long, int) const {
+        const uint32_t d = __ldg(dir + c);
+        if (d >= 8u) return;  // pit: idx_ds == idx0, nothing to copy
+        if (not_nodata(ld_cg(out + c), nd)) return;
+        const T a = ld_cg(out + ((long long)c + pfd_slot_off((int)d, ncol)));
+        if (not_nodata(a, nd)) out[c] = a;
+    }
+};
+
+// ---- core.fillnodata_downstream (core.py:149-188): up-sweep, pull in descending upstream index ------------
+// HOW: 0 = max, 1 = min, 2 = sum. A cell is filled only if its ORIGINAL value is nodata; it is written by its own
+// step only, so out[c] still holds the original value when its turn comes.
+template <typename T, int HOW>
+struct FillDownOp {
+    const uint8_t* upmask;
+    T* out;
+    long long ncol;
+    NoData nd;
+    __device__ __forceinline__ void operator()(cell_t c, long long, int) const {
+        uint32_t m = __ldg(upmask + c);
+        if (!m) return;
+        T acc = ld_cg(out + c);
+        if (not_nodata(acc, nd)) return;
+        bool changed = false;
+        while (m) {
+            const int k = 31 - __clz(m);
+            m ^= 1u << k;
+            const T v = ld_cg(out + ((long long)c + pfd_slot_off(k, ncol)));
+            if (!not_nodata(v, nd)) continue;
+            if (!not_nodata(acc, nd)) acc = v;
+            else if (HOW == 0) acc = (v > acc) ? v : acc;   // max(data_out[idx0], data_out[idx_ds])
+            else if (HOW == 1) acc = (v < acc) ? v : acc;
+            else acc = acc_add(acc, v);
+            changed = true;
+        }
+        if (changed) out[c] = acc;
+    }
+};
+
+// ---- streams.stream_order ("classic" / Hack, streams.py:191-225): down-sweep -----------------------------
+template <typename IDX>
+struct ClassicOrderOp {
+    const uint8_t* dir;
+    const uint8_t* upmask;
+    const uint8_t* mask;  // may be null
+    const IDX* us_main;
+    uint8_t* out;
+    long long ncol;
+    __device__ __forceinline__ void operator()(cell_t c, long long, int) const {
+        if (mask && !__ldg(mask + c)) return;
+        const uint32_t d = __ldg(dir + c);
+        if (d >= 8u) {
+            out[c] = 1;
+            return;
+        }
+        const long long ds = (long long)c + pfd_slot_off((int)d, ncol);
+        uint32_t m = __ldg(upmask + ds);
+        int nup = 0;  // core.upstream_count(mask=mask): upstream cells of ds that are in the mask
+        if (!mask) nup = __popc(m);
+        else
+            while (m) {
+                const int k = __ffs(m) - 1;
+                m &= m - 1;
+                nup += __ldg(mask + (ds + pfd_slot_off(k, ncol))) ? 1 : 0;
+            }
+        const uint8_t sds = ld_cg(out + ds);
+        const bool side = nup > 1 && (long long)__ldg(us_main + ds) != (long long)c;
+        out[c] = side ? (uint8_t)(sds + 1) : sds;
+    }
+};
+
+// core.main_upstream (core.py:191-219): upstream neighbour with the largest uparea (> upa_min), first wins on ties
+template <typename T, typename IDX>
+__global__ void main_upstream_kernel(const uint8_t* __restrict__ upmask, const T* __restrict__ uparea, int64_t n,
+                                     long long ncol, T upa_min, IDX* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t m = upmask[i];
+        T best = upa_min;
+        IDX arg = (IDX)-1;
+        while (m) {  // ascending upstream index = the reference's scan order
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            const int64_t u = i + pfd_slot_off(k, ncol);
+            const T v = uparea[u];
+            if (v > best) {
+                best = v;
+                arg = (IDX)u;
+            }
+        }
+        out[i] = arg;
+    }
+}
+
+// core.upstream_count with a mask (core.py:50-61): upstream cells that are in the mask; -9 on nodata
+__global__ void upstream_count_mask_kernel(const uint8_t* __restrict__ dir, const uint8_t* __restrict__ upmask,
+                                           const uint8_t* __restrict__ mask, int64_t n, long long ncol,
+                                           int8_t* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (dir[i] == PFD_DIR_NODATA) {
+            out[i] = -9;
+            continue;
+        }
+        uint32_t m = upmask[i];
+        int cnt = 0;
+        while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            cnt += mask[i + pfd_slot_off(k, ncol)] ? 1 : 0;
+        }
+        out[i] = (int8_t)cnt;
+    }
+}
+
 // ---- core.rank as a replay (when the BFS ran without it) -----------------------------------------------
 struct RankOp {
     int32_t* rank;

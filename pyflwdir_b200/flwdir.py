@@ -77,6 +77,13 @@ class Flwdir(object):
         return self._idxs_ds
 
     @property
+    def idxs_us_main(self):
+        """Linear indices of main upstream cell, i.e. the upstream cell with the largest contributing area."""
+        if "idxs_us_main" in self._cached:
+            return self._cached["idxs_us_main"]
+        return self.main_upstream()
+
+    @property
     def idxs_seq(self):
         """Linear indices of valid cells ordered from down- to upstream."""
         if self._seq is None:
@@ -155,6 +162,13 @@ class Flwdir(object):
     def _raster_shape(self):
         raise NotImplementedError
 
+    def main_upstream(self, uparea=None):
+        """Index of the upstream cell with the largest upstream area, mv at headwaters (flwdir.py:252-258)."""
+        idxs_us_main = self._dev.main_upstream(self._check_data(uparea, "uparea"), 0.0, self._idx_dtype)
+        if self.cache:
+            self._cached.update(idxs_us_main=idxs_us_main)
+        return idxs_us_main
+
     def add_pits(self, idxs=None, streams=None):
         """Add pits to the flow direction (flwdir.py:260-279)."""
         idxs1 = self._check_idxs_xy(idxs, streams=streams)
@@ -191,10 +205,22 @@ class Flwdir(object):
                 if self.cache:
                     self._cached.update(strord=strord)
         elif type.lower() == "classic":
-            raise NotImplementedError('stream_order(type="classic") is outside the accelerated hot path')
+            strord = self._dev.stream_order_classic(self.idxs_us_main, mask)
         else:
             raise ValueError(f'Unknown stream order type: "{type}"')
         return strord.reshape(self.shape)
+
+    def fillnodata(self, data, nodata, direction="down", how="max"):
+        """Returns data where cells with nodata value have been filled with the nearest up- or downstream valid
+        neighbor value (flwdir.py:360-392)."""
+        direction = str(direction).lower()
+        dflat = self._check_data(data, "data")
+        if direction not in ("up", "down"):
+            raise ValueError('Unknown flow direction: {direction}, select from ["up", "down"].')
+        if how not in ("min", "max", "sum"):
+            raise ValueError(f'Unknown how: "{how}", select from ["min", "max", "sum"].')
+        dout = self._dev.fillnodata(dflat, nodata, direction, how)
+        return dout.reshape(np.shape(data) if np.size(data) == self.size else self.shape)
 
     def upstream_area(self):
         """Upstream area from the cached/unit cell area (flwdir.py:549-565)."""
@@ -240,8 +266,8 @@ class Flwdir(object):
         return idxs
 
     # ------------------------------------------------------------------ not in scope
-    for _name in ("main_upstream", "path", "snap", "inflow_idxs", "outflow_idxs", "stream_distance", "smooth_rivlen",
-                  "subbasins_streamorder", "subbasins_pfafstetter", "subbasins_area", "fillnodata", "moving_average",
+    for _name in ("path", "snap", "inflow_idxs", "outflow_idxs", "stream_distance", "smooth_rivlen",
+                  "subbasins_streamorder", "subbasins_pfafstetter", "subbasins_area", "moving_average",
                   "moving_median", "upstream_sum", "vectorize", "streams", "geofeatures", "dem_adjust", "dem_dig_d4",
                   "floodplains", "classify_estuaries", "ucat_area", "ucat_outlets", "ucat_volume", "subgrid_rivlen",
                   "subgrid_rivslp", "subgrid_rivavg", "subgrid_rivmed", "subgrid_rivlen2", "upscale", "upscale_error",

@@ -3,7 +3,8 @@
 :211-273, idxs_seq :292-297, set_transform :318-337, to_array :341-360, basins :564-599, upstream_area :770-801,
 hand :1485-1511, _check_data :1548-1559) with every kernel running on the GPU.
 
-Only the D8 flow-direction type is accelerated; "ldd" / "nextxy" rasters raise NotImplementedError.
+The D8 and PCRaster LDD flow-direction types are accelerated (same parse kernel, different code table);
+"nextxy" rasters raise NotImplementedError.
 """
 import pickle
 
@@ -16,9 +17,8 @@ from .gis_utils import Affine
 
 __all__ = ["FlwdirRaster", "from_array"]
 
-FTYPES = ("d8", "ldd", "nextxy")  # pyflwdir.py:26-30; only "d8" is implemented here
-_D8_MV = np.uint8(247)            # core_d8.py:17
-_D8_PV = np.array([0, 255], dtype=np.uint8)  # core_d8.py:18
+FTYPES = ("d8", "ldd", "nextxy")  # pyflwdir.py:26-30; "d8" and "ldd" are implemented here
+_MV = {"d8": np.uint8(247), "ldd": np.uint8(255)}  # core_d8.py:17, core_ldd.py:15
 
 
 def _get_idxs_dtype(n):
@@ -44,43 +44,47 @@ def from_array(data, ftype="infer", check_ftype=True, mask=None, transform=gis.I
     """
     infer = ftype == "infer"
     if infer:
-        # the reference tries d8, ldd, nextxy in that order (pyflwdir.py:39-48); only d8 exists here
+        # the reference tries d8, ldd, nextxy in that order (pyflwdir.py:39-48); d8 and ldd exist here
         if not _is_d8_candidate(data):
             raise ValueError("The flow direction type could not be inferred.")
-        ftype = "d8"
         check_ftype = False
-    if ftype == "nextxy":
-        shape, ndim = data[0].shape, data[0].ndim
+        candidates = ["d8", "ldd"]
     else:
+        candidates = [ftype]
+        if ftype == "nextxy":
+            shape, ndim = data[0].shape, data[0].ndim
+    if ftype != "nextxy":
         ndim, shape = data.ndim, data.shape
     if ndim != 2:
         raise ValueError("The FlwdirRaster should be 2 dimensional")
-    if ftype not in FTYPES:
+    if not infer and ftype not in FTYPES:
         ftypes_str = '" ,"'.join(FTYPES)
         raise ValueError(f'Unknown flow direction type: "{ftype}", select from {ftypes_str}')
-    if ftype != "d8":
-        raise NotImplementedError(f'ftype "{ftype}" is not accelerated by pyflwdir_b200 (D8 only)')
+    if ftype == "nextxy":
+        raise NotImplementedError('ftype "nextxy" is not accelerated by pyflwdir_b200 (D8 and LDD only)')
     invalid_msg = f'The flow direction data with type "{ftype}" is invalid.'
     if not _is_d8_candidate(data):
         if check_ftype:
             raise ValueError(invalid_msg)
-        raise ValueError("D8 data must be a 2-D uint8 array")
-    if mask is not None:
-        if mask.shape != data.shape:
-            raise ValueError('"mask" shape does not match with data shape')
-        data = np.where(mask != 0, data, _D8_MV)
+        raise ValueError("flow direction data must be a 2-D uint8 array")
+    if mask is not None and mask.shape != data.shape:
+        raise ValueError('"mask" shape does not match with data shape')
 
     dtype = _get_idxs_dtype(shape[0] * shape[1])
     dev = _device.DeviceGraph(device)
-    try:
-        dev.parse_d8(data)
-    except ValueError as err:
-        if getattr(err, "status", None) == _lib.ERR_INVALID_D8:
+    for k, ft in enumerate(candidates):
+        try:
             # illegal codes are refused even with check_ftype=False (the reference would mis-parse them)
-            if infer:
-                raise ValueError("The flow direction type could not be inferred.") from None
-            raise ValueError(invalid_msg) from None
-        raise
+            dev.parse_d8(data if mask is None else np.where(mask != 0, data, _MV[ft]), ftype=ft)
+            ftype = ft
+            break
+        except ValueError as err:
+            if getattr(err, "status", None) != _lib.ERR_INVALID_D8:
+                raise
+            if k + 1 == len(candidates):
+                if infer:
+                    raise ValueError("The flow direction type could not be inferred.") from None
+                raise ValueError(invalid_msg) from None
     idxs_pit = dev.fetch(_lib.ARR_PITS, dtype)
     is_outlet = dev.fetch(_lib.ARR_PIT_IS_OUTLET)
     idxs_outlet = idxs_pit[is_outlet != 0]  # pits whose code is 0/255 (pyflwdir.py:193)
@@ -106,8 +110,8 @@ class FlwdirRaster(Flwdir):
         if ftype not in FTYPES:
             ftypes_str = '" ,"'.join(FTYPES)
             raise ValueError(f'Unknown flow direction type: "{ftype}", select from {ftypes_str}')
-        if ftype != "d8":
-            raise NotImplementedError(f'ftype "{ftype}" is not accelerated by pyflwdir_b200 (D8 only)')
+        if ftype == "nextxy":
+            raise NotImplementedError('ftype "nextxy" is not accelerated by pyflwdir_b200 (D8 and LDD only)')
         self.ftype = ftype
         if len(shape) != 2 or shape[0] * shape[1] != self.size:
             raise ValueError(f"Invalid FlwdirRaster: shape {shape} does not match size {self.size}")
@@ -175,6 +179,8 @@ class FlwdirRaster(Flwdir):
             ftype = self.ftype
         if ftype == "d8":
             return self._dev.fetch(_lib.ARR_D8).reshape(self.shape)
+        if ftype == "ldd":
+            return self._dev.fetch(_lib.ARR_LDD).reshape(self.shape)
         if ftype in FTYPES:
             raise NotImplementedError(f'to_array(ftype="{ftype}") is outside the accelerated hot path')
         raise ValueError(f'ftype "{ftype}" unknown')
@@ -274,6 +280,6 @@ class FlwdirRaster(Flwdir):
     for _name in ("repair_loops_raster", "subbasins_streamorder", "subbasins_pfafstetter", "subbasins_area",
                   "streams", "geofeatures", "vectorize", "stream_distance", "dem_adjust", "dem_dig_d4", "floodplains",
                   "upscale", "upscale_error", "subgrid_rivlen", "subgrid_rivslp", "subgrid_rivavg", "subgrid_rivmed",
-                  "ucat_area", "ucat_outlets", "ucat_volume", "inflow_idxs", "outflow_idxs", "main_upstream"):
+                  "ucat_area", "ucat_outlets", "ucat_volume", "inflow_idxs", "outflow_idxs"):
         locals()[_name] = _not_in_scope(_name)
     del _name

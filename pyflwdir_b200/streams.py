@@ -1,5 +1,5 @@
 """Sweeps over the flow sequence on the GPU; mirrors /root/reference/pyflwdir/streams.py (accuflux :15-41,
-accuflux_ds :44-70, strahler_order :228-269). The device always sweeps its own "walk" sequence (the one
+accuflux_ds :44-70, stream_order :191-225, strahler_order :228-269). The device always sweeps its own "walk" sequence (the one
 `core.idxs_seq` returns); `seq` is only checked for covering the same cells."""
 import numpy as np
 
@@ -18,6 +18,13 @@ def accuflux_ds(idxs_ds, seq, data, nodata, shape=None, ncol=None):
     g = _functional.graph(idxs_ds, shape, ncol)
     _functional.check_seq(g, seq, "accuflux_ds")
     return g.accuflux(np.asarray(data).ravel(), nodata, "down")
+
+
+def stream_order(idxs_ds, seq, idxs_us_main, mask=None, mv=-1, shape=None, ncol=None):
+    """Returns the classic or Hack's "bottum up" stream order (uint8; streams.py:191-225)."""
+    g = _functional.graph(idxs_ds, shape, ncol)
+    _functional.check_seq(g, seq, "stream_order")
+    return g.stream_order_classic(idxs_us_main, mask)
 
 
 def strahler_order(idxs_ds, seq, mask=None, shape=None, ncol=None):

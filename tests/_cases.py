@@ -32,8 +32,12 @@ def case_inputs(name, d8, seed):
     data_i64 = rng.integers(-50, 1000, size=shape, dtype=np.int64)
     elevtn = (oracle.synth_elevation(shape[0], shape[1], seed=seed + 7) * np.float32(1000.0)).astype(np.float32)
     smask = rng.random(shape) < 0.6
+    gaps = rng.random(shape) < 0.7  # sparse data for fillnodata
+    fill_i64 = np.where(gaps, np.int64(-9999), data_i64)
+    fill_f32 = np.where(gaps, np.float32(-1.5), data_f32)
+    fill_f64 = np.where(gaps, np.nan, data_f64)
     return dict(data_f32=data_f32, data_f64=data_f64, data_f32_nd=data_f32_nd, data_i64=data_i64,
-                elevtn=elevtn, smask=smask)
+                elevtn=elevtn, smask=smask, fill_i64=fill_i64, fill_f32=fill_f32, fill_f64=fill_f64)
 
 
 _small = None
@@ -139,6 +143,17 @@ def run_oracle_case(d8, aux, area=None):
     out["sub_ids"] = sub_ids
     out["basins_sub"] = o.basins.basins(idxs_ds, sub_idxs, seq, sub_ids).reshape(shape)
     out["to_array"] = o.core_d8.to_array(idxs_ds, shape)
+    out["us_main"] = o.core.main_upstream(idxs_ds, out["uparea_cell"].ravel())
+    if area is not None:
+        out["us_main_km2"] = o.core.main_upstream(idxs_ds, out["uparea_km2"].ravel())
+    out["strord_classic"] = o.streams.stream_order(idxs_ds, seq, out["us_main"]).reshape(shape)
+    out["strord_classic_mask"] = o.streams.stream_order(idxs_ds, seq, out["us_main"], mask=aux["smask"].ravel()).reshape(shape)
+    out["fill_up_i64"] = o.core.fillnodata_upstream_any(idxs_ds, seq, aux["fill_i64"].ravel(), -9999).reshape(shape)
+    out["fill_up_f64nan"] = o.core.fillnodata_upstream_any(idxs_ds, seq, aux["fill_f64"].ravel(), np.nan).reshape(shape)
+    out["fill_down_max_f32"] = o.core.fillnodata_downstream(idxs_ds, seq, aux["fill_f32"].ravel(), -1.5, how="max").reshape(shape)
+    out["fill_down_min_i64"] = o.core.fillnodata_downstream(idxs_ds, seq, aux["fill_i64"].ravel(), -9999, how="min").reshape(shape)
+    out["fill_down_sum_f32"] = o.core.fillnodata_downstream(idxs_ds, seq, aux["fill_f32"].ravel(), -1.5, how="sum").reshape(shape)
+    out["to_array_ldd"] = o.core_ldd.to_array(idxs_ds, shape)
     return out
 
 
@@ -179,4 +194,15 @@ def run_api_case(pf, d8, aux, transform=None, latlon=False):
     out["sub_ids"] = sub_ids
     out["basins_sub"] = flw.basins(idxs=sub_idxs, ids=sub_ids)
     out["to_array"] = flw.to_array()
+    # SURVEY.md §8f "next" rows
+    out["us_main"] = flw.main_upstream()
+    out["us_main_km2"] = flw.main_upstream(uparea=out["uparea_km2"])
+    out["strord_classic"] = flw.stream_order(type="classic")
+    out["strord_classic_mask"] = flw.stream_order(type="classic", mask=aux["smask"])
+    out["fill_up_i64"] = flw.fillnodata(aux["fill_i64"], -9999, direction="up")
+    out["fill_up_f64nan"] = flw.fillnodata(aux["fill_f64"], np.nan, direction="up")
+    out["fill_down_max_f32"] = flw.fillnodata(aux["fill_f32"], -1.5, direction="down", how="max")
+    out["fill_down_min_i64"] = flw.fillnodata(aux["fill_i64"], -9999, direction="down", how="min")
+    out["fill_down_sum_f32"] = flw.fillnodata(aux["fill_f32"], -1.5, direction="down", how="sum")
+    out["to_array_ldd"] = flw.to_array("ldd")
     return out

@@ -25,48 +25,13 @@ from oracle import reference  # noqa: E402
 import oracle  # noqa: E402
 
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from _cases import RHINE_TRANSFORM, case_inputs, sha  # noqa: E402
+from _cases import RHINE_TRANSFORM, case_inputs, run_api_case, sha  # noqa: E402
 
 
-def run_case(pf, name, d8, seed, transform=None, latlon=False, dtype_override=None):
-    """Returns dict of reference outputs for one D8 raster."""
-    kw = {}
-    if transform is not None:
-        kw = dict(transform=transform, latlon=latlon)
-    flw = pf.from_array(d8, ftype="d8", cache=False, **kw)
+def run_case(pf, name, d8, seed, transform=None, latlon=False):
+    """Reference outputs for one D8 raster: the very same API calls the GPU tests make (tests/_cases.py)."""
     aux = case_inputs(name, d8, seed)
-    out = {}
-    out["idxs_ds"] = flw.idxs_ds
-    out["idxs_pit"] = flw.idxs_pit
-    out["idxs_outlet"] = flw.idxs_outlet
-    out["rank"] = flw.rank
-    out["idxs_seq"] = flw.idxs_seq
-    out["nnodes"] = np.int64(flw.nnodes)
-    out["isvalid"] = np.bool_(flw.isvalid)
-    out["n_upstream"] = flw.n_upstream
-    out["uparea_cell"] = flw.upstream_area()
-    out["uparea_km2"] = flw.upstream_area("km2")
-    out["basins"] = flw.basins()
-    out["strord"] = flw.stream_order()
-    out["strord_mask"] = flw.stream_order(mask=aux["smask"])
-    out["accu_f32"] = flw.accuflux(aux["data_f32"], nodata=-9999)
-    out["accu_f64"] = flw.accuflux(aux["data_f64"], nodata=-9999.0)
-    out["accu_f32_nd"] = flw.accuflux(aux["data_f32_nd"], nodata=-9999)
-    out["accu_i64"] = flw.accuflux(aux["data_i64"], nodata=-9999)
-    out["accu_ds_f64"] = flw.accuflux(aux["data_f64"], nodata=-9999.0, direction="down")
-    out["accu_ds_i64"] = flw.accuflux(aux["data_i64"], nodata=-9999, direction="down")
-    drain = out["uparea_cell"] > max(4, int(0.002 * d8.size))
-    out["hand_f32"] = flw.hand(drain, aux["elevtn"])
-    out["hand_f64"] = flw.hand(drain, aux["elevtn"].astype(np.float64) * 1.1)
-    # sub-basins from custom outlets with custom ids (every 37th cell of the sequence)
-    seq = flw.idxs_seq
-    sub_idxs = seq[:: max(1, seq.size // 23)][:40]
-    sub_ids = (np.arange(sub_idxs.size, dtype=np.int64) * 3 + 5).astype(np.int32)
-    out["sub_idxs"] = sub_idxs
-    out["sub_ids"] = sub_ids
-    out["basins_sub"] = flw.basins(idxs=sub_idxs, ids=sub_ids)
-    out["to_array"] = flw.to_array()
-    return out, aux
+    return run_api_case(pf, d8, aux, transform=transform, latlon=latlon), aux
 
 
 def main():
@@ -113,6 +78,16 @@ def main():
         ids, pits, n = rd8.from_array(d8_small, dtype=dt)
         small_outputs[f"flwdir_asc/idxs_ds_{np.dtype(dt).name}"] = ids
         small_outputs[f"flwdir_asc/idxs_pit_{np.dtype(dt).name}"] = pits
+
+    # --- PCRaster LDD (core_ldd.py): the 160x200 fixture converted with the reference's own d8_to_ldd
+    ldd = pf.d8_to_ldd(d8_large).astype(np.uint8)
+    flw_ldd = pf.from_array(ldd)  # ftype inferred
+    assert flw_ldd.ftype == "ldd"
+    small_inputs["ldd_flwdir1/ldd"] = ldd
+    for k, v in dict(idxs_ds=flw_ldd.idxs_ds, idxs_pit=flw_ldd.idxs_pit, idxs_outlet=flw_ldd.idxs_outlet,
+                     to_array=flw_ldd.to_array(), to_array_d8=flw_ldd.to_array("d8"), uparea_cell=flw_ldd.upstream_area(),
+                     d8_to_ldd=ldd, ldd_to_d8=pf.ldd_to_d8(ldd).astype(np.uint8)).items():
+        small_outputs[f"ldd_flwdir1/{k}"] = np.asarray(v)
 
     # --- drdc over all 256 codes (core_d8.py:22-39), including the illegal ones
     drdc = np.array([rd8.drdc(np.uint8(i)) for i in range(256)], dtype=np.int8)

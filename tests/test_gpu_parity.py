@@ -92,7 +92,7 @@ def test_synth_generator_host_equals_device(pfb):
 
 def test_errors(pfb):
     with pytest.raises(ValueError, match="could not be inferred"):
-        pfb.from_array(np.full((4, 4), 3, dtype=np.uint8))
+        pfb.from_array(np.full((4, 4), 10, dtype=np.uint8))  # neither a D8 nor an LDD code
     with pytest.raises(ValueError, match="should be 2 dimensional"):
         pfb.from_array(np.zeros(16, dtype=np.uint8), ftype="d8")
     with pytest.raises(ValueError, match='type "d8" is invalid'):
@@ -175,3 +175,53 @@ def test_module_level_functions(pfb):
         assert np.array_equal(hand.reshape(d8.shape), cs.golden(name, "hand_f32"))
     with pytest.raises(ValueError, match="outside 8 neighbors"):
         core_d8.to_array(np.array([5, 1, 2, 3, 4, 5], dtype=np.int32), (2, 3))
+
+
+def test_ldd(pfb):
+    """PCRaster LDD rasters (core_ldd.py): inferred ftype, same graph as the D8 original, to_array both ways."""
+    from pyflwdir_b200 import core_ldd
+
+    s = cs.small()
+    ldd = s["in/ldd_flwdir1/ldd"]
+    flw = pfb.from_array(ldd)  # d8 is tried first and refused, then ldd (pyflwdir.py:39-48)
+    assert flw.ftype == "ldd"
+    assert np.array_equal(flw.idxs_ds, s["out/ldd_flwdir1/idxs_ds"])
+    assert np.array_equal(flw.idxs_pit, s["out/ldd_flwdir1/idxs_pit"])
+    assert np.array_equal(flw.idxs_outlet, s["out/ldd_flwdir1/idxs_outlet"])
+    assert np.array_equal(flw.to_array(), s["out/ldd_flwdir1/to_array"])
+    assert np.array_equal(flw.to_array("d8"), s["out/ldd_flwdir1/to_array_d8"])
+    assert np.array_equal(flw.upstream_area(), s["out/ldd_flwdir1/uparea_cell"])
+    d8 = cs.case_d8("flwdir1_asc")
+    assert np.array_equal(pfb.d8_to_ldd(d8), s["out/ldd_flwdir1/d8_to_ldd"])
+    assert np.array_equal(pfb.ldd_to_d8(ldd), s["out/ldd_flwdir1/ldd_to_d8"])
+    ids, pits, n = core_ldd.from_array(ldd, dtype=np.uint32)
+    assert np.array_equal(ids.astype(np.int64), s["out/ldd_flwdir1/idxs_ds"].astype(np.uint32).astype(np.int64))
+    assert core_ldd.isvalid(ldd) and not core_ldd.isvalid(d8)
+    assert np.array_equal(core_ldd.to_array(s["out/ldd_flwdir1/idxs_ds"], ldd.shape), s["out/ldd_flwdir1/to_array"])
+    with pytest.raises(ValueError, match='type "ldd" is invalid'):
+        pfb.from_array(d8, ftype="ldd")
+    # unaligned width + mask through the LDD table
+    lddu = np.ascontiguousarray(ldd[:, :197])
+    ids_o, pits_o, _ = oracle.core_ldd.from_array(lddu, dtype=np.int32)
+    flwu = pfb.from_array(lddu, ftype="ldd")
+    assert np.array_equal(flwu.idxs_ds, ids_o) and np.array_equal(flwu.idxs_pit, pits_o)
+
+
+def test_next_rows_module_level(pfb):
+    """main_upstream / classic stream order / fillnodata through the module-level mirrors."""
+    from pyflwdir_b200 import core, streams
+
+    name = "flwdir1_asc"
+    d8 = cs.case_d8(name)
+    aux = cs.case_inputs(name, d8, cs.case_seed(name))
+    ids, seq = cs.golden(name, "idxs_ds"), cs.golden(name, "idxs_seq")
+    um = core.main_upstream(ids, cs.golden(name, "uparea_cell").ravel())
+    assert np.array_equal(um, cs.golden(name, "us_main")) and um.dtype == ids.dtype
+    so = streams.stream_order(ids, seq, um, mask=aux["smask"].ravel())
+    assert np.array_equal(so.reshape(d8.shape), cs.golden(name, "strord_classic_mask"))
+    assert np.array_equal(core.upstream_count(ids, mask=aux["smask"].ravel()),
+                          oracle.core.upstream_count(ids, mask=aux["smask"].ravel()))
+    f = core.fillnodata_downstream(ids, seq, aux["fill_f32"].ravel(), -1.5, how="sum")
+    assert np.array_equal(f.reshape(d8.shape), cs.golden(name, "fill_down_sum_f32"))
+    f = core.fillnodata_upstream(ids, seq, aux["fill_f64"].ravel(), np.nan)
+    assert np.array_equal(f.reshape(d8.shape), cs.golden(name, "fill_up_f64nan"), equal_nan=True)

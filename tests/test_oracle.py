@@ -94,3 +94,13 @@ def test_oracle_vs_live_reference(seed, oracle_lib):
     assert np.array_equal(out["accu_f64"], flw.accuflux(aux["data_f64"], nodata=-9999.0))
     drain = out["uparea_cell"] > max(4, int(0.002 * d8.size))
     assert np.array_equal(out["hand_f32"], flw.hand(drain, aux["elevtn"]))
+
+
+def test_oracle_ldd_golden(oracle_lib):
+    """core_ldd.from_array / to_array restatement against the reference on the LDD version of flwdir1.asc."""
+    ldd = cs.small()["in/ldd_flwdir1/ldd"]
+    ids, pits, n = oracle.core_ldd.from_array(ldd, dtype=np.int32)
+    assert np.array_equal(ids, cs.small()["out/ldd_flwdir1/idxs_ds"]) and ids.dtype == np.int32
+    assert np.array_equal(pits, cs.small()["out/ldd_flwdir1/idxs_pit"])
+    assert np.array_equal(oracle.core_ldd.to_array(ids, ldd.shape), cs.small()["out/ldd_flwdir1/to_array"])
+    assert np.array_equal(oracle.core_d8.to_array(ids, ldd.shape), cs.small()["out/ldd_flwdir1/to_array_d8"])
