@@ -32,7 +32,9 @@ def test_from_array_input_errors():
     with pytest.raises(ValueError, match='"mask" shape does not match'):
         pfb.from_array(np.zeros((3, 3), dtype=np.uint8), ftype="d8", mask=np.ones((2, 2)))
     with pytest.raises(NotImplementedError):
-        pfb.from_array(np.ones((3, 3), dtype=np.uint8), ftype="ldd")
+        pfb.from_array((np.ones((3, 3), dtype=np.int32), np.ones((3, 3), dtype=np.int32)), ftype="nextxy")
+    with pytest.raises(ValueError, match='type "ldd" is invalid'):
+        pfb.from_array(np.zeros((3, 3), dtype=np.int16), ftype="ldd")
 
 
 def test_affine():
