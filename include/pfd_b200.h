@@ -163,6 +163,12 @@ int pfd_upstream_count(pfd_handle* h, const uint8_t* mask, int8_t* out);
 /* streams.stream_order, "classic" / Hack (pyflwdir/streams.py:191-225); mask may be NULL */
 int pfd_stream_order_classic(pfd_handle* h, const void* idxs_us_main, int idx_dtype, const uint8_t* mask, uint8_t* out);
 
+/* streams.stream_distance (pyflwdir/streams.py:272-315, interpreted Python in the reference): distance to the
+ * outlet or to the next downstream cell of `mask` (N bytes or NULL). real_length != 0: float32 metres, hop lengths
+ * from hop_table[nrow][3][2] = float32(gis_utils.distance) per (row, row delta + 1, |column delta|) built by the
+ * host; else int32 cell counts. out is -9999 outside the sequence. */
+int pfd_stream_distance(pfd_handle* h, const uint8_t* mask, int real_length, const float* hop_table, void* out);
+
 /* ---- fused headline pass ------------------------------------------------------------------------------ */
 /*
  * parse + order + rank + upstream_area(cell) + basins() in one call (BASELINE.json metric). Any output may be

@@ -306,7 +306,47 @@ def _strahler_order(idxs_ds, seq, mask=None):
     return out
 
 
-streams = types.SimpleNamespace(accuflux=_accuflux, accuflux_ds=_accuflux_ds, strahler_order=_strahler_order,
+def _stream_distance(idxs_ds, seq, ncol, mask=None, real_length=True, latlon=False, transform=(1.0, 0.0, 0.0, 0.0, -1.0, 0.0)):
+    """pyflwdir/streams.py:272-315 (plain Python in the reference) with gis_utils.distance (gis_utils.py:451-486)
+    restated inline; NumPy-2 scalar arithmetic (float32 array element + Python float -> float32)."""
+    import math
+
+    xres, yres, north = transform[0], transform[4], transform[5]
+
+    def dmy(lat):
+        rl = math.radians(lat)
+        return 111132.92 + (-559.82 * math.cos(2.0 * rl)) + (1.175 * math.cos(4.0 * rl)) + (-0.0023 * math.cos(6.0 * rl))
+
+    def dmx(lat):
+        rl = math.radians(lat)
+        return (111412.84 * math.cos(rl)) + (-93.5 * math.cos(3.0 * rl)) + (0.118 * math.cos(5.0 * rl))
+
+    def distance(idx0, idx1):
+        r0, r1 = int(idx0 // ncol), int(idx1 // ncol)
+        dr = abs(r1 - r0)
+        dc = abs(int(idx1 % ncol) - int(idx0 % ncol))
+        if latlon:
+            lat = north + (r0 + r1) / 2.0 * yres
+            dy = 0.0 if dr == 0 else dmy(lat) * yres
+            dx = 0.0 if dc == 0 else dmx(lat) * xres
+        else:
+            dy, dx = xres, yres
+        return math.hypot(dy * dr, dx * dc)
+
+    dist = np.full(idxs_ds.size, -9999.0, dtype=np.float32 if real_length else np.int32)
+    dist[seq] = 0
+    d = 1
+    for idx0 in seq.tolist():
+        idx_ds = int(idxs_ds[idx0])
+        if idx0 == idx_ds or (mask is not None and mask[idx0]):
+            continue
+        if real_length:
+            d = distance(idx0, idx_ds)
+        dist[idx0] = dist[idx_ds] + d
+    return dist
+
+
+streams = types.SimpleNamespace(stream_distance=_stream_distance, accuflux=_accuflux, accuflux_ds=_accuflux_ds, strahler_order=_strahler_order,
                                 stream_order=lambda *a, **k: _stream_order_classic(*a, **k))
 
 

@@ -249,6 +249,20 @@ class DeviceGraph:
                                                   _lib.ptr(out)))
         return out
 
+    def stream_distance(self, mask=None, hop_table=None):
+        """hop_table None -> int32 cell counts, else float32 with the given [nrow, 3, 2] float32 hop lengths."""
+        m = None
+        if mask is not None:
+            m = np.ascontiguousarray(mask)
+            m = m.view(np.uint8) if m.dtype == np.bool_ else (m != 0).astype(np.uint8)
+            if m.size != self.size:
+                raise ValueError('"mask" size does not match.')
+        real = hop_table is not None
+        out = _lib.out_array(self.size, np.float32 if real else np.int32)
+        tab = np.ascontiguousarray(hop_table, dtype=np.float32) if real else None
+        self._ck(self._l.pfd_stream_distance(self._h, _lib.ptr(m), 1 if real else 0, _lib.ptr(tab), _lib.ptr(out)))
+        return out
+
     # -- instrumentation
     @property
     def launches(self):

@@ -1486,6 +1486,40 @@ extern "C" int pfd_stream_order_classic(pfd_handle* h, const void* idxs_us_main,
     return PFD_OK;
 }
 
+
+// streams.stream_distance (pyflwdir/streams.py:272-315). hop_table: nrow*3*2 float32 (host or device) when
+// real_length, else NULL; out: N float32 (real_length) or N int32, -9999 outside the sequence.
+extern "C" int pfd_stream_distance(pfd_handle* h, const uint8_t* mask, int real_length, const float* hop_table, void* out) {
+    PFD_TRY(check_handle(h));
+    stage_reset(h);
+    if (!out || (real_length && !hop_table)) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_stream_distance: null array");
+    PFD_TRY(order_impl(h, false, false));
+    const int64_t n = h->n;
+    const size_t bytes = (size_t)n * 4;
+    void* out_dev = nullptr;
+    PFD_TRY(pfd_stage_out(h, out, bytes, 3, &out_dev));
+    const void *mask_dev = nullptr, *hop_dev = nullptr;
+    if (mask) PFD_TRY(pfd_stage_in(h, mask, (size_t)n, 4, &mask_dev));
+    if (real_length) PFD_TRY(pfd_stage_in(h, hop_table, (size_t)h->nrow * 6 * sizeof(float), 5, &hop_dev));
+    int rc;
+    if (real_length) {
+        fill_kernel<float><<<grid_for(n, 256, 4), 256, 0, h->stream>>>((float*)out_dev, n, -9999.0f);
+        PFD_LAUNCH_CHECK(h);
+        StreamDistOp<true> op{(const uint8_t*)h->dir.p, (const uint8_t*)mask_dev, (const float*)hop_dev, out_dev, h->ncol};
+        rc = run_sweep<StreamDistOp<true>, false>(h, op, 0);
+    } else {
+        fill_kernel<int32_t><<<grid_for(n, 256, 4), 256, 0, h->stream>>>((int32_t*)out_dev, n, -9999);
+        PFD_LAUNCH_CHECK(h);
+        StreamDistOp<false> op{(const uint8_t*)h->dir.p, (const uint8_t*)mask_dev, nullptr, out_dev, h->ncol};
+        rc = run_sweep<StreamDistOp<false>, false>(h, op, 0);
+    }
+    PFD_TRY(rc);
+    PFD_TRY(pfd_finish_out(h, out, out_dev, bytes));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    return PFD_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // fused headline pass
 // ---------------------------------------------------------------------------------------------------------

@@ -272,6 +272,42 @@ __global__ void upstream_count_mask_kernel(const uint8_t* __restrict__ dir, cons
     }
 }
 
+// ---- streams.stream_distance (streams.py:272-315, interpreted Python in the reference): down-sweep -------------
+// REAL: float32 distances, the length of a hop comes from a host-built table indexed by (row of the cell, row
+// delta + 1, |column delta|) holding float32(gis_utils.distance(...)) -- NumPy-2 scalar semantics: the Python float
+// is cast to float32, then added in float32. !REAL: int32 cell counts.
+template <bool REAL>
+struct StreamDistOp {
+    const uint8_t* dir;
+    const uint8_t* mask;   // may be null: distance to the outlet
+    const float* hop;      // [nrow][3][2], REAL only
+    void* out;
+    long long ncol;
+    __device__ __forceinline__ void operator()(cell_t c, long long, int) const {
+        const uint32_t d = __ldg(dir + c);
+        const bool stop = d >= 8u || (mask && __ldg(mask + c));
+        if (REAL) {
+            float* o = (float*)out;
+            if (stop) {
+                o[c] = 0.0f;
+                return;
+            }
+            const long long ds = (long long)c + pfd_slot_off((int)d, ncol);
+            const long long r0 = (long long)c / ncol;
+            const int dr = pfd_slot_dr((int)d), dc = pfd_slot_dc((int)d);
+            const float len = __ldg(hop + (r0 * 3 + (dr + 1)) * 2 + (dc != 0 ? 1 : 0));
+            o[c] = __fadd_rn(ld_cg(o + ds), len);
+        } else {
+            int32_t* o = (int32_t*)out;
+            if (stop) {
+                o[c] = 0;
+                return;
+            }
+            o[c] = ld_cg(o + ((long long)c + pfd_slot_off((int)d, ncol))) + 1;
+        }
+    }
+};
+
 // ---- core.rank as a replay (when the BFS ran without it) -----------------------------------------------
 struct RankOp {
     int32_t* rank;

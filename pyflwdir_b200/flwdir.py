@@ -266,7 +266,7 @@ class Flwdir(object):
         return idxs
 
     # ------------------------------------------------------------------ not in scope
-    for _name in ("path", "snap", "inflow_idxs", "outflow_idxs", "stream_distance", "smooth_rivlen",
+    for _name in ("path", "snap", "inflow_idxs", "outflow_idxs", "smooth_rivlen",
                   "subbasins_streamorder", "subbasins_pfafstetter", "subbasins_area", "moving_average",
                   "moving_median", "upstream_sum", "vectorize", "streams", "geofeatures", "dem_adjust", "dem_dig_d4",
                   "floodplains", "classify_estuaries", "ucat_area", "ucat_outlets", "ucat_volume", "subgrid_rivlen",

@@ -116,3 +116,37 @@ def area_grid(transform, shape, latlon=False, unit="m2"):
         return reggrid_area(lat, lon) / AREA_FACTORS[unit]
     area0 = abs(transform[0] * transform[4]) / AREA_FACTORS[unit]
     return np.full(shape, area0, dtype=np.float32)
+
+
+def degree_metres_y(lat):
+    """Vertical length of a degree in metres at a given latitude; gis_utils.py:415-430 (scalar, libm cos)."""
+    radlat = math.radians(lat)
+    return 111132.92 + (-559.82 * math.cos(2.0 * radlat)) + (1.175 * math.cos(4.0 * radlat)) + (-0.0023 * math.cos(6.0 * radlat))
+
+
+def degree_metres_x(lat):
+    """Horizontal length of a degree in metres at a given latitude; gis_utils.py:433-447."""
+    radlat = math.radians(lat)
+    return (111412.84 * math.cos(radlat)) + (-93.5 * math.cos(3.0 * radlat)) + (0.118 * math.cos(5.0 * radlat))
+
+
+def hop_length_table(nrow, transform, latlon):
+    """float32 table [nrow, 3, 2] of gis_utils.distance(idx0, idx1, ...) (gis_utils.py:451-486) for a hop that starts in
+    row r0 with row delta dr in (-1, 0, 1) and |column delta| dc in (0, 1) -- everything the distance depends on.
+    Reproduces the reference including its quirk for projected rasters (dy = xres, dx = yres)."""
+    xres, yres, north = transform[0], transform[4], transform[5]
+    tab = np.zeros((nrow, 3, 2), dtype=np.float64)
+    if not latlon:
+        for j, dr in enumerate((-1, 0, 1)):
+            for dc in (0, 1):
+                tab[:, j, dc] = math.hypot(xres * abs(dr), yres * dc)
+    else:
+        for r0 in range(nrow):
+            for j, d in enumerate((-1, 0, 1)):
+                lat = north + (r0 + (r0 + d)) / 2.0 * yres
+                dr = abs(d)
+                dy = 0.0 if dr == 0 else degree_metres_y(lat) * yres
+                dx1 = degree_metres_x(lat) * xres
+                tab[r0, j, 0] = math.hypot(dy * dr, 0.0)
+                tab[r0, j, 1] = math.hypot(dy * dr, dx1 * 1)
+    return tab.astype(np.float32)

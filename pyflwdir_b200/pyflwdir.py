@@ -251,6 +251,17 @@ class FlwdirRaster(Flwdir):
         uparea[~self.mask.ravel()] = -9999
         return uparea.reshape(self.shape)
 
+    # ------------------------------------------------------------------ streams
+    def stream_distance(self, mask=None, unit="cell"):
+        """Distance to the outlet or to the next downstream True cell of `mask` (pyflwdir.py:837-863 ->
+        streams.stream_distance): int32 cell counts for unit="cell", float32 metres for unit="m"."""
+        unit = str(unit).lower()
+        if unit not in ["m", "cell"]:
+            raise ValueError(f'Unknown unit: {unit}, select from "m", "cell"')
+        mask = self._check_data(mask, "mask", optional=True)
+        table = gis.hop_length_table(self.shape[0], self.transform, self.latlon) if unit != "cell" else None
+        return self._dev.stream_distance(mask, table).reshape(self.shape)
+
     # ------------------------------------------------------------------ elevation
     def hand(self, drain, elevtn):
         """Height above the nearest drain (pyflwdir.py:1485-1511 -> dem.height_above_nearest_drain)."""
@@ -278,7 +289,7 @@ class FlwdirRaster(Flwdir):
         return super()._check_idxs_xy(idxs, streams)
 
     for _name in ("repair_loops_raster", "subbasins_streamorder", "subbasins_pfafstetter", "subbasins_area",
-                  "streams", "geofeatures", "vectorize", "stream_distance", "dem_adjust", "dem_dig_d4", "floodplains",
+                  "streams", "geofeatures", "vectorize", "dem_adjust", "dem_dig_d4", "floodplains",
                   "upscale", "upscale_error", "subgrid_rivlen", "subgrid_rivslp", "subgrid_rivavg", "subgrid_rivmed",
                   "ucat_area", "ucat_outlets", "ucat_volume", "inflow_idxs", "outflow_idxs"):
         locals()[_name] = _not_in_scope(_name)

@@ -96,7 +96,7 @@ def check(name, key, arr):
     assert sha(arr) == hashes()[name][key], f"{name}/{key}: SHA-256 differs from the reference's"
 
 
-def run_oracle_case(d8, aux, area=None):
+def run_oracle_case(d8, aux, area=None, transform=(1.0, 0.0, 0.0, 0.0, -1.0, 0.0), latlon=False):
     """The whole hot path on the CPU oracle, mirroring make_golden.run_case (which runs the real reference).
     `area` = flat cell-area vector [m2] for upstream_area("km2") (host-side input, see gis_utils.area_grid)."""
     o = oracle
@@ -154,6 +154,13 @@ def run_oracle_case(d8, aux, area=None):
     out["fill_down_min_i64"] = o.core.fillnodata_downstream(idxs_ds, seq, aux["fill_i64"].ravel(), -9999, how="min").reshape(shape)
     out["fill_down_sum_f32"] = o.core.fillnodata_downstream(idxs_ds, seq, aux["fill_f32"].ravel(), -1.5, how="sum").reshape(shape)
     out["to_array_ldd"] = o.core_ldd.to_array(idxs_ds, shape)
+    sm = aux["smask"].ravel()
+    sd = lambda mask, real: o.streams.stream_distance(idxs_ds, seq, shape[1], mask=mask, real_length=real, latlon=latlon,
+                                                      transform=tuple(transform)[:6]).reshape(shape)
+    out["sdist_cell"] = sd(None, False)
+    out["sdist_cell_mask"] = sd(sm, False)
+    out["sdist_m"] = sd(None, True)
+    out["sdist_m_mask"] = sd(sm, True)
     return out
 
 
@@ -205,4 +212,8 @@ def run_api_case(pf, d8, aux, transform=None, latlon=False):
     out["fill_down_min_i64"] = flw.fillnodata(aux["fill_i64"], -9999, direction="down", how="min")
     out["fill_down_sum_f32"] = flw.fillnodata(aux["fill_f32"], -1.5, direction="down", how="sum")
     out["to_array_ldd"] = flw.to_array("ldd")
+    out["sdist_cell"] = flw.stream_distance()
+    out["sdist_cell_mask"] = flw.stream_distance(mask=aux["smask"])
+    out["sdist_m"] = flw.stream_distance(unit="m")
+    out["sdist_m_mask"] = flw.stream_distance(mask=aux["smask"], unit="m")
     return out

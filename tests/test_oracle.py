@@ -27,7 +27,7 @@ def test_oracle_rhine_golden(oracle_lib):
         assert cs.sha(v) == cs.hashes()["rhine"]["_aux"][k], f"aux input {k} drifted"
     area = gis_utils.area_grid(gis_utils.Affine(*cs.RHINE_TRANSFORM), d8.shape, latlon=True)
     assert np.array_equal(area[:, 0], cs.small()["out/rhine/area_col0"])
-    out = cs.run_oracle_case(d8, aux, area=area.ravel())
+    out = cs.run_oracle_case(d8, aux, area=area.ravel(), transform=cs.RHINE_TRANSFORM, latlon=True)
     for key, val in out.items():
         cs.check("rhine", key, val)
     assert int(out["rank"].max()) == cs.hashes()["rhine"]["_max_rank"] == 1674
