@@ -108,7 +108,6 @@ __global__ void stash_pit_ids_kernel(const cell_t* __restrict__ pits, long long 
 struct TileShared {
     uint32_t P[TL_CELLS];
     uint32_t A[TL_CELLS];
-    uint8_t dir[TL_CELLS];
 };
 #define TP_PACK(n, h) ((uint32_t)(n) | ((uint32_t)(h) << 12))
 #define TP_N(p) ((p) & 0xFFFu)
@@ -212,8 +211,6 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 
     uint32_t dirs[(TL_CPT + 3) / 4], own[TL_CPT];
     tl_load_dirs<THREADS>(dir, nrow, ncol, r0, c0, dirs);
-#pragma unroll
-    for (int it = 0; it < TL_CPT; ++it) s.dir[(ly0 + TL_RPI * it) * TL_W + lx] = (uint8_t)tl_dir_of(dirs, it);
     tl_local_solve<THREADS>(s, dirs, own);
 
     // (1) per-cell results for phase C
@@ -244,7 +241,8 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
     uint32_t rd = PFD_DIR_NODATA;
     if (threadIdx.x < TL_NRING) {
         ri = tl_ring_cell(threadIdx.x);
-        rd = s.dir[ri];
+        const int rly = ri >> 6, rlx = ri & (TL_W - 1);
+        if (r0 + rly < nrow && c0 + rlx < ncol) rd = __ldg(dir + g00 + (long long)rly * ncol + rlx);  // L1/L2 hit
         if (rd < 8u && s.P[ri] == (uint32_t)ri) {  // exit cell
             const uint32_t ti = tl_exit_slot(tile, (uint32_t)ntx, ri >> 6, ri & (TL_W - 1), rd);
             atomicAdd(W + ti, s.A[ri]);
