@@ -169,6 +169,12 @@ int pfd_stream_order_classic(pfd_handle* h, const void* idxs_us_main, int idx_dt
  * host; else int32 cell counts. out is -9999 outside the sequence. */
 int pfd_stream_distance(pfd_handle* h, const uint8_t* mask, int real_length, const float* hop_table, void* out);
 
+/* dem.floodplains (pyflwdir/dem.py:333-379, interpreted Python in the reference): floodplain mask from a HAND
+ * threshold that scales with the drain's upstream area (h ~ A**b). drainh_init: N float32 holding
+ * float32(uparea ** b) at the drain cells (uparea >= upa_min) and -9999 elsewhere -- the power is evaluated by the
+ * host exactly as the reference does; elevtn: N float32 / float64; out: N int8 (-1 outside the sequence). */
+int pfd_floodplains(pfd_handle* h, const float* drainh_init, const void* elevtn, int elev_dtype, int8_t* out);
+
 /* ---- fused headline pass ------------------------------------------------------------------------------ */
 /*
  * parse + order + rank + upstream_area(cell) + basins() in one call (BASELINE.json metric). Any output may be

@@ -379,7 +379,31 @@ def _hand(idxs_ds, seq, drain, elevtn):
     return out
 
 
-dem = types.SimpleNamespace(height_above_nearest_drain=_hand)
+def _floodplains(idxs_ds, seq, elevtn, uparea, upa_min=1000.0, b=0.3):
+    """pyflwdir/dem.py:333-379 (plain Python in the reference; numpy-scalar arithmetic kept as is)."""
+    drainh = np.full(uparea.size, -9999.0, dtype=np.float32)
+    drainz = np.full(uparea.size, -9999.0, dtype=np.float32)
+    fldpln = np.full(uparea.size, -1, dtype=np.int8)
+    fldpln[seq] = 0
+    for idx0 in seq:
+        if uparea[idx0] >= upa_min:
+            drainh[idx0] = uparea[idx0] ** b
+            drainz[idx0] = elevtn[idx0]
+            fldpln[idx0] = 1
+        else:
+            idx_ds = idxs_ds[idx0]
+            if fldpln[idx_ds] == 1:
+                z0 = drainz[idx_ds]
+                h0 = drainh[idx_ds]
+                dh = elevtn[idx0] - z0
+                if dh <= h0:
+                    fldpln[idx0] = 1
+                    drainz[idx0] = z0
+                    drainh[idx0] = h0
+    return fldpln
+
+
+dem = types.SimpleNamespace(height_above_nearest_drain=_hand, floodplains=_floodplains)
 
 
 # ----------------------------------------------------------------------------- synthetic input (host)

@@ -263,6 +263,17 @@ class DeviceGraph:
         self._ck(self._l.pfd_stream_distance(self._h, _lib.ptr(m), 1 if real else 0, _lib.ptr(tab), _lib.ptr(out)))
         return out
 
+    def floodplains(self, drainh_init, elevtn):
+        dh = np.ascontiguousarray(drainh_init, dtype=np.float32)
+        e = np.ascontiguousarray(elevtn)
+        if e.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+            e = e.astype(np.float64)
+        if dh.size != self.size or e.size != self.size:
+            raise ValueError('"elevtn" size does not match.')
+        out = _lib.out_array(self.size, np.int8)
+        self._ck(self._l.pfd_floodplains(self._h, _lib.ptr(dh), _lib.ptr(e), _lib.dtype_code(e.dtype), _lib.ptr(out)))
+        return out
+
     # -- instrumentation
     @property
     def launches(self):

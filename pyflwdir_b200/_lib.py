@@ -56,6 +56,7 @@ SYMBOLS = {
     "pfd_upstream_count": (_int, [_vp, _vp, _vp]),
     "pfd_stream_order_classic": (_int, [_vp, _vp, _int, _vp, _vp]),
     "pfd_stream_distance": (_int, [_vp, _vp, _int, _vp, _vp]),
+    "pfd_floodplains": (_int, [_vp, _vp, _vp, _int, _vp]),
     "pfd_d8_flow_all": (_int, [_vp, _vp, _i64, _i64, _vp, _int, _vp, _vp, _vp, _pi64, _pi64, _pi64]),
     "pfd_comm_unique_id": (_int, [_vp, _i64]),
     "pfd_comm_init": (_int, [_vp, _int, _int, _vp]),

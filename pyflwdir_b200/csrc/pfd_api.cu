@@ -1520,6 +1520,42 @@ extern "C" int pfd_stream_distance(pfd_handle* h, const uint8_t* mask, int real_
     return PFD_OK;
 }
 
+
+// dem.floodplains (pyflwdir/dem.py:333-379). drainh_init: N float32 = float32(uparea ** b) at drain cells, -9999
+// elsewhere (host-evaluated); elevtn: N float32 / float64; out: N int8 (-1 outside the sequence, else 0 / 1).
+extern "C" int pfd_floodplains(pfd_handle* h, const float* drainh_init, const void* elevtn, int elev_dtype, int8_t* out) {
+    PFD_TRY(check_handle(h));
+    stage_reset(h);
+    if (!drainh_init || !elevtn || !out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_floodplains: null array");
+    if (elev_dtype != PFD_F32 && elev_dtype != PFD_F64) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_floodplains: elevtn must be float32 or float64");
+    PFD_TRY(order_impl(h, false, false));
+    const int64_t n = h->n;
+    void* out_dev = nullptr;
+    PFD_TRY(pfd_stage_out(h, out, (size_t)n, 3, &out_dev));
+    const void* elev_dev = nullptr;
+    PFD_TRY(pfd_stage_in(h, elevtn, (size_t)n * pfd_dtype_size(elev_dtype), 5, &elev_dev));
+    // working copies of drainh (modified in place) and drainz
+    PFD_TRY(pfd_reserve(h, h->scratch[4], (size_t)n * sizeof(float)));
+    PFD_TRY(pfd_reserve(h, h->scratch[2], (size_t)n * sizeof(float)));
+    float* drainh = (float*)h->scratch[4].p;
+    float* drainz = (float*)h->scratch[2].p;
+    PFD_CUDA(h, cudaMemcpyAsync(drainh, drainh_init, (size_t)n * sizeof(float), cudaMemcpyDefault, h->stream));
+    PFD_CUDA(h, cudaMemsetAsync(out_dev, 0xFF, (size_t)n, h->stream));  // -1
+    int rc;
+    if (elev_dtype == PFD_F32) {
+        FloodplainOp<float> op{(const uint8_t*)h->dir.p, (const float*)elev_dev, drainh, drainz, (int8_t*)out_dev, h->ncol};
+        rc = run_sweep<FloodplainOp<float>, false>(h, op, 0);
+    } else {
+        FloodplainOp<double> op{(const uint8_t*)h->dir.p, (const double*)elev_dev, drainh, drainz, (int8_t*)out_dev, h->ncol};
+        rc = run_sweep<FloodplainOp<double>, false>(h, op, 0);
+    }
+    PFD_TRY(rc);
+    PFD_TRY(pfd_finish_out(h, out, out_dev, (size_t)n));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    return PFD_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // fused headline pass
 // ---------------------------------------------------------------------------------------------------------

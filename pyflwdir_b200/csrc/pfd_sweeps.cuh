@@ -308,6 +308,43 @@ struct StreamDistOp {
     }
 };
 
+template <typename T>
+__device__ __forceinline__ T elev_sub(T a, T b);
+
+// ---- dem.floodplains (dem.py:333-379, interpreted Python in the reference): down-sweep ------------------------
+// drainh arrives pre-loaded by the host with float32(uparea ** b) at the drain cells (uparea >= upa_min) and -9999
+// elsewhere (pow is evaluated on the host exactly as the reference does); drainz is scratch.
+template <typename T>
+struct FloodplainOp {
+    const uint8_t* dir;
+    const T* elevtn;
+    float* drainh;
+    float* drainz;
+    int8_t* out;
+    long long ncol;
+    __device__ __forceinline__ void operator()(cell_t c, long long, int) const {
+        const float h_own = drainh[c];
+        if (h_own != -9999.0f) {  // drain cell
+            drainz[c] = (float)__ldg(elevtn + c);
+            out[c] = 1;
+            return;
+        }
+        int8_t f = 0;
+        const uint32_t d = __ldg(dir + c);
+        const long long ds = ds_of(c, d, ncol);
+        if (ds != (long long)c && ld_cg(out + ds) == 1) {
+            const float z0 = ld_cg(drainz + ds), h0 = ld_cg(drainh + ds);
+            const T dh = elev_sub<T>(__ldg(elevtn + c), (T)z0);  // elevtn's dtype (float32 - float32, float64 - float32)
+            if (dh <= (T)h0) {
+                f = 1;
+                drainz[c] = z0;
+                drainh[c] = h0;
+            }
+        }
+        out[c] = f;
+    }
+};
+
 // ---- core.rank as a replay (when the BFS ran without it) -----------------------------------------------
 struct RankOp {
     int32_t* rank;

@@ -269,7 +269,7 @@ class Flwdir(object):
     for _name in ("path", "snap", "inflow_idxs", "outflow_idxs", "smooth_rivlen",
                   "subbasins_streamorder", "subbasins_pfafstetter", "subbasins_area", "moving_average",
                   "moving_median", "upstream_sum", "vectorize", "streams", "geofeatures", "dem_adjust", "dem_dig_d4",
-                  "floodplains", "classify_estuaries", "ucat_area", "ucat_outlets", "ucat_volume", "subgrid_rivlen",
+                  "classify_estuaries", "ucat_area", "ucat_outlets", "ucat_volume", "subgrid_rivlen",
                   "subgrid_rivslp", "subgrid_rivavg", "subgrid_rivmed", "subgrid_rivlen2", "upscale", "upscale_error",
                   "accuflux_ds"):
         locals()[_name] = _not_in_scope(_name)

@@ -268,6 +268,19 @@ class FlwdirRaster(Flwdir):
         hand = self._dev.hand(self._check_data(drain, "drain"), self._check_data(elevtn, "elevtn"))
         return hand.reshape(self.shape)
 
+    def floodplains(self, elevtn, uparea=None, upa_min=1000, b=0.3):
+        """Floodplain boundaries from a HAND threshold that scales with upstream area, h ~ A**b
+        (pyflwdir.py:1513-1546 -> dem.floodplains, dem.py:333-379). int8: 1 floodplain, 0 not, -1 outside the sequence."""
+        elev = self._check_data(elevtn, "elevtn")
+        upa = self._check_data(uparea, "uparea", unit="km2")
+        # uparea ** b for the drain cells only, with numpy scalars exactly as the reference's Python loop evaluates it
+        drain = np.flatnonzero(upa >= upa_min)
+        drainh = np.full(self.size, -9999.0, dtype=np.float32)
+        if drain.size:
+            drainh[drain] = np.array([u ** b for u in upa[drain]], dtype=np.float64).astype(np.float32) \
+                if upa.dtype != np.float32 else np.array([u ** b for u in upa[drain]], dtype=np.float32)
+        return self._dev.floodplains(drainh, elev).reshape(self.shape)
+
     # ------------------------------------------------------------------ shortcuts
     def _check_data(self, data, name, optional=False, flatten=True, **kwargs):
         if data is None and optional:
@@ -289,7 +302,7 @@ class FlwdirRaster(Flwdir):
         return super()._check_idxs_xy(idxs, streams)
 
     for _name in ("repair_loops_raster", "subbasins_streamorder", "subbasins_pfafstetter", "subbasins_area",
-                  "streams", "geofeatures", "vectorize", "dem_adjust", "dem_dig_d4", "floodplains",
+                  "streams", "geofeatures", "vectorize", "dem_adjust", "dem_dig_d4",
                   "upscale", "upscale_error", "subgrid_rivlen", "subgrid_rivslp", "subgrid_rivavg", "subgrid_rivmed",
                   "ucat_area", "ucat_outlets", "ucat_volume", "inflow_idxs", "outflow_idxs"):
         locals()[_name] = _not_in_scope(_name)

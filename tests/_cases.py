@@ -161,6 +161,12 @@ def run_oracle_case(d8, aux, area=None, transform=(1.0, 0.0, 0.0, 0.0, -1.0, 0.0
     out["sdist_cell_mask"] = sd(sm, False)
     out["sdist_m"] = sd(None, True)
     out["sdist_m_mask"] = sd(sm, True)
+    if area is not None:
+        ukm = out["uparea_km2"]
+        upa_min = float(np.quantile(ukm[ukm > 0], 0.97)) if (ukm > 0).any() else 1.0
+        out["fldpln_f32"] = o.dem.floodplains(idxs_ds, seq, aux["elevtn"].ravel(), ukm.ravel(), upa_min=upa_min, b=0.3).reshape(shape)
+    out["fldpln_f64"] = o.dem.floodplains(idxs_ds, seq, (aux["elevtn"].astype(np.float64) * 1.1).ravel(),
+                                          out["uparea_cell"].ravel(), upa_min=max(4, int(0.002 * d8.size)), b=0.5).reshape(shape)
     return out
 
 
@@ -216,4 +222,8 @@ def run_api_case(pf, d8, aux, transform=None, latlon=False):
     out["sdist_cell_mask"] = flw.stream_distance(mask=aux["smask"])
     out["sdist_m"] = flw.stream_distance(unit="m")
     out["sdist_m_mask"] = flw.stream_distance(mask=aux["smask"], unit="m")
+    upa_min = float(np.quantile(out["uparea_km2"][out["uparea_km2"] > 0], 0.97)) if (out["uparea_km2"] > 0).any() else 1.0
+    out["fldpln_f32"] = flw.floodplains(aux["elevtn"], upa_min=upa_min, b=0.3)
+    out["fldpln_f64"] = flw.floodplains(aux["elevtn"].astype(np.float64) * 1.1, uparea=out["uparea_cell"],
+                                        upa_min=max(4, int(0.002 * d8.size)), b=0.5)
     return out
