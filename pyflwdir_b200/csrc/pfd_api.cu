@@ -58,12 +58,6 @@ __global__ void widen_cells_kernel(const cell_t* __restrict__ in, int64_t n, IDX
         out[i] = (IDX)in[i];
 }
 
-template <typename IDX>
-__global__ void narrow_cells_kernel(const IDX* __restrict__ in, int64_t n, cell_t* __restrict__ out) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        out[i] = (cell_t)in[i];
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // library / handle
 // ---------------------------------------------------------------------------------------------------------

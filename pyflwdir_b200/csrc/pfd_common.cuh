@@ -141,8 +141,6 @@ struct pfd_handle {
 
     // staging / scratch
     DevBuf scratch[6];
-    void* pinned = nullptr;
-    size_t pinned_cap = 0;
 
     // instrumentation
     int64_t launches = 0;

@@ -168,7 +168,6 @@ __global__ void __launch_bounds__(BFS_THREADS) bfs_kernel(BfsParams P) {
     cg::grid_group grid = cg::this_grid();
     __shared__ unsigned int s_warp[BFS_THREADS / 32];
     __shared__ unsigned long long s_prefix;
-    __shared__ unsigned long long s_state[3];
 
     unsigned int lev = __ldcg(&P.st->cur_level);
     for (;;) {
@@ -215,7 +214,6 @@ __global__ void __launch_bounds__(BFS_THREADS) bfs_kernel(BfsParams P) {
         grid.sync();
         ++lev;
     }
-    (void)s_state;
 }
 
 // rank / basins initialisation: nodata -> -9999, valid -> -1 (cells the BFS never reaches keep -1 = "does not

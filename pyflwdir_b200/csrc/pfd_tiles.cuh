@@ -484,7 +484,6 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
         }
     }
     __syncthreads();
-#ifndef TL_EXPERIMENT_NOWALK
     if (threadIdx.x < s.wl_count) {
         int i = (int)s.wl_cell[threadIdx.x];
         const uint32_t w = s.wl_w[threadIdx.x];
@@ -495,7 +494,6 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
             i = ni;
         }
     }
-#endif
     __syncthreads();
 #pragma unroll
     for (int it = 0; it < TL_CPT; ++it) up[it] += s.X[(ly0 + TL_RPI * it) * TL_W + lx];

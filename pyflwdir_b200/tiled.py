@@ -104,6 +104,26 @@ class RowBlockSolver:
         self._ck(self._l.pfd_tiled_local(self._h, rank, nranks, pit_id_offset, self._basins_dev, C.byref(tab), C.byref(n)))
         return tab, n.value
 
+    def flow_all(self, block, halo_top, halo_bot, glob_row0, idx_dtype):
+        """parse + solve of this rank's row block with the exchanges over NCCL (comm_init first; a handle without a
+        communicator solves a whole raster alone). Returns (idxs_ds, rank, uparea, basins, n_pits_global)."""
+        block = np.ascontiguousarray(block, dtype=np.uint8)
+        self.nrow = block.shape[0] - halo_top - halo_bot
+        self.ncol = block.shape[1]
+        n = self.nrow * self.ncol
+        idxs = np.empty(n, dtype=idx_dtype)
+        rank = np.empty(n, dtype=np.int32)
+        upa = np.empty(n, dtype=np.int32)
+        bas = np.empty(n, dtype=np.uint32)
+        bas_dev = self.dev_alloc(n * 4)
+        npg = C.c_int64()
+        self._ck(self._l.pfd_d8_flow_all_tiled(self._h, _lib.ptr(block), self.nrow, self.ncol, halo_top, halo_bot,
+                                               glob_row0, _lib.ptr(idxs), _lib.dtype_code(idx_dtype), _lib.ptr(rank),
+                                               _lib.ptr(upa), bas_dev, None, C.byref(npg)))
+        self._ck(self._l.pfd_memcpy(self._h, _lib.ptr(bas), bas_dev, n * 4))
+        shape = (self.nrow, self.ncol)
+        return idxs, rank.reshape(shape), upa.reshape(shape), bas.reshape(shape), npg.value
+
     def read_table(self, tab, n):
         out = np.empty(n, dtype=np.uint32)
         if n:
