@@ -44,6 +44,9 @@ UNIT = "Mcells/s"
 # tile solver kernels: phase A reads dir (1) and writes loc + cnt (8); phase C reads dir + loc + cnt (9) and writes
 # rank + basins + uparea (12); the whole fused step has a 17 B/cell lower bound (d8 in, four int32 outputs)
 ALG_BYTES = {"parse": 5.0, "bfs": 12.0, "sweep": 8.0, "tile_a": 9.0, "tile_b": 0.0, "tile_c": 21.0}
+# fused-parse path (device-resident buffers): phase A reads the raw D8 codes (1) and writes dir (1) + loc + cnt (8);
+# phase C reads dir + loc + cnt (9) and writes idxs_ds (4; 8 when int64) + rank + basins + uparea (12)
+ALG_BYTES_FUSED = {"tile_a": 10.0, "tile_c": 25.0}
 STEP_BYTES_FUSED, STEP_BYTES_UNFUSED = 17.0, 29.0
 KERNEL_NAMES = {"parse": "parse_kernel", "bfs": "bfs_kernel", "sweep": "sweep_kernel<AccuUpOp<int>>",
                 "tile_a": "tile_phase_a_kernel", "tile_b": "slots_round_kernel", "tile_c": "tile_phase_c_kernel"}
@@ -200,8 +203,11 @@ class Workload:
         g = self.l.pfd_last_stage_ms
         tiles = self.l.pfd_get_info(self.h, b"tiles") == 1
         if tiles:
-            return {"parse": g(self.h, 0), "pits": g(self.h, 1), "tile_a": g(self.h, 6), "tile_b": g(self.h, 7),
-                    "tile_c": g(self.h, 8), "total": g(self.h, 4)}
+            st = {"parse": g(self.h, 0), "pits": g(self.h, 1), "tile_a": g(self.h, 6), "tile_b": g(self.h, 7),
+                  "tile_c": g(self.h, 8), "total": g(self.h, 4)}
+            if st["parse"] == 0.0:  # fused-parse path: no separate parse pass ran
+                del st["parse"]
+            return st
         return {"parse": g(self.h, 0), "pits": g(self.h, 1), "order": g(self.h, 2), "sweep": g(self.h, 3),
                 "total": g(self.h, 4), "bfs": g(self.h, 5)}
 
@@ -409,6 +415,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = every GPU owns `size` rows of a (N*size) x size raster (default); "
                          "strong = ONE size x size raster split into N row blocks (BASELINE config 4 with --size 65536)")
+    ap.add_argument("--no-fuse", action="store_true", help="run the separate parse pass even on device-resident buffers")
     ap.add_argument("--no-e2e", action="store_true", help="skip the pinned-host end-to-end arm (very large rasters)")
     ap.add_argument("--extras", action="store_true", help="also time the secondary configs (order, Strahler, HAND sweeps)")
     args = ap.parse_args()
@@ -428,6 +435,7 @@ def main():
     else:
         w = Workload(args.size, args.seed, device)
         w.ck(w.l.pfd_set_option(w.h, b"tiles", 1 if args.solver == "tiles" else 0))
+        w.ck(w.l.pfd_set_option(w.h, b"fuse_parse", 0 if args.no_fuse else 1))
     cells = w.cells
 
     # ---- device-resident arm. The clock sampler (rank 0) runs from before the warm-up until after a >= 1.2 s
@@ -477,16 +485,21 @@ def main():
     # ---- roofline of the dominant kernel
     peak, peak_src = peaks()
     kern = max((k for k in ("parse", "bfs", "sweep", "tile_a", "tile_c") if k in stage_avg), key=lambda k: stage_avg[k])
-    achieved = ALG_BYTES[kern] * cells / (stage_avg[kern] / 1e3) / 1e9
+    alg_bytes = dict(ALG_BYTES)
+    fused = "parse" not in stage_avg and "tile_a" in stage_avg
+    if fused:
+        alg_bytes.update(ALG_BYTES_FUSED)
+        alg_bytes["tile_c"] += np.dtype(getattr(w, "idx_dtype", np.int32)).itemsize - 4
+    achieved = alg_bytes[kern] * cells / (stage_avg[kern] / 1e3) / 1e9
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(f"{kern}_{args.size}")
+            traffic = json.load(f).get(f"{kern}{'_fused' if fused else ''}_{args.size}")
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": KERNEL_NAMES[kern],
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "algorithmic_bytes_per_cell": ALG_BYTES[kern],
+                "peak_source": peak_src, "algorithmic_bytes_per_cell": alg_bytes[kern], "fused_parse": fused,
                 "kernel_ms": stage_avg[kern], "stage_ms": stage_avg,
                 "step": {"algorithmic_bytes_per_cell": STEP_BYTES_FUSED, "unfused_bytes_per_cell": STEP_BYTES_UNFUSED,
                          "achieved_gbs_per_gpu": STEP_BYTES_FUSED * cells / (ms_total / args.steps / 1e3) / 1e9,

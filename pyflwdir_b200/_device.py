@@ -78,6 +78,40 @@ class DeviceGraph:
         self._set_shape(nrow, ncol, nv.value, npit.value, nout.value)
         return idxs
 
+    def flow_all(self, d8, idx_dtype=np.int32, resident=True):
+        """pfd_d8_flow_all: parse + rank + upstream_area("cell") + basins() in one call. With `resident` the raster
+        and the four outputs live in device buffers for the call (the fused-parse path of the library); otherwise
+        host buffers are handed to the library. Returns (idxs_ds, rank, uparea, basins) as flat host arrays."""
+        d8 = np.ascontiguousarray(d8, dtype=np.uint8)
+        nrow, ncol = d8.shape
+        n = d8.size
+        idx_dtype = np.dtype(idx_dtype)
+        outs = [_lib.out_array(n, idx_dtype), _lib.out_array(n, np.int32), _lib.out_array(n, np.int32),
+                _lib.out_array(n, np.uint32)]
+        nv, npit, nn = C.c_int64(), C.c_int64(), C.c_int64()
+        if resident:
+            bufs = []
+            try:
+                for nbytes in [n] + [o.nbytes for o in outs]:
+                    p = C.c_void_p()
+                    self._ck(self._l.pfd_dev_alloc(self._h, max(int(nbytes), 16), C.byref(p)))
+                    bufs.append(p)
+                self._ck(self._l.pfd_memcpy(self._h, bufs[0], _lib.ptr(d8), n))
+                self._ck(self._l.pfd_d8_flow_all(self._h, bufs[0], nrow, ncol, bufs[1], _lib.dtype_code(idx_dtype), bufs[2],
+                                                 bufs[3], bufs[4], C.byref(nv), C.byref(npit), C.byref(nn)))
+                for o, b in zip(outs, bufs[1:]):
+                    self._ck(self._l.pfd_memcpy(self._h, _lib.ptr(o), b, o.nbytes))
+            finally:
+                for b in bufs:
+                    self._l.pfd_dev_free(self._h, b)
+        else:
+            self._ck(self._l.pfd_d8_flow_all(self._h, _lib.ptr(d8), nrow, ncol, _lib.ptr(outs[0]), _lib.dtype_code(idx_dtype),
+                                             _lib.ptr(outs[1]), _lib.ptr(outs[2]), _lib.ptr(outs[3]), C.byref(nv),
+                                             C.byref(npit), C.byref(nn)))
+        self._set_shape(nrow, ncol, nv.value, npit.value, 0)
+        self.n_outlets = self.info("n_outlets")
+        return tuple(outs)
+
     def load_idxs_ds(self, idxs_ds, shape):
         idxs_ds = np.ascontiguousarray(idxs_ds)
         if idxs_ds.dtype not in _IDX_DTYPES:

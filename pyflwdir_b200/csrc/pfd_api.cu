@@ -152,6 +152,7 @@ extern "C" void pfd_destroy(pfd_handle* h) {
     cudaEventDestroy(h->ev_total[0]);
     cudaEventDestroy(h->ev_total[1]);
     cudaEventDestroy(h->ev_copy);
+    if (h->h_counters) cudaFreeHost(h->h_counters);
     cudaStreamSynchronize(h->copy_stream);
     cudaStreamDestroy(h->copy_stream);
     cudaStreamDestroy(h->stream);
@@ -224,14 +225,14 @@ extern "C" int pfd_timer_stop(pfd_handle* h, double* ms) {
 
 extern "C" double pfd_last_stage_ms(const pfd_handle* h, int stage) {
     if (!h || stage < 0 || stage >= PFD_NSTAGE) return 0.0;
-    return h->stage_ms[stage];
+    return h->stage_used[stage] ? h->stage_ms[stage] : 0.0;  // 0: the stage did not run in the last call
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // parse
 // ---------------------------------------------------------------------------------------------------------
 static void invalidate(pfd_handle* h) {
-    h->parsed = h->ordered = h->have_rank = h->have_basins = h->have_uparea = false;
+    h->parsed = h->ordered = h->have_rank = h->have_basins = h->have_uparea = h->have_upmask = false;
     h->n_valid = h->n_pits = h->n_outlets = h->nnodes = h->nlevels = 0;
 }
 
@@ -318,6 +319,7 @@ static int parse_device(pfd_handle* h, const uint8_t* d8_dev, int64_t nrow_owned
     h->dir_off = (int64_t)halo_top * ncol;
     h->tiled = (halo_top || halo_bot || glob_row0 != 0);
     h->parsed = true;
+    h->have_upmask = true;
     h->ordered = h->have_rank = h->have_basins = h->have_uparea = false;
     return PFD_OK;
 }
@@ -500,9 +502,9 @@ static int tiles_phase_a(pfd_handle* h, TileCtx& T, uint32_t* basin_dev, unsigne
             (const cell_t*)h->pits.p, h->n_pits, h->dir_off, pit_id_offset, basin_dev);
         PFD_LAUNCH_CHECK(h);
     }
-    tile_phase_a_kernel<TLA_THREADS, TLA_MINBLOCKS><<<grid, TLA_THREADS, 0, h->stream>>>(
+    tile_phase_a_kernel<TLA_THREADS, TLA_MINBLOCKS, false><<<grid, TLA_THREADS, 0, h->stream>>>(
         T.dir, h->nrow, h->ncol, T.ntx, basin_dev, (uint2*)h->tile_loc.p, T.B[0].acc, T.B[0].nxt, T.B[0].rh, T.B[0].ch,
-        T.term, T.term_h);
+        T.term, T.term_h, nullptr, nullptr, nullptr, 0);
     PFD_LAUNCH_CHECK(h);
     return PFD_OK;
 }
@@ -537,17 +539,24 @@ static int tiles_phase_b(pfd_handle* h, TileCtx& T) {
     StageTimer t(h, PFD_STAGE_TILE_B);
     PFD_TRY(slots_solve(h, T.B, T.recv, T.nslots, T.flag, 1, tiles_protect(h, T, false)));
     slots_finalize_kernel<<<grid_for(T.nslots, 256, 2, 148 * 16), 256, 0, h->stream>>>(
-        T.B[0], T.B[1], (const int*)(T.flag + 3), T.term, T.term_h, T.nslots, T.srank, T.sbasin);
+        T.B[0], T.B[1], (const int*)(T.flag + 3), T.term, T.term_h, T.nslots, T.srank, T.sbasin, nullptr, 0, 0);
     PFD_LAUNCH_CHECK(h);
     return PFD_OK;
 }
 
-static int tiles_phase_c(pfd_handle* h, TileCtx& T, int32_t* rank_dev, uint32_t* basin_dev, int32_t* uparea_dev) {
+// idxs_dev (optional, fused-parse path): idxs_ds in `idx_dtype` is written by the same kernel
+static int tiles_phase_c(pfd_handle* h, TileCtx& T, int32_t* rank_dev, uint32_t* basin_dev, int32_t* uparea_dev,
+                         void* idxs_dev = nullptr, int idx_dtype = PFD_I32) {
     StageTimer t(h, PFD_STAGE_TILE_C);
     const dim3 grid((unsigned)T.ntx, (unsigned)T.nty);
-    tile_phase_c_kernel<TLC_THREADS, TLC_MINBLOCKS><<<grid, TLC_THREADS, 0, h->stream>>>(
-        T.dir, h->nrow, h->ncol, T.ntx, (const uint2*)h->tile_loc.p, T.B[0].acc, T.srank, T.sbasin, rank_dev, basin_dev,
-        uparea_dev);
+#define LAUNCH_C(M)                                                                                                   \
+    tile_phase_c_kernel<TLC_THREADS, TLC_MINBLOCKS, M><<<grid, TLC_THREADS, 0, h->stream>>>(                            \
+        T.dir, h->nrow, h->ncol, T.ntx, (const uint2*)h->tile_loc.p, T.B[0].acc, T.srank, T.sbasin, rank_dev, basin_dev, \
+        uparea_dev, idxs_dev)
+    if (!idxs_dev) LAUNCH_C(0);
+    else if (idx_dtype == PFD_I64) LAUNCH_C(2);
+    else LAUNCH_C(1);
+#undef LAUNCH_C
     PFD_LAUNCH_CHECK(h);
     return PFD_OK;
 }
@@ -559,6 +568,128 @@ static int tiles_solve(pfd_handle* h, int32_t* rank_dev, uint32_t* basin_dev, in
     PFD_TRY(tiles_phase_a(h, T, basin_dev, 0));
     PFD_TRY(tiles_phase_b(h, T));
     PFD_TRY(tiles_phase_c(h, T, rank_dev, basin_dev, uparea_dev));
+    return PFD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused headline path (pfd_d8_flow_all with device-resident buffers): the raster is read ONCE as raw D8 codes by
+// phase A, which derives + writes `dir` itself; idxs_ds is written by phase C next to rank / basins / uparea. The
+// separate parse pass (7 B/cell) disappears. Pits are numbered (count -> scan -> scatter -> stash) from the `dir`
+// phase A wrote; the host needs the pit count to size the pit list, and waits for it WHILE the reduced-graph solve
+// (which does not depend on the pit numbering) runs on the GPU. `upmask` is not produced here: ensure_upmask()
+// derives it from `dir` the first time an ordering / sweep entry point asks for it.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void upmask_from_dir_kernel(const uint8_t* __restrict__ dir, long long nrow, long long ncol, uint8_t* __restrict__ upmask) {
+    const long long n = nrow * ncol;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / ncol, c = i % ncol;
+        uint32_t m = 0;
+        if (dir[i] != PFD_DIR_NODATA) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const long long rr = r + pfd_slot_dr(k), cc = c + pfd_slot_dc(k);
+                if (rr >= 0 && rr < nrow && cc >= 0 && cc < ncol && __ldg(dir + rr * ncol + cc) == (uint8_t)(7 - k)) m |= 1u << k;
+            }
+        }
+        upmask[i] = (uint8_t)m;
+    }
+}
+
+static int ensure_upmask(pfd_handle* h) {
+    if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, "no raster parsed on this handle");
+    if (h->have_upmask) return PFD_OK;
+    const int64_t npad = (h->n + PC_CHUNK - 1) / PC_CHUNK * PC_CHUNK;
+    PFD_TRY(pfd_reserve(h, h->upmask, (size_t)npad));
+    upmask_from_dir_kernel<<<grid_for(h->n, 256, 4), 256, 0, h->stream>>>((const uint8_t*)h->dir.p, h->nrow, h->ncol,
+                                                                          (uint8_t*)h->upmask.p);
+    PFD_LAUNCH_CHECK(h);
+    h->have_upmask = true;
+    return PFD_OK;
+}
+
+static int flow_all_fused(pfd_handle* h, const uint8_t* d8_dev, int64_t nrow, int64_t ncol, void* idxs_dev, int idx_dtype,
+                          int32_t* rank_dev, uint32_t* basin_dev, int32_t* uparea_dev) {
+    const int64_t n = nrow * ncol;
+    const int64_t npad = (n + PC_CHUNK - 1) / PC_CHUNK * PC_CHUNK;
+    PFD_TRY(pfd_reserve(h, h->dir, (size_t)npad));
+    PFD_TRY(pfd_reserve(h, h->counters, 8 * sizeof(unsigned long long)));
+    if (!h->h_counters) PFD_CUDA(h, cudaHostAlloc((void**)&h->h_counters, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+    PFD_CUDA(h, cudaMemsetAsync(h->counters.p, 0, 8 * sizeof(unsigned long long), h->stream));
+    if (npad > n) PFD_CUDA(h, cudaMemsetAsync((uint8_t*)h->dir.p + n, 0xFF, (size_t)(npad - n), h->stream));
+    unsigned int* flag = reinterpret_cast<unsigned int*>((unsigned long long*)h->counters.p + 3);
+    h->nrow = nrow;
+    h->ncol = ncol;
+    h->n = n;
+    h->dir_off = 0;
+    h->tiled = false;
+    h->parsed = true;  // tiles_setup checks it; invalidate() on any failure below
+    h->have_upmask = false;
+    TileCtx T;
+    int rc = tiles_setup(h, T, false);
+    if (rc != PFD_OK) {
+        invalidate(h);
+        return rc;
+    }
+    const dim3 grid((unsigned)T.ntx, (unsigned)T.nty);
+    {
+        StageTimer t(h, PFD_STAGE_TILE_A);
+        PFD_CUDA(h, cudaMemsetAsync(T.B[0].acc, 0, T.arr, h->stream));
+        halo_slots_init_kernel<<<grid_for(2 * T.ntx * TL_RING, 256), 256, 0, h->stream>>>(T.B[0], T.term, T.term_h, T.ntx, T.nty);
+        PFD_LAUNCH_CHECK(h);
+        const int al4 = (ncol % 4 == 0) && ((uintptr_t)d8_dev % 4 == 0);
+        tile_phase_a_kernel<TLA_THREADS, TLA_MINBLOCKS, true><<<grid, TLA_THREADS, 0, h->stream>>>(
+            nullptr, nrow, ncol, T.ntx, nullptr, (uint2*)h->tile_loc.p, T.B[0].acc, T.B[0].nxt, T.B[0].rh, T.B[0].ch, T.term,
+            T.term_h, d8_dev, (uint8_t*)h->dir.p, flag, al4);
+        PFD_LAUNCH_CHECK(h);
+    }
+    const int64_t nblk = npad / PC_CHUNK;
+    {
+        StageTimer t(h, PFD_STAGE_PITS);
+        PFD_TRY(pfd_reserve(h, h->blk_counts, (size_t)nblk * sizeof(uint32_t)));
+        PFD_TRY(pfd_reserve(h, h->blk_offsets, (size_t)(nblk + 1) * sizeof(unsigned long long)));
+        pit_count_kernel<<<(unsigned)nblk, 256, 0, h->stream>>>((const uint8_t*)h->dir.p, (uint32_t*)h->blk_counts.p,
+                                                               (unsigned long long*)h->counters.p);
+        PFD_LAUNCH_CHECK(h);
+        scan_counts_kernel<<<1, 1024, 0, h->stream>>>((const uint32_t*)h->blk_counts.p, nblk,
+                                                     (unsigned long long*)h->blk_offsets.p);
+        PFD_LAUNCH_CHECK(h);
+        PFD_CUDA(h, cudaMemcpyAsync(h->h_counters, h->counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                    h->stream));
+        PFD_CUDA(h, cudaEventRecord(h->ev_copy, h->stream));
+    }
+    {
+        // stage B = reduced-graph solve, pit list + id stash (queued once the host knows the pit count), finalize
+        StageTimer t(h, PFD_STAGE_TILE_B);
+        PFD_TRY(slots_solve(h, T.B, T.recv, T.nslots, T.flag, 1, tiles_protect(h, T, false)));
+        PFD_CUDA(h, cudaEventSynchronize(h->ev_copy));  // the solve keeps the GPU busy meanwhile
+        const unsigned int flags = (unsigned int)h->h_counters[3];
+        h->n_valid = (int64_t)h->h_counters[0];
+        h->n_pits = (int64_t)h->h_counters[1];
+        h->n_outlets = (int64_t)h->h_counters[2];
+        if ((flags & 1u) || h->n_pits == 0 || h->n_pits >= (1ll << 31)) {
+            const int64_t np = h->n_pits;
+            cudaStreamSynchronize(h->stream);
+            invalidate(h);
+            if (flags & 1u)
+                return pfd_fail(h, PFD_ERR_INVALID_D8, "raster holds values outside the D8 code set {0,1,2,4,8,16,32,64,128,247,255}");
+            if (np == 0) return pfd_fail(h, PFD_ERR_NO_PITS, "Invalid FlwdirRaster: no pits found");
+            return pfd_fail(h, PFD_ERR_UNSUPPORTED, "tile solver: more than 2^31 pits");
+        }
+        PFD_TRY(pfd_reserve(h, h->pits, (size_t)h->n_pits * sizeof(cell_t)));
+        PFD_TRY(pfd_reserve(h, h->pit_outlet, (size_t)h->n_pits));
+        pit_scatter_kernel<<<(unsigned)nblk, 256, 0, h->stream>>>((const uint8_t*)h->dir.p, (const unsigned long long*)h->blk_offsets.p,
+                                                                 (cell_t*)h->pits.p, (uint8_t*)h->pit_outlet.p);
+        PFD_LAUNCH_CHECK(h);
+        if (basin_dev) {
+            stash_pit_ids_kernel<<<grid_for(h->n_pits, 256, 1, 148 * 16), 256, 0, h->stream>>>((const cell_t*)h->pits.p, h->n_pits, 0,
+                                                                                              0ull, basin_dev);
+            PFD_LAUNCH_CHECK(h);
+        }
+        slots_finalize_kernel<<<grid_for(T.nslots, 256, 2, 148 * 16), 256, 0, h->stream>>>(
+            T.B[0], T.B[1], (const int*)(T.flag + 3), T.term, T.term_h, T.nslots, T.srank, T.sbasin, basin_dev, ncol, T.ntx);
+        PFD_LAUNCH_CHECK(h);
+    }
+    PFD_TRY(tiles_phase_c(h, T, rank_dev, basin_dev, uparea_dev, idxs_dev, idx_dtype));
     return PFD_OK;
 }
 
@@ -693,7 +824,7 @@ extern "C" int pfd_tiled_finish(pfd_handle* h, int32_t* rank_out, int32_t* upare
         SlotProtect noprot{1, 0, 0, 0};
         PFD_TRY(slots_solve(h, G, grecv, nb, gflag, 0, noprot));
         slots_finalize_kernel<<<grid_for(nb, 256), 256, 0, h->stream>>>(G[0], G[1], (const int*)(gflag + 3), gterm, gterm_h, nb,
-                                                                        grank, gbasin);
+                                                                        grank, gbasin, nullptr, 0, 0);
         PFD_LAUNCH_CHECK(h);
         // restore the local reduced graph, add the remote inflow, make the halo slots terminals, solve again
         for (int f = 0; f < 4; ++f) {
@@ -849,16 +980,23 @@ extern "C" int pfd_set_option(pfd_handle* h, const char* name, int64_t value) {
         h->use_tiles = value ? 1 : 0;
         return PFD_OK;
     }
+    if (name && strcmp(name, "fuse_parse") == 0) {
+        h->fuse_parse = value ? 1 : 0;
+        return PFD_OK;
+    }
     return pfd_fail(h, PFD_ERR_INVALID_ARG, std::string("pfd_set_option: unknown option ") + (name ? name : "(null)"));
 }
 
 extern "C" int64_t pfd_get_info(const pfd_handle* h, const char* name) {
     if (!h || !name) return -1;
     if (strcmp(name, "tiles") == 0) return h->use_tiles;
+    if (strcmp(name, "fuse_parse") == 0) return h->fuse_parse;
+    if (strcmp(name, "have_upmask") == 0) return h->have_upmask ? 1 : 0;
     if (strcmp(name, "tile_rounds") == 0) return h->tile_rounds;
     if (strcmp(name, "nlevels") == 0) return h->nlevels;
     if (strcmp(name, "nnodes") == 0) return h->nnodes;
     if (strcmp(name, "n_pits") == 0) return h->n_pits;
+    if (strcmp(name, "n_outlets") == 0) return h->n_outlets;
     if (strcmp(name, "n_valid") == 0) return h->n_valid;
     if (strcmp(name, "num_sms") == 0) return h->num_sms;
     return -1;
@@ -963,6 +1101,7 @@ static int order_impl(pfd_handle* h, bool want_rank, bool want_basins) {
         }
         for (;;) {
             BfsParams P;
+            PFD_TRY(ensure_upmask(h));
             P.upmask = (const uint8_t*)h->upmask.p;
             P.seq = (cell_t*)h->seq.p;
             P.bseq = (uint32_t*)h->bseq.p;
@@ -1110,6 +1249,7 @@ extern "C" int pfd_fetch(pfd_handle* h, int which, void* out, int idx_dtype) {
     case PFD_ARR_N_UPSTREAM: {
         void* dev = nullptr;
         PFD_TRY(pfd_stage_out(h, out, (size_t)n, 2, &dev));
+        PFD_TRY(ensure_upmask(h));
         upstream_count_kernel<<<grid_for(n, 256, 4), 256, 0, h->stream>>>((const uint8_t*)h->dir.p, (const uint8_t*)h->upmask.p, n, (int8_t*)dev);
         PFD_LAUNCH_CHECK(h);
         PFD_TRY(pfd_finish_out(h, out, dev, (size_t)n));
@@ -1146,6 +1286,7 @@ static int accuflux_typed(pfd_handle* h, const void* data_dev, void* out_dev, co
     if (data_dev != out_dev)
         PFD_CUDA(h, cudaMemcpyAsync(out_dev, data_dev, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
     if (direction == 0) {
+        PFD_TRY(ensure_upmask(h));
         AccuUpOp<T> op{(const uint8_t*)h->upmask.p, (T*)out_dev, h->ncol, nd};
         return run_sweep<AccuUpOp<T>, true>(h, op, 0);
     }
@@ -1198,6 +1339,7 @@ static int uparea_cells_device(pfd_handle* h, int32_t* out_dev) {
     uparea_init_kernel<<<grid_for(n, 256, 4, 1ll << 30), 256, 0, h->stream>>>((const uint8_t*)h->dir.p, n, out_dev);
     PFD_LAUNCH_CHECK(h);
     NoData nd{-9999.0, -9999, 1};
+    PFD_TRY(ensure_upmask(h));
     AccuUpOp<int32_t> op{(const uint8_t*)h->upmask.p, out_dev, h->ncol, nd};
     return run_sweep<AccuUpOp<int32_t>, true>(h, op, 0);
 }
@@ -1293,6 +1435,7 @@ extern "C" int pfd_strahler(pfd_handle* h, const uint8_t* mask, uint8_t* out) {
     const void* mask_dev = nullptr;
     if (mask) PFD_TRY(pfd_stage_in(h, mask, bytes, 4, &mask_dev));
     PFD_CUDA(h, cudaMemsetAsync(out_dev, 0, bytes, h->stream));
+    PFD_TRY(ensure_upmask(h));
     StrahlerOp op{(const uint8_t*)h->upmask.p, (const uint8_t*)mask_dev, (uint8_t*)out_dev, h->ncol};
     PFD_TRY((run_sweep<StrahlerOp, true>(h, op, 0)));
     PFD_TRY(pfd_finish_out(h, out, out_dev, bytes));
@@ -1340,13 +1483,16 @@ static int fillnodata_typed(pfd_handle* h, void* out_dev, const NoData& nd, int 
         return run_sweep<FillUpGenericOp<T>, false>(h, op, 1);
     }
     if (how == 0) {
+        PFD_TRY(ensure_upmask(h));
         FillDownOp<T, 0> op{(const uint8_t*)h->upmask.p, (T*)out_dev, h->ncol, nd};
         return run_sweep<FillDownOp<T, 0>, true>(h, op, 0);
     }
     if (how == 1) {
+        PFD_TRY(ensure_upmask(h));
         FillDownOp<T, 1> op{(const uint8_t*)h->upmask.p, (T*)out_dev, h->ncol, nd};
         return run_sweep<FillDownOp<T, 1>, true>(h, op, 0);
     }
+    PFD_TRY(ensure_upmask(h));
     FillDownOp<T, 2> op{(const uint8_t*)h->upmask.p, (T*)out_dev, h->ncol, nd};
     return run_sweep<FillDownOp<T, 2>, true>(h, op, 0);
 }
@@ -1390,6 +1536,7 @@ template <typename T>
 static int main_upstream_typed(pfd_handle* h, const void* up_dev, double upa_min, void* out_dev, int idx_dtype) {
     const int g = grid_for(h->n, 256, 4);
     const T mn = (T)upa_min;
+    PFD_TRY(ensure_upmask(h));
     if (pfd_dtype_size(idx_dtype) == 4)
         main_upstream_kernel<T, uint32_t><<<g, 256, 0, h->stream>>>((const uint8_t*)h->upmask.p, (const T*)up_dev, h->n, h->ncol, mn, (uint32_t*)out_dev);
     else
@@ -1435,9 +1582,11 @@ extern "C" int pfd_upstream_count(pfd_handle* h, const uint8_t* mask, int8_t* ou
     if (mask) {
         const void* mdev = nullptr;
         PFD_TRY(pfd_stage_in(h, mask, (size_t)n, 4, &mdev));
+        PFD_TRY(ensure_upmask(h));
         upstream_count_mask_kernel<<<grid_for(n, 256, 4), 256, 0, h->stream>>>((const uint8_t*)h->dir.p, (const uint8_t*)h->upmask.p,
                                                                               (const uint8_t*)mdev, n, h->ncol, (int8_t*)dev);
     } else {
+        PFD_TRY(ensure_upmask(h));
         upstream_count_kernel<<<grid_for(n, 256, 4), 256, 0, h->stream>>>((const uint8_t*)h->dir.p, (const uint8_t*)h->upmask.p, n, (int8_t*)dev);
     }
     PFD_LAUNCH_CHECK(h);
@@ -1461,6 +1610,7 @@ extern "C" int pfd_stream_order_classic(pfd_handle* h, const void* idxs_us_main,
     if (mask) PFD_TRY(pfd_stage_in(h, mask, bytes, 4, &mask_dev));
     PFD_TRY(pfd_stage_in(h, idxs_us_main, (size_t)h->n * isz, 5, &main_dev));
     PFD_CUDA(h, cudaMemsetAsync(out_dev, 0, bytes, h->stream));
+    PFD_TRY(ensure_upmask(h));
     const uint8_t *dir = (const uint8_t*)h->dir.p, *upm = (const uint8_t*)h->upmask.p;
     int rc;
     if (idx_dtype == PFD_I32) {
@@ -1560,6 +1710,36 @@ extern "C" int pfd_d8_flow_all(pfd_handle* h, const uint8_t* d8, int64_t nrow, i
     stage_reset(h);
     cudaEventRecord(h->ev_start[PFD_STAGE_TOTAL], h->stream);
     h->stage_used[PFD_STAGE_TOTAL] = true;
+    // Fused path: everything device-resident (the D2H copy of a host idxs_ds is better overlapped with the solve,
+    // which needs the separate parse pass) and the tile solver enabled.
+    const bool all_dev = d8 && pfd_is_device_ptr(d8) && (!idxs_ds_out || pfd_is_device_ptr(idxs_ds_out)) &&
+                         (!rank_out || pfd_is_device_ptr(rank_out)) && (!uparea_out || pfd_is_device_ptr(uparea_out)) &&
+                         (!basins_out || pfd_is_device_ptr(basins_out));
+    if (h->use_tiles && h->fuse_parse && all_dev) {
+        PFD_TRY(check_shape(h, nrow, ncol, "pfd_d8_flow_all"));
+        if (idxs_ds_out && idx_dtype != PFD_I32 && idx_dtype != PFD_U32 && idx_dtype != PFD_I64)
+            return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_d8_flow_all: idx_dtype must be int32, uint32 or int64");
+        if (idxs_ds_out && idx_dtype == PFD_I32 && nrow * ncol >= 2147483647ll)
+            return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_d8_flow_all: int32 indices cannot address this raster");
+        invalidate(h);
+        void* rk = rank_out;
+        bool tmp_rank = false;
+        if (!rk && nnodes) {  // nnodes needs the rank
+            PFD_TRY(pfd_reserve(h, h->rank, (size_t)nrow * ncol * 4));
+            rk = h->rank.p;
+            tmp_rank = true;
+        }
+        PFD_TRY(flow_all_fused(h, d8, nrow, ncol, idxs_ds_out, idx_dtype, (int32_t*)rk, basins_out, uparea_out));
+        if (nnodes) PFD_TRY(count_ranked(h, (const int32_t*)rk, &h->nnodes));
+        if (tmp_rank) h->have_rank = true;
+        cudaEventRecord(h->ev_stop[PFD_STAGE_TOTAL], h->stream);
+        PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+        stage_collect(h);
+        if (n_valid) *n_valid = h->n_valid;
+        if (n_pits) *n_pits = h->n_pits;
+        if (nnodes) *nnodes = h->nnodes;
+        return PFD_OK;
+    }
     PFD_TRY(parse_impl(h, d8, nrow, ncol, idxs_ds_out, idx_dtype, /*overlap_idxs_copy=*/true));
     if (h->n_pits == 0) return pfd_fail(h, PFD_ERR_NO_PITS, "Invalid FlwdirRaster: no pits found");
     const size_t b4 = (size_t)h->n * 4;

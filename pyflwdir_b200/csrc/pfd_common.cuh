@@ -133,6 +133,9 @@ struct pfd_handle {
     DevBuf tile_loc;           // uint2 [n]: per cell (local terminal | hops << 12, in-tile subtree size)
     DevBuf uparea;            // int32 [n] cached cell-count upstream area (tile solver)
     bool have_uparea = false;
+    bool have_upmask = false;  // false after the fused-parse path: derived from dir on demand (ensure_upmask)
+    unsigned long long* h_counters = nullptr;  // page-locked mirror of `counters` (read while the GPU keeps working)
+    int fuse_parse = 1;       // option "fuse_parse": pfd_d8_flow_all on device buffers parses inside the tile solver
     int use_tiles = 1;        // option "tiles": 1 = tile-hierarchical solver for rank/basins/uparea, 0 = BFS + sweeps
     int tile_rounds = 0;      // reduced-graph doubling rounds of the last solve
     int nsegs = 0;

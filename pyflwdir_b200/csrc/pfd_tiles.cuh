@@ -194,15 +194,114 @@ __device__ __forceinline__ void tl_load_dirs(const uint8_t* __restrict__ dir, lo
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Fused parse (single-GPU headline path): the tile's raw D8 codes plus a one-cell halo are staged in shared
+// memory (32-bit loads for the interior, out-of-raster cells read as 247), every thread derives the `dir` byte
+// of its own cells exactly like parse_kernel (core_d8.py:42-67: pit / forced pit when the downstream cell is
+// nodata or off the raster / nodata; illegal codes raise the invalid flag, core_d8.py:115-122) and writes it to
+// global memory, so that the separate parse pass over the raster disappears from pfd_d8_flow_all.
+// ---------------------------------------------------------------------------------------------------------
+#define TLF_STRIDE 72   // bytes per staged row: 3 pad | left halo | 64 cells | right halo | 3 pad
+#define TLF_X0 4        // byte offset of the tile's first column inside a staged row (word aligned)
+struct TileCodes {
+    uint8_t c[(TL_H + 2) * TLF_STRIDE];
+};
+
+template <int THREADS>
+__device__ __forceinline__ void tl_stage_codes(TileCodes& sc, const uint8_t* __restrict__ d8, long long nrow, long long ncol,
+                                               long long r0, long long c0, bool al4) {
+    // interior: 64 rows x 16 words
+    for (int w = threadIdx.x; w < TL_H * (TL_W / 4); w += THREADS) {
+        const int row = w >> 4, wx = w & 15;
+        const long long r = r0 + row, c = c0 + 4 * wx;
+        uint32_t v = 0xF7F7F7F7u;
+        if (r < nrow && c < ncol) {
+            const uint8_t* p = d8 + r * ncol + c;
+            if (al4) {
+                v = __ldg(reinterpret_cast<const uint32_t*>(p));  // ncol % 4 == 0: the word never straddles the row end
+            } else {
+                v = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) v |= ((c + b < ncol) ? (uint32_t)__ldg(p + b) : 247u) << (8 * b);
+            }
+        }
+        *reinterpret_cast<uint32_t*>(&sc.c[(row + 1) * TLF_STRIDE + TLF_X0 + 4 * wx]) = v;
+    }
+    // halo: top / bottom rows (66 cells each), left / right columns (64 cells each)
+    for (int k = threadIdx.x; k < 2 * (TL_W + 2) + 2 * TL_H; k += THREADS) {
+        int sy, sx;  // staged coordinates: row 0..65, column -1..64
+        if (k < TL_W + 2) {
+            sy = 0;
+            sx = k - 1;
+        } else if (k < 2 * (TL_W + 2)) {
+            sy = TL_H + 1;
+            sx = k - (TL_W + 2) - 1;
+        } else if (k < 2 * (TL_W + 2) + TL_H) {
+            sy = k - 2 * (TL_W + 2) + 1;
+            sx = -1;
+        } else {
+            sy = k - 2 * (TL_W + 2) - TL_H + 1;
+            sx = TL_W;
+        }
+        const long long r = r0 + sy - 1, c = c0 + sx;
+        uint8_t v = 247;
+        if (r >= 0 && r < nrow && c >= 0 && c < ncol) v = __ldg(d8 + r * ncol + c);
+        sc.c[sy * TLF_STRIDE + TLF_X0 + sx] = v;
+    }
+}
+
+// D8 code -> neighbour slot (codes are powers of two): log2 E0 SE1 S2 SW3 W4 NW5 N6 NE7 -> slot 4 7 6 5 3 0 1 2
+__device__ __forceinline__ uint32_t tl_code_slot(uint32_t code) { return (0x21035674u >> (4 * (__ffs((int)code) - 1))) & 7u; }
+
+// dir bytes of the thread's own cells from the staged codes (packed 4 per word like tl_load_dirs); returns false
+// when one of them is not a legal D8 code
+template <int THREADS>
+__device__ __forceinline__ bool tl_parse_dirs(const TileCodes& sc, uint32_t* dirs) {
+    constexpr int TL_CPT = TL_CELLS / THREADS, TL_RPI = THREADS / TL_W;
+    const int lx = threadIdx.x & (TL_W - 1);
+    const int ly0 = threadIdx.x >> 6;
+    bool ok = true;
+#pragma unroll
+    for (int w = 0; w < (TL_CPT + 3) / 4; ++w) dirs[w] = 0;
+#pragma unroll
+    for (int it = 0; it < TL_CPT; ++it) {
+        const int ly = ly0 + TL_RPI * it;
+        const int at = (ly + 1) * TLF_STRIDE + TLF_X0 + lx;
+        const uint32_t code = sc.c[at];
+        uint32_t d;
+        if (code == 247u) {
+            d = PFD_DIR_NODATA;
+        } else if (code == 0u || code == 255u) {
+            d = PFD_DIR_PIT;
+        } else if (code & (code - 1u)) {
+            ok = false;
+            d = PFD_DIR_NODATA;
+        } else {
+            const uint32_t k = tl_code_slot(code);
+            const uint32_t nb = sc.c[at + pfd_slot_dr((int)k) * TLF_STRIDE + pfd_slot_dc((int)k)];
+            d = (nb == 247u) ? (uint32_t)PFD_DIR_FPIT : k;
+        }
+        dirs[it >> 2] |= d << (8 * (it & 3));
+    }
+    return ok;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Phase A: local solve; per cell (local terminal, hops) -> loc[], in-tile subtree size -> cnt[]; ring nodes; W
 // ---------------------------------------------------------------------------------------------------------
-template <int THREADS, int MINBLOCKS>
+// FUSED = false: `dir` is the parsed direction raster, pit terminals carry the pit ordinal found in `pit_ids`.
+// FUSED = true : `d8` holds raw D8 codes; the kernel derives the directions itself, writes them to `dir_out`
+//                (and flags illegal codes); pit terminals carry TERM_PIT | local cell index, resolved to the pit
+//                ordinal by slots_finalize_kernel once the pits have been numbered.
+template <int THREADS, int MINBLOCKS, bool FUSED>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
     tile_phase_a_kernel(const uint8_t* __restrict__ dir, long long nrow, long long ncol, long long ntx,
                         const uint32_t* pit_ids, uint2* __restrict__ loccnt, uint32_t* __restrict__ W, uint32_t* __restrict__ s_nxt, uint32_t* __restrict__ s_rh,
-                        uint32_t* __restrict__ s_ch, uint32_t* __restrict__ s_term, uint32_t* __restrict__ s_term_h) {
+                        uint32_t* __restrict__ s_ch, uint32_t* __restrict__ s_term, uint32_t* __restrict__ s_term_h,
+                        const uint8_t* __restrict__ d8, uint8_t* __restrict__ dir_out, unsigned int* __restrict__ invalid_flag,
+                        int al4) {
     constexpr int TL_CPT = TL_CELLS / THREADS, TL_RPI = THREADS / TL_W;
     __shared__ TileShared s;
+    __shared__ TileCodes sc;  // FUSED only (the compiler drops it otherwise)
     const uint32_t tile = (uint32_t)(((long long)blockIdx.y + 1) * ntx + blockIdx.x);  // +1: halo tile row
     const long long r0 = (long long)blockIdx.y * TL_H, c0 = (long long)blockIdx.x * TL_W;
     const int lx = threadIdx.x & (TL_W - 1);
@@ -210,7 +309,21 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
     const long long g00 = r0 * ncol + c0;  // global index of the tile's first cell
 
     uint32_t dirs[(TL_CPT + 3) / 4], own[TL_CPT];
-    tl_load_dirs<THREADS>(dir, nrow, ncol, r0, c0, dirs);
+    if (FUSED) {
+        tl_stage_codes<THREADS>(sc, d8, nrow, ncol, r0, c0, al4 != 0);
+        __syncthreads();
+        if (!tl_parse_dirs<THREADS>(sc, dirs)) atomicOr(invalid_flag, 1u);
+        __syncthreads();  // every neighbour code has been read: the staged codes may now be replaced by the dirs
+#pragma unroll
+        for (int it = 0; it < TL_CPT; ++it) {
+            const int ly = ly0 + TL_RPI * it;
+            const uint32_t d = tl_dir_of(dirs, it);
+            sc.c[(ly + 1) * TLF_STRIDE + TLF_X0 + lx] = (uint8_t)d;  // read back by the ring threads below
+            if (r0 + ly < nrow && c0 + lx < ncol) dir_out[g00 + (long long)ly * ncol + lx] = (uint8_t)d;
+        }
+    } else {
+        tl_load_dirs<THREADS>(dir, nrow, ncol, r0, c0, dirs);
+    }
     tl_local_solve<THREADS>(s, dirs, own);
 
     // (1) per-cell results for phase C
@@ -234,7 +347,8 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
         const uint32_t d = tl_dir_of(dirs, it);
         if (d == PFD_DIR_PIT || d == PFD_DIR_FPIT) {
             const int ly = ly0 + TL_RPI * it;
-            s.A[ly * TL_W + lx] = TERM_PIT | (pit_ids ? (pit_ids[g00 + (long long)ly * ncol + lx] - 1u) : 0u);
+            if (FUSED) s.A[ly * TL_W + lx] = TERM_PIT | (uint32_t)(ly * TL_W + lx);
+            else s.A[ly * TL_W + lx] = TERM_PIT | (pit_ids ? (pit_ids[g00 + (long long)ly * ncol + lx] - 1u) : 0u);
         }
     }
     int ri = -1;
@@ -242,7 +356,8 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
     if (threadIdx.x < TL_NRING) {
         ri = tl_ring_cell(threadIdx.x);
         const int rly = ri >> 6, rlx = ri & (TL_W - 1);
-        if (r0 + rly < nrow && c0 + rlx < ncol) rd = __ldg(dir + g00 + (long long)rly * ncol + rlx);  // L1/L2 hit
+        if (FUSED) rd = sc.c[(rly + 1) * TLF_STRIDE + TLF_X0 + rlx];  // out-of-raster cells were staged as nodata
+        else if (r0 + rly < nrow && c0 + rlx < ncol) rd = __ldg(dir + g00 + (long long)rly * ncol + rlx);  // L1/L2 hit
         if (rd < 8u && s.P[ri] == (uint32_t)ri) {  // exit cell
             const uint32_t ti = tl_exit_slot(tile, (uint32_t)ntx, ri >> 6, ri & (TL_W - 1), rd);
             atomicAdd(W + ti, s.A[ri]);
@@ -386,10 +501,14 @@ __global__ void __launch_bounds__(256, 8) slots_solve_kernel(SlotBuf b0, SlotBuf
 }
 
 // rounds: number of rounds the solve executed (device) -> the final node state is on side (*rounds & 1)
+// pit_stash != null (fused-parse path): pit terminals hold TERM_PIT | local cell index of the pit inside the tile
+// of slot `last`; the basin id (pit ordinal + 1) is read from the pit's own cell of the basin buffer, where
+// stash_pit_ids_kernel left it.
 __global__ void __launch_bounds__(256) slots_finalize_kernel(SlotBuf b0, SlotBuf b1, const int* __restrict__ rounds,
                                                              const uint32_t* __restrict__ term,
                                                              const uint32_t* __restrict__ term_h, long long nslots,
-                                                             int32_t* __restrict__ rank, uint32_t* __restrict__ basin) {
+                                                             int32_t* __restrict__ rank, uint32_t* __restrict__ basin,
+                                                             const uint32_t* __restrict__ pit_stash, long long ncol, long long ntx) {
     const SlotBuf cur = (*rounds & 1) ? b1 : b0;
     for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < nslots; s += (long long)gridDim.x * blockDim.x) {
         const uint32_t last = cur.nxt[s];
@@ -398,7 +517,14 @@ __global__ void __launch_bounds__(256) slots_finalize_kernel(SlotBuf b0, SlotBuf
         uint32_t b = 0;
         if ((t & TERM_PIT) && cur.nxt[last] == last && term[s] != SLOT_INVALID) {
             rk = (int32_t)(cur.ch[s] + term_h[last]);
-            b = (t & ~TERM_PIT) + 1u;
+            if (pit_stash) {
+                const long long tl = (long long)(last / TL_RING);  // slot-array tile index (halo tile row included)
+                const long long ty = tl / ntx - 1, tx = tl % ntx;
+                const uint32_t li = t & (uint32_t)(TL_CELLS - 1);
+                b = __ldg(pit_stash + (ty * TL_H + (li >> 6)) * ncol + tx * TL_W + (li & (TL_W - 1)));
+            } else {
+                b = (t & ~TERM_PIT) + 1u;
+            }
         }
         rank[s] = rk;
         basin[s] = b;
@@ -409,9 +535,15 @@ __global__ void __launch_bounds__(256) slots_finalize_kernel(SlotBuf b0, SlotBuf
 // Phase C: no second solve. acc = in-tile count (phase A) + the outside inflows of the tile's entry cells walked
 // down their local paths (sparse: ~90 entry cells per tile); rank / basin = hops + solution of the local terminal.
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tl_cp_async4(uint32_t* smem_dst, const uint32_t* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void tl_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 struct TileSharedC {
     uint32_t X[TL_CELLS];   // extra inflow per cell, later basin id per terminal
-    uint32_t T[TL_CELLS];   // in-tile successor while the walkers run, then rank at the terminal
+    uint32_t R[TL_CELLS];   // pit cells: stashed basin id (fetched with the first loads); later rank at the terminal
+    uint16_t S[TL_CELLS];   // in-tile successor, for the walkers
     uint32_t wl_cell[TL_RING];  // walker list
     uint32_t wl_w[TL_RING];
     uint32_t ring_t[TL_RING];   // per ring position: rank at the terminal if the cell is an exit cell, else TL_NOT_EXIT
@@ -421,12 +553,14 @@ struct TileSharedC {
 };
 #define TL_NOT_EXIT 0xFFFFFFFEu
 
-template <int THREADS, int MINBLOCKS>
+// IDXMODE: 0 = no idxs_ds output, 1 = 32-bit (int32 / uint32 share the bit pattern), 2 = int64 -- the fused-parse path
+// writes idxs_ds (core_d8.from_array, core_d8.py:42-67) from here, next to the other per-cell outputs.
+template <int THREADS, int MINBLOCKS, int IDXMODE>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
     tile_phase_c_kernel(const uint8_t* __restrict__ dir, long long nrow, long long ncol, long long ntx,
                         const uint2* __restrict__ loccnt, const uint32_t* __restrict__ inflow, const int32_t* __restrict__ s_rank,
                         const uint32_t* __restrict__ s_basin, int32_t* __restrict__ rank_out, uint32_t* basin_out,
-                        int32_t* __restrict__ uparea_out) {
+                        int32_t* __restrict__ uparea_out, void* __restrict__ idxs_out) {
     constexpr int TL_CPT = TL_CELLS / THREADS, TL_RPI = THREADS / TL_W;
     __shared__ TileSharedC s;
     const uint32_t tile = (uint32_t)(((long long)blockIdx.y + 1) * ntx + blockIdx.x);  // +1: halo tile row
@@ -471,7 +605,11 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
         own[it] = lc.x;
         up[it] = lc.y;
         s.X[i] = 0;
-        s.T[i] = (uint32_t)tl_local_next(i, tl_dir_of(dirs, it));  // in-tile successor, for the walkers below
+        const uint32_t d = tl_dir_of(dirs, it);
+        s.S[i] = (uint16_t)tl_local_next(i, d);  // in-tile successor, for the walkers below
+        // pit cells: basin id stashed by stash_pit_ids_kernel at the pit's own cell (requested now, used much later)
+        // (asynchronous 4-byte copy straight into shared memory: no register is held across the kernel)
+        if ((d == PFD_DIR_PIT || d == PFD_DIR_FPIT) && basin_out) tl_cp_async4(&s.R[i], basin_out + g);
     }
     __syncthreads();
     // entry cells with outside inflow become walkers
@@ -489,7 +627,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
         const uint32_t w = s.wl_w[threadIdx.x];
         for (int step = 0; step < TL_CELLS; ++step) {
             atomicAdd(&s.X[i], w);
-            const int ni = (int)s.T[i];
+            const int ni = (int)s.S[i];
             if (ni == i) break;
             i = ni;
         }
@@ -499,19 +637,20 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
     for (int it = 0; it < TL_CPT; ++it) up[it] += s.X[(ly0 + TL_RPI * it) * TL_W + lx];
     __syncthreads();
     // terminals publish (rank at the terminal, basin id): pits by their owner, exit cells by the ring threads
+    tl_cp_async_wait();
 #pragma unroll
     for (int it = 0; it < TL_CPT; ++it) {
         const uint32_t d = tl_dir_of(dirs, it);
         if (d == PFD_DIR_PIT || d == PFD_DIR_FPIT) {
             const int ly = ly0 + TL_RPI * it;
             const int i = ly * TL_W + lx;
-            s.T[i] = 0;
-            s.X[i] = basin_out ? basin_out[g00 + (long long)ly * ncol + lx] : 0u;  // stashed by stash_pit_ids_kernel
+            s.X[i] = basin_out ? s.R[i] : 0u;  // own asynchronous copy, completed by tl_cp_async_wait() above
+            s.R[i] = 0;
         }
     }
     if (threadIdx.x < TL_NRING && s.ring_t[threadIdx.x] != TL_NOT_EXIT) {  // exit cell: one hop above the entry cell
         const int ri = tl_ring_cell(threadIdx.x);                           // of the neighbouring tile
-        s.T[ri] = s.ring_t[threadIdx.x];
+        s.R[ri] = s.ring_t[threadIdx.x];
         s.X[ri] = s.ring_b[threadIdx.x];
     }
     __syncthreads();
@@ -527,7 +666,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
             ua = 1;
             if (own[it] != TL_LOC_INVALID) {
                 const uint32_t root = TP_N(own[it]);
-                const uint32_t tr = s.T[root];
+                const uint32_t tr = s.R[root];
                 if (tr != 0xFFFFFFFFu) {
                     rk = (int32_t)(tr + TP_H(own[it]));
                     b = s.X[root];
@@ -539,6 +678,15 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
         if (rank_out) rank_out[g] = rk;
         if (basin_out) basin_out[g] = b;
         if (uparea_out) uparea_out[g] = ua;
+        if (IDXMODE == 1) {
+            // wrap-around 32-bit arithmetic gives the right low word for int32 and uint32 alike
+            const uint32_t g32 = (uint32_t)g;
+            const uint32_t off = (uint32_t)pfd_slot_dr((int)(d & 7u)) * (uint32_t)ncol + (uint32_t)pfd_slot_dc((int)(d & 7u));
+            reinterpret_cast<uint32_t*>(idxs_out)[g] = (d < 8u) ? g32 + off : ((d == PFD_DIR_NODATA) ? 0xFFFFFFFFu : g32);
+        } else if (IDXMODE == 2) {
+            reinterpret_cast<long long*>(idxs_out)[g] =
+                (d < 8u) ? g + pfd_slot_off((int)d, ncol) : ((d == PFD_DIR_NODATA) ? -1ll : g);
+        }
     }
 }
 
