@@ -502,9 +502,10 @@ static int tiles_phase_a(pfd_handle* h, TileCtx& T, uint32_t* basin_dev, unsigne
             (const cell_t*)h->pits.p, h->n_pits, h->dir_off, pit_id_offset, basin_dev);
         PFD_LAUNCH_CHECK(h);
     }
+    const int al4 = (h->ncol % 4 == 0) && ((uintptr_t)T.dir % 4 == 0);  // tile_loc is cudaMalloc-aligned
     tile_phase_a_kernel<TLA_THREADS, TLA_MINBLOCKS, false><<<grid, TLA_THREADS, 0, h->stream>>>(
         T.dir, h->nrow, h->ncol, T.ntx, basin_dev, (uint2*)h->tile_loc.p, T.B[0].acc, T.B[0].nxt, T.B[0].rh, T.B[0].ch,
-        T.term, T.term_h, nullptr, nullptr, nullptr, 0);
+        T.term, T.term_h, nullptr, nullptr, nullptr, al4);
     PFD_LAUNCH_CHECK(h);
     return PFD_OK;
 }
@@ -549,10 +550,21 @@ static int tiles_phase_c(pfd_handle* h, TileCtx& T, int32_t* rank_dev, uint32_t*
                          void* idxs_dev = nullptr, int idx_dtype = PFD_I32) {
     StageTimer t(h, PFD_STAGE_TILE_C);
     const dim3 grid((unsigned)T.ntx, (unsigned)T.nty);
+    auto al16 = [](const void* p) { return !p || (uintptr_t)p % 16 == 0; };
+    const int al4 = (h->ncol % 4 == 0) && ((uintptr_t)T.dir % 4 == 0) && al16(rank_dev) && al16(basin_dev) && al16(uparea_dev) &&
+                    al16(idxs_dev);
+    const size_t smem = sizeof(TileSharedC);
 #define LAUNCH_C(M)                                                                                                   \
-    tile_phase_c_kernel<TLC_THREADS, TLC_MINBLOCKS, M><<<grid, TLC_THREADS, 0, h->stream>>>(                            \
-        T.dir, h->nrow, h->ncol, T.ntx, (const uint2*)h->tile_loc.p, T.B[0].acc, T.srank, T.sbasin, rank_dev, basin_dev, \
-        uparea_dev, idxs_dev)
+    do {                                                                                                              \
+        if (!h->c_attr_set[M]) { /* the attribute is per device (context) and per instantiation */                   \
+            PFD_CUDA(h, cudaFuncSetAttribute(tile_phase_c_kernel<TLC_THREADS, TLC_MINBLOCKS, M>,                      \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
+            h->c_attr_set[M] = true;                                                                                  \
+        }                                                                                                             \
+        tile_phase_c_kernel<TLC_THREADS, TLC_MINBLOCKS, M><<<grid, TLC_THREADS, smem, h->stream>>>(                    \
+            T.dir, h->nrow, h->ncol, T.ntx, (const uint2*)h->tile_loc.p, T.B[0].acc, T.srank, T.sbasin, rank_dev,    \
+            basin_dev, uparea_dev, idxs_dev, al4);                                                                   \
+    } while (0)
     if (!idxs_dev) LAUNCH_C(0);
     else if (idx_dtype == PFD_I64) LAUNCH_C(2);
     else LAUNCH_C(1);

@@ -52,7 +52,58 @@ __host__ __device__ __forceinline__ int64_t pfd_slot_off(int k, int64_t ncol) {
 
 typedef uint32_t cell_t;  // internal cell index: rasters up to 2^32 cells
 
+
 __device__ __forceinline__ uint32_t splat4(uint32_t b) { return b * 0x01010101u; }
+
+// ---------------------------------------------------------------------------------------------------------
+// core_d8.from_array / core_ldd.from_array (core_d8.py:42-67, core_ldd.py:41-66) for FOUR horizontally adjacent cells
+// at once with byte-SIMD compares. Inputs: the 3x3 neighbourhood of 32-bit words around the word `w` that holds the
+// four codes (a* = row above, b0 / b2 = left / right word, c* = row below); cells outside the raster must read as
+// the nodata code, which makes "flows off the raster" and "flows into nodata" the same test (core_d8.py:58-61).
+// Outputs: dirw (dir byte per cell), upw (upstream mask per cell). Returns the per-byte mask of LEGAL codes
+// (core_d8.py:115-122): 0xFFFFFFFF when all four are legal.
+// ---------------------------------------------------------------------------------------------------------
+template <int FT>
+__device__ __forceinline__ uint32_t pfd_parse_word(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b0, uint32_t w, uint32_t b2,
+                                                   uint32_t c0, uint32_t c1, uint32_t c2, uint32_t& dirw_out, uint32_t& upw_out) {
+    // neighbour words per slot: byte j = code of the slot-k neighbour of my cell j
+    uint32_t nb[8];
+    nb[0] = __byte_perm(a0, a1, 0x6543);  // NW: shift right by one cell
+    nb[1] = a1;                           // N
+    nb[2] = __byte_perm(a1, a2, 0x4321);  // NE: shift left by one cell
+    nb[3] = __byte_perm(b0, w, 0x6543);   // W
+    nb[4] = __byte_perm(w, b2, 0x4321);   // E
+    nb[5] = __byte_perm(c0, c1, 0x6543);  // SW
+    nb[6] = c1;                           // S
+    nb[7] = __byte_perm(c1, c2, 0x4321);  // SE
+
+    const uint32_t nodata = __vcmpeq4(w, splat4(pfd_nodata_code<FT>()));
+    uint32_t pit, legal;
+    if (FT == 0) {
+        pit = __vcmpeq4(w, 0u) | __vcmpeq4(w, splat4(255u));
+        // legal codes: 0 or a power of two, 247, 255 (core_d8.py:19)
+        legal = __vcmpeq4(w & __vsub4(w, splat4(1u)), 0u) | nodata | pit;
+    } else {
+        pit = __vcmpeq4(w, splat4(5u));
+        // legal codes: 1..9 and 255 (core_ldd.py:17)
+        legal = __vcmpltu4(__vsub4(w, splat4(1u)), splat4(9u)) | nodata;
+    }
+    uint32_t dirw = 0, forced = 0, upw = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t sel = __vcmpeq4(w, splat4(pfd_code<FT>(k)));
+        dirw |= sel & splat4((uint32_t)k);
+        forced |= sel & __vcmpeq4(nb[k], splat4(pfd_nodata_code<FT>()));
+        upw |= __vcmpeq4(nb[k], splat4(pfd_code<FT>(7 - k))) & splat4(1u << k);
+    }
+    dirw = (dirw & ~forced) | (forced & splat4(PFD_DIR_FPIT));
+    dirw |= pit & splat4(PFD_DIR_PIT);
+    dirw |= nodata;  // 0xFF
+    upw &= ~nodata;
+    dirw_out = dirw;
+    upw_out = upw;
+    return legal;
+}
 
 // L2-only loads for data that other SMs write inside the same persistent kernel
 template <typename T>
@@ -133,6 +184,7 @@ struct pfd_handle {
     DevBuf tile_loc;           // uint2 [n]: per cell (local terminal | hops << 12, in-tile subtree size)
     DevBuf uparea;            // int32 [n] cached cell-count upstream area (tile solver)
     bool have_uparea = false;
+    bool c_attr_set[3] = {false, false, false};  // dynamic shared memory opt-in done for tile_phase_c_kernel<.., M>
     bool have_upmask = false;  // false after the fused-parse path: derived from dir on demand (ensure_upmask)
     unsigned long long* h_counters = nullptr;  // page-locked mirror of `counters` (read while the GPU keeps working)
     int fuse_parse = 1;       // option "fuse_parse": pfd_d8_flow_all on device buffers parses inside the tile solver

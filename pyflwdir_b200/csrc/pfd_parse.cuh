@@ -70,42 +70,8 @@ __global__ void __launch_bounds__(256) parse_kernel(const uint8_t* __restrict__ 
         const uint32_t a0 = tile[tr][tw], a1 = tile[tr][tw + 1], a2 = tile[tr][tw + 2];
         const uint32_t b0 = tile[tr + 1][tw], w = tile[tr + 1][tw + 1], b2 = tile[tr + 1][tw + 2];
         const uint32_t c0 = tile[tr + 2][tw], c1 = tile[tr + 2][tw + 1], c2 = tile[tr + 2][tw + 2];
-        // neighbour words per slot: byte j = code of the slot-k neighbour of my cell j
-        uint32_t nb[8];
-        nb[0] = __byte_perm(a0, a1, 0x6543);  // NW: shift right by one cell
-        nb[1] = a1;                           // N
-        nb[2] = __byte_perm(a1, a2, 0x4321);  // NE: shift left by one cell
-        nb[3] = __byte_perm(b0, w, 0x6543);   // W
-        nb[4] = __byte_perm(w, b2, 0x4321);   // E
-        nb[5] = __byte_perm(c0, c1, 0x6543);  // SW
-        nb[6] = c1;                           // S
-        nb[7] = __byte_perm(c1, c2, 0x4321);  // SE
-
-        const uint32_t nodata = __vcmpeq4(w, splat4(pfd_nodata_code<FT>()));
-        uint32_t pit, legal;
-        if (FT == 0) {
-            pit = __vcmpeq4(w, 0u) | __vcmpeq4(w, splat4(255u));
-            // legal codes: 0 or a power of two, 247, 255 (core_d8.py:19)
-            legal = __vcmpeq4(w & __vsub4(w, splat4(1u)), 0u) | nodata | pit;
-        } else {
-            pit = __vcmpeq4(w, splat4(5u));
-            // legal codes: 1..9 and 255 (core_ldd.py:17)
-            legal = __vcmpltu4(__vsub4(w, splat4(1u)), splat4(9u)) | nodata;
-        }
-        if (legal != 0xFFFFFFFFu) bad = true;
-
-        uint32_t dirw = 0, forced = 0, upw = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t sel = __vcmpeq4(w, splat4(pfd_code<FT>(k)));
-            dirw |= sel & splat4((uint32_t)k);
-            forced |= sel & __vcmpeq4(nb[k], splat4(pfd_nodata_code<FT>()));
-            upw |= __vcmpeq4(nb[k], splat4(pfd_code<FT>(7 - k))) & splat4(1u << k);
-        }
-        dirw = (dirw & ~forced) | (forced & splat4(PFD_DIR_FPIT));
-        dirw |= pit & splat4(PFD_DIR_PIT);
-        dirw |= nodata;  // 0xFF
-        upw &= ~nodata;
+        uint32_t dirw, upw;
+        if (pfd_parse_word<FT>(a0, a1, a2, b0, w, b2, c0, c1, c2, dirw, upw) != 0xFFFFFFFFu) bad = true;
 
         const int64_t i0 = r * ncol + c;
         if (ALIGNED) {

@@ -103,18 +103,50 @@ __global__ void stash_pit_ids_kernel(const cell_t* __restrict__ pits, long long 
         basin[(long long)pits[k] - cell_off] = (uint32_t)(id_off + (unsigned long long)k + 1ull);
 }
 
-// Shared state of one tile in phase A: P packs (next cell : 12 bits | hops to it : 20 bits), A is the accumulate
-// buffer.
+// Thread layout of the tile kernels: 1024 threads, thread t owns the FOUR horizontally adjacent cells 4t .. 4t+3
+// (row t >> 4, columns 4 * (t & 15) ..), so that its own cells are one 32-bit word of direction bytes and 128-bit
+// vectors in global memory.
+#define TQ_ROW ((int)(threadIdx.x >> 4))
+#define TQ_COL0 ((int)((threadIdx.x & 15u) << 2))
+#define TQ_I0 ((int)(threadIdx.x << 2))
+// Shared-memory position of local cell i = 4t + j: plane j, entry t. A warp touching cell j of its 32 quads hits 32
+// consecutive words (no bank conflict), so do the typical gathers (a neighbour of every such cell), and the thread's
+// own cells sit at compile-time offsets (j * 4 KiB) from one per-thread base address.
+#define TPHYS(i) ((((i) & 3) << 10) | ((i) >> 2))
+
+// Shared state of one tile in phase A. P packs (shared-memory ADDRESS of the P entry of the next cell : 18 bits |
+// hops to it : 13 bits); A is the accumulate buffer, laid out right behind P so that &A[x] == &P[x] + 16 KiB.
 struct TileShared {
     uint32_t P[TL_CELLS];
     uint32_t A[TL_CELLS];
 };
-#define TP_PACK(n, h) ((uint32_t)(n) | ((uint32_t)(h) << 12))
+#define TPK_MASK 0x3FFFFu
+#define TPK_SHIFT 18
+#define TL_A_OFF (TL_CELLS * 4)
+// per-cell record handed from phase A to phase C: TPHYS position of the local terminal | hops << 12
 #define TP_N(p) ((p) & 0xFFFu)
 #define TP_H(p) ((p) >> 12)
 #define TL_LOC_INVALID 0xFFFFFFFFu
 
-__device__ __forceinline__ uint32_t tl_dir_of(const uint32_t* dirs, int it) { return (dirs[it >> 2] >> (8 * (it & 3))) & 0xFFu; }
+// shared-memory accesses by 32-bit shared-window address: one LDS / STS / RED each, no address arithmetic left to
+// the compiler inside the solve loop (the issue-bound part of phase A)
+__device__ __forceinline__ uint32_t tl_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int OFF>
+__device__ __forceinline__ uint32_t tl_lds(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF) : "memory");
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ void tl_sts(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u32 [%0+%2], %1;" ::"r"(a), "r"(v), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void tl_red_add(uint32_t a, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0+%2], %1;" ::"r"(a), "r"(v), "n"(OFF) : "memory");
+}
+
+__device__ __forceinline__ uint32_t tl_dir_of(uint32_t dirw, int j) { return (dirw >> (8 * j)) & 0xFFu; }
 
 // local index of the next cell inside the tile, or i itself when the link leaves the tile / the cell is a pit
 __device__ __forceinline__ int tl_local_next(int i, uint32_t d) {
@@ -123,87 +155,82 @@ __device__ __forceinline__ int tl_local_next(int i, uint32_t d) {
     return (y >= 0 && y < TL_H && x >= 0 && x < TL_W) ? y * TL_W + x : i;
 }
 
-// Local solve of phase A. On return own[it] (mirrored in s.P) = packed (local terminal, hop distance) of every owned
-// cell and s.A[i] = subtree sum of the unit weights inside the tile.
+// Local solve of phase A. baseP = shared address of P[0]. On return own[j] (mirrored in P) = packed (address of the
+// local terminal's P entry, hop distance) of every owned cell and A = subtree sum of the unit weights inside the tile.
 // Round k (Jacobi): every cell whose 2^k-th ancestor exists (hops == 2^k) snapshots its A and its ancestor's P,
 // then -- after a barrier -- adds the snapshot to that ancestor (A_{k+1}[anc] += A_k[d]) and jumps
 // (next <- next[next], hops += hops[next]). A cell stays active only while its hop count is an exact power of two,
 // i.e. its chain is not exhausted; the loop ends when no cell of the tile is active (<= 12 rounds without loops).
-template <int THREADS>
-__device__ __forceinline__ void tl_local_solve(TileShared& s, const uint32_t* dirs, uint32_t* own) {
-    constexpr int TL_CPT = TL_CELLS / THREADS, TL_RPI = THREADS / TL_W;
-    const int lx = threadIdx.x & (TL_W - 1);
-    const int ly0 = threadIdx.x >> 6;
-    uint32_t active = 0;
-#pragma unroll
-    for (int it = 0; it < TL_CPT; ++it) {
-        const int i = (ly0 + TL_RPI * it) * TL_W + lx;
-        const uint32_t d = tl_dir_of(dirs, it);
-        const int ni = tl_local_next(i, d);
-        own[it] = TP_PACK(ni, ni != i ? 1 : 0);
-        if (ni != i) active |= 1u << it;
-        s.P[i] = own[it];
-        s.A[i] = (d != PFD_DIR_NODATA) ? 1u : 0u;
-    }
+// The body is branch-free: inactive cells repeat harmless loads, only the RED / STS are predicated.
+__device__ __forceinline__ void tl_local_solve(uint32_t baseP, uint32_t dirw, uint32_t* own) {
+    const int i0 = TQ_I0;
+    const uint32_t ownP = baseP + (threadIdx.x << 2);  // plane 0 entry of the thread; plane j at + j * 4096
+    bool act[4];
+#define TL_FOR4(BODY) { { constexpr int j = 0; BODY } { constexpr int j = 1; BODY } { constexpr int j = 2; BODY } { constexpr int j = 3; BODY } }
+    TL_FOR4({
+        const uint32_t d = tl_dir_of(dirw, j);
+        const int ni = tl_local_next(i0 + j, d);
+        act[j] = ni != i0 + j;
+        own[j] = (baseP + ((uint32_t)TPHYS(ni) << 2)) | (act[j] ? (1u << TPK_SHIFT) : 0u);
+        tl_sts<j * 4096>(ownP, own[j]);
+        tl_sts<TL_A_OFF + j * 4096>(ownP, (d != PFD_DIR_NODATA) ? 1u : 0u);
+    })
     __syncthreads();
     for (int k = 0; k < TL_MAXROUNDS; ++k) {
         const uint32_t two_k = 1u << k;
-        uint32_t pn[TL_CPT], a[TL_CPT];
-#pragma unroll
-        for (int it = 0; it < TL_CPT; ++it) {
-            if (active & (1u << it)) {
-                pn[it] = s.P[TP_N(own[it])];
-                a[it] = s.A[(ly0 + TL_RPI * it) * TL_W + lx];
-            }
-        }
+        uint32_t pn[4], a[4];
+        TL_FOR4({
+            pn[j] = tl_lds<0>(own[j] & TPK_MASK);
+            a[j] = tl_lds<TL_A_OFF + j * 4096>(ownP);
+        })
         __syncthreads();  // every snapshot is taken before any update
-        uint32_t next_active = 0;
-#pragma unroll
-        for (int it = 0; it < TL_CPT; ++it) {
-            if (active & (1u << it)) {
-                atomicAdd(&s.A[TP_N(own[it])], a[it]);
-                const uint32_t h = two_k + TP_H(pn[it]);
-                own[it] = TP_PACK(TP_N(pn[it]), h);
-                s.P[(ly0 + TL_RPI * it) * TL_W + lx] = own[it];
-                if (h == (two_k << 1)) next_active |= 1u << it;
+        bool any = false;
+        TL_FOR4({
+            if (act[j]) tl_red_add<TL_A_OFF>(own[j] & TPK_MASK, a[j]);
+            const uint32_t hp = pn[j] >> TPK_SHIFT;
+            const uint32_t nw = (pn[j] & TPK_MASK) | ((hp + two_k) << TPK_SHIFT);
+            if (act[j]) {
+                own[j] = nw;
+                tl_sts<j * 4096>(ownP, nw);
             }
-        }
-        active = next_active;
-        if (!__syncthreads_or((int)active)) break;
+            act[j] = act[j] && (hp == two_k);
+            any = any || act[j];
+        })
+        if (!__syncthreads_or((int)any)) break;
     }
 }
 
-// load the direction bytes this thread owns (rows ly0 + TL_RPI*it, column lx) packed 4 per word; cells outside the
-// raster read as nodata
-template <int THREADS>
-__device__ __forceinline__ void tl_load_dirs(const uint8_t* __restrict__ dir, long long nrow, long long ncol,
-                                             long long r0, long long c0, uint32_t* dirs) {
-    constexpr int TL_CPT = TL_CELLS / THREADS, TL_RPI = THREADS / TL_W;
-    const int lx = threadIdx.x & (TL_W - 1);
-    const int ly0 = threadIdx.x >> 6;
-    const long long c = c0 + lx;
+// the direction bytes of the thread's four cells as one word; cells outside the raster read as nodata.
+// al4: ncol % 4 == 0 and the base pointer is 4-byte aligned (a quad never straddles the row end)
+__device__ __forceinline__ uint32_t tl_load_dirs(const uint8_t* __restrict__ dir, long long nrow, long long ncol,
+                                                 long long r0, long long c0, bool al4) {
+    const long long r = r0 + TQ_ROW, c = c0 + TQ_COL0;
+    uint32_t w = 0xFFFFFFFFu;
+    if (r < nrow && c < ncol) {
+        const uint8_t* p = dir + r * ncol + c;
+        if (al4) {
+            w = __ldg(reinterpret_cast<const uint32_t*>(p));
+        } else {
+            w = 0;
 #pragma unroll
-    for (int w = 0; w < (TL_CPT + 3) / 4; ++w) dirs[w] = 0;
-#pragma unroll
-    for (int it = 0; it < TL_CPT; ++it) {
-        const long long r = r0 + ly0 + TL_RPI * it;
-        uint32_t d = PFD_DIR_NODATA;
-        if (r < nrow && c < ncol) d = __ldg(dir + r * ncol + c);
-        dirs[it >> 2] |= d << (8 * (it & 3));
+            for (int b = 0; b < 4; ++b) w |= ((c + b < ncol) ? (uint32_t)__ldg(p + b) : (uint32_t)PFD_DIR_NODATA) << (8 * b);
+        }
     }
+    return w;
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // Fused parse (single-GPU headline path): the tile's raw D8 codes plus a one-cell halo are staged in shared
-// memory (32-bit loads for the interior, out-of-raster cells read as 247), every thread derives the `dir` byte
-// of its own cells exactly like parse_kernel (core_d8.py:42-67: pit / forced pit when the downstream cell is
-// nodata or off the raster / nodata; illegal codes raise the invalid flag, core_d8.py:115-122) and writes it to
-// global memory, so that the separate parse pass over the raster disappears from pfd_d8_flow_all.
+// memory (32-bit loads for the interior, out-of-raster cells read as 247), every thread derives the `dir` bytes
+// of its four cells with the same byte-SIMD routine as parse_kernel (pfd_parse_word; core_d8.py:42-67: pit /
+// forced pit when the downstream cell is nodata or off the raster / nodata; illegal codes raise the invalid flag,
+// core_d8.py:115-122) and writes them to global memory, so that the separate parse pass over the raster
+// disappears from pfd_d8_flow_all.
 // ---------------------------------------------------------------------------------------------------------
 #define TLF_STRIDE 72   // bytes per staged row: 3 pad | left halo | 64 cells | right halo | 3 pad
 #define TLF_X0 4        // byte offset of the tile's first column inside a staged row (word aligned)
 struct TileCodes {
-    uint8_t c[(TL_H + 2) * TLF_STRIDE];
+    __align__(16) uint8_t c[(TL_H + 2) * TLF_STRIDE];
 };
 
 template <int THREADS>
@@ -249,40 +276,15 @@ __device__ __forceinline__ void tl_stage_codes(TileCodes& sc, const uint8_t* __r
     }
 }
 
-// D8 code -> neighbour slot (codes are powers of two): log2 E0 SE1 S2 SW3 W4 NW5 N6 NE7 -> slot 4 7 6 5 3 0 1 2
-__device__ __forceinline__ uint32_t tl_code_slot(uint32_t code) { return (0x21035674u >> (4 * (__ffs((int)code) - 1))) & 7u; }
-
-// dir bytes of the thread's own cells from the staged codes (packed 4 per word like tl_load_dirs); returns false
-// when one of them is not a legal D8 code
-template <int THREADS>
-__device__ __forceinline__ bool tl_parse_dirs(const TileCodes& sc, uint32_t* dirs) {
-    constexpr int TL_CPT = TL_CELLS / THREADS, TL_RPI = THREADS / TL_W;
-    const int lx = threadIdx.x & (TL_W - 1);
-    const int ly0 = threadIdx.x >> 6;
-    bool ok = true;
-#pragma unroll
-    for (int w = 0; w < (TL_CPT + 3) / 4; ++w) dirs[w] = 0;
-#pragma unroll
-    for (int it = 0; it < TL_CPT; ++it) {
-        const int ly = ly0 + TL_RPI * it;
-        const int at = (ly + 1) * TLF_STRIDE + TLF_X0 + lx;
-        const uint32_t code = sc.c[at];
-        uint32_t d;
-        if (code == 247u) {
-            d = PFD_DIR_NODATA;
-        } else if (code == 0u || code == 255u) {
-            d = PFD_DIR_PIT;
-        } else if (code & (code - 1u)) {
-            ok = false;
-            d = PFD_DIR_NODATA;
-        } else {
-            const uint32_t k = tl_code_slot(code);
-            const uint32_t nb = sc.c[at + pfd_slot_dr((int)k) * TLF_STRIDE + pfd_slot_dc((int)k)];
-            d = (nb == 247u) ? (uint32_t)PFD_DIR_FPIT : k;
-        }
-        dirs[it >> 2] |= d << (8 * (it & 3));
-    }
-    return ok;
+// dir bytes of the thread's four cells from the staged codes; *legal = false when one of them is not a D8 code
+__device__ __forceinline__ uint32_t tl_parse_dirs(const TileCodes& sc, bool* legal) {
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(&sc.c[TQ_ROW * TLF_STRIDE + TLF_X0 + TQ_COL0 - 4]);
+    constexpr int RW = TLF_STRIDE / 4;
+    uint32_t dirw, upw;
+    const uint32_t ok = pfd_parse_word<0>(row[0], row[1], row[2], row[RW], row[RW + 1], row[RW + 2], row[2 * RW],
+                                          row[2 * RW + 1], row[2 * RW + 2], dirw, upw);
+    *legal = ok == 0xFFFFFFFFu;
+    return dirw;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -292,6 +294,7 @@ __device__ __forceinline__ bool tl_parse_dirs(const TileCodes& sc, uint32_t* dir
 // FUSED = true : `d8` holds raw D8 codes; the kernel derives the directions itself, writes them to `dir_out`
 //                (and flags illegal codes); pit terminals carry TERM_PIT | local cell index, resolved to the pit
 //                ordinal by slots_finalize_kernel once the pits have been numbered.
+// al4: ncol % 4 == 0 and every raster-sized buffer is 16-byte aligned -> 32 / 128-bit accesses for the quad.
 template <int THREADS, int MINBLOCKS, bool FUSED>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
     tile_phase_a_kernel(const uint8_t* __restrict__ dir, long long nrow, long long ncol, long long ntx,
@@ -299,69 +302,82 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
                         uint32_t* __restrict__ s_ch, uint32_t* __restrict__ s_term, uint32_t* __restrict__ s_term_h,
                         const uint8_t* __restrict__ d8, uint8_t* __restrict__ dir_out, unsigned int* __restrict__ invalid_flag,
                         int al4) {
-    constexpr int TL_CPT = TL_CELLS / THREADS, TL_RPI = THREADS / TL_W;
-    __shared__ TileShared s;
+    static_assert(THREADS == TL_CELLS / 4, "one quad of cells per thread");
+    __shared__ __align__(16) TileShared s;
     __shared__ TileCodes sc;  // FUSED only (the compiler drops it otherwise)
     const uint32_t tile = (uint32_t)(((long long)blockIdx.y + 1) * ntx + blockIdx.x);  // +1: halo tile row
     const long long r0 = (long long)blockIdx.y * TL_H, c0 = (long long)blockIdx.x * TL_W;
-    const int lx = threadIdx.x & (TL_W - 1);
-    const int ly0 = threadIdx.x >> 6;
+    const int ly = TQ_ROW, lx0 = TQ_COL0, i0 = TQ_I0;
     const long long g00 = r0 * ncol + c0;  // global index of the tile's first cell
+    const long long g0 = g00 + (long long)ly * ncol + lx0;  // global index of the thread's first cell
+    const bool row_in = r0 + ly < nrow;
+    const bool quad_in = row_in && c0 + lx0 + 3 < ncol;  // all four cells inside the raster
 
-    uint32_t dirs[(TL_CPT + 3) / 4], own[TL_CPT];
+    uint32_t dirw, own[4];
     if (FUSED) {
         tl_stage_codes<THREADS>(sc, d8, nrow, ncol, r0, c0, al4 != 0);
         __syncthreads();
-        if (!tl_parse_dirs<THREADS>(sc, dirs)) atomicOr(invalid_flag, 1u);
+        bool legal;
+        dirw = tl_parse_dirs(sc, &legal);
+        if (!legal) atomicOr(invalid_flag, 1u);
         __syncthreads();  // every neighbour code has been read: the staged codes may now be replaced by the dirs
+        *reinterpret_cast<uint32_t*>(&sc.c[(ly + 1) * TLF_STRIDE + TLF_X0 + lx0]) = dirw;  // read back by the ring threads
+        if (al4 && quad_in) {
+            *reinterpret_cast<uint32_t*>(dir_out + g0) = dirw;
+        } else if (row_in) {
 #pragma unroll
-        for (int it = 0; it < TL_CPT; ++it) {
-            const int ly = ly0 + TL_RPI * it;
-            const uint32_t d = tl_dir_of(dirs, it);
-            sc.c[(ly + 1) * TLF_STRIDE + TLF_X0 + lx] = (uint8_t)d;  // read back by the ring threads below
-            if (r0 + ly < nrow && c0 + lx < ncol) dir_out[g00 + (long long)ly * ncol + lx] = (uint8_t)d;
+            for (int j = 0; j < 4; ++j)
+                if (c0 + lx0 + j < ncol) dir_out[g0 + j] = (uint8_t)tl_dir_of(dirw, j);
         }
     } else {
-        tl_load_dirs<THREADS>(dir, nrow, ncol, r0, c0, dirs);
+        dirw = tl_load_dirs(dir, nrow, ncol, r0, c0, al4 != 0);
     }
-    tl_local_solve<THREADS>(s, dirs, own);
+    const uint32_t baseP = tl_smem_addr(&s.P[0]);
+    const uint32_t ownP = baseP + (threadIdx.x << 2);
+    tl_local_solve(baseP, dirw, own);
 
     // (1) per-cell results for phase C
+    {
+        uint32_t loc[4], c4[4];
+        TL_FOR4({
+            c4[j] = tl_lds<TL_A_OFF + j * 4096>(ownP);
+            const uint32_t root = own[j] & TPK_MASK;
+            // a terminal is (next = itself, hops = 0)
+            loc[j] = (tl_lds<0>(root) != root) ? TL_LOC_INVALID : (((root - baseP) >> 2) | ((own[j] >> TPK_SHIFT) << 12));
+        })
+        if (al4 && quad_in) {
+            uint4* o = reinterpret_cast<uint4*>(loccnt + g0);  // (local terminal | hops, in-tile count) x 4
+            o[0] = make_uint4(loc[0], c4[0], loc[1], c4[1]);
+            o[1] = make_uint4(loc[2], c4[2], loc[3], c4[3]);
+        } else if (row_in) {
 #pragma unroll
-    for (int it = 0; it < TL_CPT; ++it) {
-        const int ly = ly0 + TL_RPI * it;
-        const int i = ly * TL_W + lx;
-        const uint32_t root = TP_N(own[it]);
-        const bool inv = s.P[root] != root;  // a terminal is (next = itself, hops = 0)
-        if (r0 + ly < nrow && c0 + lx < ncol) {
-            const long long g = g00 + (long long)ly * ncol + lx;
-            loccnt[g] = make_uint2(inv ? TL_LOC_INVALID : own[it], s.A[i]);  // (local terminal | hops, in-tile count)
+            for (int j = 0; j < 4; ++j)
+                if (c0 + lx0 + j < ncol) loccnt[g0 + j] = make_uint2(loc[j], c4[j]);
         }
     }
     __syncthreads();
     // (2) terminals publish their descriptor through their A slot: pits by their owner thread, exit cells (always
     //     ring cells) by one thread per ring position, which also hands the exit cell's in-tile subtree size to the
     //     entry cell it drains into
-#pragma unroll
-    for (int it = 0; it < TL_CPT; ++it) {
-        const uint32_t d = tl_dir_of(dirs, it);
+    TL_FOR4({
+        const uint32_t d = tl_dir_of(dirw, j);
         if (d == PFD_DIR_PIT || d == PFD_DIR_FPIT) {
-            const int ly = ly0 + TL_RPI * it;
-            if (FUSED) s.A[ly * TL_W + lx] = TERM_PIT | (uint32_t)(ly * TL_W + lx);
-            else s.A[ly * TL_W + lx] = TERM_PIT | (pit_ids ? (pit_ids[g00 + (long long)ly * ncol + lx] - 1u) : 0u);
+            if (FUSED) tl_sts<TL_A_OFF + j * 4096>(ownP, TERM_PIT | (uint32_t)(i0 + j));
+            else tl_sts<TL_A_OFF + j * 4096>(ownP, TERM_PIT | (pit_ids ? (pit_ids[g0 + j] - 1u) : 0u));
         }
-    }
+    })
     int ri = -1;
-    uint32_t rd = PFD_DIR_NODATA;
+    uint32_t rd = PFD_DIR_NODATA, rP = 0;
     if (threadIdx.x < TL_NRING) {
         ri = tl_ring_cell(threadIdx.x);
+        rP = baseP + ((uint32_t)TPHYS(ri) << 2);
         const int rly = ri >> 6, rlx = ri & (TL_W - 1);
         if (FUSED) rd = sc.c[(rly + 1) * TLF_STRIDE + TLF_X0 + rlx];  // out-of-raster cells were staged as nodata
         else if (r0 + rly < nrow && c0 + rlx < ncol) rd = __ldg(dir + g00 + (long long)rly * ncol + rlx);  // L1/L2 hit
-        if (rd < 8u && s.P[ri] == (uint32_t)ri) {  // exit cell
-            const uint32_t ti = tl_exit_slot(tile, (uint32_t)ntx, ri >> 6, ri & (TL_W - 1), rd);
-            atomicAdd(W + ti, s.A[ri]);
-            s.A[ri] = ti;
+        if (rd < 8u && tl_lds<0>(rP) == rP) {  // exit cell
+            const uint32_t ti = tl_exit_slot(tile, (uint32_t)ntx, rly, rlx, rd);
+            atomicAdd(W + ti, tl_lds<TL_A_OFF>(rP));
+            tl_sts<TL_A_OFF>(rP, ti);
         }
     }
     __syncthreads();
@@ -369,11 +385,11 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
     if (ri >= 0) {
         const uint32_t slot = tile * TL_RING + threadIdx.x;
         uint32_t nx = slot, rh = 0, ch = 0, term = SLOT_INVALID, th = 0;
-        const uint32_t p = s.P[ri];
-        const uint32_t root = TP_N(p);
-        if (rd != PFD_DIR_NODATA && s.P[root] == root) {
-            const uint32_t ti = s.A[root];
-            const uint32_t dist = TP_H(p);
+        const uint32_t p = tl_lds<0>(rP);
+        const uint32_t root = p & TPK_MASK;
+        if (rd != PFD_DIR_NODATA && tl_lds<0>(root) == root) {
+            const uint32_t ti = tl_lds<TL_A_OFF>(root);
+            const uint32_t dist = p >> TPK_SHIFT;
             if (ti & TERM_PIT) {
                 term = ti;
                 th = dist;
@@ -534,6 +550,8 @@ __global__ void __launch_bounds__(256) slots_finalize_kernel(SlotBuf b0, SlotBuf
 // ---------------------------------------------------------------------------------------------------------
 // Phase C: no second solve. acc = in-tile count (phase A) + the outside inflows of the tile's entry cells walked
 // down their local paths (sparse: ~90 entry cells per tile); rank / basin = hops + solution of the local terminal.
+// The walkers follow 4-step successor records (S12 / S34: 1st..4th in-tile successor of every cell, built with two
+// pointer-jumping steps), so their serial chain is one shared-memory round trip per FOUR cells.
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tl_cp_async4(uint32_t* smem_dst, const uint32_t* gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
@@ -543,7 +561,8 @@ __device__ __forceinline__ void tl_cp_async_wait() { asm volatile("cp.async.wait
 struct TileSharedC {
     uint32_t X[TL_CELLS];   // extra inflow per cell, later basin id per terminal
     uint32_t R[TL_CELLS];   // pit cells: stashed basin id (fetched with the first loads); later rank at the terminal
-    uint16_t S[TL_CELLS];   // in-tile successor, for the walkers
+    uint32_t S12[TL_CELLS];  // 1st | 2nd << 16 in-tile successor of the cell (a terminal repeats itself)
+    uint32_t S34[TL_CELLS];  // 3rd | 4th << 16
     uint32_t wl_cell[TL_RING];  // walker list
     uint32_t wl_w[TL_RING];
     uint32_t ring_t[TL_RING];   // per ring position: rank at the terminal if the cell is an exit cell, else TL_NOT_EXIT
@@ -555,34 +574,39 @@ struct TileSharedC {
 
 // IDXMODE: 0 = no idxs_ds output, 1 = 32-bit (int32 / uint32 share the bit pattern), 2 = int64 -- the fused-parse path
 // writes idxs_ds (core_d8.from_array, core_d8.py:42-67) from here, next to the other per-cell outputs.
+// Dynamic shared memory: sizeof(TileSharedC). al4: see tile_phase_a_kernel.
 template <int THREADS, int MINBLOCKS, int IDXMODE>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
     tile_phase_c_kernel(const uint8_t* __restrict__ dir, long long nrow, long long ncol, long long ntx,
                         const uint2* __restrict__ loccnt, const uint32_t* __restrict__ inflow, const int32_t* __restrict__ s_rank,
                         const uint32_t* __restrict__ s_basin, int32_t* __restrict__ rank_out, uint32_t* basin_out,
-                        int32_t* __restrict__ uparea_out, void* __restrict__ idxs_out) {
-    constexpr int TL_CPT = TL_CELLS / THREADS, TL_RPI = THREADS / TL_W;
-    __shared__ TileSharedC s;
+                        int32_t* __restrict__ uparea_out, void* __restrict__ idxs_out, int al4) {
+    static_assert(THREADS == TL_CELLS / 4, "one quad of cells per thread");
+    extern __shared__ __align__(16) unsigned char tl_smem_raw[];
+    TileSharedC& s = *reinterpret_cast<TileSharedC*>(tl_smem_raw);
     const uint32_t tile = (uint32_t)(((long long)blockIdx.y + 1) * ntx + blockIdx.x);  // +1: halo tile row
     const long long r0 = (long long)blockIdx.y * TL_H, c0 = (long long)blockIdx.x * TL_W;
-    const int lx = threadIdx.x & (TL_W - 1);
-    const int ly0 = threadIdx.x >> 6;
+    const int ly = TQ_ROW, lx0 = TQ_COL0, i0 = TQ_I0;
     const long long g00 = r0 * ncol + c0;
+    const long long g0 = g00 + (long long)ly * ncol + lx0;
+    const bool row_in = r0 + ly < nrow;
+    const bool quad_in = row_in && c0 + lx0 + 3 < ncol;
+    const bool vec = al4 && quad_in;
 
     // one thread per ring position: everything it needs from global memory is requested up front, together with
     // the per-cell loads below (entry inflow; for exit cells the solution of the entry cell they drain into)
     // (the results are parked in shared memory so that they do not occupy registers across the kernel)
     if (threadIdx.x < TL_NRING) {
         const int ri = tl_ring_cell(threadIdx.x);
-        const int ly = ri >> 6, lxr = ri & (TL_W - 1);
+        const int rly = ri >> 6, lxr = ri & (TL_W - 1);
         uint32_t rw = 0, rt = TL_NOT_EXIT, rb = 0;
-        if (r0 + ly < nrow && c0 + lxr < ncol) {
-            const long long g = g00 + (long long)ly * ncol + lxr;
+        if (r0 + rly < nrow && c0 + lxr < ncol) {
+            const long long g = g00 + (long long)rly * ncol + lxr;
             const uint32_t rd = __ldg(dir + g);
             const uint32_t rloc = __ldg(&loccnt[g].x);
             if (uparea_out && rloc != TL_LOC_INVALID) rw = __ldg(inflow + tile * TL_RING + threadIdx.x);
-            if (rd < 8u && rloc == (uint32_t)ri) {  // exit cell
-                const uint32_t slot = tl_exit_slot(tile, (uint32_t)ntx, ly, lxr, rd);
+            if (rd < 8u && rloc == (uint32_t)TPHYS(ri)) {  // exit cell (terminal = itself, 0 hops)
+                const uint32_t slot = tl_exit_slot(tile, (uint32_t)ntx, rly, lxr, rd);
                 const int32_t rrank = __ldg(s_rank + slot);
                 rt = (rrank < 0) ? 0xFFFFFFFFu : (uint32_t)(rrank + 1);
                 rb = (rrank < 0) ? 0u : __ldg(s_basin + slot);
@@ -592,24 +616,34 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
         s.ring_t[threadIdx.x] = rt;
         s.ring_b[threadIdx.x] = rb;
     }
-    uint32_t dirs[(TL_CPT + 3) / 4], own[TL_CPT], up[TL_CPT];
-    tl_load_dirs<THREADS>(dir, nrow, ncol, r0, c0, dirs);
+    const uint32_t dirw = tl_load_dirs(dir, nrow, ncol, r0, c0, al4 != 0);
     if (threadIdx.x == 0) s.wl_count = 0;
+    uint32_t own[4], up[4], n1[4];
+    if (vec) {
+        const uint4* lc = reinterpret_cast<const uint4*>(loccnt + g0);
+        const uint4 v0 = __ldg(lc), v1 = __ldg(lc + 1);
+        own[0] = v0.x, up[0] = v0.y, own[1] = v0.z, up[1] = v0.w;
+        own[2] = v1.x, up[2] = v1.y, own[3] = v1.z, up[3] = v1.w;
+    } else {
 #pragma unroll
-    for (int it = 0; it < TL_CPT; ++it) {
-        const int ly = ly0 + TL_RPI * it;
-        const int i = ly * TL_W + lx;
-        const bool inside = r0 + ly < nrow && c0 + lx < ncol;
-        const long long g = g00 + (long long)ly * ncol + lx;
-        const uint2 lc = inside ? __ldg(loccnt + g) : make_uint2(TL_LOC_INVALID, 0u);
-        own[it] = lc.x;
-        up[it] = lc.y;
-        s.X[i] = 0;
-        const uint32_t d = tl_dir_of(dirs, it);
-        s.S[i] = (uint16_t)tl_local_next(i, d);  // in-tile successor, for the walkers below
-        // pit cells: basin id stashed by stash_pit_ids_kernel at the pit's own cell (requested now, used much later)
-        // (asynchronous 4-byte copy straight into shared memory: no register is held across the kernel)
-        if ((d == PFD_DIR_PIT || d == PFD_DIR_FPIT) && basin_out) tl_cp_async4(&s.R[i], basin_out + g);
+        for (int j = 0; j < 4; ++j) {
+            const uint2 lc = (row_in && c0 + lx0 + j < ncol) ? __ldg(loccnt + g0 + j) : make_uint2(TL_LOC_INVALID, 0u);
+            own[j] = lc.x;
+            up[j] = lc.y;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t d = tl_dir_of(dirw, j);
+        n1[j] = (uint32_t)TPHYS(tl_local_next(i0 + j, d));  // positions, not cell numbers, from here on
+        // pit cells: basin id stashed by stash_pit_ids_kernel at the pit's own cell (requested now, used much later;
+        // asynchronous 4-byte copy straight into shared memory: no register is held across the kernel)
+        if ((d == PFD_DIR_PIT || d == PFD_DIR_FPIT) && basin_out) tl_cp_async4(&s.R[TPHYS(i0 + j)], basin_out + g0 + j);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        s.X[TPHYS(i0 + j)] = 0u;
+        s.S12[TPHYS(i0 + j)] = n1[j];
     }
     __syncthreads();
     // entry cells with outside inflow become walkers
@@ -617,75 +651,119 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
         const uint32_t my_w = s.ring_w[threadIdx.x];
         if (my_w != 0u) {
             const uint32_t k = atomicAdd(&s.wl_count, 1u);
-            s.wl_cell[k] = (uint32_t)tl_ring_cell(threadIdx.x);
+            s.wl_cell[k] = (uint32_t)TPHYS(tl_ring_cell(threadIdx.x));
             s.wl_w[k] = my_w;
         }
     }
+    // successor records, jump 1: 2nd successor. Concurrent readers only use the low half of S12, which does not change.
+    uint32_t x12[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x12[j] = n1[j] | ((s.S12[n1[j]] & 0xFFFFu) << 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s.S12[TPHYS(i0 + j)] = x12[j];
+    __syncthreads();
+    // jump 2: S12 of the 2nd successor holds its 1st | 2nd successor = my 3rd | 4th
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s.S34[TPHYS(i0 + j)] = s.S12[x12[j] >> 16];
     __syncthreads();
     if (threadIdx.x < s.wl_count) {
-        int i = (int)s.wl_cell[threadIdx.x];
+        uint32_t i = s.wl_cell[threadIdx.x];
         const uint32_t w = s.wl_w[threadIdx.x];
-        for (int step = 0; step < TL_CELLS; ++step) {
+        for (int step = 0; step <= TL_CELLS / 4; ++step) {
+            const uint32_t s12 = s.S12[i], s34 = s.S34[i];
+            const uint32_t m1 = s12 & 0xFFFFu, m2 = s12 >> 16, m3 = s34 & 0xFFFFu, m4 = s34 >> 16;
             atomicAdd(&s.X[i], w);
-            const int ni = (int)s.S[i];
-            if (ni == i) break;
-            i = ni;
+            if (m1 == i) break;
+            atomicAdd(&s.X[m1], w);
+            if (m2 == m1) break;
+            atomicAdd(&s.X[m2], w);
+            if (m3 == m2) break;
+            atomicAdd(&s.X[m3], w);
+            if (m4 == m3) break;
+            i = m4;
         }
     }
     __syncthreads();
 #pragma unroll
-    for (int it = 0; it < TL_CPT; ++it) up[it] += s.X[(ly0 + TL_RPI * it) * TL_W + lx];
+    for (int j = 0; j < 4; ++j) up[j] += s.X[TPHYS(i0 + j)];
     __syncthreads();
     // terminals publish (rank at the terminal, basin id): pits by their owner, exit cells by the ring threads
     tl_cp_async_wait();
 #pragma unroll
-    for (int it = 0; it < TL_CPT; ++it) {
-        const uint32_t d = tl_dir_of(dirs, it);
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t d = tl_dir_of(dirw, j);
         if (d == PFD_DIR_PIT || d == PFD_DIR_FPIT) {
-            const int ly = ly0 + TL_RPI * it;
-            const int i = ly * TL_W + lx;
-            s.X[i] = basin_out ? s.R[i] : 0u;  // own asynchronous copy, completed by tl_cp_async_wait() above
-            s.R[i] = 0;
+            s.X[TPHYS(i0 + j)] = basin_out ? s.R[TPHYS(i0 + j)] : 0u;  // own asynchronous copy, completed by tl_cp_async_wait() above
+            s.R[TPHYS(i0 + j)] = 0;
         }
     }
     if (threadIdx.x < TL_NRING && s.ring_t[threadIdx.x] != TL_NOT_EXIT) {  // exit cell: one hop above the entry cell
         const int ri = tl_ring_cell(threadIdx.x);                           // of the neighbouring tile
-        s.R[ri] = s.ring_t[threadIdx.x];
-        s.X[ri] = s.ring_b[threadIdx.x];
+        s.R[TPHYS(ri)] = s.ring_t[threadIdx.x];
+        s.X[TPHYS(ri)] = s.ring_b[threadIdx.x];
     }
     __syncthreads();
+    int32_t rk[4], ua[4];
+    uint32_t bs[4];
 #pragma unroll
-    for (int it = 0; it < TL_CPT; ++it) {
-        const int ly = ly0 + TL_RPI * it;
-        if (r0 + ly >= nrow || c0 + lx >= ncol) continue;
-        const uint32_t d = tl_dir_of(dirs, it);
-        int32_t rk = -9999, ua = -9999;
-        uint32_t b = 0;
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t d = tl_dir_of(dirw, j);
+        rk[j] = -9999, ua[j] = -9999, bs[j] = 0;
         if (d != PFD_DIR_NODATA) {
-            rk = -1;
-            ua = 1;
-            if (own[it] != TL_LOC_INVALID) {
-                const uint32_t root = TP_N(own[it]);
+            rk[j] = -1;
+            ua[j] = 1;
+            if (own[j] != TL_LOC_INVALID) {
+                const uint32_t root = TP_N(own[j]);
                 const uint32_t tr = s.R[root];
                 if (tr != 0xFFFFFFFFu) {
-                    rk = (int32_t)(tr + TP_H(own[it]));
-                    b = s.X[root];
-                    ua = (int32_t)up[it];
+                    rk[j] = (int32_t)(tr + TP_H(own[j]));
+                    bs[j] = s.X[root];
+                    ua[j] = (int32_t)up[j];
                 }
             }
         }
-        const long long g = g00 + (long long)ly * ncol + lx;
-        if (rank_out) rank_out[g] = rk;
-        if (basin_out) basin_out[g] = b;
-        if (uparea_out) uparea_out[g] = ua;
+    }
+    if (vec) {
+        if (rank_out) *reinterpret_cast<int4*>(rank_out + g0) = make_int4(rk[0], rk[1], rk[2], rk[3]);
+        if (basin_out) *reinterpret_cast<uint4*>(basin_out + g0) = make_uint4(bs[0], bs[1], bs[2], bs[3]);
+        if (uparea_out) *reinterpret_cast<int4*>(uparea_out + g0) = make_int4(ua[0], ua[1], ua[2], ua[3]);
+    } else if (row_in) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (c0 + lx0 + j >= ncol) continue;
+            if (rank_out) rank_out[g0 + j] = rk[j];
+            if (basin_out) basin_out[g0 + j] = bs[j];
+            if (uparea_out) uparea_out[g0 + j] = ua[j];
+        }
+    }
+    if (IDXMODE != 0) {
+        // idxs_ds: wrap-around 32-bit arithmetic gives the right low word for int32 and uint32 alike
+        long long ds[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t d = tl_dir_of(dirw, j);
+            const long long g = g0 + j;
+            ds[j] = (d < 8u) ? g + pfd_slot_off((int)d, ncol) : ((d == PFD_DIR_NODATA) ? -1ll : g);
+        }
         if (IDXMODE == 1) {
-            // wrap-around 32-bit arithmetic gives the right low word for int32 and uint32 alike
-            const uint32_t g32 = (uint32_t)g;
-            const uint32_t off = (uint32_t)pfd_slot_dr((int)(d & 7u)) * (uint32_t)ncol + (uint32_t)pfd_slot_dc((int)(d & 7u));
-            reinterpret_cast<uint32_t*>(idxs_out)[g] = (d < 8u) ? g32 + off : ((d == PFD_DIR_NODATA) ? 0xFFFFFFFFu : g32);
-        } else if (IDXMODE == 2) {
-            reinterpret_cast<long long*>(idxs_out)[g] =
-                (d < 8u) ? g + pfd_slot_off((int)d, ncol) : ((d == PFD_DIR_NODATA) ? -1ll : g);
+            uint32_t* o = reinterpret_cast<uint32_t*>(idxs_out) + g0;
+            if (vec) {
+                *reinterpret_cast<uint4*>(o) = make_uint4((uint32_t)ds[0], (uint32_t)ds[1], (uint32_t)ds[2], (uint32_t)ds[3]);
+            } else if (row_in) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (c0 + lx0 + j < ncol) o[j] = (uint32_t)ds[j];
+            }
+        } else {
+            long long* o = reinterpret_cast<long long*>(idxs_out) + g0;
+            if (vec) {
+                *reinterpret_cast<longlong2*>(o) = make_longlong2(ds[0], ds[1]);
+                *reinterpret_cast<longlong2*>(o + 2) = make_longlong2(ds[2], ds[3]);
+            } else if (row_in) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (c0 + lx0 + j < ncol) o[j] = ds[j];
+            }
         }
     }
 }
