@@ -291,22 +291,32 @@ __device__ __forceinline__ uint32_t tl_parse_dirs(const TileCodes& sc, bool* leg
 // Phase A: local solve; per cell (local terminal, hops) -> loc[], in-tile subtree size -> cnt[]; ring nodes; W
 // ---------------------------------------------------------------------------------------------------------
 // FUSED = false: `dir` is the parsed direction raster, pit terminals carry the pit ordinal found in `pit_ids`.
-// FUSED = true : `d8` holds raw D8 codes; the kernel derives the directions itself, writes them to `dir_out`
-//                (and flags illegal codes); pit terminals carry TERM_PIT | local cell index, resolved to the pit
-//                ordinal by slots_finalize_kernel once the pits have been numbered.
+// FUSED = true : the tile's raw D8 codes (+ halo) are already staged in `sc`; the directions are derived here and
+//                written to `dir_out` (illegal codes raise the flag); pit terminals carry TERM_PIT | local cell index,
+//                resolved to the pit ordinal by slots_finalize_kernel once the pits have been numbered.
 // al4: ncol % 4 == 0 and every raster-sized buffer is 16-byte aligned -> 32 / 128-bit accesses for the quad.
-template <int THREADS, int MINBLOCKS, bool FUSED>
-__global__ void __launch_bounds__(THREADS, MINBLOCKS)
-    tile_phase_a_kernel(const uint8_t* __restrict__ dir, long long nrow, long long ncol, long long ntx,
-                        const uint32_t* pit_ids, uint2* __restrict__ loccnt, uint32_t* __restrict__ W, uint32_t* __restrict__ s_nxt, uint32_t* __restrict__ s_rh,
-                        uint32_t* __restrict__ s_ch, uint32_t* __restrict__ s_term, uint32_t* __restrict__ s_term_h,
-                        const uint8_t* __restrict__ d8, uint8_t* __restrict__ dir_out, unsigned int* __restrict__ invalid_flag,
-                        int al4) {
-    static_assert(THREADS == TL_CELLS / 4, "one quad of cells per thread");
-    __shared__ __align__(16) TileShared s;
-    __shared__ TileCodes sc;  // FUSED only (the compiler drops it otherwise)
-    const uint32_t tile = (uint32_t)(((long long)blockIdx.y + 1) * ntx + blockIdx.x);  // +1: halo tile row
-    const long long r0 = (long long)blockIdx.y * TL_H, c0 = (long long)blockIdx.x * TL_W;
+struct PhaseAArgs {
+    const uint8_t* dir;
+    long long nrow, ncol, ntx;
+    const uint32_t* pit_ids;
+    uint2* loccnt;
+    uint32_t *W, *s_nxt, *s_rh, *s_ch, *s_term, *s_term_h;
+    const uint8_t* d8;
+    uint8_t* dir_out;
+    unsigned int* invalid_flag;
+    int al4;
+};
+
+template <bool FUSED>
+__device__ __forceinline__ void tl_phase_a_tile(TileShared& s, TileCodes& sc, const PhaseAArgs& A, long long ty, long long tx) {
+    const uint8_t* __restrict__ dir = A.dir;
+    const long long nrow = A.nrow, ncol = A.ncol, ntx = A.ntx;
+    const uint32_t* pit_ids = A.pit_ids;
+    uint2* __restrict__ loccnt = A.loccnt;
+    uint32_t* __restrict__ W = A.W;
+    const int al4 = A.al4;
+    const uint32_t tile = (uint32_t)((ty + 1) * ntx + tx);  // +1: halo tile row
+    const long long r0 = ty * TL_H, c0 = tx * TL_W;
     const int ly = TQ_ROW, lx0 = TQ_COL0, i0 = TQ_I0;
     const long long g00 = r0 * ncol + c0;  // global index of the tile's first cell
     const long long g0 = g00 + (long long)ly * ncol + lx0;  // global index of the thread's first cell
@@ -315,19 +325,17 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 
     uint32_t dirw, own[4];
     if (FUSED) {
-        tl_stage_codes<THREADS>(sc, d8, nrow, ncol, r0, c0, al4 != 0);
-        __syncthreads();
         bool legal;
         dirw = tl_parse_dirs(sc, &legal);
-        if (!legal) atomicOr(invalid_flag, 1u);
+        if (!legal) atomicOr(A.invalid_flag, 1u);
         __syncthreads();  // every neighbour code has been read: the staged codes may now be replaced by the dirs
         *reinterpret_cast<uint32_t*>(&sc.c[(ly + 1) * TLF_STRIDE + TLF_X0 + lx0]) = dirw;  // read back by the ring threads
         if (al4 && quad_in) {
-            *reinterpret_cast<uint32_t*>(dir_out + g0) = dirw;
+            *reinterpret_cast<uint32_t*>(A.dir_out + g0) = dirw;
         } else if (row_in) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (c0 + lx0 + j < ncol) dir_out[g0 + j] = (uint8_t)tl_dir_of(dirw, j);
+                if (c0 + lx0 + j < ncol) A.dir_out[g0 + j] = (uint8_t)tl_dir_of(dirw, j);
         }
     } else {
         dirw = tl_load_dirs(dir, nrow, ncol, r0, c0, al4 != 0);
@@ -400,11 +408,85 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
                 term = 0;
             }
         }
-        s_nxt[slot] = nx;
-        s_rh[slot] = rh;
-        s_ch[slot] = ch;
-        s_term[slot] = term;
-        s_term_h[slot] = th;
+        A.s_nxt[slot] = nx;
+        A.s_rh[slot] = rh;
+        A.s_ch[slot] = ch;
+        A.s_term[slot] = term;
+        A.s_term_h[slot] = th;
+    }
+}
+
+// one CTA per tile (blockIdx = tile column, tile row): any raster shape / alignment
+template <int THREADS, int MINBLOCKS, bool FUSED>
+__global__ void __launch_bounds__(THREADS, MINBLOCKS) tile_phase_a_kernel(PhaseAArgs A) {
+    static_assert(THREADS == TL_CELLS / 4, "one quad of cells per thread");
+    __shared__ __align__(16) TileShared s;
+    __shared__ TileCodes sc;  // FUSED only (the compiler drops it otherwise)
+    if (FUSED) {
+        tl_stage_codes<THREADS>(sc, A.d8, A.nrow, A.ncol, (long long)blockIdx.y * TL_H, (long long)blockIdx.x * TL_W, A.al4 != 0);
+        __syncthreads();
+    }
+    tl_phase_a_tile<FUSED>(s, sc, A, blockIdx.y, blockIdx.x);
+}
+
+// asynchronous global -> shared copies (LDGSTS): no register is tied up while the data is in flight
+__device__ __forceinline__ void tl_cp_async4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void tl_cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void tl_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tl_cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tl_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// codes of tile (ty, tx) plus halo -> sc, as 66 rows x 18 words [c0 - 4, c0 + 68); requires ncol % 4 == 0 and a
+// 4-byte aligned raster, so that every word lies entirely inside or entirely outside the raster
+template <int THREADS>
+__device__ __forceinline__ void tl_prefetch_codes(TileCodes& sc, const uint8_t* __restrict__ d8, long long nrow, long long ncol,
+                                                  long long r0, long long c0) {
+    for (int w = threadIdx.x; w < (TL_H + 2) * (TLF_STRIDE / 4); w += THREADS) {
+        const int row = w / (TLF_STRIDE / 4), cw = w - row * (TLF_STRIDE / 4);
+        const long long r = r0 - 1 + row, c = c0 - 4 + 4 * cw;
+        uint8_t* dst = &sc.c[row * TLF_STRIDE + 4 * cw];
+        if (r >= 0 && r < nrow && c >= 0 && c < ncol) tl_cp_async4(dst, d8 + r * ncol + c);
+        else *reinterpret_cast<uint32_t*>(dst) = 0xF7F7F7F7u;
+    }
+}
+
+// Persistent fused phase A: gridDim.x CTAs stride over the tiles; while tile n is solved the raw codes of tile
+// n + gridDim.x stream into the other staging buffer (cp.async), so the load latency that heads every tile in the
+// one-CTA-per-tile version is hidden behind the solve. Requires al4.
+// Tiles are handed out dynamically (tile_ctr, zeroed before the launch; the first gridDim.x tiles are implicit):
+// thread 0 draws the tile after the next one at the top of every iteration, one barrier before anybody needs it.
+template <int THREADS, int MINBLOCKS>
+__global__ void __launch_bounds__(THREADS, MINBLOCKS) tile_phase_a_pipe_kernel(PhaseAArgs A, long long nty, unsigned int* tile_ctr) {
+    static_assert(THREADS == TL_CELLS / 4, "one quad of cells per thread");
+    __shared__ __align__(16) TileShared s;
+    __shared__ TileCodes sc2[2];
+    __shared__ uint32_t next_tile[2];
+    // 32-bit tile arithmetic (64-bit divisions per tile and thread would cost more than the parse itself)
+    const uint32_t ntx = (uint32_t)A.ntx, ntiles = ntx * (uint32_t)nty;
+    uint32_t t = blockIdx.x;
+    if (t >= ntiles) return;
+    uint32_t ty = t / ntx, tx = t - ty * ntx;
+    tl_prefetch_codes<THREADS>(sc2[0], A.d8, A.nrow, A.ncol, (long long)ty * TL_H, (long long)tx * TL_W);
+    tl_cp_async_commit();
+    if (threadIdx.x == 0) next_tile[0] = atomicAdd(tile_ctr, 1u) + gridDim.x;
+    __syncthreads();
+    for (int it = 0;; ++it) {
+        const uint32_t tn = next_tile[it & 1];
+        if (threadIdx.x == 0) next_tile[(it + 1) & 1] = (tn < ntiles) ? atomicAdd(tile_ctr, 1u) + gridDim.x : ntiles;
+        const uint32_t tyn = tn / ntx, txn = tn - tyn * ntx;
+        if (tn < ntiles) tl_prefetch_codes<THREADS>(sc2[(it + 1) & 1], A.d8, A.nrow, A.ncol, (long long)tyn * TL_H, (long long)txn * TL_W);
+        tl_cp_async_commit();
+        tl_cp_async_wait_group<1>();  // everything but the prefetch just issued: the codes of tile t have landed
+        __syncthreads();
+        tl_phase_a_tile<true>(s, sc2[it & 1], A, ty, tx);
+        if (tn >= ntiles) break;
+        t = tn, ty = tyn, tx = txn;
+        __syncthreads();  // the ring threads are done with this staging buffer and with P / A
     }
 }
 
@@ -553,11 +635,6 @@ __global__ void __launch_bounds__(256) slots_finalize_kernel(SlotBuf b0, SlotBuf
 // The walkers follow 4-step successor records (S12 / S34: 1st..4th in-tile successor of every cell, built with two
 // pointer-jumping steps), so their serial chain is one shared-memory round trip per FOUR cells.
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tl_cp_async4(uint32_t* smem_dst, const uint32_t* gmem_src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void tl_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
 struct TileSharedC {
     uint32_t X[TL_CELLS];   // extra inflow per cell, later basin id per terminal
     uint32_t R[TL_CELLS];   // pit cells: stashed basin id (fetched with the first loads); later rank at the terminal
@@ -565,206 +642,306 @@ struct TileSharedC {
     uint32_t S34[TL_CELLS];  // 3rd | 4th << 16
     uint32_t wl_cell[TL_RING];  // walker list
     uint32_t wl_w[TL_RING];
-    uint32_t ring_t[TL_RING];   // per ring position: rank at the terminal if the cell is an exit cell, else TL_NOT_EXIT
+    int32_t ring_t[TL_RING];    // per ring position: reduced-graph rank of the entry cell an exit cell drains into, else TL_NOT_EXIT
     uint32_t ring_b[TL_RING];   //                    basin id behind that exit
     uint32_t ring_w[TL_RING];   //                    outside inflow of the (entry) cell
     uint32_t wl_count;
+    uint32_t next_tile[2];      // persistent kernel: dynamically drawn tiles (see tile_phase_a_pipe_kernel)
 };
-#define TL_NOT_EXIT 0xFFFFFFFEu
+#define TL_NOT_EXIT ((int32_t)0x80000000)
+
+// landing zone of the asynchronous prefetch of the NEXT tile (persistent kernel); every thread copies and later reads
+// its own quad, the ring threads additionally read the entries of the ring cells
+struct TilePrefC {
+    uint2 LC[TL_CELLS];          // (loc, cnt) in tile-local row-major order
+    uint32_t DIRW[TL_CELLS / 4]; // direction bytes, one word per quad
+    uint32_t ring_w[TL_RING];    // inflow weights of the tile's ring slots
+};
+
+struct PhaseCArgs {
+    const uint8_t* dir;
+    long long nrow, ncol, ntx, nty;
+    const uint2* loccnt;
+    const uint32_t* inflow;
+    const int32_t* s_rank;
+    const uint32_t* s_basin;
+    int32_t* rank_out;
+    uint32_t* basin_out;
+    int32_t* uparea_out;
+    void* idxs_out;
+    int al4;
+    unsigned int* tile_ctr;  // PIPE: dynamic tile counter, zeroed before the launch
+};
+
+// prefetch of tile (ty, tx): requires al4 (quads entirely inside or outside the raster, 16-byte aligned rows)
+__device__ __forceinline__ void tl_c_prefetch(TilePrefC& pf, const PhaseCArgs& A, long long ty, long long tx) {
+    const long long r0 = ty * TL_H, c0 = tx * TL_W;
+    const int ly = TQ_ROW, lx0 = TQ_COL0, i0 = TQ_I0;
+    const long long g0 = (r0 + ly) * A.ncol + c0 + lx0;
+    if (r0 + ly < A.nrow && c0 + lx0 < A.ncol) {
+        tl_cp_async16(&pf.LC[i0], A.loccnt + g0);
+        tl_cp_async16(&pf.LC[i0 + 2], A.loccnt + g0 + 2);
+        tl_cp_async4(&pf.DIRW[threadIdx.x], A.dir + g0);
+    } else {
+        uint4* lc = reinterpret_cast<uint4*>(&pf.LC[i0]);
+        lc[0] = make_uint4(TL_LOC_INVALID, 0u, TL_LOC_INVALID, 0u);
+        lc[1] = make_uint4(TL_LOC_INVALID, 0u, TL_LOC_INVALID, 0u);
+        pf.DIRW[threadIdx.x] = 0xFFFFFFFFu;
+    }
+    if (threadIdx.x < TL_RING && A.uparea_out)
+        tl_cp_async4(&pf.ring_w[threadIdx.x], A.inflow + (uint32_t)((ty + 1) * A.ntx + tx) * TL_RING + threadIdx.x);
+}
 
 // IDXMODE: 0 = no idxs_ds output, 1 = 32-bit (int32 / uint32 share the bit pattern), 2 = int64 -- the fused-parse path
 // writes idxs_ds (core_d8.from_array, core_d8.py:42-67) from here, next to the other per-cell outputs.
-// Dynamic shared memory: sizeof(TileSharedC). al4: see tile_phase_a_kernel.
-template <int THREADS, int MINBLOCKS, int IDXMODE>
-__global__ void __launch_bounds__(THREADS, MINBLOCKS)
-    tile_phase_c_kernel(const uint8_t* __restrict__ dir, long long nrow, long long ncol, long long ntx,
-                        const uint2* __restrict__ loccnt, const uint32_t* __restrict__ inflow, const int32_t* __restrict__ s_rank,
-                        const uint32_t* __restrict__ s_basin, int32_t* __restrict__ rank_out, uint32_t* basin_out,
-                        int32_t* __restrict__ uparea_out, void* __restrict__ idxs_out, int al4) {
+// PIPE = false: one CTA per tile (blockIdx = tile column, tile row), any shape / alignment; dynamic shared memory
+//               sizeof(TileSharedC).
+// PIPE = true : persistent CTAs stride over the tiles (requires al4); while tile n is processed, (loc, cnt), dir and the
+//               ring inflows of tile n + gridDim.x stream into shared memory with cp.async, and the dependent fetches
+//               of the current tile (pit basin ids, solution behind every exit cell) are asynchronous copies as well, so
+//               no global-memory latency is exposed except for the first tile of a CTA. Dynamic shared memory
+//               sizeof(TileSharedC) + sizeof(TilePrefC).
+template <int THREADS, int MINBLOCKS, int IDXMODE, bool PIPE>
+__global__ void __launch_bounds__(THREADS, MINBLOCKS) tile_phase_c_kernel(PhaseCArgs A) {
     static_assert(THREADS == TL_CELLS / 4, "one quad of cells per thread");
     extern __shared__ __align__(16) unsigned char tl_smem_raw[];
     TileSharedC& s = *reinterpret_cast<TileSharedC*>(tl_smem_raw);
-    const uint32_t tile = (uint32_t)(((long long)blockIdx.y + 1) * ntx + blockIdx.x);  // +1: halo tile row
-    const long long r0 = (long long)blockIdx.y * TL_H, c0 = (long long)blockIdx.x * TL_W;
+    TilePrefC& pf = *reinterpret_cast<TilePrefC*>(tl_smem_raw + ((sizeof(TileSharedC) + 15) / 16) * 16);  // PIPE only
+    const uint8_t* __restrict__ dir = A.dir;
+    const long long nrow = A.nrow, ncol = A.ncol, ntx = A.ntx;
+    const uint2* __restrict__ loccnt = A.loccnt;
+    int32_t* __restrict__ rank_out = A.rank_out;
+    uint32_t* basin_out = A.basin_out;
+    int32_t* __restrict__ uparea_out = A.uparea_out;
+    const int al4 = A.al4;
     const int ly = TQ_ROW, lx0 = TQ_COL0, i0 = TQ_I0;
-    const long long g00 = r0 * ncol + c0;
-    const long long g0 = g00 + (long long)ly * ncol + lx0;
-    const bool row_in = r0 + ly < nrow;
-    const bool quad_in = row_in && c0 + lx0 + 3 < ncol;
-    const bool vec = al4 && quad_in;
+    // 32-bit tile arithmetic: 64-bit divisions per tile and thread are not affordable here
+    const uint32_t ntx32 = (uint32_t)ntx, ntiles = ntx32 * (uint32_t)A.nty;
+    uint32_t t = PIPE ? blockIdx.x : 0u;
+    uint32_t ty32 = PIPE ? t / ntx32 : blockIdx.y, tx32 = PIPE ? t - ty32 * ntx32 : blockIdx.x;
+    if (PIPE) {
+        if (t >= ntiles) return;
+        tl_c_prefetch(pf, A, ty32, tx32);
+        tl_cp_async_commit();
+        if (threadIdx.x == 0) s.next_tile[0] = atomicAdd(A.tile_ctr, 1u) + gridDim.x;
+        __syncthreads();
+    }
+    for (int it = 0;; ++it) {
+        const long long ty = ty32, tx = tx32;
+        // PIPE: the tile after this one (drawn one iteration ago), and thread 0 draws the one after that
+        const uint32_t tn = PIPE ? s.next_tile[it & 1] : 0u;
+        if (PIPE && threadIdx.x == 0) s.next_tile[(it + 1) & 1] = (tn < ntiles) ? atomicAdd(A.tile_ctr, 1u) + gridDim.x : ntiles;
+        const uint32_t tyn = PIPE ? tn / ntx32 : 0u, txn = tn - tyn * ntx32;
+        const uint32_t tile = (uint32_t)((ty + 1) * ntx + tx);  // +1: halo tile row
+        const long long r0 = ty * TL_H, c0 = tx * TL_W;
+        const long long g00 = r0 * ncol + c0;
+        const long long g0 = g00 + (long long)ly * ncol + lx0;
+        const bool row_in = r0 + ly < nrow;
+        const bool quad_in = row_in && c0 + lx0 + 3 < ncol;
+        const bool vec = al4 && quad_in;
 
-    // one thread per ring position: everything it needs from global memory is requested up front, together with
-    // the per-cell loads below (entry inflow; for exit cells the solution of the entry cell they drain into)
-    // (the results are parked in shared memory so that they do not occupy registers across the kernel)
-    if (threadIdx.x < TL_NRING) {
-        const int ri = tl_ring_cell(threadIdx.x);
-        const int rly = ri >> 6, lxr = ri & (TL_W - 1);
-        uint32_t rw = 0, rt = TL_NOT_EXIT, rb = 0;
-        if (r0 + rly < nrow && c0 + lxr < ncol) {
-            const long long g = g00 + (long long)rly * ncol + lxr;
-            const uint32_t rd = __ldg(dir + g);
-            const uint32_t rloc = __ldg(&loccnt[g].x);
-            if (uparea_out && rloc != TL_LOC_INVALID) rw = __ldg(inflow + tile * TL_RING + threadIdx.x);
-            if (rd < 8u && rloc == (uint32_t)TPHYS(ri)) {  // exit cell (terminal = itself, 0 hops)
-                const uint32_t slot = tl_exit_slot(tile, (uint32_t)ntx, rly, lxr, rd);
-                const int32_t rrank = __ldg(s_rank + slot);
-                rt = (rrank < 0) ? 0xFFFFFFFFu : (uint32_t)(rrank + 1);
-                rb = (rrank < 0) ? 0u : __ldg(s_basin + slot);
+        uint32_t dirw, own[4], up[4], n1[4];
+        if (PIPE) {
+            tl_cp_async_wait_group<0>();  // my part of the prefetch of this tile
+            const uint4* lc = reinterpret_cast<const uint4*>(&pf.LC[i0]);
+            const uint4 v0 = lc[0], v1 = lc[1];
+            own[0] = v0.x, up[0] = v0.y, own[1] = v0.z, up[1] = v0.w;
+            own[2] = v1.x, up[2] = v1.y, own[3] = v1.z, up[3] = v1.w;
+            dirw = pf.DIRW[threadIdx.x];
+            __syncthreads();  // everybody's part has landed: the ring threads read other threads' entries
+        }
+        // one thread per ring position: entry inflow; for exit cells the solution of the entry cell they drain into
+        // (parked in shared memory so that nothing occupies registers across the kernel)
+        if (threadIdx.x < TL_NRING) {
+            const int ri = tl_ring_cell(threadIdx.x);
+            const int rly = ri >> 6, lxr = ri & (TL_W - 1);
+            uint32_t rw = 0;
+            bool is_exit = false;
+            if (r0 + rly < nrow && c0 + lxr < ncol) {
+                const long long g = g00 + (long long)rly * ncol + lxr;
+                const uint32_t rd = PIPE ? ((pf.DIRW[ri >> 2] >> (8 * (ri & 3))) & 0xFFu) : (uint32_t)__ldg(dir + g);
+                const uint32_t rloc = PIPE ? pf.LC[ri].x : __ldg(&loccnt[g].x);
+                if (uparea_out && rloc != TL_LOC_INVALID)
+                    rw = PIPE ? pf.ring_w[threadIdx.x] : __ldg(A.inflow + tile * TL_RING + threadIdx.x);
+                if (rd < 8u && rloc == (uint32_t)TPHYS(ri)) {  // exit cell (terminal = itself, 0 hops)
+                    const uint32_t slot = tl_exit_slot(tile, (uint32_t)ntx, rly, lxr, rd);
+                    is_exit = true;
+                    if (PIPE) {
+                        tl_cp_async4(&s.ring_t[threadIdx.x], A.s_rank + slot);
+                        tl_cp_async4(&s.ring_b[threadIdx.x], A.s_basin + slot);
+                    } else {
+                        s.ring_t[threadIdx.x] = __ldg(A.s_rank + slot);
+                        s.ring_b[threadIdx.x] = __ldg(A.s_basin + slot);
+                    }
+                }
             }
+            s.ring_w[threadIdx.x] = rw;
+            if (!is_exit) s.ring_t[threadIdx.x] = TL_NOT_EXIT;
         }
-        s.ring_w[threadIdx.x] = rw;
-        s.ring_t[threadIdx.x] = rt;
-        s.ring_b[threadIdx.x] = rb;
-    }
-    const uint32_t dirw = tl_load_dirs(dir, nrow, ncol, r0, c0, al4 != 0);
-    if (threadIdx.x == 0) s.wl_count = 0;
-    uint32_t own[4], up[4], n1[4];
-    if (vec) {
-        const uint4* lc = reinterpret_cast<const uint4*>(loccnt + g0);
-        const uint4 v0 = __ldg(lc), v1 = __ldg(lc + 1);
-        own[0] = v0.x, up[0] = v0.y, own[1] = v0.z, up[1] = v0.w;
-        own[2] = v1.x, up[2] = v1.y, own[3] = v1.z, up[3] = v1.w;
-    } else {
+        if (!PIPE) {
+            dirw = tl_load_dirs(dir, nrow, ncol, r0, c0, al4 != 0);
+            if (vec) {
+                const uint4* lc = reinterpret_cast<const uint4*>(loccnt + g0);
+                const uint4 v0 = __ldg(lc), v1 = __ldg(lc + 1);
+                own[0] = v0.x, up[0] = v0.y, own[1] = v0.z, up[1] = v0.w;
+                own[2] = v1.x, up[2] = v1.y, own[3] = v1.z, up[3] = v1.w;
+            } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint2 lc = (row_in && c0 + lx0 + j < ncol) ? __ldg(loccnt + g0 + j) : make_uint2(TL_LOC_INVALID, 0u);
-            own[j] = lc.x;
-            up[j] = lc.y;
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const uint32_t d = tl_dir_of(dirw, j);
-        n1[j] = (uint32_t)TPHYS(tl_local_next(i0 + j, d));  // positions, not cell numbers, from here on
-        // pit cells: basin id stashed by stash_pit_ids_kernel at the pit's own cell (requested now, used much later;
-        // asynchronous 4-byte copy straight into shared memory: no register is held across the kernel)
-        if ((d == PFD_DIR_PIT || d == PFD_DIR_FPIT) && basin_out) tl_cp_async4(&s.R[TPHYS(i0 + j)], basin_out + g0 + j);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        s.X[TPHYS(i0 + j)] = 0u;
-        s.S12[TPHYS(i0 + j)] = n1[j];
-    }
-    __syncthreads();
-    // entry cells with outside inflow become walkers
-    if (threadIdx.x < TL_NRING) {
-        const uint32_t my_w = s.ring_w[threadIdx.x];
-        if (my_w != 0u) {
-            const uint32_t k = atomicAdd(&s.wl_count, 1u);
-            s.wl_cell[k] = (uint32_t)TPHYS(tl_ring_cell(threadIdx.x));
-            s.wl_w[k] = my_w;
-        }
-    }
-    // successor records, jump 1: 2nd successor. Concurrent readers only use the low half of S12, which does not change.
-    uint32_t x12[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) x12[j] = n1[j] | ((s.S12[n1[j]] & 0xFFFFu) << 16);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) s.S12[TPHYS(i0 + j)] = x12[j];
-    __syncthreads();
-    // jump 2: S12 of the 2nd successor holds its 1st | 2nd successor = my 3rd | 4th
-#pragma unroll
-    for (int j = 0; j < 4; ++j) s.S34[TPHYS(i0 + j)] = s.S12[x12[j] >> 16];
-    __syncthreads();
-    if (threadIdx.x < s.wl_count) {
-        uint32_t i = s.wl_cell[threadIdx.x];
-        const uint32_t w = s.wl_w[threadIdx.x];
-        for (int step = 0; step <= TL_CELLS / 4; ++step) {
-            const uint32_t s12 = s.S12[i], s34 = s.S34[i];
-            const uint32_t m1 = s12 & 0xFFFFu, m2 = s12 >> 16, m3 = s34 & 0xFFFFu, m4 = s34 >> 16;
-            atomicAdd(&s.X[i], w);
-            if (m1 == i) break;
-            atomicAdd(&s.X[m1], w);
-            if (m2 == m1) break;
-            atomicAdd(&s.X[m2], w);
-            if (m3 == m2) break;
-            atomicAdd(&s.X[m3], w);
-            if (m4 == m3) break;
-            i = m4;
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 4; ++j) up[j] += s.X[TPHYS(i0 + j)];
-    __syncthreads();
-    // terminals publish (rank at the terminal, basin id): pits by their owner, exit cells by the ring threads
-    tl_cp_async_wait();
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const uint32_t d = tl_dir_of(dirw, j);
-        if (d == PFD_DIR_PIT || d == PFD_DIR_FPIT) {
-            s.X[TPHYS(i0 + j)] = basin_out ? s.R[TPHYS(i0 + j)] : 0u;  // own asynchronous copy, completed by tl_cp_async_wait() above
-            s.R[TPHYS(i0 + j)] = 0;
-        }
-    }
-    if (threadIdx.x < TL_NRING && s.ring_t[threadIdx.x] != TL_NOT_EXIT) {  // exit cell: one hop above the entry cell
-        const int ri = tl_ring_cell(threadIdx.x);                           // of the neighbouring tile
-        s.R[TPHYS(ri)] = s.ring_t[threadIdx.x];
-        s.X[TPHYS(ri)] = s.ring_b[threadIdx.x];
-    }
-    __syncthreads();
-    int32_t rk[4], ua[4];
-    uint32_t bs[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const uint32_t d = tl_dir_of(dirw, j);
-        rk[j] = -9999, ua[j] = -9999, bs[j] = 0;
-        if (d != PFD_DIR_NODATA) {
-            rk[j] = -1;
-            ua[j] = 1;
-            if (own[j] != TL_LOC_INVALID) {
-                const uint32_t root = TP_N(own[j]);
-                const uint32_t tr = s.R[root];
-                if (tr != 0xFFFFFFFFu) {
-                    rk[j] = (int32_t)(tr + TP_H(own[j]));
-                    bs[j] = s.X[root];
-                    ua[j] = (int32_t)up[j];
+                for (int j = 0; j < 4; ++j) {
+                    const uint2 lc = (row_in && c0 + lx0 + j < ncol) ? __ldg(loccnt + g0 + j) : make_uint2(TL_LOC_INVALID, 0u);
+                    own[j] = lc.x;
+                    up[j] = lc.y;
                 }
             }
         }
-    }
-    if (vec) {
-        if (rank_out) *reinterpret_cast<int4*>(rank_out + g0) = make_int4(rk[0], rk[1], rk[2], rk[3]);
-        if (basin_out) *reinterpret_cast<uint4*>(basin_out + g0) = make_uint4(bs[0], bs[1], bs[2], bs[3]);
-        if (uparea_out) *reinterpret_cast<int4*>(uparea_out + g0) = make_int4(ua[0], ua[1], ua[2], ua[3]);
-    } else if (row_in) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (c0 + lx0 + j >= ncol) continue;
-            if (rank_out) rank_out[g0 + j] = rk[j];
-            if (basin_out) basin_out[g0 + j] = bs[j];
-            if (uparea_out) uparea_out[g0 + j] = ua[j];
-        }
-    }
-    if (IDXMODE != 0) {
-        // idxs_ds: wrap-around 32-bit arithmetic gives the right low word for int32 and uint32 alike
-        long long ds[4];
+        if (threadIdx.x == 0) s.wl_count = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const uint32_t d = tl_dir_of(dirw, j);
-            const long long g = g0 + j;
-            ds[j] = (d < 8u) ? g + pfd_slot_off((int)d, ncol) : ((d == PFD_DIR_NODATA) ? -1ll : g);
+            n1[j] = (uint32_t)TPHYS(tl_local_next(i0 + j, d));  // positions, not cell numbers, from here on
+            // pit cells: basin id stashed by stash_pit_ids_kernel at the pit's own cell (requested now, used much
+            // later; asynchronous 4-byte copy straight into shared memory)
+            if ((d == PFD_DIR_PIT || d == PFD_DIR_FPIT) && basin_out) tl_cp_async4(&s.R[TPHYS(i0 + j)], basin_out + g0 + j);
         }
-        if (IDXMODE == 1) {
-            uint32_t* o = reinterpret_cast<uint32_t*>(idxs_out) + g0;
-            if (vec) {
-                *reinterpret_cast<uint4*>(o) = make_uint4((uint32_t)ds[0], (uint32_t)ds[1], (uint32_t)ds[2], (uint32_t)ds[3]);
-            } else if (row_in) {
+        if (PIPE) tl_cp_async_commit();  // group "current tile": pit basin ids + exit solutions
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (c0 + lx0 + j < ncol) o[j] = (uint32_t)ds[j];
-            }
-        } else {
-            long long* o = reinterpret_cast<long long*>(idxs_out) + g0;
-            if (vec) {
-                *reinterpret_cast<longlong2*>(o) = make_longlong2(ds[0], ds[1]);
-                *reinterpret_cast<longlong2*>(o + 2) = make_longlong2(ds[2], ds[3]);
-            } else if (row_in) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (c0 + lx0 + j < ncol) o[j] = ds[j];
+        for (int j = 0; j < 4; ++j) {
+            s.X[TPHYS(i0 + j)] = 0u;
+            s.S12[TPHYS(i0 + j)] = n1[j];
+        }
+        __syncthreads();
+        if (PIPE) {  // the landing zone is free again (own data in registers, ring threads done): fetch the next tile
+            if (tn < ntiles) tl_c_prefetch(pf, A, tyn, txn);
+            tl_cp_async_commit();
+        }
+        // entry cells with outside inflow become walkers
+        if (threadIdx.x < TL_NRING) {
+            const uint32_t my_w = s.ring_w[threadIdx.x];
+            if (my_w != 0u) {
+                const uint32_t k = atomicAdd(&s.wl_count, 1u);
+                s.wl_cell[k] = (uint32_t)TPHYS(tl_ring_cell(threadIdx.x));
+                s.wl_w[k] = my_w;
             }
         }
+        // successor records, jump 1: 2nd successor. Concurrent readers only use the low half of S12, which does not change.
+        uint32_t x12[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x12[j] = n1[j] | ((s.S12[n1[j]] & 0xFFFFu) << 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s.S12[TPHYS(i0 + j)] = x12[j];
+        __syncthreads();
+        // jump 2: S12 of the 2nd successor holds its 1st | 2nd successor = my 3rd | 4th
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s.S34[TPHYS(i0 + j)] = s.S12[x12[j] >> 16];
+        __syncthreads();
+        if (threadIdx.x < s.wl_count) {
+            uint32_t i = s.wl_cell[threadIdx.x];
+            const uint32_t w = s.wl_w[threadIdx.x];
+            for (int step = 0; step <= TL_CELLS / 4; ++step) {
+                const uint32_t s12 = s.S12[i], s34 = s.S34[i];
+                const uint32_t m1 = s12 & 0xFFFFu, m2 = s12 >> 16, m3 = s34 & 0xFFFFu, m4 = s34 >> 16;
+                atomicAdd(&s.X[i], w);
+                if (m1 == i) break;
+                atomicAdd(&s.X[m1], w);
+                if (m2 == m1) break;
+                atomicAdd(&s.X[m2], w);
+                if (m3 == m2) break;
+                atomicAdd(&s.X[m3], w);
+                if (m4 == m3) break;
+                i = m4;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) up[j] += s.X[TPHYS(i0 + j)];
+        // the asynchronous copies of the current tile (not the prefetch of the next one) must have landed
+        if (PIPE) tl_cp_async_wait_group<1>();
+        else tl_cp_async_wait();
+        __syncthreads();
+        // terminals publish (rank at the terminal, basin id): pits by their owner, exit cells by the ring threads
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t d = tl_dir_of(dirw, j);
+            if (d == PFD_DIR_PIT || d == PFD_DIR_FPIT) {
+                s.X[TPHYS(i0 + j)] = basin_out ? s.R[TPHYS(i0 + j)] : 0u;  // own asynchronous copy
+                s.R[TPHYS(i0 + j)] = 0;
+            }
+        }
+        if (threadIdx.x < TL_NRING) {
+            const int32_t rrank = s.ring_t[threadIdx.x];  // own (asynchronous) copy
+            if (rrank != TL_NOT_EXIT) {                   // exit cell: one hop above the entry cell of the neighbouring tile
+                const int ri = tl_ring_cell(threadIdx.x);
+                s.R[TPHYS(ri)] = (rrank < 0) ? 0xFFFFFFFFu : (uint32_t)(rrank + 1);
+                s.X[TPHYS(ri)] = (rrank < 0) ? 0u : s.ring_b[threadIdx.x];
+            }
+        }
+        __syncthreads();
+        int32_t rk[4], ua[4];
+        uint32_t bs[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t d = tl_dir_of(dirw, j);
+            rk[j] = -9999, ua[j] = -9999, bs[j] = 0;
+            if (d != PFD_DIR_NODATA) {
+                rk[j] = -1;
+                ua[j] = 1;
+                if (own[j] != TL_LOC_INVALID) {
+                    const uint32_t root = TP_N(own[j]);
+                    const uint32_t tr = s.R[root];
+                    if (tr != 0xFFFFFFFFu) {
+                        rk[j] = (int32_t)(tr + TP_H(own[j]));
+                        bs[j] = s.X[root];
+                        ua[j] = (int32_t)up[j];
+                    }
+                }
+            }
+        }
+        if (vec) {
+            if (rank_out) *reinterpret_cast<int4*>(rank_out + g0) = make_int4(rk[0], rk[1], rk[2], rk[3]);
+            if (basin_out) *reinterpret_cast<uint4*>(basin_out + g0) = make_uint4(bs[0], bs[1], bs[2], bs[3]);
+            if (uparea_out) *reinterpret_cast<int4*>(uparea_out + g0) = make_int4(ua[0], ua[1], ua[2], ua[3]);
+        } else if (row_in) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (c0 + lx0 + j >= ncol) continue;
+                if (rank_out) rank_out[g0 + j] = rk[j];
+                if (basin_out) basin_out[g0 + j] = bs[j];
+                if (uparea_out) uparea_out[g0 + j] = ua[j];
+            }
+        }
+        if (IDXMODE != 0) {
+            // idxs_ds: wrap-around 32-bit arithmetic gives the right low word for int32 and uint32 alike
+            long long ds[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t d = tl_dir_of(dirw, j);
+                const long long g = g0 + j;
+                ds[j] = (d < 8u) ? g + pfd_slot_off((int)d, ncol) : ((d == PFD_DIR_NODATA) ? -1ll : g);
+            }
+            if (IDXMODE == 1) {
+                uint32_t* o = reinterpret_cast<uint32_t*>(A.idxs_out) + g0;
+                if (vec) {
+                    *reinterpret_cast<uint4*>(o) = make_uint4((uint32_t)ds[0], (uint32_t)ds[1], (uint32_t)ds[2], (uint32_t)ds[3]);
+                } else if (row_in) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (c0 + lx0 + j < ncol) o[j] = (uint32_t)ds[j];
+                }
+            } else {
+                long long* o = reinterpret_cast<long long*>(A.idxs_out) + g0;
+                if (vec) {
+                    *reinterpret_cast<longlong2*>(o) = make_longlong2(ds[0], ds[1]);
+                    *reinterpret_cast<longlong2*>(o + 2) = make_longlong2(ds[2], ds[3]);
+                } else if (row_in) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (c0 + lx0 + j < ncol) o[j] = ds[j];
+                }
+            }
+        }
+        if (!PIPE || tn >= ntiles) break;
+        t = tn, ty32 = tyn, tx32 = txn;
+        __syncthreads();  // shared state is re-initialised by the next tile
     }
 }
 

@@ -33,6 +33,9 @@ def _rasters():
     codes = np.array([0, 1, 2, 4, 8, 16, 32, 64, 128, 247, 255], np.uint8)
     out["random130x67"] = codes[rng.integers(0, codes.size, size=(130, 67))]  # loops, forced pits, nodata
     out["random64x64"] = codes[rng.integers(0, codes.size, size=(64, 64))]
+    out["random200x192"] = codes[rng.integers(0, codes.size, size=(200, 192))]  # aligned width, partial tile rows
+    z = oracle.synth_elevation(640, 1024, seed=8)  # more tiles than one wave of a small grid
+    out["synth640x1024"] = oracle.synth_d8(z, sea_level=float(np.quantile(z, 0.02)))
     out["row1x200"] = codes[rng.integers(0, codes.size, size=(1, 200))]
     out["col200x1"] = codes[rng.integers(0, codes.size, size=(200, 1))]
     return out
@@ -64,6 +67,12 @@ def test_fused_flow_all_matches_oracle(name):
         assert np.array_equal(dev.strahler(), oracle.streams.strahler_order(ids, seq))
         nup = oracle.core.upstream_count(ids)
         assert np.array_equal(dev.fetch(_lib.ARR_N_UPSTREAM), nup)
+        # persistent tile kernels with cp.async prefetch (optional variant; takes effect on 4-aligned widths)
+        dev.set_option("tile_pipe", 1)
+        piped = dev.flow_all(d8, np.int32, resident=True)
+        dev.set_option("tile_pipe", 0)
+        for a, b in zip(got, piped):
+            assert np.array_equal(a, b)
         # and identical to the separate-parse path on the same handle
         dev.set_option("fuse_parse", 0)
         ref = dev.flow_all(d8, np.int32, resident=True)
