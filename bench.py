@@ -497,7 +497,13 @@ def main():
             traffic = json.load(f).get(f"{kern}{'_fused' if fused else ''}_{args.size}")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": KERNEL_NAMES[kern],
+    per_kernel = {}
+    for k in ("parse", "tile_a", "tile_c", "bfs", "sweep"):
+        if stage_avg.get(k):
+            gbs = alg_bytes[k] * cells / (stage_avg[k] / 1e3) / 1e9
+            per_kernel[KERNEL_NAMES[k]] = {"algorithmic_bytes_per_cell": alg_bytes[k], "ms": stage_avg[k], "achieved": gbs,
+                                           "frac": gbs / peak}
+    roofline = {"bound": "hbm", "kernel": KERNEL_NAMES[kern], "per_kernel": per_kernel,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_cell": alg_bytes[kern], "fused_parse": fused,
                 "kernel_ms": stage_avg[kern], "stage_ms": stage_avg,

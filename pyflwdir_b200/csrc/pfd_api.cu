@@ -559,34 +559,19 @@ static int tiles_phase_c(pfd_handle* h, TileCtx& T, int32_t* rank_dev, uint32_t*
     A.rank_out = rank_dev, A.basin_out = basin_dev, A.uparea_out = uparea_dev, A.idxs_out = idxs_dev;
     A.al4 = (h->ncol % 4 == 0) && ((uintptr_t)T.dir % 4 == 0) && al16(rank_dev) && al16(basin_dev) && al16(uparea_dev) &&
             al16(idxs_dev);
-    // aligned rasters: persistent CTAs with the next tile streaming in behind the current one; otherwise one CTA per tile
-    const bool pipe = A.al4 && h->tile_pipe;
-    const size_t smem = pipe ? ((sizeof(TileSharedC) + 15) / 16) * 16 + sizeof(TilePrefC) : sizeof(TileSharedC);
-    const long long ntiles = T.ntx * T.nty;
-    const dim3 pgrid((unsigned)std::min<long long>(ntiles, (long long)TLC_MINBLOCKS * h->num_sms));
-    if (pipe) {  // dynamic tile counter: high word of counters[7]
-        PFD_TRY(pfd_reserve(h, h->counters, 8 * sizeof(unsigned long long)));
-        A.tile_ctr = reinterpret_cast<unsigned int*>((unsigned long long*)h->counters.p + 7) + 1;
-        PFD_CUDA(h, cudaMemsetAsync(A.tile_ctr, 0, sizeof(unsigned int), h->stream));
-    }
-#define LAUNCH_C2(M, P)                                                                                               \
+    const size_t smem = sizeof(TileSharedC);
+#define LAUNCH_C(M)                                                                                                   \
     do {                                                                                                              \
-        if (!h->c_attr_set[M][P]) { /* the attribute is per device (context) and per instantiation */                \
-            PFD_CUDA(h, cudaFuncSetAttribute(tile_phase_c_kernel<TLC_THREADS, TLC_MINBLOCKS, M, P>,                   \
+        if (!h->c_attr_set[M]) { /* the attribute is per device (context) and per instantiation */                   \
+            PFD_CUDA(h, cudaFuncSetAttribute(tile_phase_c_kernel<TLC_THREADS, TLC_MINBLOCKS, M>,                      \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
-            h->c_attr_set[M][P] = true;                                                                               \
+            h->c_attr_set[M] = true;                                                                                  \
         }                                                                                                             \
-        tile_phase_c_kernel<TLC_THREADS, TLC_MINBLOCKS, M, P><<<(P) ? pgrid : grid, TLC_THREADS, smem, h->stream>>>(A); \
-    } while (0)
-#define LAUNCH_C(M)                  \
-    do {                             \
-        if (pipe) LAUNCH_C2(M, true); \
-        else LAUNCH_C2(M, false);    \
+        tile_phase_c_kernel<TLC_THREADS, TLC_MINBLOCKS, M><<<grid, TLC_THREADS, smem, h->stream>>>(A);                 \
     } while (0)
     if (!idxs_dev) LAUNCH_C(0);
     else if (idx_dtype == PFD_I64) LAUNCH_C(2);
     else LAUNCH_C(1);
-#undef LAUNCH_C2
 #undef LAUNCH_C
     PFD_LAUNCH_CHECK(h);
     return PFD_OK;
@@ -673,15 +658,7 @@ static int flow_all_fused(pfd_handle* h, const uint8_t* d8_dev, int64_t nrow, in
         A.s_term = T.term, A.s_term_h = T.term_h;
         A.d8 = d8_dev, A.dir_out = (uint8_t*)h->dir.p, A.invalid_flag = flag;
         A.al4 = (ncol % 4 == 0) && ((uintptr_t)d8_dev % 4 == 0);
-        if (A.al4 && h->tile_pipe) {
-            const long long ntiles = T.ntx * T.nty;
-            const unsigned pg = (unsigned)std::min<long long>(ntiles, (long long)TLA_MINBLOCKS * h->num_sms);
-            // tile counter: low word of counters[7], zeroed with the rest of the counters above
-            tile_phase_a_pipe_kernel<TLA_THREADS, TLA_MINBLOCKS><<<pg, TLA_THREADS, 0, h->stream>>>(
-                A, T.nty, reinterpret_cast<unsigned int*>((unsigned long long*)h->counters.p + 7));
-        } else {
-            tile_phase_a_kernel<TLA_THREADS, TLA_MINBLOCKS, true><<<grid, TLA_THREADS, 0, h->stream>>>(A);
-        }
+        tile_phase_a_kernel<TLA_THREADS, TLA_MINBLOCKS, true><<<grid, TLA_THREADS, 0, h->stream>>>(A);
         PFD_LAUNCH_CHECK(h);
     }
     const int64_t nblk = npad / PC_CHUNK;
@@ -1026,10 +1003,6 @@ extern "C" int pfd_set_option(pfd_handle* h, const char* name, int64_t value) {
         h->fuse_parse = value ? 1 : 0;
         return PFD_OK;
     }
-    if (name && strcmp(name, "tile_pipe") == 0) {
-        h->tile_pipe = value ? 1 : 0;
-        return PFD_OK;
-    }
     return pfd_fail(h, PFD_ERR_INVALID_ARG, std::string("pfd_set_option: unknown option ") + (name ? name : "(null)"));
 }
 
@@ -1037,7 +1010,6 @@ extern "C" int64_t pfd_get_info(const pfd_handle* h, const char* name) {
     if (!h || !name) return -1;
     if (strcmp(name, "tiles") == 0) return h->use_tiles;
     if (strcmp(name, "fuse_parse") == 0) return h->fuse_parse;
-    if (strcmp(name, "tile_pipe") == 0) return h->tile_pipe;
     if (strcmp(name, "have_upmask") == 0) return h->have_upmask ? 1 : 0;
     if (strcmp(name, "tile_rounds") == 0) return h->tile_rounds;
     if (strcmp(name, "nlevels") == 0) return h->nlevels;

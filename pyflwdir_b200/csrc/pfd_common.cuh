@@ -184,9 +184,7 @@ struct pfd_handle {
     DevBuf tile_loc;           // uint2 [n]: per cell (local terminal | hops << 12, in-tile subtree size)
     DevBuf uparea;            // int32 [n] cached cell-count upstream area (tile solver)
     bool have_uparea = false;
-    bool c_attr_set[3][2] = {};  // dynamic shared memory opt-in done for tile_phase_c_kernel<.., IDXMODE, PIPE>
-    int tile_pipe = 0;           // option "tile_pipe": persistent tile kernels with cp.async prefetch on aligned rasters
-                                 // (measured slower than one CTA per tile on B200, DESIGN.md: off by default)
+    bool c_attr_set[3] = {false, false, false};  // dynamic shared memory opt-in done for tile_phase_c_kernel<.., IDXMODE>
     bool have_upmask = false;  // false after the fused-parse path: derived from dir on demand (ensure_upmask)
     unsigned long long* h_counters = nullptr;  // page-locked mirror of `counters` (read while the GPU keeps working)
     int fuse_parse = 1;       // option "fuse_parse": pfd_d8_flow_all on device buffers parses inside the tile solver

@@ -441,55 +441,6 @@ template <int N>
 __device__ __forceinline__ void tl_cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tl_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// codes of tile (ty, tx) plus halo -> sc, as 66 rows x 18 words [c0 - 4, c0 + 68); requires ncol % 4 == 0 and a
-// 4-byte aligned raster, so that every word lies entirely inside or entirely outside the raster
-template <int THREADS>
-__device__ __forceinline__ void tl_prefetch_codes(TileCodes& sc, const uint8_t* __restrict__ d8, long long nrow, long long ncol,
-                                                  long long r0, long long c0) {
-    for (int w = threadIdx.x; w < (TL_H + 2) * (TLF_STRIDE / 4); w += THREADS) {
-        const int row = w / (TLF_STRIDE / 4), cw = w - row * (TLF_STRIDE / 4);
-        const long long r = r0 - 1 + row, c = c0 - 4 + 4 * cw;
-        uint8_t* dst = &sc.c[row * TLF_STRIDE + 4 * cw];
-        if (r >= 0 && r < nrow && c >= 0 && c < ncol) tl_cp_async4(dst, d8 + r * ncol + c);
-        else *reinterpret_cast<uint32_t*>(dst) = 0xF7F7F7F7u;
-    }
-}
-
-// Persistent fused phase A: gridDim.x CTAs stride over the tiles; while tile n is solved the raw codes of tile
-// n + gridDim.x stream into the other staging buffer (cp.async), so the load latency that heads every tile in the
-// one-CTA-per-tile version is hidden behind the solve. Requires al4.
-// Tiles are handed out dynamically (tile_ctr, zeroed before the launch; the first gridDim.x tiles are implicit):
-// thread 0 draws the tile after the next one at the top of every iteration, one barrier before anybody needs it.
-template <int THREADS, int MINBLOCKS>
-__global__ void __launch_bounds__(THREADS, MINBLOCKS) tile_phase_a_pipe_kernel(PhaseAArgs A, long long nty, unsigned int* tile_ctr) {
-    static_assert(THREADS == TL_CELLS / 4, "one quad of cells per thread");
-    __shared__ __align__(16) TileShared s;
-    __shared__ TileCodes sc2[2];
-    __shared__ uint32_t next_tile[2];
-    // 32-bit tile arithmetic (64-bit divisions per tile and thread would cost more than the parse itself)
-    const uint32_t ntx = (uint32_t)A.ntx, ntiles = ntx * (uint32_t)nty;
-    uint32_t t = blockIdx.x;
-    if (t >= ntiles) return;
-    uint32_t ty = t / ntx, tx = t - ty * ntx;
-    tl_prefetch_codes<THREADS>(sc2[0], A.d8, A.nrow, A.ncol, (long long)ty * TL_H, (long long)tx * TL_W);
-    tl_cp_async_commit();
-    if (threadIdx.x == 0) next_tile[0] = atomicAdd(tile_ctr, 1u) + gridDim.x;
-    __syncthreads();
-    for (int it = 0;; ++it) {
-        const uint32_t tn = next_tile[it & 1];
-        if (threadIdx.x == 0) next_tile[(it + 1) & 1] = (tn < ntiles) ? atomicAdd(tile_ctr, 1u) + gridDim.x : ntiles;
-        const uint32_t tyn = tn / ntx, txn = tn - tyn * ntx;
-        if (tn < ntiles) tl_prefetch_codes<THREADS>(sc2[(it + 1) & 1], A.d8, A.nrow, A.ncol, (long long)tyn * TL_H, (long long)txn * TL_W);
-        tl_cp_async_commit();
-        tl_cp_async_wait_group<1>();  // everything but the prefetch just issued: the codes of tile t have landed
-        __syncthreads();
-        tl_phase_a_tile<true>(s, sc2[it & 1], A, ty, tx);
-        if (tn >= ntiles) break;
-        t = tn, ty = tyn, tx = txn;
-        __syncthreads();  // the ring threads are done with this staging buffer and with P / A
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // Phase B: synchronous doubling rounds over the ring slots
 // ---------------------------------------------------------------------------------------------------------
@@ -646,17 +597,8 @@ struct TileSharedC {
     uint32_t ring_b[TL_RING];   //                    basin id behind that exit
     uint32_t ring_w[TL_RING];   //                    outside inflow of the (entry) cell
     uint32_t wl_count;
-    uint32_t next_tile[2];      // persistent kernel: dynamically drawn tiles (see tile_phase_a_pipe_kernel)
 };
 #define TL_NOT_EXIT ((int32_t)0x80000000)
-
-// landing zone of the asynchronous prefetch of the NEXT tile (persistent kernel); every thread copies and later reads
-// its own quad, the ring threads additionally read the entries of the ring cells
-struct TilePrefC {
-    uint2 LC[TL_CELLS];          // (loc, cnt) in tile-local row-major order
-    uint32_t DIRW[TL_CELLS / 4]; // direction bytes, one word per quad
-    uint32_t ring_w[TL_RING];    // inflow weights of the tile's ring slots
-};
 
 struct PhaseCArgs {
     const uint8_t* dir;
@@ -670,43 +612,19 @@ struct PhaseCArgs {
     int32_t* uparea_out;
     void* idxs_out;
     int al4;
-    unsigned int* tile_ctr;  // PIPE: dynamic tile counter, zeroed before the launch
 };
-
-// prefetch of tile (ty, tx): requires al4 (quads entirely inside or outside the raster, 16-byte aligned rows)
-__device__ __forceinline__ void tl_c_prefetch(TilePrefC& pf, const PhaseCArgs& A, long long ty, long long tx) {
-    const long long r0 = ty * TL_H, c0 = tx * TL_W;
-    const int ly = TQ_ROW, lx0 = TQ_COL0, i0 = TQ_I0;
-    const long long g0 = (r0 + ly) * A.ncol + c0 + lx0;
-    if (r0 + ly < A.nrow && c0 + lx0 < A.ncol) {
-        tl_cp_async16(&pf.LC[i0], A.loccnt + g0);
-        tl_cp_async16(&pf.LC[i0 + 2], A.loccnt + g0 + 2);
-        tl_cp_async4(&pf.DIRW[threadIdx.x], A.dir + g0);
-    } else {
-        uint4* lc = reinterpret_cast<uint4*>(&pf.LC[i0]);
-        lc[0] = make_uint4(TL_LOC_INVALID, 0u, TL_LOC_INVALID, 0u);
-        lc[1] = make_uint4(TL_LOC_INVALID, 0u, TL_LOC_INVALID, 0u);
-        pf.DIRW[threadIdx.x] = 0xFFFFFFFFu;
-    }
-    if (threadIdx.x < TL_RING && A.uparea_out)
-        tl_cp_async4(&pf.ring_w[threadIdx.x], A.inflow + (uint32_t)((ty + 1) * A.ntx + tx) * TL_RING + threadIdx.x);
-}
 
 // IDXMODE: 0 = no idxs_ds output, 1 = 32-bit (int32 / uint32 share the bit pattern), 2 = int64 -- the fused-parse path
 // writes idxs_ds (core_d8.from_array, core_d8.py:42-67) from here, next to the other per-cell outputs.
-// PIPE = false: one CTA per tile (blockIdx = tile column, tile row), any shape / alignment; dynamic shared memory
-//               sizeof(TileSharedC).
-// PIPE = true : persistent CTAs stride over the tiles (requires al4); while tile n is processed, (loc, cnt), dir and the
-//               ring inflows of tile n + gridDim.x stream into shared memory with cp.async, and the dependent fetches
-//               of the current tile (pit basin ids, solution behind every exit cell) are asynchronous copies as well, so
-//               no global-memory latency is exposed except for the first tile of a CTA. Dynamic shared memory
-//               sizeof(TileSharedC) + sizeof(TilePrefC).
-template <int THREADS, int MINBLOCKS, int IDXMODE, bool PIPE>
+// One CTA per tile (blockIdx = tile column, tile row); dynamic shared memory sizeof(TileSharedC).
+// (Variants that process several tiles per CTA and stream the next tile in with cp.async behind the current one --
+// persistent with a dynamic tile counter, or 4 adjacent tiles per CTA -- were measured 7-15 % SLOWER on B200 for both
+// tile phases: DESIGN.md section 4.3.)
+template <int THREADS, int MINBLOCKS, int IDXMODE>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS) tile_phase_c_kernel(PhaseCArgs A) {
     static_assert(THREADS == TL_CELLS / 4, "one quad of cells per thread");
     extern __shared__ __align__(16) unsigned char tl_smem_raw[];
     TileSharedC& s = *reinterpret_cast<TileSharedC*>(tl_smem_raw);
-    TilePrefC& pf = *reinterpret_cast<TilePrefC*>(tl_smem_raw + ((sizeof(TileSharedC) + 15) / 16) * 16);  // PIPE only
     const uint8_t* __restrict__ dir = A.dir;
     const long long nrow = A.nrow, ncol = A.ncol, ntx = A.ntx;
     const uint2* __restrict__ loccnt = A.loccnt;
@@ -715,23 +633,8 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) tile_phase_c_kernel(PhaseC
     int32_t* __restrict__ uparea_out = A.uparea_out;
     const int al4 = A.al4;
     const int ly = TQ_ROW, lx0 = TQ_COL0, i0 = TQ_I0;
-    // 32-bit tile arithmetic: 64-bit divisions per tile and thread are not affordable here
-    const uint32_t ntx32 = (uint32_t)ntx, ntiles = ntx32 * (uint32_t)A.nty;
-    uint32_t t = PIPE ? blockIdx.x : 0u;
-    uint32_t ty32 = PIPE ? t / ntx32 : blockIdx.y, tx32 = PIPE ? t - ty32 * ntx32 : blockIdx.x;
-    if (PIPE) {
-        if (t >= ntiles) return;
-        tl_c_prefetch(pf, A, ty32, tx32);
-        tl_cp_async_commit();
-        if (threadIdx.x == 0) s.next_tile[0] = atomicAdd(A.tile_ctr, 1u) + gridDim.x;
-        __syncthreads();
-    }
-    for (int it = 0;; ++it) {
-        const long long ty = ty32, tx = tx32;
-        // PIPE: the tile after this one (drawn one iteration ago), and thread 0 draws the one after that
-        const uint32_t tn = PIPE ? s.next_tile[it & 1] : 0u;
-        if (PIPE && threadIdx.x == 0) s.next_tile[(it + 1) & 1] = (tn < ntiles) ? atomicAdd(A.tile_ctr, 1u) + gridDim.x : ntiles;
-        const uint32_t tyn = PIPE ? tn / ntx32 : 0u, txn = tn - tyn * ntx32;
+    {
+        const long long ty = blockIdx.y, tx = blockIdx.x;
         const uint32_t tile = (uint32_t)((ty + 1) * ntx + tx);  // +1: halo tile row
         const long long r0 = ty * TL_H, c0 = tx * TL_W;
         const long long g00 = r0 * ncol + c0;
@@ -741,44 +644,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) tile_phase_c_kernel(PhaseC
         const bool vec = al4 && quad_in;
 
         uint32_t dirw, own[4], up[4], n1[4];
-        if (PIPE) {
-            tl_cp_async_wait_group<0>();  // my part of the prefetch of this tile
-            const uint4* lc = reinterpret_cast<const uint4*>(&pf.LC[i0]);
-            const uint4 v0 = lc[0], v1 = lc[1];
-            own[0] = v0.x, up[0] = v0.y, own[1] = v0.z, up[1] = v0.w;
-            own[2] = v1.x, up[2] = v1.y, own[3] = v1.z, up[3] = v1.w;
-            dirw = pf.DIRW[threadIdx.x];
-            __syncthreads();  // everybody's part has landed: the ring threads read other threads' entries
-        }
-        // one thread per ring position: entry inflow; for exit cells the solution of the entry cell they drain into
-        // (parked in shared memory so that nothing occupies registers across the kernel)
-        if (threadIdx.x < TL_NRING) {
-            const int ri = tl_ring_cell(threadIdx.x);
-            const int rly = ri >> 6, lxr = ri & (TL_W - 1);
-            uint32_t rw = 0;
-            bool is_exit = false;
-            if (r0 + rly < nrow && c0 + lxr < ncol) {
-                const long long g = g00 + (long long)rly * ncol + lxr;
-                const uint32_t rd = PIPE ? ((pf.DIRW[ri >> 2] >> (8 * (ri & 3))) & 0xFFu) : (uint32_t)__ldg(dir + g);
-                const uint32_t rloc = PIPE ? pf.LC[ri].x : __ldg(&loccnt[g].x);
-                if (uparea_out && rloc != TL_LOC_INVALID)
-                    rw = PIPE ? pf.ring_w[threadIdx.x] : __ldg(A.inflow + tile * TL_RING + threadIdx.x);
-                if (rd < 8u && rloc == (uint32_t)TPHYS(ri)) {  // exit cell (terminal = itself, 0 hops)
-                    const uint32_t slot = tl_exit_slot(tile, (uint32_t)ntx, rly, lxr, rd);
-                    is_exit = true;
-                    if (PIPE) {
-                        tl_cp_async4(&s.ring_t[threadIdx.x], A.s_rank + slot);
-                        tl_cp_async4(&s.ring_b[threadIdx.x], A.s_basin + slot);
-                    } else {
-                        s.ring_t[threadIdx.x] = __ldg(A.s_rank + slot);
-                        s.ring_b[threadIdx.x] = __ldg(A.s_basin + slot);
-                    }
-                }
-            }
-            s.ring_w[threadIdx.x] = rw;
-            if (!is_exit) s.ring_t[threadIdx.x] = TL_NOT_EXIT;
-        }
-        if (!PIPE) {
+        {  // per-cell loads first: they are in flight while the ring threads chase their dependent loads
             dirw = tl_load_dirs(dir, nrow, ncol, r0, c0, al4 != 0);
             if (vec) {
                 const uint4* lc = reinterpret_cast<const uint4*>(loccnt + g0);
@@ -794,6 +660,29 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) tile_phase_c_kernel(PhaseC
                 }
             }
         }
+        // one thread per ring position: entry inflow; for exit cells the solution of the entry cell they drain into
+        // (parked in shared memory so that nothing occupies registers across the kernel)
+        if (threadIdx.x < TL_NRING) {
+            const int ri = tl_ring_cell(threadIdx.x);
+            const int rly = ri >> 6, lxr = ri & (TL_W - 1);
+            uint32_t rw = 0;
+            bool is_exit = false;
+            if (r0 + rly < nrow && c0 + lxr < ncol) {
+                const long long g = g00 + (long long)rly * ncol + lxr;
+                const uint32_t rd = __ldg(dir + g);
+                const uint32_t rloc = __ldg(&loccnt[g].x);
+                if (uparea_out && rloc != TL_LOC_INVALID) rw = __ldg(A.inflow + tile * TL_RING + threadIdx.x);
+                if (rd < 8u && rloc == (uint32_t)TPHYS(ri)) {  // exit cell (terminal = itself, 0 hops)
+                    const uint32_t slot = tl_exit_slot(tile, (uint32_t)ntx, rly, lxr, rd);
+                    is_exit = true;
+                    // asynchronous copies: consumed after the walkers, nothing waits for them before
+                    tl_cp_async4(&s.ring_t[threadIdx.x], A.s_rank + slot);
+                    tl_cp_async4(&s.ring_b[threadIdx.x], A.s_basin + slot);
+                }
+            }
+            s.ring_w[threadIdx.x] = rw;
+            if (!is_exit) s.ring_t[threadIdx.x] = TL_NOT_EXIT;
+        }
         if (threadIdx.x == 0) s.wl_count = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -803,17 +692,12 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) tile_phase_c_kernel(PhaseC
             // later; asynchronous 4-byte copy straight into shared memory)
             if ((d == PFD_DIR_PIT || d == PFD_DIR_FPIT) && basin_out) tl_cp_async4(&s.R[TPHYS(i0 + j)], basin_out + g0 + j);
         }
-        if (PIPE) tl_cp_async_commit();  // group "current tile": pit basin ids + exit solutions
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             s.X[TPHYS(i0 + j)] = 0u;
             s.S12[TPHYS(i0 + j)] = n1[j];
         }
         __syncthreads();
-        if (PIPE) {  // the landing zone is free again (own data in registers, ring threads done): fetch the next tile
-            if (tn < ntiles) tl_c_prefetch(pf, A, tyn, txn);
-            tl_cp_async_commit();
-        }
         // entry cells with outside inflow become walkers
         if (threadIdx.x < TL_NRING) {
             const uint32_t my_w = s.ring_w[threadIdx.x];
@@ -854,9 +738,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) tile_phase_c_kernel(PhaseC
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < 4; ++j) up[j] += s.X[TPHYS(i0 + j)];
-        // the asynchronous copies of the current tile (not the prefetch of the next one) must have landed
-        if (PIPE) tl_cp_async_wait_group<1>();
-        else tl_cp_async_wait();
+        tl_cp_async_wait();  // my asynchronous copies (pit basin ids, exit solutions) have landed
         __syncthreads();
         // terminals publish (rank at the terminal, basin id): pits by their owner, exit cells by the ring threads
 #pragma unroll
@@ -939,9 +821,6 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) tile_phase_c_kernel(PhaseC
                 }
             }
         }
-        if (!PIPE || tn >= ntiles) break;
-        t = tn, ty32 = tyn, tx32 = txn;
-        __syncthreads();  // shared state is re-initialised by the next tile
     }
 }
 

@@ -67,12 +67,6 @@ def test_fused_flow_all_matches_oracle(name):
         assert np.array_equal(dev.strahler(), oracle.streams.strahler_order(ids, seq))
         nup = oracle.core.upstream_count(ids)
         assert np.array_equal(dev.fetch(_lib.ARR_N_UPSTREAM), nup)
-        # persistent tile kernels with cp.async prefetch (optional variant; takes effect on 4-aligned widths)
-        dev.set_option("tile_pipe", 1)
-        piped = dev.flow_all(d8, np.int32, resident=True)
-        dev.set_option("tile_pipe", 0)
-        for a, b in zip(got, piped):
-            assert np.array_equal(a, b)
         # and identical to the separate-parse path on the same handle
         dev.set_option("fuse_parse", 0)
         ref = dev.flow_all(d8, np.int32, resident=True)
