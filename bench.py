@@ -328,6 +328,97 @@ def extras(w, size, seed):
     return res
 
 
+def extras_widened(w, size, seed, cpu_size):
+    """The widened rows of SURVEY.md §8f on the same raster: every entry point timed device-resident (CUDA events, best
+    of 3, ordering already cached) next to the oracle port of the same reference function on a `cpu_size`^2 raster of
+    the same generator (1 host thread). Returns {name: {"gpu_ms", "gpu_mcells_s", "cpu_mcells_s"}}."""
+    import oracle
+
+    l, L, h, n = w.l, w.L, w.h, w.cells
+    i32, f32 = L.DTYPES[np.dtype(np.int32)], L.DTYPES[np.dtype(np.float32)]
+    z_dev = w.dev_alloc(n * 4)
+    w.ck(l.pfd_synth_elevation(h, size, size, size, octaves_for(size), seed, z_dev))
+    w.ck(l.pfd_d8_parse(h, w.d8_dev, size, size, 1, None, 0, None, None, None))
+    w.ck(l.pfd_order(h, None, None))
+    upa_dev, out4_dev, out1_dev, um_dev = w.out_dev[2], w.out_dev[1], w.dev_alloc(n), w.dev_alloc(n * 4)
+    w.ck(l.pfd_upstream_area_cells(h, upa_dev))
+    upa = np.empty(n, np.int32)
+    w.ck(l.pfd_memcpy(h, L.ptr(upa), upa_dev, n * 4))
+    mask_dev = w.dev_alloc(n)
+    mask_h = (upa > 100).astype(np.uint8)  # (named: L.ptr() does not keep a temporary alive)
+    w.ck(l.pfd_memcpy(h, mask_dev, L.ptr(mask_h), n))
+    # sparse data for fillnodata: keep ~30 % of the elevations, the rest is nodata
+    rng = np.random.default_rng(seed + 5)
+    zh = np.empty(n, np.float32)
+    w.ck(l.pfd_memcpy(h, L.ptr(zh), z_dev, n * 4))
+    gaps = rng.random(n) < 0.7
+    sparse_dev = w.dev_alloc(n * 4)
+    sparse_h = np.where(gaps, np.float32(-9999.0), zh)
+    w.ck(l.pfd_memcpy(h, sparse_dev, L.ptr(sparse_h), n * 4))
+    drainh = np.where(upa >= 1000, np.power(upa.astype(np.float64), 0.3), -9999.0).astype(np.float32)
+    drainh_dev = w.dev_alloc(n * 4)
+    w.ck(l.pfd_memcpy(h, drainh_dev, L.ptr(drainh), n * 4))
+    del zh, gaps, drainh, sparse_h, mask_h
+
+    def best(fn, reps=3):
+        fn()
+        return min(w.timer(fn, 1) for _ in range(reps))
+
+    gpu = {}
+    gpu["main_upstream"] = best(lambda: w.ck(l.pfd_main_upstream(h, upa_dev, i32, C.c_double(0.0), um_dev, i32)))
+    gpu["upstream_count_masked"] = best(lambda: w.ck(l.pfd_upstream_count(h, mask_dev, out1_dev)))
+    gpu["stream_order_classic"] = best(lambda: w.ck(l.pfd_stream_order_classic(h, um_dev, i32, None, out1_dev)))
+    gpu["accuflux_ds_f32"] = best(lambda: w.ck(l.pfd_accuflux(h, z_dev, f32, C.c_double(-9999.0), 0, 0, 1, out4_dev)))
+    gpu["fillnodata_up_f32"] = best(lambda: w.ck(l.pfd_fillnodata(h, sparse_dev, f32, C.c_double(-9999.0), 0, 0, 0, 0, out4_dev)))
+    gpu["fillnodata_down_max_f32"] = best(lambda: w.ck(l.pfd_fillnodata(h, sparse_dev, f32, C.c_double(-9999.0), 0, 0, 1, 0, out4_dev)))
+    gpu["stream_distance_cells"] = best(lambda: w.ck(l.pfd_stream_distance(h, mask_dev, 0, None, out4_dev)))
+    gpu["floodplains"] = best(lambda: w.ck(l.pfd_floodplains(h, drainh_dev, z_dev, f32, out1_dev)))
+    ldd_dev = w.dev_alloc(n)
+    w.ck(l.pfd_fetch(h, L.ARR_LDD, ldd_dev, 0))
+    gpu["ldd_parse"] = best(lambda: w.ck(l.pfd_ldd_parse(h, ldd_dev, size, size, w.out_dev[0], i32, None, None)))
+    gpu["to_array_d8"] = best(lambda: w.ck(l.pfd_fetch(h, L.ARR_D8, out1_dev, 0)))
+    for pdev in (z_dev, out1_dev, um_dev, mask_dev, sparse_dev, drainh_dev, ldd_dev):
+        w.ck(l.pfd_dev_free(h, pdev))
+
+    # CPU port on a bounded sample of the same generator
+    oracle.build()
+    d8, _ = host_raster(cpu_size, seed)
+    m = d8.size
+    zc = oracle.synth_elevation(cpu_size, cpu_size, seed=seed, octaves=octaves_for(cpu_size), nref=cpu_size).ravel()
+    ids, pits, _ = oracle.core_d8.from_array(d8, dtype=np.int32)
+    seq = oracle.core.idxs_seq(ids, pits)
+    upc = oracle.streams.accuflux(ids, seq, np.ones(m, np.int32), -9999)
+    cmask = upc > 100
+    sparse = np.where(np.random.default_rng(seed + 5).random(m) < 0.7, np.float32(-9999.0), zc)
+
+    def cpu_time(fn):
+        t0 = time.perf_counter()
+        r = fn()
+        return time.perf_counter() - t0, r
+
+    cpu = {}
+    cpu["main_upstream"], um = cpu_time(lambda: oracle.core.main_upstream(ids, upc, 0.0))
+    cpu["upstream_count_masked"], _ = cpu_time(lambda: oracle.core.upstream_count(ids, mask=cmask))
+    cpu["stream_order_classic"], _ = cpu_time(lambda: oracle.streams.stream_order(ids, seq, um))
+    cpu["accuflux_ds_f32"], _ = cpu_time(lambda: oracle.streams.accuflux_ds(ids, seq, zc, -9999.0))
+    cpu["fillnodata_up_f32"], _ = cpu_time(lambda: oracle.core.fillnodata_upstream_any(ids, seq, sparse, -9999.0))
+    cpu["fillnodata_down_max_f32"], _ = cpu_time(lambda: oracle.core.fillnodata_downstream(ids, seq, sparse, -9999.0, "max"))
+    cpu["stream_distance_cells"], _ = cpu_time(lambda: oracle.streams.stream_distance(ids, seq, cpu_size, mask=cmask, real_length=False))
+    cpu["floodplains"], _ = cpu_time(lambda: oracle.dem.floodplains(ids, seq, zc, upc, 1000.0, 0.3))
+    ldd = oracle.core_ldd.to_array(ids, d8.shape) if hasattr(oracle, "core_ldd") else None
+    if ldd is not None:
+        cpu["ldd_parse"], _ = cpu_time(lambda: oracle.core_ldd.from_array(ldd, dtype=np.int32))
+    cpu["to_array_d8"], _ = cpu_time(lambda: oracle.core_d8.to_array(ids, d8.shape))
+    res = {}
+    for k, ms in gpu.items():
+        res[k] = {"gpu_ms": ms, "gpu_mcells_s": n / (ms / 1e3) / 1e6,
+                  "cpu_mcells_s": (m / cpu[k] / 1e6) if k in cpu else None}
+    res["note"] = (f"GPU: {size}^2 raster, device-resident buffers, ordering cached, best of 3; CPU: oracle port of the same "
+                   f"reference function on a {cpu_size}^2 raster of the same generator, 1 thread (the reference's "
+                   "stream_distance / floodplains are interpreted Python and far slower than this C port)")
+    return res
+
+
 def cpu_path(d8, repeat=1):
     """The reference's CPU path on `d8` via the oracle port: seconds per stage (best of `repeat`)."""
     import oracle
@@ -514,6 +605,7 @@ def main():
     extra = None
     if args.extras and world == 1:
         extra = extras(w, args.size, args.seed)
+        extra["widened"] = extras_widened(w, args.size, args.seed, min(args.size, 2048))
 
     # ---- CPU baseline (rank 0, N = 1 only)
     cpu = None
