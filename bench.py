@@ -121,6 +121,9 @@ def dist_setup(n_gpus):
     import torch.distributed as dist
 
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     dist.init_process_group(backend="gloo")
     return dist, dist.get_rank(), dist.get_world_size(), int(os.environ.get("LOCAL_RANK", "0"))
 
@@ -575,9 +578,10 @@ def main():
 
     # ---- roofline of the dominant kernel
     peak, peak_src = peaks()
-    kern = max((k for k in ("parse", "bfs", "sweep", "tile_a", "tile_c") if k in stage_avg), key=lambda k: stage_avg[k])
+    kern = max((k for k in ("parse", "bfs", "sweep", "tile_a", "tile_c") if stage_avg.get(k, 0.0) > 0.0), key=lambda k: stage_avg[k])
     alg_bytes = dict(ALG_BYTES)
-    fused = "parse" not in stage_avg and "tile_a" in stage_avg
+    stage_avg = {k: v for k, v in stage_avg.items() if v > 0.0}  # stages that did not run in this path report 0
+    fused = world == 1 and not args.no_fuse and "parse" not in stage_avg and "tile_a" in stage_avg
     if fused:
         alg_bytes.update(ALG_BYTES_FUSED)
         alg_bytes["tile_c"] += np.dtype(getattr(w, "idx_dtype", np.int32)).itemsize - 4
