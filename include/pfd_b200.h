@@ -58,7 +58,8 @@ typedef enum pfd_array {
     PFD_ARR_N_UPSTREAM = 5,/* int8, N               -- core.upstream_count           */
     PFD_ARR_D8 = 6,        /* uint8, N              -- core_d8.to_array              */
     PFD_ARR_LEVEL_OFFSETS = 7, /* int64, nlevels+1: start of every rank level inside SEQ */
-    PFD_ARR_LDD = 8        /* uint8, N              -- core_ldd.to_array             */
+    PFD_ARR_LDD = 8,       /* uint8, N              -- core_ldd.to_array             */
+    PFD_ARR_SUBBASIN_OUTLETS = 9 /* idx dtype, n_outlets of the last pfd_subbasins_streamorder call (2nd return value) */
 } pfd_array;
 
 /* ---- library / device ------------------------------------------------------------------------------- */
@@ -174,6 +175,19 @@ int pfd_stream_distance(pfd_handle* h, const uint8_t* mask, int real_length, con
  * float32(uparea ** b) at the drain cells (uparea >= upa_min) and -9999 elsewhere -- the power is evaluated by the
  * host exactly as the reference does; elevtn: N float32 / float64; out: N int8 (-1 outside the sequence). */
 int pfd_floodplains(pfd_handle* h, const float* drainh_init, const void* elevtn, int elev_dtype, int8_t* out);
+
+/* arithmetics.upstream_sum (pyflwdir/arithmetics.py:150-169), Flwdir.upstream_sum (pyflwdir/flwdir.py:412-433): per cell
+ * the sum of the values of its direct upstream neighbours, with the reference's nodata rule (a cell whose own or whose
+ * downstream value is nodata gets nodata ASSIGNED when the scan reaches it, which wipes earlier additions). data / out:
+ * N elements of `dtype` (any 1/2/4/8-byte integer, float32, float64); nodata as in pfd_accuflux. Bit-exact for floats. */
+int pfd_upstream_sum(pfd_handle* h, const void* data, int dtype, double nodata_f, int64_t nodata_i, int nodata_is_int,
+                     void* out);
+/* basins.subbasins_streamorder (pyflwdir/basins.py:67-103), FlwdirRaster.subbasins_streamorder (pyflwdir/pyflwdir.py:601-629):
+ * subbasins of every stream segment with order >= min_sto (min_sto < 0: relative to the maximum order). strord: N uint8;
+ * mask: N bytes or NULL; subbas_out: N int32 (0 = no subbasin); ids follow the reference (outlets numbered along
+ * seq[::-1]). The outlet cells (2nd return value) are fetched with pfd_fetch(PFD_ARR_SUBBASIN_OUTLETS). */
+int pfd_subbasins_streamorder(pfd_handle* h, const uint8_t* strord, const uint8_t* mask, int64_t min_sto, int32_t* subbas_out,
+                              int64_t* n_outlets);
 
 /* ---- fused headline pass ------------------------------------------------------------------------------ */
 /*

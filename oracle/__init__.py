@@ -251,6 +251,32 @@ def _stream_order_classic(idxs_ds, seq, idxs_us_main, mask=None, mv=None):
     return out
 
 
+def _upstream_sum(idxs_ds, data, nodata=-9999.0, mv=None):
+    """pyflwdir/arithmetics.py:150-169"""
+    a, sfx = _idx(idxs_ds)
+    data = np.ascontiguousarray(data)
+    tsfx = _DATA_SFX[data.dtype]
+    out = np.empty(data.size, dtype=data.dtype)
+    nd_f, nd_i, nd_is_int = _nodata_args(nodata)
+    _fn(f"orc_upstream_sum_{tsfx}", sfx)(_p(a), _p(data), C.c_int64(data.size), nd_f, nd_i, nd_is_int, _p(out))
+    return out
+
+
+def _subbasins_streamorder(idxs_ds, seq, strord, mask=None, min_sto=-2):
+    """pyflwdir/basins.py:67-103 -> (int32 map, outlet indices)"""
+    a, sfx = _idx(idxs_ds)
+    s = np.ascontiguousarray(seq).astype(a.dtype)
+    so = np.ascontiguousarray(strord, dtype=np.uint8)
+    m = None if mask is None else np.ascontiguousarray(mask).astype(np.uint8)
+    sub = np.empty(a.size, dtype=np.int32)
+    idxs = np.empty(max(s.size, 1), dtype=a.dtype)
+    n = _fn("orc_subbasins_streamorder", sfx, C.c_int64)(_p(a), _p(s), C.c_int64(s.size), _p(so), None if m is None else _p(m),
+                                                         C.c_int64(int(min_sto)), C.c_int64(a.size), _p(sub), _p(idxs))
+    return sub, idxs[: int(n)].copy()
+
+
+arithmetics = types.SimpleNamespace(upstream_sum=_upstream_sum)
+
 core = types.SimpleNamespace(
     fillnodata_upstream_any=_fillnodata_upstream_any,
     fillnodata_downstream=_fillnodata_downstream,
@@ -360,7 +386,7 @@ def _basins(idxs_ds, idxs_pit, seq, ids=None):
     return _fillnodata_upstream(idxs_ds, seq, b, 0)
 
 
-basins = types.SimpleNamespace(basins=_basins)
+basins = types.SimpleNamespace(basins=_basins, subbasins_streamorder=_subbasins_streamorder)
 
 
 def _hand(idxs_ds, seq, drain, elevtn):

@@ -181,6 +181,38 @@ class DeviceGraph:
                                       0 if direction == "up" else 1, _lib.ptr(out)))
         return out
 
+    def upstream_sum(self, data, nodata):
+        """arithmetics.upstream_sum: sum of the values of the direct upstream neighbours."""
+        data = np.ascontiguousarray(data)
+        if data.size != self.size:
+            raise ValueError('"data" size does not match.')
+        if data.dtype == np.bool_:
+            raise TypeError("upstream_sum: boolean data is not supported")
+        out = _lib.out_array(data.size, data.dtype)
+        nd_f, nd_i, nd_is = nodata_args(nodata)
+        self._ck(self._l.pfd_upstream_sum(self._h, _lib.ptr(data), _lib.dtype_code(data.dtype), nd_f, nd_i, nd_is,
+                                          _lib.ptr(out)))
+        return out
+
+    def subbasins_streamorder(self, strord, mask=None, min_sto=-2, idx_dtype=np.int32):
+        """basins.subbasins_streamorder -> (int32 map, outlet indices)."""
+        strord = np.ascontiguousarray(strord, dtype=np.uint8)
+        if strord.size != self.size:
+            raise ValueError('"strord" size does not match.')
+        m = None
+        if mask is not None:
+            m = np.ascontiguousarray(mask).astype(np.uint8, copy=False)
+            if m.size != self.size:
+                raise ValueError('"mask" size does not match.')
+        out = _lib.out_array(self.size, np.int32)
+        k = C.c_int64()
+        self._ck(self._l.pfd_subbasins_streamorder(self._h, _lib.ptr(strord), _lib.ptr(m), int(min_sto), _lib.ptr(out),
+                                                   C.byref(k)))
+        idxs = np.empty(k.value, dtype=idx_dtype)
+        if k.value:
+            self._ck(self._l.pfd_fetch(self._h, _lib.ARR_SUBBASIN_OUTLETS, _lib.ptr(idxs), _lib.dtype_code(idx_dtype)))
+        return out, idxs
+
     def upstream_area_cells(self):
         out = _lib.out_array(self.size, np.int32)
         self._ck(self._l.pfd_upstream_area_cells(self._h, _lib.ptr(out)))

@@ -23,7 +23,8 @@ DTYPES = {
 }
 
 # pfd_array
-ARR_IDXS_DS, ARR_PITS, ARR_PIT_IS_OUTLET, ARR_SEQ, ARR_RANK, ARR_N_UPSTREAM, ARR_D8, ARR_LEVEL_OFFSETS, ARR_LDD = range(9)
+ARR_IDXS_DS, ARR_PITS, ARR_PIT_IS_OUTLET, ARR_SEQ, ARR_RANK, ARR_N_UPSTREAM, ARR_D8, ARR_LEVEL_OFFSETS, ARR_LDD, \
+    ARR_SUBBASIN_OUTLETS = range(10)
 
 # every symbol include/pfd_b200.h declares: name -> (restype, argtypes)
 _vp, _i64, _int, _u32 = C.c_void_p, C.c_int64, C.c_int, C.c_uint32
@@ -57,6 +58,8 @@ SYMBOLS = {
     "pfd_stream_order_classic": (_int, [_vp, _vp, _int, _vp, _vp]),
     "pfd_stream_distance": (_int, [_vp, _vp, _int, _vp, _vp]),
     "pfd_floodplains": (_int, [_vp, _vp, _vp, _int, _vp]),
+    "pfd_upstream_sum": (_int, [_vp, _vp, _int, C.c_double, _i64, _int, _vp]),
+    "pfd_subbasins_streamorder": (_int, [_vp, _vp, _vp, _i64, _vp, _pi64]),
     "pfd_d8_flow_all": (_int, [_vp, _vp, _i64, _i64, _vp, _int, _vp, _vp, _vp, _pi64, _pi64, _pi64]),
     "pfd_comm_unique_id": (_int, [_vp, _i64]),
     "pfd_comm_init": (_int, [_vp, _int, _int, _vp]),

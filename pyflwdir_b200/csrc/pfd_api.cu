@@ -3,6 +3,7 @@
 #include "pfd_order.cuh"
 #include "pfd_parse.cuh"
 #include "pfd_sweeps.cuh"
+#include "pfd_compact.cuh"
 #include "pfd_tiles.cuh"
 #include "pfd_synth.h"
 
@@ -140,7 +141,7 @@ extern "C" void pfd_destroy(pfd_handle* h) {
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->dir, &h->upmask, &h->pits, &h->pit_outlet, &h->seq, &h->bseq, &h->rank, &h->basins,
                       &h->level_off, &h->bfs_state, &h->chunk_status, &h->blk_counts, &h->blk_offsets, &h->counters,
-                      &h->segs, &h->tslots, &h->uparea, &h->tile_loc, &h->btab, &h->bgraph, &h->mg_counts};
+                      &h->segs, &h->tslots, &h->uparea, &h->tile_loc, &h->btab, &h->bgraph, &h->mg_counts, &h->sub_idxs};
     for (DevBuf* b : bufs) pfd_release(*b);
     for (DevBuf& b : h->scratch) pfd_release(b);
     for (int s = 0; s < PFD_NSTAGE; ++s) {
@@ -233,7 +234,7 @@ extern "C" double pfd_last_stage_ms(const pfd_handle* h, int stage) {
 // ---------------------------------------------------------------------------------------------------------
 static void invalidate(pfd_handle* h) {
     h->parsed = h->ordered = h->have_rank = h->have_basins = h->have_uparea = h->have_upmask = false;
-    h->n_valid = h->n_pits = h->n_outlets = h->nnodes = h->nlevels = 0;
+    h->n_valid = h->n_pits = h->n_outlets = h->nnodes = h->nlevels = h->n_sub = 0;
 }
 
 // d8_dev: device pointer. idxs_dev: device pointer or null.
@@ -1284,6 +1285,9 @@ extern "C" int pfd_fetch(pfd_handle* h, int which, void* out, int idx_dtype) {
         PFD_TRY(pfd_finish_out(h, out, dev, (size_t)n));
         break;
     }
+    case PFD_ARR_SUBBASIN_OUTLETS:
+        PFD_TRY(copy_cells_out(h, (const cell_t*)h->sub_idxs.p, h->n_sub, out, idx_dtype));
+        break;
     case PFD_ARR_LEVEL_OFFSETS:
         PFD_TRY(order_impl(h, false, false));
         PFD_CUDA(h, cudaMemcpyAsync(out, h->level_off.p, (size_t)(h->nlevels + 1) * sizeof(long long), cudaMemcpyDefault, h->stream));
@@ -1802,6 +1806,109 @@ extern "C" int pfd_d8_flow_all(pfd_handle* h, const uint8_t* d8, int64_t nrow, i
     if (n_valid) *n_valid = h->n_valid;
     if (n_pits) *n_pits = h->n_pits;
     if (nnodes) *nnodes = h->nnodes;
+    return PFD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// further rows of SURVEY.md §8f: arithmetics.upstream_sum, basins.subbasins_streamorder
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+static int upstream_sum_typed(pfd_handle* h, const void* data_dev, void* out_dev, const NoData& nd) {
+    // arr_sum[idx0] = nodata casts the nodata value to the data dtype
+    const T ndv = nd.is_int ? (T)nd.i : (T)nd.f;
+    upstream_sum_kernel<T><<<grid_for(h->n, 256, 4), 256, 0, h->stream>>>((const uint8_t*)h->dir.p, (const uint8_t*)h->upmask.p,
+                                                                       (const T*)data_dev, h->n, h->ncol, nd, ndv, (T*)out_dev);
+    PFD_LAUNCH_CHECK(h);
+    return PFD_OK;
+}
+
+extern "C" int pfd_upstream_sum(pfd_handle* h, const void* data, int dtype, double nodata_f, int64_t nodata_i, int nodata_is_int,
+                                void* out) {
+    PFD_TRY(check_handle(h));
+    stage_reset(h);
+    if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, "pfd_upstream_sum: no raster parsed on this handle");
+    if (h->tiled) return pfd_fail(h, PFD_ERR_UNSUPPORTED, "this handle holds a row block: only the pfd_tiled_* entry points apply");
+    if (!data || !out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_upstream_sum: null array");
+    const size_t esz = pfd_dtype_size(dtype);
+    if (!esz) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_upstream_sum: unknown dtype");
+    const size_t bytes = (size_t)h->n * esz;
+    void* out_dev = nullptr;
+    const void* data_dev = nullptr;
+    PFD_TRY(pfd_stage_out(h, out, bytes, 3, &out_dev));
+    PFD_TRY(pfd_stage_in(h, data, bytes, 5, &data_dev));
+    if (data_dev == out_dev) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_upstream_sum: data and out must not alias");
+    PFD_TRY(ensure_upmask(h));
+    NoData nd{nodata_f, (long long)nodata_i, nodata_is_int};
+    int rc;
+    switch (dtype) {
+    case PFD_I8: rc = upstream_sum_typed<int8_t>(h, data_dev, out_dev, nd); break;
+    case PFD_U8: rc = upstream_sum_typed<uint8_t>(h, data_dev, out_dev, nd); break;
+    case PFD_I16: rc = upstream_sum_typed<int16_t>(h, data_dev, out_dev, nd); break;
+    case PFD_U16: rc = upstream_sum_typed<uint16_t>(h, data_dev, out_dev, nd); break;
+    case PFD_I32: rc = upstream_sum_typed<int32_t>(h, data_dev, out_dev, nd); break;
+    case PFD_U32: rc = upstream_sum_typed<uint32_t>(h, data_dev, out_dev, nd); break;
+    case PFD_I64: rc = upstream_sum_typed<int64_t>(h, data_dev, out_dev, nd); break;
+    case PFD_U64: rc = upstream_sum_typed<uint64_t>(h, data_dev, out_dev, nd); break;
+    case PFD_F32: rc = upstream_sum_typed<float>(h, data_dev, out_dev, nd); break;
+    default: rc = upstream_sum_typed<double>(h, data_dev, out_dev, nd); break;
+    }
+    PFD_TRY(rc);
+    PFD_TRY(pfd_finish_out(h, out, out_dev, bytes));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    return PFD_OK;
+}
+
+extern "C" int pfd_subbasins_streamorder(pfd_handle* h, const uint8_t* strord, const uint8_t* mask, int64_t min_sto,
+                                         int32_t* subbas_out, int64_t* n_outlets) {
+    PFD_TRY(check_handle(h));
+    stage_reset(h);
+    if (!strord || !subbas_out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_subbasins_streamorder: null array");
+    PFD_TRY(order_impl(h, false, false));
+    const int64_t n = h->n, m = h->nnodes;
+    const void *so_dev = nullptr, *mask_dev = nullptr;
+    PFD_TRY(pfd_stage_in(h, strord, (size_t)n, 5, &so_dev));
+    if (mask) PFD_TRY(pfd_stage_in(h, mask, (size_t)n, 4, &mask_dev));
+    void* out_dev = nullptr;
+    PFD_TRY(pfd_stage_out(h, subbas_out, (size_t)n * sizeof(int32_t), 3, &out_dev));
+    if (min_sto < 0) {  // relative to the global maximum (basins.py:88-89)
+        unsigned int* mx = reinterpret_cast<unsigned int*>((unsigned long long*)h->counters.p + 6);
+        PFD_CUDA(h, cudaMemsetAsync(mx, 0, sizeof(unsigned int), h->stream));
+        max_u8_kernel<<<grid_for(n, 256, 16, 148 * 8), 256, 0, h->stream>>>((const uint8_t*)so_dev, n, mx);
+        PFD_LAUNCH_CHECK(h);
+        unsigned int hmx = 0;
+        PFD_CUDA(h, cudaMemcpyAsync(&hmx, mx, sizeof(hmx), cudaMemcpyDeviceToHost, h->stream));
+        PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+        min_sto += (int64_t)hmx;
+    }
+    const int min_sto_i = (int)std::max<int64_t>(std::min<int64_t>(min_sto, 1 << 20), -(1 << 20));
+    SubbasinOutletPred pred{(const uint8_t*)h->dir.p, (const uint8_t*)so_dev, (const uint8_t*)mask_dev, min_sto_i, h->ncol};
+    const int64_t nblk = std::max<int64_t>(1, (m + CP_CHUNK - 1) / CP_CHUNK);
+    PFD_TRY(pfd_reserve(h, h->blk_counts, (size_t)nblk * sizeof(uint32_t)));
+    PFD_TRY(pfd_reserve(h, h->blk_offsets, (size_t)(nblk + 1) * sizeof(unsigned long long)));
+    PFD_CUDA(h, cudaMemsetAsync(out_dev, 0, (size_t)n * sizeof(int32_t), h->stream));
+    // outlets are numbered while walking the sequence from up- to downstream (seq[::-1], basins.py:92)
+    compact_count_kernel<SubbasinOutletPred, true><<<(unsigned)nblk, CP_THREADS, 0, h->stream>>>(
+        (const cell_t*)h->seq.p, m, pred, (uint32_t*)h->blk_counts.p);
+    PFD_LAUNCH_CHECK(h);
+    scan_counts_kernel<<<1, 1024, 0, h->stream>>>((const uint32_t*)h->blk_counts.p, nblk, (unsigned long long*)h->blk_offsets.p);
+    PFD_LAUNCH_CHECK(h);
+    unsigned long long total = 0;
+    PFD_CUDA(h, cudaMemcpyAsync(&total, (unsigned long long*)h->blk_offsets.p + nblk, sizeof(total), cudaMemcpyDeviceToHost, h->stream));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->n_sub = (int64_t)total;
+    PFD_TRY(pfd_reserve(h, h->sub_idxs, (size_t)std::max<int64_t>(h->n_sub, 1) * sizeof(cell_t)));
+    if (h->n_sub > 0) {
+        compact_scatter_kernel<SubbasinOutletPred, true, int32_t><<<(unsigned)nblk, CP_THREADS, 0, h->stream>>>(
+            (const cell_t*)h->seq.p, m, pred, (const unsigned long long*)h->blk_offsets.p, (cell_t*)h->sub_idxs.p, (int32_t*)out_dev);
+        PFD_LAUNCH_CHECK(h);
+        FillUpOp<int32_t> op{(const uint8_t*)h->dir.p, (int32_t*)out_dev, h->ncol};  // core.fillnodata_upstream(.., 0)
+        PFD_TRY((run_sweep<FillUpOp<int32_t>, false>(h, op, 0)));
+    }
+    PFD_TRY(pfd_finish_out(h, subbas_out, out_dev, (size_t)n * sizeof(int32_t)));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    if (n_outlets) *n_outlets = h->n_sub;
     return PFD_OK;
 }
 

@@ -181,6 +181,8 @@ struct pfd_handle {
     int mg_rank = 0, mg_nranks = 0, mg_halo_top = 0, mg_halo_bot = 0;
     uint32_t* mg_basins = nullptr;
     void* nccl_comm = nullptr;
+    DevBuf sub_idxs;           // cell_t [n_sub] outlets of the last pfd_subbasins_streamorder call
+    int64_t n_sub = 0;
     DevBuf tile_loc;           // uint2 [n]: per cell (local terminal | hops << 12, in-tile subtree size)
     DevBuf uparea;            // int32 [n] cached cell-count upstream area (tile solver)
     bool have_uparea = false;

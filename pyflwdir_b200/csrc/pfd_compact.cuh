@@ -1,0 +1,141 @@
+// pfd_compact.cuh -- ordered stream compaction over the cell sequence, and the entry points built on it / next to it:
+//   basins.subbasins_streamorder   (pyflwdir/basins.py:67-103): outlets numbered in seq[::-1] order
+//   arithmetics.upstream_sum       (pyflwdir/arithmetics.py:150-169): element-wise, order-exact
+#pragma once
+#include "pfd_sweeps.cuh"
+
+// ---------------------------------------------------------------------------------------------------------
+// Ordered compaction. Position q in [0, m) maps to cell seq[q] (REVERSED: seq[m-1-q]); the cells whose predicate holds
+// are written to out_cells in ascending q and, optionally, label[cell] = 1-based ordinal. Every thread owns
+// CP_PER_THREAD consecutive positions, so order is preserved with one block-wide exclusive scan.
+// Pass 1 counts per chunk, scan_counts_kernel (pfd_parse.cuh) turns counts into offsets, pass 2 writes.
+// ---------------------------------------------------------------------------------------------------------
+#define CP_THREADS 256
+#define CP_PER_THREAD 8
+#define CP_CHUNK (CP_THREADS * CP_PER_THREAD)
+
+template <class Pred, bool REVERSED>
+__device__ __forceinline__ uint32_t cp_flags(const cell_t* __restrict__ seq, long long m, const Pred& pred, long long q0,
+                                             cell_t* cells) {
+    uint32_t flags = 0;
+#pragma unroll
+    for (int e = 0; e < CP_PER_THREAD; ++e) {
+        const long long q = q0 + e;
+        if (q < m) {
+            const cell_t c = __ldg(seq + (REVERSED ? m - 1 - q : q));
+            cells[e] = c;
+            if (pred(c)) flags |= 1u << e;
+        }
+    }
+    return flags;
+}
+
+template <class Pred, bool REVERSED>
+__global__ void __launch_bounds__(CP_THREADS) compact_count_kernel(const cell_t* __restrict__ seq, long long m, Pred pred,
+                                                                   uint32_t* __restrict__ blk_counts) {
+    __shared__ uint32_t s_w[CP_THREADS / 32];
+    cell_t cells[CP_PER_THREAD];
+    const long long q0 = (long long)blockIdx.x * CP_CHUNK + (long long)threadIdx.x * CP_PER_THREAD;
+    uint32_t cnt = __popc(cp_flags<Pred, REVERSED>(seq, m, pred, q0, cells));
+    cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < CP_THREADS / 32; ++w) t += s_w[w];
+        blk_counts[blockIdx.x] = t;
+    }
+}
+
+template <class Pred, bool REVERSED, typename LABEL>
+__global__ void __launch_bounds__(CP_THREADS) compact_scatter_kernel(const cell_t* __restrict__ seq, long long m, Pred pred,
+                                                                     const unsigned long long* __restrict__ blk_off,
+                                                                     cell_t* __restrict__ out_cells, LABEL* __restrict__ label) {
+    __shared__ uint32_t s_w[CP_THREADS / 32];
+    cell_t cells[CP_PER_THREAD];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long q0 = (long long)blockIdx.x * CP_CHUNK + (long long)threadIdx.x * CP_PER_THREAD;
+    const uint32_t flags = cp_flags<Pred, REVERSED>(seq, m, pred, q0, cells);
+    const uint32_t cnt = __popc(flags);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    unsigned long long o = blk_off[blockIdx.x] + (incl - cnt);
+    for (int w = 0; w < warp; ++w) o += s_w[w];
+#pragma unroll
+    for (int e = 0; e < CP_PER_THREAD; ++e) {
+        if (flags & (1u << e)) {
+            out_cells[o] = cells[e];
+            if (label) label[cells[e]] = (LABEL)(o + 1ull);
+            ++o;
+        }
+    }
+}
+
+// basins.subbasins_streamorder (basins.py:90-100): an outlet is a cell of stream order >= min_sto (and inside the
+// mask) whose downstream cell has another stream order, or a pit
+struct SubbasinOutletPred {
+    const uint8_t* dir;
+    const uint8_t* strord;
+    const uint8_t* mask;  // may be null
+    int min_sto;
+    long long ncol;
+    __device__ __forceinline__ bool operator()(cell_t c) const {
+        const uint32_t so = __ldg(strord + c);
+        if ((mask && __ldg(mask + c) == 0) || (int)so < min_sto) return false;
+        const uint32_t d = __ldg(dir + c);
+        if (d >= 8u) return true;  // idx_ds == idx0
+        return so != (uint32_t)__ldg(strord + ((long long)c + pfd_slot_off((int)d, ncol)));
+    }
+};
+
+__global__ void max_u8_kernel(const uint8_t* __restrict__ a, int64_t n, unsigned int* __restrict__ out) {
+    unsigned int mx = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        mx = max(mx, (unsigned int)a[i]);
+    mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(out, mx);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// arithmetics.upstream_sum (arithmetics.py:150-169). The reference walks idx0 = 0..N-1 and either adds data[idx0] to
+// arr_sum[idx_ds] or -- when data[idx0] or data[idx_ds] is nodata -- ASSIGNS nodata to arr_sum[idx0], wiping what the
+// upstream cells with a smaller index added before. Per cell D that is: the valid upstream neighbours below D in
+// index order (slots 0..3), then the assignment at idx0 = D, then the neighbours above D (slots 4..7).
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void upstream_sum_kernel(const uint8_t* __restrict__ dir, const uint8_t* __restrict__ upmask, const T* __restrict__ data,
+                                    int64_t n, long long ncol, NoData nd, T ndv, T* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t d = dir[i];
+        T acc = (T)0;
+        if (d != PFD_DIR_NODATA) {
+            const bool valid = not_nodata<T>(data[i], nd);
+            const bool wipe = d < 8u && (!valid || !not_nodata<T>(data[i + pfd_slot_off((int)d, ncol)], nd));
+            const uint32_t m = upmask[i];
+            if (valid) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (m & (1u << k)) {
+                        const T v = data[i + pfd_slot_off(k, ncol)];
+                        if (not_nodata<T>(v, nd)) acc = acc_add<T>(acc, v);
+                    }
+            }
+            if (wipe) acc = ndv;
+            if (valid) {
+#pragma unroll
+                for (int k = 4; k < 8; ++k)
+                    if (m & (1u << k)) {
+                        const T v = data[i + pfd_slot_off(k, ncol)];
+                        if (not_nodata<T>(v, nd)) acc = acc_add<T>(acc, v);
+                    }
+            }
+        }
+        out[i] = acc;
+    }
+}

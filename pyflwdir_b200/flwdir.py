@@ -210,6 +210,11 @@ class Flwdir(object):
             raise ValueError(f'Unknown stream order type: "{type}"')
         return strord.reshape(self.shape)
 
+    def upstream_sum(self, data, mv=-9999):
+        """Returns sum of next upstream values (flwdir.py:412-433 -> arithmetics.upstream_sum)."""
+        dflat = self._check_data(data, "data")
+        return self._dev.upstream_sum(dflat, mv).reshape(np.shape(data))
+
     def fillnodata(self, data, nodata, direction="down", how="max"):
         """Returns data where cells with nodata value have been filled with the nearest up- or downstream valid
         neighbor value (flwdir.py:360-392)."""
@@ -267,8 +272,8 @@ class Flwdir(object):
 
     # ------------------------------------------------------------------ not in scope
     for _name in ("path", "snap", "inflow_idxs", "outflow_idxs", "smooth_rivlen",
-                  "subbasins_streamorder", "subbasins_pfafstetter", "subbasins_area", "moving_average",
-                  "moving_median", "upstream_sum", "vectorize", "streams", "geofeatures", "dem_adjust", "dem_dig_d4",
+                  "subbasins_pfafstetter", "subbasins_area", "moving_average",
+                  "moving_median", "vectorize", "streams", "geofeatures", "dem_adjust", "dem_dig_d4",
                   "classify_estuaries", "ucat_area", "ucat_outlets", "ucat_volume", "subgrid_rivlen",
                   "subgrid_rivslp", "subgrid_rivavg", "subgrid_rivmed", "subgrid_rivlen2", "upscale", "upscale_error",
                   "accuflux_ds"):

@@ -237,6 +237,14 @@ class FlwdirRaster(Flwdir):
         return basids.reshape(self.shape)
 
     # ------------------------------------------------------------------ accumulate
+    def subbasins_streamorder(self, strord=None, mask=None, min_sto=-2):
+        """Returns map with basin IDs, with one basin for each stream with a minimal stream order (pyflwdir.py:601-629 ->
+        basins.subbasins_streamorder): (int32 map, linear indices of the subbasin outlets)."""
+        subbas, idxs_out = self._dev.subbasins_streamorder(
+            self._check_data(strord, "strord"), self._check_data(mask, "mask", optional=True), min_sto,
+            idx_dtype=self._idx_dtype)
+        return subbas.reshape(self.shape), idxs_out
+
     def upstream_area(self, unit="cell"):
         """Upstream area map (pyflwdir.py:770-801). "cell": int32 counts by the dedicated device sweep; other
         units accumulate the cell-area grid in its own dtype (float64 if latlon, else float32)."""
@@ -301,7 +309,7 @@ class FlwdirRaster(Flwdir):
             idxs = self.index(*xy)
         return super()._check_idxs_xy(idxs, streams)
 
-    for _name in ("repair_loops_raster", "subbasins_streamorder", "subbasins_pfafstetter", "subbasins_area",
+    for _name in ("repair_loops_raster", "subbasins_pfafstetter", "subbasins_area",
                   "streams", "geofeatures", "vectorize", "dem_adjust", "dem_dig_d4",
                   "upscale", "upscale_error", "subgrid_rivlen", "subgrid_rivslp", "subgrid_rivavg", "subgrid_rivmed",
                   "ucat_area", "ucat_outlets", "ucat_volume", "inflow_idxs", "outflow_idxs"):

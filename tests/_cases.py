@@ -167,6 +167,13 @@ def run_oracle_case(d8, aux, area=None, transform=(1.0, 0.0, 0.0, 0.0, -1.0, 0.0
         out["fldpln_f32"] = o.dem.floodplains(idxs_ds, seq, aux["elevtn"].ravel(), ukm.ravel(), upa_min=upa_min, b=0.3).reshape(shape)
     out["fldpln_f64"] = o.dem.floodplains(idxs_ds, seq, (aux["elevtn"].astype(np.float64) * 1.1).ravel(),
                                           out["uparea_cell"].ravel(), upa_min=max(4, int(0.002 * d8.size)), b=0.5).reshape(shape)
+    out["upsum_f32"] = o.arithmetics.upstream_sum(idxs_ds, aux["data_f32_nd"].ravel(), -9999).reshape(shape)
+    out["upsum_i64"] = o.arithmetics.upstream_sum(idxs_ds, aux["fill_i64"].ravel(), -9999).reshape(shape)
+    out["upsum_f64"] = o.arithmetics.upstream_sum(idxs_ds, aux["data_f64"].ravel(), -9999.0).reshape(shape)
+    sub, sidx = o.basins.subbasins_streamorder(idxs_ds, seq, out["strord"].ravel(), None, -2)
+    out["subbas_so"], out["subbas_so_idxs"] = sub.reshape(shape), sidx
+    sub, sidx = o.basins.subbasins_streamorder(idxs_ds, seq, out["strord"].ravel(), sm, 2)
+    out["subbas_so_mask"], out["subbas_so_mask_idxs"] = sub.reshape(shape), sidx
     return out
 
 
@@ -226,4 +233,9 @@ def run_api_case(pf, d8, aux, transform=None, latlon=False):
     out["fldpln_f32"] = flw.floodplains(aux["elevtn"], upa_min=upa_min, b=0.3)
     out["fldpln_f64"] = flw.floodplains(aux["elevtn"].astype(np.float64) * 1.1, uparea=out["uparea_cell"],
                                         upa_min=max(4, int(0.002 * d8.size)), b=0.5)
+    out["upsum_f32"] = flw.upstream_sum(aux["data_f32_nd"], mv=-9999)
+    out["upsum_i64"] = flw.upstream_sum(aux["fill_i64"], mv=-9999)
+    out["upsum_f64"] = flw.upstream_sum(aux["data_f64"], mv=-9999.0)
+    out["subbas_so"], out["subbas_so_idxs"] = flw.subbasins_streamorder(min_sto=-2)
+    out["subbas_so_mask"], out["subbas_so_mask_idxs"] = flw.subbasins_streamorder(min_sto=2, mask=aux["smask"])
     return out
