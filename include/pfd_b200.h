@@ -189,6 +189,13 @@ int pfd_upstream_sum(pfd_handle* h, const void* data, int dtype, double nodata_f
 int pfd_subbasins_streamorder(pfd_handle* h, const uint8_t* strord, const uint8_t* mask, int64_t min_sto, int32_t* subbas_out,
                               int64_t* n_outlets);
 
+/* basins.subbasins_area (pyflwdir/basins.py:194-233), FlwdirRaster.subbasins_area (pyflwdir/pyflwdir.py:665-692): moving
+ * upstream from the outlets a new subbasin starts at tributaries / interbasins with more than area_min contributing area.
+ * idxs_us_main: N indices (core.main_upstream, e.g. from pfd_main_upstream); uparea: N int32 / int64 / float32 / float64;
+ * subbas_out: N uint32; outlet cells via pfd_fetch(PFD_ARR_SUBBASIN_OUTLETS). */
+int pfd_subbasins_area(pfd_handle* h, const void* idxs_us_main, int idx_dtype, const void* uparea, int dtype, double area_min,
+                       uint32_t* subbas_out, int64_t* n_outlets);
+
 /* ---- fused headline pass ------------------------------------------------------------------------------ */
 /*
  * parse + order + rank + upstream_area(cell) + basins() in one call (BASELINE.json metric). Any output may be

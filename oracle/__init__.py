@@ -275,6 +275,21 @@ def _subbasins_streamorder(idxs_ds, seq, strord, mask=None, min_sto=-2):
     return sub, idxs[: int(n)].copy()
 
 
+def _subbasins_area(idxs_ds, seq, idxs_us_main, uparea, area_min):
+    """pyflwdir/basins.py:194-233 -> (uint32 map, outlet indices)"""
+    a, sfx = _idx(idxs_ds)
+    s = np.ascontiguousarray(seq).astype(a.dtype)
+    um = np.ascontiguousarray(idxs_us_main).astype(a.dtype)
+    upa = np.ascontiguousarray(uparea)
+    tsfx = {np.dtype(np.int32): "i32", np.dtype(np.int64): "i64", np.dtype(np.float32): "f32",
+            np.dtype(np.float64): "f64"}[upa.dtype]
+    sub = np.empty(a.size, dtype=np.uint32)
+    idxs = np.empty(max(s.size, 1), dtype=a.dtype)
+    n = _fn(f"orc_subbasins_area_{tsfx}", sfx, C.c_int64)(_p(a), _p(s), C.c_int64(s.size), _p(um), _p(upa),
+                                                          C.c_double(float(area_min)), C.c_int64(a.size), _p(sub), _p(idxs))
+    return sub, idxs[: int(n)].copy()
+
+
 arithmetics = types.SimpleNamespace(upstream_sum=_upstream_sum)
 
 core = types.SimpleNamespace(
@@ -386,7 +401,7 @@ def _basins(idxs_ds, idxs_pit, seq, ids=None):
     return _fillnodata_upstream(idxs_ds, seq, b, 0)
 
 
-basins = types.SimpleNamespace(basins=_basins, subbasins_streamorder=_subbasins_streamorder)
+basins = types.SimpleNamespace(basins=_basins, subbasins_streamorder=_subbasins_streamorder, subbasins_area=_subbasins_area)
 
 
 def _hand(idxs_ds, seq, drain, elevtn):

@@ -213,6 +213,25 @@ class DeviceGraph:
             self._ck(self._l.pfd_fetch(self._h, _lib.ARR_SUBBASIN_OUTLETS, _lib.ptr(idxs), _lib.dtype_code(idx_dtype)))
         return out, idxs
 
+    def subbasins_area(self, idxs_us_main, uparea, area_min, idx_dtype=np.int32):
+        """basins.subbasins_area -> (uint32 map, outlet indices)."""
+        um = np.ascontiguousarray(idxs_us_main)
+        if um.dtype not in _IDX_DTYPES or um.size != self.size:
+            raise ValueError('"idxs_us_main" must be an index array of the raster size')
+        upa = np.ascontiguousarray(uparea)
+        if upa.size != self.size:
+            raise ValueError('"uparea" size does not match.')
+        if upa.dtype not in (np.dtype(np.int32), np.dtype(np.int64), np.dtype(np.float32), np.dtype(np.float64)):
+            upa = upa.astype(np.float64)
+        out = _lib.out_array(self.size, np.uint32)
+        k = C.c_int64()
+        self._ck(self._l.pfd_subbasins_area(self._h, _lib.ptr(um), _lib.dtype_code(um.dtype), _lib.ptr(upa),
+                                            _lib.dtype_code(upa.dtype), C.c_double(float(area_min)), _lib.ptr(out), C.byref(k)))
+        idxs = np.empty(k.value, dtype=idx_dtype)
+        if k.value:
+            self._ck(self._l.pfd_fetch(self._h, _lib.ARR_SUBBASIN_OUTLETS, _lib.ptr(idxs), _lib.dtype_code(idx_dtype)))
+        return out, idxs
+
     def upstream_area_cells(self):
         out = _lib.out_array(self.size, np.int32)
         self._ck(self._l.pfd_upstream_area_cells(self._h, _lib.ptr(out)))

@@ -1812,6 +1812,32 @@ extern "C" int pfd_d8_flow_all(pfd_handle* h, const uint8_t* d8, int64_t nrow, i
 // ---------------------------------------------------------------------------------------------------------
 // further rows of SURVEY.md §8f: arithmetics.upstream_sum, basins.subbasins_streamorder
 // ---------------------------------------------------------------------------------------------------------
+// ordered numbering of the cells selected by `pred` (positions of the sequence, optionally reversed) into
+// h->sub_idxs / labels; leaves the count in h->n_sub
+template <class Pred, bool REVERSED, typename LABEL>
+static int number_outlets(pfd_handle* h, Pred pred, LABEL* label_dev) {
+    const int64_t m = h->nnodes;
+    const int64_t nblk = std::max<int64_t>(1, (m + CP_CHUNK - 1) / CP_CHUNK);
+    PFD_TRY(pfd_reserve(h, h->blk_counts, (size_t)nblk * sizeof(uint32_t)));
+    PFD_TRY(pfd_reserve(h, h->blk_offsets, (size_t)(nblk + 1) * sizeof(unsigned long long)));
+    compact_count_kernel<Pred, REVERSED><<<(unsigned)nblk, CP_THREADS, 0, h->stream>>>((const cell_t*)h->seq.p, m, pred,
+                                                                                     (uint32_t*)h->blk_counts.p);
+    PFD_LAUNCH_CHECK(h);
+    scan_counts_kernel<<<1, 1024, 0, h->stream>>>((const uint32_t*)h->blk_counts.p, nblk, (unsigned long long*)h->blk_offsets.p);
+    PFD_LAUNCH_CHECK(h);
+    unsigned long long total = 0;
+    PFD_CUDA(h, cudaMemcpyAsync(&total, (unsigned long long*)h->blk_offsets.p + nblk, sizeof(total), cudaMemcpyDeviceToHost, h->stream));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->n_sub = (int64_t)total;
+    PFD_TRY(pfd_reserve(h, h->sub_idxs, (size_t)std::max<int64_t>(h->n_sub, 1) * sizeof(cell_t)));
+    if (h->n_sub > 0) {
+        compact_scatter_kernel<Pred, REVERSED, LABEL><<<(unsigned)nblk, CP_THREADS, 0, h->stream>>>(
+            (const cell_t*)h->seq.p, m, pred, (const unsigned long long*)h->blk_offsets.p, (cell_t*)h->sub_idxs.p, label_dev);
+        PFD_LAUNCH_CHECK(h);
+    }
+    return PFD_OK;
+}
+
 template <typename T>
 static int upstream_sum_typed(pfd_handle* h, const void* data_dev, void* out_dev, const NoData& nd) {
     // arr_sum[idx0] = nodata casts the nodata value to the data dtype
@@ -1865,7 +1891,7 @@ extern "C" int pfd_subbasins_streamorder(pfd_handle* h, const uint8_t* strord, c
     stage_reset(h);
     if (!strord || !subbas_out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_subbasins_streamorder: null array");
     PFD_TRY(order_impl(h, false, false));
-    const int64_t n = h->n, m = h->nnodes;
+    const int64_t n = h->n;
     const void *so_dev = nullptr, *mask_dev = nullptr;
     PFD_TRY(pfd_stage_in(h, strord, (size_t)n, 5, &so_dev));
     if (mask) PFD_TRY(pfd_stage_in(h, mask, (size_t)n, 4, &mask_dev));
@@ -1883,29 +1909,73 @@ extern "C" int pfd_subbasins_streamorder(pfd_handle* h, const uint8_t* strord, c
     }
     const int min_sto_i = (int)std::max<int64_t>(std::min<int64_t>(min_sto, 1 << 20), -(1 << 20));
     SubbasinOutletPred pred{(const uint8_t*)h->dir.p, (const uint8_t*)so_dev, (const uint8_t*)mask_dev, min_sto_i, h->ncol};
-    const int64_t nblk = std::max<int64_t>(1, (m + CP_CHUNK - 1) / CP_CHUNK);
-    PFD_TRY(pfd_reserve(h, h->blk_counts, (size_t)nblk * sizeof(uint32_t)));
-    PFD_TRY(pfd_reserve(h, h->blk_offsets, (size_t)(nblk + 1) * sizeof(unsigned long long)));
     PFD_CUDA(h, cudaMemsetAsync(out_dev, 0, (size_t)n * sizeof(int32_t), h->stream));
     // outlets are numbered while walking the sequence from up- to downstream (seq[::-1], basins.py:92)
-    compact_count_kernel<SubbasinOutletPred, true><<<(unsigned)nblk, CP_THREADS, 0, h->stream>>>(
-        (const cell_t*)h->seq.p, m, pred, (uint32_t*)h->blk_counts.p);
-    PFD_LAUNCH_CHECK(h);
-    scan_counts_kernel<<<1, 1024, 0, h->stream>>>((const uint32_t*)h->blk_counts.p, nblk, (unsigned long long*)h->blk_offsets.p);
-    PFD_LAUNCH_CHECK(h);
-    unsigned long long total = 0;
-    PFD_CUDA(h, cudaMemcpyAsync(&total, (unsigned long long*)h->blk_offsets.p + nblk, sizeof(total), cudaMemcpyDeviceToHost, h->stream));
-    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
-    h->n_sub = (int64_t)total;
-    PFD_TRY(pfd_reserve(h, h->sub_idxs, (size_t)std::max<int64_t>(h->n_sub, 1) * sizeof(cell_t)));
+    PFD_TRY((number_outlets<SubbasinOutletPred, true, int32_t>(h, pred, (int32_t*)out_dev)));
     if (h->n_sub > 0) {
-        compact_scatter_kernel<SubbasinOutletPred, true, int32_t><<<(unsigned)nblk, CP_THREADS, 0, h->stream>>>(
-            (const cell_t*)h->seq.p, m, pred, (const unsigned long long*)h->blk_offsets.p, (cell_t*)h->sub_idxs.p, (int32_t*)out_dev);
-        PFD_LAUNCH_CHECK(h);
         FillUpOp<int32_t> op{(const uint8_t*)h->dir.p, (int32_t*)out_dev, h->ncol};  // core.fillnodata_upstream(.., 0)
         PFD_TRY((run_sweep<FillUpOp<int32_t>, false>(h, op, 0)));
     }
     PFD_TRY(pfd_finish_out(h, subbas_out, out_dev, (size_t)n * sizeof(int32_t)));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    if (n_outlets) *n_outlets = h->n_sub;
+    return PFD_OK;
+}
+
+template <typename T, typename IDX>
+static int subbasins_area_typed(pfd_handle* h, const void* main_dev, const void* upa_dev, double area_min, uint32_t* out_dev) {
+    const int64_t n = h->n;
+    PFD_TRY(pfd_reserve(h, h->scratch[2], (size_t)n * sizeof(T)));
+    PFD_TRY(pfd_reserve(h, h->scratch[1], (size_t)n));
+    T* upa_out = (T*)h->scratch[2].p;
+    uint8_t* flag = (uint8_t*)h->scratch[1].p;
+    PFD_CUDA(h, cudaMemcpyAsync(upa_out, upa_dev, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
+    PFD_CUDA(h, cudaMemsetAsync(flag, 0, (size_t)n, h->stream));
+    PFD_CUDA(h, cudaMemsetAsync(out_dev, 0, (size_t)n * sizeof(uint32_t), h->stream));
+    SubbasinsAreaOp<T, IDX> op{(const uint8_t*)h->dir.p, (const uint8_t*)h->upmask.p, (const IDX*)main_dev, (const T*)upa_dev,
+                               upa_out, flag, area_min, h->ncol};
+    PFD_TRY((run_sweep<SubbasinsAreaOp<T, IDX>, false>(h, op, 0)));
+    FlagPred pred{flag};
+    PFD_TRY((number_outlets<FlagPred, false, uint32_t>(h, pred, out_dev)));  // numbered along seq (basins.py:208-223)
+    if (h->n_sub > 0) {
+        FillUpOp<uint32_t> fill{(const uint8_t*)h->dir.p, out_dev, h->ncol};  // core.fillnodata_upstream(.., 0)
+        PFD_TRY((run_sweep<FillUpOp<uint32_t>, false>(h, fill, 0)));
+    }
+    return PFD_OK;
+}
+
+extern "C" int pfd_subbasins_area(pfd_handle* h, const void* idxs_us_main, int idx_dtype, const void* uparea, int dtype,
+                                  double area_min, uint32_t* subbas_out, int64_t* n_outlets) {
+    PFD_TRY(check_handle(h));
+    stage_reset(h);
+    if (!idxs_us_main || !uparea || !subbas_out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_subbasins_area: null array");
+    const size_t isz = pfd_dtype_size(idx_dtype), esz = pfd_dtype_size(dtype);
+    if ((isz != 4 && isz != 8) || idx_dtype == PFD_F32 || idx_dtype == PFD_F64)
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_subbasins_area: index dtype must be a 32/64-bit integer");
+    if (dtype != PFD_I32 && dtype != PFD_I64 && dtype != PFD_F32 && dtype != PFD_F64)
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_subbasins_area: uparea must be int32, int64, float32 or float64");
+    PFD_TRY(order_impl(h, false, false));
+    PFD_TRY(ensure_upmask(h));
+    const int64_t n = h->n;
+    void* out_dev = nullptr;
+    PFD_TRY(pfd_stage_out(h, subbas_out, (size_t)n * sizeof(uint32_t), 3, &out_dev));
+    const void *main_dev = nullptr, *upa_dev = nullptr;
+    PFD_TRY(pfd_stage_in(h, idxs_us_main, (size_t)n * isz, 5, &main_dev));
+    PFD_TRY(pfd_stage_in(h, uparea, (size_t)n * esz, 4, &upa_dev));
+    int rc;
+#define SUBAREA(T)                                                                                                  \
+    (isz == 4 ? subbasins_area_typed<T, uint32_t>(h, main_dev, upa_dev, area_min, (uint32_t*)out_dev)               \
+              : subbasins_area_typed<T, int64_t>(h, main_dev, upa_dev, area_min, (uint32_t*)out_dev))
+    switch (dtype) {
+    case PFD_I32: rc = SUBAREA(int32_t); break;
+    case PFD_I64: rc = SUBAREA(int64_t); break;
+    case PFD_F32: rc = SUBAREA(float); break;
+    default: rc = SUBAREA(double); break;
+    }
+#undef SUBAREA
+    PFD_TRY(rc);
+    PFD_TRY(pfd_finish_out(h, subbas_out, out_dev, (size_t)n * sizeof(uint32_t)));
     PFD_CUDA(h, cudaStreamSynchronize(h->stream));
     stage_collect(h);
     if (n_outlets) *n_outlets = h->n_sub;

@@ -139,3 +139,75 @@ __global__ void upstream_sum_kernel(const uint8_t* __restrict__ dir, const uint8
         out[i] = acc;
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// basins.subbasins_area (basins.py:194-233). The reference walks the sequence from down- to upstream; the cells
+// that share a downstream cell are consecutive and ascending in it (core.idxs_seq), and they are the only ones that
+// touch each other's state (upa_out of the parent, of themselves and of the parent's main-stem child). So one thread
+// per PARENT replays its children in ascending index inside a level-synchronous sweep: bit-identical, no races.
+// flag[c] = 1 marks the subbasin outlets; they are numbered afterwards in sequence order (ordered compaction).
+// ---------------------------------------------------------------------------------------------------------
+template <typename T> struct SubDiff {  // (a - b) as the reference's numba typing evaluates it, converted for `> area_min`
+    static __device__ __forceinline__ double gap(T a, T b) { return (double)((long long)a - (long long)b); }
+};
+template <> struct SubDiff<float> {
+    static __device__ __forceinline__ double gap(float a, float b) { return (double)__fsub_rn(a, b); }
+};
+template <> struct SubDiff<double> {
+    static __device__ __forceinline__ double gap(double a, double b) { return __dsub_rn(a, b); }
+};
+template <typename T>
+__device__ __forceinline__ T sub_wrap(T a, T b) {
+    typedef typename AccT<T>::U U;
+    return (T)((U)a - (U)b);
+}
+template <>
+__device__ __forceinline__ float sub_wrap<float>(float a, float b) { return __fsub_rn(a, b); }
+template <>
+__device__ __forceinline__ double sub_wrap<double>(double a, double b) { return __dsub_rn(a, b); }
+
+template <typename T, typename IDX>
+struct SubbasinsAreaOp {
+    const uint8_t* dir;
+    const uint8_t* upmask;
+    const IDX* us_main;
+    const T* uparea;
+    T* upa_out;     // pre-initialised with uparea
+    uint8_t* flag;  // pre-initialised with 0
+    double area_min;
+    long long ncol;
+    __device__ __forceinline__ void operator()(cell_t c, long long, int) const {
+        if (__ldg(dir + c) >= 8u) flag[c] = 1;  // pit: a subbasin of its own (basins.py:211-214)
+        uint32_t m = __ldg(upmask + c);
+        if (!m) return;
+        T upa_p = ld_cg(upa_out + c);  // upa_out[idx_ds]
+        const T uparea_p = __ldg(uparea + c);
+        const IDX mainv = __ldg(us_main + c);
+        const long long main = (mainv == (IDX)-1) ? -1ll : (long long)mainv;
+        while (m) {  // children in ascending index = their order in the sequence
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            const long long ch = (long long)c + pfd_slot_off(k, ncol);
+            const T upa = __ldg(uparea + ch);
+            if (SubDiff<T>::gap(upa_p, upa) > area_min && (double)upa > area_min) {
+                const bool conf = SubDiff<T>::gap(uparea_p, upa) > area_min;
+                const bool trib = main != ch;
+                if (!conf || trib) {
+                    flag[ch] = 1;
+                    upa_out[ch] = upa;
+                }
+                if (trib) {
+                    upa_p = sub_wrap<T>(upa_p, upa);
+                    if (main >= 0) upa_out[main] = upa_p;
+                }
+            } else {
+                upa_out[ch] = upa_p;
+            }
+        }
+    }
+};
+
+struct FlagPred {
+    const uint8_t* flag;
+    __device__ __forceinline__ bool operator()(cell_t c) const { return __ldg(flag + c) != 0; }
+};

@@ -272,7 +272,7 @@ class Flwdir(object):
 
     # ------------------------------------------------------------------ not in scope
     for _name in ("path", "snap", "inflow_idxs", "outflow_idxs", "smooth_rivlen",
-                  "subbasins_pfafstetter", "subbasins_area", "moving_average",
+                  "subbasins_pfafstetter", "moving_average",
                   "moving_median", "vectorize", "streams", "geofeatures", "dem_adjust", "dem_dig_d4",
                   "classify_estuaries", "ucat_area", "ucat_outlets", "ucat_volume", "subgrid_rivlen",
                   "subgrid_rivslp", "subgrid_rivavg", "subgrid_rivmed", "subgrid_rivlen2", "upscale", "upscale_error",

@@ -245,6 +245,13 @@ class FlwdirRaster(Flwdir):
             idx_dtype=self._idx_dtype)
         return subbas.reshape(self.shape), idxs_out
 
+    def subbasins_area(self, area_min, uparea=None):
+        """Returns map with basin IDs, with a minimal area of `area_min` (pyflwdir.py:665-692 -> basins.subbasins_area):
+        (uint32 map, linear indices of the subbasin outlets)."""
+        subbas, idxs_out = self._dev.subbasins_area(
+            self.idxs_us_main, self._check_data(uparea, "uparea", unit="km2"), area_min, idx_dtype=self._idx_dtype)
+        return subbas.reshape(self.shape), idxs_out
+
     def upstream_area(self, unit="cell"):
         """Upstream area map (pyflwdir.py:770-801). "cell": int32 counts by the dedicated device sweep; other
         units accumulate the cell-area grid in its own dtype (float64 if latlon, else float32)."""
@@ -309,7 +316,7 @@ class FlwdirRaster(Flwdir):
             idxs = self.index(*xy)
         return super()._check_idxs_xy(idxs, streams)
 
-    for _name in ("repair_loops_raster", "subbasins_pfafstetter", "subbasins_area",
+    for _name in ("repair_loops_raster", "subbasins_pfafstetter",
                   "streams", "geofeatures", "vectorize", "dem_adjust", "dem_dig_d4",
                   "upscale", "upscale_error", "subgrid_rivlen", "subgrid_rivslp", "subgrid_rivavg", "subgrid_rivmed",
                   "ucat_area", "ucat_outlets", "ucat_volume", "inflow_idxs", "outflow_idxs"):

@@ -174,6 +174,13 @@ def run_oracle_case(d8, aux, area=None, transform=(1.0, 0.0, 0.0, 0.0, -1.0, 0.0
     out["subbas_so"], out["subbas_so_idxs"] = sub.reshape(shape), sidx
     sub, sidx = o.basins.subbasins_streamorder(idxs_ds, seq, out["strord"].ravel(), sm, 2)
     out["subbas_so_mask"], out["subbas_so_mask_idxs"] = sub.reshape(shape), sidx
+    if area is not None:
+        ukm = out["uparea_km2"]
+        amin = float(np.quantile(ukm[ukm > 0], 0.9)) if (ukm > 0).any() else 1.0
+        sub, sidx = o.basins.subbasins_area(idxs_ds, seq, out["us_main"], ukm.ravel(), amin)
+        out["subbas_area_km2"], out["subbas_area_km2_idxs"] = sub.reshape(shape), sidx
+    sub, sidx = o.basins.subbasins_area(idxs_ds, seq, out["us_main"], out["uparea_cell"].ravel(), max(3, d8.size // 400))
+    out["subbas_area_cell"], out["subbas_area_cell_idxs"] = sub.reshape(shape), sidx
     return out
 
 
@@ -238,4 +245,8 @@ def run_api_case(pf, d8, aux, transform=None, latlon=False):
     out["upsum_f64"] = flw.upstream_sum(aux["data_f64"], mv=-9999.0)
     out["subbas_so"], out["subbas_so_idxs"] = flw.subbasins_streamorder(min_sto=-2)
     out["subbas_so_mask"], out["subbas_so_mask_idxs"] = flw.subbasins_streamorder(min_sto=2, mask=aux["smask"])
+    ukm = out["uparea_km2"]
+    amin = float(np.quantile(ukm[ukm > 0], 0.9)) if (ukm > 0).any() else 1.0
+    out["subbas_area_km2"], out["subbas_area_km2_idxs"] = flw.subbasins_area(amin)
+    out["subbas_area_cell"], out["subbas_area_cell_idxs"] = flw.subbasins_area(max(3, d8.size // 400), uparea=out["uparea_cell"])
     return out
