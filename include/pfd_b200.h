@@ -196,6 +196,17 @@ int pfd_subbasins_streamorder(pfd_handle* h, const uint8_t* strord, const uint8_
 int pfd_subbasins_area(pfd_handle* h, const void* idxs_us_main, int idx_dtype, const void* uparea, int dtype, double area_min,
                        uint32_t* subbas_out, int64_t* n_outlets);
 
+/* arithmetics.moving_average / moving_median (pyflwdir/arithmetics.py:67-147) over core._window (pyflwdir/core.py:368-398),
+ * Flwdir.moving_average / moving_median (pyflwdir/flwdir.py:435-505): per cell the weighted mean / nan-median over the n
+ * cells upstream along idxs_us_main, the cell itself and the n cells downstream (strord != NULL: downstream only while the
+ * stream order does not grow). data / out: N float32 or float64; weights: NULL (ones) or N float64 (wdtype = PFD_F64, the only dtype the
+ * reference's numba typing accepts); 0 <= n <= 64;
+ * nodata may be NaN. Bit-exact (float64 accumulation in window order; numba's own quick-select for the median). */
+int pfd_moving_average(pfd_handle* h, const void* data, int dtype, const void* weights, int wdtype, int n,
+                       const void* idxs_us_main, int idx_dtype, const uint8_t* strord, double nodata, void* out);
+int pfd_moving_median(pfd_handle* h, const void* data, int dtype, int n, const void* idxs_us_main, int idx_dtype,
+                      const uint8_t* strord, double nodata, void* out);
+
 /* ---- fused headline pass ------------------------------------------------------------------------------ */
 /*
  * parse + order + rank + upstream_area(cell) + basins() in one call (BASELINE.json metric). Any output may be

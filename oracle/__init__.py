@@ -290,7 +290,37 @@ def _subbasins_area(idxs_ds, seq, idxs_us_main, uparea, area_min):
     return sub, idxs[: int(n)].copy()
 
 
-arithmetics = types.SimpleNamespace(upstream_sum=_upstream_sum)
+_FSFX = {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64"}
+
+
+def _moving_average(data, weights, n, idxs_ds, idxs_us_main, strord=None, nodata=-9999.0, mv=None):
+    """pyflwdir/arithmetics.py:67-103"""
+    a, sfx = _idx(idxs_ds)
+    um = np.ascontiguousarray(idxs_us_main).astype(a.dtype)
+    data = np.ascontiguousarray(data)
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+    so = None if strord is None else np.ascontiguousarray(strord, dtype=np.uint8)
+    out = np.empty(data.size, dtype=data.dtype)
+    _fn(f"orc_moving_average_{_FSFX[data.dtype]}_f64", sfx)(
+        _p(data), None if w is None else _p(w), C.c_int(int(n)), _p(a), _p(um), None if so is None else _p(so),
+        C.c_double(float(nodata)), C.c_int64(data.size), _p(out))
+    return out
+
+
+def _moving_median(data, n, idxs_ds, idxs_us_main, strord=None, nodata=-9999.0, mv=None):
+    """pyflwdir/arithmetics.py:106-147"""
+    a, sfx = _idx(idxs_ds)
+    um = np.ascontiguousarray(idxs_us_main).astype(a.dtype)
+    data = np.ascontiguousarray(data)
+    so = None if strord is None else np.ascontiguousarray(strord, dtype=np.uint8)
+    out = np.empty(data.size, dtype=data.dtype)
+    _fn(f"orc_moving_median_{_FSFX[data.dtype]}", sfx)(
+        _p(data), C.c_int(int(n)), _p(a), _p(um), None if so is None else _p(so), C.c_double(float(nodata)),
+        C.c_int64(data.size), _p(out))
+    return out
+
+
+arithmetics = types.SimpleNamespace(upstream_sum=_upstream_sum, moving_average=_moving_average, moving_median=_moving_median)
 
 core = types.SimpleNamespace(
     fillnodata_upstream_any=_fillnodata_upstream_any,

@@ -232,6 +232,48 @@ class DeviceGraph:
             self._ck(self._l.pfd_fetch(self._h, _lib.ARR_SUBBASIN_OUTLETS, _lib.ptr(idxs), _lib.dtype_code(idx_dtype)))
         return out, idxs
 
+    def _window_args(self, data, idxs_us_main, strord):
+        data = np.ascontiguousarray(data)
+        if data.size != self.size:
+            raise ValueError('"data" size does not match.')
+        if data.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise TypeError("moving window: data must be float32 or float64")
+        um = np.ascontiguousarray(idxs_us_main)
+        if um.dtype not in _IDX_DTYPES or um.size != self.size:
+            raise ValueError('"idxs_us_main" must be an index array of the raster size')
+        so = None
+        if strord is not None:
+            so = np.ascontiguousarray(strord, dtype=np.uint8)
+            if so.size != self.size:
+                raise ValueError('"strord" size does not match.')
+        return data, um, so
+
+    def moving_average(self, data, weights, n, idxs_us_main, strord=None, nodata=-9999.0):
+        """arithmetics.moving_average"""
+        data, um, so = self._window_args(data, idxs_us_main, strord)
+        w, wcode = None, 0
+        if weights is not None:
+            w = np.ascontiguousarray(weights)
+            if w.size != self.size:
+                raise ValueError('"weights" size does not match.')
+            # arithmetics.py:101 only types with float64 weights (np.ones() in the other branch): anything else is upcast
+            if w.dtype != np.dtype(np.float64):
+                w = w.astype(np.float64)
+            wcode = _lib.dtype_code(w.dtype)
+        out = _lib.out_array(data.size, data.dtype)
+        self._ck(self._l.pfd_moving_average(self._h, _lib.ptr(data), _lib.dtype_code(data.dtype), _lib.ptr(w), wcode, int(n),
+                                            _lib.ptr(um), _lib.dtype_code(um.dtype), _lib.ptr(so), C.c_double(float(nodata)),
+                                            _lib.ptr(out)))
+        return out
+
+    def moving_median(self, data, n, idxs_us_main, strord=None, nodata=-9999.0):
+        """arithmetics.moving_median"""
+        data, um, so = self._window_args(data, idxs_us_main, strord)
+        out = _lib.out_array(data.size, data.dtype)
+        self._ck(self._l.pfd_moving_median(self._h, _lib.ptr(data), _lib.dtype_code(data.dtype), int(n), _lib.ptr(um),
+                                           _lib.dtype_code(um.dtype), _lib.ptr(so), C.c_double(float(nodata)), _lib.ptr(out)))
+        return out
+
     def upstream_area_cells(self):
         out = _lib.out_array(self.size, np.int32)
         self._ck(self._l.pfd_upstream_area_cells(self._h, _lib.ptr(out)))

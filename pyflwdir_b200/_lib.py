@@ -61,6 +61,8 @@ SYMBOLS = {
     "pfd_upstream_sum": (_int, [_vp, _vp, _int, C.c_double, _i64, _int, _vp]),
     "pfd_subbasins_streamorder": (_int, [_vp, _vp, _vp, _i64, _vp, _pi64]),
     "pfd_subbasins_area": (_int, [_vp, _vp, _int, _vp, _int, C.c_double, _vp, _pi64]),
+    "pfd_moving_average": (_int, [_vp, _vp, _int, _vp, _int, _int, _vp, _int, _vp, C.c_double, _vp]),
+    "pfd_moving_median": (_int, [_vp, _vp, _int, _int, _vp, _int, _vp, C.c_double, _vp]),
     "pfd_d8_flow_all": (_int, [_vp, _vp, _i64, _i64, _vp, _int, _vp, _vp, _vp, _pi64, _pi64, _pi64]),
     "pfd_comm_unique_id": (_int, [_vp, _i64]),
     "pfd_comm_init": (_int, [_vp, _int, _int, _vp]),

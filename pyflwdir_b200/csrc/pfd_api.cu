@@ -1982,6 +1982,77 @@ extern "C" int pfd_subbasins_area(pfd_handle* h, const void* idxs_us_main, int i
     return PFD_OK;
 }
 
+template <typename T, bool MEDIAN>
+static int moving_window_typed(pfd_handle* h, const void* data_dev, const void* w_dev, int nwin, const void* main_dev, size_t isz,
+                               const void* so_dev, double nodata, void* out_dev, unsigned int* flag) {
+    const int g = grid_for(h->n, 128, 1, 148 * 64);
+    if (isz == 4)
+        moving_window_kernel<T, uint32_t, MEDIAN><<<g, 128, 0, h->stream>>>(
+            (const uint8_t*)h->dir.p, (const uint32_t*)main_dev, (const uint8_t*)so_dev, (const T*)data_dev, (const double*)w_dev, h->n,
+            h->ncol, nwin, nodata, (T*)out_dev, flag);
+    else
+        moving_window_kernel<T, int64_t, MEDIAN><<<g, 128, 0, h->stream>>>(
+            (const uint8_t*)h->dir.p, (const int64_t*)main_dev, (const uint8_t*)so_dev, (const T*)data_dev, (const double*)w_dev, h->n,
+            h->ncol, nwin, nodata, (T*)out_dev, flag);
+    PFD_LAUNCH_CHECK(h);
+    return PFD_OK;
+}
+
+// shared driver of pfd_moving_average (median = 0) and pfd_moving_median (median = 1)
+static int moving_window(pfd_handle* h, const char* who, int median, const void* data, int dtype, const void* weights, int wdtype,
+                         int nwin, const void* idxs_us_main, int idx_dtype, const uint8_t* strord, double nodata, void* out) {
+    PFD_TRY(check_handle(h));
+    stage_reset(h);
+    if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, std::string(who) + ": no raster parsed on this handle");
+    if (h->tiled) return pfd_fail(h, PFD_ERR_UNSUPPORTED, "this handle holds a row block: only the pfd_tiled_* entry points apply");
+    if (!data || !idxs_us_main || !out) return pfd_fail(h, PFD_ERR_INVALID_ARG, std::string(who) + ": null array");
+    if (dtype != PFD_F32 && dtype != PFD_F64) return pfd_fail(h, PFD_ERR_INVALID_ARG, std::string(who) + ": data must be float32 or float64");
+    if (weights && wdtype != PFD_F64)  // arithmetics.py:101 only types with float64 weights
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, std::string(who) + ": weights must be float64");
+    if (nwin < 0 || nwin > MW_NMAX) return pfd_fail(h, PFD_ERR_UNSUPPORTED, std::string(who) + ": n must be in 0..64");
+    const size_t isz = pfd_dtype_size(idx_dtype), esz = pfd_dtype_size(dtype);
+    if ((isz != 4 && isz != 8) || idx_dtype == PFD_F32 || idx_dtype == PFD_F64)
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, std::string(who) + ": index dtype must be a 32/64-bit integer");
+    const int64_t n = h->n;
+    void* out_dev = nullptr;
+    const void *data_dev = nullptr, *w_dev = nullptr, *main_dev = nullptr, *so_dev = nullptr;
+    PFD_TRY(pfd_stage_out(h, out, (size_t)n * esz, 3, &out_dev));
+    PFD_TRY(pfd_stage_in(h, data, (size_t)n * esz, 5, &data_dev));
+    PFD_TRY(pfd_stage_in(h, idxs_us_main, (size_t)n * isz, 4, &main_dev));
+    if (weights) PFD_TRY(pfd_stage_in(h, weights, (size_t)n * pfd_dtype_size(wdtype), 2, &w_dev));
+    if (strord) PFD_TRY(pfd_stage_in(h, strord, (size_t)n, 1, &so_dev));
+    if (data_dev == out_dev) return pfd_fail(h, PFD_ERR_INVALID_ARG, std::string(who) + ": data and out must not alias");
+    PFD_TRY(pfd_reserve(h, h->counters, 8 * sizeof(unsigned long long)));
+    unsigned int* flag = reinterpret_cast<unsigned int*>((unsigned long long*)h->counters.p + 5);
+    PFD_CUDA(h, cudaMemsetAsync(flag, 0, sizeof(unsigned int), h->stream));
+    int rc;
+    if (median) {
+        rc = dtype == PFD_F32 ? moving_window_typed<float, true>(h, data_dev, nullptr, nwin, main_dev, isz, so_dev, nodata, out_dev, flag)
+                              : moving_window_typed<double, true>(h, data_dev, nullptr, nwin, main_dev, isz, so_dev, nodata, out_dev, flag);
+    } else {
+        rc = dtype == PFD_F32 ? moving_window_typed<float, false>(h, data_dev, w_dev, nwin, main_dev, isz, so_dev, nodata, out_dev, flag)
+                              : moving_window_typed<double, false>(h, data_dev, w_dev, nwin, main_dev, isz, so_dev, nodata, out_dev, flag);
+    }
+    PFD_TRY(rc);
+    unsigned int hflag = 0;
+    PFD_CUDA(h, cudaMemcpyAsync(&hflag, flag, sizeof(hflag), cudaMemcpyDeviceToHost, h->stream));
+    PFD_TRY(pfd_finish_out(h, out, out_dev, (size_t)n * esz));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    if (hflag & 8u) return pfd_fail(h, PFD_ERR_INVALID_ARG, std::string(who) + ": idxs_us_main holds an index outside the raster");
+    return PFD_OK;
+}
+
+extern "C" int pfd_moving_average(pfd_handle* h, const void* data, int dtype, const void* weights, int wdtype, int n,
+                                  const void* idxs_us_main, int idx_dtype, const uint8_t* strord, double nodata, void* out) {
+    return moving_window(h, "pfd_moving_average", 0, data, dtype, weights, wdtype, n, idxs_us_main, idx_dtype, strord, nodata, out);
+}
+
+extern "C" int pfd_moving_median(pfd_handle* h, const void* data, int dtype, int n, const void* idxs_us_main, int idx_dtype,
+                                 const uint8_t* strord, double nodata, void* out) {
+    return moving_window(h, "pfd_moving_median", 1, data, dtype, nullptr, 0, n, idxs_us_main, idx_dtype, strord, nodata, out);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // synthetic input
 // ---------------------------------------------------------------------------------------------------------

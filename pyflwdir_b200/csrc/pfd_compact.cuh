@@ -211,3 +211,152 @@ struct FlagPred {
     const uint8_t* flag;
     __device__ __forceinline__ bool operator()(cell_t c) const { return __ldg(flag + c) != 0; }
 };
+
+// ---------------------------------------------------------------------------------------------------------
+// arithmetics.moving_average / moving_median (arithmetics.py:67-147) over core._window (core.py:368-398): for every
+// cell the n cells upstream along the main-upstream links, the cell, and the n cells downstream (optionally only
+// while the stream order does not grow). One thread per cell; the window is visited in the reference's order
+// (farthest upstream cell first), the weighted mean accumulates in float64 exactly like arithmetics._average, and
+// the median uses numba's own median-of-three quick-select (numba/np/arraymath.py _partition / _select /
+// _select_two), so that even the sign of a zero that ties with another zero comes out identical.
+// ---------------------------------------------------------------------------------------------------------
+#define MW_NMAX 64
+
+template <typename T>
+__device__ __forceinline__ bool mw_is_nodata(T v, double nodata, bool nan_nodata) {
+    return nan_nodata ? isnan(v) : ((double)v == nodata);
+}
+
+// `w0 * v0` with float64 weights (the only weights dtype arithmetics.py:101 types with): a float64 product, no fma
+__device__ __forceinline__ double mw_prod(double w, float v) { return __dmul_rn(w, (double)v); }
+__device__ __forceinline__ double mw_prod(double w, double v) { return __dmul_rn(w, v); }
+
+template <typename T>
+__device__ __forceinline__ int mw_partition(T* A, int low, int high) {
+    const int mid = (low + high) >> 1;
+    T t;
+    if (A[mid] < A[low]) { t = A[low]; A[low] = A[mid]; A[mid] = t; }
+    if (A[high] < A[mid]) { t = A[high]; A[high] = A[mid]; A[mid] = t; }
+    if (A[mid] < A[low]) { t = A[low]; A[low] = A[mid]; A[mid] = t; }
+    const T pivot = A[mid];
+    t = A[high]; A[high] = A[mid]; A[mid] = t;
+    int i = low, j = high - 1;
+    while (true) {
+        while (i < high && A[i] < pivot) ++i;
+        while (j >= low && pivot < A[j]) --j;
+        if (i >= j) break;
+        t = A[i]; A[i] = A[j]; A[j] = t;
+        ++i;
+        --j;
+    }
+    t = A[i]; A[i] = A[high]; A[high] = t;
+    return i;
+}
+template <typename T>
+__device__ __forceinline__ T mw_select(T* A, int k, int low, int high) {
+    int i = mw_partition(A, low, high);
+    while (i != k) {
+        if (i < k) low = i + 1;
+        else high = i - 1;
+        i = mw_partition(A, low, high);
+    }
+    return A[k];
+}
+template <typename T>
+__device__ __forceinline__ void mw_select_two(T* A, int k, int low, int high) {
+    while (true) {
+        const int i = mw_partition(A, low, high);
+        if (i < k) low = i + 1;
+        else if (i > k + 1) high = i - 1;
+        else if (i == k) { mw_select(A, k + 1, i + 1, high); break; }
+        else { mw_select(A, k, low, i - 1); break; }
+    }
+}
+
+// MEDIAN = false: weighted mean (weights may be null = ones), MEDIAN = true: nan-median
+template <typename T, typename IDX, bool MEDIAN>
+__global__ void moving_window_kernel(const uint8_t* __restrict__ dir, const IDX* __restrict__ us_main,
+                                     const uint8_t* __restrict__ strord, const T* __restrict__ data,
+                                     const double* __restrict__ weights, int64_t n, long long ncol, int nwin, double nodata,
+                                     T* __restrict__ out, unsigned int* __restrict__ flag) {
+    const bool nan_nodata = isnan(nodata);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const T d0 = data[i];
+        if ((double)d0 == nodata) {  // `data[idx0] == nodata` (never true for a NaN nodata)
+            out[i] = (T)nodata;
+            continue;
+        }
+        // n upstream cells along the main-upstream links
+        long long up[MW_NMAX];
+        int nu = 0;
+        long long cur = i;
+        while (nu < nwin) {
+            const IDX u = us_main[cur];
+            if (u == (IDX)-1) break;
+            if ((long long)u < 0 || (long long)u >= n) {
+                atomicOr(flag, 8u);
+                break;
+            }
+            cur = (long long)u;
+            up[nu++] = cur;
+        }
+        const uint32_t so0 = strord ? (uint32_t)strord[i] : 0u;
+        if (!MEDIAN) {
+            double v = 0.0, w = 0.0;
+            auto add = [&](long long c) {
+                const T v0 = data[c];
+                if (mw_is_nodata<T>(v0, nodata, nan_nodata)) return;
+                if (weights) {
+                    const double w0 = weights[c];
+                    v = __dadd_rn(v, mw_prod(w0, v0));
+                    w = __dadd_rn(w, w0);
+                } else {
+                    v = __dadd_rn(v, mw_prod(1.0, v0));
+                    w = __dadd_rn(w, 1.0);
+                }
+            };
+            for (int k = nu - 1; k >= 0; --k) add(up[k]);
+            add(i);
+            cur = i;
+            for (int t = 0; t < nwin; ++t) {
+                const uint32_t d = dir[cur];
+                if (d >= 8u) break;  // pit or nodata
+                const long long ds = cur + pfd_slot_off((int)d, ncol);
+                if (strord && (uint32_t)strord[ds] > so0) break;
+                cur = ds;
+                add(cur);
+            }
+            out[i] = (T)((w != 0.0) ? __ddiv_rn(v, w) : nodata);
+        } else {
+            T a[2 * MW_NMAX + 1];
+            int m = 0;
+            auto push = [&](long long c) {
+                const T v0 = data[c];
+                if (isnan(v0) || (!nan_nodata && (double)v0 == nodata)) return;  // -> NaN -> dropped by nanmedian
+                a[m++] = v0;
+            };
+            for (int k = nu - 1; k >= 0; --k) push(up[k]);
+            push(i);
+            cur = i;
+            for (int t = 0; t < nwin; ++t) {
+                const uint32_t d = dir[cur];
+                if (d >= 8u) break;
+                const long long ds = cur + pfd_slot_off((int)d, ncol);
+                if (strord && (uint32_t)strord[ds] > so0) break;
+                cur = ds;
+                push(cur);
+            }
+            T r;
+            if (m == 0) {
+                r = (T)nan("");
+            } else if ((m & 1) == 0) {
+                const int half = m >> 1;
+                mw_select_two(a, half - 1, 0, m - 1);
+                r = (T)((double)acc_add<T>(a[half - 1], a[half]) / 2.0);
+            } else {
+                r = mw_select(a, m >> 1, 0, m - 1);
+            }
+            out[i] = r;
+        }
+    }
+}

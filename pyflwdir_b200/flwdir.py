@@ -215,6 +215,21 @@ class Flwdir(object):
         dflat = self._check_data(data, "data")
         return self._dev.upstream_sum(dflat, mv).reshape(np.shape(data))
 
+    def moving_average(self, data, n, weights=None, restrict_strord=False, strord=None, nodata=-9999.0):
+        """Take the moving weighted average over the flow direction network (flwdir.py:435-470 ->
+        arithmetics.moving_average): n up- and n downstream neighbours along the main stem."""
+        dout = self._dev.moving_average(
+            self._check_data(data, "data"), self._check_data(weights, "weights", optional=True), n, self.idxs_us_main,
+            strord=self._check_data(strord, "strord", optional=not restrict_strord), nodata=nodata)
+        return dout.reshape(np.shape(data))
+
+    def moving_median(self, data, n, restrict_strord=False, strord=None, nodata=-9999.0):
+        """Take the moving median over the flow direction network (flwdir.py:472-505 -> arithmetics.moving_median)."""
+        dout = self._dev.moving_median(
+            self._check_data(data, "data"), n, self.idxs_us_main,
+            strord=self._check_data(strord, "strord", optional=not restrict_strord), nodata=nodata)
+        return dout.reshape(np.shape(data))
+
     def fillnodata(self, data, nodata, direction="down", how="max"):
         """Returns data where cells with nodata value have been filled with the nearest up- or downstream valid
         neighbor value (flwdir.py:360-392)."""
@@ -272,8 +287,7 @@ class Flwdir(object):
 
     # ------------------------------------------------------------------ not in scope
     for _name in ("path", "snap", "inflow_idxs", "outflow_idxs", "smooth_rivlen",
-                  "subbasins_pfafstetter", "moving_average",
-                  "moving_median", "vectorize", "streams", "geofeatures", "dem_adjust", "dem_dig_d4",
+                  "subbasins_pfafstetter", "vectorize", "streams", "geofeatures", "dem_adjust", "dem_dig_d4",
                   "classify_estuaries", "ucat_area", "ucat_outlets", "ucat_volume", "subgrid_rivlen",
                   "subgrid_rivslp", "subgrid_rivavg", "subgrid_rivmed", "subgrid_rivlen2", "upscale", "upscale_error",
                   "accuflux_ds"):

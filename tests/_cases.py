@@ -181,6 +181,15 @@ def run_oracle_case(d8, aux, area=None, transform=(1.0, 0.0, 0.0, 0.0, -1.0, 0.0
         out["subbas_area_km2"], out["subbas_area_km2_idxs"] = sub.reshape(shape), sidx
     sub, sidx = o.basins.subbasins_area(idxs_ds, seq, out["us_main"], out["uparea_cell"].ravel(), max(3, d8.size // 400))
     out["subbas_area_cell"], out["subbas_area_cell_idxs"] = sub.reshape(shape), sidx
+    um, so = out["us_main"], out["strord"].ravel()
+    ar = o.arithmetics
+    out["movavg_f32"] = ar.moving_average(aux["data_f32_nd"].ravel(), None, 3, idxs_ds, um, None, -9999.0).reshape(shape)
+    out["movavg_f64_w"] = ar.moving_average(aux["data_f64"].ravel(), aux["data_f64"].ravel(), 5, idxs_ds, um, so, -9999.0).reshape(shape)
+    out["movavg_f32_w"] = ar.moving_average(aux["fill_f32"].ravel(), aux["data_f64"].ravel(), 2, idxs_ds, um, None, -1.5).reshape(shape)
+    out["movavg_f64_nan"] = ar.moving_average(aux["fill_f64"].ravel(), None, 4, idxs_ds, um, None, np.nan).reshape(shape)
+    out["movmed_f32"] = ar.moving_median(aux["data_f32_nd"].ravel(), 3, idxs_ds, um, None, -9999.0).reshape(shape)
+    out["movmed_f64_so"] = ar.moving_median(aux["data_f64"].ravel(), 4, idxs_ds, um, so, -9999.0).reshape(shape)
+    out["movmed_f32_sparse"] = ar.moving_median(aux["fill_f32"].ravel(), 6, idxs_ds, um, None, -1.5).reshape(shape)
     return out
 
 
@@ -249,4 +258,11 @@ def run_api_case(pf, d8, aux, transform=None, latlon=False):
     amin = float(np.quantile(ukm[ukm > 0], 0.9)) if (ukm > 0).any() else 1.0
     out["subbas_area_km2"], out["subbas_area_km2_idxs"] = flw.subbasins_area(amin)
     out["subbas_area_cell"], out["subbas_area_cell_idxs"] = flw.subbasins_area(max(3, d8.size // 400), uparea=out["uparea_cell"])
+    out["movavg_f32"] = flw.moving_average(aux["data_f32_nd"], 3, nodata=-9999.0)
+    out["movavg_f64_w"] = flw.moving_average(aux["data_f64"], 5, weights=aux["data_f64"], restrict_strord=True, strord=out["strord"], nodata=-9999.0)
+    out["movavg_f32_w"] = flw.moving_average(aux["fill_f32"], 2, weights=aux["data_f64"], nodata=-1.5)
+    out["movavg_f64_nan"] = flw.moving_average(aux["fill_f64"], 4, nodata=np.nan)
+    out["movmed_f32"] = flw.moving_median(aux["data_f32_nd"], 3, nodata=-9999.0)
+    out["movmed_f64_so"] = flw.moving_median(aux["data_f64"], 4, restrict_strord=True, strord=out["strord"], nodata=-9999.0)
+    out["movmed_f32_sparse"] = flw.moving_median(aux["fill_f32"], 6, nodata=-1.5)
     return out
