@@ -59,7 +59,10 @@ typedef enum pfd_array {
     PFD_ARR_D8 = 6,        /* uint8, N              -- core_d8.to_array              */
     PFD_ARR_LEVEL_OFFSETS = 7, /* int64, nlevels+1: start of every rank level inside SEQ */
     PFD_ARR_LDD = 8,       /* uint8, N              -- core_ldd.to_array             */
-    PFD_ARR_SUBBASIN_OUTLETS = 9 /* idx dtype, n_outlets of the last pfd_subbasins_streamorder call (2nd return value) */
+    PFD_ARR_SUBBASIN_OUTLETS = 9, /* idx dtype, n cells selected by the last pfd_subbasins_* / pfd_inflow_idxs / pfd_outflow_idxs /
+                                   * pfd_region_outlets call (their index-array return value) */
+    PFD_ARR_REGION_LABELS = 10, /* int64, n labels of the last pfd_region_outlets / pfd_region_slices call */
+    PFD_ARR_REGION_SLICES = 11  /* int32 [n][4] (row start, row stop, col start, col stop) of the last pfd_region_slices call */
 } pfd_array;
 
 /* ---- library / device ------------------------------------------------------------------------------- */
@@ -206,6 +209,45 @@ int pfd_moving_average(pfd_handle* h, const void* data, int dtype, const void* w
                        const void* idxs_us_main, int idx_dtype, const uint8_t* strord, double nodata, void* out);
 int pfd_moving_median(pfd_handle* h, const void* data, int dtype, int n, const void* idxs_us_main, int idx_dtype,
                       const uint8_t* strord, double nodata, void* out);
+
+/* ---- local traces and region post-processing ---------------------------------------------------------- */
+/* Flwdir.downstream (pyflwdir/flwdir.py:394-410): out[i] = data[idxs_ds[i]] for cells with a downstream link, data[i] for
+ * pits and nodata cells. data / out: N values of `dtype` (any of pfd_dtype; moved by size). */
+int pfd_downstream(pfd_handle* h, const void* data, int dtype, void* out);
+
+/* core.path / core.snap (pyflwdir/core.py:400-480) over core._trace (:309-364): from every start cell follow the
+ * downstream links (direction = 0) or idxs_us_main (direction = 1; N indices of idx_dtype) until a pit / headwater, a
+ * mask cell (mask: NULL or N uint8, the hit is included) or until the next hop would exceed max_length
+ * (has_max_length = 0 <=> None). hop_table: NULL (unit "cell", every hop counts 1.0) or nrow*3*2 float64 =
+ * gis_utils.distance (pyflwdir/gis_utils.py:452-486) per (row of the cell, row delta + 1, column delta != 0).
+ * starts: n0 int64. Per start: counts_out (cells in the trace, start included), ends_out (last cell = core.snap's
+ * index), dists_out (float64; core.snap casts to float32); any of them may be NULL. paths_out: NULL, or room for
+ * paths_capacity >= sum(counts) indices of path_dtype, traces back to back in start order (core.path). Fails with
+ * PFD_ERR_INVALID_ARG for an index outside the raster and PFD_ERR_UNSUPPORTED for a trace that never ends. */
+int pfd_trace(pfd_handle* h, const int64_t* starts, int64_t n0, int direction, const void* idxs_us_main, int idx_dtype,
+              const uint8_t* mask, int has_max_length, double max_length, const double* hop_table, int64_t* counts_out,
+              int64_t* ends_out, double* dists_out, void* paths_out, int path_dtype, int64_t paths_capacity);
+
+/* core.inflow_idxs / core.outflow_idxs (pyflwdir/core.py:483-514): most upstream cells draining INTO / most downstream
+ * cells INSIDE the region (N uint8), in the reference's order (seq[::-1] / seq). *n_out = count; the indices are
+ * fetched with pfd_fetch(PFD_ARR_SUBBASIN_OUTLETS). */
+int pfd_inflow_idxs(pfd_handle* h, const uint8_t* region, int64_t* n_out);
+int pfd_outflow_idxs(pfd_handle* h, const uint8_t* region, int64_t* n_out);
+
+/* basins.interbasin_mask (pyflwdir/basins.py:23-64): most downstream contiguous area within region (N uint8), optionally
+ * reduced to the cells that drain to a stream cell (stream: NULL or N uint8). out: N uint8 (0 / 1). */
+int pfd_interbasin_mask(pfd_handle* h, const uint8_t* region, const uint8_t* stream, uint8_t* out);
+
+/* regions.region_outlets (pyflwdir/regions.py:132-163): outlet cell(s) of every region label > 0, sorted by label with
+ * numba's argsort (ties keep the reference's order). regions: N values of PFD_I32 / PFD_U32 / PFD_I64 / PFD_U64.
+ * *n_out = count; pfd_fetch(PFD_ARR_REGION_LABELS) -> int64 labels, pfd_fetch(PFD_ARR_SUBBASIN_OUTLETS) -> cells. */
+int pfd_region_outlets(pfd_handle* h, const void* regions, int dtype, int64_t* n_out);
+
+/* regions.region_slices (pyflwdir/regions.py:58-86, scipy.ndimage.find_objects): bounding rows / columns of every label
+ * > 0 present in regions (dtype as above; labels up to 2^28). *n_labels = count; pfd_fetch(PFD_ARR_REGION_LABELS) ->
+ * ascending int64 labels (np.unique), pfd_fetch(PFD_ARR_REGION_SLICES) -> int32 [n][4]. region_bounds (:89-129) turns
+ * these into coordinates on the host. */
+int pfd_region_slices(pfd_handle* h, const void* regions, int dtype, int64_t* n_labels);
 
 /* ---- fused headline pass ------------------------------------------------------------------------------ */
 /*

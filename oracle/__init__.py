@@ -334,6 +334,151 @@ core = types.SimpleNamespace(
 )
 
 
+def _hop_table64(nrow, latlon, transform):
+    """float64 table [nrow, 3, 2] of gis_utils.distance (gis_utils.py:452-486) for a D8 hop: (row of idx0, row delta + 1,
+    column delta != 0). Includes the reference's swap for projected rasters (dy = xres, dx = yres)."""
+    import math
+
+    xres, yres, north = transform[0], transform[4], transform[5]
+    tab = np.zeros((nrow, 3, 2), dtype=np.float64)
+    for r0 in range(nrow):
+        for j, d in enumerate((-1, 0, 1)):
+            dr = abs(d)
+            for dc in (0, 1):
+                if latlon:
+                    lat = north + (r0 + (r0 + d)) / 2.0 * yres
+                    rl = math.radians(lat)
+                    dy = 0.0 if dr == 0 else (111132.92 + (-559.82 * math.cos(2.0 * rl)) + (1.175 * math.cos(4.0 * rl))
+                                              + (-0.0023 * math.cos(6.0 * rl))) * yres
+                    dx = 0.0 if dc == 0 else ((111412.84 * math.cos(rl)) + (-93.5 * math.cos(3.0 * rl))
+                                              + (0.118 * math.cos(5.0 * rl))) * xres
+                else:
+                    dy, dx = xres, yres
+                tab[r0, j, dc] = math.hypot(dy * dr, dx * dc)
+    return tab
+
+
+def _path_impl(idxs0, idxs_nxt, ncol, mask, max_length, real_length, latlon, transform, want_paths):
+    a, sfx = _idx(idxs_nxt)
+    starts = np.ascontiguousarray(idxs0).astype(np.int64)
+    m = None if mask is None else np.ascontiguousarray(mask).astype(np.uint8)
+    hop = None
+    if real_length and ncol is not None:
+        hop = _hop_table64(a.size // int(ncol), latlon, transform)
+    n0 = starts.size
+    counts = np.zeros(n0, dtype=np.int64)
+    ends = np.zeros(n0, dtype=np.int64)
+    dists = np.zeros(n0, dtype=np.float64)
+    f = _fn("orc_path", sfx)
+    args = [_p(starts), C.c_int64(n0), _p(a), C.c_int64(int(ncol) if ncol is not None else 1), None if m is None else _p(m),
+            C.c_int(0 if max_length is None else 1), C.c_double(0.0 if max_length is None else float(max_length)),
+            None if hop is None else _p(hop), _p(counts), _p(ends), _p(dists)]
+    f(*args, None)
+    if not want_paths:
+        return ends, dists
+    flat = np.empty(max(int(counts.sum()), 1), dtype=a.dtype)
+    f(*args, _p(flat))
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    return [flat[offs[i]:offs[i + 1]].copy() for i in range(n0)], dists
+
+
+def _path(idxs0, idxs_nxt, ncol=None, mask=None, max_length=None, real_length=False, latlon=False,
+          transform=(1.0, 0.0, 0.0, 0.0, -1.0, 0.0), mv=None):
+    """pyflwdir/core.py:400-438 -> (list of index arrays, float64 distances)"""
+    return _path_impl(idxs0, idxs_nxt, ncol, mask, max_length, real_length, latlon, transform, True)
+
+
+def _snap(idxs0, idxs_nxt, ncol=None, mask=None, max_length=None, real_length=False, latlon=False,
+          transform=(1.0, 0.0, 0.0, 0.0, -1.0, 0.0), mv=None):
+    """pyflwdir/core.py:441-480 -> (end indices in idxs0's dtype, float32 distances)"""
+    ends, dists = _path_impl(idxs0, idxs_nxt, ncol, mask, max_length, real_length, latlon, transform, False)
+    return ends.astype(np.asarray(idxs0).dtype), dists.astype(np.float32)
+
+
+def _io_idxs(name, idxs_ds, seq, region):
+    a, sfx = _idx(idxs_ds)
+    s = np.ascontiguousarray(seq).astype(a.dtype)
+    r = np.ascontiguousarray(region).astype(np.uint8)
+    out = np.empty(max(a.size, 1), dtype=a.dtype)
+    n = _fn(name, sfx, C.c_int64)(_p(a), _p(s), C.c_int64(s.size), _p(r), C.c_int64(a.size), _p(out))
+    return out[: int(n)].copy()
+
+
+def _inflow_idxs(idxs_ds, seq, region):
+    """pyflwdir/core.py:483-497"""
+    return _io_idxs("orc_inflow_idxs", idxs_ds, seq, region)
+
+
+def _outflow_idxs(idxs_ds, seq, region):
+    """pyflwdir/core.py:500-514"""
+    return _io_idxs("orc_outflow_idxs", idxs_ds, seq, region)
+
+
+def _interbasin_mask(idxs_ds, seq, region, stream=None):
+    """pyflwdir/basins.py:23-64"""
+    a, sfx = _idx(idxs_ds)
+    s = np.ascontiguousarray(seq).astype(a.dtype)
+    r = np.ascontiguousarray(region).astype(np.uint8)
+    st = None if stream is None else np.ascontiguousarray(stream).astype(np.uint8)
+    out = np.empty(a.size, dtype=np.uint8)
+    _fn("orc_interbasin_mask", sfx)(_p(a), _p(s), C.c_int64(s.size), _p(r), None if st is None else _p(st), C.c_int64(a.size), _p(out))
+    return out.astype(np.bool_)
+
+
+def _region_outlets(regions, idxs_ds, seq):
+    """pyflwdir/regions.py:132-163 -> (labels in regions' dtype, outlet indices)"""
+    a, sfx = _idx(idxs_ds)
+    s = np.ascontiguousarray(seq).astype(a.dtype)
+    reg = np.asarray(regions)
+    r64 = np.ascontiguousarray(reg.ravel()).astype(np.int64)
+    lbs = np.empty(max(s.size, 1), dtype=np.int64)
+    idxs = np.empty(max(s.size, 1), dtype=a.dtype)
+    n = int(_fn("orc_region_outlets", sfx, C.c_int64)(_p(r64), _p(a), _p(s), C.c_int64(s.size), _p(lbs), _p(idxs)))
+    return lbs[:n].astype(reg.dtype), idxs[:n].copy()
+
+
+core.path = _path
+core.snap = _snap
+core.inflow_idxs = _inflow_idxs
+core.outflow_idxs = _outflow_idxs
+
+
+def _region_bounds(regions, transform=(1.0, 0.0, 0.0, 0.0, -1.0, 0.0)):
+    """pyflwdir/regions.py:58-129 (region_slices + region_bounds); scipy.ndimage.find_objects replaced by its definition:
+    per label > 0 the smallest row / column slices that hold every cell with that label."""
+    regions = np.asarray(regions)
+    nrow, ncol = regions.shape
+    lbs = np.unique(regions[regions > 0])
+    a, b, c, d, e, f = [float(v) for v in tuple(transform)[:6]]
+    xres, yres = a, e
+    lons = (np.arange(ncol) + 0.5) * a + (np.zeros(ncol) + 0.5) * b + c  # gis_utils.affine_to_coords, gis_utils.py:340-358
+    lats = (np.zeros(nrow) + 0.5) * d + (np.arange(nrow) + 0.5) * e + f
+    iy = np.array([0, -1])
+    ix = iy.copy()
+    if yres < 0:
+        iy = iy[::-1]
+    if xres < 0:
+        ix = ix[::-1]
+    dx, dy = np.abs(xres) / 2, np.abs(yres) / 2
+    rows, cols = np.nonzero(regions > 0)
+    order = np.argsort(regions[rows, cols], kind="stable")
+    rows, cols = rows[order], cols[order]
+    first = np.flatnonzero(np.diff(regions[rows, cols], prepend=0) != 0)  # start of every label's run
+    r0, r1 = np.minimum.reduceat(rows, first), np.maximum.reduceat(rows, first)
+    c0, c1 = np.minimum.reduceat(cols, first), np.maximum.reduceat(cols, first)
+    bboxs = []
+    for k in range(lbs.size):
+        xmin, xmax = lons[c0[k]: c1[k] + 1][ix]
+        ymin, ymax = lats[r0[k]: r1[k] + 1][iy]
+        bboxs.append([xmin - dx, ymin - dy, xmax + dx, ymax + dy])
+    bboxs = np.asarray(bboxs)
+    total_bbox = np.hstack([bboxs[:, :2].min(axis=0), bboxs[:, 2:].max(axis=0)])
+    return lbs, bboxs, total_bbox
+
+
+regions = types.SimpleNamespace(region_outlets=_region_outlets, region_bounds=_region_bounds)
+
+
 # ----------------------------------------------------------------------------- streams
 def _nodata_args(nodata):
     is_int = isinstance(nodata, (int, np.integer)) and not isinstance(nodata, (bool, np.bool_))
@@ -431,7 +576,8 @@ def _basins(idxs_ds, idxs_pit, seq, ids=None):
     return _fillnodata_upstream(idxs_ds, seq, b, 0)
 
 
-basins = types.SimpleNamespace(basins=_basins, subbasins_streamorder=_subbasins_streamorder, subbasins_area=_subbasins_area)
+basins = types.SimpleNamespace(basins=_basins, subbasins_streamorder=_subbasins_streamorder, subbasins_area=_subbasins_area,
+                               interbasin_mask=_interbasin_mask)
 
 
 def _hand(idxs_ds, seq, drain, elevtn):

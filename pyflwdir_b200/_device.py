@@ -274,6 +274,117 @@ class DeviceGraph:
                                            _lib.dtype_code(um.dtype), _lib.ptr(so), C.c_double(float(nodata)), _lib.ptr(out)))
         return out
 
+    # -- local traces and region post-processing
+    def _mask_u8(self, a, name):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a)
+        if a.size != self.size:
+            raise ValueError(f'"{name}" size does not match.')
+        return a.astype(np.uint8, copy=False) if a.dtype != np.bool_ else a.view(np.uint8)
+
+    def downstream(self, data):
+        """Flwdir.downstream: value of the next downstream cell."""
+        data = np.ascontiguousarray(data)
+        if data.size != self.size:
+            raise ValueError('"data" size does not match.')
+        out = _lib.out_array(self.size, data.dtype)
+        self._ck(self._l.pfd_downstream(self._h, _lib.ptr(data), _lib.dtype_code(data.dtype), _lib.ptr(out)))
+        return out
+
+    def trace(self, idxs0, direction="down", idxs_us_main=None, mask=None, max_length=None, hop_table=None, paths_dtype=None):
+        """core.path (paths_dtype given) / core.snap (paths_dtype None) -> (paths or None, ends int64, dists float64)."""
+        starts = np.ascontiguousarray(idxs0, dtype=np.int64).ravel()
+        n0 = starts.size
+        up = 1 if direction == "up" else 0
+        um, ucode = None, 0
+        if up:
+            um = np.ascontiguousarray(idxs_us_main)
+            if um.dtype not in _IDX_DTYPES or um.size != self.size:
+                raise ValueError('"idxs_us_main" must be an index array of the raster size')
+            ucode = _lib.dtype_code(um.dtype)
+        m = self._mask_u8(mask, "mask")
+        hop = None if hop_table is None else np.ascontiguousarray(hop_table, dtype=np.float64)
+        if hop is not None and hop.size != self.shape[0] * 6:
+            raise ValueError("hop table must hold nrow * 3 * 2 lengths")
+        counts = np.zeros(n0, dtype=np.int64)
+        ends = np.zeros(n0, dtype=np.int64)
+        dists = np.zeros(n0, dtype=np.float64)
+        has_max, mx = (0, 0.0) if max_length is None else (1, float(max_length))
+
+        def call(paths, pcode, cap):
+            self._ck(self._l.pfd_trace(self._h, _lib.ptr(starts), n0, up, _lib.ptr(um), ucode, _lib.ptr(m), has_max, C.c_double(mx),
+                                       _lib.ptr(hop), _lib.ptr(counts), _lib.ptr(ends), _lib.ptr(dists), _lib.ptr(paths), pcode, cap))
+
+        call(None, 0, 0)
+        if paths_dtype is None:
+            return None, ends, dists
+        total = int(counts.sum())
+        flat = np.empty(max(total, 1), dtype=paths_dtype)
+        if n0:
+            call(flat, _lib.dtype_code(paths_dtype), total)
+        offs = np.concatenate([[0], np.cumsum(counts)])
+        return [flat[offs[i]:offs[i + 1]].copy() for i in range(n0)], ends, dists
+
+    def _fetch_selected(self, k, idx_dtype):
+        idxs = np.empty(k, dtype=idx_dtype)
+        if k:
+            self._ck(self._l.pfd_fetch(self._h, _lib.ARR_SUBBASIN_OUTLETS, _lib.ptr(idxs), _lib.dtype_code(idx_dtype)))
+        return idxs
+
+    def inflow_idxs(self, region, idx_dtype=np.int32):
+        k = C.c_int64()
+        self._ck(self._l.pfd_inflow_idxs(self._h, _lib.ptr(self._mask_u8(region, "region")), C.byref(k)))
+        return self._fetch_selected(k.value, idx_dtype)
+
+    def outflow_idxs(self, region, idx_dtype=np.int32):
+        k = C.c_int64()
+        self._ck(self._l.pfd_outflow_idxs(self._h, _lib.ptr(self._mask_u8(region, "region")), C.byref(k)))
+        return self._fetch_selected(k.value, idx_dtype)
+
+    def interbasin_mask(self, region, stream=None):
+        out = _lib.out_array(self.size, np.uint8)
+        self._ck(self._l.pfd_interbasin_mask(self._h, _lib.ptr(self._mask_u8(region, "region")),
+                                             _lib.ptr(self._mask_u8(stream, "stream")), _lib.ptr(out)))
+        return out.view(np.bool_)
+
+    @staticmethod
+    def _region_array(regions):
+        reg = np.ascontiguousarray(regions)
+        if reg.dtype.kind not in "iu":
+            raise TypeError("regions must be an integer array")
+        if reg.dtype.itemsize < 4:  # small integer labels are widened for the device
+            reg = reg.astype(np.int32)
+        return reg
+
+    def region_outlets(self, regions, idx_dtype=np.int32):
+        """regions.region_outlets -> (labels in the dtype of regions, outlet cells)."""
+        rdt = np.asarray(regions).dtype
+        reg = self._region_array(regions)
+        if reg.size != self.size:
+            raise ValueError('"regions" size does not match.')
+        k = C.c_int64()
+        self._ck(self._l.pfd_region_outlets(self._h, _lib.ptr(reg), _lib.dtype_code(reg.dtype), C.byref(k)))
+        lbs = np.empty(k.value, dtype=np.int64)
+        if k.value:
+            self._ck(self._l.pfd_fetch(self._h, _lib.ARR_REGION_LABELS, _lib.ptr(lbs), 0))
+        return lbs.astype(rdt), self._fetch_selected(k.value, idx_dtype)
+
+    def region_slices(self, regions):
+        """regions.region_slices -> (ascending labels in the dtype of regions, int32 [n, 4] row / column slices)."""
+        rdt = np.asarray(regions).dtype
+        reg = self._region_array(regions)
+        if reg.size != self.size:
+            raise ValueError('"regions" size does not match.')
+        k = C.c_int64()
+        self._ck(self._l.pfd_region_slices(self._h, _lib.ptr(reg), _lib.dtype_code(reg.dtype), C.byref(k)))
+        lbs = np.empty(k.value, dtype=np.int64)
+        sl = np.empty((k.value, 4), dtype=np.int32)
+        if k.value:
+            self._ck(self._l.pfd_fetch(self._h, _lib.ARR_REGION_LABELS, _lib.ptr(lbs), 0))
+            self._ck(self._l.pfd_fetch(self._h, _lib.ARR_REGION_SLICES, _lib.ptr(sl), 0))
+        return lbs.astype(rdt), sl
+
     def upstream_area_cells(self):
         out = _lib.out_array(self.size, np.int32)
         self._ck(self._l.pfd_upstream_area_cells(self._h, _lib.ptr(out)))

@@ -24,7 +24,7 @@ DTYPES = {
 
 # pfd_array
 ARR_IDXS_DS, ARR_PITS, ARR_PIT_IS_OUTLET, ARR_SEQ, ARR_RANK, ARR_N_UPSTREAM, ARR_D8, ARR_LEVEL_OFFSETS, ARR_LDD, \
-    ARR_SUBBASIN_OUTLETS = range(10)
+    ARR_SUBBASIN_OUTLETS, ARR_REGION_LABELS, ARR_REGION_SLICES = range(12)
 
 # every symbol include/pfd_b200.h declares: name -> (restype, argtypes)
 _vp, _i64, _int, _u32 = C.c_void_p, C.c_int64, C.c_int, C.c_uint32
@@ -63,6 +63,13 @@ SYMBOLS = {
     "pfd_subbasins_area": (_int, [_vp, _vp, _int, _vp, _int, C.c_double, _vp, _pi64]),
     "pfd_moving_average": (_int, [_vp, _vp, _int, _vp, _int, _int, _vp, _int, _vp, C.c_double, _vp]),
     "pfd_moving_median": (_int, [_vp, _vp, _int, _int, _vp, _int, _vp, C.c_double, _vp]),
+    "pfd_downstream": (_int, [_vp, _vp, _int, _vp]),
+    "pfd_trace": (_int, [_vp, _vp, _i64, _int, _vp, _int, _vp, _int, C.c_double, _vp, _vp, _vp, _vp, _vp, _int, _i64]),
+    "pfd_inflow_idxs": (_int, [_vp, _vp, _pi64]),
+    "pfd_outflow_idxs": (_int, [_vp, _vp, _pi64]),
+    "pfd_interbasin_mask": (_int, [_vp, _vp, _vp, _vp]),
+    "pfd_region_outlets": (_int, [_vp, _vp, _int, _pi64]),
+    "pfd_region_slices": (_int, [_vp, _vp, _int, _pi64]),
     "pfd_d8_flow_all": (_int, [_vp, _vp, _i64, _i64, _vp, _int, _vp, _vp, _vp, _pi64, _pi64, _pi64]),
     "pfd_comm_unique_id": (_int, [_vp, _i64]),
     "pfd_comm_init": (_int, [_vp, _int, _int, _vp]),

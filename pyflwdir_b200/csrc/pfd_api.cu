@@ -4,6 +4,7 @@
 #include "pfd_parse.cuh"
 #include "pfd_sweeps.cuh"
 #include "pfd_compact.cuh"
+#include "pfd_local.cuh"
 #include "pfd_tiles.cuh"
 #include "pfd_synth.h"
 
@@ -1288,6 +1289,14 @@ extern "C" int pfd_fetch(pfd_handle* h, int which, void* out, int idx_dtype) {
     case PFD_ARR_SUBBASIN_OUTLETS:
         PFD_TRY(copy_cells_out(h, (const cell_t*)h->sub_idxs.p, h->n_sub, out, idx_dtype));
         break;
+    case PFD_ARR_REGION_LABELS:
+        if (!h->have_sub_labels) return pfd_fail(h, PFD_ERR_STATE, "pfd_fetch: no pfd_region_outlets / pfd_region_slices result on this handle");
+        if (h->n_sub) PFD_CUDA(h, cudaMemcpyAsync(out, h->sub_labels.p, (size_t)h->n_sub * sizeof(int64_t), cudaMemcpyDefault, h->stream));
+        break;
+    case PFD_ARR_REGION_SLICES:
+        if (!h->have_sub_slices) return pfd_fail(h, PFD_ERR_STATE, "pfd_fetch: no pfd_region_slices result on this handle");
+        if (h->n_sub) PFD_CUDA(h, cudaMemcpyAsync(out, h->sub_slices.p, (size_t)h->n_sub * sizeof(int4), cudaMemcpyDefault, h->stream));
+        break;
     case PFD_ARR_LEVEL_OFFSETS:
         PFD_TRY(order_impl(h, false, false));
         PFD_CUDA(h, cudaMemcpyAsync(out, h->level_off.p, (size_t)(h->nlevels + 1) * sizeof(long long), cudaMemcpyDefault, h->stream));
@@ -1814,14 +1823,15 @@ extern "C" int pfd_d8_flow_all(pfd_handle* h, const uint8_t* d8, int64_t nrow, i
 // ---------------------------------------------------------------------------------------------------------
 // ordered numbering of the cells selected by `pred` (positions of the sequence, optionally reversed) into
 // h->sub_idxs / labels; leaves the count in h->n_sub
-template <class Pred, bool REVERSED, typename LABEL>
-static int number_outlets(pfd_handle* h, Pred pred, LABEL* label_dev) {
-    const int64_t m = h->nnodes;
+// ordered compaction of the positions [0, m) whose cell (seq[q], seq[m-1-q] or q itself: REVERSED = 0 / 1 / 2) satisfies
+// pred -> h->sub_idxs / h->n_sub; label_dev (may be null) receives the 1-based ordinal per selected cell
+template <class Pred, int REVERSED, typename LABEL>
+static int compact_cells(pfd_handle* h, const cell_t* seq, int64_t m, Pred pred, LABEL* label_dev) {
+    h->have_sub_labels = h->have_sub_slices = false;
     const int64_t nblk = std::max<int64_t>(1, (m + CP_CHUNK - 1) / CP_CHUNK);
     PFD_TRY(pfd_reserve(h, h->blk_counts, (size_t)nblk * sizeof(uint32_t)));
     PFD_TRY(pfd_reserve(h, h->blk_offsets, (size_t)(nblk + 1) * sizeof(unsigned long long)));
-    compact_count_kernel<Pred, REVERSED><<<(unsigned)nblk, CP_THREADS, 0, h->stream>>>((const cell_t*)h->seq.p, m, pred,
-                                                                                     (uint32_t*)h->blk_counts.p);
+    compact_count_kernel<Pred, REVERSED><<<(unsigned)nblk, CP_THREADS, 0, h->stream>>>(seq, m, pred, (uint32_t*)h->blk_counts.p);
     PFD_LAUNCH_CHECK(h);
     scan_counts_kernel<<<1, 1024, 0, h->stream>>>((const uint32_t*)h->blk_counts.p, nblk, (unsigned long long*)h->blk_offsets.p);
     PFD_LAUNCH_CHECK(h);
@@ -1832,10 +1842,14 @@ static int number_outlets(pfd_handle* h, Pred pred, LABEL* label_dev) {
     PFD_TRY(pfd_reserve(h, h->sub_idxs, (size_t)std::max<int64_t>(h->n_sub, 1) * sizeof(cell_t)));
     if (h->n_sub > 0) {
         compact_scatter_kernel<Pred, REVERSED, LABEL><<<(unsigned)nblk, CP_THREADS, 0, h->stream>>>(
-            (const cell_t*)h->seq.p, m, pred, (const unsigned long long*)h->blk_offsets.p, (cell_t*)h->sub_idxs.p, label_dev);
+            seq, m, pred, (const unsigned long long*)h->blk_offsets.p, (cell_t*)h->sub_idxs.p, label_dev);
         PFD_LAUNCH_CHECK(h);
     }
     return PFD_OK;
+}
+template <class Pred, int REVERSED, typename LABEL>
+static int number_outlets(pfd_handle* h, Pred pred, LABEL* label_dev) {
+    return compact_cells<Pred, REVERSED, LABEL>(h, (const cell_t*)h->seq.p, h->nnodes, pred, label_dev);
 }
 
 template <typename T>
@@ -2051,6 +2065,371 @@ extern "C" int pfd_moving_average(pfd_handle* h, const void* data, int dtype, co
 extern "C" int pfd_moving_median(pfd_handle* h, const void* data, int dtype, int n, const void* idxs_us_main, int idx_dtype,
                                  const uint8_t* strord, double nodata, void* out) {
     return moving_window(h, "pfd_moving_median", 1, data, dtype, nullptr, 0, n, idxs_us_main, idx_dtype, strord, nodata, out);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// local traces and region post-processing (pfd_local.cuh)
+// ---------------------------------------------------------------------------------------------------------
+static int require_raster(pfd_handle* h, const char* who) {
+    PFD_TRY(check_handle(h));
+    if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, std::string(who) + ": no raster parsed on this handle");
+    if (h->tiled) return pfd_fail(h, PFD_ERR_UNSUPPORTED, "this handle holds a row block: only the pfd_tiled_* entry points apply");
+    return PFD_OK;
+}
+
+extern "C" int pfd_downstream(pfd_handle* h, const void* data, int dtype, void* out) {
+    PFD_TRY(require_raster(h, "pfd_downstream"));
+    stage_reset(h);
+    if (!data || !out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_downstream: null array");
+    const size_t esz = pfd_dtype_size(dtype);
+    if (!esz) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_downstream: unknown dtype");
+    const int64_t n = h->n;
+    void* out_dev = nullptr;
+    const void* data_dev = nullptr;
+    PFD_TRY(pfd_stage_out(h, out, (size_t)n * esz, 3, &out_dev));
+    PFD_TRY(pfd_stage_in(h, data, (size_t)n * esz, 5, &data_dev));
+    if (data_dev == out_dev) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_downstream: data and out must not alias");
+    const int g = grid_for(n, 256, 4);
+    const uint8_t* dir = (const uint8_t*)h->dir.p;
+    switch (esz) {
+    case 1: downstream_kernel<uint8_t><<<g, 256, 0, h->stream>>>(dir, (const uint8_t*)data_dev, n, h->ncol, (uint8_t*)out_dev); break;
+    case 2: downstream_kernel<uint16_t><<<g, 256, 0, h->stream>>>(dir, (const uint16_t*)data_dev, n, h->ncol, (uint16_t*)out_dev); break;
+    case 4: downstream_kernel<uint32_t><<<g, 256, 0, h->stream>>>(dir, (const uint32_t*)data_dev, n, h->ncol, (uint32_t*)out_dev); break;
+    default: downstream_kernel<uint64_t><<<g, 256, 0, h->stream>>>(dir, (const uint64_t*)data_dev, n, h->ncol, (uint64_t*)out_dev); break;
+    }
+    PFD_LAUNCH_CHECK(h);
+    PFD_TRY(pfd_finish_out(h, out, out_dev, (size_t)n * esz));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    return PFD_OK;
+}
+
+template <typename IDX, typename OUT>
+static void launch_trace(pfd_handle* h, int up, const void* main_dev, const uint8_t* mask_dev, const int64_t* starts_dev, int64_t n0,
+                         int has_max, double max_length, const double* hop_dev, const long long* offsets, int64_t* counts,
+                         int64_t* ends, double* dists, void* paths, unsigned int* flag) {
+    const int g = grid_for(n0, 64, 1, 148 * 32);
+    if (up)
+        trace_kernel<IDX, OUT, true><<<g, 64, 0, h->stream>>>((const uint8_t*)h->dir.p, (const IDX*)main_dev, mask_dev, starts_dev, n0, h->n,
+                                                             h->ncol, has_max, max_length, hop_dev, offsets, counts, ends, dists,
+                                                             (OUT*)paths, flag);
+    else
+        trace_kernel<IDX, OUT, false><<<g, 64, 0, h->stream>>>((const uint8_t*)h->dir.p, (const IDX*)main_dev, mask_dev, starts_dev, n0, h->n,
+                                                              h->ncol, has_max, max_length, hop_dev, offsets, counts, ends, dists,
+                                                              (OUT*)paths, flag);
+}
+
+extern "C" int pfd_trace(pfd_handle* h, const int64_t* starts, int64_t n0, int direction, const void* idxs_us_main, int idx_dtype,
+                         const uint8_t* mask, int has_max_length, double max_length, const double* hop_table, int64_t* counts_out,
+                         int64_t* ends_out, double* dists_out, void* paths_out, int path_dtype, int64_t paths_capacity) {
+    PFD_TRY(require_raster(h, "pfd_trace"));
+    stage_reset(h);
+    if (n0 < 0 || (n0 > 0 && !starts)) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_trace: null start indices");
+    if (direction != 0 && direction != 1) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_trace: direction must be 0 (down) or 1 (up)");
+    if (direction == 1 && !idxs_us_main) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_trace: upstream traces need idxs_us_main");
+    const size_t isz = direction == 1 ? pfd_dtype_size(idx_dtype) : 4;
+    if ((isz != 4 && isz != 8) || (direction == 1 && (idx_dtype == PFD_F32 || idx_dtype == PFD_F64)))
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_trace: index dtype must be a 32/64-bit integer");
+    const size_t psz = paths_out ? pfd_dtype_size(path_dtype) : 4;
+    if ((psz != 4 && psz != 8) || (paths_out && (path_dtype == PFD_F32 || path_dtype == PFD_F64)))
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_trace: path dtype must be a 32/64-bit integer");
+    if (n0 == 0) return PFD_OK;
+    const int64_t n = h->n;
+    const void *starts_dev = nullptr, *mask_dev = nullptr, *main_dev = nullptr, *hop_dev = nullptr;
+    PFD_TRY(pfd_stage_in(h, starts, (size_t)n0 * sizeof(int64_t), 1, &starts_dev));
+    if (mask) PFD_TRY(pfd_stage_in(h, mask, (size_t)n, 4, &mask_dev));
+    if (direction == 1) PFD_TRY(pfd_stage_in(h, idxs_us_main, (size_t)n * isz, 5, &main_dev));
+    if (hop_table) PFD_TRY(pfd_stage_in(h, hop_table, (size_t)h->nrow * 6 * sizeof(double), 2, &hop_dev));
+    // per-start results: counts | ends | dists | offsets
+    PFD_TRY(pfd_reserve(h, h->scratch[0], (size_t)(4 * n0 + 1) * 8));
+    int64_t* counts = (int64_t*)h->scratch[0].p;
+    int64_t* ends = counts + n0;
+    double* dists = (double*)(ends + n0);
+    long long* offsets = (long long*)(dists + n0);
+    PFD_TRY(pfd_reserve(h, h->counters, 8 * sizeof(unsigned long long)));
+    unsigned int* flag = reinterpret_cast<unsigned int*>((unsigned long long*)h->counters.p + 5);
+    PFD_CUDA(h, cudaMemsetAsync(flag, 0, sizeof(unsigned int), h->stream));
+#define TRACE(PATHS, OFFS)                                                                                                   \
+    do {                                                                                                                     \
+        if (isz == 4 && psz == 4)                                                                                            \
+            launch_trace<uint32_t, uint32_t>(h, direction, main_dev, (const uint8_t*)mask_dev, (const int64_t*)starts_dev, n0, \
+                                             has_max_length, max_length, (const double*)hop_dev, OFFS, counts, ends, dists, PATHS, flag); \
+        else if (isz == 4)                                                                                                   \
+            launch_trace<uint32_t, int64_t>(h, direction, main_dev, (const uint8_t*)mask_dev, (const int64_t*)starts_dev, n0, \
+                                            has_max_length, max_length, (const double*)hop_dev, OFFS, counts, ends, dists, PATHS, flag); \
+        else if (psz == 4)                                                                                                   \
+            launch_trace<int64_t, uint32_t>(h, direction, main_dev, (const uint8_t*)mask_dev, (const int64_t*)starts_dev, n0, \
+                                            has_max_length, max_length, (const double*)hop_dev, OFFS, counts, ends, dists, PATHS, flag); \
+        else                                                                                                                 \
+            launch_trace<int64_t, int64_t>(h, direction, main_dev, (const uint8_t*)mask_dev, (const int64_t*)starts_dev, n0,  \
+                                           has_max_length, max_length, (const double*)hop_dev, OFFS, counts, ends, dists, PATHS, flag); \
+        PFD_LAUNCH_CHECK(h);                                                                                                 \
+    } while (0)
+    TRACE(nullptr, nullptr);
+    unsigned int hflag = 0;
+    if (paths_out) {
+        trace_offsets_kernel<<<1, 32, 0, h->stream>>>(counts, n0, offsets);
+        PFD_LAUNCH_CHECK(h);
+        long long total = 0;
+        PFD_CUDA(h, cudaMemcpyAsync(&total, offsets + n0, sizeof(total), cudaMemcpyDeviceToHost, h->stream));
+        PFD_CUDA(h, cudaMemcpyAsync(&hflag, flag, sizeof(hflag), cudaMemcpyDeviceToHost, h->stream));
+        PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (!hflag) {
+            if (total > paths_capacity) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_trace: paths_out is too small for the traces");
+            void* paths_dev = nullptr;
+            PFD_TRY(pfd_stage_out(h, paths_out, (size_t)std::max<long long>(total, 1) * psz, 3, &paths_dev));
+            TRACE(paths_dev, offsets);
+            PFD_TRY(pfd_finish_out(h, paths_out, paths_dev, (size_t)total * psz));
+        }
+    }
+#undef TRACE
+    if (counts_out) PFD_CUDA(h, cudaMemcpyAsync(counts_out, counts, (size_t)n0 * 8, cudaMemcpyDefault, h->stream));
+    if (ends_out) PFD_CUDA(h, cudaMemcpyAsync(ends_out, ends, (size_t)n0 * 8, cudaMemcpyDefault, h->stream));
+    if (dists_out) PFD_CUDA(h, cudaMemcpyAsync(dists_out, dists, (size_t)n0 * 8, cudaMemcpyDefault, h->stream));
+    PFD_CUDA(h, cudaMemcpyAsync(&hflag, flag, sizeof(hflag), cudaMemcpyDeviceToHost, h->stream));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    if (hflag & 8u) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_trace: index outside the raster (start cell or idxs_us_main)");
+    if (hflag & 16u) return pfd_fail(h, PFD_ERR_UNSUPPORTED, "pfd_trace: a trace does not end (loop in the flow directions and no stop condition)");
+    return PFD_OK;
+}
+
+// shared driver of pfd_inflow_idxs (inflow = 1) and pfd_outflow_idxs (inflow = 0)
+static int inout_idxs(pfd_handle* h, const char* who, int inflow, const uint8_t* region, int64_t* n_out) {
+    PFD_TRY(require_raster(h, who));
+    stage_reset(h);
+    if (!region) return pfd_fail(h, PFD_ERR_INVALID_ARG, std::string(who) + ": null array");
+    PFD_TRY(order_impl(h, false, false));
+    const int64_t n = h->n;
+    const void* region_dev = nullptr;
+    PFD_TRY(pfd_stage_in(h, region, (size_t)n, 4, &region_dev));
+    PFD_TRY(pfd_reserve(h, h->scratch[1], (size_t)n));
+    uint8_t* st = (uint8_t*)h->scratch[1].p;
+    PFD_CUDA(h, cudaMemsetAsync(st, 1, (size_t)n, h->stream));
+    h->have_sub_labels = h->have_sub_slices = false;
+    StateBit2Pred pred{st};
+    if (inflow) {
+        PFD_TRY(ensure_upmask(h));
+        InflowOp op{(const uint8_t*)h->upmask.p, (const uint8_t*)region_dev, st, h->ncol};
+        PFD_TRY((run_sweep<InflowOp, true>(h, op, 0)));
+        PFD_TRY((number_outlets<StateBit2Pred, 1, uint32_t>(h, pred, nullptr)));  // appended while walking seq[::-1]
+    } else {
+        OutflowOp op{(const uint8_t*)h->dir.p, (const uint8_t*)region_dev, st, h->ncol};
+        PFD_TRY((run_sweep<OutflowOp, false>(h, op, 0)));
+        PFD_TRY((number_outlets<StateBit2Pred, 0, uint32_t>(h, pred, nullptr)));
+    }
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    if (n_out) *n_out = h->n_sub;
+    return PFD_OK;
+}
+extern "C" int pfd_inflow_idxs(pfd_handle* h, const uint8_t* region, int64_t* n_out) {
+    return inout_idxs(h, "pfd_inflow_idxs", 1, region, n_out);
+}
+extern "C" int pfd_outflow_idxs(pfd_handle* h, const uint8_t* region, int64_t* n_out) {
+    return inout_idxs(h, "pfd_outflow_idxs", 0, region, n_out);
+}
+
+extern "C" int pfd_interbasin_mask(pfd_handle* h, const uint8_t* region, const uint8_t* stream, uint8_t* out) {
+    PFD_TRY(require_raster(h, "pfd_interbasin_mask"));
+    stage_reset(h);
+    if (!region || !out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_interbasin_mask: null array");
+    PFD_TRY(order_impl(h, false, false));
+    const int64_t n = h->n;
+    const void* region_dev = nullptr;
+    void* out_dev = nullptr;
+    PFD_TRY(pfd_stage_in(h, region, (size_t)n, 4, &region_dev));
+    PFD_TRY(pfd_stage_out(h, out, (size_t)n, 3, &out_dev));
+    PFD_TRY(pfd_reserve(h, h->scratch[1], (size_t)n));
+    uint8_t* st = (uint8_t*)h->scratch[1].p;
+    if (stream) {
+        PFD_CUDA(h, cudaMemcpyAsync(st, stream, (size_t)n, cudaMemcpyDefault, h->stream));
+        PFD_TRY(ensure_upmask(h));
+        AnyUpstreamOp any{(const uint8_t*)h->upmask.p, st, h->ncol};
+        PFD_TRY((run_sweep<AnyUpstreamOp, true>(h, any, 0)));
+    } else {
+        PFD_CUDA(h, cudaMemsetAsync(st, 1, (size_t)n, h->stream));
+    }
+    InterbasinOp op{(const uint8_t*)h->dir.p, (const uint8_t*)region_dev, st, h->ncol};
+    PFD_TRY((run_sweep<InterbasinOp, false>(h, op, 1)));
+    and_mask_kernel<<<grid_for(n, 256, 4), 256, 0, h->stream>>>(st, (const uint8_t*)region_dev, n, (uint8_t*)out_dev);
+    PFD_LAUNCH_CHECK(h);
+    PFD_TRY(pfd_finish_out(h, out, out_dev, (size_t)n));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    return PFD_OK;
+}
+
+// np.argsort as numba compiles it (numba/misc/quicksort.py: median-of-three partition, explicit stack, insertion sort
+// below 15 elements) -- regions.region_outlets sorts its outlets with it (regions.py:162), and the order of equal
+// labels depends on the exact algorithm. Host side: the list holds one entry per outlet.
+static void numba_argsort_i64(const std::vector<int64_t>& A, std::vector<int64_t>& R) {
+    const int64_t n = (int64_t)A.size();
+    R.resize((size_t)n);
+    for (int64_t i = 0; i < n; ++i) R[(size_t)i] = i;
+    if (n < 2) return;
+    auto key = [&](int64_t pos) { return A[(size_t)R[(size_t)pos]]; };
+    auto partition = [&](int64_t low, int64_t high) {
+        const int64_t mid = (low + high) >> 1;
+        if (key(mid) < key(low)) std::swap(R[(size_t)low], R[(size_t)mid]);
+        if (key(high) < key(mid)) std::swap(R[(size_t)high], R[(size_t)mid]);
+        if (key(mid) < key(low)) std::swap(R[(size_t)low], R[(size_t)mid]);
+        const int64_t pivot = key(mid);
+        std::swap(R[(size_t)high], R[(size_t)mid]);
+        int64_t i = low, j = high - 1;
+        while (true) {
+            while (i < high && key(i) < pivot) ++i;
+            while (j >= low && pivot < key(j)) --j;
+            if (i >= j) break;
+            std::swap(R[(size_t)i], R[(size_t)j]);
+            ++i;
+            --j;
+        }
+        std::swap(R[(size_t)i], R[(size_t)high]);
+        return i;
+    };
+    std::vector<std::pair<int64_t, int64_t>> stack;
+    stack.emplace_back(0, n - 1);
+    while (!stack.empty()) {
+        int64_t low = stack.back().first, high = stack.back().second;
+        stack.pop_back();
+        while (high - low >= 15) {
+            const int64_t i = partition(low, high);
+            if (high - i > i - low) {
+                if (high > i) stack.emplace_back(i + 1, high);
+                high = i - 1;
+            } else {
+                if (i > low) stack.emplace_back(low, i - 1);
+                low = i + 1;
+            }
+        }
+        for (int64_t i = low + 1; i <= high; ++i) {  // insertion sort
+            const int64_t k = R[(size_t)i];
+            const int64_t v = A[(size_t)k];
+            int64_t j = i;
+            while (j > low && v < A[(size_t)R[(size_t)(j - 1)]]) {
+                R[(size_t)j] = R[(size_t)(j - 1)];
+                --j;
+            }
+            R[(size_t)j] = k;
+        }
+    }
+}
+
+template <typename T>
+static int region_outlets_typed(pfd_handle* h, const void* reg_dev) {
+    RegionOutletPred<T> pred{(const uint8_t*)h->dir.p, (const T*)reg_dev, h->ncol};
+    PFD_TRY((number_outlets<RegionOutletPred<T>, 1, uint32_t>(h, pred, nullptr)));  // found while walking seq[::-1]
+    PFD_TRY(pfd_reserve(h, h->sub_labels, (size_t)std::max<int64_t>(h->n_sub, 1) * sizeof(int64_t)));
+    if (h->n_sub > 0) {
+        gather_labels_kernel<T><<<grid_for(h->n_sub, 256), 256, 0, h->stream>>>((const cell_t*)h->sub_idxs.p, h->n_sub, (const T*)reg_dev,
+                                                                              (int64_t*)h->sub_labels.p);
+        PFD_LAUNCH_CHECK(h);
+    }
+    return PFD_OK;
+}
+
+static int region_dtype_ok(int dtype) { return dtype == PFD_I32 || dtype == PFD_U32 || dtype == PFD_I64 || dtype == PFD_U64; }
+
+extern "C" int pfd_region_outlets(pfd_handle* h, const void* regions, int dtype, int64_t* n_out) {
+    PFD_TRY(require_raster(h, "pfd_region_outlets"));
+    stage_reset(h);
+    if (!regions) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_region_outlets: null array");
+    if (!region_dtype_ok(dtype)) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_region_outlets: regions must be a 32/64-bit integer array");
+    PFD_TRY(order_impl(h, false, false));
+    const void* reg_dev = nullptr;
+    PFD_TRY(pfd_stage_in(h, regions, (size_t)h->n * pfd_dtype_size(dtype), 5, &reg_dev));
+    h->have_sub_labels = h->have_sub_slices = false;
+    int rc;
+    switch (dtype) {
+    case PFD_I32: rc = region_outlets_typed<int32_t>(h, reg_dev); break;
+    case PFD_U32: rc = region_outlets_typed<uint32_t>(h, reg_dev); break;
+    case PFD_I64: rc = region_outlets_typed<int64_t>(h, reg_dev); break;
+    default: rc = region_outlets_typed<uint64_t>(h, reg_dev); break;
+    }
+    PFD_TRY(rc);
+    const int64_t m = h->n_sub;
+    if (m > 1) {  // sort = np.argsort(lbs); lbs[sort], idxs_out[sort] (regions.py:162-163)
+        std::vector<int64_t> lbs((size_t)m), order;
+        std::vector<cell_t> cells((size_t)m), cells2((size_t)m);
+        PFD_CUDA(h, cudaMemcpyAsync(lbs.data(), h->sub_labels.p, (size_t)m * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+        PFD_CUDA(h, cudaMemcpyAsync(cells.data(), h->sub_idxs.p, (size_t)m * sizeof(cell_t), cudaMemcpyDeviceToHost, h->stream));
+        PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+        numba_argsort_i64(lbs, order);
+        std::vector<int64_t> lbs2((size_t)m);
+        for (int64_t i = 0; i < m; ++i) {
+            lbs2[(size_t)i] = lbs[(size_t)order[(size_t)i]];
+            cells2[(size_t)i] = cells[(size_t)order[(size_t)i]];
+        }
+        PFD_CUDA(h, cudaMemcpyAsync(h->sub_labels.p, lbs2.data(), (size_t)m * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+        PFD_CUDA(h, cudaMemcpyAsync(h->sub_idxs.p, cells2.data(), (size_t)m * sizeof(cell_t), cudaMemcpyHostToDevice, h->stream));
+        PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->have_sub_labels = true;
+    stage_collect(h);
+    if (n_out) *n_out = m;
+    return PFD_OK;
+}
+
+#define PFD_MAX_REGION_LABEL (1ll << 28)
+
+template <typename T>
+static int region_slices_typed(pfd_handle* h, const void* reg_dev) {
+    const int64_t n = h->n;
+    unsigned long long* mx = (unsigned long long*)h->counters.p + 6;
+    PFD_CUDA(h, cudaMemsetAsync(mx, 0, sizeof(unsigned long long), h->stream));
+    max_label_kernel<T><<<grid_for(n, 256, 8, 148 * 8), 256, 0, h->stream>>>((const T*)reg_dev, n, mx);
+    PFD_LAUNCH_CHECK(h);
+    unsigned long long hmx = 0;
+    PFD_CUDA(h, cudaMemcpyAsync(&hmx, mx, sizeof(hmx), cudaMemcpyDeviceToHost, h->stream));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->n_sub = 0;
+    if (hmx == 0) return PFD_OK;
+    if (hmx > (unsigned long long)PFD_MAX_REGION_LABEL)
+        return pfd_fail(h, PFD_ERR_UNSUPPORTED, "pfd_region_slices: labels above 2^28 are not supported");
+    const int64_t nlab = (int64_t)hmx;
+    PFD_TRY(pfd_reserve(h, h->scratch[2], (size_t)nlab * sizeof(int4)));
+    int4* box = (int4*)h->scratch[2].p;
+    region_box_init_kernel<<<grid_for(nlab, 256), 256, 0, h->stream>>>(box, nlab);
+    PFD_LAUNCH_CHECK(h);
+    region_box_kernel<T><<<grid_for(n, 256, 4), 256, 0, h->stream>>>((const T*)reg_dev, h->nrow, h->ncol, box);
+    PFD_LAUNCH_CHECK(h);
+    BoxPresentPred pred{box};
+    PFD_TRY((compact_cells<BoxPresentPred, 2, uint32_t>(h, nullptr, nlab, pred, nullptr)));  // present labels, ascending
+    PFD_TRY(pfd_reserve(h, h->sub_labels, (size_t)std::max<int64_t>(h->n_sub, 1) * sizeof(int64_t)));
+    PFD_TRY(pfd_reserve(h, h->sub_slices, (size_t)std::max<int64_t>(h->n_sub, 1) * sizeof(int4)));
+    if (h->n_sub > 0) {
+        region_slices_kernel<<<grid_for(h->n_sub, 256), 256, 0, h->stream>>>((const cell_t*)h->sub_idxs.p, h->n_sub, box,
+                                                                           (int64_t*)h->sub_labels.p, (int4*)h->sub_slices.p);
+        PFD_LAUNCH_CHECK(h);
+    }
+    return PFD_OK;
+}
+
+extern "C" int pfd_region_slices(pfd_handle* h, const void* regions, int dtype, int64_t* n_labels) {
+    PFD_TRY(require_raster(h, "pfd_region_slices"));
+    stage_reset(h);
+    if (!regions) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_region_slices: null array");
+    if (!region_dtype_ok(dtype)) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_region_slices: regions must be a 32/64-bit integer array");
+    if (h->nrow >= (1ll << 31) || h->ncol >= (1ll << 31)) return pfd_fail(h, PFD_ERR_UNSUPPORTED, "pfd_region_slices: raster side above 2^31");
+    const void* reg_dev = nullptr;
+    PFD_TRY(pfd_stage_in(h, regions, (size_t)h->n * pfd_dtype_size(dtype), 5, &reg_dev));
+    PFD_TRY(pfd_reserve(h, h->counters, 8 * sizeof(unsigned long long)));
+    h->have_sub_labels = h->have_sub_slices = false;
+    int rc;
+    switch (dtype) {
+    case PFD_I32: rc = region_slices_typed<int32_t>(h, reg_dev); break;
+    case PFD_U32: rc = region_slices_typed<uint32_t>(h, reg_dev); break;
+    case PFD_I64: rc = region_slices_typed<int64_t>(h, reg_dev); break;
+    default: rc = region_slices_typed<uint64_t>(h, reg_dev); break;
+    }
+    PFD_TRY(rc);
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->have_sub_labels = h->have_sub_slices = true;
+    stage_collect(h);
+    if (n_labels) *n_labels = h->n_sub;
+    return PFD_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -183,6 +183,9 @@ struct pfd_handle {
     void* nccl_comm = nullptr;
     DevBuf sub_idxs;           // cell_t [n_sub] outlets of the last pfd_subbasins_streamorder call
     int64_t n_sub = 0;
+    DevBuf sub_labels;         // int64 [n_sub] labels of the last pfd_region_outlets / pfd_region_slices call
+    DevBuf sub_slices;         // int4 [n_sub] (row start, row stop, col start, col stop) of the last pfd_region_slices call
+    bool have_sub_labels = false, have_sub_slices = false;
     DevBuf tile_loc;           // uint2 [n]: per cell (local terminal | hops << 12, in-tile subtree size)
     DevBuf uparea;            // int32 [n] cached cell-count upstream area (tile solver)
     bool have_uparea = false;

@@ -5,7 +5,7 @@
 #include "pfd_sweeps.cuh"
 
 // ---------------------------------------------------------------------------------------------------------
-// Ordered compaction. Position q in [0, m) maps to cell seq[q] (REVERSED: seq[m-1-q]); the cells whose predicate holds
+// Ordered compaction. Position q in [0, m) maps to cell seq[q] (REVERSED = 1: seq[m-1-q], 2: q itself); the cells whose predicate holds
 // are written to out_cells in ascending q and, optionally, label[cell] = 1-based ordinal. Every thread owns
 // CP_PER_THREAD consecutive positions, so order is preserved with one block-wide exclusive scan.
 // Pass 1 counts per chunk, scan_counts_kernel (pfd_parse.cuh) turns counts into offsets, pass 2 writes.
@@ -14,7 +14,7 @@
 #define CP_PER_THREAD 8
 #define CP_CHUNK (CP_THREADS * CP_PER_THREAD)
 
-template <class Pred, bool REVERSED>
+template <class Pred, int REVERSED>
 __device__ __forceinline__ uint32_t cp_flags(const cell_t* __restrict__ seq, long long m, const Pred& pred, long long q0,
                                              cell_t* cells) {
     uint32_t flags = 0;
@@ -22,7 +22,7 @@ __device__ __forceinline__ uint32_t cp_flags(const cell_t* __restrict__ seq, lon
     for (int e = 0; e < CP_PER_THREAD; ++e) {
         const long long q = q0 + e;
         if (q < m) {
-            const cell_t c = __ldg(seq + (REVERSED ? m - 1 - q : q));
+            const cell_t c = (REVERSED == 2) ? (cell_t)q : __ldg(seq + (REVERSED == 1 ? m - 1 - q : q));
             cells[e] = c;
             if (pred(c)) flags |= 1u << e;
         }
@@ -30,7 +30,7 @@ __device__ __forceinline__ uint32_t cp_flags(const cell_t* __restrict__ seq, lon
     return flags;
 }
 
-template <class Pred, bool REVERSED>
+template <class Pred, int REVERSED>
 __global__ void __launch_bounds__(CP_THREADS) compact_count_kernel(const cell_t* __restrict__ seq, long long m, Pred pred,
                                                                    uint32_t* __restrict__ blk_counts) {
     __shared__ uint32_t s_w[CP_THREADS / 32];
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(CP_THREADS) compact_count_kernel(const cell_t*
     }
 }
 
-template <class Pred, bool REVERSED, typename LABEL>
+template <class Pred, int REVERSED, typename LABEL>
 __global__ void __launch_bounds__(CP_THREADS) compact_scatter_kernel(const cell_t* __restrict__ seq, long long m, Pred pred,
                                                                      const unsigned long long* __restrict__ blk_off,
                                                                      cell_t* __restrict__ out_cells, LABEL* __restrict__ label) {

@@ -1,0 +1,250 @@
+// pfd_local.cuh -- local traces and region post-processing around the ordered flow graph:
+//   Flwdir.downstream                    (pyflwdir/flwdir.py:394-410)
+//   core._trace / path / snap            (pyflwdir/core.py:309-364, 400-480)
+//   core.inflow_idxs / outflow_idxs      (pyflwdir/core.py:483-514)
+//   basins.interbasin_mask               (pyflwdir/basins.py:23-64)
+//   regions.region_outlets               (pyflwdir/regions.py:132-163)
+//   regions.region_slices / region_bounds (pyflwdir/regions.py:58-129, scipy.ndimage.find_objects)
+#pragma once
+#include "pfd_compact.cuh"
+
+// ---- Flwdir.downstream: data_out[mask] = data[idxs_ds[mask]]; pits and nodata cells keep their own value --------
+template <typename W>
+__global__ void downstream_kernel(const uint8_t* __restrict__ dir, const W* __restrict__ data, int64_t n, long long ncol,
+                                  W* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t d = dir[i];
+        out[i] = data[d < 8u ? i + pfd_slot_off((int)d, ncol) : i];
+    }
+}
+
+// ---- core._trace for a batch of start cells (core.path / core.snap): one thread per start ------------------------
+// Downstream traces read the 1-byte dir graph, upstream traces the caller's idxs_us_main. hop = NULL (cells) or the
+// host-built float64 table of gis_utils.distance per (row of the cell, row delta + 1, column delta != 0).
+// paths = NULL: count / end / distance only; else the trace of start i is written at paths[offsets[i] ...].
+// flag bits: 8 = index outside the raster, 16 = trace longer than the raster (a loop without a stop condition).
+template <typename IDX, typename OUT, bool UP>
+__global__ void trace_kernel(const uint8_t* __restrict__ dir, const IDX* __restrict__ us_main, const uint8_t* __restrict__ mask,
+                             const int64_t* __restrict__ starts, int64_t n0, int64_t n, long long ncol, int has_max,
+                             double max_length, const double* __restrict__ hop, const long long* __restrict__ offsets,
+                             int64_t* __restrict__ counts, int64_t* __restrict__ ends, double* __restrict__ dists,
+                             OUT* __restrict__ paths, unsigned int* __restrict__ flag) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n0; t += (int64_t)gridDim.x * blockDim.x) {
+        long long cur = starts[t];
+        if (cur < 0 || cur >= n) {
+            atomicOr(flag, 8u);
+            counts[t] = 0;
+            ends[t] = -1;
+            dists[t] = 0.0;
+            continue;
+        }
+        OUT* dst = paths ? paths + offsets[t] : nullptr;
+        long long cnt = 0;
+        double dist = 0.0, d = 1.0;
+        if (dst) dst[cnt] = (OUT)cur;
+        ++cnt;
+        while (!mask || mask[cur] == 0) {
+            long long nx;
+            if (!UP) {
+                const uint32_t c = dir[cur];
+                if (c >= 8u) break;  // pit (idx1 == idx0) or nodata (idx1 == mv)
+                nx = cur + pfd_slot_off((int)c, ncol);
+            } else {
+                const IDX u = us_main[cur];
+                if (u == (IDX)-1 || (long long)u == cur) break;
+                nx = (long long)u;
+                if (nx < 0 || nx >= n) {
+                    atomicOr(flag, 8u);
+                    break;
+                }
+            }
+            if (hop) {
+                const long long r0 = cur / ncol, r1 = nx / ncol;
+                const long long drow = r1 - r0;
+                if (drow < -1 || drow > 1) {
+                    atomicOr(flag, 8u);
+                    break;
+                }
+                d = hop[(r0 * 3 + (drow + 1)) * 2 + ((nx - r1 * ncol) != (cur - r0 * ncol) ? 1 : 0)];
+            }
+            if (has_max && __dadd_rn(dist, d) > max_length) break;
+            dist = __dadd_rn(dist, d);
+            cur = nx;
+            if (cnt > n) {
+                atomicOr(flag, 16u);
+                break;
+            }
+            if (dst) dst[cnt] = (OUT)cur;
+            ++cnt;
+        }
+        counts[t] = cnt;
+        ends[t] = cur;
+        dists[t] = dist;
+    }
+}
+
+// exclusive scan of the trace lengths (a handful of starts: one thread)
+__global__ void trace_offsets_kernel(const int64_t* __restrict__ counts, int64_t n0, long long* __restrict__ offsets) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        long long o = 0;
+        for (int64_t i = 0; i < n0; ++i) {
+            offsets[i] = o;
+            o += counts[i];
+        }
+        offsets[n0] = o;
+    }
+}
+
+// ---- core.outflow_idxs: down-sweep. state byte: bit 0 = the reference's `mask`, bit 1 = "appended" -----------------
+struct OutflowOp {
+    const uint8_t* dir;
+    const uint8_t* region;
+    uint8_t* st;  // pre-initialised with 1
+    long long ncol;
+    __device__ __forceinline__ void operator()(cell_t c, long long, int) const {
+        const uint32_t d = __ldg(dir + c);
+        const bool pit = d >= 8u;
+        const long long ds = pit ? (long long)c : (long long)c + pfd_slot_off((int)d, ncol);
+        const uint32_t m_ds = pit ? 1u : ((uint32_t)ld_cg(st + ds) & 1u);
+        const bool out = m_ds && __ldg(region + c) && (pit || !__ldg(region + ds));
+        st[c] = out ? (uint8_t)2 : (uint8_t)m_ds;
+    }
+};
+
+// ---- core.inflow_idxs: up-sweep, parent-centric. The reference overwrites mask[idx_ds] once per upstream cell while it
+// walks seq[::-1]; the last writer is the upstream cell that comes FIRST in seq = the one with the smallest index
+// (siblings are consecutive and ascending in core.idxs_seq). ------------------------------------------------------------
+struct InflowOp {
+    const uint8_t* upmask;
+    const uint8_t* region;
+    uint8_t* st;  // pre-initialised with 1
+    long long ncol;
+    __device__ __forceinline__ void operator()(cell_t c, long long, int) const {
+        uint32_t m = __ldg(upmask + c);
+        if (!m) return;  // headwater: mask stays True
+        const bool rc = __ldg(region + c) != 0;
+        bool first = true;
+        while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            const long long u = (long long)c + pfd_slot_off(k, ncol);
+            const uint32_t mu = (uint32_t)ld_cg(st + u) & 1u;
+            const bool in = mu && rc && !__ldg(region + u);
+            if (in) st[u] = (uint8_t)(mu | 2u);
+            if (first) {
+                st[c] = in ? (uint8_t)0 : (uint8_t)mu;
+                first = false;
+            }
+        }
+    }
+};
+
+struct StateBit2Pred {
+    const uint8_t* st;
+    __device__ __forceinline__ bool operator()(cell_t c) const { return (__ldg(st + c) & 2u) != 0; }
+};
+
+// ---- basins.interbasin_mask ------------------------------------------------------------------------------------------
+// step 1 (stream given): a cell is True if it or any cell upstream of it is a stream cell (up-sweep, OR of the children)
+struct AnyUpstreamOp {
+    const uint8_t* upmask;
+    uint8_t* st;  // pre-initialised with the stream mask
+    long long ncol;
+    __device__ __forceinline__ void operator()(cell_t c, long long, int) const {
+        if (ld_cg(st + c)) return;
+        uint32_t m = __ldg(upmask + c);
+        while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            if (ld_cg(st + ((long long)c + pfd_slot_off(k, ncol)))) {
+                st[c] = 1;
+                return;
+            }
+        }
+    }
+};
+// step 2: propagate upstream, cut where the flow enters the region (down-sweep)
+struct InterbasinOp {
+    const uint8_t* dir;
+    const uint8_t* region;
+    uint8_t* st;
+    long long ncol;
+    __device__ __forceinline__ void operator()(cell_t c, long long, int) const {
+        const uint32_t d = __ldg(dir + c);
+        if (d >= 8u) return;  // pit: mask[idx0] = mask[idx_ds] is a no-op
+        const long long ds = (long long)c + pfd_slot_off((int)d, ncol);
+        uint8_t v = ld_cg(st + ds);
+        if (!__ldg(region + c) && __ldg(region + ds)) v = 0;
+        st[c] = v;
+    }
+};
+__global__ void and_mask_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int64_t n, uint8_t* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (a[i] && b[i]) ? 1 : 0;
+}
+
+// ---- regions.region_outlets: cell inside a region (label > 0) whose downstream cell carries another label, or a pit ---
+template <typename T>
+struct RegionOutletPred {
+    const uint8_t* dir;
+    const T* regions;
+    long long ncol;
+    __device__ __forceinline__ bool operator()(cell_t c) const {
+        const T lb = __ldg(regions + c);
+        if (!(lb > (T)0)) return false;
+        const uint32_t d = __ldg(dir + c);
+        if (d >= 8u) return true;
+        return __ldg(regions + ((long long)c + pfd_slot_off((int)d, ncol))) != lb;
+    }
+};
+template <typename T>
+__global__ void gather_labels_kernel(const cell_t* __restrict__ cells, int64_t m, const T* __restrict__ regions, int64_t* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (int64_t)regions[cells[i]];
+}
+
+// ---- regions.region_slices (scipy.ndimage.find_objects): bounding rows / columns of every label > 0 ------------------
+template <typename T>
+__global__ void max_label_kernel(const T* __restrict__ regions, int64_t n, unsigned long long* __restrict__ out) {
+    unsigned long long mx = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const T v = regions[i];
+        if (v > (T)0) mx = max(mx, (unsigned long long)v);
+    }
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(out, mx);
+}
+// box[l] = (min row, max row, min col, max col) of label l + 1. Only cells on the edge of a run of equal labels can
+// hold an extreme, so interior cells issue no atomics.
+__global__ void region_box_init_kernel(int4* __restrict__ box, int64_t nlab) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nlab; i += (int64_t)gridDim.x * blockDim.x)
+        box[i] = make_int4(0x7FFFFFFF, -1, 0x7FFFFFFF, -1);
+}
+template <typename T>
+__global__ void region_box_kernel(const T* __restrict__ regions, long long nrow, long long ncol, int4* __restrict__ box) {
+    const int64_t n = nrow * ncol;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const T lb = regions[i];
+        if (!(lb > (T)0)) continue;
+        const long long r = i / ncol, c = i - r * ncol;
+        int* b = reinterpret_cast<int*>(box + ((unsigned long long)lb - 1ull));
+        if (r == 0 || regions[i - ncol] != lb) atomicMin(b + 0, (int)r);
+        if (r == nrow - 1 || regions[i + ncol] != lb) atomicMax(b + 1, (int)r);
+        if (c == 0 || regions[i - 1] != lb) atomicMin(b + 2, (int)c);
+        if (c == ncol - 1 || regions[i + 1] != lb) atomicMax(b + 3, (int)c);
+    }
+}
+struct BoxPresentPred {
+    const int4* box;
+    __device__ __forceinline__ bool operator()(cell_t l) const { return __ldg(reinterpret_cast<const int*>(box + l) + 1) >= 0; }
+};
+// slices[k] = (row start, row stop, col start, col stop) of the k-th present label; labels[k] = its value
+__global__ void region_slices_kernel(const cell_t* __restrict__ present, int64_t m, const int4* __restrict__ box,
+                                     int64_t* __restrict__ labels, int4* __restrict__ slices) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        const cell_t l = present[i];
+        const int4 b = box[l];
+        labels[i] = (int64_t)l + 1;
+        slices[i] = make_int4(b.x, b.y + 1, b.z, b.w + 1);
+    }
+}

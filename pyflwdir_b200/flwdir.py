@@ -230,6 +230,24 @@ class Flwdir(object):
             strord=self._check_data(strord, "strord", optional=not restrict_strord), nodata=nodata)
         return dout.reshape(np.shape(data))
 
+    # ------------------------------------------------------------------ local methods
+    def path(self, idxs=None, mask=None, max_length=None, direction="down"):
+        """Returns paths of indices in down- or upstream direction from the starting points until a pit / headwater,
+        a True cell in mask (included) or max_length [cells] is reached (flwdir.py:309-356 -> core.path)."""
+        direction = str(direction).lower()
+        if direction not in ["up", "down"]:
+            msg = 'Unknown flow direction: {direction}, select from ["up", "down"].'
+            raise ValueError(msg)
+        paths, _, dist = self._dev.trace(
+            np.atleast_1d(idxs).ravel(), direction, self.idxs_us_main if direction == "up" else None,
+            self._check_data(mask, "mask", optional=True), max_length, None, paths_dtype=self._idx_dtype)
+        return paths, dist
+
+    def downstream(self, data):
+        """Returns next downstream value (flwdir.py:394-410)."""
+        dflat = self._check_data(data, "data")
+        return self._dev.downstream(dflat).reshape(np.shape(data))
+
     def fillnodata(self, data, nodata, direction="down", how="max"):
         """Returns data where cells with nodata value have been filled with the nearest up- or downstream valid
         neighbor value (flwdir.py:360-392)."""
@@ -281,12 +299,14 @@ class Flwdir(object):
 
     def _check_idxs_xy(self, idxs, streams=None):
         idxs = np.atleast_1d(idxs).ravel()
+        # snap to streams (flwdir.py:805-811)
+        streams = self._check_data(streams, "streams", optional=True)
         if streams is not None:
-            raise NotImplementedError("snapping pits to streams is outside the accelerated hot path")
+            idxs = self.snap(idxs=idxs, mask=streams)[0]
         return idxs
 
     # ------------------------------------------------------------------ not in scope
-    for _name in ("path", "snap", "inflow_idxs", "outflow_idxs", "smooth_rivlen",
+    for _name in ("smooth_rivlen",
                   "subbasins_pfafstetter", "vectorize", "streams", "geofeatures", "dem_adjust", "dem_dig_d4",
                   "classify_estuaries", "ucat_area", "ucat_outlets", "ucat_volume", "subgrid_rivlen",
                   "subgrid_rivslp", "subgrid_rivavg", "subgrid_rivmed", "subgrid_rivlen2", "upscale", "upscale_error",

@@ -130,8 +130,8 @@ def degree_metres_x(lat):
     return (111412.84 * math.cos(radlat)) + (-93.5 * math.cos(3.0 * radlat)) + (0.118 * math.cos(5.0 * radlat))
 
 
-def hop_length_table(nrow, transform, latlon):
-    """float32 table [nrow, 3, 2] of gis_utils.distance(idx0, idx1, ...) (gis_utils.py:451-486) for a hop that starts in
+def hop_length_table(nrow, transform, latlon, dtype=np.float32):
+    """float32 (stream_distance) or float64 (core._trace) table [nrow, 3, 2] of gis_utils.distance(idx0, idx1, ...) (gis_utils.py:451-486) for a hop that starts in
     row r0 with row delta dr in (-1, 0, 1) and |column delta| dc in (0, 1) -- everything the distance depends on.
     Reproduces the reference including its quirk for projected rasters (dy = xres, dx = yres)."""
     xres, yres, north = transform[0], transform[4], transform[5]
@@ -149,4 +149,4 @@ def hop_length_table(nrow, transform, latlon):
                 dx1 = degree_metres_x(lat) * xres
                 tab[r0, j, 0] = math.hypot(dy * dr, 0.0)
                 tab[r0, j, 1] = math.hypot(dy * dr, dx1 * 1)
-    return tab.astype(np.float32)
+    return tab.astype(dtype)

@@ -211,6 +211,83 @@ class FlwdirRaster(Flwdir):
         r, c = idxs // ncol, idxs % ncol
         return self.transform * (c + 0.5, r + 0.5)
 
+    # ------------------------------------------------------------------ local traces
+    def _trace_args(self, unit, direction):
+        unit = str(unit).lower()
+        if unit not in ["m", "cell"]:
+            raise ValueError(f'Unknown unit: {unit}, select from ["m", "cell"].')
+        direction = str(direction).lower()
+        if direction not in ["up", "down"]:
+            msg = 'Unknown flow direction: {direction}, select from ["up", "down"].'
+            raise ValueError(msg)
+        hop = gis.hop_length_table(self.shape[0], self.transform, self.latlon, dtype=np.float64) if unit == "m" else None
+        return direction, hop
+
+    def path(self, idxs=None, xy=None, mask=None, max_length=None, unit="cell", direction="down"):
+        """Returns paths of indices in down- or upstream direction from the starting points until a pit / headwater, a
+        True cell in mask (included) or max_length is exceeded (pyflwdir.py:443-500 -> core.path, core.py:400-438)."""
+        direction, hop = self._trace_args(unit, direction)
+        paths, _, dist = self._dev.trace(
+            self._check_idxs_xy(idxs, xy), direction, self.idxs_us_main if direction == "up" else None,
+            self._check_data(mask, "mask", optional=True), max_length, hop, paths_dtype=self._idx_dtype)
+        return paths, dist
+
+    def snap(self, idxs=None, xy=None, mask=None, max_length=None, unit="cell", direction="down"):
+        """Returns the last index of the trace from every starting point and the distance to it
+        (pyflwdir.py:502-560 -> core.snap, core.py:441-480: indices in the dtype of idxs, float32 distances)."""
+        direction, hop = self._trace_args(unit, direction)
+        idxs0 = self._check_idxs_xy(idxs, xy)
+        _, ends, dist = self._dev.trace(
+            idxs0, direction, self.idxs_us_main if direction == "up" else None,
+            self._check_data(mask, "mask", optional=True), max_length, hop)
+        return ends.astype(idxs0.dtype), dist.astype(np.float32)
+
+    def inflow_idxs(self, region):
+        """Returns linear indices of most upstream cells within region (pyflwdir.py:804-818 -> core.inflow_idxs)."""
+        return self._dev.inflow_idxs(self._check_data(region, "region"), self._idx_dtype)
+
+    def outflow_idxs(self, region):
+        """Returns linear indices of most downstream cells within region (pyflwdir.py:820-835 -> core.outflow_idxs)."""
+        return self._dev.outflow_idxs(self._check_data(region, "region"), self._idx_dtype)
+
+    # ------------------------------------------------------------------ regions
+    def basin_outlets(self, basins):
+        """Returns the linear index of the outlet cell of `basins` (pyflwdir.py:720-740 -> regions.region_outlets)."""
+        return self._dev.region_outlets(self._check_data(basins, "basins"), self._idx_dtype)
+
+    def basin_bounds(self, basins=None, **kwargs):
+        """Returns the basin labels, their bounding boxes [xmin, ymin, xmax, ymax] and the total bounding box
+        (pyflwdir.py:694-718 -> regions.region_bounds, regions.py:89-129; the label extents come from the device)."""
+        regions = self._check_data(basins, "basins", flatten=False, **kwargs)
+        if regions.ndim != 2:
+            raise ValueError('The "regions" array should be two dimensional')
+        lbs, sl = self._dev.region_slices(regions)
+        if lbs.size == 0:
+            raise ValueError("No regions found in data")
+        xres, yres = self.transform[0], self.transform[4]
+        lons, lats = gis.affine_to_coords(self.transform, regions.shape)
+        iy = np.array([0, -1])
+        ix = iy.copy()
+        if yres < 0:
+            iy = iy[::-1]
+        if xres < 0:
+            ix = ix[::-1]
+        dx = np.abs(xres) / 2
+        dy = np.abs(yres) / 2
+        bboxs = []
+        for r0, r1, c0, c1 in sl.tolist():
+            xmin, xmax = lons[c0:c1][ix]
+            ymin, ymax = lats[r0:r1][iy]
+            bboxs.append([xmin - dx, ymin - dy, xmax + dx, ymax + dy])
+        bboxs = np.asarray(bboxs)
+        total_bbox = np.hstack([bboxs[:, :2].min(axis=0), bboxs[:, 2:].max(axis=0)])
+        return lbs, bboxs, total_bbox
+
+    def interbasin_mask(self, region, stream=None):
+        """Returns most downstream contiguous area within region (pyflwdir.py:742-766 -> basins.interbasin_mask)."""
+        mask = self._dev.interbasin_mask(self._check_data(region, "region"), self._check_data(stream, "stream", optional=True))
+        return mask.reshape(self.shape)
+
     # ------------------------------------------------------------------ basins
     def basins(self, idxs=None, xy=None, ids=None, **kwargs):
         """(Sub)basin map with a unique ID for every (sub)basin (pyflwdir.py:564-599 -> basins.basins)."""
@@ -319,6 +396,6 @@ class FlwdirRaster(Flwdir):
     for _name in ("repair_loops_raster", "subbasins_pfafstetter",
                   "streams", "geofeatures", "vectorize", "dem_adjust", "dem_dig_d4",
                   "upscale", "upscale_error", "subgrid_rivlen", "subgrid_rivslp", "subgrid_rivavg", "subgrid_rivmed",
-                  "ucat_area", "ucat_outlets", "ucat_volume", "inflow_idxs", "outflow_idxs"):
+                  "ucat_area", "ucat_outlets", "ucat_volume"):
         locals()[_name] = _not_in_scope(_name)
     del _name

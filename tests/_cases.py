@@ -96,6 +96,27 @@ def check(name, key, arr):
     assert sha(arr) == hashes()[name][key], f"{name}/{key}: SHA-256 differs from the reference's"
 
 
+def local_inputs(d8, seq, aux):
+    """Deterministic start cells / region masks / label rasters for the local-trace and region cases."""
+    nrow, ncol = d8.shape
+    starts = np.asarray(seq[:: max(1, seq.size // 37)][:60]).astype(np.int64)
+    nod = np.flatnonzero(d8.ravel() == 247)[:2].astype(np.int64)
+    starts = np.concatenate([starts, nod])
+    region = np.zeros(d8.shape, dtype=np.bool_)
+    region[nrow // 4: max(nrow // 4 + 1, 3 * nrow // 4), ncol // 5: max(ncol // 5 + 1, 4 * ncol // 5)] = True
+    rr, cc = np.arange(nrow)[:, None], np.arange(ncol)[None, :]
+    blocks = (((rr // 7) % 3) * 3 + ((cc // 9) % 3)).astype(np.int32)  # labels 0..8 repeated over the raster: ties
+    labels = ((rr // max(1, nrow // 5)) * 7 + (cc // max(1, ncol // 4)) * 3 + 2).astype(np.int64)  # gaps in the numbering
+    labels[aux["smask"] & (rr % 3 == 0)] = 0
+    return starts, region, blocks, labels
+
+
+def _flat_paths(paths):
+    counts = np.array([p.size for p in paths], dtype=np.int64)
+    flat = np.concatenate(paths) if len(paths) else np.zeros(0, dtype=np.int64)
+    return flat, counts
+
+
 def run_oracle_case(d8, aux, area=None, transform=(1.0, 0.0, 0.0, 0.0, -1.0, 0.0), latlon=False):
     """The whole hot path on the CPU oracle, mirroring make_golden.run_case (which runs the real reference).
     `area` = flat cell-area vector [m2] for upstream_area("km2") (host-side input, see gis_utils.area_grid)."""
@@ -190,6 +211,31 @@ def run_oracle_case(d8, aux, area=None, transform=(1.0, 0.0, 0.0, 0.0, -1.0, 0.0
     out["movmed_f32"] = ar.moving_median(aux["data_f32_nd"].ravel(), 3, idxs_ds, um, None, -9999.0).reshape(shape)
     out["movmed_f64_so"] = ar.moving_median(aux["data_f64"].ravel(), 4, idxs_ds, um, so, -9999.0).reshape(shape)
     out["movmed_f32_sparse"] = ar.moving_median(aux["fill_f32"].ravel(), 6, idxs_ds, um, None, -1.5).reshape(shape)
+    # local traces and region post-processing
+    starts, region, blocks, labels = local_inputs(d8, seq, aux)
+    tr6 = tuple(transform)[:6]
+    upc = out["uparea_cell"].ravel()
+    stream = upc > max(4, int(0.002 * d8.size))
+    for tag, nxt in (("down", idxs_ds), ("up", um)):
+        for key, kw in (("", {}), ("_mask", dict(mask=stream)), ("_max", dict(max_length=7.5)),
+                        ("_m", dict(mask=stream, max_length=3000.0 * abs(tr6[0]) * (111e3 if latlon else 1.0) / 1e3,
+                                    real_length=True, ncol=shape[1], latlon=latlon, transform=tr6))):
+            paths, dist = o.core.path(starts, nxt, **kw)
+            out[f"path_{tag}{key}"], out[f"path_{tag}{key}_n"] = _flat_paths(paths)
+            out[f"path_{tag}{key}_dist"] = dist
+            out[f"snap_{tag}{key}"], out[f"snap_{tag}{key}_dist"] = o.core.snap(starts, nxt, **kw)
+    out["downstream_f32"] = np.where(mask, aux["data_f32"].ravel()[np.where(mask, idxs_ds, 0).astype(np.int64)],
+                                     aux["data_f32"].ravel()).reshape(shape)
+    out["downstream_i64"] = np.where(mask, aux["data_i64"].ravel()[np.where(mask, idxs_ds, 0).astype(np.int64)],
+                                     aux["data_i64"].ravel()).reshape(shape)
+    out["inflow_idxs"] = o.core.inflow_idxs(idxs_ds, seq, region.ravel())
+    out["outflow_idxs"] = o.core.outflow_idxs(idxs_ds, seq, region.ravel())
+    out["interbasin"] = o.basins.interbasin_mask(idxs_ds, seq, region.ravel()).reshape(shape)
+    out["interbasin_stream"] = o.basins.interbasin_mask(idxs_ds, seq, region.ravel(), stream).reshape(shape)
+    out["outlets_basins_lbs"], out["outlets_basins_idxs"] = o.regions.region_outlets(out["basins"], idxs_ds, seq)
+    out["outlets_blocks_lbs"], out["outlets_blocks_idxs"] = o.regions.region_outlets(blocks, idxs_ds, seq)
+    out["bounds_basins_lbs"], out["bounds_basins_boxes"], out["bounds_basins_total"] = o.regions.region_bounds(out["basins"], tr6)
+    out["bounds_labels_lbs"], out["bounds_labels_boxes"], out["bounds_labels_total"] = o.regions.region_bounds(labels, tr6)
     return out
 
 
@@ -265,4 +311,25 @@ def run_api_case(pf, d8, aux, transform=None, latlon=False):
     out["movmed_f32"] = flw.moving_median(aux["data_f32_nd"], 3, nodata=-9999.0)
     out["movmed_f64_so"] = flw.moving_median(aux["data_f64"], 4, restrict_strord=True, strord=out["strord"], nodata=-9999.0)
     out["movmed_f32_sparse"] = flw.moving_median(aux["fill_f32"], 6, nodata=-1.5)
+    # local traces and region post-processing
+    starts, region, blocks, labels = local_inputs(d8, seq, aux)
+    stream = out["uparea_cell"] > max(4, int(0.002 * d8.size))
+    xres = abs(flw.transform[0])
+    for tag in ("down", "up"):
+        for key, kw in (("", {}), ("_mask", dict(mask=stream)), ("_max", dict(max_length=7.5)),
+                        ("_m", dict(mask=stream, max_length=3000.0 * xres * (111e3 if latlon else 1.0) / 1e3, unit="m"))):
+            paths, dist = flw.path(idxs=starts, direction=tag, **kw)
+            out[f"path_{tag}{key}"], out[f"path_{tag}{key}_n"] = _flat_paths(list(paths))
+            out[f"path_{tag}{key}_dist"] = dist
+            out[f"snap_{tag}{key}"], out[f"snap_{tag}{key}_dist"] = flw.snap(idxs=starts, direction=tag, **kw)
+    out["downstream_f32"] = flw.downstream(aux["data_f32"])
+    out["downstream_i64"] = flw.downstream(aux["data_i64"])
+    out["inflow_idxs"] = flw.inflow_idxs(region)
+    out["outflow_idxs"] = flw.outflow_idxs(region)
+    out["interbasin"] = flw.interbasin_mask(region)
+    out["interbasin_stream"] = flw.interbasin_mask(region, stream=stream)
+    out["outlets_basins_lbs"], out["outlets_basins_idxs"] = flw.basin_outlets(out["basins"])
+    out["outlets_blocks_lbs"], out["outlets_blocks_idxs"] = flw.basin_outlets(blocks)
+    out["bounds_basins_lbs"], out["bounds_basins_boxes"], out["bounds_basins_total"] = flw.basin_bounds()
+    out["bounds_labels_lbs"], out["bounds_labels_boxes"], out["bounds_labels_total"] = flw.basin_bounds(basins=labels)
     return out

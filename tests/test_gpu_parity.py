@@ -225,3 +225,44 @@ def test_next_rows_module_level(pfb):
     assert np.array_equal(f.reshape(d8.shape), cs.golden(name, "fill_down_sum_f32"))
     f = core.fillnodata_upstream(ids, seq, aux["fill_f64"].ravel(), np.nan)
     assert np.array_equal(f.reshape(d8.shape), cs.golden(name, "fill_up_f64nan"), equal_nan=True)
+
+
+def test_local_traces_errors_and_snapped_pits(pfb):
+    """pfd_trace refuses start cells outside the raster and traces that never end; add_pits(streams=...) snaps the new
+    pits to the stream mask first (flwdir.py:805-811), like the reference."""
+    z = oracle.synth_elevation(200, 260, seed=12)
+    d8 = oracle.synth_d8(z, sea_level=float(np.quantile(z, 0.05)))
+    flw = pfb.from_array(d8, ftype="d8")
+    with pytest.raises(ValueError, match="outside the raster"):
+        flw.path(idxs=np.array([d8.size + 3]))
+    with pytest.raises(ValueError, match="outside the raster"):
+        flw.snap(idxs=np.array([-5]))
+    with pytest.raises(ValueError, match="Either idxs or xy"):
+        flw.path()
+    with pytest.raises(ValueError, match="Unknown unit"):
+        flw.snap(idxs=np.array([1]), unit="km")
+    # xy start points go through FlwdirRaster.index
+    xs, ys = flw.xy(np.array([5 * 260 + 7, 100 * 260 + 31]))
+    p_xy, d_xy = flw.path(xy=(xs, ys))
+    p_ix, d_ix = flw.path(idxs=np.array([5 * 260 + 7, 100 * 260 + 31]))
+    assert all(np.array_equal(a, b) for a, b in zip(p_xy, p_ix)) and np.array_equal(d_xy, d_ix)
+    # a 2-cell loop without a stop condition does not end
+    loop = np.array([[1, 16, 0]], dtype=np.uint8)
+    flw_loop = pfb.from_array(loop, ftype="d8")
+    with pytest.raises(ValueError, match="does not end"):
+        flw_loop.path(idxs=np.array([0]))
+    paths, dist = flw_loop.path(idxs=np.array([0]), max_length=4)
+    assert paths[0].tolist() == [0, 1, 0, 1, 0] and dist[0] == 4.0
+    # add_pits with a stream mask
+    ids, pits, _ = oracle.core_d8.from_array(d8, dtype=np.int32)
+    seq = oracle.core.idxs_seq(ids, pits)
+    upa = oracle.streams.accuflux(ids, seq, np.ones(d8.size, np.int32), -9999)
+    streams = (upa > 40).reshape(d8.shape)
+    new = seq[:: seq.size // 9][1:6].astype(np.int64)
+    snapped, _ = oracle.core.snap(new, ids, mask=streams.ravel())
+    flw.add_pits(idxs=new, streams=streams)
+    want = np.unique(np.concatenate([pits, snapped.astype(pits.dtype)]))
+    assert np.array_equal(flw.idxs_pit, want)
+    ids2 = ids.copy()
+    ids2[snapped] = snapped
+    assert np.array_equal(flw.idxs_seq, oracle.core.idxs_seq(ids2, want))
