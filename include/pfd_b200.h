@@ -62,7 +62,8 @@ typedef enum pfd_array {
     PFD_ARR_SUBBASIN_OUTLETS = 9, /* idx dtype, n cells selected by the last pfd_subbasins_* / pfd_inflow_idxs / pfd_outflow_idxs /
                                    * pfd_region_outlets call (their index-array return value) */
     PFD_ARR_REGION_LABELS = 10, /* int64, n labels of the last pfd_region_outlets / pfd_region_slices call */
-    PFD_ARR_REGION_SLICES = 11  /* int32 [n][4] (row start, row stop, col start, col stop) of the last pfd_region_slices call */
+    PFD_ARR_REGION_SLICES = 11, /* int32 [n][4] (row start, row stop, col start, col stop) of the last pfd_region_slices call */
+    PFD_ARR_NEXTXY = 12         /* int32 [2][N] -- core_nextxy.to_array (nextx plane, then nexty plane) */
 } pfd_array;
 
 /* ---- library / device ------------------------------------------------------------------------------- */
@@ -101,6 +102,14 @@ int pfd_d8_parse(pfd_handle* h, const uint8_t* d8, int64_t nrow, int64_t ncol, i
 /* core_ldd.from_array (pyflwdir/core_ldd.py:41-66): PCRaster LDD codes 1..9 (5 = pit), 255 = nodata; same kernel. */
 int pfd_ldd_parse(pfd_handle* h, const uint8_t* ldd, int64_t nrow, int64_t ncol, void* idxs_ds_out, int idx_dtype,
                   int64_t* n_valid, int64_t* n_pits);
+
+/* core_nextxy.from_array (pyflwdir/core_nextxy.py:24-67): CaMa-Flood NEXTXY raster = two int32 planes with the one-based
+ * column (nextx) and row (nexty) of the downstream cell; -9 / -10 = pit, -9999 = nodata. check_values != 0: fail with
+ * PFD_ERR_INVALID_D8 unless core_nextxy.isvalid (:86-103) holds. n_outlets = pits whose nextx is -9 / -10
+ * (pyflwdir.py:193). A link that leaves the 8 neighbours of its cell is refused with PFD_ERR_UNSUPPORTED (the device
+ * graph stores the slot of the downstream neighbour in one byte). pfd_fetch(PFD_ARR_NEXTXY) is core_nextxy.to_array. */
+int pfd_nextxy_parse(pfd_handle* h, const int32_t* nextx, const int32_t* nexty, int64_t nrow, int64_t ncol, int check_values,
+                     void* idxs_ds_out, int idx_dtype, int64_t* n_valid, int64_t* n_pits, int64_t* n_outlets);
 
 /*
  * Constructor path FlwdirRaster(idxs_ds, shape, "d8", ...) (pyflwdir/pyflwdir.py:211-273): load a graph from

@@ -479,6 +479,36 @@ def _region_bounds(regions, transform=(1.0, 0.0, 0.0, 0.0, -1.0, 0.0)):
 regions = types.SimpleNamespace(region_outlets=_region_outlets, region_bounds=_region_bounds)
 
 
+# ----------------------------------------------------------------------------- core_nextxy
+def _nextxy_from_array(flwdir, dtype=np.intp):
+    """pyflwdir/core_nextxy.py:24-67"""
+    nextx, nexty = flwdir
+    nextx = np.ascontiguousarray(nextx, dtype=np.int32)
+    nexty = np.ascontiguousarray(nexty, dtype=np.int32)
+    dt = np.dtype(dtype)
+    if dt == np.dtype(np.intp) and dt not in _SFX:  # pragma: no cover
+        dt = np.dtype(np.int64)
+    sfx = _SFX[dt]
+    nrow, ncol = nextx.shape
+    idxs_ds = np.empty(nextx.size, dtype=dt)
+    pits = np.empty(nextx.size, dtype=dt)
+    npits = C.c_int64()
+    n = _fn("orc_nextxy_from_array", sfx, C.c_int64)(_p(nextx), _p(nexty), C.c_int64(nrow), C.c_int64(ncol), _p(idxs_ds), _p(pits),
+                                                     C.byref(npits))
+    return idxs_ds, pits[: npits.value].copy(), int(n)
+
+
+def _nextxy_to_array(idxs_ds, shape, mv=None):
+    """pyflwdir/core_nextxy.py:37-39,70-83"""
+    a, sfx = _idx(idxs_ds)
+    out = np.empty((2, a.size), dtype=np.int32)
+    _fn("orc_nextxy_to_array", sfx)(_p(a), C.c_int64(a.size), C.c_int64(shape[1]), _p(out[0]), _p(out[1]))
+    return out.reshape((2,) + tuple(shape))
+
+
+core_nextxy = types.SimpleNamespace(from_array=_nextxy_from_array, to_array=_nextxy_to_array)
+
+
 # ----------------------------------------------------------------------------- streams
 def _nodata_args(nodata):
     is_int = isinstance(nodata, (int, np.integer)) and not isinstance(nodata, (bool, np.bool_))

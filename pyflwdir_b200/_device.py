@@ -78,6 +78,23 @@ class DeviceGraph:
         self._set_shape(nrow, ncol, nv.value, npit.value, nout.value)
         return idxs
 
+    def parse_nextxy(self, nextx, nexty, idx_dtype=None, want_idxs=False, check=True):
+        """core_nextxy.from_array on the device. Two 2-D int32 planes (host) -> optional idxs_ds."""
+        nextx = np.ascontiguousarray(nextx, dtype=np.int32)
+        nexty = np.ascontiguousarray(nexty, dtype=np.int32)
+        if nextx.ndim != 2 or nextx.shape != nexty.shape:
+            raise ValueError("NEXTXY planes must be two 2-D arrays of the same shape")
+        nrow, ncol = nextx.shape
+        nv, npit, nout = C.c_int64(), C.c_int64(), C.c_int64()
+        idxs, code = None, 0
+        if want_idxs:
+            idxs = _lib.out_array(nextx.size, idx_dtype)
+            code = _lib.dtype_code(idx_dtype)
+        self._ck(self._l.pfd_nextxy_parse(self._h, _lib.ptr(nextx), _lib.ptr(nexty), nrow, ncol, 1 if check else 0, _lib.ptr(idxs),
+                                          code, C.byref(nv), C.byref(npit), C.byref(nout)))
+        self._set_shape(nrow, ncol, nv.value, npit.value, nout.value)
+        return idxs
+
     def flow_all(self, d8, idx_dtype=np.int32, resident=True):
         """pfd_d8_flow_all: parse + rank + upstream_area("cell") + basins() in one call. With `resident` the raster
         and the four outputs live in device buffers for the call (the fused-parse path of the library); otherwise
@@ -155,6 +172,8 @@ class DeviceGraph:
             out = _lib.out_array(self.size, np.int8)
         elif which in (_lib.ARR_D8, _lib.ARR_LDD):
             out = _lib.out_array(self.size, np.uint8)
+        elif which == _lib.ARR_NEXTXY:
+            out = _lib.out_array(2 * self.size, np.int32)
         elif which == _lib.ARR_LEVEL_OFFSETS:
             if self.nlevels is None:
                 self.order()

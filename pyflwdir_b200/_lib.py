@@ -24,7 +24,7 @@ DTYPES = {
 
 # pfd_array
 ARR_IDXS_DS, ARR_PITS, ARR_PIT_IS_OUTLET, ARR_SEQ, ARR_RANK, ARR_N_UPSTREAM, ARR_D8, ARR_LEVEL_OFFSETS, ARR_LDD, \
-    ARR_SUBBASIN_OUTLETS, ARR_REGION_LABELS, ARR_REGION_SLICES = range(12)
+    ARR_SUBBASIN_OUTLETS, ARR_REGION_LABELS, ARR_REGION_SLICES, ARR_NEXTXY = range(13)
 
 # every symbol include/pfd_b200.h declares: name -> (restype, argtypes)
 _vp, _i64, _int, _u32 = C.c_void_p, C.c_int64, C.c_int, C.c_uint32
@@ -44,6 +44,7 @@ SYMBOLS = {
     "pfd_synchronize": (_int, [_vp]),
     "pfd_d8_parse": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _int, _pi64, _pi64, _pi64]),
     "pfd_ldd_parse": (_int, [_vp, _vp, _i64, _i64, _vp, _int, _pi64, _pi64]),
+    "pfd_nextxy_parse": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _vp, _int, _pi64, _pi64, _pi64]),
     "pfd_load_idxs_ds": (_int, [_vp, _vp, _int, _i64, _i64, _pi64, _pi64]),
     "pfd_order": (_int, [_vp, _pi64, _pi64]),
     "pfd_fetch": (_int, [_vp, _int, _vp, _int]),

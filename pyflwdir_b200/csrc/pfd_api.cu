@@ -238,6 +238,44 @@ static void invalidate(pfd_handle* h) {
     h->n_valid = h->n_pits = h->n_outlets = h->nnodes = h->nlevels = h->n_sub = 0;
 }
 
+// pit list in ascending index order + n_valid / n_pits / n_outlets from the dir bytes; fails on the parse flag
+static int pits_stage(pfd_handle* h, int64_t npad, int ftype) {
+    const int64_t nblk = npad / PC_CHUNK;
+    {
+        StageTimer t(h, PFD_STAGE_PITS);
+        PFD_TRY(pfd_reserve(h, h->blk_counts, (size_t)nblk * sizeof(uint32_t)));
+        PFD_TRY(pfd_reserve(h, h->blk_offsets, (size_t)(nblk + 1) * sizeof(unsigned long long)));
+        pit_count_kernel<<<(unsigned)nblk, 256, 0, h->stream>>>((const uint8_t*)h->dir.p, (uint32_t*)h->blk_counts.p,
+                                                               (unsigned long long*)h->counters.p);
+        PFD_LAUNCH_CHECK(h);
+        scan_counts_kernel<<<1, 1024, 0, h->stream>>>((const uint32_t*)h->blk_counts.p, nblk,
+                                                     (unsigned long long*)h->blk_offsets.p);
+        PFD_LAUNCH_CHECK(h);
+        unsigned long long hc[4];
+        PFD_CUDA(h, cudaMemcpyAsync(hc, h->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, h->stream));
+        PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+        const unsigned int flags = (unsigned int)hc[3];
+        if (flags & 1u) {
+            invalidate(h);
+            return pfd_fail(h, PFD_ERR_INVALID_D8, ftype == 0 ? "raster holds values outside the D8 code set {0,1,2,4,8,16,32,64,128,247,255}"
+                                                   : ftype == 1 ? "raster holds values outside the LDD code set {1..9,255}"
+                                                                : "NEXTXY data is invalid (core_nextxy.isvalid)");
+        }
+        h->n_valid = (int64_t)hc[0];
+        h->n_pits = (int64_t)hc[1];
+        h->n_outlets = (int64_t)hc[2];
+        PFD_TRY(pfd_reserve(h, h->pits, (size_t)std::max<int64_t>(h->n_pits, 1) * sizeof(cell_t)));
+        PFD_TRY(pfd_reserve(h, h->pit_outlet, (size_t)std::max<int64_t>(h->n_pits, 1)));
+        if (h->n_pits > 0) {
+            pit_scatter_kernel<<<(unsigned)nblk, 256, 0, h->stream>>>((const uint8_t*)h->dir.p,
+                                                                     (const unsigned long long*)h->blk_offsets.p,
+                                                                     (cell_t*)h->pits.p, (uint8_t*)h->pit_outlet.p);
+            PFD_LAUNCH_CHECK(h);
+        }
+    }
+    return PFD_OK;
+}
+
 // d8_dev: device pointer. idxs_dev: device pointer or null.
 // d8_dev holds halo_top + nrow + halo_bot rows (halo rows only feed the forced-pit test of the block's edge rows);
 // idxs_dev (optional) receives the nrow owned rows as global linear indices (first owned row = glob_row0).
@@ -283,38 +321,7 @@ static int parse_device(pfd_handle* h, const uint8_t* d8_dev, int64_t nrow_owned
         if (halo_top) PFD_CUDA(h, cudaMemsetAsync(h->dir.p, 0xFF, (size_t)ncol, h->stream));
         if (halo_bot) PFD_CUDA(h, cudaMemsetAsync((uint8_t*)h->dir.p + (n - ncol), 0xFF, (size_t)ncol, h->stream));
     }
-    const int64_t nblk = npad / PC_CHUNK;
-    {
-        StageTimer t(h, PFD_STAGE_PITS);
-        PFD_TRY(pfd_reserve(h, h->blk_counts, (size_t)nblk * sizeof(uint32_t)));
-        PFD_TRY(pfd_reserve(h, h->blk_offsets, (size_t)(nblk + 1) * sizeof(unsigned long long)));
-        pit_count_kernel<<<(unsigned)nblk, 256, 0, h->stream>>>((const uint8_t*)h->dir.p, (uint32_t*)h->blk_counts.p,
-                                                               (unsigned long long*)h->counters.p);
-        PFD_LAUNCH_CHECK(h);
-        scan_counts_kernel<<<1, 1024, 0, h->stream>>>((const uint32_t*)h->blk_counts.p, nblk,
-                                                     (unsigned long long*)h->blk_offsets.p);
-        PFD_LAUNCH_CHECK(h);
-        unsigned long long hc[4];
-        PFD_CUDA(h, cudaMemcpyAsync(hc, h->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, h->stream));
-        PFD_CUDA(h, cudaStreamSynchronize(h->stream));
-        const unsigned int flags = (unsigned int)hc[3];
-        if (flags & 1u) {
-            invalidate(h);
-            return pfd_fail(h, PFD_ERR_INVALID_D8, ftype == 0 ? "raster holds values outside the D8 code set {0,1,2,4,8,16,32,64,128,247,255}"
-                                                              : "raster holds values outside the LDD code set {1..9,255}");
-        }
-        h->n_valid = (int64_t)hc[0];
-        h->n_pits = (int64_t)hc[1];
-        h->n_outlets = (int64_t)hc[2];
-        PFD_TRY(pfd_reserve(h, h->pits, (size_t)std::max<int64_t>(h->n_pits, 1) * sizeof(cell_t)));
-        PFD_TRY(pfd_reserve(h, h->pit_outlet, (size_t)std::max<int64_t>(h->n_pits, 1)));
-        if (h->n_pits > 0) {
-            pit_scatter_kernel<<<(unsigned)nblk, 256, 0, h->stream>>>((const uint8_t*)h->dir.p,
-                                                                     (const unsigned long long*)h->blk_offsets.p,
-                                                                     (cell_t*)h->pits.p, (uint8_t*)h->pit_outlet.p);
-            PFD_LAUNCH_CHECK(h);
-        }
-    }
+    PFD_TRY(pits_stage(h, npad, ftype));
     h->nrow = nrow_owned;
     h->ncol = ncol;
     h->n = nrow_owned * ncol;
@@ -385,6 +392,73 @@ extern "C" int pfd_ldd_parse(pfd_handle* h, const uint8_t* ldd, int64_t nrow, in
     stage_collect(h);
     if (n_valid) *n_valid = h->n_valid;
     if (n_pits) *n_pits = h->n_pits;
+    return PFD_OK;
+}
+
+// core_nextxy.from_array (pyflwdir/core_nextxy.py:24-67): CaMa-Flood NEXTXY rasters. The device graph stores one byte per
+// cell (slot of the downstream neighbour), so every link has to stay inside the 8-neighbourhood; a raster with longer
+// links (e.g. across the date line) is refused with PFD_ERR_UNSUPPORTED.
+extern "C" int pfd_nextxy_parse(pfd_handle* h, const int32_t* nextx, const int32_t* nexty, int64_t nrow, int64_t ncol, int check_values,
+                                void* idxs_ds_out, int idx_dtype, int64_t* n_valid, int64_t* n_pits, int64_t* n_outlets) {
+    PFD_TRY(check_handle(h));
+    stage_reset(h);
+    PFD_TRY(check_shape(h, nrow, ncol, "pfd_nextxy_parse"));
+    if (!nextx || !nexty) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_nextxy_parse: null array");
+    if (idxs_ds_out && idx_dtype != PFD_I32 && idx_dtype != PFD_U32 && idx_dtype != PFD_I64)
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_nextxy_parse: idx_dtype must be int32, uint32 or int64");
+    const int64_t n = nrow * ncol;
+    if (idxs_ds_out && idx_dtype == PFD_I32 && n >= 2147483647ll)
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_nextxy_parse: int32 indices cannot address this raster");
+    invalidate(h);
+    const void *x_dev = nullptr, *y_dev = nullptr;
+    PFD_TRY(pfd_stage_in(h, nextx, (size_t)n * 4, 0, &x_dev));
+    PFD_TRY(pfd_stage_in(h, nexty, (size_t)n * 4, 2, &y_dev));
+    void* idxs_dev = nullptr;
+    const size_t ibytes = (size_t)n * pfd_dtype_size(idx_dtype);
+    if (idxs_ds_out) PFD_TRY(pfd_stage_out(h, idxs_ds_out, ibytes, 1, &idxs_dev));
+    const int64_t npad = (n + PC_CHUNK - 1) / PC_CHUNK * PC_CHUNK;
+    PFD_TRY(pfd_reserve(h, h->dir, (size_t)npad));
+    PFD_TRY(pfd_reserve(h, h->upmask, (size_t)npad));
+    PFD_TRY(pfd_reserve(h, h->counters, 8 * sizeof(unsigned long long)));
+    PFD_CUDA(h, cudaMemsetAsync(h->counters.p, 0, 8 * sizeof(unsigned long long), h->stream));
+    if (npad > n) PFD_CUDA(h, cudaMemsetAsync((uint8_t*)h->dir.p + n, 0xFF, (size_t)(npad - n), h->stream));
+    unsigned int* flag = reinterpret_cast<unsigned int*>((unsigned long long*)h->counters.p + 3);
+    unsigned int* flag2 = reinterpret_cast<unsigned int*>((unsigned long long*)h->counters.p + 4);
+    {
+        StageTimer t(h, PFD_STAGE_PARSE);
+        const int g = grid_for(n, 256, 2);
+        const int idxmode = !idxs_dev ? 0 : (idx_dtype == PFD_I64 ? 2 : 1);
+#define LAUNCH_NX(M)                                                                                                    \
+    nextxy_parse_kernel<M><<<g, 256, 0, h->stream>>>((const int32_t*)x_dev, (const int32_t*)y_dev, nrow, ncol, check_values, \
+                                                     (uint8_t*)h->dir.p, idxs_dev, flag, flag2)
+        if (idxmode == 0) LAUNCH_NX(0);
+        else if (idxmode == 1) LAUNCH_NX(1);
+        else LAUNCH_NX(2);
+#undef LAUNCH_NX
+        PFD_LAUNCH_CHECK(h);
+    }
+    PFD_TRY(pits_stage(h, npad, 2));
+    unsigned int hflag2 = 0;
+    PFD_CUDA(h, cudaMemcpyAsync(&hflag2, flag2, sizeof(hflag2), cudaMemcpyDeviceToHost, h->stream));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (hflag2 & 2u) {
+        invalidate(h);
+        return pfd_fail(h, PFD_ERR_UNSUPPORTED, "pfd_nextxy_parse: a downstream link leaves the 8 neighbours of its cell (or points at the cell itself)");
+    }
+    h->nrow = nrow;
+    h->ncol = ncol;
+    h->n = n;
+    h->dir_off = 0;
+    h->tiled = false;
+    h->parsed = true;
+    h->have_upmask = false;  // derived from dir on demand (ensure_upmask)
+    h->ordered = h->have_rank = h->have_basins = h->have_uparea = false;
+    if (idxs_ds_out) PFD_TRY(pfd_finish_out(h, idxs_ds_out, idxs_dev, ibytes));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    if (n_valid) *n_valid = h->n_valid;
+    if (n_pits) *n_pits = h->n_pits;
+    if (n_outlets) *n_outlets = h->n_outlets;
     return PFD_OK;
 }
 
@@ -1284,6 +1358,14 @@ extern "C" int pfd_fetch(pfd_handle* h, int which, void* out, int idx_dtype) {
         else dir_to_codes_kernel<1><<<grid_for(n, 256, 4), 256, 0, h->stream>>>((const uint8_t*)h->dir.p, n, (uint8_t*)dev);
         PFD_LAUNCH_CHECK(h);
         PFD_TRY(pfd_finish_out(h, out, dev, (size_t)n));
+        break;
+    }
+    case PFD_ARR_NEXTXY: {
+        void* dev = nullptr;
+        PFD_TRY(pfd_stage_out(h, out, (size_t)n * 8, 2, &dev));
+        dir_to_nextxy_kernel<<<grid_for(n, 256, 4), 256, 0, h->stream>>>((const uint8_t*)h->dir.p, n, h->ncol, (int32_t*)dev, (int32_t*)dev + n);
+        PFD_LAUNCH_CHECK(h);
+        PFD_TRY(pfd_finish_out(h, out, dev, (size_t)n * 8));
         break;
     }
     case PFD_ARR_SUBBASIN_OUTLETS:

@@ -70,7 +70,7 @@ __global__ void trace_kernel(const uint8_t* __restrict__ dir, const IDX* __restr
             if (has_max && __dadd_rn(dist, d) > max_length) break;
             dist = __dadd_rn(dist, d);
             cur = nx;
-            if (cnt > n) {
+            if (has_max ? !(d > 0.0) : (cnt > n)) {  // more cells than the raster holds (or hops of no length): a loop
                 atomicOr(flag, 16u);
                 break;
             }

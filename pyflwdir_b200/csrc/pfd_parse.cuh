@@ -339,3 +339,71 @@ __global__ void __launch_bounds__(256) pit_scatter_kernel(const uint8_t* __restr
     }
     (void)total;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// core_nextxy.from_array / to_array (pyflwdir/core_nextxy.py:24-83): one-based (column, row) of the downstream cell in
+// two int32 planes; -9 / -10 = pit (river mouth / inland), -9999 = nodata. Element-wise; the only gather is the
+// "downstream cell is nodata" test. flag bit 1: core_nextxy.isvalid (:86-103) fails (only when check != 0);
+// flag2 bit 2: a link that the 1-byte dir graph cannot hold.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool nextxy_ispit(int32_t v) { return v == -9 || v == -10; }
+
+template <int IDXMODE>
+__global__ void nextxy_parse_kernel(const int32_t* __restrict__ nextx, const int32_t* __restrict__ nexty, int64_t nrow, int64_t ncol,
+                                    int check, uint8_t* __restrict__ dir, void* __restrict__ idxs, unsigned int* __restrict__ flag,
+                                    unsigned int* __restrict__ flag2) {
+    const int64_t n = nrow * ncol;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t x = nextx[i], y = nexty[i];
+        if (check) {
+            const bool m = x == -9999 || nextxy_ispit(x);
+            if (m ? (x != y) : (x < 0)) atomicOr(flag, 1u);
+        }
+        uint32_t d;
+        int64_t ds = -1;
+        if (x == -9999) {
+            d = PFD_DIR_NODATA;
+        } else {
+            const bool pit = nextxy_ispit(x) || nextxy_ispit(y);
+            const int64_t r_ds = (int64_t)y - 1, c_ds = (int64_t)x - 1;
+            const bool outside = r_ds >= nrow || c_ds >= ncol || r_ds < 0 || c_ds < 0;
+            const int64_t ids = c_ds + r_ds * ncol;
+            if (pit || outside || nextx[ids] == -9999) {
+                d = nextxy_ispit(x) ? PFD_DIR_PIT : PFD_DIR_FPIT;  // outlet <=> nextx in (-9, -10) (pyflwdir.py:193)
+                ds = i;
+            } else {
+                const int64_t r = i / ncol, c = i - r * ncol;
+                const int64_t dr = r_ds - r, dc = c_ds - c;
+                if (dr < -1 || dr > 1 || dc < -1 || dc > 1 || (dr == 0 && dc == 0)) {
+                    atomicOr(flag2, 2u);
+                    d = PFD_DIR_FPIT;
+                    ds = i;
+                } else {
+                    const int k3 = (int)(dr + 1) * 3 + (int)(dc + 1);
+                    d = (uint32_t)(k3 < 4 ? k3 : k3 - 1);
+                    ds = ids;
+                }
+            }
+        }
+        dir[i] = (uint8_t)d;
+        if (IDXMODE == 1) ((uint32_t*)idxs)[i] = (uint32_t)ds;
+        else if (IDXMODE == 2) ((int64_t*)idxs)[i] = ds;
+    }
+}
+
+__global__ void dir_to_nextxy_kernel(const uint8_t* __restrict__ dir, int64_t n, int64_t ncol, int32_t* __restrict__ nextx,
+                                     int32_t* __restrict__ nexty) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t d = dir[i];
+        int32_t x = -9999, y = -9999;
+        if (d < 8u) {
+            const int64_t ds = i + pfd_slot_off((int)d, ncol);
+            x = (int32_t)(ds % ncol + 1);
+            y = (int32_t)(ds / ncol + 1);
+        } else if (d != PFD_DIR_NODATA) {
+            x = y = -9;  // core_nextxy._pv[0] for every pit
+        }
+        nextx[i] = x;
+        nexty[i] = y;
+    }
+}

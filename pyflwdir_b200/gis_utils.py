@@ -71,6 +71,11 @@ class Affine(_AffineBase):
 IDENTITY = Affine(1.0, 0.0, 0.0, 0.0, -1.0, 0.0)
 
 
+def transform_from_bounds(west, south, east, north, width, height):
+    """Affine transformation of a georeferenced raster given its bounds and its size in pixels; gis_utils.py:162-170."""
+    return Affine.translation(west, north) * Affine.scale((east - west) / width, (south - north) / height)
+
+
 def affine_to_coords(affine, shape):
     """Pixel-centre x (per column) and y (per row) coordinates; gis_utils.py:340-358."""
     height, width = shape

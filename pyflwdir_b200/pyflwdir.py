@@ -3,21 +3,21 @@
 :211-273, idxs_seq :292-297, set_transform :318-337, to_array :341-360, basins :564-599, upstream_area :770-801,
 hand :1485-1511, _check_data :1548-1559) with every kernel running on the GPU.
 
-The D8 and PCRaster LDD flow-direction types are accelerated (same parse kernel, different code table);
-"nextxy" rasters raise NotImplementedError.
+The D8 and PCRaster LDD flow-direction types share one parse kernel (different code table); CaMa-Flood "nextxy"
+rasters are parsed by an element-wise kernel as long as every link stays inside the 8-neighbourhood.
 """
 import pickle
 
 import numpy as np
 
-from . import _device, _lib
+from . import _device, _lib, core_nextxy
 from . import gis_utils as gis
 from .flwdir import Flwdir, _not_in_scope
 from .gis_utils import Affine
 
 __all__ = ["FlwdirRaster", "from_array"]
 
-FTYPES = ("d8", "ldd", "nextxy")  # pyflwdir.py:26-30; "d8" and "ldd" are implemented here
+FTYPES = ("d8", "ldd", "nextxy")  # pyflwdir.py:26-30
 _MV = {"d8": np.uint8(247), "ldd": np.uint8(255)}  # core_d8.py:17, core_ldd.py:15
 
 
@@ -43,35 +43,60 @@ def from_array(data, ftype="infer", check_ftype=True, mask=None, transform=gis.I
     `idxs_seq`, `rank` are materialised on the host only when read.
     """
     infer = ftype == "infer"
+    is_xy = core_nextxy.isformat(data)
     if infer:
-        # the reference tries d8, ldd, nextxy in that order (pyflwdir.py:39-48); d8 and ldd exist here
-        if not _is_d8_candidate(data):
+        # the reference tries d8, ldd, nextxy in that order (pyflwdir.py:39-48)
+        if not (_is_d8_candidate(data) or is_xy):
             raise ValueError("The flow direction type could not be inferred.")
         check_ftype = False
-        candidates = ["d8", "ldd"]
+        candidates = ["nextxy"] if is_xy else ["d8", "ldd"]
     else:
         candidates = [ftype]
-        if ftype == "nextxy":
-            shape, ndim = data[0].shape, data[0].ndim
-    if ftype != "nextxy":
+    if ftype == "nextxy" or (infer and is_xy):
+        shape, ndim = data[0].shape, data[0].ndim
+    else:
         ndim, shape = data.ndim, data.shape
     if ndim != 2:
         raise ValueError("The FlwdirRaster should be 2 dimensional")
     if not infer and ftype not in FTYPES:
         ftypes_str = '" ,"'.join(FTYPES)
         raise ValueError(f'Unknown flow direction type: "{ftype}", select from {ftypes_str}')
-    if ftype == "nextxy":
-        raise NotImplementedError('ftype "nextxy" is not accelerated by pyflwdir_b200 (D8 and LDD only)')
     invalid_msg = f'The flow direction data with type "{ftype}" is invalid.'
-    if not _is_d8_candidate(data):
+    dtype = _get_idxs_dtype(shape[0] * shape[1])
+    dev = None
+    if candidates == ["nextxy"]:
+        if not is_xy:
+            if check_ftype:
+                raise ValueError(invalid_msg)
+            raise TypeError("NEXTXY flwdir data not understood")
+        nextx, nexty = data
+        if infer or check_ftype:  # core_nextxy.isvalid (core_nextxy.py:86-103): the value tests run in the parse kernel
+            ok = (isinstance(nextx, np.ndarray) and isinstance(nexty, np.ndarray) and nextx.dtype == "int32"
+                  and nexty.dtype == "int32" and nextx.shape == nexty.shape)
+            if not ok:
+                raise ValueError("The flow direction type could not be inferred." if infer else invalid_msg)
+        if mask is not None:
+            if mask.shape != np.shape(data):  # the reference compares with the [2, nrow, ncol] stack (pyflwdir.py:185-188)
+                raise ValueError('"mask" shape does not match with data shape')
+            nextx, nexty = np.where(mask != 0, np.asarray(data), core_nextxy._mv)
+        dev = _device.DeviceGraph(device)
+        try:
+            dev.parse_nextxy(nextx, nexty, check=infer or check_ftype)
+        except ValueError as err:
+            if getattr(err, "status", None) != _lib.ERR_INVALID_D8:
+                raise
+            raise ValueError("The flow direction type could not be inferred." if infer else invalid_msg) from None
+        ftype = "nextxy"
+        candidates = []
+    elif not _is_d8_candidate(data):
         if check_ftype:
             raise ValueError(invalid_msg)
         raise ValueError("flow direction data must be a 2-D uint8 array")
-    if mask is not None and mask.shape != data.shape:
+    elif mask is not None and mask.shape != data.shape:
         raise ValueError('"mask" shape does not match with data shape')
 
-    dtype = _get_idxs_dtype(shape[0] * shape[1])
-    dev = _device.DeviceGraph(device)
+    if dev is None:
+        dev = _device.DeviceGraph(device)
     for k, ft in enumerate(candidates):
         try:
             # illegal codes are refused even with check_ftype=False (the reference would mis-parse them)
@@ -110,8 +135,6 @@ class FlwdirRaster(Flwdir):
         if ftype not in FTYPES:
             ftypes_str = '" ,"'.join(FTYPES)
             raise ValueError(f'Unknown flow direction type: "{ftype}", select from {ftypes_str}')
-        if ftype == "nextxy":
-            raise NotImplementedError('ftype "nextxy" is not accelerated by pyflwdir_b200 (D8 and LDD only)')
         self.ftype = ftype
         if len(shape) != 2 or shape[0] * shape[1] != self.size:
             raise ValueError(f"Invalid FlwdirRaster: shape {shape} does not match size {self.size}")
@@ -145,6 +168,15 @@ class FlwdirRaster(Flwdir):
     @property
     def ncells(self):
         return self.nnodes
+
+    @property
+    def idxs_seq(self):
+        """Linear indices of valid cells ordered from down- to upstream (pyflwdir.py:292-297: "walk", except for
+        nextxy rasters, which the reference orders with np.argsort of the rank; ties inside a rank level then follow
+        numpy's unstable sort. The device sweeps always run over the "walk" sequence.)"""
+        if self._seq is None:
+            self.order_cells(method="walk" if self.ftype != "nextxy" else "sort")
+        return self._seq
 
     @property
     def area(self):
@@ -181,8 +213,8 @@ class FlwdirRaster(Flwdir):
             return self._dev.fetch(_lib.ARR_D8).reshape(self.shape)
         if ftype == "ldd":
             return self._dev.fetch(_lib.ARR_LDD).reshape(self.shape)
-        if ftype in FTYPES:
-            raise NotImplementedError(f'to_array(ftype="{ftype}") is outside the accelerated hot path')
+        if ftype == "nextxy":
+            return self._dev.fetch(_lib.ARR_NEXTXY).reshape((2,) + self.shape)
         raise ValueError(f'ftype "{ftype}" unknown')
 
     @staticmethod

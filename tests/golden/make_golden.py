@@ -89,6 +89,28 @@ def main():
                      d8_to_ldd=ldd, ldd_to_d8=pf.ldd_to_d8(ldd).astype(np.uint8)).items():
         small_outputs[f"ldd_flwdir1/{k}"] = np.asarray(v)
 
+    # --- CaMa-Flood NEXTXY (core_nextxy.py): the 160x200 fixture written with the reference's own to_array, two river
+    #     mouths turned into inland pits (-10), one cell with a pit in the nexty plane only, a masked-out corner
+    flw_d8 = pf.from_array(d8_large, ftype="d8")
+    nxy = flw_d8.to_array("nextxy").astype(np.int32)
+    pit_cells = flw_d8.idxs_pit
+    for idx in pit_cells[:2]:
+        nxy[:, idx // d8_large.shape[1], idx % d8_large.shape[1]] = -10
+    free = np.flatnonzero((nxy[0].ravel() > 0))[37]
+    nxy[1, free // d8_large.shape[1], free % d8_large.shape[1]] = -9
+    nxy[:, :9, :13] = -9999
+    flw_xy = pf.from_array(nxy)  # ftype inferred
+    assert flw_xy.ftype == "nextxy"
+    small_inputs["nextxy_flwdir1/nextxy"] = nxy
+    mask_xy = np.ones(nxy.shape, dtype=np.uint8)
+    mask_xy[:, 100:, 150:] = 0
+    flw_xy_m = pf.from_array(nxy, ftype="nextxy", mask=mask_xy)
+    for k, v in dict(idxs_ds=flw_xy.idxs_ds, idxs_pit=flw_xy.idxs_pit, idxs_outlet=flw_xy.idxs_outlet, idxs_seq=flw_xy.idxs_seq,
+                     to_array=flw_xy.to_array(), to_array_d8=flw_xy.to_array("d8"), uparea_cell=flw_xy.upstream_area(),
+                     basins=flw_xy.basins(), masked_idxs_ds=flw_xy_m.idxs_ds, masked_idxs_pit=flw_xy_m.idxs_pit,
+                     d8_to_nextxy=flw_d8.to_array("nextxy")).items():
+        small_outputs[f"nextxy_flwdir1/{k}"] = np.asarray(v)
+
     # --- drdc over all 256 codes (core_d8.py:22-39), including the illegal ones
     drdc = np.array([rd8.drdc(np.uint8(i)) for i in range(256)], dtype=np.int8)
     small_outputs["drdc_table"] = drdc

@@ -266,3 +266,56 @@ def test_local_traces_errors_and_snapped_pits(pfb):
     ids2 = ids.copy()
     ids2[snapped] = snapped
     assert np.array_equal(flw.idxs_seq, oracle.core.idxs_seq(ids2, want))
+
+
+def test_nextxy(pfb):
+    """CaMa-Flood NEXTXY codec (core_nextxy.py) against the reference's golden outputs: inferred ftype, -10 pits, a pit in
+    the nexty plane only, mask=, to_array in all three formats, and the refusal of links longer than one cell."""
+    from pyflwdir_b200 import core_nextxy
+
+    s = cs.small()
+    nxy = s["in/nextxy_flwdir1/nextxy"]
+    shape = nxy.shape[1:]
+    for data in (nxy, (nxy[0], nxy[1])):
+        flw = pfb.from_array(data)  # ftype inferred
+        assert flw.ftype == "nextxy" and flw.shape == shape
+        # idxs_seq of a nextxy raster = np.argsort(rank) in the reference: ties follow numpy's unstable sort
+        seq, want = flw.idxs_seq, s["out/nextxy_flwdir1/idxs_seq"]
+        rank = flw.rank.ravel()
+        assert seq.dtype == want.dtype and np.array_equal(np.sort(seq), np.sort(want)) and np.all(np.diff(rank[seq]) >= 0)
+        for key, got in dict(idxs_ds=flw.idxs_ds, idxs_pit=flw.idxs_pit, idxs_outlet=flw.idxs_outlet,
+                             to_array=flw.to_array(), to_array_d8=flw.to_array("d8"), uparea_cell=flw.upstream_area(),
+                             basins=flw.basins()).items():
+            want = s[f"out/nextxy_flwdir1/{key}"]
+            assert np.asarray(got).dtype == want.dtype, key
+            assert np.array_equal(got, want), key
+    mask = np.ones(nxy.shape, dtype=np.uint8)
+    mask[:, 100:, 150:] = 0
+    flw_m = pfb.from_array(nxy, ftype="nextxy", mask=mask)
+    assert np.array_equal(flw_m.idxs_ds, s["out/nextxy_flwdir1/masked_idxs_ds"])
+    assert np.array_equal(flw_m.idxs_pit, s["out/nextxy_flwdir1/masked_idxs_pit"])
+    d8 = cs.case_d8("flwdir1_asc")
+    assert np.array_equal(pfb.from_array(d8, ftype="d8").to_array("nextxy"), s["out/nextxy_flwdir1/d8_to_nextxy"])
+    # module-level mirror
+    ids, pits, n = core_nextxy.from_array(nxy, dtype=np.uint32)
+    assert ids.dtype == np.uint32 and np.array_equal(ids.astype(np.int64), s["out/nextxy_flwdir1/idxs_ds"].astype(np.uint32).astype(np.int64))
+    assert np.array_equal(core_nextxy.to_array(s["out/nextxy_flwdir1/idxs_ds"], shape), s["out/nextxy_flwdir1/to_array"])
+    assert core_nextxy.isvalid(nxy) and not core_nextxy.isvalid(nxy.astype(np.int64))
+    bad = nxy.copy()
+    bad[0, 50, 50] = -3
+    assert not core_nextxy.isvalid(bad)
+    with pytest.raises(ValueError, match='type "nextxy" is invalid'):
+        pfb.from_array(bad, ftype="nextxy")
+    far = nxy.copy()
+    far[:, 60, 60] = (150, 120)  # a link across the raster: valid NEXTXY, but not representable here
+    with pytest.raises(ValueError, match="leaves the 8 neighbours"):
+        pfb.from_array(far, ftype="nextxy")
+    # read_nextxy: CaMa-Flood binary layout
+    import os
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as tmp:
+        fn = os.path.join(tmp, "nextxy.bin")
+        nxy.tofile(fn)
+        data, transform = pfb.read_nextxy(fn, shape[0], shape[1], [0.0, -10.0, 20.0, 6.0])
+        assert np.array_equal(data, nxy) and tuple(transform)[:6] == (0.1, 0.0, 0.0, 0.0, -0.1, 6.0)

@@ -31,8 +31,10 @@ def test_from_array_input_errors():
         pfb.from_array(np.zeros((3, 3), dtype=np.uint8), ftype="d16")
     with pytest.raises(ValueError, match='"mask" shape does not match'):
         pfb.from_array(np.zeros((3, 3), dtype=np.uint8), ftype="d8", mask=np.ones((2, 2)))
-    with pytest.raises(NotImplementedError):
-        pfb.from_array((np.ones((3, 3), dtype=np.int32), np.ones((3, 3), dtype=np.int32)), ftype="nextxy")
+    with pytest.raises(ValueError, match='type "nextxy" is invalid'):
+        pfb.from_array((np.ones((3, 3), dtype=np.int64), np.ones((3, 3), dtype=np.int32)), ftype="nextxy")
+    with pytest.raises(ValueError, match="should be 2 dimensional"):  # data[0] of a 2-D raster is a row (pyflwdir.py:168-170)
+        pfb.from_array(np.zeros((3, 3), dtype=np.uint8), ftype="nextxy")
     with pytest.raises(ValueError, match='type "ldd" is invalid'):
         pfb.from_array(np.zeros((3, 3), dtype=np.int16), ftype="ldd")
 

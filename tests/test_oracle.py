@@ -104,3 +104,23 @@ def test_oracle_ldd_golden(oracle_lib):
     assert np.array_equal(pits, cs.small()["out/ldd_flwdir1/idxs_pit"])
     assert np.array_equal(oracle.core_ldd.to_array(ids, ldd.shape), cs.small()["out/ldd_flwdir1/to_array"])
     assert np.array_equal(oracle.core_d8.to_array(ids, ldd.shape), cs.small()["out/ldd_flwdir1/to_array_d8"])
+
+
+def test_oracle_nextxy_golden():
+    """core_nextxy.from_array / to_array against the reference's outputs (incl. -10 pits and a nexty-only pit)."""
+    s = cs.small()
+    nxy = s["in/nextxy_flwdir1/nextxy"]
+    ids, pits, n = oracle.core_nextxy.from_array(nxy, dtype=np.int32)
+    assert np.array_equal(ids, s["out/nextxy_flwdir1/idxs_ds"]) and ids.dtype == s["out/nextxy_flwdir1/idxs_ds"].dtype
+    assert np.array_equal(pits, s["out/nextxy_flwdir1/idxs_pit"])
+    assert np.array_equal(oracle.core_nextxy.to_array(ids, nxy.shape[1:]), s["out/nextxy_flwdir1/to_array"])
+    assert np.array_equal(oracle.core_d8.to_array(ids, nxy.shape[1:]), s["out/nextxy_flwdir1/to_array_d8"])
+    # the reference orders nextxy rasters with np.argsort(rank) (pyflwdir.py:296): same cells, rank-sorted, but the
+    # order inside a rank level is numpy's unstable sort, not core.idxs_seq
+    seq, want = oracle.core.idxs_seq(ids, pits), s["out/nextxy_flwdir1/idxs_seq"]
+    rank = oracle.core.rank(ids)[0]
+    assert np.array_equal(np.sort(seq), np.sort(want)) and np.all(np.diff(rank[want]) >= 0) and np.all(np.diff(rank[seq]) >= 0)
+    masked = nxy.copy()
+    masked[:, 100:, 150:] = -9999
+    ids_m, pits_m, _ = oracle.core_nextxy.from_array(masked, dtype=np.int32)
+    assert np.array_equal(ids_m, s["out/nextxy_flwdir1/masked_idxs_ds"]) and np.array_equal(pits_m, s["out/nextxy_flwdir1/masked_idxs_pit"])
