@@ -380,7 +380,37 @@ def extras_widened(w, size, seed, cpu_size):
     w.ck(l.pfd_fetch(h, L.ARR_LDD, ldd_dev, 0))
     gpu["ldd_parse"] = best(lambda: w.ck(l.pfd_ldd_parse(h, ldd_dev, size, size, w.out_dev[0], i32, None, None)))
     gpu["to_array_d8"] = best(lambda: w.ck(l.pfd_fetch(h, L.ARR_D8, out1_dev, 0)))
-    for pdev in (z_dev, out1_dev, um_dev, mask_dev, sparse_dev, drainh_dev, ldd_dev):
+    # later rows: arithmetics, subbasins, local / region post-processing, NEXTXY codec
+    f64 = L.DTYPES[np.dtype(np.float64)]
+    u32 = L.DTYPES[np.dtype(np.uint32)]
+    so_dev = w.dev_alloc(n)
+    w.ck(l.pfd_strahler(h, None, so_dev))
+    k64 = C.c_int64()
+    gpu["upstream_sum_f32"] = best(lambda: w.ck(l.pfd_upstream_sum(h, z_dev, f32, C.c_double(-9999.0), 0, 0, out4_dev)))
+    gpu["subbasins_streamorder"] = best(lambda: w.ck(l.pfd_subbasins_streamorder(h, so_dev, None, -2, out4_dev, C.byref(k64))))
+    gpu["subbasins_area"] = best(lambda: w.ck(l.pfd_subbasins_area(h, um_dev, i32, upa_dev, i32, C.c_double(5000.0), out4_dev, C.byref(k64))))
+    gpu["moving_average_n3_f32"] = best(lambda: w.ck(l.pfd_moving_average(h, z_dev, f32, None, 0, 3, um_dev, i32, None, C.c_double(-9999.0), out4_dev)))
+    gpu["moving_median_n3_f32"] = best(lambda: w.ck(l.pfd_moving_median(h, z_dev, f32, 3, um_dev, i32, None, C.c_double(-9999.0), out4_dev)))
+    gpu["downstream_f32"] = best(lambda: w.ck(l.pfd_downstream(h, z_dev, f32, out4_dev)))
+    region_h = np.zeros((size, size), np.uint8)
+    region_h[size // 4: 3 * size // 4, size // 5: 4 * size // 5] = 1
+    region_dev = w.dev_alloc(n)
+    w.ck(l.pfd_memcpy(h, region_dev, L.ptr(region_h), n))
+    gpu["outflow_idxs"] = best(lambda: w.ck(l.pfd_outflow_idxs(h, region_dev, C.byref(k64))))
+    gpu["inflow_idxs"] = best(lambda: w.ck(l.pfd_inflow_idxs(h, region_dev, C.byref(k64))))
+    gpu["interbasin_mask_stream"] = best(lambda: w.ck(l.pfd_interbasin_mask(h, region_dev, mask_dev, out1_dev)))
+    bas_dev = w.out_dev[3]
+    w.ck(l.pfd_basins(h, None, 0, i32, None, u32, bas_dev))
+    gpu["region_outlets_basins"] = best(lambda: w.ck(l.pfd_region_outlets(h, bas_dev, u32, C.byref(k64))))
+    gpu["region_slices_basins"] = best(lambda: w.ck(l.pfd_region_slices(h, bas_dev, u32, C.byref(k64))))
+    starts_h = np.ascontiguousarray(np.random.default_rng(seed + 9).integers(0, n, size=4096), dtype=np.int64)
+    cnt_h, end_h, dist_h = np.empty(4096, np.int64), np.empty(4096, np.int64), np.empty(4096, np.float64)
+    gpu["snap_4096_starts"] = best(lambda: w.ck(l.pfd_trace(h, L.ptr(starts_h), 4096, 0, None, 0, mask_dev, 0, C.c_double(0.0), None,
+                                                           L.ptr(cnt_h), L.ptr(end_h), L.ptr(dist_h), None, 0, 0)))
+    nxy_dev = w.dev_alloc(n * 8)
+    w.ck(l.pfd_fetch(h, L.ARR_NEXTXY, nxy_dev, 0))
+    gpu["nextxy_parse"] = best(lambda: w.ck(l.pfd_nextxy_parse(h, nxy_dev, C.c_void_p(nxy_dev.value + n * 4), size, size, 1, w.out_dev[0], i32, None, None, None)))
+    for pdev in (z_dev, out1_dev, um_dev, mask_dev, sparse_dev, drainh_dev, ldd_dev, so_dev, region_dev, nxy_dev):
         w.ck(l.pfd_dev_free(h, pdev))
 
     # CPU port on a bounded sample of the same generator
@@ -412,6 +442,22 @@ def extras_widened(w, size, seed, cpu_size):
     if ldd is not None:
         cpu["ldd_parse"], _ = cpu_time(lambda: oracle.core_ldd.from_array(ldd, dtype=np.int32))
     cpu["to_array_d8"], _ = cpu_time(lambda: oracle.core_d8.to_array(ids, d8.shape))
+    so = oracle.streams.strahler_order(ids, seq)
+    cpu["upstream_sum_f32"], _ = cpu_time(lambda: oracle.arithmetics.upstream_sum(ids, zc, -9999.0))
+    cpu["subbasins_streamorder"], _ = cpu_time(lambda: oracle.basins.subbasins_streamorder(ids, seq, so, None, -2))
+    cpu["subbasins_area"], _ = cpu_time(lambda: oracle.basins.subbasins_area(ids, seq, um, upc, 5000.0))
+    cpu["moving_average_n3_f32"], _ = cpu_time(lambda: oracle.arithmetics.moving_average(zc, None, 3, ids, um, None, -9999.0))
+    cpu["moving_median_n3_f32"], _ = cpu_time(lambda: oracle.arithmetics.moving_median(zc, 3, ids, um, None, -9999.0))
+    creg = np.zeros(d8.shape, np.uint8)
+    creg[cpu_size // 4: 3 * cpu_size // 4, cpu_size // 5: 4 * cpu_size // 5] = 1
+    creg = creg.ravel()
+    cpu["outflow_idxs"], _ = cpu_time(lambda: oracle.core.outflow_idxs(ids, seq, creg))
+    cpu["inflow_idxs"], _ = cpu_time(lambda: oracle.core.inflow_idxs(ids, seq, creg))
+    cpu["interbasin_mask_stream"], _ = cpu_time(lambda: oracle.basins.interbasin_mask(ids, seq, creg, cmask))
+    cbas = oracle.basins.basins(ids, pits, seq)
+    cpu["region_outlets_basins"], _ = cpu_time(lambda: oracle.regions.region_outlets(cbas, ids, seq))
+    cnxy = oracle.core_nextxy.to_array(ids, d8.shape)
+    cpu["nextxy_parse"], _ = cpu_time(lambda: oracle.core_nextxy.from_array(cnxy, dtype=np.int32))
     res = {}
     for k, ms in gpu.items():
         res[k] = {"gpu_ms": ms, "gpu_mcells_s": n / (ms / 1e3) / 1e6,
