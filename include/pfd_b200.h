@@ -63,7 +63,9 @@ typedef enum pfd_array {
                                    * pfd_region_outlets call (their index-array return value) */
     PFD_ARR_REGION_LABELS = 10, /* int64, n labels of the last pfd_region_outlets / pfd_region_slices call */
     PFD_ARR_REGION_SLICES = 11, /* int32 [n][4] (row start, row stop, col start, col stop) of the last pfd_region_slices call */
-    PFD_ARR_NEXTXY = 12         /* int32 [2][N] -- core_nextxy.to_array (nextx plane, then nexty plane) */
+    PFD_ARR_NEXTXY = 12,        /* int32 [2][N] -- core_nextxy.to_array (nextx plane, then nexty plane) */
+    PFD_ARR_STREAM_OFFSETS = 13,/* int64 [n_streams + 1]: start of every segment of the last pfd_streams call inside STREAM_CELLS */
+    PFD_ARR_STREAM_CELLS = 14   /* idx dtype [n_cells]: the segments of the last pfd_streams call, back to back */
 } pfd_array;
 
 /* ---- library / device ------------------------------------------------------------------------------- */
@@ -257,6 +259,13 @@ int pfd_region_outlets(pfd_handle* h, const void* regions, int dtype, int64_t* n
  * ascending int64 labels (np.unique), pfd_fetch(PFD_ARR_REGION_SLICES) -> int32 [n][4]. region_bounds (:89-129) turns
  * these into coordinates on the host. */
 int pfd_region_slices(pfd_handle* h, const void* regions, int dtype, int64_t* n_labels);
+
+/* streams.streams (pyflwdir/streams.py:131-188): linear indices per stream segment between two confluences of the masked
+ * network (mask: NULL = all cells, or N uint8), in the reference's order (segment starts found while walking seq[::-1]);
+ * segments longer than max_len > 0 cells are split into pieces that share their end points; a zero-length [pit, pit]
+ * segment follows every segment that ends in a pit. *n_streams / *n_cells = number of segments / of indices; fetch with
+ * pfd_fetch(PFD_ARR_STREAM_OFFSETS) (int64 [n_streams + 1]) and pfd_fetch(PFD_ARR_STREAM_CELLS) (idx dtype). */
+int pfd_streams(pfd_handle* h, const uint8_t* mask, int64_t max_len, int64_t* n_streams, int64_t* n_cells);
 
 /* ---- fused headline pass ------------------------------------------------------------------------------ */
 /*

@@ -592,7 +592,22 @@ def _stream_distance(idxs_ds, seq, ncol, mask=None, real_length=True, latlon=Fal
     return dist
 
 
-streams = types.SimpleNamespace(stream_distance=_stream_distance, accuflux=_accuflux, accuflux_ds=_accuflux_ds, strahler_order=_strahler_order,
+
+def _streams(idxs_ds, seq, mask=None, max_len=0, mv=None):
+    """pyflwdir/streams.py:131-188 -> list of index arrays"""
+    a, sfx = _idx(idxs_ds)
+    s = np.ascontiguousarray(seq).astype(a.dtype)
+    m = None if mask is None else np.ascontiguousarray(mask).astype(np.uint8)
+    f = _fn("orc_streams", sfx, C.c_int64)
+    ncell = C.c_int64()
+    args = [_p(a), _p(s), C.c_int64(s.size), None if m is None else _p(m), C.c_int64(int(max_len)), C.c_int64(a.size)]
+    nseg = int(f(*args, None, None, C.byref(ncell)))
+    offs = np.zeros(nseg + 1, dtype=np.int64)
+    cells = np.empty(max(ncell.value, 1), dtype=a.dtype)
+    f(*args, _p(offs), _p(cells), C.byref(ncell))
+    return [cells[offs[i]:offs[i + 1]] for i in range(nseg)]
+
+streams = types.SimpleNamespace(streams=_streams, stream_distance=_stream_distance, accuflux=_accuflux, accuflux_ds=_accuflux_ds, strahler_order=_strahler_order,
                                 stream_order=lambda *a, **k: _stream_order_classic(*a, **k))
 
 

@@ -404,6 +404,17 @@ class DeviceGraph:
             self._ck(self._l.pfd_fetch(self._h, _lib.ARR_REGION_SLICES, _lib.ptr(sl), 0))
         return lbs.astype(rdt), sl
 
+    def streams(self, mask=None, max_len=0, idx_dtype=np.int32):
+        """streams.streams -> list of index arrays (one per stream segment)."""
+        ns, nc = C.c_int64(), C.c_int64()
+        self._ck(self._l.pfd_streams(self._h, _lib.ptr(self._mask_u8(mask, "mask")), int(max_len), C.byref(ns), C.byref(nc)))
+        offs = np.empty(ns.value + 1, dtype=np.int64)
+        self._ck(self._l.pfd_fetch(self._h, _lib.ARR_STREAM_OFFSETS, _lib.ptr(offs), 0))
+        cells = np.empty(max(nc.value, 1), dtype=idx_dtype)
+        if nc.value:
+            self._ck(self._l.pfd_fetch(self._h, _lib.ARR_STREAM_CELLS, _lib.ptr(cells), _lib.dtype_code(idx_dtype)))
+        return np.split(cells[: nc.value], offs[1:-1]) if ns.value else []
+
     def upstream_area_cells(self):
         out = _lib.out_array(self.size, np.int32)
         self._ck(self._l.pfd_upstream_area_cells(self._h, _lib.ptr(out)))

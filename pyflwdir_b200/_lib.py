@@ -24,7 +24,8 @@ DTYPES = {
 
 # pfd_array
 ARR_IDXS_DS, ARR_PITS, ARR_PIT_IS_OUTLET, ARR_SEQ, ARR_RANK, ARR_N_UPSTREAM, ARR_D8, ARR_LEVEL_OFFSETS, ARR_LDD, \
-    ARR_SUBBASIN_OUTLETS, ARR_REGION_LABELS, ARR_REGION_SLICES, ARR_NEXTXY = range(13)
+    ARR_SUBBASIN_OUTLETS, ARR_REGION_LABELS, ARR_REGION_SLICES, ARR_NEXTXY, ARR_STREAM_OFFSETS, \
+    ARR_STREAM_CELLS = range(15)
 
 # every symbol include/pfd_b200.h declares: name -> (restype, argtypes)
 _vp, _i64, _int, _u32 = C.c_void_p, C.c_int64, C.c_int, C.c_uint32
@@ -70,6 +71,7 @@ SYMBOLS = {
     "pfd_outflow_idxs": (_int, [_vp, _vp, _pi64]),
     "pfd_interbasin_mask": (_int, [_vp, _vp, _vp, _vp]),
     "pfd_region_outlets": (_int, [_vp, _vp, _int, _pi64]),
+    "pfd_streams": (_int, [_vp, _vp, _i64, _pi64, _pi64]),
     "pfd_region_slices": (_int, [_vp, _vp, _int, _pi64]),
     "pfd_d8_flow_all": (_int, [_vp, _vp, _i64, _i64, _vp, _int, _vp, _vp, _vp, _pi64, _pi64, _pi64]),
     "pfd_comm_unique_id": (_int, [_vp, _i64]),

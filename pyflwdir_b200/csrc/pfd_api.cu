@@ -236,6 +236,7 @@ extern "C" double pfd_last_stage_ms(const pfd_handle* h, int stage) {
 static void invalidate(pfd_handle* h) {
     h->parsed = h->ordered = h->have_rank = h->have_basins = h->have_uparea = h->have_upmask = false;
     h->n_valid = h->n_pits = h->n_outlets = h->nnodes = h->nlevels = h->n_sub = 0;
+    h->n_streams = -1;
 }
 
 // pit list in ascending index order + n_valid / n_pits / n_outlets from the dir bytes; fails on the parse flag
@@ -1370,6 +1371,14 @@ extern "C" int pfd_fetch(pfd_handle* h, int which, void* out, int idx_dtype) {
     }
     case PFD_ARR_SUBBASIN_OUTLETS:
         PFD_TRY(copy_cells_out(h, (const cell_t*)h->sub_idxs.p, h->n_sub, out, idx_dtype));
+        break;
+    case PFD_ARR_STREAM_OFFSETS:
+        if (h->n_streams < 0) return pfd_fail(h, PFD_ERR_STATE, "pfd_fetch: no pfd_streams result on this handle");
+        PFD_CUDA(h, cudaMemcpyAsync(out, h->stream_off.p, (size_t)(h->n_streams + 1) * sizeof(long long), cudaMemcpyDefault, h->stream));
+        break;
+    case PFD_ARR_STREAM_CELLS:
+        if (h->n_streams < 0) return pfd_fail(h, PFD_ERR_STATE, "pfd_fetch: no pfd_streams result on this handle");
+        PFD_TRY(copy_cells_out(h, (const cell_t*)h->stream_cells.p, h->n_stream_cells, out, idx_dtype));
         break;
     case PFD_ARR_REGION_LABELS:
         if (!h->have_sub_labels) return pfd_fail(h, PFD_ERR_STATE, "pfd_fetch: no pfd_region_outlets / pfd_region_slices result on this handle");
@@ -2511,6 +2520,66 @@ extern "C" int pfd_region_slices(pfd_handle* h, const void* regions, int dtype, 
     h->have_sub_labels = h->have_sub_slices = true;
     stage_collect(h);
     if (n_labels) *n_labels = h->n_sub;
+    return PFD_OK;
+}
+
+// streams.streams (pyflwdir/streams.py:131-188)
+extern "C" int pfd_streams(pfd_handle* h, const uint8_t* mask, int64_t max_len, int64_t* n_streams, int64_t* n_cells) {
+    PFD_TRY(require_raster(h, "pfd_streams"));
+    stage_reset(h);
+    PFD_TRY(order_impl(h, false, false));
+    PFD_TRY(ensure_upmask(h));
+    const int64_t n = h->n;
+    h->n_streams = -1;
+    const void* mask_dev = nullptr;
+    if (mask) PFD_TRY(pfd_stage_in(h, mask, (size_t)n, 4, &mask_dev));
+    PFD_TRY(pfd_reserve(h, h->scratch[1], (size_t)n));
+    uint8_t* st = (uint8_t*)h->scratch[1].p;
+    PFD_CUDA(h, cudaMemsetAsync(st, 0, (size_t)n, h->stream));
+    StreamStartOp op{(const uint8_t*)h->upmask.p, (const uint8_t*)mask_dev, st, h->ncol};
+    PFD_TRY((run_sweep<StreamStartOp, true>(h, op, 0)));
+    StateBit2Pred pred{st};
+    PFD_TRY((number_outlets<StateBit2Pred, 1, uint32_t>(h, pred, nullptr)));  // segments start while walking seq[::-1]
+    const int64_t ns = h->n_sub;
+    int64_t npieces = 0, ncells = 0;
+    PFD_TRY(pfd_reserve(h, h->stream_off, sizeof(long long)));
+    if (ns > 0) {
+        // per start: len | npiece | ncell (uint32 each), then the two exclusive scans (uint64 [ns + 1] each)
+        PFD_TRY(pfd_reserve(h, h->scratch[0], (size_t)ns * 3 * sizeof(uint32_t)));
+        PFD_TRY(pfd_reserve(h, h->scratch[2], (size_t)(ns + 1) * 2 * sizeof(unsigned long long)));
+        uint32_t* len = (uint32_t*)h->scratch[0].p;
+        uint32_t* npiece = len + ns;
+        uint32_t* ncell = npiece + ns;
+        unsigned long long* piece_off = (unsigned long long*)h->scratch[2].p;
+        unsigned long long* cell_off = piece_off + (ns + 1);
+        const int g = grid_for(ns, 128, 1, 148 * 16);
+        stream_count_kernel<<<g, 128, 0, h->stream>>>((const uint8_t*)h->dir.p, (const uint8_t*)h->upmask.p, (const uint8_t*)mask_dev,
+                                                     (const cell_t*)h->sub_idxs.p, ns, h->ncol, max_len, len, npiece, ncell);
+        PFD_LAUNCH_CHECK(h);
+        scan_counts_kernel<<<1, 1024, 0, h->stream>>>(npiece, ns, piece_off);
+        PFD_LAUNCH_CHECK(h);
+        scan_counts_kernel<<<1, 1024, 0, h->stream>>>(ncell, ns, cell_off);
+        PFD_LAUNCH_CHECK(h);
+        unsigned long long tot[2] = {0, 0};
+        PFD_CUDA(h, cudaMemcpyAsync(&tot[0], piece_off + ns, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        PFD_CUDA(h, cudaMemcpyAsync(&tot[1], cell_off + ns, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+        npieces = (int64_t)tot[0];
+        ncells = (int64_t)tot[1];
+        PFD_TRY(pfd_reserve(h, h->stream_off, (size_t)(npieces + 1) * sizeof(long long)));
+        PFD_TRY(pfd_reserve(h, h->stream_cells, (size_t)std::max<int64_t>(ncells, 1) * sizeof(cell_t)));
+        stream_write_kernel<<<g, 128, 0, h->stream>>>((const uint8_t*)h->dir.p, (const cell_t*)h->sub_idxs.p, ns, h->ncol, max_len, len,
+                                                     piece_off, cell_off, (long long*)h->stream_off.p, (cell_t*)h->stream_cells.p);
+        PFD_LAUNCH_CHECK(h);
+    }
+    const long long last = (long long)ncells;
+    PFD_CUDA(h, cudaMemcpyAsync((long long*)h->stream_off.p + npieces, &last, sizeof(last), cudaMemcpyHostToDevice, h->stream));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->n_streams = npieces;
+    h->n_stream_cells = ncells;
+    stage_collect(h);
+    if (n_streams) *n_streams = npieces;
+    if (n_cells) *n_cells = ncells;
     return PFD_OK;
 }
 

@@ -186,6 +186,8 @@ struct pfd_handle {
     DevBuf sub_labels;         // int64 [n_sub] labels of the last pfd_region_outlets / pfd_region_slices call
     DevBuf sub_slices;         // int4 [n_sub] (row start, row stop, col start, col stop) of the last pfd_region_slices call
     bool have_sub_labels = false, have_sub_slices = false;
+    DevBuf stream_off, stream_cells;  // int64 [n_streams + 1] / cell_t [n_stream_cells] of the last pfd_streams call
+    int64_t n_streams = -1, n_stream_cells = 0;
     DevBuf tile_loc;           // uint2 [n]: per cell (local terminal | hops << 12, in-tile subtree size)
     DevBuf uparea;            // int32 [n] cached cell-count upstream area (tile solver)
     bool have_uparea = false;

@@ -248,3 +248,123 @@ __global__ void region_slices_kernel(const cell_t* __restrict__ present, int64_t
         slices[i] = make_int4(b.x, b.y + 1, b.z, b.w + 1);
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// streams.streams (pyflwdir/streams.py:131-188): the stream segments between confluences of the masked network.
+// The reference walks seq[::-1] and starts a segment at every masked cell no earlier segment ran through; a segment
+// runs downstream (also across unmasked cells) until a cell with more than one masked upstream neighbour or a pit.
+// "Some segment runs through c" is a 1-bit up-sweep: through[c] = mask[c] or (nup[c] <= 1 and any upstream neighbour
+// is run through); a masked cell starts a segment unless it is reached that way. The starts are compacted in
+// seq[::-1] order, every start is traced twice (lengths -> exclusive scans -> cells), one thread per start.
+// ---------------------------------------------------------------------------------------------------------
+struct StreamStartOp {
+    const uint8_t* upmask;
+    const uint8_t* mask;  // may be null = every cell
+    uint8_t* st;          // bit 0 = a segment runs through the cell, bit 1 = the cell starts a segment; pre-set to 0
+    long long ncol;
+    __device__ __forceinline__ void operator()(cell_t c, long long, int) const {
+        uint32_t m = __ldg(upmask + c);
+        int nup = 0;
+        bool any = false;
+        while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            const long long u = (long long)c + pfd_slot_off(k, ncol);
+            nup += (!mask || __ldg(mask + u)) ? 1 : 0;
+            any = any || (ld_cg(st + u) & 1u);
+        }
+        const bool in = !mask || __ldg(mask + c);
+        const bool reached = nup <= 1 && any;
+        st[c] = (uint8_t)(((in || reached) ? 1u : 0u) | ((in && !reached) ? 2u : 0u));
+    }
+};
+
+// number of masked upstream neighbours > 1 (core.upstream_count with a mask, core.py:50-61)
+__device__ __forceinline__ bool stream_confluence(const uint8_t* __restrict__ upmask, const uint8_t* __restrict__ mask, long long c,
+                                                  long long ncol) {
+    uint32_t m = upmask[c];
+    if (!mask) return __popc(m) > 1;
+    int nup = 0;
+    while (m) {
+        const int k = __ffs(m) - 1;
+        m &= m - 1;
+        nup += mask[c + pfd_slot_off(k, ncol)] ? 1 : 0;
+    }
+    return nup > 1;
+}
+
+// split of a segment of l cells (streams.py:168-180): k pieces of n cells (+ the shared end point)
+__device__ __forceinline__ void stream_split(long long l, long long max_len, long long& k, long long& n) {
+    k = 1;
+    n = l;
+    if (max_len > 0 && l > max_len && ((double)l / (double)max_len) > 1.5) {
+        k = (long long)rint((double)l / (double)max_len);  // Python round(): half to even
+        n = (long long)rint((double)l / (double)k);
+    }
+}
+__device__ __forceinline__ long long stream_piece_len(long long i, long long k, long long n, long long l) {
+    const long long from = min(i * n, l);
+    const long long to = (i + 1 == k) ? l : min(n * (i + 1) + 1, l);
+    return max(to - from, 0ll);
+}
+
+// pass 1: length of every segment (bit 31: it ends in a pit), number of output pieces and indices
+__global__ void stream_count_kernel(const uint8_t* __restrict__ dir, const uint8_t* __restrict__ upmask, const uint8_t* __restrict__ mask,
+                                    const cell_t* __restrict__ starts, long long nstart, long long ncol, long long max_len,
+                                    uint32_t* __restrict__ len, uint32_t* __restrict__ npiece, uint32_t* __restrict__ ncell) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nstart; t += (long long)gridDim.x * blockDim.x) {
+        long long cur = starts[t], l = 1;
+        bool pit;
+        while (true) {
+            const uint32_t d = dir[cur];
+            pit = d >= 8u;
+            if (pit) break;
+            cur += pfd_slot_off((int)d, ncol);
+            ++l;
+            if (stream_confluence(upmask, mask, cur, ncol)) break;
+        }
+        long long k, n;
+        stream_split(l, max_len, k, n);
+        long long cells = 0;
+        if (k == 1) cells = l;
+        else
+            for (long long i = 0; i < k; ++i) cells += stream_piece_len(i, k, n, l);
+        len[t] = (uint32_t)l | (pit ? 0x80000000u : 0u);
+        npiece[t] = (uint32_t)(k + (pit ? 1 : 0));
+        ncell[t] = (uint32_t)(cells + (pit ? 2 : 0));
+    }
+}
+
+// pass 2: write the indices of every piece and its start offset
+__global__ void stream_write_kernel(const uint8_t* __restrict__ dir, const cell_t* __restrict__ starts, long long nstart, long long ncol,
+                                    long long max_len, const uint32_t* __restrict__ len, const unsigned long long* __restrict__ piece_off,
+                                    const unsigned long long* __restrict__ cell_off, long long* __restrict__ offsets,
+                                    cell_t* __restrict__ cells) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nstart; t += (long long)gridDim.x * blockDim.x) {
+        const uint32_t lw = len[t];
+        const long long l = (long long)(lw & 0x7FFFFFFFu);
+        const bool pit = (lw >> 31) != 0;
+        long long k, n;
+        stream_split(l, max_len, k, n);
+        unsigned long long po = piece_off[t], base = cell_off[t];
+        long long cur = starts[t], i = 0;
+        offsets[po] = (long long)base;
+        for (long long p = 0; p < l; ++p) {
+            if (p > 0) cur += pfd_slot_off((int)dir[cur], ncol);
+            cells[base + (unsigned long long)(p - i * n)] = (cell_t)cur;
+            if (i + 1 < k && p == n * (i + 1)) {  // shared end point: last index of piece i, first of piece i + 1
+                base += (unsigned long long)(n + 1);
+                ++i;
+                offsets[po + (unsigned long long)i] = (long long)base;
+                cells[base] = (cell_t)cur;
+            }
+        }
+        unsigned long long end = base + (unsigned long long)(l - min(i * n, l));
+        for (long long j = i + 1; j < k; ++j) offsets[po + (unsigned long long)j] = (long long)end;  // pieces beyond the end are empty
+        if (pit) {
+            offsets[po + (unsigned long long)k] = (long long)end;
+            cells[end] = (cell_t)cur;
+            cells[end + 1] = (cell_t)cur;
+        }
+    }
+}

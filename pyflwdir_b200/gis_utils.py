@@ -155,3 +155,62 @@ def hop_length_table(nrow, transform, latlon, dtype=np.float32):
                 tab[r0, j, 0] = math.hypot(dy * dr, 0.0)
                 tab[r0, j, 1] = math.hypot(dy * dr, dx1 * 1)
     return tab.astype(dtype)
+
+
+def xy(transform, rows, cols, offset="center"):
+    """x and y coordinates of pixels at `rows` and `cols`; gis_utils.py:183-223."""
+    rows, cols = np.asarray(rows), np.asarray(cols)
+    offs = {"center": (0.5, 0.5), "ul": (0, 0), "ur": (1, 0), "ll": (0, 1), "lr": (1, 1)}
+    if offset not in offs:
+        raise ValueError("Invalid offset")
+    coff, roff = offs[offset]
+    xs, ys = transform * transform.translation(coff, roff) * (cols, rows)
+    return xs, ys
+
+
+def idxs_to_coords(idxs, transform, shape, offset="center"):
+    """Coordinates of linear raster indices; gis_utils.py:264-298."""
+    idxs = np.asarray(idxs).astype(int)
+    size = np.multiply(*shape)
+    if np.any(np.logical_or(idxs < 0, idxs >= size)):
+        raise IndexError("idxs coordinates outside domain")
+    ncol = shape[1]
+    return xy(transform, idxs // ncol, idxs % ncol, offset=offset)
+
+
+def features(flowpaths, xs=None, ys=None, transform=None, shape=None, **kwargs):
+    """LineString geo-feature (dict) per flow path; gis_utils.py:490-549. Host side, like the reference: the output is a
+    list of Python dicts."""
+    if xs is None or ys is None:
+        if transform is None or shape is None:
+            raise ValueError("transform and shape should be provided if xs and ys are None")
+        _size = shape[0] * shape[1]
+    else:
+        _size = xs.size
+    for key in kwargs:
+        if not isinstance(kwargs[key], np.ndarray) or kwargs[key].size != _size:
+            raise ValueError(f'Kwargs map "{key}" should be ndarrays of same size as coordinates')
+    # coordinates of all paths in one vectorised pass (element-wise identical to the reference's per-path calls)
+    paths = [np.asarray(idxs) for idxs in flowpaths if len(idxs) >= 2]
+    feats = list()
+    if not paths:
+        return feats
+    flat = np.concatenate(paths)
+    if xs is None or ys is None:
+        xi, yi = idxs_to_coords(flat, transform, shape)
+    else:
+        xi, yi = np.asarray(xs).ravel()[flat], np.asarray(ys).ravel()[flat]
+    coords = list(zip(xi, yi))  # numpy scalars, like the reference
+    o = 0
+    for idxs in paths:
+        n = len(idxs)
+        idx0 = idxs[0]
+        pit = idxs[-1] == idxs[-2]
+        props = {key: kwargs[key].flat[idx0] for key in kwargs}
+        feats.append({
+            "type": "Feature",
+            "geometry": {"type": "LineString", "coordinates": coords[o:o + n]},
+            "properties": {"idx": idx0, "idx_ds": idxs[-1], "pit": pit, **props},
+        })
+        o += n
+    return feats

@@ -320,6 +320,39 @@ class FlwdirRaster(Flwdir):
         mask = self._dev.interbasin_mask(self._check_data(region, "region"), self._check_data(stream, "stream", optional=True))
         return mask.reshape(self.shape)
 
+    # ------------------------------------------------------------------ vectorize
+    def vectorize(self, mask=None, xs=None, ys=None, direction="down", **kwargs):
+        """Returns each flow direction as a linestring geo-feature (pyflwdir.py:865-892 -> core.flwdir_tuples, core.py:266-275:
+        one [cell, next cell] pair per valid cell)."""
+        nxt = self.idxs_ds if direction == "down" else self.idxs_us_main
+        valid = nxt != self._mv
+        m = self._check_data(mask, "mask", optional=True)
+        if m is not None:
+            valid &= m == 1
+        idx0 = np.flatnonzero(valid).astype(nxt.dtype)
+        pairs = np.stack([idx0, nxt[idx0]], axis=1)
+        return self.geofeatures(list(pairs), xs=xs, ys=ys, **kwargs)
+
+    def streams(self, mask=None, min_sto=1, xs=None, ys=None, idxs_out=None, max_len=0, direction="up", **kwargs):
+        """Returns a list of stream segments (between two confluences) as linestring geo-features
+        (pyflwdir.py:894-974 -> streams.streams, streams.py:131-188, on the device; gis_utils.features on the host)."""
+        if mask is not None:
+            mask = self._check_data(mask, "mask")
+        elif min_sto > 1:
+            strord = self._check_data(kwargs.get("strord"), "strord")
+            mask = strord >= min_sto
+            kwargs.update(strord=strord)  # add strord column
+        if idxs_out is not None:
+            raise NotImplementedError("streams(idxs_out=...) needs subgrid.segment_indices, which is outside the D8 hot path "
+                                      "that pyflwdir_b200 accelerates")
+        idxs = self._dev.streams(mask, max_len, self._idx_dtype)
+        return self.geofeatures(idxs, xs=xs, ys=ys, **kwargs)
+
+    def geofeatures(self, flowpaths, xs=None, ys=None, **kwargs):
+        """Returns geo-features of flowpaths defined by a list of arrays of linear indices (pyflwdir.py:976-1011)."""
+        return gis.features(flowpaths=flowpaths, xs=self._check_data(xs, "xs", optional=True),
+                            ys=self._check_data(ys, "ys", optional=True), transform=self.transform, shape=self.shape, **kwargs)
+
     # ------------------------------------------------------------------ basins
     def basins(self, idxs=None, xy=None, ids=None, **kwargs):
         """(Sub)basin map with a unique ID for every (sub)basin (pyflwdir.py:564-599 -> basins.basins)."""
@@ -426,7 +459,7 @@ class FlwdirRaster(Flwdir):
         return super()._check_idxs_xy(idxs, streams)
 
     for _name in ("repair_loops_raster", "subbasins_pfafstetter",
-                  "streams", "geofeatures", "vectorize", "dem_adjust", "dem_dig_d4",
+                  "dem_adjust", "dem_dig_d4",
                   "upscale", "upscale_error", "subgrid_rivlen", "subgrid_rivslp", "subgrid_rivavg", "subgrid_rivmed",
                   "ucat_area", "ucat_outlets", "ucat_volume"):
         locals()[_name] = _not_in_scope(_name)

@@ -32,3 +32,10 @@ def strahler_order(idxs_ds, seq, mask=None, shape=None, ncol=None):
     g = _functional.graph(idxs_ds, shape, ncol)
     _functional.check_seq(g, seq, "strahler_order")
     return g.strahler(mask)
+
+
+def streams(idxs_ds, seq, mask=None, max_len=0, mv=-1, shape=None, ncol=None):
+    """Returns list of linear indices per stream of equal stream order (streams.py:131-188)."""
+    g = _functional.graph(idxs_ds, shape, ncol)
+    _functional.check_seq(g, seq, "streams")
+    return g.streams(mask, max_len, np.asarray(idxs_ds).dtype)

@@ -15,6 +15,7 @@ RHINE_TRANSFORM = (0.008333333333325754, 0.0, 3.5666666664997138, 0.0, -0.008333
 
 SMALL_CASES = ["flwdir_asc", "flwdir1_asc", "loop3x3", "random48x61", "synth96x130"]
 HASH_CASES = ["rhine", "synth512x768"]
+FEATS_MAX_CELLS = 40000  # geo-feature cases (Python dict per segment) run on rasters up to this size
 
 
 def sha(a):
@@ -115,6 +116,35 @@ def _flat_paths(paths):
     counts = np.array([p.size for p in paths], dtype=np.int64)
     flat = np.concatenate(paths) if len(paths) else np.zeros(0, dtype=np.int64)
     return flat, counts
+
+
+def _feats_arrays(feats, prefix, out, props=()):
+    """Geo-features (list of dicts) -> comparable arrays."""
+    out[f"{prefix}_idx"] = np.array([f["properties"]["idx"] for f in feats], dtype=np.int64)
+    out[f"{prefix}_idx_ds"] = np.array([f["properties"]["idx_ds"] for f in feats], dtype=np.int64)
+    out[f"{prefix}_pit"] = np.array([bool(f["properties"]["pit"]) for f in feats], dtype=np.bool_)
+    out[f"{prefix}_n"] = np.array([len(f["geometry"]["coordinates"]) for f in feats], dtype=np.int64)
+    xy = [c for f in feats for c in f["geometry"]["coordinates"]]
+    out[f"{prefix}_xy"] = np.array(xy, dtype=np.float64).reshape(-1, 2)
+    for key in props:
+        out[f"{prefix}_{key}"] = np.array([f["properties"][key] for f in feats])
+
+
+def _oracle_feats(paths, prefix, out, transform, ncol, props=None):
+    """gis_utils.features (gis_utils.py:490-549) over index lists, with Affine * translation(0.5, 0.5) * (cols, rows)
+    spelled out (gis_utils.py:222)."""
+    a, b, c, d, e, f = [float(v) for v in tuple(transform)[:6]]
+    cx, cy = a * 0.5 + b * 0.5 + c, d * 0.5 + e * 0.5 + f
+    paths = [p for p in paths if len(p) >= 2]
+    out[f"{prefix}_idx"] = np.array([p[0] for p in paths], dtype=np.int64)
+    out[f"{prefix}_idx_ds"] = np.array([p[-1] for p in paths], dtype=np.int64)
+    out[f"{prefix}_pit"] = np.array([p[-1] == p[-2] for p in paths], dtype=np.bool_)
+    out[f"{prefix}_n"] = np.array([len(p) for p in paths], dtype=np.int64)
+    flat = np.concatenate(paths).astype(np.int64) if paths else np.zeros(0, np.int64)
+    rows, cols = flat // ncol, flat % ncol
+    out[f"{prefix}_xy"] = np.stack([cols * a + rows * b + cx, cols * d + rows * e + cy], axis=1).reshape(-1, 2)
+    for key, arr in (props or {}).items():
+        out[f"{prefix}_{key}"] = np.asarray(arr).ravel()[out[f"{prefix}_idx"]]
 
 
 def run_oracle_case(d8, aux, area=None, transform=(1.0, 0.0, 0.0, 0.0, -1.0, 0.0), latlon=False):
@@ -236,6 +266,16 @@ def run_oracle_case(d8, aux, area=None, transform=(1.0, 0.0, 0.0, 0.0, -1.0, 0.0
     out["outlets_blocks_lbs"], out["outlets_blocks_idxs"] = o.regions.region_outlets(blocks, idxs_ds, seq)
     out["bounds_basins_lbs"], out["bounds_basins_boxes"], out["bounds_basins_total"] = o.regions.region_bounds(out["basins"], tr6)
     out["bounds_labels_lbs"], out["bounds_labels_boxes"], out["bounds_labels_total"] = o.regions.region_bounds(labels, tr6)
+    # stream segments and flow-direction vectors as geo-features
+    so2 = out["strord"].ravel() >= 2
+    _oracle_feats(o.streams.streams(idxs_ds, seq, so2, 0), "streams_so2", out, tr6, shape[1],
+                  props=dict(strord=out["strord"], uparea=out["uparea_cell"]))
+    if d8.size <= FEATS_MAX_CELLS:
+        _oracle_feats(o.streams.streams(idxs_ds, seq, None, 7), "streams_len7", out, tr6, shape[1])
+        _oracle_feats(o.streams.streams(idxs_ds, seq, aux["smask"].ravel(), 3), "streams_gaps", out, tr6, shape[1])
+        vmask = aux["smask"].ravel()
+        pairs = [np.array([i, idxs_ds[i]]) for i in np.flatnonzero(mask & vmask)]
+        _oracle_feats(pairs, "vector", out, tr6, shape[1])
     return out
 
 
@@ -332,4 +372,10 @@ def run_api_case(pf, d8, aux, transform=None, latlon=False):
     out["outlets_blocks_lbs"], out["outlets_blocks_idxs"] = flw.basin_outlets(blocks)
     out["bounds_basins_lbs"], out["bounds_basins_boxes"], out["bounds_basins_total"] = flw.basin_bounds()
     out["bounds_labels_lbs"], out["bounds_labels_boxes"], out["bounds_labels_total"] = flw.basin_bounds(basins=labels)
+    # stream segments and flow-direction vectors as geo-features
+    _feats_arrays(flw.streams(min_sto=2, strord=out["strord"], uparea=out["uparea_cell"]), "streams_so2", out, props=("strord", "uparea"))
+    if d8.size <= FEATS_MAX_CELLS:  # one Python dict per segment / cell: small rasters only
+        _feats_arrays(flw.streams(max_len=7), "streams_len7", out)
+        _feats_arrays(flw.streams(mask=aux["smask"], max_len=3), "streams_gaps", out)
+        _feats_arrays(flw.vectorize(mask=aux["smask"]), "vector", out)
     return out

@@ -319,3 +319,22 @@ def test_nextxy(pfb):
         nxy.tofile(fn)
         data, transform = pfb.read_nextxy(fn, shape[0], shape[1], [0.0, -10.0, 20.0, 6.0])
         assert np.array_equal(data, nxy) and tuple(transform)[:6] == (0.1, 0.0, 0.0, 0.0, -0.1, 6.0)
+
+
+def test_streams_raw_segments(pfb):
+    """streams.streams on a 1024 x 1536 raster against the oracle, as raw index lists (no geo-features): no mask, a
+    contiguous stream mask, a mask with gaps; unsplit and split segments."""
+    from pyflwdir_b200 import streams as gstreams
+
+    z = oracle.synth_elevation(1024, 1536, seed=44)
+    d8 = oracle.synth_d8(z, sea_level=float(np.quantile(z, 0.04)))
+    ids, pits, _ = oracle.core_d8.from_array(d8, dtype=np.int32)
+    seq = oracle.core.idxs_seq(ids, pits)
+    upa = oracle.streams.accuflux(ids, seq, np.ones(d8.size, np.int32), -9999)
+    gaps = np.random.default_rng(9).random(d8.size) < 0.5
+    for mask, max_len in ((None, 0), (None, 5), (upa > 25, 0), (upa > 25, 12), (gaps, 2)):
+        got = gstreams.streams(ids, seq, mask, max_len, shape=d8.shape)
+        want = oracle.streams.streams(ids, seq, mask, max_len)
+        assert len(got) == len(want)
+        assert np.array_equal(np.array([g.size for g in got]), np.array([w.size for w in want]))
+        assert np.array_equal(np.concatenate(got), np.concatenate(want)) and got[0].dtype == want[0].dtype
