@@ -267,6 +267,15 @@ int pfd_region_slices(pfd_handle* h, const void* regions, int dtype, int64_t* n_
  * pfd_fetch(PFD_ARR_STREAM_OFFSETS) (int64 [n_streams + 1]) and pfd_fetch(PFD_ARR_STREAM_CELLS) (idx dtype). */
 int pfd_streams(pfd_handle* h, const uint8_t* mask, int64_t max_len, int64_t* n_streams, int64_t* n_cells);
 
+/* basins.subbasins_pfafstetter (pyflwdir/basins.py:106-191): Pfafstetter coding of every basin down to `depth` levels
+ * (1..8): per label the four largest tributaries (odd digits) and the interbasins between them (even digits), on the
+ * classic stream order of the masked network (mask: NULL or N uint8, e.g. uparea >= upa_min). idxs_us_main: N indices;
+ * uparea: N values of PFD_I32 / PFD_I64 / PFD_F32 / PFD_F64. pfafbas_out: N int64 (the reference's int32 % int64).
+ * *n_outlets = number of subbasin outlet cells, fetched with pfd_fetch(PFD_ARR_SUBBASIN_OUTLETS) in the reference's
+ * order (pits first, then label by label). Ties between equal upstream areas are broken like numba's argsort does. */
+int pfd_subbasins_pfafstetter(pfd_handle* h, const void* idxs_us_main, int idx_dtype, const void* uparea, int dtype,
+                              const uint8_t* mask, int depth, int64_t* pfafbas_out, int64_t* n_outlets);
+
 /* ---- fused headline pass ------------------------------------------------------------------------------ */
 /*
  * parse + order + rank + upstream_area(cell) + basins() in one call (BASELINE.json metric). Any output may be

@@ -621,8 +621,26 @@ def _basins(idxs_ds, idxs_pit, seq, ids=None):
     return _fillnodata_upstream(idxs_ds, seq, b, 0)
 
 
+
+def _subbasins_pfafstetter(idxs_pit, idxs_ds, seq, idxs_us_main, uparea, mask=None, depth=1, mv=None):
+    """pyflwdir/basins.py:106-191 -> (pfafstetter map, outlet indices)"""
+    a, sfx = _idx(idxs_ds)
+    s = np.ascontiguousarray(seq).astype(a.dtype)
+    pits = np.ascontiguousarray(idxs_pit).astype(a.dtype)
+    um = np.ascontiguousarray(idxs_us_main).astype(a.dtype)
+    upa = np.ascontiguousarray(uparea, dtype=np.float64)
+    m = None if mask is None else np.ascontiguousarray(mask).astype(np.uint8)
+    out = np.empty(a.size, dtype=np.int32)
+    idxs = np.empty(max(a.size, 1), dtype=a.dtype)
+    n = int(_fn("orc_subbasins_pfafstetter", sfx, C.c_int64)(
+        _p(pits), C.c_int64(pits.size), _p(a), _p(s), C.c_int64(s.size), _p(um), _p(upa), None if m is None else _p(m),
+        C.c_int(int(depth)), C.c_int64(a.size), _p(out), _p(idxs)))
+    if n < 0:
+        raise IndexError("subbasins_pfafstetter: missing main-upstream index")
+    return out.astype(np.int64), idxs[:n].copy()  # numba: int32 % int64 -> int64
+
 basins = types.SimpleNamespace(basins=_basins, subbasins_streamorder=_subbasins_streamorder, subbasins_area=_subbasins_area,
-                               interbasin_mask=_interbasin_mask)
+                               interbasin_mask=_interbasin_mask, subbasins_pfafstetter=_subbasins_pfafstetter)
 
 
 def _hand(idxs_ds, seq, drain, elevtn):

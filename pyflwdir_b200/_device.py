@@ -251,6 +251,23 @@ class DeviceGraph:
             self._ck(self._l.pfd_fetch(self._h, _lib.ARR_SUBBASIN_OUTLETS, _lib.ptr(idxs), _lib.dtype_code(idx_dtype)))
         return out, idxs
 
+    def subbasins_pfafstetter(self, idxs_us_main, uparea, mask=None, depth=1, idx_dtype=np.int32):
+        """basins.subbasins_pfafstetter -> (int64 map, outlet indices)."""
+        um = np.ascontiguousarray(idxs_us_main)
+        if um.dtype not in _IDX_DTYPES or um.size != self.size:
+            raise ValueError('"idxs_us_main" must be an index array of the raster size')
+        upa = np.ascontiguousarray(uparea)
+        if upa.size != self.size:
+            raise ValueError('"uparea" size does not match.')
+        if upa.dtype not in (np.dtype(np.int32), np.dtype(np.int64), np.dtype(np.float32), np.dtype(np.float64)):
+            upa = upa.astype(np.float64)
+        out = _lib.out_array(self.size, np.int64)
+        k = C.c_int64()
+        self._ck(self._l.pfd_subbasins_pfafstetter(self._h, _lib.ptr(um), _lib.dtype_code(um.dtype), _lib.ptr(upa),
+                                                   _lib.dtype_code(upa.dtype), _lib.ptr(self._mask_u8(mask, "mask")), int(depth),
+                                                   _lib.ptr(out), C.byref(k)))
+        return out, self._fetch_selected(k.value, idx_dtype)
+
     def _window_args(self, data, idxs_us_main, strord):
         data = np.ascontiguousarray(data)
         if data.size != self.size:

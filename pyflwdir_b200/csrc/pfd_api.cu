@@ -2583,6 +2583,185 @@ extern "C" int pfd_streams(pfd_handle* h, const uint8_t* mask, int64_t max_len, 
     return PFD_OK;
 }
 
+// basins.subbasins_pfafstetter (pyflwdir/basins.py:106-191)
+struct TmpBufs {  // device scratch that lives for one call
+    std::vector<DevBuf*> all;
+    ~TmpBufs() {
+        for (DevBuf* b : all) {
+            pfd_release(*b);
+            delete b;
+        }
+    }
+    DevBuf* get() {
+        all.push_back(new DevBuf());
+        return all.back();
+    }
+};
+
+extern "C" int pfd_subbasins_pfafstetter(pfd_handle* h, const void* idxs_us_main, int idx_dtype, const void* uparea, int dtype,
+                                         const uint8_t* mask, int depth, int64_t* pfafbas_out, int64_t* n_outlets) {
+    PFD_TRY(require_raster(h, "pfd_subbasins_pfafstetter"));
+    stage_reset(h);
+    if (!idxs_us_main || !uparea || !pfafbas_out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_subbasins_pfafstetter: null array");
+    const size_t isz = pfd_dtype_size(idx_dtype), esz = pfd_dtype_size(dtype);
+    if ((isz != 4 && isz != 8) || idx_dtype == PFD_F32 || idx_dtype == PFD_F64)
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_subbasins_pfafstetter: index dtype must be a 32/64-bit integer");
+    if (dtype != PFD_I32 && dtype != PFD_I64 && dtype != PFD_F32 && dtype != PFD_F64)
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_subbasins_pfafstetter: uparea must be int32, int64, float32 or float64");
+    if (depth < 1 || depth > 8) return pfd_fail(h, PFD_ERR_UNSUPPORTED, "pfd_subbasins_pfafstetter: depth must be in 1..8");
+    PFD_TRY(order_impl(h, false, false));
+    PFD_TRY(ensure_upmask(h));
+    const int64_t n = h->n;
+    void* out_dev = nullptr;
+    PFD_TRY(pfd_stage_out(h, pfafbas_out, (size_t)n * sizeof(int64_t), 3, &out_dev));
+    const void *main_dev = nullptr, *upa_dev = nullptr, *mask_dev = nullptr;
+    PFD_TRY(pfd_stage_in(h, idxs_us_main, (size_t)n * isz, 5, &main_dev));
+    PFD_TRY(pfd_stage_in(h, uparea, (size_t)n * esz, 4, &upa_dev));
+    if (mask) PFD_TRY(pfd_stage_in(h, mask, (size_t)n, 2, &mask_dev));
+    PFD_TRY(pfd_reserve(h, h->counters, 8 * sizeof(unsigned long long)));
+    unsigned int* flag = reinterpret_cast<unsigned int*>((unsigned long long*)h->counters.p + 5);
+    PFD_CUDA(h, cudaMemsetAsync(flag, 0, sizeof(unsigned int), h->stream));
+    TmpBufs tmp;
+    DevBuf *b_so = tmp.get(), *b_pb = tmp.get(), *b_in = tmp.get(), *b_pos = tmp.get(), *b_upa = tmp.get(), *b_main = tmp.get();
+    PFD_TRY(pfd_reserve(h, *b_so, (size_t)n));
+    PFD_TRY(pfd_reserve(h, *b_pb, (size_t)n * sizeof(int32_t)));
+    PFD_TRY(pfd_reserve(h, *b_in, (size_t)n));
+    PFD_TRY(pfd_reserve(h, *b_pos, (size_t)n * sizeof(uint32_t)));
+    PFD_TRY(pfd_reserve(h, *b_upa, (size_t)n * sizeof(double)));
+    const int g = grid_for(n, 256, 4);
+    // classic stream order of the masked network, orders above depth + 1 dropped (basins.py:120-121)
+    uint8_t* so = (uint8_t*)b_so->p;
+    PFD_CUDA(h, cudaMemsetAsync(so, 0, (size_t)n, h->stream));
+    {
+        const uint8_t *dir = (const uint8_t*)h->dir.p, *upm = (const uint8_t*)h->upmask.p;
+        int rc;
+        if (idx_dtype == PFD_I32) {
+            ClassicOrderOp<int32_t> op{dir, upm, (const uint8_t*)mask_dev, (const int32_t*)main_dev, so, h->ncol};
+            rc = run_sweep<ClassicOrderOp<int32_t>, false>(h, op, 0);
+        } else if (idx_dtype == PFD_U32) {
+            ClassicOrderOp<uint32_t> op{dir, upm, (const uint8_t*)mask_dev, (const uint32_t*)main_dev, so, h->ncol};
+            rc = run_sweep<ClassicOrderOp<uint32_t>, false>(h, op, 0);
+        } else {
+            ClassicOrderOp<int64_t> op{dir, upm, (const uint8_t*)mask_dev, (const int64_t*)main_dev, so, h->ncol};
+            rc = run_sweep<ClassicOrderOp<int64_t>, false>(h, op, 0);
+        }
+        PFD_TRY(rc);
+    }
+    pf_prepare_kernel<<<g, 256, 0, h->stream>>>(so, n, depth);
+    PFD_LAUNCH_CHECK(h);
+    PFD_CUDA(h, cudaMemsetAsync(b_pos->p, 0, (size_t)n * sizeof(uint32_t), h->stream));
+    pf_pos_kernel<<<grid_for(h->nnodes, 256, 4), 256, 0, h->stream>>>((const cell_t*)h->seq.p, h->nnodes, (uint32_t*)b_pos->p);
+    PFD_LAUNCH_CHECK(h);
+    const uint32_t* main32 = (const uint32_t*)main_dev;  // int32 -1 and uint32 mv are both 0xFFFFFFFF
+    if (isz == 8) {
+        PFD_TRY(pfd_reserve(h, *b_main, (size_t)n * sizeof(uint32_t)));
+        pf_main32_kernel<int64_t><<<g, 256, 0, h->stream>>>((const int64_t*)main_dev, n, (uint32_t*)b_main->p, flag);
+        PFD_LAUNCH_CHECK(h);
+        main32 = (const uint32_t*)b_main->p;
+    }
+    switch (dtype) {
+    case PFD_I32: pf_to_double_kernel<int32_t><<<g, 256, 0, h->stream>>>((const int32_t*)upa_dev, n, (double*)b_upa->p); break;
+    case PFD_I64: pf_to_double_kernel<int64_t><<<g, 256, 0, h->stream>>>((const int64_t*)upa_dev, n, (double*)b_upa->p); break;
+    case PFD_F32: pf_to_double_kernel<float><<<g, 256, 0, h->stream>>>((const float*)upa_dev, n, (double*)b_upa->p); break;
+    default: pf_to_double_kernel<double><<<g, 256, 0, h->stream>>>((const double*)upa_dev, n, (double*)b_upa->p); break;
+    }
+    PFD_LAUNCH_CHECK(h);
+    PFD_CUDA(h, cudaMemsetAsync(b_pb->p, 0, (size_t)n * sizeof(int32_t), h->stream));
+    PFD_CUDA(h, cudaMemsetAsync(b_in->p, 0, (size_t)n, h->stream));
+    PfGraph G{(const uint8_t*)h->dir.p, (const uint8_t*)h->upmask.p, so, main32, (const uint32_t*)b_pos->p, (const double*)b_upa->p,
+              (int32_t*)b_pb->p, (uint8_t*)b_in->p, h->ncol, depth};
+
+    // round 0: one label per pit (basins.py:131-141)
+    int64_t nlab = h->n_pits, nout_total = h->n_pits;
+    DevBuf *b_lab = tmp.get(), *b_labo = tmp.get(), *b_outl = tmp.get();
+    PFD_TRY(pfd_reserve(h, *b_lab, (size_t)std::max<int64_t>(nlab, 1) * sizeof(long long)));
+    PFD_TRY(pfd_reserve(h, *b_labo, (size_t)std::max<int64_t>(nlab, 1) * sizeof(uint32_t)));
+    PFD_TRY(pfd_reserve(h, *b_outl, (size_t)std::max<int64_t>(nout_total, 1) * sizeof(cell_t)));
+    if (nlab > 0) {
+        pf_init_pits_kernel<<<grid_for(nlab, 128), 128, 0, h->stream>>>(G, (const cell_t*)h->pits.p, nlab, (long long*)b_lab->p,
+                                                                       (uint32_t*)b_labo->p, (cell_t*)b_outl->p);
+        PFD_LAUNCH_CHECK(h);
+    }
+    for (int d0 = 1; d0 <= depth && nlab > 0; ++d0) {
+        const int gl = grid_for(nlab, 64, 1, 148 * 32);
+        DevBuf *b_cnt = tmp.get(), *b_off = tmp.get();
+        PFD_TRY(pfd_reserve(h, *b_cnt, (size_t)nlab * sizeof(uint32_t)));
+        PFD_TRY(pfd_reserve(h, *b_off, (size_t)(nlab + 1) * sizeof(unsigned long long)));
+        pf_count_kernel<<<gl, 64, 0, h->stream>>>(G, (const long long*)b_lab->p, (const uint32_t*)b_labo->p, nlab, (uint32_t*)b_cnt->p);
+        PFD_LAUNCH_CHECK(h);
+        scan_counts_kernel<<<1, 1024, 0, h->stream>>>((const uint32_t*)b_cnt->p, nlab, (unsigned long long*)b_off->p);
+        PFD_LAUNCH_CHECK(h);
+        unsigned long long ncand = 0;
+        PFD_CUDA(h, cudaMemcpyAsync(&ncand, (unsigned long long*)b_off->p + nlab, sizeof(ncand), cudaMemcpyDeviceToHost, h->stream));
+        PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (ncand == 0) break;
+        DevBuf *b_cand = tmp.get(), *b_key = tmp.get(), *b_R = tmp.get(), *b_cl = tmp.get(), *b_co = tmp.get(), *b_nc = tmp.get(),
+               *b_oc = tmp.get(), *b_no = tmp.get(), *b_coff = tmp.get(), *b_ooff = tmp.get();
+        PFD_TRY(pfd_reserve(h, *b_cand, (size_t)ncand * sizeof(uint32_t)));
+        PFD_TRY(pfd_reserve(h, *b_key, (size_t)ncand * sizeof(double)));
+        PFD_TRY(pfd_reserve(h, *b_R, (size_t)ncand * sizeof(uint32_t)));
+        PFD_TRY(pfd_reserve(h, *b_cl, (size_t)nlab * 8 * sizeof(long long)));
+        PFD_TRY(pfd_reserve(h, *b_co, (size_t)nlab * 8 * sizeof(uint32_t)));
+        PFD_TRY(pfd_reserve(h, *b_nc, (size_t)nlab * sizeof(uint32_t)));
+        PFD_TRY(pfd_reserve(h, *b_oc, (size_t)nlab * 8 * sizeof(uint32_t)));
+        PFD_TRY(pfd_reserve(h, *b_no, (size_t)nlab * sizeof(uint32_t)));
+        PFD_TRY(pfd_reserve(h, *b_coff, (size_t)(nlab + 1) * sizeof(unsigned long long)));
+        PFD_TRY(pfd_reserve(h, *b_ooff, (size_t)(nlab + 1) * sizeof(unsigned long long)));
+        pf_process_kernel<<<gl, 64, 0, h->stream>>>(G, (const long long*)b_lab->p, (const uint32_t*)b_labo->p, nlab, d0,
+                                                   (const unsigned long long*)b_off->p, (uint32_t*)b_cand->p, (double*)b_key->p,
+                                                   (uint32_t*)b_R->p, (long long*)b_cl->p, (uint32_t*)b_co->p, (uint32_t*)b_nc->p,
+                                                   (uint32_t*)b_oc->p, (uint32_t*)b_no->p, flag);
+        PFD_LAUNCH_CHECK(h);
+        scan_counts_kernel<<<1, 1024, 0, h->stream>>>((const uint32_t*)b_nc->p, nlab, (unsigned long long*)b_coff->p);
+        PFD_LAUNCH_CHECK(h);
+        scan_counts_kernel<<<1, 1024, 0, h->stream>>>((const uint32_t*)b_no->p, nlab, (unsigned long long*)b_ooff->p);
+        PFD_LAUNCH_CHECK(h);
+        unsigned long long tot[2] = {0, 0};
+        PFD_CUDA(h, cudaMemcpyAsync(&tot[0], (unsigned long long*)b_coff->p + nlab, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        PFD_CUDA(h, cudaMemcpyAsync(&tot[1], (unsigned long long*)b_ooff->p + nlab, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+        const int64_t nnext = (int64_t)tot[0], nadd = (int64_t)tot[1];
+        DevBuf *b_nlab = tmp.get(), *b_nlabo = tmp.get(), *b_noutl = tmp.get();
+        PFD_TRY(pfd_reserve(h, *b_nlab, (size_t)std::max<int64_t>(nnext, 1) * sizeof(long long)));
+        PFD_TRY(pfd_reserve(h, *b_nlabo, (size_t)std::max<int64_t>(nnext, 1) * sizeof(uint32_t)));
+        PFD_TRY(pfd_reserve(h, *b_noutl, (size_t)(nout_total + nadd + 1) * sizeof(cell_t)));
+        PFD_CUDA(h, cudaMemcpyAsync(b_noutl->p, b_outl->p, (size_t)nout_total * sizeof(cell_t), cudaMemcpyDeviceToDevice, h->stream));
+        pf_gather_kernel<<<gl, 64, 0, h->stream>>>(nlab, (const long long*)b_cl->p, (const uint32_t*)b_co->p, (const uint32_t*)b_nc->p,
+                                                  (const unsigned long long*)b_coff->p, (const uint32_t*)b_oc->p, (const uint32_t*)b_no->p,
+                                                  (const unsigned long long*)b_ooff->p, (long long*)b_nlab->p, (uint32_t*)b_nlabo->p,
+                                                  (cell_t*)b_noutl->p + nout_total);
+        PFD_LAUNCH_CHECK(h);
+        b_lab = b_nlab;
+        b_labo = b_nlabo;
+        b_outl = b_noutl;
+        nlab = nnext;
+        nout_total += nadd;
+    }
+    // pfafbas = core.fillnodata_upstream(idxs_ds, seq, pfaf_branch, 0) % 10**depth (basins.py:190)
+    {
+        FillUpOp<int32_t> fill{(const uint8_t*)h->dir.p, (int32_t*)b_pb->p, h->ncol};
+        PFD_TRY((run_sweep<FillUpOp<int32_t>, false>(h, fill, 0)));
+    }
+    long long mod = 1;
+    for (int i = 0; i < depth; ++i) mod *= 10;
+    pf_mod_kernel<<<g, 256, 0, h->stream>>>((const int32_t*)b_pb->p, n, mod, (int64_t*)out_dev);
+    PFD_LAUNCH_CHECK(h);
+    h->have_sub_labels = h->have_sub_slices = false;
+    h->n_sub = nout_total;
+    PFD_TRY(pfd_reserve(h, h->sub_idxs, (size_t)std::max<int64_t>(nout_total, 1) * sizeof(cell_t)));
+    PFD_CUDA(h, cudaMemcpyAsync(h->sub_idxs.p, b_outl->p, (size_t)nout_total * sizeof(cell_t), cudaMemcpyDeviceToDevice, h->stream));
+    unsigned int hflag = 0;
+    PFD_CUDA(h, cudaMemcpyAsync(&hflag, flag, sizeof(hflag), cudaMemcpyDeviceToHost, h->stream));
+    PFD_TRY(pfd_finish_out(h, pfafbas_out, out_dev, (size_t)n * sizeof(int64_t)));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    if (hflag & 8u) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_subbasins_pfafstetter: idxs_us_main holds an index outside the raster");
+    if (hflag & 32u)
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_subbasins_pfafstetter: idxs_us_main misses the main upstream cell of a confluence");
+    if (n_outlets) *n_outlets = nout_total;
+    return PFD_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // synthetic input
 // ---------------------------------------------------------------------------------------------------------

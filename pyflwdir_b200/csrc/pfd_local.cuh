@@ -368,3 +368,283 @@ __global__ void stream_write_kernel(const uint8_t* __restrict__ dir, const cell_
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// basins.subbasins_pfafstetter (pyflwdir/basins.py:106-191). The reference pops labels from a FIFO; a label owns a
+// "stem" (the main-upstream chain that carries it), picks its four largest unlabelled tributaries, labels them (odd
+// digits) and carves the stem into interbasins (even digits); the new labels go to the back of the FIFO, so the FIFO is
+// processed depth by depth, and the stems and tributary subtrees of the labels of one depth are disjoint. One depth =
+// one round here, one thread per label: count the candidate tributaries along the stem -> scan -> collect them, restore
+// sequence order, numba's argsort on -uparea (ties!), label, emit children / outlets into per-label slots -> ordered
+// compaction into the next round's label list and the outlet list.
+// ---------------------------------------------------------------------------------------------------------
+#define PF_MV 0xFFFFFFFFu
+
+__global__ void pf_prepare_kernel(uint8_t* __restrict__ strord, int64_t n, int depth) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if ((int)strord[i] > depth + 1) strord[i] = 0;
+}
+__global__ void pf_pos_kernel(const cell_t* __restrict__ seq, int64_t m, uint32_t* __restrict__ pos) {
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < m; q += (int64_t)gridDim.x * blockDim.x) pos[seq[q]] = (uint32_t)q;
+}
+template <typename IDX>
+__global__ void pf_main32_kernel(const IDX* __restrict__ us_main, int64_t n, uint32_t* __restrict__ out, unsigned int* __restrict__ flag) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const IDX u = us_main[i];
+        uint32_t v = PF_MV;
+        if (u != (IDX)-1) {
+            if ((long long)u < 0 || (long long)u >= n) atomicOr(flag, 8u);
+            else v = (uint32_t)u;
+        }
+        out[i] = v;
+    }
+}
+template <typename T>
+__global__ void pf_to_double_kernel(const T* __restrict__ a, int64_t n, double* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (double)a[i];
+}
+
+struct PfGraph {
+    const uint8_t* dir;
+    const uint8_t* upmask;
+    const uint8_t* strord;
+    const uint32_t* main;   // idxs_us_main as uint32, PF_MV at headwaters
+    const uint32_t* pos;    // position of a cell inside seq
+    const double* uparea;
+    int32_t* pb;            // pfaf_branch
+    uint8_t* inidx;         // 1 where the cell is already in the outlet list (`idx1 not in idxs`)
+    long long ncol;
+    int depth;
+};
+
+// label its outlet, then the main stem upstream of it while the stream order is non-zero (basins.py:134-141,163-169)
+__device__ __forceinline__ void pf_label_stem(const PfGraph& G, uint32_t cell, long long label) {
+    G.pb[cell] = (int32_t)label;
+    while (true) {
+        const uint32_t u = G.main[cell];
+        if (u == PF_MV || G.strord[u] == 0) break;
+        cell = u;
+        G.pb[cell] = (int32_t)label;
+    }
+}
+
+__device__ __forceinline__ long long pf_pow10(int e) {
+    long long p = 1;
+    for (int i = 0; i < e; ++i) p *= 10;
+    return p;
+}
+
+__global__ void pf_init_pits_kernel(PfGraph G, const cell_t* __restrict__ pits, long long npits, long long* __restrict__ lab,
+                                    uint32_t* __restrict__ lab_out, cell_t* __restrict__ outlets) {
+    long long base = 1;
+    for (int d0 = 1; d0 < G.depth; ++d0) base += pf_pow10(d0);
+    const long long p = pf_pow10(G.depth);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npits; i += (long long)gridDim.x * blockDim.x) {
+        const uint32_t c = pits[i];
+        const long long label = base + (i + 1) * p;
+        lab[i] = label;
+        lab_out[i] = c;
+        outlets[i] = c;
+        G.inidx[c] = 1;
+        pf_label_stem(G, c, label);
+    }
+}
+
+// visits the unlabelled tributaries attached to the stem of (label, outlet): cells t that drain into a stem cell c with
+// strord[t] > 0 and strord[t] > strord[c] (basins.py:107-114) and pfaf_branch[t] == 0
+template <class F>
+__device__ __forceinline__ void pf_for_candidates(const PfGraph& G, long long label, uint32_t outlet, F f) {
+    uint32_t c = outlet;
+    while ((long long)G.pb[c] == label) {
+        uint32_t m = G.upmask[c];
+        const uint32_t sc = G.strord[c];
+        while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t t = (uint32_t)((long long)c + pfd_slot_off(k, G.ncol));
+            const uint32_t st = G.strord[t];
+            if (st > 0 && st > sc && G.pb[t] == 0) f(t);
+        }
+        const uint32_t u = G.main[c];
+        if (u == PF_MV) break;
+        c = u;
+    }
+}
+
+__global__ void pf_count_kernel(PfGraph G, const long long* __restrict__ lab, const uint32_t* __restrict__ lab_out, long long nlab,
+                                uint32_t* __restrict__ cnt) {
+    for (long long l = blockIdx.x * (long long)blockDim.x + threadIdx.x; l < nlab; l += (long long)gridDim.x * blockDim.x) {
+        uint32_t n = 0;
+        pf_for_candidates(G, lab[l], lab_out[l], [&](uint32_t) { ++n; });
+        cnt[l] = n;
+    }
+}
+
+// numba's `a < b` for float keys (numba/np/numpy_support.py lt_floats): NaNs sort last
+__device__ __forceinline__ bool pf_lt(double a, double b) { return a < b || (isnan(b) && !isnan(a)); }
+
+// np.argsort as numba compiles it (numba/misc/quicksort.py), on keys A[0..n) with the index array R
+__device__ void pf_numba_argsort(const double* A, long long n, uint32_t* R) {
+    for (long long i = 0; i < n; ++i) R[i] = (uint32_t)i;
+    if (n < 2) return;
+    long long slo[100], shi[100];
+    int ns = 1;
+    slo[0] = 0;
+    shi[0] = n - 1;
+    while (ns > 0) {
+        --ns;
+        long long low = slo[ns], high = shi[ns];
+        while (high - low >= 15) {
+            const long long mid = (low + high) >> 1;
+            uint32_t t;
+            if (pf_lt(A[R[mid]], A[R[low]])) { t = R[low]; R[low] = R[mid]; R[mid] = t; }
+            if (pf_lt(A[R[high]], A[R[mid]])) { t = R[high]; R[high] = R[mid]; R[mid] = t; }
+            if (pf_lt(A[R[mid]], A[R[low]])) { t = R[low]; R[low] = R[mid]; R[mid] = t; }
+            const double pivot = A[R[mid]];
+            t = R[high]; R[high] = R[mid]; R[mid] = t;
+            long long i = low, j = high - 1;
+            while (true) {
+                while (i < high && pf_lt(A[R[i]], pivot)) ++i;
+                while (j >= low && pf_lt(pivot, A[R[j]])) --j;
+                if (i >= j) break;
+                t = R[i]; R[i] = R[j]; R[j] = t;
+                ++i;
+                --j;
+            }
+            t = R[i]; R[i] = R[high]; R[high] = t;
+            if (high - i > i - low) {
+                if (high > i && ns < 100) { slo[ns] = i + 1; shi[ns] = high; ++ns; }
+                high = i - 1;
+            } else {
+                if (i > low && ns < 100) { slo[ns] = low; shi[ns] = i - 1; ++ns; }
+                low = i + 1;
+            }
+        }
+        for (long long i = low + 1; i <= high; ++i) {
+            const uint32_t k = R[i];
+            const double v = A[k];
+            long long j = i;
+            while (j > low && pf_lt(v, A[R[j - 1]])) {
+                R[j] = R[j - 1];
+                --j;
+            }
+            R[j] = k;
+        }
+    }
+}
+
+// ascending heap sort of the candidate cells by their sequence position (unique keys)
+__device__ void pf_sort_by_pos(const uint32_t* __restrict__ pos, uint32_t* c, long long n) {
+    auto sift = [&](long long root, long long end) {
+        while (true) {
+            long long child = 2 * root + 1;
+            if (child > end) break;
+            if (child + 1 <= end && pos[c[child]] < pos[c[child + 1]]) ++child;
+            if (pos[c[root]] < pos[c[child]]) {
+                const uint32_t t = c[root]; c[root] = c[child]; c[child] = t;
+                root = child;
+            } else break;
+        }
+    };
+    for (long long s = (n - 2) / 2; s >= 0; --s) sift(s, n - 1);
+    for (long long e = n - 1; e > 0; --e) {
+        const uint32_t t = c[0]; c[0] = c[e]; c[e] = t;
+        sift(0, e - 1);
+    }
+}
+
+// one label: basins.py:142-187. Children / outlets go to the label's 8 slots.
+__global__ void pf_process_kernel(PfGraph G, const long long* __restrict__ lab, const uint32_t* __restrict__ lab_out, long long nlab,
+                                  int d0, const unsigned long long* __restrict__ off, uint32_t* __restrict__ cand,
+                                  double* __restrict__ key, uint32_t* __restrict__ R, long long* __restrict__ child_lab,
+                                  uint32_t* __restrict__ child_out, uint32_t* __restrict__ nchild, uint32_t* __restrict__ out_cells,
+                                  uint32_t* __restrict__ nout, unsigned int* __restrict__ flag) {
+    for (long long l = blockIdx.x * (long long)blockDim.x + threadIdx.x; l < nlab; l += (long long)gridDim.x * blockDim.x) {
+        const long long pfaf0 = lab[l];
+        const long long n = (long long)(off[l + 1] - off[l]);
+        uint32_t nc = 0, no = 0;
+        if (n > 0) {
+            uint32_t* c = cand + off[l];
+            double* kk = key + off[l];
+            uint32_t* r = R + off[l];
+            long long w = 0;
+            pf_for_candidates(G, pfaf0, lab_out[l], [&](uint32_t t) { c[w++] = t; });
+            pf_sort_by_pos(G.pos, c, n);  // the order of idxs_trib (sequence order)
+            for (long long i = 0; i < n; ++i) kk[i] = -G.uparea[c[i]];
+            pf_numba_argsort(kk, n, r);   // idxs0[np.argsort(-uparea[idxs0])]
+            const int n4 = (int)min(n, 4ll);
+            uint32_t t4[4], o4[4];
+            double k4[4];
+            for (int i = 0; i < n4; ++i) {
+                t4[i] = c[r[i]];
+                const uint32_t d = G.dir[t4[i]];
+                k4[i] = -G.uparea[(long long)t4[i] + pfd_slot_off((int)d, G.ncol)];
+            }
+            pf_numba_argsort(k4, n4, o4);  // down- to upstream along the stem
+            const long long p = pf_pow10(G.depth - d0);
+            long long pfaf_int_ds = pfaf0;
+            for (int i = 0; i < n4; ++i) {
+                const uint32_t idx = t4[o4[i]];
+                out_cells[l * 8 + no++] = idx;
+                G.inidx[idx] = 1;
+                const uint32_t ds = (uint32_t)((long long)idx + pfd_slot_off((int)G.dir[idx], G.ncol));
+                uint32_t idx1 = G.main[ds];
+                const long long pfaf_sub = pfaf0 + (long long)(i * 2 + 1) * p;
+                pf_label_stem(G, idx, pfaf_sub);
+                if (d0 < G.depth) {
+                    child_lab[l * 8 + nc] = pfaf_sub;
+                    child_out[l * 8 + nc] = idx;
+                    ++nc;
+                }
+                if (idx1 == PF_MV) {  // the reference would index with -1 here
+                    atomicOr(flag, 32u);
+                    break;
+                }
+                if (!G.inidx[idx1]) {
+                    out_cells[l * 8 + no++] = idx1;
+                    G.inidx[idx1] = 1;
+                    const long long pfaf_int = pfaf0 + (long long)(i + 1) * 2 * p;
+                    const uint32_t int_outlet = idx1;
+                    G.pb[idx1] = (int32_t)pfaf_int;
+                    while (true) {
+                        const uint32_t u = G.main[idx1];
+                        if (u == PF_MV || (long long)G.pb[u] != pfaf_int_ds) break;
+                        idx1 = u;
+                        G.pb[idx1] = (int32_t)pfaf_int;
+                    }
+                    pfaf_int_ds = pfaf_int;
+                    if (d0 < G.depth) {
+                        child_lab[l * 8 + nc] = pfaf_int;
+                        child_out[l * 8 + nc] = int_outlet;
+                        ++nc;
+                    }
+                }
+            }
+        }
+        nchild[l] = nc;
+        nout[l] = no;
+    }
+}
+
+__global__ void pf_gather_kernel(long long nlab, const long long* __restrict__ child_lab, const uint32_t* __restrict__ child_out,
+                                 const uint32_t* __restrict__ nchild, const unsigned long long* __restrict__ child_off,
+                                 const uint32_t* __restrict__ out_cells, const uint32_t* __restrict__ nout,
+                                 const unsigned long long* __restrict__ out_off, long long* __restrict__ next_lab,
+                                 uint32_t* __restrict__ next_out, cell_t* __restrict__ outlets_tail) {
+    for (long long l = blockIdx.x * (long long)blockDim.x + threadIdx.x; l < nlab; l += (long long)gridDim.x * blockDim.x) {
+        for (uint32_t j = 0; j < nchild[l]; ++j) {
+            next_lab[child_off[l] + j] = child_lab[l * 8 + j];
+            next_out[child_off[l] + j] = child_out[l * 8 + j];
+        }
+        for (uint32_t j = 0; j < nout[l]; ++j) outlets_tail[out_off[l] + j] = out_cells[l * 8 + j];
+    }
+}
+
+// pfaf_branch % 10**depth with Python's sign rule, as int64 (numba: int32 % int64 -> int64)
+__global__ void pf_mod_kernel(const int32_t* __restrict__ pb, int64_t n, long long mod, int64_t* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        long long m = (long long)pb[i] % mod;
+        if (m < 0) m += mod;
+        out[i] = m;
+    }
+}

@@ -307,7 +307,7 @@ class Flwdir(object):
 
     # ------------------------------------------------------------------ not in scope
     for _name in ("smooth_rivlen",
-                  "subbasins_pfafstetter", "dem_adjust", "dem_dig_d4",
+                  "dem_adjust", "dem_dig_d4",
                   "classify_estuaries", "ucat_area", "ucat_outlets", "ucat_volume", "subgrid_rivlen",
                   "subgrid_rivslp", "subgrid_rivavg", "subgrid_rivmed", "subgrid_rivlen2", "upscale", "upscale_error",
                   "accuflux_ds"):

@@ -387,6 +387,15 @@ class FlwdirRaster(Flwdir):
             idx_dtype=self._idx_dtype)
         return subbas.reshape(self.shape), idxs_out
 
+    def subbasins_pfafstetter(self, depth=1, uparea=None, upa_min=0.0):
+        """Returns the pfafstetter subbasins and the linear indices of their outlet cells
+        (pyflwdir.py:631-663 -> basins.subbasins_pfafstetter, basins.py:106-191)."""
+        uparea = self._check_data(uparea, "uparea")
+        mask = uparea >= upa_min if upa_min is not None else None
+        subbas, idxs_out = self._dev.subbasins_pfafstetter(self.idxs_us_main, uparea, mask=mask, depth=depth,
+                                                           idx_dtype=self._idx_dtype)
+        return subbas.reshape(self.shape), idxs_out
+
     def subbasins_area(self, area_min, uparea=None):
         """Returns map with basin IDs, with a minimal area of `area_min` (pyflwdir.py:665-692 -> basins.subbasins_area):
         (uint32 map, linear indices of the subbasin outlets)."""
@@ -458,7 +467,7 @@ class FlwdirRaster(Flwdir):
             idxs = self.index(*xy)
         return super()._check_idxs_xy(idxs, streams)
 
-    for _name in ("repair_loops_raster", "subbasins_pfafstetter",
+    for _name in ("repair_loops_raster",
                   "dem_adjust", "dem_dig_d4",
                   "upscale", "upscale_error", "subgrid_rivlen", "subgrid_rivslp", "subgrid_rivavg", "subgrid_rivmed",
                   "ucat_area", "ucat_outlets", "ucat_volume"):

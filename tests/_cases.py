@@ -276,6 +276,11 @@ def run_oracle_case(d8, aux, area=None, transform=(1.0, 0.0, 0.0, 0.0, -1.0, 0.0
         vmask = aux["smask"].ravel()
         pairs = [np.array([i, idxs_ds[i]]) for i in np.flatnonzero(mask & vmask)]
         _oracle_feats(pairs, "vector", out, tr6, shape[1])
+    # Pfafstetter subbasins
+    upc_flat = out["uparea_cell"].ravel()
+    for key, depth, upa_min in (("pfaf_d1", 1, 0.0), ("pfaf_d2", 2, 0.0), ("pfaf_d3_min", 3, 5.0)):
+        sub, sidx = o.basins.subbasins_pfafstetter(idxs_pit, idxs_ds, seq, um, upc_flat, mask=upc_flat >= upa_min, depth=depth)
+        out[key], out[key + "_idxs"] = sub.reshape(shape), sidx
     return out
 
 
@@ -378,4 +383,7 @@ def run_api_case(pf, d8, aux, transform=None, latlon=False):
         _feats_arrays(flw.streams(max_len=7), "streams_len7", out)
         _feats_arrays(flw.streams(mask=aux["smask"], max_len=3), "streams_gaps", out)
         _feats_arrays(flw.vectorize(mask=aux["smask"]), "vector", out)
+    # Pfafstetter subbasins
+    for key, depth, upa_min in (("pfaf_d1", 1, 0.0), ("pfaf_d2", 2, 0.0), ("pfaf_d3_min", 3, 5.0)):
+        out[key], out[key + "_idxs"] = flw.subbasins_pfafstetter(depth=depth, upa_min=upa_min)
     return out

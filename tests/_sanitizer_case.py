@@ -9,6 +9,9 @@ for name in ["flwdir1_asc", "random48x61", "synth96x130"]:
     out = cs.run_api_case(pfb, d8, aux)
     for k, v in out.items():
         cs.check(name, k, v)
+nxy = cs.small()["in/nextxy_flwdir1/nextxy"]
+flw = pfb.from_array(nxy)
+assert np.array_equal(flw.to_array(), cs.small()["out/nextxy_flwdir1/to_array"])
 z = oracle.synth_elevation(200, 150, seed=41)
 d8 = oracle.synth_d8(z, sea_level=float(np.quantile(z, 0.05)))
 got = tiled.solve_emulated(d8, 3)
