@@ -276,6 +276,12 @@ int pfd_streams(pfd_handle* h, const uint8_t* mask, int64_t max_len, int64_t* n_
 int pfd_subbasins_pfafstetter(pfd_handle* h, const void* idxs_us_main, int idx_dtype, const void* uparea, int dtype,
                               const uint8_t* mask, int depth, int64_t* pfafbas_out, int64_t* n_outlets);
 
+/* rivers.classify_estuary (pyflwdir/rivers.py:11-53): estuaries by width convergence. est_init: N int8, 1 at the pits with
+ * elevtn <= max_elevtn (selected by the caller, rivers.py:38-39), 0 elsewhere; rivdst / rivwth: N float32 or float64;
+ * out: N int8 (>= 1 where estuary, 2 at the upstream end). */
+int pfd_classify_estuary(pfd_handle* h, const int8_t* est_init, const void* rivdst, int dst_dtype, const void* rivwth,
+                         int wth_dtype, double min_convergence, int8_t* out);
+
 /* ---- fused headline pass ------------------------------------------------------------------------------ */
 /*
  * parse + order + rank + upstream_area(cell) + basins() in one call (BASELINE.json metric). Any output may be

@@ -509,6 +509,23 @@ def _nextxy_to_array(idxs_ds, shape, mv=None):
 core_nextxy = types.SimpleNamespace(from_array=_nextxy_from_array, to_array=_nextxy_to_array)
 
 
+# ----------------------------------------------------------------------------- rivers
+def _classify_estuary(idxs_ds, seq, idxs_pit, rivdst, rivwth, elevtn, max_elevtn=0, min_convergence=1e-2):
+    """pyflwdir/rivers.py:11-53"""
+    a, sfx = _idx(idxs_ds)
+    s = np.ascontiguousarray(seq).astype(a.dtype)
+    rivdst, rivwth = np.ascontiguousarray(rivdst), np.ascontiguousarray(rivwth)
+    est = np.zeros(a.size, np.int8)
+    pits = np.asarray(idxs_pit)
+    est[pits[np.asarray(elevtn)[pits] <= max_elevtn]] = 1
+    _fn(f"orc_classify_estuary_{_FSFX[rivdst.dtype]}_{_FSFX[rivwth.dtype]}", sfx)(
+        _p(a), _p(s), C.c_int64(s.size), _p(rivdst), _p(rivwth), C.c_double(float(min_convergence)), _p(est))
+    return est
+
+
+rivers = types.SimpleNamespace(classify_estuary=_classify_estuary)
+
+
 # ----------------------------------------------------------------------------- streams
 def _nodata_args(nodata):
     is_int = isinstance(nodata, (int, np.integer)) and not isinstance(nodata, (bool, np.bool_))

@@ -268,6 +268,23 @@ class DeviceGraph:
                                                    _lib.ptr(out), C.byref(k)))
         return out, self._fetch_selected(k.value, idx_dtype)
 
+    def classify_estuary(self, est_init, rivdst, rivwth, min_convergence):
+        """rivers.classify_estuary -> int8 map."""
+        arrs = []
+        for a, name in ((rivdst, "rivdst"), (rivwth, "rivwth")):
+            a = np.ascontiguousarray(a)
+            if a.size != self.size:
+                raise ValueError(f'"{name}" size does not match.')
+            if a.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+                a = a.astype(np.float64)
+            arrs.append(a)
+        est_init = np.ascontiguousarray(est_init, dtype=np.int8)
+        out = _lib.out_array(self.size, np.int8)
+        self._ck(self._l.pfd_classify_estuary(self._h, _lib.ptr(est_init), _lib.ptr(arrs[0]), _lib.dtype_code(arrs[0].dtype),
+                                              _lib.ptr(arrs[1]), _lib.dtype_code(arrs[1].dtype), C.c_double(float(min_convergence)),
+                                              _lib.ptr(out)))
+        return out
+
     def _window_args(self, data, idxs_us_main, strord):
         data = np.ascontiguousarray(data)
         if data.size != self.size:

@@ -72,6 +72,7 @@ SYMBOLS = {
     "pfd_interbasin_mask": (_int, [_vp, _vp, _vp, _vp]),
     "pfd_region_outlets": (_int, [_vp, _vp, _int, _pi64]),
     "pfd_subbasins_pfafstetter": (_int, [_vp, _vp, _int, _vp, _int, _vp, _int, _vp, _pi64]),
+    "pfd_classify_estuary": (_int, [_vp, _vp, _vp, _int, _vp, _int, C.c_double, _vp]),
     "pfd_streams": (_int, [_vp, _vp, _i64, _pi64, _pi64]),
     "pfd_region_slices": (_int, [_vp, _vp, _int, _pi64]),
     "pfd_d8_flow_all": (_int, [_vp, _vp, _i64, _i64, _vp, _int, _vp, _vp, _vp, _pi64, _pi64, _pi64]),

@@ -2762,6 +2762,42 @@ extern "C" int pfd_subbasins_pfafstetter(pfd_handle* h, const void* idxs_us_main
     return PFD_OK;
 }
 
+// rivers.classify_estuary (pyflwdir/rivers.py:11-53). est_init: N int8 with 1 at the estuary outlets (pits with
+// elevtn <= max_elevtn; selected by the caller), 0 elsewhere.
+template <typename TD, typename TW>
+static int estuary_typed(pfd_handle* h, const void* dst_dev, const void* wth_dev, double min_convergence, int8_t* est) {
+    EstuaryOp<TD, TW> op{(const uint8_t*)h->dir.p, (const TD*)dst_dev, (const TW*)wth_dev, est, min_convergence, h->ncol};
+    return run_sweep<EstuaryOp<TD, TW>, false>(h, op, 1);
+}
+extern "C" int pfd_classify_estuary(pfd_handle* h, const int8_t* est_init, const void* rivdst, int dst_dtype, const void* rivwth,
+                                    int wth_dtype, double min_convergence, int8_t* out) {
+    PFD_TRY(require_raster(h, "pfd_classify_estuary"));
+    stage_reset(h);
+    if (!est_init || !rivdst || !rivwth || !out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_classify_estuary: null array");
+    if ((dst_dtype != PFD_F32 && dst_dtype != PFD_F64) || (wth_dtype != PFD_F32 && wth_dtype != PFD_F64))
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_classify_estuary: rivdst / rivwth must be float32 or float64");
+    PFD_TRY(order_impl(h, false, false));
+    const int64_t n = h->n;
+    void* out_dev = nullptr;
+    PFD_TRY(pfd_stage_out(h, out, (size_t)n, 3, &out_dev));
+    const void *dst_dev = nullptr, *wth_dev = nullptr;
+    PFD_TRY(pfd_stage_in(h, rivdst, (size_t)n * pfd_dtype_size(dst_dtype), 5, &dst_dev));
+    PFD_TRY(pfd_stage_in(h, rivwth, (size_t)n * pfd_dtype_size(wth_dtype), 4, &wth_dev));
+    if (out_dev != (const void*)est_init) PFD_CUDA(h, cudaMemcpyAsync(out_dev, est_init, (size_t)n, cudaMemcpyDefault, h->stream));
+    int rc;
+    if (dst_dtype == PFD_F32)
+        rc = wth_dtype == PFD_F32 ? estuary_typed<float, float>(h, dst_dev, wth_dev, min_convergence, (int8_t*)out_dev)
+                                  : estuary_typed<float, double>(h, dst_dev, wth_dev, min_convergence, (int8_t*)out_dev);
+    else
+        rc = wth_dtype == PFD_F32 ? estuary_typed<double, float>(h, dst_dev, wth_dev, min_convergence, (int8_t*)out_dev)
+                                  : estuary_typed<double, double>(h, dst_dev, wth_dev, min_convergence, (int8_t*)out_dev);
+    PFD_TRY(rc);
+    PFD_TRY(pfd_finish_out(h, out, out_dev, (size_t)n));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    stage_collect(h);
+    return PFD_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // synthetic input
 // ---------------------------------------------------------------------------------------------------------

@@ -648,3 +648,30 @@ __global__ void pf_mod_kernel(const int32_t* __restrict__ pb, int64_t n, long lo
         out[i] = m;
     }
 }
+
+// ---- rivers.classify_estuary (pyflwdir/rivers.py:11-53): down-sweep. A cell whose downstream cell is estuary joins it
+// if the river keeps widening downstream fast enough, else it marks the downstream cell as the upstream end (2). The
+// parent's value is only tested for != 0, so the siblings' concurrent `= 2` writes do not change any decision. ----------
+template <typename TD, typename TW>
+struct EstuaryOp {
+    const uint8_t* dir;
+    const TD* rivdst;
+    const TW* rivwth;
+    int8_t* est;  // pre-initialised: 1 at the pits with elevtn <= max_elevtn, else 0
+    double min_convergence;
+    long long ncol;
+    __device__ __forceinline__ void operator()(cell_t c, long long, int) const {
+        const uint32_t d = __ldg(dir + c);
+        if (d >= 8u) return;  // idx == idx_ds
+        const long long ds = (long long)c + pfd_slot_off((int)d, ncol);
+        if (ld_cg(est + ds) == 0) return;
+        const TD dst_ds = __ldg(rivdst + ds);
+        const TD dx = elev_sub<TD>(__ldg(rivdst + c), dst_ds);
+        const TW dw = elev_sub<TW>(__ldg(rivwth + ds), __ldg(rivwth + c));
+        bool conv;
+        if (sizeof(TD) == 4 && sizeof(TW) == 4) conv = (double)__fdiv_rn((float)dw, (float)dx) > min_convergence;  // float32 / float32
+        else conv = __ddiv_rn((double)dw, (double)dx) > min_convergence;
+        if ((dst_ds == (TD)0 && dw <= (TW)0) || (dx > (TD)0 && conv)) est[c] = 1;
+        else est[ds] = 2;  // most upstream estuary link
+    }
+};

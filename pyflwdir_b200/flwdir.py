@@ -230,6 +230,55 @@ class Flwdir(object):
             strord=self._check_data(strord, "strord", optional=not restrict_strord), nodata=nodata)
         return dout.reshape(np.shape(data))
 
+    # ------------------------------------------------------------------ rivers
+    @property
+    def distnc(self):
+        """Distance to outlet [m] (flwdir.py:206-213)"""
+        if "distnc" in self._cached:
+            return self._cached["distnc"]
+        return np.ones(self.size, dtype=np.float32)
+
+    def classify_estuaries(self, elevtn, rivwth, rivdst=None, min_convergence=1e-2, max_elevtn=0):
+        """Classifies estuaries based on a minimum width convergence (flwdir.py:666-696 -> rivers.classify_estuary,
+        rivers.py:11-53): int8, >= 1 where estuary, 2 at the upstream end of an estuary. Flat, like the reference."""
+        rivdst = self.distnc if rivdst is None else rivdst
+        rivdst = self._check_data(rivdst, "rivdst")
+        rivwth = self._check_data(rivwth, "rivwth")
+        elevtn = self._check_data(elevtn, "elevtn")
+        est = np.zeros(self.size, np.int8)
+        pits = self.idxs_pit
+        est[pits[elevtn[pits] <= max_elevtn]] = 1  # rivers.py:38-39
+        return self._dev.classify_estuary(est, rivdst, rivwth, min_convergence)
+
+    def river_depth(self, qbankfull, rivwth, zs=None, rivdst=None, rivslp=None, manning=0.03, method="manning",
+                    min_rivdph=1, min_rivslp=1e-5, **kwargs):
+        """Return an estimated river depth based on manning's equation for a rectangular river profile
+        (flwdir.py:698-778; element-wise numpy on the host like the reference, `downstream` and `fillnodata` on the device).
+        The experimental "gvf" solver (rivers.rivdph_gvf: one scipy solve_ivp call per cell) is not provided."""
+        methods = ["manning", "gvf"]
+        if method not in methods:
+            raise ValueError(f"Method unknown {method}, select from {methods}")
+        manning = self._check_data(manning, "manning")
+        qbankfull = self._check_data(qbankfull, "qbankfull")
+        rivwth = self._check_data(rivwth, "rivwth")
+        _opt = method == "manning" and rivslp is not None
+        rivslp = self._check_data(rivslp, "rivslp", optional=True)
+        rivdst = self._check_data(rivdst, "rivdst", optional=_opt)
+        zs = self._check_data(zs, "zs", optional=_opt)
+        if method == "gvf":
+            raise NotImplementedError('river_depth(method="gvf") integrates an ODE per cell with scipy on the host and is outside '
+                                      "the D8 hot path that pyflwdir_b200 accelerates")
+        if rivslp is None:
+            dz = zs - self.downstream(zs)
+            dx = rivdst - self.downstream(rivdst)
+            rivslp = np.where(dx >= 1, dz / np.maximum(1, dx), -9999)
+            rivslp = self.fillnodata(rivslp, nodata=-9999)
+        rivslp = np.maximum(min_rivslp, rivslp)
+        rivdph = ((manning * qbankfull) / (np.sqrt(rivslp) * rivwth)) ** (3 / 5)
+        rivdph = np.maximum(min_rivdph, rivdph)
+        rivdph[self.idxs_ds == self._mv] = -9999.0
+        return rivdph.reshape(self.shape)
+
     # ------------------------------------------------------------------ local methods
     def path(self, idxs=None, mask=None, max_length=None, direction="down"):
         """Returns paths of indices in down- or upstream direction from the starting points until a pit / headwater,
@@ -306,10 +355,6 @@ class Flwdir(object):
         return idxs
 
     # ------------------------------------------------------------------ not in scope
-    for _name in ("smooth_rivlen",
-                  "dem_adjust", "dem_dig_d4",
-                  "classify_estuaries", "ucat_area", "ucat_outlets", "ucat_volume", "subgrid_rivlen",
-                  "subgrid_rivslp", "subgrid_rivavg", "subgrid_rivmed", "subgrid_rivlen2", "upscale", "upscale_error",
-                  "accuflux_ds"):
+    for _name in ("smooth_rivlen", "dem_adjust"):
         locals()[_name] = _not_in_scope(_name)
     del _name

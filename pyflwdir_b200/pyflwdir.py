@@ -189,6 +189,30 @@ class FlwdirRaster(Flwdir):
                 self._cached.update(area=area)
         return area
 
+    @property
+    def bounds(self):
+        """Returns the raster bounding box [xmin, ymin, xmax, ymax] (pyflwdir.py:409-412 -> gis_utils.array_bounds)."""
+        w, n = self.transform.xoff, self.transform.yoff
+        e, s = self.transform * (self.shape[1], self.shape[0])
+        return np.array((w, s, e, n), dtype=np.float64)
+
+    @property
+    def extent(self):
+        """Returns the raster extent in cartopy format [xmin, xmax, ymin, ymax]."""
+        xmin, ymin, xmax, ymax = self.bounds
+        return np.array([xmin, xmax, ymin, ymax], dtype=np.float64)
+
+    @property
+    def distnc(self):
+        """Distance to outlet [m] (pyflwdir.py:420-429)"""
+        if "distnc" in self._cached:
+            distnc = self._cached["distnc"]
+        else:
+            distnc = self.stream_distance(unit="m")
+            if self.cache:
+                self._cached.update(distnc=distnc)
+        return distnc
+
     # ------------------------------------------------------------------ set / modify
     def set_transform(self, transform, latlon=False):
         """Set transform affine (pyflwdir.py:318-337)."""
@@ -467,9 +491,7 @@ class FlwdirRaster(Flwdir):
             idxs = self.index(*xy)
         return super()._check_idxs_xy(idxs, streams)
 
-    for _name in ("repair_loops_raster",
-                  "dem_adjust", "dem_dig_d4",
-                  "upscale", "upscale_error", "subgrid_rivlen", "subgrid_rivslp", "subgrid_rivavg", "subgrid_rivmed",
-                  "ucat_area", "ucat_outlets", "ucat_volume"):
+    for _name in ("dem_dig_d4", "upscale", "upscale_error", "ucat_outlets", "ucat_area", "ucat_volume",
+                  "subgrid_rivlen", "subgrid_rivslp", "subgrid_rivavg", "subgrid_rivmed"):
         locals()[_name] = _not_in_scope(_name)
     del _name
