@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpfd_b200.so")
+LIB_PATH = os.environ.get("PFD_B200_LIB") or os.path.join(_HERE, "libpfd_b200.so")  # override: kernel experiments
 
 # pfd_status
 OK, ERR_CUDA, ERR_INVALID_ARG, ERR_INVALID_D8, ERR_NO_PITS, ERR_STATE, ERR_UNSUPPORTED, ERR_OOM, ERR_NCCL = range(9)
