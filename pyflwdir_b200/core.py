@@ -1,5 +1,6 @@
 """Format-agnostic graph kernels on the GPU; mirrors /root/reference/pyflwdir/core.py (rank :17-47,
-upstream_count :50-61, idxs_seq :87-117, fillnodata_upstream :120-146, pit_indices :225-232).
+upstream_count :50-61, idxs_seq :87-117, fillnodata_upstream :120-146, pit_indices :225-232, path :400-438,
+snap :441-480, inflow_idxs / outflow_idxs :483-514).
 `shape=` / `ncol=` are optional extensions (the raster width is inferred from the links otherwise)."""
 import numpy as np
 
@@ -60,3 +61,51 @@ def fillnodata_downstream(idxs_ds, seq, data, nodata, how="max", shape=None, nco
     g = _functional.graph(idxs_ds, shape, ncol)
     _functional.check_seq(g, seq, "fillnodata_downstream")
     return g.fillnodata(np.asarray(data).ravel(), nodata, "down", how)
+
+
+def _trace(idxs0, idxs_nxt, ncol, mask, max_length, real_length, latlon, transform, shape, paths):
+    from . import gis_utils as gis
+
+    idxs_nxt = np.asarray(idxs_nxt)
+    n = idxs_nxt.size
+    # idxs_nxt is idxs_ds (downstream trace) or idxs_us_main (upstream trace): the former holds self-links at the pits
+    own = np.arange(n, dtype=np.int64)
+    nx = idxs_nxt.astype(np.int64)
+    down = bool(np.any(nx == own))
+    if not down:
+        raise NotImplementedError("core.path / core.snap along idxs_us_main need the downstream links as well: use "
+                                  "FlwdirRaster.path(direction='up') / snap(direction='up')")
+    if shape is None and ncol is not None:
+        shape = (n // int(ncol), int(ncol))
+    g = _functional.graph(idxs_nxt, shape, None)
+    hop = gis.hop_length_table(g.shape[0], transform, latlon, dtype=np.float64) if (real_length and ncol is not None) else None
+    return g.trace(np.atleast_1d(idxs0), "down", None, mask, max_length, hop, paths_dtype=idxs_nxt.dtype if paths else None)
+
+
+def path(idxs0, idxs_nxt, ncol=None, mask=None, max_length=None, real_length=False, latlon=False,
+         transform=(1.0, 0.0, 0.0, 0.0, -1.0, 0.0), mv=_mv, shape=None):
+    """Traces from every start cell along idxs_nxt -> (list of index arrays, float64 distances); core.py:400-438"""
+    paths, _, dist = _trace(idxs0, idxs_nxt, ncol, mask, max_length, real_length, latlon, transform, shape, True)
+    return paths, dist
+
+
+def snap(idxs0, idxs_nxt, ncol=None, mask=None, max_length=None, real_length=False, latlon=False,
+         transform=(1.0, 0.0, 0.0, 0.0, -1.0, 0.0), mv=_mv, shape=None):
+    """Last cell of every trace -> (indices in the dtype of idxs0, float32 distances); core.py:441-480"""
+    idxs0 = np.atleast_1d(idxs0)
+    _, ends, dist = _trace(idxs0, idxs_nxt, ncol, mask, max_length, real_length, latlon, transform, shape, False)
+    return ends.astype(idxs0.dtype), dist.astype(np.float32)
+
+
+def inflow_idxs(idxs_ds, seq, region, shape=None, ncol=None):
+    """returns linear indices of most upstream cells within region (core.py:483-497)"""
+    g = _functional.graph(idxs_ds, shape, ncol)
+    _functional.check_seq(g, seq, "inflow_idxs")
+    return g.inflow_idxs(np.asarray(region).ravel(), np.asarray(idxs_ds).dtype)
+
+
+def outflow_idxs(idxs_ds, seq, region, shape=None, ncol=None):
+    """returns linear indices of most downstream cells within region (core.py:500-514)"""
+    g = _functional.graph(idxs_ds, shape, ncol)
+    _functional.check_seq(g, seq, "outflow_idxs")
+    return g.outflow_idxs(np.asarray(region).ravel(), np.asarray(idxs_ds).dtype)

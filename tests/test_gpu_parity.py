@@ -338,3 +338,52 @@ def test_streams_raw_segments(pfb):
         assert len(got) == len(want)
         assert np.array_equal(np.array([g.size for g in got]), np.array([w.size for w in want]))
         assert np.array_equal(np.concatenate(got), np.concatenate(want)) and got[0].dtype == want[0].dtype
+
+
+def test_later_rows_module_level(pfb):
+    """The module-level mirrors of the later rows (arithmetics / basins / core / regions / rivers / streams) against the
+    golden outputs of the reference on tests/data/flwdir1.asc."""
+    from pyflwdir_b200 import arithmetics, basins, core, regions, rivers, streams
+
+    name = "flwdir1_asc"
+    d8 = cs.case_d8(name)
+    aux = cs.case_inputs(name, d8, cs.case_seed(name))
+    g = lambda key: cs.golden(name, key)
+    ids, seq, pits, um = g("idxs_ds"), g("idxs_seq"), g("idxs_pit"), g("us_main")
+    shape = d8.shape
+    so, upa = g("strord").ravel(), g("uparea_cell").ravel()
+    assert np.array_equal(arithmetics.moving_average(aux["data_f32_nd"].ravel(), None, 3, ids, um).reshape(shape), g("movavg_f32"),
+                          equal_nan=True)
+    assert np.array_equal(arithmetics.moving_median(aux["data_f64"].ravel(), 4, ids, um, strord=so).reshape(shape),
+                          g("movmed_f64_so"), equal_nan=True)
+    assert np.array_equal(arithmetics.upstream_sum(ids, aux["data_f64"].ravel(), -9999.0).reshape(shape), g("upsum_f64"))
+    sub, idxs = basins.subbasins_pfafstetter(pits, ids, seq, um, upa, mask=upa >= 0.0, depth=2)
+    assert np.array_equal(sub.reshape(shape), g("pfaf_d2")) and np.array_equal(idxs, g("pfaf_d2_idxs")) and idxs.dtype == ids.dtype
+    sub, idxs = basins.subbasins_streamorder(ids, seq, so, None, -2)
+    assert np.array_equal(sub.reshape(shape), g("subbas_so")) and np.array_equal(idxs, g("subbas_so_idxs"))
+    sub, idxs = basins.subbasins_area(ids, seq, um, upa, max(3, d8.size // 400))
+    assert np.array_equal(sub.reshape(shape), g("subbas_area_cell")) and np.array_equal(idxs, g("subbas_area_cell_idxs"))
+    starts, region, blocks, labels = cs.local_inputs(d8, seq, aux)
+    stream = upa > max(4, int(0.002 * d8.size))
+    assert np.array_equal(basins.interbasin_mask(ids, seq, region.ravel(), stream).reshape(shape), g("interbasin_stream"))
+    assert np.array_equal(core.inflow_idxs(ids, seq, region.ravel()), g("inflow_idxs"))
+    assert np.array_equal(core.outflow_idxs(ids, seq, region.ravel()), g("outflow_idxs"))
+    paths, dist = core.path(starts, ids, mask=stream)
+    assert np.array_equal(np.concatenate(paths), g("path_down_mask")) and np.array_equal(dist, g("path_down_mask_dist"))
+    ends, dist = core.snap(starts, ids, max_length=7.5)
+    assert np.array_equal(ends, g("snap_down_max")) and np.array_equal(dist, g("snap_down_max_dist")) and dist.dtype == np.float32
+    lbs, idxs = regions.region_outlets(blocks, ids, seq)
+    assert np.array_equal(lbs, g("outlets_blocks_lbs")) and np.array_equal(idxs, g("outlets_blocks_idxs")) and lbs.dtype == blocks.dtype
+    lbs, boxes, total = regions.region_bounds(labels)
+    assert np.array_equal(lbs, g("bounds_labels_lbs")) and np.array_equal(boxes, g("bounds_labels_boxes"))
+    assert np.array_equal(total, g("bounds_labels_total"))
+    lbs2, slices = regions.region_slices(labels)
+    assert len(slices) == lbs.size and all(np.all(labels[s] == lb) or (labels[s] == lb).any() for lb, s in zip(lbs2, slices))
+    segs = streams.streams(ids, seq, so >= 2, 0)
+    segs = [s for s in segs if s.size >= 2]
+    assert np.array_equal(np.array([s[0] for s in segs]), g("streams_so2_idx")) and np.array_equal(
+        np.array([s.size for s in segs]), g("streams_so2_n"))
+    distnc = g("sdist_m").ravel()
+    rivwth32 = np.sqrt(np.abs(upa).astype(np.float32)) + aux["data_f32"].ravel()
+    elev0 = aux["elevtn"].ravel() - np.float32(np.median(aux["elevtn"].ravel()[pits]))
+    assert np.array_equal(rivers.classify_estuary(ids, seq, pits, distnc, rivwth32, elev0, 0, 1e-2), g("estuary_f32"))
