@@ -337,8 +337,13 @@ core = types.SimpleNamespace(
 def _hop_table64(nrow, latlon, transform):
     """float64 table [nrow, 3, 2] of gis_utils.distance (gis_utils.py:452-486) for a D8 hop: (row of idx0, row delta + 1,
     column delta != 0). Includes the reference's swap for projected rasters (dy = xres, dx = yres)."""
+    import ctypes
+    import ctypes.util
     import math
 
+    libm = C.CDLL(ctypes.util.find_library("m") or "libm.so.6")  # numba's math.hypot is the C library's hypot
+    libm.hypot.restype = C.c_double
+    libm.hypot.argtypes = [C.c_double, C.c_double]
     xres, yres, north = transform[0], transform[4], transform[5]
     tab = np.zeros((nrow, 3, 2), dtype=np.float64)
     for r0 in range(nrow):
@@ -354,7 +359,7 @@ def _hop_table64(nrow, latlon, transform):
                                               + (0.118 * math.cos(5.0 * rl))) * xres
                 else:
                     dy, dx = xres, yres
-                tab[r0, j, dc] = math.hypot(dy * dr, dx * dc)
+                tab[r0, j, dc] = libm.hypot(float(dy * dr), float(dx * dc))
     return tab
 
 

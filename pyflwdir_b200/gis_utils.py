@@ -135,16 +135,38 @@ def degree_metres_x(lat):
     return (111412.84 * math.cos(radlat)) + (-93.5 * math.cos(3.0 * radlat)) + (0.118 * math.cos(5.0 * radlat))
 
 
+_libm = None
+
+
+def _libm_hypot(x, y):
+    """hypot of the C library: what numba's math.hypot lowers to (numba/cpython/mathimpl.py hypot_float_impl). CPython's
+    own math.hypot is a different (correctly rounded) algorithm and differs from glibc's in the last bit for ~0.2 % of
+    the arguments."""
+    global _libm
+    if _libm is None:
+        import ctypes
+        import ctypes.util
+
+        lib = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+        lib.hypot.restype = ctypes.c_double
+        lib.hypot.argtypes = [ctypes.c_double, ctypes.c_double]
+        _libm = lib
+    return _libm.hypot(x, y)
+
+
 def hop_length_table(nrow, transform, latlon, dtype=np.float32):
-    """float32 (stream_distance) or float64 (core._trace) table [nrow, 3, 2] of gis_utils.distance(idx0, idx1, ...) (gis_utils.py:451-486) for a hop that starts in
+    """Table [nrow, 3, 2] of gis_utils.distance(idx0, idx1, ...) (gis_utils.py:451-486) for a hop that starts in
     row r0 with row delta dr in (-1, 0, 1) and |column delta| dc in (0, 1) -- everything the distance depends on.
-    Reproduces the reference including its quirk for projected rasters (dy = xres, dx = yres)."""
+    float32: for streams.stream_distance, interpreted Python in the reference (CPython's math.hypot, the sum kept in
+    float32); float64: for core._trace, compiled by numba (the C library's hypot). Reproduces the reference including
+    its quirk for projected rasters (dy = xres, dx = yres)."""
+    hyp = math.hypot if np.dtype(dtype) == np.float32 else _libm_hypot
     xres, yres, north = transform[0], transform[4], transform[5]
     tab = np.zeros((nrow, 3, 2), dtype=np.float64)
     if not latlon:
         for j, dr in enumerate((-1, 0, 1)):
             for dc in (0, 1):
-                tab[:, j, dc] = math.hypot(xres * abs(dr), yres * dc)
+                tab[:, j, dc] = hyp(float(xres) * abs(dr), float(yres) * dc)
     else:
         for r0 in range(nrow):
             for j, d in enumerate((-1, 0, 1)):
@@ -152,8 +174,8 @@ def hop_length_table(nrow, transform, latlon, dtype=np.float32):
                 dr = abs(d)
                 dy = 0.0 if dr == 0 else degree_metres_y(lat) * yres
                 dx1 = degree_metres_x(lat) * xres
-                tab[r0, j, 0] = math.hypot(dy * dr, 0.0)
-                tab[r0, j, 1] = math.hypot(dy * dr, dx1 * 1)
+                tab[r0, j, 0] = hyp(dy * dr, 0.0)
+                tab[r0, j, 1] = hyp(dy * dr, dx1 * 1)
     return tab.astype(dtype)
 
 

@@ -112,6 +112,15 @@ def local_inputs(d8, seq, aux):
     return starts, region, blocks, labels
 
 
+def row_starts(d8, seq):
+    """One start cell per raster row (the first cell of the row that drains to a pit): metric traces then touch the
+    hop-length table of every row."""
+    seq = np.sort(np.asarray(seq).astype(np.int64))
+    rows = seq // d8.shape[1]
+    first = np.flatnonzero(np.diff(rows, prepend=-1) != 0)
+    return seq[first]
+
+
 def _flat_paths(paths):
     counts = np.array([p.size for p in paths], dtype=np.int64)
     flat = np.concatenate(paths) if len(paths) else np.zeros(0, dtype=np.int64)
@@ -254,6 +263,13 @@ def run_oracle_case(d8, aux, area=None, transform=(1.0, 0.0, 0.0, 0.0, -1.0, 0.0
             out[f"path_{tag}{key}"], out[f"path_{tag}{key}_n"] = _flat_paths(paths)
             out[f"path_{tag}{key}_dist"] = dist
             out[f"snap_{tag}{key}"], out[f"snap_{tag}{key}_dist"] = o.core.snap(starts, nxt, **kw)
+    rs = row_starts(d8, seq)
+    for tag, nxt in (("down", idxs_ds), ("up", um)):
+        kw = dict(max_length=40.0 * abs(tr6[0]) * (111e3 if latlon else 1.0), real_length=True, ncol=shape[1], latlon=latlon, transform=tr6)
+        paths, dist = o.core.path(rs, nxt, **kw)
+        out[f"path_{tag}_rows"], out[f"path_{tag}_rows_n"] = _flat_paths(paths)
+        out[f"path_{tag}_rows_dist"] = dist
+        out[f"snap_{tag}_rows"], out[f"snap_{tag}_rows_dist"] = o.core.snap(rs, nxt, **kw)
     out["downstream_f32"] = np.where(mask, aux["data_f32"].ravel()[np.where(mask, idxs_ds, 0).astype(np.int64)],
                                      aux["data_f32"].ravel()).reshape(shape)
     out["downstream_i64"] = np.where(mask, aux["data_i64"].ravel()[np.where(mask, idxs_ds, 0).astype(np.int64)],
@@ -385,6 +401,13 @@ def run_api_case(pf, d8, aux, transform=None, latlon=False):
             out[f"path_{tag}{key}"], out[f"path_{tag}{key}_n"] = _flat_paths(list(paths))
             out[f"path_{tag}{key}_dist"] = dist
             out[f"snap_{tag}{key}"], out[f"snap_{tag}{key}_dist"] = flw.snap(idxs=starts, direction=tag, **kw)
+    rs = row_starts(d8, seq)
+    for tag in ("down", "up"):
+        kw = dict(max_length=40.0 * xres * (111e3 if latlon else 1.0), unit="m", direction=tag)
+        paths, dist = flw.path(idxs=rs, **kw)
+        out[f"path_{tag}_rows"], out[f"path_{tag}_rows_n"] = _flat_paths(list(paths))
+        out[f"path_{tag}_rows_dist"] = dist
+        out[f"snap_{tag}_rows"], out[f"snap_{tag}_rows_dist"] = flw.snap(idxs=rs, **kw)
     out["downstream_f32"] = flw.downstream(aux["data_f32"])
     out["downstream_i64"] = flw.downstream(aux["data_i64"])
     out["inflow_idxs"] = flw.inflow_idxs(region)
