@@ -174,3 +174,59 @@ def test_pinned_pool_recycles(monkeypatch):
     assert pool.total == 16 << 20 and d.flags.owndata
     assert pool.empty(10, np.int32).flags.owndata           # tiny results are never pinned
     del b, c, d
+
+
+def test_geo_helpers_and_features():
+    """Host-side geometry helpers behind path(unit="m") / streams / basin_bounds: transform_from_bounds, xy,
+    idxs_to_coords, the two hop-length tables, gis_utils.features (vectorised, same dicts as the reference's loop)."""
+    import ctypes
+    import ctypes.util
+    import math
+
+    t = gis.transform_from_bounds(0.0, -10.0, 20.0, 6.0, 200, 160)
+    assert tuple(t)[:6] == (0.1, 0.0, 0.0, 0.0, -0.1, 6.0)
+    x, y = gis.xy(t, np.array([0, 3]), np.array([0, 7]))
+    assert np.array_equal(x, 0.1 * np.array([0, 7]) + 0.0 * np.array([0, 3]) + (0.1 * 0.5 + 0.0 * 0.5 + 0.0))
+    assert np.array_equal(y, 0.0 * np.array([0, 7]) + -0.1 * np.array([0, 3]) + (0.0 * 0.5 + -0.1 * 0.5 + 6.0))
+    with pytest.raises(ValueError, match="Invalid offset"):
+        gis.xy(t, 0, 0, offset="middle")
+    xs, ys = gis.idxs_to_coords(np.array([0, 201]), t, (160, 200))
+    assert np.array_equal(xs, gis.xy(t, [0, 1], [0, 1])[0]) and np.array_equal(ys, gis.xy(t, [0, 1], [0, 1])[1])
+    with pytest.raises(IndexError, match="outside domain"):
+        gis.idxs_to_coords(np.array([160 * 200]), t, (160, 200))
+
+    # hop lengths: float32 table = CPython's math.hypot (interpreted stream_distance), float64 = the C library's (numba)
+    tr = gis.Affine(*cs.RHINE_TRANSFORM)
+    t32 = gis.hop_length_table(50, tr, True)
+    t64 = gis.hop_length_table(50, tr, True, dtype=np.float64)
+    assert t32.dtype == np.float32 and t64.dtype == np.float64 and t32.shape == t64.shape == (50, 3, 2)
+    libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    libm.hypot.restype = ctypes.c_double
+    libm.hypot.argtypes = [ctypes.c_double, ctypes.c_double]
+    r0, d = 17, 1
+    lat = tr[5] + (r0 + (r0 + d)) / 2.0 * tr[4]
+    dy, dx = gis.degree_metres_y(lat) * tr[4], gis.degree_metres_x(lat) * tr[0]
+    assert t64[r0, 2, 1] == libm.hypot(dy, dx) and t32[r0, 2, 1] == np.float32(math.hypot(dy, dx))
+    lat0 = tr[5] + (r0 + r0) / 2.0 * tr[4]  # a hop inside the row
+    assert t64[r0, 1, 0] == 0.0 and t64[r0, 1, 1] == libm.hypot(0.0, gis.degree_metres_x(lat0) * tr[0])
+    proj = gis.hop_length_table(3, gis.Affine(30.0, 0, 0, 0, -20.0, 0), False, dtype=np.float64)
+    assert proj[0, 0, 0] == 30.0 and proj[0, 1, 1] == 20.0  # the reference's swap: dy = xres, dx = yres
+
+    # features: one dict per path with >= 2 cells
+    paths = [np.array([0, 1, 201], dtype=np.int32), np.array([5], dtype=np.int32), np.array([402, 402], dtype=np.int32)]
+    upa = np.arange(160 * 200, dtype=np.float64).reshape(160, 200)
+    feats = gis.features(paths, transform=t, shape=(160, 200), uparea=upa)
+    assert len(feats) == 2
+    f0, f1 = feats
+    assert f0["type"] == "Feature" and f0["geometry"]["type"] == "LineString"
+    want = list(zip(*gis.idxs_to_coords(paths[0], t, (160, 200))))
+    assert f0["geometry"]["coordinates"] == want and isinstance(f0["geometry"]["coordinates"][0][0], np.float64)
+    assert f0["properties"] == {"idx": 0, "idx_ds": 201, "pit": False, "uparea": 0.0} and f0["properties"]["idx"].dtype == np.int32
+    assert f1["properties"]["pit"] and f1["properties"]["uparea"] == 402.0
+    xs2, ys2 = np.arange(160 * 200) * 2.0, np.arange(160 * 200) * -1.0
+    assert gis.features(paths[:1], xs=xs2, ys=ys2)[0]["geometry"]["coordinates"] == [(0.0, 0.0), (2.0, -1.0), (402.0, -201.0)]
+    with pytest.raises(ValueError, match="transform and shape should be provided"):
+        gis.features(paths)
+    with pytest.raises(ValueError, match='Kwargs map "uparea"'):
+        gis.features(paths, transform=t, shape=(160, 200), uparea=np.ones((2, 2)))
+    assert gis.features([np.array([3])], transform=t, shape=(160, 200)) == []
