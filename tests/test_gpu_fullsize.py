@@ -110,3 +110,60 @@ def test_tiled_equals_single_gpu_4096():
     assert np.array_equal(got["rank"], flw.rank)
     assert np.array_equal(got["uparea"], flw.upstream_area())
     assert np.array_equal(got["basins"], flw.basins())
+
+
+def test_later_rows_oracle_parity_3072():
+    """The later rows with the most intricate ordering rules (stream segments, Pfafstetter coding, region outlets with
+    ties, inflow / outflow cells, moving median, estuaries) against the oracle on a 3072^2 raster (9.4 M cells)."""
+    import pyflwdir_b200 as pfb
+
+    size = 3072
+    d8, z = _synth_on_device(size, 9, sea_quantile=0.03)
+    flw = pfb.from_array(d8, ftype="d8")
+    ids, pits, _ = oracle.core_d8.from_array(d8, dtype=np.int32)
+    seq = oracle.core.idxs_seq(ids, pits)
+    assert np.array_equal(flw.idxs_seq, seq)
+    upa = flw.upstream_area()
+    um = flw.idxs_us_main
+    assert np.array_equal(um, oracle.core.main_upstream(ids, upa.ravel()))
+    # stream segments of the channel network, split at 25 cells
+    mask = upa > 200
+    got = flw._dev.streams(mask, 25, np.int32)
+    want = oracle.streams.streams(ids, seq, mask.ravel(), 25)
+    assert len(got) == len(want) and np.array_equal(np.concatenate(got), np.concatenate(want))
+    assert np.array_equal(np.array([g.size for g in got]), np.array([w.size for w in want]))
+    # Pfafstetter, two levels, small tributaries masked out
+    sub, sidx = flw.subbasins_pfafstetter(depth=2, upa_min=50)
+    wsub, widx = oracle.basins.subbasins_pfafstetter(pits, ids, seq, um, upa.ravel(), mask=(upa >= 50).ravel(), depth=2)
+    assert np.array_equal(sub.ravel(), wsub) and np.array_equal(sidx, widx)
+    # region outlets on a label raster with many ties, inflow / outflow of a window, interbasin mask
+    rr, cc = np.arange(size)[:, None], np.arange(size)[None, :]
+    blocks = (((rr // 97) % 5) * 5 + ((cc // 131) % 5)).astype(np.int32)
+    lbs, oidx = flw.basin_outlets(blocks)
+    wl, wi = oracle.regions.region_outlets(blocks, ids, seq)
+    assert np.array_equal(lbs, wl) and np.array_equal(oidx, wi)
+    region = np.zeros((size, size), np.bool_)
+    region[size // 5: 3 * size // 5, size // 4: 3 * size // 4] = True
+    assert np.array_equal(flw.inflow_idxs(region), oracle.core.inflow_idxs(ids, seq, region.ravel()))
+    assert np.array_equal(flw.outflow_idxs(region), oracle.core.outflow_idxs(ids, seq, region.ravel()))
+    assert np.array_equal(flw.interbasin_mask(region, stream=mask).ravel(),
+                          oracle.basins.interbasin_mask(ids, seq, region.ravel(), mask.ravel()))
+    # bounding boxes of all basins against numpy
+    bas = flw.basins()
+    lbs, boxes, total = flw.basin_bounds(basins=bas)
+    assert np.array_equal(lbs, np.arange(1, pits.size + 1, dtype=np.uint32))
+    rows, cols = np.nonzero(bas)
+    lab = bas[rows, cols].astype(np.int64) - 1
+    rmin = np.full(pits.size, size, np.int64); np.minimum.at(rmin, lab, rows)
+    rmax = np.full(pits.size, -1, np.int64); np.maximum.at(rmax, lab, rows)
+    cmin = np.full(pits.size, size, np.int64); np.minimum.at(cmin, lab, cols)
+    cmax = np.full(pits.size, -1, np.int64); np.maximum.at(cmax, lab, cols)
+    assert np.array_equal(boxes, np.stack([cmin, -(rmax + 1.0), cmax + 1.0, -rmin.astype(np.float64)], axis=1))
+    # moving median of the elevation along the main stem, estuary classification
+    got = flw.moving_median(z, 5, nodata=-9999.0)
+    assert np.array_equal(got.ravel(), oracle.arithmetics.moving_median(z.ravel(), 5, ids, um, None, -9999.0), equal_nan=True)
+    rivwth = np.sqrt(np.abs(upa).astype(np.float32))
+    dist = flw.stream_distance(unit="cell").astype(np.float32)
+    est = flw.classify_estuaries(z - np.float32(np.median(z.ravel()[pits])), rivwth, rivdst=dist)
+    assert np.array_equal(est, oracle.rivers.classify_estuary(ids, seq, pits, dist.ravel(), rivwth.ravel(),
+                                                              z.ravel() - np.float32(np.median(z.ravel()[pits])), 0, 1e-2))
