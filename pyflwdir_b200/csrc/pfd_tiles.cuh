@@ -413,6 +413,13 @@ __device__ __forceinline__ void tl_phase_a_tile(TileShared& s, TileCodes& sc, co
         A.s_ch[slot] = ch;
         A.s_term[slot] = term;
         A.s_term_h[slot] = th;
+    } else if (threadIdx.x < TL_RING) {  // the 4 padding slots of the tile: inert nodes (the solve streams over every slot)
+        const uint32_t slot = tile * TL_RING + threadIdx.x;
+        A.s_nxt[slot] = slot;
+        A.s_rh[slot] = 0u;
+        A.s_ch[slot] = 0u;
+        A.s_term[slot] = SLOT_INVALID;
+        A.s_term_h[slot] = 0u;
     }
 }
 
