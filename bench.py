@@ -407,6 +407,17 @@ def extras_widened(w, size, seed, cpu_size):
     cnt_h, end_h, dist_h = np.empty(4096, np.int64), np.empty(4096, np.int64), np.empty(4096, np.float64)
     gpu["snap_4096_starts"] = best(lambda: w.ck(l.pfd_trace(h, L.ptr(starts_h), 4096, 0, None, 0, mask_dev, 0, C.c_double(0.0), None,
                                                            L.ptr(cnt_h), L.ptr(end_h), L.ptr(dist_h), None, 0, 0)))
+    i64 = L.DTYPES[np.dtype(np.int64)]
+    pf_dev = w.dev_alloc(n * 8)
+    n2 = C.c_int64()
+    gpu["subbasins_pfafstetter_d2"] = best(lambda: w.ck(l.pfd_subbasins_pfafstetter(h, um_dev, i32, upa_dev, i32, mask_dev, 2, pf_dev, C.byref(k64))))
+    gpu["streams_mask_len25"] = best(lambda: w.ck(l.pfd_streams(h, mask_dev, 25, C.byref(k64), C.byref(n2))))
+    est_h = np.zeros(n, np.int8)
+    est_dev = w.dev_alloc(n)
+    w.ck(l.pfd_memcpy(h, est_dev, L.ptr(est_h), n))
+    gpu["classify_estuary_f32"] = best(lambda: w.ck(l.pfd_classify_estuary(h, est_dev, z_dev, f32, z_dev, f32, C.c_double(1e-2), out1_dev)))
+    w.ck(l.pfd_dev_free(h, pf_dev))
+    w.ck(l.pfd_dev_free(h, est_dev))
     nxy_dev = w.dev_alloc(n * 8)
     w.ck(l.pfd_fetch(h, L.ARR_NEXTXY, nxy_dev, 0))
     gpu["nextxy_parse"] = best(lambda: w.ck(l.pfd_nextxy_parse(h, nxy_dev, C.c_void_p(nxy_dev.value + n * 4), size, size, 1, w.out_dev[0], i32, None, None, None)))
@@ -456,6 +467,9 @@ def extras_widened(w, size, seed, cpu_size):
     cpu["interbasin_mask_stream"], _ = cpu_time(lambda: oracle.basins.interbasin_mask(ids, seq, creg, cmask))
     cbas = oracle.basins.basins(ids, pits, seq)
     cpu["region_outlets_basins"], _ = cpu_time(lambda: oracle.regions.region_outlets(cbas, ids, seq))
+    cpu["subbasins_pfafstetter_d2"], _ = cpu_time(lambda: oracle.basins.subbasins_pfafstetter(pits, ids, seq, um, upc, mask=cmask, depth=2))
+    cpu["streams_mask_len25"], _ = cpu_time(lambda: oracle.streams.streams(ids, seq, cmask, 25))
+    cpu["classify_estuary_f32"], _ = cpu_time(lambda: oracle.rivers.classify_estuary(ids, seq, pits, zc, zc, zc, -1e9, 1e-2))
     cnxy = oracle.core_nextxy.to_array(ids, d8.shape)
     cpu["nextxy_parse"], _ = cpu_time(lambda: oracle.core_nextxy.from_array(cnxy, dtype=np.int32))
     res = {}
