@@ -109,3 +109,21 @@ def outflow_idxs(idxs_ds, seq, region, shape=None, ncol=None):
     g = _functional.graph(idxs_ds, shape, ncol)
     _functional.check_seq(g, seq, "outflow_idxs")
     return g.outflow_idxs(np.asarray(region).ravel(), np.asarray(idxs_ds).dtype)
+
+
+def loop_indices(idxs_ds, mv=_mv, shape=None, ncol=None):
+    """Returns indices of loop cells, i.e. cells which do not drain to a pit (core.py:235-243)"""
+    ranks = rank(idxs_ds, mv, shape, ncol)[0]
+    return np.flatnonzero(ranks == -1).astype(np.asarray(idxs_ds).dtype)
+
+
+def headwater_indices(idxs_ds, mask=None, mv=_mv, shape=None, ncol=None):
+    """Returns indices of headwater cells, i.e. cells with no upstream neighbors (core.py:246-250)"""
+    nup = upstream_count(idxs_ds, mv, mask, shape, ncol)
+    return np.where(nup == 0)[0].astype(np.asarray(idxs_ds).dtype)
+
+
+def confluence_indices(idxs_ds, mask=None, mv=_mv, shape=None, ncol=None):
+    """Returns indices of confluence cells, i.e. cells with two or more upstream neighbors (core.py:253-257)"""
+    nup = upstream_count(idxs_ds, mv, mask, shape, ncol)
+    return np.where(nup > 1)[0].astype(np.asarray(idxs_ds).dtype)

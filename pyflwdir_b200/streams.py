@@ -3,7 +3,7 @@ accuflux_ds :44-70, stream_order :191-225, strahler_order :228-269). The device 
 `core.idxs_seq` returns); `seq` is only checked for covering the same cells."""
 import numpy as np
 
-from . import _functional
+from . import _functional, _lib
 
 
 def accuflux(idxs_ds, seq, data, nodata, shape=None, ncol=None):
@@ -39,3 +39,26 @@ def streams(idxs_ds, seq, mask=None, max_len=0, mv=-1, shape=None, ncol=None):
     g = _functional.graph(idxs_ds, shape, ncol)
     _functional.check_seq(g, seq, "streams")
     return g.streams(mask, max_len, np.asarray(idxs_ds).dtype)
+
+
+def upstream_area(idxs_ds, seq, ncol, latlon=False, transform=(1.0, 0.0, 0.0, 0.0, -1.0, 0.0), area_factor=1, nodata=-9999.0,
+                  dtype=np.float64):
+    """Returns the accumulated upstream area without an area grid in memory (streams.py:72-128): the local cell area
+    (per row for a geographic CRS) is evaluated on the host, the accumulation runs on the device in `dtype`."""
+    from . import gis_utils as gis
+
+    idxs_ds = np.asarray(idxs_ds)
+    nrow = idxs_ds.size // int(ncol)
+    g = _functional.graph(idxs_ds, (nrow, int(ncol)), None)
+    _functional.check_seq(g, seq, "upstream_area")
+    xres, yres, north = transform[0], transform[4], transform[5]
+    uparea = np.full(idxs_ds.size, nodata, dtype=dtype)
+    inseq = g.fetch(_lib.ARR_RANK) >= 0
+    if latlon:
+        lats = [north + (r + 0.5) * yres for r in range(nrow)]
+        rows = gis.cellarea(np.asarray(lats, dtype=np.float64), xres, yres) / area_factor
+        local = np.repeat(rows, int(ncol))
+        uparea[inseq] = local[inseq]
+    else:
+        uparea[inseq] = abs(xres * yres) / area_factor
+    return g.accuflux(uparea, nodata, "up")

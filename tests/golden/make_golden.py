@@ -133,6 +133,16 @@ def main():
         pf.from_array(rhine, ftype="d8", transform=RHINE_TRANSFORM, latlon=True).area[:, 0]
     )
 
+    # --- streams.upstream_area (no area grid): rhine in m2 / km2 (geographic), the 160x200 fixture in cells (int32)
+    import pyflwdir.streams as rstreams
+    flw_r = pf.from_array(rhine, ftype="d8", transform=RHINE_TRANSFORM, latlon=True)
+    ua = rstreams.upstream_area(flw_r.idxs_ds, flw_r.idxs_seq, rhine.shape[1], latlon=True, transform=flw_r.transform, area_factor=1e6)
+    hashes["cases"]["rhine"]["streams_uparea_km2"] = sha(ua)
+    flw_l = pf.from_array(d8_large, ftype="d8")
+    small_outputs["flwdir1_asc/streams_uparea_i32"] = rstreams.upstream_area(flw_l.idxs_ds, flw_l.idxs_seq, d8_large.shape[1], dtype=np.int32)
+    small_outputs["flwdir1_asc/streams_uparea_f32"] = rstreams.upstream_area(
+        flw_l.idxs_ds, flw_l.idxs_seq, d8_large.shape[1], transform=(30.0, 0.0, 0.0, 0.0, -20.0, 0.0), area_factor=1e4, dtype=np.float32)
+
     # --- a mid-size synthetic (512 x 768, with sea): hashes only, input regenerated in the tests
     z = oracle.synth_elevation(512, 768, seed=21)
     sea = float(np.quantile(z, 0.05))

@@ -387,3 +387,30 @@ def test_later_rows_module_level(pfb):
     rivwth32 = np.sqrt(np.abs(upa).astype(np.float32)) + aux["data_f32"].ravel()
     elev0 = aux["elevtn"].ravel() - np.float32(np.median(aux["elevtn"].ravel()[pits]))
     assert np.array_equal(rivers.classify_estuary(ids, seq, pits, distnc, rivwth32, elev0, 0, 1e-2), g("estuary_f32"))
+
+
+def test_small_mirrors(pfb):
+    """streams.upstream_area (no area grid) against the reference's outputs; loop / headwater / confluence indices
+    against their definitions."""
+    from pyflwdir_b200 import core, streams
+
+    s = cs.small()
+    d8 = cs.case_d8("flwdir1_asc")
+    ids, seq = cs.golden("flwdir1_asc", "idxs_ds"), cs.golden("flwdir1_asc", "idxs_seq")
+    got = streams.upstream_area(ids, seq, d8.shape[1], dtype=np.int32)
+    assert got.dtype == np.int32 and np.array_equal(got, s["out/flwdir1_asc/streams_uparea_i32"])
+    got = streams.upstream_area(ids, seq, d8.shape[1], transform=(30.0, 0.0, 0.0, 0.0, -20.0, 0.0), area_factor=1e4, dtype=np.float32)
+    assert got.dtype == np.float32 and np.array_equal(got, s["out/flwdir1_asc/streams_uparea_f32"])
+    rhine = cs.case_d8("rhine")
+    flw = pfb.from_array(rhine, ftype="d8", transform=cs.RHINE_TRANSFORM, latlon=True)
+    got = streams.upstream_area(flw.idxs_ds, flw.idxs_seq, rhine.shape[1], latlon=True, transform=flw.transform, area_factor=1e6)
+    assert got.dtype == np.float64 and cs.sha(got) == cs.hashes()["rhine"]["streams_uparea_km2"]
+    # index lists
+    rnd = cs.case_d8("random48x61")  # has loops
+    rids = cs.golden("random48x61", "idxs_ds")
+    rank = cs.golden("random48x61", "rank").ravel()
+    nup = cs.golden("random48x61", "n_upstream").ravel()
+    assert np.array_equal(core.loop_indices(rids, shape=rnd.shape), np.flatnonzero(rank == -1)) and (rank == -1).any()
+    assert np.array_equal(core.headwater_indices(rids, shape=rnd.shape), np.flatnonzero(nup == 0))
+    assert np.array_equal(core.confluence_indices(rids, shape=rnd.shape), np.flatnonzero(nup > 1))
+    assert core.loop_indices(rids, shape=rnd.shape).dtype == rids.dtype
