@@ -330,12 +330,12 @@ class FlwdirRaster(Flwdir):
             ix = ix[::-1]
         dx = np.abs(xres) / 2
         dy = np.abs(yres) / 2
-        bboxs = []
-        for r0, r1, c0, c1 in sl.tolist():
-            xmin, xmax = lons[c0:c1][ix]
-            ymin, ymax = lats[r0:r1][iy]
-            bboxs.append([xmin - dx, ymin - dy, xmax + dx, ymax + dy])
-        bboxs = np.asarray(bboxs)
+        # lons[xslice][ix], lats[yslice][iy] of regions.py:123-125 for all labels at once (first / last cell of the slice)
+        r0, r1, c0, c1 = sl[:, 0], sl[:, 1] - 1, sl[:, 2], sl[:, 3] - 1
+        xends, yends = (c0, c1), (r0, r1)
+        xmin, xmax = lons[xends[ix[0]]], lons[xends[ix[1]]]
+        ymin, ymax = lats[yends[iy[0]]], lats[yends[iy[1]]]
+        bboxs = np.stack([xmin - dx, ymin - dy, xmax + dx, ymax + dy], axis=1)
         total_bbox = np.hstack([bboxs[:, :2].min(axis=0), bboxs[:, 2:].max(axis=0)])
         return lbs, bboxs, total_bbox
 
