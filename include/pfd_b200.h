@@ -130,7 +130,9 @@ int pfd_load_idxs_ds(pfd_handle* h, const void* idxs_ds, int idx_dtype, int64_t 
  */
 int pfd_order(pfd_handle* h, int64_t* nnodes, int64_t* nlevels);
 
-/* Copy a cached array out (host or device destination). idx_dtype is used for the index-typed arrays. */
+/* Copy a cached array out (host or device destination); the pfd_array entries above name the reference array each one
+ * is (core_d8.from_array, core.idxs_seq, core.rank, core.upstream_count, core_d8 / core_ldd / core_nextxy.to_array under
+ * pyflwdir/). idx_dtype is used for the index-typed arrays. */
 int pfd_fetch(pfd_handle* h, int which, void* out, int idx_dtype);
 
 /* ---- sweeps ------------------------------------------------------------------------------------------ */
@@ -284,8 +286,11 @@ int pfd_classify_estuary(pfd_handle* h, const int8_t* est_init, const void* rivd
 
 /* ---- fused headline pass ------------------------------------------------------------------------------ */
 /*
- * parse + order + rank + upstream_area(cell) + basins() in one call (BASELINE.json metric). Any output may be
- * NULL. Equivalent to pfd_d8_parse + pfd_order + pfd_fetch(RANK) + pfd_upstream_area_cells + pfd_basins(NULL).
+ * parse + order + rank + upstream_area(cell) + basins() in one call (BASELINE.json metric): core_d8.from_array
+ * (pyflwdir/core_d8.py:42-67), core.rank (pyflwdir/core.py:17-47), streams.accuflux of ones with -9999 on nodata
+ * (pyflwdir/streams.py:15-41, pyflwdir/pyflwdir.py:770-801) and basins.basins over all pits (pyflwdir/basins.py:12-18).
+ * Any output may be NULL. Equivalent to pfd_d8_parse + pfd_order + pfd_fetch(RANK) + pfd_upstream_area_cells +
+ * pfd_basins(NULL).
  */
 int pfd_d8_flow_all(pfd_handle* h, const uint8_t* d8, int64_t nrow, int64_t ncol, void* idxs_ds_out,
                     int idx_dtype, int32_t* rank_out, int32_t* uparea_out, uint32_t* basins_out,
