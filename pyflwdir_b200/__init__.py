@@ -9,8 +9,8 @@ from . import arithmetics, basins, core, core_conversion, core_d8, core_ldd, cor
 from .core_nextxy import read_nextxy
 from .core_conversion import d8_to_ldd, ldd_to_d8
 from .gis_utils import Affine
-from .pyflwdir import FlwdirRaster, from_array, _get_idxs_dtype
+from .pyflwdir import FlwdirRaster, from_array, from_dem, _get_idxs_dtype
 from .flwdir import Flwdir
 
 __version__ = "0.1.0"
-__all__ = ["FlwdirRaster", "Flwdir", "from_array", "gis_utils", "Affine", "d8_to_ldd", "ldd_to_d8", "read_nextxy"]
+__all__ = ["FlwdirRaster", "Flwdir", "from_array", "from_dem", "gis_utils", "Affine", "d8_to_ldd", "ldd_to_d8", "read_nextxy"]

@@ -15,7 +15,7 @@ from . import gis_utils as gis
 from .flwdir import Flwdir, _not_in_scope
 from .gis_utils import Affine
 
-__all__ = ["FlwdirRaster", "from_array"]
+__all__ = ["FlwdirRaster", "from_array", "from_dem"]
 
 FTYPES = ("d8", "ldd", "nextxy")  # pyflwdir.py:26-30
 _MV = {"d8": np.uint8(247), "ldd": np.uint8(255)}  # core_d8.py:17, core_ldd.py:15
@@ -117,6 +117,16 @@ def from_array(data, ftype="infer", check_ftype=True, mask=None, transform=gis.I
         idxs_ds=None, idxs_pit=idxs_pit, idxs_outlet=idxs_outlet, shape=shape, ftype=ftype, transform=transform,
         latlon=latlon, _dev=dev, _idx_dtype=dtype, **kwargs,
     )
+
+
+def from_dem(data, nodata=-9999.0, max_depth=-1.0, transform=gis.IDENTITY, latlon=False, **kwargs):
+    """Flow directions derived from elevation (pyflwdir.py:51-102 -> dem.fill_depressions, dem.py:17-143). Not provided:
+    the D8 raster the reference derives is defined by the pop order of its priority queue cell by cell (inside every
+    filled depression a lowest-index-first search), which a data-parallel algorithm cannot reproduce bit for bit; run
+    `pyflwdir.from_dem(...).to_array()` on the reference and pass the D8 raster to `from_array` here."""
+    raise NotImplementedError(
+        "from_dem / dem.fill_depressions (priority-flood) is outside the D8 hot path that pyflwdir_b200 accelerates "
+        "(DESIGN.md §1); derive the D8 raster with Deltares/pyflwdir and parse it with pyflwdir_b200.from_array")
 
 
 class FlwdirRaster(Flwdir):

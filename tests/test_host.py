@@ -230,3 +230,14 @@ def test_geo_helpers_and_features():
     with pytest.raises(ValueError, match='Kwargs map "uparea"'):
         gis.features(paths, transform=t, shape=(160, 200), uparea=np.ones((2, 2)))
     assert gis.features([np.array([3])], transform=t, shape=(160, 200)) == []
+
+
+def test_out_of_scope_entry_points_raise():
+    """What stays on the reference side of the boundary says so instead of computing something else."""
+    from pyflwdir_b200 import dem
+
+    for fn, args in ((pfb.from_dem, (np.zeros((4, 4), np.float32),)), (dem.fill_depressions, (np.zeros((4, 4), np.float32),)),
+                     (dem.adjust_elevation, (None, None, None)), (dem.dig_4connectivity, (None, None, None, (1, 1))),
+                     (dem.slope, (np.zeros((4, 4), np.float32),))):
+        with pytest.raises(NotImplementedError, match="outside the D8 hot path"):
+            fn(*args)
