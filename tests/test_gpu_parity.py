@@ -387,6 +387,10 @@ def test_later_rows_module_level(pfb):
     rivwth32 = np.sqrt(np.abs(upa).astype(np.float32)) + aux["data_f32"].ravel()
     elev0 = aux["elevtn"].ravel() - np.float32(np.median(aux["elevtn"].ravel()[pits]))
     assert np.array_equal(rivers.classify_estuary(ids, seq, pits, distnc, rivwth32, elev0, 0, 1e-2), g("estuary_f32"))
+    from pyflwdir_b200 import dem
+
+    fp = dem.floodplains(ids, seq, (aux["elevtn"].astype(np.float64) * 1.1).ravel(), upa, upa_min=max(4, int(0.002 * d8.size)), b=0.5)
+    assert np.array_equal(fp.reshape(shape), g("fldpln_f64")) and fp.dtype == np.int8
 
 
 def test_small_mirrors(pfb):
