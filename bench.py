@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the D8 flow-network hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--size 8192] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--size 32768] [--impl ours|reference]
 
 One "step" = the whole hot path on one synthetic D8 raster (SURVEY.md §8d generator, "rough" Perlin fBm with
 K = log2(n)-2 octaves, steepest descent, no depression filling):
@@ -13,15 +13,17 @@ Outputs of a step: idxs_ds int32, rank int32, upstream area int32, basins uint32
   e2e   : the same C-ABI call with PINNED HOST buffers: H2D of the raster and D2H of the four outputs are inside
           the timed region.
   roofline     : the dominant kernel of the step (largest share of device time), algorithmic bytes / event time.
-  cpu_baseline : the CPU oracle (single-threaded C port of the reference's numba kernels) on the same raster.
+  cpu_baseline : the reference's own numba CPU path (installed by oracle/make_ref.sh into the git-ignored oracle/_ref,
+          kind "reference"; else the C oracle port, kind "port") on a --cpu-size^2 sample of the same generator.
 
 N > 1 (launched by torchrun, one process per GPU): ONE raster of (N*size) x size cells is row-tiled across the GPUs,
 each rank owning `size` rows (+ one halo row per neighbour): weak scaling with the real exchange step of the path
 (pit-count all-gather + one NCCL all-reduce of the boundary tables per step, pfd_d8_flow_all_tiled). torch.distributed
 (gloo) is used only to hand out the NCCL unique id and for the barrier / max-reduce of the timings.
 
---impl reference: times the reference's CPU implementation of the path (the oracle port; the numba reference
-itself cannot travel to the GPU box) on the host cores, same metric / config, bounded sample per step.
+--impl reference: times the reference's CPU implementation of the path on the host cores -- the UNMODIFIED numba
+reference from oracle/_ref (oracle/make_ref.sh) when present, else the C oracle port -- same metric / config, each step
+one pass over a --cpu-size^2 sample of the same generator (the numba kernels are single-threaded).
 """
 import argparse
 import ctypes as C
@@ -160,21 +162,21 @@ def octaves_for(n):
 class Workload:
     """Synthetic raster on the device + resident / pinned output buffers."""
 
-    def __init__(self, size, seed, device):
+    def __init__(self, size, seed, device, nrow=None):
         from pyflwdir_b200 import _lib
 
         self.L = _lib
         self.l = _lib.lib()
-        self.n = size
-        self.cells = size * size
+        self.n = size if nrow is None else nrow   # rows
+        self.ncol = size
+        self.cells = self.n * size
         h = C.c_void_p()
         _lib.check(self.l.pfd_create(device, C.byref(h)))
         self.h = h
         self.d8_dev = self.dev_alloc(self.cells)
-        z_dev = self.dev_alloc(self.cells * 4)
-        self.ck(self.l.pfd_synth_elevation(h, size, size, size, octaves_for(size), seed, z_dev))
-        self.ck(self.l.pfd_synth_d8(h, z_dev, size, size, C.c_float(-np.inf), self.d8_dev))
-        self.ck(self.l.pfd_dev_free(h, z_dev))
+        # same generator call as the row blocks of the multi-GPU arm (bit-identical to synth_elevation + synth_d8)
+        self.ck(self.l.pfd_synth_d8_block(h, 0, self.n, size, self.n, size, octaves_for(size), seed, C.c_float(-np.inf), self.d8_dev))
+        self.ck(self.l.pfd_set_option(h, b"release_scratch", 1))  # the generator's float plane
         self.idx_dtype = np.int32 if self.cells < 2**31 - 1 else (np.uint32 if self.cells < 2**32 - 2 else np.int64)
         idx_b = np.dtype(self.idx_dtype).itemsize
         self.out_dev = [self.dev_alloc(self.cells * idx_b)] + [self.dev_alloc(self.cells * 4) for _ in range(3)]  # idxs_ds, rank, uparea, basins
@@ -189,17 +191,33 @@ class Workload:
 
     def step_resident(self):
         o = self.out_dev
-        self.ck(self.l.pfd_d8_flow_all(self.h, self.d8_dev, self.n, self.n, o[0], self.L.DTYPES[np.dtype(self.idx_dtype)],
+        self.ck(self.l.pfd_d8_flow_all(self.h, self.d8_dev, self.n, self.ncol, o[0], self.L.DTYPES[np.dtype(self.idx_dtype)],
                                        o[1], o[2], o[3], None, None, None))
 
+    def checksums(self, index_offset=0, row0=0, nrow=None):
+        """pfd_checksum of (idxs_ds, rank, uparea, basins) over rows [row0, row0 + nrow) of the resident outputs."""
+        nrow = self.n if nrow is None else nrow
+        out = []
+        for p, b in zip(self.out_dev, (np.dtype(self.idx_dtype).itemsize, 4, 4, 4)):
+            v = C.c_uint64()
+            q = C.c_void_p(p.value + row0 * self.ncol * b)
+            self.ck(self.l.pfd_checksum(self.h, q, b, nrow * self.ncol, index_offset, C.byref(v)))
+            out.append(int(v.value))
+        return out
+
+    def free(self):
+        for p in [self.d8_dev] + self.out_dev:
+            self.l.pfd_dev_free(self.h, p)
+        self.l.pfd_destroy(self.h)
+
     def make_host(self):
-        self.d8_host = self.L.PinnedArray((self.n, self.n), np.uint8)
+        self.d8_host = self.L.PinnedArray((self.n, self.ncol), np.uint8)
         self.ck(self.l.pfd_memcpy(self.h, self.L.ptr(self.d8_host.array), self.d8_dev, self.cells))
         self.out_host = [self.L.PinnedArray(self.cells, dt) for dt in (self.idx_dtype, np.int32, np.int32, np.uint32)]
 
     def step_host(self):
         o = [self.L.ptr(a.array) for a in self.out_host]
-        self.ck(self.l.pfd_d8_flow_all(self.h, self.L.ptr(self.d8_host.array), self.n, self.n, o[0],
+        self.ck(self.l.pfd_d8_flow_all(self.h, self.L.ptr(self.d8_host.array), self.n, self.ncol, o[0],
                                        self.L.DTYPES[np.dtype(self.idx_dtype)], o[1], o[2], o[3], None, None, None))
 
     def stage_ms(self):
@@ -229,7 +247,7 @@ class Workload:
 class TiledWorkload(Workload):
     """Rank `rank` of `world`: rows [rank*size, (rank+1)*size) of a (world*size) x size raster, one GPU per rank."""
 
-    def __init__(self, size, seed, device, rank, world, dist, strong=False):
+    def __init__(self, size, seed, device, rank, world, dist, strong=False, rows_per_rank=None):
         from pyflwdir_b200 import _lib, tiled
 
         self.L = _lib
@@ -242,9 +260,9 @@ class TiledWorkload(Workload):
             self.n = r1 - self.row0          # rows owned by this rank
             self.nrow_global = size
         else:
-            self.n = size
-            self.row0 = rank * size
-            self.nrow_global = world * size
+            self.n = size if rows_per_rank is None else rows_per_rank
+            self.row0 = rank * self.n
+            self.nrow_global = world * self.n
         self.cells = self.n * size
         self.rank, self.world = rank, world
         h = C.c_void_p()
@@ -260,6 +278,7 @@ class TiledWorkload(Workload):
         self.d8_dev = self.dev_alloc(ext)
         self.ck(self.l.pfd_synth_d8_block(h, self.row0 - self.ht, self.n + self.ht + self.hb, size, self.nrow_global, size,
                                           octaves_for(size), seed, C.c_float(-np.inf), self.d8_dev))
+        self.ck(self.l.pfd_set_option(h, b"release_scratch", 1))
         self.ext_bytes = ext
         ncells_global = self.nrow_global * size
         self.idx_dtype = np.int32 if ncells_global < 2**31 - 1 else (np.uint32 if ncells_global < 2**32 - 2 else np.int64)
@@ -285,6 +304,12 @@ class TiledWorkload(Workload):
         o = [self.L.ptr(a.array) for a in self.out_host]
         self._call(self.L.ptr(self.d8_host.array), o[0], o[1], o[2], self.out_dev[3])
         self.ck(self.l.pfd_memcpy(self.h, o[3], self.out_dev[3], self.cells * 4))  # basins travel through a device buffer
+
+    def free(self):
+        for p in [self.d8_dev] + self.out_dev:
+            self.l.pfd_dev_free(self.h, p)
+        self.l.pfd_comm_destroy(self.h)
+        self.l.pfd_destroy(self.h)
 
 
 def extras(w, size, seed):
@@ -482,72 +507,122 @@ def extras_widened(w, size, seed, cpu_size):
     return res
 
 
-def cpu_path(d8, repeat=1):
-    """The reference's CPU path on `d8` via the oracle port: seconds per stage (best of `repeat`)."""
-    import oracle
+CPU_STAGES = ("from_array", "rank", "idxs_seq", "accuflux", "basins")
 
-    best = None
-    for _ in range(repeat):
-        t = {}
-        t0 = time.perf_counter()
-        ids, pits, _ = oracle.core_d8.from_array(d8, dtype=np.int32)
-        t["from_array"] = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        oracle.core.rank(ids)
-        t["rank"] = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        seq = oracle.core.idxs_seq(ids, pits)
-        t["idxs_seq"] = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        oracle.streams.accuflux(ids, seq, np.ones(d8.size, np.int32), -9999)
-        t["accuflux"] = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        oracle.basins.basins(ids, pits, seq)
-        t["basins"] = time.perf_counter() - t0
-        t["total"] = sum(t.values())
-        if best is None or t["total"] < best["total"]:
-            best = t
-    return best
+
+def cpu_modules():
+    """(kind, core_d8, core, streams, basins): the reference's numba modules when installed, else the oracle port."""
+    import oracle
+    from oracle import reference
+
+    if reference.available() and os.environ.get("PFD_BENCH_CPU", "reference") != "port":
+        try:
+            pf = reference.load()
+            import importlib
+
+            mods = [importlib.import_module(f"pyflwdir.{m}") for m in ("core_d8", "core", "streams", "basins")]
+            return ("reference",) + tuple(mods)
+        except Exception as exc:  # numba / reference import problem on this box: say so and time the port
+            print(f"bench.py: reference import failed ({exc!r}); timing the oracle port", file=sys.stderr)
+    oracle.build()
+    return "port", oracle.core_d8, oracle.core, oracle.streams, oracle.basins
+
+
+def cpu_path(mods, d8):
+    """One pass of the reference's CPU path on `d8`: seconds per stage. The reference needs idxs_seq for its accuflux /
+    basins sweeps (pyflwdir.py:292-297), so it is part of its path; the GPU path needs no ordering for these outputs."""
+    kind, core_d8, core, streams, basins = mods
+    t = {}
+    t0 = time.perf_counter()
+    ids, pits, _ = core_d8.from_array(d8, dtype=np.int32)
+    t["from_array"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    core.rank(ids, mv=np.int32(-1)) if kind == "reference" else core.rank(ids)
+    t["rank"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    seq = core.idxs_seq(ids, pits, mv=np.int32(-1)) if kind == "reference" else core.idxs_seq(ids, pits)
+    t["idxs_seq"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    streams.accuflux(ids, seq, np.ones(d8.size, np.int32), -9999)
+    t["accuflux"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    basins.basins(ids, pits, seq)
+    t["basins"] = time.perf_counter() - t0
+    t["total"] = sum(t.values())
+    return t
+
+
+def cpu_warm(mods):
+    """JIT-compile the numba kernels on a 256^2 raster outside any timed region."""
+    d8, _ = host_raster(256, 1)
+    cpu_path(mods, d8)
+
+
+def cpu_describe(mods, cs, st):
+    kind = mods[0]
+    what = ("UNMODIFIED reference (Deltares/pyflwdir numba kernels, JIT warm, single-threaded by construction)"
+            if kind == "reference" else "oracle C port of the numba kernels")
+    return (f"{cs}x{cs} sample of the same generator/seed, {what}, 1 thread of {os.cpu_count()} host cores; s/stage: " +
+            ", ".join(f"{k}={v:.3f}" for k, v in st.items()))
 
 
 def host_raster(size, seed):
-    """Synthetic raster built on the HOST (oracle generator, OpenMP over rows, bit-identical to the CUDA one):
-    the reference arm touches nothing of the GPU path."""
+    """Synthetic raster built on the HOST (oracle generator, bit-identical to the CUDA one): the reference arm touches
+    nothing of the GPU path."""
     import oracle
 
+    oracle.build()
     z = oracle.synth_elevation(size, size, seed=seed, octaves=octaves_for(size), nref=size)
     return oracle.synth_d8(z), "synthetic (host generator)"
 
 
+def workload_config(args, world=1, w=None):
+    """The `config` object: identical for both arms of one invocation (ours / --impl reference)."""
+    if world == 1:
+        what = f"synthetic {args.size}x{args.size} D8 raster"
+        par = "single GPU"
+    else:
+        nrow_global = args.size if args.scaling == "strong" else world * args.size
+        what = f"ONE synthetic {nrow_global}x{args.size} D8 raster row-tiled over {world} GPUs"
+        par = f"row-tiled x{world}: pit-count all-gather + 1 NCCL all-reduce of boundary tables per step"
+    return {
+        "workload": what + f" (rough Perlin fBm, {octaves_for(args.size)} octaves, steepest descent, no depression filling): "
+                           "parse->idxs_ds + rank + upstream_area(cell) + basins (BASELINE.json configs[2] size, configs[1] "
+                           "outputs)",
+        "seed": args.seed,
+        "cpu_sample": f"{args.cpu_size}x{args.cpu_size} raster of the same generator per CPU step (throughput is flat in "
+                      "size, BASELINE.md section 2); the CPU path also computes idxs_seq, which its sweeps need",
+        "l2": "per-step working set ~26 B/cell x N cells (>= 1.7 GB at 8192^2) exceeds the 126 MB L2; no flush needed",
+        "parallelism": par,
+    }
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port, 1 thread) on the host cores."""
+    """--impl reference: the reference's CPU path on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import oracle
-
-    oracle.build()
-    total_steps = args.steps + args.warmup
-    size = args.size if total_steps <= 6 else min(args.size, 4096)
-    d8, data = host_raster(size, args.seed)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    mods = cpu_modules()
+    cpu_warm(mods)
+    d8, data = host_raster(args.cpu_size, args.seed)
     cells = d8.size
     for _ in range(args.warmup):
-        cpu_path(d8)
+        cpu_path(mods, d8)
     t0 = time.perf_counter()
     stages = None
     for _ in range(args.steps):
-        stages = cpu_path(d8)
+        st = cpu_path(mods, d8)
+        stages = st if stages is None or st["total"] < stages["total"] else stages
     dt = time.perf_counter() - t0
     value = cells * args.steps / dt / 1e6
-    sample = f"{size}x{size} raster of the same generator (full workload is {args.size}x{args.size}); stages s/step: " + \
-        ", ".join(f"{k}={v:.2f}" for k, v in stages.items())
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int32", "data": data,
-        "config": {"workload": f"synthetic {args.size}x{args.size} D8 raster: parse + rank + idxs_seq + accuflux(cell) + basins",
-                   "seed": args.seed},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": mods[0], "sample": cpu_describe(mods, args.cpu_size, stages),
+                         "accuflux_plus_basins_mcells_s": cells / (stages["accuflux"] + stages["basins"]) / 1e6},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -560,17 +635,23 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--size", type=int, default=8192, help="raster is size x size (BASELINE.json configs[1]: 8192)")
+    ap.add_argument("--size", type=int, default=32768,
+                    help="raster is size x size (default: the north-star size, BASELINE.json configs[2]; configs[1] is 8192); "
+                         "N > 1: rows per GPU (weak) or the whole raster (strong)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-size", type=int, default=0, help="raster size of the CPU baseline sample (default: --size)")
+    ap.add_argument("--cpu-size", type=int, default=4096,
+                    help="side of the raster the CPU arm / cpu_baseline samples per step (same generator; both arms use it)")
     ap.add_argument("--solver", default="tiles", choices=["tiles", "bfs"], help="rank/basins/uparea solver")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = every GPU owns `size` rows of a (N*size) x size raster (default); "
                          "strong = ONE size x size raster split into N row blocks (BASELINE config 4 with --size 65536)")
     ap.add_argument("--no-fuse", action="store_true", help="run the separate parse pass even on device-resident buffers")
     ap.add_argument("--no-e2e", action="store_true", help="skip the pinned-host end-to-end arm (very large rasters)")
+    ap.add_argument("--verify-full", action="store_true",
+                    help="N>1: compare the FULL-size outputs with a single-GPU solve of the whole raster on rank 0 (needs the "
+                         "raster to fit one GPU; the multi-rank buffers are freed first)")
     ap.add_argument("--extras", action="store_true", help="also time the secondary configs (order, Strahler, HAND sweeps)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -584,6 +665,7 @@ def main():
     if _lib.device_count() == 0:
         raise SystemExit("bench.py: no CUDA device -- pyflwdir_b200 has no CPU fallback")
     device = local_rank % _lib.device_count()
+    numa_node = _lib.bind_to_device_numa_node(device) if world > 1 else None  # before any pinned allocation
     if world > 1:
         w = TiledWorkload(args.size, args.seed, device, rank, world, dist, strong=(args.scaling == "strong"))
     else:
@@ -633,7 +715,7 @@ def main():
         idx_b = np.dtype(getattr(w, "idx_dtype", np.int32)).itemsize
         e2e = {"value": cells_total * args.steps / (e2e_ms / 1e3) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": int(getattr(w, "ext_bytes", cells)), "d2h_bytes_per_step": int((12 + idx_b) * cells),
-               "ms_per_step": e2e_ms / args.steps, "note": "bytes are per GPU"}
+               "ms_per_step": e2e_ms / args.steps, "note": "bytes are per GPU", "numa_node_rank0": numa_node}
     launches_total = int(reduce_sum(dist, launches))
 
     # ---- roofline of the dominant kernel
@@ -671,21 +753,19 @@ def main():
         extra = extras(w, args.size, args.seed)
         extra["widened"] = extras_widened(w, args.size, args.seed, min(args.size, 2048))
 
-    # ---- CPU baseline (rank 0, N = 1 only)
+    # ---- parity of what was just timed (size-independent properties at full size; N > 1: the same NCCL path on a
+    # reduced raster against a single-GPU solve of that raster)
+    parity = parity_check(w, dist, rank, world, device, args)
+
+    # ---- CPU baseline (rank 0, N = 1 only): the reference's own numba path when oracle/_ref is there
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        import oracle
-
-        oracle.build()
-        cs = args.cpu_size or args.size
-        if cs == args.size:
-            d8 = np.array(w.d8_host.array, copy=True)
-        else:
-            d8, _ = host_raster(cs, args.seed)
-        st = cpu_path(d8)
-        cpu = {"value": d8.size / st["total"] / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"{cs}x{cs} raster (same generator/seed), oracle C port of the numba kernels, 1 thread of "
-                         f"{os.cpu_count()} host cores; s/stage: " + ", ".join(f"{k}={v:.2f}" for k, v in st.items()),
+        mods = cpu_modules()
+        cpu_warm(mods)
+        d8, _ = host_raster(args.cpu_size, args.seed)
+        st = min((cpu_path(mods, d8) for _ in range(3)), key=lambda t: t["total"])  # best of 3
+        cpu = {"value": d8.size / st["total"] / 1e6, "unit": UNIT, "cores": 1, "kind": mods[0],
+               "sample": cpu_describe(mods, args.cpu_size, st),
                "accuflux_plus_basins_mcells_s": d8.size / (st["accuflux"] + st["basins"]) / 1e6}
 
     if rank == 0:
@@ -693,21 +773,84 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": (f"synthetic {args.size}x{args.size} D8 raster" if world == 1 else
-                                    f"ONE synthetic {w.nrow_global}x{args.size} D8 raster row-tiled over {world} GPUs "
-                                    f"({w.n} rows + halo per GPU)") +
-                                   f" (rough Perlin fBm, {octaves_for(args.size)} octaves, steepest descent): "
-                                   "parse->idxs_ds + rank + upstream_area(cell) + basins",
-                       "seed": args.seed, "l2": "per-step working set ~26 B/cell x N cells (>= 1.7 GB at 8192^2) exceeds the 126 MB L2; no flush needed",
-                       "parallelism": (f"row-tiled x{world}: pit-count all-gather + 1 NCCL all-reduce of boundary tables per step"
-                                       if world > 1 else "single GPU")},
-            "e2e": e2e,
+            "config": workload_config(args, world, w),
+            "e2e": e2e, "parity_ok": parity["ok"], "parity": parity,
             "gpu_launches": launches_total, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "extra": extra,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
-    return 0
+    return 0 if parity["ok"] else 3
+
+
+def gather_objects(dist, obj):
+    if dist is None:
+        return [obj]
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, obj)
+    return out
+
+
+def parity_check(w, dist, rank, world, device, args):
+    """Checks on the outputs the timed region produced (device-resident arm).
+    (a) full size, every N: conservation laws that tie the four outputs together across ALL ranks --
+        sum of upstream_area over the pits (rank == 0) == number of cells that drain to a pit (rank >= 0);
+        number of pits == max basin id == global pit count.
+    (b) N > 1: the same pfd_d8_flow_all_tiled / NCCL path on a reduced raster (world x 1024 rows x 4096 columns, or the
+        full raster with --verify-full) against rank 0's single-GPU pfd_d8_flow_all of the WHOLE raster, by position-
+        dependent checksums of idxs_ds / rank / upstream_area / basins (additive over row blocks)."""
+    res = {"ok": True}
+    w.step_resident()
+    # (a)
+    host = []
+    for p, dt in zip(w.out_dev[1:], (np.int32, np.int32, np.uint32)):
+        a = np.empty(w.cells, dt)
+        w.ck(w.l.pfd_memcpy(w.h, w.L.ptr(a), p, w.cells * 4))
+        host.append(a)
+    rk, upa, bas = host
+    is_pit = rk == 0
+    mine = {"ranked": int(np.count_nonzero(rk >= 0)), "pit_upa": int(upa[is_pit].astype(np.int64).sum()),
+            "pits": int(np.count_nonzero(is_pit)), "max_basin": int(bas.max()),
+            "npits_reported": int(getattr(w, "n_pits_global", C.c_int64(-1)).value)}
+    del host, rk, upa, bas, is_pit
+    allr = gather_objects(dist, mine)
+    ranked, pit_upa, pits = (sum(r[k] for r in allr) for k in ("ranked", "pit_upa", "pits"))
+    max_basin = max(r["max_basin"] for r in allr)
+    res["conservation"] = {"cells_draining_to_pits": ranked, "sum_uparea_at_pits": pit_upa, "pits": pits, "max_basin_id": max_basin}
+    ok = ranked == pit_upa and pits == max_basin and ranked > 0
+    if world > 1:
+        ok = ok and all(r["npits_reported"] == pits for r in allr)
+    res["ok"] = bool(ok)
+    # (b)
+    if world > 1:
+        full = args.verify_full
+        if full:
+            cs = w.checksums(index_offset=w.row0 * w.ncol)
+            shape = (w.nrow_global, w.ncol)
+            w.free()
+        else:
+            rows = 1024
+            shape = (world * rows, 4096)
+            tw = TiledWorkload(shape[1], args.seed + 1, device, rank, world, dist, strong=False, rows_per_rank=rows)
+            tw.step_resident()
+            cs = tw.checksums(index_offset=tw.row0 * tw.ncol)
+            tw.free()
+        allc = gather_objects(dist, cs)
+        total = [sum(c[i] for c in allc) % (1 << 64) for i in range(4)]
+        want = [None]
+        if rank == 0:
+            sw = Workload(shape[1], args.seed if full else args.seed + 1, device, nrow=shape[0])
+            sw.ck(sw.l.pfd_set_option(sw.h, b"tiles", 1))
+            sw.step_resident()
+            want = [sw.checksums()]
+            sw.free()
+        if dist is not None:
+            dist.broadcast_object_list(want, src=0)
+        match = total == want[0]
+        res["vs_single_gpu"] = {"raster": f"{shape[0]}x{shape[1]}", "full_size": bool(full), "outputs": ["idxs_ds", "rank", "uparea", "basins"],
+                                "checksums_match": bool(match)}
+        res["ok"] = bool(res["ok"] and match)
+    return res
 
 
 if __name__ == "__main__":

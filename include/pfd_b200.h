@@ -72,6 +72,9 @@ typedef enum pfd_array {
 const char* pfd_version(void);
 int pfd_device_count(void);                       /* 0 when no CUDA device is usable */
 const char* pfd_status_string(int status);
+/* PCI bus id ("0000:1b:00.0") of CUDA device `device`: lets a one-process-per-GPU host bind itself to the GPU's NUMA node
+ * before it allocates pinned buffers (pyflwdir_b200/_lib.py bind_to_device_numa_node). */
+int pfd_device_pci_bus_id(int device, char* out, int capacity);
 
 /* ---- handle ------------------------------------------------------------------------------------------ */
 int pfd_create(int device, pfd_handle** out);
@@ -342,6 +345,25 @@ int pfd_set_option(pfd_handle* h, const char* name, int64_t value);
 int64_t pfd_get_info(const pfd_handle* h, const char* name);
 
 /* ---- instrumentation ---------------------------------------------------------------------------------- */
+/* Position-dependent 64-bit checksum of `count` elements of `elem_bytes` (1, 2, 4 or 8) bytes (device or host array):
+ * sum over i of (v[i] + 1) * ((i + index_offset) * 0x9E3779B97F4A7C15 | 1) mod 2^64. Additive over consecutive blocks,
+ * so the checksums of the row blocks of a multi-GPU run add up to the checksum of the single-GPU array (bench.py's
+ * parity_ok, the full-size tests). No reference counterpart: verification plumbing. */
+/* Element-wise verification of FINISHED outputs against their defining recurrences (csrc/pfd_verify.cuh): one independent
+ * pass re-evaluates, for every cell, the reference's per-cell statement from the finished values of the cell's graph
+ * neighbours and compares bit for bit -- a proof of the whole array at any raster size (the oracle only runs at small sizes).
+ * n_bad counts the violating cells (0 = the array is exactly what the reference returns for the raster parsed on h).
+ *   pfd_verify_flow     n_bad[5] = idxs_ds (core_d8.py:42-67), rank (core.py:17-47), basins (core.py:120-146), upstream
+ *                       area in cells (streams.py:15-41 via pyflwdir.py:790-800), pit numbering (basins.py:14-16); any array may be NULL
+ *   pfd_verify_strahler streams.strahler_order (streams.py:228-269)        pfd_verify_hand  dem.height_above_nearest_drain (dem.py:299-330)
+ *   pfd_verify_accuflux streams.accuflux, any dtype, in the walk order (descending upstream index) */
+int pfd_verify_flow(pfd_handle* h, const void* idxs_ds, int idx_dtype, const int32_t* rank, const int32_t* uparea,
+                    const uint32_t* basins, int64_t* n_bad);
+int pfd_verify_strahler(pfd_handle* h, const uint8_t* mask, const uint8_t* strord, int64_t* n_bad);
+int pfd_verify_hand(pfd_handle* h, const uint8_t* drain, const void* elevtn, int elev_dtype, const double* hand, int64_t* n_bad);
+int pfd_verify_accuflux(pfd_handle* h, const void* data, int dtype, double nodata_f, int64_t nodata_i, int nodata_is_int,
+                        const void* accu, int64_t* n_bad);
+int pfd_checksum(pfd_handle* h, const void* data, int elem_bytes, int64_t count, uint64_t index_offset, uint64_t* out);
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t pfd_launch_count(const pfd_handle* h);
 /* CUDA-event stopwatch on the handle's stream: device time between the two calls, in ms */

@@ -1,29 +1,40 @@
-"""Import the REAL reference (Deltares/pyflwdir, numba) when it is mounted at /root/reference.
+"""Import the REAL reference (Deltares/pyflwdir, numba): from /root/reference when it is mounted (this container),
+else from the git-ignored install under oracle/_ref/ (oracle/make_ref.sh), which travels to the GPU box with the
+gpurun snapshot.
 
-Used only by tests/golden/make_golden.py (golden-vector generation) and by CPU tests that pin the C oracle
-against the live reference. /root/reference does not exist on the GPU box: everything that runs there uses the
-committed golden vectors instead. TEST INFRASTRUCTURE ONLY."""
+Used by tests/golden/make_golden.py (golden-vector generation), by CPU tests that pin the C oracle against the live
+reference, and by bench.py's CPU legs (`--impl reference`, `cpu_baseline`). TEST / MEASUREMENT INFRASTRUCTURE ONLY:
+nothing under pyflwdir_b200/ imports it."""
 import importlib
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("PFD_REFERENCE_ROOT", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+REFERENCE_ROOT = os.environ.get("PFD_REFERENCE_ROOT", "/root/reference")  # data files (tests/data, examples) live only here
+_CANDIDATES = [os.environ.get("PFD_REFERENCE_ROOT", "/root/reference"), os.path.join(HERE, "_ref")]
+
+
+def root():
+    for r in _CANDIDATES:
+        if r and os.path.isfile(os.path.join(r, "pyflwdir", "__init__.py")):
+            return r
+    return None
 
 
 def available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "pyflwdir"))
+    return root() is not None
 
 
 def load():
     """Returns the reference `pyflwdir` module (numba JIT cache redirected to a writable dir)."""
-    if not available():
-        raise ImportError("reference not mounted")
+    r = root()
+    if r is None:
+        raise ImportError("reference not found (neither /root/reference nor oracle/_ref; run oracle/make_ref.sh)")
     os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/pfd_numba_cache")
-    stubs = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_stubs")
     try:
         importlib.import_module("affine")
     except ImportError:
-        sys.path.insert(0, stubs)
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+        sys.path.insert(0, os.path.join(HERE, "_stubs"))
+    if r not in sys.path:
+        sys.path.insert(0, r)
     return importlib.import_module("pyflwdir")

@@ -220,7 +220,8 @@ class DeviceGraph:
             raise ValueError('"strord" size does not match.')
         m = None
         if mask is not None:
-            m = np.ascontiguousarray(mask).astype(np.uint8, copy=False)
+            m = np.ascontiguousarray(mask)
+            m = m.view(np.uint8) if m.dtype == np.bool_ else (m != 0).view(np.uint8)
             if m.size != self.size:
                 raise ValueError('"mask" size does not match.')
         out = _lib.out_array(self.size, np.int32)
@@ -334,7 +335,8 @@ class DeviceGraph:
         a = np.ascontiguousarray(a)
         if a.size != self.size:
             raise ValueError(f'"{name}" size does not match.')
-        return a.astype(np.uint8, copy=False) if a.dtype != np.bool_ else a.view(np.uint8)
+        # any nonzero value is True (like numpy's truth value in the reference), not just values that survive a uint8 cast
+        return (a != 0).view(np.uint8) if a.dtype != np.bool_ else a.view(np.uint8)
 
     def downstream(self, data):
         """Flwdir.downstream: value of the next downstream cell."""

@@ -34,6 +34,7 @@ SYMBOLS = {
     "pfd_version": (C.c_char_p, []),
     "pfd_device_count": (_int, []),
     "pfd_status_string": (C.c_char_p, [_int]),
+    "pfd_device_pci_bus_id": (_int, [_int, C.c_char_p, _int]),
     "pfd_create": (_int, [_int, C.POINTER(_vp)]),
     "pfd_destroy": (None, [_vp]),
     "pfd_last_error": (C.c_char_p, [_vp]),
@@ -89,6 +90,11 @@ SYMBOLS = {
     "pfd_set_option": (_int, [_vp, C.c_char_p, _i64]),
     "pfd_get_info": (_i64, [_vp, C.c_char_p]),
     "pfd_synth_d8_block": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _int, _u32, C.c_float, _vp]),
+    "pfd_verify_flow": (_int, [_vp, _vp, _int, _vp, _vp, _vp, _pi64]),
+    "pfd_verify_strahler": (_int, [_vp, _vp, _vp, _pi64]),
+    "pfd_verify_hand": (_int, [_vp, _vp, _vp, _int, _vp, _pi64]),
+    "pfd_verify_accuflux": (_int, [_vp, _vp, _int, C.c_double, _i64, _int, _vp, _pi64]),
+    "pfd_checksum": (_int, [_vp, _vp, _int, _i64, C.c_uint64, C.POINTER(C.c_uint64)]),
     "pfd_launch_count": (_i64, [_vp]),
     "pfd_timer_start": (_int, [_vp]),
     "pfd_timer_stop": (_int, [_vp, C.POINTER(C.c_double)]),
@@ -126,6 +132,39 @@ def lib():
 
 def device_count():
     return int(lib().pfd_device_count())
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_device_numa_node(device):
+    """One process per GPU: run this process on the CPUs of the GPU's NUMA node, so that the pinned buffers it allocates
+    afterwards (first touched by this process) sit next to the GPU's PCIe root and the D2H / H2D copies of several ranks
+    do not all cross the socket interconnect. Returns the node (or None when the topology is not exposed)."""
+    buf = C.create_string_buffer(32)
+    if lib().pfd_device_pci_bus_id(int(device), buf, 32) != OK:
+        return None
+    bus = buf.value.decode().lower()
+    try:
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read()) & set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except (OSError, ValueError):
+        return None
 
 
 def check(status, handle=None):

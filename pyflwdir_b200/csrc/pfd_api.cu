@@ -6,6 +6,7 @@
 #include "pfd_compact.cuh"
 #include "pfd_local.cuh"
 #include "pfd_tiles.cuh"
+#include "pfd_verify.cuh"
 #include "pfd_synth.h"
 
 #include <nccl.h>
@@ -72,6 +73,15 @@ extern "C" int pfd_device_count(void) {
         return 0;
     }
     return n;
+}
+
+extern "C" int pfd_device_pci_bus_id(int device, char* out, int capacity) {
+    if (!out || capacity < 16) return pfd_fail(nullptr, PFD_ERR_INVALID_ARG, "pfd_device_pci_bus_id: need a buffer of >= 16 bytes");
+    if (cudaDeviceGetPCIBusId(out, capacity, device) != cudaSuccess) {
+        cudaGetLastError();
+        return pfd_fail(nullptr, PFD_ERR_CUDA, "pfd_device_pci_bus_id: no such device");
+    }
+    return PFD_OK;
 }
 
 extern "C" const char* pfd_status_string(int s) {
@@ -142,7 +152,8 @@ extern "C" void pfd_destroy(pfd_handle* h) {
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->dir, &h->upmask, &h->pits, &h->pit_outlet, &h->seq, &h->bseq, &h->rank, &h->basins,
                       &h->level_off, &h->bfs_state, &h->chunk_status, &h->blk_counts, &h->blk_offsets, &h->counters,
-                      &h->segs, &h->tslots, &h->uparea, &h->tile_loc, &h->btab, &h->bgraph, &h->mg_counts, &h->sub_idxs};
+                      &h->segs, &h->tslots, &h->uparea, &h->tile_loc, &h->btab, &h->bgraph, &h->mg_counts, &h->sub_idxs,
+                      &h->sub_labels, &h->sub_slices, &h->stream_off, &h->stream_cells, &h->verify};
     for (DevBuf* b : bufs) pfd_release(*b);
     for (DevBuf& b : h->scratch) pfd_release(b);
     for (int s = 0; s < PFD_NSTAGE; ++s) {
@@ -206,6 +217,41 @@ extern "C" int pfd_synchronize(pfd_handle* h) {
 }
 
 extern "C" int64_t pfd_launch_count(const pfd_handle* h) { return h ? h->launches : 0; }
+
+// position-dependent checksum (verification plumbing, include/pfd_b200.h)
+template <typename T>
+__global__ void checksum_kernel(const T* __restrict__ v, int64_t n, unsigned long long off, unsigned long long* __restrict__ out) {
+    unsigned long long acc = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        acc += ((unsigned long long)v[i] + 1ull) * ((((unsigned long long)i + off) * 0x9E3779B97F4A7C15ull) | 1ull);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+extern "C" int pfd_checksum(pfd_handle* h, const void* data, int elem_bytes, int64_t count, uint64_t index_offset, uint64_t* out) {
+    PFD_TRY(check_handle(h));
+    if (!data || !out || count < 0 || (elem_bytes != 1 && elem_bytes != 2 && elem_bytes != 4 && elem_bytes != 8))
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_checksum: bad argument");
+    PFD_TRY(pfd_reserve(h, h->counters, 8 * sizeof(unsigned long long)));
+    unsigned long long* ctr = (unsigned long long*)h->counters.p + 6;
+    PFD_CUDA(h, cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), h->stream));
+    const void* dev = nullptr;
+    PFD_TRY(pfd_stage_in(h, data, (size_t)count * elem_bytes, 2, &dev));
+    if (count > 0) {
+        const int g = grid_for(count, 256, 8, 148 * 16);
+        if (elem_bytes == 1) checksum_kernel<uint8_t><<<g, 256, 0, h->stream>>>((const uint8_t*)dev, count, index_offset, ctr);
+        else if (elem_bytes == 2) checksum_kernel<uint16_t><<<g, 256, 0, h->stream>>>((const uint16_t*)dev, count, index_offset, ctr);
+        else if (elem_bytes == 4) checksum_kernel<uint32_t><<<g, 256, 0, h->stream>>>((const uint32_t*)dev, count, index_offset, ctr);
+        else checksum_kernel<unsigned long long><<<g, 256, 0, h->stream>>>((const unsigned long long*)dev, count, index_offset, ctr);
+        PFD_LAUNCH_CHECK(h);
+    }
+    unsigned long long v = 0;
+    PFD_CUDA(h, cudaMemcpyAsync(&v, ctr, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    *out = v;
+    return PFD_OK;
+}
 
 // CUDA-event bracket on the handle's stream (bench.py times K steps between start and stop)
 extern "C" int pfd_timer_start(pfd_handle* h) {
@@ -1080,6 +1126,11 @@ extern "C" int pfd_set_option(pfd_handle* h, const char* name, int64_t value) {
         h->fuse_parse = value ? 1 : 0;
         return PFD_OK;
     }
+    if (name && strcmp(name, "release_scratch") == 0) {  // give the staging buffers back (very large rasters)
+        PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+        for (auto& b : h->scratch) pfd_release(b);
+        return PFD_OK;
+    }
     return pfd_fail(h, PFD_ERR_INVALID_ARG, std::string("pfd_set_option: unknown option ") + (name ? name : "(null)"));
 }
 
@@ -1826,10 +1877,9 @@ extern "C" int pfd_floodplains(pfd_handle* h, const float* drainh_init, const vo
 // ---------------------------------------------------------------------------------------------------------
 // fused headline pass
 // ---------------------------------------------------------------------------------------------------------
-extern "C" int pfd_d8_flow_all(pfd_handle* h, const uint8_t* d8, int64_t nrow, int64_t ncol, void* idxs_ds_out,
-                               int idx_dtype, int32_t* rank_out, int32_t* uparea_out, uint32_t* basins_out,
-                               int64_t* n_valid, int64_t* n_pits, int64_t* nnodes) {
-    PFD_TRY(check_handle(h));
+static int flow_all_impl(pfd_handle* h, const uint8_t* d8, int64_t nrow, int64_t ncol, void* idxs_ds_out,
+                         int idx_dtype, int32_t* rank_out, int32_t* uparea_out, uint32_t* basins_out,
+                         int64_t* n_valid, int64_t* n_pits, int64_t* nnodes) {
     stage_reset(h);
     cudaEventRecord(h->ev_start[PFD_STAGE_TOTAL], h->stream);
     h->stage_used[PFD_STAGE_TOTAL] = true;
@@ -1907,6 +1957,150 @@ extern "C" int pfd_d8_flow_all(pfd_handle* h, const uint8_t* d8, int64_t nrow, i
     if (n_pits) *n_pits = h->n_pits;
     if (nnodes) *nnodes = h->nnodes;
     return PFD_OK;
+}
+
+extern "C" int pfd_d8_flow_all(pfd_handle* h, const uint8_t* d8, int64_t nrow, int64_t ncol, void* idxs_ds_out,
+                               int idx_dtype, int32_t* rank_out, int32_t* uparea_out, uint32_t* basins_out,
+                               int64_t* n_valid, int64_t* n_pits, int64_t* nnodes) {
+    PFD_TRY(check_handle(h));
+    const int rc = flow_all_impl(h, d8, nrow, ncol, idxs_ds_out, idx_dtype, rank_out, uparea_out, basins_out, n_valid, n_pits, nnodes);
+    if (rc != PFD_OK) {
+        // every error exit: nothing may still be in flight into the caller's buffers, and the handle holds no half-built graph
+        const std::string msg = h->err;
+        if (h->copy_pending) {
+            cudaStreamSynchronize(h->copy_stream);
+            h->copy_pending = false;
+        }
+        cudaStreamSynchronize(h->stream);
+        cudaGetLastError();
+        invalidate(h);
+        h->err = msg;
+    }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// verification plumbing (pfd_verify.cuh): finished outputs against their defining recurrences, any raster size
+// ---------------------------------------------------------------------------------------------------------
+static int verify_begin(pfd_handle* h, const char* who, VerifyCounts** vc) {
+    PFD_TRY(check_handle(h));
+    if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, std::string(who) + ": no raster parsed on this handle");
+    if (h->tiled) return pfd_fail(h, PFD_ERR_UNSUPPORTED, std::string(who) + ": this handle holds a row block");
+    PFD_TRY(ensure_upmask(h));
+    PFD_TRY(pfd_reserve(h, h->verify, sizeof(VerifyCounts)));
+    PFD_CUDA(h, cudaMemsetAsync(h->verify.p, 0, sizeof(VerifyCounts), h->stream));
+    *vc = (VerifyCounts*)h->verify.p;
+    return PFD_OK;
+}
+
+static int verify_end(pfd_handle* h, int64_t* n_bad, int first, int count) {
+    VerifyCounts host;
+    PFD_CUDA(h, cudaMemcpyAsync(&host, h->verify.p, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < count; ++k) n_bad[k] = (int64_t)host.bad[first + k];
+    return PFD_OK;
+}
+
+extern "C" int pfd_verify_flow(pfd_handle* h, const void* idxs_ds, int idx_dtype, const int32_t* rank, const int32_t* uparea,
+                               const uint32_t* basins, int64_t* n_bad) {
+    VerifyCounts* vc = nullptr;
+    PFD_TRY(verify_begin(h, "pfd_verify_flow", &vc));
+    if (!n_bad) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_verify_flow: n_bad is null");
+    if (idxs_ds && idx_dtype != PFD_I32 && idx_dtype != PFD_U32 && idx_dtype != PFD_I64 && idx_dtype != PFD_U64)
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_verify_flow: bad index dtype");
+    const int64_t n = h->n;
+    const void *di = nullptr, *dr = nullptr, *du = nullptr, *db = nullptr;
+    if (idxs_ds) PFD_TRY(pfd_stage_in(h, idxs_ds, (size_t)n * pfd_dtype_size(idx_dtype), 2, &di));
+    if (rank) PFD_TRY(pfd_stage_in(h, rank, (size_t)n * 4, 3, &dr));
+    if (uparea) PFD_TRY(pfd_stage_in(h, uparea, (size_t)n * 4, 4, &du));
+    if (basins) PFD_TRY(pfd_stage_in(h, basins, (size_t)n * 4, 5, &db));
+    const int g = grid_for(n, 256, 4, 148 * 32);
+    const uint8_t *dir = (const uint8_t*)h->dir.p, *um = (const uint8_t*)h->upmask.p;
+    if (idx_dtype == PFD_I64 || idx_dtype == PFD_U64)
+        verify_flow_kernel<int64_t><<<g, 256, 0, h->stream>>>(dir, um, n, h->ncol, (const int64_t*)di, (const int32_t*)dr,
+                                                              (const int32_t*)du, (const uint32_t*)db, vc);
+    else
+        verify_flow_kernel<uint32_t><<<g, 256, 0, h->stream>>>(dir, um, n, h->ncol, (const uint32_t*)di, (const int32_t*)dr,
+                                                               (const int32_t*)du, (const uint32_t*)db, vc);
+    PFD_LAUNCH_CHECK(h);
+    if (basins && h->n_pits > 0) {
+        verify_pit_ids_kernel<<<grid_for(h->n_pits, 256), 256, 0, h->stream>>>((const cell_t*)h->pits.p, h->n_pits, (const uint32_t*)db, vc);
+        PFD_LAUNCH_CHECK(h);
+    }
+    return verify_end(h, n_bad, 0, 5);
+}
+
+extern "C" int pfd_verify_strahler(pfd_handle* h, const uint8_t* mask, const uint8_t* strord, int64_t* n_bad) {
+    VerifyCounts* vc = nullptr;
+    PFD_TRY(verify_begin(h, "pfd_verify_strahler", &vc));
+    if (!strord || !n_bad) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_verify_strahler: null argument");
+    PFD_TRY(tiles_usable(h) ? tiles_ensure(h, true, false, false) : order_impl(h, true, false));
+    const int64_t n = h->n;
+    const void *dm = nullptr, *ds = nullptr;
+    if (mask) PFD_TRY(pfd_stage_in(h, mask, (size_t)n, 4, &dm));
+    PFD_TRY(pfd_stage_in(h, strord, (size_t)n, 5, &ds));
+    verify_strahler_kernel<<<grid_for(n, 256, 4, 148 * 32), 256, 0, h->stream>>>(
+        (const uint8_t*)h->dir.p, (const uint8_t*)h->upmask.p, (const int32_t*)h->rank.p, (const uint8_t*)dm, n, h->ncol,
+        (const uint8_t*)ds, vc);
+    PFD_LAUNCH_CHECK(h);
+    return verify_end(h, n_bad, 5, 1);
+}
+
+extern "C" int pfd_verify_hand(pfd_handle* h, const uint8_t* drain, const void* elevtn, int elev_dtype, const double* hand,
+                               int64_t* n_bad) {
+    VerifyCounts* vc = nullptr;
+    PFD_TRY(verify_begin(h, "pfd_verify_hand", &vc));
+    if (!drain || !elevtn || !hand || !n_bad) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_verify_hand: null argument");
+    if (elev_dtype != PFD_F32 && elev_dtype != PFD_F64) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_verify_hand: elevtn must be float32 or float64");
+    PFD_TRY(tiles_usable(h) ? tiles_ensure(h, true, false, false) : order_impl(h, true, false));
+    const int64_t n = h->n;
+    const void *dd = nullptr, *de = nullptr, *dh = nullptr;
+    PFD_TRY(pfd_stage_in(h, drain, (size_t)n, 2, &dd));
+    PFD_TRY(pfd_stage_in(h, elevtn, (size_t)n * pfd_dtype_size(elev_dtype), 4, &de));
+    PFD_TRY(pfd_stage_in(h, hand, (size_t)n * 8, 5, &dh));
+    const int g = grid_for(n, 256, 4, 148 * 32);
+    if (elev_dtype == PFD_F32)
+        verify_hand_kernel<float><<<g, 256, 0, h->stream>>>((const uint8_t*)h->dir.p, (const int32_t*)h->rank.p, (const uint8_t*)dd,
+                                                            (const float*)de, n, h->ncol, (const double*)dh, vc);
+    else
+        verify_hand_kernel<double><<<g, 256, 0, h->stream>>>((const uint8_t*)h->dir.p, (const int32_t*)h->rank.p, (const uint8_t*)dd,
+                                                             (const double*)de, n, h->ncol, (const double*)dh, vc);
+    PFD_LAUNCH_CHECK(h);
+    return verify_end(h, n_bad, 5, 1);
+}
+
+template <typename T>
+static void verify_accuflux_launch(pfd_handle* h, const void* data, const NoData& nd, const void* accu, VerifyCounts* vc) {
+    verify_accuflux_kernel<T><<<grid_for(h->n, 256, 4, 148 * 32), 256, 0, h->stream>>>(
+        (const uint8_t*)h->dir.p, (const uint8_t*)h->upmask.p, (const int32_t*)h->rank.p, (const T*)data, nd, h->n, h->ncol,
+        (const T*)accu, vc);
+}
+
+extern "C" int pfd_verify_accuflux(pfd_handle* h, const void* data, int dtype, double nodata_f, int64_t nodata_i, int nodata_is_int,
+                                   const void* accu, int64_t* n_bad) {
+    VerifyCounts* vc = nullptr;
+    PFD_TRY(verify_begin(h, "pfd_verify_accuflux", &vc));
+    const size_t esz = pfd_dtype_size(dtype);
+    if (!data || !accu || !n_bad || !esz) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_verify_accuflux: bad argument");
+    PFD_TRY(tiles_usable(h) ? tiles_ensure(h, true, false, false) : order_impl(h, true, false));
+    const void *dd = nullptr, *da = nullptr;
+    PFD_TRY(pfd_stage_in(h, data, (size_t)h->n * esz, 4, &dd));
+    PFD_TRY(pfd_stage_in(h, accu, (size_t)h->n * esz, 5, &da));
+    NoData nd{nodata_f, (long long)nodata_i, nodata_is_int};
+    switch (dtype) {
+    case PFD_I8: verify_accuflux_launch<int8_t>(h, dd, nd, da, vc); break;
+    case PFD_U8: verify_accuflux_launch<uint8_t>(h, dd, nd, da, vc); break;
+    case PFD_I16: verify_accuflux_launch<int16_t>(h, dd, nd, da, vc); break;
+    case PFD_U16: verify_accuflux_launch<uint16_t>(h, dd, nd, da, vc); break;
+    case PFD_I32: verify_accuflux_launch<int32_t>(h, dd, nd, da, vc); break;
+    case PFD_U32: verify_accuflux_launch<uint32_t>(h, dd, nd, da, vc); break;
+    case PFD_I64: verify_accuflux_launch<int64_t>(h, dd, nd, da, vc); break;
+    case PFD_U64: verify_accuflux_launch<uint64_t>(h, dd, nd, da, vc); break;
+    case PFD_F32: verify_accuflux_launch<float>(h, dd, nd, da, vc); break;
+    default: verify_accuflux_launch<double>(h, dd, nd, da, vc); break;
+    }
+    PFD_LAUNCH_CHECK(h);
+    return verify_end(h, n_bad, 5, 1);
 }
 
 // ---------------------------------------------------------------------------------------------------------

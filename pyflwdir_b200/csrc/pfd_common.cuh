@@ -175,6 +175,7 @@ struct pfd_handle {
     DevBuf segs;              // SweepSeg schedule of the level replays
     DevBuf tslots;            // reduced-graph (tile ring) arrays of the tile solver
     DevBuf mg_counts;
+    DevBuf verify;            // VerifyCounts of the pfd_verify_* entry points
     DevBuf btab, bgraph;       // row-tiled multi-GPU solve: boundary tables, boundary graph state
     int64_t dir_off = 0;       // offset of the first OWNED row inside dir (halo row of a row block)
     bool tiled = false;        // parsed as a row block of a larger raster (only the tiled entry points apply)

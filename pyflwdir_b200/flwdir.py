@@ -250,34 +250,11 @@ class Flwdir(object):
         est[pits[elevtn[pits] <= max_elevtn]] = 1  # rivers.py:38-39
         return self._dev.classify_estuary(est, rivdst, rivwth, min_convergence)
 
-    def river_depth(self, qbankfull, rivwth, zs=None, rivdst=None, rivslp=None, manning=0.03, method="manning",
-                    min_rivdph=1, min_rivslp=1e-5, **kwargs):
-        """Return an estimated river depth based on manning's equation for a rectangular river profile
-        (flwdir.py:698-778; element-wise numpy on the host like the reference, `downstream` and `fillnodata` on the device).
-        The experimental "gvf" solver (rivers.rivdph_gvf: one scipy solve_ivp call per cell) is not provided."""
-        methods = ["manning", "gvf"]
-        if method not in methods:
-            raise ValueError(f"Method unknown {method}, select from {methods}")
-        manning = self._check_data(manning, "manning")
-        qbankfull = self._check_data(qbankfull, "qbankfull")
-        rivwth = self._check_data(rivwth, "rivwth")
-        _opt = method == "manning" and rivslp is not None
-        rivslp = self._check_data(rivslp, "rivslp", optional=True)
-        rivdst = self._check_data(rivdst, "rivdst", optional=_opt)
-        zs = self._check_data(zs, "zs", optional=_opt)
-        if method == "gvf":
-            raise NotImplementedError('river_depth(method="gvf") integrates an ODE per cell with scipy on the host and is outside '
-                                      "the D8 hot path that pyflwdir_b200 accelerates")
-        if rivslp is None:
-            dz = zs - self.downstream(zs)
-            dx = rivdst - self.downstream(rivdst)
-            rivslp = np.where(dx >= 1, dz / np.maximum(1, dx), -9999)
-            rivslp = self.fillnodata(rivslp, nodata=-9999)
-        rivslp = np.maximum(min_rivslp, rivslp)
-        rivdph = ((manning * qbankfull) / (np.sqrt(rivslp) * rivwth)) ** (3 / 5)
-        rivdph = np.maximum(min_rivdph, rivdph)
-        rivdph[self.idxs_ds == self._mv] = -9999.0
-        return rivdph.reshape(self.shape)
+    def river_depth(self, *args, **kwargs):
+        """Out of scope (rivers / hydraulics): element-wise host numpy in the reference
+        (flwdir.py:698-778). Hand `idxs_ds` / `idxs_seq` of this object to the unmodified reference for it."""
+        raise NotImplementedError("river_depth is outside the D8 hot path that pyflwdir_b200 accelerates; use the reference "
+                                  "on this object's idxs_ds / idxs_seq (they are bit-identical to the reference's)")
 
     # ------------------------------------------------------------------ local methods
     def path(self, idxs=None, mask=None, max_length=None, direction="down"):

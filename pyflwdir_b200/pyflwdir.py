@@ -260,20 +260,23 @@ class FlwdirRaster(Flwdir):
 
     # ------------------------------------------------------------------ spatial helpers
     def index(self, xs, ys, **kwargs):
-        """Linear cell indices of x, y coordinates (row-major), -1 outside the raster."""
+        """Linear cell indices of x, y coordinates (pyflwdir.py:388-406 -> gis_utils.coords_to_idxs,
+        gis_utils.py:304-338): raises IndexError for coordinates outside the raster, like the reference."""
         xs, ys = np.atleast_1d(xs), np.atleast_1d(ys)
         cols, rows = ~self.transform * (xs, ys)
         cols, rows = np.floor(cols).astype(np.int64), np.floor(rows).astype(np.int64)
         nrow, ncol = self.shape
-        idxs = rows * ncol + cols
-        outside = (rows < 0) | (rows >= nrow) | (cols < 0) | (cols >= ncol)
-        idxs[outside] = -1
-        return idxs
+        if np.any((rows < 0) | (rows >= nrow) | (cols < 0) | (cols >= ncol)):
+            raise IndexError("XY coordinates outside domain")
+        return rows * ncol + cols
 
     def xy(self, idxs, **kwargs):
-        """Cell-centre x, y coordinates of linear indices."""
+        """Cell-centre x, y coordinates of linear indices (pyflwdir.py:408-424 -> gis_utils.idxs_to_coords,
+        gis_utils.py:264-301): raises IndexError for indices outside the raster, like the reference."""
         idxs = np.atleast_1d(idxs)
-        ncol = self.shape[1]
+        nrow, ncol = self.shape
+        if np.any((idxs < 0) | (idxs >= nrow * ncol)):
+            raise IndexError("idxs coordinates outside domain")
         r, c = idxs // ncol, idxs % ncol
         return self.transform * (c + 0.5, r + 0.5)
 

@@ -304,17 +304,6 @@ def run_oracle_case(d8, aux, area=None, transform=(1.0, 0.0, 0.0, 0.0, -1.0, 0.0
     out["estuary_f32"] = o.rivers.classify_estuary(idxs_ds, seq, idxs_pit, distnc, rivwth32, elev0, 0, 1e-2)
     out["estuary_f64"] = o.rivers.classify_estuary(idxs_ds, seq, idxs_pit, distnc.astype(np.float64) * 0.5,
                                                    rivwth32.astype(np.float64), elev0, 1.5, 1e-3)
-    zs = aux["elevtn"].ravel().astype(np.float64)
-    dstf = distnc.astype(np.float64)
-    ds_of = np.where(mask, idxs_ds, np.arange(d8.size)).astype(np.int64)
-    dz, dx = zs - zs[ds_of], dstf - dstf[ds_of]
-    rivslp = np.where(dx >= 1, dz / np.maximum(1, dx), -9999)
-    rivslp = o.core.fillnodata_downstream(idxs_ds, seq, rivslp, -9999, "max")
-    rivslp = np.maximum(1e-5, rivslp)
-    rivdph = ((np.full(d8.size, 0.03) * aux["data_f64"].ravel()) / (np.sqrt(rivslp) * rivwth32)) ** (3 / 5)
-    rivdph = np.maximum(1, rivdph)
-    rivdph[~mask] = -9999.0
-    out["rivdph_manning"] = rivdph.reshape(shape)
     return out
 
 
@@ -434,6 +423,4 @@ def run_api_case(pf, d8, aux, transform=None, latlon=False):
     out["estuary_f32"] = flw.classify_estuaries(elev0, rivwth32)
     out["estuary_f64"] = flw.classify_estuaries(elev0, rivwth32.astype(np.float64), rivdst=flw.distnc.astype(np.float64) * 0.5,
                                                 min_convergence=1e-3, max_elevtn=1.5)
-    out["rivdph_manning"] = flw.river_depth(aux["data_f64"], rivwth32, zs=aux["elevtn"].astype(np.float64),
-                                            rivdst=flw.distnc.astype(np.float64))
     return out

@@ -33,12 +33,30 @@ def test_reference_arm_json_contract():
     import json
 
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--size", "256",
-                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+                          "--cpu-size", "256", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300,
+                         cwd=ROOT)
     assert out.returncode == 0, out.stderr
     line = json.loads(out.stdout.strip().splitlines()[-1])
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["impl"] == "reference" and line["unit"] == "Mcells/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1
-    assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
+    # the real numba reference when it is installed (oracle/make_ref.sh or /root/reference), else the C port
+    from oracle import reference
+
+    assert line["cpu_baseline"]["kind"] == ("reference" if reference.available() else "port")
+    assert line["cpu_baseline"]["cores"] == 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"] and "cpu_sample" in line["config"]
+
+
+def test_reference_arm_port_fallback():
+    """Without the reference install the CPU arm times the oracle port and says so."""
+    import json
+
+    env = dict(os.environ, PFD_BENCH_CPU="port")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--size", "256",
+                          "--cpu-size", "256", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300,
+                         cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["cpu_baseline"]["kind"] == "port"
