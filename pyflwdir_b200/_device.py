@@ -31,6 +31,10 @@ class DeviceGraph:
         import os
         if os.environ.get("PFD_TILES", "1") == "0":
             self.set_option("tiles", 0)
+        # PFD_TILE_SWEEPS=0 selects the level replays over the BFS order for accuflux / Strahler / HAND instead of the
+        # tile-dataflow sweeps (identical results; used by the parity tests)
+        if os.environ.get("PFD_TILE_SWEEPS", "1") == "0":
+            self.set_option("tile_sweeps", 0)
         self.shape = None
         self.size = 0
         self.n_valid = self.n_pits = self.n_outlets = 0

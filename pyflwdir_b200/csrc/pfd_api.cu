@@ -6,6 +6,7 @@
 #include "pfd_compact.cuh"
 #include "pfd_local.cuh"
 #include "pfd_tiles.cuh"
+#include "pfd_tilesweep.cuh"
 #include "pfd_verify.cuh"
 #include "pfd_synth.h"
 
@@ -153,7 +154,7 @@ extern "C" void pfd_destroy(pfd_handle* h) {
     DevBuf* bufs[] = {&h->dir, &h->upmask, &h->pits, &h->pit_outlet, &h->seq, &h->bseq, &h->rank, &h->basins,
                       &h->level_off, &h->bfs_state, &h->chunk_status, &h->blk_counts, &h->blk_offsets, &h->counters,
                       &h->segs, &h->tslots, &h->uparea, &h->tile_loc, &h->btab, &h->bgraph, &h->mg_counts, &h->sub_idxs,
-                      &h->sub_labels, &h->sub_slices, &h->stream_off, &h->stream_cells, &h->verify};
+                      &h->sub_labels, &h->sub_slices, &h->stream_off, &h->stream_cells, &h->verify, &h->ts_done, &h->ts_lists};
     for (DevBuf* b : bufs) pfd_release(*b);
     for (DevBuf& b : h->scratch) pfd_release(b);
     for (int s = 0; s < PFD_NSTAGE; ++s) {
@@ -1126,6 +1127,10 @@ extern "C" int pfd_set_option(pfd_handle* h, const char* name, int64_t value) {
         h->fuse_parse = value ? 1 : 0;
         return PFD_OK;
     }
+    if (name && strcmp(name, "tile_sweeps") == 0) {  // 1 = tile-dataflow sweeps (default), 0 = level replays over the BFS order
+        h->tile_sweeps = value ? 1 : 0;
+        return PFD_OK;
+    }
     if (name && strcmp(name, "release_scratch") == 0) {  // give the staging buffers back (very large rasters)
         PFD_CUDA(h, cudaStreamSynchronize(h->stream));
         for (auto& b : h->scratch) pfd_release(b);
@@ -1140,6 +1145,8 @@ extern "C" int64_t pfd_get_info(const pfd_handle* h, const char* name) {
     if (strcmp(name, "fuse_parse") == 0) return h->fuse_parse;
     if (strcmp(name, "have_upmask") == 0) return h->have_upmask ? 1 : 0;
     if (strcmp(name, "tile_rounds") == 0) return h->tile_rounds;
+    if (strcmp(name, "tile_sweeps") == 0) return h->tile_sweeps;
+    if (strcmp(name, "sweep_passes") == 0) return h->sweep_passes;
     if (strcmp(name, "nlevels") == 0) return h->nlevels;
     if (strcmp(name, "nnodes") == 0) return h->nnodes;
     if (strcmp(name, "n_pits") == 0) return h->n_pits;
@@ -1452,11 +1459,87 @@ extern "C" int pfd_fetch(pfd_handle* h, int which, void* out, int idx_dtype) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// tile-dataflow sweeps (pfd_tilesweep.cuh): no cell ordering needed
+// ---------------------------------------------------------------------------------------------------------
+static int ts_prepare(pfd_handle* h, TsArgs& A, const char* who) {
+    if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, std::string(who) + ": no raster parsed on this handle");
+    if (h->tiled) return pfd_fail(h, PFD_ERR_UNSUPPORTED, "this handle holds a row block: only the pfd_tiled_* entry points apply");
+    const long long ntx = (h->ncol + TS_T - 1) / TS_T, nty = (h->nrow + TS_T - 1) / TS_T;
+    const long long ntiles = ntx * nty;
+    if (ntiles >= (1ll << 31)) return pfd_fail(h, PFD_ERR_UNSUPPORTED, std::string(who) + ": too many tiles");
+    PFD_TRY(pfd_reserve(h, h->ts_done, (size_t)ntiles * TS_BMW * sizeof(uint32_t)));
+    PFD_TRY(pfd_reserve(h, h->ts_lists, (size_t)ntiles * 3 * sizeof(uint32_t) + sizeof(TsCtl)));
+    uint32_t* base = (uint32_t*)h->ts_lists.p;
+    A.dir = (const uint8_t*)h->dir.p + h->dir_off;
+    A.nrow = h->nrow, A.ncol = h->ncol, A.ntx = (int)ntx, A.nty = (int)nty;
+    A.done = (uint32_t*)h->ts_done.p;
+    A.list[0] = base, A.list[1] = base + ntiles, A.stamp = base + 2 * ntiles;
+    A.ctl = (TsCtl*)(base + 3 * ntiles);
+    PFD_CUDA(h, cudaMemsetAsync(A.stamp, 0, (size_t)ntiles * sizeof(uint32_t) + sizeof(TsCtl), h->stream));
+    return PFD_OK;
+}
+
+static int ts_launch(pfd_handle* h, void* kern, size_t smem, const TsArgs& A, void* op_ptr) {
+    PFD_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    PFD_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TS_THREADS, smem));
+    if (per_sm < 1) return pfd_fail(h, PFD_ERR_CUDA, "tile sweep kernel cannot be made resident");
+    const long long ntiles = (long long)A.ntx * A.nty;
+    const long long grid = std::max<long long>(1, std::min<long long>((long long)per_sm * h->num_sms, ntiles));
+    void* args[] = {(void*)&A, op_ptr};
+    StageTimer t(h, PFD_STAGE_SWEEP);
+    PFD_CUDA(h, cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(TS_THREADS), args, smem, h->stream));
+    h->launches++;
+    return PFD_OK;
+}
+
+static int ts_result(pfd_handle* h, const TsArgs& A, unsigned long long* resolved) {
+    TsCtl c;
+    PFD_CUDA(h, cudaMemcpyAsync(&c, A.ctl, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->sweep_passes = (int)c.passes;
+    *resolved = c.resolved;
+    return PFD_OK;
+}
+
+
+// Up-sweep over the whole raster; `op.out` receives the result. Cells that drain to no pit keep op.init().
+template <class Op>
+static int run_tile_up(pfd_handle* h, Op op, const char* who) {
+    TsArgs A;
+    PFD_TRY(ts_prepare(h, A, who));
+    PFD_TRY(ts_launch(h, (void*)tile_up_sweep_kernel<Op>, sizeof(TsSharedUp<typename Op::V>), A, (void*)&op));
+    unsigned long long resolved = 0;
+    PFD_TRY(ts_result(h, A, &resolved));
+    if ((int64_t)resolved != h->n_valid) {
+        // loops: the trees hanging on them were resolved by the dataflow but are outside the reference's `seq`
+        PFD_TRY(tiles_usable(h) ? tiles_ensure(h, true, false, false) : order_impl(h, true, false));
+        ts_reset_unranked_kernel<Op><<<grid_for(h->n, 256, 4, 148 * 32), 256, 0, h->stream>>>(
+            (const uint8_t*)h->dir.p + h->dir_off, (const int32_t*)h->rank.p, h->n, op);
+        PFD_LAUNCH_CHECK(h);
+    }
+    return PFD_OK;
+}
+
+template <class Op>
+static int run_tile_down(pfd_handle* h, Op op, const char* who) {
+    TsArgs A;
+    PFD_TRY(ts_prepare(h, A, who));
+    PFD_TRY(ts_launch(h, (void*)tile_down_sweep_kernel<Op>, sizeof(TsSharedDown<typename Op::V>), A, (void*)&op));
+    unsigned long long resolved = 0;
+    return ts_result(h, A, &resolved);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // sweeps
 // ---------------------------------------------------------------------------------------------------------
 template <typename T>
 static int accuflux_typed(pfd_handle* h, const void* data_dev, void* out_dev, const NoData& nd, int direction) {
     const int64_t n = h->n;
+    if (direction == 0 && h->tile_sweeps) {
+        AccuUpTileOp<T> op{(const T*)data_dev, (T*)out_dev, nd};
+        return run_tile_up(h, op, "pfd_accuflux");
+    }
     if (data_dev != out_dev)
         PFD_CUDA(h, cudaMemcpyAsync(out_dev, data_dev, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
     if (direction == 0) {
@@ -1476,7 +1559,8 @@ extern "C" int pfd_accuflux(pfd_handle* h, const void* data, int dtype, double n
     if (direction != 0 && direction != 1) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_accuflux: direction must be 0 (up) or 1 (down)");
     const size_t esz = pfd_dtype_size(dtype);
     if (!esz) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_accuflux: unknown dtype");
-    PFD_TRY(order_impl(h, false, false));
+    if (!(direction == 0 && h->tile_sweeps)) PFD_TRY(order_impl(h, false, false));
+    else if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, "pfd_accuflux: no raster parsed on this handle");
     const size_t bytes = (size_t)h->n * esz;
     void* out_dev = nullptr;
     PFD_TRY(pfd_stage_out(h, out, bytes, 3, &out_dev));
@@ -1602,16 +1686,27 @@ extern "C" int pfd_strahler(pfd_handle* h, const uint8_t* mask, uint8_t* out) {
     PFD_TRY(check_handle(h));
     stage_reset(h);
     if (!out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_strahler: out is null");
-    PFD_TRY(order_impl(h, false, false));
+    if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, "pfd_strahler: no raster parsed on this handle");
+    if (!h->tile_sweeps) PFD_TRY(order_impl(h, false, false));
     const size_t bytes = (size_t)h->n;
     void* out_dev = nullptr;
     PFD_TRY(pfd_stage_out(h, out, bytes, 3, &out_dev));
     const void* mask_dev = nullptr;
     if (mask) PFD_TRY(pfd_stage_in(h, mask, bytes, 4, &mask_dev));
-    PFD_CUDA(h, cudaMemsetAsync(out_dev, 0, bytes, h->stream));
-    PFD_TRY(ensure_upmask(h));
-    StrahlerOp op{(const uint8_t*)h->upmask.p, (const uint8_t*)mask_dev, (uint8_t*)out_dev, h->ncol};
-    PFD_TRY((run_sweep<StrahlerOp, true>(h, op, 0)));
+    if (h->tile_sweeps) {
+        if (mask) {
+            StrahlerTileOp<true> op{(const uint8_t*)mask_dev, (uint8_t*)out_dev};
+            PFD_TRY(run_tile_up(h, op, "pfd_strahler"));
+        } else {
+            StrahlerTileOp<false> op{nullptr, (uint8_t*)out_dev};
+            PFD_TRY(run_tile_up(h, op, "pfd_strahler"));
+        }
+    } else {
+        PFD_CUDA(h, cudaMemsetAsync(out_dev, 0, bytes, h->stream));
+        PFD_TRY(ensure_upmask(h));
+        StrahlerOp op{(const uint8_t*)h->upmask.p, (const uint8_t*)mask_dev, (uint8_t*)out_dev, h->ncol};
+        PFD_TRY((run_sweep<StrahlerOp, true>(h, op, 0)));
+    }
     PFD_TRY(pfd_finish_out(h, out, out_dev, bytes));
     PFD_CUDA(h, cudaStreamSynchronize(h->stream));
     stage_collect(h);
@@ -1623,7 +1718,8 @@ extern "C" int pfd_hand(pfd_handle* h, const uint8_t* drain, const void* elevtn,
     stage_reset(h);
     if (!drain || !elevtn || !out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_hand: null array");
     if (elev_dtype != PFD_F32 && elev_dtype != PFD_F64) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_hand: elevtn must be float32 or float64");
-    PFD_TRY(order_impl(h, false, false));
+    if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, "pfd_hand: no raster parsed on this handle");
+    if (!h->tile_sweeps) PFD_TRY(order_impl(h, false, false));
     const int64_t n = h->n;
     const size_t bytes = (size_t)n * sizeof(double);
     void* out_dev = nullptr;
@@ -1631,6 +1727,19 @@ extern "C" int pfd_hand(pfd_handle* h, const uint8_t* drain, const void* elevtn,
     const void *drain_dev = nullptr, *elev_dev = nullptr;
     PFD_TRY(pfd_stage_in(h, drain, (size_t)n, 4, &drain_dev));
     PFD_TRY(pfd_stage_in(h, elevtn, (size_t)n * pfd_dtype_size(elev_dtype), 5, &elev_dev));
+    if (h->tile_sweeps) {
+        if (elev_dtype == PFD_F32) {
+            HandTileOp<float> op{(const uint8_t*)drain_dev, (const float*)elev_dev, (double*)out_dev};
+            PFD_TRY(run_tile_down(h, op, "pfd_hand"));
+        } else {
+            HandTileOp<double> op{(const uint8_t*)drain_dev, (const double*)elev_dev, (double*)out_dev};
+            PFD_TRY(run_tile_down(h, op, "pfd_hand"));
+        }
+        PFD_TRY(pfd_finish_out(h, out, out_dev, bytes));
+        PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+        stage_collect(h);
+        return PFD_OK;
+    }
     fill_kernel<double><<<grid_for(n, 256, 4), 256, 0, h->stream>>>((double*)out_dev, n, -9999.0);
     PFD_LAUNCH_CHECK(h);
     if (elev_dtype == PFD_F32) {
@@ -3053,7 +3162,7 @@ extern "C" int pfd_synth_d8(pfd_handle* h, const float* z, int64_t nrow, int64_t
 extern "C" int pfd_synth_d8_block(pfd_handle* h, int64_t row0, int64_t nrow, int64_t ncol, int64_t nrow_global, int64_t nref,
                                   int octaves, uint32_t seed, float sea_level, uint8_t* d8_out) {
     PFD_TRY(check_handle(h));
-    PFD_TRY(check_shape(h, nrow + 2, ncol, "pfd_synth_d8_block"));
+    PFD_TRY(check_shape(h, nrow, ncol, "pfd_synth_d8_block"));
     if (!d8_out || row0 < 0 || row0 + nrow > nrow_global || nref < 8 || octaves < 1)
         return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_synth_d8_block: bad argument");
     const int64_t top = row0 > 0 ? 1 : 0, bot = (row0 + nrow < nrow_global) ? 1 : 0;

@@ -175,6 +175,9 @@ struct pfd_handle {
     DevBuf segs;              // SweepSeg schedule of the level replays
     DevBuf tslots;            // reduced-graph (tile ring) arrays of the tile solver
     DevBuf mg_counts;
+    DevBuf ts_done, ts_lists;  // tile-dataflow sweeps: done bitmap; work lists + stamps + control block
+    int tile_sweeps = 1;       // option "tile_sweeps"
+    int sweep_passes = 0;      // passes of the last tile-dataflow sweep
     DevBuf verify;            // VerifyCounts of the pfd_verify_* entry points
     DevBuf btab, bgraph;       // row-tiled multi-GPU solve: boundary tables, boundary graph state
     int64_t dir_off = 0;       // offset of the first OWNED row inside dir (halo row of a row block)

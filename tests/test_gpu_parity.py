@@ -22,9 +22,11 @@ def pfb():
 
 @pytest.fixture(params=["tiles", "bfs"])
 def solver(request, monkeypatch):
-    """Both implementations of rank / basins() / upstream_area("cell"): the tile-hierarchical solver (default)
-    and the level-synchronous BFS + sweeps."""
+    """Both implementations of rank / basins() / upstream_area("cell") -- the tile-hierarchical solver (default) and the
+    level-synchronous BFS + sweeps -- and of accuflux / Strahler / HAND: tile-dataflow sweeps (default) and level
+    replays over the BFS order."""
     monkeypatch.setenv("PFD_TILES", "1" if request.param == "tiles" else "0")
+    monkeypatch.setenv("PFD_TILE_SWEEPS", "1" if request.param == "tiles" else "0")
     return request.param
 
 
