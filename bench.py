@@ -312,7 +312,7 @@ class TiledWorkload(Workload):
         self.l.pfd_destroy(self.h)
 
 
-def extras(w, size, seed):
+def extras(w, size, seed, skip_level=False):
     """Secondary configs of BASELINE.json on the same raster (device-resident, CUDA events, best of 3): the exact
     idxs_seq ordering (level-synchronous BFS), Strahler order, float64 accuflux and HAND level sweeps."""
     l, L, h, n = w.l, w.L, w.h, w.cells
@@ -325,7 +325,6 @@ def extras(w, size, seed):
     drain_dev = w.dev_alloc(n)
     w.ck(l.pfd_memcpy(h, drain_dev, L.ptr(drain), n))
     f64_dev, out8_dev, out1_dev = w.dev_alloc(n * 8), w.dev_alloc(n * 8), w.dev_alloc(n)
-    w.ck(l.pfd_accuflux(h, w.out_dev[2], L.DTYPES[np.dtype(np.int32)], -9999.0, -9999, 1, 0, w.out_dev[1]))  # warm the sweep path
 
     def best(fn, reps=3, prep=None):
         t = []
@@ -336,21 +335,36 @@ def extras(w, size, seed):
         return min(t)
 
     res = {}
-    reparse = lambda: w.ck(l.pfd_d8_parse(h, w.d8_dev, size, size, 1, None, 0, None, None, None))
-    res["order_idxs_seq_ms"] = best(lambda: w.ck(l.pfd_order(h, None, None)), prep=reparse)
-    res["nlevels"] = int(l.pfd_get_info(h, b"nlevels"))
-    res["strahler_sweep_ms"] = best(lambda: w.ck(l.pfd_strahler(h, None, out1_dev)))
-    # float64 data = the float elevation promoted on the device would need a kernel; use the int32 uparea as int64-free
-    res["accuflux_i32_sweep_ms"] = best(lambda: w.ck(l.pfd_accuflux(h, w.out_dev[2], L.DTYPES[np.dtype(np.int32)], -9999.0,
-                                                                      -9999, 1, 0, w.out_dev[1])))
-    res["accuflux_f32_sweep_ms"] = best(lambda: w.ck(l.pfd_accuflux(h, z_dev, L.DTYPES[np.dtype(np.float32)], -9999.0, 0, 0,
-                                                                      0, w.out_dev[1])))
-    res["hand_sweep_ms"] = best(lambda: w.ck(l.pfd_hand(h, drain_dev, z_dev, L.DTYPES[np.dtype(np.float32)], out8_dev)))
-    for k in list(res):
-        if k.endswith("_ms"):
-            res[k.replace("_ms", "_mcells_s")] = n / (res[k] / 1e3) / 1e6
-    res["note"] = ("device-resident, same raster; sweeps run over the cached ordering; config 3 (accuflux + Strahler) = "
-                   "tile solver + order + strahler sweep, config 5 (HAND) = tile solver + order + hand sweep")
+    f32, i32 = L.DTYPES[np.dtype(np.float32)], L.DTYPES[np.dtype(np.int32)]
+    calls = {
+        "strahler": lambda: w.ck(l.pfd_strahler(h, None, out1_dev)),
+        "accuflux_i32": lambda: w.ck(l.pfd_accuflux(h, w.out_dev[2], i32, -9999.0, -9999, 1, 0, w.out_dev[1])),
+        "accuflux_f32": lambda: w.ck(l.pfd_accuflux(h, z_dev, f32, -9999.0, 0, 0, 0, w.out_dev[1])),
+        "hand": lambda: w.ck(l.pfd_hand(h, drain_dev, z_dev, f32, out8_dev)),
+    }
+    # tile-dataflow sweeps (default): no ordering needed
+    w.ck(l.pfd_set_option(h, b"tile_sweeps", 1))
+    tile = {}
+    for k, fn in calls.items():
+        fn()
+        tile[k + "_ms"] = best(fn)
+        tile[k + "_passes"] = int(l.pfd_get_info(h, b"sweep_passes"))
+        tile[k + "_mcells_s"] = n / (tile[k + "_ms"] / 1e3) / 1e6
+    res["tile_dataflow"] = tile
+    if not skip_level:
+        # level replays over the BFS order (round-1 path, option tile_sweeps = 0)
+        w.ck(l.pfd_set_option(h, b"tile_sweeps", 0))
+        reparse = lambda: w.ck(l.pfd_d8_parse(h, w.d8_dev, size, size, 1, None, 0, None, None, None))
+        lev = {"order_idxs_seq_ms": best(lambda: w.ck(l.pfd_order(h, None, None)), prep=reparse)}
+        lev["nlevels"] = int(l.pfd_get_info(h, b"nlevels"))
+        for k, fn in calls.items():
+            fn()
+            lev[k + "_ms"] = best(fn)
+            lev[k + "_mcells_s"] = n / (lev[k + "_ms"] / 1e3) / 1e6
+        res["level_replay"] = lev
+        w.ck(l.pfd_set_option(h, b"tile_sweeps", 1))
+    res["note"] = ("device-resident, same raster, best of 3, CUDA events. BASELINE config 3 (accuflux + Strahler) = the headline "
+                   "step + strahler; config 5 (HAND) = headline step + hand; level_replay additionally needs order_idxs_seq")
     for p in (z_dev, drain_dev, f64_dev, out8_dev, out1_dev):
         w.ck(l.pfd_dev_free(h, p))
     return res
@@ -652,7 +666,9 @@ def main():
     ap.add_argument("--verify-full", action="store_true",
                     help="N>1: compare the FULL-size outputs with a single-GPU solve of the whole raster on rank 0 (needs the "
                          "raster to fit one GPU; the multi-rank buffers are freed first)")
-    ap.add_argument("--extras", action="store_true", help="also time the secondary configs (order, Strahler, HAND sweeps)")
+    ap.add_argument("--extras", nargs="?", const="sweeps", default=None, choices=["tile", "sweeps", "all"],
+                    help="also time the secondary configs: Strahler / accuflux / HAND sweeps (tile = tile-dataflow only, sweeps = "
+                         "also the level replays + ordering, all = plus every widened entry point)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -750,8 +766,9 @@ def main():
 
     extra = None
     if args.extras and world == 1:
-        extra = extras(w, args.size, args.seed)
-        extra["widened"] = extras_widened(w, args.size, args.seed, min(args.size, 2048))
+        extra = extras(w, args.size, args.seed, skip_level=args.extras == "tile")
+        if args.extras == "all":
+            extra["widened"] = extras_widened(w, args.size, args.seed, min(args.size, 2048))
 
     # ---- parity of what was just timed (size-independent properties at full size; N > 1: the same NCCL path on a
     # reduced raster against a single-GPU solve of that raster)

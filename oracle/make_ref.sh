@@ -25,4 +25,9 @@ else
     cp "$SRC"/pyflwdir/*.py "$DST/pyflwdir/"
     echo "make_ref.sh: pip install unavailable (no flit_core offline); placed the package directory in $DST"
 fi
+# the reference's own test files + fixtures (run against pyflwdir_b200 by tests/reference_suite.py on the GPU box)
+rm -rf "$DST/tests"
+mkdir -p "$DST/tests/data"
+cp "$SRC"/tests/*.py "$DST/tests/"
+cp "$SRC"/tests/data/* "$DST/tests/data/"
 ( cd "$SRC" && git rev-parse HEAD 2>/dev/null || echo unknown ) > "$DST/REFERENCE_COMMIT" || true

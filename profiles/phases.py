@@ -1,0 +1,68 @@
+"""Instruction share per phase of the tile-sweep kernels (line ranges of pfd_tilesweep.cuh), from the ncu source page.
+    python profiles/phases.py file.csv <kernel substring>"""
+import bisect
+import csv
+import sys
+
+rows = list(csv.reader(open(sys.argv[1])))
+want = sys.argv[2]
+funcs, cur, fname, hdr = {}, None, None, None
+for r in rows:
+    if not r:
+        continue
+    if r[0] == "File Path":
+        fname = r[1].split("/")[-1]
+        continue
+    if r[0] == "Function Name":
+        cur = r[1]
+        funcs.setdefault(cur, [])
+        continue
+    if r[0] == "Line No":
+        hdr = r
+        continue
+    if hdr is None or cur is None or len(r) < 10 or r[2] != "-":
+        continue
+    try:
+        smp = int(r[hdr.index("# Samples")])
+        ins = int(r[hdr.index("Instructions Executed")])
+        thr = int(r[hdr.index("Thread Instructions Executed")])
+    except ValueError:
+        continue
+    funcs[cur].append((ins, smp, thr, fname, int(r[0]) if r[0].isdigit() else -1))
+src = open("/root/repo/pyflwdir_b200/csrc/pfd_tilesweep.cuh").read().splitlines()
+
+
+def find(pat):
+    for i, l in enumerate(src, 1):
+        if pat in l:
+            return i
+
+
+names = [("stage_graph", "void ts_stage_graph"), ("load16", "void ts_load16"), ("store16", "void ts_store16"),
+         ("bitmap", "void ts_store_bitmap"), ("activate", "void ts_activate"), ("act_bit", "ts_act_bit_of(int si)"),
+         ("scan_word", "void ts_scan_word"), ("live/halo", "ts_live4(uint32_t"), ("structs", "struct TsSharedUp"),
+         ("up_step", "int ts_up_step"), ("up head+stage", "void ts_up_visit"), ("up masks", "// upstream / pending masks of the own cells"),
+         ("up walk", "// dataflow walk: one cell of one chain"), ("up store", "// store: pass 1 writes every cell of the tile (pending"),
+         ("up kernel loop", "// All passes in one cooperative launch"), ("ops", "// streams.accuflux (up): accu"),
+         ("down structs", "// Down-sweep. Op:"), ("down head", "void ts_down_visit"), ("down roots", "// roots: sources, pits, exit cells"),
+         ("down rounds", "// rounds: a lane resolves one child"), ("down store", "    // store\n"), ("down kernel", "tile_down_sweep_kernel(TsArgs"),
+         ("hand op", "struct HandTileOp")]
+marks = sorted([(n, find(p)) for n, p in names if find(p)], key=lambda m: m[1])
+for f, out in funcs.items():
+    if want not in f:
+        continue
+    ti = sum(o[0] for o in out)
+    print(f[:70], "total warp instr", ti)
+    agg = {}
+    for ins, smp, thr, fn, ln in out:
+        if fn != "pfd_tilesweep.cuh":
+            key = "other:" + fn
+        else:
+            i = bisect.bisect_right([m[1] for m in marks], ln) - 1
+            key = marks[i][0] if i >= 0 else "top"
+        a = agg.setdefault(key, [0, 0, 0])
+        a[0] += ins
+        a[1] += smp
+        a[2] += thr
+    for k, (ins, smp, thr) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:16]:
+        print(f"  {k:30s} {ins * 100 / ti:5.1f}% ins  thr/warp {thr / max(ins, 1):5.1f}  samples {smp}")

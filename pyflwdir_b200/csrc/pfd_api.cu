@@ -1131,6 +1131,10 @@ extern "C" int pfd_set_option(pfd_handle* h, const char* name, int64_t value) {
         h->tile_sweeps = value ? 1 : 0;
         return PFD_OK;
     }
+    if (name && strcmp(name, "sweep_max_passes") == 0) {  // profiling only
+        h->ts_max_passes = (int)value;
+        return PFD_OK;
+    }
     if (name && strcmp(name, "release_scratch") == 0) {  // give the staging buffers back (very large rasters)
         PFD_CUDA(h, cudaStreamSynchronize(h->stream));
         for (auto& b : h->scratch) pfd_release(b);
@@ -1147,6 +1151,7 @@ extern "C" int64_t pfd_get_info(const pfd_handle* h, const char* name) {
     if (strcmp(name, "tile_rounds") == 0) return h->tile_rounds;
     if (strcmp(name, "tile_sweeps") == 0) return h->tile_sweeps;
     if (strcmp(name, "sweep_passes") == 0) return h->sweep_passes;
+    if (strcmp(name, "sweep_visits") == 0) return h->sweep_visits;
     if (strcmp(name, "nlevels") == 0) return h->nlevels;
     if (strcmp(name, "nnodes") == 0) return h->nnodes;
     if (strcmp(name, "n_pits") == 0) return h->n_pits;
@@ -1461,7 +1466,7 @@ extern "C" int pfd_fetch(pfd_handle* h, int which, void* out, int idx_dtype) {
 // ---------------------------------------------------------------------------------------------------------
 // tile-dataflow sweeps (pfd_tilesweep.cuh): no cell ordering needed
 // ---------------------------------------------------------------------------------------------------------
-static int ts_prepare(pfd_handle* h, TsArgs& A, const char* who) {
+static int ts_prepare(pfd_handle* h, TsArgs& A, const char* who, std::initializer_list<const void*> arrays) {
     if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, std::string(who) + ": no raster parsed on this handle");
     if (h->tiled) return pfd_fail(h, PFD_ERR_UNSUPPORTED, "this handle holds a row block: only the pfd_tiled_* entry points apply");
     const long long ntx = (h->ncol + TS_T - 1) / TS_T, nty = (h->nrow + TS_T - 1) / TS_T;
@@ -1469,13 +1474,17 @@ static int ts_prepare(pfd_handle* h, TsArgs& A, const char* who) {
     if (ntiles >= (1ll << 31)) return pfd_fail(h, PFD_ERR_UNSUPPORTED, std::string(who) + ": too many tiles");
     PFD_TRY(pfd_reserve(h, h->ts_done, (size_t)ntiles * TS_BMW * sizeof(uint32_t)));
     PFD_TRY(pfd_reserve(h, h->ts_lists, (size_t)ntiles * 3 * sizeof(uint32_t) + sizeof(TsCtl)));
-    uint32_t* base = (uint32_t*)h->ts_lists.p;
+    // control block first (it holds a 64-bit counter), then the stamps, then the two work lists
+    A.ctl = (TsCtl*)h->ts_lists.p;
+    uint32_t* base = (uint32_t*)((char*)h->ts_lists.p + sizeof(TsCtl));
     A.dir = (const uint8_t*)h->dir.p + h->dir_off;
     A.nrow = h->nrow, A.ncol = h->ncol, A.ntx = (int)ntx, A.nty = (int)nty;
+    A.max_passes = h->ts_max_passes;
+    A.al16 = (h->ncol % 16 == 0) && ((uintptr_t)A.dir % 16 == 0);
+    for (const void* q : arrays) A.al16 = A.al16 && ((uintptr_t)q % 16 == 0);
     A.done = (uint32_t*)h->ts_done.p;
-    A.list[0] = base, A.list[1] = base + ntiles, A.stamp = base + 2 * ntiles;
-    A.ctl = (TsCtl*)(base + 3 * ntiles);
-    PFD_CUDA(h, cudaMemsetAsync(A.stamp, 0, (size_t)ntiles * sizeof(uint32_t) + sizeof(TsCtl), h->stream));
+    A.stamp = base, A.list[0] = base + ntiles, A.list[1] = base + 2 * ntiles;
+    PFD_CUDA(h, cudaMemsetAsync(h->ts_lists.p, 0, sizeof(TsCtl) + (size_t)ntiles * sizeof(uint32_t), h->stream));
     return PFD_OK;
 }
 
@@ -1498,6 +1507,7 @@ static int ts_result(pfd_handle* h, const TsArgs& A, unsigned long long* resolve
     PFD_CUDA(h, cudaMemcpyAsync(&c, A.ctl, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
     PFD_CUDA(h, cudaStreamSynchronize(h->stream));
     h->sweep_passes = (int)c.passes;
+    h->sweep_visits = (int64_t)c.visits;
     *resolved = c.resolved;
     return PFD_OK;
 }
@@ -1507,11 +1517,11 @@ static int ts_result(pfd_handle* h, const TsArgs& A, unsigned long long* resolve
 template <class Op>
 static int run_tile_up(pfd_handle* h, Op op, const char* who) {
     TsArgs A;
-    PFD_TRY(ts_prepare(h, A, who));
+    PFD_TRY(ts_prepare(h, A, who, {op.out, op.init_src(), op.aux_src()}));
     PFD_TRY(ts_launch(h, (void*)tile_up_sweep_kernel<Op>, sizeof(TsSharedUp<typename Op::V>), A, (void*)&op));
     unsigned long long resolved = 0;
     PFD_TRY(ts_result(h, A, &resolved));
-    if ((int64_t)resolved != h->n_valid) {
+    if ((int64_t)resolved != h->n_valid && h->ts_max_passes == 0) {
         // loops: the trees hanging on them were resolved by the dataflow but are outside the reference's `seq`
         PFD_TRY(tiles_usable(h) ? tiles_ensure(h, true, false, false) : order_impl(h, true, false));
         ts_reset_unranked_kernel<Op><<<grid_for(h->n, 256, 4, 148 * 32), 256, 0, h->stream>>>(
@@ -1524,7 +1534,7 @@ static int run_tile_up(pfd_handle* h, Op op, const char* who) {
 template <class Op>
 static int run_tile_down(pfd_handle* h, Op op, const char* who) {
     TsArgs A;
-    PFD_TRY(ts_prepare(h, A, who));
+    PFD_TRY(ts_prepare(h, A, who, {op.out}));
     PFD_TRY(ts_launch(h, (void*)tile_down_sweep_kernel<Op>, sizeof(TsSharedDown<typename Op::V>), A, (void*)&op));
     unsigned long long resolved = 0;
     return ts_result(h, A, &resolved);
@@ -1567,6 +1577,8 @@ extern "C" int pfd_accuflux(pfd_handle* h, const void* data, int dtype, double n
     const void* data_dev = nullptr;
     if (pfd_is_device_ptr(data)) {
         data_dev = data;
+    } else if (direction == 0 && h->tile_sweeps) {  // the tile sweep reads `data` and writes `out` (never in place: cells
+        PFD_TRY(pfd_stage_in(h, data, bytes, 4, &data_dev));  // outside `seq` are reset from the data afterwards)
     } else {  // host data goes straight into the output buffer (accu = data.copy())
         PFD_CUDA(h, cudaMemcpyAsync(out_dev, data, bytes, cudaMemcpyHostToDevice, h->stream));
         data_dev = out_dev;

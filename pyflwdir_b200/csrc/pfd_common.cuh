@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <initializer_list>
 #include <string>
 #include <vector>
 
@@ -177,7 +178,9 @@ struct pfd_handle {
     DevBuf mg_counts;
     DevBuf ts_done, ts_lists;  // tile-dataflow sweeps: done bitmap; work lists + stamps + control block
     int tile_sweeps = 1;       // option "tile_sweeps"
+    int ts_max_passes = 0;     // option "sweep_max_passes" (profiling)
     int sweep_passes = 0;      // passes of the last tile-dataflow sweep
+    int64_t sweep_visits = 0;  // tile visits of the last tile-dataflow sweep
     DevBuf verify;            // VerifyCounts of the pfd_verify_* entry points
     DevBuf btab, bgraph;       // row-tiled multi-GPU solve: boundary tables, boundary graph state
     int64_t dir_off = 0;       // offset of the first OWNED row inside dir (halo row of a row block)

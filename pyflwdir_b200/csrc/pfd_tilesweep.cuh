@@ -13,37 +13,42 @@
 //
 // Here the raster is cut into 64x64 tiles and the dependency chains are followed INSIDE shared memory:
 //   * a tile visit stages the tile's 1-byte directions (+ one-cell halo), the values and done-flags of the halo
-//     cells, and the cell data; then
+//     cells, and the cell data (128-bit loads); the upstream / pending masks of all cells are derived with byte-SIMD
+//     compares, four cells per 32-bit word; then
 //       up:   every thread starts at its ready cells (no pending upstream neighbour) and walks downstream for as long
 //             as it is the LAST ARRIVER at the next cell (one shared-memory atomic clears its bit in the cell's
-//             pending mask) -- barrier-free dataflow, float sums bit-exact without float atomics;
+//             pending mask) -- barrier-free dataflow, float sums bit-exact without float atomics; a lane that ends a
+//             chain picks its next start cell at once, so the warp stays converged on the one-step loop body;
 //       down: resolved roots (pits, drain cells, exit cells whose downstream halo cell is resolved) spread upstream:
 //             a thread follows the first child itself and queues the others for the next round;
 //     cells whose chain crosses the tile edge stay pending; finished cells are written once, coalesced.
 //   * pass 1 visits every tile; a tile that resolves a cell on its edge ACTIVATES the neighbour tile that waits for
 //     it; pass p + 1 visits the activated tiles only. One persistent cooperative kernel runs all passes (grid.sync()
 //     between them, work lists in HBM); the number of passes is the largest number of tile crossings of a dependency
-//     chain (9-12 on the benchmark terrain, where 90 % of the cells resolve in pass 1 and a tile is visited 3.7 times
-//     on average).
+//     chain (9-25 on the benchmark terrain, where 90 % of the cells resolve in pass 1).
 // HBM traffic per cell: dir 1 B + data + value once in pass 1, a few bytes for the revisits.
 #pragma once
 #include "pfd_common.cuh"
 #include "pfd_sweeps.cuh"
 
 #define TS_T 64                 // tile edge
-#define TS_S 66                 // shared-memory row stride: tile + one-cell halo
-#define TS_N (TS_S * TS_S)      // 4356 staged cells
+#define TS_S 72                 // shared-memory row stride in cells: 3 pad | left halo | 64 cells | right halo | 3 pad
+#define TS_X0 4                 // column of the tile's first cell inside a staged row (word aligned)
+#define TS_ROWS (TS_T + 2)
+#define TS_N (TS_S * TS_ROWS)   // 4752 staged cells
 #define TS_THREADS 256
 #define TS_BMW 128              // done-bitmap words per tile (tile-major: word = ly * 2 + (lx >> 5), bit = lx & 31)
-#define TS_CPT (TS_T * TS_T / TS_THREADS)  // own cells per thread
+#define TS_CPT 16               // own cells per thread: 16 consecutive cells of one row (one 128-bit vector of bytes)
 
 #define TSF_DONE 1u   // value final
 #define TSF_NEW 2u    // ... and computed in this visit
 #define TSF_SRC 4u    // down-sweep: value does not depend on the downstream cell (drain cell)
+#define TSF_EXIT 8u   // the downstream cell lies outside the tile
 
 struct TsCtl {
     unsigned int count[4];           // work-list length of pass p at [p & 3]
     unsigned long long resolved;     // cells resolved so far
+    unsigned long long visits;       // tile visits so far
     unsigned int passes;             // passes executed
     unsigned int pad;
 };
@@ -52,37 +57,42 @@ struct TsArgs {
     const uint8_t* dir;
     long long nrow, ncol;
     int ntx, nty;
+    int max_passes;      // > 0: stop after that many passes (profiling only: the result is incomplete)
+    int al16;            // ncol % 16 == 0 and every raster-sized array is 16-byte aligned: 128-bit global accesses
     uint32_t* done;      // [ntiles][TS_BMW]
     uint32_t* list[2];   // work lists (tile ids)
     uint32_t* stamp;     // last pass a tile was queued for
     TsCtl* ctl;
 };
 
-__device__ __forceinline__ int ts_si(int ly, int lx) { return (ly + 1) * TS_S + lx + 1; }
-__device__ __forceinline__ int ts_noff(int k) { return pfd_slot_dr(k) * TS_S + pfd_slot_dc(k); }
+__device__ __forceinline__ int ts_si(int ly, int lx) { return (ly + 1) * TS_S + lx + TS_X0; }
+// shared-memory offset of the neighbour in slot k (NW N NE W E SW S SE): -73 -72 -71 -1 1 71 72 73 as packed int8
+__device__ __forceinline__ int ts_noff(int k) {
+    return (int)(int8_t)(0x494847'01FF'B9B8B7ull >> (8 * k));
+}
+static_assert(TS_S == 72, "ts_noff is tabulated for a row stride of 72");
 
-// own cell j of thread t: consecutive threads own consecutive columns (coalesced global rows)
-#define TS_OWN(j, ly, lx)                                  \
-    const int ts_i__ = (int)threadIdx.x + TS_THREADS * (j); \
-    const int ly = ts_i__ >> 6, lx = ts_i__ & (TS_T - 1)
+// own cells of thread t: row t >> 2, columns (t & 3) * 16 .. + 15
+#define TS_ROW ((int)(threadIdx.x >> 2))
+#define TS_COL0 ((int)((threadIdx.x & 3u) << 4))
 
 // halo cell k (0 .. 259): top row, bottom row (66 cells each), left column, right column (64 each) -> (hy, hx) in -1 .. 64
 __device__ __forceinline__ void ts_halo_cell(int k, int& hy, int& hx) {
-    if (k < TS_S) {
+    if (k < TS_T + 2) {
         hy = -1;
         hx = k - 1;
-    } else if (k < 2 * TS_S) {
+    } else if (k < 2 * (TS_T + 2)) {
         hy = TS_T;
-        hx = k - TS_S - 1;
-    } else if (k < 2 * TS_S + TS_T) {
-        hy = k - 2 * TS_S;
+        hx = k - (TS_T + 2) - 1;
+    } else if (k < 2 * (TS_T + 2) + TS_T) {
+        hy = k - 2 * (TS_T + 2);
         hx = -1;
     } else {
-        hy = k - 2 * TS_S - TS_T;
+        hy = k - 2 * (TS_T + 2) - TS_T;
         hx = TS_T;
     }
 }
-#define TS_NHALO (2 * TS_S + 2 * TS_T)
+#define TS_NHALO (2 * (TS_T + 2) + 2 * TS_T)
 
 __device__ __forceinline__ bool ts_in_raster(const TsArgs& A, long long r, long long c) {
     return r >= 0 && r < A.nrow && c >= 0 && c < A.ncol;
@@ -95,15 +105,37 @@ __device__ __forceinline__ uint32_t ts_done_bit(const TsArgs& A, long long r, lo
     return (__ldcg(A.done + t * TS_BMW + ly * 2 + (lx >> 5)) >> (lx & 31)) & 1u;
 }
 
+// 16 bits -> 16 bytes of 0 / 1 (four words)
+__device__ __forceinline__ uint32_t ts_spread4(uint32_t b) {  // low 4 bits -> 4 bytes
+    return ((b & 1u) | ((b & 2u) << 7) | ((b & 4u) << 14) | ((b & 8u) << 21));
+}
+
 // directions of the tile and its halo (cells outside the raster read as nodata) + done flags (pass > 1)
-__device__ __forceinline__ void ts_stage_graph(uint8_t* sdir, uint8_t* sflag, const TsArgs& A, long long r0, long long c0, int pass) {
-#pragma unroll 4
-    for (int j = 0; j < TS_CPT; ++j) {
-        TS_OWN(j, ly, lx);
-        const long long r = r0 + ly, c = c0 + lx;
-        const bool in = r < A.nrow && c < A.ncol;
-        sdir[ts_si(ly, lx)] = in ? __ldg(A.dir + r * A.ncol + c) : (uint8_t)PFD_DIR_NODATA;
-        sflag[ts_si(ly, lx)] = (pass > 1 && in) ? (uint8_t)ts_done_bit(A, r, c) : (uint8_t)0;
+__device__ __forceinline__ void ts_stage_graph(uint8_t* sdir, uint8_t* sflag, const TsArgs& A, int tile, long long r0, long long c0,
+                                               int pass) {
+    {
+        const int ly = TS_ROW, lx0 = TS_COL0;
+        const long long r = r0 + ly, c = c0 + lx0;
+        uint32_t* dw = reinterpret_cast<uint32_t*>(sdir + ts_si(ly, lx0));
+        uint32_t* fw = reinterpret_cast<uint32_t*>(sflag + ts_si(ly, lx0));
+        uint32_t w[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+        if (r < A.nrow && c < A.ncol) {
+            const uint8_t* p = A.dir + r * A.ncol + c;
+            if (A.al16 && c + 15 < A.ncol) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+                w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t b = (c + j < A.ncol) ? (uint32_t)__ldg(p + j) : (uint32_t)PFD_DIR_NODATA;
+                    w[j >> 2] = (w[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | (b << (8 * (j & 3)));
+                }
+            }
+        }
+        dw[0] = w[0], dw[1] = w[1], dw[2] = w[2], dw[3] = w[3];
+        uint32_t bits = 0;
+        if (pass > 1) bits = __ldcg(A.done + (long long)tile * TS_BMW + ly * 2 + (lx0 >> 5)) >> (lx0 & 31);
+        fw[0] = ts_spread4(bits), fw[1] = ts_spread4(bits >> 4), fw[2] = ts_spread4(bits >> 8), fw[3] = ts_spread4(bits >> 12);
     }
     for (int k = threadIdx.x; k < TS_NHALO; k += TS_THREADS) {
         int hy, hx;
@@ -115,13 +147,55 @@ __device__ __forceinline__ void ts_stage_graph(uint8_t* sdir, uint8_t* sflag, co
     }
 }
 
-// done bitmap of the tile from the flags; returns nothing. 128 words, one per thread t < 128.
+// 16 consecutive values global -> shared (src == nullptr: zero fill). smem index must be a multiple of 4 elements.
+template <typename V, bool CG>
+__device__ __forceinline__ void ts_load16(V* sdst, const V* gsrc, bool vec, int nvalid) {
+    if (!gsrc) {
+        uint32_t* d = reinterpret_cast<uint32_t*>(sdst);
+#pragma unroll
+        for (int i = 0; i < (int)(4 * sizeof(V)); ++i) d[i] = 0u;
+        return;
+    }
+    if (vec) {
+        const uint4* g = reinterpret_cast<const uint4*>(gsrc);
+        uint32_t* d = reinterpret_cast<uint32_t*>(sdst);
+#pragma unroll
+        for (int q = 0; q < (int)sizeof(V); ++q) {
+            const uint4 v = CG ? __ldcg(g + q) : __ldg(g + q);
+            d[4 * q] = v.x, d[4 * q + 1] = v.y, d[4 * q + 2] = v.z, d[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll 4
+        for (int j = 0; j < 16; ++j)
+            if (j < nvalid) sdst[j] = CG ? ld_cg(gsrc + j) : gsrc[j];
+    }
+}
+
+template <typename V>
+__device__ __forceinline__ void ts_store16(V* gdst, const V* ssrc, bool vec, int nvalid, uint32_t sel) {
+    if (vec && sel == 0xFFFFu) {
+        uint4* g = reinterpret_cast<uint4*>(gdst);
+        const uint32_t* d = reinterpret_cast<const uint32_t*>(ssrc);
+#pragma unroll
+        for (int q = 0; q < (int)sizeof(V); ++q) g[q] = make_uint4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
+    } else {
+#pragma unroll 4
+        for (int j = 0; j < 16; ++j)
+            if (j < nvalid && ((sel >> j) & 1u)) gdst[j] = ssrc[j];
+    }
+}
+
+// done bitmap of the tile from the flags: 128 words, one per thread t < 128
 __device__ __forceinline__ void ts_store_bitmap(const uint8_t* sflag, const TsArgs& A, int tile) {
     if (threadIdx.x < TS_BMW) {
         const int ly = threadIdx.x >> 1, x0 = (threadIdx.x & 1) * 32;
+        const uint32_t* fw = reinterpret_cast<const uint32_t*>(sflag + ts_si(ly, x0));
         uint32_t w = 0;
-#pragma unroll 8
-        for (int b = 0; b < 32; ++b) w |= (uint32_t)(sflag[ts_si(ly, x0 + b)] & TSF_DONE) << b;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t f = fw[q] & 0x01010101u;  // done bits of 4 cells -> 4 bits
+            w |= ((f | (f >> 7) | (f >> 14) | (f >> 21)) & 0xFu) << (4 * q);
+        }
         A.done[(long long)tile * TS_BMW + threadIdx.x] = w;
     }
 }
@@ -141,10 +215,77 @@ __device__ __forceinline__ void ts_activate(const TsArgs& A, int tile, uint32_t 
     }
 }
 
-// which neighbour tile holds halo position (hy, hx)
-__device__ __forceinline__ uint32_t ts_act_bit(int hy, int hx) {
+// which neighbour tile holds the staged position si (a halo position)
+__device__ __forceinline__ uint32_t ts_act_bit_of(int si) {
+    const int hy = si / TS_S - 1, hx = si % TS_S - TS_X0;
     const int tyo = hy < 0 ? 0 : (hy >= TS_T ? 2 : 1), txo = hx < 0 ? 0 : (hx >= TS_T ? 2 : 1);
     return 1u << (tyo * 3 + txo);
+}
+
+// Byte-SIMD neighbourhood scan of the 4 cells held by word `wi` of staged row `row` (row 1 .. 64, wi 1 .. 16):
+//   ups  (per byte) bit k: the neighbour in slot k drains into the cell
+//   pend (per byte) bit k: ... and is not resolved yet          (FLAGS = false: nothing is resolved, pend = ups)
+template <bool FLAGS>
+__device__ __forceinline__ void ts_scan_word(const uint8_t* sdir, const uint8_t* sflag, int row, int wi, uint32_t& ups_out,
+                                             uint32_t& pend_out) {
+    const uint32_t* d = reinterpret_cast<const uint32_t*>(sdir) + row * (TS_S / 4) + wi;
+    const uint32_t* f = reinterpret_cast<const uint32_t*>(sflag) + row * (TS_S / 4) + wi;
+    constexpr int RW = TS_S / 4;
+    uint32_t nd[8], nf[8];
+    nd[0] = __byte_perm(d[-RW - 1], d[-RW], 0x6543);
+    nd[1] = d[-RW];
+    nd[2] = __byte_perm(d[-RW], d[-RW + 1], 0x4321);
+    nd[3] = __byte_perm(d[-1], d[0], 0x6543);
+    nd[4] = __byte_perm(d[0], d[1], 0x4321);
+    nd[5] = __byte_perm(d[RW - 1], d[RW], 0x6543);
+    nd[6] = d[RW];
+    nd[7] = __byte_perm(d[RW], d[RW + 1], 0x4321);
+    if (FLAGS) {
+        nf[0] = __byte_perm(f[-RW - 1], f[-RW], 0x6543);
+        nf[1] = f[-RW];
+        nf[2] = __byte_perm(f[-RW], f[-RW + 1], 0x4321);
+        nf[3] = __byte_perm(f[-1], f[0], 0x6543);
+        nf[4] = __byte_perm(f[0], f[1], 0x4321);
+        nf[5] = __byte_perm(f[RW - 1], f[RW], 0x6543);
+        nf[6] = f[RW];
+        nf[7] = __byte_perm(f[RW], f[RW + 1], 0x4321);
+    }
+    uint32_t ups = 0, pend = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t eq = __vcmpeq4(nd[k], splat4(7u - k));
+        ups |= eq & splat4(1u << k);
+        if (FLAGS) pend |= eq & __vcmpeq4(nf[k] & 0x01010101u, 0u) & splat4(1u << k);
+    }
+    ups_out = ups;
+    pend_out = FLAGS ? pend : ups;
+}
+
+// per byte 0xFF where the cell takes part in this visit: not nodata, not resolved
+__device__ __forceinline__ uint32_t ts_live4(uint32_t dirw, uint32_t flagw) {
+    return ~__vcmpeq4(dirw, 0xFFFFFFFFu) & __vcmpeq4(flagw & 0x01010101u, 0u);
+}
+
+// upstream slots that lie in the halo, per byte, for the 4 cells of word q (0 .. 3) of the thread's 16 cells
+__device__ __forceinline__ uint32_t ts_halo_slots4(int ly, int lx0, int q) {
+    uint32_t m = (ly == 0 ? 0x07u : 0u) | (ly == TS_T - 1 ? 0xE0u : 0u);
+    uint32_t w = splat4(m);
+    if (lx0 == 0 && q == 0) w |= 0x29u;                        // NW, W, SW of the first column
+    if (lx0 == TS_T - 16 && q == 3) w |= 0x94u << 24;          // NE, E, SE of the last column
+    return w;
+}
+
+// Warp-aggregated append: every lane of the (converged) warp calls it; lanes with `want` get consecutive positions
+// base + (*counter before) .. One shared-memory atomic per warp.
+__device__ __forceinline__ void ts_push(uint16_t* q, uint32_t base, uint32_t* counter, bool want, int cell) {
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, want);
+    if (m) {
+        const int lane = threadIdx.x & 31;
+        uint32_t pos = 0;
+        if (lane == __ffs(m) - 1) pos = atomicAdd(counter, (uint32_t)__popc(m));
+        pos = __shfl_sync(0xFFFFFFFFu, pos, __ffs(m) - 1);
+        if (want) q[base + pos + __popc(m & ((1u << lane) - 1u))] = (uint16_t)cell;
+    }
 }
 
 template <typename V>
@@ -155,14 +296,50 @@ struct TsSharedUp {
     uint8_t dir[TS_N];
     uint8_t flag[TS_N];
     uint8_t aux[TS_N];         // Op-specific byte per cell (Strahler: mask)
+    uint16_t q[TS_T * TS_T];   // ready cells in the order they became ready: round r works on q[lo_r, lo_r + wcnt[r % 3])
+    uint32_t wcnt[3];
     uint32_t act;
     uint32_t newly;
 };
 
+// One cell of an up-sweep chain: fold the upstream values into `cur`, mark it resolved, and clear its bit in the pending
+// mask of the downstream cell. Returns the downstream cell when this lane was the LAST ARRIVER there (the chain goes
+// on), -1 when the chain ends here (pit, tile edge, or another lane arrives later).
+template <class Op>
+__device__ __forceinline__ int ts_up_step(TsSharedUp<typename Op::V>& s, const Op& op, int cur) {
+    uint32_t m = s.ups[cur];
+    const uint8_t own_aux = Op::AUX ? s.aux[cur] : (uint8_t)0;
+    typename Op::State st = op.begin(s.val[cur], own_aux);
+    while (m) {  // descending slot = descending linear index
+        const int k = 31 - __clz(m);
+        m ^= 1u << k;
+        const int u = cur + ts_noff(k);
+        op.step(st, s.val[u], Op::AUX ? s.aux[u] : (uint8_t)0);
+    }
+    s.val[cur] = op.end(st, own_aux);
+    const uint32_t f = s.flag[cur];
+    s.flag[cur] = (uint8_t)(f | TSF_DONE | TSF_NEW);
+    const uint32_t d = s.dir[cur];
+    int next = -1;
+    if (d < 8u) {  // (a pit ends the chain)
+        const int ds = cur + ts_noff((int)d);
+        if (f & TSF_EXIT) {  // leaves the tile: the neighbour tile may continue in the next pass
+            atomicOr(&s.act, ts_act_bit_of(ds));
+        } else {
+            __threadfence_block();  // my value is visible before my bit disappears
+            const unsigned sh = 8u * (ds & 3), bit = 1u << (7u - d);
+            const uint32_t old = atomicAnd(&s.pendw[ds >> 2], ~(bit << sh));
+            if (((old >> sh) & 0xFFu & ~bit) == 0u) next = ds;  // last arriver: the chain goes on (else somebody else continues)
+            __threadfence_block();
+        }
+    }
+    return next;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Up-sweep. Op:  typedef V; static const bool AUX;
-//   V init(g)                      value of a cell before anything was added (accuflux: data[g]; Strahler: 0)
-//   uint8 aux(g)                   (AUX) byte staged per cell incl. halo
+//   const V* init_src()            array holding the value of a cell before anything was added (accuflux: data), nullptr = 0
+//   const uint8_t* aux_src()       (AUX) byte staged per cell incl. halo
 //   State begin(own, own_aux); step(State&, v_up, aux_up) for the upstream neighbours in DESCENDING linear index; V end(State, own_aux)
 //   V* out
 // ---------------------------------------------------------------------------------------------------------
@@ -170,114 +347,120 @@ template <class Op>
 __device__ __forceinline__ void ts_up_visit(TsSharedUp<typename Op::V>& s, const TsArgs& A, const Op& op, int tile, int pass) {
     typedef typename Op::V V;
     const long long r0 = (long long)(tile / A.ntx) * TS_T, c0 = (long long)(tile % A.ntx) * TS_T;
+    const int ly = TS_ROW, lx0 = TS_COL0;
+    const int base = ts_si(ly, lx0);
+    const long long r = r0 + ly, c = c0 + lx0;
+    const bool row_in = r < A.nrow && c < A.ncol;
+    const int nvalid = row_in ? (int)min((long long)16, A.ncol - c) : 0;
+    const bool vec = A.al16 && nvalid == 16;
+    const long long g0 = r * A.ncol + c;
     if (threadIdx.x == 0) {
         s.act = 0;
         s.newly = 0;
+        s.wcnt[0] = s.wcnt[1] = s.wcnt[2] = 0;
     }
-    ts_stage_graph(s.dir, s.flag, A, r0, c0, pass);
+    ts_stage_graph(s.dir, s.flag, A, tile, r0, c0, pass);
     // values: pass 1 starts from the cell's own datum; later passes read what earlier visits stored (final for done
     // cells, the own datum for pending ones)
-#pragma unroll 4
-    for (int j = 0; j < TS_CPT; ++j) {
-        TS_OWN(j, ly, lx);
-        const long long r = r0 + ly, c = c0 + lx;
-        if (r < A.nrow && c < A.ncol) {
-            const long long g = r * A.ncol + c;
-            s.val[ts_si(ly, lx)] = (pass == 1) ? op.init(g) : ld_cg(op.out + g);
-            if (Op::AUX) s.aux[ts_si(ly, lx)] = op.aux(g);
-        }
+    if (row_in) {
+        if (pass == 1) ts_load16<V, false>(&s.val[base], op.init_src() ? op.init_src() + g0 : nullptr, vec, nvalid);
+        else ts_load16<V, true>(&s.val[base], op.out + g0, vec, nvalid);
+        if (Op::AUX) ts_load16<uint8_t, false>(&s.aux[base], op.aux_src() + g0, vec, nvalid);
     }
-    __syncthreads();  // flags of the halo are staged
+    __syncthreads();  // dir + flags (incl. halo) are staged
     if (pass > 1 || Op::AUX) {
         for (int k = threadIdx.x; k < TS_NHALO; k += TS_THREADS) {
             int hy, hx;
             ts_halo_cell(k, hy, hx);
-            const long long r = r0 + hy, c = c0 + hx;
-            if (ts_in_raster(A, r, c)) {
-                const long long g = r * A.ncol + c;
+            const long long hr = r0 + hy, hc = c0 + hx;
+            if (ts_in_raster(A, hr, hc)) {
+                const long long g = hr * A.ncol + hc;
                 if (s.flag[ts_si(hy, hx)] & TSF_DONE) s.val[ts_si(hy, hx)] = ld_cg(op.out + g);
-                if (Op::AUX) s.aux[ts_si(hy, hx)] = op.aux(g);
+                if (Op::AUX) s.aux[ts_si(hy, hx)] = __ldg(op.aux_src() + g);
             }
         }
     }
-    // upstream / pending masks of the own cells
+    // upstream / pending masks of the own cells (4 cells per word), start cells, exit flags
     uint32_t start = 0;
-#pragma unroll 4
-    for (int j = 0; j < TS_CPT; ++j) {
-        TS_OWN(j, ly, lx);
-        const int c = ts_si(ly, lx);
-        uint32_t ups = 0, pend = 0;
-        const bool live = s.dir[c] != PFD_DIR_NODATA && !(s.flag[c] & TSF_DONE);
-        if (live) {
+    {
+        const uint32_t* dw = reinterpret_cast<const uint32_t*>(s.dir + base);
+        uint32_t* fw = reinterpret_cast<uint32_t*>(s.flag + base);
+        uint32_t* uw = reinterpret_cast<uint32_t*>(s.ups + base);
+        uint32_t* pw = s.pendw + (base >> 2);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int n = c + ts_noff(k);
-                if (s.dir[n] == (uint8_t)(7 - k)) {
-                    ups |= 1u << k;
-                    if (!(s.flag[n] & TSF_DONE)) pend |= 1u << k;
+        for (int q = 0; q < 4; ++q) {
+            uint32_t ups, pend;
+            if (pass == 1) ts_scan_word<false>(s.dir, s.flag, ly + 1, (TS_X0 + lx0) / 4 + q, ups, pend);
+            else ts_scan_word<true>(s.dir, s.flag, ly + 1, (TS_X0 + lx0) / 4 + q, ups, pend);
+            const uint32_t live = ts_live4(dw[q], fw[q]);
+            ups &= live;
+            pend &= live;
+            uw[q] = ups;
+            pw[q] = pend;
+            const uint32_t st = live & __vcmpeq4(pend, 0u);  // 0xFF per ready cell
+            start |= (((st & 1u) | ((st >> 7) & 2u) | ((st >> 14) & 4u) | ((st >> 21) & 8u))) << (4 * q);
+        }
+        // cells whose downstream neighbour lies outside the tile (ring cells only)
+        if (ly == 0 || ly == TS_T - 1 || lx0 == 0 || lx0 == TS_T - 16) {
+#pragma unroll 1
+            for (int j = 0; j < 16; ++j) {
+                const int lx = lx0 + j;
+                if (!(ly == 0 || ly == TS_T - 1 || lx == 0 || lx == TS_T - 1)) continue;
+                const uint32_t d = s.dir[base + j];
+                if (d < 8u) {
+                    const int y = ly + pfd_slot_dr((int)d), x = lx + pfd_slot_dc((int)d);
+                    if (y < 0 || y >= TS_T || x < 0 || x >= TS_T) s.flag[base + j] |= (uint8_t)TSF_EXIT;
                 }
             }
-            if (pend == 0) start |= 1u << j;
-        }
-        s.ups[c] = (uint8_t)ups;
-        reinterpret_cast<uint8_t*>(s.pendw)[c] = (uint8_t)pend;
-    }
-    __syncthreads();
-    // dataflow walk
-    for (int j = 0; j < TS_CPT; ++j) {
-        if (!((start >> j) & 1u)) continue;
-        TS_OWN(j, ly, lx);
-        int c = ts_si(ly, lx);
-        for (;;) {
-            uint32_t m = s.ups[c];
-            const uint8_t own_aux = Op::AUX ? s.aux[c] : (uint8_t)0;
-            typename Op::State st = op.begin(s.val[c], own_aux);
-            while (m) {  // descending slot = descending linear index
-                const int k = 31 - __clz(m);
-                m ^= 1u << k;
-                const int u = c + ts_noff(k);
-                op.step(st, s.val[u], Op::AUX ? s.aux[u] : (uint8_t)0);
-            }
-            s.val[c] = op.end(st, own_aux);
-            s.flag[c] = (uint8_t)(TSF_DONE | TSF_NEW);
-            const uint32_t d = s.dir[c];
-            if (d >= 8u) break;  // pit
-            const int ds = c + ts_noff((int)d);
-            const int hy = ds / TS_S - 1, hx = ds % TS_S - 1;
-            if (hy < 0 || hy >= TS_T || hx < 0 || hx >= TS_T) {  // leaves the tile: the neighbour may continue next pass
-                atomicOr(&s.act, ts_act_bit(hy, hx));
-                break;
-            }
-            __threadfence_block();  // my value is visible before my bit disappears
-            const unsigned sh = 8u * (ds & 3), bit = 1u << (7u - d);
-            const uint32_t old = atomicAnd(&s.pendw[ds >> 2], ~(bit << sh));
-            if (((old >> sh) & 0xFFu & ~bit) != 0u) break;  // somebody else arrives later and continues
-            __threadfence_block();
-            c = ds;
         }
     }
     __syncthreads();
+    // In-tile dataflow, level by level: round 0 holds the ready cells (no pending upstream neighbour); a lane resolves
+    // ONE cell per round and, when it was the last arriver at the downstream cell, appends that cell to the next round
+    // (warp-aggregated). The frontier stays compacted, so the lanes of a warp all work, and the long chains (rivers) of
+    // the tile end up side by side in one warp instead of one per warp.
+#pragma unroll 1
+    for (int j = 0; j < TS_CPT; ++j) ts_push(s.q, 0u, &s.wcnt[0], (start >> j) & 1u, base + j);
+    uint32_t lo = 0;
+    for (int rd = 0;; ++rd) {
+        __syncthreads();
+        const uint32_t n = s.wcnt[rd % 3];
+        if (n == 0) break;
+        if (threadIdx.x == 0) s.wcnt[(rd + 2) % 3] = 0;
+        uint32_t* cn = &s.wcnt[(rd + 1) % 3];
+        for (uint32_t e0 = threadIdx.x & ~31u; e0 < n; e0 += TS_THREADS) {  // warp-uniform trip count
+            const uint32_t e = e0 + (threadIdx.x & 31u);
+            int next = -1;
+            if (e < n) next = ts_up_step<Op>(s, op, s.q[lo + e]);
+            ts_push(s.q, lo + n, cn, next >= 0, next);
+        }
+        lo += n;
+    }
     // store: pass 1 writes every cell of the tile (pending and nodata cells keep their own datum, like accu = data.copy()),
     // later passes only what this visit resolved
     uint32_t cnt = 0;
-#pragma unroll 4
-    for (int j = 0; j < TS_CPT; ++j) {
-        TS_OWN(j, ly, lx);
-        const long long r = r0 + ly, c = c0 + lx;
-        if (r < A.nrow && c < A.ncol) {
-            const uint32_t f = s.flag[ts_si(ly, lx)];
-            if (pass == 1 || (f & TSF_NEW)) op.out[r * A.ncol + c] = s.val[ts_si(ly, lx)];
-            cnt += (f & TSF_NEW) ? 1u : 0u;
+    if (row_in) {
+        const uint32_t* fw = reinterpret_cast<const uint32_t*>(s.flag + base);
+        uint32_t sel = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t f = fw[q] & 0x02020202u;
+            sel |= (((f >> 1) | (f >> 8) | (f >> 15) | (f >> 22)) & 0xFu) << (4 * q);
         }
+        cnt = __popc(sel);
+        if (pass == 1) sel = 0xFFFFu;
+        if (sel) ts_store16<V>(op.out + g0, &s.val[base], vec, nvalid, sel);
     }
     cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s.newly, cnt);
     __threadfence();  // a tile running in the same pass may read my done bits: the values are out before the bits
     __syncthreads();
     ts_store_bitmap(s.flag, A, tile);
-    __syncthreads();
     ts_activate(A, tile, s.act, pass);
-    if (threadIdx.x == 0 && s.newly) atomicAdd(&A.ctl->resolved, (unsigned long long)s.newly);
+    if (threadIdx.x == 32) {
+        if (s.newly) atomicAdd(&A.ctl->resolved, (unsigned long long)s.newly);
+        atomicAdd(&A.ctl->visits, 1ull);
+    }
     __syncthreads();  // shared memory is reused by the next visit
 }
 
@@ -291,7 +474,7 @@ __global__ void __launch_bounds__(TS_THREADS) tile_up_sweep_kernel(TsArgs A, Op 
     int pass = 1;
     for (;; ++pass) {
         const unsigned int count = (pass == 1) ? ntiles : __ldcg(&A.ctl->count[pass & 3]);
-        if (count == 0) break;
+        if (count == 0 || (A.max_passes > 0 && pass > A.max_passes)) break;
         if (blockIdx.x == 0 && threadIdx.x == 0) A.ctl->count[(pass + 2) & 3] = 0u;  // last read two passes ago
         const uint32_t* list = A.list[pass & 1];
         for (unsigned int w = blockIdx.x; w < count; w += gridDim.x)
@@ -306,13 +489,14 @@ __global__ void __launch_bounds__(TS_THREADS) tile_up_sweep_kernel(TsArgs A, Op 
 template <typename T>
 struct AccuUpTileOp {
     typedef T V;
+    typedef T State;
     static const bool AUX = false;
     const T* data;
     T* out;
     NoData nd;
-    __device__ __forceinline__ T init(long long g) const { return __ldg(data + g); }
-    __device__ __forceinline__ uint8_t aux(long long) const { return 0; }
-    typedef T State;
+    __host__ __device__ __forceinline__ const T* init_src() const { return data; }
+    __host__ __device__ __forceinline__ const uint8_t* aux_src() const { return nullptr; }
+    __device__ __forceinline__ T init(long long g) const { return data[g]; }
     __device__ __forceinline__ T begin(T own, uint8_t) const { return own; }
     __device__ __forceinline__ void step(T& acc, T up, uint8_t) const {
         if (not_nodata(acc, nd) && not_nodata(up, nd)) acc = acc_add(acc, up);
@@ -327,11 +511,12 @@ struct StrahlerTileOp {
     static const bool AUX = MASKED;
     const uint8_t* mask;
     uint8_t* out;
-    __device__ __forceinline__ uint8_t init(long long) const { return 0; }
-    __device__ __forceinline__ uint8_t aux(long long g) const { return __ldg(mask + g); }
     struct State {
         uint8_t so, smax;
     };
+    __host__ __device__ __forceinline__ const uint8_t* init_src() const { return nullptr; }
+    __host__ __device__ __forceinline__ const uint8_t* aux_src() const { return mask; }
+    __device__ __forceinline__ uint8_t init(long long) const { return 0; }
     __device__ __forceinline__ State begin(uint8_t, uint8_t) const { return State{0, 0}; }
     __device__ __forceinline__ void step(State& st, uint8_t sto, uint8_t up_aux) const {
         if (MASKED && !up_aux) return;
@@ -365,7 +550,9 @@ __global__ void ts_reset_unranked_kernel(const uint8_t* __restrict__ dir, const 
 template <typename V>
 struct TsSharedDown {
     V val[TS_N];
-    uint16_t q[2][TS_T * TS_T];
+    uint16_t q[TS_T * TS_T];  // resolved cells in the order they were resolved: round r expands q[lo_r, lo_r + qcnt[r % 3])
+    uint8_t kids[TS_N];   // per cell: unresolved upstream neighbours inside the tile
+    uint8_t outm[TS_N];   // per cell: unresolved upstream neighbours in the halo (their tiles wait for this cell)
     uint8_t dir[TS_N];
     uint8_t flag[TS_N];
     uint32_t qcnt[3];
@@ -377,24 +564,44 @@ template <class Op>
 __device__ __forceinline__ void ts_down_visit(TsSharedDown<typename Op::V>& s, const TsArgs& A, const Op& op, int tile, int pass) {
     typedef typename Op::V V;
     const long long r0 = (long long)(tile / A.ntx) * TS_T, c0 = (long long)(tile % A.ntx) * TS_T;
+    const int ly = TS_ROW, lx0 = TS_COL0;
+    const int base = ts_si(ly, lx0);
+    const long long r = r0 + ly, c = c0 + lx0;
+    const bool row_in = r < A.nrow && c < A.ncol;
+    const int nvalid = row_in ? (int)min((long long)16, A.ncol - c) : 0;
+    const bool vec = A.al16 && nvalid == 16;
+    const long long g0 = r * A.ncol + c;
     if (threadIdx.x == 0) {
         s.act = 0;
         s.newly = 0;
         s.qcnt[0] = s.qcnt[1] = s.qcnt[2] = 0;
     }
-    ts_stage_graph(s.dir, s.flag, A, r0, c0, pass);
+    ts_stage_graph(s.dir, s.flag, A, tile, r0, c0, pass);
     __syncthreads();
-    // per-cell terms; values of the resolved halo cells
+    // children masks (4 cells per word); per-cell terms; values of the resolved halo cells
+    {
+        uint32_t* kw = reinterpret_cast<uint32_t*>(s.kids + base);
+        uint32_t* ow = reinterpret_cast<uint32_t*>(s.outm + base);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t ups, pend;
+            if (pass == 1) ts_scan_word<false>(s.dir, s.flag, ly + 1, (TS_X0 + lx0) / 4 + q, ups, pend);
+            else ts_scan_word<true>(s.dir, s.flag, ly + 1, (TS_X0 + lx0) / 4 + q, ups, pend);
+            const uint32_t halo = ts_halo_slots4(ly, lx0, q);
+            kw[q] = pend & ~halo;
+            ow[q] = pend & halo;
+        }
+    }
+    uint32_t live16 = 0;
 #pragma unroll 4
-    for (int j = 0; j < TS_CPT; ++j) {
-        TS_OWN(j, ly, lx);
-        const long long r = r0 + ly, c = c0 + lx;
-        const int ci = ts_si(ly, lx);
+    for (int j = 0; j < 16; ++j) {
+        const int ci = base + j;
         const uint32_t d = s.dir[ci];
         if (d != PFD_DIR_NODATA && !(s.flag[ci] & TSF_DONE)) {
-            const long long g = r * A.ncol + c;
+            const long long g = g0 + j;
             s.val[ci] = op.prep(g, d, (d < 8u) ? g + pfd_slot_off((int)d, A.ncol) : g);
             if (op.source(g)) s.flag[ci] |= (uint8_t)TSF_SRC;
+            live16 |= 1u << j;
         }
     }
     if (pass > 1) {
@@ -406,12 +613,11 @@ __device__ __forceinline__ void ts_down_visit(TsSharedDown<typename Op::V>& s, c
     }
     __syncthreads();
     // roots: sources, pits, exit cells whose downstream (halo) cell is resolved
-#pragma unroll 4
-    for (int j = 0; j < TS_CPT; ++j) {
-        TS_OWN(j, ly, lx);
-        const int ci = ts_si(ly, lx);
+    while (live16) {
+        const int j = __ffs(live16) - 1;
+        live16 &= live16 - 1;
+        const int ci = base + j;
         const uint32_t d = s.dir[ci], f = s.flag[ci];
-        if (d == PFD_DIR_NODATA || (f & TSF_DONE)) continue;
         bool root = false;
         V v = s.val[ci];
         if (f & TSF_SRC) {
@@ -421,73 +627,94 @@ __device__ __forceinline__ void ts_down_visit(TsSharedDown<typename Op::V>& s, c
             v = op.pit(v);
             root = true;
         } else {
-            const int ds = ci + ts_noff((int)d);
-            const int hy = ds / TS_S - 1, hx = ds % TS_S - 1;
-            if ((hy < 0 || hy >= TS_T || hx < 0 || hx >= TS_T) && (s.flag[ds] & TSF_DONE)) {
-                v = op.down(s.val[ds], v);
-                root = true;
+            const int lx = lx0 + j;
+            const int y = ly + pfd_slot_dr((int)d), x = lx + pfd_slot_dc((int)d);
+            if (y < 0 || y >= TS_T || x < 0 || x >= TS_T) {
+                const int ds = ci + ts_noff((int)d);
+                if (s.flag[ds] & TSF_DONE) {
+                    v = op.down(s.val[ds], v);
+                    root = true;
+                }
             }
         }
         if (root) {
             s.val[ci] = v;
             s.flag[ci] = (uint8_t)(f | TSF_DONE | TSF_NEW);
-            s.q[0][atomicAdd(&s.qcnt[0], 1u)] = (uint16_t)ci;
+            s.q[atomicAdd(&s.qcnt[0], 1u)] = (uint16_t)ci;
         }
     }
-    // rounds: a thread follows the first child itself and queues the others
-    for (int r = 0;; ++r) {
+    // rounds, level by level: a lane takes ONE resolved cell per round, resolves its unresolved in-tile children and
+    // appends them to the next round (warp-aggregated, so the frontier stays compacted)
+    uint32_t lo = 0;
+    for (int rd = 0;; ++rd) {
         __syncthreads();
-        const uint32_t cnt = s.qcnt[r % 3];
+        const uint32_t cnt = s.qcnt[rd % 3];
         if (cnt == 0) break;
-        if (threadIdx.x == 0) s.qcnt[(r + 2) % 3] = 0;
-        const uint16_t* qin = s.q[r & 1];
-        uint16_t* qout = s.q[(r + 1) & 1];
-        for (uint32_t e = threadIdx.x; e < cnt; e += TS_THREADS) {
-            int c = qin[e];
-            for (;;) {
-                const V vc = s.val[c];
-                int first = -1;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int n = c + ts_noff(k);
-                    if (s.dir[n] != (uint8_t)(7 - k)) continue;
-                    const int hy = n / TS_S - 1, hx = n % TS_S - 1;
-                    if (hy < 0 || hy >= TS_T || hx < 0 || hx >= TS_T) {  // the neighbour tile waits for this cell
-                        if (!(s.flag[n] & TSF_DONE)) atomicOr(&s.act, ts_act_bit(hy, hx));
-                        continue;
-                    }
-                    if (s.flag[n] & TSF_DONE) continue;  // a source, already resolved
-                    s.val[n] = op.down(vc, s.val[n]);
-                    s.flag[n] = (uint8_t)(TSF_DONE | TSF_NEW);
-                    if (first < 0) first = n;
-                    else qout[atomicAdd(&s.qcnt[(r + 1) % 3], 1u)] = (uint16_t)n;
+        if (threadIdx.x == 0) s.qcnt[(rd + 2) % 3] = 0;
+        uint32_t* qn = &s.qcnt[(rd + 1) % 3];
+        for (uint32_t e0 = threadIdx.x & ~31u; e0 < cnt; e0 += TS_THREADS) {  // warp-uniform trip count
+            const uint32_t e = e0 + (threadIdx.x & 31u);
+            uint32_t m = 0;
+            int p = 0;
+            V vp = V();
+            if (e < cnt) {
+                p = s.q[lo + e];
+                m = s.kids[p];
+                vp = s.val[p];
+                uint32_t om = s.outm[p];
+                while (om) {  // a neighbour tile waits for this cell
+                    const int k = __ffs(om) - 1;
+                    om &= om - 1;
+                    atomicOr(&s.act, ts_act_bit_of(p + ts_noff(k)));
                 }
-                if (first < 0) break;
-                c = first;
+            }
+            while (__any_sync(0xFFFFFFFFu, m != 0u)) {
+                int n = -1;
+                if (m) {
+                    const int k = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int c = p + ts_noff(k);
+                    const uint32_t f = s.flag[c];
+                    if (!(f & TSF_DONE)) {  // (a source was resolved as a root)
+                        s.val[c] = op.down(vp, s.val[c]);
+                        s.flag[c] = (uint8_t)(f | TSF_DONE | TSF_NEW);
+                        n = c;
+                    }
+                }
+                ts_push(s.q, lo + cnt, qn, n >= 0, n);
             }
         }
+        lo += cnt;
     }
     // store
     uint32_t cnt = 0;
-#pragma unroll 4
-    for (int j = 0; j < TS_CPT; ++j) {
-        TS_OWN(j, ly, lx);
-        const long long r = r0 + ly, c = c0 + lx;
-        if (r < A.nrow && c < A.ncol) {
-            const uint32_t f = s.flag[ts_si(ly, lx)];
-            if (f & TSF_NEW) op.out[r * A.ncol + c] = s.val[ts_si(ly, lx)];
-            else if (pass == 1) op.out[r * A.ncol + c] = op.fill();
-            cnt += (f & TSF_NEW) ? 1u : 0u;
+    if (row_in) {
+        const uint32_t* fw = reinterpret_cast<const uint32_t*>(s.flag + base);
+        uint32_t sel = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t f = fw[q] & 0x02020202u;
+            sel |= (((f >> 1) | (f >> 8) | (f >> 15) | (f >> 22)) & 0xFu) << (4 * q);
         }
+        cnt = __popc(sel);
+        if (pass == 1) {  // every cell is written: what is not resolved (yet, or never) holds the fill value
+#pragma unroll 4
+            for (int j = 0; j < 16; ++j)
+                if (!((sel >> j) & 1u)) s.val[base + j] = op.fill();
+            sel = 0xFFFFu;
+        }
+        if (sel) ts_store16<V>(op.out + g0, &s.val[base], vec, nvalid, sel);
     }
     cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s.newly, cnt);
-    __threadfence();  // a tile running in the same pass may read my done bits: the values are out before the bits
+    __threadfence();
     __syncthreads();
     ts_store_bitmap(s.flag, A, tile);
-    __syncthreads();
     ts_activate(A, tile, s.act, pass);
-    if (threadIdx.x == 0 && s.newly) atomicAdd(&A.ctl->resolved, (unsigned long long)s.newly);
+    if (threadIdx.x == 32) {
+        if (s.newly) atomicAdd(&A.ctl->resolved, (unsigned long long)s.newly);
+        atomicAdd(&A.ctl->visits, 1ull);
+    }
     __syncthreads();
 }
 
@@ -500,7 +727,7 @@ __global__ void __launch_bounds__(TS_THREADS) tile_down_sweep_kernel(TsArgs A, O
     int pass = 1;
     for (;; ++pass) {
         const unsigned int count = (pass == 1) ? ntiles : __ldcg(&A.ctl->count[pass & 3]);
-        if (count == 0) break;
+        if (count == 0 || (A.max_passes > 0 && pass > A.max_passes)) break;
         if (blockIdx.x == 0 && threadIdx.x == 0) A.ctl->count[(pass + 2) & 3] = 0u;
         const uint32_t* list = A.list[pass & 1];
         for (unsigned int w = blockIdx.x; w < count; w += gridDim.x)
