@@ -343,7 +343,7 @@ def extras(w, size, seed, skip_level=False):
         "hand": lambda: w.ck(l.pfd_hand(h, drain_dev, z_dev, f32, out8_dev)),
     }
     # tile-dataflow sweeps (default): no ordering needed
-    w.ck(l.pfd_set_option(h, b"tile_sweeps", 1))
+    w.ck(l.pfd_set_option(h, b"tile_sweeps", 2))
     tile = {}
     for k, fn in calls.items():
         fn()

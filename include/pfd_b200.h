@@ -180,6 +180,9 @@ int pfd_fillnodata(pfd_handle* h, const void* data, int dtype, double nodata_f, 
 int pfd_main_upstream(pfd_handle* h, const void* uparea, int dtype, double upa_min, void* out, int idx_dtype);
 /* core.upstream_count (pyflwdir/core.py:50-61) with an optional mask of the cells that count (N bytes or NULL) */
 int pfd_upstream_count(pfd_handle* h, const uint8_t* mask, int8_t* out);
+/* core.upstream_matrix (pyflwdir/core.py:67-84): out[N][d] = upstream cells of every cell in ascending linear index, padded
+ * with mv (-1 / all ones); d = largest in-degree, returned in *d_out. out == NULL: size query only. */
+int pfd_upstream_matrix(pfd_handle* h, void* out, int idx_dtype, int64_t d_capacity, int64_t* d_out);
 /* streams.stream_order, "classic" / Hack (pyflwdir/streams.py:191-225); mask may be NULL */
 int pfd_stream_order_classic(pfd_handle* h, const void* idxs_us_main, int idx_dtype, const uint8_t* mask, uint8_t* out);
 

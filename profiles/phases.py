@@ -32,20 +32,22 @@ for r in rows:
 src = open("/root/repo/pyflwdir_b200/csrc/pfd_tilesweep.cuh").read().splitlines()
 
 
+TEXT = "\n".join(src)
+
+
 def find(pat):
-    for i, l in enumerate(src, 1):
-        if pat in l:
-            return i
+    k = TEXT.find(pat)
+    return TEXT.count("\n", 0, k) + 1 if k >= 0 else None
 
 
 names = [("stage_graph", "void ts_stage_graph"), ("load16", "void ts_load16"), ("store16", "void ts_store16"),
-         ("bitmap", "void ts_store_bitmap"), ("activate", "void ts_activate"), ("act_bit", "ts_act_bit_of(int si)"),
-         ("scan_word", "void ts_scan_word"), ("live/halo", "ts_live4(uint32_t"), ("structs", "struct TsSharedUp"),
-         ("up_step", "int ts_up_step"), ("up head+stage", "void ts_up_visit"), ("up masks", "// upstream / pending masks of the own cells"),
-         ("up walk", "// dataflow walk: one cell of one chain"), ("up store", "// store: pass 1 writes every cell of the tile (pending"),
+         ("activate", "void ts_activate"), ("act_bit", "uint32_t ts_act_bit"), ("scan_word", "void ts_scan_word"),
+         ("live/halo/popc", "ts_live4(uint32_t"), ("push", "void ts_push"), ("structs", "struct TsShared"), ("finish", "void ts_finish"),
+         ("up_step", "int ts_up_step"), ("up head+stage", "void ts_up_visit"), ("up records", "// per-cell records (4 cells per word of the planes)"),
+         ("up fill q", "// In-tile dataflow, level by level"), ("up rounds", "    uint32_t lo = 0;\n    for (int rd = 0;; ++rd) {\n        ts_sync<NT>();\n        const uint32_t n"),
          ("up kernel loop", "// All passes in one cooperative launch"), ("ops", "// streams.accuflux (up): accu"),
-         ("down structs", "// Down-sweep. Op:"), ("down head", "void ts_down_visit"), ("down roots", "// roots: sources, pits, exit cells"),
-         ("down rounds", "// rounds: a lane resolves one child"), ("down store", "    // store\n"), ("down kernel", "tile_down_sweep_kernel(TsArgs"),
+         ("down head", "void ts_down_visit"), ("down records+roots", "// records: unresolved children inside the tile"),
+         ("down rounds", "// rounds, level by level: a lane takes ONE resolved cell"), ("down kernel", "tile_down_sweep_kernel(TsArgs"),
          ("hand op", "struct HandTileOp")]
 marks = sorted([(n, find(p)) for n, p in names if find(p)], key=lambda m: m[1])
 for f, out in funcs.items():

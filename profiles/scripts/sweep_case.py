@@ -11,7 +11,7 @@ import bench  # noqa: E402
 
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-mode = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+mode = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 maxp = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 w = bench.Workload(size, 0, 0)
 l, L, h, n = w.l, w.L, w.h, w.cells

@@ -31,10 +31,11 @@ class DeviceGraph:
         import os
         if os.environ.get("PFD_TILES", "1") == "0":
             self.set_option("tiles", 0)
-        # PFD_TILE_SWEEPS=0 selects the level replays over the BFS order for accuflux / Strahler / HAND instead of the
-        # tile-dataflow sweeps (identical results; used by the parity tests)
-        if os.environ.get("PFD_TILE_SWEEPS", "1") == "0":
-            self.set_option("tile_sweeps", 0)
+        # accuflux / Strahler / HAND engine: default 1 = tile-dataflow sweeps unless the BFS ordering is already cached;
+        # PFD_TILE_SWEEPS=2 always tile-dataflow, =0 always level replays over the BFS order (identical results; used by
+        # the parity tests)
+        if os.environ.get("PFD_TILE_SWEEPS", "1") in ("0", "2"):
+            self.set_option("tile_sweeps", int(os.environ["PFD_TILE_SWEEPS"]))
         self.shape = None
         self.size = 0
         self.n_valid = self.n_pits = self.n_outlets = 0
@@ -532,6 +533,15 @@ class DeviceGraph:
         self._ck(self._l.pfd_main_upstream(self._h, _lib.ptr(up), _lib.dtype_code(up.dtype), float(upa_min),
                                            _lib.ptr(out), _lib.dtype_code(fetch)))
         return out.astype(idx_dtype, copy=False)
+
+    def upstream_matrix(self, idx_dtype=np.int32):
+        """core.upstream_matrix -> (N, d) upstream indices in ascending order, padded with mv."""
+        d = C.c_int64()
+        self._ck(self._l.pfd_upstream_matrix(self._h, None, _lib.dtype_code(idx_dtype), 0, C.byref(d)))
+        out = np.empty((self.size, d.value), dtype=idx_dtype)
+        if d.value:
+            self._ck(self._l.pfd_upstream_matrix(self._h, _lib.ptr(out), _lib.dtype_code(idx_dtype), d.value, C.byref(d)))
+        return out
 
     def upstream_count(self, mask=None):
         m = None

@@ -58,6 +58,7 @@ SYMBOLS = {
     "pfd_fillnodata": (_int, [_vp, _vp, _int, C.c_double, _i64, _int, _int, _int, _vp]),
     "pfd_main_upstream": (_int, [_vp, _vp, _int, C.c_double, _vp, _int]),
     "pfd_upstream_count": (_int, [_vp, _vp, _vp]),
+    "pfd_upstream_matrix": (_int, [_vp, _vp, _int, _i64, _pi64]),
     "pfd_stream_order_classic": (_int, [_vp, _vp, _int, _vp, _vp]),
     "pfd_stream_distance": (_int, [_vp, _vp, _int, _vp, _vp]),
     "pfd_floodplains": (_int, [_vp, _vp, _vp, _int, _vp]),

@@ -22,6 +22,16 @@ def upstream_count(idxs_ds, mv=_mv, mask=None, shape=None, ncol=None):
     return _functional.graph(idxs_ds, shape, ncol).upstream_count(mask)
 
 
+def upstream_matrix(idxs_ds, mv=_mv, shape=None, ncol=None):
+    """Returns a 2D array with upstream cell indices for each cell, shape (idxs_ds.size, max number of upstream cells per
+    cell), rows in ascending upstream index, padded with mv (core.py:67-84)."""
+    idxs_ds = np.asarray(idxs_ds)
+    g = _functional.graph(idxs_ds, shape=shape, ncol=ncol)
+    dt = idxs_ds.dtype
+    out = g.upstream_matrix(np.int64 if dt.itemsize == 8 else np.uint32 if dt == np.uint32 else np.int32)
+    return out.astype(dt, copy=False) if out.dtype != dt else out
+
+
 def main_upstream(idxs_ds, uparea, upa_min=0.0, mv=_mv, shape=None, ncol=None):
     """Returns the index of the upstream cell with the largest uparea, mv (-1) at headwaters (core.py:191-219)."""
     dt = np.asarray(idxs_ds).dtype

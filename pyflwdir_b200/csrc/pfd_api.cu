@@ -1127,8 +1127,11 @@ extern "C" int pfd_set_option(pfd_handle* h, const char* name, int64_t value) {
         h->fuse_parse = value ? 1 : 0;
         return PFD_OK;
     }
-    if (name && strcmp(name, "tile_sweeps") == 0) {  // 1 = tile-dataflow sweeps (default), 0 = level replays over the BFS order
-        h->tile_sweeps = value ? 1 : 0;
+    if (name && strcmp(name, "tile_sweeps") == 0) {
+        // 1 (default): tile-dataflow sweeps unless the BFS ordering of this raster is already cached (then its level
+        // replay is the cheaper one: 32 vs 46 ms for Strahler at 32768^2; the ordering itself costs 40 ms);
+        // 2: always tile-dataflow; 0: always level replays over the BFS order
+        h->tile_sweeps = (int)value;
         return PFD_OK;
     }
     if (name && strcmp(name, "sweep_max_passes") == 0) {  // profiling only
@@ -1466,6 +1469,11 @@ extern "C" int pfd_fetch(pfd_handle* h, int which, void* out, int idx_dtype) {
 // ---------------------------------------------------------------------------------------------------------
 // tile-dataflow sweeps (pfd_tilesweep.cuh): no cell ordering needed
 // ---------------------------------------------------------------------------------------------------------
+#ifndef TS_NT_OVERRIDE
+#define TS_NT_OVERRIDE 0  // -DTS_NT_OVERRIDE=32|64|128|256: threads per tile visit for every tile sweep (tuning)
+#endif
+static bool use_tile_sweeps(const pfd_handle* h) { return h->tile_sweeps == 2 || (h->tile_sweeps == 1 && !h->ordered); }
+
 static int ts_prepare(pfd_handle* h, TsArgs& A, const char* who, std::initializer_list<const void*> arrays) {
     if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, std::string(who) + ": no raster parsed on this handle");
     if (h->tiled) return pfd_fail(h, PFD_ERR_UNSUPPORTED, "this handle holds a row block: only the pfd_tiled_* entry points apply");
@@ -1488,16 +1496,16 @@ static int ts_prepare(pfd_handle* h, TsArgs& A, const char* who, std::initialize
     return PFD_OK;
 }
 
-static int ts_launch(pfd_handle* h, void* kern, size_t smem, const TsArgs& A, void* op_ptr) {
+static int ts_launch(pfd_handle* h, void* kern, int nt, size_t smem, const TsArgs& A, void* op_ptr) {
     PFD_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    PFD_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TS_THREADS, smem));
+    PFD_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, smem));
     if (per_sm < 1) return pfd_fail(h, PFD_ERR_CUDA, "tile sweep kernel cannot be made resident");
     const long long ntiles = (long long)A.ntx * A.nty;
     const long long grid = std::max<long long>(1, std::min<long long>((long long)per_sm * h->num_sms, ntiles));
     void* args[] = {(void*)&A, op_ptr};
     StageTimer t(h, PFD_STAGE_SWEEP);
-    PFD_CUDA(h, cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(TS_THREADS), args, smem, h->stream));
+    PFD_CUDA(h, cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3((unsigned)nt), args, smem, h->stream));
     h->launches++;
     return PFD_OK;
 }
@@ -1518,7 +1526,10 @@ template <class Op>
 static int run_tile_up(pfd_handle* h, Op op, const char* who) {
     TsArgs A;
     PFD_TRY(ts_prepare(h, A, who, {op.out, op.init_src(), op.aux_src()}));
-    PFD_TRY(ts_launch(h, (void*)tile_up_sweep_kernel<Op>, sizeof(TsSharedUp<typename Op::V>), A, (void*)&op));
+    // threads per tile visit (measured on B200 at 8192^2, profiles/r2_sweeps.md: 32 / 64 / 128 / 256 threads = 5.2 / 3.7 / 3.2 /
+    // 4.0 ms for uint8 values, 7.5 / 5.1 / 4.3 / 4.2 ms for float32): warps in flight per SM matter more than tiles in flight
+    constexpr int NT = TS_NT_OVERRIDE ? TS_NT_OVERRIDE : (sizeof(typename Op::V) == 1 ? 128 : 256);
+    PFD_TRY(ts_launch(h, (void*)tile_up_sweep_kernel<NT, Op>, NT, sizeof(TsShared<typename Op::V, Op::AUX>), A, (void*)&op));
     unsigned long long resolved = 0;
     PFD_TRY(ts_result(h, A, &resolved));
     if ((int64_t)resolved != h->n_valid && h->ts_max_passes == 0) {
@@ -1535,7 +1546,8 @@ template <class Op>
 static int run_tile_down(pfd_handle* h, Op op, const char* who) {
     TsArgs A;
     PFD_TRY(ts_prepare(h, A, who, {op.out}));
-    PFD_TRY(ts_launch(h, (void*)tile_down_sweep_kernel<Op>, sizeof(TsSharedDown<typename Op::V>), A, (void*)&op));
+    constexpr int NT = TS_NT_OVERRIDE ? TS_NT_OVERRIDE : 256;  // (HAND at 8192^2: 16.4 / 7.9 / 8.0 / 7.2 ms for 32 / 64 / 128 / 256)
+    PFD_TRY(ts_launch(h, (void*)tile_down_sweep_kernel<NT, Op>, NT, sizeof(TsShared<typename Op::V, false>), A, (void*)&op));
     unsigned long long resolved = 0;
     return ts_result(h, A, &resolved);
 }
@@ -1546,7 +1558,7 @@ static int run_tile_down(pfd_handle* h, Op op, const char* who) {
 template <typename T>
 static int accuflux_typed(pfd_handle* h, const void* data_dev, void* out_dev, const NoData& nd, int direction) {
     const int64_t n = h->n;
-    if (direction == 0 && h->tile_sweeps) {
+    if (direction == 0 && use_tile_sweeps(h)) {
         AccuUpTileOp<T> op{(const T*)data_dev, (T*)out_dev, nd};
         return run_tile_up(h, op, "pfd_accuflux");
     }
@@ -1569,7 +1581,7 @@ extern "C" int pfd_accuflux(pfd_handle* h, const void* data, int dtype, double n
     if (direction != 0 && direction != 1) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_accuflux: direction must be 0 (up) or 1 (down)");
     const size_t esz = pfd_dtype_size(dtype);
     if (!esz) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_accuflux: unknown dtype");
-    if (!(direction == 0 && h->tile_sweeps)) PFD_TRY(order_impl(h, false, false));
+    if (!(direction == 0 && use_tile_sweeps(h))) PFD_TRY(order_impl(h, false, false));
     else if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, "pfd_accuflux: no raster parsed on this handle");
     const size_t bytes = (size_t)h->n * esz;
     void* out_dev = nullptr;
@@ -1577,7 +1589,7 @@ extern "C" int pfd_accuflux(pfd_handle* h, const void* data, int dtype, double n
     const void* data_dev = nullptr;
     if (pfd_is_device_ptr(data)) {
         data_dev = data;
-    } else if (direction == 0 && h->tile_sweeps) {  // the tile sweep reads `data` and writes `out` (never in place: cells
+    } else if (direction == 0 && use_tile_sweeps(h)) {  // the tile sweep reads `data` and writes `out` (never in place: cells
         PFD_TRY(pfd_stage_in(h, data, bytes, 4, &data_dev));  // outside `seq` are reset from the data afterwards)
     } else {  // host data goes straight into the output buffer (accu = data.copy())
         PFD_CUDA(h, cudaMemcpyAsync(out_dev, data, bytes, cudaMemcpyHostToDevice, h->stream));
@@ -1699,13 +1711,14 @@ extern "C" int pfd_strahler(pfd_handle* h, const uint8_t* mask, uint8_t* out) {
     stage_reset(h);
     if (!out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_strahler: out is null");
     if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, "pfd_strahler: no raster parsed on this handle");
-    if (!h->tile_sweeps) PFD_TRY(order_impl(h, false, false));
+    const bool tile = use_tile_sweeps(h);
+    if (!tile) PFD_TRY(order_impl(h, false, false));
     const size_t bytes = (size_t)h->n;
     void* out_dev = nullptr;
     PFD_TRY(pfd_stage_out(h, out, bytes, 3, &out_dev));
     const void* mask_dev = nullptr;
     if (mask) PFD_TRY(pfd_stage_in(h, mask, bytes, 4, &mask_dev));
-    if (h->tile_sweeps) {
+    if (tile) {
         if (mask) {
             StrahlerTileOp<true> op{(const uint8_t*)mask_dev, (uint8_t*)out_dev};
             PFD_TRY(run_tile_up(h, op, "pfd_strahler"));
@@ -1731,7 +1744,8 @@ extern "C" int pfd_hand(pfd_handle* h, const uint8_t* drain, const void* elevtn,
     if (!drain || !elevtn || !out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_hand: null array");
     if (elev_dtype != PFD_F32 && elev_dtype != PFD_F64) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_hand: elevtn must be float32 or float64");
     if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, "pfd_hand: no raster parsed on this handle");
-    if (!h->tile_sweeps) PFD_TRY(order_impl(h, false, false));
+    const bool tile = use_tile_sweeps(h);
+    if (!tile) PFD_TRY(order_impl(h, false, false));
     const int64_t n = h->n;
     const size_t bytes = (size_t)n * sizeof(double);
     void* out_dev = nullptr;
@@ -1739,7 +1753,7 @@ extern "C" int pfd_hand(pfd_handle* h, const uint8_t* drain, const void* elevtn,
     const void *drain_dev = nullptr, *elev_dev = nullptr;
     PFD_TRY(pfd_stage_in(h, drain, (size_t)n, 4, &drain_dev));
     PFD_TRY(pfd_stage_in(h, elevtn, (size_t)n * pfd_dtype_size(elev_dtype), 5, &elev_dev));
-    if (h->tile_sweeps) {
+    if (tile) {
         if (elev_dtype == PFD_F32) {
             HandTileOp<float> op{(const uint8_t*)drain_dev, (const float*)elev_dev, (double*)out_dev};
             PFD_TRY(run_tile_down(h, op, "pfd_hand"));
@@ -1863,6 +1877,63 @@ extern "C" int pfd_main_upstream(pfd_handle* h, const void* uparea, int dtype, d
     }
     PFD_TRY(rc);
     PFD_TRY(pfd_finish_out(h, out, out_dev, (size_t)h->n * isz));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    return PFD_OK;
+}
+
+// core.upstream_matrix (core.py:67-84): row i = the upstream cells of i in ascending linear index, padded with mv
+__global__ void max_indegree_kernel(const uint8_t* __restrict__ upmask, int64_t n, unsigned int* __restrict__ out) {
+    unsigned int m = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = max(m, (unsigned int)__popc((unsigned int)upmask[i]));
+    m = __reduce_max_sync(0xFFFFFFFFu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+template <typename IDX>
+__global__ void upstream_matrix_kernel(const uint8_t* __restrict__ upmask, int64_t n, int64_t ncol, int d, IDX* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t m = upmask[i];
+        for (int j = 0; j < d; ++j) {
+            IDX v = (IDX)-1;
+            if (m) {
+                const int k = __ffs(m) - 1;
+                m &= m - 1;
+                v = (IDX)(i + pfd_slot_off(k, ncol));
+            }
+            out[i * d + j] = v;
+        }
+    }
+}
+
+extern "C" int pfd_upstream_matrix(pfd_handle* h, void* out, int idx_dtype, int64_t d_capacity, int64_t* d_out) {
+    PFD_TRY(check_handle(h));
+    if (!h->parsed || h->tiled) return pfd_fail(h, PFD_ERR_STATE, "pfd_upstream_matrix: no (whole) raster parsed on this handle");
+    if (!d_out) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_upstream_matrix: d_out is null");
+    PFD_TRY(ensure_upmask(h));
+    PFD_TRY(pfd_reserve(h, h->counters, 8 * sizeof(unsigned long long)));
+    unsigned int* ctr = reinterpret_cast<unsigned int*>((unsigned long long*)h->counters.p + 6);
+    PFD_CUDA(h, cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), h->stream));
+    max_indegree_kernel<<<grid_for(h->n, 256, 8, 148 * 8), 256, 0, h->stream>>>((const uint8_t*)h->upmask.p, h->n, ctr);
+    PFD_LAUNCH_CHECK(h);
+    unsigned int d = 0;
+    PFD_CUDA(h, cudaMemcpyAsync(&d, ctr, sizeof(d), cudaMemcpyDeviceToHost, h->stream));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    *d_out = (int64_t)d;
+    if (!out) return PFD_OK;  // size query
+    if (d_capacity < (int64_t)d) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_upstream_matrix: out holds fewer columns than the largest in-degree");
+    const size_t isz = pfd_dtype_size(idx_dtype);
+    if ((isz != 4 && isz != 8) || idx_dtype == PFD_F32 || idx_dtype == PFD_F64)
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_upstream_matrix: index dtype must be a 32/64-bit integer");
+    if (d == 0) return PFD_OK;
+    const size_t bytes = (size_t)h->n * d * isz;
+    void* dev = nullptr;
+    PFD_TRY(pfd_stage_out(h, out, bytes, 3, &dev));
+    const int g = grid_for(h->n, 256, 2);
+    if (isz == 4) upstream_matrix_kernel<uint32_t><<<g, 256, 0, h->stream>>>((const uint8_t*)h->upmask.p, h->n, h->ncol, (int)d, (uint32_t*)dev);
+    else upstream_matrix_kernel<int64_t><<<g, 256, 0, h->stream>>>((const uint8_t*)h->upmask.p, h->n, h->ncol, (int)d, (int64_t*)dev);
+    PFD_LAUNCH_CHECK(h);
+    PFD_TRY(pfd_finish_out(h, out, dev, bytes));
     PFD_CUDA(h, cudaStreamSynchronize(h->stream));
     return PFD_OK;
 }

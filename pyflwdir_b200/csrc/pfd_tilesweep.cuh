@@ -36,14 +36,12 @@
 #define TS_X0 4                 // column of the tile's first cell inside a staged row (word aligned)
 #define TS_ROWS (TS_T + 2)
 #define TS_N (TS_S * TS_ROWS)   // 4752 staged cells
-#define TS_THREADS 256
 #define TS_BMW 128              // done-bitmap words per tile (tile-major: word = ly * 2 + (lx >> 5), bit = lx & 31)
-#define TS_CPT 16               // own cells per thread: 16 consecutive cells of one row (one 128-bit vector of bytes)
+#define TS_NCHUNK (TS_T * TS_T / 16)  // a chunk = 16 consecutive cells of one row (one 128-bit vector of bytes); thread t works on
+                                     // chunks t, t + NT, ...: row ch >> 2, columns (ch & 3) * 16 .. + 15
 
-#define TSF_DONE 1u   // value final
-#define TSF_NEW 2u    // ... and computed in this visit
-#define TSF_SRC 4u    // down-sweep: value does not depend on the downstream cell (drain cell)
-#define TSF_EXIT 8u   // the downstream cell lies outside the tile
+#define TSF_DONE 1u   // staged flag plane: value final (resolved by an earlier visit)
+#define TSF_SRC 4u    // staged flag plane, down-sweep: value does not depend on the downstream cell (drain cell)
 
 struct TsCtl {
     unsigned int count[4];           // work-list length of pass p at [p & 3]
@@ -72,9 +70,12 @@ __device__ __forceinline__ int ts_noff(int k) {
 }
 static_assert(TS_S == 72, "ts_noff is tabulated for a row stride of 72");
 
-// own cells of thread t: row t >> 2, columns (t & 3) * 16 .. + 15
-#define TS_ROW ((int)(threadIdx.x >> 2))
-#define TS_COL0 ((int)((threadIdx.x & 3u) << 4))
+// CTA-wide barrier: a one-warp CTA only needs the warp to reconverge (shared memory is ordered by __syncwarp)
+template <int NT>
+__device__ __forceinline__ void ts_sync() {
+    if (NT == 32) __syncwarp();
+    else __syncthreads();
+}
 
 // halo cell k (0 .. 259): top row, bottom row (66 cells each), left column, right column (64 each) -> (hy, hx) in -1 .. 64
 __device__ __forceinline__ void ts_halo_cell(int k, int& hy, int& hx) {
@@ -110,11 +111,13 @@ __device__ __forceinline__ uint32_t ts_spread4(uint32_t b) {  // low 4 bits -> 4
     return ((b & 1u) | ((b & 2u) << 7) | ((b & 4u) << 14) | ((b & 8u) << 21));
 }
 
-// directions of the tile and its halo (cells outside the raster read as nodata) + done flags (pass > 1)
-__device__ __forceinline__ void ts_stage_graph(uint8_t* sdir, uint8_t* sflag, const TsArgs& A, int tile, long long r0, long long c0,
-                                               int pass) {
-    {
-        const int ly = TS_ROW, lx0 = TS_COL0;
+// directions of the tile and its halo (cells outside the raster read as nodata) + done flags of earlier visits (pass > 1)
+// into the staged byte planes; the tile's own done bits also go to oldbm
+template <int NT>
+__device__ __forceinline__ void ts_stage_graph(uint8_t* sdir, uint8_t* sflag, uint32_t* oldbm, const TsArgs& A, int tile,
+                                               long long r0, long long c0, int pass) {
+    for (int ch = threadIdx.x; ch < TS_NCHUNK; ch += NT) {
+        const int ly = ch >> 2, lx0 = (ch & 3) << 4;
         const long long r = r0 + ly, c = c0 + lx0;
         uint32_t* dw = reinterpret_cast<uint32_t*>(sdir + ts_si(ly, lx0));
         uint32_t* fw = reinterpret_cast<uint32_t*>(sflag + ts_si(ly, lx0));
@@ -134,10 +137,11 @@ __device__ __forceinline__ void ts_stage_graph(uint8_t* sdir, uint8_t* sflag, co
         }
         dw[0] = w[0], dw[1] = w[1], dw[2] = w[2], dw[3] = w[3];
         uint32_t bits = 0;
-        if (pass > 1) bits = __ldcg(A.done + (long long)tile * TS_BMW + ly * 2 + (lx0 >> 5)) >> (lx0 & 31);
+        if (pass > 1) bits = __ldcg(A.done + (long long)tile * TS_BMW + (ch >> 1)) >> (lx0 & 31);
         fw[0] = ts_spread4(bits), fw[1] = ts_spread4(bits >> 4), fw[2] = ts_spread4(bits >> 8), fw[3] = ts_spread4(bits >> 12);
     }
-    for (int k = threadIdx.x; k < TS_NHALO; k += TS_THREADS) {
+    for (int k = threadIdx.x; k < TS_BMW; k += NT) oldbm[k] = (pass > 1) ? __ldcg(A.done + (long long)tile * TS_BMW + k) : 0u;
+    for (int k = threadIdx.x; k < TS_NHALO; k += NT) {
         int hy, hx;
         ts_halo_cell(k, hy, hx);
         const long long r = r0 + hy, c = c0 + hx;
@@ -185,21 +189,6 @@ __device__ __forceinline__ void ts_store16(V* gdst, const V* ssrc, bool vec, int
     }
 }
 
-// done bitmap of the tile from the flags: 128 words, one per thread t < 128
-__device__ __forceinline__ void ts_store_bitmap(const uint8_t* sflag, const TsArgs& A, int tile) {
-    if (threadIdx.x < TS_BMW) {
-        const int ly = threadIdx.x >> 1, x0 = (threadIdx.x & 1) * 32;
-        const uint32_t* fw = reinterpret_cast<const uint32_t*>(sflag + ts_si(ly, x0));
-        uint32_t w = 0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const uint32_t f = fw[q] & 0x01010101u;  // done bits of 4 cells -> 4 bits
-            w |= ((f | (f >> 7) | (f >> 14) | (f >> 21)) & 0xFu) << (4 * q);
-        }
-        A.done[(long long)tile * TS_BMW + threadIdx.x] = w;
-    }
-}
-
 // the neighbour tiles recorded in `act` (bit (tyo + 1) * 3 + (txo + 1)) are queued for pass + 1
 __device__ __forceinline__ void ts_activate(const TsArgs& A, int tile, uint32_t act, int pass) {
     if (threadIdx.x < 9 && ((act >> threadIdx.x) & 1u)) {
@@ -215,22 +204,22 @@ __device__ __forceinline__ void ts_activate(const TsArgs& A, int tile, uint32_t 
     }
 }
 
-// which neighbour tile holds the staged position si (a halo position)
-__device__ __forceinline__ uint32_t ts_act_bit_of(int si) {
-    const int hy = si / TS_S - 1, hx = si % TS_S - TS_X0;
-    const int tyo = hy < 0 ? 0 : (hy >= TS_T ? 2 : 1), txo = hx < 0 ? 0 : (hx >= TS_T ? 2 : 1);
+// which neighbour tile holds the cell (y, x) in tile coordinates (a cell outside 0 .. 63)
+__device__ __forceinline__ uint32_t ts_act_bit(int y, int x) {
+    const int tyo = y < 0 ? 0 : (y >= TS_T ? 2 : 1), txo = x < 0 ? 0 : (x >= TS_T ? 2 : 1);
     return 1u << (tyo * 3 + txo);
 }
 
 // Byte-SIMD neighbourhood scan of the 4 cells held by word `wi` of staged row `row` (row 1 .. 64, wi 1 .. 16):
 //   ups  (per byte) bit k: the neighbour in slot k drains into the cell
-//   pend (per byte) bit k: ... and is not resolved yet          (FLAGS = false: nothing is resolved, pend = ups)
-template <bool FLAGS>
+//   pend (per byte) bit k: ... and is not resolved yet (and, NOSRC, is not a source cell)
+template <bool FLAGS, bool NOSRC>
 __device__ __forceinline__ void ts_scan_word(const uint8_t* sdir, const uint8_t* sflag, int row, int wi, uint32_t& ups_out,
                                              uint32_t& pend_out) {
     const uint32_t* d = reinterpret_cast<const uint32_t*>(sdir) + row * (TS_S / 4) + wi;
     const uint32_t* f = reinterpret_cast<const uint32_t*>(sflag) + row * (TS_S / 4) + wi;
     constexpr int RW = TS_S / 4;
+    constexpr uint32_t FM = (FLAGS ? 0x01010101u : 0u) | (NOSRC ? 0x04040404u : 0u);
     uint32_t nd[8], nf[8];
     nd[0] = __byte_perm(d[-RW - 1], d[-RW], 0x6543);
     nd[1] = d[-RW];
@@ -240,7 +229,7 @@ __device__ __forceinline__ void ts_scan_word(const uint8_t* sdir, const uint8_t*
     nd[5] = __byte_perm(d[RW - 1], d[RW], 0x6543);
     nd[6] = d[RW];
     nd[7] = __byte_perm(d[RW], d[RW + 1], 0x4321);
-    if (FLAGS) {
+    if (FM) {
         nf[0] = __byte_perm(f[-RW - 1], f[-RW], 0x6543);
         nf[1] = f[-RW];
         nf[2] = __byte_perm(f[-RW], f[-RW + 1], 0x4321);
@@ -255,10 +244,10 @@ __device__ __forceinline__ void ts_scan_word(const uint8_t* sdir, const uint8_t*
     for (int k = 0; k < 8; ++k) {
         const uint32_t eq = __vcmpeq4(nd[k], splat4(7u - k));
         ups |= eq & splat4(1u << k);
-        if (FLAGS) pend |= eq & __vcmpeq4(nf[k] & 0x01010101u, 0u) & splat4(1u << k);
+        if (FM) pend |= eq & __vcmpeq4(nf[k] & FM, 0u) & splat4(1u << k);
     }
     ups_out = ups;
-    pend_out = FLAGS ? pend : ups;
+    pend_out = FM ? pend : ups;
 }
 
 // per byte 0xFF where the cell takes part in this visit: not nodata, not resolved
@@ -266,13 +255,25 @@ __device__ __forceinline__ uint32_t ts_live4(uint32_t dirw, uint32_t flagw) {
     return ~__vcmpeq4(dirw, 0xFFFFFFFFu) & __vcmpeq4(flagw & 0x01010101u, 0u);
 }
 
-// upstream slots that lie in the halo, per byte, for the 4 cells of word q (0 .. 3) of the thread's 16 cells
+// upstream slots that lie in the halo, per byte, for the 4 cells of word q (0 .. 3) of the chunk at (ly, lx0)
 __device__ __forceinline__ uint32_t ts_halo_slots4(int ly, int lx0, int q) {
     uint32_t m = (ly == 0 ? 0x07u : 0u) | (ly == TS_T - 1 ? 0xE0u : 0u);
     uint32_t w = splat4(m);
     if (lx0 == 0 && q == 0) w |= 0x29u;                        // NW, W, SW of the first column
     if (lx0 == TS_T - 16 && q == 3) w |= 0x94u << 24;          // NE, E, SE of the last column
     return w;
+}
+
+// per-byte population count
+__device__ __forceinline__ uint32_t ts_popc4(uint32_t x) {
+    x = x - ((x >> 1) & 0x55555555u);
+    x = (x & 0x33333333u) + ((x >> 2) & 0x33333333u);
+    return (x + (x >> 4)) & 0x0F0F0F0Fu;
+}
+
+// four bytes 0x00 / 0xFF -> four bits
+__device__ __forceinline__ uint32_t ts_gather4(uint32_t b) {
+    return (b & 1u) | ((b >> 7) & 2u) | ((b >> 14) & 4u) | ((b >> 21) & 8u);
 }
 
 // Warp-aggregated append: every lane of the (converged) warp calls it; lanes with `want` get consecutive positions
@@ -288,52 +289,65 @@ __device__ __forceinline__ void ts_push(uint16_t* q, uint32_t base, uint32_t* co
     }
 }
 
-template <typename V>
-struct TsSharedUp {
+// Shared state of one tile visit. The staged byte planes (directions, flags) are only needed until the per-cell records
+// are built; the frontier queue takes their place afterwards.
+//   up   rec = ups mask (8) | dir nibble (4) | number of pending upstream neighbours (4)
+//   down rec = unresolved in-tile children mask (8) | unresolved halo children mask (8)
+template <typename V, bool AUX>
+struct TsShared {
     V val[TS_N];
-    uint32_t pendw[TS_N / 4];  // per cell (byte): upstream neighbours still pending; cleared with shared-memory atomics
-    uint8_t ups[TS_N];         // per cell: all upstream neighbours (bit k = slot k)
-    uint8_t dir[TS_N];
-    uint8_t flag[TS_N];
-    uint8_t aux[TS_N];         // Op-specific byte per cell (Strahler: mask)
-    uint16_t q[TS_T * TS_T];   // ready cells in the order they became ready: round r works on q[lo_r, lo_r + wcnt[r % 3])
-    uint32_t wcnt[3];
+    uint16_t rec[TS_N];
+    union {
+        struct {
+            uint8_t dir[TS_N];
+            uint8_t flag[TS_N];
+        } pl;
+        uint16_t q[TS_T * TS_T];  // cells (ly * 64 + lx) in the order they became ready: round r works on q[lo_r, lo_r + cnt[r % 3])
+    } u;
+    uint8_t aux[AUX ? TS_N : 16];  // Op-specific byte per cell (Strahler: mask)
+    uint32_t oldbm[TS_BMW];        // resolved by earlier visits
+    uint32_t newbm[TS_BMW];        // resolved by this visit
+    uint32_t cnt[3];
     uint32_t act;
     uint32_t newly;
 };
 
-// One cell of an up-sweep chain: fold the upstream values into `cur`, mark it resolved, and clear its bit in the pending
-// mask of the downstream cell. Returns the downstream cell when this lane was the LAST ARRIVER there (the chain goes
-// on), -1 when the chain ends here (pit, tile edge, or another lane arrives later).
-template <class Op>
-__device__ __forceinline__ int ts_up_step(TsSharedUp<typename Op::V>& s, const Op& op, int cur) {
-    uint32_t m = s.ups[cur];
-    const uint8_t own_aux = Op::AUX ? s.aux[cur] : (uint8_t)0;
-    typename Op::State st = op.begin(s.val[cur], own_aux);
-    while (m) {  // descending slot = descending linear index
-        const int k = 31 - __clz(m);
-        m ^= 1u << k;
-        const int u = cur + ts_noff(k);
-        op.step(st, s.val[u], Op::AUX ? s.aux[u] : (uint8_t)0);
-    }
-    s.val[cur] = op.end(st, own_aux);
-    const uint32_t f = s.flag[cur];
-    s.flag[cur] = (uint8_t)(f | TSF_DONE | TSF_NEW);
-    const uint32_t d = s.dir[cur];
-    int next = -1;
-    if (d < 8u) {  // (a pit ends the chain)
-        const int ds = cur + ts_noff((int)d);
-        if (f & TSF_EXIT) {  // leaves the tile: the neighbour tile may continue in the next pass
-            atomicOr(&s.act, ts_act_bit_of(ds));
-        } else {
-            __threadfence_block();  // my value is visible before my bit disappears
-            const unsigned sh = 8u * (ds & 3), bit = 1u << (7u - d);
-            const uint32_t old = atomicAnd(&s.pendw[ds >> 2], ~(bit << sh));
-            if (((old >> sh) & 0xFFu & ~bit) == 0u) next = ds;  // last arriver: the chain goes on (else somebody else continues)
-            __threadfence_block();
+// write back what this visit resolved (pass 1: every cell), publish the done bitmap, queue the neighbour tiles
+template <int NT, typename V, bool AUX, class Op>
+__device__ __forceinline__ void ts_finish(TsShared<V, AUX>& s, const TsArgs& A, const Op& op, int tile, int pass, long long r0,
+                                          long long c0, bool fill_unresolved) {
+    uint32_t cnt = 0;
+    for (int ch = threadIdx.x; ch < TS_NCHUNK; ch += NT) {
+        const int ly = ch >> 2, lx0 = (ch & 3) << 4;
+        const long long r = r0 + ly, c = c0 + lx0;
+        if (r < A.nrow && c < A.ncol) {
+            const int nvalid = (int)min((long long)16, A.ncol - c);
+            const bool vec = A.al16 && nvalid == 16;
+            uint32_t sel = (s.newbm[ch >> 1] >> (lx0 & 31)) & 0xFFFFu;
+            cnt += __popc(sel);
+            V* sv = &s.val[ts_si(ly, lx0)];
+            if (pass == 1) {
+                if (fill_unresolved) {
+#pragma unroll 4
+                    for (int j = 0; j < 16; ++j)
+                        if (!((sel >> j) & 1u)) sv[j] = op.fill();
+                }
+                sel = 0xFFFFu;
+            }
+            if (sel) ts_store16<V>(op.out + (r * A.ncol + c), sv, vec, nvalid, sel);
         }
     }
-    return next;
+    cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s.newly, cnt);
+    __threadfence();  // a tile running in the same pass may read my done bits: the values are out before the bits
+    ts_sync<NT>();
+    for (int k = threadIdx.x; k < TS_BMW; k += NT) A.done[(long long)tile * TS_BMW + k] = s.oldbm[k] | s.newbm[k];
+    ts_activate(A, tile, s.act, pass);
+    if (threadIdx.x == 16) {
+        if (s.newly) atomicAdd(&A.ctl->resolved, (unsigned long long)s.newly);
+        atomicAdd(&A.ctl->visits, 1ull);
+    }
+    ts_sync<NT>();  // shared memory is reused by the next visit
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -343,132 +357,147 @@ __device__ __forceinline__ int ts_up_step(TsSharedUp<typename Op::V>& s, const O
 //   State begin(own, own_aux); step(State&, v_up, aux_up) for the upstream neighbours in DESCENDING linear index; V end(State, own_aux)
 //   V* out
 // ---------------------------------------------------------------------------------------------------------
+// One cell of the frontier: fold the upstream values into the cell, mark it resolved, and take one off the pending
+// count of the downstream cell. Returns the downstream cell when this lane was the LAST ARRIVER there (it joins the
+// next round), -1 otherwise (pit, tile edge, or another lane arrives later).
 template <class Op>
-__device__ __forceinline__ void ts_up_visit(TsSharedUp<typename Op::V>& s, const TsArgs& A, const Op& op, int tile, int pass) {
+__device__ __forceinline__ int ts_up_step(TsShared<typename Op::V, Op::AUX>& s, const Op& op, int i) {
+    const int ly = i >> 6, lx = i & (TS_T - 1);
+    const int c = ts_si(ly, lx);
+    const uint32_t r = s.rec[c];
+    uint32_t m = r & 0xFFu;
+    const uint32_t d = (r >> 8) & 0xFu;
+    const uint8_t own_aux = Op::AUX ? s.aux[c] : (uint8_t)0;
+    typename Op::State st = op.begin(s.val[c], own_aux);
+    while (m) {  // descending slot = descending linear index
+        const int k = 31 - __clz(m);
+        m ^= 1u << k;
+        const int u = c + ts_noff(k);
+        op.step(st, s.val[u], Op::AUX ? s.aux[u] : (uint8_t)0);
+    }
+    s.val[c] = op.end(st, own_aux);
+    atomicOr(&s.newbm[i >> 5], 1u << (i & 31));
+    int next = -1;
+    if (d < 8u) {  // (a pit ends the chain)
+        const int y = ly + pfd_slot_dr((int)d), x = lx + pfd_slot_dc((int)d);
+        if ((unsigned)y < (unsigned)TS_T && (unsigned)x < (unsigned)TS_T) {
+            const int ds = c + ts_noff((int)d);
+            const unsigned sh = 16u * (ds & 1);
+            const uint32_t old = atomicSub(reinterpret_cast<uint32_t*>(s.rec) + (ds >> 1), 0x1000u << sh);
+            if (((old >> (sh + 12)) & 0xFu) == 1u) next = y * TS_T + x;  // last arriver (else somebody else continues)
+        } else {
+            atomicOr(&s.act, ts_act_bit(y, x));  // leaves the tile: the neighbour tile may continue in the next pass
+        }
+    }
+    return next;
+}
+
+template <int NT, class Op>
+__device__ __forceinline__ void ts_up_visit(TsShared<typename Op::V, Op::AUX>& s, const TsArgs& A, const Op& op, int tile, int pass) {
     typedef typename Op::V V;
     const long long r0 = (long long)(tile / A.ntx) * TS_T, c0 = (long long)(tile % A.ntx) * TS_T;
-    const int ly = TS_ROW, lx0 = TS_COL0;
-    const int base = ts_si(ly, lx0);
-    const long long r = r0 + ly, c = c0 + lx0;
-    const bool row_in = r < A.nrow && c < A.ncol;
-    const int nvalid = row_in ? (int)min((long long)16, A.ncol - c) : 0;
-    const bool vec = A.al16 && nvalid == 16;
-    const long long g0 = r * A.ncol + c;
     if (threadIdx.x == 0) {
         s.act = 0;
         s.newly = 0;
-        s.wcnt[0] = s.wcnt[1] = s.wcnt[2] = 0;
+        s.cnt[0] = s.cnt[1] = s.cnt[2] = 0;
     }
-    ts_stage_graph(s.dir, s.flag, A, tile, r0, c0, pass);
+    for (int k = threadIdx.x; k < TS_BMW; k += NT) s.newbm[k] = 0u;
+    ts_stage_graph<NT>(s.u.pl.dir, s.u.pl.flag, s.oldbm, A, tile, r0, c0, pass);
     // values: pass 1 starts from the cell's own datum; later passes read what earlier visits stored (final for done
     // cells, the own datum for pending ones)
-    if (row_in) {
-        if (pass == 1) ts_load16<V, false>(&s.val[base], op.init_src() ? op.init_src() + g0 : nullptr, vec, nvalid);
-        else ts_load16<V, true>(&s.val[base], op.out + g0, vec, nvalid);
-        if (Op::AUX) ts_load16<uint8_t, false>(&s.aux[base], op.aux_src() + g0, vec, nvalid);
+    for (int ch = threadIdx.x; ch < TS_NCHUNK; ch += NT) {
+        const int ly = ch >> 2, lx0 = (ch & 3) << 4;
+        const long long r = r0 + ly, c = c0 + lx0;
+        if (r < A.nrow && c < A.ncol) {
+            const int nvalid = (int)min((long long)16, A.ncol - c);
+            const bool vec = A.al16 && nvalid == 16;
+            const long long g0 = r * A.ncol + c;
+            const int base = ts_si(ly, lx0);
+            if (pass == 1) ts_load16<V, false>(&s.val[base], op.init_src() ? op.init_src() + g0 : nullptr, vec, nvalid);
+            else ts_load16<V, true>(&s.val[base], op.out + g0, vec, nvalid);
+            if (Op::AUX) ts_load16<uint8_t, false>(&s.aux[base], op.aux_src() + g0, vec, nvalid);
+        }
     }
-    __syncthreads();  // dir + flags (incl. halo) are staged
+    ts_sync<NT>();  // dir + flags (incl. halo) are staged
     if (pass > 1 || Op::AUX) {
-        for (int k = threadIdx.x; k < TS_NHALO; k += TS_THREADS) {
+        for (int k = threadIdx.x; k < TS_NHALO; k += NT) {
             int hy, hx;
             ts_halo_cell(k, hy, hx);
             const long long hr = r0 + hy, hc = c0 + hx;
             if (ts_in_raster(A, hr, hc)) {
                 const long long g = hr * A.ncol + hc;
-                if (s.flag[ts_si(hy, hx)] & TSF_DONE) s.val[ts_si(hy, hx)] = ld_cg(op.out + g);
+                if (s.u.pl.flag[ts_si(hy, hx)] & TSF_DONE) s.val[ts_si(hy, hx)] = ld_cg(op.out + g);
                 if (Op::AUX) s.aux[ts_si(hy, hx)] = __ldg(op.aux_src() + g);
             }
         }
     }
-    // upstream / pending masks of the own cells (4 cells per word), start cells, exit flags
-    uint32_t start = 0;
-    {
-        const uint32_t* dw = reinterpret_cast<const uint32_t*>(s.dir + base);
-        uint32_t* fw = reinterpret_cast<uint32_t*>(s.flag + base);
-        uint32_t* uw = reinterpret_cast<uint32_t*>(s.ups + base);
-        uint32_t* pw = s.pendw + (base >> 2);
+    // per-cell records (4 cells per word of the planes); the ready cells are remembered in registers until the planes are dead
+    uint32_t start[(TS_NCHUNK / NT + 1) / 2];
+#pragma unroll
+    for (int t = 0; t < (TS_NCHUNK / NT + 1) / 2; ++t) start[t] = 0;
+#pragma unroll
+    for (int it = 0; it < TS_NCHUNK / NT; ++it) {
+        const int ch = threadIdx.x + it * NT;
+        const int ly = ch >> 2, lx0 = (ch & 3) << 4;
+        const int base = ts_si(ly, lx0);
+        const uint32_t* dw = reinterpret_cast<const uint32_t*>(s.u.pl.dir + base);
+        const uint32_t* fw = reinterpret_cast<const uint32_t*>(s.u.pl.flag + base);
+        uint32_t* rw = reinterpret_cast<uint32_t*>(s.rec + base);
+        uint32_t st16 = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             uint32_t ups, pend;
-            if (pass == 1) ts_scan_word<false>(s.dir, s.flag, ly + 1, (TS_X0 + lx0) / 4 + q, ups, pend);
-            else ts_scan_word<true>(s.dir, s.flag, ly + 1, (TS_X0 + lx0) / 4 + q, ups, pend);
+            if (pass == 1) ts_scan_word<false, false>(s.u.pl.dir, s.u.pl.flag, ly + 1, (TS_X0 + lx0) / 4 + q, ups, pend);
+            else ts_scan_word<true, false>(s.u.pl.dir, s.u.pl.flag, ly + 1, (TS_X0 + lx0) / 4 + q, ups, pend);
             const uint32_t live = ts_live4(dw[q], fw[q]);
             ups &= live;
             pend &= live;
-            uw[q] = ups;
-            pw[q] = pend;
-            const uint32_t st = live & __vcmpeq4(pend, 0u);  // 0xFF per ready cell
-            start |= (((st & 1u) | ((st >> 7) & 2u) | ((st >> 14) & 4u) | ((st >> 21) & 8u))) << (4 * q);
+            const uint32_t hi = (dw[q] & 0x0F0F0F0Fu) | (ts_popc4(pend) << 4);  // dir nibble | pending count
+            rw[2 * q] = __byte_perm(ups, hi, 0x5140);
+            rw[2 * q + 1] = __byte_perm(ups, hi, 0x7362);
+            st16 |= ts_gather4(live & __vcmpeq4(pend, 0u)) << (4 * q);
         }
-        // cells whose downstream neighbour lies outside the tile (ring cells only)
-        if (ly == 0 || ly == TS_T - 1 || lx0 == 0 || lx0 == TS_T - 16) {
-#pragma unroll 1
-            for (int j = 0; j < 16; ++j) {
-                const int lx = lx0 + j;
-                if (!(ly == 0 || ly == TS_T - 1 || lx == 0 || lx == TS_T - 1)) continue;
-                const uint32_t d = s.dir[base + j];
-                if (d < 8u) {
-                    const int y = ly + pfd_slot_dr((int)d), x = lx + pfd_slot_dc((int)d);
-                    if (y < 0 || y >= TS_T || x < 0 || x >= TS_T) s.flag[base + j] |= (uint8_t)TSF_EXIT;
-                }
-            }
-        }
+        start[it >> 1] |= st16 << (16 * (it & 1));
     }
-    __syncthreads();
+    ts_sync<NT>();  // the planes are dead: the queue takes their place
     // In-tile dataflow, level by level: round 0 holds the ready cells (no pending upstream neighbour); a lane resolves
     // ONE cell per round and, when it was the last arriver at the downstream cell, appends that cell to the next round
     // (warp-aggregated). The frontier stays compacted, so the lanes of a warp all work, and the long chains (rivers) of
     // the tile end up side by side in one warp instead of one per warp.
+#pragma unroll
+    for (int it = 0; it < TS_NCHUNK / NT; ++it) {
+        const int ch = threadIdx.x + it * NT;
+        const uint32_t st16 = (start[it >> 1] >> (16 * (it & 1))) & 0xFFFFu;
+        if (__any_sync(0xFFFFFFFFu, st16 != 0u)) {
 #pragma unroll 1
-    for (int j = 0; j < TS_CPT; ++j) ts_push(s.q, 0u, &s.wcnt[0], (start >> j) & 1u, base + j);
+            for (int j = 0; j < 16; ++j) ts_push(s.u.q, 0u, &s.cnt[0], (st16 >> j) & 1u, ch * 16 + j);
+        }
+    }
     uint32_t lo = 0;
     for (int rd = 0;; ++rd) {
-        __syncthreads();
-        const uint32_t n = s.wcnt[rd % 3];
+        ts_sync<NT>();
+        const uint32_t n = s.cnt[rd % 3];
         if (n == 0) break;
-        if (threadIdx.x == 0) s.wcnt[(rd + 2) % 3] = 0;
-        uint32_t* cn = &s.wcnt[(rd + 1) % 3];
-        for (uint32_t e0 = threadIdx.x & ~31u; e0 < n; e0 += TS_THREADS) {  // warp-uniform trip count
+        if (threadIdx.x == 0) s.cnt[(rd + 2) % 3] = 0;
+        uint32_t* cn = &s.cnt[(rd + 1) % 3];
+        for (uint32_t e0 = threadIdx.x & ~31u; e0 < n; e0 += NT) {  // warp-uniform trip count
             const uint32_t e = e0 + (threadIdx.x & 31u);
             int next = -1;
-            if (e < n) next = ts_up_step<Op>(s, op, s.q[lo + e]);
-            ts_push(s.q, lo + n, cn, next >= 0, next);
+            if (e < n) next = ts_up_step<Op>(s, op, s.u.q[lo + e]);
+            ts_push(s.u.q, lo + n, cn, next >= 0, next);
         }
         lo += n;
     }
-    // store: pass 1 writes every cell of the tile (pending and nodata cells keep their own datum, like accu = data.copy()),
+    // pass 1 writes every cell of the tile (pending and nodata cells keep their own datum, like accu = data.copy()),
     // later passes only what this visit resolved
-    uint32_t cnt = 0;
-    if (row_in) {
-        const uint32_t* fw = reinterpret_cast<const uint32_t*>(s.flag + base);
-        uint32_t sel = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t f = fw[q] & 0x02020202u;
-            sel |= (((f >> 1) | (f >> 8) | (f >> 15) | (f >> 22)) & 0xFu) << (4 * q);
-        }
-        cnt = __popc(sel);
-        if (pass == 1) sel = 0xFFFFu;
-        if (sel) ts_store16<V>(op.out + g0, &s.val[base], vec, nvalid, sel);
-    }
-    cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
-    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s.newly, cnt);
-    __threadfence();  // a tile running in the same pass may read my done bits: the values are out before the bits
-    __syncthreads();
-    ts_store_bitmap(s.flag, A, tile);
-    ts_activate(A, tile, s.act, pass);
-    if (threadIdx.x == 32) {
-        if (s.newly) atomicAdd(&A.ctl->resolved, (unsigned long long)s.newly);
-        atomicAdd(&A.ctl->visits, 1ull);
-    }
-    __syncthreads();  // shared memory is reused by the next visit
+    ts_finish<NT>(s, A, op, tile, pass, r0, c0, false);
 }
 
 // All passes in one cooperative launch. grid-stride over the work list of the pass (pass 1: every tile).
-template <class Op>
-__global__ void __launch_bounds__(TS_THREADS) tile_up_sweep_kernel(TsArgs A, Op op) {
+template <int NT, class Op>
+__global__ void __launch_bounds__(NT) tile_up_sweep_kernel(TsArgs A, Op op) {
     extern __shared__ __align__(16) unsigned char ts_smem_raw[];
-    TsSharedUp<typename Op::V>& s = *reinterpret_cast<TsSharedUp<typename Op::V>*>(ts_smem_raw);
+    TsShared<typename Op::V, Op::AUX>& s = *reinterpret_cast<TsShared<typename Op::V, Op::AUX>*>(ts_smem_raw);
     cg::grid_group grid = cg::this_grid();
     const unsigned int ntiles = (unsigned int)(A.ntx * A.nty);
     int pass = 1;
@@ -478,7 +507,7 @@ __global__ void __launch_bounds__(TS_THREADS) tile_up_sweep_kernel(TsArgs A, Op 
         if (blockIdx.x == 0 && threadIdx.x == 0) A.ctl->count[(pass + 2) & 3] = 0u;  // last read two passes ago
         const uint32_t* list = A.list[pass & 1];
         for (unsigned int w = blockIdx.x; w < count; w += gridDim.x)
-            ts_up_visit<Op>(s, A, op, (pass == 1) ? (int)w : (int)__ldcg(list + w), pass);
+            ts_up_visit<NT, Op>(s, A, op, (pass == 1) ? (int)w : (int)__ldcg(list + w), pass);
         __threadfence();
         grid.sync();
     }
@@ -497,6 +526,7 @@ struct AccuUpTileOp {
     __host__ __device__ __forceinline__ const T* init_src() const { return data; }
     __host__ __device__ __forceinline__ const uint8_t* aux_src() const { return nullptr; }
     __device__ __forceinline__ T init(long long g) const { return data[g]; }
+    __device__ __forceinline__ T fill() const { return T(); }
     __device__ __forceinline__ T begin(T own, uint8_t) const { return own; }
     __device__ __forceinline__ void step(T& acc, T up, uint8_t) const {
         if (not_nodata(acc, nd) && not_nodata(up, nd)) acc = acc_add(acc, up);
@@ -517,6 +547,7 @@ struct StrahlerTileOp {
     __host__ __device__ __forceinline__ const uint8_t* init_src() const { return nullptr; }
     __host__ __device__ __forceinline__ const uint8_t* aux_src() const { return mask; }
     __device__ __forceinline__ uint8_t init(long long) const { return 0; }
+    __device__ __forceinline__ uint8_t fill() const { return 0; }
     __device__ __forceinline__ State begin(uint8_t, uint8_t) const { return State{0, 0}; }
     __device__ __forceinline__ void step(State& st, uint8_t sto, uint8_t up_aux) const {
         if (MASKED && !up_aux) return;
@@ -547,125 +578,134 @@ __global__ void ts_reset_unranked_kernel(const uint8_t* __restrict__ dir, const 
 //   V fill()                value of the cells the sweep never reaches (nodata, cells draining to no pit)
 //   V* out
 // ---------------------------------------------------------------------------------------------------------
-template <typename V>
-struct TsSharedDown {
-    V val[TS_N];
-    uint16_t q[TS_T * TS_T];  // resolved cells in the order they were resolved: round r expands q[lo_r, lo_r + qcnt[r % 3])
-    uint8_t kids[TS_N];   // per cell: unresolved upstream neighbours inside the tile
-    uint8_t outm[TS_N];   // per cell: unresolved upstream neighbours in the halo (their tiles wait for this cell)
-    uint8_t dir[TS_N];
-    uint8_t flag[TS_N];
-    uint32_t qcnt[3];
-    uint32_t act;
-    uint32_t newly;
-};
-
-template <class Op>
-__device__ __forceinline__ void ts_down_visit(TsSharedDown<typename Op::V>& s, const TsArgs& A, const Op& op, int tile, int pass) {
+template <int NT, class Op>
+__device__ __forceinline__ void ts_down_visit(TsShared<typename Op::V, false>& s, const TsArgs& A, const Op& op, int tile, int pass) {
     typedef typename Op::V V;
     const long long r0 = (long long)(tile / A.ntx) * TS_T, c0 = (long long)(tile % A.ntx) * TS_T;
-    const int ly = TS_ROW, lx0 = TS_COL0;
-    const int base = ts_si(ly, lx0);
-    const long long r = r0 + ly, c = c0 + lx0;
-    const bool row_in = r < A.nrow && c < A.ncol;
-    const int nvalid = row_in ? (int)min((long long)16, A.ncol - c) : 0;
-    const bool vec = A.al16 && nvalid == 16;
-    const long long g0 = r * A.ncol + c;
     if (threadIdx.x == 0) {
         s.act = 0;
         s.newly = 0;
-        s.qcnt[0] = s.qcnt[1] = s.qcnt[2] = 0;
+        s.cnt[0] = s.cnt[1] = s.cnt[2] = 0;
     }
-    ts_stage_graph(s.dir, s.flag, A, tile, r0, c0, pass);
-    __syncthreads();
-    // children masks (4 cells per word); per-cell terms; values of the resolved halo cells
-    {
-        uint32_t* kw = reinterpret_cast<uint32_t*>(s.kids + base);
-        uint32_t* ow = reinterpret_cast<uint32_t*>(s.outm + base);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint32_t ups, pend;
-            if (pass == 1) ts_scan_word<false>(s.dir, s.flag, ly + 1, (TS_X0 + lx0) / 4 + q, ups, pend);
-            else ts_scan_word<true>(s.dir, s.flag, ly + 1, (TS_X0 + lx0) / 4 + q, ups, pend);
-            const uint32_t halo = ts_halo_slots4(ly, lx0, q);
-            kw[q] = pend & ~halo;
-            ow[q] = pend & halo;
-        }
-    }
-    uint32_t live16 = 0;
+    for (int k = threadIdx.x; k < TS_BMW; k += NT) s.newbm[k] = 0u;
+    ts_stage_graph<NT>(s.u.pl.dir, s.u.pl.flag, s.oldbm, A, tile, r0, c0, pass);
+    ts_sync<NT>();
+    // per-cell terms of the unresolved cells, source flags; values of the resolved halo cells
+    for (int ch = threadIdx.x; ch < TS_NCHUNK; ch += NT) {
+        const int ly = ch >> 2, lx0 = (ch & 3) << 4;
+        const int base = ts_si(ly, lx0);
+        const long long g0 = (r0 + ly) * A.ncol + c0 + lx0;
 #pragma unroll 4
-    for (int j = 0; j < 16; ++j) {
-        const int ci = base + j;
-        const uint32_t d = s.dir[ci];
-        if (d != PFD_DIR_NODATA && !(s.flag[ci] & TSF_DONE)) {
-            const long long g = g0 + j;
-            s.val[ci] = op.prep(g, d, (d < 8u) ? g + pfd_slot_off((int)d, A.ncol) : g);
-            if (op.source(g)) s.flag[ci] |= (uint8_t)TSF_SRC;
-            live16 |= 1u << j;
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t d = s.u.pl.dir[base + j];
+            if (d != PFD_DIR_NODATA && !(s.u.pl.flag[base + j] & TSF_DONE)) {
+                const long long g = g0 + j;
+                s.val[base + j] = op.prep(g, d, (d < 8u) ? g + pfd_slot_off((int)d, A.ncol) : g);
+                if (op.source(g)) s.u.pl.flag[base + j] |= (uint8_t)TSF_SRC;
+            }
         }
     }
     if (pass > 1) {
-        for (int k = threadIdx.x; k < TS_NHALO; k += TS_THREADS) {
+        for (int k = threadIdx.x; k < TS_NHALO; k += NT) {
             int hy, hx;
             ts_halo_cell(k, hy, hx);
-            if (s.flag[ts_si(hy, hx)] & TSF_DONE) s.val[ts_si(hy, hx)] = ld_cg(op.out + ((r0 + hy) * A.ncol + c0 + hx));
+            if (s.u.pl.flag[ts_si(hy, hx)] & TSF_DONE) s.val[ts_si(hy, hx)] = ld_cg(op.out + ((r0 + hy) * A.ncol + c0 + hx));
         }
     }
-    __syncthreads();
-    // roots: sources, pits, exit cells whose downstream (halo) cell is resolved
-    while (live16) {
-        const int j = __ffs(live16) - 1;
-        live16 &= live16 - 1;
-        const int ci = base + j;
-        const uint32_t d = s.dir[ci], f = s.flag[ci];
-        bool root = false;
-        V v = s.val[ci];
-        if (f & TSF_SRC) {
-            v = op.source_value();
-            root = true;
-        } else if (d >= 8u) {
-            v = op.pit(v);
-            root = true;
-        } else {
-            const int lx = lx0 + j;
-            const int y = ly + pfd_slot_dr((int)d), x = lx + pfd_slot_dc((int)d);
-            if (y < 0 || y >= TS_T || x < 0 || x >= TS_T) {
-                const int ds = ci + ts_noff((int)d);
-                if (s.flag[ds] & TSF_DONE) {
-                    v = op.down(s.val[ds], v);
-                    root = true;
+    ts_sync<NT>();
+    // records: unresolved children inside the tile / in the halo (sources are nobody's children: they are roots).
+    // Roots: sources, pits, exit cells whose downstream (halo) cell is resolved -- resolved right here, queued below.
+    uint32_t roots[(TS_NCHUNK / NT + 1) / 2];
+#pragma unroll
+    for (int t = 0; t < (TS_NCHUNK / NT + 1) / 2; ++t) roots[t] = 0;
+#pragma unroll
+    for (int it = 0; it < TS_NCHUNK / NT; ++it) {
+        const int ch = threadIdx.x + it * NT;
+        const int ly = ch >> 2, lx0 = (ch & 3) << 4;
+        const int base = ts_si(ly, lx0);
+        const uint32_t* dw = reinterpret_cast<const uint32_t*>(s.u.pl.dir + base);
+        const uint32_t* fw = reinterpret_cast<const uint32_t*>(s.u.pl.flag + base);
+        uint32_t* rw = reinterpret_cast<uint32_t*>(s.rec + base);
+        uint32_t live16 = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t ups, pend;
+            if (pass == 1) ts_scan_word<false, true>(s.u.pl.dir, s.u.pl.flag, ly + 1, (TS_X0 + lx0) / 4 + q, ups, pend);
+            else ts_scan_word<true, true>(s.u.pl.dir, s.u.pl.flag, ly + 1, (TS_X0 + lx0) / 4 + q, ups, pend);
+            const uint32_t halo = ts_halo_slots4(ly, lx0, q);
+            const uint32_t kids = pend & ~halo, outm = pend & halo;
+            rw[2 * q] = __byte_perm(kids, outm, 0x5140);
+            rw[2 * q + 1] = __byte_perm(kids, outm, 0x7362);
+            live16 |= ts_gather4(ts_live4(dw[q], fw[q])) << (4 * q);
+        }
+        uint32_t root16 = 0;
+        while (live16) {
+            const int j = __ffs(live16) - 1;
+            live16 &= live16 - 1;
+            const int ci = base + j;
+            const uint32_t d = s.u.pl.dir[ci], f = s.u.pl.flag[ci];
+            bool root = false;
+            V v = s.val[ci];
+            if (f & TSF_SRC) {
+                v = op.source_value();
+                root = true;
+            } else if (d >= 8u) {
+                v = op.pit(v);
+                root = true;
+            } else {
+                const int y = ly + pfd_slot_dr((int)d), x = lx0 + j + pfd_slot_dc((int)d);
+                if (!((unsigned)y < (unsigned)TS_T && (unsigned)x < (unsigned)TS_T)) {
+                    const int ds = ci + ts_noff((int)d);
+                    if (s.u.pl.flag[ds] & TSF_DONE) {
+                        v = op.down(s.val[ds], v);
+                        root = true;
+                    }
                 }
             }
+            if (root) {
+                s.val[ci] = v;
+                root16 |= 1u << j;
+            }
         }
-        if (root) {
-            s.val[ci] = v;
-            s.flag[ci] = (uint8_t)(f | TSF_DONE | TSF_NEW);
-            s.q[atomicAdd(&s.qcnt[0], 1u)] = (uint16_t)ci;
+        roots[it >> 1] |= root16 << (16 * (it & 1));
+    }
+    ts_sync<NT>();  // the planes are dead: the queue takes their place
+#pragma unroll
+    for (int it = 0; it < TS_NCHUNK / NT; ++it) {
+        const int ch = threadIdx.x + it * NT;
+        const uint32_t r16 = (roots[it >> 1] >> (16 * (it & 1))) & 0xFFFFu;
+        if (r16) atomicOr(&s.newbm[ch >> 1], r16 << ((ch & 1) * 16));
+        if (__any_sync(0xFFFFFFFFu, r16 != 0u)) {
+#pragma unroll 1
+            for (int j = 0; j < 16; ++j) ts_push(s.u.q, 0u, &s.cnt[0], (r16 >> j) & 1u, ch * 16 + j);
         }
     }
     // rounds, level by level: a lane takes ONE resolved cell per round, resolves its unresolved in-tile children and
     // appends them to the next round (warp-aggregated, so the frontier stays compacted)
     uint32_t lo = 0;
     for (int rd = 0;; ++rd) {
-        __syncthreads();
-        const uint32_t cnt = s.qcnt[rd % 3];
+        ts_sync<NT>();
+        const uint32_t cnt = s.cnt[rd % 3];
         if (cnt == 0) break;
-        if (threadIdx.x == 0) s.qcnt[(rd + 2) % 3] = 0;
-        uint32_t* qn = &s.qcnt[(rd + 1) % 3];
-        for (uint32_t e0 = threadIdx.x & ~31u; e0 < cnt; e0 += TS_THREADS) {  // warp-uniform trip count
+        if (threadIdx.x == 0) s.cnt[(rd + 2) % 3] = 0;
+        uint32_t* qn = &s.cnt[(rd + 1) % 3];
+        for (uint32_t e0 = threadIdx.x & ~31u; e0 < cnt; e0 += NT) {  // warp-uniform trip count
             const uint32_t e = e0 + (threadIdx.x & 31u);
             uint32_t m = 0;
-            int p = 0;
+            int ly = 0, lx = 0, p = 0;
             V vp = V();
             if (e < cnt) {
-                p = s.q[lo + e];
-                m = s.kids[p];
+                const int i = s.u.q[lo + e];
+                ly = i >> 6, lx = i & (TS_T - 1);
+                p = ts_si(ly, lx);
+                const uint32_t r = s.rec[p];
+                m = r & 0xFFu;
                 vp = s.val[p];
-                uint32_t om = s.outm[p];
+                uint32_t om = r >> 8;
                 while (om) {  // a neighbour tile waits for this cell
                     const int k = __ffs(om) - 1;
                     om &= om - 1;
-                    atomicOr(&s.act, ts_act_bit_of(p + ts_noff(k)));
+                    atomicOr(&s.act, ts_act_bit(ly + pfd_slot_dr(k), lx + pfd_slot_dc(k)));
                 }
             }
             while (__any_sync(0xFFFFFFFFu, m != 0u)) {
@@ -674,54 +714,23 @@ __device__ __forceinline__ void ts_down_visit(TsSharedDown<typename Op::V>& s, c
                     const int k = __ffs(m) - 1;
                     m &= m - 1;
                     const int c = p + ts_noff(k);
-                    const uint32_t f = s.flag[c];
-                    if (!(f & TSF_DONE)) {  // (a source was resolved as a root)
-                        s.val[c] = op.down(vp, s.val[c]);
-                        s.flag[c] = (uint8_t)(f | TSF_DONE | TSF_NEW);
-                        n = c;
-                    }
+                    s.val[c] = op.down(vp, s.val[c]);
+                    n = (ly + pfd_slot_dr(k)) * TS_T + lx + pfd_slot_dc(k);
+                    atomicOr(&s.newbm[n >> 5], 1u << (n & 31));
                 }
-                ts_push(s.q, lo + cnt, qn, n >= 0, n);
+                ts_push(s.u.q, lo + cnt, qn, n >= 0, n);
             }
         }
         lo += cnt;
     }
-    // store
-    uint32_t cnt = 0;
-    if (row_in) {
-        const uint32_t* fw = reinterpret_cast<const uint32_t*>(s.flag + base);
-        uint32_t sel = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t f = fw[q] & 0x02020202u;
-            sel |= (((f >> 1) | (f >> 8) | (f >> 15) | (f >> 22)) & 0xFu) << (4 * q);
-        }
-        cnt = __popc(sel);
-        if (pass == 1) {  // every cell is written: what is not resolved (yet, or never) holds the fill value
-#pragma unroll 4
-            for (int j = 0; j < 16; ++j)
-                if (!((sel >> j) & 1u)) s.val[base + j] = op.fill();
-            sel = 0xFFFFu;
-        }
-        if (sel) ts_store16<V>(op.out + g0, &s.val[base], vec, nvalid, sel);
-    }
-    cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
-    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s.newly, cnt);
-    __threadfence();
-    __syncthreads();
-    ts_store_bitmap(s.flag, A, tile);
-    ts_activate(A, tile, s.act, pass);
-    if (threadIdx.x == 32) {
-        if (s.newly) atomicAdd(&A.ctl->resolved, (unsigned long long)s.newly);
-        atomicAdd(&A.ctl->visits, 1ull);
-    }
-    __syncthreads();
+    // pass 1 writes every cell: what is not resolved (yet, or never) holds the fill value
+    ts_finish<NT>(s, A, op, tile, pass, r0, c0, true);
 }
 
-template <class Op>
-__global__ void __launch_bounds__(TS_THREADS) tile_down_sweep_kernel(TsArgs A, Op op) {
+template <int NT, class Op>
+__global__ void __launch_bounds__(NT) tile_down_sweep_kernel(TsArgs A, Op op) {
     extern __shared__ __align__(16) unsigned char ts_smem_raw[];
-    TsSharedDown<typename Op::V>& s = *reinterpret_cast<TsSharedDown<typename Op::V>*>(ts_smem_raw);
+    TsShared<typename Op::V, false>& s = *reinterpret_cast<TsShared<typename Op::V, false>*>(ts_smem_raw);
     cg::grid_group grid = cg::this_grid();
     const unsigned int ntiles = (unsigned int)(A.ntx * A.nty);
     int pass = 1;
@@ -731,7 +740,7 @@ __global__ void __launch_bounds__(TS_THREADS) tile_down_sweep_kernel(TsArgs A, O
         if (blockIdx.x == 0 && threadIdx.x == 0) A.ctl->count[(pass + 2) & 3] = 0u;
         const uint32_t* list = A.list[pass & 1];
         for (unsigned int w = blockIdx.x; w < count; w += gridDim.x)
-            ts_down_visit<Op>(s, A, op, (pass == 1) ? (int)w : (int)__ldcg(list + w), pass);
+            ts_down_visit<NT, Op>(s, A, op, (pass == 1) ? (int)w : (int)__ldcg(list + w), pass);
         __threadfence();
         grid.sync();
     }

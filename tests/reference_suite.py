@@ -22,6 +22,10 @@ SUBMODULES = ["core", "core_d8", "core_ldd", "core_nextxy", "core_conversion", "
 def alias():
     if ROOT not in sys.path:
         sys.path.insert(0, ROOT)
+    try:
+        importlib.import_module("affine")
+    except ImportError:  # the tests import affine.Affine: same stand-in the oracle uses
+        sys.path.insert(0, os.path.join(ROOT, "oracle", "_stubs"))
     import pyflwdir_b200
 
     sys.modules["pyflwdir"] = pyflwdir_b200

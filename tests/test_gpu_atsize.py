@@ -205,6 +205,7 @@ def test_sweeps_verified_at_size(size):
     L, l = _lib()
     w = bench.Workload(size, 1 if size == 32768 else 3, 0)
     h, n = w.h, w.cells
+    w.ck(l.pfd_set_option(h, b"tile_sweeps", 2))  # the tile-dataflow sweeps (the level replays are covered at 4096^2)
     w.step_resident()
     nb = C.c_int64()
     so_dev = w.dev_alloc(n)

@@ -26,7 +26,7 @@ def solver(request, monkeypatch):
     level-synchronous BFS + sweeps -- and of accuflux / Strahler / HAND: tile-dataflow sweeps (default) and level
     replays over the BFS order."""
     monkeypatch.setenv("PFD_TILES", "1" if request.param == "tiles" else "0")
-    monkeypatch.setenv("PFD_TILE_SWEEPS", "1" if request.param == "tiles" else "0")
+    monkeypatch.setenv("PFD_TILE_SWEEPS", "2" if request.param == "tiles" else "0")
     return request.param
 
 
@@ -420,3 +420,33 @@ def test_small_mirrors(pfb):
     assert np.array_equal(core.headwater_indices(rids, shape=rnd.shape), np.flatnonzero(nup == 0))
     assert np.array_equal(core.confluence_indices(rids, shape=rnd.shape), np.flatnonzero(nup > 1))
     assert core.loop_indices(rids, shape=rnd.shape).dtype == rids.dtype
+
+
+def test_upstream_matrix_and_dump_load(pfb, tmp_path):
+    """core.upstream_matrix (core.py:67-84) against its definition on a raster with loops, and the pickle round trip
+    FlwdirRaster.dump / load (flwdir.py:290-306, pyflwdir.py:362-373)."""
+    from pyflwdir_b200 import core
+
+    d8 = cs.case_d8("random48x61")
+    ids = cs.golden("random48x61", "idxs_ds")
+    got = core.upstream_matrix(ids, shape=d8.shape)
+    nup = cs.golden("random48x61", "n_upstream").ravel()
+    d = int(nup.max())
+    want = np.full((ids.size, d), -1, dtype=ids.dtype)
+    fill = np.zeros(ids.size, np.int64)
+    for i0 in range(ids.size):  # the reference's loop: upstream cells land in ascending index
+        ds = ids[i0]
+        if ds != i0 and ds != -1:
+            want[ds, fill[ds]] = i0
+            fill[ds] += 1
+    assert got.dtype == ids.dtype and got.shape == want.shape and np.array_equal(got, want)
+    rhine = cs.case_d8("rhine")
+    flw = pfb.from_array(rhine, ftype="d8", transform=cs.RHINE_TRANSFORM, latlon=True)
+    seq = flw.idxs_seq
+    fn = str(tmp_path / "flw.pkl")
+    flw.dump(fn)
+    flw2 = pfb.FlwdirRaster.load(fn)
+    assert flw2.shape == flw.shape and flw2.ftype == "d8" and flw2.latlon and tuple(flw2.transform) == tuple(flw.transform)
+    assert np.array_equal(flw2.idxs_ds, flw.idxs_ds) and np.array_equal(flw2.idxs_pit, flw.idxs_pit)
+    assert np.array_equal(flw2.idxs_seq, seq) and flw2.nnodes == flw.nnodes
+    assert np.array_equal(flw2.upstream_area(), flw.upstream_area()) and cs.sha(flw2.basins()) == cs.hashes()["rhine"]["basins"]
