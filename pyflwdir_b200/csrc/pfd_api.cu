@@ -167,6 +167,7 @@ extern "C" void pfd_destroy(pfd_handle* h) {
     cudaEventDestroy(h->ev_total[1]);
     cudaEventDestroy(h->ev_copy);
     if (h->h_counters) cudaFreeHost(h->h_counters);
+    if (h->h_gather) cudaFreeHost(h->h_gather);
     cudaStreamSynchronize(h->copy_stream);
     cudaStreamDestroy(h->copy_stream);
     cudaStreamDestroy(h->stream);
@@ -662,18 +663,19 @@ static SlotProtect tiles_protect(const pfd_handle* h, const TileCtx& T, bool fir
     return p;
 }
 
-static int tiles_phase_b(pfd_handle* h, TileCtx& T) {
+// pit_stash != null (fused-parse paths): pit terminals carry the pit's local cell index; the id sits in the basin buffer
+static int tiles_phase_b(pfd_handle* h, TileCtx& T, const uint32_t* pit_stash = nullptr) {
     StageTimer t(h, PFD_STAGE_TILE_B);
     PFD_TRY(slots_solve(h, T.B, T.recv, T.nslots, T.flag, 1, tiles_protect(h, T, false)));
     slots_finalize_kernel<<<grid_for(T.nslots, 256, 2, 148 * 16), 256, 0, h->stream>>>(
-        T.B[0], T.B[1], (const int*)(T.flag + 3), T.term, T.term_h, T.nslots, T.srank, T.sbasin, nullptr, 0, 0);
+        T.B[0], T.B[1], (const int*)(T.flag + 3), T.term, T.term_h, T.nslots, T.srank, T.sbasin, pit_stash, h->ncol, T.ntx, T.nty);
     PFD_LAUNCH_CHECK(h);
     return PFD_OK;
 }
 
 // idxs_dev (optional, fused-parse path): idxs_ds in `idx_dtype` is written by the same kernel
 static int tiles_phase_c(pfd_handle* h, TileCtx& T, int32_t* rank_dev, uint32_t* basin_dev, int32_t* uparea_dev,
-                         void* idxs_dev = nullptr, int idx_dtype = PFD_I32) {
+                         void* idxs_dev = nullptr, int idx_dtype = PFD_I32, long long idx_base = 0) {
     StageTimer t(h, PFD_STAGE_TILE_C);
     const dim3 grid((unsigned)T.ntx, (unsigned)T.nty);
     auto al16 = [](const void* p) { return !p || (uintptr_t)p % 16 == 0; };
@@ -681,6 +683,7 @@ static int tiles_phase_c(pfd_handle* h, TileCtx& T, int32_t* rank_dev, uint32_t*
     A.dir = T.dir, A.nrow = h->nrow, A.ncol = h->ncol, A.ntx = T.ntx, A.nty = T.nty;
     A.loccnt = (const uint2*)h->tile_loc.p, A.inflow = T.B[0].acc, A.s_rank = T.srank, A.s_basin = T.sbasin;
     A.rank_out = rank_dev, A.basin_out = basin_dev, A.uparea_out = uparea_dev, A.idxs_out = idxs_dev;
+    A.idx_base = idx_base;
     A.al4 = (h->ncol % 4 == 0) && ((uintptr_t)T.dir % 4 == 0) && al16(rank_dev) && al16(basin_dev) && al16(uparea_dev) &&
             al16(idxs_dev);
     const size_t smem = sizeof(TileSharedC);
@@ -855,6 +858,102 @@ static void boundary_tables(pfd_handle* h, BoundaryTables& bt) {
     bt.bas = p + 3 * nb;
 }
 
+// Fused row-block path: phase A parses the block itself (the neighbours' edge rows of D8 codes are read for the
+// forced-pit test only), so the separate parse pass over the block disappears, as on a single GPU. Queues: phase A, the pit
+// count + scan, and the copy of {n_valid, n_pits, n_outlets, flags} to the page-locked mirror (event ev_copy).
+static int tiled_fused_begin(pfd_handle* h, const uint8_t* d8_owned, int64_t nrow, int64_t ncol, int halo_top, int halo_bot) {
+    const int64_t n = nrow * ncol;
+    const int64_t npad = (n + PC_CHUNK - 1) / PC_CHUNK * PC_CHUNK;
+    PFD_TRY(pfd_reserve(h, h->dir, (size_t)npad));
+    PFD_TRY(pfd_reserve(h, h->counters, 8 * sizeof(unsigned long long)));
+    if (!h->h_counters) PFD_CUDA(h, cudaHostAlloc((void**)&h->h_counters, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+    PFD_CUDA(h, cudaMemsetAsync(h->counters.p, 0, 8 * sizeof(unsigned long long), h->stream));
+    if (npad > n) PFD_CUDA(h, cudaMemsetAsync((uint8_t*)h->dir.p + n, 0xFF, (size_t)(npad - n), h->stream));
+    unsigned int* flag = reinterpret_cast<unsigned int*>((unsigned long long*)h->counters.p + 3);
+    h->nrow = nrow, h->ncol = ncol, h->n = n;
+    h->dir_off = 0;
+    h->tiled = true;
+    h->parsed = true;
+    h->have_upmask = false;
+    h->mg_halo_top = halo_top, h->mg_halo_bot = halo_bot;
+    TileCtx T;
+    PFD_TRY(tiles_setup(h, T, true));
+    {
+        StageTimer t(h, PFD_STAGE_TILE_A);
+        PFD_CUDA(h, cudaMemsetAsync(T.B[0].acc, 0, T.arr, h->stream));
+        halo_slots_init_kernel<<<grid_for(2 * T.ntx * TL_RING, 256), 256, 0, h->stream>>>(T.B[0], T.term, T.term_h, T.ntx, T.nty);
+        PFD_LAUNCH_CHECK(h);
+        PhaseAArgs A{};
+        A.nrow = nrow, A.ncol = ncol, A.ntx = T.ntx;
+        A.loccnt = (uint2*)h->tile_loc.p, A.W = T.B[0].acc, A.s_nxt = T.B[0].nxt, A.s_rh = T.B[0].rh, A.s_ch = T.B[0].ch;
+        A.s_term = T.term, A.s_term_h = T.term_h;
+        A.d8 = d8_owned, A.dir_out = (uint8_t*)h->dir.p, A.invalid_flag = flag;
+        A.al4 = (ncol % 4 == 0) && ((uintptr_t)d8_owned % 4 == 0);
+        A.halo_top = halo_top, A.halo_bot = halo_bot;
+        tile_phase_a_kernel<TLA_THREADS, TLA_MINBLOCKS, true><<<dim3((unsigned)T.ntx, (unsigned)T.nty), TLA_THREADS, 0, h->stream>>>(A);
+        PFD_LAUNCH_CHECK(h);
+    }
+    const int64_t nblk = npad / PC_CHUNK;
+    {
+        StageTimer t(h, PFD_STAGE_PITS);
+        PFD_TRY(pfd_reserve(h, h->blk_counts, (size_t)nblk * sizeof(uint32_t)));
+        PFD_TRY(pfd_reserve(h, h->blk_offsets, (size_t)(nblk + 1) * sizeof(unsigned long long)));
+        pit_count_kernel<<<(unsigned)nblk, 256, 0, h->stream>>>((const uint8_t*)h->dir.p, (uint32_t*)h->blk_counts.p,
+                                                               (unsigned long long*)h->counters.p);
+        PFD_LAUNCH_CHECK(h);
+        scan_counts_kernel<<<1, 1024, 0, h->stream>>>((const uint32_t*)h->blk_counts.p, nblk, (unsigned long long*)h->blk_offsets.p);
+        PFD_LAUNCH_CHECK(h);
+    }
+    return PFD_OK;
+}
+
+// the pit list of the block once the host knows the count (h->n_pits etc. already set from the counters)
+static int tiled_fused_pits(pfd_handle* h) {
+    const int64_t npad = (h->n + PC_CHUNK - 1) / PC_CHUNK * PC_CHUNK;
+    PFD_TRY(pfd_reserve(h, h->pits, (size_t)std::max<int64_t>(h->n_pits, 1) * sizeof(cell_t)));
+    PFD_TRY(pfd_reserve(h, h->pit_outlet, (size_t)std::max<int64_t>(h->n_pits, 1)));
+    if (h->n_pits > 0) {
+        pit_scatter_kernel<<<(unsigned)(npad / PC_CHUNK), 256, 0, h->stream>>>((const uint8_t*)h->dir.p, (const unsigned long long*)h->blk_offsets.p,
+                                                                             (cell_t*)h->pits.p, (uint8_t*)h->pit_outlet.p);
+        PFD_LAUNCH_CHECK(h);
+    }
+    return PFD_OK;
+}
+
+// basin id (global pit ordinal + 1) of every pit of the block at the pit's own cell of the basin buffer
+static int tiled_fused_stash(pfd_handle* h, uint32_t* basin_dev, int64_t pit_id_offset) {
+    if (basin_dev && h->n_pits > 0) {
+        stash_pit_ids_kernel<<<grid_for(h->n_pits, 256, 1, 148 * 16), 256, 0, h->stream>>>((const cell_t*)h->pits.p, h->n_pits, 0,
+                                                                                          (unsigned long long)pit_id_offset, basin_dev);
+        PFD_LAUNCH_CHECK(h);
+    }
+    return PFD_OK;
+}
+
+// keep the state after phase A (the local reduced graph is solved again once the remote inflow is known), first local solve
+static int tiled_local_solve1(pfd_handle* h, TileCtx& T) {
+    for (int f = 0; f < 4; ++f) {
+        uint32_t* dst = f == 0 ? T.init.nxt : f == 1 ? T.init.rh : f == 2 ? T.init.ch : T.init.acc;
+        uint32_t* src = f == 0 ? T.B[0].nxt : f == 1 ? T.B[0].rh : f == 2 ? T.B[0].ch : T.B[0].acc;
+        PFD_CUDA(h, cudaMemcpyAsync(dst, src, T.arr, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    StageTimer t(h, PFD_STAGE_TILE_B);
+    return slots_solve(h, T.B, T.recv, T.nslots, T.flag, 1, tiles_protect(h, T, true));
+}
+
+// this rank's contribution to the boundary tables
+static int tiled_local_fill(pfd_handle* h, TileCtx& T, int rank, const uint32_t* pit_stash) {
+    const long long nb = boundary_entries(h);
+    PFD_CUDA(h, cudaMemsetAsync(h->btab.p, 0, (size_t)(4 * nb) * sizeof(uint32_t), h->stream));
+    BoundaryTables bt;
+    boundary_tables(h, bt);
+    boundary_fill_kernel<<<grid_for(2 * h->ncol, 256), 256, 0, h->stream>>>(
+        T.B[0], T.B[1], (const int*)(T.flag + 3), T.term, T.term_h, h->nrow, h->ncol, T.ntx, T.nty, rank, h->mg_halo_top,
+        h->mg_halo_bot, bt, pit_stash);
+    PFD_LAUNCH_CHECK(h);
+    return PFD_OK;
+}
+
 extern "C" int pfd_tiled_parse(pfd_handle* h, const uint8_t* d8_block, int64_t nrow_owned, int64_t ncol, int halo_top,
                                int halo_bot, int64_t glob_row0, void* idxs_ds_out, int idx_dtype, int64_t* n_valid,
                                int64_t* n_pits) {
@@ -869,6 +968,27 @@ extern "C" int pfd_tiled_parse(pfd_handle* h, const uint8_t* d8_block, int64_t n
     const int64_t next = (nrow_owned + halo_top + halo_bot) * ncol;
     const void* d8_dev = nullptr;
     PFD_TRY(pfd_stage_in(h, d8_block, (size_t)next, 0, &d8_dev));
+    h->mg_fused = h->use_tiles && h->fuse_parse;
+    if (h->mg_fused) {  // the block is parsed inside phase A; idxs_ds is written by pfd_tiled_finish
+        h->mg_idxs_user = idxs_ds_out, h->mg_idx_dtype = idx_dtype, h->mg_glob_row0 = glob_row0;
+        int rc = tiled_fused_begin(h, (const uint8_t*)d8_dev + (int64_t)halo_top * ncol, nrow_owned, ncol, halo_top, halo_bot);
+        unsigned long long hc[4] = {0, 0, 0, 0};
+        if (rc == PFD_OK && cudaMemcpyAsync(hc, h->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) rc = PFD_ERR_CUDA;
+        if (rc == PFD_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = pfd_fail(h, PFD_ERR_CUDA, "pfd_tiled_parse: phase A failed");
+        if (rc == PFD_OK && (hc[3] & 1ull))
+            rc = pfd_fail(h, PFD_ERR_INVALID_D8, "raster holds values outside the D8 code set {0,1,2,4,8,16,32,64,128,247,255}");
+        if (rc != PFD_OK) {
+            invalidate(h);
+            return rc;
+        }
+        h->n_valid = (int64_t)hc[0], h->n_pits = (int64_t)hc[1], h->n_outlets = (int64_t)hc[2];
+        PFD_TRY(tiled_fused_pits(h));
+        PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+        stage_collect(h);
+        if (n_valid) *n_valid = h->n_valid;
+        if (n_pits) *n_pits = h->n_pits;
+        return PFD_OK;
+    }
     void* idxs_dev = nullptr;
     const size_t ibytes = (size_t)(nrow_owned * ncol) * pfd_dtype_size(idx_dtype);
     if (idxs_ds_out) PFD_TRY(pfd_stage_out(h, idxs_ds_out, ibytes, 1, &idxs_dev));
@@ -899,28 +1019,21 @@ extern "C" int pfd_tiled_local(pfd_handle* h, int rank, int nranks, int64_t pit_
     h->mg_nranks = nranks;
     h->mg_basins = basins_out;
     TileCtx T;
-    PFD_TRY(tiles_setup(h, T, nranks > 1));
-    PFD_TRY(tiles_phase_a(h, T, basins_out, (unsigned long long)pit_id_offset));
+    PFD_TRY(tiles_setup(h, T, h->mg_fused || nranks > 1));
+    if (h->mg_fused) {
+        if (!basins_out) {  // the pit ids travel through a basin buffer: use the handle's own
+            PFD_TRY(pfd_reserve(h, h->basins, (size_t)h->n * sizeof(uint32_t)));
+            h->mg_basins = basins_out = (uint32_t*)h->basins.p;
+        }
+        PFD_TRY(tiled_fused_stash(h, basins_out, pit_id_offset));
+    } else {
+        PFD_TRY(tiles_phase_a(h, T, basins_out, (unsigned long long)pit_id_offset));
+    }
     const long long nb = boundary_entries(h);
     PFD_TRY(pfd_reserve(h, h->btab, (size_t)std::max<long long>(4 * nb, 1) * sizeof(uint32_t)));
     if (nranks > 1) {
-        // keep the state after phase A: the local reduced graph is solved again once the remote inflow is known
-        for (int f = 0; f < 4; ++f) {
-            uint32_t* dst = f == 0 ? T.init.nxt : f == 1 ? T.init.rh : f == 2 ? T.init.ch : T.init.acc;
-            uint32_t* src = f == 0 ? T.B[0].nxt : f == 1 ? T.B[0].rh : f == 2 ? T.B[0].ch : T.B[0].acc;
-            PFD_CUDA(h, cudaMemcpyAsync(dst, src, T.arr, cudaMemcpyDeviceToDevice, h->stream));
-        }
-        {
-            StageTimer t(h, PFD_STAGE_TILE_B);
-            PFD_TRY(slots_solve(h, T.B, T.recv, T.nslots, T.flag, 1, tiles_protect(h, T, true)));
-        }
-        PFD_CUDA(h, cudaMemsetAsync(h->btab.p, 0, (size_t)(4 * nb) * sizeof(uint32_t), h->stream));
-        BoundaryTables bt;
-        boundary_tables(h, bt);
-        boundary_fill_kernel<<<grid_for(2 * h->ncol, 256), 256, 0, h->stream>>>(
-            T.B[0], T.B[1], (const int*)(T.flag + 3), T.term, T.term_h, h->nrow, h->ncol, T.ntx, T.nty, rank, h->mg_halo_top,
-            h->mg_halo_bot, bt);
-        PFD_LAUNCH_CHECK(h);
+        PFD_TRY(tiled_local_solve1(h, T));
+        PFD_TRY(tiled_local_fill(h, T, rank, h->mg_fused ? basins_out : nullptr));
     }
     PFD_CUDA(h, cudaStreamSynchronize(h->stream));
     stage_collect(h);
@@ -930,17 +1043,27 @@ extern "C" int pfd_tiled_local(pfd_handle* h, int rank, int nranks, int64_t pit_
 }
 
 // After the boundary tables were all-reduced: boundary graph, second local solve, per-tile finalisation.
+static int tiled_finish_impl(pfd_handle* h, int32_t* rank_out, int32_t* uparea_out, uint32_t* basins_out);
+
 extern "C" int pfd_tiled_finish(pfd_handle* h, int32_t* rank_out, int32_t* uparea_out, uint32_t* basins_out) {
     PFD_TRY(check_handle(h));
     stage_reset(h);
+    return tiled_finish_impl(h, rank_out, uparea_out, basins_out);
+}
+
+static int tiled_finish_impl(pfd_handle* h, int32_t* rank_out, int32_t* uparea_out, uint32_t* basins_out) {
     if (!h->parsed || h->mg_nranks < 1) return pfd_fail(h, PFD_ERR_STATE, "pfd_tiled_finish: call pfd_tiled_local first");
-    if (basins_out != h->mg_basins) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_tiled_finish: basins_out differs from pfd_tiled_local");
+    if (basins_out != h->mg_basins && !(h->mg_fused && !basins_out))
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_tiled_finish: basins_out differs from pfd_tiled_local");
+    if (h->mg_fused && !basins_out) basins_out = h->mg_basins;  // internal buffer (results not requested)
     const size_t b4 = (size_t)h->n * 4;
-    void *rk = nullptr, *up = nullptr;
+    void *rk = nullptr, *up = nullptr, *ix = nullptr;
     if (rank_out) PFD_TRY(pfd_stage_out(h, rank_out, b4, 2, &rk));
     if (uparea_out) PFD_TRY(pfd_stage_out(h, uparea_out, b4, 3, &up));
+    const size_t ibytes = (size_t)h->n * pfd_dtype_size(h->mg_idx_dtype);
+    if (h->mg_fused && h->mg_idxs_user) PFD_TRY(pfd_stage_out(h, h->mg_idxs_user, ibytes, 1, &ix));
     TileCtx T;
-    PFD_TRY(tiles_setup(h, T, h->mg_nranks > 1));
+    PFD_TRY(tiles_setup(h, T, h->mg_fused || h->mg_nranks > 1));
     if (h->mg_nranks > 1) {
         const long long nb = boundary_entries(h);
         // boundary graph: 12 node arrays + results, solved redundantly on every rank
@@ -980,8 +1103,14 @@ extern "C" int pfd_tiled_finish(pfd_handle* h, int32_t* rank_out, int32_t* upare
             T.term, T.term_h);
         PFD_LAUNCH_CHECK(h);
     }
-    PFD_TRY(tiles_phase_b(h, T));
-    PFD_TRY(tiles_phase_c(h, T, (int32_t*)rk, basins_out, (int32_t*)up));
+    if (h->mg_fused) {
+        PFD_TRY(tiles_phase_b(h, T, basins_out));
+        PFD_TRY(tiles_phase_c(h, T, (int32_t*)rk, basins_out, (int32_t*)up, ix, h->mg_idx_dtype, (long long)h->mg_glob_row0 * h->ncol));
+        if (ix) PFD_TRY(pfd_finish_out(h, h->mg_idxs_user, ix, ibytes));
+    } else {
+        PFD_TRY(tiles_phase_b(h, T));
+        PFD_TRY(tiles_phase_c(h, T, (int32_t*)rk, basins_out, (int32_t*)up));
+    }
     if (rank_out) PFD_TRY(pfd_finish_out(h, rank_out, rk, b4));
     if (uparea_out) PFD_TRY(pfd_finish_out(h, uparea_out, up, b4));
     PFD_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -1019,6 +1148,17 @@ extern "C" int pfd_comm_init(pfd_handle* h, int rank, int nranks, const void* un
     h->nccl_comm = (void*)comm;
     h->mg_rank = rank;
     h->mg_nranks = nranks;
+    // buffers of exchange #1 are allocated now, so that a rank that fails later can still tell the others
+    PFD_TRY(pfd_reserve(h, h->counters, 8 * sizeof(unsigned long long)));
+    PFD_TRY(pfd_reserve(h, h->mg_counts, (size_t)(4 * nranks + 4) * sizeof(unsigned long long)));
+    if (h->h_gather && h->h_gather_ranks < nranks) {
+        cudaFreeHost(h->h_gather);
+        h->h_gather = nullptr;
+    }
+    if (!h->h_gather) {
+        PFD_CUDA(h, cudaHostAlloc((void**)&h->h_gather, (size_t)(4 * nranks) * sizeof(unsigned long long), cudaHostAllocDefault));
+        h->h_gather_ranks = nranks;
+    }
     return PFD_OK;
 }
 
@@ -1043,7 +1183,7 @@ extern "C" int pfd_comm_barrier(pfd_handle* h) {
 
 // parse + order-free solve of one row block, exchanges over NCCL. Outputs (device or host, any may be NULL except
 // that basins_out, when given, must be a device buffer) hold the nrow_owned rows of this rank.
-extern "C" int pfd_d8_flow_all_tiled(pfd_handle* h, const uint8_t* d8_block, int64_t nrow_owned, int64_t ncol, int halo_top,
+static int flow_all_tiled_unfused(pfd_handle* h, const uint8_t* d8_block, int64_t nrow_owned, int64_t ncol, int halo_top,
                                      int halo_bot, int64_t glob_row0, void* idxs_ds_out, int idx_dtype, int32_t* rank_out,
                                      int32_t* uparea_out, uint32_t* basins_out, int64_t* n_valid, int64_t* n_pits_global) {
     PFD_TRY(check_handle(h));
@@ -1082,6 +1222,144 @@ extern "C" int pfd_d8_flow_all_tiled(pfd_handle* h, const uint8_t* d8_block, int
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, h->ev_total[0], h->ev_total[1]) == cudaSuccess) h->stage_ms[PFD_STAGE_TOTAL] = ms;
     if (n_valid) *n_valid = nv;
+    if (n_pits_global) *n_pits_global = total;
+    return PFD_OK;
+}
+
+// A rank that fails after exchange #1 tears the communicator down, so that its peers' collectives return an error
+// instead of waiting forever.
+static int tiled_abort(pfd_handle* h, int rc) {
+    if (rc != PFD_OK && h->nccl_comm && h->mg_nranks > 1) {
+        const std::string msg = h->err;
+        ncclCommAbort((ncclComm_t)h->nccl_comm);
+        h->nccl_comm = nullptr;
+        h->err = msg + " (communicator aborted)";
+    }
+    return rc;
+}
+
+// parse + order-free solve of one row block, exchanges over NCCL. Outputs (device or host, any may be NULL) hold the
+// nrow_owned rows of this rank. ONE program with the single-GPU step: the block is parsed inside phase A; the host
+// waits once, for the pit counts, while the first local solve keeps the GPU busy.
+//   exchange #1  all-gather of {n_valid, n_pits, n_outlets, flags} per rank -> global basin-id offset of the block, and
+//                ERROR AGREEMENT: a rank whose block is invalid (or that failed locally) says so here, and every rank
+//                returns an error instead of entering exchange #2;
+//   exchange #2  ONE all-reduce (uint32 sum) of the boundary tables.
+extern "C" int pfd_d8_flow_all_tiled(pfd_handle* h, const uint8_t* d8_block, int64_t nrow_owned, int64_t ncol, int halo_top,
+                                     int halo_bot, int64_t glob_row0, void* idxs_ds_out, int idx_dtype, int32_t* rank_out,
+                                     int32_t* uparea_out, uint32_t* basins_out, int64_t* n_valid, int64_t* n_pits_global) {
+    PFD_TRY(check_handle(h));
+    if (!(h->use_tiles && h->fuse_parse))
+        return flow_all_tiled_unfused(h, d8_block, nrow_owned, ncol, halo_top, halo_bot, glob_row0, idxs_ds_out, idx_dtype, rank_out,
+                                      uparea_out, basins_out, n_valid, n_pits_global);
+    const int nranks = h->nccl_comm ? h->mg_nranks : 1, rank = h->nccl_comm ? h->mg_rank : 0;
+    stage_reset(h);
+    cudaEventRecord(h->ev_total[0], h->stream);
+    // ---- local part 1 (any failure is carried into exchange #1, not returned early: the peers must not be left waiting)
+    int rc = PFD_OK;
+    const void* d8_dev = nullptr;
+    if (!d8_block) rc = pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_d8_flow_all_tiled: d8_block is null");
+    else if ((halo_top | halo_bot) & ~1) rc = pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_d8_flow_all_tiled: halo flags must be 0 or 1");
+    else if (idxs_ds_out && idx_dtype != PFD_I32 && idx_dtype != PFD_U32 && idx_dtype != PFD_I64)
+        rc = pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_d8_flow_all_tiled: idx_dtype must be int32, uint32 or int64");
+    else if (nranks > 1 && rank < nranks - 1 && (nrow_owned % TL_H) != 0)
+        rc = pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_d8_flow_all_tiled: row blocks (except the last) must be multiples of 64 rows");
+    else if (basins_out && !pfd_is_device_ptr(basins_out))
+        rc = pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_d8_flow_all_tiled: basins_out must be a device buffer (it carries the pit ids)");
+    if (rc == PFD_OK) rc = check_shape(h, nrow_owned + 2, ncol, "pfd_d8_flow_all_tiled");
+    invalidate(h);
+    if (rc == PFD_OK) rc = pfd_stage_in(h, d8_block, (size_t)((nrow_owned + halo_top + halo_bot) * ncol), 0, &d8_dev);
+    h->mg_fused = true;
+    h->mg_idxs_user = idxs_ds_out, h->mg_idx_dtype = idx_dtype, h->mg_glob_row0 = glob_row0;
+    h->mg_rank = rank, h->mg_nranks = nranks;
+    if (rc == PFD_OK && !basins_out) {
+        rc = pfd_reserve(h, h->basins, (size_t)(nrow_owned * ncol) * sizeof(uint32_t));
+        basins_out = (uint32_t*)h->basins.p;
+    }
+    h->mg_basins = basins_out;
+    if (rc == PFD_OK) rc = tiled_fused_begin(h, (const uint8_t*)d8_dev + (int64_t)halo_top * ncol, nrow_owned, ncol, halo_top, halo_bot);
+    // ---- exchange #1
+    unsigned long long mine[4] = {0, 0, 0, 0};
+    unsigned long long* all = mine;
+    if (nranks > 1) {
+        unsigned long long* d = (unsigned long long*)h->mg_counts.p;  // [4 * nranks] gathered, [4] send slot behind
+        unsigned long long* send = d + 4 * nranks;
+        if (rc != PFD_OK) {  // failure marker in the flags word
+            const unsigned long long fail[4] = {0, 0, 0, (1ull << 32) | (unsigned long long)rc};
+            cudaMemcpyAsync(send, fail, sizeof(fail), cudaMemcpyHostToDevice, h->stream);
+        } else {
+            cudaMemcpyAsync(send, h->counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, h->stream);
+        }
+        if (ncclAllGather(send, d, 4, ncclUint64, (ncclComm_t)h->nccl_comm, h->stream) != ncclSuccess)
+            return tiled_abort(h, pfd_fail(h, PFD_ERR_NCCL, "pfd_d8_flow_all_tiled: ncclAllGather failed"));
+        cudaMemcpyAsync(h->h_gather, d, (size_t)(4 * nranks) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream);
+        all = h->h_gather;
+    } else if (rc == PFD_OK) {
+        cudaMemcpyAsync(h->h_counters, h->counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream);
+        all = h->h_counters;
+    }
+    cudaEventRecord(h->ev_copy, h->stream);
+    // the first local solve does not need the pit numbering: it keeps the GPU busy while the host waits for the counts
+    TileCtx T;
+    int rc_solve = PFD_OK;
+    if (rc == PFD_OK) {
+        rc_solve = tiles_setup(h, T, true);
+        if (rc_solve == PFD_OK) rc_solve = pfd_reserve(h, h->btab, (size_t)std::max<long long>(4 * boundary_entries(h), 1) * sizeof(uint32_t));
+        if (rc_solve == PFD_OK && nranks > 1) rc_solve = tiled_local_solve1(h, T);
+    }
+    if (cudaEventSynchronize(h->ev_copy) != cudaSuccess) return tiled_abort(h, pfd_fail(h, PFD_ERR_CUDA, "pfd_d8_flow_all_tiled: exchange #1 failed"));
+    // ---- agreement
+    int bad_rank = -1;
+    bool invalid_codes = false;
+    long long offset = 0, total = 0;
+    for (int g = 0; g < nranks; ++g) {
+        const unsigned long long f = (nranks > 1 || rc == PFD_OK) ? all[4 * g + 3] : ((1ull << 32) | (unsigned long long)rc);
+        if ((f >> 32) && bad_rank < 0) bad_rank = g;
+        if (f & 1ull) {
+            invalid_codes = true;
+            if (bad_rank < 0) bad_rank = g;
+        }
+        if (g < rank) offset += (long long)all[4 * g + 1];
+        total += (long long)all[4 * g + 1];
+    }
+    if (bad_rank >= 0 || total >= (1ll << 31) || total == 0) {
+        cudaStreamSynchronize(h->stream);
+        cudaGetLastError();
+        const std::string own = h->err;
+        invalidate(h);
+        if (rc != PFD_OK) {
+            h->err = own;
+            return rc;
+        }
+        if (bad_rank == rank && invalid_codes)
+            return pfd_fail(h, PFD_ERR_INVALID_D8, "raster holds values outside the D8 code set {0,1,2,4,8,16,32,64,128,247,255}");
+        if (bad_rank >= 0 && invalid_codes)
+            return pfd_fail(h, PFD_ERR_INVALID_D8, "the row block of rank " + std::to_string(bad_rank) + " holds values outside the D8 code set");
+        if (bad_rank >= 0)
+            return pfd_fail(h, PFD_ERR_NCCL, "rank " + std::to_string(bad_rank) + " failed before exchange #1 (status " +
+                                                 std::to_string((int)(all[4 * bad_rank + 3] & 0xFFFFFFFFull)) + ")");
+        if (total == 0) return pfd_fail(h, PFD_ERR_NO_PITS, "Invalid FlwdirRaster: no pits found");
+        return pfd_fail(h, PFD_ERR_UNSUPPORTED, "pfd_d8_flow_all_tiled: more than 2^31 pits");
+    }
+    h->n_valid = (int64_t)all[4 * rank + 0], h->n_pits = (int64_t)all[4 * rank + 1], h->n_outlets = (int64_t)all[4 * rank + 2];
+    // ---- local part 2, exchange #2, finish: a failure from here on aborts the communicator
+    rc = rc_solve;
+    if (rc == PFD_OK) rc = tiled_fused_pits(h);
+    if (rc == PFD_OK) rc = tiled_fused_stash(h, basins_out, offset);
+    if (rc == PFD_OK && nranks > 1) rc = tiled_local_fill(h, T, rank, basins_out);
+    if (rc != PFD_OK) return tiled_abort(h, rc);
+    if (nranks > 1) {
+        const long long nb = boundary_entries(h);
+        if (nb > 0 && ncclAllReduce(h->btab.p, h->btab.p, (size_t)(4 * nb), ncclUint32, ncclSum, (ncclComm_t)h->nccl_comm, h->stream) != ncclSuccess)
+            return tiled_abort(h, pfd_fail(h, PFD_ERR_NCCL, "pfd_d8_flow_all_tiled: ncclAllReduce failed"));
+    }
+    rc = tiled_finish_impl(h, rank_out, uparea_out, basins_out == (uint32_t*)h->basins.p ? nullptr : basins_out);
+    if (rc != PFD_OK) return tiled_abort(h, rc);
+    cudaEventRecord(h->ev_total[1], h->stream);
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev_total[0], h->ev_total[1]) == cudaSuccess) h->stage_ms[PFD_STAGE_TOTAL] = ms;
+    if (n_valid) *n_valid = h->n_valid;
     if (n_pits_global) *n_pits_global = total;
     return PFD_OK;
 }

@@ -187,6 +187,12 @@ struct pfd_handle {
     bool tiled = false;        // parsed as a row block of a larger raster (only the tiled entry points apply)
     int mg_rank = 0, mg_nranks = 0, mg_halo_top = 0, mg_halo_bot = 0;
     uint32_t* mg_basins = nullptr;
+    bool mg_fused = false;       // row block parsed inside phase A (fused): idxs_ds is written by pfd_tiled_finish
+    void* mg_idxs_user = nullptr; // caller's idxs_ds buffer of the fused row-block path (host or device)
+    int mg_idx_dtype = 0;
+    int64_t mg_glob_row0 = 0;
+    unsigned long long* h_gather = nullptr;  // page-locked: per-rank {n_valid, n_pits, n_outlets, flags} of exchange #1
+    int h_gather_ranks = 0;
     void* nccl_comm = nullptr;
     DevBuf sub_idxs;           // cell_t [n_sub] outlets of the last pfd_subbasins_streamorder call
     int64_t n_sub = 0;

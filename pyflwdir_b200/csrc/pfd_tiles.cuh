@@ -233,9 +233,11 @@ struct TileCodes {
     __align__(16) uint8_t c[(TL_H + 2) * TLF_STRIDE];
 };
 
+// row_lo / row_hi: rows that may be READ: [0, nrow) for a whole raster; a row block of a larger raster also has the
+// neighbour's edge row at -1 / nrow (they only feed the forced-pit test of the block's edge rows, core_d8.py:58-61)
 template <int THREADS>
 __device__ __forceinline__ void tl_stage_codes(TileCodes& sc, const uint8_t* __restrict__ d8, long long nrow, long long ncol,
-                                               long long r0, long long c0, bool al4) {
+                                               long long r0, long long c0, bool al4, long long row_lo, long long row_hi) {
     // interior: 64 rows x 16 words
     for (int w = threadIdx.x; w < TL_H * (TL_W / 4); w += THREADS) {
         const int row = w >> 4, wx = w & 15;
@@ -271,7 +273,7 @@ __device__ __forceinline__ void tl_stage_codes(TileCodes& sc, const uint8_t* __r
         }
         const long long r = r0 + sy - 1, c = c0 + sx;
         uint8_t v = 247;
-        if (r >= 0 && r < nrow && c >= 0 && c < ncol) v = __ldg(d8 + r * ncol + c);
+        if (r >= row_lo && r < row_hi && c >= 0 && c < ncol) v = __ldg(d8 + r * ncol + c);
         sc.c[sy * TLF_STRIDE + TLF_X0 + sx] = v;
     }
 }
@@ -305,6 +307,7 @@ struct PhaseAArgs {
     uint8_t* dir_out;
     unsigned int* invalid_flag;
     int al4;
+    int halo_top, halo_bot;  // FUSED, row block of a larger raster: d8 has the neighbour's edge row above / below
 };
 
 template <bool FUSED>
@@ -430,7 +433,8 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) tile_phase_a_kernel(PhaseA
     __shared__ __align__(16) TileShared s;
     __shared__ TileCodes sc;  // FUSED only (the compiler drops it otherwise)
     if (FUSED) {
-        tl_stage_codes<THREADS>(sc, A.d8, A.nrow, A.ncol, (long long)blockIdx.y * TL_H, (long long)blockIdx.x * TL_W, A.al4 != 0);
+        tl_stage_codes<THREADS>(sc, A.d8, A.nrow, A.ncol, (long long)blockIdx.y * TL_H, (long long)blockIdx.x * TL_W, A.al4 != 0,
+                                -(long long)A.halo_top, A.nrow + A.halo_bot);
         __syncthreads();
     }
     tl_phase_a_tile<FUSED>(s, sc, A, blockIdx.y, blockIdx.x);
@@ -564,7 +568,8 @@ __global__ void __launch_bounds__(256) slots_finalize_kernel(SlotBuf b0, SlotBuf
                                                              const uint32_t* __restrict__ term,
                                                              const uint32_t* __restrict__ term_h, long long nslots,
                                                              int32_t* __restrict__ rank, uint32_t* __restrict__ basin,
-                                                             const uint32_t* __restrict__ pit_stash, long long ncol, long long ntx) {
+                                                             const uint32_t* __restrict__ pit_stash, long long ncol, long long ntx,
+                                                             long long nty = (1ll << 40)) {
     const SlotBuf cur = (*rounds & 1) ? b1 : b0;
     for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < nslots; s += (long long)gridDim.x * blockDim.x) {
         const uint32_t last = cur.nxt[s];
@@ -577,7 +582,9 @@ __global__ void __launch_bounds__(256) slots_finalize_kernel(SlotBuf b0, SlotBuf
                 const long long tl = (long long)(last / TL_RING);  // slot-array tile index (halo tile row included)
                 const long long ty = tl / ntx - 1, tx = tl % ntx;
                 const uint32_t li = t & (uint32_t)(TL_CELLS - 1);
-                b = __ldg(pit_stash + (ty * TL_H + (li >> 6)) * ncol + tx * TL_W + (li & (TL_W - 1)));
+                // halo slots of a row block (tile rows -1 / nty) are pit-like terminals that carry the basin id itself
+                if (ty < 0 || ty >= nty) b = (t & ~TERM_PIT) + 1u;
+                else b = __ldg(pit_stash + (ty * TL_H + (li >> 6)) * ncol + tx * TL_W + (li & (TL_W - 1)));
             } else {
                 b = (t & ~TERM_PIT) + 1u;
             }
@@ -618,6 +625,7 @@ struct PhaseCArgs {
     uint32_t* basin_out;
     int32_t* uparea_out;
     void* idxs_out;
+    long long idx_base;  // global linear index of the first owned cell (row block of a larger raster), else 0
     int al4;
 };
 
@@ -804,7 +812,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) tile_phase_c_kernel(PhaseC
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint32_t d = tl_dir_of(dirw, j);
-                const long long g = g0 + j;
+                const long long g = A.idx_base + g0 + j;
                 ds[j] = (d < 8u) ? g + pfd_slot_off((int)d, ncol) : ((d == PFD_DIR_NODATA) ? -1ll : g);
             }
             if (IDXMODE == 1) {
@@ -866,7 +874,10 @@ __global__ void halo_slots_init_kernel(SlotBuf b0, uint32_t* __restrict__ term, 
 // side_sel 0: my top boundary (boundary rank-1), 1: my bottom boundary (boundary rank)
 __global__ void boundary_fill_kernel(SlotBuf b0, SlotBuf b1, const int* __restrict__ rounds, const uint32_t* __restrict__ term,
                                      const uint32_t* __restrict__ term_h, long long nrow, long long ncol, long long ntx,
-                                     long long nty, int rank, int has_top, int has_bot, BoundaryTables T) {
+                                     long long nty, int rank, int has_top, int has_bot, BoundaryTables T,
+                                     const uint32_t* __restrict__ pit_stash) {
+    // pit_stash != null (fused-parse path): pit terminals hold TERM_PIT | local cell index inside the tile of slot `last`;
+    // the basin id was stashed at the pit's own cell of the basin buffer (see slots_finalize_kernel)
     const SlotBuf cur = (*rounds & 1) ? b1 : b0;
     const long long per_row = ntx * TL_RING;
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < 2 * ncol; k += (long long)gridDim.x * blockDim.x) {
@@ -903,7 +914,14 @@ __global__ void boundary_fill_kernel(SlotBuf b0, SlotBuf b1, const int* __restri
                 } else if (t & TERM_PIT) {
                     nx = 1;
                     hop = cur.ch[s] + term_h[last];
-                    bas = (t & ~TERM_PIT) + 1u;
+                    if (pit_stash) {
+                        const long long tl = (long long)(last / TL_RING);
+                        const long long ty = tl / ntx - 1, tx = tl % ntx;
+                        const uint32_t li = t & (uint32_t)(TL_CELLS - 1);
+                        bas = __ldg(pit_stash + (ty * TL_H + (li >> 6)) * ncol + tx * TL_W + (li & (TL_W - 1)));
+                    } else {
+                        bas = (t & ~TERM_PIT) + 1u;
+                    }
                 }
             }
         }

@@ -45,6 +45,11 @@ class RowBlockSolver:
         self._h = h
         self._dev_bufs = []
         self.nrow = self.ncol = 0
+        import os
+        # PFD_FUSE_PARSE=0: separate parse pass over the block instead of parsing inside phase A (identical results;
+        # used by the parity tests). In the fused path idxs_ds is written by finish() / flow_all().
+        if os.environ.get("PFD_FUSE_PARSE", "1") == "0":
+            self._ck(self._l.pfd_set_option(self._h, b"fuse_parse", 0))
 
     def _ck(self, rc):
         _lib.check(rc, self._h)

@@ -43,5 +43,24 @@ if rank == 0:
     assert np.array_equal(np.concatenate([p["bas"] for p in parts]).ravel(), oracle.basins.basins(ids_o, pits_o, seq))
     print("NCCL_TILED_OK", world, flush=True)
 dist.barrier()
+# error agreement: ONE rank's block holds an illegal code -> every rank returns an error instead of hanging in a collective
+bad = d8.copy()
+rb0, rb1 = blocks[world - 1]
+bad[(rb0 + rb1) // 2, 7] = 3
+blk, ht, hb = tiled.block_with_halo(bad, r0, r1)
+try:
+    solver.flow_all(blk, ht, hb, r0, _get_idxs_dtype(d8.size))
+    raised = None
+except ValueError as err:
+    raised = str(err)
+oks = [None] * world
+dist.all_gather_object(oks, raised)
+if rank == 0:
+    assert all(o is not None and "D8 code set" in o for o in oks), oks
+    print("NCCL_ERROR_AGREEMENT_OK", world, flush=True)
+# ... and the communicator is still usable afterwards
+ids2, rk2, upa2, bas2, _ = solver.flow_all(*tiled.block_with_halo(d8, r0, r1), r0, _get_idxs_dtype(d8.size))
+assert np.array_equal(ids2, ids) and np.array_equal(rk2, rk) and np.array_equal(upa2, upa) and np.array_equal(bas2, bas)
+dist.barrier()
 solver.close()
 dist.destroy_process_group()

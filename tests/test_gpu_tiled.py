@@ -10,6 +10,14 @@ import oracle
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["fused", "separate-parse"], autouse=True)
+def parse_mode(request, monkeypatch):
+    """Both row-block paths: the block parsed inside phase A (default, the same program as the single-GPU step) and
+    the separate parse pass."""
+    monkeypatch.setenv("PFD_FUSE_PARSE", "1" if request.param == "fused" else "0")
+    return request.param
+
+
 def _oracle_whole(d8):
     dtype = oracle.get_idxs_dtype(d8.size)
     ids, pits, _ = oracle.core_d8.from_array(d8, dtype=dtype)
