@@ -930,13 +930,9 @@ static int tiled_fused_stash(pfd_handle* h, uint32_t* basin_dev, int64_t pit_id_
     return PFD_OK;
 }
 
-// keep the state after phase A (the local reduced graph is solved again once the remote inflow is known), first local solve
+// keep the one-hop links of phase A (the remote inflow is added along them later); THE solve of the local reduced graph
 static int tiled_local_solve1(pfd_handle* h, TileCtx& T) {
-    for (int f = 0; f < 4; ++f) {
-        uint32_t* dst = f == 0 ? T.init.nxt : f == 1 ? T.init.rh : f == 2 ? T.init.ch : T.init.acc;
-        uint32_t* src = f == 0 ? T.B[0].nxt : f == 1 ? T.B[0].rh : f == 2 ? T.B[0].ch : T.B[0].acc;
-        PFD_CUDA(h, cudaMemcpyAsync(dst, src, T.arr, cudaMemcpyDeviceToDevice, h->stream));
-    }
+    PFD_CUDA(h, cudaMemcpyAsync(T.init.nxt, T.B[0].nxt, T.arr, cudaMemcpyDeviceToDevice, h->stream));
     StageTimer t(h, PFD_STAGE_TILE_B);
     return slots_solve(h, T.B, T.recv, T.nslots, T.flag, 1, tiles_protect(h, T, true));
 }
@@ -1042,7 +1038,7 @@ extern "C" int pfd_tiled_local(pfd_handle* h, int rank, int nranks, int64_t pit_
     return PFD_OK;
 }
 
-// After the boundary tables were all-reduced: boundary graph, second local solve, per-tile finalisation.
+// After the boundary tables were all-reduced: boundary graph, remote inflow along the local chains, per-tile finalisation.
 static int tiled_finish_impl(pfd_handle* h, int32_t* rank_out, int32_t* uparea_out, uint32_t* basins_out);
 
 extern "C" int pfd_tiled_finish(pfd_handle* h, int32_t* rank_out, int32_t* uparea_out, uint32_t* basins_out) {
@@ -1092,23 +1088,28 @@ static int tiled_finish_impl(pfd_handle* h, int32_t* rank_out, int32_t* uparea_o
         slots_finalize_kernel<<<grid_for(nb, 256), 256, 0, h->stream>>>(G[0], G[1], (const int*)(gflag + 3), gterm, gterm_h, nb,
                                                                         grank, gbasin, nullptr, 0, 0);
         PFD_LAUNCH_CHECK(h);
-        // restore the local reduced graph, add the remote inflow, make the halo slots terminals, solve again
-        for (int f = 0; f < 4; ++f) {
-            uint32_t* src = f == 0 ? T.init.nxt : f == 1 ? T.init.rh : f == 2 ? T.init.ch : T.init.acc;
-            uint32_t* dst = f == 0 ? T.B[0].nxt : f == 1 ? T.B[0].rh : f == 2 ? T.B[0].ch : T.B[0].acc;
-            PFD_CUDA(h, cudaMemcpyAsync(dst, src, T.arr, cudaMemcpyDeviceToDevice, h->stream));
-        }
+        // No second solve of the local reduced graph: the first one already left, for every ring node, its local
+        // terminal, the hops to it and the local inflow. The halo slots now become pit-like terminals carrying (rank,
+        // basin) of the neighbour's entry -- picked up by the finalisation below --, and the remote inflow of my own
+        // boundary entries is added along their local chains (one-hop links saved before the first solve).
         boundary_writeback_kernel<<<grid_for(2 * h->ncol, 256), 256, 0, h->stream>>>(
             grank, gbasin, G[0].acc, h->nrow, h->ncol, T.ntx, h->mg_rank, h->mg_halo_top, h->mg_halo_bot, T.B[0].acc,
-            T.term, T.term_h);
+            T.term, T.term_h, T.init.nxt, T.B[0], T.B[1], (const int*)(T.flag + 3), T.nslots);
         PFD_LAUNCH_CHECK(h);
+        {
+            StageTimer t(h, PFD_STAGE_TILE_B);
+            slots_finalize_kernel<<<grid_for(T.nslots, 256, 2, 148 * 16), 256, 0, h->stream>>>(
+                T.B[0], T.B[1], (const int*)(T.flag + 3), T.term, T.term_h, T.nslots, T.srank, T.sbasin,
+                h->mg_fused ? basins_out : nullptr, h->ncol, T.ntx, T.nty);
+            PFD_LAUNCH_CHECK(h);
+        }
     }
     if (h->mg_fused) {
-        PFD_TRY(tiles_phase_b(h, T, basins_out));
+        if (h->mg_nranks == 1) PFD_TRY(tiles_phase_b(h, T, basins_out));  // (several ranks: solved in pfd_tiled_local)
         PFD_TRY(tiles_phase_c(h, T, (int32_t*)rk, basins_out, (int32_t*)up, ix, h->mg_idx_dtype, (long long)h->mg_glob_row0 * h->ncol));
         if (ix) PFD_TRY(pfd_finish_out(h, h->mg_idxs_user, ix, ibytes));
     } else {
-        PFD_TRY(tiles_phase_b(h, T));
+        if (h->mg_nranks == 1) PFD_TRY(tiles_phase_b(h, T));
         PFD_TRY(tiles_phase_c(h, T, (int32_t*)rk, basins_out, (int32_t*)up));
     }
     if (rank_out) PFD_TRY(pfd_finish_out(h, rank_out, rk, b4));

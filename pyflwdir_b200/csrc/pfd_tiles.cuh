@@ -954,11 +954,14 @@ __global__ void boundary_build_kernel(BoundaryTables T, long long nb, SlotBuf b0
 }
 
 // boundary solution -> my halo slots become pit-like terminals carrying (rank, basin) of the neighbour's entry;
-// my own boundary entries receive the total remote inflow X on top of their local weight
+// my own boundary entries receive the total remote inflow X on top of the local inflow of the first solve
 __global__ void boundary_writeback_kernel(const int32_t* __restrict__ brank, const uint32_t* __restrict__ bbasin,
                                           const uint32_t* __restrict__ bx, long long nrow, long long ncol, long long ntx,
                                           int rank, int has_top, int has_bot, uint32_t* __restrict__ w,
-                                          uint32_t* __restrict__ term, uint32_t* __restrict__ term_h) {
+                                          uint32_t* __restrict__ term, uint32_t* __restrict__ term_h,
+                                          const uint32_t* __restrict__ nxt0, SlotBuf b0, SlotBuf b1,
+                                          const int* __restrict__ rounds, long long nslots) {
+    const SlotBuf cur = (*rounds & 1) ? b1 : b0;
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < 2 * ncol; k += (long long)gridDim.x * blockDim.x) {
         const int bottom = k >= ncol;
         const long long c = bottom ? k - ncol : k;
@@ -970,7 +973,23 @@ __global__ void boundary_writeback_kernel(const int32_t* __restrict__ brank, con
         const int32_t rk = brank[nb_b];
         term[hs] = (rk >= 0) ? (TERM_PIT | (bbasin[nb_b] - 1u)) : SLOT_INVALID;
         term_h[hs] = (rk >= 0) ? (uint32_t)rk : 0u;
-        const uint32_t s = tl_slot_of(bottom ? nrow - 1 : 0, c, ntx);
-        if (bx[own_b]) atomicAdd(w + s, bx[own_b]);  // a 1-row block has the same slot on both of its boundaries
+        // The remote inflow X of my own boundary entry travels down the entry's local chain: every ring node on it gets
+        // + X (what a second solve of the local reduced graph would deliver). nxt0 = the one-hop links as phase A left
+        // them; chains end in a terminal (pit node or halo slot: next == itself).
+        const uint32_t x = bx[own_b];
+        if (x) {
+            uint32_t s = tl_slot_of(bottom ? nrow - 1 : 0, c, ntx);
+            // only chains that END (the first solve left their terminal in cur.nxt): a chain that runs into a loop across
+            // tiles has no end, and its cells drain to no pit anyway (upstream area 1, like every cell outside `seq`)
+            const uint32_t last = cur.nxt[s];
+            if (cur.nxt[last] == last) {
+                for (long long guard = 0; guard < nslots; ++guard) {
+                    atomicAdd(w + s, x);
+                    const uint32_t n = nxt0[s];
+                    if (n == s) break;
+                    s = n;
+                }
+            }
+        }
     }
 }
