@@ -1,11 +1,37 @@
-"""Region (label raster) post-processing on the GPU; mirrors /root/reference/pyflwdir/regions.py (region_slices :58-86,
-region_bounds :89-129, region_outlets :132-163)."""
+"""Region (label raster) post-processing; mirrors /root/reference/pyflwdir/regions.py (region_sum :16-32, region_area :35-55,
+region_slices :58-86, region_bounds :89-129, region_outlets :132-163). Slices / bounds / outlets run on the GPU; the two
+label statistics are host-side numpy like the reference's scipy.ndimage calls (float64 sums in raster order)."""
 import numpy as np
 
 from . import _device, _functional
 from . import gis_utils as gis
 
-__all__ = ["region_bounds", "region_slices", "region_outlets"]
+__all__ = ["region_bounds", "region_slices", "region_outlets", "region_sum", "region_area"]
+
+
+def region_sum(data, regions):
+    """Returns the sum of values in `data` for each unique label (> 0) in `regions` -> (labels, float64 sums).
+    Same accumulation as scipy.ndimage.sum(data, regions, index=labels): float64, cells added in raster order."""
+    data, regions = np.asarray(data), np.asarray(regions)
+    if data.shape != regions.shape:
+        raise ValueError("input and labels must have the same shape")
+    sel = regions > 0
+    lbs, inv = np.unique(regions[sel], return_inverse=True)
+    sums = np.bincount(inv.ravel(), weights=data[sel].astype(np.float64, copy=False), minlength=lbs.size)
+    return lbs, sums
+
+
+def region_area(regions, transform=gis.IDENTITY, latlon=False):
+    """Returns the area [m2] for each unique label in `regions` -> (labels, areas)"""
+    regions = np.asarray(regions)
+    area = gis.area_grid(transform=transform, shape=regions.shape, latlon=latlon)
+    return region_sum(area, regions)
+
+
+def region_dissolve(regions, labels=None, idxs=None, transform=gis.IDENTITY, latlon=False, **kwargs):
+    """Out of scope (regions post-processing built on gis_utils.spread2d, a priority-queue spread)."""
+    raise NotImplementedError("region_dissolve needs gis_utils.spread2d, which is outside the D8 hot path that pyflwdir_b200 "
+                              "accelerates; use the reference on the label raster")
 
 
 def region_slices(regions, device=0):

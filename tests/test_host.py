@@ -241,3 +241,24 @@ def test_out_of_scope_entry_points_raise():
                      (dem.slope, (np.zeros((4, 4), np.float32),))):
         with pytest.raises(NotImplementedError, match="outside the D8 hot path"):
             fn(*args)
+
+
+def test_region_sum_and_area_match_scipy():
+    """regions.region_sum / region_area (regions.py:16-55): same labels and bit-identical float64 sums as the
+    reference's scipy.ndimage.sum call."""
+    from scipy import ndimage
+
+    from pyflwdir_b200 import gis_utils as gis
+    from pyflwdir_b200 import regions
+
+    rng = np.random.default_rng(3)
+    reg = rng.integers(0, 40, size=(120, 77)).astype(np.int32) * (rng.random((120, 77)) > 0.2)
+    for data in (rng.random((120, 77)), rng.random((120, 77)).astype(np.float32) * 1e3, rng.integers(-5, 99, (120, 77))):
+        lbs, sums = regions.region_sum(data, reg)
+        want_lbs = np.unique(reg[reg > 0])
+        assert np.array_equal(lbs, want_lbs) and np.array_equal(sums, ndimage.sum(data, reg, index=want_lbs))
+    t = gis.Affine(0.01, 0.0, 4.0, 0.0, -0.01, 52.0)
+    lbs, area = regions.region_area(reg, transform=t, latlon=True)
+    assert np.array_equal(area, ndimage.sum(gis.area_grid(t, reg.shape, latlon=True), reg, index=lbs))
+    with pytest.raises(NotImplementedError):
+        regions.region_dissolve(reg, labels=[1])
