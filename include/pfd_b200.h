@@ -331,6 +331,30 @@ int pfd_tiled_local(pfd_handle* h, int rank, int nranks, int64_t pit_id_offset, 
                     void** table_dev, int64_t* table_len);
 int pfd_tiled_finish(pfd_handle* h, int32_t* rank_out, int32_t* uparea_out, uint32_t* basins_out);
 
+/* ---- row-block (multi-GPU) sweeps of the order-sensitive outputs ------------------------------------------- */
+/*
+ * streams.strahler_order (kind 0, unmasked; pyflwdir/streams.py:228-269), streams.accuflux up (kind 1, any dtype;
+ * streams.py:15-41) and dem.height_above_nearest_drain (kind 2; pyflwdir/dem.py:299-330) across the row blocks of ONE
+ * raster, on handles that hold a row block (pfd_tiled_parse / pfd_d8_flow_all_tiled). These outputs cannot be
+ * re-associated, so every rank sweeps its block extended by the neighbours' edge rows and the ranks swap the values +
+ * done flags of their edge rows between rounds until a round resolves nothing anywhere (SURVEY.md §8e "neighbour
+ * send/recv rounds"). Bit-identical to the single-GPU call. data: accuflux data / HAND elevtn of the OWN rows; drain:
+ * HAND only. pfd_sweep_tiled drives the rounds over NCCL (ncclSend / ncclRecv between row neighbours + one all-reduce
+ * of the progress counter per round); the step functions let a caller emulate the exchange (tests):
+ *   begin -> swap(edges -> halo) -> { round -> swap(edges -> halo) }* -> end
+ * pfd_sweep_tiled_edges(which = 0 my first row | 1 my last row) packs [dir | done | value | aux] of that row;
+ * pfd_sweep_tiled_halo(which = 0 the row above my block | 1 the row below) installs a neighbour's record.
+ * Rasters with loops are refused by the up-sweeps (PFD_ERR_UNSUPPORTED): use the single-GPU call.
+ */
+int pfd_sweep_tiled_begin(pfd_handle* h, int kind, const void* data, int dtype, const uint8_t* drain, double nodata_f,
+                          int64_t nodata_i, int nodata_is_int);
+int pfd_sweep_tiled_round(pfd_handle* h, int64_t* newly_resolved);
+int pfd_sweep_tiled_edges(pfd_handle* h, int which, void** buf_dev, int64_t* nbytes);
+int pfd_sweep_tiled_halo(pfd_handle* h, int which, const void* record);
+int pfd_sweep_tiled_end(pfd_handle* h, void* out, int64_t* resolved);
+int pfd_sweep_tiled(pfd_handle* h, int kind, const void* data, int dtype, const uint8_t* drain, double nodata_f,
+                    int64_t nodata_i, int nodata_is_int, void* out, int64_t* rounds);
+
 /* ---- synthetic input (bench / tests) ---------------------------------------------------- */
 /* z: nrow*ncol float32 (device or host) elevation; d8 from z by strict steepest descent. */
 int pfd_synth_elevation(pfd_handle* h, int64_t nrow, int64_t ncol, int64_t nref, int octaves, uint32_t seed,

@@ -86,6 +86,12 @@ SYMBOLS = {
     "pfd_tiled_parse": (_int, [_vp, _vp, _i64, _i64, _int, _int, _i64, _vp, _int, _pi64, _pi64]),
     "pfd_tiled_local": (_int, [_vp, _int, _int, _i64, _vp, C.POINTER(_vp), _pi64]),
     "pfd_tiled_finish": (_int, [_vp, _vp, _vp, _vp]),
+    "pfd_sweep_tiled_begin": (_int, [_vp, _int, _vp, _int, _vp, C.c_double, _i64, _int]),
+    "pfd_sweep_tiled_round": (_int, [_vp, _pi64]),
+    "pfd_sweep_tiled_edges": (_int, [_vp, _int, C.POINTER(_vp), _pi64]),
+    "pfd_sweep_tiled_halo": (_int, [_vp, _int, _vp]),
+    "pfd_sweep_tiled_end": (_int, [_vp, _vp, _pi64]),
+    "pfd_sweep_tiled": (_int, [_vp, _int, _vp, _int, _vp, C.c_double, _i64, _int, _vp, _pi64]),
     "pfd_synth_elevation": (_int, [_vp, _i64, _i64, _i64, _int, _u32, _vp]),
     "pfd_synth_d8": (_int, [_vp, _vp, _i64, _i64, C.c_float, _vp]),
     "pfd_set_option": (_int, [_vp, C.c_char_p, _i64]),

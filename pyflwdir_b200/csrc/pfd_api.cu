@@ -1766,6 +1766,7 @@ static int ts_prepare(pfd_handle* h, TsArgs& A, const char* who, std::initialize
     uint32_t* base = (uint32_t*)((char*)h->ts_lists.p + sizeof(TsCtl));
     A.dir = (const uint8_t*)h->dir.p + h->dir_off;
     A.nrow = h->nrow, A.ncol = h->ncol, A.ntx = (int)ntx, A.nty = (int)nty;
+    A.own_lo = 0, A.own_hi = h->nrow, A.fdone = nullptr, A.first_pass = 1;
     A.max_passes = h->ts_max_passes;
     A.al16 = (h->ncol % 16 == 0) && ((uintptr_t)A.dir % 16 == 0);
     for (const void* q : arrays) A.al16 = A.al16 && ((uintptr_t)q % 16 == 0);
@@ -1829,6 +1830,292 @@ static int run_tile_down(pfd_handle* h, Op op, const char* who) {
     PFD_TRY(ts_launch(h, (void*)tile_down_sweep_kernel<NT, Op>, NT, sizeof(TsShared<typename Op::V, false>), A, (void*)&op));
     unsigned long long resolved = 0;
     return ts_result(h, A, &resolved);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Row-block (multi-GPU) tile sweeps: Strahler, accuflux (any dtype), HAND across the row blocks of ONE raster.
+// These outputs are order-sensitive / not re-associable, so the single all-reduce of the integer path does not apply
+// (SURVEY.md section 8e): every rank sweeps its block extended by the neighbours' edge rows ("foreign" rows: never
+// resolved here), then the ranks swap the values + done flags of their edge rows and resume from the edge tiles, until
+// a round resolves nothing anywhere. The number of rounds is the largest number of block-boundary crossings of a
+// dependency chain + 1. Bit-identical to the single-GPU sweep: the same per-cell statement on the same final values.
+// Step functions (the exchange is NCCL send/recv in pfd_sweep_tiled, or emulated by the caller in tests):
+//   pfd_sweep_tiled_begin -> { pfd_sweep_tiled_round, pfd_sweep_tiled_edges (pack), swap, pfd_sweep_tiled_halo (unpack) }* -> pfd_sweep_tiled_end
+// ---------------------------------------------------------------------------------------------------------
+static size_t sw_edge_bytes(const pfd_handle* h) { return (size_t)h->ncol * (2 + h->sw.vsz + h->sw.asz); }
+
+// edge record of one row: [dir ncol][done ncol][value ncol * vsz][aux ncol * asz]
+__global__ void sw_pack_kernel(const uint8_t* __restrict__ dir, const uint32_t* __restrict__ done, const uint8_t* __restrict__ out,
+                               const uint8_t* __restrict__ aux, long long row, long long ncol, int ntx, int vsz, int asz,
+                               uint8_t* __restrict__ buf) {
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < ncol; c += (long long)gridDim.x * blockDim.x) {
+        buf[c] = dir[row * ncol + c];
+        const long long t = (row >> 6) * ntx + (c >> 6);
+        buf[ncol + c] = (uint8_t)((done[t * TS_BMW + (row & 63) * 2 + ((c & 63) >> 5)] >> (c & 31)) & 1u);
+        for (int b = 0; b < vsz; ++b) buf[2 * ncol + c * vsz + b] = out[(row * ncol + c) * vsz + b];
+        for (int b = 0; b < asz; ++b) buf[(2 + vsz) * ncol + c * asz + b] = aux[(row * ncol + c) * asz + b];
+    }
+}
+
+__global__ void sw_unpack_kernel(const uint8_t* __restrict__ buf, long long row, long long ncol, int vsz, int asz,
+                                 uint8_t* __restrict__ dir, uint8_t* __restrict__ fdone, uint8_t* __restrict__ out,
+                                 uint8_t* __restrict__ aux) {
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < ncol; c += (long long)gridDim.x * blockDim.x) {
+        dir[row * ncol + c] = buf[c];
+        fdone[c] = buf[ncol + c];
+        for (int b = 0; b < vsz; ++b) out[(row * ncol + c) * vsz + b] = buf[2 * ncol + c * vsz + b];
+        for (int b = 0; b < asz; ++b) aux[(row * ncol + c) * asz + b] = buf[(2 + vsz) * ncol + c * asz + b];
+    }
+}
+
+static int sw_args(pfd_handle* h, TsArgs& A) {
+    const long long nrow_ext = h->nrow + 2, ncol = h->ncol;
+    const long long ntx = (ncol + TS_T - 1) / TS_T, nty = (nrow_ext + TS_T - 1) / TS_T;
+    const long long ntiles = ntx * nty;
+    if (ntiles >= (1ll << 31)) return pfd_fail(h, PFD_ERR_UNSUPPORTED, "pfd_sweep_tiled: too many tiles");
+    PFD_TRY(pfd_reserve(h, h->ts_done, (size_t)ntiles * TS_BMW * sizeof(uint32_t)));
+    PFD_TRY(pfd_reserve(h, h->ts_lists, (size_t)ntiles * 3 * sizeof(uint32_t) + sizeof(TsCtl)));
+    A.ctl = (TsCtl*)h->ts_lists.p;
+    uint32_t* base = (uint32_t*)((char*)h->ts_lists.p + sizeof(TsCtl));
+    A.dir = (const uint8_t*)h->sw_dir.p;
+    A.nrow = nrow_ext, A.ncol = ncol, A.ntx = (int)ntx, A.nty = (int)nty;
+    A.own_lo = 1, A.own_hi = h->nrow + 1, A.fdone = (const uint8_t*)h->sw_fdone.p, A.first_pass = h->sw.next_pass;
+    A.max_passes = 0;
+    A.al16 = (ncol % 16 == 0) && ((uintptr_t)h->sw.data % 16 == 0) && ((uintptr_t)h->sw.drain % 16 == 0);
+    A.done = (uint32_t*)h->ts_done.p;
+    A.stamp = base, A.list[0] = base + ntiles, A.list[1] = base + 2 * ntiles;
+    return PFD_OK;
+}
+
+extern "C" int pfd_sweep_tiled_begin(pfd_handle* h, int kind, const void* data, int dtype, const uint8_t* drain, double nodata_f,
+                                     int64_t nodata_i, int nodata_is_int) {
+    PFD_TRY(check_handle(h));
+    if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, "pfd_sweep_tiled_begin: parse a row block first (pfd_tiled_parse / pfd_d8_flow_all_tiled)");
+    if (kind < 0 || kind > 2) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_sweep_tiled_begin: kind must be 0 (strahler), 1 (accuflux), 2 (hand)");
+    const size_t esz = pfd_dtype_size(dtype);
+    if (kind == 1 && (!data || !esz)) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_sweep_tiled_begin: accuflux needs data of a known dtype");
+    if (kind == 2 && (!data || !drain || (dtype != PFD_F32 && dtype != PFD_F64)))
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_sweep_tiled_begin: hand needs drain and float32 / float64 elevtn");
+    auto& w = h->sw;
+    w = pfd_handle::SweepShard();
+    w.kind = kind, w.dtype = dtype;
+    w.vsz = kind == 0 ? 1 : kind == 1 ? (int)esz : 8;
+    w.asz = kind == 2 ? (int)esz : 0;
+    w.nodata_f = nodata_f, w.nodata_i = nodata_i, w.nodata_is_int = nodata_is_int;
+    const int64_t n = h->n, ncol = h->ncol, next = (h->nrow + 2) * ncol;
+    PFD_TRY(pfd_reserve(h, h->sw_dir, (size_t)next));
+    PFD_TRY(pfd_reserve(h, h->sw_out, (size_t)next * w.vsz));
+    PFD_TRY(pfd_reserve(h, h->sw_aux, (size_t)std::max<int64_t>(next * w.asz, 16)));
+    PFD_TRY(pfd_reserve(h, h->sw_fdone, (size_t)(2 * ncol)));
+    for (int k = 0; k < 4; ++k) PFD_TRY(pfd_reserve(h, h->sw_edge[k], sw_edge_bytes(h)));
+    // extended direction raster: the neighbours' edge rows start as nodata (no neighbour / nothing received yet)
+    PFD_CUDA(h, cudaMemsetAsync(h->sw_dir.p, 0xFF, (size_t)next, h->stream));
+    PFD_CUDA(h, cudaMemcpyAsync((uint8_t*)h->sw_dir.p + ncol, (const uint8_t*)h->dir.p + h->dir_off, (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
+    PFD_CUDA(h, cudaMemsetAsync(h->sw_fdone.p, 0, (size_t)(2 * ncol), h->stream));
+    // per-cell inputs of the own rows, on the device; addressed as rows 1 .. nrow of the extended raster
+    const void* ddev = nullptr;
+    if (kind == 1) {
+        PFD_TRY(pfd_stage_in(h, data, (size_t)n * esz, 4, &ddev));
+        w.data = (const uint8_t*)ddev - (size_t)ncol * esz;
+    } else if (kind == 2) {
+        PFD_TRY(pfd_stage_in(h, data, (size_t)n * esz, 4, &ddev));
+        PFD_CUDA(h, cudaMemsetAsync(h->sw_aux.p, 0, (size_t)next * esz, h->stream));
+        PFD_CUDA(h, cudaMemcpyAsync((uint8_t*)h->sw_aux.p + (size_t)ncol * esz, ddev, (size_t)n * esz, cudaMemcpyDeviceToDevice, h->stream));
+        const void* drdev = nullptr;
+        PFD_TRY(pfd_stage_in(h, drain, (size_t)n, 5, &drdev));
+        w.drain = (const uint8_t*)drdev - ncol;
+    }
+    TsArgs A;
+    PFD_TRY(sw_args(h, A));
+    const long long ntiles = (long long)A.ntx * A.nty;
+    PFD_CUDA(h, cudaMemsetAsync(h->ts_lists.p, 0, sizeof(TsCtl) + (size_t)ntiles * sizeof(uint32_t), h->stream));
+    PFD_CUDA(h, cudaMemsetAsync(h->ts_done.p, 0, (size_t)ntiles * TS_BMW * sizeof(uint32_t), h->stream));  // (the first swap packs it)
+    w.active = true;
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    return PFD_OK;
+}
+
+template <typename T>
+static int sw_launch_accu(pfd_handle* h, const TsArgs& A) {
+    AccuUpTileOp<T> op{(const T*)h->sw.data, (T*)h->sw_out.p, NoData{h->sw.nodata_f, h->sw.nodata_i, h->sw.nodata_is_int}};
+    constexpr int NT = TS_NT_OVERRIDE ? TS_NT_OVERRIDE : (sizeof(T) == 1 ? 128 : 256);
+    return ts_launch(h, (void*)tile_up_sweep_kernel<NT, AccuUpTileOp<T>>, NT, sizeof(TsShared<T, false>), A, (void*)&op);
+}
+
+// one round: every pass the block can make on its own (first round: every tile; later: from the tiles at the block edges)
+extern "C" int pfd_sweep_tiled_round(pfd_handle* h, int64_t* newly_resolved) {
+    PFD_TRY(check_handle(h));
+    auto& w = h->sw;
+    if (!w.active) return pfd_fail(h, PFD_ERR_STATE, "pfd_sweep_tiled_round: call pfd_sweep_tiled_begin first");
+    TsArgs A;
+    PFD_TRY(sw_args(h, A));
+    if (w.next_pass > 1) {  // resume: the tile rows that see a foreign row
+        std::vector<uint32_t> tiles;
+        std::vector<long long> rows = {0, (long long)A.nty - 1, (long long)A.nty - 2};
+        std::sort(rows.begin(), rows.end());
+        rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+        for (long long ty : rows)
+            if (ty >= 0)
+                for (int tx = 0; tx < A.ntx; ++tx) tiles.push_back((uint32_t)(ty * A.ntx + tx));
+        const unsigned int cnt[4] = {0, 0, 0, 0};
+        PFD_CUDA(h, cudaMemcpyAsync(A.ctl->count, cnt, sizeof(cnt), cudaMemcpyHostToDevice, h->stream));
+        const unsigned int c = (unsigned int)tiles.size();
+        PFD_CUDA(h, cudaMemcpyAsync(&A.ctl->count[w.next_pass & 3], &c, sizeof(c), cudaMemcpyHostToDevice, h->stream));
+        PFD_CUDA(h, cudaMemcpyAsync(A.list[w.next_pass & 1], tiles.data(), tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+        PFD_CUDA(h, cudaStreamSynchronize(h->stream));  // `tiles` is a local vector
+    }
+    int rc;
+    if (w.kind == 0) {
+        StrahlerTileOp<false> op{nullptr, (uint8_t*)h->sw_out.p};
+        constexpr int NT = TS_NT_OVERRIDE ? TS_NT_OVERRIDE : 128;
+        rc = ts_launch(h, (void*)tile_up_sweep_kernel<NT, StrahlerTileOp<false>>, NT, sizeof(TsShared<uint8_t, false>), A, (void*)&op);
+    } else if (w.kind == 1) {
+        switch (w.dtype) {
+        case PFD_I8: rc = sw_launch_accu<int8_t>(h, A); break;
+        case PFD_U8: rc = sw_launch_accu<uint8_t>(h, A); break;
+        case PFD_I16: rc = sw_launch_accu<int16_t>(h, A); break;
+        case PFD_U16: rc = sw_launch_accu<uint16_t>(h, A); break;
+        case PFD_I32: rc = sw_launch_accu<int32_t>(h, A); break;
+        case PFD_U32: rc = sw_launch_accu<uint32_t>(h, A); break;
+        case PFD_I64: rc = sw_launch_accu<int64_t>(h, A); break;
+        case PFD_U64: rc = sw_launch_accu<uint64_t>(h, A); break;
+        case PFD_F32: rc = sw_launch_accu<float>(h, A); break;
+        default: rc = sw_launch_accu<double>(h, A); break;
+        }
+    } else {
+        constexpr int NT = TS_NT_OVERRIDE ? TS_NT_OVERRIDE : 256;
+        if (w.dtype == PFD_F32) {
+            HandTileOp<float> op{w.drain, (const float*)h->sw_aux.p, (double*)h->sw_out.p};
+            rc = ts_launch(h, (void*)tile_down_sweep_kernel<NT, HandTileOp<float>>, NT, sizeof(TsShared<double, false>), A, (void*)&op);
+        } else {
+            HandTileOp<double> op{w.drain, (const double*)h->sw_aux.p, (double*)h->sw_out.p};
+            rc = ts_launch(h, (void*)tile_down_sweep_kernel<NT, HandTileOp<double>>, NT, sizeof(TsShared<double, false>), A, (void*)&op);
+        }
+    }
+    PFD_TRY(rc);
+    TsCtl c;
+    PFD_CUDA(h, cudaMemcpyAsync(&c, A.ctl, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (newly_resolved) *newly_resolved = (int64_t)(c.resolved - w.resolved);
+    w.resolved = c.resolved;
+    w.next_pass = std::max<int>((int)c.passes + 1, w.next_pass + 1);
+    h->sweep_passes = (int)c.passes;
+    return PFD_OK;
+}
+
+// which: 0 = my first row (for the rank above), 1 = my last row (for the rank below). Returns the packed record (device).
+extern "C" int pfd_sweep_tiled_edges(pfd_handle* h, int which, void** buf_dev, int64_t* nbytes) {
+    PFD_TRY(check_handle(h));
+    auto& w = h->sw;
+    if (!w.active || (which & ~1)) return pfd_fail(h, PFD_ERR_STATE, "pfd_sweep_tiled_edges: bad state / argument");
+    TsArgs A;
+    PFD_TRY(sw_args(h, A));
+    const long long row = which == 0 ? 1 : h->nrow;
+    sw_pack_kernel<<<grid_for(h->ncol, 256), 256, 0, h->stream>>>((const uint8_t*)h->sw_dir.p, (const uint32_t*)h->ts_done.p,
+                                                                 (const uint8_t*)h->sw_out.p, (const uint8_t*)h->sw_aux.p, row, h->ncol,
+                                                                 A.ntx, w.vsz, w.asz, (uint8_t*)h->sw_edge[which].p);
+    PFD_LAUNCH_CHECK(h);
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (buf_dev) *buf_dev = h->sw_edge[which].p;
+    if (nbytes) *nbytes = (int64_t)sw_edge_bytes(h);
+    return PFD_OK;
+}
+
+// which: 0 = the row above my block (the last row of the rank above), 1 = the row below. record: device or host, as packed
+// by the neighbour's pfd_sweep_tiled_edges; NULL = take what was received into the handle's own buffer (NCCL path).
+extern "C" int pfd_sweep_tiled_halo(pfd_handle* h, int which, const void* record) {
+    PFD_TRY(check_handle(h));
+    auto& w = h->sw;
+    if (!w.active || (which & ~1)) return pfd_fail(h, PFD_ERR_STATE, "pfd_sweep_tiled_halo: bad state / argument");
+    if (record) PFD_CUDA(h, cudaMemcpyAsync(h->sw_edge[2 + which].p, record, sw_edge_bytes(h), cudaMemcpyDefault, h->stream));
+    const long long row = which == 0 ? 0 : h->nrow + 1;
+    sw_unpack_kernel<<<grid_for(h->ncol, 256), 256, 0, h->stream>>>((const uint8_t*)h->sw_edge[2 + which].p, row, h->ncol, w.vsz, w.asz,
+                                                                   (uint8_t*)h->sw_dir.p, (uint8_t*)h->sw_fdone.p + (which ? h->ncol : 0),
+                                                                   (uint8_t*)h->sw_out.p, (uint8_t*)h->sw_aux.p);
+    PFD_LAUNCH_CHECK(h);
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    return PFD_OK;
+}
+
+// own rows of the result -> out (host or device); *resolved = cells of this block that were resolved
+extern "C" int pfd_sweep_tiled_end(pfd_handle* h, void* out, int64_t* resolved) {
+    PFD_TRY(check_handle(h));
+    auto& w = h->sw;
+    if (!w.active) return pfd_fail(h, PFD_ERR_STATE, "pfd_sweep_tiled_end: call pfd_sweep_tiled_begin first");
+    if (out)
+        PFD_CUDA(h, cudaMemcpyAsync(out, (const uint8_t*)h->sw_out.p + (size_t)h->ncol * w.vsz, (size_t)h->n * w.vsz, cudaMemcpyDefault, h->stream));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (resolved) *resolved = (int64_t)w.resolved;
+    w.active = false;
+    return PFD_OK;
+}
+
+// NCCL composition of the step functions above: neighbour send/recv of the packed edge rows, one all-reduce of the
+// progress counter per round. kind / data / dtype / drain / nodata as in pfd_sweep_tiled_begin; out = own rows.
+extern "C" int pfd_sweep_tiled(pfd_handle* h, int kind, const void* data, int dtype, const uint8_t* drain, double nodata_f,
+                               int64_t nodata_i, int nodata_is_int, void* out, int64_t* rounds_out) {
+    PFD_TRY(check_handle(h));
+    const int nranks = h->nccl_comm ? h->mg_nranks : 1, rank = h->nccl_comm ? h->mg_rank : 0;
+    int rc = pfd_sweep_tiled_begin(h, kind, data, dtype, drain, nodata_f, nodata_i, nodata_is_int);
+    // error agreement before the first exchange: a rank that could not set up says so
+    PFD_TRY(pfd_reserve(h, h->mg_counts, (size_t)(4 * std::max(nranks, 1) + 4) * sizeof(unsigned long long)));
+    unsigned long long* dcount = (unsigned long long*)h->mg_counts.p;
+    auto allreduce3 = [&](unsigned long long a, unsigned long long b, unsigned long long c, unsigned long long* res) -> int {
+        const unsigned long long v[3] = {a, b, c};
+        PFD_CUDA(h, cudaMemcpyAsync(dcount, v, sizeof(v), cudaMemcpyHostToDevice, h->stream));
+        if (nranks > 1) PFD_NCCL(h, ncclAllReduce(dcount, dcount, 3, ncclUint64, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
+        PFD_CUDA(h, cudaMemcpyAsync(res, dcount, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+        PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+        return PFD_OK;
+    };
+    unsigned long long res[3];
+    {
+        const int rc2 = allreduce3(rc != PFD_OK ? 1ull : 0ull, 0, 0, res);
+        if (rc != PFD_OK) return rc;
+        PFD_TRY(rc2);
+        if (res[0]) return pfd_fail(h, PFD_ERR_NCCL, "pfd_sweep_tiled: another rank failed to set up the sweep");
+    }
+    auto exchange = [&]() -> int {
+        if (nranks == 1) return PFD_OK;
+        const size_t nb = sw_edge_bytes(h);
+        if (rank > 0) PFD_TRY(pfd_sweep_tiled_edges(h, 0, nullptr, nullptr));
+        if (rank < nranks - 1) PFD_TRY(pfd_sweep_tiled_edges(h, 1, nullptr, nullptr));
+        PFD_NCCL(h, ncclGroupStart());
+        if (rank > 0) {
+            PFD_NCCL(h, ncclSend(h->sw_edge[0].p, nb, ncclUint8, rank - 1, (ncclComm_t)h->nccl_comm, h->stream));
+            PFD_NCCL(h, ncclRecv(h->sw_edge[2].p, nb, ncclUint8, rank - 1, (ncclComm_t)h->nccl_comm, h->stream));
+        }
+        if (rank < nranks - 1) {
+            PFD_NCCL(h, ncclSend(h->sw_edge[1].p, nb, ncclUint8, rank + 1, (ncclComm_t)h->nccl_comm, h->stream));
+            PFD_NCCL(h, ncclRecv(h->sw_edge[3].p, nb, ncclUint8, rank + 1, (ncclComm_t)h->nccl_comm, h->stream));
+        }
+        PFD_NCCL(h, ncclGroupEnd());
+        if (rank > 0) PFD_TRY(pfd_sweep_tiled_halo(h, 0, nullptr));
+        if (rank < nranks - 1) PFD_TRY(pfd_sweep_tiled_halo(h, 1, nullptr));
+        return PFD_OK;
+    };
+    // the neighbours' edge rows of directions (and elevations) must be in place before the first round
+    rc = exchange();
+    if (rc != PFD_OK) return tiled_abort(h, rc);
+    int rounds = 0;
+    for (;;) {
+        int64_t newly = 0;
+        rc = pfd_sweep_tiled_round(h, &newly);
+        if (rc == PFD_OK) rc = exchange();
+        if (rc != PFD_OK) return tiled_abort(h, rc);
+        ++rounds;
+        rc = allreduce3((unsigned long long)newly, 0, 0, res);
+        if (rc != PFD_OK) return tiled_abort(h, rc);
+        if (res[0] == 0) break;  // a round that resolved nothing anywhere
+    }
+    int64_t resolved = 0;
+    PFD_TRY(pfd_sweep_tiled_end(h, out, &resolved));
+    PFD_TRY(allreduce3((unsigned long long)resolved, (unsigned long long)h->n_valid, 0, res));
+    if (rounds_out) *rounds_out = rounds;
+    if (kind != 2 && res[0] != res[1])
+        return pfd_fail(h, PFD_ERR_UNSUPPORTED, "pfd_sweep_tiled: the raster has cells that drain to no pit (loops); the row-block "
+                                               "up-sweeps do not reset the trees hanging on them -- use the single-GPU call");
+    return PFD_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------

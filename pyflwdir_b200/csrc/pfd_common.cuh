@@ -181,6 +181,18 @@ struct pfd_handle {
     int ts_max_passes = 0;     // option "sweep_max_passes" (profiling)
     int sweep_passes = 0;      // passes of the last tile-dataflow sweep
     int64_t sweep_visits = 0;  // tile visits of the last tile-dataflow sweep
+    // row-block (multi-GPU) tile sweeps: the block extended by one foreign row above and below
+    struct SweepShard {
+        bool active = false;
+        int kind = 0, dtype = 0, vsz = 0, asz = 0, next_pass = 1;
+        const void* data = nullptr;      // accuflux data / (unused) of the own rows, device
+        const uint8_t* drain = nullptr;  // HAND drain mask of the own rows, device
+        double nodata_f = 0.0;
+        long long nodata_i = 0;
+        int nodata_is_int = 0;
+        unsigned long long resolved = 0;  // cells resolved so far (all rounds)
+    } sw;
+    DevBuf sw_dir, sw_out, sw_aux, sw_fdone, sw_edge[4];  // ext rows; [0,1] = send top / bottom, [2,3] = receive top / bottom
     DevBuf verify;            // VerifyCounts of the pfd_verify_* entry points
     DevBuf btab, bgraph;       // row-tiled multi-GPU solve: boundary tables, boundary graph state
     int64_t dir_off = 0;       // offset of the first OWNED row inside dir (halo row of a row block)

@@ -42,6 +42,8 @@
 
 #define TSF_DONE 1u   // staged flag plane: value final (resolved by an earlier visit)
 #define TSF_SRC 4u    // staged flag plane, down-sweep: value does not depend on the downstream cell (drain cell)
+#define TSF_FOREIGN 8u  // staged flag plane: the cell belongs to the neighbour rank's row block (never resolved here; its
+                        // done flag and value arrive with the halo exchange)
 
 struct TsCtl {
     unsigned int count[4];           // work-list length of pass p at [p & 3]
@@ -55,6 +57,10 @@ struct TsArgs {
     const uint8_t* dir;
     long long nrow, ncol;
     int ntx, nty;
+    long long own_lo, own_hi;  // rows [own_lo, own_hi) are resolved here (whole raster: 0, nrow); a row block of a larger
+                               // raster is extended by the neighbours' edge rows own_lo - 1 / own_hi ("foreign" rows)
+    const uint8_t* fdone;      // [2][ncol] done flags of the two foreign rows (row-block sweeps only, else null)
+    int first_pass;            // 1: fresh sweep over every tile; > 1: resume with the work list already in list[first_pass & 1]
     int max_passes;      // > 0: stop after that many passes (profiling only: the result is incomplete)
     int al16;            // ncol % 16 == 0 and every raster-sized array is 16-byte aligned: 128-bit global accesses
     uint32_t* done;      // [ntiles][TS_BMW]
@@ -138,7 +144,16 @@ __device__ __forceinline__ void ts_stage_graph(uint8_t* sdir, uint8_t* sflag, ui
         dw[0] = w[0], dw[1] = w[1], dw[2] = w[2], dw[3] = w[3];
         uint32_t bits = 0;
         if (pass > 1) bits = __ldcg(A.done + (long long)tile * TS_BMW + (ch >> 1)) >> (lx0 & 31);
-        fw[0] = ts_spread4(bits), fw[1] = ts_spread4(bits >> 4), fw[2] = ts_spread4(bits >> 8), fw[3] = ts_spread4(bits >> 12);
+        uint32_t f4[4] = {ts_spread4(bits), ts_spread4(bits >> 4), ts_spread4(bits >> 8), ts_spread4(bits >> 12)};
+        if (A.fdone && (r < A.own_lo || r >= A.own_hi) && r < A.nrow && c < A.ncol) {  // a foreign row
+            const uint8_t* fd = A.fdone + (r < A.own_lo ? 0 : A.ncol) + c;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t b = TSF_FOREIGN | ((c + j < A.ncol && __ldcg(fd + j)) ? TSF_DONE : 0u);
+                f4[j >> 2] = (f4[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | (b << (8 * (j & 3)));
+            }
+        }
+        fw[0] = f4[0], fw[1] = f4[1], fw[2] = f4[2], fw[3] = f4[3];
     }
     for (int k = threadIdx.x; k < TS_BMW; k += NT) oldbm[k] = (pass > 1) ? __ldcg(A.done + (long long)tile * TS_BMW + k) : 0u;
     for (int k = threadIdx.x; k < TS_NHALO; k += NT) {
@@ -147,7 +162,10 @@ __device__ __forceinline__ void ts_stage_graph(uint8_t* sdir, uint8_t* sflag, ui
         const long long r = r0 + hy, c = c0 + hx;
         const bool in = ts_in_raster(A, r, c);
         sdir[ts_si(hy, hx)] = in ? __ldg(A.dir + r * A.ncol + c) : (uint8_t)PFD_DIR_NODATA;
-        sflag[ts_si(hy, hx)] = (pass > 1 && in) ? (uint8_t)ts_done_bit(A, r, c) : (uint8_t)0;
+        uint8_t f = (pass > 1 && in) ? (uint8_t)ts_done_bit(A, r, c) : (uint8_t)0;
+        if (A.fdone && in && (r < A.own_lo || r >= A.own_hi))
+            f = (uint8_t)(TSF_FOREIGN | (__ldcg(A.fdone + (r < A.own_lo ? 0 : A.ncol) + c) ? TSF_DONE : 0u));
+        sflag[ts_si(hy, hx)] = f;
     }
 }
 
@@ -219,7 +237,7 @@ __device__ __forceinline__ void ts_scan_word(const uint8_t* sdir, const uint8_t*
     const uint32_t* d = reinterpret_cast<const uint32_t*>(sdir) + row * (TS_S / 4) + wi;
     const uint32_t* f = reinterpret_cast<const uint32_t*>(sflag) + row * (TS_S / 4) + wi;
     constexpr int RW = TS_S / 4;
-    constexpr uint32_t FM = (FLAGS ? 0x01010101u : 0u) | (NOSRC ? 0x04040404u : 0u);
+    constexpr uint32_t FM = (FLAGS ? 0x01010101u : 0u) | (NOSRC ? 0x0C0C0C0Cu : 0u);  // (down-sweep: sources and foreign cells are nobody's children)
     uint32_t nd[8], nf[8];
     nd[0] = __byte_perm(d[-RW - 1], d[-RW], 0x6543);
     nd[1] = d[-RW];
@@ -252,7 +270,7 @@ __device__ __forceinline__ void ts_scan_word(const uint8_t* sdir, const uint8_t*
 
 // per byte 0xFF where the cell takes part in this visit: not nodata, not resolved
 __device__ __forceinline__ uint32_t ts_live4(uint32_t dirw, uint32_t flagw) {
-    return ~__vcmpeq4(dirw, 0xFFFFFFFFu) & __vcmpeq4(flagw & 0x01010101u, 0u);
+    return ~__vcmpeq4(dirw, 0xFFFFFFFFu) & __vcmpeq4(flagw & 0x09090909u, 0u);  // not nodata, not done, not foreign
 }
 
 // upstream slots that lie in the halo, per byte, for the 4 cells of word q (0 .. 3) of the chunk at (ly, lx0)
@@ -310,6 +328,7 @@ struct TsShared {
     uint32_t cnt[3];
     uint32_t act;
     uint32_t newly;
+    int ylo, yhi;                  // tile rows [ylo, yhi) are owned (0, 64 unless the tile holds a foreign row)
 };
 
 // write back what this visit resolved (pass 1: every cell), publish the done bitmap, queue the neighbour tiles
@@ -380,14 +399,14 @@ __device__ __forceinline__ int ts_up_step(TsShared<typename Op::V, Op::AUX>& s, 
     int next = -1;
     if (d < 8u) {  // (a pit ends the chain)
         const int y = ly + pfd_slot_dr((int)d), x = lx + pfd_slot_dc((int)d);
-        if ((unsigned)y < (unsigned)TS_T && (unsigned)x < (unsigned)TS_T) {
+        if ((unsigned)(y - s.ylo) < (unsigned)(s.yhi - s.ylo) && (unsigned)x < (unsigned)TS_T) {
             const int ds = c + ts_noff((int)d);
             const unsigned sh = 16u * (ds & 1);
             const uint32_t old = atomicSub(reinterpret_cast<uint32_t*>(s.rec) + (ds >> 1), 0x1000u << sh);
             if (((old >> (sh + 12)) & 0xFu) == 1u) next = y * TS_T + x;  // last arriver (else somebody else continues)
-        } else {
+        } else if (!((unsigned)y < (unsigned)TS_T && (unsigned)x < (unsigned)TS_T)) {
             atomicOr(&s.act, ts_act_bit(y, x));  // leaves the tile: the neighbour tile may continue in the next pass
-        }
+        }  // (else: a foreign row inside the tile -- the neighbour rank continues after the halo exchange)
     }
     return next;
 }
@@ -400,6 +419,8 @@ __device__ __forceinline__ void ts_up_visit(TsShared<typename Op::V, Op::AUX>& s
         s.act = 0;
         s.newly = 0;
         s.cnt[0] = s.cnt[1] = s.cnt[2] = 0;
+        s.ylo = (int)max(0ll, A.own_lo - r0);
+        s.yhi = (int)min((long long)TS_T, A.own_hi - r0);
     }
     for (int k = threadIdx.x; k < TS_BMW; k += NT) s.newbm[k] = 0u;
     ts_stage_graph<NT>(s.u.pl.dir, s.u.pl.flag, s.oldbm, A, tile, r0, c0, pass);
@@ -413,13 +434,14 @@ __device__ __forceinline__ void ts_up_visit(TsShared<typename Op::V, Op::AUX>& s
             const bool vec = A.al16 && nvalid == 16;
             const long long g0 = r * A.ncol + c;
             const int base = ts_si(ly, lx0);
-            if (pass == 1) ts_load16<V, false>(&s.val[base], op.init_src() ? op.init_src() + g0 : nullptr, vec, nvalid);
-            else ts_load16<V, true>(&s.val[base], op.out + g0, vec, nvalid);
+            if (pass == 1 && r >= A.own_lo && r < A.own_hi)
+                ts_load16<V, false>(&s.val[base], op.init_src() ? op.init_src() + g0 : nullptr, vec, nvalid);
+            else ts_load16<V, true>(&s.val[base], op.out + g0, vec, nvalid);  // (a foreign row: what the neighbour sent)
             if (Op::AUX) ts_load16<uint8_t, false>(&s.aux[base], op.aux_src() + g0, vec, nvalid);
         }
     }
     ts_sync<NT>();  // dir + flags (incl. halo) are staged
-    if (pass > 1 || Op::AUX) {
+    if (pass > 1 || Op::AUX || A.fdone) {
         for (int k = threadIdx.x; k < TS_NHALO; k += NT) {
             int hy, hx;
             ts_halo_cell(k, hy, hx);
@@ -500,7 +522,7 @@ __global__ void __launch_bounds__(NT) tile_up_sweep_kernel(TsArgs A, Op op) {
     TsShared<typename Op::V, Op::AUX>& s = *reinterpret_cast<TsShared<typename Op::V, Op::AUX>*>(ts_smem_raw);
     cg::grid_group grid = cg::this_grid();
     const unsigned int ntiles = (unsigned int)(A.ntx * A.nty);
-    int pass = 1;
+    int pass = A.first_pass;
     for (;; ++pass) {
         const unsigned int count = (pass == 1) ? ntiles : __ldcg(&A.ctl->count[pass & 3]);
         if (count == 0 || (A.max_passes > 0 && pass > A.max_passes)) break;
@@ -605,11 +627,21 @@ __device__ __forceinline__ void ts_down_visit(TsShared<typename Op::V, false>& s
             }
         }
     }
-    if (pass > 1) {
+    if (pass > 1 || A.fdone) {
         for (int k = threadIdx.x; k < TS_NHALO; k += NT) {
             int hy, hx;
             ts_halo_cell(k, hy, hx);
             if (s.u.pl.flag[ts_si(hy, hx)] & TSF_DONE) s.val[ts_si(hy, hx)] = ld_cg(op.out + ((r0 + hy) * A.ncol + c0 + hx));
+        }
+        if (A.fdone) {  // resolved foreign cells inside the tile: what the neighbour sent
+            for (int ch = threadIdx.x; ch < TS_NCHUNK; ch += NT) {
+                const int ly = ch >> 2, lx0 = (ch & 3) << 4;
+                const long long r = r0 + ly;
+                if (r >= A.own_lo && r < A.own_hi) continue;
+#pragma unroll 4
+                for (int j = 0; j < 16; ++j)
+                    if (s.u.pl.flag[ts_si(ly, lx0 + j)] & TSF_DONE) s.val[ts_si(ly, lx0 + j)] = ld_cg(op.out + (r * A.ncol + c0 + lx0 + j));
+            }
         }
     }
     ts_sync<NT>();
@@ -653,13 +685,12 @@ __device__ __forceinline__ void ts_down_visit(TsShared<typename Op::V, false>& s
                 v = op.pit(v);
                 root = true;
             } else {
-                const int y = ly + pfd_slot_dr((int)d), x = lx0 + j + pfd_slot_dc((int)d);
-                if (!((unsigned)y < (unsigned)TS_T && (unsigned)x < (unsigned)TS_T)) {
-                    const int ds = ci + ts_noff((int)d);
-                    if (s.u.pl.flag[ds] & TSF_DONE) {
-                        v = op.down(s.val[ds], v);
-                        root = true;
-                    }
+                // the downstream cell was resolved BEFORE this visit: it lies in the halo or in a foreign row (an own cell
+                // of the tile resolves its children in the visit that resolves it)
+                const int ds = ci + ts_noff((int)d);
+                if (s.u.pl.flag[ds] & TSF_DONE) {
+                    v = op.down(s.val[ds], v);
+                    root = true;
                 }
             }
             if (root) {
@@ -733,7 +764,7 @@ __global__ void __launch_bounds__(NT) tile_down_sweep_kernel(TsArgs A, Op op) {
     TsShared<typename Op::V, false>& s = *reinterpret_cast<TsShared<typename Op::V, false>*>(ts_smem_raw);
     cg::grid_group grid = cg::this_grid();
     const unsigned int ntiles = (unsigned int)(A.ntx * A.nty);
-    int pass = 1;
+    int pass = A.first_pass;
     for (;; ++pass) {
         const unsigned int count = (pass == 1) ? ntiles : __ldcg(&A.ctl->count[pass & 3]);
         if (count == 0 || (A.max_passes > 0 && pass > A.max_passes)) break;

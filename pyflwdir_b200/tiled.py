@@ -129,6 +129,67 @@ class RowBlockSolver:
         shape = (self.nrow, self.ncol)
         return idxs, rank.reshape(shape), upa.reshape(shape), bas.reshape(shape), npg.value
 
+    # -- row-block sweeps of the order-sensitive outputs (Strahler, accuflux, HAND)
+    KINDS = {"strahler": 0, "accuflux": 1, "hand": 2}
+
+    def _sweep_args(self, kind, data, drain, nodata):
+        k = self.KINDS[kind]
+        n = self.nrow * self.ncol
+        code, dref, mref = 0, None, None
+        nodata_f, nodata_i, is_int = 0.0, 0, 0
+        if k == 1:
+            dref = np.ascontiguousarray(data).reshape(-1)
+            code = _lib.dtype_code(dref.dtype)
+            is_int = int(np.issubdtype(dref.dtype, np.integer) and float(nodata) == int(nodata))
+            nodata_f, nodata_i = float(nodata), int(nodata) if is_int else 0
+        elif k == 2:
+            dref = np.ascontiguousarray(data).reshape(-1)
+            if dref.dtype not in (np.float32, np.float64):
+                dref = dref.astype(np.float64)
+            code = _lib.dtype_code(dref.dtype)
+            mref = np.ascontiguousarray(drain).reshape(-1)
+            mref = mref.view(np.uint8) if mref.dtype == np.bool_ else (mref == 1).view(np.uint8)
+        if dref is not None and dref.size != n:
+            raise ValueError('"data" size does not match.')
+        out_dtype = np.uint8 if k == 0 else (dref.dtype if k == 1 else np.float64)
+        return k, dref, code, mref, nodata_f, nodata_i, is_int, out_dtype
+
+    def sweep_begin(self, kind, data=None, drain=None, nodata=-9999):
+        k, dref, code, mref, nf, ni, is_int, self._sweep_dtype = self._sweep_args(kind, data, drain, nodata)
+        self._ck(self._l.pfd_sweep_tiled_begin(self._h, k, _lib.ptr(dref), code, _lib.ptr(mref), C.c_double(nf), ni, is_int))
+
+    def sweep_round(self):
+        n = C.c_int64()
+        self._ck(self._l.pfd_sweep_tiled_round(self._h, C.byref(n)))
+        return n.value
+
+    def sweep_edges(self, which):
+        """packed [dir | done | value | aux] record of my first (0) / last (1) row, as host bytes"""
+        p, nb = C.c_void_p(), C.c_int64()
+        self._ck(self._l.pfd_sweep_tiled_edges(self._h, which, C.byref(p), C.byref(nb)))
+        buf = np.empty(nb.value, np.uint8)
+        self._ck(self._l.pfd_memcpy(self._h, _lib.ptr(buf), p, nb.value))
+        return buf
+
+    def sweep_halo(self, which, record):
+        self._ck(self._l.pfd_sweep_tiled_halo(self._h, which, _lib.ptr(np.ascontiguousarray(record))))
+
+    def sweep_end(self):
+        out = np.empty(self.nrow * self.ncol, self._sweep_dtype)
+        res = C.c_int64()
+        self._ck(self._l.pfd_sweep_tiled_end(self._h, _lib.ptr(out), C.byref(res)))
+        return out.reshape(self.nrow, self.ncol), res.value
+
+    def sweep(self, kind, data=None, drain=None, nodata=-9999):
+        """Strahler order / accuflux / HAND of this rank's row block with the halo rounds over NCCL (after flow_all or
+        parse on a handle with a communicator). Returns (own rows of the result, number of rounds)."""
+        k, dref, code, mref, nf, ni, is_int, out_dtype = self._sweep_args(kind, data, drain, nodata)
+        out = np.empty(self.nrow * self.ncol, out_dtype)
+        rounds = C.c_int64()
+        self._ck(self._l.pfd_sweep_tiled(self._h, k, _lib.ptr(dref), code, _lib.ptr(mref), C.c_double(nf), ni, is_int,
+                                         _lib.ptr(out), C.byref(rounds)))
+        return out.reshape(self.nrow, self.ncol), rounds.value
+
     def read_table(self, tab, n):
         out = np.empty(n, dtype=np.uint32)
         if n:
@@ -179,6 +240,46 @@ def solve_emulated(d8, nranks, device=0):
         return dict(idxs_ds=np.concatenate(idxs), rank=np.concatenate([o[0] for o in outs]),
                     uparea=np.concatenate([o[1] for o in outs]), basins=np.concatenate([o[2] for o in outs]),
                     n_pits=int(np.sum(npits)), blocks=blocks)
+    finally:
+        for s in solvers:
+            s.close()
+
+
+def sweep_emulated(d8, nranks, kind, data=None, drain=None, nodata=-9999, device=0):
+    """Strahler order / accuflux / HAND of `d8` over `nranks` row blocks on ONE GPU, the halo exchange of every round done
+    on the host: the same step functions the NCCL path (RowBlockSolver.sweep) drives. Returns (result, rounds)."""
+    d8 = np.ascontiguousarray(d8, dtype=np.uint8)
+    nrow, ncol = d8.shape
+    blocks = split_rows(nrow, nranks)
+    R = len(blocks)
+    solvers = [RowBlockSolver(device) for _ in blocks]
+
+    def part(a, r0, r1):
+        return None if a is None else np.ascontiguousarray(np.asarray(a).reshape(nrow, ncol)[r0:r1])
+
+    def swap():
+        recs = [(s.sweep_edges(0) if g > 0 else None, s.sweep_edges(1) if g < R - 1 else None) for g, s in enumerate(solvers)]
+        for g, s in enumerate(solvers):
+            if g > 0:
+                s.sweep_halo(0, recs[g - 1][1])
+            if g < R - 1:
+                s.sweep_halo(1, recs[g + 1][0])
+
+    try:
+        for s, (r0, r1) in zip(solvers, blocks):
+            blk, ht, hb = block_with_halo(d8, r0, r1)
+            s.parse(blk, ht, hb, r0, None)
+            s.sweep_begin(kind, part(data, r0, r1), part(drain, r0, r1), nodata)
+        swap()
+        rounds = 0
+        while True:
+            newly = sum(s.sweep_round() for s in solvers)
+            swap()
+            rounds += 1
+            if newly == 0:
+                break
+        outs = [s.sweep_end() for s in solvers]
+        return np.concatenate([o[0] for o in outs]), rounds, sum(o[1] for o in outs)
     finally:
         for s in solvers:
             s.close()

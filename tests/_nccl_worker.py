@@ -43,6 +43,29 @@ if rank == 0:
     assert np.array_equal(np.concatenate([p["bas"] for p in parts]).ravel(), oracle.basins.basins(ids_o, pits_o, seq))
     print("NCCL_TILED_OK", world, flush=True)
 dist.barrier()
+# the order-sensitive outputs across the row blocks: halo rounds over ncclSend / ncclRecv between row neighbours
+area = (np.abs(z) + np.float32(0.25)).astype(np.float32)
+so, rounds = solver.sweep("strahler")
+acc, _ = solver.sweep("accuflux", data=area[r0:r1], nodata=-9999.0)
+upa_all = None
+np.savez(os.path.join(out_dir, f"sweep{rank}.npz"), so=so, acc=acc)
+dist.barrier()
+parts = [np.load(os.path.join(out_dir, f"sweep{g}.npz")) for g in range(world)]
+ids_o, pits_o, _ = oracle.core_d8.from_array(d8, dtype=np.int32)
+seq_o = oracle.core.idxs_seq(ids_o, pits_o)
+upa_o = oracle.streams.accuflux(ids_o, seq_o, np.ones(d8.size, np.int32), -9999).reshape(d8.shape)
+drain = upa_o > 60
+hand, _ = solver.sweep("hand", data=z[r0:r1], drain=drain[r0:r1])
+np.save(os.path.join(out_dir, f"hand{rank}.npy"), hand)
+dist.barrier()
+if rank == 0:
+    assert np.array_equal(np.concatenate([p["so"] for p in parts]).ravel(), oracle.streams.strahler_order(ids_o, seq_o))
+    assert np.array_equal(np.concatenate([p["acc"] for p in parts]).ravel(), oracle.streams.accuflux(ids_o, seq_o, area.ravel(), -9999.0))
+    hands = np.concatenate([np.load(os.path.join(out_dir, f"hand{g}.npy")) for g in range(world)])
+    assert np.array_equal(hands.ravel(), oracle.dem.height_above_nearest_drain(ids_o, seq_o, drain.ravel(), z.ravel()))
+    assert rounds >= 2
+    print("NCCL_SWEEPS_OK", world, rounds, flush=True)
+dist.barrier()
 # error agreement: ONE rank's block holds an illegal code -> every rank returns an error instead of hanging in a collective
 bad = d8.copy()
 rb0, rb1 = blocks[world - 1]

@@ -28,4 +28,5 @@ def test_tiled_over_nccl(world, tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert f"NCCL_TILED_OK {world}" in out.stdout
+    assert f"NCCL_SWEEPS_OK {world}" in out.stdout
     assert f"NCCL_ERROR_AGREEMENT_OK {world}" in out.stdout

@@ -85,3 +85,62 @@ def test_tiled_rhine():
     h = cs.hashes()["rhine"]
     assert cs.sha(got["rank"]) == h["rank"] and cs.sha(got["uparea"]) == h["uparea_cell"]
     assert cs.sha(got["basins"]) == h["basins"] and cs.sha(got["idxs_ds"]) == h["idxs_ds"]
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3, 5])
+def test_tiled_sweeps_strahler_accuflux_hand(nranks):
+    """The order-sensitive outputs across row blocks (halo rounds emulated on the host): bit-identical to the oracle on
+    the whole raster -- Strahler order, float32 / float64 / int32 accuflux with nodata, HAND with float32 / float64 elevation."""
+    from pyflwdir_b200 import tiled
+
+    z = oracle.synth_elevation(448, 333, seed=43)
+    d8 = oracle.synth_d8(z, sea_level=float(np.quantile(z, 0.04)))
+    ids, pits, _ = oracle.core_d8.from_array(d8, dtype=np.int32)
+    seq = oracle.core.idxs_seq(ids, pits)
+    got, rounds, resolved = tiled.sweep_emulated(d8, nranks, "strahler")
+    want = oracle.streams.strahler_order(ids, seq)
+    bad = np.flatnonzero(got.ravel() != want)
+    assert bad.size == 0, (bad.size, bad[:8] // d8.shape[1], bad[:8] % d8.shape[1], got.ravel()[bad[:8]], want[bad[:8]], rounds)
+    assert resolved == seq.size
+    assert rounds >= (2 if nranks > 1 else 1)
+    rng = np.random.default_rng(5)
+    for data, nodata in ((np.abs(z) + np.float32(0.25), -9999.0), (z.astype(np.float64) * 1e-3, -9999.0),
+                         (rng.integers(0, 50, z.shape).astype(np.int32), -9999)):
+        data = np.ascontiguousarray(data).copy()
+        data.ravel()[rng.integers(0, data.size, 40)] = nodata
+        got, _, _ = tiled.sweep_emulated(d8, nranks, "accuflux", data=data, nodata=nodata)
+        assert got.dtype == data.dtype and np.array_equal(got.ravel(), oracle.streams.accuflux(ids, seq, data.ravel(), nodata))
+    upa = oracle.streams.accuflux(ids, seq, np.ones(d8.size, np.int32), -9999)
+    for drain, elev in ((upa > 60, z), (np.zeros(d8.size, np.bool_), z.astype(np.float64))):
+        got, _, _ = tiled.sweep_emulated(d8, nranks, "hand", data=elev, drain=drain)
+        want = oracle.dem.height_above_nearest_drain(ids, seq, np.asarray(drain).ravel(), np.asarray(elev).ravel())
+        assert got.dtype == np.float64 and np.array_equal(got.ravel(), want)
+
+
+def test_tiled_sweeps_zigzag_and_wide():
+    """A river that crosses a block boundary many times (many rounds) and a raster wider than tall with an unaligned width."""
+    from pyflwdir_b200 import tiled
+
+    d8 = np.full((130, 70), 247, np.uint8)
+    # a zig-zag channel around the block boundary (rows 127 | 128 for two blocks) flowing west -> east, pit at the east end
+    r = 127
+    for c in range(0, 68):
+        d8[r, c] = 2 if r == 127 else 128  # SE from the upper row, NE from the lower row
+        r = 128 if r == 127 else 127
+    d8[r, 68] = 0
+    ids, pits, _ = oracle.core_d8.from_array(d8, dtype=np.int32)
+    seq = oracle.core.idxs_seq(ids, pits)
+    got, rounds, _ = tiled.sweep_emulated(d8, 2, "strahler")
+    assert np.array_equal(got.ravel(), oracle.streams.strahler_order(ids, seq)) and rounds > 30
+    area = np.linspace(0.5, 3.0, d8.size, dtype=np.float32).reshape(d8.shape)
+    got, _, _ = tiled.sweep_emulated(d8, 2, "accuflux", data=area, nodata=-9999.0)
+    assert np.array_equal(got.ravel(), oracle.streams.accuflux(ids, seq, area.ravel(), -9999.0))
+    elev = np.linspace(9.0, 1.0, d8.size, dtype=np.float32).reshape(d8.shape)
+    got, _, _ = tiled.sweep_emulated(d8, 2, "hand", data=elev, drain=np.zeros(d8.shape, np.bool_))
+    assert np.array_equal(got.ravel(), oracle.dem.height_above_nearest_drain(ids, seq, np.zeros(d8.size, np.bool_), elev.ravel()))
+    z = oracle.synth_elevation(200, 1001, seed=44)
+    d8 = oracle.synth_d8(z)
+    ids, pits, _ = oracle.core_d8.from_array(d8, dtype=np.int32)
+    seq = oracle.core.idxs_seq(ids, pits)
+    got, _, _ = tiled.sweep_emulated(d8, 3, "strahler")
+    assert np.array_equal(got.ravel(), oracle.streams.strahler_order(ids, seq))
