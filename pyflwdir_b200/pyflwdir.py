@@ -35,12 +35,14 @@ def _is_d8_candidate(data):
 
 
 def from_array(data, ftype="infer", check_ftype=True, mask=None, transform=gis.IDENTITY, latlon=False,
-               device=0, **kwargs):
+               device=0, devices=None, **kwargs):
     """Flow direction raster array parsed to actionable format (GPU resident).
 
-    Same signature and errors as the reference's `pyflwdir.from_array`; `device` (CUDA ordinal) is the only
-    extension. The D8 raster is parsed by one CUDA kernel into the device flow graph; `idxs_ds`, `idxs_pit`,
+    Same signature and errors as the reference's `pyflwdir.from_array`; `device` (CUDA ordinal) and `devices` are the
+    only extensions. The D8 raster is parsed by one CUDA kernel into the device flow graph; `idxs_ds`, `idxs_pit`,
     `idxs_seq`, `rank` are materialised on the host only when read.
+    devices=[0, 1, ...] (D8 rasters): the raster is row-tiled over those GPUs (multigpu.MultiDeviceGraph): idxs_ds, rank,
+    upstream_area(), basins(), stream_order(), accuflux(), hand() come from all of them over NCCL, bit-identical to one GPU.
     """
     infer = ftype == "infer"
     is_xy = core_nextxy.isformat(data)
@@ -96,7 +98,15 @@ def from_array(data, ftype="infer", check_ftype=True, mask=None, transform=gis.I
         raise ValueError('"mask" shape does not match with data shape')
 
     if dev is None:
-        dev = _device.DeviceGraph(device)
+        if devices is not None and len(devices) > 1:
+            if candidates not in (["d8"], ["d8", "ldd"]):
+                raise ValueError('devices=[...] supports ftype "d8"')
+            from . import multigpu
+
+            dev = multigpu.MultiDeviceGraph(devices)
+            candidates = ["d8"]
+        else:
+            dev = _device.DeviceGraph(device if not devices else devices[0])
     for k, ft in enumerate(candidates):
         try:
             # illegal codes are refused even with check_ftype=False (the reference would mis-parse them)

@@ -140,8 +140,10 @@ class RowBlockSolver:
         if k == 1:
             dref = np.ascontiguousarray(data).reshape(-1)
             code = _lib.dtype_code(dref.dtype)
-            is_int = int(np.issubdtype(dref.dtype, np.integer) and float(nodata) == int(nodata))
-            nodata_f, nodata_i = float(nodata), int(nodata) if is_int else 0
+            from ._device import nodata_args  # numba's typing of `x != nodata` (int nodata: int64 compare)
+
+            nf, ni, nis = nodata_args(nodata)
+            nodata_f, nodata_i, is_int = nf.value, ni.value, nis.value
         elif k == 2:
             dref = np.ascontiguousarray(data).reshape(-1)
             if dref.dtype not in (np.float32, np.float64):

@@ -30,3 +30,35 @@ def test_tiled_over_nccl(world, tmp_path):
     assert f"NCCL_TILED_OK {world}" in out.stdout
     assert f"NCCL_SWEEPS_OK {world}" in out.stdout
     assert f"NCCL_ERROR_AGREEMENT_OK {world}" in out.stdout
+
+
+def test_from_array_devices_matches_single_gpu():
+    """The drop-in surface over two GPUs in ONE process (from_array(..., devices=[0, 1])): every sharded output equals the
+    single-GPU object's, bit for bit, and the oracle's."""
+    import numpy as np
+
+    import oracle
+    import pyflwdir_b200 as pfb
+    from pyflwdir_b200 import _lib
+
+    if _lib.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    z = oracle.synth_elevation(700, 520, seed=23)
+    d8 = oracle.synth_d8(z, sea_level=float(np.quantile(z, 0.04)))
+    one = pfb.from_array(d8, ftype="d8")
+    two = pfb.from_array(d8, ftype="d8", devices=[0, 1])
+    assert np.array_equal(two.idxs_ds, one.idxs_ds) and np.array_equal(two.idxs_pit, one.idxs_pit)
+    assert np.array_equal(two.rank, one.rank)
+    assert np.array_equal(two.upstream_area(), one.upstream_area()) and np.array_equal(two.basins(), one.basins())
+    assert np.array_equal(two.stream_order(), one.stream_order())
+    area = (np.abs(z) + np.float32(0.5)).astype(np.float32)
+    assert np.array_equal(two.accuflux(area), one.accuflux(area))
+    assert np.array_equal(two.upstream_area("km2"), one.upstream_area("km2"))
+    drain = one.upstream_area() > 80
+    assert np.array_equal(two.hand(drain, z), one.hand(drain, z))
+    ids, pits, _ = oracle.core_d8.from_array(d8, dtype=np.int32)
+    seq = oracle.core.idxs_seq(ids, pits)
+    assert np.array_equal(two.stream_order().ravel(), oracle.streams.strahler_order(ids, seq))
+    assert np.array_equal(two.hand(drain, z).ravel(), oracle.dem.height_above_nearest_drain(ids, seq, drain.ravel(), z.ravel()))
+    # unsharded entry points still work (devices[0])
+    assert np.array_equal(two.idxs_seq, seq)
