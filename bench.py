@@ -666,7 +666,7 @@ def main():
     ap.add_argument("--verify-full", action="store_true",
                     help="N>1: compare the FULL-size outputs with a single-GPU solve of the whole raster on rank 0 (needs the "
                          "raster to fit one GPU; the multi-rank buffers are freed first)")
-    ap.add_argument("--extras", nargs="?", const="sweeps", default=None, choices=["tile", "sweeps", "all"],
+    ap.add_argument("--extras", nargs="?", const="sweeps", default=None, choices=["none", "tile", "sweeps", "all"],
                     help="also time the secondary configs: Strahler / accuflux / HAND sweeps (tile = tile-dataflow only, sweeps = "
                          "also the level replays + ordering, all = plus every widened entry point)")
     args = ap.parse_args()
@@ -723,6 +723,16 @@ def main():
     e2e = None
     if not args.no_e2e:
         w.make_host()
+        # the host link under the same concurrency: every rank copies its uparea output D2H at the same time (plain
+        # cudaMemcpy into pinned memory). e2e is bound by this number, not by the kernels (0.3 s of copies vs 0.02 s of GPU work)
+        probe_bytes = cells * 4
+        w.ck(w.l.pfd_memcpy(w.h, w.L.ptr(w.out_host[2].array), w.out_dev[2], probe_bytes))
+        barrier(dist)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            w.ck(w.l.pfd_memcpy(w.h, w.L.ptr(w.out_host[2].array), w.out_dev[2], probe_bytes))
+        probe_s = reduce_max(dist, (time.perf_counter() - t0) / 3)
+        d2h_gbs_per_gpu = probe_bytes / probe_s / 1e9
         for _ in range(2):
             w.step_host()
         barrier(dist)
@@ -731,7 +741,10 @@ def main():
         idx_b = np.dtype(getattr(w, "idx_dtype", np.int32)).itemsize
         e2e = {"value": cells_total * args.steps / (e2e_ms / 1e3) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": int(getattr(w, "ext_bytes", cells)), "d2h_bytes_per_step": int((12 + idx_b) * cells),
-               "ms_per_step": e2e_ms / args.steps, "note": "bytes are per GPU", "numa_node_rank0": numa_node}
+               "ms_per_step": e2e_ms / args.steps, "note": "bytes are per GPU", "numa_node_rank0": numa_node,
+               "host_link": {"d2h_gbs_per_gpu_all_ranks_concurrent": d2h_gbs_per_gpu,
+                             "copy_bound_ms_per_step": (int(getattr(w, "ext_bytes", cells)) + (12 + idx_b) * cells) / d2h_gbs_per_gpu / 1e6,
+                             "note": "plain pinned cudaMemcpy D2H, every rank at once: the e2e step is bound by it"}}
     launches_total = int(reduce_sum(dist, launches))
 
     # ---- roofline of the dominant kernel
@@ -764,10 +777,22 @@ def main():
                          "achieved_gbs_per_gpu": STEP_BYTES_FUSED * cells / (ms_total / args.steps / 1e3) / 1e9,
                          "frac_per_gpu": STEP_BYTES_FUSED * cells / (ms_total / args.steps / 1e3) / 1e9 / peak}}
 
+    # BASELINE configs 3 / 5 on the same raster (N = 1): Strahler order, float accuflux and HAND by the tile-dataflow sweeps.
+    # --extras sweeps adds the level replays over the BFS order, --extras all every widened entry point.
     extra = None
-    if args.extras and world == 1:
-        extra = extras(w, args.size, args.seed, skip_level=args.extras == "tile")
-        if args.extras == "all":
+    if world == 1 and args.extras != "none":
+        mode = args.extras or "tile"
+        extra = extras(w, args.size, args.seed, skip_level=mode == "tile")
+        t = extra["tile_dataflow"]
+        step_ms = ms_total / args.steps
+        extra["baseline_configs"] = {
+            "config3_accuflux_plus_strahler_ms": step_ms + t["strahler_ms"],
+            "config3_mcells_s": cells / ((step_ms + t["strahler_ms"]) / 1e3) / 1e6,
+            "config5_accuflux_mask_hand_ms": step_ms + t["hand_ms"],
+            "config5_mcells_s": cells / ((step_ms + t["hand_ms"]) / 1e3) / 1e6,
+            "note": f"this {args.size}^2 raster: headline step (parse + rank + accuflux + basins) + the sweep; BASELINE quotes "
+                    "config 5 at 16384^2 (run with --size 16384)"}
+        if mode == "all":
             extra["widened"] = extras_widened(w, args.size, args.seed, min(args.size, 2048))
 
     # ---- parity of what was just timed (size-independent properties at full size; N > 1: the same NCCL path on a
