@@ -41,3 +41,46 @@ def isvalid(flwdir, _all=_all, device=0):
             return False
         raise
     return True
+
+
+# ---- scalar helpers on a handful of cells (host; not part of the hot path) ------------------------------------
+def drdc(dd):
+    """D8 code -> (row offset, column offset); pits and anything else map to (0, 0) like core_d8.py:22-39 for the legal codes"""
+    hit = np.argwhere(_ds == np.uint8(dd))
+    if dd in (0, 255) or hit.size == 0:
+        return 0, 0
+    return int(hit[0, 0]) - 1, int(hit[0, 1]) - 1
+
+
+def ispit(dd):
+    """True if D8 pit (core_d8.py:125-127)"""
+    return np.logical_or(np.asarray(dd) == _pv[0], np.asarray(dd) == _pv[1])
+
+
+def isnodata(dd):
+    """True if D8 nodata (core_d8.py:130-132)"""
+    return np.asarray(dd) == _mv
+
+
+def _downstream_idx(idx0, flwdir_flat, shape, mv=np.intp(-1)):
+    """linear index of the downstream cell of idx0; mv when it lies outside the raster (core_d8.py:70-83)"""
+    nrow, ncol = shape
+    r0, c0 = idx0 // ncol, idx0 % ncol
+    dr, dc = drdc(flwdir_flat[idx0])
+    r, c = r0 + dr, c0 + dc
+    if 0 <= r < nrow and 0 <= c < ncol:
+        return np.intp(r * ncol + c)
+    return mv
+
+
+def _upstream_idx(idx0, flwdir_flat, shape, dtype=np.intp):
+    """linear indices of the cells that drain into idx0 (core_d8.py:137-154)"""
+    nrow, ncol = shape
+    r0, c0 = idx0 // ncol, idx0 % ncol
+    out = []
+    for dr in (-1, 0, 1):
+        for dc in (-1, 0, 1):
+            r, c = r0 + dr, c0 + dc
+            if (dr or dc) and 0 <= r < nrow and 0 <= c < ncol and flwdir_flat[r * ncol + c] == _us[dr + 1, dc + 1]:
+                out.append(r * ncol + c)
+    return np.array(out, dtype=dtype)

@@ -41,3 +41,45 @@ def isvalid(flwdir, _all=_all, device=0):
             return False
         raise
     return True
+
+
+# ---- scalar helpers on a handful of cells (host; not part of the hot path) ------------------------------------
+def drdc(dd):
+    """LDD code -> (row offset, column offset); the pit code 5 maps to (0, 0) (core_ldd.py:20-38)"""
+    hit = np.argwhere(_ds == np.uint8(dd))
+    if hit.size == 0:
+        return 0, 0
+    return int(hit[0, 0]) - 1, int(hit[0, 1]) - 1
+
+
+def ispit(dd):
+    """True if LDD pit"""
+    return np.asarray(dd) == _pv
+
+
+def isnodata(dd):
+    """True if LDD nodata"""
+    return np.asarray(dd) == _mv
+
+
+def _downstream_idx(idx0, flwdir_flat, shape, mv=np.intp(-1)):
+    """linear index of the downstream cell of idx0; mv when it lies outside the raster"""
+    nrow, ncol = shape
+    dr, dc = drdc(flwdir_flat[idx0])
+    r, c = idx0 // ncol + dr, idx0 % ncol + dc
+    if 0 <= r < nrow and 0 <= c < ncol:
+        return np.intp(r * ncol + c)
+    return mv
+
+
+def _upstream_idx(idx0, flwdir_flat, shape, dtype=np.intp):
+    """linear indices of the cells that drain into idx0"""
+    nrow, ncol = shape
+    r0, c0 = idx0 // ncol, idx0 % ncol
+    out = []
+    for dr in (-1, 0, 1):
+        for dc in (-1, 0, 1):
+            r, c = r0 + dr, c0 + dc
+            if (dr or dc) and 0 <= r < nrow and 0 <= c < ncol and flwdir_flat[r * ncol + c] == _us[dr + 1, dc + 1]:
+                out.append(r * ncol + c)
+    return np.array(out, dtype=dtype)

@@ -37,6 +37,9 @@
 #define TS_ROWS (TS_T + 2)
 #define TS_N (TS_S * TS_ROWS)   // 4752 staged cells
 #define TS_BMW 128              // done-bitmap words per tile (tile-major: word = ly * 2 + (lx >> 5), bit = lx & 31)
+#ifndef TS_TAIL
+#define TS_TAIL 32              // a frontier of at most this many cells is finished by warp 0 alone (no CTA barriers per round)
+#endif
 #define TS_NCHUNK (TS_T * TS_T / 16)  // a chunk = 16 consecutive cells of one row (one 128-bit vector of bytes); thread t works on
                                      // chunks t, t + NT, ...: row ch >> 2, columns (ch & 3) * 16 .. + 15
 
@@ -498,8 +501,29 @@ __device__ __forceinline__ void ts_up_visit(TsShared<typename Op::V, Op::AUX>& s
     uint32_t lo = 0;
     for (int rd = 0;; ++rd) {
         ts_sync<NT>();
-        const uint32_t n = s.cnt[rd % 3];
+        uint32_t n = s.cnt[rd % 3];
         if (n == 0) break;
+        if (NT > 32 && n <= TS_TAIL) {
+            // The tail -- a few ready cells, i.e. the rivers of the tile (and all there is in most revisits): warp 0
+            // finishes the remaining rounds alone. No CTA barrier and no idle warps spinning through the round loop.
+            if (threadIdx.x < 32) {
+                for (int r2 = rd; n != 0; ++r2) {
+                    if (threadIdx.x == 0) s.cnt[(r2 + 2) % 3] = 0;
+                    uint32_t* cn = &s.cnt[(r2 + 1) % 3];
+                    for (uint32_t e0 = 0; e0 < n; e0 += 32) {
+                        const uint32_t e = e0 + threadIdx.x;
+                        int next = -1;
+                        if (e < n) next = ts_up_step<Op>(s, op, s.u.q[lo + e]);
+                        ts_push(s.u.q, lo + n, cn, next >= 0, next);
+                    }
+                    __syncwarp();
+                    lo += n;
+                    n = *(volatile uint32_t*)cn;
+                }
+            }
+            ts_sync<NT>();
+            break;
+        }
         if (threadIdx.x == 0) s.cnt[(rd + 2) % 3] = 0;
         uint32_t* cn = &s.cnt[(rd + 1) % 3];
         for (uint32_t e0 = threadIdx.x & ~31u; e0 < n; e0 += NT) {  // warp-uniform trip count
@@ -600,6 +624,43 @@ __global__ void ts_reset_unranked_kernel(const uint8_t* __restrict__ dir, const 
 //   V fill()                value of the cells the sweep never reaches (nodata, cells draining to no pit)
 //   V* out
 // ---------------------------------------------------------------------------------------------------------
+// One entry of the round (called by all 32 lanes of a warp): the lane's resolved cell resolves its unresolved in-tile
+// children and appends them to the next round (warp-aggregated, so the frontier stays compacted).
+template <class Op>
+__device__ __forceinline__ void ts_down_expand(TsShared<typename Op::V, false>& s, const Op& op, uint32_t lo, uint32_t cnt, uint32_t e,
+                                               uint32_t* qn) {
+    typedef typename Op::V V;
+    uint32_t m = 0;
+    int ly = 0, lx = 0, p = 0;
+    V vp = V();
+    if (e < cnt) {
+        const int i = s.u.q[lo + e];
+        ly = i >> 6, lx = i & (TS_T - 1);
+        p = ts_si(ly, lx);
+        const uint32_t r = s.rec[p];
+        m = r & 0xFFu;
+        vp = s.val[p];
+        uint32_t om = r >> 8;
+        while (om) {  // a neighbour tile waits for this cell
+            const int k = __ffs(om) - 1;
+            om &= om - 1;
+            atomicOr(&s.act, ts_act_bit(ly + pfd_slot_dr(k), lx + pfd_slot_dc(k)));
+        }
+    }
+    while (__any_sync(0xFFFFFFFFu, m != 0u)) {
+        int n = -1;
+        if (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            const int c = p + ts_noff(k);
+            s.val[c] = op.down(vp, s.val[c]);
+            n = (ly + pfd_slot_dr(k)) * TS_T + lx + pfd_slot_dc(k);
+            atomicOr(&s.newbm[n >> 5], 1u << (n & 31));
+        }
+        ts_push(s.u.q, lo + cnt, qn, n >= 0, n);
+    }
+}
+
 template <int NT, class Op>
 __device__ __forceinline__ void ts_down_visit(TsShared<typename Op::V, false>& s, const TsArgs& A, const Op& op, int tile, int pass) {
     typedef typename Op::V V;
@@ -620,7 +681,7 @@ __device__ __forceinline__ void ts_down_visit(TsShared<typename Op::V, false>& s
 #pragma unroll 4
         for (int j = 0; j < 16; ++j) {
             const uint32_t d = s.u.pl.dir[base + j];
-            if (d != PFD_DIR_NODATA && !(s.u.pl.flag[base + j] & TSF_DONE)) {
+            if (d != PFD_DIR_NODATA && !(s.u.pl.flag[base + j] & (TSF_DONE | TSF_FOREIGN))) {  // (own, unresolved cells only)
                 const long long g = g0 + j;
                 s.val[base + j] = op.prep(g, d, (d < 8u) ? g + pfd_slot_off((int)d, A.ncol) : g);
                 if (op.source(g)) s.u.pl.flag[base + j] |= (uint8_t)TSF_SRC;
@@ -716,42 +777,26 @@ __device__ __forceinline__ void ts_down_visit(TsShared<typename Op::V, false>& s
     uint32_t lo = 0;
     for (int rd = 0;; ++rd) {
         ts_sync<NT>();
-        const uint32_t cnt = s.cnt[rd % 3];
+        uint32_t cnt = s.cnt[rd % 3];
         if (cnt == 0) break;
+        if (NT > 32 && cnt <= TS_TAIL) {  // the tail: warp 0 finishes the remaining rounds alone (see the up-sweep)
+            if (threadIdx.x < 32) {
+                for (int r2 = rd; cnt != 0; ++r2) {
+                    if (threadIdx.x == 0) s.cnt[(r2 + 2) % 3] = 0;
+                    uint32_t* qn = &s.cnt[(r2 + 1) % 3];
+                    for (uint32_t e0 = 0; e0 < cnt; e0 += 32) ts_down_expand<Op>(s, op, lo, cnt, e0 + threadIdx.x, qn);
+                    __syncwarp();
+                    lo += cnt;
+                    cnt = *(volatile uint32_t*)qn;
+                }
+            }
+            ts_sync<NT>();
+            break;
+        }
         if (threadIdx.x == 0) s.cnt[(rd + 2) % 3] = 0;
         uint32_t* qn = &s.cnt[(rd + 1) % 3];
-        for (uint32_t e0 = threadIdx.x & ~31u; e0 < cnt; e0 += NT) {  // warp-uniform trip count
-            const uint32_t e = e0 + (threadIdx.x & 31u);
-            uint32_t m = 0;
-            int ly = 0, lx = 0, p = 0;
-            V vp = V();
-            if (e < cnt) {
-                const int i = s.u.q[lo + e];
-                ly = i >> 6, lx = i & (TS_T - 1);
-                p = ts_si(ly, lx);
-                const uint32_t r = s.rec[p];
-                m = r & 0xFFu;
-                vp = s.val[p];
-                uint32_t om = r >> 8;
-                while (om) {  // a neighbour tile waits for this cell
-                    const int k = __ffs(om) - 1;
-                    om &= om - 1;
-                    atomicOr(&s.act, ts_act_bit(ly + pfd_slot_dr(k), lx + pfd_slot_dc(k)));
-                }
-            }
-            while (__any_sync(0xFFFFFFFFu, m != 0u)) {
-                int n = -1;
-                if (m) {
-                    const int k = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int c = p + ts_noff(k);
-                    s.val[c] = op.down(vp, s.val[c]);
-                    n = (ly + pfd_slot_dr(k)) * TS_T + lx + pfd_slot_dc(k);
-                    atomicOr(&s.newbm[n >> 5], 1u << (n & 31));
-                }
-                ts_push(s.u.q, lo + cnt, qn, n >= 0, n);
-            }
-        }
+        for (uint32_t e0 = threadIdx.x & ~31u; e0 < cnt; e0 += NT)  // warp-uniform trip count
+            ts_down_expand<Op>(s, op, lo, cnt, e0 + (threadIdx.x & 31u), qn);
         lo += cnt;
     }
     // pass 1 writes every cell: what is not resolved (yet, or never) holds the fill value
