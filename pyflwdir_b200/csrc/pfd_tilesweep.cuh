@@ -37,9 +37,6 @@
 #define TS_ROWS (TS_T + 2)
 #define TS_N (TS_S * TS_ROWS)   // 4752 staged cells
 #define TS_BMW 128              // done-bitmap words per tile (tile-major: word = ly * 2 + (lx >> 5), bit = lx & 31)
-#ifndef TS_TAIL
-#define TS_TAIL 32              // a frontier of at most this many cells is finished by warp 0 alone (no CTA barriers per round)
-#endif
 #define TS_NCHUNK (TS_T * TS_T / 16)  // a chunk = 16 consecutive cells of one row (one 128-bit vector of bytes); thread t works on
                                      // chunks t, t + NT, ...: row ch >> 2, columns (ch & 3) * 16 .. + 15
 
@@ -501,29 +498,8 @@ __device__ __forceinline__ void ts_up_visit(TsShared<typename Op::V, Op::AUX>& s
     uint32_t lo = 0;
     for (int rd = 0;; ++rd) {
         ts_sync<NT>();
-        uint32_t n = s.cnt[rd % 3];
+        const uint32_t n = s.cnt[rd % 3];
         if (n == 0) break;
-        if (NT > 32 && n <= TS_TAIL) {
-            // The tail -- a few ready cells, i.e. the rivers of the tile (and all there is in most revisits): warp 0
-            // finishes the remaining rounds alone. No CTA barrier and no idle warps spinning through the round loop.
-            if (threadIdx.x < 32) {
-                for (int r2 = rd; n != 0; ++r2) {
-                    if (threadIdx.x == 0) s.cnt[(r2 + 2) % 3] = 0;
-                    uint32_t* cn = &s.cnt[(r2 + 1) % 3];
-                    for (uint32_t e0 = 0; e0 < n; e0 += 32) {
-                        const uint32_t e = e0 + threadIdx.x;
-                        int next = -1;
-                        if (e < n) next = ts_up_step<Op>(s, op, s.u.q[lo + e]);
-                        ts_push(s.u.q, lo + n, cn, next >= 0, next);
-                    }
-                    __syncwarp();
-                    lo += n;
-                    n = *(volatile uint32_t*)cn;
-                }
-            }
-            ts_sync<NT>();
-            break;
-        }
         if (threadIdx.x == 0) s.cnt[(rd + 2) % 3] = 0;
         uint32_t* cn = &s.cnt[(rd + 1) % 3];
         for (uint32_t e0 = threadIdx.x & ~31u; e0 < n; e0 += NT) {  // warp-uniform trip count
@@ -541,7 +517,7 @@ __device__ __forceinline__ void ts_up_visit(TsShared<typename Op::V, Op::AUX>& s
 
 // All passes in one cooperative launch. grid-stride over the work list of the pass (pass 1: every tile).
 template <int NT, class Op>
-__global__ void __launch_bounds__(NT) tile_up_sweep_kernel(TsArgs A, Op op) {
+__global__ void __launch_bounds__(NT, 1024 / NT) tile_up_sweep_kernel(TsArgs A, Op op) {  // (at most 64 registers: occupancy)
     extern __shared__ __align__(16) unsigned char ts_smem_raw[];
     TsShared<typename Op::V, Op::AUX>& s = *reinterpret_cast<TsShared<typename Op::V, Op::AUX>*>(ts_smem_raw);
     cg::grid_group grid = cg::this_grid();
@@ -777,22 +753,8 @@ __device__ __forceinline__ void ts_down_visit(TsShared<typename Op::V, false>& s
     uint32_t lo = 0;
     for (int rd = 0;; ++rd) {
         ts_sync<NT>();
-        uint32_t cnt = s.cnt[rd % 3];
+        const uint32_t cnt = s.cnt[rd % 3];
         if (cnt == 0) break;
-        if (NT > 32 && cnt <= TS_TAIL) {  // the tail: warp 0 finishes the remaining rounds alone (see the up-sweep)
-            if (threadIdx.x < 32) {
-                for (int r2 = rd; cnt != 0; ++r2) {
-                    if (threadIdx.x == 0) s.cnt[(r2 + 2) % 3] = 0;
-                    uint32_t* qn = &s.cnt[(r2 + 1) % 3];
-                    for (uint32_t e0 = 0; e0 < cnt; e0 += 32) ts_down_expand<Op>(s, op, lo, cnt, e0 + threadIdx.x, qn);
-                    __syncwarp();
-                    lo += cnt;
-                    cnt = *(volatile uint32_t*)qn;
-                }
-            }
-            ts_sync<NT>();
-            break;
-        }
         if (threadIdx.x == 0) s.cnt[(rd + 2) % 3] = 0;
         uint32_t* qn = &s.cnt[(rd + 1) % 3];
         for (uint32_t e0 = threadIdx.x & ~31u; e0 < cnt; e0 += NT)  // warp-uniform trip count
@@ -804,7 +766,7 @@ __device__ __forceinline__ void ts_down_visit(TsShared<typename Op::V, false>& s
 }
 
 template <int NT, class Op>
-__global__ void __launch_bounds__(NT) tile_down_sweep_kernel(TsArgs A, Op op) {
+__global__ void __launch_bounds__(NT, 1024 / NT) tile_down_sweep_kernel(TsArgs A, Op op) {
     extern __shared__ __align__(16) unsigned char ts_smem_raw[];
     TsShared<typename Op::V, false>& s = *reinterpret_cast<TsShared<typename Op::V, false>*>(ts_smem_raw);
     cg::grid_group grid = cg::this_grid();
