@@ -57,11 +57,23 @@ def graph(idxs_ds, shape=None, ncol=None, device=0):
     return g
 
 
-def check_seq(g, seq, what):
-    """The sweeps run over the device's own "walk" sequence; a caller-supplied `seq` must cover the same cells."""
-    if seq is not None:
-        nn = g.order()[0]
-        if np.asarray(seq).size != nn:
+def check_seq(g, seq, what, order_sensitive=False):
+    """The sweeps run over the device's own "walk" sequence (what `core.idxs_seq` / `FlwdirRaster.idxs_seq` return). A
+    caller-supplied `seq` must cover the same cells; when the RESULT depends on the order inside `seq` (float sums over the
+    upstream cells, label / segment numbering in sequence order) a different order -- e.g. the `np.argsort(rank)` sequence of
+    the reference's test fixtures -- would give different values in the reference, so it is refused instead of silently
+    answering for the walk order (first row)."""
+    if seq is None:
+        return
+    seq = np.asarray(seq)
+    nn = g.order()[0]
+    if seq.size != nn:
+        raise NotImplementedError(
+            f"{what}: `seq` holds {seq.size} cells but {nn} cells drain to a pit; sweeps over a "
+            "partial sequence are outside the accelerated hot path")
+    if order_sensitive:
+        walk = g.fetch(_lib.ARR_SEQ, np.int64 if seq.dtype.itemsize == 8 else np.int32)
+        if not np.array_equal(walk, seq.ravel()):
             raise NotImplementedError(
-                f"{what}: `seq` holds {np.asarray(seq).size} cells but {nn} cells drain to a pit; sweeps over a "
-                "partial sequence are outside the accelerated hot path")
+                f"{what}: the result depends on the order of the cells inside `seq`, and the device sweeps the \"walk\" order "
+                "(core.idxs_seq); pass that sequence (FlwdirRaster.idxs_seq), or integer data for accumulations")

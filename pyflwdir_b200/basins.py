@@ -27,7 +27,7 @@ def interbasin_mask(idxs_ds, seq, region, stream=None, shape=None, ncol=None):
 def subbasins_streamorder(idxs_ds, seq, strord, mask=None, min_sto=-2, shape=None, ncol=None):
     """Returns map with basin IDs, with a basin ID for subbasins of each stream order (basins.py:67-103)"""
     g = _functional.graph(idxs_ds, shape, ncol)
-    _functional.check_seq(g, seq, "subbasins_streamorder")
+    _functional.check_seq(g, seq, "subbasins_streamorder", order_sensitive=True)  # labels are numbered in sequence order
     return g.subbasins_streamorder(np.asarray(strord).ravel(), None if mask is None else np.asarray(mask).ravel(), min_sto,
                                    np.asarray(idxs_ds).dtype)
 
@@ -35,7 +35,7 @@ def subbasins_streamorder(idxs_ds, seq, strord, mask=None, min_sto=-2, shape=Non
 def subbasins_pfafstetter(idxs_pit, idxs_ds, seq, idxs_us_main, uparea, mask=None, depth=1, mv=-1, shape=None, ncol=None):
     """Returns the pfafstetter subbasin map and outlet indices (basins.py:106-191)"""
     g = _functional.graph(idxs_ds, shape, ncol)
-    _functional.check_seq(g, seq, "subbasins_pfafstetter")
+    _functional.check_seq(g, seq, "subbasins_pfafstetter", order_sensitive=True)
     if not np.array_equal(np.asarray(idxs_pit).astype(np.int64), g.fetch(_lib.ARR_PITS, np.int64)):
         raise NotImplementedError("subbasins_pfafstetter from a subset of the pits is outside the accelerated hot path")
     return g.subbasins_pfafstetter(idxs_us_main, np.asarray(uparea).ravel(), None if mask is None else np.asarray(mask).ravel(),
@@ -45,5 +45,5 @@ def subbasins_pfafstetter(idxs_pit, idxs_ds, seq, idxs_us_main, uparea, mask=Non
 def subbasins_area(idxs_ds, seq, idxs_us_main, uparea, area_min, shape=None, ncol=None):
     """Returns map with basin IDs, with a minimal area of `area_min` (basins.py:194-233)"""
     g = _functional.graph(idxs_ds, shape, ncol)
-    _functional.check_seq(g, seq, "subbasins_area")
+    _functional.check_seq(g, seq, "subbasins_area", order_sensitive=True)
     return g.subbasins_area(idxs_us_main, np.asarray(uparea).ravel(), area_min, np.asarray(idxs_ds).dtype)

@@ -69,7 +69,7 @@ def fillnodata_downstream(idxs_ds, seq, data, nodata, how="max", shape=None, nco
     confluences with how = "max" | "min" | "sum" (core.py:149-188)."""
     assert how in ["min", "max", "sum"]
     g = _functional.graph(idxs_ds, shape, ncol)
-    _functional.check_seq(g, seq, "fillnodata_downstream")
+    _functional.check_seq(g, seq, "fillnodata_downstream", order_sensitive=how == "sum" and np.asarray(data).dtype.kind == "f")
     return g.fillnodata(np.asarray(data).ravel(), nodata, "down", how)
 
 
@@ -110,14 +110,14 @@ def snap(idxs0, idxs_nxt, ncol=None, mask=None, max_length=None, real_length=Fal
 def inflow_idxs(idxs_ds, seq, region, shape=None, ncol=None):
     """returns linear indices of most upstream cells within region (core.py:483-497)"""
     g = _functional.graph(idxs_ds, shape, ncol)
-    _functional.check_seq(g, seq, "inflow_idxs")
+    _functional.check_seq(g, seq, "inflow_idxs", order_sensitive=True)  # the indices come back in sequence order
     return g.inflow_idxs(np.asarray(region).ravel(), np.asarray(idxs_ds).dtype)
 
 
 def outflow_idxs(idxs_ds, seq, region, shape=None, ncol=None):
     """returns linear indices of most downstream cells within region (core.py:500-514)"""
     g = _functional.graph(idxs_ds, shape, ncol)
-    _functional.check_seq(g, seq, "outflow_idxs")
+    _functional.check_seq(g, seq, "outflow_idxs", order_sensitive=True)
     return g.outflow_idxs(np.asarray(region).ravel(), np.asarray(idxs_ds).dtype)
 
 

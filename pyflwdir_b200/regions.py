@@ -75,5 +75,5 @@ def region_outlets(regions, idxs_ds, seq, shape=None, ncol=None):
     if shape is None and regions.ndim == 2:
         shape = regions.shape
     g = _functional.graph(idxs_ds, shape, ncol)
-    _functional.check_seq(g, seq, "region_outlets")
+    _functional.check_seq(g, seq, "region_outlets", order_sensitive=True)  # ties between outlets follow the sequence
     return g.region_outlets(regions.ravel(), np.asarray(idxs_ds).dtype)

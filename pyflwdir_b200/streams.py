@@ -1,6 +1,7 @@
 """Sweeps over the flow sequence on the GPU; mirrors /root/reference/pyflwdir/streams.py (accuflux :15-41,
 accuflux_ds :44-70, stream_order :191-225, strahler_order :228-269). The device always sweeps its own "walk" sequence (the one
-`core.idxs_seq` returns); `seq` is only checked for covering the same cells."""
+`core.idxs_seq` returns): `seq` must cover the same cells, and where the result depends on the order inside `seq` (float
+sums, segment numbering) it must BE that sequence (`_functional.check_seq`)."""
 import numpy as np
 
 from . import _functional, _lib
@@ -9,7 +10,7 @@ from . import _functional, _lib
 def accuflux(idxs_ds, seq, data, nodata, shape=None, ncol=None):
     """Returns maps of accumulate upstream <data>"""
     g = _functional.graph(idxs_ds, shape, ncol)
-    _functional.check_seq(g, seq, "accuflux")
+    _functional.check_seq(g, seq, "accuflux", order_sensitive=np.asarray(data).dtype.kind == "f")  # float sums follow seq
     return g.accuflux(np.asarray(data).ravel(), nodata, "up")
 
 
@@ -37,7 +38,7 @@ def strahler_order(idxs_ds, seq, mask=None, shape=None, ncol=None):
 def streams(idxs_ds, seq, mask=None, max_len=0, mv=-1, shape=None, ncol=None):
     """Returns list of linear indices per stream of equal stream order (streams.py:131-188)."""
     g = _functional.graph(idxs_ds, shape, ncol)
-    _functional.check_seq(g, seq, "streams")
+    _functional.check_seq(g, seq, "streams", order_sensitive=True)  # segments are listed in sequence order
     return g.streams(mask, max_len, np.asarray(idxs_ds).dtype)
 
 
@@ -50,7 +51,7 @@ def upstream_area(idxs_ds, seq, ncol, latlon=False, transform=(1.0, 0.0, 0.0, 0.
     idxs_ds = np.asarray(idxs_ds)
     nrow = idxs_ds.size // int(ncol)
     g = _functional.graph(idxs_ds, (nrow, int(ncol)), None)
-    _functional.check_seq(g, seq, "upstream_area")
+    _functional.check_seq(g, seq, "upstream_area", order_sensitive=np.dtype(dtype).kind == "f")
     xres, yres, north = transform[0], transform[4], transform[5]
     uparea = np.full(idxs_ds.size, nodata, dtype=dtype)
     inseq = g.fetch(_lib.ARR_RANK) >= 0

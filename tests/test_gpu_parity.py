@@ -450,3 +450,29 @@ def test_upstream_matrix_and_dump_load(pfb, tmp_path):
     assert np.array_equal(flw2.idxs_ds, flw.idxs_ds) and np.array_equal(flw2.idxs_pit, flw.idxs_pit)
     assert np.array_equal(flw2.idxs_seq, seq) and flw2.nnodes == flw.nnodes
     assert np.array_equal(flw2.upstream_area(), flw.upstream_area()) and cs.sha(flw2.basins()) == cs.hashes()["rhine"]["basins"]
+
+
+def test_module_level_seq_order_is_honoured_or_refused(pfb):
+    """The module-level mirrors sweep the "walk" order. A caller-supplied `seq` in another valid order (the reference's
+    fixtures use np.argsort(rank)) is accepted where the result cannot depend on it (integer accumulation, Strahler, HAND)
+    and refused where it would (float sums, label numbering) -- never silently answered for a different order."""
+    from pyflwdir_b200 import basins, dem, streams
+
+    d8 = cs.case_d8("flwdir1_asc")
+    ids, walk = cs.golden("flwdir1_asc", "idxs_ds"), cs.golden("flwdir1_asc", "idxs_seq")
+    rank = cs.golden("flwdir1_asc", "rank").ravel()
+    sort_seq = np.argsort(rank, kind="stable")[-walk.size:].astype(walk.dtype)
+    assert not np.array_equal(sort_seq, walk) and np.all(np.diff(rank[sort_seq]) >= 0)
+    ones = np.ones(ids.size, np.int32)
+    upa = streams.accuflux(ids, sort_seq, ones, -9999, shape=d8.shape)
+    assert np.array_equal(upa, oracle.streams.accuflux(ids, sort_seq, ones, -9999))  # integers: any valid order
+    assert np.array_equal(streams.strahler_order(ids, sort_seq, shape=d8.shape), oracle.streams.strahler_order(ids, sort_seq))
+    elev = np.random.default_rng(1).random(ids.size, dtype=np.float32)
+    assert np.array_equal(dem.height_above_nearest_drain(ids, sort_seq, upa > 20, elev, shape=d8.shape),
+                          oracle.dem.height_above_nearest_drain(ids, sort_seq, upa > 20, elev))
+    area = np.random.default_rng(2).random(ids.size)
+    assert np.array_equal(streams.accuflux(ids, walk, area, -9999, shape=d8.shape), oracle.streams.accuflux(ids, walk, area, -9999))
+    with pytest.raises(NotImplementedError, match="order of the cells"):
+        streams.accuflux(ids, sort_seq, area, -9999, shape=d8.shape)
+    with pytest.raises(NotImplementedError, match="order of the cells"):
+        basins.subbasins_streamorder(ids, sort_seq, streams.strahler_order(ids, walk, shape=d8.shape), shape=d8.shape)
