@@ -355,6 +355,27 @@ int pfd_sweep_tiled_end(pfd_handle* h, void* out, int64_t* resolved);
 int pfd_sweep_tiled(pfd_handle* h, int kind, const void* data, int dtype, const uint8_t* drain, double nodata_f,
                     int64_t nodata_i, int nodata_is_int, void* out, int64_t* rounds);
 
+/* ---- the step before the path ----------------------------------------------------------- */
+/*
+ * dem.fill_depressions (pyflwdir/dem.py:17-143; pyflwdir.from_dem, pyflwdir/pyflwdir.py:51-102, is this followed by
+ * pfd_d8_parse): depression-filled elevation and the D8 codes of the reference's priority flood, bit for bit. Does not
+ * touch the raster parsed on the handle.
+ *   elevtn / elevtn_out : nrow*ncol values of PFD_F32 or PFD_F64. Integer rasters are passed as PFD_F64 with int_delv = 1
+ *                         (numba's typing of the loop: arithmetic in float64, the raise truncated to the integer type).
+ *   outlets_mode        : 0 = outlets="edge", 1 = outlets="min", 2 = idxs_pit (n_pit int64 linear indices).
+ *   nodata              : may be NaN. has_elv_max / elv_max: the optional elv_max of outlets="edge".
+ *   connectivity        : 4 or 8.  max_depth: must be negative (fill everything); >= 0 -> PFD_ERR_UNSUPPORTED.
+ *   stats (may be NULL) : int64[12] = relaxation passes (levels, tie labels), cells in tie components, tie components,
+ *                         cells no outlet reaches, initial outlets, final band (float32 bits), largest component, largest
+ *                         key drift seen (float32 bits), number of label + replay rounds, microseconds spent on the levels / on the rest.
+ * PFD_ERR_INVALID_ARG with the reference's message when elv_max leaves no outlet ("No initial outlet cells found.").
+ * Float32 rasters: raising a cell (z1 += z0 - z1) is inexact, the reference's heap keys drift around the pour level; the
+ * replay follows them exactly (csrc/pfd_fill.cuh), widening the band of "tied" levels until it covers the drift.
+ */
+int pfd_fill_depressions(pfd_handle* h, const void* elevtn, int elev_dtype, int64_t nrow, int64_t ncol, int outlets_mode,
+                         const int64_t* idxs_pit, int64_t n_pit, double nodata, double max_depth, int has_elv_max,
+                         double elv_max, int connectivity, int int_delv, void* elevtn_out, uint8_t* d8_out, int64_t* stats);
+
 /* ---- synthetic input (bench / tests) ---------------------------------------------------- */
 /* z: nrow*ncol float32 (device or host) elevation; d8 from z by strict steepest descent. */
 int pfd_synth_elevation(pfd_handle* h, int64_t nrow, int64_t ncol, int64_t nref, int octaves, uint32_t seed,

@@ -705,7 +705,38 @@ def _floodplains(idxs_ds, seq, elevtn, uparea, upa_min=1000.0, b=0.3):
     return fldpln
 
 
-dem = types.SimpleNamespace(height_above_nearest_drain=_hand, floodplains=_floodplains)
+def _fill_depressions(elevtn, outlets="edge", idxs_pit=None, nodata=-9999.0, max_depth=-1.0, elv_max=None, connectivity=8):
+    """pyflwdir/dem.py:17-143 -> (filled elevation, d8). float32 / float64 / integer elevation rasters."""
+    e = np.ascontiguousarray(elevtn)
+    if e.ndim != 2:
+        raise ValueError("elevtn must be 2D")
+    if connectivity not in (4, 8):
+        raise ValueError('"connectivity" should either be 4 or 8')
+    int_delv = 0
+    if e.dtype == np.float32:
+        w, sfx = e, "f32"
+    elif e.dtype == np.float64:
+        w, sfx = e, "f64"
+    elif np.issubdtype(e.dtype, np.integer):
+        w, sfx, int_delv = e.astype(np.float64), "f64", 1
+    else:
+        raise TypeError("oracle fill_depressions: float32 / float64 / integer elevation only")
+    mode = 2 if idxs_pit is not None else {"edge": 0, "min": 1}.get(outlets, 0)
+    pits = np.ascontiguousarray(idxs_pit if idxs_pit is not None else [], dtype=np.int64)
+    out = np.empty_like(w)
+    d8 = np.empty(w.shape, dtype=np.uint8)
+    rc = getattr(lib(), f"orc_fill_depressions_{sfx}")(
+        _p(w), C.c_int64(w.shape[0]), C.c_int64(w.shape[1]), C.c_int(mode), _p(pits), C.c_int64(pits.size),
+        C.c_double(nodata), C.c_double(max_depth), C.c_int(elv_max is not None and mode != 2),
+        C.c_double(0.0 if elv_max is None else elv_max), C.c_int(connectivity), C.c_int(int_delv), _p(out), _p(d8))
+    if rc == 1:
+        raise ValueError("No initial outlet cells found.")
+    if rc != 0:
+        raise MemoryError("oracle fill_depressions")
+    return out.astype(e.dtype, copy=False), d8
+
+
+dem = types.SimpleNamespace(height_above_nearest_drain=_hand, floodplains=_floodplains, fill_depressions=_fill_depressions)
 
 
 # ----------------------------------------------------------------------------- synthetic input (host)

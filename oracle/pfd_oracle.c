@@ -14,6 +14,7 @@
  *   streams.accuflux / accuflux_ds / strahler_order
  *                                             /root/reference/pyflwdir/streams.py:15-41,44-70,228-269
  *   dem.height_above_nearest_drain            /root/reference/pyflwdir/dem.py:299-330
+ *   dem.fill_depressions (pfd_oracle_fill.inc)  /root/reference/pyflwdir/dem.py:17-143
  * Parity is PINNED: tests/golden/make_golden.py imports the real reference (numba) in the build
  * container and writes golden vectors; tests/test_oracle.py checks this library against them (and
  * against the live reference whenever /root/reference is present).
@@ -99,6 +100,18 @@ int orc_d8_check_values(const uint8_t* flwdir, int64_t size) {
 #include "pfd_oracle_body.inc"
 #undef IDX
 #undef SFX
+
+/* ---- dem.fill_depressions (dem.py:17-143): one instance per elevation type ---- */
+#define FILL_T float
+#define FILL_SFX f32
+#include "pfd_oracle_fill.inc"
+#undef FILL_T
+#undef FILL_SFX
+#define FILL_T double
+#define FILL_SFX f64
+#include "pfd_oracle_fill.inc"
+#undef FILL_T
+#undef FILL_SFX
 
 /* ---- synthetic input (not part of the reference): SURVEY.md §8(d) generator, host version ---- */
 /* The generator (NOT part of the measured path) is split over rows with pthreads so that the CPU-only reference arm

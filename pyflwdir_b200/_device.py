@@ -63,6 +63,40 @@ class DeviceGraph:
     def info(self, name):
         return int(self._l.pfd_get_info(self._h, name.encode()))
 
+    # -- the step before the path: dem.fill_depressions (does not touch the parsed raster of this handle)
+    def fill_depressions(self, elevtn, outlets="edge", idxs_pit=None, nodata=-9999.0, max_depth=-1.0, elv_max=None,
+                         connectivity=8):
+        e = np.asarray(elevtn)
+        if e.ndim != 2:
+            raise ValueError("elevtn should be a 2D array")
+        int_delv = 0
+        if e.dtype in (np.float32, np.float64):
+            w = np.ascontiguousarray(e)
+        elif np.issubdtype(e.dtype, np.integer) or e.dtype == np.bool_:
+            w, int_delv = np.ascontiguousarray(e, dtype=np.float64), 1  # numba's typing of the loop for integer rasters
+        else:
+            w = np.ascontiguousarray(e, dtype=np.float64)
+        if outlets not in ("edge", "min"):
+            outlets = "edge"  # the reference only tests `outlets == "min"`
+        mode = 2 if idxs_pit is not None else (1 if outlets == "min" else 0)
+        pits = np.ascontiguousarray([] if idxs_pit is None else idxs_pit, dtype=np.int64).ravel()
+        out = _lib.out_array(w.size, w.dtype)
+        d8 = _lib.out_array(w.size, np.uint8)
+        stats = np.zeros(12, dtype=np.int64)
+        self._ck(self._l.pfd_fill_depressions(
+            self._h, _lib.ptr(w), _lib.dtype_code(w.dtype), w.shape[0], w.shape[1], mode, _lib.ptr(pits) if pits.size else None,
+            pits.size, C.c_double(float(nodata)), C.c_double(float(max_depth)), int(elv_max is not None and mode != 2),
+            C.c_double(0.0 if elv_max is None else float(elv_max)), int(connectivity), int_delv, _lib.ptr(out), _lib.ptr(d8),
+            _lib.ptr(stats)))
+        self.fill_stats = dict(zip(("level_passes", "label_passes", "tied_cells", "tie_components", "unreached", "outlets", "band",
+                                    "largest_component", "max_drift", "tries", "levels_us", "ties_us"), stats.tolist()))
+        for k in ("band", "max_drift"):  # float32 bit patterns
+            self.fill_stats[k] = float(np.array([self.fill_stats[k]], dtype=np.uint32).view(np.float32)[0])
+        out = np.array(out).reshape(w.shape)
+        if int_delv:
+            out = out.astype(e.dtype)
+        return out, np.array(d8).reshape(w.shape)
+
     # -- parse
     def parse_d8(self, d8, idx_dtype=None, want_idxs=False, ftype="d8"):
         """core_d8.from_array / core_ldd.from_array on the device. 2-D uint8 raster (host) -> optional idxs_ds."""

@@ -96,6 +96,8 @@ SYMBOLS = {
     "pfd_synth_d8": (_int, [_vp, _vp, _i64, _i64, C.c_float, _vp]),
     "pfd_set_option": (_int, [_vp, C.c_char_p, _i64]),
     "pfd_get_info": (_i64, [_vp, C.c_char_p]),
+    "pfd_fill_depressions": (_int, [_vp, _vp, _int, _i64, _i64, _int, _vp, _i64, C.c_double, C.c_double, _int, C.c_double, _int, _int,
+                             _vp, _vp, _vp]),
     "pfd_synth_d8_block": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _int, _u32, C.c_float, _vp]),
     "pfd_verify_flow": (_int, [_vp, _vp, _int, _vp, _vp, _vp, _pi64]),
     "pfd_verify_strahler": (_int, [_vp, _vp, _vp, _pi64]),

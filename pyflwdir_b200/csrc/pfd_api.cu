@@ -3830,3 +3830,45 @@ extern "C" int pfd_synth_d8_block(pfd_handle* h, int64_t row0, int64_t nrow, int
     PFD_CUDA(h, cudaStreamSynchronize(h->stream));
     return PFD_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// dem.fill_depressions (pyflwdir/dem.py:17-143) -- SURVEY.md §8f-3; kernels in pfd_fill.cuh
+// ---------------------------------------------------------------------------------------------------------
+#include "pfd_fill.cuh"
+
+extern "C" int pfd_fill_depressions(pfd_handle* h, const void* elevtn, int elev_dtype, int64_t nrow, int64_t ncol, int outlets_mode,
+                                    const int64_t* idxs_pit, int64_t n_pit, double nodata, double max_depth, int has_elv_max,
+                                    double elv_max, int connectivity, int int_delv, void* elevtn_out, uint8_t* d8_out, int64_t* stats) {
+    PFD_TRY(check_handle(h));
+    if (!elevtn || !elevtn_out || !d8_out || nrow < 0 || ncol < 0) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_fill_depressions: bad argument");
+    if (elev_dtype != PFD_F32 && elev_dtype != PFD_F64)
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_fill_depressions: elevtn must be float32 or float64 (integers: pass float64 with int_delv)");
+    if (connectivity != 4 && connectivity != 8) return pfd_fail(h, PFD_ERR_INVALID_ARG, "\"connectivity\" should either be 4 or 8");
+    if (outlets_mode < 0 || outlets_mode > 2 || (outlets_mode == 2 && n_pit > 0 && !idxs_pit))
+        return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_fill_depressions: outlets_mode is 0 (edge), 1 (min) or 2 (idxs_pit)");
+    if (max_depth >= 0)
+        return pfd_fail(h, PFD_ERR_UNSUPPORTED,
+                        "pfd_fill_depressions: max_depth >= 0 (re-opening of visited cells, dem.py:121-132) is not implemented on the device");
+    const int64_t n = nrow * ncol;
+    if (n >= (1ll << 31)) return pfd_fail(h, PFD_ERR_UNSUPPORTED, "pfd_fill_depressions: rasters of 2^31 cells or more are not supported");
+    if (n == 0) return PFD_OK;
+    const size_t esz = pfd_dtype_size(elev_dtype);
+    const void* elev_dev = nullptr;
+    void* out_dev = nullptr;
+    void* d8_dev = nullptr;
+    const void* pit_dev = nullptr;
+    PFD_TRY(pfd_stage_in(h, elevtn, (size_t)n * esz, 0, &elev_dev));
+    PFD_TRY(pfd_stage_out(h, elevtn_out, (size_t)n * esz, 1, &out_dev));
+    PFD_TRY(pfd_stage_out(h, d8_out, (size_t)n, 2, &d8_dev));
+    if (outlets_mode == 2 && n_pit > 0) PFD_TRY(pfd_stage_in(h, idxs_pit, (size_t)n_pit * sizeof(int64_t), 3, &pit_dev));
+    if (elev_dtype == PFD_F32)
+        PFD_TRY((fd_fill_impl<float, float>(h, (const float*)elev_dev, nrow, ncol, outlets_mode, (const int64_t*)pit_dev, n_pit, nodata, has_elv_max,
+                                            elv_max, connectivity, int_delv, (float*)out_dev, (uint8_t*)d8_dev, stats)));
+    else
+        PFD_TRY((fd_fill_impl<double, double>(h, (const double*)elev_dev, nrow, ncol, outlets_mode, (const int64_t*)pit_dev, n_pit, nodata,
+                                              has_elv_max, elv_max, connectivity, int_delv, (double*)out_dev, (uint8_t*)d8_dev, stats)));
+    PFD_TRY(pfd_finish_out(h, elevtn_out, out_dev, (size_t)n * esz));
+    PFD_TRY(pfd_finish_out(h, d8_out, d8_dev, (size_t)n));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    return PFD_OK;
+}

@@ -1,8 +1,36 @@
-"""Elevation-coupled sweeps on the GPU; mirrors /root/reference/pyflwdir/dem.py (height_above_nearest_drain :299-330,
-floodplains :333-379). The serial DEM-conditioning algorithms of that module are not provided."""
+"""Elevation-coupled algorithms on the GPU; mirrors /root/reference/pyflwdir/dem.py (fill_depressions :17-143,
+height_above_nearest_drain :299-330, floodplains :333-379). The remaining serial DEM-conditioning algorithms of that module
+are not provided."""
 import numpy as np
 
-from . import _functional
+from . import _device, _functional
+
+__all__ = ["fill_depressions", "height_above_nearest_drain", "floodplains"]
+
+
+def fill_depressions(elevtn, outlets="edge", idxs_pit=None, nodata=-9999.0, max_depth=-1.0, elv_max=None, connectivity=8,
+                     device=0):
+    """Fill local depressions in elevation data and derive local D8 flow directions (Wang & Liu 2006), the reference's
+    priority flood (dem.py:17-143) reproduced bit for bit on the GPU (csrc/pfd_fill.cuh): levels by parallel min/max
+    relaxation, the heap order inside flats / filled lakes replayed per tie component.
+
+    Outlets are the edge cells of the valid elevation cells (`outlets='edge'`, optionally only those with elevation
+    <= `elv_max`), the lowest edge cell (`outlets='min'`) or the cells `idxs_pit`. `connectivity` is 4 or 8.
+    `max_depth >= 0` (pits at depressions deeper than max_depth) is not implemented: NotImplementedError.
+
+    Returns (elevtn_out, d8): the depression-filled elevation (dtype of `elevtn`) and uint8 D8 flow directions."""
+    if connectivity not in (4, 8):
+        raise ValueError('"connectivity" should either be 4 or 8')
+    if max_depth >= 0:
+        raise NotImplementedError(
+            "dem.fill_depressions(max_depth >= 0) re-opens visited cells in heap order (pyflwdir/dem.py:121-132); only "
+            "max_depth < 0 (fill every depression) is implemented on the device -- use Deltares/pyflwdir for it")
+    g = _device.DeviceGraph(device)
+    try:
+        return g.fill_depressions(elevtn, outlets=outlets, idxs_pit=idxs_pit, nodata=nodata, max_depth=max_depth,
+                                  elv_max=elv_max, connectivity=connectivity)
+    finally:
+        g.close()
 
 
 def height_above_nearest_drain(idxs_ds, seq, drain, elevtn, shape=None, ncol=None):
@@ -37,7 +65,6 @@ def _serial(name, where):
     return fn
 
 
-fill_depressions = _serial("fill_depressions", "pyflwdir/dem.py:17-143, priority-flood")
 adjust_elevation = _serial("adjust_elevation", "pyflwdir/dem.py:146-168")
 dig_4connectivity = _serial("dig_4connectivity", "pyflwdir/dem.py:404-439")
 slope = _serial("slope", "pyflwdir/dem.py:228-296; its hypot is the C library's, which is not correctly rounded")

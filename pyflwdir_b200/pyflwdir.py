@@ -129,14 +129,14 @@ def from_array(data, ftype="infer", check_ftype=True, mask=None, transform=gis.I
     )
 
 
-def from_dem(data, nodata=-9999.0, max_depth=-1.0, transform=gis.IDENTITY, latlon=False, **kwargs):
-    """Flow directions derived from elevation (pyflwdir.py:51-102 -> dem.fill_depressions, dem.py:17-143). Not provided:
-    the D8 raster the reference derives is defined by the pop order of its priority queue cell by cell (inside every
-    filled depression a lowest-index-first search), which a data-parallel algorithm cannot reproduce bit for bit; run
-    `pyflwdir.from_dem(...).to_array()` on the reference and pass the D8 raster to `from_array` here."""
-    raise NotImplementedError(
-        "from_dem / dem.fill_depressions (priority-flood) is outside the D8 hot path that pyflwdir_b200 accelerates "
-        "(DESIGN.md §1); derive the D8 raster with Deltares/pyflwdir and parse it with pyflwdir_b200.from_array")
+def from_dem(data, nodata=-9999.0, max_depth=-1.0, transform=gis.IDENTITY, latlon=False, outlets="edge", **kwargs):
+    """Flow direction raster derived from digital elevation data (pyflwdir.py:51-102): dem.fill_depressions on the GPU
+    (outlets at the edge of the valid cells, or only the lowest one with outlets="min"; depressions filled to their pour
+    point) followed by from_array on the resulting D8 raster. `max_depth >= 0` is not implemented (see dem.fill_depressions)."""
+    from . import dem
+
+    d8 = dem.fill_depressions(data, nodata=nodata, max_depth=max_depth, outlets=outlets, device=kwargs.get("device", 0))[1]
+    return from_array(d8, ftype="d8", check_ftype=False, transform=transform, latlon=latlon, **kwargs)
 
 
 class FlwdirRaster(Flwdir):

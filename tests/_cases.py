@@ -424,3 +424,55 @@ def run_api_case(pf, d8, aux, transform=None, latlon=False):
     out["estuary_f64"] = flw.classify_estuaries(elev0, rivwth32.astype(np.float64), rivdst=flw.distnc.astype(np.float64) * 0.5,
                                                 min_convergence=1e-3, max_elevtn=1.5)
     return out
+
+
+# ----------------------------------------------------------------------------- dem.fill_depressions cases
+def fill_cases():
+    """name -> (elevation raster, kwargs) of the dem.fill_depressions parity cases: the reference's own test rasters
+    (tests/conftest.py:57-60 rand(15, 10) seed 2345; tests/test_dem.py:13-22 Wang & Liu's example), ties (integer-valued
+    and integer-typed rasters: every level is a flat), nodata holes, both connectivities and all outlet modes."""
+    wl = np.array([[15, 15, 14, 15, 12, 6, 12], [14, 13, 10, 12, 15, 17, 15], [15, 15, 9, 11, 8, 15, 15],
+                   [16, 17, 8, 16, 15, 7, 5], [19, 18, 19, 18, 17, 15, 14]])
+    np.random.seed(2345)
+    rand1510 = np.random.rand(15, 10)
+    rng = np.random.default_rng(77)
+    f32 = rng.random((40, 50), dtype=np.float32) * np.float32(100.0)
+    f32_holes = f32.copy()
+    f32_holes[rng.random(f32.shape) < 0.12] = -9999.0
+    ties = rng.integers(0, 6, size=(30, 33)).astype(np.float32)
+    ties_holes = ties.copy()
+    ties_holes[rng.random(ties.shape) < 0.1] = -9999.0
+    i32 = rng.integers(0, 25, size=(37, 29)).astype(np.int32)
+    f64r = np.round(rng.random((33, 41)) * 20.0, 1)  # float64 with many float32-key ties
+    nanr = rng.random((25, 31))
+    nanr[rng.random(nanr.shape) < 0.15] = np.nan
+    z = oracle.synth_elevation(96, 130, seed=5)
+    zsea = np.where(z < np.quantile(z, 0.1), np.float32(-9999.0), z * np.float32(500.0)).astype(np.float32)
+    cases = {
+        "rand15x10": (rand1510, {}),
+        "rand15x10_min": (rand1510, dict(outlets="min")),
+        "wangliu_f32": (wl.astype(np.float32), {}),
+        "wangliu_i32": (wl.astype(np.int32), {}),
+        "wangliu_min": (wl.astype(np.float32), dict(outlets="min")),
+        "wangliu_c4": (wl.astype(np.float32), dict(connectivity=4)),
+        "f32_40x50": (f32, {}),
+        "f32_holes": (f32_holes, {}),
+        "f32_holes_c4": (f32_holes, dict(connectivity=4)),
+        "f32_elvmax": (f32, dict(elv_max=30.0)),
+        "f32_pits": (f32, dict(idxs_pit=np.array([7, 1033, 1999]))),
+        "ties_f32": (ties, {}),
+        "ties_f32_c4": (ties, dict(connectivity=4)),
+        "ties_holes_min": (ties_holes, dict(outlets="min")),
+        "ties_i32": (i32, {}),
+        "round_f64": (f64r, {}),
+        "nan_nodata": (nanr, dict(nodata=np.nan)),
+        "synth_sea": (zsea, {}),
+        "synth_f64": (z.astype(np.float64), {}),
+    }
+    return cases
+
+
+def fill_mid_case():
+    """512 x 768 synthetic terrain (hash-only golden)."""
+    z = oracle.synth_elevation(512, 768, seed=31)
+    return (z * np.float32(800.0)).astype(np.float32), {}

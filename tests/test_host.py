@@ -236,11 +236,15 @@ def test_out_of_scope_entry_points_raise():
     """What stays on the reference side of the boundary says so instead of computing something else."""
     from pyflwdir_b200 import dem
 
-    for fn, args in ((pfb.from_dem, (np.zeros((4, 4), np.float32),)), (dem.fill_depressions, (np.zeros((4, 4), np.float32),)),
-                     (dem.adjust_elevation, (None, None, None)), (dem.dig_4connectivity, (None, None, None, (1, 1))),
+    for fn, args in ((dem.adjust_elevation, (None, None, None)), (dem.dig_4connectivity, (None, None, None, (1, 1))),
                      (dem.slope, (np.zeros((4, 4), np.float32),))):
         with pytest.raises(NotImplementedError, match="outside the D8 hot path"):
             fn(*args)
+    # the one branch of the priority flood that is not restated on the device says so before touching the GPU
+    with pytest.raises(NotImplementedError, match="max_depth"):
+        dem.fill_depressions(np.zeros((4, 4), np.float32), max_depth=2.0)
+    with pytest.raises(ValueError, match="connectivity"):
+        dem.fill_depressions(np.zeros((4, 4), np.float32), connectivity=6)
 
 
 def test_region_sum_and_area_match_scipy():

@@ -117,3 +117,57 @@ def test_oracle_nextxy_golden():
     masked[:, 100:, 150:] = -9999
     ids_m, pits_m, _ = oracle.core_nextxy.from_array(masked, dtype=np.int32)
     assert np.array_equal(ids_m, s["out/nextxy_flwdir1/masked_idxs_ds"]) and np.array_equal(pits_m, s["out/nextxy_flwdir1/masked_idxs_pit"])
+
+
+def _fill_golden():
+    import os
+
+    return dict(np.load(os.path.join(cs.GOLDEN, "fill_cases.npz")))
+
+
+@pytest.mark.parametrize("name", sorted(cs.fill_cases()))
+def test_oracle_fill_depressions_golden(name, oracle_lib):
+    """oracle/pfd_oracle_fill.inc against the reference's dem.fill_depressions outputs (tests/golden/make_golden_fill.py)."""
+    g = _fill_golden()
+    a, kw = cs.fill_cases()[name]
+    filled, d8 = oracle.dem.fill_depressions(a.copy(), **kw)
+    assert filled.dtype == g[f"{name}/filled"].dtype
+    assert np.array_equal(filled, g[f"{name}/filled"], equal_nan=True), f"{name}: filled elevation differs from the reference"
+    assert np.array_equal(d8, g[f"{name}/d8"]), f"{name}: d8 differs from the reference"
+
+
+def test_oracle_fill_depressions_mid_hash(oracle_lib):
+    import json
+    import os
+
+    a, kw = cs.fill_mid_case()
+    want = json.load(open(os.path.join(cs.GOLDEN, "fill_hashes.json")))["synth512x768"]
+    assert cs.sha(a) == want["input"], "synthetic input drifted"
+    filled, d8 = oracle.dem.fill_depressions(a, **kw)
+    assert cs.sha(filled) == want["filled"] and cs.sha(d8) == want["d8"]
+
+
+@pytest.mark.skipif(not reference.available(), reason="/root/reference not mounted")
+def test_oracle_fill_depressions_vs_live_reference(oracle_lib):
+    """fresh random rasters (ties, holes, every outlet mode, both connectivities, max_depth) against the numba reference"""
+    reference.load()
+    from pyflwdir import dem as rdem
+
+    rng = np.random.default_rng(123)
+    for trial in range(24):
+        nr, nc = int(rng.integers(3, 30)), int(rng.integers(3, 30))
+        kind = trial % 4
+        a = [rng.random((nr, nc)), rng.random((nr, nc)).astype(np.float32) * 9, rng.integers(0, 5, (nr, nc)).astype(np.float32),
+             rng.integers(0, 20, (nr, nc)).astype(np.int32)][kind]
+        if kind != 3 and trial % 3 == 0:
+            a[rng.random((nr, nc)) < 0.15] = -9999
+        for kw in (dict(), dict(outlets="min"), dict(connectivity=4), dict(idxs_pit=np.array([0, a.size // 2]))):
+            r = rdem.fill_depressions(a.copy(), **kw)
+            o = oracle.dem.fill_depressions(a.copy(), **kw)
+            assert np.array_equal(r[0], o[0]) and np.array_equal(r[1], o[1]) and r[0].dtype == o[0].dtype, (trial, kw)
+    a = rng.random((20, 24)).astype(np.float32) * 10
+    a[0, :] += 100; a[-1, :] += 100; a[:, 0] += 100; a[:, -1] += 100  # the revisit of max_depth stays inside the raster
+    for md in (0.5, 2.0):
+        r = rdem.fill_depressions(a.copy(), max_depth=md)
+        o = oracle.dem.fill_depressions(a.copy(), max_depth=md)
+        assert np.array_equal(r[0], o[0]) and np.array_equal(r[1], o[1])
