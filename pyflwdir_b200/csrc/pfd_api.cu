@@ -632,7 +632,7 @@ static int tiles_phase_a(pfd_handle* h, TileCtx& T, uint32_t* basin_dev, unsigne
     A.loccnt = (uint2*)h->tile_loc.p, A.W = T.B[0].acc, A.s_nxt = T.B[0].nxt, A.s_rh = T.B[0].rh, A.s_ch = T.B[0].ch;
     A.s_term = T.term, A.s_term_h = T.term_h;
     A.al4 = (h->ncol % 4 == 0) && ((uintptr_t)T.dir % 4 == 0);  // tile_loc is cudaMalloc-aligned
-    tile_phase_a_kernel<TLA_THREADS, TLA_MINBLOCKS, false><<<grid, TLA_THREADS, 0, h->stream>>>(A);
+    tl_launch_phase_a<false>(grid, h->stream, A);
     PFD_LAUNCH_CHECK(h);
     return PFD_OK;
 }
@@ -785,7 +785,7 @@ static int flow_all_fused(pfd_handle* h, const uint8_t* d8_dev, int64_t nrow, in
         A.s_term = T.term, A.s_term_h = T.term_h;
         A.d8 = d8_dev, A.dir_out = (uint8_t*)h->dir.p, A.invalid_flag = flag;
         A.al4 = (ncol % 4 == 0) && ((uintptr_t)d8_dev % 4 == 0);
-        tile_phase_a_kernel<TLA_THREADS, TLA_MINBLOCKS, true><<<grid, TLA_THREADS, 0, h->stream>>>(A);
+        tl_launch_phase_a<true>(grid, h->stream, A);
         PFD_LAUNCH_CHECK(h);
     }
     const int64_t nblk = npad / PC_CHUNK;
@@ -890,7 +890,7 @@ static int tiled_fused_begin(pfd_handle* h, const uint8_t* d8_owned, int64_t nro
         A.d8 = d8_owned, A.dir_out = (uint8_t*)h->dir.p, A.invalid_flag = flag;
         A.al4 = (ncol % 4 == 0) && ((uintptr_t)d8_owned % 4 == 0);
         A.halo_top = halo_top, A.halo_bot = halo_bot;
-        tile_phase_a_kernel<TLA_THREADS, TLA_MINBLOCKS, true><<<dim3((unsigned)T.ntx, (unsigned)T.nty), TLA_THREADS, 0, h->stream>>>(A);
+        tl_launch_phase_a<true>(dim3((unsigned)T.ntx, (unsigned)T.nty), h->stream, A);
         PFD_LAUNCH_CHECK(h);
     }
     const int64_t nblk = npad / PC_CHUNK;

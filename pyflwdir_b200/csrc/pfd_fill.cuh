@@ -54,7 +54,7 @@ __device__ __forceinline__ bool fd_is_nodata(T z, double nodata, int nodata_nan)
 }
 
 struct FdCounters {
-    unsigned long long n_outlets, minkey, n_tied, n_roots, pool_top, root_fill, err_pit, n_drift, n_unreached, max_drift, max_comp, max_abs;
+    unsigned long long n_outlets, minkey, n_tied, n_roots, pool_top, root_fill, err_pit, n_drift, n_unreached, max_drift, max_comp, max_abs, big_fill;
 };
 
 // dem.py:70-71,81-86 + gis_utils.get_edge (gis_utils.py:118-144): validity, initial outlets, their keys
@@ -366,12 +366,15 @@ __global__ void fd_count_kernel(const uint32_t* __restrict__ label, int64_t n, u
     if (roots) atomicAdd(&cnt->n_roots, roots);
 }
 
+#define FD_BIG 2048     // components of at least this many cells are replayed by a warp (fd_simulate_warp_kernel)
+#define FDW_CAP 24576   // heap entries that fit the warp's shared memory (192 KiB)
 // every component gets a slice of the heap pool; cnt[root] becomes the fill counter of that slice
 __global__ void fd_roots_kernel(const uint32_t* __restrict__ label, int64_t n, uint32_t* __restrict__ cntarr, uint32_t* __restrict__ off,
-                                uint32_t* __restrict__ roots, FdCounters* cnt) {
+                                uint32_t* __restrict__ roots, unsigned long long nroots, FdCounters* cnt) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         if (label[i] != (uint32_t)i) continue;
-        roots[atomicAdd(&cnt->root_fill, 1ull)] = (uint32_t)i;
+        if (cntarr[i] >= FD_BIG) roots[nroots - 1 - atomicAdd(&cnt->big_fill, 1ull)] = (uint32_t)i;  // big ones from the back
+        else roots[atomicAdd(&cnt->root_fill, 1ull)] = (uint32_t)i;
         off[i] = (uint32_t)atomicAdd(&cnt->pool_top, (unsigned long long)cntarr[i]);
         atomicMax(&cnt->max_comp, (unsigned long long)cntarr[i]);
         cntarr[i] = 0;
@@ -429,8 +432,16 @@ __device__ __forceinline__ void fd_sift_down(unsigned long long* hp, uint32_t n,
 
 // visit of cell y by a popped cell with key z0 (dem.py:119-120,133-135): returns the key y is pushed with, writes elevtn + delv
 template <typename T, typename W>
+__device__ __forceinline__ float fd_visit_z(T zy, T* __restrict__ out, uint32_t y, float z0, int int_delv);
+
+template <typename T, typename W>
 __device__ __forceinline__ float fd_visit(const T* __restrict__ elev, T* __restrict__ out, uint32_t y, float z0, int int_delv) {
-    const W z1 = (W)elev[y];
+    return fd_visit_z<T, W>(elev[y], out, y, z0, int_delv);
+}
+
+template <typename T, typename W>
+__device__ __forceinline__ float fd_visit_z(T zy, T* __restrict__ out, uint32_t y, float z0, int int_delv) {
+    const W z1 = (W)zy;
     const W dz = (W)z0 - z1;
     W delv = (W)0, z1n = z1;
     if (dz > (W)0) {
@@ -502,6 +513,128 @@ __global__ void fd_simulate_kernel(const uint32_t* __restrict__ roots, uint32_t 
         }
     }
     if (worst > 0.0f) atomicMax(&cnt->max_drift, (unsigned long long)__float_as_uint(worst));  // non-negative floats order like their bits
+    if (ndrift) atomicAdd(&cnt->n_drift, ndrift);
+}
+
+// The same replay for a BIG component, by one warp: the heap (32-ary) lives in shared memory while it fits -- a pop is a chain of
+// dependent reads, ~17 levels of global-memory latency per pop in the one-thread version --, the 32 children of a node are read by
+// the 32 lanes at once, and the eight neighbours of the popped cell are visited by eight lanes at once.
+__device__ __forceinline__ unsigned long long fd_shfl64(unsigned long long v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
+
+#define FDW_ARY 32  // heap fan-out = warp width: one shared-memory read + two warp reductions (REDUX) per level, 3 levels for 24 k entries
+__device__ __forceinline__ void fd_wsift_down(unsigned long long* hp, uint32_t n, uint32_t i, unsigned long long v, int lane) {
+    for (;;) {
+        const uint32_t c0 = FDW_ARY * i + 1;
+        if (c0 >= n) break;
+        const unsigned long long cv = (c0 + lane < n) ? hp[c0 + lane] : ~0ull;
+        const uint32_t hi = (uint32_t)(cv >> 32), lo = (uint32_t)cv;
+        const uint32_t mh = __reduce_min_sync(0xFFFFFFFFu, hi);
+        const uint32_t ml = __reduce_min_sync(0xFFFFFFFFu, hi == mh ? lo : 0xFFFFFFFFu);
+        const unsigned long long m = ((unsigned long long)mh << 32) | ml;
+        if (m >= v) break;
+        const uint32_t which = __ffs(__ballot_sync(0xFFFFFFFFu, cv == m)) - 1;  // entries are distinct
+        if (lane == 0) hp[i] = m;
+        i = c0 + which;
+    }
+    if (lane == 0) hp[i] = v;
+    __syncwarp();
+}
+
+template <typename T, typename W>
+__global__ void __launch_bounds__(32) fd_simulate_warp_kernel(const uint32_t* __restrict__ roots, const uint32_t* __restrict__ off,
+                                                              const uint32_t* __restrict__ cntarr, unsigned long long* __restrict__ pool,
+                                                              const uint32_t* __restrict__ S, const uint32_t* __restrict__ label,
+                                                              const T* __restrict__ elev, uint8_t* flags, uint32_t* __restrict__ Tord,
+                                                              uint8_t* d8, T* __restrict__ out, int64_t nrow, int64_t ncol, uint32_t nbmask,
+                                                              int int_delv, float max_drift, FdCounters* cnt) {
+    extern __shared__ unsigned long long fd_sheap[];
+    const int lane = threadIdx.x;
+    const uint32_t root = roots[blockIdx.x];
+    unsigned long long* gheap = pool + off[root];
+    uint32_t n = cntarr[root];
+    unsigned long long* hp = gheap;
+    bool in_smem = n <= FDW_CAP;
+    if (in_smem) {
+        for (uint32_t i = lane; i < n; i += 32) fd_sheap[i] = gheap[i];
+        hp = fd_sheap;
+    }
+    __syncwarp();
+    if (n > 1)
+        for (int32_t i = (int32_t)((n - 2) / FDW_ARY); i >= 0; --i) fd_wsift_down(hp, n, (uint32_t)i, hp[i], lane);
+    const int32_t nr = (int32_t)nrow, nc = (int32_t)ncol;
+    const bool nb_lane = lane < 9 && ((nbmask >> lane) & 1u);
+    uint32_t t = 0;
+    float worst = 0.0f;
+    unsigned long long ndrift = 0;
+    while (n > 0) {
+        const unsigned long long top = hp[0];
+        --n;
+        if (n > 0) fd_wsift_down(hp, n, 0, hp[n], lane);
+        const uint32_t p = (uint32_t)(top & 0x7FFFFFFFull);
+        const float z0 = fd_unord((uint32_t)(top >> 32));
+        if (lane == 0) Tord[p] = t;
+        ++t;
+        const int32_t pr = (int32_t)(p / (uint32_t)nc), pc = (int32_t)(p - (uint32_t)pr * (uint32_t)nc);
+        bool push = false;
+        unsigned long long e = 0;
+        if (lane < 9) {  // lane k looks at cell k of the 3 x 3 window (k = 4: the popped cell itself); all loads issued at once
+            const int32_t rr = pr + lane / 3 - 1, cc = pc + lane % 3 - 1;
+            if (rr >= 0 && rr < nr && cc >= 0 && cc < nc) {
+                const uint32_t y = (uint32_t)rr * (uint32_t)nc + (uint32_t)cc;
+                uint8_t fy = flags[y];
+                const uint32_t ly = label[y], sy = S[y];
+                const T zy = elev[y];
+                if (lane == 4) {
+                    if (!(fy & FDF_DISC)) {  // an initial outlet that no neighbour visited before it popped: it visits itself (d8 = 0)
+                        flags[y] = fy | FDF_DISC;
+                        d8[y] = 0;
+                        fd_visit_z<T, W>(zy, out, y, z0, int_delv);
+                    }
+                } else if (nb_lane && ly == root && !(fy & FDF_DISC)) {
+                    fy |= FDF_DISC;
+                    d8[y] = fd_us[lane];
+                    const float kf = fd_visit_z<T, W>(zy, out, y, z0, int_delv);
+                    const uint32_t ky = fd_ord(kf);
+                    const float drift = ky == sy ? 0.0f : fabsf(kf - fd_unord(sy));
+                    worst = fmaxf(worst, drift);
+                    ndrift += !(drift <= max_drift);
+                    if (!(fy & FDF_QUEUED)) {
+                        fy |= FDF_QUEUED;
+                        push = true;
+                        e = ((unsigned long long)ky << 32) | (unsigned long long)y;
+                    }
+                    flags[y] = fy;
+                }
+            }
+        }
+        uint32_t pm = __ballot_sync(0xFFFFFFFFu, push);
+        while (pm) {
+            const int src = __ffs(pm) - 1;
+            pm &= pm - 1;
+            const unsigned long long ev = fd_shfl64(e, src);
+            if (in_smem && n == FDW_CAP) {  // the frontier outgrew shared memory: continue in the component's pool slice
+                __syncwarp();
+                for (uint32_t i = lane; i < n; i += 32) gheap[i] = fd_sheap[i];
+                hp = gheap;
+                in_smem = false;
+                __syncwarp();
+            }
+            if (lane == 0) {
+                uint32_t i = n;  // sift up
+                while (i > 0) {
+                    const uint32_t par = (i - 1) / FDW_ARY;
+                    const unsigned long long pv = hp[par];
+                    if (pv <= ev) break;
+                    hp[i] = pv;
+                    i = par;
+                }
+                hp[i] = ev;
+            }
+            ++n;
+        }
+        __syncwarp();
+    }
+    if (worst > 0.0f) atomicMax(&cnt->max_drift, (unsigned long long)__float_as_uint(worst));
     if (ndrift) atomicAdd(&cnt->n_drift, ndrift);
 }
 
@@ -704,13 +837,39 @@ static int fd_fill_impl(pfd_handle* h, const T* elev, int64_t nrow, int64_t ncol
         if (hc.n_tied > 0) {
             PFD_TRY(sc.alloc(h, (void**)&pool, (size_t)hc.n_tied * 8));
             PFD_TRY(sc.alloc(h, (void**)&roots, (size_t)hc.n_roots * 4));
-            fd_roots_kernel<<<grid, 256, 0, h->stream>>>(label, n, cntarr, off, roots, cnt);
+            const unsigned long long nroots = hc.n_roots;
+            fd_roots_kernel<<<grid, 256, 0, h->stream>>>(label, n, cntarr, off, roots, nroots, cnt);
             PFD_LAUNCH_CHECK(h);
             fd_sources_kernel<<<grid, 256, 0, h->stream>>>(S, label, nrow, ncol, nbmask, flags, cntarr, off, pool);
             PFD_LAUNCH_CHECK(h);
-            fd_simulate_kernel<T, W><<<(unsigned)((hc.n_roots + 31) / 32), 32, 0, h->stream>>>(
-                roots, (uint32_t)hc.n_roots, off, cntarr, pool, S, label, elev, flags, Tord, d8, out, nrow, ncol, nbmask, int_delv, max_drift, cnt);
-            PFD_LAUNCH_CHECK(h);
+            PFD_CUDA(h, cudaMemcpyAsync(&hc, cnt, sizeof(hc), cudaMemcpyDeviceToHost, h->stream));
+            PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+            const unsigned long long nbig = hc.big_fill, nsmall = nroots - nbig;
+            // the few long replays (one warp each) run next to the many short ones (one thread each) on a second stream
+            cudaStream_t s2 = (nbig > 0 && nsmall > 0 && h->copy_stream && h->ev_copy) ? h->copy_stream : h->stream;
+            if (s2 != h->stream) {
+                PFD_CUDA(h, cudaEventRecord(h->ev_copy, h->stream));
+                PFD_CUDA(h, cudaStreamWaitEvent(s2, h->ev_copy, 0));
+            }
+            if (nbig > 0) {
+                static bool attr_set[2] = {false, false};
+                if (!attr_set[sizeof(W) == 8]) {
+                    PFD_CUDA(h, cudaFuncSetAttribute(fd_simulate_warp_kernel<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, FDW_CAP * 8));
+                    attr_set[sizeof(W) == 8] = true;
+                }
+                fd_simulate_warp_kernel<T, W><<<(unsigned)nbig, 32, FDW_CAP * 8, h->stream>>>(
+                    roots + nsmall, off, cntarr, pool, S, label, elev, flags, Tord, d8, out, nrow, ncol, nbmask, int_delv, max_drift, cnt);
+                PFD_LAUNCH_CHECK(h);
+            }
+            if (nsmall > 0) {
+                fd_simulate_kernel<T, W><<<(unsigned)((nsmall + 31) / 32), 32, 0, s2>>>(
+                    roots, (uint32_t)nsmall, off, cntarr, pool, S, label, elev, flags, Tord, d8, out, nrow, ncol, nbmask, int_delv, max_drift, cnt);
+                PFD_LAUNCH_CHECK(h);
+            }
+            if (s2 != h->stream) {
+                PFD_CUDA(h, cudaEventRecord(h->ev_copy, s2));
+                PFD_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
+            }
         }
         PFD_CUDA(h, cudaMemcpyAsync(&hc, cnt, sizeof(hc), cudaMemcpyDeviceToHost, h->stream));
         PFD_CUDA(h, cudaStreamSynchronize(h->stream));
