@@ -462,6 +462,17 @@ def extras_widened(w, size, seed, cpu_size):
     gpu["nextxy_parse"] = best(lambda: w.ck(l.pfd_nextxy_parse(h, nxy_dev, C.c_void_p(nxy_dev.value + n * 4), size, size, 1, w.out_dev[0], i32, None, None, None)))
     for pdev in (z_dev, out1_dev, um_dev, mask_dev, sparse_dev, drainh_dev, ldd_dev, so_dev, region_dev, nxy_dev):
         w.ck(l.pfd_dev_free(h, pdev))
+    # the step before the path: dem.fill_depressions of the synthetic terrain in metres (float32,
+    # z * 700 + 2000), device-resident in and out, on at most 8192^2 cells
+    fsz = min(size, 8192)
+    fz = (oracle.synth_elevation(fsz, fsz, seed=seed, octaves=octaves_for(fsz), nref=fsz) * np.float32(700.0) + np.float32(2000.0)).astype(np.float32)
+    fin_dev, fout_dev, fd8_dev = w.dev_alloc(fz.size * 4), w.dev_alloc(fz.size * 4), w.dev_alloc(fz.size)
+    w.ck(l.pfd_memcpy(h, fin_dev, L.ptr(fz), fz.size * 4))
+    fstats = np.zeros(12, np.int64)
+    fill_ms = best(lambda: w.ck(l.pfd_fill_depressions(h, fin_dev, f32, fsz, fsz, 0, None, 0, C.c_double(-9999.0), C.c_double(-1.0), 0,
+                                                       C.c_double(0.0), 8, 0, fout_dev, fd8_dev, L.ptr(fstats))), reps=2)
+    for pdev in (fin_dev, fout_dev, fd8_dev):
+        w.ck(l.pfd_dev_free(h, pdev))
 
     # CPU port on a bounded sample of the same generator
     oracle.build()
@@ -515,6 +526,25 @@ def extras_widened(w, size, seed, cpu_size):
     for k, ms in gpu.items():
         res[k] = {"gpu_ms": ms, "gpu_mcells_s": n / (ms / 1e3) / 1e6,
                   "cpu_mcells_s": (m / cpu[k] / 1e6) if k in cpu else None}
+    # fill_depressions: the CPU arm is the numba reference itself when oracle/_ref is there (else the C port), 1024^2 sample
+    csz = min(cpu_size, 1024)
+    fzc = np.ascontiguousarray(fz[:csz, :csz])
+    fill_kind, fill_fn = "port", oracle.dem.fill_depressions
+    try:
+        from oracle import reference as _ref
+        if _ref.available():
+            _ref.load()
+            from pyflwdir import dem as _rdem
+            _rdem.fill_depressions(fzc[:64, :64].copy())  # JIT
+            fill_kind, fill_fn = "reference", _rdem.fill_depressions
+    except Exception:
+        pass
+    t_fill, _ = cpu_time(lambda: fill_fn(fzc.copy()))
+    res["fill_depressions"] = {"gpu_ms": fill_ms, "gpu_mcells_s": fz.size / (fill_ms / 1e3) / 1e6, "cpu_mcells_s": fzc.size / t_fill / 1e6,
+                               "cpu_kind": fill_kind, "gpu_raster": f"{fsz}^2 float32", "cpu_raster": f"{csz}^2",
+                               "level_passes": int(fstats[0]), "label_passes": int(fstats[1]), "tied_cells": int(fstats[2]),
+                               "tie_components": int(fstats[3]), "largest_component": int(fstats[7]),
+                               "levels_ms": fstats[10] / 1e3, "ties_ms": fstats[11] / 1e3}
     res["note"] = (f"GPU: {size}^2 raster, device-resident buffers, ordering cached, best of 3; CPU: oracle port of the same "
                    f"reference function on a {cpu_size}^2 raster of the same generator, 1 thread (the reference's "
                    "stream_distance / floodplains are interpreted Python and far slower than this C port)")

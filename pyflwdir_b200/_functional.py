@@ -13,8 +13,8 @@ def infer_ncol(idxs_ds):
     idxs_ds = np.asarray(idxs_ds)
     n = idxs_ds.size
     i = np.arange(n, dtype=np.int64)
-    ds = idxs_ds.astype(np.int64)
-    mv = np.int64(-1) if idxs_ds.dtype.kind == "i" else np.int64(np.iinfo(idxs_ds.dtype).max)
+    ds = idxs_ds.astype(np.int64)  # uint64: the missing value 2**64 - 1 wraps to -1
+    mv = np.int64(-1) if idxs_ds.dtype.kind == "i" or idxs_ds.dtype.itemsize == 8 else np.int64(np.iinfo(idxs_ds.dtype).max)
     link = (ds != mv) & (ds != i)
     if idxs_ds.dtype == np.uint32:
         link &= idxs_ds != np.uint32(0xFFFFFFFF)
