@@ -119,10 +119,6 @@ __global__ void stash_pit_ids_kernel(const cell_t* __restrict__ pits, long long 
 struct TileShared {
     uint32_t P[TL_CELLS];
     uint32_t A[TL_CELLS];
-#ifdef TL_ONEBAR
-    uint32_t P1[TL_CELLS];  // second pointer buffer / second inbox of the one-barrier rounds (experiment, see tl_local_solve_1b)
-    uint32_t D1[TL_CELLS];
-#endif
 };
 #define TPK_MASK 0x3FFFFu
 #define TPK_SHIFT 18
@@ -203,184 +199,6 @@ __device__ __forceinline__ void tl_local_solve(uint32_t baseP, uint32_t dirw, ui
         if (!__syncthreads_or((int)any)) break;
     }
 }
-
-#ifdef TL_COMPACT
-// EXPERIMENT (profiles/scripts/ab.sh): after TL_SWITCH full rounds (97 / 90 / 75 / 50 / 23 / 5 % of the cells still move in
-// rounds 0 .. 5) the moving cells are compacted into a shared work list and the remaining rounds run over the list only --
-// the other threads just meet the barriers.
-#ifndef TL_SWITCH
-#define TL_SWITCH 3
-#endif
-struct TileWorkList {
-    uint16_t l[2][TL_CELLS];  // TPHYS positions of the moving cells, ping-pong
-    uint32_t n[2];
-};
-
-__device__ __forceinline__ void tl_local_solve_compact(uint32_t baseP, uint32_t dirw, uint32_t* own, TileWorkList& wl) {
-    const int i0 = TQ_I0;
-    const uint32_t ownP = baseP + (threadIdx.x << 2);
-    bool act[4];
-    TL_FOR4({
-        const uint32_t d = tl_dir_of(dirw, j);
-        const int ni = tl_local_next(i0 + j, d);
-        act[j] = ni != i0 + j;
-        own[j] = (baseP + ((uint32_t)TPHYS(ni) << 2)) | (act[j] ? (1u << TPK_SHIFT) : 0u);
-        tl_sts<j * 4096>(ownP, own[j]);
-        tl_sts<TL_A_OFF + j * 4096>(ownP, (d != PFD_DIR_NODATA) ? 1u : 0u);
-    })
-    if (threadIdx.x < 2) wl.n[threadIdx.x] = 0;
-    __syncthreads();
-    bool done = false;
-#pragma unroll
-    for (int k = 0; k < TL_SWITCH; ++k) {
-        const uint32_t two_k = 1u << k;
-        uint32_t pn[4], a[4];
-        TL_FOR4({
-            pn[j] = tl_lds<0>(own[j] & TPK_MASK);
-            a[j] = tl_lds<TL_A_OFF + j * 4096>(ownP);
-        })
-        __syncthreads();  // every snapshot is taken before any update
-        bool any = false;
-        TL_FOR4({
-            if (act[j]) tl_red_add<TL_A_OFF>(own[j] & TPK_MASK, a[j]);
-            const uint32_t hp = pn[j] >> TPK_SHIFT;
-            const uint32_t nw = (pn[j] & TPK_MASK) | ((hp + two_k) << TPK_SHIFT);
-            if (act[j]) {
-                own[j] = nw;
-                tl_sts<j * 4096>(ownP, nw);
-            }
-            act[j] = act[j] && (hp == two_k);
-            any = any || act[j];
-        })
-        if (k + 1 < TL_SWITCH) {
-            if (!__syncthreads_or((int)any)) {
-                done = true;
-                break;
-            }
-        }
-    }
-    if (done) return;
-    {  // the list of the cells that still move: per-warp exclusive scan of the per-thread counts, one shared atomic per warp
-        const uint32_t nact = (uint32_t)act[0] + (uint32_t)act[1] + (uint32_t)act[2] + (uint32_t)act[3];
-        uint32_t incl = nact;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if ((int)(threadIdx.x & 31u) >= o) incl += v;
-        }
-        uint32_t base = 0;
-        if ((threadIdx.x & 31u) == 31u && incl) base = atomicAdd(&wl.n[0], incl);
-        base = __shfl_sync(0xFFFFFFFFu, base, 31);
-        uint32_t pos = base + incl - nact;
-        TL_FOR4({
-            if (act[j]) wl.l[0][pos++] = (uint16_t)(j * 1024 + (int)threadIdx.x);  // TPHYS position of cell i0 + j
-        })
-    }
-    __syncthreads();
-    int cur = 0;
-    for (int k = TL_SWITCH; k < TL_MAXROUNDS; ++k) {
-        const uint32_t two_k = 1u << k;
-        const uint32_t n = wl.n[cur];
-        if (n == 0) break;
-        uint32_t cp[4], ow[4], a[4], pn[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const uint32_t idx = threadIdx.x + e * 1024u;
-            if (e * 1024u < n) {  // warp-uniform
-                cp[e] = baseP + ((idx < n ? (uint32_t)wl.l[cur][idx] : 0u) << 2);
-                ow[e] = tl_lds<0>(cp[e]);
-                a[e] = tl_lds<TL_A_OFF>(cp[e]);
-                pn[e] = tl_lds<0>(ow[e] & TPK_MASK);
-            }
-        }
-        if (threadIdx.x == 0) wl.n[cur ^ 1] = 0;
-        __syncthreads();
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const uint32_t idx = threadIdx.x + e * 1024u;
-            if (e * 1024u < n) {
-                bool still = false;
-                if (idx < n) {
-                    tl_red_add<TL_A_OFF>(ow[e] & TPK_MASK, a[e]);
-                    const uint32_t hp = pn[e] >> TPK_SHIFT;
-                    tl_sts<0>(cp[e], (pn[e] & TPK_MASK) | ((hp + two_k) << TPK_SHIFT));
-                    still = hp == two_k;
-                }
-                const uint32_t m = __ballot_sync(0xFFFFFFFFu, still);
-                if (m) {
-                    const int leader = __ffs(m) - 1;
-                    uint32_t base = 0;
-                    if ((int)(threadIdx.x & 31u) == leader) base = atomicAdd(&wl.n[cur ^ 1], (uint32_t)__popc(m));
-                    base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                    if (still) wl.l[cur ^ 1][base + __popc(m & ((1u << (threadIdx.x & 31u)) - 1u))] = (uint16_t)((cp[e] - baseP) >> 2);
-                }
-            }
-        }
-        __syncthreads();
-        cur ^= 1;
-    }
-    TL_FOR4({ own[j] = tl_lds<j * 4096>(ownP); })  // the registers missed the list rounds
-}
-#endif
-
-#ifdef TL_ONEBAR
-// EXPERIMENT (profiles/scripts/ab.sh): the same doubling with ONE barrier per round. The pointer words are double-buffered
-// (round k reads buffer k & 1 and writes the other one), the running subtree sum of a cell lives in a register of its owner,
-// and what other cells push at it lands in an inbox that is double-buffered as well: the inbox read in round k was filled in
-// round k - 1 and is zeroed for round k + 1. Five shared-memory operations per cell and round instead of four, one barrier
-// instead of two. Layout: P0 | D0 (= A) | P1 | D1; on return P0 / A hold the final state like tl_local_solve.
-template <int PC, int DC, int PN, int DN>
-__device__ __forceinline__ bool tl_round_1b(uint32_t ownP, uint32_t* own, uint32_t* acc, bool* act, uint32_t two_k) {
-    bool any = false;
-    TL_FOR4({
-        const uint32_t inc = tl_lds<DC + j * 4096>(ownP);
-        tl_sts<DC + j * 4096>(ownP, 0u);
-        acc[j] += inc;
-        const uint32_t pn = tl_lds<PC>(own[j] & TPK_MASK);
-        if (act[j]) tl_red_add<DN>(own[j] & TPK_MASK, acc[j]);
-        const uint32_t hp = pn >> TPK_SHIFT;
-        const uint32_t nw = (pn & TPK_MASK) | ((hp + two_k) << TPK_SHIFT);
-        if (act[j]) own[j] = nw;
-        tl_sts<PN + j * 4096>(ownP, own[j]);
-        act[j] = act[j] && (hp == two_k);
-        any = any || act[j];
-    })
-    return any;
-}
-
-__device__ __forceinline__ void tl_local_solve_1b(uint32_t baseP, uint32_t dirw, uint32_t* own) {
-    const int i0 = TQ_I0;
-    const uint32_t ownP = baseP + (threadIdx.x << 2);
-    bool act[4];
-    uint32_t acc[4];
-    TL_FOR4({
-        const uint32_t d = tl_dir_of(dirw, j);
-        const int ni = tl_local_next(i0 + j, d);
-        act[j] = ni != i0 + j;
-        own[j] = (baseP + ((uint32_t)TPHYS(ni) << 2)) | (act[j] ? (1u << TPK_SHIFT) : 0u);
-        tl_sts<j * 4096>(ownP, own[j]);
-        tl_sts<TL_A_OFF + j * 4096>(ownP, 0u);
-        tl_sts<3 * TL_A_OFF + j * 4096>(ownP, 0u);
-        acc[j] = (d != PFD_DIR_NODATA) ? 1u : 0u;
-    })
-    __syncthreads();
-    int last = 1;  // the inbox that received the pushes of the last executed round
-    for (int k = 0; k < TL_MAXROUNDS; k += 2) {
-        bool any = tl_round_1b<0, TL_A_OFF, 2 * TL_A_OFF, 3 * TL_A_OFF>(ownP, own, acc, act, 1u << k);
-        last = 1;
-        if (!__syncthreads_or((int)any) || k + 1 >= TL_MAXROUNDS) break;
-        any = tl_round_1b<2 * TL_A_OFF, 3 * TL_A_OFF, 0, TL_A_OFF>(ownP, own, acc, act, 2u << k);
-        last = 0;
-        if (!__syncthreads_or((int)any)) break;
-    }
-    TL_FOR4({
-        acc[j] += last ? tl_lds<3 * TL_A_OFF + j * 4096>(ownP) : tl_lds<TL_A_OFF + j * 4096>(ownP);
-        tl_sts<j * 4096>(ownP, own[j]);
-        tl_sts<TL_A_OFF + j * 4096>(ownP, acc[j]);
-    })
-    __syncthreads();
-}
-#endif
 
 // the direction bytes of the thread's four cells as one word; cells outside the raster read as nodata.
 // al4: ncol % 4 == 0 and the base pointer is 4-byte aligned (a quad never straddles the row end)
@@ -527,13 +345,7 @@ __device__ __forceinline__ void tl_phase_a_tile(TileShared& s, TileCodes& sc, co
     }
     const uint32_t baseP = tl_smem_addr(&s.P[0]);
     const uint32_t ownP = baseP + (threadIdx.x << 2);
-#ifdef TL_ONEBAR
-    tl_local_solve_1b(baseP, dirw, own);
-#elif defined(TL_COMPACT)
-    tl_local_solve_compact(baseP, dirw, own, *reinterpret_cast<TileWorkList*>(reinterpret_cast<unsigned char*>(&sc) + ((sizeof(TileCodes) + 15) & ~15)));
-#else
     tl_local_solve(baseP, dirw, own);
-#endif
 
     // (1) per-cell results for phase C
     {
@@ -618,14 +430,8 @@ __device__ __forceinline__ void tl_phase_a_tile(TileShared& s, TileCodes& sc, co
 template <int THREADS, int MINBLOCKS, bool FUSED>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS) tile_phase_a_kernel(PhaseAArgs A) {
     static_assert(THREADS == TL_CELLS / 4, "one quad of cells per thread");
-#if defined(TL_ONEBAR) || defined(TL_COMPACT)
-    extern __shared__ __align__(16) unsigned char tl_dyn_smem[];
-    TileShared& s = *reinterpret_cast<TileShared*>(tl_dyn_smem);
-    TileCodes& sc = *reinterpret_cast<TileCodes*>(tl_dyn_smem + sizeof(TileShared));
-#else
     __shared__ __align__(16) TileShared s;
     __shared__ TileCodes sc;  // FUSED only (the compiler drops it otherwise)
-#endif
     if (FUSED) {
         tl_stage_codes<THREADS>(sc, A.d8, A.nrow, A.ncol, (long long)blockIdx.y * TL_H, (long long)blockIdx.x * TL_W, A.al4 != 0,
                                 -(long long)A.halo_top, A.nrow + A.halo_bot);
@@ -634,23 +440,9 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS) tile_phase_a_kernel(PhaseA
     tl_phase_a_tile<FUSED>(s, sc, A, blockIdx.y, blockIdx.x);
 }
 
-#ifdef TL_ONEBAR
-#define TL_A_DYN_SMEM (sizeof(TileShared) + sizeof(TileCodes))
-#elif defined(TL_COMPACT)
-#define TL_A_DYN_SMEM (sizeof(TileShared) + ((sizeof(TileCodes) + 15) & ~15) + sizeof(TileWorkList))
-#else
-#define TL_A_DYN_SMEM 0
-#endif
 template <bool FUSED>
 static void tl_launch_phase_a(dim3 grid, cudaStream_t stream, const PhaseAArgs& A) {
-#if defined(TL_ONEBAR) || defined(TL_COMPACT)
-    static bool attr_set = false;  // experiment builds only: one device per process
-    if (!attr_set) {
-        cudaFuncSetAttribute(tile_phase_a_kernel<TLA_THREADS, TLA_MINBLOCKS, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_A_DYN_SMEM);
-        attr_set = true;
-    }
-#endif
-    tile_phase_a_kernel<TLA_THREADS, TLA_MINBLOCKS, FUSED><<<grid, TLA_THREADS, TL_A_DYN_SMEM, stream>>>(A);
+    tile_phase_a_kernel<TLA_THREADS, TLA_MINBLOCKS, FUSED><<<grid, TLA_THREADS, 0, stream>>>(A);
 }
 
 // asynchronous global -> shared copies (LDGSTS): no register is tied up while the data is in flight
