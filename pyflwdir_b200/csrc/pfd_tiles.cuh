@@ -227,10 +227,18 @@ __device__ __forceinline__ uint32_t tl_load_dirs(const uint8_t* __restrict__ dir
 // core_d8.py:115-122) and writes them to global memory, so that the separate parse pass over the raster
 // disappears from pfd_d8_flow_all.
 // ---------------------------------------------------------------------------------------------------------
+#ifdef TL_BULK          // the 64 interior rows of an interior tile arrive by bulk asynchronous copies (TMA unit, UBLKCP): 16-byte aligned rows
+#define TLF_STRIDE 80   // bytes per staged row: 15 pad | left halo | 64 cells | right halo | 15 pad
+#define TLF_X0 16
+#else
 #define TLF_STRIDE 72   // bytes per staged row: 3 pad | left halo | 64 cells | right halo | 3 pad
 #define TLF_X0 4        // byte offset of the tile's first column inside a staged row (word aligned)
+#endif
 struct TileCodes {
     __align__(16) uint8_t c[(TL_H + 2) * TLF_STRIDE];
+#ifdef TL_BULK
+    __align__(8) unsigned long long mbar;
+#endif
 };
 
 // row_lo / row_hi: rows that may be READ: [0, nrow) for a whole raster; a row block of a larger raster also has the
@@ -238,6 +246,26 @@ struct TileCodes {
 template <int THREADS>
 __device__ __forceinline__ void tl_stage_codes(TileCodes& sc, const uint8_t* __restrict__ d8, long long nrow, long long ncol,
                                                long long r0, long long c0, bool al4, long long row_lo, long long row_hi) {
+#ifdef TL_BULK
+    // interior tile of an aligned raster: one thread arms an mbarrier with the 4 KiB it expects and issues one 64-byte bulk copy
+    // per row; everybody else goes on to the halo and meets the data at the mbarrier
+    const bool bulk = (ncol % 16 == 0) && ((reinterpret_cast<uintptr_t>(d8) & 15) == 0) && r0 + TL_H <= nrow && c0 + TL_W <= ncol;
+    const uint32_t mb = tl_smem_addr(&sc.mbar);
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(TL_H * TL_W) : "memory");
+            const uint8_t* src = d8 + r0 * ncol + c0;
+            uint32_t dst = tl_smem_addr(&sc.c[TLF_STRIDE + TLF_X0]);
+#pragma unroll 8
+            for (int row = 0; row < TL_H; ++row, src += ncol, dst += TLF_STRIDE)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                             "r"(TL_W), "r"(mb)
+                             : "memory");
+        }
+    } else
+#endif
     // interior: 64 rows x 16 words
     for (int w = threadIdx.x; w < TL_H * (TL_W / 4); w += THREADS) {
         const int row = w >> 4, wx = w & 15;
@@ -276,6 +304,14 @@ __device__ __forceinline__ void tl_stage_codes(TileCodes& sc, const uint8_t* __r
         if (r >= row_lo && r < row_hi && c >= 0 && c < ncol) v = __ldg(d8 + r * ncol + c);
         sc.c[sy * TLF_STRIDE + TLF_X0 + sx] = v;
     }
+#ifdef TL_BULK
+    if (bulk) {
+        __syncthreads();  // the mbarrier is initialised before anybody polls it
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tTL_BULK_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@!p bra TL_BULK_WAIT;\n\t}" ::"r"(mb)
+            : "memory");
+    }
+#endif
 }
 
 // dir bytes of the thread's four cells from the staged codes; *legal = false when one of them is not a D8 code
