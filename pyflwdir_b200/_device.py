@@ -36,6 +36,9 @@ class DeviceGraph:
         # the parity tests)
         if os.environ.get("PFD_TILE_SWEEPS", "1") in ("0", "2"):
             self.set_option("tile_sweeps", int(os.environ["PFD_TILE_SWEEPS"]))
+        # HAND: PFD_HAND_PATHSUM=0 skips the re-associated path sums (pfd_hand.cuh) and goes straight to the hop-by-hop sweeps
+        if os.environ.get("PFD_HAND_PATHSUM", "1") == "0":
+            self.set_option("hand_pathsum", 0)
         self.shape = None
         self.size = 0
         self.n_valid = self.n_pits = self.n_outlets = 0

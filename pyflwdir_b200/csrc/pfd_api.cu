@@ -154,7 +154,8 @@ extern "C" void pfd_destroy(pfd_handle* h) {
     DevBuf* bufs[] = {&h->dir, &h->upmask, &h->pits, &h->pit_outlet, &h->seq, &h->bseq, &h->rank, &h->basins,
                       &h->level_off, &h->bfs_state, &h->chunk_status, &h->blk_counts, &h->blk_offsets, &h->counters,
                       &h->segs, &h->tslots, &h->uparea, &h->tile_loc, &h->btab, &h->bgraph, &h->mg_counts, &h->sub_idxs,
-                      &h->sub_labels, &h->sub_slices, &h->stream_off, &h->stream_cells, &h->verify, &h->ts_done, &h->ts_lists};
+                      &h->sub_labels, &h->sub_slices, &h->stream_off, &h->stream_cells, &h->verify, &h->ts_done, &h->ts_lists,
+                      &h->hand_root, &h->hand_sum, &h->hand_slots, &h->sw_dir, &h->sw_out, &h->sw_aux, &h->sw_fdone};
     for (DevBuf* b : bufs) pfd_release(*b);
     for (DevBuf& b : h->scratch) pfd_release(b);
     for (int s = 0; s < PFD_NSTAGE; ++s) {
@@ -1406,6 +1407,10 @@ extern "C" int pfd_set_option(pfd_handle* h, const char* name, int64_t value) {
         h->fuse_parse = value ? 1 : 0;
         return PFD_OK;
     }
+    if (name && strcmp(name, "hand_pathsum") == 0) {
+        h->hand_pathsum = value ? 1 : 0;
+        return PFD_OK;
+    }
     if (name && strcmp(name, "tile_sweeps") == 0) {
         // 1 (default): tile-dataflow sweeps unless the BFS ordering of this raster is already cached (then its level
         // replay is the cheaper one: 32 vs 46 ms for Strahler at 32768^2; the ordering itself costs 40 ms);
@@ -1432,6 +1437,8 @@ extern "C" int64_t pfd_get_info(const pfd_handle* h, const char* name) {
     if (strcmp(name, "have_upmask") == 0) return h->have_upmask ? 1 : 0;
     if (strcmp(name, "tile_rounds") == 0) return h->tile_rounds;
     if (strcmp(name, "tile_sweeps") == 0) return h->tile_sweeps;
+    if (strcmp(name, "hand_pathsum") == 0) return h->hand_pathsum;
+    if (strcmp(name, "hand_engine") == 0) return h->hand_engine;
     if (strcmp(name, "sweep_passes") == 0) return h->sweep_passes;
     if (strcmp(name, "sweep_visits") == 0) return h->sweep_visits;
     if (strcmp(name, "nlevels") == 0) return h->nlevels;
@@ -2304,6 +2311,8 @@ extern "C" int pfd_strahler(pfd_handle* h, const uint8_t* mask, uint8_t* out) {
     return PFD_OK;
 }
 
+#include "pfd_hand.cuh"
+
 extern "C" int pfd_hand(pfd_handle* h, const uint8_t* drain, const void* elevtn, int elev_dtype, double* out) {
     PFD_TRY(check_handle(h));
     stage_reset(h);
@@ -2311,7 +2320,7 @@ extern "C" int pfd_hand(pfd_handle* h, const uint8_t* drain, const void* elevtn,
     if (elev_dtype != PFD_F32 && elev_dtype != PFD_F64) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_hand: elevtn must be float32 or float64");
     if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, "pfd_hand: no raster parsed on this handle");
     const bool tile = use_tile_sweeps(h);
-    if (!tile) PFD_TRY(order_impl(h, false, false));
+    if (!tile && !(h->hand_pathsum && !h->tiled)) PFD_TRY(order_impl(h, false, false));
     const int64_t n = h->n;
     const size_t bytes = (size_t)n * sizeof(double);
     void* out_dev = nullptr;
@@ -2319,6 +2328,21 @@ extern "C" int pfd_hand(pfd_handle* h, const uint8_t* drain, const void* elevtn,
     const void *drain_dev = nullptr, *elev_dev = nullptr;
     PFD_TRY(pfd_stage_in(h, drain, (size_t)n, 4, &drain_dev));
     PFD_TRY(pfd_stage_in(h, elevtn, (size_t)n * pfd_dtype_size(elev_dtype), 5, &elev_dev));
+    if (h->hand_pathsum && !h->tiled) {
+        // re-associated path sums (pfd_hand.cuh), accepted only when every cell satisfies the reference's statement bit for bit
+        unsigned long long bad = 0;
+        if (elev_dtype == PFD_F32) PFD_TRY(hand_pathsum<float>(h, (const uint8_t*)drain_dev, (const float*)elev_dev, (double*)out_dev, &bad));
+        else PFD_TRY(hand_pathsum<double>(h, (const uint8_t*)drain_dev, (const double*)elev_dev, (double*)out_dev, &bad));
+        if (bad == 0) {
+            h->hand_engine = 1;
+            PFD_TRY(pfd_finish_out(h, out, out_dev, bytes));
+            PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+            stage_collect(h);
+            return PFD_OK;
+        }
+    }
+    h->hand_engine = tile ? 2 : 3;
+    if (!tile) PFD_TRY(order_impl(h, false, false));  // (no-op when the ordering is cached)
     if (tile) {
         if (elev_dtype == PFD_F32) {
             HandTileOp<float> op{(const uint8_t*)drain_dev, (const float*)elev_dev, (double*)out_dev};

@@ -193,6 +193,9 @@ struct pfd_handle {
         unsigned long long resolved = 0;  // cells resolved so far (all rounds)
     } sw;
     DevBuf sw_dir, sw_out, sw_aux, sw_fdone, sw_edge[4];  // ext rows; [0,1] = send top / bottom, [2,3] = receive top / bottom
+    DevBuf hand_root, hand_sum, hand_slots;  // path-sum HAND (pfd_hand.cuh): per-cell (root, segment sum), ring nodes
+    int hand_pathsum = 1;      // option "hand_pathsum": 1 = try the re-associated path sums first (verified, else hop by hop)
+    int hand_engine = 0;       // info "hand_engine": what produced the last pfd_hand result (1 path sums, 2 tile sweep, 3 level replay)
     DevBuf verify;            // VerifyCounts of the pfd_verify_* entry points
     DevBuf btab, bgraph;       // row-tiled multi-GPU solve: boundary tables, boundary graph state
     int64_t dir_off = 0;       // offset of the first OWNED row inside dir (halo row of a row block)

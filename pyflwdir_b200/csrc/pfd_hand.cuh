@@ -1,0 +1,283 @@
+// pfd_hand.cuh -- dem.height_above_nearest_drain (pyflwdir/dem.py:299-330) as a tile-hierarchical PATH SUM.
+//
+// The reference walks the sequence downstream -> upstream and sets hand[i] = hand[ds] + float64(elevtn[i] - elevtn[ds]) (the
+// difference formed in elevtn's type), 0 at drain cells and pits: a left fold of float64 additions along every flow path. The
+// terms are float32 (or float64) differences of neighbouring elevations, a few dozen bits wide, and their running sums stay
+// far inside the 53 bits of a double -- so on real rasters every one of those additions is EXACT, and exact sums may be
+// re-associated freely. This file computes the path sums with pointer doubling instead of hop by hop:
+//   phase A (one CTA per 64 x 64 tile): every cell carries the summary of the path segment to its current ancestor,
+//       (sum of the hop terms, "passed a drain cell" flag); summaries compose associatively (a segment that already passed a
+//       drain cell ignores what lies downstream), so ancestor <- ancestor's ancestor doubles the segment per round (double-
+//       buffered in shared memory, one barrier per round) until the ancestor is a pit or the cell where the path leaves the tile;
+//   phase B: the same doubling over the ring nodes of all tiles (node = border cell, successor = the border cell of the
+//       neighbouring tile its path enters) until every node knows its sum down to the pit -- or that it never gets there;
+//   phase C: hand = own segment (+ the solved sum behind the exit cell); -9999 for nodata and for cells that reach no pit,
+//       exactly the cells outside the reference's sequence.
+// Then hand_check_kernel re-evaluates the reference's statement for EVERY cell from the finished values (hand[i] == hand[ds] +
+// dz bit for bit, 0 at drains and pits, -9999 exactly where the downstream cell is -9999). Zero violations prove the array
+// equal to the reference's (induction from the pits upstream); a single violation -- an addition that was not exact -- and
+// pfd_hand discards the result and runs the hop-by-hop sweep (pfd_tilesweep.cuh / pfd_sweeps.cuh) instead.
+#pragma once
+#include "pfd_tiles.cuh"
+
+#define HD_SINK 0x7FFFFFFEu     // node successor: the path ended in a pit (value final)
+#define HD_INVALID 0x7FFFFFFFu  // node reaches no pit (loop, nodata)
+#define HD_HIT 0x80000000u      // node / cell flag: the segment already passed a drain cell
+#define HD_ROOT_NONE 0xFFFFu
+#define HD_ROOT_EXIT 0x4000u
+#define HD_ROOT_HIT 0x8000u
+
+template <typename T>
+__device__ __forceinline__ double hd_dz(T a, T b) { return (double)(T)(a - b); }
+template <>
+__device__ __forceinline__ double hd_dz<float>(float a, float b) { return (double)__fsub_rn(a, b); }
+template <>
+__device__ __forceinline__ double hd_dz<double>(double a, double b) { return __dsub_rn(a, b); }
+
+struct HandTileShared {
+    double D[2][TL_CELLS];
+    uint16_t nx[2][TL_CELLS];  // in-tile index of the current ancestor | HD_ROOT_HIT
+    double wexit[TL_RING];     // exit cells: their own hop term
+    uint32_t eslot[TL_RING];   //             ring slot of the cell they drain into | HD_HIT when they are drain cells
+    uint8_t kind[TL_CELLS];    // 0 inner, 1 pit, 2 exit, 3 nodata
+};
+
+template <typename T>
+__global__ void __launch_bounds__(1024, 2) hand_tile_a_kernel(const uint8_t* __restrict__ dir, const uint8_t* __restrict__ drain,
+                                                              const T* __restrict__ elev, long long nrow, long long ncol, long long ntx,
+                                                              uint16_t* __restrict__ hroot, double* __restrict__ hD,
+                                                              uint32_t* __restrict__ s_nxt, double* __restrict__ s_val) {
+    extern __shared__ __align__(16) unsigned char hd_smem[];
+    HandTileShared& s = *reinterpret_cast<HandTileShared*>(hd_smem);
+    const long long ty = blockIdx.y, tx = blockIdx.x;
+    const uint32_t tile = (uint32_t)((ty + 1) * ntx + tx);
+    const long long r0 = ty * TL_H, c0 = tx * TL_W;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = threadIdx.x + 1024 * j;
+        const int ly = i >> 6, lx = i & 63;
+        const long long r = r0 + ly, c = c0 + lx;
+        uint32_t d = PFD_DIR_NODATA;
+        long long g = 0;
+        if (r < nrow && c < ncol) {
+            g = r * ncol + c;
+            d = dir[g];
+        }
+        uint16_t nx = (uint16_t)i;
+        double D = 0.0;
+        uint8_t kind = 3;
+        if (d != PFD_DIR_NODATA) {
+            if (d >= 8u) {
+                kind = 1;
+            } else {
+                const bool dr = drain[g] == 1;
+                const double w = dr ? 0.0 : hd_dz<T>(elev[g], elev[g + pfd_slot_off((int)d, ncol)]);
+                const int y = ly + pfd_slot_dr((int)d), x = lx + pfd_slot_dc((int)d);
+                if ((unsigned)y < (unsigned)TL_H && (unsigned)x < (unsigned)TL_W) {
+                    kind = 0;
+                    nx = (uint16_t)((y << 6) | x) | (dr ? HD_ROOT_HIT : 0);
+                    D = w;
+                } else {
+                    kind = 2;
+                    const int rp = tl_ring_pos(ly, lx);
+                    s.wexit[rp] = w;
+                    s.eslot[rp] = tl_exit_slot(tile, (uint32_t)ntx, ly, lx, d) | (dr ? HD_HIT : 0u);
+                }
+            }
+        }
+        s.kind[i] = kind;
+        s.nx[0][i] = nx;
+        s.D[0][i] = D;
+    }
+    __syncthreads();
+    int fin = 0;
+    for (int k = 0; k < TL_MAXROUNDS; ++k) {
+        const int cur = k & 1, nb = cur ^ 1;
+        bool ch = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = threadIdx.x + 1024 * j;
+            const uint32_t a = s.nx[cur][i];
+            const uint32_t n = a & 0xFFFu;
+            const uint32_t an = s.nx[cur][n];
+            const double Di = s.D[cur][i];
+            s.D[nb][i] = (a & HD_ROOT_HIT) ? Di : __dadd_rn(Di, s.D[cur][n]);  // (a root carries the empty segment: + 0)
+            s.nx[nb][i] = (uint16_t)((an & 0xFFFu) | ((a | an) & HD_ROOT_HIT));
+            ch |= (an & 0xFFFu) != n;
+        }
+        fin = nb;
+        if (!__syncthreads_or((int)ch)) break;
+    }
+    // per-cell records for phase C
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = threadIdx.x + 1024 * j;
+        const long long r = r0 + (i >> 6), c = c0 + (i & 63);
+        if (r < nrow && c < ncol) {
+            const uint32_t a = s.nx[fin][i];
+            const uint32_t root = a & 0xFFFu;
+            uint16_t rec = HD_ROOT_NONE;
+            // (an in-tile loop never settles on a root; one of 2^k cells comes back to itself, which is no root either)
+            if (s.kind[i] != 3 && s.kind[root] != 0 && (s.nx[fin][root] & 0xFFFu) == root)
+                rec = (uint16_t)(root | (a & HD_ROOT_HIT) | (s.kind[root] == 2 ? HD_ROOT_EXIT : 0));
+            hroot[r * ncol + c] = rec;
+            hD[r * ncol + c] = s.D[fin][i];
+        }
+    }
+    // ring nodes
+    if (threadIdx.x < TL_RING) {
+        uint32_t nxt = HD_INVALID;
+        double val = 0.0;
+        if (threadIdx.x < TL_NRING) {
+            const int ri = tl_ring_cell(threadIdx.x);
+            const uint32_t a = s.nx[fin][ri];
+            const uint32_t root = a & 0xFFFu;
+            if (s.kind[ri] != 3 && s.kind[root] != 0 && (s.nx[fin][root] & 0xFFFu) == root) {
+                const uint32_t hit = (a & HD_ROOT_HIT) ? HD_HIT : 0u;
+                val = s.D[fin][ri];
+                if (s.kind[root] == 1) {
+                    nxt = HD_SINK | hit;
+                } else {
+                    const int rp = tl_ring_pos((int)(root >> 6), (int)(root & 63u));
+                    if (!hit) val = __dadd_rn(val, s.wexit[rp]);
+                    nxt = s.eslot[rp] | hit;
+                }
+            }
+        }
+        s_nxt[tile * TL_RING + threadIdx.x] = nxt;
+        s_val[tile * TL_RING + threadIdx.x] = val;
+    }
+}
+
+// one doubling round over the ring nodes [lo, hi): (successor, sum, flag) <- composed with the successor's
+__global__ void hand_slots_round_kernel(const uint32_t* __restrict__ nxt_c, const double* __restrict__ val_c, uint32_t* __restrict__ nxt_n,
+                                        double* __restrict__ val_n, long long lo, long long hi, unsigned int* __restrict__ changed) {
+    bool ch = false;
+    for (long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
+        const uint32_t a = nxt_c[i];
+        const uint32_t j = a & 0x7FFFFFFFu;
+        if (j >= HD_SINK) {  // final: mirrored into the other buffer once
+            if (nxt_n[i] != a) {
+                nxt_n[i] = a;
+                val_n[i] = val_c[i];
+            }
+            continue;
+        }
+        const uint32_t b = nxt_c[j];
+        const double v = val_c[i];
+        val_n[i] = (a & HD_HIT) ? v : __dadd_rn(v, val_c[j]);
+        nxt_n[i] = (b & 0x7FFFFFFFu) | ((a | b) & HD_HIT);
+        ch = true;
+    }
+    if (ch) *changed = 1u;
+}
+
+__global__ void __launch_bounds__(1024) hand_tile_c_kernel(const uint8_t* __restrict__ dir, const uint16_t* __restrict__ hroot,
+                                                           const double* __restrict__ hD, const uint32_t* __restrict__ s_nxt,
+                                                           const double* __restrict__ s_val, long long nrow, long long ncol, long long ntx,
+                                                           double* __restrict__ out) {
+    __shared__ double ringval[TL_RING];
+    __shared__ uint8_t ringok[TL_RING];
+    const long long ty = blockIdx.y, tx = blockIdx.x;
+    const uint32_t tile = (uint32_t)((ty + 1) * ntx + tx);
+    const long long r0 = ty * TL_H, c0 = tx * TL_W;
+    if (threadIdx.x < TL_RING) {
+        const uint32_t a = s_nxt[tile * TL_RING + threadIdx.x];
+        ringok[threadIdx.x] = (a & 0x7FFFFFFFu) == HD_SINK;
+        ringval[threadIdx.x] = s_val[tile * TL_RING + threadIdx.x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = threadIdx.x + 1024 * j;
+        const long long r = r0 + (i >> 6), c = c0 + (i & 63);
+        if (r >= nrow || c >= ncol) continue;
+        const long long g = r * ncol + c;
+        const uint32_t rec = hroot[g];
+        double h = -9999.0;
+        if (rec != HD_ROOT_NONE) {
+            const double D = hD[g];
+            if (!(rec & HD_ROOT_EXIT)) {
+                h = D;
+            } else {
+                const uint32_t root = rec & 0xFFFu;
+                const int rp = tl_ring_pos((int)(root >> 6), (int)(root & 63u));
+                if (ringok[rp]) h = (rec & HD_ROOT_HIT) ? D : __dadd_rn(D, ringval[rp]);
+            }
+        }
+        out[g] = h;
+    }
+}
+
+// the reference's per-cell statement, from the finished values: counts the cells that violate it
+template <typename T>
+__global__ void hand_check_kernel(const uint8_t* __restrict__ dir, const uint8_t* __restrict__ drain, const T* __restrict__ elev, int64_t n,
+                                  int64_t ncol, const double* __restrict__ hand, unsigned long long* __restrict__ n_bad) {
+    unsigned long long bad = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t d = dir[i];
+        double want = -9999.0;
+        if (d != PFD_DIR_NODATA) {
+            if (d >= 8u) {
+                want = 0.0;  // a pit: in the sequence, hand[pit] + 0
+            } else {
+                const int64_t ds = i + pfd_slot_off((int)d, ncol);
+                const double hds = hand[ds];
+                if (__double_as_longlong(hds) != __double_as_longlong(-9999.0))  // (else: the cell drains to no pit either)
+                    want = drain[i] == 1 ? 0.0 : __dadd_rn(hds, hd_dz<T>(elev[i], elev[ds]));
+            }
+        }
+        bad += __double_as_longlong(hand[i]) != __double_as_longlong(want);
+    }
+    bad = __reduce_add_sync(0xFFFFFFFFu, (unsigned)bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(n_bad, bad);
+}
+
+// Host side: returns the number of cells that violate the reference's statement (0 = the result is the reference's)
+template <typename T>
+static int hand_pathsum(pfd_handle* h, const uint8_t* drain_dev, const T* elev_dev, double* out_dev, unsigned long long* n_bad) {
+    const long long nrow = h->nrow, ncol = h->ncol, n = h->n;
+    const long long ntx = (ncol + TL_W - 1) / TL_W, nty = (nrow + TL_H - 1) / TL_H;
+    const long long nslots = (nty + 2) * ntx * TL_RING;
+    if (nslots >= (long long)HD_SINK) return pfd_fail(h, PFD_ERR_UNSUPPORTED, "pfd_hand: too many ring nodes");
+    const uint8_t* dir = (const uint8_t*)h->dir.p + h->dir_off;
+    PFD_TRY(pfd_reserve(h, h->hand_root, (size_t)n * sizeof(uint16_t)));
+    PFD_TRY(pfd_reserve(h, h->hand_sum, (size_t)n * sizeof(double)));
+    PFD_TRY(pfd_reserve(h, h->hand_slots, (size_t)nslots * 2 * (sizeof(uint32_t) + sizeof(double)) + 64));
+    uint16_t* hroot = (uint16_t*)h->hand_root.p;
+    double* hD = (double*)h->hand_sum.p;
+    double* sval[2] = {(double*)h->hand_slots.p, (double*)h->hand_slots.p + nslots};
+    uint32_t* snxt[2] = {(uint32_t*)(sval[1] + nslots), (uint32_t*)(sval[1] + nslots) + nslots};
+    unsigned int* changed = (unsigned int*)(snxt[1] + nslots);
+    unsigned long long* bad = (unsigned long long*)(changed + 2);
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[sizeof(T) == 8]) {
+        PFD_CUDA(h, cudaFuncSetAttribute(hand_tile_a_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HandTileShared)));
+        attr_set[sizeof(T) == 8] = true;
+    }
+    const dim3 grid((unsigned)ntx, (unsigned)nty);
+    hand_tile_a_kernel<T><<<grid, 1024, sizeof(HandTileShared), h->stream>>>(dir, drain_dev, elev_dev, nrow, ncol, ntx, hroot, hD, snxt[0], sval[0]);
+    PFD_LAUNCH_CHECK(h);
+    PFD_CUDA(h, cudaMemsetAsync(snxt[1], 0, (size_t)nslots * sizeof(uint32_t), h->stream));
+    const long long lo = ntx * TL_RING, hi = (nty + 1) * ntx * TL_RING;
+    int fin = 0;
+    for (int k = 0; k < 48; ++k) {
+        const int cur = k & 1, nb = cur ^ 1;
+        PFD_CUDA(h, cudaMemsetAsync(changed, 0, sizeof(unsigned int), h->stream));
+        hand_slots_round_kernel<<<grid_for(hi - lo, 256, 2, 148 * 16), 256, 0, h->stream>>>(snxt[cur], sval[cur], snxt[nb], sval[nb], lo, hi, changed);
+        PFD_LAUNCH_CHECK(h);
+        fin = nb;
+        unsigned int ch = 0;
+        PFD_CUDA(h, cudaMemcpyAsync(&ch, changed, sizeof(ch), cudaMemcpyDeviceToHost, h->stream));
+        PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (!ch) break;
+    }
+    hand_tile_c_kernel<<<grid, 1024, 0, h->stream>>>(dir, hroot, hD, snxt[fin], sval[fin], nrow, ncol, ntx, out_dev);
+    PFD_LAUNCH_CHECK(h);
+    PFD_CUDA(h, cudaMemsetAsync(bad, 0, sizeof(unsigned long long), h->stream));
+    hand_check_kernel<T><<<grid_for(n, 256, 4, 148 * 32), 256, 0, h->stream>>>(dir, drain_dev, elev_dev, n, ncol, out_dev, bad);
+    PFD_LAUNCH_CHECK(h);
+    PFD_CUDA(h, cudaMemcpyAsync(n_bad, bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    return PFD_OK;
+}
