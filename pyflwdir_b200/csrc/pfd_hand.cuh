@@ -209,28 +209,53 @@ __global__ void __launch_bounds__(1024) hand_tile_c_kernel(const uint8_t* __rest
     }
 }
 
-// the reference's per-cell statement, from the finished values: counts the cells that violate it
+// the reference's per-cell statement, from the finished values: counts the cells that violate it (four independent cells per
+// thread and trip, so that the two dependent rounds of loads -- the cell, then its downstream cell -- overlap)
 template <typename T>
-__global__ void hand_check_kernel(const uint8_t* __restrict__ dir, const uint8_t* __restrict__ drain, const T* __restrict__ elev, int64_t n,
-                                  int64_t ncol, const double* __restrict__ hand, unsigned long long* __restrict__ n_bad) {
-    unsigned long long bad = 0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t d = dir[i];
-        double want = -9999.0;
-        if (d != PFD_DIR_NODATA) {
-            if (d >= 8u) {
-                want = 0.0;  // a pit: in the sequence, hand[pit] + 0
-            } else {
-                const int64_t ds = i + pfd_slot_off((int)d, ncol);
-                const double hds = hand[ds];
-                if (__double_as_longlong(hds) != __double_as_longlong(-9999.0))  // (else: the cell drains to no pit either)
-                    want = drain[i] == 1 ? 0.0 : __dadd_rn(hds, hd_dz<T>(elev[i], elev[ds]));
+__global__ void __launch_bounds__(256) hand_check_kernel(const uint8_t* __restrict__ dir, const uint8_t* __restrict__ drain,
+                                                         const T* __restrict__ elev, int64_t n, int64_t ncol,
+                                                         const double* __restrict__ hand, unsigned long long* __restrict__ n_bad) {
+    unsigned int bad = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        uint32_t d[4];
+        uint8_t dr[4];
+        T e[4];
+        double got[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t i = i0 + k * stride;
+            d[k] = PFD_DIR_NODATA;
+            got[k] = -9999.0;
+            if (i < n) {
+                d[k] = dir[i];
+                dr[k] = drain[i];
+                e[k] = elev[i];
+                got[k] = hand[i];
             }
         }
-        bad += __double_as_longlong(hand[i]) != __double_as_longlong(want);
+        double hds[4];
+        T eds[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (d[k] < 8u) {
+                const int64_t ds = i0 + k * stride + pfd_slot_off((int)d[k], ncol);
+                hds[k] = hand[ds];
+                eds[k] = elev[ds];
+            }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double want = -9999.0;
+            if (d[k] != PFD_DIR_NODATA) {
+                if (d[k] >= 8u) want = 0.0;  // a pit: in the sequence, hand[pit] + 0
+                else if (__double_as_longlong(hds[k]) != __double_as_longlong(-9999.0))  // (else: the cell drains to no pit either)
+                    want = dr[k] == 1 ? 0.0 : __dadd_rn(hds[k], hd_dz<T>(e[k], eds[k]));
+            }
+            bad += (i0 + k * stride < n) && __double_as_longlong(got[k]) != __double_as_longlong(want);
+        }
     }
-    bad = __reduce_add_sync(0xFFFFFFFFu, (unsigned)bad);
-    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(n_bad, bad);
+    bad = __reduce_add_sync(0xFFFFFFFFu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(n_bad, (unsigned long long)bad);
 }
 
 // Host side: returns the number of cells that violate the reference's statement (0 = the result is the reference's)
