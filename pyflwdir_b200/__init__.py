@@ -5,7 +5,7 @@ Host code is plain Python + numpy calling hand-written CUDA through a C ABI (cty
 PyTorch, no Triton, no CPU fallback: without the built `libpfd_b200.so` and a CUDA device every compute call
 raises. See DESIGN.md for the kernels and INTEGRATION.md for the drop-in boundary.
 """
-from . import arithmetics, basins, core, core_conversion, core_d8, core_ldd, core_nextxy, dem, geotiff, gis_utils, regions, rivers, streams
+from . import arithmetics, basins, core, core_conversion, core_d8, core_ldd, core_nextxy, dem, geotiff, gis_utils, regions, rivers, streams, subgrid, upscale
 from .core_nextxy import read_nextxy
 from .core_conversion import d8_to_ldd, ldd_to_d8
 from .gis_utils import Affine
