@@ -90,6 +90,14 @@ __global__ void __launch_bounds__(1024, 2) hand_tile_a_kernel(const uint8_t* __r
         s.D[0][i] = D;
     }
     __syncthreads();
+    // own (ancestor, sum) live in registers; shared memory only publishes them to the cells that point here
+    uint32_t own_a[4];
+    double own_d[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        own_a[j] = s.nx[0][threadIdx.x + 1024 * j];
+        own_d[j] = s.D[0][threadIdx.x + 1024 * j];
+    }
     int fin = 0;
     for (int k = 0; k < TL_MAXROUNDS; ++k) {
         const int cur = k & 1, nb = cur ^ 1;
@@ -97,12 +105,12 @@ __global__ void __launch_bounds__(1024, 2) hand_tile_a_kernel(const uint8_t* __r
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int i = threadIdx.x + 1024 * j;
-            const uint32_t a = s.nx[cur][i];
-            const uint32_t n = a & 0xFFFu;
+            const uint32_t n = own_a[j] & 0xFFFu;
             const uint32_t an = s.nx[cur][n];
-            const double Di = s.D[cur][i];
-            s.D[nb][i] = (a & HD_ROOT_HIT) ? Di : __dadd_rn(Di, s.D[cur][n]);  // (a root carries the empty segment: + 0)
-            s.nx[nb][i] = (uint16_t)((an & 0xFFFu) | ((a | an) & HD_ROOT_HIT));
+            if (!(own_a[j] & HD_ROOT_HIT)) own_d[j] = __dadd_rn(own_d[j], s.D[cur][n]);  // (a root carries the empty segment: + 0)
+            own_a[j] = (an & 0xFFFu) | ((own_a[j] | an) & HD_ROOT_HIT);
+            s.D[nb][i] = own_d[j];
+            s.nx[nb][i] = (uint16_t)own_a[j];
             ch |= (an & 0xFFFu) != n;
         }
         fin = nb;
