@@ -469,8 +469,16 @@ def extras_widened(w, size, seed, cpu_size):
     fin_dev, fout_dev, fd8_dev = w.dev_alloc(fz.size * 4), w.dev_alloc(fz.size * 4), w.dev_alloc(fz.size)
     w.ck(l.pfd_memcpy(h, fin_dev, L.ptr(fz), fz.size * 4))
     fstats = np.zeros(12, np.int64)
-    fill_ms = best(lambda: w.ck(l.pfd_fill_depressions(h, fin_dev, f32, fsz, fsz, 0, None, 0, C.c_double(-9999.0), C.c_double(-1.0), 0,
-                                                       C.c_double(0.0), 8, 0, fout_dev, fd8_dev, L.ptr(fstats))), reps=2)
+    fill_call = lambda: w.ck(l.pfd_fill_depressions(h, fin_dev, f32, fsz, fsz, 0, None, 0, C.c_double(-9999.0), C.c_double(-1.0), 0,
+                                                    C.c_double(0.0), 8, 0, fout_dev, fd8_dev, L.ptr(fstats)))
+    fill_ms = best(fill_call, reps=2)
+    fstats0 = fstats.copy()
+    # the same terrain on a regional slope (3 m per cell along the diagonal): depressions stay local, as in a real DEM -- without
+    # it the fBm surface has basin-scale sinks whose lakes (millions of cells) are replayed serially
+    fzt = (fz + (np.arange(fsz, dtype=np.float32)[:, None] + np.arange(fsz, dtype=np.float32)[None, :]) * np.float32(1.5)).astype(np.float32)
+    w.ck(l.pfd_memcpy(h, fin_dev, L.ptr(fzt), fzt.size * 4))
+    fill_t_ms = best(fill_call, reps=2)
+    fstats1 = fstats.copy()
     for pdev in (fin_dev, fout_dev, fd8_dev):
         w.ck(l.pfd_dev_free(h, pdev))
 
@@ -540,11 +548,15 @@ def extras_widened(w, size, seed, cpu_size):
     except Exception:
         pass
     t_fill, _ = cpu_time(lambda: fill_fn(fzc.copy()))
-    res["fill_depressions"] = {"gpu_ms": fill_ms, "gpu_mcells_s": fz.size / (fill_ms / 1e3) / 1e6, "cpu_mcells_s": fzc.size / t_fill / 1e6,
-                               "cpu_kind": fill_kind, "gpu_raster": f"{fsz}^2 float32", "cpu_raster": f"{csz}^2",
-                               "level_passes": int(fstats[0]), "label_passes": int(fstats[1]), "tied_cells": int(fstats[2]),
-                               "tie_components": int(fstats[3]), "largest_component": int(fstats[7]),
-                               "levels_ms": fstats[10] / 1e3, "ties_ms": fstats[11] / 1e3}
+    def fill_entry(ms, st, t_cpu, what):
+        return {"gpu_ms": ms, "gpu_mcells_s": fz.size / (ms / 1e3) / 1e6, "cpu_mcells_s": fzc.size / t_cpu / 1e6, "cpu_kind": fill_kind,
+                "terrain": what, "gpu_raster": f"{fsz}^2 float32", "cpu_raster": f"{csz}^2", "level_passes": int(st[0]),
+                "label_passes": int(st[1]), "tied_cells": int(st[2]), "tie_components": int(st[3]), "largest_component": int(st[7]),
+                "levels_ms": st[10] / 1e3, "ties_ms": st[11] / 1e3}
+
+    res["fill_depressions"] = fill_entry(fill_ms, fstats0, t_fill, "rough fBm in metres, no regional slope: basin-scale sinks")
+    t_fill_t, _ = cpu_time(lambda: fill_fn(np.ascontiguousarray(fzt[:csz, :csz])))
+    res["fill_depressions_sloped"] = fill_entry(fill_t_ms, fstats1, t_fill_t, "the same + 3 m per cell of regional slope: local depressions")
     res["note"] = (f"GPU: {size}^2 raster, device-resident buffers, ordering cached, best of 3; CPU: oracle port of the same "
                    f"reference function on a {cpu_size}^2 raster of the same generator, 1 thread (the reference's "
                    "stream_distance / floodplains are interpreted Python and far slower than this C port)")
