@@ -366,8 +366,12 @@ __global__ void fd_count_kernel(const uint32_t* __restrict__ label, int64_t n, u
     if (roots) atomicAdd(&cnt->n_roots, roots);
 }
 
+#ifndef FD_BIG
 #define FD_BIG 2048     // components of at least this many cells are replayed by a warp (fd_simulate_warp_kernel)
-#define FDW_CAP 24576   // heap entries that fit the warp's shared memory (192 KiB)
+#endif
+#ifndef FDW_CAP
+#define FDW_CAP 24576   // heap entries that fit the warp's shared memory (192 KiB); tests build with a tiny value to exercise the spill
+#endif
 // every component gets a slice of the heap pool; cnt[root] becomes the fill counter of that slice
 __global__ void fd_roots_kernel(const uint32_t* __restrict__ label, int64_t n, uint32_t* __restrict__ cntarr, uint32_t* __restrict__ off,
                                 uint32_t* __restrict__ roots, unsigned long long nroots, FdCounters* cnt) {

@@ -120,3 +120,20 @@ def test_fill_depressions_float32_key_drift():
         got = g.fill_depressions(z)
         assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), (trial, g.fill_stats)
         g.close()
+
+
+def test_fill_depressions_degenerate_rasters():
+    """all nodata, one cell, one row / column, one flat (a single tie component, replayed by a warp), a flat with holes"""
+    cases = [np.full((7, 9), -9999.0, dtype=np.float32), np.array([[3.5]]), np.arange(17, dtype=np.float64)[None, :] % 5,
+             (np.arange(23, dtype=np.float32)[:, None] * np.float32(0.5)) % np.float32(3.0), np.zeros((90, 110), dtype=np.float32),
+             np.ones((64, 64), dtype=np.int32)]
+    holes = np.zeros((120, 97), dtype=np.float64)
+    holes[np.random.default_rng(8).random(holes.shape) < 0.3] = -9999.0
+    cases.append(holes)
+    for a in cases:
+        for kw in (dict(), dict(connectivity=4), dict(outlets="min")):
+            if kw.get("outlets") == "min" and not np.any(a != -9999.0):
+                continue  # (the reference pops an empty heap there)
+            want = oracle.dem.fill_depressions(a.copy(), **kw)
+            got = dem.fill_depressions(a.copy(), **kw)
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), (a.shape, a.dtype, kw)
