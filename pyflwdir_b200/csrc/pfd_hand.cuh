@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(1024, 2) hand_tile_a_kernel(const uint8_t* __r
             const uint32_t root = a & 0xFFFu;
             uint16_t rec = HD_ROOT_NONE;
             // (an in-tile loop never settles on a root; one of 2^k cells comes back to itself, which is no root either)
-            if (s.kind[i] != 3 && s.kind[root] != 0 && (s.nx[fin][root] & 0xFFFu) == root)
+            // and a path that runs into a nodata cell (possible in graphs loaded from idxs_ds arrays) reaches no pit
+            if (s.kind[i] != 3 && (s.kind[root] == 1 || s.kind[root] == 2) && (s.nx[fin][root] & 0xFFFu) == root)
                 rec = (uint16_t)(root | (a & HD_ROOT_HIT) | (s.kind[root] == 2 ? HD_ROOT_EXIT : 0));
             hroot[r * ncol + c] = rec;
             hD[r * ncol + c] = s.D[fin][i];
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(1024, 2) hand_tile_a_kernel(const uint8_t* __r
             const int ri = tl_ring_cell(threadIdx.x);
             const uint32_t a = s.nx[fin][ri];
             const uint32_t root = a & 0xFFFu;
-            if (s.kind[ri] != 3 && s.kind[root] != 0 && (s.nx[fin][root] & 0xFFFu) == root) {
+            if (s.kind[ri] != 3 && (s.kind[root] == 1 || s.kind[root] == 2) && (s.nx[fin][root] & 0xFFFu) == root) {
                 const uint32_t hit = (a & HD_ROOT_HIT) ? HD_HIT : 0u;
                 val = s.D[fin][ri];
                 if (s.kind[root] == 1) {
