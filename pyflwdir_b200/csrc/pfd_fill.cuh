@@ -21,11 +21,11 @@
 // float64) and the pushed key is float32(z1): for float32 rasters the result can miss z0 by an ulp or, when z0 and z1 differ
 // in sign or magnitude, by much more, so the keys inside a filled lake DRIFT around the pour level and so does the pop order.
 // The replay therefore works with the actual keys and the actual arithmetic, and "equal level" in (3) means "within BAND
-// (an absolute elevation difference, first 16 ulps of max |z|) of each other": everything the heap might order differently from the drift-free levels of (1) is inside
+// (an absolute elevation difference; 0 = exact ties at first, 16 ulps of max |z| or more once a raise has drifted) of each other": everything the heap might order differently from the drift-free levels of (1) is inside
 // one component and is replayed exactly; across components (and for cells in none) levels differ by more than BAND and the
 // order follows (1). The replay checks that no key drifted by more than BAND / 4 from its level (1); if one did, the labelling
 // and the replay are repeated with a wider band (x 32 or 8 x the drift seen; in the limit the whole raster is one component, i.e. the reference's
-// own serial loop). Float64 / integer rasters reproduce z0 exactly and start with BAND = 0.
+// own serial loop). Float64 / integer rasters reproduce z0 exactly and never leave BAND = 0.
 // max_depth >= 0 (re-opening of visited cells, dem.py:121-132) is not restated: PFD_ERR_UNSUPPORTED.
 #pragma once
 #include "pfd_common.cuh"
@@ -813,10 +813,11 @@ static int fd_fill_impl(pfd_handle* h, const T* elev, int64_t nrow, int64_t ncol
     const auto t_levels = std::chrono::steady_clock::now();
     // (3) tie components and their replay; the band widens until no key drifted half a band away from its level
     uint32_t *M = A1, *label = A2, *link = A3, *cntarr = A1, *off = A3, *Tord = A4;
-    // "tied" = levels within `band` (absolute) of each other. Raising is exact in float64 (band 0: exact ties only); in float32
-    // one raise misses the pour level by about an ulp of the larger operand, so the first band is 16 ulps of max |z|.
+    // "tied" = levels within `band` (absolute) of each other. The first attempt takes exact ties only (band 0): raising is exact in
+    // float64, and in float32 whenever z0 - z1 fits 24 bits (elevations of one sign and similar magnitude); a raise that misses its
+    // pour level is seen by the replay as drift, and the band widens to 16 ulps of max |z| or 8 x the drift seen.
     const float zmax = uint_as_float_host((uint32_t)max_abs_bits);
-    float band = sizeof(W) == 8 ? 0.0f : zmax * 1.9073486e-06f;  // 2^-19
+    float band = 0.0f;  // exact ties first: any raise that misses its pour level (possible in float32 only) shows up as drift
     for (;; ++tries) {
         const float max_drift = band * 0.25f;
         fd_tie_kernel<<<grid, 256, 0, h->stream>>>(S, nrow, ncol, nbmask, band, M, label, link);
@@ -883,7 +884,7 @@ static int fd_fill_impl(pfd_handle* h, const T* elev, int64_t nrow, int64_t ncol
         if (band > 3.0e38f) return pfd_fail(h, PFD_ERR_CUDA, "pfd_fill_depressions: internal error (drift with an unbounded band)");
         // some key drifted too far from its level: everything it may have been ordered against must share its heap
         const float seen = uint_as_float_host((uint32_t)hc.max_drift);
-        float nb = band > 0.0f ? band * 32.0f : 0.0f;
+        float nb = band > 0.0f ? band * 32.0f : zmax * 1.9073486e-06f;  // first widening: 16 ulps of max |z| (2^-19 relative)
         if (!(nb >= seen * 8.0f)) nb = seen * 8.0f;
         band = (nb > 3.0e38f || nb != nb) ? INFINITY : nb;
         fd_reset_flags_kernel<<<grid, 256, 0, h->stream>>>(flags, n);
