@@ -158,6 +158,7 @@ extern "C" void pfd_destroy(pfd_handle* h) {
                       &h->hand_root, &h->hand_sum, &h->hand_slots, &h->sw_dir, &h->sw_out, &h->sw_aux, &h->sw_fdone};
     for (DevBuf* b : bufs) pfd_release(*b);
     for (DevBuf& b : h->scratch) pfd_release(b);
+    for (DevBuf& b : h->fill_bufs) pfd_release(b);
     for (int s = 0; s < PFD_NSTAGE; ++s) {
         cudaEventDestroy(h->ev_start[s]);
         cudaEventDestroy(h->ev_stop[s]);
@@ -1425,6 +1426,10 @@ extern "C" int pfd_set_option(pfd_handle* h, const char* name, int64_t value) {
     if (name && strcmp(name, "release_scratch") == 0) {  // give the staging buffers back (very large rasters)
         PFD_CUDA(h, cudaStreamSynchronize(h->stream));
         for (auto& b : h->scratch) pfd_release(b);
+        for (auto& b : h->fill_bufs) pfd_release(b);
+        pfd_release(h->hand_root);
+        pfd_release(h->hand_sum);
+        pfd_release(h->hand_slots);
         return PFD_OK;
     }
     return pfd_fail(h, PFD_ERR_INVALID_ARG, std::string("pfd_set_option: unknown option ") + (name ? name : "(null)"));

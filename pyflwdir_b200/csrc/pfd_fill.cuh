@@ -707,23 +707,18 @@ __global__ void fd_reset_flags_kernel(uint8_t* __restrict__ flags, int64_t n) {
 // ---------------------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------------------
-struct FdScratch {  // temporary device buffers of one call
-    std::vector<void*> ptrs;
-    ~FdScratch() {
-        for (void* p : ptrs) cudaFree(p);
-    }
-    int alloc(pfd_handle* h, void** p, size_t bytes) {
-        PFD_CUDA(h, cudaMalloc(p, bytes ? bytes : 16));
-        ptrs.push_back(*p);
+struct FdScratch {  // device buffers of one call: slots of the handle that persist (and only grow) across calls
+    pfd_handle* h;
+    int next = 0;
+    explicit FdScratch(pfd_handle* handle) : h(handle) {}
+    int alloc(pfd_handle*, void** p, size_t bytes) {
+        if (next >= (int)(sizeof(h->fill_bufs) / sizeof(h->fill_bufs[0]))) return pfd_fail(h, PFD_ERR_STATE, "pfd_fill_depressions: out of buffer slots");
+        PFD_TRY(pfd_reserve(h, h->fill_bufs[next], bytes));
+        *p = h->fill_bufs[next++].p;
         return PFD_OK;
     }
-    void release(void* p) {
-        for (size_t i = 0; i < ptrs.size(); ++i)
-            if (ptrs[i] == p) {
-                cudaFree(p);
-                ptrs.erase(ptrs.begin() + i);
-                return;
-            }
+    void release(void* p) {  // the last slot handed out can be handed out again (heap pool / root list of a retry)
+        if (next > 0 && h->fill_bufs[next - 1].p == p) --next;
     }
 };
 
@@ -738,21 +733,29 @@ static inline uint32_t float_as_uint_host(float f) {
     return u;
 }
 
-// runs a tile kernel over the active tiles until no tile changes anything; `launch(cur, next)` queues one pass
+// runs a tile kernel over the active tiles until no tile changes anything; `launch(cur, next, changed)` queues one pass. Passes are
+// queued four at a time between two looks at the flags (a pass after convergence finds no active tile and costs next to nothing)
+#define FD_BATCH 4
 template <class Launch>
 static int fd_converge(pfd_handle* h, int64_t ntiles, uint8_t* act[2], unsigned int* changed_dev, Launch launch, int* passes_out) {
     PFD_CUDA(h, cudaMemsetAsync(act[0], 1, (size_t)ntiles, h->stream));
-    int passes = 0;
-    for (int cur = 0;; cur ^= 1) {
-        PFD_CUDA(h, cudaMemsetAsync(act[cur ^ 1], 0, (size_t)ntiles, h->stream));
-        PFD_CUDA(h, cudaMemsetAsync(changed_dev, 0, sizeof(unsigned int), h->stream));
-        launch(act[cur], act[cur ^ 1]);
-        PFD_LAUNCH_CHECK(h);
-        ++passes;
-        unsigned int changed = 0;
-        PFD_CUDA(h, cudaMemcpyAsync(&changed, changed_dev, sizeof(changed), cudaMemcpyDeviceToHost, h->stream));
+    int passes = 0, cur = 0;
+    for (;;) {
+        PFD_CUDA(h, cudaMemsetAsync(changed_dev, 0, FD_BATCH * sizeof(unsigned int), h->stream));
+        for (int p = 0; p < FD_BATCH; ++p, cur ^= 1) {
+            PFD_CUDA(h, cudaMemsetAsync(act[cur ^ 1], 0, (size_t)ntiles, h->stream));
+            launch(act[cur], act[cur ^ 1], changed_dev + p);
+            PFD_LAUNCH_CHECK(h);
+        }
+        unsigned int changed[FD_BATCH];
+        PFD_CUDA(h, cudaMemcpyAsync(changed, changed_dev, sizeof(changed), cudaMemcpyDeviceToHost, h->stream));
         PFD_CUDA(h, cudaStreamSynchronize(h->stream));
-        if (!changed) break;
+        bool done = false;
+        for (int p = 0; p < FD_BATCH && !done; ++p) {
+            ++passes;
+            done = changed[p] == 0;
+        }
+        if (done) break;
     }
     if (passes_out) *passes_out = passes;
     return PFD_OK;
@@ -765,7 +768,7 @@ static int fd_fill_impl(pfd_handle* h, const T* elev, int64_t nrow, int64_t ncol
     const int64_t n = nrow * ncol;
     const uint32_t nbmask = connectivity == 4 ? FD_NB4 : FD_NB8;
     const int nodata_nan = nodata != nodata;
-    FdScratch sc;
+    FdScratch sc(h);
     uint8_t* flags = nullptr;
     uint32_t *S = nullptr, *A1 = nullptr, *A2 = nullptr, *A3 = nullptr, *A4 = nullptr;
     FdCounters* cnt = nullptr;
@@ -777,7 +780,7 @@ static int fd_fill_impl(pfd_handle* h, const T* elev, int64_t nrow, int64_t ncol
     PFD_TRY(sc.alloc(h, (void**)&A3, (size_t)n * 4));
     PFD_TRY(sc.alloc(h, (void**)&A4, (size_t)n * 4));
     PFD_TRY(sc.alloc(h, (void**)&cnt, sizeof(FdCounters)));
-    PFD_TRY(sc.alloc(h, (void**)&changed, sizeof(unsigned int)));
+    PFD_TRY(sc.alloc(h, (void**)&changed, 16 * sizeof(unsigned int)));
     FdCounters hc;
     memset(&hc, 0, sizeof(hc));
     hc.minkey = ~0ull;
@@ -806,8 +809,8 @@ static int fd_fill_impl(pfd_handle* h, const T* elev, int64_t nrow, int64_t ncol
     PFD_TRY(sc.alloc(h, (void**)&act[0], (size_t)(lty * ltx)));
     PFD_TRY(sc.alloc(h, (void**)&act[1], (size_t)(lty * ltx)));
     int passes_levels = 0, passes_labels = 0, tries = 0;
-    PFD_TRY(fd_converge(h, nty * ntx, act, changed, [&](const uint8_t* cur, uint8_t* next) {
-        fd_relax_kernel<T><<<(unsigned)(nty * ntx), 1024, 0, h->stream>>>(elev, flags, S, nrow, ncol, nty, ntx, nbmask, cur, next, changed);
+    PFD_TRY(fd_converge(h, nty * ntx, act, changed, [&](const uint8_t* cur, uint8_t* next, unsigned int* chg) {
+        fd_relax_kernel<T><<<(unsigned)(nty * ntx), 1024, 0, h->stream>>>(elev, flags, S, nrow, ncol, nty, ntx, nbmask, cur, next, chg);
     }, &passes_levels));
 
     const auto t_levels = std::chrono::steady_clock::now();
@@ -825,8 +828,8 @@ static int fd_fill_impl(pfd_handle* h, const T* elev, int64_t nrow, int64_t ncol
         fd_tie2_kernel<<<grid, 256, 0, h->stream>>>(S, M, link, nrow, ncol, nbmask, band, label);
         PFD_LAUNCH_CHECK(h);
         int lp = 0;
-        PFD_TRY(fd_converge(h, lty * ltx, act, changed, [&](const uint8_t* cur, uint8_t* next) {
-            fd_label_kernel<<<(unsigned)(lty * ltx), 256, 0, h->stream>>>(S, M, label, link, nrow, ncol, lty, ltx, nbmask, band, cur, next, changed);
+        PFD_TRY(fd_converge(h, lty * ltx, act, changed, [&](const uint8_t* cur, uint8_t* next, unsigned int* chg) {
+            fd_label_kernel<<<(unsigned)(lty * ltx), 256, 0, h->stream>>>(S, M, label, link, nrow, ncol, lty, ltx, nbmask, band, cur, next, chg);
         }, &lp));
         passes_labels += lp;
         // heap slices (cnt = A1, off = A3)
@@ -878,8 +881,8 @@ static int fd_fill_impl(pfd_handle* h, const T* elev, int64_t nrow, int64_t ncol
         }
         PFD_CUDA(h, cudaMemcpyAsync(&hc, cnt, sizeof(hc), cudaMemcpyDeviceToHost, h->stream));
         PFD_CUDA(h, cudaStreamSynchronize(h->stream));
-        if (pool) sc.release(pool);
         if (roots) sc.release(roots);
+        if (pool) sc.release(pool);
         if (hc.n_drift == 0) break;
         if (band > 3.0e38f) return pfd_fail(h, PFD_ERR_CUDA, "pfd_fill_depressions: internal error (drift with an unbounded band)");
         // some key drifted too far from its level: everything it may have been ordered against must share its heap
