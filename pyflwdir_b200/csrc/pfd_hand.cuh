@@ -52,17 +52,37 @@ __global__ void __launch_bounds__(1024, 2) hand_tile_a_kernel(const uint8_t* __r
     const long long ty = blockIdx.y, tx = blockIdx.x;
     const uint32_t tile = (uint32_t)((ty + 1) * ntx + tx);
     const long long r0 = ty * TL_H, c0 = tx * TL_W;
+    // loads in two waves (all directions, then everything that depends on them) so that the four cells of a thread overlap
+    uint32_t dd[4];
+    long long gg[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = threadIdx.x + 1024 * j;
+        const long long r = r0 + (i >> 6), c = c0 + (i & 63);
+        dd[j] = PFD_DIR_NODATA;
+        gg[j] = 0;
+        if (r < nrow && c < ncol) {
+            gg[j] = r * ncol + c;
+            dd[j] = dir[gg[j]];
+        }
+    }
+    uint8_t drn[4];
+    T ee[4], eds[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        drn[j] = 0;
+        ee[j] = eds[j] = (T)0;
+        if (dd[j] < 8u) {
+            drn[j] = drain[gg[j]];
+            ee[j] = elev[gg[j]];
+            eds[j] = elev[gg[j] + pfd_slot_off((int)dd[j], ncol)];
+        }
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int i = threadIdx.x + 1024 * j;
         const int ly = i >> 6, lx = i & 63;
-        const long long r = r0 + ly, c = c0 + lx;
-        uint32_t d = PFD_DIR_NODATA;
-        long long g = 0;
-        if (r < nrow && c < ncol) {
-            g = r * ncol + c;
-            d = dir[g];
-        }
+        const uint32_t d = dd[j];
         uint16_t nx = (uint16_t)i;
         double D = 0.0;
         uint8_t kind = 3;
@@ -70,8 +90,8 @@ __global__ void __launch_bounds__(1024, 2) hand_tile_a_kernel(const uint8_t* __r
             if (d >= 8u) {
                 kind = 1;
             } else {
-                const bool dr = drain[g] == 1;
-                const double w = dr ? 0.0 : hd_dz<T>(elev[g], elev[g + pfd_slot_off((int)d, ncol)]);
+                const bool dr = drn[j] == 1;
+                const double w = dr ? 0.0 : hd_dz<T>(ee[j], eds[j]);
                 const int y = ly + pfd_slot_dr((int)d), x = lx + pfd_slot_dc((int)d);
                 if ((unsigned)y < (unsigned)TL_H && (unsigned)x < (unsigned)TL_W) {
                     kind = 0;
