@@ -421,6 +421,19 @@ __global__ void fd_sources_kernel(const uint32_t* __restrict__ S, const uint32_t
     }
 }
 
+// linear index -> row without a hardware division (a dependent ~20-instruction sequence on the replay's critical path):
+// row = (i * magic) >> (31 + shift) is exact for i < 2^31 with magic = ceil(2^(31 + shift) / ncol), shift = ceil(log2(ncol))
+struct FdDiv {
+    uint32_t magic, shift;
+};
+static FdDiv fd_make_div(uint32_t ncol) {
+    uint32_t s = 0;
+    while ((1ull << s) < ncol) ++s;
+    const unsigned long long num = 1ull << (31 + s);
+    return FdDiv{(uint32_t)((num + ncol - 1) / ncol), 31 + s};
+}
+__device__ __forceinline__ uint32_t fd_row_of(uint32_t i, FdDiv dv) { return (uint32_t)(((unsigned long long)i * dv.magic) >> dv.shift); }
+
 // (3b) one thread replays the heap loop (dem.py:112-142) of one tie component with the reference's keys and arithmetic
 __device__ __forceinline__ void fd_sift_down(unsigned long long* hp, uint32_t n, uint32_t i, unsigned long long v) {
     for (;;) {
@@ -461,7 +474,7 @@ __global__ void fd_simulate_kernel(const uint32_t* __restrict__ roots, uint32_t 
                                    const uint32_t* __restrict__ cntarr, unsigned long long* __restrict__ pool, const uint32_t* __restrict__ S,
                                    const uint32_t* __restrict__ label, const T* __restrict__ elev, uint8_t* flags, uint32_t* __restrict__ Tord,
                                    uint8_t* d8, T* __restrict__ out, int64_t nrow, int64_t ncol, uint32_t nbmask, int int_delv,
-                                   float max_drift, FdCounters* cnt) {
+                                   float max_drift, FdDiv dv, FdCounters* cnt) {
     const uint32_t k0 = blockIdx.x * blockDim.x + threadIdx.x;
     if (k0 >= nroots) return;
     const uint32_t root = roots[k0];
@@ -485,7 +498,7 @@ __global__ void fd_simulate_kernel(const uint32_t* __restrict__ roots, uint32_t 
             d8[p] = 0;
             fd_visit<T, W>(elev, out, p, z0, int_delv);
         }
-        const int32_t pr = (int32_t)(p / (uint32_t)nc), pc = (int32_t)(p - (uint32_t)pr * (uint32_t)nc);
+        const int32_t pr = (int32_t)fd_row_of(p, dv), pc = (int32_t)(p - (uint32_t)pr * (uint32_t)nc);
         for (int k = 0; k < 9; ++k) {
             if (!((nbmask >> k) & 1u)) continue;
             const int32_t rr = pr + k / 3 - 1, cc = pc + k % 3 - 1;
@@ -550,7 +563,7 @@ __global__ void __launch_bounds__(32) fd_simulate_warp_kernel(const uint32_t* __
                                                               const uint32_t* __restrict__ S, const uint32_t* __restrict__ label,
                                                               const T* __restrict__ elev, uint8_t* flags, uint32_t* __restrict__ Tord,
                                                               uint8_t* d8, T* __restrict__ out, int64_t nrow, int64_t ncol, uint32_t nbmask,
-                                                              int int_delv, float max_drift, FdCounters* cnt) {
+                                                              int int_delv, float max_drift, FdDiv dv, FdCounters* cnt) {
     extern __shared__ unsigned long long fd_sheap[];
     const int lane = threadIdx.x;
     const uint32_t root = roots[blockIdx.x];
@@ -578,7 +591,7 @@ __global__ void __launch_bounds__(32) fd_simulate_warp_kernel(const uint32_t* __
         const float z0 = fd_unord((uint32_t)(top >> 32));
         if (lane == 0) Tord[p] = t;
         ++t;
-        const int32_t pr = (int32_t)(p / (uint32_t)nc), pc = (int32_t)(p - (uint32_t)pr * (uint32_t)nc);
+        const int32_t pr = (int32_t)fd_row_of(p, dv), pc = (int32_t)(p - (uint32_t)pr * (uint32_t)nc);
         bool push = false;
         unsigned long long e = 0;
         if (lane < 9) {  // lane k looks at cell k of the 3 x 3 window (k = 4: the popped cell itself); all loads issued at once
@@ -768,6 +781,7 @@ static int fd_fill_impl(pfd_handle* h, const T* elev, int64_t nrow, int64_t ncol
     const int64_t n = nrow * ncol;
     const uint32_t nbmask = connectivity == 4 ? FD_NB4 : FD_NB8;
     const int nodata_nan = nodata != nodata;
+    const FdDiv dv = fd_make_div((uint32_t)ncol);
     FdScratch sc(h);
     uint8_t* flags = nullptr;
     uint32_t *S = nullptr, *A1 = nullptr, *A2 = nullptr, *A3 = nullptr, *A4 = nullptr;
@@ -866,12 +880,12 @@ static int fd_fill_impl(pfd_handle* h, const T* elev, int64_t nrow, int64_t ncol
                     attr_set[sizeof(W) == 8] = true;
                 }
                 fd_simulate_warp_kernel<T, W><<<(unsigned)nbig, 32, FDW_CAP * 8, h->stream>>>(
-                    roots + nsmall, off, cntarr, pool, S, label, elev, flags, Tord, d8, out, nrow, ncol, nbmask, int_delv, max_drift, cnt);
+                    roots + nsmall, off, cntarr, pool, S, label, elev, flags, Tord, d8, out, nrow, ncol, nbmask, int_delv, max_drift, dv, cnt);
                 PFD_LAUNCH_CHECK(h);
             }
             if (nsmall > 0) {
                 fd_simulate_kernel<T, W><<<(unsigned)((nsmall + 31) / 32), 32, 0, s2>>>(
-                    roots, (uint32_t)nsmall, off, cntarr, pool, S, label, elev, flags, Tord, d8, out, nrow, ncol, nbmask, int_delv, max_drift, cnt);
+                    roots, (uint32_t)nsmall, off, cntarr, pool, S, label, elev, flags, Tord, d8, out, nrow, ncol, nbmask, int_delv, max_drift, dv, cnt);
                 PFD_LAUNCH_CHECK(h);
             }
             if (s2 != h->stream) {
