@@ -344,7 +344,9 @@ int pfd_tiled_finish(pfd_handle* h, int32_t* rank_out, int32_t* uparea_out, uint
  *   begin -> swap(edges -> halo) -> { round -> swap(edges -> halo) }* -> end
  * pfd_sweep_tiled_edges(which = 0 my first row | 1 my last row) packs [dir | done | value | aux] of that row;
  * pfd_sweep_tiled_halo(which = 0 the row above my block | 1 the row below) installs a neighbour's record.
- * Rasters with loops are refused by the up-sweeps (PFD_ERR_UNSUPPORTED): use the single-GPU call.
+ * Rasters with loops are refused by the up-sweeps (PFD_ERR_UNSUPPORTED): use the single-GPU call. The HAND down-sweep starts at
+ * every drain cell, so a drain cell that drains to no pit (above a loop; outside the reference's sequence) gets 0 instead of
+ * -9999 here: callers with such rasters use the single-GPU pfd_hand (pyflwdir_b200.multigpu does, from the rank it already has).
  */
 int pfd_sweep_tiled_begin(pfd_handle* h, int kind, const void* data, int dtype, const uint8_t* drain, double nodata_f,
                           int64_t nodata_i, int nodata_is_int);

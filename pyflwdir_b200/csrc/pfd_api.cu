@@ -2318,6 +2318,11 @@ extern "C" int pfd_strahler(pfd_handle* h, const uint8_t* mask, uint8_t* out) {
 
 #include "pfd_hand.cuh"
 
+__global__ void hand_reset_unranked_kernel(const uint8_t* __restrict__ dir, const int32_t* __restrict__ rank, int64_t n, double* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (dir[i] != PFD_DIR_NODATA && rank[i] < 0) out[i] = -9999.0;
+}
+
 extern "C" int pfd_hand(pfd_handle* h, const uint8_t* drain, const void* elevtn, int elev_dtype, double* out) {
     PFD_TRY(check_handle(h));
     stage_reset(h);
@@ -2333,9 +2338,11 @@ extern "C" int pfd_hand(pfd_handle* h, const uint8_t* drain, const void* elevtn,
     const void *drain_dev = nullptr, *elev_dev = nullptr;
     PFD_TRY(pfd_stage_in(h, drain, (size_t)n, 4, &drain_dev));
     PFD_TRY(pfd_stage_in(h, elevtn, (size_t)n * pfd_dtype_size(elev_dtype), 5, &elev_dev));
+    bool pathsum_ran = false;
     if (h->hand_pathsum && !h->tiled) {
         // re-associated path sums (pfd_hand.cuh), accepted only when every cell satisfies the reference's statement bit for bit
         unsigned long long bad = 0;
+        pathsum_ran = true;
         if (elev_dtype == PFD_F32) PFD_TRY(hand_pathsum<float>(h, (const uint8_t*)drain_dev, (const float*)elev_dev, (double*)out_dev, &bad));
         else PFD_TRY(hand_pathsum<double>(h, (const uint8_t*)drain_dev, (const double*)elev_dev, (double*)out_dev, &bad));
         if (bad == 0) {
@@ -2355,6 +2362,16 @@ extern "C" int pfd_hand(pfd_handle* h, const uint8_t* drain, const void* elevtn,
         } else {
             HandTileOp<double> op{(const uint8_t*)drain_dev, (const double*)elev_dev, (double*)out_dev};
             PFD_TRY(run_tile_down(h, op, "pfd_hand"));
+        }
+        // the dataflow starts at every drain cell, also at one that drains to no pit (above a loop): the reference only knows the
+        // cells of its sequence. Which cells those are: from the path structure of the rejected attempt, else from the rank.
+        if (pathsum_ran) {
+            PFD_TRY(hand_mask_unreached(h, (double*)out_dev));
+        } else {
+            PFD_TRY(tiles_usable(h) ? tiles_ensure(h, true, false, false) : order_impl(h, true, false));
+            hand_reset_unranked_kernel<<<grid_for(n, 256, 4, 148 * 32), 256, 0, h->stream>>>((const uint8_t*)h->dir.p + h->dir_off, (const int32_t*)h->rank.p, n,
+                                                                                             (double*)out_dev);
+            PFD_LAUNCH_CHECK(h);
         }
         PFD_TRY(pfd_finish_out(h, out, out_dev, bytes));
         PFD_CUDA(h, cudaStreamSynchronize(h->stream));

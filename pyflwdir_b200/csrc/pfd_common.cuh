@@ -196,6 +196,7 @@ struct pfd_handle {
     DevBuf fill_bufs[12];      // pfd_fill_depressions (pfd_fill.cuh): levels, labels, heap pool ... (kept between calls)
     DevBuf hand_root, hand_sum, hand_slots;  // path-sum HAND (pfd_hand.cuh): per-cell (root, segment sum), ring nodes
     int hand_pathsum = 1;      // option "hand_pathsum": 1 = try the re-associated path sums first (verified, else hop by hop)
+    int hand_fin = 0;          // which ring-node buffer holds the final state of the last path-sum attempt
     int hand_engine = 0;       // info "hand_engine": what produced the last pfd_hand result (1 path sums, 2 tile sweep, 3 level replay)
     DevBuf verify;            // VerifyCounts of the pfd_verify_* entry points
     DevBuf btab, bgraph;       // row-tiled multi-GPU solve: boundary tables, boundary graph state

@@ -238,6 +238,31 @@ __global__ void __launch_bounds__(1024) hand_tile_c_kernel(const uint8_t* __rest
     }
 }
 
+// -9999 for every cell that reaches no pit, decided by the path structure alone (valid whether or not the sums were exact): the
+// hop-by-hop tile sweep treats every drain cell as a source, also one that sits above a loop, outside the reference's sequence
+__global__ void __launch_bounds__(1024) hand_mask_unreached_kernel(const uint16_t* __restrict__ hroot, const uint32_t* __restrict__ s_nxt,
+                                                                   long long nrow, long long ncol, long long ntx, double* __restrict__ out) {
+    __shared__ uint8_t ringok[TL_RING];
+    const long long ty = blockIdx.y, tx = blockIdx.x;
+    const uint32_t tile = (uint32_t)((ty + 1) * ntx + tx);
+    const long long r0 = ty * TL_H, c0 = tx * TL_W;
+    if (threadIdx.x < TL_RING) ringok[threadIdx.x] = (s_nxt[tile * TL_RING + threadIdx.x] & 0x7FFFFFFFu) == HD_SINK;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = threadIdx.x + 1024 * j;
+        const long long r = r0 + (i >> 6), c = c0 + (i & 63);
+        if (r >= nrow || c >= ncol) continue;
+        const uint32_t rec = hroot[r * ncol + c];
+        bool reached = rec != HD_ROOT_NONE;
+        if (reached && (rec & HD_ROOT_EXIT)) {
+            const uint32_t root = rec & 0xFFFu;
+            reached = ringok[tl_ring_pos((int)(root >> 6), (int)(root & 63u))];
+        }
+        if (!reached) out[r * ncol + c] = -9999.0;
+    }
+}
+
 // the reference's per-cell statement, from the finished values: counts the cells that violate it (four independent cells per
 // thread and trip, so that the two dependent rounds of loads -- the cell, then its downstream cell -- overlap)
 template <typename T>
@@ -326,6 +351,7 @@ static int hand_pathsum(pfd_handle* h, const uint8_t* drain_dev, const T* elev_d
         PFD_CUDA(h, cudaStreamSynchronize(h->stream));
         if (!ch) break;
     }
+    h->hand_fin = fin;
     hand_tile_c_kernel<<<grid, 1024, 0, h->stream>>>(dir, hroot, hD, snxt[fin], sval[fin], nrow, ncol, ntx, out_dev);
     PFD_LAUNCH_CHECK(h);
     PFD_CUDA(h, cudaMemsetAsync(bad, 0, sizeof(unsigned long long), h->stream));
@@ -333,5 +359,19 @@ static int hand_pathsum(pfd_handle* h, const uint8_t* drain_dev, const T* elev_d
     PFD_LAUNCH_CHECK(h);
     PFD_CUDA(h, cudaMemcpyAsync(n_bad, bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+    return PFD_OK;
+}
+
+// after a REJECTED path-sum attempt the hop-by-hop engine wrote `out`; the path structure of the attempt still says which cells
+// reach a pit
+static int hand_mask_unreached(pfd_handle* h, double* out_dev) {
+    const long long nrow = h->nrow, ncol = h->ncol;
+    const long long ntx = (ncol + TL_W - 1) / TL_W, nty = (nrow + TL_H - 1) / TL_H;
+    const long long nslots = (nty + 2) * ntx * TL_RING;
+    double* sval1 = (double*)h->hand_slots.p + nslots;
+    uint32_t* snxt[2] = {(uint32_t*)(sval1 + nslots), (uint32_t*)(sval1 + nslots) + nslots};
+    hand_mask_unreached_kernel<<<dim3((unsigned)ntx, (unsigned)nty), 1024, 0, h->stream>>>((const uint16_t*)h->hand_root.p, snxt[h->hand_fin], nrow, ncol,
+                                                                                            ntx, out_dev);
+    PFD_LAUNCH_CHECK(h);
     return PFD_OK;
 }

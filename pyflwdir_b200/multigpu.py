@@ -132,7 +132,9 @@ class MultiDeviceGraph(_device.DeviceGraph):
         return super().accuflux(data, nodata, direction)
 
     def hand(self, drain, elevtn):
-        if self._solvers:
+        # (loops: the row-block dataflow starts at every drain cell, also at one above a loop, which is outside the reference's
+        # sequence -- those rasters go to the single-GPU call, which knows which cells reach a pit)
+        if self._solvers and self._no_loops():
             drain, elevtn = np.ascontiguousarray(drain), np.ascontiguousarray(elevtn)
             if drain.size != self.size:
                 raise ValueError('"drain" size does not match.')

@@ -65,3 +65,25 @@ def test_inexact_sums_fall_back_to_the_sweep():
     got = flw.hand(drain, elev)
     assert np.array_equal(got, want)
     assert flw._dev.info("hand_engine") in (2, 3), "inexact float64 sums must not be accepted"
+
+
+def test_drain_cells_above_loops_all_engines():
+    """a drain cell that drains to no pit is outside the reference's sequence (-9999 there and upstream of it): path sums, the
+    tile-dataflow fallback (after a rejected attempt and with the attempt switched off) and the level replay agree with the oracle"""
+    rng = np.random.default_rng(77)
+    legal = np.array([32, 64, 128, 16, 0, 1, 8, 4, 2, 247, 255], dtype=np.uint8)
+    p = np.array([1, 1, 1, 1, 0.03, 1, 1, 1, 1, 0.1, 0.03])
+    d8 = legal[rng.choice(legal.size, size=(411, 305), p=p / p.sum())]
+    drain = rng.random(d8.shape) < 0.04
+    exact = rng.random(d8.shape, dtype=np.float32) * np.float32(100.0)
+    inexact = (rng.random(d8.shape) + 2.0) * 10.0 ** rng.integers(-25, 25, size=d8.shape)
+    for elev, engines in ((exact, (1,)), (inexact, (2, 3))):
+        want = _oracle_hand(d8, drain, elev)
+        assert np.any((want == -9999.0) & (d8 != 247)), "the case must hold cells outside the sequence"
+        flw = pfb.from_array(d8, ftype="d8", check_ftype=False)
+        assert np.array_equal(flw.hand(drain, elev), want) and flw._dev.info("hand_engine") in engines
+        flw._dev.set_option("hand_pathsum", 0)
+        flw._dev.set_option("tile_sweeps", 2)
+        assert np.array_equal(flw.hand(drain, elev), want) and flw._dev.info("hand_engine") == 2
+        flw._dev.set_option("tile_sweeps", 0)
+        assert np.array_equal(flw.hand(drain, elev), want) and flw._dev.info("hand_engine") == 3
