@@ -874,10 +874,9 @@ static int fd_fill_impl(pfd_handle* h, const T* elev, int64_t nrow, int64_t ncol
                 PFD_CUDA(h, cudaStreamWaitEvent(s2, h->ev_copy, 0));
             }
             if (nbig > 0) {
-                static bool attr_set[2] = {false, false};
-                if (!attr_set[sizeof(W) == 8]) {
+                if (!h->fill_attr_set[sizeof(W) == 8]) {
                     PFD_CUDA(h, cudaFuncSetAttribute(fd_simulate_warp_kernel<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, FDW_CAP * 8));
-                    attr_set[sizeof(W) == 8] = true;
+                    h->fill_attr_set[sizeof(W) == 8] = true;
                 }
                 fd_simulate_warp_kernel<T, W><<<(unsigned)nbig, 32, FDW_CAP * 8, h->stream>>>(
                     roots + nsmall, off, cntarr, pool, S, label, elev, flags, Tord, d8, out, nrow, ncol, nbmask, int_delv, max_drift, dv, cnt);

@@ -329,10 +329,9 @@ static int hand_pathsum(pfd_handle* h, const uint8_t* drain_dev, const T* elev_d
     uint32_t* snxt[2] = {(uint32_t*)(sval[1] + nslots), (uint32_t*)(sval[1] + nslots) + nslots};
     unsigned int* changed = (unsigned int*)(snxt[1] + nslots);
     unsigned long long* bad = (unsigned long long*)(changed + 2);
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[sizeof(T) == 8]) {
+    if (!h->hand_attr_set[sizeof(T) == 8]) {
         PFD_CUDA(h, cudaFuncSetAttribute(hand_tile_a_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HandTileShared)));
-        attr_set[sizeof(T) == 8] = true;
+        h->hand_attr_set[sizeof(T) == 8] = true;
     }
     const dim3 grid((unsigned)ntx, (unsigned)nty);
     hand_tile_a_kernel<T><<<grid, 1024, sizeof(HandTileShared), h->stream>>>(dir, drain_dev, elev_dev, nrow, ncol, ntx, hroot, hD, snxt[0], sval[0]);

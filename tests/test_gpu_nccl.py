@@ -62,3 +62,31 @@ def test_from_array_devices_matches_single_gpu():
     assert np.array_equal(two.hand(drain, z).ravel(), oracle.dem.height_above_nearest_drain(ids, seq, drain.ravel(), z.ravel()))
     # unsharded entry points still work (devices[0])
     assert np.array_equal(two.idxs_seq, seq)
+
+
+def test_fill_and_hand_on_the_second_device():
+    """kernels that opt into large dynamic shared memory (the warp replay of dem.fill_depressions, phase A of the path-sum HAND) on
+    device 1 after device 0 in the same process: the opt-in is per device"""
+    import numpy as np
+
+    import oracle
+    import pyflwdir_b200 as pfb
+    from pyflwdir_b200 import _lib, dem
+
+    if _lib.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    flat = np.full((130, 140), 5.0, dtype=np.float32)  # one tie component of > 2048 cells: warp replay
+    flat[0, :] = flat[-1, :] = flat[:, 0] = flat[:, -1] = 9.0
+    flat[0, 70] = 1.0
+    z = oracle.synth_elevation(300, 260, seed=5)
+    d8 = oracle.synth_d8(z)
+    ids, pits, _ = oracle.core_d8.from_array(d8, dtype=np.int32)
+    seq = oracle.core.idxs_seq(ids, pits)
+    want_fill = oracle.dem.fill_depressions(flat)
+    for device in (0, 1, 0):
+        got = dem.fill_depressions(flat, device=device)
+        assert np.array_equal(got[0], want_fill[0]) and np.array_equal(got[1], want_fill[1])
+        flw = pfb.from_array(d8, ftype="d8", device=device)
+        drain = flw.upstream_area() > 60
+        assert np.array_equal(flw.hand(drain, z).ravel(), oracle.dem.height_above_nearest_drain(ids, seq, drain.ravel(), z.ravel()))
+        assert flw._dev.info("hand_engine") == 1
