@@ -7,9 +7,11 @@ module returns exactly those three things (+ nodata) so that the same two lines 
     flw = pyflwdir_b200.from_array(d8, ftype="d8", transform=transform, latlon=latlon)
 
 Scope: classic (32-bit offset) TIFF, little or big endian, one sample per pixel, strips or tiles, 8/16/32/64-bit integers
-and 32/64-bit floats, compression none / deflate (8, 32946) / PackBits (32773), predictor 1 or 2 (horizontal differencing),
+and 32/64-bit floats, compression none / LZW (5) / deflate (8, 32946) / PackBits (32773), predictor 1, 2 (horizontal differencing)
+or 3 (floating point),
 north-up georeferencing by ModelPixelScale + ModelTiepoint or ModelTransformation, GDAL_NODATA. Anything else raises
-NotImplementedError naming the tag. `write` produces an uncompressed or deflate-compressed striped file that `read`,
+NotImplementedError naming the tag. (LZW is decoded in pure Python, about 1 MB/s: fine for the example rasters, slow for
+gigabyte files -- deflate goes through zlib.) `write` produces an uncompressed or deflate-compressed striped file that `read`,
 rasterio and GDAL open."""
 import struct
 import zlib
@@ -71,6 +73,40 @@ def _unpackbits(data, size):
     return bytes(out[:size])
 
 
+def _unlzw(data, size):
+    """TIFF LZW (compression 5): MSB-first codes of 9..12 bits, 256 = clear, 257 = end of information, early change."""
+    out = bytearray()
+    table = [bytes((i,)) for i in range(256)] + [b"", b""]
+    nbits, bitbuf, bitcnt, prev = 9, 0, 0, None
+    for byte in data:
+        bitbuf = (bitbuf << 8) | byte
+        bitcnt += 8
+        while bitcnt >= nbits:
+            bitcnt -= nbits
+            code = (bitbuf >> bitcnt) & ((1 << nbits) - 1)
+            if code == 257:
+                return bytes(out[:size])
+            if code == 256:
+                table = table[:258]
+                nbits, prev = 9, None
+                continue
+            if prev is None:
+                entry = table[code]
+            elif code < len(table):
+                entry = table[code]
+                table.append(prev + entry[:1])
+            else:
+                entry = prev + prev[:1]
+                table.append(entry)
+            out += entry
+            prev = entry
+            if len(table) >= (1 << nbits) - 1 and nbits < 12:
+                nbits += 1
+            if len(out) >= size:
+                return bytes(out[:size])
+    return bytes(out[:size])
+
+
 def read(path):
     """Returns (array 2D, transform Affine, latlon bool, nodata or None)."""
     with open(path, "rb") as f:
@@ -91,9 +127,9 @@ def read(path):
         raise NotImplementedError(f"BitsPerSample (258) = {bits}, SampleFormat (339) = {fmt}")
     dtype = np.dtype(f"{bo}{kind}{bits // 8}")
     comp, pred = _first(t, 259, 1), _first(t, 317, 1)
-    if comp not in (1, 8, 32946, 32773):
-        raise NotImplementedError(f"Compression (259) = {comp}: only none / deflate / PackBits are supported")
-    if pred not in (1, 2) or (pred == 2 and kind == "f"):
+    if comp not in (1, 5, 8, 32946, 32773):
+        raise NotImplementedError(f"Compression (259) = {comp}: only none / LZW / deflate / PackBits are supported")
+    if pred not in (1, 2, 3) or (pred == 2 and kind == "f") or (pred == 3 and kind != "f"):
         raise NotImplementedError(f"Predictor (317) = {pred}")
     tiled = 322 in t
     if tiled:
@@ -114,7 +150,14 @@ def read(path):
                 raw = zlib.decompress(raw)
             elif comp == 32773:
                 raw = _unpackbits(raw, size)
-            blk = np.frombuffer(raw[:size], dtype=dtype).reshape(rows, bw).astype(out.dtype)
+            elif comp == 5:
+                raw = _unlzw(raw, size)
+            if pred == 3:  # floating-point predictor: bytes of a row differenced, then the byte planes stored most significant first
+                b = np.frombuffer(raw[:size], dtype=np.uint8).reshape(rows, bw * dtype.itemsize)
+                b = np.cumsum(b, axis=1, dtype=np.uint8).reshape(rows, dtype.itemsize, bw)
+                blk = np.ascontiguousarray(b.transpose(0, 2, 1)).view(np.dtype(f">{kind}{bits // 8}")).reshape(rows, bw).astype(out.dtype)
+            else:
+                blk = np.frombuffer(raw[:size], dtype=dtype).reshape(rows, bw).astype(out.dtype)
             if pred == 2:
                 blk = np.cumsum(blk, axis=1, dtype=out.dtype)
             r0, c0 = by * bh, bx * bw

@@ -51,3 +51,43 @@ def test_reference_examples():
     assert tuple(t)[:6] == cs.RHINE_TRANSFORM and latlon is True
     elv, t2, _, nd = geotiff.read(os.path.join(EXAMPLES, "rhine_elv0.tif"))
     assert elv.dtype == np.float32 and elv.shape == d8.shape and nd == -9999.0 and tuple(t2)[:6] == cs.RHINE_TRANSFORM
+
+
+@pytest.mark.parametrize("compression", ["tiff_lzw", "tiff_adobe_deflate", "packbits", "raw"])
+def test_reads_files_written_by_an_independent_encoder(tmp_path, compression):
+    """PIL writes, geotiff.read decodes: LZW (the usual compression of distributed GeoTIFFs), deflate, PackBits, none"""
+    from PIL import Image
+
+    rng = np.random.default_rng(1)
+    fn = str(tmp_path / "p.tif")
+    for dtype in (np.uint8, np.int32, np.float32):
+        for shape in ((1, 1), (7, 13), (120, 201), (40, 700)):
+            for x in ((rng.random(shape) * 200).astype(dtype), (np.add.outer(np.arange(shape[0]), np.arange(shape[1])) // 7).astype(dtype)):
+                Image.fromarray(x).save(fn, compression=compression)
+                y = geotiff.read(fn)[0]
+                assert y.dtype == x.dtype and np.array_equal(x, y), (dtype, shape, compression)
+
+
+def test_floating_point_predictor(tmp_path):
+    """Predictor 3 (TIFF Technical Note 3), encoded here straight from its definition: per row the bytes of the samples are
+    regrouped into planes, most significant byte first, and the resulting byte string is differenced"""
+    import struct
+    import zlib
+
+    rng = np.random.default_rng(2)
+    x = (rng.random((37, 53)) * 1000 - 300).astype(np.float32)
+    rows = []
+    for r in range(x.shape[0]):
+        planes = x[r].astype(">f4").view(np.uint8).reshape(-1, 4).T.reshape(-1).astype(np.int16)  # plane 0 = most significant bytes
+        rows.append((np.diff(planes, prepend=0) & 0xFF).astype(np.uint8).tobytes())
+    data = zlib.compress(b"".join(rows))
+    fn = str(tmp_path / "f.tif")
+    tags = [(256, 4, x.shape[1]), (257, 4, x.shape[0]), (258, 3, 32), (259, 3, 8), (262, 3, 1), (273, 4, 8 + 2 + 12 * 11 + 4),
+            (277, 3, 1), (278, 4, x.shape[0]), (279, 4, len(data)), (317, 3, 3), (339, 3, 3)]
+    with open(fn, "wb") as f:
+        f.write(b"II" + struct.pack("<HI", 42, 8) + struct.pack("<H", len(tags)))
+        for tag, typ, val in tags:
+            f.write(struct.pack("<HHI", tag, typ, 1) + (struct.pack("<I", val) if typ == 4 else struct.pack("<HH", val, 0)))
+        f.write(struct.pack("<I", 0) + data)
+    y = geotiff.read(fn)[0]
+    assert y.dtype == np.float32 and np.array_equal(x, y)
