@@ -20,12 +20,21 @@
 // Raising a cell is ARITHMETIC in the raster's own type (z1 += z0 - z1; float32 rasters: float32, float64 / integer rasters:
 // float64) and the pushed key is float32(z1): for float32 rasters the result can miss z0 by an ulp or, when z0 and z1 differ
 // in sign or magnitude, by much more, so the keys inside a filled lake DRIFT around the pour level and so does the pop order.
-// The replay therefore works with the actual keys and the actual arithmetic, and "equal level" in (3) means "within BAND
-// (an absolute elevation difference; 0 = exact ties at first, 16 ulps of max |z| or more once a raise has drifted) of each other": everything the heap might order differently from the drift-free levels of (1) is inside
-// one component and is replayed exactly; across components (and for cells in none) levels differ by more than BAND and the
-// order follows (1). The replay checks that no key drifted by more than BAND / 4 from its level (1); if one did, the labelling
-// and the replay are repeated with a wider band (x 32 or 8 x the drift seen; in the limit the whole raster is one component, i.e. the reference's
-// own serial loop). Float64 / integer rasters reproduce z0 exactly and never leave BAND = 0.
+// The replay therefore works with the actual keys and the actual arithmetic, and "equal level" in (3) means "within BAND of each
+// other" (an absolute elevation difference; 0 = exact ties at first, 16 ulps of max |z| or more once a raise has drifted):
+// everything the heap might order differently from the drift-free levels of (1) is inside one component and is replayed
+// exactly; across components (and for cells in none) levels differ by more than BAND and the order follows (1). The replay
+// checks that no key drifted by more than BAND / 4 from its level (1); if one did, the labelling and the replay are repeated with
+// a wider band (x 32 or 8 x the drift seen; in the limit the whole raster is one component, i.e. the reference's own serial
+// loop). Float64 / integer rasters reproduce z0 exactly and never leave BAND = 0.
+// Why that is sound. Let every key lie within d of its cell's level (checked: d <= BAND / 4) and let u, v be cells whose levels
+// differ by more than BAND > 2d, level(u) < level(v). Then the heap pops u before v: walk from u along smallest-level neighbours to
+// an outlet -- levels never rise on that walk, so every cell on it has a key below key(v); the first cell of the walk (from the
+// outlet side) that is not yet popped when v pops is already in the heap (an outlet, or visited when its predecessor popped)
+// with a smaller key than v, which contradicts v being the minimum. So a cell's parent is among its neighbours within BAND of
+// the smallest level; two or more of those share a component by construction ("connectors"), a single one needs no order. A cell
+// visited from outside its component is visited by a neighbour more than BAND below it, hence never raised, hence its key is
+// its own float32 elevation whatever the drift elsewhere: the set queued before a component starts, and their keys, are exact.
 // max_depth >= 0 (re-opening of visited cells, dem.py:121-132) is not restated: PFD_ERR_UNSUPPORTED.
 #pragma once
 #include "pfd_common.cuh"
