@@ -342,6 +342,12 @@ def extras(w, size, seed, skip_level=False):
         "accuflux_f32": lambda: w.ck(l.pfd_accuflux(h, z_dev, f32, -9999.0, 0, 0, 0, w.out_dev[1])),
         "hand": lambda: w.ck(l.pfd_hand(h, drain_dev, z_dev, f32, out8_dev)),
     }
+    # HAND as verified path sums (pfd_hand.cuh, the default engine of pfd_hand): no ordering, no passes
+    calls["hand"]()
+    res["hand_pathsum"] = {"hand_ms": best(calls["hand"]), "engine": int(l.pfd_get_info(h, b"hand_engine")),
+                           "note": "engine 1 = path sums accepted by the per-cell proof; 2 / 3 = a hop-by-hop engine answered"}
+    res["hand_pathsum"]["hand_mcells_s"] = n / (res["hand_pathsum"]["hand_ms"] / 1e3) / 1e6
+    w.ck(l.pfd_set_option(h, b"hand_pathsum", 0))  # the two sections below time the hop-by-hop engines
     # tile-dataflow sweeps (default): no ordering needed
     w.ck(l.pfd_set_option(h, b"tile_sweeps", 2))
     tile = {}
@@ -363,8 +369,10 @@ def extras(w, size, seed, skip_level=False):
             lev[k + "_mcells_s"] = n / (lev[k + "_ms"] / 1e3) / 1e6
         res["level_replay"] = lev
         w.ck(l.pfd_set_option(h, b"tile_sweeps", 1))
+    w.ck(l.pfd_set_option(h, b"hand_pathsum", 1))
     res["note"] = ("device-resident, same raster, best of 3, CUDA events. BASELINE config 3 (accuflux + Strahler) = the headline "
-                   "step + strahler; config 5 (HAND) = headline step + hand; level_replay additionally needs order_idxs_seq")
+                   "step + strahler; config 5 (HAND) = headline step + hand (hand_pathsum when its engine is 1, else the tile-dataflow "
+                   "sweep); level_replay additionally needs order_idxs_seq")
     for p in (z_dev, drain_dev, f64_dev, out8_dev, out1_dev):
         w.ck(l.pfd_dev_free(h, p))
     return res
@@ -827,11 +835,14 @@ def main():
         extra = extras(w, args.size, args.seed, skip_level=mode == "tile")
         t = extra["tile_dataflow"]
         step_ms = ms_total / args.steps
+        hp = extra["hand_pathsum"]
+        hand_ms = hp["hand_ms"] if hp["engine"] == 1 else t["hand_ms"]  # what a pfd_hand call costs with the default options
         extra["baseline_configs"] = {
             "config3_accuflux_plus_strahler_ms": step_ms + t["strahler_ms"],
             "config3_mcells_s": cells / ((step_ms + t["strahler_ms"]) / 1e3) / 1e6,
-            "config5_accuflux_mask_hand_ms": step_ms + t["hand_ms"],
-            "config5_mcells_s": cells / ((step_ms + t["hand_ms"]) / 1e3) / 1e6,
+            "config5_accuflux_mask_hand_ms": step_ms + hand_ms,
+            "config5_mcells_s": cells / ((step_ms + hand_ms) / 1e3) / 1e6,
+            "config5_hand_engine": "path sums (verified)" if hp["engine"] == 1 else "tile-dataflow sweep",
             "note": f"this {args.size}^2 raster: headline step (parse + rank + accuflux + basins) + the sweep; BASELINE quotes "
                     "config 5 at 16384^2 (run with --size 16384)"}
         if mode == "all":
