@@ -40,6 +40,10 @@
 #include "pfd_common.cuh"
 #include <chrono>
 
+#define FD_T 64            // tile of the level relaxation
+#define FD_TS (FD_T + 2)
+#define FL_T 32            // tile of the label propagation
+#define FL_TS (FL_T + 2)
 #define FD_UNREACHED 0xFFFFFFFFu
 #define FD_NONE 0xFFFFFFFFu
 enum { FDF_VALID = 1, FDF_OUTLET = 2, FDF_TIED = 4, FDF_QUEUED = 8, FDF_DISC = 16, FDF_SRCDISC = 32 };
@@ -62,6 +66,12 @@ __device__ __forceinline__ bool fd_is_nodata(T z, double nodata, int nodata_nan)
     return nodata_nan ? (z != z) : ((double)z == nodata);
 }
 
+__device__ __forceinline__ void fd_mark_neighbours(uint8_t* active_next, int64_t ty, int64_t tx, int64_t nty, int64_t ntx, int dy, int dx) {
+    if (dy != 0 && ty + dy >= 0 && ty + dy < nty) active_next[(ty + dy) * ntx + tx] = 1;
+    if (dx != 0 && tx + dx >= 0 && tx + dx < ntx) active_next[ty * ntx + tx + dx] = 1;
+    if (dy != 0 && dx != 0 && ty + dy >= 0 && ty + dy < nty && tx + dx >= 0 && tx + dx < ntx) active_next[(ty + dy) * ntx + tx + dx] = 1;
+}
+
 struct FdCounters {
     unsigned long long n_outlets, minkey, n_tied, n_roots, pool_top, root_fill, err_pit, n_drift, n_unreached, max_drift, max_comp, max_abs, big_fill;
 };
@@ -70,7 +80,7 @@ struct FdCounters {
 template <typename T>
 __global__ void fd_init_kernel(const T* __restrict__ elev, int64_t nrow, int64_t ncol, double nodata, int nodata_nan, uint32_t nbmask,
                                int mode, int has_elv_max, double elv_max, uint8_t* __restrict__ flags, uint32_t* __restrict__ S,
-                               FdCounters* cnt) {
+                               uint8_t* __restrict__ act0, int64_t ntx, FdCounters* cnt) {
     const int64_t n = nrow * ncol;
     float zmax = 0.0f;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -90,6 +100,12 @@ __global__ void fd_init_kernel(const T* __restrict__ elev, int64_t nrow, int64_t
                 if (edge && (!has_elv_max || (double)z <= elv_max)) {
                     f |= FDF_OUTLET;
                     s = fd_ord((float)z);
+                    // the flood starts in the tiles that hold an outlet (and next door, when the outlet sits on a tile edge)
+                    const int64_t ty = r / FD_T, tx = c / FD_T;
+                    const int ly = (int)(r - ty * FD_T), lx = (int)(c - tx * FD_T);
+                    act0[ty * ntx + tx] = 1;
+                    fd_mark_neighbours(act0, ty, tx, (nrow + FD_T - 1) / FD_T, ntx, ly == 0 ? -1 : (ly == FD_T - 1 ? 1 : 0),
+                                       lx == 0 ? -1 : (lx == FD_T - 1 ? 1 : 0));
                     atomicAdd(&cnt->n_outlets, 1ull);
                     if (mode == 1) atomicMin(&cnt->minkey, ((unsigned long long)s << 32) | (unsigned long long)i);
                 }
@@ -100,7 +116,8 @@ __global__ void fd_init_kernel(const T* __restrict__ elev, int64_t nrow, int64_t
         flags[i] = f;
         S[i] = s;
     }
-    if (zmax > 0.0f) atomicMax(&cnt->max_abs, (unsigned long long)__float_as_uint(zmax));
+    const uint32_t zb = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(zmax));  // (non-negative floats order like their bits)
+    if ((threadIdx.x & 31) == 0 && zb) atomicMax(&cnt->max_abs, (unsigned long long)zb);
 }
 
 // outlets="min" (dem.py:104-107): only the smallest (key, 1, row, col) stays an outlet
@@ -116,7 +133,8 @@ __global__ void fd_keep_min_kernel(int64_t n, uint8_t* __restrict__ flags, uint3
 // idxs_pit given (dem.py:87-90)
 template <typename T>
 __global__ void fd_pits_kernel(const T* __restrict__ elev, int64_t n, const int64_t* __restrict__ idxs, int64_t npit,
-                               uint8_t* __restrict__ flags, uint32_t* __restrict__ S, FdCounters* cnt) {
+                               uint8_t* __restrict__ flags, uint32_t* __restrict__ S, uint8_t* __restrict__ act0, int64_t ncol, int64_t ntx,
+                               FdCounters* cnt) {
     for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < npit; k += (int64_t)gridDim.x * blockDim.x) {
         int64_t i = idxs[k];
         if (i < 0) i += n;
@@ -126,6 +144,13 @@ __global__ void fd_pits_kernel(const T* __restrict__ elev, int64_t n, const int6
         }
         flags[i] |= FDF_OUTLET;  // duplicates write the same values
         S[i] = fd_ord((float)elev[i]);
+        {
+            const int64_t r = i / ncol, c = i - r * ncol, ty = r / FD_T, tx = c / FD_T;
+            const int ly = (int)(r - ty * FD_T), lx = (int)(c - tx * FD_T);
+            act0[ty * ntx + tx] = 1;
+            fd_mark_neighbours(act0, ty, tx, (n / ncol + FD_T - 1) / FD_T, ntx, ly == 0 ? -1 : (ly == FD_T - 1 ? 1 : 0),
+                               lx == 0 ? -1 : (lx == FD_T - 1 ? 1 : 0));
+        }
         atomicAdd(&cnt->n_outlets, 1ull);
     }
 }
@@ -133,14 +158,7 @@ __global__ void fd_pits_kernel(const T* __restrict__ elev, int64_t n, const int6
 // ---------------------------------------------------------------------------------------------------------
 // (1) levels: S(x) <- max(key(x), min over neighbours S(y)) until nothing moves, one CTA per active 64x64 tile
 // ---------------------------------------------------------------------------------------------------------
-#define FD_T 64
-#define FD_TS (FD_T + 2)
 
-__device__ __forceinline__ void fd_mark_neighbours(uint8_t* active_next, int64_t ty, int64_t tx, int64_t nty, int64_t ntx, int dy, int dx) {
-    if (dy != 0 && ty + dy >= 0 && ty + dy < nty) active_next[(ty + dy) * ntx + tx] = 1;
-    if (dx != 0 && tx + dx >= 0 && tx + dx < ntx) active_next[ty * ntx + tx + dx] = 1;
-    if (dy != 0 && dx != 0 && ty + dy >= 0 && ty + dy < nty && tx + dx >= 0 && tx + dx < ntx) active_next[(ty + dy) * ntx + tx + dx] = 1;
-}
 
 template <typename T>
 __global__ void __launch_bounds__(1024) fd_relax_kernel(const T* __restrict__ elev, const uint8_t* __restrict__ flags, uint32_t* __restrict__ S,
@@ -220,7 +238,8 @@ __device__ __forceinline__ bool fd_near(uint32_t a, uint32_t b, float band) { re
 __device__ __forceinline__ bool fd_nearmin(uint32_t b, uint32_t m, float band) { return b == m || fd_unord(b) - fd_unord(m) <= band; }
 
 __global__ void fd_tie_kernel(const uint32_t* __restrict__ S, int64_t nrow, int64_t ncol, uint32_t nbmask, float band,
-                              uint32_t* __restrict__ M, uint32_t* __restrict__ label, uint32_t* __restrict__ link) {
+                              uint32_t* __restrict__ M, uint32_t* __restrict__ label, uint32_t* __restrict__ link, uint8_t* __restrict__ act0,
+                              int64_t ltx) {
     const int64_t n = nrow * ncol;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t s = S[i];
@@ -253,12 +272,17 @@ __global__ void fd_tie_kernel(const uint32_t* __restrict__ S, int64_t nrow, int6
         M[i] = m;
         label[i] = lab;
         link[i] = lk;
+        if (lab != FD_NONE || lk != FD_NONE) {  // label propagation starts in the tiles that hold a tied cell or a connector
+            const int64_t r = i / ncol, c = i - r * ncol;
+            act0[(r / FL_T) * ltx + c / FL_T] = 1;
+        }
     }
 }
 
 // the candidates of a connector join the labelled cells (even when they have no tied neighbour themselves)
 __global__ void fd_tie2_kernel(const uint32_t* __restrict__ S, const uint32_t* __restrict__ M, const uint32_t* __restrict__ link,
-                               int64_t nrow, int64_t ncol, uint32_t nbmask, float band, uint32_t* __restrict__ label) {
+                               int64_t nrow, int64_t ncol, uint32_t nbmask, float band, uint32_t* __restrict__ label, uint8_t* __restrict__ act0,
+                               int64_t ltx) {
     const int64_t n = nrow * ncol;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         if (link[i] == FD_NONE) continue;
@@ -271,7 +295,10 @@ __global__ void fd_tie2_kernel(const uint32_t* __restrict__ S, const uint32_t* _
             if (rr < 0 || rr >= nrow || cc < 0 || cc >= ncol) continue;
             const int64_t y = rr * ncol + cc;
             const uint32_t sy = S[y];
-            if (sy != FD_UNREACHED && fd_nearmin(sy, m, band) && label[y] == FD_NONE) label[y] = (uint32_t)y;  // racing writers store the same value
+            if (sy != FD_UNREACHED && fd_nearmin(sy, m, band) && label[y] == FD_NONE) {
+                label[y] = (uint32_t)y;  // racing writers store the same value
+                act0[(rr / FL_T) * ltx + cc / FL_T] = 1;
+            }
         }
     }
 }
@@ -279,8 +306,6 @@ __global__ void fd_tie2_kernel(const uint32_t* __restrict__ S, const uint32_t* _
 // min-label propagation, one CTA (256 threads, 4 cells each) per active 32x32 tile:
 //   labelled y : label <- min(label of tied labelled neighbours, link of adjacent connectors whose candidate y is)
 //   connector x: link  <- min(label of its candidates)
-#define FL_T 32
-#define FL_TS (FL_T + 2)
 __global__ void __launch_bounds__(256) fd_label_kernel(const uint32_t* __restrict__ S, const uint32_t* __restrict__ M, uint32_t* __restrict__ label,
                                                        uint32_t* __restrict__ link, int64_t nrow, int64_t ncol, int64_t nty, int64_t ntx,
                                                        uint32_t nbmask, float band, const uint8_t* __restrict__ active_cur,
@@ -760,7 +785,7 @@ static inline uint32_t float_as_uint_host(float f) {
 #define FD_BATCH 4
 template <class Launch>
 static int fd_converge(pfd_handle* h, int64_t ntiles, uint8_t* act[2], unsigned int* changed_dev, Launch launch, int* passes_out) {
-    PFD_CUDA(h, cudaMemsetAsync(act[0], 1, (size_t)ntiles, h->stream));
+    // act[0] holds the tiles to start from (set by the kernels that created the state to relax)
     int passes = 0, cur = 0;
     for (;;) {
         PFD_CUDA(h, cudaMemsetAsync(changed_dev, 0, FD_BATCH * sizeof(unsigned int), h->stream));
@@ -809,13 +834,20 @@ static int fd_fill_impl(pfd_handle* h, const T* elev, int64_t nrow, int64_t ncol
     hc.minkey = ~0ull;
     PFD_CUDA(h, cudaMemcpyAsync(cnt, &hc, sizeof(hc), cudaMemcpyHostToDevice, h->stream));
     const int grid = grid_for(n, 256, 4);
-    fd_init_kernel<T><<<grid, 256, 0, h->stream>>>(elev, nrow, ncol, nodata, nodata_nan, nbmask, mode, has_elv_max, elv_max, flags, S, cnt);
+    const int64_t nty = (nrow + FD_T - 1) / FD_T, ntx = (ncol + FD_T - 1) / FD_T;
+    const int64_t lty = (nrow + FL_T - 1) / FL_T, ltx = (ncol + FL_T - 1) / FL_T;
+    uint8_t* act[2] = {nullptr, nullptr};
+    PFD_TRY(sc.alloc(h, (void**)&act[0], (size_t)(lty * ltx)));
+    PFD_TRY(sc.alloc(h, (void**)&act[1], (size_t)(lty * ltx)));
+    PFD_CUDA(h, cudaMemsetAsync(act[0], 0, (size_t)(nty * ntx), h->stream));
+    fd_init_kernel<T><<<grid, 256, 0, h->stream>>>(elev, nrow, ncol, nodata, nodata_nan, nbmask, mode, has_elv_max, elv_max, flags, S, act[0], ntx,
+                                                   cnt);
     PFD_LAUNCH_CHECK(h);
     if (mode == 1) {
         fd_keep_min_kernel<<<grid, 256, 0, h->stream>>>(n, flags, S, cnt);
         PFD_LAUNCH_CHECK(h);
     } else if (mode == 2) {
-        fd_pits_kernel<T><<<grid_for(npit > 0 ? npit : 1, 256, 1), 256, 0, h->stream>>>(elev, n, idxs_pit, npit, flags, S, cnt);
+        fd_pits_kernel<T><<<grid_for(npit > 0 ? npit : 1, 256, 1), 256, 0, h->stream>>>(elev, n, idxs_pit, npit, flags, S, act[0], ncol, ntx, cnt);
         PFD_LAUNCH_CHECK(h);
     }
     PFD_CUDA(h, cudaMemcpyAsync(&hc, cnt, sizeof(hc), cudaMemcpyDeviceToHost, h->stream));
@@ -826,11 +858,6 @@ static int fd_fill_impl(pfd_handle* h, const T* elev, int64_t nrow, int64_t ncol
 
     // (1) levels
     const auto t_start = std::chrono::steady_clock::now();
-    const int64_t nty = (nrow + FD_T - 1) / FD_T, ntx = (ncol + FD_T - 1) / FD_T;
-    const int64_t lty = (nrow + FL_T - 1) / FL_T, ltx = (ncol + FL_T - 1) / FL_T;
-    uint8_t* act[2] = {nullptr, nullptr};
-    PFD_TRY(sc.alloc(h, (void**)&act[0], (size_t)(lty * ltx)));
-    PFD_TRY(sc.alloc(h, (void**)&act[1], (size_t)(lty * ltx)));
     int passes_levels = 0, passes_labels = 0, tries = 0;
     PFD_TRY(fd_converge(h, nty * ntx, act, changed, [&](const uint8_t* cur, uint8_t* next, unsigned int* chg) {
         fd_relax_kernel<T><<<(unsigned)(nty * ntx), 1024, 0, h->stream>>>(elev, flags, S, nrow, ncol, nty, ntx, nbmask, cur, next, chg);
@@ -846,9 +873,10 @@ static int fd_fill_impl(pfd_handle* h, const T* elev, int64_t nrow, int64_t ncol
     float band = 0.0f;  // exact ties first: any raise that misses its pour level (possible in float32 only) shows up as drift
     for (;; ++tries) {
         const float max_drift = band * 0.25f;
-        fd_tie_kernel<<<grid, 256, 0, h->stream>>>(S, nrow, ncol, nbmask, band, M, label, link);
+        PFD_CUDA(h, cudaMemsetAsync(act[0], 0, (size_t)(lty * ltx), h->stream));
+        fd_tie_kernel<<<grid, 256, 0, h->stream>>>(S, nrow, ncol, nbmask, band, M, label, link, act[0], ltx);
         PFD_LAUNCH_CHECK(h);
-        fd_tie2_kernel<<<grid, 256, 0, h->stream>>>(S, M, link, nrow, ncol, nbmask, band, label);
+        fd_tie2_kernel<<<grid, 256, 0, h->stream>>>(S, M, link, nrow, ncol, nbmask, band, label, act[0], ltx);
         PFD_LAUNCH_CHECK(h);
         int lp = 0;
         PFD_TRY(fd_converge(h, lty * ltx, act, changed, [&](const uint8_t* cur, uint8_t* next, unsigned int* chg) {
