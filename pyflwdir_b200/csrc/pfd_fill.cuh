@@ -42,6 +42,9 @@
 
 #define FD_T 64            // tile of the level relaxation
 #define FD_TS (FD_T + 2)
+#ifndef FD_SWEEPS
+#define FD_SWEEPS 2         // in-place sweeps of the level relaxation between two barriers (one down, one up; 2 / 3 / 4 / 8 / 16: 12.0 / 12.3 / 12.9 / 15.0 / 19.1 ms at 8192^2)
+#endif
 #define FL_T 32            // tile of the label propagation
 #define FL_TS (FL_T + 2)
 #define FD_UNREACHED 0xFFFFFFFFu
@@ -178,10 +181,12 @@ __global__ void __launch_bounds__(1024) fd_relax_kernel(const T* __restrict__ el
     uint32_t kz[4], orig[4];
     bool upd[4];
     int pos[4];
-    const int lx = threadIdx.x & 63, ly0 = threadIdx.x >> 6;
+    // a thread owns four vertically adjacent cells and relaxes them in place top-down, then bottom-up: a level travels four rows per
+    // sweep along a column instead of one; several sweeps run between two barriers (any interleaving reaches the same fixpoint)
+    const int lx = threadIdx.x & 63, ly0 = (threadIdx.x >> 6) << 2;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int ly = ly0 + 16 * j;
+        const int ly = ly0 + j;
         const int64_t r = r0 + ly, c = c0 + lx;
         pos[j] = (ly + 1) * FD_TS + lx + 1;
         upd[j] = false;
@@ -198,17 +203,21 @@ __global__ void __launch_bounds__(1024) fd_relax_kernel(const T* __restrict__ el
     volatile uint32_t* vS = sS;
     for (;;) {
         bool ch = false;
+#pragma unroll 1
+        for (int sweep = 0; sweep < FD_SWEEPS; ++sweep) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (!upd[j]) continue;
-            uint32_t m = FD_UNREACHED;
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = (sweep & 1) ? 3 - jj : jj;
+                if (!upd[j]) continue;
+                uint32_t m = FD_UNREACHED;
 #pragma unroll
-            for (int k = 0; k < 9; ++k)
-                if ((nbmask >> k) & 1u) m = min(m, vS[pos[j] + (k / 3 - 1) * FD_TS + (k % 3 - 1)]);
-            const uint32_t ns = max(kz[j], m);
-            if (ns < vS[pos[j]]) {
-                vS[pos[j]] = ns;
-                ch = true;
+                for (int k = 0; k < 9; ++k)
+                    if ((nbmask >> k) & 1u) m = min(m, vS[pos[j] + (k / 3 - 1) * FD_TS + (k % 3 - 1)]);
+                const uint32_t ns = max(kz[j], m);
+                if (ns < vS[pos[j]]) {
+                    vS[pos[j]] = ns;
+                    ch = true;
+                }
             }
         }
         if (!__syncthreads_or((int)ch)) break;
@@ -218,7 +227,7 @@ __global__ void __launch_bounds__(1024) fd_relax_kernel(const T* __restrict__ el
     for (int j = 0; j < 4; ++j) {
         const uint32_t v = sS[pos[j]];
         if (v != orig[j]) {
-            const int ly = ly0 + 16 * j;
+            const int ly = ly0 + j;
             S[(r0 + ly) * ncol + c0 + lx] = v;
             any = true;
             const int dy = (ly == 0) ? -1 : ((ly == FD_T - 1) ? 1 : 0), dx = (lx == 0) ? -1 : ((lx == FD_T - 1) ? 1 : 0);
