@@ -137,3 +137,16 @@ def test_fill_depressions_degenerate_rasters():
             want = oracle.dem.fill_depressions(a.copy(), **kw)
             got = dem.fill_depressions(a.copy(), **kw)
             assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), (a.shape, a.dtype, kw)
+
+
+def test_fill_depressions_sloped_terrain_4096_vs_oracle():
+    """4096^2 terrain on a regional slope (local depressions: many small tie components, the level wavefront crosses 64 tiles),
+    float32 and float64, against the oracle"""
+    n = 4096
+    z = oracle.synth_elevation(n, n, seed=6)
+    a = (z * np.float32(700.0) + np.float32(2000.0)
+         + (np.arange(n, dtype=np.float32)[:, None] + np.arange(n, dtype=np.float32)[None, :]) * np.float32(1.5)).astype(np.float32)
+    for arr in (a, a.astype(np.float64)):
+        want = oracle.dem.fill_depressions(arr)
+        got = dem.fill_depressions(arr)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), arr.dtype
