@@ -2223,6 +2223,8 @@ extern "C" int pfd_upstream_area_cells(pfd_handle* h, int32_t* out) {
     return PFD_OK;
 }
 
+#include "pfd_hand.cuh"  // path summaries by pointer doubling: HAND, and the label / value filling of the two functions below
+
 template <typename IDX, typename U>
 static int basins_custom(pfd_handle* h, const void* idx_dev, const void* ids_dev, int64_t k, void* out_dev) {
     unsigned int* flag = reinterpret_cast<unsigned int*>((unsigned long long*)h->counters.p + 5);
@@ -2236,6 +2238,8 @@ static int basins_custom(pfd_handle* h, const void* idx_dev, const void* ids_dev
     PFD_CUDA(h, cudaMemcpyAsync(&hflag, flag, sizeof(hflag), cudaMemcpyDeviceToHost, h->stream));
     PFD_CUDA(h, cudaStreamSynchronize(h->stream));
     if (hflag & 4u) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_basins: outlet index out of bounds");
+    if (h->hand_pathsum && !h->tiled) return fill_up_paths<U>(h, (U*)out_dev, HasNonZero<U>{});  // no cell ordering needed
+    PFD_TRY(order_impl(h, false, false));
     FillUpOp<U> op{(const uint8_t*)h->dir.p, (U*)out_dev, h->ncol};
     return run_sweep<FillUpOp<U>, false>(h, op, 0);
 }
@@ -2259,7 +2263,7 @@ extern "C" int pfd_basins(pfd_handle* h, const void* outlets, int64_t n_outlets,
         return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_basins: outlet indices must be 32/64-bit integers");
     if (!usz || ids_dtype == PFD_F32 || ids_dtype == PFD_F64)
         return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_basins: ids must be an integer dtype");
-    PFD_TRY(order_impl(h, false, false));
+    if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, "pfd_basins: no raster parsed on this handle");
     const size_t bytes = (size_t)h->n * usz;
     void* out_dev = nullptr;
     PFD_TRY(pfd_stage_out(h, out, bytes, 3, &out_dev));
@@ -2315,8 +2319,6 @@ extern "C" int pfd_strahler(pfd_handle* h, const uint8_t* mask, uint8_t* out) {
     stage_collect(h);
     return PFD_OK;
 }
-
-#include "pfd_hand.cuh"
 
 __global__ void hand_reset_unranked_kernel(const uint8_t* __restrict__ dir, const int32_t* __restrict__ rank, int64_t n, double* __restrict__ out) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -2400,6 +2402,8 @@ extern "C" int pfd_hand(pfd_handle* h, const uint8_t* drain, const void* elevtn,
 template <typename T>
 static int fillnodata_typed(pfd_handle* h, void* out_dev, const NoData& nd, int direction, int how) {
     if (direction == 0) {
+        if (h->hand_pathsum && !h->tiled) return fill_up_paths<T>(h, (T*)out_dev, HasData<T>{nd});  // no cell ordering needed
+        PFD_TRY(order_impl(h, false, false));
         FillUpGenericOp<T> op{(const uint8_t*)h->dir.p, (T*)out_dev, h->ncol, nd};
         return run_sweep<FillUpGenericOp<T>, false>(h, op, 1);
     }
@@ -2427,7 +2431,8 @@ extern "C" int pfd_fillnodata(pfd_handle* h, const void* data, int dtype, double
         return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_fillnodata: direction must be 0/1 and how 0 (max) / 1 (min) / 2 (sum)");
     const size_t esz = pfd_dtype_size(dtype);
     if (!esz) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_fillnodata: unknown dtype");
-    PFD_TRY(order_impl(h, false, false));
+    if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, "pfd_fillnodata: no raster parsed on this handle");
+    if (direction != 0) PFD_TRY(order_impl(h, false, false));  // (direction 0 orders only when it has to fall back to the level replay)
     const size_t bytes = (size_t)h->n * esz;
     void* out_dev = nullptr;
     PFD_TRY(pfd_stage_out(h, out, bytes, 3, &out_dev));

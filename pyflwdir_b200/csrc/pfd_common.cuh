@@ -193,7 +193,7 @@ struct pfd_handle {
         unsigned long long resolved = 0;  // cells resolved so far (all rounds)
     } sw;
     DevBuf sw_dir, sw_out, sw_aux, sw_fdone, sw_edge[4];  // ext rows; [0,1] = send top / bottom, [2,3] = receive top / bottom
-    bool fill_attr_set[2] = {false, false}, hand_attr_set[2] = {false, false};  // dynamic shared memory opt-ins (per device, so per handle)
+    bool fill_attr_set[2] = {false, false}, hand_attr_set[48] = {};  // dynamic shared memory opt-ins (per device, so per handle)
     DevBuf fill_bufs[12];      // pfd_fill_depressions (pfd_fill.cuh): levels, labels, heap pool ... (kept between calls)
     DevBuf hand_root, hand_sum, hand_slots;  // path-sum HAND (pfd_hand.cuh): per-cell (root, segment sum), ring nodes
     int hand_pathsum = 1;      // option "hand_pathsum": 1 = try the re-associated path sums first (verified, else hop by hop)

@@ -42,10 +42,32 @@ struct HandTileShared {
     uint8_t kind[TL_CELLS];    // 0 inner, 1 pit, 2 exit, 3 nodata
 };
 
+// What a cell contributes to the path summaries. hit(g): the cell's value does not depend on what lies downstream (HAND: a drain
+// cell; label filling: a cell that has a value of its own), hit_value(g): the segment sum frozen there, w(g, g_ds): the hop term
+// of a cell that is not hit.
 template <typename T>
-__global__ void __launch_bounds__(1024, 2) hand_tile_a_kernel(const uint8_t* __restrict__ dir, const uint8_t* __restrict__ drain,
-                                                              const T* __restrict__ elev, long long nrow, long long ncol, long long ntx,
-                                                              uint16_t* __restrict__ hroot, double* __restrict__ hD,
+struct HandSrc {
+    const uint8_t* drain;
+    const T* elev;
+    __device__ __forceinline__ bool hit(long long g) const { return drain[g] == 1; }
+    __device__ __forceinline__ double hit_value(long long) const { return 0.0; }
+    __device__ __forceinline__ double w(long long g, long long g_ds) const { return hd_dz<T>(elev[g], elev[g_ds]); }
+};
+// core.fillnodata_upstream (pyflwdir/core.py:120-146; basins.basins, pyflwdir/basins.py:12-18, is this on a raster of outlet ids):
+// every cell without a value takes the value of the first cell downstream that has one. No arithmetic at all: the "sum" carries
+// (index of that cell + 1), exact in a double, and the result is gathered from there.
+template <typename U, class Has>
+struct FillSrc {
+    const U* data;
+    Has has;
+    __device__ __forceinline__ bool hit(long long g) const { return has(data[g]); }
+    __device__ __forceinline__ double hit_value(long long g) const { return (double)(g + 1); }
+    __device__ __forceinline__ double w(long long, long long) const { return 0.0; }
+};
+
+template <class Src>
+__global__ void __launch_bounds__(1024, 2) hand_tile_a_kernel(const uint8_t* __restrict__ dir, Src src, long long nrow, long long ncol,
+                                                              long long ntx, uint16_t* __restrict__ hroot, double* __restrict__ hD,
                                                               uint32_t* __restrict__ s_nxt, double* __restrict__ s_val) {
     extern __shared__ __align__(16) unsigned char hd_smem[];
     HandTileShared& s = *reinterpret_cast<HandTileShared*>(hd_smem);
@@ -66,16 +88,16 @@ __global__ void __launch_bounds__(1024, 2) hand_tile_a_kernel(const uint8_t* __r
             dd[j] = dir[gg[j]];
         }
     }
-    uint8_t drn[4];
-    T ee[4], eds[4];
+    bool hitf[4];
+    double wv[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        drn[j] = 0;
-        ee[j] = eds[j] = (T)0;
-        if (dd[j] < 8u) {
-            drn[j] = drain[gg[j]];
-            ee[j] = elev[gg[j]];
-            eds[j] = elev[gg[j] + pfd_slot_off((int)dd[j], ncol)];
+        hitf[j] = false;
+        wv[j] = 0.0;
+        if (dd[j] != PFD_DIR_NODATA) {
+            hitf[j] = src.hit(gg[j]);
+            if (hitf[j]) wv[j] = src.hit_value(gg[j]);
+            else if (dd[j] < 8u) wv[j] = src.w(gg[j], gg[j] + pfd_slot_off((int)dd[j], ncol));
         }
     }
 #pragma unroll
@@ -88,20 +110,22 @@ __global__ void __launch_bounds__(1024, 2) hand_tile_a_kernel(const uint8_t* __r
         uint8_t kind = 3;
         if (d != PFD_DIR_NODATA) {
             if (d >= 8u) {
-                kind = 1;
+                kind = 1;  // a pit: the root of its paths; one that is hit carries its value into every segment that ends there
+                if (hitf[j]) {
+                    nx |= HD_ROOT_HIT;
+                    D = wv[j];
+                }
             } else {
-                const bool dr = drn[j] == 1;
-                const double w = dr ? 0.0 : hd_dz<T>(ee[j], eds[j]);
                 const int y = ly + pfd_slot_dr((int)d), x = lx + pfd_slot_dc((int)d);
                 if ((unsigned)y < (unsigned)TL_H && (unsigned)x < (unsigned)TL_W) {
                     kind = 0;
-                    nx = (uint16_t)((y << 6) | x) | (dr ? HD_ROOT_HIT : 0);
-                    D = w;
+                    nx = (uint16_t)((y << 6) | x) | (hitf[j] ? HD_ROOT_HIT : 0);
+                    D = wv[j];
                 } else {
                     kind = 2;
                     const int rp = tl_ring_pos(ly, lx);
-                    s.wexit[rp] = w;
-                    s.eslot[rp] = tl_exit_slot(tile, (uint32_t)ntx, ly, lx, d) | (dr ? HD_HIT : 0u);
+                    s.wexit[rp] = wv[j];
+                    s.eslot[rp] = tl_exit_slot(tile, (uint32_t)ntx, ly, lx, d) | (hitf[j] ? HD_HIT : 0u);
                 }
             }
         }
@@ -201,10 +225,26 @@ __global__ void hand_slots_round_kernel(const uint32_t* __restrict__ nxt_c, cons
     if (ch) *changed = 1u;
 }
 
+struct HandOut {  // hand[g] = the path sum, -9999 where no pit is reached
+    double* out;
+    __device__ __forceinline__ void operator()(long long g, double h) const { out[g] = h; }
+};
+template <typename U>
+struct FillOut {  // in place: a cell without a value takes the value of the cell the "sum" names (sources never change)
+    U* data;
+    __device__ __forceinline__ void operator()(long long g, double h) const {
+        if (h > 0.0) {
+            const long long src = (long long)h - 1;
+            if (src != g) data[g] = data[src];
+        }
+    }
+};
+
+template <class Out>
 __global__ void __launch_bounds__(1024) hand_tile_c_kernel(const uint8_t* __restrict__ dir, const uint16_t* __restrict__ hroot,
                                                            const double* __restrict__ hD, const uint32_t* __restrict__ s_nxt,
                                                            const double* __restrict__ s_val, long long nrow, long long ncol, long long ntx,
-                                                           double* __restrict__ out) {
+                                                           Out out) {
     __shared__ double ringval[TL_RING];
     __shared__ uint8_t ringok[TL_RING];
     const long long ty = blockIdx.y, tx = blockIdx.x;
@@ -234,7 +274,7 @@ __global__ void __launch_bounds__(1024) hand_tile_c_kernel(const uint8_t* __rest
                 if (ringok[rp]) h = (rec & HD_ROOT_HIT) ? D : __dadd_rn(D, ringval[rp]);
             }
         }
-        out[g] = h;
+        out(g, h);
     }
 }
 
@@ -312,13 +352,22 @@ __global__ void __launch_bounds__(256) hand_check_kernel(const uint8_t* __restri
     if ((threadIdx.x & 31) == 0 && bad) atomicAdd(n_bad, (unsigned long long)bad);
 }
 
-// Host side: returns the number of cells that violate the reference's statement (0 = the result is the reference's)
-template <typename T>
-static int hand_pathsum(pfd_handle* h, const uint8_t* drain_dev, const T* elev_dev, double* out_dev, unsigned long long* n_bad) {
+// Host side. Phases A - C for any source / output pair; the ring-node buffers stay on the handle.
+static int hd_next_slot = 0;
+template <class Src>
+static int hd_slot() {  // one flag per instantiation of phase A (its shared-memory opt-in is per device, hence kept per handle)
+    static const int slot = hd_next_slot++;
+    return slot;
+}
+
+template <class Src, class Out>
+static int hd_solve(pfd_handle* h, Src src, Out outf) {
+    const int attr_slot = hd_slot<Src>();
+    if (attr_slot >= (int)(sizeof(h->hand_attr_set) / sizeof(h->hand_attr_set[0]))) return pfd_fail(h, PFD_ERR_STATE, "path sums: out of attribute slots");
     const long long nrow = h->nrow, ncol = h->ncol, n = h->n;
     const long long ntx = (ncol + TL_W - 1) / TL_W, nty = (nrow + TL_H - 1) / TL_H;
     const long long nslots = (nty + 2) * ntx * TL_RING;
-    if (nslots >= (long long)HD_SINK) return pfd_fail(h, PFD_ERR_UNSUPPORTED, "pfd_hand: too many ring nodes");
+    if (nslots >= (long long)HD_SINK) return pfd_fail(h, PFD_ERR_UNSUPPORTED, "path sums: too many ring nodes");
     const uint8_t* dir = (const uint8_t*)h->dir.p + h->dir_off;
     PFD_TRY(pfd_reserve(h, h->hand_root, (size_t)n * sizeof(uint16_t)));
     PFD_TRY(pfd_reserve(h, h->hand_sum, (size_t)n * sizeof(double)));
@@ -328,13 +377,12 @@ static int hand_pathsum(pfd_handle* h, const uint8_t* drain_dev, const T* elev_d
     double* sval[2] = {(double*)h->hand_slots.p, (double*)h->hand_slots.p + nslots};
     uint32_t* snxt[2] = {(uint32_t*)(sval[1] + nslots), (uint32_t*)(sval[1] + nslots) + nslots};
     unsigned int* changed = (unsigned int*)(snxt[1] + nslots);
-    unsigned long long* bad = (unsigned long long*)(changed + 2);
-    if (!h->hand_attr_set[sizeof(T) == 8]) {
-        PFD_CUDA(h, cudaFuncSetAttribute(hand_tile_a_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HandTileShared)));
-        h->hand_attr_set[sizeof(T) == 8] = true;
+    if (!h->hand_attr_set[attr_slot]) {
+        PFD_CUDA(h, cudaFuncSetAttribute(hand_tile_a_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HandTileShared)));
+        h->hand_attr_set[attr_slot] = true;
     }
     const dim3 grid((unsigned)ntx, (unsigned)nty);
-    hand_tile_a_kernel<T><<<grid, 1024, sizeof(HandTileShared), h->stream>>>(dir, drain_dev, elev_dev, nrow, ncol, ntx, hroot, hD, snxt[0], sval[0]);
+    hand_tile_a_kernel<Src><<<grid, 1024, sizeof(HandTileShared), h->stream>>>(dir, src, nrow, ncol, ntx, hroot, hD, snxt[0], sval[0]);
     PFD_LAUNCH_CHECK(h);
     PFD_CUDA(h, cudaMemsetAsync(snxt[1], 0, (size_t)nslots * sizeof(uint32_t), h->stream));
     const long long lo = ntx * TL_RING, hi = (nty + 1) * ntx * TL_RING;
@@ -351,15 +399,42 @@ static int hand_pathsum(pfd_handle* h, const uint8_t* drain_dev, const T* elev_d
         if (!ch) break;
     }
     h->hand_fin = fin;
-    hand_tile_c_kernel<<<grid, 1024, 0, h->stream>>>(dir, hroot, hD, snxt[fin], sval[fin], nrow, ncol, ntx, out_dev);
+    hand_tile_c_kernel<Out><<<grid, 1024, 0, h->stream>>>(dir, hroot, hD, snxt[fin], sval[fin], nrow, ncol, ntx, outf);
     PFD_LAUNCH_CHECK(h);
+    return PFD_OK;
+}
+
+// HAND: the path sums, then the proof; *n_bad = number of cells that violate the reference's statement (0 = the result is the
+// reference's)
+template <typename T>
+static int hand_pathsum(pfd_handle* h, const uint8_t* drain_dev, const T* elev_dev, double* out_dev, unsigned long long* n_bad) {
+    PFD_TRY((hd_solve(h, HandSrc<T>{drain_dev, elev_dev}, HandOut{out_dev})));
+    const long long ntx = (h->ncol + TL_W - 1) / TL_W, nty = (h->nrow + TL_H - 1) / TL_H;
+    const long long nslots = (nty + 2) * ntx * TL_RING;
+    unsigned long long* bad = (unsigned long long*)((unsigned int*)((uint32_t*)((double*)h->hand_slots.p + 2 * nslots) + 2 * nslots) + 2);
     PFD_CUDA(h, cudaMemsetAsync(bad, 0, sizeof(unsigned long long), h->stream));
-    hand_check_kernel<T><<<grid_for(n, 256, 4, 148 * 32), 256, 0, h->stream>>>(dir, drain_dev, elev_dev, n, ncol, out_dev, bad);
+    hand_check_kernel<T><<<grid_for(h->n, 256, 4, 148 * 32), 256, 0, h->stream>>>((const uint8_t*)h->dir.p + h->dir_off, drain_dev, elev_dev, h->n,
+                                                                                  h->ncol, out_dev, bad);
     PFD_LAUNCH_CHECK(h);
     PFD_CUDA(h, cudaMemcpyAsync(n_bad, bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     PFD_CUDA(h, cudaStreamSynchronize(h->stream));
     return PFD_OK;
 }
+
+// core.fillnodata_upstream in place: `has(v)` says which cells hold a value of their own
+template <typename U, class Has>
+static int fill_up_paths(pfd_handle* h, U* data_dev, Has has) {
+    return hd_solve(h, FillSrc<U, Has>{data_dev, has}, FillOut<U>{data_dev});
+}
+template <typename U>
+struct HasNonZero {
+    __device__ __forceinline__ bool operator()(U v) const { return v != (U)0; }
+};
+template <typename T>
+struct HasData {
+    NoData nd;
+    __device__ __forceinline__ bool operator()(T v) const { return not_nodata(v, nd); }
+};
 
 // after a REJECTED path-sum attempt the hop-by-hop engine wrote `out`; the path structure of the attempt still says which cells
 // reach a pit
