@@ -389,7 +389,13 @@ int pfd_synth_d8_block(pfd_handle* h, int64_t row0, int64_t nrow, int64_t ncol, 
 
 /* ---- options / introspection ------------------------------------------------------------------------- */
 /* "tiles" = 1 (default): rank / basins() / upstream_area("cell") come from the tile-hierarchical solver
- * (pfd_tiles.cuh); 0: from the level-synchronous BFS + sweeps. Results are identical bit for bit. */
+ * (pfd_tiles.cuh); 0: from the level-synchronous BFS + sweeps. Results are identical bit for bit.
+ * "tile_sweeps" = 1 (default): accuflux / Strahler / HAND fallback by the tile-dataflow sweeps unless the BFS ordering is already
+ * cached; 2: always; 0: level replays over the BFS order. "hand_pathsum" = 1 (default): pfd_hand tries the re-associated path sums
+ * first (accepted only when every cell satisfies the reference's statement bit for bit, pfd_hand.cuh), and pfd_basins with custom
+ * outlets / pfd_fillnodata(direction up) use the same path summaries (no ordering needed); 0: the sweeps only.
+ * "fuse_parse", "sweep_max_passes", "release_scratch": see pfd_api.cu. pfd_get_info: "hand_engine" (1 path sums, 2 tile sweep,
+ * 3 level replay answered the last pfd_hand), "sweep_passes", "tile_rounds", "nnodes", "n_pits", "nlevels", ... */
 int pfd_set_option(pfd_handle* h, const char* name, int64_t value);
 /* "tiles", "tile_rounds", "nlevels", "nnodes", "n_pits", "n_valid", "num_sms"; -1 if unknown */
 int64_t pfd_get_info(const pfd_handle* h, const char* name);
