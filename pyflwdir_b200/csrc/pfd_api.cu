@@ -2620,13 +2620,22 @@ extern "C" int pfd_stream_distance(pfd_handle* h, const uint8_t* mask, int real_
     PFD_TRY(check_handle(h));
     stage_reset(h);
     if (!out || (real_length && !hop_table)) return pfd_fail(h, PFD_ERR_INVALID_ARG, "pfd_stream_distance: null array");
-    PFD_TRY(order_impl(h, false, false));
+    if (!h->parsed) return pfd_fail(h, PFD_ERR_STATE, "pfd_stream_distance: no raster parsed on this handle");
+    const bool paths = !real_length && h->hand_pathsum && !h->tiled;  // integer hop counts: path summaries, no ordering
+    if (!paths) PFD_TRY(order_impl(h, false, false));
     const int64_t n = h->n;
     const size_t bytes = (size_t)n * 4;
     void* out_dev = nullptr;
     PFD_TRY(pfd_stage_out(h, out, bytes, 3, &out_dev));
     const void *mask_dev = nullptr, *hop_dev = nullptr;
     if (mask) PFD_TRY(pfd_stage_in(h, mask, (size_t)n, 4, &mask_dev));
+    if (paths) {
+        PFD_TRY((hd_solve(h, HopSrc{(const uint8_t*)mask_dev}, HopOut{(int32_t*)out_dev})));
+        PFD_TRY(pfd_finish_out(h, out, out_dev, bytes));
+        PFD_CUDA(h, cudaStreamSynchronize(h->stream));
+        stage_collect(h);
+        return PFD_OK;
+    }
     if (real_length) PFD_TRY(pfd_stage_in(h, hop_table, (size_t)h->nrow * 6 * sizeof(float), 5, &hop_dev));
     int rc;
     if (real_length) {

@@ -65,6 +65,15 @@ struct FillSrc {
     __device__ __forceinline__ double w(long long, long long) const { return 0.0; }
 };
 
+// streams.stream_distance(real_length=False) (pyflwdir/streams.py:272-315): hops to the first masked cell downstream (or the pit),
+// int32 -- unit hop terms, exact
+struct HopSrc {
+    const uint8_t* mask;  // may be null: distance to the pit
+    __device__ __forceinline__ bool hit(long long g) const { return mask && mask[g]; }
+    __device__ __forceinline__ double hit_value(long long) const { return 0.0; }
+    __device__ __forceinline__ double w(long long, long long) const { return 1.0; }
+};
+
 template <class Src>
 __global__ void __launch_bounds__(1024, 2) hand_tile_a_kernel(const uint8_t* __restrict__ dir, Src src, long long nrow, long long ncol,
                                                               long long ntx, uint16_t* __restrict__ hroot, double* __restrict__ hD,
@@ -228,6 +237,10 @@ __global__ void hand_slots_round_kernel(const uint32_t* __restrict__ nxt_c, cons
 struct HandOut {  // hand[g] = the path sum, -9999 where no pit is reached
     double* out;
     __device__ __forceinline__ void operator()(long long g, double h) const { out[g] = h; }
+};
+struct HopOut {  // int32 hop counts, -9999 where no pit is reached
+    int32_t* out;
+    __device__ __forceinline__ void operator()(long long g, double h) const { out[g] = (int32_t)h; }
 };
 template <typename U>
 struct FillOut {  // in place: a cell without a value takes the value of the cell the "sum" names (sources never change)
