@@ -1,7 +1,7 @@
 """Host-side georeferencing helpers needed by the hot path's wrappers.
 
-Only what `FlwdirRaster.upstream_area(unit != "cell")` and `set_transform` touch: an `Affine` value type (the
-`affine` package is not a dependency here), `IDENTITY`, `AREA_FACTORS`, and the per-row cell-area grid.
+Only what `FlwdirRaster.upstream_area(unit != "cell")` and `set_transform` touch: an `Affine` value type (`affine.Affine` when that
+package is installed, else an equivalent 9-tuple defined here), `IDENTITY`, `AREA_FACTORS`, and the per-row cell-area grid.
 Mirrors /root/reference/pyflwdir/gis_utils.py:10-13 (constants), :340-358 (pixel-centre coordinates),
 :379-402 (reggrid_area / area_grid), :405-412 (cellarea). The area grid is an O(nrow) host computation that
 only produces the `data` vector of an accumulation; it stays on the host.
@@ -17,7 +17,7 @@ AREA_FACTORS = {"m2": 1.0, "ha": 1e4, "km2": 1e6, "cell": 1}  # gis_utils.py:11
 _AffineBase = namedtuple("Affine", "a b c d e f g h i")
 
 
-class Affine(_AffineBase):
+class _OwnAffine(_AffineBase):
     """2-D affine transform (x, y) = A * (col, row); a 9-tuple like `affine.Affine` (indexable, iterable)."""
 
     __slots__ = ()
@@ -47,8 +47,8 @@ class Affine(_AffineBase):
         return self.f
 
     def __mul__(self, other):
-        if isinstance(other, Affine):
-            return Affine(
+        if isinstance(other, _OwnAffine):
+            return _OwnAffine(
                 self.a * other.a + self.b * other.d,
                 self.a * other.b + self.b * other.e,
                 self.a * other.c + self.b * other.f + self.c,
@@ -64,8 +64,13 @@ class Affine(_AffineBase):
         if det == 0:
             raise ValueError("Affine transform is not invertible")
         ia, ib, id_, ie = self.e / det, -self.b / det, -self.d / det, self.a / det
-        return Affine(ia, ib, -self.c * ia - self.f * ib, id_, ie, -self.c * id_ - self.f * ie)
+        return _OwnAffine(ia, ib, -self.c * ia - self.f * ib, id_, ie, -self.c * id_ - self.f * ie)
 
+
+try:  # the reference's own dependency, when it is installed: transforms then are the very type callers already hold
+    from affine import Affine
+except ImportError:  # not a dependency here
+    Affine = _OwnAffine
 
 # N->S oriented identity, gis_utils.py:13
 IDENTITY = Affine(1.0, 0.0, 0.0, 0.0, -1.0, 0.0)
